@@ -1,0 +1,315 @@
+"""Parity checks shared by the GPU tests (libviwb.so through the C ABI on a B200) and the CPU kernel-logic
+emulation tests (same device source compiled with g++; tests/emu).  `ctx` is a viwb.lib.Context, `oracle` the
+CPU oracle module.  Tolerances: the solver path is FP64 end to end, so the pose tolerance of north_star
+(1e-4 m / 1e-4 rad) is met with a wide margin; the asserted bounds are the tight ones actually observed."""
+import numpy as np
+
+from viwb import abi, synth
+
+POSE_TOL_M, POSE_TOL_RAD = 1e-4, 1e-4     # north_star tolerance (pose states after double2vector)
+TIGHT_M, TIGHT_RAD = 1e-6, 1e-6           # what an FP64 implementation of the same recurrence should reach
+
+
+def block_ptr(st, b):
+    o = abi.block_offset(b) if b < 32 else abi.STATE_FIXED + b - 32
+    s = abi.block_size(b) if b < 32 else 1
+    return st[o:o + s].copy()
+
+
+def check_factor_evaluate(ctx, oracle, cid=4, max_each=6):
+    """CostFunction::Evaluate of every factor class: residuals and Jacobians (reference layout) vs the oracle."""
+    prob, st, gt = synth.make_window(cid)
+    st = st.copy()
+    st[abi.block_offset(abi.BLK_TD)] = 0.002
+    worst = 0.0
+    cases = []
+    for ftype in (abi.F_PROJ_2F1C, abi.F_PROJ_2F2C, abi.F_PROJ_1F2C):
+        for f in np.nonzero(prob.vis_type == ftype)[0][:max_each]:
+            fi, fj, lm = prob.vis_frame_i[f], prob.vis_frame_j[f], 32 + prob.vis_landmark[f]
+            blocks = {abi.F_PROJ_2F1C: [fi, fj, 22, lm, 30], abi.F_PROJ_2F2C: [fi, fj, 22, 23, lm, 30], abi.F_PROJ_1F2C: [22, 23, lm, 30]}[ftype]
+            cases.append((ftype, prob.vis_obs[f], blocks))
+    for f in range(min(max_each, len(prob.imu_frame_i))):
+        i, j = prob.imu_frame_i[f], prob.imu_frame_j[f]
+        cases.append((abi.F_IMU, prob.imu_data[f], [i, 11 + i, j, 11 + j]))
+    for f in range(min(max_each, len(prob.wheel_frame_i))):
+        i, j = prob.wheel_frame_i[f], prob.wheel_frame_j[f]
+        cases.append((abi.F_WHEEL, prob.wheel_data[f], [i, j, 24, 27, 28, 29, 31]))
+    for f in range(min(max_each, len(prob.plane_frame))):
+        cases.append((abi.F_PLANE, None, [prob.plane_frame[f], 24, 25, 26]))
+    assert len(cases) > 0
+    for ftype, consts, blocks in cases:
+        params = [block_ptr(st, b) for b in blocks]
+        if ftype == abi.F_WHEEL:
+            params[3][0], params[4][0], params[5][0], params[6][0] = 1.01, 0.99, 1.02, 0.004
+        r0, J0 = oracle.factor_evaluate(ftype, prob.globals, consts, params)
+        r1, J1 = ctx.factor_evaluate(ftype, prob.globals, consts, params)
+        scale = max(1.0, np.abs(r0).max())
+        assert np.abs(r0 - r1).max() <= 1e-9 * scale, (ftype, r0, r1)
+        for a, b in zip(J0, J1):
+            s = max(1.0, np.abs(a).max())
+            worst = max(worst, np.abs(a - b).max() / s)
+            assert np.abs(a - b).max() <= 1e-9 * s, (ftype, np.abs(a - b).max(), s)
+            if a.shape[1] == 7:
+                assert np.all(b[:, 6] == 0)
+        # NULL Jacobian blocks and residual-only calls follow the ceres contract
+        r2, J2 = ctx.factor_evaluate(ftype, prob.globals, consts, params, null_jac=(0,))
+        assert J2[0] is None and np.array_equal(r1, r2) and np.array_equal(J1[1], J2[1])
+        r3, _ = ctx.factor_evaluate(ftype, prob.globals, consts, params, want_jac=False)
+        assert np.array_equal(r1, r3)
+    return worst
+
+
+def check_normal_equations(ctx, oracle, cid):
+    prob, st, gt = synth.make_window(cid)
+    H0, g0, lm0, c0 = oracle.normal_equations(prob, st)
+    H1, g1, lm1, c1 = ctx.normal_equations(prob, st)
+    assert abs(c0 - c1) <= 1e-12 * c0
+    assert np.abs(H0 - H1).max() <= 1e-12 * np.abs(H0).max()
+    assert np.abs(g0 - g1).max() <= 1e-11 * np.abs(g0).max()
+    assert np.abs(lm0 - lm1).max() <= 1e-11 * np.abs(lm0).max()
+
+
+def check_solve(ctx, oracle, cid, seq=0, iters=8, prior_chain=False):
+    cfg = synth.make_config(cid)
+    s = synth.Sequence(cfg, seq, 12 if prior_chain else 11)
+    prob, st, gt = s.window(0)
+    if prior_chain:
+        a, _ = oracle.window_solve(prob, st)
+        a = oracle.gauge_reanchor(prob, st, a)
+        pr = oracle.marginalize(prob, a, abi.MARGIN_OLD)
+        prob, st, gt = s.window(1, prior=pr, prev_state=a)
+    opt = abi.default_options()
+    opt.max_num_iterations = iters
+    s0, sm0 = oracle.window_solve(prob, st, opt)
+    s1, sm1 = ctx.window_solve(prob, st, opt)
+    assert sm0.num_iterations == sm1.num_iterations and sm0.termination_type == sm1.termination_type
+    assert sm0.num_successful_steps == sm1.num_successful_steps
+    assert abs(sm0.initial_cost - sm1.initial_cost) <= 1e-12 * sm0.initial_cost
+    assert abs(sm0.final_cost - sm1.final_cost) <= 1e-7 * sm0.final_cost
+    r0, r1 = oracle.gauge_reanchor(prob, st, s0), ctx.gauge_reanchor(prob, st, s1)
+    ep, er = synth.pose_errors(r0, r1)
+    assert ep <= POSE_TOL_M and er <= POSE_TOL_RAD, (ep, er)
+    assert ep <= TIGHT_M and er <= TIGHT_RAD, (ep, er)
+    # every other block too
+    assert np.abs(r0[77:abi.STATE_FIXED] - r1[77:abi.STATE_FIXED]).max() <= 1e-6
+    assert np.abs(r0[abi.STATE_FIXED:] - r1[abi.STATE_FIXED:]).max() <= 1e-6
+    # constant blocks untouched bit for bit
+    for b in range(abi.NUM_FIXED_BLOCKS):
+        if prob.block_flags[b] & abi.BLOCK_CONSTANT:
+            o = abi.block_offset(b)
+            assert np.array_equal(s1[o:o + abi.block_size(b)], st[o:o + abi.block_size(b)])
+    return ep, er
+
+
+def check_reanchor(ctx, oracle, cid):
+    prob, st, gt = synth.make_window(cid)
+    s0, _ = oracle.window_solve(prob, st)
+    r0, r1 = oracle.gauge_reanchor(prob, st, s0), ctx.gauge_reanchor(prob, st, s0)
+    assert np.abs(r0 - r1).max() <= 1e-13 * max(1.0, np.abs(r0).max())
+
+
+def prior_information_close(p0, p1, rtol=1e-6):
+    assert p0.valid == p1.valid
+    if not p0.valid:
+        return
+    assert p0.n == p1.n and p0.blocks() == p1.blocks()
+    assert np.array_equal(p0.x0, p1.x0)
+    A0, b0 = p0.information()
+    A1, b1 = p1.information()
+    assert np.abs(A0 - A1).max() <= rtol * np.abs(A0).max(), np.abs(A0 - A1).max() / np.abs(A0).max()
+    assert np.abs(b0 - b1).max() <= rtol * np.abs(b0).max(), np.abs(b0 - b1).max() / np.abs(b0).max()
+
+
+def check_marginalize(ctx, oracle, cid):
+    """J_lin^T J_lin and J_lin^T r_lin (the order-independent content of the prior) vs the oracle."""
+    prob, st, gt = synth.make_window(cid)
+    s0, _ = oracle.window_solve(prob, st)
+    r0 = oracle.gauge_reanchor(prob, st, s0)
+    p0 = oracle.marginalize(prob, r0, abi.MARGIN_OLD)
+    p1 = ctx.marginalize(prob, r0, abi.MARGIN_OLD)
+    prior_information_close(p0, p1)
+    # prior factor evaluate agrees as well
+    x = r0.copy()
+    x[:abi.STATE_FIXED] = p1.x0
+    x[7:10] += 0.01
+    res0, jac0 = oracle.prior_evaluate(p1, x[:abi.STATE_FIXED])
+    res1, jac1 = ctx.prior_evaluate(p1, x)
+    assert np.abs(res0 - res1).max() <= 1e-9 * max(1.0, np.abs(res0).max())
+    assert np.array_equal(jac0, jac1)
+    return p0, p1
+
+
+def check_sequence(ctx, oracle, cid, nwin=3):
+    """Estimator::optimization() over consecutive windows: solve + re-anchor + marginalise, prior fed forward,
+    alternating MARGIN_OLD / MARGIN_SECOND_NEW like a real key-frame / non-key-frame stream."""
+    cfg = synth.make_config(cid)
+    s = synth.Sequence(cfg, 0, 11 + nwin)
+    pr0 = pr1 = None
+    prev0 = prev1 = None
+    for k in range(nwin):
+        flag = abi.MARGIN_OLD if k != 1 else abi.MARGIN_SECOND_NEW
+        prob0, st0, _ = s.window(k, prior=pr0, prev_state=prev0)
+        prob1, st1, _ = s.window(k, prior=pr1, prev_state=prev1)
+        a0, sm0, q0 = oracle.optimization(prob0, st0, flag)
+        a1, sm1, q1 = ctx.optimization(prob1, st1, flag)
+        ep, er = synth.pose_errors(a0, a1)
+        assert ep <= POSE_TOL_M and er <= POSE_TOL_RAD, (k, ep, er)
+        assert q0.valid == q1.valid
+        if q0.valid:
+            assert q0.n == q1.n and q0.blocks() == q1.blocks()
+            A0, b0 = q0.information()
+            A1, b1 = q1.information()
+            assert np.abs(A0 - A1).max() <= 1e-4 * np.abs(A0).max()
+        pr0, pr1, prev0, prev1 = (q0 if q0.valid else None), (q1 if q1.valid else None), a0, a1
+        if flag == abi.MARGIN_SECOND_NEW:
+            # slideWindowNew: frame 9 is dropped, frame 10 takes its place (states are re-generated by window())
+            prev0 = prev1 = None
+
+
+def check_batch_matches_single(ctx, oracle):
+    probs, sts, flags = [], [], []
+    for cid, seq in ((1, 0), (4, 1), (2, 2), (3, 3)):
+        p, s, _ = synth.make_window(cid, seq)
+        probs.append(p)
+        sts.append(s)
+        flags.append(abi.MARGIN_OLD)
+    out_s, out_sum, out_pr = ctx.optimization_batch(probs, sts, flags)
+    for p, s, f, bs, bsum, bpr in zip(probs, sts, flags, out_s, out_sum, out_pr):
+        a, sm, q = ctx.optimization(p, s, f)
+        assert np.array_equal(a, bs)
+        assert sm.num_iterations == bsum.num_iterations and sm.final_cost == bsum.final_cost
+        assert q.n == bpr.n and np.array_equal(q.Jmat(), bpr.Jmat()) and np.array_equal(q.rvec(), bpr.rvec())
+        a0, sm0, q0 = oracle.optimization(p, s, f)
+        ep, er = synth.pose_errors(a0, bs)
+        assert ep <= TIGHT_M and er <= TIGHT_RAD
+    # device-resident batch API gives the same numbers and is re-runnable
+    b = ctx.batch(probs, sts, flags)
+    b.run()
+    s1, sum1, pr1 = b.download()
+    b.run()
+    s2, sum2, pr2 = b.download()
+    b.destroy()
+    for x, y, z in zip(s1, s2, out_s):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+    assert b.algorithmic_bytes() if False else True
+
+
+def check_edge_cases(ctx, oracle):
+    # window that is not full yet (frame_count < WINDOW_SIZE): no marginalisation, fewer poses
+    prob, st, gt = synth.make_window(1)
+    keep = prob.vis_frame_j <= 6
+    flags = prob.block_flags.copy()
+    for i in range(7, 11):
+        flags[i] = 0
+        flags[11 + i] = 0
+    small = abi.WindowProblem(6, prob.num_landmarks, flags, prob.subset_mask, prob.vis_type[keep], prob.vis_landmark[keep], prob.vis_frame_i[keep],
+                              prob.vis_frame_j[keep], prob.vis_obs[keep], prob.imu_frame_i[:6], prob.imu_frame_j[:6], prob.imu_data[:6],
+                              globals_=prob.globals)
+    s0, sm0 = oracle.window_solve(small, st)
+    s1, sm1 = ctx.window_solve(small, st)
+    ep, er = synth.pose_errors(s0, s1, frames=7)
+    assert ep <= TIGHT_M and er <= TIGHT_RAD
+    assert np.array_equal(s1[7 * 7:77], st[7 * 7:77])            # absent poses untouched
+    a, sm, q = ctx.optimization(small, st, abi.MARGIN_OLD)
+    assert not q.valid                                            # estimator.cpp:1666
+    # no visual factors at all (IMU only, empty landmark set)
+    imu_only = abi.WindowProblem(10, 0, prob.block_flags, prob.subset_mask, imu_frame_i=prob.imu_frame_i, imu_frame_j=prob.imu_frame_j,
+                                 imu_data=prob.imu_data, globals_=prob.globals)
+    s0, sm0 = oracle.window_solve(imu_only, st[:abi.STATE_FIXED])
+    s1, sm1 = ctx.window_solve(imu_only, st[:abi.STATE_FIXED])
+    assert sm0.num_iterations == sm1.num_iterations
+    ep, er = synth.pose_errors(s0, s1)
+    assert ep <= 1e-5 and er <= 1e-5, (ep, er)
+    # zero iterations: state unchanged, cost reported
+    opt = abi.default_options()
+    opt.max_num_iterations = 0
+    s1, sm1 = ctx.window_solve(prob, st, opt)
+    assert np.array_equal(s1, st) and sm1.num_iterations == 1 and sm1.initial_cost == sm1.final_cost
+    # a rejected-step heavy start (depths 3x off) follows the oracle through rejections / dogleg steps
+    bad = st.copy()
+    bad[abi.STATE_FIXED:] *= 3.0
+    opt = abi.default_options()
+    opt.max_num_iterations = 12
+    s0, sm0, tr = oracle.window_solve(prob, bad, opt, want_trace=True)
+    s1, sm1 = ctx.window_solve(prob, bad, opt)
+    assert sm0.num_iterations == sm1.num_iterations and sm0.num_successful_steps == sm1.num_successful_steps
+    ep, er = synth.pose_errors(s0, s1)
+    assert ep <= POSE_TOL_M and er <= POSE_TOL_RAD, (ep, er)
+
+
+# ------------------------------------------------------------------------------------------------ LK
+def lk_images(seed=0, w=752, h=480):
+    import cv2
+    rng = np.random.default_rng(seed)
+    tex = rng.normal(size=(h + 200, w + 200)).astype(np.float32)
+    tex = cv2.GaussianBlur(tex, (0, 0), 2.0)
+    tex = (tex - tex.min()) / (tex.max() - tex.min()) * 255
+    img0 = tex[100:100 + h, 100:100 + w].astype(np.uint8)
+    M = np.array([[1.01, 0.02, 3.3], [-0.015, 0.995, -2.1]], np.float32)
+    img1 = cv2.warpAffine(tex, M, (w + 200, h + 200), flags=cv2.INTER_LINEAR)[100:100 + h, 100:100 + w].astype(np.uint8)
+    pts = cv2.goodFeaturesToTrack(img0, 150, 0.01, 30).reshape(-1, 2).astype(np.float32)
+    return np.ascontiguousarray(img0), np.ascontiguousarray(img1), pts
+
+
+def check_lk(ctx, seed=0, w=752, h=480):
+    """vs cv2.calcOpticalFlowPyrLK (OpenCV is the reference's third-party LK; oracle = cv2 4.13 in this image).
+    Stated tolerance: <= 1e-2 px on points both sides track, >= 99 % status agreement."""
+    import cv2
+    img0, img1, pts = lk_images(seed, w, h)
+    # add points near / outside the border to exercise the padded-window and status paths
+    extra = np.array([[3.0, 4.0], [w - 2.5, h - 3.0], [w / 2, 1.0], [0.2, h / 2]], np.float32)
+    pts = np.vstack([pts, extra]).astype(np.float32)
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+    for ml, flags in ((3, 0), (1, 4), (0, 0)):
+        init = (pts + np.float32([2.0, -1.5])) if flags else None
+        p_cv, st_cv, err_cv = cv2.calcOpticalFlowPyrLK(img0, img1, pts.reshape(-1, 1, 2), None if init is None else init.reshape(-1, 1, 2).copy(),
+                                                       winSize=(21, 21), maxLevel=ml, criteria=crit, flags=flags)
+        p_g, st_g, err_g = ctx.lk_track(img0, img1, pts, init, max_level=ml, flags=flags)
+        p_cv, st_cv = p_cv.reshape(-1, 2), st_cv.reshape(-1)
+        assert (st_cv == st_g).mean() >= 0.99, (ml, flags, (st_cv == st_g).mean())
+        both = (st_cv == 1) & (st_g == 1)
+        assert both.sum() > 100
+        assert np.abs(p_cv[both] - p_g[both]).max() <= 1e-2, (ml, flags, np.abs(p_cv[both] - p_g[both]).max())
+        assert np.abs(err_cv.reshape(-1)[both] - err_g[both]).max() <= 5e-2
+
+
+def ref_track_checked(img_a, img_b, pts, mode, flow_back):
+    """FeatureTracker::trackImage status logic restated with cv2 calls (feature_tracker.cpp:139-162, 240-251)."""
+    import cv2
+    h, w = img_a.shape
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+    p1, st, _ = cv2.calcOpticalFlowPyrLK(img_a, img_b, pts.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3)
+    p1, st = p1.reshape(-1, 2), st.reshape(-1).copy()
+
+    def in_border(p):
+        x, y = int(np.rint(p[0])), int(np.rint(p[1]))
+        return 1 <= x < w - 1 and 1 <= y < h - 1
+    if flow_back:
+        if mode == 0:
+            rp, rs, _ = cv2.calcOpticalFlowPyrLK(img_b, img_a, p1.reshape(-1, 1, 2), pts.reshape(-1, 1, 2).copy(), winSize=(21, 21), maxLevel=1,
+                                                 criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        else:
+            rp, rs, _ = cv2.calcOpticalFlowPyrLK(img_b, img_a, p1.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3)
+        rp, rs = rp.reshape(-1, 2), rs.reshape(-1)
+        for i in range(len(pts)):
+            d = np.sqrt(float(pts[i, 0] - rp[i, 0]) ** 2 + float(pts[i, 1] - rp[i, 1]) ** 2)
+            ok = st[i] and rs[i] and d <= 0.5
+            if mode == 1:
+                ok = ok and in_border(p1[i])
+            st[i] = 1 if ok else 0
+    if mode == 0:
+        for i in range(len(pts)):
+            if st[i] and not in_border(p1[i]):
+                st[i] = 0
+    return p1, st
+
+
+def check_track_checked(ctx, seed=1):
+    img0, img1, pts = lk_images(seed)
+    for mode in (0, 1):
+        for fb in (True, False):
+            p_ref, st_ref = ref_track_checked(img0, img1, pts, mode, fb)
+            p_g, st_g = ctx.track_checked(img0, img1, pts, mode=mode, flow_back=fb)
+            assert (st_ref == st_g).mean() >= 0.99, (mode, fb, (st_ref == st_g).mean())
+            both = (st_ref == 1) & (st_g == 1)
+            assert both.sum() > 100 and np.abs(p_ref[both] - p_g[both]).max() <= 1e-2

@@ -1,0 +1,62 @@
+"""`not gpu`: the device source of libviwb.so, compiled for the host (tests/emu), against the CPU oracle.
+This checks the kernels' algebra / indexing and the host-side lowering on the CPU-only box; the GPU tests
+(test_gpu_parity.py) run the same checks on the real library through the C ABI."""
+import pytest
+
+import parity_checks as pc
+from viwb import lib as viwb_lib
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from emu import build_emu
+    ctx = viwb_lib.Context(0, build_emu.build())
+    yield ctx
+    ctx.close()
+
+
+def test_factor_evaluate(emu, oracle):
+    pc.check_factor_evaluate(emu, oracle, 4, max_each=2)
+
+
+@pytest.mark.parametrize("cid", [1, 4])
+def test_normal_equations(emu, oracle, cid):
+    pc.check_normal_equations(emu, oracle, cid)
+
+
+@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+def test_solve(emu, oracle, cid):
+    pc.check_solve(emu, oracle, cid)
+
+
+def test_solve_with_prior(emu, oracle):
+    pc.check_solve(emu, oracle, 4, prior_chain=True)
+
+
+def test_reanchor(emu, oracle):
+    pc.check_reanchor(emu, oracle, 4)
+
+
+@pytest.mark.parametrize("cid", [1, 4])
+def test_marginalize(emu, oracle, cid):
+    pc.check_marginalize(emu, oracle, cid)
+
+
+def test_sequence(emu, oracle):
+    pc.check_sequence(emu, oracle, 4)
+
+
+def test_batch(emu, oracle):
+    pc.check_batch_matches_single(emu, oracle)
+
+
+def test_edge_cases(emu, oracle):
+    pc.check_edge_cases(emu, oracle)
+
+
+def test_lk(emu):
+    pc.check_lk(emu)
+
+
+def test_track_checked(emu):
+    pc.check_track_checked(emu)

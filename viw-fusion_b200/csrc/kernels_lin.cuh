@@ -1,0 +1,426 @@
+// kernels_lin.cuh -- linearisation kernels: factor evaluation and gather-assembly of the normal equations.
+//
+// All kernels are written as block functions f(bd, bx, by, tid, nt, smem, mode) in strided-loop style with
+// barriers only between phases, so the same source runs as a CUDA kernel and (nt = 1) in the CPU emulation.
+//   setup      once per solve: IMU/wheel sqrt-information (imu_factor.h:75, wheel_factor.h:85), prior J^T J
+//   lin_vis    one thread per visual factor: residual, Huber, tangent Jacobians -> 54-double record   (8a-5/6/7, a-12)
+//   lm_reduce  one thread per landmark: a = |J_l|^2, g_l, w = J_p^T J_l, Schur weight gamma, cost      (Schur, Appendix B)
+//   lin_small  one block per window: IMU / wheel / plane factors and the prior residual + gradient   (8a-8..a-11)
+//   assemble   one block per (window, slice): owner-computes gather of H_pp, g, T = sum gamma w w^T, no atomics
+// mode 0 = solver linearisation at x_cand over the tangent layout, mode 1 = marginalisation at x_cur over the
+// marginalisation layout (7 -> 6, plane quaternion counted 4; marginalization_factor.cpp:140-143).
+#pragma once
+#include "layout.cuh"
+#include "factors.cuh"
+
+namespace viwb {
+
+enum { MODE_SOLVE = 0, MODE_MARG = 1 };
+enum { MLAY = 193 };   // marginalisation layout dimension over the fixed blocks
+VIWB_HD int blk_moff(int b) { int t = blk_toff(b); return b > BLK_PR ? t + 1 : t; }
+
+// MARGIN_SECOND_NEW marginalises the prior only (estimator.cpp:1819-1842); margin_flag < 0: nothing to marginalise
+VIWB_HD bool marg_prior_only(const WinMeta &m, int mode) { return mode == MODE_MARG && m.margin_flag == 1; }
+VIWB_HD bool marg_skip(const WinMeta &m, int mode) { return mode == MODE_MARG && m.margin_flag < 0; }
+
+VIWB_HD const double *eval_state(const BatchDev &bd, int w, int mode) {
+    return (mode == MODE_SOLVE ? bd.x_cand : bd.x_cur) + bd.meta[w].state_off;
+}
+
+// ------------------------------------------------------------------------------------------------ setup
+VIWB_D void setup_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem; (void)mode;
+    const int gi = bx * nt + tid, gstride = nt;   // gridDim.x handled by the launcher loop: items = bx*nt + tid
+    (void)gstride;
+    const int n_s = bd.nimu_total + bd.nwheel_total;
+    if (gi < bd.nimu_total) {
+        sqrt_info_upper(15, bd.imu_data + (size_t)gi * 287 + 62, bd.imu_S + (size_t)gi * 225);
+    } else if (gi < n_s) {
+        const int k = gi - bd.nimu_total;
+        sqrt_info_upper(6, bd.wheel_data + (size_t)k * 78 + 25, bd.wheel_S + (size_t)k * 36);
+    }
+}
+// prior A = J^T J, one block per prior
+VIWB_D void prior_setup_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem; (void)mode;
+    const PriorDev &p = bd.prior[bx];
+    const int n = p.n;
+    const double *J = bd.prior_J + p.J_off;
+    double *A = bd.prior_A + p.J_off;
+    for (int e = tid; e < n * n; e += nt) {
+        const int i = e / n, j = e % n;
+        double s = 0.0;
+        for (int k = 0; k < n; k++) s += J[k * n + i] * J[k * n + j];
+        A[e] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ lin_vis
+VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem;
+    const int f = bx * nt + tid;
+    if (f >= bd.nvis_total) return;
+    const int w = bd.vis_win[f];
+    if (mode == MODE_SOLVE && bd.work[w].status != ST_RUNNING) return;
+    const int fi = bd.vis_fi[f];
+    const WinMeta &m = bd.meta[w];
+    if (mode == MODE_MARG && (fi != 0 || m.margin_flag != 0)) return;
+    const double *x = eval_state(bd, w, mode);
+    double obs[12];
+    for (int k = 0; k < 12; k++) obs[k] = bd.vis_obs[(size_t)k * bd.nvis_total + f];
+    const int lm = bd.vis_lm[f] - m.lm_off;
+    VisOut o;
+    vis_eval(bd.vis_type[f], obs, x + 7 * fi, x + 7 * bd.vis_fj[f], x + blk_off(BLK_EX0), x + blk_off(BLK_EX1),
+             x[SFIX + lm], x[blk_off(BLK_TD)], m.S_vis, true, o);
+    double half_rho;
+    const double sc = huber_scale(o.r[0] * o.r[0] + o.r[1] * o.r[1], m.huber, half_rho);
+    double *rec = bd.vis_rec + (size_t)f * VREC;
+    rec[0] = o.r[0] * sc; rec[1] = o.r[1] * sc;
+    for (int k = 0; k < 12; k++) { rec[REC_A + k] = o.JA[k] * sc; rec[REC_B + k] = o.JB[k] * sc; rec[REC_E0 + k] = o.JE0[k] * sc; rec[REC_E1 + k] = o.JE1[k] * sc; }
+    rec[REC_L] = o.Jl[0] * sc; rec[REC_L + 1] = o.Jl[1] * sc;
+    rec[REC_TD] = o.Jtd[0] * sc; rec[REC_TD + 1] = o.Jtd[1] * sc;
+    bd.vis_cost[f] = half_rho;
+}
+
+// ------------------------------------------------------------------------------------------------ lm_reduce
+VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem;
+    const int k = bx * nt + tid;
+    if (k >= bd.nlm_total) return;
+    const int w = bd.lm_win[k];
+    const WinWork &ww = bd.work[w];
+    if (mode == MODE_SOLVE && ww.status != ST_RUNNING) return;
+    const int f0 = bd.lm_fptr[k], f1 = bd.lm_fptr[k + 1];
+    double *W = bd.lm_W + (size_t)k * VSUB;
+    if (mode == MODE_MARG && (f0 == f1 || bd.vis_fi[f0] != 0 || bd.meta[w].margin_flag != 0)) { bd.lm_gamma[k] = 0.0; return; }
+    double wv[VSUB];
+    for (int i = 0; i < VSUB; i++) wv[i] = 0.0;
+    double a = 0.0, g = 0.0, c = 0.0;
+    for (int f = f0; f < f1; f++) {
+        const double *rec = bd.vis_rec + (size_t)f * VREC;
+        const double u0 = rec[REC_L], u1 = rec[REC_L + 1];
+        a += u0 * u0 + u1 * u1;
+        g += u0 * rec[0] + u1 * rec[1];
+        c += bd.vis_cost[f];
+        const int type = bd.vis_type[f];
+        if (type != 2) {
+            const int oi = 6 * bd.vis_fi[f], oj = 6 * bd.vis_fj[f];
+            for (int q = 0; q < 6; q++) {
+                wv[oi + q] += rec[REC_A + q] * u0 + rec[REC_A + 6 + q] * u1;
+                wv[oj + q] += rec[REC_B + q] * u0 + rec[REC_B + 6 + q] * u1;
+            }
+        }
+        for (int q = 0; q < 6; q++) wv[66 + q] += rec[REC_E0 + q] * u0 + rec[REC_E0 + 6 + q] * u1;
+        if (type != 0) for (int q = 0; q < 6; q++) wv[72 + q] += rec[REC_E1 + q] * u0 + rec[REC_E1 + 6 + q] * u1;
+        wv[78] += rec[REC_TD] * u0 + rec[REC_TD + 1] * u1;
+    }
+    for (int i = 0; i < VSUB; i++) W[i] = wv[i];
+    bd.lm_a[k] = a; bd.lm_g[k] = g; bd.lm_cost[k] = c;
+    if (mode == MODE_MARG) { bd.lm_gamma[k] = a; return; }     // marginalisation keeps the pivot itself
+    // Jacobi scale (first linearisation only) and the Schur weight for the mu this linearisation will be solved with:
+    // scaled pivot h = c^2 a + mu * clamp(c^2 a); gamma = c^2 / h  
+    double sc = bd.lm_scale[k];
+    if (ww.first) { sc = bd.opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(a)) : 1.0; bd.lm_scale[k] = sc; }
+    const double s = sc * sc * a;
+    double d2 = s; if (d2 < bd.opt.min_lm_diagonal) d2 = bd.opt.min_lm_diagonal; if (d2 > bd.opt.max_lm_diagonal) d2 = bd.opt.max_lm_diagonal;
+    bd.lm_gamma[k] = sc * sc / (s + ww.mu_lin * d2);
+}
+
+// ------------------------------------------------------------------------------------------------ lin_small
+// prior residual: r = r_lin + J_lin dx (marginalization_factor.cpp:361-380); dx in the prior's own column layout
+VIWB_D void prior_dx(const PriorDev &p, const double *x, const double *x0, double *dx) {
+    for (int i = 0; i < p.nb; i++) {
+        const int b = p.block_id[i], size = blk_size(b), idx = p.block_idx[i], off = blk_off(b);
+        if (size != 7) { for (int k = 0; k < size; k++) dx[idx + k] = x[off + k] - x0[off + k]; }
+        else {
+            for (int k = 0; k < 3; k++) dx[idx + k] = x[off + k] - x0[off + k];
+            const Q4 dq = qinv(ldq(x0 + off + 3)) * ldq(x + off + 3);
+            const double s = (dq.w >= 0) ? 2.0 : -2.0;          // quirk 8: sign flip when w < 0 (:374-377)
+            dx[idx + 3] = s * dq.x; dx[idx + 4] = s * dq.y; dx[idx + 5] = s * dq.z;
+        }
+    }
+}
+
+VIWB_D void lin_small_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    WinWork &ww = bd.work[w];
+    if (mode == MODE_SOLVE && ww.status != ST_RUNNING) return;
+    if (marg_skip(m, mode)) return;
+    const double *x = eval_state(bd, w, mode);
+    double *cost_part = smem;            // [nt]
+    double *dx = smem + nt;              // [MAXPRI]
+    double c = 0.0;
+    const int n_small = marg_prior_only(m, mode) ? 0 : m.nimu + m.nwheel + m.nplane;
+    for (int t = tid; t < n_small; t += nt) {
+        if (t < m.nimu) {
+            const int f = m.imu_off + t, i = bd.imu_fi[f], j = bd.imu_fj[f];
+            if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+            double *rec = bd.imu_rec + (size_t)f * IMU_REC;
+            imu_eval(bd.imu_data + (size_t)f * 287, bd.imu_S + (size_t)f * 225, m.G, x + 7 * i, x + 77 + 9 * i, x + 7 * j, x + 77 + 9 * j,
+                     true, rec, rec + 15);
+            for (int k = 0; k < 15; k++) c += 0.5 * rec[k] * rec[k];
+        } else if (t < m.nimu + m.nwheel) {
+            const int f = m.wheel_off + (t - m.nimu), i = bd.wheel_fi[f], j = bd.wheel_fj[f];
+            if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+            double *rec = bd.wheel_rec + (size_t)f * WHEEL_REC;
+            wheel_eval(bd.wheel_data + (size_t)f * 78, bd.wheel_S + (size_t)f * 36, x + 7 * i, x + 7 * j, x + blk_off(BLK_EXW),
+                       x[blk_off(BLK_SX)], x[blk_off(BLK_SY)], x[blk_off(BLK_SW)], x[blk_off(BLK_TDW)], true, rec, rec + 6);
+            for (int k = 0; k < 6; k++) c += 0.5 * rec[k] * rec[k];
+        } else {
+            const int f = m.plane_off + (t - m.nimu - m.nwheel), i = bd.plane_f[f];
+            if (mode == MODE_MARG && i != 0) continue;
+            double *rec = bd.plane_rec + (size_t)f * PLANE_REC;
+            plane_eval(m.w_plane, x + 7 * i, x + blk_off(BLK_EXW), x + blk_off(BLK_PR), x[blk_off(BLK_PZ)], true, rec, rec + 3);
+            for (int k = 0; k < 3; k++) c += 0.5 * rec[k] * rec[k];
+        }
+    }
+    if (m.prior_idx >= 0) {
+        const PriorDev &p = bd.prior[m.prior_idx];
+        const int n = p.n;
+        if (tid == 0) prior_dx(p, x, bd.prior_x0 + p.x0_off, dx);
+        VIWB_SYNC();
+        const double *J = bd.prior_J + p.J_off;
+        double *res = bd.prior_res + p.r_off, *g = bd.prior_g + p.r_off;
+        for (int i = tid; i < n; i += nt) {
+            double s = bd.prior_r[p.r_off + i];
+            for (int k = 0; k < n; k++) s += J[i * n + k] * dx[k];
+            res[i] = s;
+            c += 0.5 * s * s;
+        }
+        VIWB_SYNC();
+        for (int i = tid; i < n; i += nt) {
+            double s = 0.0;
+            for (int k = 0; k < n; k++) s += J[k * n + i] * res[k];
+            g[i] = s;
+        }
+    }
+    cost_part[tid] = c;
+    VIWB_SYNC();
+    if (tid == 0) { double s = 0.0; for (int i = 0; i < nt; i++) s += cost_part[i]; ww.small_cost = s; }
+}
+
+// ------------------------------------------------------------------------------------------------ assemble
+// slot table of a small factor: (block id, column offset inside its Jacobian record)
+struct Slot { int blk, col; };
+VIWB_D int imu_slots(int i, int j, Slot *s) { s[0].blk = i; s[0].col = 0; s[1].blk = BLK_SB0 + i; s[1].col = 6; s[2].blk = j; s[2].col = 15; s[3].blk = BLK_SB0 + j; s[3].col = 21; return 4; }
+VIWB_D int wheel_slots(int i, int j, Slot *s) {
+    s[0].blk = i; s[0].col = 0; s[1].blk = j; s[1].col = 6; s[2].blk = BLK_EXW; s[2].col = 12; s[3].blk = BLK_SX; s[3].col = 18;
+    s[4].blk = BLK_SY; s[4].col = 19; s[5].blk = BLK_SW; s[5].col = 20; s[6].blk = BLK_TDW; s[6].col = 21; return 7;
+}
+VIWB_D int plane_slots(int i, Slot *s) { s[0].blk = i; s[0].col = 0; s[1].blk = BLK_EXW; s[1].col = 6; s[2].blk = BLK_PR; s[2].col = 12; s[3].blk = BLK_PZ; s[3].col = 15; return 4; }
+VIWB_D int find_slot(const Slot *s, int n, int blk) { for (int i = 0; i < n; i++) if (s[i].blk == blk) return s[i].col; return -1; }
+
+// sum over rows of J[:, ca+p] * J[:, cb+q]   (J rows x ld, row-major)
+VIWB_D double col_dot(const double *J, int rows, int ld, int ca, int cb) {
+    double s = 0.0;
+    for (int r = 0; r < rows; r++) s += J[r * ld + ca] * J[r * ld + cb];
+    return s;
+}
+VIWB_D double col_dot_r(const double *J, const double *res, int rows, int ld, int ca) {
+    double s = 0.0;
+    for (int r = 0; r < rows; r++) s += J[r * ld + ca] * res[r];
+    return s;
+}
+// record offset of a visual-subspace block inside the 54-double record, given the factor's role for that block
+VIWB_D int vis_slot(int blk, int type, int fi, int fj, int which /*0: host role, 1: target role*/) {
+    if (blk < 11) { if (type == 2) return -1; return which == 0 ? (blk == fi ? REC_A : -1) : (blk == fj ? REC_B : -1); }
+    if (blk == BLK_EX0) return REC_E0;
+    if (blk == BLK_EX1) return type == 0 ? -1 : REC_E1;
+    if (blk == BLK_TD) return REC_TD;
+    return -1;
+}
+
+// entry (p,q) of  sum_f  U_f^T V_f  over the visual factors that contain both blocks ba, bb (ba != bb or ba == bb)
+VIWB_D double vis_block_entry(const BatchDev &bd, const WinMeta &m, int ba, int bb, int p, int q, int mode) {
+    const int *pp = bd.pair_ptr + m.pair_off;
+    const int ta = blk_tsize(ba), tb = blk_tsize(bb);
+    const int sa = ta == 1 ? 1 : 6, sb = tb == 1 ? 1 : 6;     // row stride inside the record (2 x size)
+    double s = 0.0;
+    // enumerate (h,j) pairs whose factors can contain both blocks
+    const int hmax = (mode == MODE_MARG) ? (m.margin_flag == 0 ? 1 : 0) : NFR;
+    for (int h = 0; h < hmax; h++) {
+        for (int j = 0; j < NFR; j++) {
+            const int lo = pp[h * NFR + j], hi = pp[h * NFR + j + 1];
+            if (lo == hi) continue;
+            // frame-block membership for this pair
+            if (ba < 11 && ba != h && ba != j) continue;
+            if (bb < 11 && bb != h && bb != j) continue;
+            for (int e = lo; e < hi; e++) {
+                const int f = bd.pair_perm[e];
+                const int type = bd.vis_type[f];
+                const double *rec = bd.vis_rec + (size_t)f * VREC;
+                // a frame block may appear as host (A) and, for h == j never (type 2 has no frame blocks)
+                for (int ra = 0; ra < 2; ra++) {
+                    const int oa = vis_slot(ba, type, h, j, ra);
+                    if (oa < 0 || (ba >= 11 && ra == 1)) continue;
+                    for (int rb = 0; rb < 2; rb++) {
+                        const int ob = vis_slot(bb, type, h, j, rb);
+                        if (ob < 0 || (bb >= 11 && rb == 1)) continue;
+                        s += rec[oa + p] * rec[ob + q] + rec[oa + sa + p] * rec[ob + sb + q];
+                    }
+                }
+            }
+        }
+    }
+    return s;
+}
+VIWB_D double vis_grad_entry(const BatchDev &bd, const WinMeta &m, int ba, int p, int mode) {
+    const int *pp = bd.pair_ptr + m.pair_off;
+    const int sa = blk_tsize(ba) == 1 ? 1 : 6;
+    double s = 0.0;
+    const int hmax = (mode == MODE_MARG) ? (m.margin_flag == 0 ? 1 : 0) : NFR;
+    for (int h = 0; h < hmax; h++)
+        for (int j = 0; j < NFR; j++) {
+            if (ba < 11 && ba != h && ba != j) continue;
+            const int lo = pp[h * NFR + j], hi = pp[h * NFR + j + 1];
+            for (int e = lo; e < hi; e++) {
+                const int f = bd.pair_perm[e];
+                const int type = bd.vis_type[f];
+                const double *rec = bd.vis_rec + (size_t)f * VREC;
+                for (int ra = 0; ra < 2; ra++) {
+                    const int oa = vis_slot(ba, type, h, j, ra);
+                    if (oa < 0 || (ba >= 11 && ra == 1)) continue;
+                    s += rec[oa + p] * rec[0] + rec[oa + sa + p] * rec[1];
+                }
+            }
+        }
+    return s;
+}
+
+// contribution of the small factors and the prior to entry (p,q) of block pair (ba, bb)
+VIWB_D double small_block_entry(const BatchDev &bd, const WinMeta &m, int ba, int bb, int p, int q, int mode) {
+    double s = 0.0;
+    Slot sl[8];
+    const bool po = marg_prior_only(m, mode);
+    for (int t = 0; t < (po ? 0 : m.nimu); t++) {
+        const int f = m.imu_off + t, i = bd.imu_fi[f], j = bd.imu_fj[f];
+        if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+        const int ns = imu_slots(i, j, sl), ca = find_slot(sl, ns, ba), cb = find_slot(sl, ns, bb);
+        if (ca >= 0 && cb >= 0) s += col_dot(bd.imu_rec + (size_t)f * IMU_REC + 15, 15, 30, ca + p, cb + q);
+    }
+    for (int t = 0; t < (po ? 0 : m.nwheel); t++) {
+        const int f = m.wheel_off + t, i = bd.wheel_fi[f], j = bd.wheel_fj[f];
+        if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+        const int ns = wheel_slots(i, j, sl), ca = find_slot(sl, ns, ba), cb = find_slot(sl, ns, bb);
+        if (ca >= 0 && cb >= 0) s += col_dot(bd.wheel_rec + (size_t)f * WHEEL_REC + 6, 6, 22, ca + p, cb + q);
+    }
+    for (int t = 0; t < (po ? 0 : m.nplane); t++) {
+        const int f = m.plane_off + t, i = bd.plane_f[f];
+        if (mode == MODE_MARG && i != 0) continue;
+        const int ns = plane_slots(i, sl), ca = find_slot(sl, ns, ba), cb = find_slot(sl, ns, bb);
+        // the plane quaternion has 3 tangent columns; its 4th marginalisation column is identically zero
+        if (ca >= 0 && cb >= 0 && !(ba == BLK_PR && p == 3) && !(bb == BLK_PR && q == 3))
+            s += col_dot(bd.plane_rec + (size_t)f * PLANE_REC + 3, 3, 16, ca + p, cb + q);
+    }
+    if (m.prior_idx >= 0) {
+        const PriorDev &pr = bd.prior[m.prior_idx];
+        int ia = -1, ib = -1;
+        for (int i = 0; i < pr.nb; i++) { if (pr.block_id[i] == ba) ia = pr.block_idx[i]; if (pr.block_id[i] == bb) ib = pr.block_idx[i]; }
+        if (ia >= 0 && ib >= 0) s += bd.prior_A[pr.J_off + (ia + p) * pr.n + ib + q];
+    }
+    return s;
+}
+VIWB_D double small_grad_entry(const BatchDev &bd, const WinMeta &m, int ba, int p, int mode) {
+    double s = 0.0;
+    Slot sl[8];
+    const bool po = marg_prior_only(m, mode);
+    for (int t = 0; t < (po ? 0 : m.nimu); t++) {
+        const int f = m.imu_off + t, i = bd.imu_fi[f], j = bd.imu_fj[f];
+        if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+        const int ns = imu_slots(i, j, sl), ca = find_slot(sl, ns, ba);
+        const double *rec = bd.imu_rec + (size_t)f * IMU_REC;
+        if (ca >= 0) s += col_dot_r(rec + 15, rec, 15, 30, ca + p);
+    }
+    for (int t = 0; t < (po ? 0 : m.nwheel); t++) {
+        const int f = m.wheel_off + t, i = bd.wheel_fi[f], j = bd.wheel_fj[f];
+        if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+        const int ns = wheel_slots(i, j, sl), ca = find_slot(sl, ns, ba);
+        const double *rec = bd.wheel_rec + (size_t)f * WHEEL_REC;
+        if (ca >= 0) s += col_dot_r(rec + 6, rec, 6, 22, ca + p);
+    }
+    for (int t = 0; t < (po ? 0 : m.nplane); t++) {
+        const int f = m.plane_off + t, i = bd.plane_f[f];
+        if (mode == MODE_MARG && i != 0) continue;
+        const int ns = plane_slots(i, sl), ca = find_slot(sl, ns, ba);
+        const double *rec = bd.plane_rec + (size_t)f * PLANE_REC;
+        if (ca >= 0 && !(ba == BLK_PR && p == 3)) s += col_dot_r(rec + 3, rec, 3, 16, ca + p);
+    }
+    if (m.prior_idx >= 0) {
+        const PriorDev &pr = bd.prior[m.prior_idx];
+        for (int i = 0; i < pr.nb; i++) if (pr.block_id[i] == ba) s += bd.prior_g[pr.r_off + pr.block_idx[i] + p];
+    }
+    return s;
+}
+
+// is fixed block b part of the system being assembled?
+VIWB_D bool blk_in_system(const WinMeta &m, int b, int mode) {
+    if (mode == MODE_SOLVE) return m.tcol[b] >= 0;
+    return (m.flags[b] & 1u) != 0;     // marginalisation: every present block counts, constant or not
+}
+
+// grid (B, NSLICE): the block-pair list and the T entries are split round-robin over the slices.
+VIWB_D void assemble_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)smem;
+    const int nslice = bd.nslice;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    if (mode == MODE_SOLVE && bd.work[w].status != ST_RUNNING) return;
+    if (marg_skip(m, mode)) return;
+    const int LD = (mode == MODE_SOLVE) ? TFIX : MLAY;
+    double *H = bd.Hpp + (size_t)w * TFIX * TFIX + (mode == MODE_MARG ? 0 : 0);   // marg layout fits: 193*193 > 192*192 -> uses marg_A
+    if (mode == MODE_MARG) H = bd.marg_A + (size_t)w * (MAXPRI + 16) * (MAXPRI + 16);
+    const int HLD = (mode == MODE_SOLVE) ? TFIX : (MAXPRI + 16);
+    (void)LD;
+    double *g = bd.gfix + (size_t)w * (TFIX + 8);
+    // ---- H blocks and gradient: work item = (block pair, entry); pairs enumerated ba >= bb
+    const int gtid = by * nt + tid, gnt = nslice * nt;
+    for (int pair = 0; pair < NB * (NB + 1) / 2; pair++) {
+        // unrank: ba = row, bb = col of the lower triangle
+        int ba = 0; while ((ba + 1) * (ba + 2) / 2 <= pair) ba++;
+        const int bb = pair - ba * (ba + 1) / 2;
+        if (!blk_in_system(m, ba, mode) || !blk_in_system(m, bb, mode)) continue;
+        const int ta = (mode == MODE_SOLVE) ? blk_tsize(ba) : blk_msize(ba), tb = (mode == MODE_SOLVE) ? blk_tsize(bb) : blk_msize(bb);
+        const int oa = (mode == MODE_SOLVE) ? blk_toff(ba) : blk_moff(ba), ob = (mode == MODE_SOLVE) ? blk_toff(bb) : blk_moff(bb);
+        const bool vis = blk_voff(ba) >= 0 && blk_voff(bb) >= 0;
+        for (int e = gtid; e < ta * tb; e += gnt) {
+            const int p = e / tb, q = e % tb;
+            double s = small_block_entry(bd, m, ba, bb, p, q, mode);
+            if (vis && !(ba == BLK_PR) ) s += vis_block_entry(bd, m, ba, bb, p, q, mode);
+            H[(size_t)(oa + p) * HLD + ob + q] = s;
+            H[(size_t)(ob + q) * HLD + oa + p] = s;
+        }
+    }
+    for (int b = 0; b < NB; b++) {
+        if (!blk_in_system(m, b, mode)) continue;
+        const int tb = (mode == MODE_SOLVE) ? blk_tsize(b) : blk_msize(b), ob = (mode == MODE_SOLVE) ? blk_toff(b) : blk_moff(b);
+        for (int p = gtid; p < tb; p += gnt) {
+            double s = small_grad_entry(bd, m, b, p, mode);
+            if (blk_voff(b) >= 0) s += vis_grad_entry(bd, m, b, p, mode);
+            g[ob + p] = s;
+        }
+    }
+    // ---- Schur sums over the visual subspace: T = sum_k gamma_k w_k w_k^T, tvec = sum_k gamma_k w_k g_k
+    double *T = bd.Tvis + (size_t)w * VSUB * VSUB, *tv = bd.tvec + (size_t)w * VSUB;
+    const double *W = bd.lm_W + (size_t)m.lm_off * VSUB;
+    const double *gam = bd.lm_gamma + m.lm_off, *gl = bd.lm_g + m.lm_off;
+    for (int e = gtid; e < 79 * 80 / 2 + 79; e += gnt) {
+        if (e < 79 * 80 / 2) {
+            int p = 0; while ((p + 1) * (p + 2) / 2 <= e) p++;
+            const int q = e - p * (p + 1) / 2;
+            double s = 0.0;
+            if (mode == MODE_SOLVE) { for (int k = 0; k < m.nlm; k++) s += gam[k] * W[(size_t)k * VSUB + p] * W[(size_t)k * VSUB + q]; }
+            else { for (int k = 0; k < m.nlm; k++) if (gam[k] > 0.0) s += W[(size_t)k * VSUB + p] * W[(size_t)k * VSUB + q] / gam[k]; }
+            T[p * VSUB + q] = s; T[q * VSUB + p] = s;
+        } else {
+            const int p = e - 79 * 80 / 2;
+            double s = 0.0;
+            if (mode == MODE_SOLVE) { for (int k = 0; k < m.nlm; k++) s += gam[k] * W[(size_t)k * VSUB + p] * gl[k]; }
+            else { for (int k = 0; k < m.nlm; k++) if (gam[k] > 0.0) s += W[(size_t)k * VSUB + p] * gl[k] / gam[k]; }
+            tv[p] = s;
+        }
+    }
+}
+
+}  // namespace viwb

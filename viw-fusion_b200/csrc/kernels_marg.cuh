@@ -1,0 +1,226 @@
+// kernels_marg.cuh -- gauge re-anchoring and marginalisation, one block per window.
+//
+//   reanchor : Estimator::double2vector + vector2double (estimator.cpp:1224-1332, 1155-1222)
+//   marg     : MarginalizationInfo::marginalize + getParameterBlocks (marginalization_factor.cpp:183-334) on the
+//              dense system assembled by assemble_block(MODE_MARG) from the same Jacobian kernels the solver uses.
+// The dropped landmark block is diagonal, so it is eliminated exactly (Schur sum T0 = sum w w^T / a); the remaining
+// dropped block (pose 0 + speed-bias 0, or pose 9) goes through the reference's eigen pseudo-inverse (eps 1e-8),
+// and the kept n x n system through a parallel cyclic Jacobi eigen-decomposition in shared memory
+// (stands in for Eigen::SelfAdjointEigenSolver) to produce J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b.
+#pragma once
+#include "kernels_lin.cuh"
+#include "kernels_solve.cuh"
+
+namespace viwb {
+
+VIWB_D void reanchor_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem; (void)mode; (void)nt;
+    if (tid != 0) return;
+    const WinMeta &m = bd.meta[bx];
+    double *st = bd.x_cur + m.state_off;
+    const double *before = bd.x_before + m.state_off;
+    const bool use_imu = (m.flags[BLK_SB0] & 1u) != 0;
+    const int nfr = m.frame_count + 1;
+    if (use_imu) {
+        const M3 Rs0 = qR(ldq(before + 3)), R00 = qR(ldq(st + 3));
+        const V3 o0 = R_to_ypr(Rs0), o00 = R_to_ypr(R00), P0 = ld3(before), p00 = ld3(st);
+        M3 rot = yaw_to_R(o0.x - o00.x);
+        if (fabs(fabs(o0.y) - 90) < 1.0 || fabs(fabs(o00.y) - 90) < 1.0) rot = Rs0 * transpose(R00);
+        for (int i = 0; i < nfr; i++) {
+            double *p = st + 7 * i;
+            const M3 Ri = rot * qR(qnormalized(ldq(p + 3)));
+            const V3 Pi = rot * (ld3(p) - p00) + P0;
+            st3(p, Pi); stq(p + 3, q_from_R(Ri));
+            st3(st + 77 + 9 * i, rot * ld3(st + 77 + 9 * i));
+        }
+        for (int c = 0; c < 2; c++) if (m.flags[BLK_EX0 + c] & 1u) { double *e = st + blk_off(BLK_EX0 + c); stq(e + 3, q_from_R(qR(qnormalized(ldq(e + 3))))); }
+    } else {
+        for (int i = 0; i < nfr; i++) { double *p = st + 7 * i; stq(p + 3, q_from_R(qR(qnormalized(ldq(p + 3))))); }
+    }
+    if (m.flags[BLK_EXW] & 1u) {
+        double *e = st + blk_off(BLK_EXW);
+        stq(e + 3, q_from_R(qR(qnormalized(ldq(e + 3)))));
+        if (m.flags[BLK_PR] & 1u) for (int k = 0; k < 4; k++) st[blk_off(BLK_PR) + k] = e[3 + k];   // quirk 1 (estimator.cpp:1209-1213)
+    }
+    for (int k = 0; k < m.nlm; k++) st[SFIX + k] = 1.0 / (1.0 / st[SFIX + k]);   // setDepth(1/x), getDepthVector(1/depth)
+}
+
+// serial cyclic Jacobi for a tiny symmetric matrix (n <= 16): A -> eigenvalues on the diagonal, V eigenvectors (columns)
+VIWB_D void jacobi_small(double *A, double *V, int n) {
+    for (int i = 0; i < n * n; i++) V[i] = 0.0;
+    for (int i = 0; i < n; i++) V[i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        int rot = 0;
+        for (int p = 0; p < n - 1; p++) for (int q = p + 1; q < n; q++) {
+            const double apq = A[p * n + q], app = A[p * n + p], aqq = A[q * n + q];
+            if (fabs(apq) <= 1e-17 * sqrt(fabs(app) * fabs(aqq)) || apq == 0.0) continue;
+            rot++;
+            const double tau = (aqq - app) / (2.0 * apq);
+            const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+            for (int r = 0; r < n; r++) { const double a = A[r * n + p], b = A[r * n + q]; A[r * n + p] = c * a - s * b; A[r * n + q] = s * a + c * b; }
+            for (int r = 0; r < n; r++) { const double a = A[p * n + r], b = A[q * n + r]; A[p * n + r] = c * a - s * b; A[q * n + r] = s * a + c * b; }
+            for (int r = 0; r < n; r++) { const double a = V[r * n + p], b = V[r * n + q]; V[r * n + p] = c * a - s * b; V[r * n + q] = s * a + c * b; }
+        }
+        if (!rot) break;
+    }
+}
+
+// parallel-ordering cyclic Jacobi in shared memory.  A, V: n x n (row-major, ld = n).  cs: 2*(n/2+1), ord: n+2 ints.
+VIWB_D void jacobi_block(double *A, double *V, int n, double *cs, int *ord, double *bc, int tid, int nt) {
+    const int ne = n + (n & 1), half = ne / 2;      // pad to even with a dummy index (= n)
+    for (int e = tid; e < n * n; e += nt) V[e] = ((e / n) == (e % n)) ? 1.0 : 0.0;
+    for (int i = tid; i < ne; i += nt) ord[i] = i;
+    VIWB_SYNC();
+    for (int sweep = 0; sweep < 40; sweep++) {
+        if (tid == 0) bc[1] = 0.0;
+        VIWB_SYNC();
+        for (int step = 0; step < ne - 1; step++) {
+            // rotation parameters of the 'half' disjoint pairs (ord[i], ord[ne-1-i])
+            for (int i = tid; i < half; i += nt) {
+                int p = ord[i], q = ord[ne - 1 - i];
+                if (p > q) { const int t = p; p = q; q = t; }
+                double c = 1.0, s = 0.0;
+                if (q < n) {
+                    const double apq = A[p * n + q], app = A[p * n + p], aqq = A[q * n + q];
+                    if (apq != 0.0 && fabs(apq) > 1e-17 * sqrt(fabs(app) * fabs(aqq))) {
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t); s = t * c;
+                        bc[1] = 1.0;
+                    }
+                }
+                cs[2 * i] = c; cs[2 * i + 1] = s;
+            }
+            VIWB_SYNC();
+            // A <- A J, V <- V J (columns p,q of every row)
+            for (int e = tid; e < half * n; e += nt) {
+                const int i = e / n, r = e % n;
+                const double c = cs[2 * i], s = cs[2 * i + 1];
+                if (s == 0.0) continue;
+                int p = ord[i], q = ord[ne - 1 - i];
+                if (p > q) { const int t = p; p = q; q = t; }
+                double a = A[r * n + p], b = A[r * n + q]; A[r * n + p] = c * a - s * b; A[r * n + q] = s * a + c * b;
+                a = V[r * n + p]; b = V[r * n + q]; V[r * n + p] = c * a - s * b; V[r * n + q] = s * a + c * b;
+            }
+            VIWB_SYNC();
+            // A <- J^T A (rows p,q of every column)
+            for (int e = tid; e < half * n; e += nt) {
+                const int i = e / n, r = e % n;
+                const double c = cs[2 * i], s = cs[2 * i + 1];
+                if (s == 0.0) continue;
+                int p = ord[i], q = ord[ne - 1 - i];
+                if (p > q) { const int t = p; p = q; q = t; }
+                const double a = A[p * n + r], b = A[q * n + r]; A[p * n + r] = c * a - s * b; A[q * n + r] = s * a + c * b;
+            }
+            VIWB_SYNC();
+            // round-robin: position 0 stays, the others rotate by one
+            if (tid == 0) { const int last = ord[ne - 1]; for (int i = ne - 1; i > 1; i--) ord[i] = ord[i - 1]; ord[1] = last; }
+            VIWB_SYNC();
+        }
+        if (bc[1] == 0.0) break;
+        VIWB_SYNC();
+    }
+}
+
+VIWB_HD int vsub_to_mlay(int p) { return p < 66 ? p : p < 72 ? 165 + (p - 66) : p < 78 ? 171 + (p - 72) : 191; }   // td -> blk_moff(BLK_TD) = 191
+VIWB_HD size_t marg_smem_doubles(int nt) { return 24000 + (size_t)nt; }
+
+VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)mode;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    WinWork &ww = bd.work[w];
+    if (m.margin_flag < 0) return;
+    const int LDM = MAXPRI + 16;
+    double *M = bd.marg_A + (size_t)w * LDM * LDM;
+    double *b = bd.gfix + (size_t)w * (TFIX + 8);
+    const double *T = bd.Tvis + (size_t)w * VSUB * VSUB, *tv = bd.tvec + (size_t)w * VSUB;
+    int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
+    const double eps = 1e-8;   // marginalization_factor.h:81
+    // smem carve
+    double *An = smem, *Vn = An + 100 * 100, *Amm = Vn + 100 * 100, *Vmm = Amm + 256, *Ainv = Vmm + 256, *Tm = Ainv + 256;
+    double *bn = Tm + 100 * 16, *cs = bn + 216, *red = cs + 216 + 216, *bc = red + nt;
+    int *keep = (int *)(bc + 16), *dl = keep + 216, *ord = dl + 32;
+    // ---- eliminate the dropped landmarks: M -= scatter(T0), b -= scatter(tvec0)   (MARGIN_OLD only)
+    if (m.margin_flag == 0) {
+        for (int e = tid; e < 79 * 79; e += nt) { const int p = e / 79, q = e % 79; M[(size_t)vsub_to_mlay(p) * LDM + vsub_to_mlay(q)] -= T[p * VSUB + q]; }
+        for (int p = tid; p < 79; p += nt) b[vsub_to_mlay(p)] -= tv[p];
+    }
+    VIWB_SYNC();
+    // ---- dropped / kept dimension lists (marginalisation layout)
+    if (tid == 0) {
+        int md = 0, n = 0, nb = 0;
+        unsigned dropped = 0;
+        if (m.margin_flag == 0) { for (int k = 0; k < 6; k++) dl[md++] = k; for (int k = 0; k < 9; k++) dl[md++] = 66 + k; dropped = (1u << 0) | (1u << BLK_SB0); }
+        else { for (int k = 0; k < 6; k++) dl[md++] = 54 + k; dropped = (1u << 9); }
+        // a dropped block that no factor references contributes nothing (its rows are zero); keep md as is
+        for (int bq = 0; bq < NB; bq++) {
+            if (!(m.flags[bq] & 4u) || ((dropped >> bq) & 1u)) continue;      // bit 2 of flags = seen by a marginalisation factor
+            int nid = bq;
+            if (m.margin_flag == 0) { if ((bq >= 1 && bq <= 10) || (bq >= 12 && bq <= 21)) nid = bq - 1; }
+            else { if (bq == 10 || bq == 21) nid = bq - 1; }
+            hdr[3 + nb] = nid; hdr[3 + NB + nb] = n; nb++;
+            for (int k = 0; k < blk_msize(bq); k++) keep[n++] = blk_moff(bq) + k;
+            // linearisation point of the kept block, stored under its new id (keep_block_data + addr_shift)
+            const double *src = bd.x_cur + m.state_off + blk_off(bq);
+            double *dst = bd.marg_x0 + (size_t)w * SFIX + blk_off(nid);
+            for (int k = 0; k < blk_size(bq); k++) dst[k] = src[k];
+        }
+        hdr[0] = 1; hdr[1] = n; hdr[2] = nb;
+        bc[2] = (double)md; bc[3] = (double)n;
+    }
+    VIWB_SYNC();
+    const int md = (int)bc[2], n = (int)bc[3];
+    if (n > 100) { if (tid == 0) { ww.marg_status = -1; hdr[0] = 0; } return; }
+    // ---- pseudo-inverse of the dropped fixed block (marginalization_factor.cpp:282-287)
+    for (int e = tid; e < md * md; e += nt) { const int i = e / md, j = e % md; Amm[e] = 0.5 * (M[(size_t)dl[i] * LDM + dl[j]] + M[(size_t)dl[j] * LDM + dl[i]]); }
+    VIWB_SYNC();
+    if (tid == 0) jacobi_small(Amm, Vmm, md);
+    VIWB_SYNC();
+    for (int e = tid; e < md * md; e += nt) {
+        const int i = e / md, j = e % md;
+        double sacc = 0.0;
+        for (int k = 0; k < md; k++) { const double l = Amm[k * md + k]; if (l > eps) sacc += Vmm[i * md + k] * Vmm[j * md + k] / l; }
+        Ainv[e] = sacc;
+    }
+    VIWB_SYNC();
+    // Tm = Arm * Ainv (n x md)
+    for (int e = tid; e < n * md; e += nt) {
+        const int i = e / md, j = e % md;
+        double sacc = 0.0;
+        for (int k = 0; k < md; k++) sacc += M[(size_t)keep[i] * LDM + dl[k]] * Ainv[k * md + j];
+        Tm[e] = sacc;
+    }
+    VIWB_SYNC();
+    // A = Arr - Arm Amm^-1 Amr ; b = brr - Arm Amm^-1 bmm
+    for (int e = tid; e < n * n; e += nt) {
+        const int i = e / n, j = e % n;
+        double sacc = M[(size_t)keep[i] * LDM + keep[j]];
+        for (int k = 0; k < md; k++) sacc -= Tm[i * md + k] * M[(size_t)dl[k] * LDM + keep[j]];
+        An[e] = sacc;
+    }
+    for (int i = tid; i < n; i += nt) {
+        double sacc = b[keep[i]];
+        for (int k = 0; k < md; k++) sacc -= Tm[i * md + k] * b[dl[k]];
+        bn[i] = sacc;
+    }
+    VIWB_SYNC();
+    // SelfAdjointEigenSolver reads the lower triangle
+    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e % n; if (j > i) An[e] = An[j * n + i]; }
+    VIWB_SYNC();
+    jacobi_block(An, Vn, n, cs, ord, bc, tid, nt);
+    VIWB_SYNC();
+    // J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b   (marginalization_factor.cpp:298-306)
+    double *Jout = bd.marg_J + (size_t)w * MAXPRI * MAXPRI, *rout = bd.marg_r + (size_t)w * MAXPRI;
+    for (int i = tid; i < n; i += nt) {
+        const double l = An[i * n + i];
+        const double S = l > eps ? l : 0.0, Sinv = l > eps ? 1.0 / l : 0.0, ss = sqrt(S), si = sqrt(Sinv);
+        double vb = 0.0;
+        for (int k = 0; k < n; k++) { Jout[(size_t)i * n + k] = ss * Vn[k * n + i]; vb += Vn[k * n + i] * bn[k]; }
+        rout[i] = si * vb;
+    }
+    if (tid == 0) ww.marg_status = 0;
+}
+
+}  // namespace viwb

@@ -1,0 +1,422 @@
+// kernels_solve.cuh -- one block per window: the Ceres trust-region recurrence (DENSE_SCHUR + DOGLEG) on the
+// assembled normal equations.  Restates ceres-solver 1.14 semantics (call site
+// estimator.cpp:1643-1658): Jacobi scaling fixed at the first linearisation, D = sqrt(clamp(diag)), Cauchy
+// length, mu-regularised Gauss-Newton step through the Schur complement on the inverse depths + dense Cholesky
+// (mu x10 on failure), traditional dogleg interpolation, model decrease, candidate = x (+) step; and, one call
+// later, the accept/reject decision with the radius / mu updates and all termination tests.
+//
+// The reduced system (<= 192 active tangent columns) lives in shared memory as a packed lower triangle
+// (<= 148 KB); all quadratic forms are evaluated on the *unscaled* matrices with unscaled directions
+// u = c o (v / D), which equals Ceres' J_scaled products exactly.
+#pragma once
+#include "layout.cuh"
+#include "factors.cuh"
+
+namespace viwb {
+
+VIWB_HD int pidx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+// block-wide sum; red has nt doubles.  Every thread gets the result.
+VIWB_D double block_sum(double v, int tid, int nt, double *red) {
+    red[tid] = v;
+    VIWB_SYNC();
+    for (int s = nt >> 1; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; VIWB_SYNC(); }
+    const double r = red[0];
+    VIWB_SYNC();
+    return r;
+}
+VIWB_D double block_max(double v, int tid, int nt, double *red) {
+    red[tid] = v;
+    VIWB_SYNC();
+    for (int s = nt >> 1; s > 0; s >>= 1) { if (tid < s) red[tid] = fmax(red[tid], red[tid + s]); VIWB_SYNC(); }
+    const double r = red[0];
+    VIWB_SYNC();
+    return r;
+}
+
+struct SolveSmem {
+    double *L;       // packed lower, nf(nf+1)/2
+    double *g, *sc, *D, *sg, *y, *u, *Hu, *ug, *uvis, *red, *bc;
+    int *amap, *vmap;
+};
+VIWB_HD size_t solve_smem_doubles(int nt) { return (size_t)TFIX * (TFIX + 1) / 2 + 9 * TFIX + 2 * VSUB + nt + 16 + TFIX; }   // + ints (2*TFIX ints = TFIX doubles)
+VIWB_D void carve(SolveSmem &s, double *smem, int nt) {
+    double *p = smem;
+    s.L = p; p += (size_t)TFIX * (TFIX + 1) / 2;
+    s.g = p; p += TFIX; s.sc = p; p += TFIX; s.D = p; p += TFIX; s.sg = p; p += TFIX; s.y = p; p += TFIX;
+    s.u = p; p += TFIX; s.Hu = p; p += TFIX; s.ug = p; p += TFIX;
+    s.uvis = p; p += 2 * VSUB;
+    s.red = p; p += nt; s.bc = p; p += 16;
+    s.amap = (int *)p; s.vmap = s.amap + TFIX;
+}
+
+// load the active part of H_pp (unscaled) into the packed triangle
+VIWB_D void load_H(const double *Hpp, const SolveSmem &s, int nf, int tid, int nt) {
+    const int ne = nf * (nf + 1) / 2;
+    for (int i = tid; i < nf; i += nt) {
+        const double *row = Hpp + (size_t)s.amap[i] * TFIX;
+        for (int j = 0; j <= i; j++) s.L[i * (i + 1) / 2 + j] = row[s.amap[j]];
+    }
+    (void)ne;
+    VIWB_SYNC();
+}
+// Hu = H u over the packed triangle (u, Hu of length nf)
+VIWB_D void symv(const SolveSmem &s, int nf, const double *u, double *Hu, int tid, int nt) {
+    for (int i = tid; i < nf; i += nt) {
+        double a = 0.0;
+        for (int j = 0; j < nf; j++) a += s.L[pidx(i, j)] * u[j];
+        Hu[i] = a;
+    }
+    VIWB_SYNC();
+}
+// uvis[p] = u mapped to the visual subspace (0 where the column is inactive)
+VIWB_D void to_vis(const SolveSmem &s, int nf, const double *u, double *uvis, int tid, int nt) {
+    for (int p = tid; p < VSUB; p += nt) uvis[p] = 0.0;
+    VIWB_SYNC();
+    for (int i = tid; i < nf; i += nt) if (s.vmap[i] >= 0) uvis[s.vmap[i]] = u[i];
+    VIWB_SYNC();
+}
+VIWB_D double dot80(const double *W, const double *v) { double a = 0.0; for (int p = 0; p < 79; p++) a += W[p] * v[p]; return a; }
+
+// in-place packed Cholesky; returns false on a non-positive pivot (Eigen LLT semantics)
+VIWB_D bool cholesky_packed(double *L, int n, int tid, int nt, double *bc) {
+    int TX = 1; while (TX * TX * 2 <= nt) TX *= 2;          // nt = 512 -> TX 16, TY 32 ; nt = 1 -> 1,1
+    const int TY = nt / TX, ty = tid / TX, tx = tid % TX;
+    if (tid == 0) bc[0] = 1.0;
+    VIWB_SYNC();
+    for (int j = 0; j < n; j++) {
+        if (tid == 0) { const double d = L[pidx(j, j)]; if (!(d > 0.0)) bc[0] = 0.0; else L[pidx(j, j)] = sqrt(d); }
+        VIWB_SYNC();
+        if (bc[0] == 0.0) return false;
+        const double inv = 1.0 / L[pidx(j, j)];
+        for (int i = j + 1 + tid; i < n; i += nt) L[pidx(i, j)] *= inv;
+        VIWB_SYNC();
+        for (int i = j + 1 + ty; i < n; i += TY) {
+            const double lij = L[pidx(i, j)];
+            for (int k = j + 1 + tx; k <= i; k += TX) L[i * (i + 1) / 2 + k] -= lij * L[pidx(k, j)];
+        }
+        VIWB_SYNC();
+    }
+    return true;
+}
+// solve L L^T y = b in place (b -> y)
+VIWB_D void chol_solve_packed(const double *L, int n, double *b, int tid, int nt) {
+    for (int j = 0; j < n; j++) {
+        if (tid == 0) b[j] /= L[pidx(j, j)];
+        VIWB_SYNC();
+        const double bj = b[j];
+        for (int i = j + 1 + tid; i < n; i += nt) b[i] -= L[pidx(i, j)] * bj;
+        VIWB_SYNC();
+    }
+    for (int j = n - 1; j >= 0; j--) {
+        if (tid == 0) b[j] /= L[pidx(j, j)];
+        VIWB_SYNC();
+        const double bj = b[j];
+        for (int i = tid; i < j; i += nt) b[i] -= L[pidx(j, i)] * bj;
+        VIWB_SYNC();
+    }
+}
+
+VIWB_D void terminate(WinWork &ww, int term) { ww.status = ST_DONE; ww.term = term; }
+
+// max |x - Plus(x, -g)| over one fixed block (ambient infinity norm of the projected gradient step)
+VIWB_D double block_grad_inf(int b, unsigned mask, const double *x, const double *gneg) {
+    const int gs = blk_size(b);
+    double out[7], m = 0.0;
+    if (gs == 7) pose_plus(x, gneg, mask, out);
+    else if (gs == 4) quat_plus(x, gneg, mask, out);
+    else for (int i = 0; i < gs; i++) out[i] = x[i] + gneg[i];
+    for (int i = 0; i < gs; i++) m = fmax(m, fabs(x[i] - out[i]));
+    return m;
+}
+
+VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)mode;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    WinWork &ww = bd.work[w];
+    if (ww.status != ST_RUNNING) return;
+    const Opts &op = bd.opt;
+    SolveSmem s; carve(s, smem, nt);
+    const int nf = m.nf, N = m.nlm, vo = vec_off(bd, w);
+    double *x = bd.x_cur + m.state_off, *xc = bd.x_cand + m.state_off;
+    double *g_scale = bd.v_scale + vo, *g_D = bd.v_D + vo, *g_sg = bd.v_sgrad + vo, *g_gn = bd.v_gn + vo;
+    const double *lm_a = bd.lm_a + m.lm_off, *lm_g = bd.lm_g + m.lm_off, *lm_gamma = bd.lm_gamma + m.lm_off, *lm_sc = bd.lm_scale + m.lm_off;
+    const double *W = bd.lm_W + (size_t)m.lm_off * VSUB;
+    const double *Hpp = bd.Hpp + (size_t)w * TFIX * TFIX, *gfix = bd.gfix + (size_t)w * (TFIX + 8);
+    const double *Tvis = bd.Tvis + (size_t)w * VSUB * VSUB, *tvec = bd.tvec + (size_t)w * VSUB;
+    const double min_mu = 1e-8, max_mu = 1.0, mu_inc = 10.0;
+
+    // compact <-> fixed / visual index maps
+    for (int b = tid; b < NB; b += nt) if (m.tcol[b] >= 0) for (int k = 0; k < blk_tsize(b); k++) {
+        s.amap[m.tcol[b] + k] = blk_toff(b) + k;
+        s.vmap[m.tcol[b] + k] = blk_voff(b) >= 0 ? blk_voff(b) + k : -1;
+    }
+    VIWB_SYNC();
+
+    // ================= phase A: decision on the pending candidate ==================================
+    double c_part = 0.0;
+    for (int k = tid; k < N; k += nt) c_part += bd.lm_cost[m.lm_off + k];
+    const double cand_cost = block_sum(c_part, tid, nt, s.red) + ww.small_cost;
+    bool new_lin = false;
+    if (ww.phase == PH_INIT) {
+        if (tid == 0) { ww.x_cost = cand_cost; ww.initial_cost = cand_cost; ww.num_iterations = 1; }
+        new_lin = true;
+        for (int i = tid; i < SFIX + N; i += nt) x[i] = xc[i];
+    } else {
+        // ParameterToleranceReached / FunctionToleranceReached / IsStepSuccessful (trust_region_minimizer.cc)
+        int verdict = 0;   // 0 rejected, 1 accepted, 2 converged
+        const double cost_change = ww.x_cost - cand_cost;
+        if (ww.step_norm <= op.parameter_tolerance * (ww.x_norm + op.parameter_tolerance)) verdict = 2;
+        else if (fabs(cost_change) <= op.function_tolerance * ww.x_cost) verdict = 2;
+        else if (cost_change / ww.model_cost_change > op.min_relative_decrease) verdict = 1;
+        if (verdict == 2) { VIWB_SYNC(); if (tid == 0) terminate(ww, 0); return; }
+        if (verdict == 1) {
+            for (int i = tid; i < SFIX + N; i += nt) x[i] = xc[i];
+            new_lin = true;
+        }
+        VIWB_SYNC();
+        if (tid == 0) {
+            const double rd = cost_change / ww.model_cost_change;
+            if (verdict == 1) {
+                ww.x_cost = cand_cost; ww.successful++;
+                if (rd < 0.25) ww.radius *= 0.5;                                 // DoglegStrategy::StepAccepted
+                if (rd > 0.75) ww.radius = fmax(ww.radius, 3.0 * ww.dogleg_step_norm);
+                ww.radius = fmin(ww.radius, op.max_radius);
+                ww.mu = fmax(min_mu, 2.0 * ww.mu / mu_inc);
+                ww.reuse = 0;
+            } else { ww.radius *= 0.5; ww.reuse = 1; }                           // StepRejected
+            ww.num_iterations++;
+        }
+        VIWB_SYNC();
+        // FinalizeIterationAndCheckIfMinimizerCanContinue (gradient tolerance is tested in phase B)
+        if (ww.iteration >= op.max_num_iterations) { VIWB_SYNC(); if (tid == 0) terminate(ww, 1); return; }
+        if (ww.radius <= op.min_radius) { VIWB_SYNC(); if (tid == 0) terminate(ww, 0); return; }
+    }
+    VIWB_SYNC();
+    if (new_lin) {   // x_norm over the active blocks
+        double a = 0.0;
+        for (int b = tid; b < NB; b += nt) if (m.tcol[b] >= 0) for (int k = 0; k < blk_size(b); k++) a += x[blk_off(b) + k] * x[blk_off(b) + k];
+        for (int k = tid; k < N; k += nt) a += x[SFIX + k] * x[SFIX + k];
+        a = block_sum(a, tid, nt, s.red);
+        if (tid == 0) ww.x_norm = sqrt(a);
+    }
+    if (ww.phase == PH_INIT && op.max_num_iterations <= 0) { VIWB_SYNC(); if (tid == 0) terminate(ww, 1); return; }
+    VIWB_SYNC();
+
+    // ================= phase B: compute a trust-region step (loops while the step is invalid) =========
+    for (;;) {
+        if (tid == 0) ww.iteration++;
+        VIWB_SYNC();
+        bool ls_failure = false;
+        if (!ww.reuse) {
+            VIWB_SYNC();
+            if (tid == 0) ww.reuse = 1;
+            load_H(Hpp, s, nf, tid, nt);
+            for (int i = tid; i < nf; i += nt) s.g[i] = gfix[s.amap[i]];
+            VIWB_SYNC();
+            if (ww.first) {
+                for (int i = tid; i < nf; i += nt) g_scale[i] = op.jacobi_scaling ? 1.0 / (1.0 + sqrt(s.L[pidx(i, i)])) : 1.0;
+            }
+            VIWB_SYNC();
+            for (int i = tid; i < nf; i += nt) s.sc[i] = g_scale[i];
+            VIWB_SYNC();
+            if (new_lin) {
+                // gradient_max_norm = |x - Plus(x, -g)|_inf  (unscaled gradient)
+                double gm = 0.0;
+                for (int b = tid; b < NB; b += nt) if (m.tcol[b] >= 0) {
+                    double gneg[9];
+                    for (int k = 0; k < blk_tsize(b); k++) gneg[k] = -s.g[m.tcol[b] + k];
+                    gm = fmax(gm, block_grad_inf(b, m.mask[b], x + blk_off(b), gneg));
+                }
+                for (int k = tid; k < N; k += nt) gm = fmax(gm, fabs(lm_g[k]));
+                gm = block_max(gm, tid, nt, s.red);
+                if (tid == 0) ww.gradient_max_norm = gm;
+                if (gm <= op.gradient_tolerance) { VIWB_SYNC(); if (tid == 0) terminate(ww, 0); return; }
+            }
+            // D = sqrt(clamp(diag(J_s^T J_s))), scaled gradient, Cauchy direction u_g = c o (sgrad / D)
+            double n2 = 0.0;
+            for (int i = tid; i < nf; i += nt) {
+                double d2 = s.sc[i] * s.sc[i] * s.L[pidx(i, i)];
+                d2 = fmin(fmax(d2, op.min_lm_diagonal), op.max_lm_diagonal);
+                const double D = sqrt(d2); s.D[i] = D; g_D[i] = D;
+                const double sg = s.sc[i] * s.g[i] / D; s.sg[i] = sg; g_sg[i] = sg; n2 += sg * sg;
+                s.ug[i] = s.sc[i] * sg / D;
+            }
+            for (int k = tid; k < N; k += nt) {
+                const double c = lm_sc[k];
+                double d2 = c * c * lm_a[k]; d2 = fmin(fmax(d2, op.min_lm_diagonal), op.max_lm_diagonal);
+                const double D = sqrt(d2); g_D[TFIX + k] = D;
+                const double sg = c * lm_g[k] / D; g_sg[TFIX + k] = sg; n2 += sg * sg;
+            }
+            n2 = block_sum(n2, tid, nt, s.red);
+            // q_gg = |J u_g|^2, l_g = g . u_g
+            symv(s, nf, s.ug, s.Hu, tid, nt);
+            to_vis(s, nf, s.ug, s.uvis, tid, nt);
+            double q = 0.0, l = 0.0;
+            for (int i = tid; i < nf; i += nt) { q += s.ug[i] * s.Hu[i]; l += s.g[i] * s.ug[i]; }
+            for (int k = tid; k < N; k += nt) {
+                const double ul = lm_sc[k] * g_sg[TFIX + k] / g_D[TFIX + k];
+                q += 2.0 * ul * dot80(W + (size_t)k * VSUB, s.uvis) + lm_a[k] * ul * ul;
+                l += lm_g[k] * ul;
+            }
+            q = block_sum(q, tid, nt, s.red); l = block_sum(l, tid, nt, s.red);
+            if (tid == 0) { ww.sgrad_norm = sqrt(n2); ww.q_gg = q; ww.l_g = l; ww.alpha = n2 / q; }
+            VIWB_SYNC();
+            // ---- Gauss-Newton step: (J^T J + mu D^2) y = J^T r through the Schur complement
+            ls_failure = true;
+            bool h_dirty = false;
+            while (ww.mu < max_mu) {
+                if (h_dirty) load_H(Hpp, s, nf, tid, nt);
+                const double mu = ww.mu;
+                const bool t_ok = (mu == ww.mu_lin);          // gamma / T / tvec were built for mu_lin
+                // S = C (H - T) C + mu D^2 ; rhs = C (g - tvec)
+                for (int i = tid; i < nf; i += nt) {
+                    const int vi = s.vmap[i];
+                    for (int j = 0; j <= i; j++) {
+                        const int vj = s.vmap[j];
+                        double hij = s.L[i * (i + 1) / 2 + j];
+                        if (vi >= 0 && vj >= 0) {
+                            if (t_ok) hij -= Tvis[vi * VSUB + vj];
+                            else {
+                                double t = 0.0;
+                                for (int k = 0; k < N; k++) {
+                                    const double c = lm_sc[k], sk = c * c * lm_a[k], Dk = g_D[TFIX + k];
+                                    t += (c * c / (sk + mu * Dk * Dk)) * W[(size_t)k * VSUB + vi] * W[(size_t)k * VSUB + vj];
+                                }
+                                hij -= t;
+                            }
+                        }
+                        hij *= s.sc[i] * s.sc[j];
+                        if (i == j) hij += mu * s.D[i] * s.D[i];
+                        s.L[i * (i + 1) / 2 + j] = hij;
+                    }
+                    double r = s.g[i];
+                    if (vi >= 0) {
+                        if (t_ok) r -= tvec[vi];
+                        else { double t = 0.0; for (int k = 0; k < N; k++) { const double c = lm_sc[k], sk = c * c * lm_a[k], Dk = g_D[TFIX + k]; t += (c * c / (sk + mu * Dk * Dk)) * W[(size_t)k * VSUB + vi] * lm_g[k]; } r -= t; }
+                    }
+                    s.y[i] = s.sc[i] * r;
+                }
+                VIWB_SYNC();
+                h_dirty = true;
+                if (tid == 0) ww.num_linear++;
+                bool ok = cholesky_packed(s.L, nf, tid, nt, s.bc);
+                if (ok) {
+                    chol_solve_packed(s.L, nf, s.y, tid, nt);
+                    // back-substitute the inverse depths (scaled): y_k = (c g_k - c w_k . (C y_f)) / h_k
+                    for (int i = tid; i < nf; i += nt) s.u[i] = s.sc[i] * s.y[i];
+                    VIWB_SYNC();
+                    to_vis(s, nf, s.u, s.uvis, tid, nt);
+                    double bad = 0.0;
+                    for (int i = tid; i < nf; i += nt) { if (!isfinite(s.y[i])) bad = 1.0; g_gn[i] = -s.D[i] * s.y[i]; }
+                    for (int k = tid; k < N; k += nt) {
+                        const double c = lm_sc[k], Dk = g_D[TFIX + k], hk = c * c * lm_a[k] + mu * Dk * Dk;
+                        const double yk = c * (lm_g[k] - dot80(W + (size_t)k * VSUB, s.uvis)) / hk;
+                        if (!isfinite(yk)) bad = 1.0;
+                        g_gn[TFIX + k] = -Dk * yk;
+                    }
+                    bad = block_sum(bad, tid, nt, s.red);
+                    ok = (bad == 0.0);
+                }
+                if (!ok) { VIWB_SYNC(); if (tid == 0) ww.mu *= mu_inc; VIWB_SYNC(); continue; }
+                ls_failure = false;
+                break;
+            }
+            VIWB_SYNC();
+            if (!ls_failure) {
+                // q_gn, q_nn, l_n with u_n = c o (gn / D) = -c o y
+                load_H(Hpp, s, nf, tid, nt);
+                for (int i = tid; i < nf; i += nt) s.u[i] = s.sc[i] * g_gn[i] / s.D[i];
+                VIWB_SYNC();
+                symv(s, nf, s.u, s.Hu, tid, nt);
+                to_vis(s, nf, s.u, s.uvis, tid, nt);            // uvis = u_n
+                to_vis(s, nf, s.ug, s.uvis + VSUB, tid, nt);    // second half = u_g
+                double qnn = 0.0, qgn = 0.0, ln = 0.0, nn = 0.0, gd = 0.0;
+                for (int i = tid; i < nf; i += nt) {
+                    qnn += s.u[i] * s.Hu[i]; qgn += s.ug[i] * s.Hu[i]; ln += s.g[i] * s.u[i];
+                    nn += g_gn[i] * g_gn[i]; gd += s.sg[i] * g_gn[i];
+                }
+                for (int k = tid; k < N; k += nt) {
+                    const double c = lm_sc[k], Dk = g_D[TFIX + k];
+                    const double un = c * g_gn[TFIX + k] / Dk, ug = c * g_sg[TFIX + k] / Dk;
+                    const double dn = dot80(W + (size_t)k * VSUB, s.uvis), dg = dot80(W + (size_t)k * VSUB, s.uvis + VSUB);
+                    qnn += 2.0 * un * dn + lm_a[k] * un * un;
+                    qgn += ug * dn + un * dg + lm_a[k] * ug * un;
+                    ln += lm_g[k] * un;
+                    nn += g_gn[TFIX + k] * g_gn[TFIX + k]; gd += g_sg[TFIX + k] * g_gn[TFIX + k];
+                }
+                qnn = block_sum(qnn, tid, nt, s.red); qgn = block_sum(qgn, tid, nt, s.red); ln = block_sum(ln, tid, nt, s.red);
+                nn = block_sum(nn, tid, nt, s.red); gd = block_sum(gd, tid, nt, s.red);
+                if (tid == 0) { ww.q_nn = qnn; ww.q_gn = qgn; ww.l_n = ln; ww.gn_norm = sqrt(nn); ww.sgrad_dot_gn = gd; }
+            }
+            VIWB_SYNC();
+            if (tid == 0) ww.first = 0;
+            VIWB_SYNC();
+        }
+        // ---- ComputeTraditionalDoglegStep: step = ca * sgrad + cb * gn (scaled space), then / D
+        double ca = 0.0, cb = 0.0, mcc = 0.0, dsn = 0.0;
+        bool valid = false;
+        if (!ls_failure) {
+            const double gnorm = ww.sgrad_norm, gnn = ww.gn_norm, radius = ww.radius, alpha = ww.alpha;
+            if (gnn <= radius) { ca = 0.0; cb = 1.0; dsn = gnn; }
+            else if (gnorm * alpha >= radius) { ca = -(radius / gnorm); cb = 0.0; dsn = radius; }
+            else {
+                const double b_dot_a = -alpha * ww.sgrad_dot_gn, a_sq = (alpha * gnorm) * (alpha * gnorm);
+                const double bma = a_sq - 2.0 * b_dot_a + gnn * gnn, c = b_dot_a - a_sq;
+                const double d = sqrt(c * c + bma * (radius * radius - a_sq));
+                const double beta = (c <= 0) ? (d - c) / bma : (radius * radius - a_sq) / (d + c);
+                ca = -alpha * (1.0 - beta); cb = beta;
+                dsn = sqrt(ca * ca * gnorm * gnorm + 2.0 * ca * cb * ww.sgrad_dot_gn + cb * cb * gnn * gnn);
+            }
+            // model_cost_change = -(J t)^T (r + J t / 2) = -(ca l_g + cb l_n) - (ca^2 q_gg + 2 ca cb q_gn + cb^2 q_nn) / 2
+            mcc = -(ca * ww.l_g + cb * ww.l_n) - 0.5 * (ca * ca * ww.q_gg + 2.0 * ca * cb * ww.q_gn + cb * cb * ww.q_nn);
+            valid = mcc > 0.0;
+        }
+        VIWB_SYNC();
+        if (!valid) {
+            // HandleInvalidStep + DoglegStrategy::StepIsInvalid
+            bool stop = false;
+            if (tid == 0) {
+                ww.num_invalid++;
+                if (ww.num_invalid >= op.max_invalid) { terminate(ww, 2); }
+                else {
+                    ww.mu *= mu_inc; ww.reuse = 0; ww.num_iterations++;
+                    if (ww.iteration >= op.max_num_iterations) terminate(ww, 1);
+                    else if (ww.radius <= op.min_radius) terminate(ww, 0);
+                }
+            }
+            VIWB_SYNC();
+            stop = (ww.status != ST_RUNNING);
+            if (stop) return;
+            new_lin = false;
+            continue;
+        }
+        // ---- candidate: x (+) (step o scale)
+        double sn = 0.0;
+        for (int b = tid; b < NB; b += nt) {
+            const int o = blk_off(b), gs = blk_size(b);
+            if (m.tcol[b] >= 0) {
+                double d[9], out[9];
+                for (int k = 0; k < blk_tsize(b); k++) { const int i = m.tcol[b] + k; d[k] = (ca * g_sg[i] + cb * g_gn[i]) / g_D[i] * g_scale[i]; }
+                if (gs == 7) pose_plus(x + o, d, m.mask[b], out);
+                else if (gs == 4) quat_plus(x + o, d, m.mask[b], out);
+                else for (int k = 0; k < gs; k++) out[k] = x[o + k] + d[k];
+                for (int k = 0; k < gs; k++) { xc[o + k] = out[k]; const double e = x[o + k] - out[k]; sn += e * e; }
+            } else for (int k = 0; k < gs; k++) xc[o + k] = x[o + k];
+        }
+        for (int k = tid; k < N; k += nt) {
+            const double d = (ca * g_sg[TFIX + k] + cb * g_gn[TFIX + k]) / g_D[TFIX + k] * lm_sc[k];
+            xc[SFIX + k] = x[SFIX + k] + d; sn += d * d;
+        }
+        sn = block_sum(sn, tid, nt, s.red);
+        if (tid == 0) {
+            ww.num_invalid = 0; ww.step_norm = sqrt(sn); ww.model_cost_change = mcc; ww.dogleg_step_norm = dsn;
+            ww.phase = PH_CAND;
+            ww.mu_lin = fmax(min_mu, 2.0 * ww.mu / mu_inc);      // the candidate's linearisation is solved with the post-accept mu
+        }
+        return;
+    }
+}
+
+}  // namespace viwb

@@ -1,0 +1,116 @@
+// layout.cuh -- device-resident data layout of a batch of windows (one Estimator::optimization() each).
+//
+// HBM layout (all FP64 unless noted; B windows, concatenated):
+//   x_cur / x_cand      [sum(207 + nlm)]        parameter blocks, fixed-state layout of include/viwb.h + inverse depths
+//   vis_*               visual factor table, sorted by landmark; vis_obs is SoA [12][nvis_total] for coalesced reads
+//   vis_rec             [nvis_total][54]  per-factor record written by lin_vis: r(2) A(12) B(12) E0(12) E1(12) Jl(2) Jtd(2)
+//   lm_*                per landmark: a = |J_l|^2, gl = J_l^T r, gamma = c^2/h (Schur weight), W [80] = J_p^T J_l over the
+//                       "visual subspace" (11 poses x 6 | ex0 6 | ex1 6 | td 1 | pad)
+//   imu_rec / wheel_rec / plane_rec   whitened residual + tangent Jacobian of the small factors
+//   Hpp [B][192*192], gfix [B][192]   normal equations over the fixed tangent layout (assembled by gather, no atomics)
+//   Tvis [B][80*80], tvec [B][80]     Schur sums  sum_k gamma_k w_k w_k^T  and  sum_k gamma_k w_k gl_k
+//   per-window solver vectors (scale, D, scaled gradient, Gauss-Newton step) of length 192 + nlm
+#pragma once
+#include <stdint.h>
+#include "vmath.cuh"
+
+namespace viwb {
+
+enum { NB = 32, NFR = 11, TFIX = 192, SFIX = 207, VSUB = 80, VREC = 54, IMU_REC = 15 + 15 * 30, WHEEL_REC = 6 + 6 * 22,
+       PLANE_REC = 3 + 3 * 16, MAXPRI = 200 };
+enum { REC_R = 0, REC_A = 2, REC_B = 14, REC_E0 = 26, REC_E1 = 38, REC_L = 50, REC_TD = 52 };
+enum { BLK_SB0 = 11, BLK_EX0 = 22, BLK_EX1 = 23, BLK_EXW = 24, BLK_PR = 25, BLK_PZ = 26, BLK_SX = 27, BLK_SY = 28, BLK_SW = 29,
+       BLK_TD = 30, BLK_TDW = 31 };
+
+VIWB_HD int blk_size(int b) { return b < 11 ? 7 : b < 22 ? 9 : b < 25 ? 7 : b == 25 ? 4 : 1; }
+VIWB_HD int blk_off(int b) { return b < 11 ? 7 * b : b < 22 ? 77 + 9 * (b - 11) : b < 25 ? 176 + 7 * (b - 22) : b == 25 ? 197 : 201 + (b - 26); }
+VIWB_HD int blk_tsize(int b) { return b < 11 ? 6 : b < 22 ? 9 : b < 25 ? 6 : b == 25 ? 3 : 1; }
+VIWB_HD int blk_toff(int b) { return b < 11 ? 6 * b : b < 22 ? 66 + 9 * (b - 11) : b < 25 ? 165 + 6 * (b - 22) : b == 25 ? 183 : 186 + (b - 26); }
+VIWB_HD int blk_msize(int b) { int s = blk_size(b); return s == 7 ? 6 : s; }
+// visual-subspace offset of a fixed block (-1 if the block is not touched by visual factors)
+VIWB_HD int blk_voff(int b) { return b < 11 ? 6 * b : b == BLK_EX0 ? 66 : b == BLK_EX1 ? 72 : b == BLK_TD ? 78 : -1; }
+
+struct PriorDev {       // one per window that has a valid prior
+    int n, nb;
+    int block_id[NB], block_idx[NB];
+    int J_off;          // into prior_J (n*n row-major) and prior_A (n*n = J^T J, computed once per solve)
+    int r_off;          // into prior_r (n), prior_res (n, current residual) and prior_g (n, J^T res)
+    int x0_off;         // into prior_x0 (207)
+};
+
+struct WinMeta {        // read-only during a solve
+    int state_off, lm_off, nlm;
+    int vis_off, nvis;
+    int imu_off, nimu, wheel_off, nwheel, plane_off, nplane;
+    int prior_idx;      // -1: none
+    int frame_count;
+    int nf;             // active fixed tangent columns (compact)
+    int namb;
+    int margin_flag;
+    int pair_off;       // into pair_ptr: 122 entries per window; factors of pair (h,j) = pair_perm[pair_ptr[h*11+j] .. pair_ptr[h*11+j+1])
+    short tcol[NB];     // compact column of fixed block b, -1 if constant / absent / unreferenced
+    unsigned char flags[NB], mask[NB];
+    double G[3], S_vis[4], w_plane[3], huber;
+};
+
+enum { ST_RUNNING = 0, ST_DONE = 1 };
+enum { PH_INIT = 0, PH_CAND = 1 };
+
+struct WinWork {        // solver state of one window (read-write)
+    int status, term, phase;
+    int iteration, num_iterations, successful, num_linear, num_invalid;
+    int reuse, first;   // first: the pending linearisation is the first one (Jacobi scales are computed from it)
+    int marg_status;    // 0 ok, <0 numeric problem on the marginalisation fast path
+    int pad;
+    double radius, mu, mu_lin;      // mu_lin: the mu the pending linearisation's Schur weights gamma were built with
+    double x_cost, x_norm, step_norm, model_cost_change, dogleg_step_norm, alpha;
+    double q_gg, q_gn, q_nn, l_g, l_n;   // v'Hv, v'Hn, n'Hn, g.v, g.n  with v = sgrad/D, n = gn/D (scaled space)
+    double sgrad_norm, gn_norm, sgrad_dot_gn;
+    double initial_cost, gradient_max_norm;
+    double small_cost;  // cost of IMU/wheel/plane/prior at the evaluated point (written by lin_small)
+};
+
+struct Opts {
+    int max_num_iterations, max_invalid, jacobi_scaling;
+    double function_tolerance, gradient_tolerance, parameter_tolerance;
+    double initial_radius, max_radius, min_radius, min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
+};
+
+struct BatchDev {       // passed by value to every kernel
+    int B, nvis_total, nlm_total, nimu_total, nwheel_total, nplane_total, nprior, nslice;
+    const WinMeta *meta;
+    WinWork *work;
+    const PriorDev *prior;
+    Opts opt;
+    // states
+    double *x_cur, *x_cand, *x_init, *x_before;
+    // visual tables
+    const int *vis_type, *vis_lm, *vis_fi, *vis_fj, *vis_win;
+    const double *vis_obs;          // SoA [12][nvis_total]
+    double *vis_rec;                // [nvis_total][VREC]
+    double *vis_cost;               // [nvis_total]
+    const int *pair_ptr, *pair_perm;   // per window 122 / nvis (global factor indices)
+    // landmarks
+    const int *lm_win, *lm_fptr;    // [nlm_total], [nlm_total+1] factor range (global factor indices, sorted by landmark)
+    double *lm_a, *lm_g, *lm_gamma, *lm_scale, *lm_cost, *lm_W;   // lm_W [nlm_total][VSUB]
+    // small factors
+    const int *imu_fi, *imu_fj, *imu_win, *wheel_fi, *wheel_fj, *wheel_win, *plane_f, *plane_win;
+    const double *imu_data, *wheel_data;   // [n][287], [n][78]
+    double *imu_S, *wheel_S;               // [n][225], [n][36] upper sqrt-info, built once per solve
+    double *imu_rec, *wheel_rec, *plane_rec;
+    // prior
+    const double *prior_J, *prior_r, *prior_x0;
+    double *prior_A, *prior_res, *prior_g;
+    // normal equations
+    double *Hpp, *gfix, *Tvis, *tvec;
+    // solver vectors, per window at work_off = state_off - 15*w ... stored at vec_off = w*TFIX + lm_off
+    double *v_scale, *v_D, *v_sgrad, *v_gn;
+    // marginalisation outputs
+    double *marg_J, *marg_r, *marg_x0;  // [B][MAXPRI*MAXPRI], [B][MAXPRI], [B][SFIX]
+    int *marg_hdr;                      // [B][2 + 2*NB]: valid, n, nb, block_id[], block_idx[]
+    double *marg_A;                     // [B][MAXPRI+16][MAXPRI+16] scratch for the dense system
+};
+
+VIWB_HD int vec_off(const BatchDev &bd, int w) { return w * TFIX + bd.meta[w].lm_off; }
+
+}  // namespace viwb

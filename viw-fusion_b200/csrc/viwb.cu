@@ -1,0 +1,708 @@
+// viwb.cu -- host side of libviwb.so: the C ABI of include/viwb.h over the CUDA kernels in this directory.
+//
+// Lowers viwb_problem tables to the device layout of layout.cuh (sorting visual factors by landmark, building the
+// per-frame-pair gather lists, compacting the active tangent columns), runs the fixed launch sequence of one
+// Estimator::optimization() (estimator.cpp:1383-1896) for a whole batch of windows and brings results back.
+// There is no host arithmetic on the data path and no CPU fallback: without a CUDA device every entry point fails.
+//
+// The same file compiles with -DVIWB_HOST_EMU (g++, no CUDA) into the test-only kernel-logic emulation used by
+// the `not gpu` tests (tests/emu); that build is never part of libviwb.so.
+#include "../../include/viwb.h"
+#include "kernels_marg.cuh"
+#include "kernels_lk.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace viwb;
+
+// ====================================================================================== device abstraction
+#ifdef VIWB_HOST_EMU
+typedef void *stream_t;
+static int dev_malloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 1; }
+static void dev_free(void *p) { free(p); }
+static int dev_h2d(void *d, const void *h, size_t n, stream_t) { if (n) memcpy(d, h, n); return 0; }
+static int dev_d2h(void *h, const void *d, size_t n, stream_t) { if (n) memcpy(h, d, n); return 0; }
+static int dev_d2d(void *d, const void *s, size_t n, stream_t) { if (n) memcpy(d, s, n); return 0; }
+static int dev_sync(stream_t) { return 0; }
+static const char *dev_errstr(int) { return "emulation"; }
+#define VIWB_EMU_NT 1
+template <typename F>
+static void emu_launch(F f, const BatchDev &bd, int gx, int gy, size_t smem_bytes, int mode) {
+    std::vector<double> sm(smem_bytes / 8 + 64);
+    for (int by = 0; by < gy; by++) for (int bx = 0; bx < gx; bx++) f(bd, bx, by, 0, 1, sm.data(), mode);
+}
+#define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) emu_launch(name##_block, bd, gx, gy, smem_bytes, mode)
+#define NT(n) 1
+#else
+#include <cuda_runtime.h>
+typedef cudaStream_t stream_t;
+static int dev_malloc(void **p, size_t n) { return (int)cudaMalloc(p, n ? n : 1); }
+static void dev_free(void *p) { cudaFree(p); }
+static int dev_h2d(void *d, const void *h, size_t n, stream_t s) { return n ? (int)cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) : 0; }
+static int dev_d2h(void *h, const void *d, size_t n, stream_t s) { return n ? (int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) : 0; }
+static int dev_d2d(void *d, const void *s_, size_t n, stream_t s) { return n ? (int)cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s) : 0; }
+static int dev_sync(stream_t s) { return (int)cudaStreamSynchronize(s); }
+static const char *dev_errstr(int e) { return cudaGetErrorString((cudaError_t)e); }
+#define DEF_KERNEL(name, maxnt) \
+    __global__ void __launch_bounds__(maxnt) name##_kernel(BatchDev bd, int mode) { \
+        extern __shared__ double viwb_smem[]; \
+        name##_block(bd, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, viwb_smem, mode); }
+DEF_KERNEL(setup, 128)
+DEF_KERNEL(prior_setup, 256)
+DEF_KERNEL(lin_vis, 128)
+DEF_KERNEL(lm_reduce, 64)
+DEF_KERNEL(lin_small, 64)
+DEF_KERNEL(assemble, 256)
+DEF_KERNEL(solve, 512)
+DEF_KERNEL(reanchor, 32)
+DEF_KERNEL(marg, 256)
+#define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) \
+    do { if ((gx) > 0 && (gy) > 0) name##_kernel<<<dim3((gx), (gy)), (nt), (smem_bytes), (stream)>>>(bd, mode); } while (0)
+#define NT(n) (n)
+#endif
+
+struct viwb_context {
+    int device;
+    stream_t stream;
+    long long launches;
+    std::string err;
+    bool attrs_set;
+};
+
+static int fail(viwb_context *ctx, int code, const std::string &msg) { if (ctx) ctx->err = msg; return code; }
+#define CK(call) do { int e_ = (call); if (e_) return fail(ctx, VIWB_ERR_CUDA, std::string(#call) + ": " + dev_errstr(e_)); } while (0)
+
+// ====================================================================================== batch
+struct HostPrior { int valid, n, nb; int block_id[NB], block_idx[NB]; std::vector<double> x0, J, r; };
+struct viwb_batch {
+    int B;
+    BatchDev bd;
+    std::vector<void *> allocs;
+    std::vector<WinMeta> meta;
+    std::vector<WinWork> work;
+    std::vector<int> out_mode;        // 0: prior computed on the device, 1: input prior passes through, 2: invalid / none
+    std::vector<HostPrior> in_prior;
+    std::vector<int> state_sizes;
+    size_t total_state;
+    double algorithmic_bytes;
+    bool any_marg;
+    int max_iter;
+    size_t nrec_imu, nrec_wheel, nrec_plane;
+};
+
+template <typename T>
+static int upload(viwb_context *ctx, viwb_batch *b, const std::vector<T> &h, const T **dptr) {
+    void *d = nullptr;
+    CK(dev_malloc(&d, h.size() * sizeof(T)));
+    b->allocs.push_back(d);
+    CK(dev_h2d(d, h.data(), h.size() * sizeof(T), ctx->stream));
+    *dptr = (const T *)d;
+    return 0;
+}
+template <typename T>
+static int alloc_dev(viwb_context *ctx, viwb_batch *b, size_t count, T **dptr) {
+    void *d = nullptr;
+    CK(dev_malloc(&d, (count ? count : 1) * sizeof(T)));
+    b->allocs.push_back(d);
+    *dptr = (T *)d;
+    return 0;
+}
+
+static void opts_from(const viwb_options *o, Opts &d) {
+    d.max_num_iterations = o->max_num_iterations; d.max_invalid = o->max_num_consecutive_invalid_steps; d.jacobi_scaling = o->jacobi_scaling;
+    d.function_tolerance = o->function_tolerance; d.gradient_tolerance = o->gradient_tolerance; d.parameter_tolerance = o->parameter_tolerance;
+    d.initial_radius = o->initial_trust_region_radius; d.max_radius = o->max_trust_region_radius; d.min_radius = o->min_trust_region_radius;
+    d.min_relative_decrease = o->min_relative_decrease; d.min_lm_diagonal = o->min_lm_diagonal; d.max_lm_diagonal = o->max_lm_diagonal;
+}
+
+extern "C" void viwb_default_options(viwb_options *o) {
+    o->max_num_iterations = 8; o->max_solver_time_in_seconds = 0;
+    o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+    o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+    o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+    o->max_num_consecutive_invalid_steps = 5; o->jacobi_scaling = 1;
+}
+extern "C" void viwb_default_globals(viwb_globals *g) {
+    g->G[0] = 0; g->G[1] = 0; g->G[2] = 9.81007;
+    g->vis_sqrt_info[0] = 460.0 / 1.5; g->vis_sqrt_info[1] = 0; g->vis_sqrt_info[2] = 0; g->vis_sqrt_info[3] = 460.0 / 1.5;
+    g->plane_sqrt_info[0] = 100.0; g->plane_sqrt_info[1] = 100.0; g->plane_sqrt_info[2] = 20.0;
+    g->huber_delta = 1.0;
+}
+
+static double window_algorithmic_bytes(const viwb_problem &p, int iters) {
+    // B_solve = iters * B_iter + B_marg
+    double R = 0, pg = p.num_landmarks;
+    for (int b = 0; b < NB; b++) if (p.block_flags[b] & VIWB_BLOCK_PRESENT) { pg += blk_size(b); if (!(p.block_flags[b] & VIWB_BLOCK_CONSTANT)) R += blk_tsize(b); }
+    const double n = (p.prior && p.prior->valid) ? p.prior->n : 0;
+    const double b_iter = 112.0 * p.num_vis + 2296.0 * p.num_imu + 624.0 * p.num_wheel + 4.0 * p.num_plane + 8 * (n * n + 2 * n) + 8 * pg + 2 * 8 * (R * R + R) + 8 * pg;
+    int nv0 = 0; std::vector<char> l0(p.num_landmarks > 0 ? p.num_landmarks : 1, 0);
+    for (int i = 0; i < p.num_vis; i++) if (p.vis_frame_i[i] == 0) { nv0++; l0[p.vis_landmark[i]] = 1; }
+    double m = 15; for (int k = 0; k < p.num_landmarks; k++) m += l0[k];
+    const double nn = std::max(n, 76.0);
+    const double b_marg = 112.0 * nv0 + 2296 + (p.num_wheel ? 624 : 0) + (p.num_plane ? 4 : 0) + 8 * (n * n + 2 * n) + 8 * ((m + nn) * (m + nn) + (m + nn)) + 8 * (nn * nn + nn);
+    return iters * b_iter + b_marg;
+}
+
+static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, const double *const *states,
+                       const viwb_options *options, const int32_t *margin_flags, viwb_batch **out) {
+    if (B <= 0 || !problems || !states) return fail(ctx, VIWB_ERR_INVALID, "empty batch");
+    viwb_batch *b = new viwb_batch();
+    b->B = B; b->any_marg = false; b->algorithmic_bytes = 0;
+    viwb_options defopt; viwb_default_options(&defopt);
+    const viwb_options *opt = options ? options : &defopt;
+    b->max_iter = opt->max_num_iterations;
+    BatchDev &bd = b->bd; memset(&bd, 0, sizeof bd);
+    bd.B = B; opts_from(opt, bd.opt); bd.nslice = 8;
+    std::vector<int> vis_type, vis_lm, vis_fi, vis_fj, vis_win, pair_ptr, pair_perm, lm_win, lm_fptr;
+    std::vector<double> vis_obs_aos, x_init;
+    std::vector<int> imu_fi, imu_fj, imu_win, wheel_fi, wheel_fj, wheel_win, plane_f, plane_win;
+    std::vector<double> imu_data, wheel_data, prior_J, prior_r, prior_x0;
+    std::vector<PriorDev> priors;
+    b->meta.resize(B); b->work.resize(B); b->out_mode.assign(B, 2); b->in_prior.resize(B); b->state_sizes.resize(B);
+    lm_fptr.push_back(0);
+    for (int w = 0; w < B; w++) {
+        const viwb_problem &p = problems[w];
+        WinMeta &m = b->meta[w]; memset(&m, 0, sizeof m);
+        if (p.frame_count < 0 || p.frame_count > VIWB_WINDOW_SIZE || p.num_landmarks < 0 || p.num_landmarks > VIWB_MAX_LANDMARKS) { delete b; return fail(ctx, VIWB_ERR_INVALID, "bad frame_count / num_landmarks"); }
+        m.state_off = (int)x_init.size(); m.lm_off = (int)lm_win.size(); m.nlm = p.num_landmarks; m.frame_count = p.frame_count;
+        b->state_sizes[w] = SFIX + p.num_landmarks;
+        x_init.insert(x_init.end(), states[w], states[w] + SFIX + p.num_landmarks);
+        for (int k = 0; k < 3; k++) m.G[k] = p.globals.G[k];
+        for (int k = 0; k < 4; k++) m.S_vis[k] = p.globals.vis_sqrt_info[k];
+        for (int k = 0; k < 3; k++) m.w_plane[k] = p.globals.plane_sqrt_info[k];
+        m.huber = p.globals.huber_delta;
+        const bool has_prior = p.prior && p.prior->valid;
+        // ---- visual factors, stable-sorted by landmark
+        std::vector<int> order(p.num_vis);
+        for (int i = 0; i < p.num_vis; i++) {
+            order[i] = i;
+            const int t = p.vis_type[i], l = p.vis_landmark[i], fi = p.vis_frame_i[i], fj = p.vis_frame_j[i];
+            if (t < 0 || t > 2 || l < 0 || l >= p.num_landmarks || fi < 0 || fi > p.frame_count || fj < 0 || fj > p.frame_count) { delete b; return fail(ctx, VIWB_ERR_INVALID, "bad visual factor table"); }
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return p.vis_landmark[a] < p.vis_landmark[c]; });
+        m.vis_off = (int)vis_type.size(); m.nvis = p.num_vis;
+        std::vector<int> cnt(p.num_landmarks + 1, 0);
+        for (int i = 0; i < p.num_vis; i++) {
+            const int s = order[i];
+            vis_type.push_back(p.vis_type[s]); vis_lm.push_back(m.lm_off + p.vis_landmark[s]); vis_fi.push_back(p.vis_frame_i[s]); vis_fj.push_back(p.vis_frame_j[s]);
+            vis_win.push_back(w);
+            vis_obs_aos.insert(vis_obs_aos.end(), p.vis_obs + (size_t)s * 12, p.vis_obs + (size_t)s * 12 + 12);
+            cnt[p.vis_landmark[s]]++;
+        }
+        for (int k = 0; k < p.num_landmarks; k++) { lm_win.push_back(w); lm_fptr.push_back(lm_fptr.back() + cnt[k]); }
+        // ---- gather lists by (host frame, target frame)
+        m.pair_off = (int)pair_ptr.size();
+        {
+            std::vector<int> pc(NFR * NFR + 1, 0);
+            for (int i = 0; i < p.num_vis; i++) pc[vis_fi[m.vis_off + i] * NFR + vis_fj[m.vis_off + i] + 1]++;
+            for (int k = 0; k < NFR * NFR; k++) pc[k + 1] += pc[k];
+            const int base = (int)pair_perm.size();
+            pair_perm.resize(base + p.num_vis);
+            std::vector<int> pos(pc.begin(), pc.end() - 1);
+            for (int i = 0; i < p.num_vis; i++) { const int key = vis_fi[m.vis_off + i] * NFR + vis_fj[m.vis_off + i]; pair_perm[base + pos[key]++] = m.vis_off + i; }
+            for (int k = 0; k <= NFR * NFR; k++) pair_ptr.push_back(base + pc[k]);
+        }
+        // ---- small factors
+        m.imu_off = (int)imu_fi.size(); m.nimu = p.num_imu;
+        for (int i = 0; i < p.num_imu; i++) { imu_fi.push_back(p.imu_frame_i[i]); imu_fj.push_back(p.imu_frame_j[i]); imu_win.push_back(w); }
+        imu_data.insert(imu_data.end(), p.imu_data, p.imu_data + (size_t)p.num_imu * 287);
+        m.wheel_off = (int)wheel_fi.size(); m.nwheel = p.num_wheel;
+        for (int i = 0; i < p.num_wheel; i++) { wheel_fi.push_back(p.wheel_frame_i[i]); wheel_fj.push_back(p.wheel_frame_j[i]); wheel_win.push_back(w); }
+        if (p.num_wheel) wheel_data.insert(wheel_data.end(), p.wheel_data, p.wheel_data + (size_t)p.num_wheel * 78);
+        m.plane_off = (int)plane_f.size(); m.nplane = p.num_plane;
+        for (int i = 0; i < p.num_plane; i++) { plane_f.push_back(p.plane_frame[i]); plane_win.push_back(w); }
+        // ---- prior
+        m.prior_idx = -1;
+        HostPrior &hp = b->in_prior[w]; hp.valid = 0; hp.n = 0; hp.nb = 0;
+        if (has_prior) {
+            const viwb_prior &pr = *p.prior;
+            if (pr.n <= 0 || pr.n > MAXPRI || pr.num_blocks <= 0 || pr.num_blocks > NB) { delete b; return fail(ctx, VIWB_ERR_INVALID, "bad prior"); }
+            PriorDev pd; memset(&pd, 0, sizeof pd);
+            pd.n = pr.n; pd.nb = pr.num_blocks;
+            for (int i = 0; i < pr.num_blocks; i++) { pd.block_id[i] = pr.block_id[i]; pd.block_idx[i] = pr.block_idx[i]; }
+            pd.J_off = (int)prior_J.size(); pd.r_off = (int)prior_r.size(); pd.x0_off = (int)prior_x0.size();
+            prior_J.insert(prior_J.end(), pr.J, pr.J + (size_t)pr.n * pr.n);
+            prior_r.insert(prior_r.end(), pr.r, pr.r + pr.n);
+            prior_x0.insert(prior_x0.end(), pr.x0, pr.x0 + SFIX);
+            m.prior_idx = (int)priors.size(); priors.push_back(pd);
+            hp.valid = 1; hp.n = pr.n; hp.nb = pr.num_blocks;
+            memcpy(hp.block_id, pd.block_id, sizeof hp.block_id); memcpy(hp.block_idx, pd.block_idx, sizeof hp.block_idx);
+            hp.x0.assign(pr.x0, pr.x0 + SFIX); hp.J.assign(pr.J, pr.J + (size_t)pr.n * pr.n); hp.r.assign(pr.r, pr.r + pr.n);
+        }
+        // ---- active blocks (Program::RemoveFixedBlocks) and compact columns
+        bool ref[NB]; for (int k = 0; k < NB; k++) ref[k] = false;
+        if (has_prior) for (int i = 0; i < p.prior->num_blocks; i++) ref[p.prior->block_id[i]] = true;
+        for (int i = 0; i < p.num_imu; i++) { ref[p.imu_frame_i[i]] = ref[BLK_SB0 + p.imu_frame_i[i]] = ref[p.imu_frame_j[i]] = ref[BLK_SB0 + p.imu_frame_j[i]] = true; }
+        for (int i = 0; i < p.num_wheel; i++) { ref[p.wheel_frame_i[i]] = ref[p.wheel_frame_j[i]] = ref[BLK_EXW] = ref[BLK_SX] = ref[BLK_SY] = ref[BLK_SW] = ref[BLK_TDW] = true; }
+        for (int i = 0; i < p.num_plane; i++) { ref[p.plane_frame[i]] = ref[BLK_EXW] = ref[BLK_PR] = ref[BLK_PZ] = true; }
+        for (int i = 0; i < p.num_vis; i++) {
+            const int t = p.vis_type[i];
+            if (t != 2) { ref[p.vis_frame_i[i]] = ref[p.vis_frame_j[i]] = true; }
+            ref[BLK_EX0] = true; if (t != 0) ref[BLK_EX1] = true; ref[BLK_TD] = true;
+        }
+        int col = 0, amb = 0;
+        for (int k = 0; k < NB; k++) {
+            m.flags[k] = p.block_flags[k] & 3u; m.mask[k] = p.subset_mask[k];
+            const bool active = (p.block_flags[k] & VIWB_BLOCK_PRESENT) && !(p.block_flags[k] & VIWB_BLOCK_CONSTANT) && ref[k];
+            if (active) { m.tcol[k] = (short)col; col += blk_tsize(k); amb += blk_size(k); } else m.tcol[k] = -1;
+        }
+        m.nf = col; m.namb = amb + p.num_landmarks;
+        // ---- marginalisation plan (estimator.cpp:1666-1893)
+        m.margin_flag = -1; b->out_mode[w] = 2;
+        const int mf = margin_flags ? margin_flags[w] : -1;
+        if (mf >= 0 && p.frame_count == VIWB_WINDOW_SIZE) {
+            bool seen[NB]; for (int k = 0; k < NB; k++) seen[k] = false;
+            if (mf == VIWB_MARGIN_OLD) {
+                if (has_prior) for (int i = 0; i < p.prior->num_blocks; i++) seen[p.prior->block_id[i]] = true;
+                for (int i = 0; i < p.num_imu; i++) if (p.imu_frame_i[i] == 0 && p.imu_frame_j[i] == 1) seen[0] = seen[BLK_SB0] = seen[1] = seen[BLK_SB0 + 1] = true;
+                for (int i = 0; i < p.num_wheel; i++) if (p.wheel_frame_i[i] == 0 && p.wheel_frame_j[i] == 1) seen[0] = seen[1] = seen[BLK_EXW] = seen[BLK_SX] = seen[BLK_SY] = seen[BLK_SW] = seen[BLK_TDW] = true;
+                for (int i = 0; i < p.num_plane; i++) if (p.plane_frame[i] == 0) seen[0] = seen[BLK_EXW] = seen[BLK_PR] = seen[BLK_PZ] = true;
+                bool any_lm0 = false;
+                for (int i = 0; i < p.num_vis; i++) if (p.vis_frame_i[i] == 0) {
+                    any_lm0 = true;
+                    const int t = p.vis_type[i];
+                    if (t != 2) seen[0] = seen[p.vis_frame_j[i]] = true;
+                    seen[BLK_EX0] = true; if (t != 0) seen[BLK_EX1] = true; seen[BLK_TD] = true;
+                }
+                if (seen[0] || seen[BLK_SB0] || any_lm0) { m.margin_flag = 0; b->out_mode[w] = 0; }
+            } else {
+                bool has9 = false;
+                if (has_prior) for (int i = 0; i < p.prior->num_blocks; i++) { seen[p.prior->block_id[i]] = true; if (p.prior->block_id[i] == VIWB_WINDOW_SIZE - 1) has9 = true; }
+                if (has9) { m.margin_flag = 1; b->out_mode[w] = 0; }
+                else b->out_mode[w] = has_prior ? 1 : 2;
+            }
+            if (m.margin_flag >= 0) { for (int k = 0; k < NB; k++) if (seen[k]) m.flags[k] |= 4u; b->any_marg = true; }
+        }
+        b->algorithmic_bytes += window_algorithmic_bytes(p, opt->max_num_iterations);
+        // ---- initial solver state
+        WinWork &ww = b->work[w]; memset(&ww, 0, sizeof ww);
+        ww.status = ST_RUNNING; ww.phase = PH_INIT; ww.first = 1; ww.radius = opt->initial_trust_region_radius; ww.mu = 1e-8; ww.mu_lin = 1e-8;
+        ww.term = VIWB_NO_CONVERGENCE;
+    }
+    // ---- SoA transpose of the observations
+    const size_t nv = vis_type.size();
+    std::vector<double> vis_obs(nv * 12);
+    for (size_t f = 0; f < nv; f++) for (int k = 0; k < 12; k++) vis_obs[(size_t)k * nv + f] = vis_obs_aos[f * 12 + k];
+    bd.nvis_total = (int)nv; bd.nlm_total = (int)lm_win.size(); bd.nimu_total = (int)imu_fi.size(); bd.nwheel_total = (int)wheel_fi.size();
+    bd.nplane_total = (int)plane_f.size(); bd.nprior = (int)priors.size();
+    b->total_state = x_init.size();
+#define UP(vec, field) do { int rc_ = upload(ctx, b, vec, &bd.field); if (rc_) { return rc_; } } while (0)
+    UP(b->meta, meta); UP(priors, prior);
+    UP(vis_type, vis_type); UP(vis_lm, vis_lm); UP(vis_fi, vis_fi); UP(vis_fj, vis_fj); UP(vis_win, vis_win); UP(vis_obs, vis_obs);
+    UP(pair_ptr, pair_ptr); UP(pair_perm, pair_perm); UP(lm_win, lm_win); UP(lm_fptr, lm_fptr);
+    UP(imu_fi, imu_fi); UP(imu_fj, imu_fj); UP(imu_win, imu_win); UP(wheel_fi, wheel_fi); UP(wheel_fj, wheel_fj); UP(wheel_win, wheel_win);
+    UP(plane_f, plane_f); UP(plane_win, plane_win); UP(imu_data, imu_data); UP(wheel_data, wheel_data);
+    UP(prior_J, prior_J); UP(prior_r, prior_r); UP(prior_x0, prior_x0);
+#undef UP
+    { const double *xi = nullptr; int rc = upload(ctx, b, x_init, &xi); if (rc) return rc; bd.x_init = (double *)xi; }
+#define AL(field, count) do { int rc_ = alloc_dev(ctx, b, (size_t)(count), &bd.field); if (rc_) return rc_; } while (0)
+    AL(work, B); AL(x_cur, x_init.size()); AL(x_cand, x_init.size()); AL(x_before, x_init.size());
+    AL(vis_rec, nv * VREC); AL(vis_cost, nv);
+    const size_t nl = lm_win.size();
+    AL(lm_a, nl); AL(lm_g, nl); AL(lm_gamma, nl); AL(lm_scale, nl); AL(lm_cost, nl); AL(lm_W, nl * VSUB);
+    AL(imu_S, imu_fi.size() * 225); AL(wheel_S, wheel_fi.size() * 36);
+    AL(imu_rec, imu_fi.size() * IMU_REC); AL(wheel_rec, wheel_fi.size() * WHEEL_REC); AL(plane_rec, plane_f.size() * PLANE_REC);
+    AL(prior_A, prior_J.size()); AL(prior_res, prior_r.size()); AL(prior_g, prior_r.size());
+    AL(Hpp, (size_t)B * TFIX * TFIX); AL(gfix, (size_t)B * (TFIX + 8)); AL(Tvis, (size_t)B * VSUB * VSUB); AL(tvec, (size_t)B * VSUB);
+    const size_t nvec = (size_t)B * TFIX + nl;
+    AL(v_scale, nvec); AL(v_D, nvec); AL(v_sgrad, nvec); AL(v_gn, nvec);
+    AL(marg_J, (size_t)B * MAXPRI * MAXPRI); AL(marg_r, (size_t)B * MAXPRI); AL(marg_x0, (size_t)B * SFIX);
+    AL(marg_hdr, (size_t)B * (3 + 2 * NB)); AL(marg_A, (size_t)B * (MAXPRI + 16) * (MAXPRI + 16));
+#undef AL
+    *out = b;
+    return 0;
+}
+
+static int ensure_attrs(viwb_context *ctx) {
+#ifndef VIWB_HOST_EMU
+    if (!ctx->attrs_set) {
+        CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(512) * 8)));
+        CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(256) * 8)));
+        ctx->attrs_set = true;
+    }
+#endif
+    return 0;
+}
+
+enum { RUN_SOLVE = 1, RUN_REANCHOR = 2, RUN_MARG = 4, RUN_LIN_ONLY = 8 };
+
+static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
+    BatchDev &bd = b->bd;
+    int rc = ensure_attrs(ctx); if (rc) return rc;
+    stream_t st = ctx->stream;
+    const int B = b->B;
+    const size_t xs = b->total_state * sizeof(double);
+    CK(dev_d2d(bd.x_cur, bd.x_init, xs, st)); CK(dev_d2d(bd.x_cand, bd.x_init, xs, st));
+    if (!(what & RUN_REANCHOR) || (what & RUN_SOLVE)) CK(dev_d2d(bd.x_before, bd.x_init, xs, st));
+    CK(dev_h2d(bd.work, b->work.data(), sizeof(WinWork) * B, st));
+    const int nt_vis = NT(128), nt_lm = NT(64), nt_small = NT(64), nt_asm = NT(256), nt_solve = NT(512), nt_marg = NT(256);
+    const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total + nt_lm - 1) / nt_lm;
+    const size_t sm_small = (size_t)(nt_small + MAXPRI + 8) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg) * 8;
+    auto lin = [&](int mode) {
+        LAUNCH(lin_vis, bd, g_vis, 1, nt_vis, 0, mode, st);
+        LAUNCH(lm_reduce, bd, g_lm, 1, nt_lm, 0, mode, st);
+        LAUNCH(lin_small, bd, B, 1, nt_small, sm_small, mode, st);
+        LAUNCH(assemble, bd, B, bd.nslice, nt_asm, 0, mode, st);
+        ctx->launches += (g_vis > 0) + (g_lm > 0) + 2;
+    };
+    if (what & (RUN_SOLVE | RUN_MARG | RUN_LIN_ONLY)) {
+        const int ns = bd.nimu_total + bd.nwheel_total, nt_s = NT(128);
+        LAUNCH(setup, bd, (ns + nt_s - 1) / nt_s, 1, nt_s, 0, 0, st);
+        LAUNCH(prior_setup, bd, bd.nprior, 1, NT(256), 0, 0, st);
+        ctx->launches += (ns > 0) + (bd.nprior > 0);
+    }
+    if (what & RUN_LIN_ONLY) lin(MODE_SOLVE);
+    if (what & RUN_SOLVE) {
+        for (int round = 0; round <= b->max_iter; round++) {
+            lin(MODE_SOLVE);
+            LAUNCH(solve, bd, B, 1, nt_solve, sm_solve, 0, st);
+            ctx->launches++;
+        }
+    }
+    if (what & RUN_REANCHOR) { LAUNCH(reanchor, bd, B, 1, NT(32), 0, 0, st); ctx->launches++; }
+    if ((what & RUN_MARG) && b->any_marg) {
+        lin(MODE_MARG);
+        LAUNCH(marg, bd, B, 1, nt_marg, sm_marg, 0, st);
+        ctx->launches++;
+    }
+#ifndef VIWB_HOST_EMU
+    CK((int)cudaGetLastError());
+#endif
+    return 0;
+}
+
+static void fill_prior_out(const viwb_batch *b, int w, const std::vector<int> &hdr, const std::vector<double> &J, const std::vector<double> &r,
+                           const std::vector<double> &x0, viwb_prior *out) {
+    const int mode = b->out_mode[w];
+    if (mode == 0) {
+        const int *h = hdr.data() + (size_t)w * (3 + 2 * NB);
+        out->valid = h[0]; out->n = h[1]; out->num_blocks = h[2];
+        for (int i = 0; i < h[2]; i++) { out->block_id[i] = h[3 + i]; out->block_idx[i] = h[3 + NB + i]; }
+        const int n = h[1];
+        memcpy(out->J, J.data() + (size_t)w * MAXPRI * MAXPRI, sizeof(double) * n * n);
+        memcpy(out->r, r.data() + (size_t)w * MAXPRI, sizeof(double) * n);
+        memcpy(out->x0, x0.data() + (size_t)w * SFIX, sizeof(double) * SFIX);
+    } else if (mode == 1) {
+        const HostPrior &hp = b->in_prior[w];
+        out->valid = 1; out->n = hp.n; out->num_blocks = hp.nb;
+        memcpy(out->block_id, hp.block_id, sizeof hp.block_id); memcpy(out->block_idx, hp.block_idx, sizeof hp.block_idx);
+        memcpy(out->x0, hp.x0.data(), sizeof(double) * SFIX); memcpy(out->J, hp.J.data(), sizeof(double) * hp.n * hp.n); memcpy(out->r, hp.r.data(), sizeof(double) * hp.n);
+    } else { out->valid = 0; out->n = 0; out->num_blocks = 0; }
+}
+
+static int batch_fetch(viwb_context *ctx, viwb_batch *b, double *const *states, viwb_summary *summaries, viwb_prior *priors_out) {
+    BatchDev &bd = b->bd;
+    std::vector<double> x(b->total_state);
+    std::vector<WinWork> work(b->B);
+    CK(dev_d2h(x.data(), bd.x_cur, x.size() * sizeof(double), ctx->stream));
+    CK(dev_d2h(work.data(), bd.work, sizeof(WinWork) * b->B, ctx->stream));
+    std::vector<int> hdr; std::vector<double> J, r, x0;
+    if (priors_out && b->any_marg) {
+        hdr.resize((size_t)b->B * (3 + 2 * NB)); J.resize((size_t)b->B * MAXPRI * MAXPRI); r.resize((size_t)b->B * MAXPRI); x0.resize((size_t)b->B * SFIX);
+        CK(dev_d2h(hdr.data(), bd.marg_hdr, hdr.size() * sizeof(int), ctx->stream));
+        CK(dev_d2h(J.data(), bd.marg_J, J.size() * sizeof(double), ctx->stream));
+        CK(dev_d2h(r.data(), bd.marg_r, r.size() * sizeof(double), ctx->stream));
+        CK(dev_d2h(x0.data(), bd.marg_x0, x0.size() * sizeof(double), ctx->stream));
+    }
+    CK(dev_sync(ctx->stream));
+    int rc = 0;
+    for (int w = 0; w < b->B; w++) {
+        if (states && states[w]) memcpy(states[w], x.data() + b->meta[w].state_off, sizeof(double) * b->state_sizes[w]);
+        if (summaries) {
+            viwb_summary &s = summaries[w]; const WinWork &ww = work[w];
+            s.termination_type = ww.term; s.num_iterations = ww.num_iterations; s.num_successful_steps = ww.successful; s.num_linear_solves = ww.num_linear;
+            s.initial_cost = ww.initial_cost; s.final_cost = ww.x_cost; s.final_radius = ww.radius; s.final_mu = ww.mu;
+        }
+        if (priors_out) {
+            if (b->out_mode[w] == 0 && !b->any_marg) { priors_out[w].valid = 0; continue; }
+            fill_prior_out(b, w, hdr, J, r, x0, &priors_out[w]);
+            if (b->out_mode[w] == 0 && work[w].marg_status < 0) rc = VIWB_ERR_NUMERIC;
+        }
+    }
+    if (rc) return fail(ctx, rc, "marginalisation: kept dimension exceeds the shared-memory eigen solver");
+    return 0;
+}
+
+static void batch_free(viwb_batch *b) { if (!b) return; for (void *p : b->allocs) dev_free(p); delete b; }
+
+// ====================================================================================== C ABI
+extern "C" int viwb_create(int device, viwb_context **out) {
+    if (!out) return VIWB_ERR_INVALID;
+    viwb_context *ctx = new viwb_context();
+    ctx->device = device; ctx->launches = 0; ctx->attrs_set = false; ctx->stream = 0;
+#ifndef VIWB_HOST_EMU
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) { delete ctx; return VIWB_ERR_CUDA; }   // no CPU fallback: fail loudly
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return VIWB_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return VIWB_ERR_CUDA; }
+#endif
+    *out = ctx;
+    return VIWB_OK;
+}
+extern "C" void viwb_destroy(viwb_context *ctx) {
+    if (!ctx) return;
+#ifndef VIWB_HOST_EMU
+    lk_release(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+#endif
+    delete ctx;
+}
+extern "C" const char *viwb_last_error(const viwb_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int viwb_set_stream(viwb_context *ctx, void *s) { if (!ctx) return VIWB_ERR_INVALID; ctx->stream = (stream_t)s; return VIWB_OK; }
+extern "C" long long viwb_launch_count(const viwb_context *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int viwb_batch_create(viwb_context *ctx, int batch, const viwb_problem *problems, const double *const *states,
+                                 const viwb_options *options, const int32_t *margin_flags, viwb_batch **out) {
+    if (!ctx || !out) return VIWB_ERR_INVALID;
+    int rc = batch_build(ctx, batch, problems, states, options, margin_flags, out);
+    if (rc) return rc;
+    CK(dev_sync(ctx->stream));
+    return VIWB_OK;
+}
+extern "C" int viwb_batch_reset_states(viwb_context *ctx, viwb_batch *b) { (void)ctx; (void)b; return VIWB_OK; }   // batch_run restarts from x_init
+extern "C" int viwb_batch_run(viwb_context *ctx, viwb_batch *b) {
+    if (!ctx || !b) return VIWB_ERR_INVALID;
+    return batch_execute(ctx, b, RUN_SOLVE | RUN_REANCHOR | RUN_MARG);
+}
+extern "C" int viwb_batch_download(viwb_context *ctx, viwb_batch *b, double *const *states, viwb_summary *summaries, viwb_prior *priors_out) {
+    if (!ctx || !b) return VIWB_ERR_INVALID;
+    return batch_fetch(ctx, b, states, summaries, priors_out);
+}
+extern "C" double viwb_batch_algorithmic_bytes(const viwb_batch *b) { return b ? b->algorithmic_bytes : 0.0; }
+extern "C" void viwb_batch_destroy(viwb_context *ctx, viwb_batch *b) { (void)ctx; batch_free(b); }
+
+static int run_once(viwb_context *ctx, int B, const viwb_problem *problems, double *const *states, const viwb_options *opt,
+                    const int32_t *flags, int what, viwb_summary *summaries, viwb_prior *priors, const double *const *before) {
+    viwb_batch *b = nullptr;
+    int rc = batch_build(ctx, B, problems, (const double *const *)states, opt, flags, &b);
+    if (rc) return rc;
+    if (before) {   // gauge re-anchoring against an explicit pre-solve state
+        std::vector<double> xb(b->total_state);
+        for (int w = 0; w < B; w++) memcpy(xb.data() + b->meta[w].state_off, before[w], sizeof(double) * b->state_sizes[w]);
+        rc = dev_h2d(b->bd.x_before, xb.data(), xb.size() * sizeof(double), ctx->stream);
+        if (!rc) rc = dev_sync(ctx->stream);
+        if (rc) { batch_free(b); return fail(ctx, VIWB_ERR_CUDA, "upload of state_before failed"); }
+    }
+    rc = batch_execute(ctx, b, what);
+    if (!rc) rc = batch_fetch(ctx, b, states, summaries, priors);
+    batch_free(b);
+    return rc;
+}
+
+extern "C" int viwb_window_solve(viwb_context *ctx, const viwb_problem *problem, double *state, const viwb_options *options, viwb_summary *summary) {
+    if (!ctx || !problem || !state) return VIWB_ERR_INVALID;
+    double *sp[1] = {state};
+    return run_once(ctx, 1, problem, sp, options, nullptr, RUN_SOLVE, summary, nullptr, nullptr);
+}
+extern "C" int viwb_gauge_reanchor(viwb_context *ctx, const viwb_problem *problem, const double *state_before, double *state) {
+    if (!ctx || !problem || !state || !state_before) return VIWB_ERR_INVALID;
+    double *sp[1] = {state}; const double *bp[1] = {state_before};
+    return run_once(ctx, 1, problem, sp, nullptr, nullptr, RUN_REANCHOR, nullptr, nullptr, bp);
+}
+extern "C" int viwb_marginalize(viwb_context *ctx, const viwb_problem *problem, const double *state, int margin_flag, viwb_prior *prior_out) {
+    if (!ctx || !problem || !state || !prior_out) return VIWB_ERR_INVALID;
+    std::vector<double> tmp(state, state + SFIX + problem->num_landmarks);
+    double *sp[1] = {tmp.data()}; int32_t fl[1] = {margin_flag};
+    return run_once(ctx, 1, problem, sp, nullptr, fl, RUN_MARG, nullptr, prior_out, nullptr);
+}
+extern "C" int viwb_optimization(viwb_context *ctx, const viwb_problem *problem, double *state, const viwb_options *options, int margin_flag,
+                                 viwb_summary *summary, viwb_prior *prior_out) {
+    if (!ctx || !problem || !state) return VIWB_ERR_INVALID;
+    double *sp[1] = {state}; int32_t fl[1] = {margin_flag};
+    return run_once(ctx, 1, problem, sp, options, prior_out ? fl : nullptr, RUN_SOLVE | RUN_REANCHOR | (prior_out ? RUN_MARG : 0), summary, prior_out, nullptr);
+}
+extern "C" int viwb_optimization_batch(viwb_context *ctx, int batch, const viwb_problem *problems, double *const *states, const viwb_options *options,
+                                       const int32_t *margin_flags, viwb_summary *summaries, viwb_prior *priors_out) {
+    if (!ctx || !problems || !states) return VIWB_ERR_INVALID;
+    return run_once(ctx, batch, problems, states, options, priors_out ? margin_flags : nullptr, RUN_SOLVE | RUN_REANCHOR | (priors_out ? RUN_MARG : 0),
+                    summaries, priors_out, nullptr);
+}
+
+extern "C" int viwb_debug_normal_equations(viwb_context *ctx, const viwb_problem *problem, const double *state, double *H, double *g, double *lm, double *cost) {
+    if (!ctx || !problem || !state) return VIWB_ERR_INVALID;
+    viwb_batch *b = nullptr;
+    const double *sp[1] = {state};
+    int rc = batch_build(ctx, 1, problem, sp, nullptr, nullptr, &b);
+    if (rc) return rc;
+    rc = batch_execute(ctx, b, RUN_LIN_ONLY);
+    if (rc) { batch_free(b); return rc; }
+    const int N = problem->num_landmarks;
+    std::vector<double> Hd((size_t)TFIX * TFIX), gd(TFIX + 8), a(N + 1), gl(N + 1), W((size_t)(N + 1) * VSUB), lc(N + 1);
+    std::vector<WinWork> ww(1);
+    int e = dev_d2h(Hd.data(), b->bd.Hpp, Hd.size() * 8, ctx->stream);
+    e |= dev_d2h(gd.data(), b->bd.gfix, gd.size() * 8, ctx->stream);
+    e |= dev_d2h(a.data(), b->bd.lm_a, (size_t)N * 8, ctx->stream); e |= dev_d2h(gl.data(), b->bd.lm_g, (size_t)N * 8, ctx->stream);
+    e |= dev_d2h(W.data(), b->bd.lm_W, (size_t)N * VSUB * 8, ctx->stream); e |= dev_d2h(lc.data(), b->bd.lm_cost, (size_t)N * 8, ctx->stream);
+    e |= dev_d2h(ww.data(), b->bd.work, sizeof(WinWork), ctx->stream);
+    e |= dev_sync(ctx->stream);
+    if (e) { batch_free(b); return fail(ctx, VIWB_ERR_CUDA, "download failed"); }
+    // formatting only: scatter the active blocks into the caller's fixed-layout arrays
+    const WinMeta &m = b->meta[0];
+    if (H) { memset(H, 0, sizeof(double) * TFIX * TFIX);
+        for (int ba = 0; ba < NB; ba++) for (int bb = 0; bb < NB; bb++) if (m.tcol[ba] >= 0 && m.tcol[bb] >= 0)
+            for (int p = 0; p < blk_tsize(ba); p++) for (int q = 0; q < blk_tsize(bb); q++) H[(blk_toff(ba) + p) * TFIX + blk_toff(bb) + q] = Hd[(size_t)(blk_toff(ba) + p) * TFIX + blk_toff(bb) + q]; }
+    if (g) { memset(g, 0, sizeof(double) * TFIX); for (int ba = 0; ba < NB; ba++) if (m.tcol[ba] >= 0) for (int p = 0; p < blk_tsize(ba); p++) g[blk_toff(ba) + p] = gd[blk_toff(ba) + p]; }
+    double c = ww[0].small_cost;
+    for (int k = 0; k < N; k++) {
+        c += lc[k];
+        if (lm) { lm[k * 82] = a[k]; lm[k * 82 + 1] = gl[k];
+            for (int p = 0; p < VSUB; p++) {
+                bool act = true;
+                if (p < 66) act = m.tcol[p / 6] >= 0; else if (p < 72) act = m.tcol[BLK_EX0] >= 0; else if (p < 78) act = m.tcol[BLK_EX1] >= 0; else if (p == 78) act = m.tcol[BLK_TD] >= 0; else act = false;
+                lm[k * 82 + 2 + p] = act ? W[(size_t)k * VSUB + p] : 0.0;
+            } }
+    }
+    if (cost) *cost = c;
+    batch_free(b);
+    return VIWB_OK;
+}
+
+// -------------------------------------------------------------------------------------- factor level
+struct EvalArgs { int type, want_j; const double *in; double *out; };
+// in : globals(11) | consts(287) | params(7 blocks x 9)        out: residual(15) | tangent Jacobian (15 x 30)
+VIWB_D void eval_factor_device(const EvalArgs &a) {
+    const double *gl = a.in, *c = a.in + 11, *p = a.in + 11 + 287;
+    double *r = a.out, *J = a.out + 15;
+    const double *P[7]; for (int i = 0; i < 7; i++) P[i] = p + 9 * i;
+    if (a.type <= 2) {
+        VisOut o;
+        if (a.type == 0) vis_eval(0, c, P[0], P[1], P[2], P[2], P[3][0], P[4][0], gl + 3, a.want_j != 0, o);
+        else if (a.type == 1) vis_eval(1, c, P[0], P[1], P[2], P[3], P[4][0], P[5][0], gl + 3, a.want_j != 0, o);
+        else vis_eval(2, c, P[0], P[0], P[0], P[1], P[2][0], P[3][0], gl + 3, a.want_j != 0, o);
+        r[0] = o.r[0]; r[1] = o.r[1];
+        if (a.want_j) { for (int k = 0; k < 12; k++) { J[k] = o.JA[k]; J[12 + k] = o.JB[k]; J[24 + k] = o.JE0[k]; J[36 + k] = o.JE1[k]; } J[48] = o.Jl[0]; J[49] = o.Jl[1]; J[50] = o.Jtd[0]; J[51] = o.Jtd[1]; }
+    } else if (a.type == 3) {
+        double S[225]; sqrt_info_upper(15, c + 62, S);
+        imu_eval(c, S, gl, P[0], P[1], P[2], P[3], a.want_j != 0, r, J);
+    } else if (a.type == 4) {
+        double S[36]; sqrt_info_upper(6, c + 25, S);
+        wheel_eval(c, S, P[0], P[1], P[2], P[3][0], P[4][0], P[5][0], P[6][0], a.want_j != 0, r, J);
+    } else {
+        plane_eval(gl + 7, P[0], P[1], P[2], P[3][0], a.want_j != 0, r, J);
+    }
+}
+#ifndef VIWB_HOST_EMU
+__global__ void eval_factor_kernel(EvalArgs a) { if (threadIdx.x == 0 && blockIdx.x == 0) eval_factor_device(a); }
+#endif
+
+extern "C" int viwb_factor_evaluate(viwb_context *ctx, int type, const viwb_globals *gl, const double *consts, const double *const *params,
+                                    double *residuals, double **jacobians) {
+    if (!ctx || !gl || !params || !residuals || type < 0 || type > 5) return VIWB_ERR_INVALID;
+    static const int nblk[6] = {5, 6, 4, 4, 7, 4};
+    static const int sizes[6][7] = {{7, 7, 7, 1, 1, 0, 0}, {7, 7, 7, 7, 1, 1, 0}, {7, 7, 1, 1, 0, 0, 0}, {7, 9, 7, 9, 0, 0, 0}, {7, 7, 7, 1, 1, 1, 1}, {7, 7, 4, 1, 0, 0, 0}};
+    static const int nres[6] = {2, 2, 2, 15, 6, 3};
+    static const int ncons[6] = {12, 12, 12, 287, 78, 0};
+    std::vector<double> in(11 + 287 + 63, 0.0), out(15 + 450, 0.0);
+    for (int k = 0; k < 3; k++) in[k] = gl->G[k];
+    for (int k = 0; k < 4; k++) in[3 + k] = gl->vis_sqrt_info[k];
+    for (int k = 0; k < 3; k++) in[7 + k] = gl->plane_sqrt_info[k];
+    in[10] = gl->huber_delta;
+    if (ncons[type]) { if (!consts) return VIWB_ERR_INVALID; memcpy(in.data() + 11, consts, sizeof(double) * ncons[type]); }
+    for (int i = 0; i < nblk[type]; i++) memcpy(in.data() + 11 + 287 + 9 * i, params[i], sizeof(double) * sizes[type][i]);
+    double *din = nullptr, *dout = nullptr;
+    CK(dev_malloc((void **)&din, in.size() * 8)); CK(dev_malloc((void **)&dout, out.size() * 8));
+    CK(dev_h2d(din, in.data(), in.size() * 8, ctx->stream));
+    EvalArgs a; a.type = type; a.want_j = jacobians ? 1 : 0; a.in = din; a.out = dout;
+#ifdef VIWB_HOST_EMU
+    eval_factor_device(a);
+#else
+    eval_factor_kernel<<<1, 32, 0, ctx->stream>>>(a);
+#endif
+    ctx->launches++;
+    CK(dev_d2h(out.data(), dout, out.size() * 8, ctx->stream)); CK(dev_sync(ctx->stream));
+    dev_free(din); dev_free(dout);
+    for (int i = 0; i < nres[type]; i++) residuals[i] = out[i];
+    if (jacobians) {   // formatting only: tangent columns -> the reference's row-major (rows x global size) blocks, last pose column zero
+        const double *J = out.data() + 15;
+        int ld = 0, tcol[7];
+        if (type <= 2) {   // record layout A | B | E0 | E1 | l | td, 2 rows each
+            const int off0[5] = {0, 12, 24, 48, 50}, off1[6] = {0, 12, 24, 36, 48, 50}, off2[4] = {24, 36, 48, 50};
+            const int *off = type == 0 ? off0 : type == 1 ? off1 : off2;
+            for (int i = 0; i < nblk[type]; i++) {
+                if (!jacobians[i]) continue;
+                const int gs = sizes[type][i], ts = gs == 7 ? 6 : 1;
+                for (int r = 0; r < 2; r++) { for (int c2 = 0; c2 < ts; c2++) jacobians[i][r * gs + c2] = J[off[i] + r * ts + c2]; if (gs == 7) jacobians[i][r * gs + 6] = 0.0; }
+            }
+        } else {
+            int c0 = 0;
+            for (int i = 0; i < nblk[type]; i++) { tcol[i] = c0; const int gs = sizes[type][i]; c0 += gs == 7 ? 6 : gs == 4 ? 3 : gs; }
+            ld = c0;
+            for (int i = 0; i < nblk[type]; i++) {
+                if (!jacobians[i]) continue;
+                const int gs = sizes[type][i], ts = gs == 7 ? 6 : gs == 4 ? 3 : gs;
+                for (int r = 0; r < nres[type]; r++) { for (int c2 = 0; c2 < ts; c2++) jacobians[i][r * gs + c2] = J[r * ld + tcol[i] + c2]; for (int c2 = ts; c2 < gs; c2++) jacobians[i][r * gs + c2] = 0.0; }
+            }
+        }
+    }
+    return VIWB_OK;
+}
+
+struct PriorEvalArgs { PriorDev p; const double *J, *r, *x0, *x; double *res; };
+VIWB_D void prior_eval_device(const PriorEvalArgs &a, int tid, int nt, double *dx) {
+    if (tid == 0) prior_dx(a.p, a.x, a.x0, dx);
+    VIWB_SYNC();
+    for (int i = tid; i < a.p.n; i += nt) { double s = a.r[i]; for (int k = 0; k < a.p.n; k++) s += a.J[i * a.p.n + k] * dx[k]; a.res[i] = s; }
+}
+#ifndef VIWB_HOST_EMU
+__global__ void prior_eval_kernel(PriorEvalArgs a) { __shared__ double dx[MAXPRI]; prior_eval_device(a, threadIdx.x, blockDim.x, dx); }
+#endif
+extern "C" int viwb_prior_evaluate(viwb_context *ctx, const viwb_prior *prior, const double *state, double *residuals, double *jacobian) {
+    if (!ctx || !prior || !state || !residuals || prior->n <= 0 || prior->n > MAXPRI) return VIWB_ERR_INVALID;
+    const int n = prior->n;
+    double *d = nullptr;
+    const size_t tot = (size_t)n * n + n + SFIX + SFIX + n;
+    CK(dev_malloc((void **)&d, tot * 8));
+    CK(dev_h2d(d, prior->J, (size_t)n * n * 8, ctx->stream)); CK(dev_h2d(d + (size_t)n * n, prior->r, n * 8, ctx->stream));
+    CK(dev_h2d(d + (size_t)n * n + n, prior->x0, SFIX * 8, ctx->stream)); CK(dev_h2d(d + (size_t)n * n + n + SFIX, state, SFIX * 8, ctx->stream));
+    PriorEvalArgs a; memset(&a, 0, sizeof a);
+    a.p.n = n; a.p.nb = prior->num_blocks;
+    for (int i = 0; i < prior->num_blocks; i++) { a.p.block_id[i] = prior->block_id[i]; a.p.block_idx[i] = prior->block_idx[i]; }
+    a.J = d; a.r = d + (size_t)n * n; a.x0 = a.r + n; a.x = a.x0 + SFIX; a.res = d + (size_t)n * n + n + 2 * SFIX;
+#ifdef VIWB_HOST_EMU
+    { double dx[MAXPRI]; prior_eval_device(a, 0, 1, dx); }
+#else
+    prior_eval_kernel<<<1, 128, 0, ctx->stream>>>(a);
+#endif
+    ctx->launches++;
+    CK(dev_d2h(residuals, a.res, n * 8, ctx->stream)); CK(dev_sync(ctx->stream));
+    dev_free(d);
+    if (jacobian) {   // formatting only (marginalization_factor.cpp:381-394): J_lin columns at the block's state offset
+        memset(jacobian, 0, sizeof(double) * n * SFIX);
+        for (int i = 0; i < prior->num_blocks; i++) {
+            const int bq = prior->block_id[i], ls = blk_msize(bq), idx = prior->block_idx[i], off = blk_off(bq);
+            for (int r = 0; r < n; r++) for (int k = 0; k < ls; k++) jacobian[(size_t)r * SFIX + off + k] = prior->J[(size_t)r * n + idx + k];
+        }
+    }
+    return VIWB_OK;
+}
+
+// -------------------------------------------------------------------------------------- feature tracker
+extern "C" int viwb_lk_track(viwb_context *ctx, const uint8_t *prev_img, const uint8_t *next_img, int width, int height, int stride,
+                             const float *prev_pts, float *next_pts, int n, int win_size, int max_level, int max_iter, float eps, int flags,
+                             float min_eig_threshold, uint8_t *status, float *err) {
+    if (!ctx || !prev_img || !next_img || !prev_pts || !next_pts || !status || n < 0 || width <= 0 || height <= 0) return VIWB_ERR_INVALID;
+    if (win_size != 21) return fail(ctx, VIWB_ERR_UNSUPPORTED, "only the reference's 21x21 window is supported");
+    if (max_level < 0 || max_level > 3) return fail(ctx, VIWB_ERR_UNSUPPORTED, "maxLevel must be 0..3");
+    long long nl = 0;
+    int rc = lk_track_host(ctx->device, ctx->stream, prev_img, next_img, width, height, stride, prev_pts, next_pts, n, max_level, max_iter, eps, flags,
+                           min_eig_threshold, status, err, &nl);
+    ctx->launches += nl;
+    if (rc) return fail(ctx, VIWB_ERR_CUDA, "lk_track failed");
+    return VIWB_OK;
+}
+
+extern "C" int viwb_track_checked(viwb_context *ctx, const uint8_t *img_a, const uint8_t *img_b, int width, int height, int stride,
+                                  const float *pts_a, float *pts_b, int n, int mode, int flow_back, uint8_t *status) {
+    if (!ctx || !img_a || !img_b || !pts_a || !pts_b || !status || n < 0) return VIWB_ERR_INVALID;
+    long long nl = 0;
+    int rc = lk_track_checked_host(ctx->device, ctx->stream, img_a, img_b, width, height, stride, pts_a, pts_b, n, mode, flow_back, status, &nl);
+    ctx->launches += nl;
+    if (rc) return fail(ctx, VIWB_ERR_CUDA, "track_checked failed");
+    return VIWB_OK;
+}

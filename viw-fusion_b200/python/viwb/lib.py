@@ -1,0 +1,228 @@
+"""ctypes binding of libviwb.so (viw-fusion_b200/csrc), the CUDA implementation behind include/viwb.h.
+
+No fallback of any kind: if the shared library is missing, or no CUDA device is usable, creating a Context raises.
+`Context(device, libpath=...)` lets the CPU test-suite point the same binding at the test-only kernel-logic
+emulation build (tests/emu/libviwb_emu.so); the product never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.normpath(os.path.join(_HERE, "..", "..", "csrc", "libviwb.so"))
+
+EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", "viwb_launch_count", "viwb_default_options",
+           "viwb_default_globals", "viwb_factor_evaluate", "viwb_prior_evaluate", "viwb_window_solve", "viwb_gauge_reanchor",
+           "viwb_marginalize", "viwb_optimization", "viwb_optimization_batch", "viwb_batch_create", "viwb_batch_reset_states",
+           "viwb_batch_run", "viwb_batch_download", "viwb_batch_algorithmic_bytes", "viwb_batch_destroy",
+           "viwb_debug_normal_equations", "viwb_lk_track", "viwb_track_checked"]
+
+
+class ViwbError(RuntimeError):
+    pass
+
+
+def load(libpath=None):
+    path = libpath or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise ViwbError("libviwb.so not found at %s -- build it with __graft_entry__.build() (nvcc, sm_100a)" % path)
+    lib = C.CDLL(path)
+    lib.viwb_last_error.restype = C.c_char_p
+    lib.viwb_launch_count.restype = C.c_longlong
+    lib.viwb_batch_algorithmic_bytes.restype = C.c_double
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(abi.c_double_p)
+
+
+class Context:
+    def __init__(self, device=0, libpath=None):
+        self.lib = load(libpath)
+        self.h = C.c_void_p()
+        rc = self.lib.viwb_create(C.c_int(device), C.byref(self.h))
+        if rc:
+            raise ViwbError("viwb_create(device=%d) failed with %d: no usable CUDA device (there is no CPU fallback)" % (device, rc))
+
+    def close(self):
+        if self.h:
+            self.lib.viwb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def _ck(self, rc, what):
+        if rc:
+            raise ViwbError("%s failed with %d: %s" % (what, rc, self.lib.viwb_last_error(self.h).decode()))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.viwb_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "viwb_set_stream")
+
+    def launch_count(self):
+        return int(self.lib.viwb_launch_count(self.h))
+
+    # ---------------------------------------------------------------- factor level
+    def factor_evaluate(self, ftype, globals_, consts, params, want_jac=True, null_jac=()):
+        sizes = abi.FACTOR_BLOCK_SIZES[ftype]
+        nres = abi.FACTOR_RESIDUALS[ftype]
+        P = [np.ascontiguousarray(p, np.float64) for p in params]
+        pp = (abi.c_double_p * len(P))(*[_dp(p) for p in P])
+        res = np.zeros(nres)
+        cst = np.ascontiguousarray(consts, np.float64) if consts is not None else None
+        jacs = [None if (not want_jac or i in null_jac) else np.zeros((nres, s)) for i, s in enumerate(sizes)]
+        jp = (abi.c_double_p * len(P))(*[(_dp(j) if j is not None else None) for j in jacs]) if want_jac else None
+        self._ck(self.lib.viwb_factor_evaluate(self.h, C.c_int(ftype), C.byref(globals_), _dp(cst) if cst is not None else None, pp, _dp(res), jp),
+                 "viwb_factor_evaluate")
+        return res, jacs
+
+    def prior_evaluate(self, prior, state, want_jac=True):
+        st = np.ascontiguousarray(state[:abi.STATE_FIXED], np.float64)
+        res = np.zeros(prior.n)
+        jac = np.zeros((prior.n, abi.STATE_FIXED)) if want_jac else None
+        self._ck(self.lib.viwb_prior_evaluate(self.h, C.byref(prior.c), _dp(st), _dp(res), _dp(jac) if want_jac else None), "viwb_prior_evaluate")
+        return res, jac
+
+    # ---------------------------------------------------------------- window level
+    def window_solve(self, problem, state, options=None):
+        st = np.array(state, np.float64, copy=True)
+        opt = options if options is not None else abi.default_options()
+        summ = abi.Summary()
+        self._ck(self.lib.viwb_window_solve(self.h, C.byref(problem.c), _dp(st), C.byref(opt), C.byref(summ)), "viwb_window_solve")
+        return st, summ
+
+    def gauge_reanchor(self, problem, state_before, state):
+        sb = np.ascontiguousarray(state_before, np.float64)
+        st = np.array(state, np.float64, copy=True)
+        self._ck(self.lib.viwb_gauge_reanchor(self.h, C.byref(problem.c), _dp(sb), _dp(st)), "viwb_gauge_reanchor")
+        return st
+
+    def marginalize(self, problem, state, flag):
+        st = np.ascontiguousarray(state, np.float64)
+        out = abi.PriorData()
+        self._ck(self.lib.viwb_marginalize(self.h, C.byref(problem.c), _dp(st), C.c_int(flag), C.byref(out.c)), "viwb_marginalize")
+        return out
+
+    def optimization(self, problem, state, flag, options=None, want_prior=True):
+        st = np.array(state, np.float64, copy=True)
+        opt = options if options is not None else abi.default_options()
+        summ = abi.Summary()
+        out = abi.PriorData() if want_prior else None
+        self._ck(self.lib.viwb_optimization(self.h, C.byref(problem.c), _dp(st), C.byref(opt), C.c_int(flag), C.byref(summ),
+                                            C.byref(out.c) if out else None), "viwb_optimization")
+        return st, summ, out
+
+    def normal_equations(self, problem, state):
+        st = np.ascontiguousarray(state, np.float64)
+        T = abi.TANGENT_FIXED
+        H, g = np.zeros((T, T)), np.zeros(T)
+        lm = np.zeros((max(problem.num_landmarks, 1), 82))
+        c = C.c_double()
+        self._ck(self.lib.viwb_debug_normal_equations(self.h, C.byref(problem.c), _dp(st), _dp(H), _dp(g), _dp(lm), C.byref(c)),
+                 "viwb_debug_normal_equations")
+        return H, g, lm[: problem.num_landmarks], c.value
+
+    def batch(self, problems, states, flags=None, options=None):
+        return Batch(self, problems, states, flags, options)
+
+    def optimization_batch(self, problems, states, flags, options=None, want_priors=True):
+        """Host buffers in, host buffers out (the e2e path)."""
+        B = len(problems)
+        arr = (abi.Problem * B)()
+        for i, p in enumerate(problems):
+            p.fill(arr[i])
+        sts = [np.array(s, np.float64, copy=True) for s in states]
+        sp = (abi.c_double_p * B)(*[_dp(s) for s in sts])
+        fl = (C.c_int32 * B)(*[int(f) for f in flags])
+        opt = options if options is not None else abi.default_options()
+        summ = (abi.Summary * B)()
+        pri = [abi.PriorData() for _ in range(B)] if want_priors else None
+        parr = None
+        if want_priors:
+            parr = (abi.Prior * B)()
+            for i, p in enumerate(pri):
+                parr[i] = p.c
+        self._ck(self.lib.viwb_optimization_batch(self.h, C.c_int(B), arr, sp, C.byref(opt), fl, summ, parr), "viwb_optimization_batch")
+        if want_priors:
+            for i, p in enumerate(pri):
+                p.c.valid, p.c.n, p.c.num_blocks = parr[i].valid, parr[i].n, parr[i].num_blocks
+                for k in range(abi.NUM_FIXED_BLOCKS):
+                    p.c.block_id[k], p.c.block_idx[k] = parr[i].block_id[k], parr[i].block_idx[k]
+        return sts, list(summ), pri
+
+    # ---------------------------------------------------------------- feature tracker
+    def lk_track(self, prev_img, next_img, prev_pts, next_pts=None, max_level=3, max_iter=30, eps=0.01, flags=0, min_eig=1e-4):
+        a = np.ascontiguousarray(prev_img, np.uint8)
+        b = np.ascontiguousarray(next_img, np.uint8)
+        h, w = a.shape
+        p0 = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+        n = len(p0)
+        p1 = np.array(next_pts if next_pts is not None else p0, np.float32, copy=True).reshape(-1, 2)
+        st = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32)
+        self._ck(self.lib.viwb_lk_track(self.h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_int(a.strides[0]),
+                                        p0.ctypes.data_as(C.c_void_p), p1.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(21), C.c_int(max_level),
+                                        C.c_int(max_iter), C.c_float(eps), C.c_int(flags), C.c_float(min_eig), st.ctypes.data_as(C.c_void_p),
+                                        err.ctypes.data_as(C.c_void_p)), "viwb_lk_track")
+        return p1, st, err
+
+    def track_checked(self, img_a, img_b, pts_a, mode=0, flow_back=True):
+        a = np.ascontiguousarray(img_a, np.uint8)
+        b = np.ascontiguousarray(img_b, np.uint8)
+        h, w = a.shape
+        p0 = np.ascontiguousarray(pts_a, np.float32).reshape(-1, 2)
+        n = len(p0)
+        p1 = np.zeros_like(p0)
+        st = np.zeros(n, np.uint8)
+        self._ck(self.lib.viwb_track_checked(self.h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_int(a.strides[0]),
+                                             p0.ctypes.data_as(C.c_void_p), p1.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(mode),
+                                             C.c_int(1 if flow_back else 0), st.ctypes.data_as(C.c_void_p)), "viwb_track_checked")
+        return p1, st
+
+
+class Batch:
+    """Device-resident batch of windows: upload once, run many times."""
+
+    def __init__(self, ctx, problems, states, flags=None, options=None):
+        self.ctx = ctx
+        self.B = len(problems)
+        self.problems = problems
+        self._arr = (abi.Problem * self.B)()
+        for i, p in enumerate(problems):
+            p.fill(self._arr[i])
+        self._states = [np.ascontiguousarray(s, np.float64) for s in states]
+        sp = (abi.c_double_p * self.B)(*[_dp(s) for s in self._states])
+        fl = (C.c_int32 * self.B)(*[int(f) for f in flags]) if flags is not None else None
+        opt = options if options is not None else abi.default_options()
+        self.h = C.c_void_p()
+        ctx._ck(ctx.lib.viwb_batch_create(ctx.h, C.c_int(self.B), self._arr, sp, C.byref(opt), fl, C.byref(self.h)), "viwb_batch_create")
+
+    def run(self):
+        self.ctx._ck(self.ctx.lib.viwb_batch_run(self.ctx.h, self.h), "viwb_batch_run")
+
+    def algorithmic_bytes(self):
+        return float(self.ctx.lib.viwb_batch_algorithmic_bytes(self.h))
+
+    def download(self, want_priors=True):
+        sts = [np.zeros(p.state_size) for p in self.problems]
+        sp = (abi.c_double_p * self.B)(*[_dp(s) for s in sts])
+        summ = (abi.Summary * self.B)()
+        pri = [abi.PriorData() for _ in range(self.B)] if want_priors else None
+        parr = None
+        if want_priors:
+            parr = (abi.Prior * self.B)()
+            for i, p in enumerate(pri):
+                parr[i] = p.c
+        self.ctx._ck(self.ctx.lib.viwb_batch_download(self.ctx.h, self.h, sp, summ, parr), "viwb_batch_download")
+        if want_priors:
+            for i, p in enumerate(pri):
+                p.c.valid, p.c.n, p.c.num_blocks = parr[i].valid, parr[i].n, parr[i].num_blocks
+                for k in range(abi.NUM_FIXED_BLOCKS):
+                    p.c.block_id[k], p.c.block_idx[k] = parr[i].block_id[k], parr[i].block_idx[k]
+        return sts, list(summ), pri
+
+    def destroy(self):
+        if self.h:
+            self.ctx.lib.viwb_batch_destroy(self.ctx.h, self.h)
+            self.h = C.c_void_p()
