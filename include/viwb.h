@@ -212,6 +212,10 @@ const char *viwb_last_error(const viwb_context *ctx);
 int viwb_set_stream(viwb_context *ctx, void *cuda_stream);
 /* number of kernels this context launched since creation (bench.py's gpu_launches) */
 long long viwb_launch_count(const viwb_context *ctx);
+/* optional CUDA-event timing around every kernel launch (used by bench.py for the live roofline numbers) */
+int viwb_set_profiling(viwb_context *ctx, int enable);
+int viwb_profile_count(viwb_context *ctx);
+int viwb_profile_get(viwb_context *ctx, int idx, char *name, int name_cap, double *total_ms, long long *launches);
 void viwb_default_options(viwb_options *opt);
 void viwb_default_globals(viwb_globals *g);
 

@@ -48,6 +48,18 @@ static int dev_d2h(void *h, const void *d, size_t n, stream_t s) { return n ? (i
 static int dev_d2d(void *d, const void *s_, size_t n, stream_t s) { return n ? (int)cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s) : 0; }
 static int dev_sync(stream_t s) { return (int)cudaStreamSynchronize(s); }
 static const char *dev_errstr(int e) { return cudaGetErrorString((cudaError_t)e); }
+// optional per-kernel CUDA-event profiler (bench.py's live roofline timing); off by default
+struct Profiler {
+    bool on = false;
+    std::vector<std::string> names; std::vector<double> ms; std::vector<long long> count;
+    struct Rec { int idx; cudaEvent_t a, b; };
+    std::vector<Rec> pending;
+    int index(const char *n) { for (size_t i = 0; i < names.size(); i++) if (names[i] == n) return (int)i; names.push_back(n); ms.push_back(0); count.push_back(0); return (int)names.size() - 1; }
+    void begin(const char *n, cudaStream_t s) { if (!on) return; Rec r; r.idx = index(n); cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, s); pending.push_back(r); }
+    void end(cudaStream_t s) { if (!on) return; cudaEventRecord(pending.back().b, s); }
+    void collect() { for (auto &r : pending) { cudaEventSynchronize(r.b); float t = 0; cudaEventElapsedTime(&t, r.a, r.b); ms[r.idx] += t; count[r.idx]++; cudaEventDestroy(r.a); cudaEventDestroy(r.b); } pending.clear(); }
+};
+static Profiler g_prof;
 #define DEF_KERNEL(name, maxnt) \
     __global__ void __launch_bounds__(maxnt) name##_kernel(BatchDev bd, int mode) { \
         extern __shared__ double viwb_smem[]; \
@@ -62,7 +74,7 @@ DEF_KERNEL(solve, 512)
 DEF_KERNEL(reanchor, 32)
 DEF_KERNEL(marg, 256)
 #define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) \
-    do { if ((gx) > 0 && (gy) > 0) name##_kernel<<<dim3((gx), (gy)), (nt), (smem_bytes), (stream)>>>(bd, mode); } while (0)
+    do { if ((gx) > 0 && (gy) > 0) { g_prof.begin((mode) == 1 ? #name "_marg" : #name, stream); name##_kernel<<<dim3((gx), (gy)), (nt), (smem_bytes), (stream)>>>(bd, mode); g_prof.end(stream); } } while (0)
 #define NT(n) (n)
 #endif
 
@@ -456,6 +468,37 @@ extern "C" void viwb_destroy(viwb_context *ctx) {
 extern "C" const char *viwb_last_error(const viwb_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" int viwb_set_stream(viwb_context *ctx, void *s) { if (!ctx) return VIWB_ERR_INVALID; ctx->stream = (stream_t)s; return VIWB_OK; }
 extern "C" long long viwb_launch_count(const viwb_context *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int viwb_set_profiling(viwb_context *ctx, int enable) {
+    if (!ctx) return VIWB_ERR_INVALID;
+#ifndef VIWB_HOST_EMU
+    g_prof.collect(); g_prof.on = enable != 0;
+    if (enable) { g_prof.names.clear(); g_prof.ms.clear(); g_prof.count.clear(); }
+#else
+    (void)enable;
+#endif
+    return VIWB_OK;
+}
+extern "C" int viwb_profile_count(viwb_context *ctx) {
+    (void)ctx;
+#ifndef VIWB_HOST_EMU
+    g_prof.collect(); return (int)g_prof.names.size();
+#else
+    return 0;
+#endif
+}
+extern "C" int viwb_profile_get(viwb_context *ctx, int idx, char *name, int name_cap, double *total_ms, long long *launches) {
+    (void)ctx;
+#ifndef VIWB_HOST_EMU
+    if (idx < 0 || idx >= (int)g_prof.names.size()) return VIWB_ERR_INVALID;
+    if (name && name_cap > 0) { strncpy(name, g_prof.names[idx].c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (total_ms) *total_ms = g_prof.ms[idx];
+    if (launches) *launches = g_prof.count[idx];
+    return VIWB_OK;
+#else
+    (void)idx; (void)name; (void)name_cap; (void)total_ms; (void)launches; return VIWB_ERR_INVALID;
+#endif
+}
 
 extern "C" int viwb_batch_create(viwb_context *ctx, int batch, const viwb_problem *problems, const double *const *states,
                                  const viwb_options *options, const int32_t *margin_flags, viwb_batch **out) {

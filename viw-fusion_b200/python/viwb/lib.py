@@ -14,7 +14,7 @@ from . import abi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.normpath(os.path.join(_HERE, "..", "..", "csrc", "libviwb.so"))
 
-EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", "viwb_launch_count", "viwb_default_options",
+EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", "viwb_launch_count", "viwb_set_profiling", "viwb_profile_count", "viwb_profile_get", "viwb_default_options",
            "viwb_default_globals", "viwb_factor_evaluate", "viwb_prior_evaluate", "viwb_window_solve", "viwb_gauge_reanchor",
            "viwb_marginalize", "viwb_optimization", "viwb_optimization_batch", "viwb_batch_create", "viwb_batch_reset_states",
            "viwb_batch_run", "viwb_batch_download", "viwb_batch_algorithmic_bytes", "viwb_batch_destroy",
@@ -62,6 +62,19 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.viwb_launch_count(self.h))
+
+    def set_profiling(self, on):
+        self._ck(self.lib.viwb_set_profiling(self.h, C.c_int(1 if on else 0)), "viwb_set_profiling")
+
+    def profile(self):
+        """{kernel name: (total ms, launches)} accumulated since set_profiling(True)."""
+        out = {}
+        for i in range(self.lib.viwb_profile_count(self.h)):
+            name = C.create_string_buffer(64)
+            ms, cnt = C.c_double(), C.c_longlong()
+            self.lib.viwb_profile_get(self.h, C.c_int(i), name, C.c_int(64), C.byref(ms), C.byref(cnt))
+            out[name.value.decode()] = (ms.value, cnt.value)
+        return out
 
     # ---------------------------------------------------------------- factor level
     def factor_evaluate(self, ftype, globals_, consts, params, want_jac=True, null_jac=()):
