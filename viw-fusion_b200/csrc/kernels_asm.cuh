@@ -1,0 +1,252 @@
+// kernels_asm.cuh -- assembly of the normal equations without atomics and without a dense H in HBM.
+//
+// The factor graph of a window is static during a solve, so the host builds an assembly plan once per batch:
+//   FRAME  item (frame a, chunk)      : list of (factor, role) touching pose a      -> F^T F (21), F^T [E0 E1 td] (78), F^T r (6)
+//   PAIR   item (frames a<b, chunk)   : list of (factor, role of a)                 -> F_a^T F_b (36)
+//   COMMON item (chunk)               : all factors                                 -> [E0 E1 td]^T [E0 E1 td] (91), ^T r (13)
+// Lists are cut into chunks of ASM_CHUNK entries; chunk c of every list is "phase" c.  Items of one phase write
+// disjoint blocks of H, so the consumer adds them phase by phase with plain stores (deterministic).
+//   asm_items  : one warp per item, lanes over the item's outputs, records streamed from HBM/L2 (54 doubles per factor)
+//   syrk       : one block per window, T = sum_k gamma_k w_k w_k^T with a shared-memory tile of W and 4x4 register tiles
+//   assemble_into(target) : called by the solve kernel (packed shared-memory triangle) and by the marginalisation
+//                kernel (dense marginalisation layout): prior J^T J, IMU / wheel / plane J^T J factor by factor,
+//                visual partial sums phase by phase.
+#pragma once
+#include "layout.cuh"
+#include "factors.cuh"
+#include "kernels_lin.cuh"
+
+namespace viwb {
+
+// slot table of a small factor: (block id, first column inside its Jacobian record), ascending columns
+struct Slot { int blk, col; };
+VIWB_D int imu_slots(int i, int j, Slot *s) { s[0].blk = i; s[0].col = 0; s[1].blk = BLK_SB0 + i; s[1].col = 6; s[2].blk = j; s[2].col = 15; s[3].blk = BLK_SB0 + j; s[3].col = 21; return 4; }
+VIWB_D int wheel_slots(int i, int j, Slot *s) {
+    s[0].blk = i; s[0].col = 0; s[1].blk = j; s[1].col = 6; s[2].blk = BLK_EXW; s[2].col = 12; s[3].blk = BLK_SX; s[3].col = 18;
+    s[4].blk = BLK_SY; s[4].col = 19; s[5].blk = BLK_SW; s[5].col = 20; s[6].blk = BLK_TDW; s[6].col = 21; return 7;
+}
+VIWB_D int plane_slots(int i, Slot *s) { s[0].blk = i; s[0].col = 0; s[1].blk = BLK_EXW; s[1].col = 6; s[2].blk = BLK_PR; s[2].col = 12; s[3].blk = BLK_PZ; s[3].col = 15; return 4; }
+
+// offset of common column c (0..12: ex0 6 | ex1 6 | td) inside a visual record, and its row stride
+VIWB_HD int common_off(int c) { return c < 6 ? REC_E0 + c : c < 12 ? REC_E1 + (c - 6) : REC_TD; }
+VIWB_HD int common_stride(int c) { return c < 12 ? 6 : 1; }
+VIWB_HD void sym_unrank(int e, int &p, int &q) { p = 0; while ((p + 1) * (p + 2) / 2 <= e) p++; q = e - p * (p + 1) / 2; }
+
+// ------------------------------------------------------------------------------------------------ asm_items
+// grid: ceil(nitems / warps_per_block); mode selects the solver or the marginalisation item table.
+VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem;
+    const int W = nt < 32 ? nt : 32, wpb = nt / W, lane = tid % W;
+    const int nitems = (mode == MODE_SOLVE) ? bd.nitems_solve : bd.nitems_marg;
+    const int it = bx * wpb + tid / W;
+    if (it >= nitems) return;
+    const int gi = (mode == MODE_SOLVE) ? it : bd.nitems_solve + it;
+    const AsmItem item = bd.items[gi];
+    if (mode == MODE_SOLVE && bd.work[item.win].status != ST_RUNNING) return;
+    double *out = bd.asm_out + (size_t)gi * ASM_STRIDE;
+    const int *list = bd.asm_list;
+    int nout;
+    if (item.kind == ITEM_FRAME) nout = 105; else if (item.kind == ITEM_PAIR) nout = 36; else nout = 104;
+    for (int o = lane; o < nout; o += W) {
+        // (ia, sa): record offset / row stride of the left operand, (ib, sb) of the right one; role-dependent parts resolved per entry
+        int ka = 0, kb = 0, pa = 0, pb = 0;      // k*: 0 = frame slot of a, 1 = frame slot of b (PAIR), 2 = common column, 3 = residual
+        if (item.kind == ITEM_FRAME) {
+            if (o < 21) { sym_unrank(o, pa, pb); ka = 0; kb = 0; }
+            else if (o < 99) { if (!item.has_common) { out[o] = 0.0; continue; } pa = (o - 21) / 13; pb = (o - 21) % 13; ka = 0; kb = 2; }
+            else { pa = o - 99; ka = 0; kb = 3; }
+        } else if (item.kind == ITEM_PAIR) { pa = o / 6; pb = o % 6; ka = 0; kb = 1; }
+        else { if (o < 91) { sym_unrank(o, pa, pb); ka = 2; kb = 2; } else { pa = o - 91; ka = 2; kb = 3; } }
+        double acc = 0.0;
+        for (int e = item.lo; e < item.hi; e++) {
+            const int ent = list[e];
+            const double *rec = bd.vis_rec + (size_t)(ent >> 1) * VREC;
+            const int role = ent & 1;
+            int ia, sa, ib, sb;
+            if (ka == 0) { ia = (role ? REC_B : REC_A) + pa; sa = 6; } else { ia = common_off(pa); sa = common_stride(pa); }
+            if (kb == 0) { ib = (role ? REC_B : REC_A) + pb; sb = 6; }
+            else if (kb == 1) { ib = (role ? REC_A : REC_B) + pb; sb = 6; }
+            else if (kb == 2) { ib = common_off(pb); sb = common_stride(pb); }
+            else { ib = 0; sb = 1; }
+            acc += rec[ia] * rec[ib] + rec[ia + sa] * rec[ib + sb];
+        }
+        out[o] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ syrk
+// T = sum_k g_k w_k w_k^T (80 x 80, symmetric, both triangles written), tvec = sum_k g_k w_k gl_k.
+// solver: g_k = gamma_k; marginalisation: g_k = 1 / a_k for the landmarks hosted in frame 0 (gamma holds a_k, 0 = skip).
+enum { SYRK_KC = 32 };
+VIWB_HD size_t syrk_smem_doubles() { return (size_t)SYRK_KC * VSUB + SYRK_KC; }
+VIWB_D void syrk_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    if (mode == MODE_SOLVE && bd.work[w].status != ST_RUNNING) return;
+    if (mode == MODE_MARG && m.margin_flag != 0) return;
+    double *Ws = smem, *gs = smem + SYRK_KC * VSUB;      // Ws[k][80] = sqrt(g_k) w_k ; gs[k] = sqrt(g_k) gl_k
+    const double *W = bd.lm_W + (size_t)m.lm_off * VSUB, *gam = bd.lm_gamma + m.lm_off, *gl = bd.lm_g + m.lm_off;
+    double *T = bd.Tvis + (size_t)w * VSUB * VSUB, *tv = bd.tvec + (size_t)w * VSUB;
+    // 4x4 tiles of the lower triangle (20 x 20 tile grid -> 210 tiles) + 20 tiles (4 entries each) for tvec
+    const int NT4 = VSUB / 4, ntiles = NT4 * (NT4 + 1) / 2;
+    for (int base = 0; base < ntiles + NT4; base += nt) {          // every thread walks the same number of rounds (barriers inside)
+        const int t = base + tid;
+        const bool live = t < ntiles + NT4, is_vec = t >= ntiles;
+        int tp = 0, tq = 0;
+        if (live && !is_vec) sym_unrank(t, tp, tq); else if (live) tp = t - ntiles;
+        double acc[16];
+        for (int i = 0; i < 16; i++) acc[i] = 0.0;
+        for (int k0 = 0; k0 < m.nlm; k0 += SYRK_KC) {
+            const int kc = (m.nlm - k0) < SYRK_KC ? (m.nlm - k0) : SYRK_KC;
+            VIWB_SYNC();
+            for (int e = tid; e < kc * VSUB; e += nt) {
+                const int k = e / VSUB, p = e % VSUB;
+                double g = gam[k0 + k];
+                if (mode == MODE_MARG) g = g > 0.0 ? 1.0 / g : 0.0;
+                const double sg = sqrt(g);
+                Ws[e] = sg * W[(size_t)(k0 + k) * VSUB + p];
+                if (p == 0) gs[k] = sg * gl[k0 + k];
+            }
+            VIWB_SYNC();
+            if (live && !is_vec) {
+                for (int k = 0; k < kc; k++) {
+                    const double *r = Ws + k * VSUB;
+                    const double a0 = r[4 * tp], a1 = r[4 * tp + 1], a2 = r[4 * tp + 2], a3 = r[4 * tp + 3];
+                    const double b0 = r[4 * tq], b1 = r[4 * tq + 1], b2 = r[4 * tq + 2], b3 = r[4 * tq + 3];
+                    acc[0] += a0 * b0; acc[1] += a0 * b1; acc[2] += a0 * b2; acc[3] += a0 * b3;
+                    acc[4] += a1 * b0; acc[5] += a1 * b1; acc[6] += a1 * b2; acc[7] += a1 * b3;
+                    acc[8] += a2 * b0; acc[9] += a2 * b1; acc[10] += a2 * b2; acc[11] += a2 * b3;
+                    acc[12] += a3 * b0; acc[13] += a3 * b1; acc[14] += a3 * b2; acc[15] += a3 * b3;
+                }
+            } else if (live) {
+                for (int k = 0; k < kc; k++) { const double *r = Ws + k * VSUB; const double g = gs[k]; for (int i = 0; i < 4; i++) acc[i] += r[4 * tp + i] * g; }
+            }
+        }
+        if (live && !is_vec) {
+            for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { T[(4 * tp + i) * VSUB + 4 * tq + j] = acc[i * 4 + j]; T[(4 * tq + j) * VSUB + 4 * tp + i] = acc[i * 4 + j]; }
+        } else if (live) { for (int i = 0; i < 4; i++) tv[4 * tp + i] = acc[i]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ assemble_into
+// A target provides:  int col(int blk, int k)  (-1 if that column is not part of the system),
+//                     void add(int i, int j, double v)  for an unordered index pair (called once per pair per phase),
+//                     void addg(int i, double v).
+struct PackedTarget {      // solver: packed lower triangle in shared memory over the compact active columns
+    double *L, *g; const short *tcol;
+    VIWB_DM int col(int blk, int k) const { return (tcol[blk] >= 0 && k < blk_tsize(blk)) ? tcol[blk] + k : -1; }
+    VIWB_DM void add(int i, int j, double v) const { if (i >= j) L[i * (i + 1) / 2 + j] += v; else L[j * (j + 1) / 2 + i] += v; }
+    VIWB_DM void addg(int i, double v) const { g[i] += v; }
+};
+struct DenseTarget {       // marginalisation: dense symmetric matrix in the marginalisation layout (global memory)
+    double *M, *g; int ld; const unsigned char *flags;
+    VIWB_DM int col(int blk, int k) const { return ((flags[blk] & 1u) && k < blk_msize(blk)) ? blk_moff(blk) + k : -1; }
+    VIWB_DM void add(int i, int j, double v) const { M[(size_t)i * ld + j] += v; if (i != j) M[(size_t)j * ld + i] += v; }
+    VIWB_DM void addg(int i, double v) const { g[i] += v; }
+};
+
+// J^T J / J^T r of one small factor: J rows x ld (row-major) with `ns` parameter slots
+template <typename Target>
+VIWB_D void add_small_factor(const Target &t, const double *rec, int rows, int ld, const Slot *sl, int ns, int tid, int nt) {
+    const double *res = rec, *J = rec + rows;
+    // local column -> (block, k)
+    for (int e = tid; e < ld * (ld + 1) / 2 + ld; e += nt) {
+        if (e < ld * (ld + 1) / 2) {
+            int p, q; sym_unrank(e, p, q);
+            int bp = -1, kp = 0, bq = -1, kq = 0;
+            for (int s = 0; s < ns; s++) { if (p >= sl[s].col) { bp = sl[s].blk; kp = p - sl[s].col; } if (q >= sl[s].col) { bq = sl[s].blk; kq = q - sl[s].col; } }
+            const int ci = t.col(bp, kp), cj = t.col(bq, kq);
+            if (ci < 0 || cj < 0) continue;
+            double v = 0.0;
+            for (int r = 0; r < rows; r++) v += J[r * ld + p] * J[r * ld + q];
+            t.add(ci, cj, v);
+        } else {
+            const int p = e - ld * (ld + 1) / 2;
+            int bp = -1, kp = 0;
+            for (int s = 0; s < ns; s++) if (p >= sl[s].col) { bp = sl[s].blk; kp = p - sl[s].col; }
+            const int ci = t.col(bp, kp);
+            if (ci < 0) continue;
+            double v = 0.0;
+            for (int r = 0; r < rows; r++) v += J[r * ld + p] * res[r];
+            t.addg(ci, v);
+        }
+    }
+    VIWB_SYNC();
+}
+
+// common column c (0..12) -> (block, k)
+VIWB_HD int common_blk(int c) { return c < 6 ? BLK_EX0 : c < 12 ? BLK_EX1 : BLK_TD; }
+VIWB_HD int common_k(int c) { return c < 6 ? c : c < 12 ? c - 6 : 0; }
+
+// Adds every contribution to the (zero-initialised by the caller) target.  All threads of the block must call it.
+template <typename Target>
+VIWB_D void assemble_into(const Target &t, const BatchDev &bd, int w, int mode, int tid, int nt) {
+    const WinMeta &m = bd.meta[w];
+    const bool prior_only = marg_prior_only(m, mode);
+    // ---- prior: A = J_lin^T J_lin (constant during the solve) and g = J_lin^T r
+    if (m.prior_idx >= 0) {
+        const PriorDev &pr = bd.prior[m.prior_idx];
+        const double *A = bd.prior_A + pr.J_off, *g = bd.prior_g + pr.r_off;
+        for (int e = tid; e < pr.nb * (pr.nb + 1) / 2; e += nt) {        // block pairs; entries inside
+            int bi, bj; sym_unrank(e, bi, bj);
+            const int ba = pr.block_id[bi], bb = pr.block_id[bj], ia = pr.block_idx[bi], ib = pr.block_idx[bj];
+            const int sa = blk_msize(ba), sb = blk_msize(bb);
+            for (int p = 0; p < sa; p++) for (int q = 0; q < (bi == bj ? p + 1 : sb); q++) {
+                const int ci = t.col(ba, p), cj = t.col(bb, q);
+                if (ci >= 0 && cj >= 0) t.add(ci, cj, A[(size_t)(ia + p) * pr.n + ib + q]);
+            }
+        }
+        for (int bi = tid; bi < pr.nb; bi += nt) {
+            const int ba = pr.block_id[bi];
+            for (int p = 0; p < blk_msize(ba); p++) { const int ci = t.col(ba, p); if (ci >= 0) t.addg(ci, g[pr.block_idx[bi] + p]); }
+        }
+    }
+    VIWB_SYNC();
+    // ---- IMU / wheel / plane: one factor at a time (consecutive factors share blocks)
+    Slot sl[8];
+    if (!prior_only) {
+        for (int k = 0; k < m.nimu; k++) {
+            const int f = m.imu_off + k, i = bd.imu_fi[f], j = bd.imu_fj[f];
+            if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+            const int ns = imu_slots(i, j, sl);
+            add_small_factor(t, bd.imu_rec + (size_t)f * IMU_REC, 15, 30, sl, ns, tid, nt);
+        }
+        for (int k = 0; k < m.nwheel; k++) {
+            const int f = m.wheel_off + k, i = bd.wheel_fi[f], j = bd.wheel_fj[f];
+            if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+            const int ns = wheel_slots(i, j, sl);
+            add_small_factor(t, bd.wheel_rec + (size_t)f * WHEEL_REC, 6, 22, sl, ns, tid, nt);
+        }
+        for (int k = 0; k < m.nplane; k++) {
+            const int f = m.plane_off + k, i = bd.plane_f[f];
+            if (mode == MODE_MARG && i != 0) continue;
+            const int ns = plane_slots(i, sl);      // plane_R: 3 tangent columns; its 4th marginalisation column stays zero
+            add_small_factor(t, bd.plane_rec + (size_t)f * PLANE_REC, 3, 16, sl, ns, tid, nt);
+        }
+    }
+    // ---- visual partial sums, phase by phase
+    const int ioff = (mode == MODE_SOLVE) ? m.item_off : bd.nitems_solve + m.mitem_off;
+    const int ni = (mode == MODE_SOLVE) ? m.nitems : (m.margin_flag == 0 ? m.nmitems : 0);
+    const int nph = (mode == MODE_SOLVE) ? m.nphases : m.nmphases;
+    for (int ph = 0; ph < nph; ph++) {
+        for (int e = tid; e < ni * ASM_STRIDE; e += nt) {
+            const int ii = e / ASM_STRIDE, o = e % ASM_STRIDE;
+            const AsmItem &item = bd.items[ioff + ii];
+            if (item.phase != ph) continue;
+            const double v = bd.asm_out[(size_t)(ioff + ii) * ASM_STRIDE + o];
+            if (item.kind == ITEM_FRAME) {
+                if (o < 21) { int p, q; sym_unrank(o, p, q); const int ci = t.col(item.a, p), cj = t.col(item.a, q); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
+                else if (o < 99) { const int p = (o - 21) / 13, c = (o - 21) % 13; const int ci = t.col(item.a, p), cj = t.col(common_blk(c), common_k(c)); if (ci >= 0 && cj >= 0 && item.has_common) t.add(ci, cj, v); }
+                else if (o < 105) { const int ci = t.col(item.a, o - 99); if (ci >= 0) t.addg(ci, v); }
+            } else if (item.kind == ITEM_PAIR) {
+                if (o < 36) { const int ci = t.col(item.a, o / 6), cj = t.col(item.b, o % 6); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
+            } else {
+                if (o < 91) { int p, q; sym_unrank(o, p, q); const int ci = t.col(common_blk(p), common_k(p)), cj = t.col(common_blk(q), common_k(q)); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
+                else if (o < 104) { const int c = o - 91; const int ci = t.col(common_blk(c), common_k(c)); if (ci >= 0) t.addg(ci, v); }
+            }
+        }
+        VIWB_SYNC();
+    }
+}
+
+}  // namespace viwb

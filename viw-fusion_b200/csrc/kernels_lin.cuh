@@ -6,7 +6,7 @@
 //   lin_vis    one thread per visual factor: residual, Huber, tangent Jacobians -> 54-double record   (8a-5/6/7, a-12)
 //   lm_reduce  one thread per landmark: a = |J_l|^2, g_l, w = J_p^T J_l, Schur weight gamma, cost      (Schur, Appendix B)
 //   lin_small  one block per window: IMU / wheel / plane factors and the prior residual + gradient   (8a-8..a-11)
-//   assemble   one block per (window, slice): owner-computes gather of H_pp, g, T = sum gamma w w^T, no atomics
+//   (assembly of the normal equations: kernels_asm.cuh)
 // mode 0 = solver linearisation at x_cand over the tangent layout, mode 1 = marginalisation at x_cur over the
 // marginalisation layout (7 -> 6, plane quaternion counted 4; marginalization_factor.cpp:140-143).
 #pragma once
@@ -199,228 +199,6 @@ VIWB_D void lin_small_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     cost_part[tid] = c;
     VIWB_SYNC();
     if (tid == 0) { double s = 0.0; for (int i = 0; i < nt; i++) s += cost_part[i]; ww.small_cost = s; }
-}
-
-// ------------------------------------------------------------------------------------------------ assemble
-// slot table of a small factor: (block id, column offset inside its Jacobian record)
-struct Slot { int blk, col; };
-VIWB_D int imu_slots(int i, int j, Slot *s) { s[0].blk = i; s[0].col = 0; s[1].blk = BLK_SB0 + i; s[1].col = 6; s[2].blk = j; s[2].col = 15; s[3].blk = BLK_SB0 + j; s[3].col = 21; return 4; }
-VIWB_D int wheel_slots(int i, int j, Slot *s) {
-    s[0].blk = i; s[0].col = 0; s[1].blk = j; s[1].col = 6; s[2].blk = BLK_EXW; s[2].col = 12; s[3].blk = BLK_SX; s[3].col = 18;
-    s[4].blk = BLK_SY; s[4].col = 19; s[5].blk = BLK_SW; s[5].col = 20; s[6].blk = BLK_TDW; s[6].col = 21; return 7;
-}
-VIWB_D int plane_slots(int i, Slot *s) { s[0].blk = i; s[0].col = 0; s[1].blk = BLK_EXW; s[1].col = 6; s[2].blk = BLK_PR; s[2].col = 12; s[3].blk = BLK_PZ; s[3].col = 15; return 4; }
-VIWB_D int find_slot(const Slot *s, int n, int blk) { for (int i = 0; i < n; i++) if (s[i].blk == blk) return s[i].col; return -1; }
-
-// sum over rows of J[:, ca+p] * J[:, cb+q]   (J rows x ld, row-major)
-VIWB_D double col_dot(const double *J, int rows, int ld, int ca, int cb) {
-    double s = 0.0;
-    for (int r = 0; r < rows; r++) s += J[r * ld + ca] * J[r * ld + cb];
-    return s;
-}
-VIWB_D double col_dot_r(const double *J, const double *res, int rows, int ld, int ca) {
-    double s = 0.0;
-    for (int r = 0; r < rows; r++) s += J[r * ld + ca] * res[r];
-    return s;
-}
-// record offset of a visual-subspace block inside the 54-double record, given the factor's role for that block
-VIWB_D int vis_slot(int blk, int type, int fi, int fj, int which /*0: host role, 1: target role*/) {
-    if (blk < 11) { if (type == 2) return -1; return which == 0 ? (blk == fi ? REC_A : -1) : (blk == fj ? REC_B : -1); }
-    if (blk == BLK_EX0) return REC_E0;
-    if (blk == BLK_EX1) return type == 0 ? -1 : REC_E1;
-    if (blk == BLK_TD) return REC_TD;
-    return -1;
-}
-
-// entry (p,q) of  sum_f  U_f^T V_f  over the visual factors that contain both blocks ba, bb (ba != bb or ba == bb)
-VIWB_D double vis_block_entry(const BatchDev &bd, const WinMeta &m, int ba, int bb, int p, int q, int mode) {
-    const int *pp = bd.pair_ptr + m.pair_off;
-    const int ta = blk_tsize(ba), tb = blk_tsize(bb);
-    const int sa = ta == 1 ? 1 : 6, sb = tb == 1 ? 1 : 6;     // row stride inside the record (2 x size)
-    double s = 0.0;
-    // enumerate (h,j) pairs whose factors can contain both blocks
-    const int hmax = (mode == MODE_MARG) ? (m.margin_flag == 0 ? 1 : 0) : NFR;
-    for (int h = 0; h < hmax; h++) {
-        for (int j = 0; j < NFR; j++) {
-            const int lo = pp[h * NFR + j], hi = pp[h * NFR + j + 1];
-            if (lo == hi) continue;
-            // frame-block membership for this pair
-            if (ba < 11 && ba != h && ba != j) continue;
-            if (bb < 11 && bb != h && bb != j) continue;
-            for (int e = lo; e < hi; e++) {
-                const int f = bd.pair_perm[e];
-                const int type = bd.vis_type[f];
-                const double *rec = bd.vis_rec + (size_t)f * VREC;
-                // a frame block may appear as host (A) and, for h == j never (type 2 has no frame blocks)
-                for (int ra = 0; ra < 2; ra++) {
-                    const int oa = vis_slot(ba, type, h, j, ra);
-                    if (oa < 0 || (ba >= 11 && ra == 1)) continue;
-                    for (int rb = 0; rb < 2; rb++) {
-                        const int ob = vis_slot(bb, type, h, j, rb);
-                        if (ob < 0 || (bb >= 11 && rb == 1)) continue;
-                        s += rec[oa + p] * rec[ob + q] + rec[oa + sa + p] * rec[ob + sb + q];
-                    }
-                }
-            }
-        }
-    }
-    return s;
-}
-VIWB_D double vis_grad_entry(const BatchDev &bd, const WinMeta &m, int ba, int p, int mode) {
-    const int *pp = bd.pair_ptr + m.pair_off;
-    const int sa = blk_tsize(ba) == 1 ? 1 : 6;
-    double s = 0.0;
-    const int hmax = (mode == MODE_MARG) ? (m.margin_flag == 0 ? 1 : 0) : NFR;
-    for (int h = 0; h < hmax; h++)
-        for (int j = 0; j < NFR; j++) {
-            if (ba < 11 && ba != h && ba != j) continue;
-            const int lo = pp[h * NFR + j], hi = pp[h * NFR + j + 1];
-            for (int e = lo; e < hi; e++) {
-                const int f = bd.pair_perm[e];
-                const int type = bd.vis_type[f];
-                const double *rec = bd.vis_rec + (size_t)f * VREC;
-                for (int ra = 0; ra < 2; ra++) {
-                    const int oa = vis_slot(ba, type, h, j, ra);
-                    if (oa < 0 || (ba >= 11 && ra == 1)) continue;
-                    s += rec[oa + p] * rec[0] + rec[oa + sa + p] * rec[1];
-                }
-            }
-        }
-    return s;
-}
-
-// contribution of the small factors and the prior to entry (p,q) of block pair (ba, bb)
-VIWB_D double small_block_entry(const BatchDev &bd, const WinMeta &m, int ba, int bb, int p, int q, int mode) {
-    double s = 0.0;
-    Slot sl[8];
-    const bool po = marg_prior_only(m, mode);
-    for (int t = 0; t < (po ? 0 : m.nimu); t++) {
-        const int f = m.imu_off + t, i = bd.imu_fi[f], j = bd.imu_fj[f];
-        if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-        const int ns = imu_slots(i, j, sl), ca = find_slot(sl, ns, ba), cb = find_slot(sl, ns, bb);
-        if (ca >= 0 && cb >= 0) s += col_dot(bd.imu_rec + (size_t)f * IMU_REC + 15, 15, 30, ca + p, cb + q);
-    }
-    for (int t = 0; t < (po ? 0 : m.nwheel); t++) {
-        const int f = m.wheel_off + t, i = bd.wheel_fi[f], j = bd.wheel_fj[f];
-        if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-        const int ns = wheel_slots(i, j, sl), ca = find_slot(sl, ns, ba), cb = find_slot(sl, ns, bb);
-        if (ca >= 0 && cb >= 0) s += col_dot(bd.wheel_rec + (size_t)f * WHEEL_REC + 6, 6, 22, ca + p, cb + q);
-    }
-    for (int t = 0; t < (po ? 0 : m.nplane); t++) {
-        const int f = m.plane_off + t, i = bd.plane_f[f];
-        if (mode == MODE_MARG && i != 0) continue;
-        const int ns = plane_slots(i, sl), ca = find_slot(sl, ns, ba), cb = find_slot(sl, ns, bb);
-        // the plane quaternion has 3 tangent columns; its 4th marginalisation column is identically zero
-        if (ca >= 0 && cb >= 0 && !(ba == BLK_PR && p == 3) && !(bb == BLK_PR && q == 3))
-            s += col_dot(bd.plane_rec + (size_t)f * PLANE_REC + 3, 3, 16, ca + p, cb + q);
-    }
-    if (m.prior_idx >= 0) {
-        const PriorDev &pr = bd.prior[m.prior_idx];
-        int ia = -1, ib = -1;
-        for (int i = 0; i < pr.nb; i++) { if (pr.block_id[i] == ba) ia = pr.block_idx[i]; if (pr.block_id[i] == bb) ib = pr.block_idx[i]; }
-        if (ia >= 0 && ib >= 0) s += bd.prior_A[pr.J_off + (ia + p) * pr.n + ib + q];
-    }
-    return s;
-}
-VIWB_D double small_grad_entry(const BatchDev &bd, const WinMeta &m, int ba, int p, int mode) {
-    double s = 0.0;
-    Slot sl[8];
-    const bool po = marg_prior_only(m, mode);
-    for (int t = 0; t < (po ? 0 : m.nimu); t++) {
-        const int f = m.imu_off + t, i = bd.imu_fi[f], j = bd.imu_fj[f];
-        if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-        const int ns = imu_slots(i, j, sl), ca = find_slot(sl, ns, ba);
-        const double *rec = bd.imu_rec + (size_t)f * IMU_REC;
-        if (ca >= 0) s += col_dot_r(rec + 15, rec, 15, 30, ca + p);
-    }
-    for (int t = 0; t < (po ? 0 : m.nwheel); t++) {
-        const int f = m.wheel_off + t, i = bd.wheel_fi[f], j = bd.wheel_fj[f];
-        if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-        const int ns = wheel_slots(i, j, sl), ca = find_slot(sl, ns, ba);
-        const double *rec = bd.wheel_rec + (size_t)f * WHEEL_REC;
-        if (ca >= 0) s += col_dot_r(rec + 6, rec, 6, 22, ca + p);
-    }
-    for (int t = 0; t < (po ? 0 : m.nplane); t++) {
-        const int f = m.plane_off + t, i = bd.plane_f[f];
-        if (mode == MODE_MARG && i != 0) continue;
-        const int ns = plane_slots(i, sl), ca = find_slot(sl, ns, ba);
-        const double *rec = bd.plane_rec + (size_t)f * PLANE_REC;
-        if (ca >= 0 && !(ba == BLK_PR && p == 3)) s += col_dot_r(rec + 3, rec, 3, 16, ca + p);
-    }
-    if (m.prior_idx >= 0) {
-        const PriorDev &pr = bd.prior[m.prior_idx];
-        for (int i = 0; i < pr.nb; i++) if (pr.block_id[i] == ba) s += bd.prior_g[pr.r_off + pr.block_idx[i] + p];
-    }
-    return s;
-}
-
-// is fixed block b part of the system being assembled?
-VIWB_D bool blk_in_system(const WinMeta &m, int b, int mode) {
-    if (mode == MODE_SOLVE) return m.tcol[b] >= 0;
-    return (m.flags[b] & 1u) != 0;     // marginalisation: every present block counts, constant or not
-}
-
-// grid (B, NSLICE): the block-pair list and the T entries are split round-robin over the slices.
-VIWB_D void assemble_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
-    (void)smem;
-    const int nslice = bd.nslice;
-    const int w = bx;
-    const WinMeta &m = bd.meta[w];
-    if (mode == MODE_SOLVE && bd.work[w].status != ST_RUNNING) return;
-    if (marg_skip(m, mode)) return;
-    const int LD = (mode == MODE_SOLVE) ? TFIX : MLAY;
-    double *H = bd.Hpp + (size_t)w * TFIX * TFIX + (mode == MODE_MARG ? 0 : 0);   // marg layout fits: 193*193 > 192*192 -> uses marg_A
-    if (mode == MODE_MARG) H = bd.marg_A + (size_t)w * (MAXPRI + 16) * (MAXPRI + 16);
-    const int HLD = (mode == MODE_SOLVE) ? TFIX : (MAXPRI + 16);
-    (void)LD;
-    double *g = bd.gfix + (size_t)w * (TFIX + 8);
-    // ---- H blocks and gradient: work item = (block pair, entry); pairs enumerated ba >= bb
-    const int gtid = by * nt + tid, gnt = nslice * nt;
-    for (int pair = 0; pair < NB * (NB + 1) / 2; pair++) {
-        // unrank: ba = row, bb = col of the lower triangle
-        int ba = 0; while ((ba + 1) * (ba + 2) / 2 <= pair) ba++;
-        const int bb = pair - ba * (ba + 1) / 2;
-        if (!blk_in_system(m, ba, mode) || !blk_in_system(m, bb, mode)) continue;
-        const int ta = (mode == MODE_SOLVE) ? blk_tsize(ba) : blk_msize(ba), tb = (mode == MODE_SOLVE) ? blk_tsize(bb) : blk_msize(bb);
-        const int oa = (mode == MODE_SOLVE) ? blk_toff(ba) : blk_moff(ba), ob = (mode == MODE_SOLVE) ? blk_toff(bb) : blk_moff(bb);
-        const bool vis = blk_voff(ba) >= 0 && blk_voff(bb) >= 0;
-        for (int e = gtid; e < ta * tb; e += gnt) {
-            const int p = e / tb, q = e % tb;
-            double s = small_block_entry(bd, m, ba, bb, p, q, mode);
-            if (vis && !(ba == BLK_PR) ) s += vis_block_entry(bd, m, ba, bb, p, q, mode);
-            H[(size_t)(oa + p) * HLD + ob + q] = s;
-            H[(size_t)(ob + q) * HLD + oa + p] = s;
-        }
-    }
-    for (int b = 0; b < NB; b++) {
-        if (!blk_in_system(m, b, mode)) continue;
-        const int tb = (mode == MODE_SOLVE) ? blk_tsize(b) : blk_msize(b), ob = (mode == MODE_SOLVE) ? blk_toff(b) : blk_moff(b);
-        for (int p = gtid; p < tb; p += gnt) {
-            double s = small_grad_entry(bd, m, b, p, mode);
-            if (blk_voff(b) >= 0) s += vis_grad_entry(bd, m, b, p, mode);
-            g[ob + p] = s;
-        }
-    }
-    // ---- Schur sums over the visual subspace: T = sum_k gamma_k w_k w_k^T, tvec = sum_k gamma_k w_k g_k
-    double *T = bd.Tvis + (size_t)w * VSUB * VSUB, *tv = bd.tvec + (size_t)w * VSUB;
-    const double *W = bd.lm_W + (size_t)m.lm_off * VSUB;
-    const double *gam = bd.lm_gamma + m.lm_off, *gl = bd.lm_g + m.lm_off;
-    for (int e = gtid; e < 79 * 80 / 2 + 79; e += gnt) {
-        if (e < 79 * 80 / 2) {
-            int p = 0; while ((p + 1) * (p + 2) / 2 <= e) p++;
-            const int q = e - p * (p + 1) / 2;
-            double s = 0.0;
-            if (mode == MODE_SOLVE) { for (int k = 0; k < m.nlm; k++) s += gam[k] * W[(size_t)k * VSUB + p] * W[(size_t)k * VSUB + q]; }
-            else { for (int k = 0; k < m.nlm; k++) if (gam[k] > 0.0) s += W[(size_t)k * VSUB + p] * W[(size_t)k * VSUB + q] / gam[k]; }
-            T[p * VSUB + q] = s; T[q * VSUB + p] = s;
-        } else {
-            const int p = e - 79 * 80 / 2;
-            double s = 0.0;
-            if (mode == MODE_SOLVE) { for (int k = 0; k < m.nlm; k++) s += gam[k] * W[(size_t)k * VSUB + p] * gl[k]; }
-            else { for (int k = 0; k < m.nlm; k++) if (gam[k] > 0.0) s += W[(size_t)k * VSUB + p] * gl[k] / gam[k]; }
-            tv[p] = s;
-        }
-    }
 }
 
 }  // namespace viwb

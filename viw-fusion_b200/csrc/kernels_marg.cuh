@@ -66,23 +66,28 @@ VIWB_D void jacobi_small(double *A, double *V, int n) {
     }
 }
 
-// parallel-ordering cyclic Jacobi in shared memory.  A, V: n x n (row-major, ld = n).  cs: 2*(n/2+1), ord: n+2 ints.
-VIWB_D void jacobi_block(double *A, double *V, int n, double *cs, int *ord, double *bc, int tid, int nt) {
+// parallel-ordering cyclic Jacobi in shared memory.  A, V: n x n with leading dimension ld (odd, so that the column
+// walks of the rotation updates are bank-conflict free); on exit diag(A) = eigenvalues, columns of V = eigenvectors.
+// Round r of the circle method pairs (ne-1, r) and ((r+i) mod (ne-1), (r-i) mod (ne-1)), i = 1..ne/2-1: all disjoint.
+VIWB_D void jacobi_pair(int i, int r, int ne, int &p, int &q) {
+    const int m1 = ne - 1;
+    if (i == 0) { p = m1; q = r; } else { p = (r + i) % m1; q = (r - i + m1) % m1; }
+    if (p > q) { const int t = p; p = q; q = t; }
+}
+VIWB_D void jacobi_block(double *A, double *V, int n, int ld, double *cs, double *bc, int tid, int nt) {
     const int ne = n + (n & 1), half = ne / 2;      // pad to even with a dummy index (= n)
-    for (int e = tid; e < n * n; e += nt) V[e] = ((e / n) == (e % n)) ? 1.0 : 0.0;
-    for (int i = tid; i < ne; i += nt) ord[i] = i;
+    const int W = nt < 32 ? nt : 32, nw = nt / W, lane = tid % W, wid = tid / W;
+    for (int i = wid; i < n; i += nw) for (int j = lane; j < n; j += W) V[i * ld + j] = (i == j) ? 1.0 : 0.0;
     VIWB_SYNC();
     for (int sweep = 0; sweep < 40; sweep++) {
         if (tid == 0) bc[1] = 0.0;
         VIWB_SYNC();
         for (int step = 0; step < ne - 1; step++) {
-            // rotation parameters of the 'half' disjoint pairs (ord[i], ord[ne-1-i])
             for (int i = tid; i < half; i += nt) {
-                int p = ord[i], q = ord[ne - 1 - i];
-                if (p > q) { const int t = p; p = q; q = t; }
+                int p, q; jacobi_pair(i, step, ne, p, q);
                 double c = 1.0, s = 0.0;
                 if (q < n) {
-                    const double apq = A[p * n + q], app = A[p * n + p], aqq = A[q * n + q];
+                    const double apq = A[p * ld + q], app = A[p * ld + p], aqq = A[q * ld + q];
                     if (apq != 0.0 && fabs(apq) > 1e-17 * sqrt(fabs(app) * fabs(aqq))) {
                         const double tau = (aqq - app) / (2.0 * apq);
                         const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
@@ -93,29 +98,24 @@ VIWB_D void jacobi_block(double *A, double *V, int n, double *cs, int *ord, doub
                 cs[2 * i] = c; cs[2 * i + 1] = s;
             }
             VIWB_SYNC();
-            // A <- A J, V <- V J (columns p,q of every row)
-            for (int e = tid; e < half * n; e += nt) {
-                const int i = e / n, r = e % n;
+            // A <- A J, V <- V J (columns p,q of every row): warps over pairs, lanes over rows
+            for (int i = wid; i < half; i += nw) {
                 const double c = cs[2 * i], s = cs[2 * i + 1];
                 if (s == 0.0) continue;
-                int p = ord[i], q = ord[ne - 1 - i];
-                if (p > q) { const int t = p; p = q; q = t; }
-                double a = A[r * n + p], b = A[r * n + q]; A[r * n + p] = c * a - s * b; A[r * n + q] = s * a + c * b;
-                a = V[r * n + p]; b = V[r * n + q]; V[r * n + p] = c * a - s * b; V[r * n + q] = s * a + c * b;
+                int p, q; jacobi_pair(i, step, ne, p, q);
+                for (int r = lane; r < n; r += W) {
+                    double a = A[r * ld + p], b = A[r * ld + q]; A[r * ld + p] = c * a - s * b; A[r * ld + q] = s * a + c * b;
+                    a = V[r * ld + p]; b = V[r * ld + q]; V[r * ld + p] = c * a - s * b; V[r * ld + q] = s * a + c * b;
+                }
             }
             VIWB_SYNC();
             // A <- J^T A (rows p,q of every column)
-            for (int e = tid; e < half * n; e += nt) {
-                const int i = e / n, r = e % n;
+            for (int i = wid; i < half; i += nw) {
                 const double c = cs[2 * i], s = cs[2 * i + 1];
                 if (s == 0.0) continue;
-                int p = ord[i], q = ord[ne - 1 - i];
-                if (p > q) { const int t = p; p = q; q = t; }
-                const double a = A[p * n + r], b = A[q * n + r]; A[p * n + r] = c * a - s * b; A[q * n + r] = s * a + c * b;
+                int p, q; jacobi_pair(i, step, ne, p, q);
+                for (int r = lane; r < n; r += W) { const double a = A[p * ld + r], b = A[q * ld + r]; A[p * ld + r] = c * a - s * b; A[q * ld + r] = s * a + c * b; }
             }
-            VIWB_SYNC();
-            // round-robin: position 0 stays, the others rotate by one
-            if (tid == 0) { const int last = ord[ne - 1]; for (int i = ne - 1; i > 1; i--) ord[i] = ord[i - 1]; ord[1] = last; }
             VIWB_SYNC();
         }
         if (bc[1] == 0.0) break;
@@ -124,7 +124,7 @@ VIWB_D void jacobi_block(double *A, double *V, int n, double *cs, int *ord, doub
 }
 
 VIWB_HD int vsub_to_mlay(int p) { return p < 66 ? p : p < 72 ? 165 + (p - 66) : p < 78 ? 171 + (p - 72) : 191; }   // td -> blk_moff(BLK_TD) = 191
-VIWB_HD size_t marg_smem_doubles(int nt) { return 24000 + (size_t)nt; }
+VIWB_HD size_t marg_smem_doubles(int nt) { return 24400 + (size_t)nt; }
 
 VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)mode;
@@ -139,9 +139,15 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
     const double eps = 1e-8;   // marginalization_factor.h:81
     // smem carve
-    double *An = smem, *Vn = An + 100 * 100, *Amm = Vn + 100 * 100, *Vmm = Amm + 256, *Ainv = Vmm + 256, *Tm = Ainv + 256;
+    double *An = smem, *Vn = An + 100 * 101, *Amm = Vn + 100 * 101, *Vmm = Amm + 256, *Ainv = Vmm + 256, *Tm = Ainv + 256;
     double *bn = Tm + 100 * 16, *cs = bn + 216, *red = cs + 216 + 216, *bc = red + nt;
-    int *keep = (int *)(bc + 16), *dl = keep + 216, *ord = dl + 32;
+    int *keep = (int *)(bc + 16), *dl = keep + 216;
+    // ---- dense system of the marginalisation factors over the marginalisation layout
+    for (int e = tid; e < MLAY * MLAY; e += nt) M[(size_t)(e / MLAY) * LDM + (e % MLAY)] = 0.0;
+    for (int i = tid; i < TFIX + 8; i += nt) b[i] = 0.0;
+    VIWB_SYNC();
+    { DenseTarget t; t.M = M; t.g = b; t.ld = LDM; t.flags = m.flags; assemble_into(t, bd, w, MODE_MARG, tid, nt); }
+    VIWB_SYNC();
     // ---- eliminate the dropped landmarks: M -= scatter(T0), b -= scatter(tvec0)   (MARGIN_OLD only)
     if (m.margin_flag == 0) {
         for (int e = tid; e < 79 * 79; e += nt) { const int p = e / 79, q = e % 79; M[(size_t)vsub_to_mlay(p) * LDM + vsub_to_mlay(q)] -= T[p * VSUB + q]; }
@@ -194,11 +200,12 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     }
     VIWB_SYNC();
     // A = Arr - Arm Amm^-1 Amr ; b = brr - Arm Amm^-1 bmm
+    const int ld = n | 1;
     for (int e = tid; e < n * n; e += nt) {
         const int i = e / n, j = e % n;
         double sacc = M[(size_t)keep[i] * LDM + keep[j]];
         for (int k = 0; k < md; k++) sacc -= Tm[i * md + k] * M[(size_t)dl[k] * LDM + keep[j]];
-        An[e] = sacc;
+        An[i * ld + j] = sacc;
     }
     for (int i = tid; i < n; i += nt) {
         double sacc = b[keep[i]];
@@ -207,17 +214,17 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     }
     VIWB_SYNC();
     // SelfAdjointEigenSolver reads the lower triangle
-    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e % n; if (j > i) An[e] = An[j * n + i]; }
+    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e % n; if (j > i) An[i * ld + j] = An[j * ld + i]; }
     VIWB_SYNC();
-    jacobi_block(An, Vn, n, cs, ord, bc, tid, nt);
+    jacobi_block(An, Vn, n, ld, cs, bc, tid, nt);
     VIWB_SYNC();
     // J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b   (marginalization_factor.cpp:298-306)
     double *Jout = bd.marg_J + (size_t)w * MAXPRI * MAXPRI, *rout = bd.marg_r + (size_t)w * MAXPRI;
     for (int i = tid; i < n; i += nt) {
-        const double l = An[i * n + i];
+        const double l = An[i * ld + i];
         const double S = l > eps ? l : 0.0, Sinv = l > eps ? 1.0 / l : 0.0, ss = sqrt(S), si = sqrt(Sinv);
         double vb = 0.0;
-        for (int k = 0; k < n; k++) { Jout[(size_t)i * n + k] = ss * Vn[k * n + i]; vb += Vn[k * n + i] * bn[k]; }
+        for (int k = 0; k < n; k++) { Jout[(size_t)i * n + k] = ss * Vn[k * ld + i]; vb += Vn[k * ld + i] * bn[k]; }
         rout[i] = si * vb;
     }
     if (tid == 0) ww.marg_status = 0;

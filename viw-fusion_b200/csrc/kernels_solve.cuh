@@ -11,6 +11,7 @@
 #pragma once
 #include "layout.cuh"
 #include "factors.cuh"
+#include "kernels_asm.cuh"
 
 namespace viwb {
 
@@ -50,14 +51,22 @@ VIWB_D void carve(SolveSmem &s, double *smem, int nt) {
     s.amap = (int *)p; s.vmap = s.amap + TFIX;
 }
 
-// load the active part of H_pp (unscaled) into the packed triangle
-VIWB_D void load_H(const double *Hpp, const SolveSmem &s, int nf, int tid, int nt) {
+// assemble the active part of H (unscaled) and g into the packed triangle / s.g, and keep a packed copy in HBM
+VIWB_D void assemble_H(const BatchDev &bd, int w, const SolveSmem &s, int nf, double *Hpk, double *gpk, int tid, int nt) {
     const int ne = nf * (nf + 1) / 2;
-    for (int i = tid; i < nf; i += nt) {
-        const double *row = Hpp + (size_t)s.amap[i] * TFIX;
-        for (int j = 0; j <= i; j++) s.L[i * (i + 1) / 2 + j] = row[s.amap[j]];
-    }
-    (void)ne;
+    for (int e = tid; e < ne; e += nt) s.L[e] = 0.0;
+    for (int i = tid; i < nf; i += nt) s.g[i] = 0.0;
+    VIWB_SYNC();
+    PackedTarget t; t.L = s.L; t.g = s.g; t.tcol = bd.meta[w].tcol;
+    assemble_into(t, bd, w, MODE_SOLVE, tid, nt);
+    for (int e = tid; e < ne; e += nt) Hpk[e] = s.L[e];
+    for (int i = tid; i < nf; i += nt) gpk[i] = s.g[i];
+    VIWB_SYNC();
+}
+// reload the packed copy (after the Cholesky factor overwrote it)
+VIWB_D void load_H(const double *Hpk, const SolveSmem &s, int nf, int tid, int nt) {
+    const int ne = nf * (nf + 1) / 2;
+    for (int e = tid; e < ne; e += nt) s.L[e] = Hpk[e];
     VIWB_SYNC();
 }
 // Hu = H u over the packed triangle (u, Hu of length nf)
@@ -131,7 +140,7 @@ VIWB_D double block_grad_inf(int b, unsigned mask, const double *x, const double
 }
 
 VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
-    (void)by; (void)mode;
+    (void)by;
     const int w = bx;
     const WinMeta &m = bd.meta[w];
     WinWork &ww = bd.work[w];
@@ -143,7 +152,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
     double *g_scale = bd.v_scale + vo, *g_D = bd.v_D + vo, *g_sg = bd.v_sgrad + vo, *g_gn = bd.v_gn + vo;
     const double *lm_a = bd.lm_a + m.lm_off, *lm_g = bd.lm_g + m.lm_off, *lm_gamma = bd.lm_gamma + m.lm_off, *lm_sc = bd.lm_scale + m.lm_off;
     const double *W = bd.lm_W + (size_t)m.lm_off * VSUB;
-    const double *Hpp = bd.Hpp + (size_t)w * TFIX * TFIX, *gfix = bd.gfix + (size_t)w * (TFIX + 8);
+    double *Hpk = bd.Hpk + (size_t)w * (TFIX * (TFIX + 1) / 2), *gpk = bd.gpk + (size_t)w * TFIX;
     const double *Tvis = bd.Tvis + (size_t)w * VSUB * VSUB, *tvec = bd.tvec + (size_t)w * VSUB;
     const double min_mu = 1e-8, max_mu = 1.0, mu_inc = 10.0;
 
@@ -153,6 +162,9 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
         s.vmap[m.tcol[b] + k] = blk_voff(b) >= 0 ? blk_voff(b) + k : -1;
     }
     VIWB_SYNC();
+
+    if (mode == 2) { assemble_H(bd, w, s, nf, Hpk, gpk, tid, nt); return; }     // debug hook: normal equations only
+    bool assembled = false;
 
     // ================= phase A: decision on the pending candidate ==================================
     double c_part = 0.0;
@@ -212,9 +224,8 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
         if (!ww.reuse) {
             VIWB_SYNC();
             if (tid == 0) ww.reuse = 1;
-            load_H(Hpp, s, nf, tid, nt);
-            for (int i = tid; i < nf; i += nt) s.g[i] = gfix[s.amap[i]];
-            VIWB_SYNC();
+            if (!assembled) { assemble_H(bd, w, s, nf, Hpk, gpk, tid, nt); assembled = true; }
+            else { load_H(Hpk, s, nf, tid, nt); for (int i = tid; i < nf; i += nt) s.g[i] = gpk[i]; VIWB_SYNC(); }
             if (ww.first) {
                 for (int i = tid; i < nf; i += nt) g_scale[i] = op.jacobi_scaling ? 1.0 / (1.0 + sqrt(s.L[pidx(i, i)])) : 1.0;
             }
@@ -267,7 +278,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
             ls_failure = true;
             bool h_dirty = false;
             while (ww.mu < max_mu) {
-                if (h_dirty) load_H(Hpp, s, nf, tid, nt);
+                if (h_dirty) load_H(Hpk, s, nf, tid, nt);
                 const double mu = ww.mu;
                 const bool t_ok = (mu == ww.mu_lin);          // gamma / T / tvec were built for mu_lin
                 // S = C (H - T) C + mu D^2 ; rhs = C (g - tvec)
@@ -326,7 +337,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
             VIWB_SYNC();
             if (!ls_failure) {
                 // q_gn, q_nn, l_n with u_n = c o (gn / D) = -c o y
-                load_H(Hpp, s, nf, tid, nt);
+                load_H(Hpk, s, nf, tid, nt);
                 for (int i = tid; i < nf; i += nt) s.u[i] = s.sc[i] * g_gn[i] / s.D[i];
                 VIWB_SYNC();
                 symv(s, nf, s.u, s.Hu, tid, nt);

@@ -30,6 +30,9 @@ VIWB_HD int blk_msize(int b) { int s = blk_size(b); return s == 7 ? 6 : s; }
 // visual-subspace offset of a fixed block (-1 if the block is not touched by visual factors)
 VIWB_HD int blk_voff(int b) { return b < 11 ? 6 * b : b == BLK_EX0 ? 66 : b == BLK_EX1 ? 72 : b == BLK_TD ? 78 : -1; }
 
+enum { ASM_STRIDE = 108, ASM_CHUNK = 256, ITEM_FRAME = 0, ITEM_PAIR = 1, ITEM_COMMON = 2 };
+struct AsmItem { int kind, win, a, b, lo, hi, phase, has_common; };
+
 struct PriorDev {       // one per window that has a valid prior
     int n, nb;
     int block_id[NB], block_idx[NB];
@@ -47,7 +50,9 @@ struct WinMeta {        // read-only during a solve
     int nf;             // active fixed tangent columns (compact)
     int namb;
     int margin_flag;
-    int pair_off;       // into pair_ptr: 122 entries per window; factors of pair (h,j) = pair_perm[pair_ptr[h*11+j] .. pair_ptr[h*11+j+1])
+    int item_off, nitems, nphases;      // assembly items of the solver linearisation (kernels_asm.cuh)
+    int mitem_off, nmitems, nmphases;   // assembly items of the marginalisation linearisation (factors hosted in frame 0)
+    int has_common;                     // any of ex0 / ex1 / td is an active column (solver); marginalisation always counts them
     short tcol[NB];     // compact column of fixed block b, -1 if constant / absent / unreferenced
     unsigned char flags[NB], mask[NB];
     double G[3], S_vis[4], w_plane[3], huber;
@@ -77,7 +82,7 @@ struct Opts {
 };
 
 struct BatchDev {       // passed by value to every kernel
-    int B, nvis_total, nlm_total, nimu_total, nwheel_total, nplane_total, nprior, nslice;
+    int B, nvis_total, nlm_total, nimu_total, nwheel_total, nplane_total, nprior, nitems_solve, nitems_marg;
     const WinMeta *meta;
     WinWork *work;
     const PriorDev *prior;
@@ -89,7 +94,10 @@ struct BatchDev {       // passed by value to every kernel
     const double *vis_obs;          // SoA [12][nvis_total]
     double *vis_rec;                // [nvis_total][VREC]
     double *vis_cost;               // [nvis_total]
-    const int *pair_ptr, *pair_perm;   // per window 122 / nvis (global factor indices)
+    // assembly plan (static per batch): items = chunks of per-frame / per-frame-pair / common factor lists
+    const struct AsmItem *items;    // solver items of all windows, then marginalisation items
+    const int *asm_list;            // list entries: (global factor index << 1) | role
+    double *asm_out;                // [nitems_total][ASM_STRIDE] partial sums written by asm_items
     // landmarks
     const int *lm_win, *lm_fptr;    // [nlm_total], [nlm_total+1] factor range (global factor indices, sorted by landmark)
     double *lm_a, *lm_g, *lm_gamma, *lm_scale, *lm_cost, *lm_W;   // lm_W [nlm_total][VSUB]
@@ -102,7 +110,7 @@ struct BatchDev {       // passed by value to every kernel
     const double *prior_J, *prior_r, *prior_x0;
     double *prior_A, *prior_res, *prior_g;
     // normal equations
-    double *Hpp, *gfix, *Tvis, *tvec;
+    double *Hpk, *gpk, *gfix, *Tvis, *tvec;   // Hpk [B][TFIX*(TFIX+1)/2] packed active H, gpk [B][TFIX] compact gradient
     // solver vectors, per window at work_off = state_off - 15*w ... stored at vec_off = w*TFIX + lm_off
     double *v_scale, *v_D, *v_sgrad, *v_gn;
     // marginalisation outputs

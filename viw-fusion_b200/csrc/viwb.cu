@@ -69,10 +69,11 @@ DEF_KERNEL(prior_setup, 256)
 DEF_KERNEL(lin_vis, 128)
 DEF_KERNEL(lm_reduce, 64)
 DEF_KERNEL(lin_small, 64)
-DEF_KERNEL(assemble, 256)
+DEF_KERNEL(asm_items, 128)
+DEF_KERNEL(syrk, 256)
 DEF_KERNEL(solve, 512)
 DEF_KERNEL(reanchor, 32)
-DEF_KERNEL(marg, 256)
+DEF_KERNEL(marg, 512)
 #define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) \
     do { if ((gx) > 0 && (gy) > 0) { g_prof.begin((mode) == 1 ? #name "_marg" : #name, stream); name##_kernel<<<dim3((gx), (gy)), (nt), (smem_bytes), (stream)>>>(bd, mode); g_prof.end(stream); } } while (0)
 #define NT(n) (n)
@@ -169,8 +170,9 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     const viwb_options *opt = options ? options : &defopt;
     b->max_iter = opt->max_num_iterations;
     BatchDev &bd = b->bd; memset(&bd, 0, sizeof bd);
-    bd.B = B; opts_from(opt, bd.opt); bd.nslice = 8;
-    std::vector<int> vis_type, vis_lm, vis_fi, vis_fj, vis_win, pair_ptr, pair_perm, lm_win, lm_fptr;
+    bd.B = B; opts_from(opt, bd.opt);
+    std::vector<int> vis_type, vis_lm, vis_fi, vis_fj, vis_win, lm_win, lm_fptr, asm_list;
+    std::vector<AsmItem> items_solve, items_marg;
     std::vector<double> vis_obs_aos, x_init;
     std::vector<int> imu_fi, imu_fj, imu_win, wheel_fi, wheel_fj, wheel_win, plane_f, plane_win;
     std::vector<double> imu_data, wheel_data, prior_J, prior_r, prior_x0;
@@ -207,18 +209,6 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
             cnt[p.vis_landmark[s]]++;
         }
         for (int k = 0; k < p.num_landmarks; k++) { lm_win.push_back(w); lm_fptr.push_back(lm_fptr.back() + cnt[k]); }
-        // ---- gather lists by (host frame, target frame)
-        m.pair_off = (int)pair_ptr.size();
-        {
-            std::vector<int> pc(NFR * NFR + 1, 0);
-            for (int i = 0; i < p.num_vis; i++) pc[vis_fi[m.vis_off + i] * NFR + vis_fj[m.vis_off + i] + 1]++;
-            for (int k = 0; k < NFR * NFR; k++) pc[k + 1] += pc[k];
-            const int base = (int)pair_perm.size();
-            pair_perm.resize(base + p.num_vis);
-            std::vector<int> pos(pc.begin(), pc.end() - 1);
-            for (int i = 0; i < p.num_vis; i++) { const int key = vis_fi[m.vis_off + i] * NFR + vis_fj[m.vis_off + i]; pair_perm[base + pos[key]++] = m.vis_off + i; }
-            for (int k = 0; k <= NFR * NFR; k++) pair_ptr.push_back(base + pc[k]);
-        }
         // ---- small factors
         m.imu_off = (int)imu_fi.size(); m.nimu = p.num_imu;
         for (int i = 0; i < p.num_imu; i++) { imu_fi.push_back(p.imu_frame_i[i]); imu_fj.push_back(p.imu_frame_j[i]); imu_win.push_back(w); }
@@ -290,6 +280,42 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
             }
             if (m.margin_flag >= 0) { for (int k = 0; k < NB; k++) if (seen[k]) m.flags[k] |= 4u; b->any_marg = true; }
         }
+        // ---- assembly plan (kernels_asm.cuh): per-frame, per-frame-pair and common factor lists cut into chunks = phases
+        m.has_common = (m.tcol[BLK_EX0] >= 0 || m.tcol[BLK_EX1] >= 0 || m.tcol[BLK_TD] >= 0) ? 1 : 0;
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1 && m.margin_flag != 0) { m.mitem_off = (int)items_marg.size(); m.nmitems = 0; m.nmphases = 0; continue; }
+            std::vector<AsmItem> &items = pass == 0 ? items_solve : items_marg;
+            const int has_common = pass == 0 ? m.has_common : 1;
+            std::vector<std::vector<int>> fl(NFR), pl(NFR * NFR);
+            std::vector<int> cl;
+            for (int i = 0; i < p.num_vis; i++) {
+                const int f = m.vis_off + i, fi = vis_fi[f], fj = vis_fj[f], t = vis_type[f];
+                if (pass == 1 && fi != 0) continue;
+                if (t != 2) {
+                    fl[fi].push_back((f << 1) | 0); fl[fj].push_back((f << 1) | 1);
+                    const int lo = fi < fj ? fi : fj, hi = fi < fj ? fj : fi;
+                    pl[lo * NFR + hi].push_back((f << 1) | (fi == lo ? 0 : 1));
+                }
+                cl.push_back(f << 1);
+            }
+            const int first = (int)items.size();
+            int nph = 0;
+            auto emit = [&](int kind, int a, int bq, const std::vector<int> &lst) {
+                for (size_t c0 = 0, ph = 0; c0 < lst.size(); c0 += ASM_CHUNK, ph++) {
+                    AsmItem it; it.kind = kind; it.win = w; it.a = a; it.b = bq; it.lo = (int)asm_list.size();
+                    const size_t c1 = std::min(lst.size(), c0 + (size_t)ASM_CHUNK);
+                    asm_list.insert(asm_list.end(), lst.begin() + c0, lst.begin() + c1);
+                    it.hi = (int)asm_list.size(); it.phase = (int)ph; it.has_common = has_common;
+                    items.push_back(it);
+                    nph = std::max(nph, (int)ph + 1);
+                }
+            };
+            for (int a = 0; a < NFR; a++) emit(ITEM_FRAME, a, a, fl[a]);
+            for (int a = 0; a < NFR; a++) for (int c = a + 1; c < NFR; c++) emit(ITEM_PAIR, a, c, pl[a * NFR + c]);
+            if (has_common) emit(ITEM_COMMON, 0, 0, cl);
+            if (pass == 0) { m.item_off = first; m.nitems = (int)items.size() - first; m.nphases = nph; }
+            else { m.mitem_off = first; m.nmitems = (int)items.size() - first; m.nmphases = nph; }
+        }
         b->algorithmic_bytes += window_algorithmic_bytes(p, opt->max_num_iterations);
         // ---- initial solver state
         WinWork &ww = b->work[w]; memset(&ww, 0, sizeof ww);
@@ -306,7 +332,10 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
 #define UP(vec, field) do { int rc_ = upload(ctx, b, vec, &bd.field); if (rc_) { return rc_; } } while (0)
     UP(b->meta, meta); UP(priors, prior);
     UP(vis_type, vis_type); UP(vis_lm, vis_lm); UP(vis_fi, vis_fi); UP(vis_fj, vis_fj); UP(vis_win, vis_win); UP(vis_obs, vis_obs);
-    UP(pair_ptr, pair_ptr); UP(pair_perm, pair_perm); UP(lm_win, lm_win); UP(lm_fptr, lm_fptr);
+    UP(lm_win, lm_win); UP(lm_fptr, lm_fptr);
+    bd.nitems_solve = (int)items_solve.size(); bd.nitems_marg = (int)items_marg.size();
+    { std::vector<AsmItem> all(items_solve); all.insert(all.end(), items_marg.begin(), items_marg.end()); UP(all, items); }
+    UP(asm_list, asm_list);
     UP(imu_fi, imu_fi); UP(imu_fj, imu_fj); UP(imu_win, imu_win); UP(wheel_fi, wheel_fi); UP(wheel_fj, wheel_fj); UP(wheel_win, wheel_win);
     UP(plane_f, plane_f); UP(plane_win, plane_win); UP(imu_data, imu_data); UP(wheel_data, wheel_data);
     UP(prior_J, prior_J); UP(prior_r, prior_r); UP(prior_x0, prior_x0);
@@ -320,7 +349,8 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     AL(imu_S, imu_fi.size() * 225); AL(wheel_S, wheel_fi.size() * 36);
     AL(imu_rec, imu_fi.size() * IMU_REC); AL(wheel_rec, wheel_fi.size() * WHEEL_REC); AL(plane_rec, plane_f.size() * PLANE_REC);
     AL(prior_A, prior_J.size()); AL(prior_res, prior_r.size()); AL(prior_g, prior_r.size());
-    AL(Hpp, (size_t)B * TFIX * TFIX); AL(gfix, (size_t)B * (TFIX + 8)); AL(Tvis, (size_t)B * VSUB * VSUB); AL(tvec, (size_t)B * VSUB);
+    AL(Hpk, (size_t)B * (TFIX * (TFIX + 1) / 2)); AL(gpk, (size_t)B * TFIX); AL(gfix, (size_t)B * (TFIX + 8));
+    AL(asm_out, (size_t)(items_solve.size() + items_marg.size()) * ASM_STRIDE); AL(Tvis, (size_t)B * VSUB * VSUB); AL(tvec, (size_t)B * VSUB);
     const size_t nvec = (size_t)B * TFIX + nl;
     AL(v_scale, nvec); AL(v_D, nvec); AL(v_sgrad, nvec); AL(v_gn, nvec);
     AL(marg_J, (size_t)B * MAXPRI * MAXPRI); AL(marg_r, (size_t)B * MAXPRI); AL(marg_x0, (size_t)B * SFIX);
@@ -334,7 +364,7 @@ static int ensure_attrs(viwb_context *ctx) {
 #ifndef VIWB_HOST_EMU
     if (!ctx->attrs_set) {
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(512) * 8)));
-        CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(256) * 8)));
+        CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(512) * 8)));
         ctx->attrs_set = true;
     }
 #endif
@@ -352,15 +382,17 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     CK(dev_d2d(bd.x_cur, bd.x_init, xs, st)); CK(dev_d2d(bd.x_cand, bd.x_init, xs, st));
     if (!(what & RUN_REANCHOR) || (what & RUN_SOLVE)) CK(dev_d2d(bd.x_before, bd.x_init, xs, st));
     CK(dev_h2d(bd.work, b->work.data(), sizeof(WinWork) * B, st));
-    const int nt_vis = NT(128), nt_lm = NT(64), nt_small = NT(64), nt_asm = NT(256), nt_solve = NT(512), nt_marg = NT(256);
+    const int nt_vis = NT(128), nt_lm = NT(64), nt_small = NT(64), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(512), nt_marg = NT(512);
     const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total + nt_lm - 1) / nt_lm;
     const size_t sm_small = (size_t)(nt_small + MAXPRI + 8) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg) * 8;
     auto lin = [&](int mode) {
         LAUNCH(lin_vis, bd, g_vis, 1, nt_vis, 0, mode, st);
         LAUNCH(lm_reduce, bd, g_lm, 1, nt_lm, 0, mode, st);
         LAUNCH(lin_small, bd, B, 1, nt_small, sm_small, mode, st);
-        LAUNCH(assemble, bd, B, bd.nslice, nt_asm, 0, mode, st);
-        ctx->launches += (g_vis > 0) + (g_lm > 0) + 2;
+        const int ni = mode == MODE_SOLVE ? bd.nitems_solve : bd.nitems_marg, wpb = nt_asm / (nt_asm < 32 ? nt_asm : 32);
+        LAUNCH(asm_items, bd, (ni + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
+        LAUNCH(syrk, bd, B, 1, nt_syrk, syrk_smem_doubles() * 8, mode, st);
+        ctx->launches += (g_vis > 0) + (g_lm > 0) + (ni > 0) + 2;
     };
     if (what & (RUN_SOLVE | RUN_MARG | RUN_LIN_ONLY)) {
         const int ns = bd.nimu_total + bd.nwheel_total, nt_s = NT(128);
@@ -368,7 +400,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
         LAUNCH(prior_setup, bd, bd.nprior, 1, NT(256), 0, 0, st);
         ctx->launches += (ns > 0) + (bd.nprior > 0);
     }
-    if (what & RUN_LIN_ONLY) lin(MODE_SOLVE);
+    if (what & RUN_LIN_ONLY) { lin(MODE_SOLVE); LAUNCH(solve, bd, B, 1, nt_solve, sm_solve, 2, st); ctx->launches++; }
     if (what & RUN_SOLVE) {
         for (int round = 0; round <= b->max_iter; round++) {
             lin(MODE_SOLVE);
@@ -576,21 +608,24 @@ extern "C" int viwb_debug_normal_equations(viwb_context *ctx, const viwb_problem
     rc = batch_execute(ctx, b, RUN_LIN_ONLY);
     if (rc) { batch_free(b); return rc; }
     const int N = problem->num_landmarks;
-    std::vector<double> Hd((size_t)TFIX * TFIX), gd(TFIX + 8), a(N + 1), gl(N + 1), W((size_t)(N + 1) * VSUB), lc(N + 1);
+    std::vector<double> Hd((size_t)TFIX * (TFIX + 1) / 2), gd(TFIX), a(N + 1), gl(N + 1), W((size_t)(N + 1) * VSUB), lc(N + 1);
     std::vector<WinWork> ww(1);
-    int e = dev_d2h(Hd.data(), b->bd.Hpp, Hd.size() * 8, ctx->stream);
-    e |= dev_d2h(gd.data(), b->bd.gfix, gd.size() * 8, ctx->stream);
+    int e = dev_d2h(Hd.data(), b->bd.Hpk, Hd.size() * 8, ctx->stream);
+    e |= dev_d2h(gd.data(), b->bd.gpk, gd.size() * 8, ctx->stream);
     e |= dev_d2h(a.data(), b->bd.lm_a, (size_t)N * 8, ctx->stream); e |= dev_d2h(gl.data(), b->bd.lm_g, (size_t)N * 8, ctx->stream);
     e |= dev_d2h(W.data(), b->bd.lm_W, (size_t)N * VSUB * 8, ctx->stream); e |= dev_d2h(lc.data(), b->bd.lm_cost, (size_t)N * 8, ctx->stream);
     e |= dev_d2h(ww.data(), b->bd.work, sizeof(WinWork), ctx->stream);
     e |= dev_sync(ctx->stream);
     if (e) { batch_free(b); return fail(ctx, VIWB_ERR_CUDA, "download failed"); }
-    // formatting only: scatter the active blocks into the caller's fixed-layout arrays
+    // formatting only: scatter the packed active triangle into the caller's fixed-layout arrays
     const WinMeta &m = b->meta[0];
     if (H) { memset(H, 0, sizeof(double) * TFIX * TFIX);
         for (int ba = 0; ba < NB; ba++) for (int bb = 0; bb < NB; bb++) if (m.tcol[ba] >= 0 && m.tcol[bb] >= 0)
-            for (int p = 0; p < blk_tsize(ba); p++) for (int q = 0; q < blk_tsize(bb); q++) H[(blk_toff(ba) + p) * TFIX + blk_toff(bb) + q] = Hd[(size_t)(blk_toff(ba) + p) * TFIX + blk_toff(bb) + q]; }
-    if (g) { memset(g, 0, sizeof(double) * TFIX); for (int ba = 0; ba < NB; ba++) if (m.tcol[ba] >= 0) for (int p = 0; p < blk_tsize(ba); p++) g[blk_toff(ba) + p] = gd[blk_toff(ba) + p]; }
+            for (int p = 0; p < blk_tsize(ba); p++) for (int q = 0; q < blk_tsize(bb); q++) {
+                const int ci = m.tcol[ba] + p, cj = m.tcol[bb] + q;
+                H[(blk_toff(ba) + p) * TFIX + blk_toff(bb) + q] = Hd[ci >= cj ? (size_t)ci * (ci + 1) / 2 + cj : (size_t)cj * (cj + 1) / 2 + ci];
+            } }
+    if (g) { memset(g, 0, sizeof(double) * TFIX); for (int ba = 0; ba < NB; ba++) if (m.tcol[ba] >= 0) for (int p = 0; p < blk_tsize(ba); p++) g[blk_toff(ba) + p] = gd[m.tcol[ba] + p]; }
     double c = ww[0].small_cost;
     for (int k = 0; k < N; k++) {
         c += lc[k];
