@@ -209,12 +209,14 @@ def main():
     sts, sums, pri = batch.download()
 
     # ---- e2e: host buffers in / out through the C ABI
-    e2e_steps = max(1, min(args.steps, 3))
-    ctx.optimization_batch(probs, states, flags)
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_call = ctx.prepare_optimization_batch(probs, states, flags)
+    e2e_call()
+    e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.optimization_batch(probs, states, flags)
+        e2e_call()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:

@@ -188,7 +188,7 @@ VIWB_D void lk_post_item(const PostArgs &a, int i) {
 #ifdef VIWB_HOST_EMU
 #define LK_LAUNCH_ITEMS(fn, args, items, stream) do { for (int i_ = 0; i_ < (items); i_++) fn(args, i_); } while (0)
 static void lk_launch_track(const LkArgs &a, void *) { std::vector<unsigned char> sm(lk_smem_bytes(1) + 64); for (int p = 0; p < a.n; p++) lk_track_block(a, p, 0, 1, sm.data()); }
-static int lk_malloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 1; }
+static int lk_malloc(void **p, size_t n) { *p = malloc(n ? n : 1); if (*p) memset(*p, 0xFF, n ? n : 1); return *p ? 0 : 1; }
 static void lk_free(void *p) { free(p); }
 static int lk_h2d(void *d, const void *h, size_t n, void *) { memcpy(d, h, n); return 0; }
 static int lk_d2h(void *h, const void *d, size_t n, void *) { memcpy(h, d, n); return 0; }

@@ -158,6 +158,7 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     if (tid == 0) {
         int md = 0, n = 0, nb = 0;
         unsigned dropped = 0;
+        for (int k = 0; k < SFIX; k++) bd.marg_x0[(size_t)w * SFIX + k] = 0.0;
         if (m.margin_flag == 0) { for (int k = 0; k < 6; k++) dl[md++] = k; for (int k = 0; k < 9; k++) dl[md++] = 66 + k; dropped = (1u << 0) | (1u << BLK_SB0); }
         else { for (int k = 0; k < 6; k++) dl[md++] = 54 + k; dropped = (1u << 9); }
         // a dropped block that no factor references contributes nothing (its rows are zero); keep md as is

@@ -2,7 +2,7 @@
 //
 // HBM layout (all FP64 unless noted; B windows, concatenated):
 //   x_cur / x_cand      [sum(207 + nlm)]        parameter blocks, fixed-state layout of include/viwb.h + inverse depths
-//   vis_*               visual factor table, sorted by landmark; vis_obs is SoA [12][nvis_total] for coalesced reads
+//   vis_*               visual factor table, sorted by landmark; vis_obs stays [nvis][12] as given
 //   vis_rec             [nvis_total][54]  per-factor record written by lin_vis: r(2) A(12) B(12) E0(12) E1(12) Jl(2) Jtd(2)
 //   lm_*                per landmark: a = |J_l|^2, gl = J_l^T r, gamma = c^2/h (Schur weight), W [80] = J_p^T J_l over the
 //                       "visual subspace" (11 poses x 6 | ex0 6 | ex1 6 | td 1 | pad)
@@ -91,7 +91,7 @@ struct BatchDev {       // passed by value to every kernel
     double *x_cur, *x_cand, *x_init, *x_before;
     // visual tables
     const int *vis_type, *vis_lm, *vis_fi, *vis_fj, *vis_win;
-    const double *vis_obs;          // SoA [12][nvis_total]
+    const double *vis_obs;          // [nvis_total][12] exactly as the caller's table (no host transpose)
     double *vis_rec;                // [nvis_total][VREC]
     double *vis_cost;               // [nvis_total]
     // assembly plan (static per batch): items = chunks of per-frame / per-frame-pair / common factor lists

@@ -23,12 +23,16 @@ using namespace viwb;
 // ====================================================================================== device abstraction
 #ifdef VIWB_HOST_EMU
 typedef void *stream_t;
-static int dev_malloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 1; }
+// poison fresh 'device' memory with NaN bytes so that reads of never-written data show up in the CPU tests
+static int dev_malloc(void **p, size_t n) { *p = malloc(n ? n : 1); if (*p) memset(*p, 0xFF, n ? n : 1); return *p ? 0 : 1; }
 static void dev_free(void *p) { free(p); }
 static int dev_h2d(void *d, const void *h, size_t n, stream_t) { if (n) memcpy(d, h, n); return 0; }
 static int dev_d2h(void *h, const void *d, size_t n, stream_t) { if (n) memcpy(h, d, n); return 0; }
 static int dev_d2d(void *d, const void *s, size_t n, stream_t) { if (n) memcpy(d, s, n); return 0; }
 static int dev_sync(stream_t) { return 0; }
+static int host_alloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+static void host_free(void *p) { free(p); }
+static int dev_d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t w, size_t rows, stream_t) { for (size_t r = 0; r < rows; r++) memcpy((char *)h + r * hp, (const char *)d + r * dp, w); return 0; }
 static const char *dev_errstr(int) { return "emulation"; }
 #define VIWB_EMU_NT 1
 template <typename F>
@@ -47,6 +51,9 @@ static int dev_h2d(void *d, const void *h, size_t n, stream_t s) { return n ? (i
 static int dev_d2h(void *h, const void *d, size_t n, stream_t s) { return n ? (int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) : 0; }
 static int dev_d2d(void *d, const void *s_, size_t n, stream_t s) { return n ? (int)cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s) : 0; }
 static int dev_sync(stream_t s) { return (int)cudaStreamSynchronize(s); }
+static int host_alloc(void **p, size_t n) { return (int)cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault); }
+static void host_free(void *p) { cudaFreeHost(p); }
+static int dev_d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t w, size_t rows, stream_t s) { return (w && rows) ? (int)cudaMemcpy2DAsync(h, hp, d, dp, w, rows, cudaMemcpyDeviceToHost, s) : 0; }
 static const char *dev_errstr(int e) { return cudaGetErrorString((cudaError_t)e); }
 // optional per-kernel CUDA-event profiler (bench.py's live roofline timing); off by default
 struct Profiler {
@@ -79,12 +86,17 @@ DEF_KERNEL(marg, 512)
 #define NT(n) (n)
 #endif
 
+// one device slab + one pinned host staging slab; cached in the context so that the host-buffer entry points do not
+// pay cudaMalloc / cudaHostAlloc on every call
+struct Arena { char *dev = nullptr; size_t dev_cap = 0; char *host = nullptr; size_t host_cap = 0; bool busy = false; };
+static void arena_release(Arena &a) { if (a.dev) dev_free(a.dev); if (a.host) host_free(a.host); a = Arena(); }
 struct viwb_context {
     int device;
     stream_t stream;
     long long launches;
     std::string err;
     bool attrs_set;
+    Arena arena;
 };
 
 static int fail(viwb_context *ctx, int code, const std::string &msg) { if (ctx) ctx->err = msg; return code; }
@@ -95,7 +107,11 @@ struct HostPrior { int valid, n, nb; int block_id[NB], block_idx[NB]; std::vecto
 struct viwb_batch {
     int B;
     BatchDev bd;
-    std::vector<void *> allocs;
+    Arena arena; bool arena_cached;      // cached: borrowed from the context (host-buffer calls), else owned
+    size_t out_bytes;
+    std::vector<int> prior_n;            // n of the prior each window will produce (known from the plan)
+    int prior_nmax;
+    WinWork *work_init_dev;              // pristine solver states, copied to bd.work at the start of every run
     std::vector<WinMeta> meta;
     std::vector<WinWork> work;
     std::vector<int> out_mode;        // 0: prior computed on the device, 1: input prior passes through, 2: invalid / none
@@ -108,23 +124,17 @@ struct viwb_batch {
     size_t nrec_imu, nrec_wheel, nrec_plane;
 };
 
-template <typename T>
-static int upload(viwb_context *ctx, viwb_batch *b, const std::vector<T> &h, const T **dptr) {
-    void *d = nullptr;
-    CK(dev_malloc(&d, h.size() * sizeof(T)));
-    b->allocs.push_back(d);
-    CK(dev_h2d(d, h.data(), h.size() * sizeof(T), ctx->stream));
-    *dptr = (const T *)d;
-    return 0;
-}
-template <typename T>
-static int alloc_dev(viwb_context *ctx, viwb_batch *b, size_t count, T **dptr) {
-    void *d = nullptr;
-    CK(dev_malloc(&d, (count ? count : 1) * sizeof(T)));
-    b->allocs.push_back(d);
-    *dptr = (T *)d;
-    return 0;
-}
+// deferred placement: every array is first registered (inputs with their host segments), then one device slab and one
+// pinned staging slab are sized, the inputs are packed into the staging slab and go over in a single H2D copy.
+struct Seg { const void *src; size_t bytes; };
+struct Req { void **field; size_t bytes; std::vector<Seg> segs; bool input; size_t off; };
+struct Placer {
+    std::vector<Req> reqs;
+    template <typename T> void in(const std::vector<T> &h, const T **field) { Req r; r.field = (void **)field; r.bytes = h.size() * sizeof(T); r.input = true; r.off = 0; if (r.bytes) r.segs.push_back({h.data(), r.bytes}); reqs.push_back(r); }
+    template <typename T> void in_segs(const std::vector<Seg> &segs, const T **field) { Req r; r.field = (void **)field; r.bytes = 0; for (auto &sg : segs) r.bytes += sg.bytes; r.segs = segs; r.input = true; r.off = 0; reqs.push_back(r); }
+    template <typename T> void work(size_t count, T **field) { Req r; r.field = (void **)field; r.bytes = (count ? count : 1) * sizeof(T); r.input = false; r.off = 0; reqs.push_back(r); }
+};
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static void opts_from(const viwb_options *o, Opts &d) {
     d.max_num_iterations = o->max_num_iterations; d.max_invalid = o->max_num_consecutive_invalid_steps; d.jacobi_scaling = o->jacobi_scaling;
@@ -161,11 +171,18 @@ static double window_algorithmic_bytes(const viwb_problem &p, int iters) {
     return iters * b_iter + b_marg;
 }
 
+static void batch_free(viwb_context *ctx, viwb_batch *b);
+static int batch_build_impl(viwb_context *ctx, int B, const viwb_problem *problems, const double *const *states,
+                            const viwb_options *options, const int32_t *margin_flags, viwb_batch **out, bool use_cached);
 static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, const double *const *states,
-                       const viwb_options *options, const int32_t *margin_flags, viwb_batch **out) {
+                       const viwb_options *options, const int32_t *margin_flags, viwb_batch **out, bool use_cached = false) {
+    return batch_build_impl(ctx, B, problems, states, options, margin_flags, out, use_cached);
+}
+static int batch_build_impl(viwb_context *ctx, int B, const viwb_problem *problems, const double *const *states,
+                            const viwb_options *options, const int32_t *margin_flags, viwb_batch **out, bool use_cached) {
     if (B <= 0 || !problems || !states) return fail(ctx, VIWB_ERR_INVALID, "empty batch");
     viwb_batch *b = new viwb_batch();
-    b->B = B; b->any_marg = false; b->algorithmic_bytes = 0;
+    b->B = B; b->any_marg = false; b->algorithmic_bytes = 0; b->arena_cached = false; b->out_bytes = 0; b->prior_nmax = 0; b->work_init_dev = nullptr;
     viwb_options defopt; viwb_default_options(&defopt);
     const viwb_options *opt = options ? options : &defopt;
     b->max_iter = opt->max_num_iterations;
@@ -173,16 +190,18 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     bd.B = B; opts_from(opt, bd.opt);
     std::vector<int> vis_type, vis_lm, vis_fi, vis_fj, vis_win, lm_win, lm_fptr, asm_list;
     std::vector<AsmItem> items_solve, items_marg;
-    std::vector<double> vis_obs_aos, x_init;
+    std::vector<double> x_init;
+    std::vector<Seg> obs_segs, imu_segs, wheel_segs, priorJ_segs;
     std::vector<int> imu_fi, imu_fj, imu_win, wheel_fi, wheel_fj, wheel_win, plane_f, plane_win;
-    std::vector<double> imu_data, wheel_data, prior_J, prior_r, prior_x0;
+    std::vector<double> prior_r, prior_x0;
+    size_t priorJ_count = 0;
     std::vector<PriorDev> priors;
-    b->meta.resize(B); b->work.resize(B); b->out_mode.assign(B, 2); b->in_prior.resize(B); b->state_sizes.resize(B);
+    b->meta.resize(B); b->work.resize(B); b->out_mode.assign(B, 2); b->in_prior.resize(B); b->state_sizes.resize(B); b->prior_n.assign(B, 0);
     lm_fptr.push_back(0);
     for (int w = 0; w < B; w++) {
         const viwb_problem &p = problems[w];
         WinMeta &m = b->meta[w]; memset(&m, 0, sizeof m);
-        if (p.frame_count < 0 || p.frame_count > VIWB_WINDOW_SIZE || p.num_landmarks < 0 || p.num_landmarks > VIWB_MAX_LANDMARKS) { delete b; return fail(ctx, VIWB_ERR_INVALID, "bad frame_count / num_landmarks"); }
+        if (p.frame_count < 0 || p.frame_count > VIWB_WINDOW_SIZE || p.num_landmarks < 0 || p.num_landmarks > VIWB_MAX_LANDMARKS) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, "bad frame_count / num_landmarks"); }
         m.state_off = (int)x_init.size(); m.lm_off = (int)lm_win.size(); m.nlm = p.num_landmarks; m.frame_count = p.frame_count;
         b->state_sizes[w] = SFIX + p.num_landmarks;
         x_init.insert(x_init.end(), states[w], states[w] + SFIX + p.num_landmarks);
@@ -191,31 +210,41 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
         for (int k = 0; k < 3; k++) m.w_plane[k] = p.globals.plane_sqrt_info[k];
         m.huber = p.globals.huber_delta;
         const bool has_prior = p.prior && p.prior->valid;
-        // ---- visual factors, stable-sorted by landmark
-        std::vector<int> order(p.num_vis);
+        // ---- visual factors, grouped by landmark (stable sort only if the caller's table is not already grouped)
+        bool grouped = true;
         for (int i = 0; i < p.num_vis; i++) {
-            order[i] = i;
             const int t = p.vis_type[i], l = p.vis_landmark[i], fi = p.vis_frame_i[i], fj = p.vis_frame_j[i];
-            if (t < 0 || t > 2 || l < 0 || l >= p.num_landmarks || fi < 0 || fi > p.frame_count || fj < 0 || fj > p.frame_count) { delete b; return fail(ctx, VIWB_ERR_INVALID, "bad visual factor table"); }
+            if (t < 0 || t > 2 || l < 0 || l >= p.num_landmarks || fi < 0 || fi > p.frame_count || fj < 0 || fj > p.frame_count) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, "bad visual factor table"); }
+            if (i && l < p.vis_landmark[i - 1]) grouped = false;
         }
-        std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return p.vis_landmark[a] < p.vis_landmark[c]; });
         m.vis_off = (int)vis_type.size(); m.nvis = p.num_vis;
         std::vector<int> cnt(p.num_landmarks + 1, 0);
-        for (int i = 0; i < p.num_vis; i++) {
-            const int s = order[i];
-            vis_type.push_back(p.vis_type[s]); vis_lm.push_back(m.lm_off + p.vis_landmark[s]); vis_fi.push_back(p.vis_frame_i[s]); vis_fj.push_back(p.vis_frame_j[s]);
-            vis_win.push_back(w);
-            vis_obs_aos.insert(vis_obs_aos.end(), p.vis_obs + (size_t)s * 12, p.vis_obs + (size_t)s * 12 + 12);
-            cnt[p.vis_landmark[s]]++;
+        if (grouped) {
+            vis_type.insert(vis_type.end(), p.vis_type, p.vis_type + p.num_vis);
+            vis_fi.insert(vis_fi.end(), p.vis_frame_i, p.vis_frame_i + p.num_vis); vis_fj.insert(vis_fj.end(), p.vis_frame_j, p.vis_frame_j + p.num_vis);
+            for (int i = 0; i < p.num_vis; i++) { vis_lm.push_back(m.lm_off + p.vis_landmark[i]); cnt[p.vis_landmark[i]]++; }
+            vis_win.insert(vis_win.end(), (size_t)p.num_vis, w);
+            if (p.num_vis) obs_segs.push_back({p.vis_obs, (size_t)p.num_vis * 12 * sizeof(double)});
+        } else {
+            std::vector<int> order(p.num_vis);
+            for (int i = 0; i < p.num_vis; i++) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return p.vis_landmark[a] < p.vis_landmark[c]; });
+            for (int i = 0; i < p.num_vis; i++) {
+                const int sidx = order[i];
+                vis_type.push_back(p.vis_type[sidx]); vis_lm.push_back(m.lm_off + p.vis_landmark[sidx]); vis_fi.push_back(p.vis_frame_i[sidx]); vis_fj.push_back(p.vis_frame_j[sidx]);
+                vis_win.push_back(w);
+                obs_segs.push_back({p.vis_obs + (size_t)sidx * 12, 12 * sizeof(double)});
+                cnt[p.vis_landmark[sidx]]++;
+            }
         }
         for (int k = 0; k < p.num_landmarks; k++) { lm_win.push_back(w); lm_fptr.push_back(lm_fptr.back() + cnt[k]); }
         // ---- small factors
         m.imu_off = (int)imu_fi.size(); m.nimu = p.num_imu;
         for (int i = 0; i < p.num_imu; i++) { imu_fi.push_back(p.imu_frame_i[i]); imu_fj.push_back(p.imu_frame_j[i]); imu_win.push_back(w); }
-        imu_data.insert(imu_data.end(), p.imu_data, p.imu_data + (size_t)p.num_imu * 287);
+        if (p.num_imu) imu_segs.push_back({p.imu_data, (size_t)p.num_imu * 287 * sizeof(double)});
         m.wheel_off = (int)wheel_fi.size(); m.nwheel = p.num_wheel;
         for (int i = 0; i < p.num_wheel; i++) { wheel_fi.push_back(p.wheel_frame_i[i]); wheel_fj.push_back(p.wheel_frame_j[i]); wheel_win.push_back(w); }
-        if (p.num_wheel) wheel_data.insert(wheel_data.end(), p.wheel_data, p.wheel_data + (size_t)p.num_wheel * 78);
+        if (p.num_wheel) wheel_segs.push_back({p.wheel_data, (size_t)p.num_wheel * 78 * sizeof(double)});
         m.plane_off = (int)plane_f.size(); m.nplane = p.num_plane;
         for (int i = 0; i < p.num_plane; i++) { plane_f.push_back(p.plane_frame[i]); plane_win.push_back(w); }
         // ---- prior
@@ -223,18 +252,18 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
         HostPrior &hp = b->in_prior[w]; hp.valid = 0; hp.n = 0; hp.nb = 0;
         if (has_prior) {
             const viwb_prior &pr = *p.prior;
-            if (pr.n <= 0 || pr.n > MAXPRI || pr.num_blocks <= 0 || pr.num_blocks > NB) { delete b; return fail(ctx, VIWB_ERR_INVALID, "bad prior"); }
+            if (pr.n <= 0 || pr.n > MAXPRI || pr.num_blocks <= 0 || pr.num_blocks > NB) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, "bad prior"); }
             PriorDev pd; memset(&pd, 0, sizeof pd);
             pd.n = pr.n; pd.nb = pr.num_blocks;
             for (int i = 0; i < pr.num_blocks; i++) { pd.block_id[i] = pr.block_id[i]; pd.block_idx[i] = pr.block_idx[i]; }
-            pd.J_off = (int)prior_J.size(); pd.r_off = (int)prior_r.size(); pd.x0_off = (int)prior_x0.size();
-            prior_J.insert(prior_J.end(), pr.J, pr.J + (size_t)pr.n * pr.n);
+            pd.J_off = (int)priorJ_count; pd.r_off = (int)prior_r.size(); pd.x0_off = (int)prior_x0.size();
+            priorJ_segs.push_back({pr.J, (size_t)pr.n * pr.n * sizeof(double)}); priorJ_count += (size_t)pr.n * pr.n;
             prior_r.insert(prior_r.end(), pr.r, pr.r + pr.n);
             prior_x0.insert(prior_x0.end(), pr.x0, pr.x0 + SFIX);
             m.prior_idx = (int)priors.size(); priors.push_back(pd);
             hp.valid = 1; hp.n = pr.n; hp.nb = pr.num_blocks;
             memcpy(hp.block_id, pd.block_id, sizeof hp.block_id); memcpy(hp.block_idx, pd.block_idx, sizeof hp.block_idx);
-            hp.x0.assign(pr.x0, pr.x0 + SFIX); hp.J.assign(pr.J, pr.J + (size_t)pr.n * pr.n); hp.r.assign(pr.r, pr.r + pr.n);
+            if (margin_flags && margin_flags[w] == VIWB_MARGIN_SECOND_NEW) { hp.x0.assign(pr.x0, pr.x0 + SFIX); hp.J.assign(pr.J, pr.J + (size_t)pr.n * pr.n); hp.r.assign(pr.r, pr.r + pr.n); }
         }
         // ---- active blocks (Program::RemoveFixedBlocks) and compact columns
         bool ref[NB]; for (int k = 0; k < NB; k++) ref[k] = false;
@@ -278,7 +307,11 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
                 if (has9) { m.margin_flag = 1; b->out_mode[w] = 0; }
                 else b->out_mode[w] = has_prior ? 1 : 2;
             }
-            if (m.margin_flag >= 0) { for (int k = 0; k < NB; k++) if (seen[k]) m.flags[k] |= 4u; b->any_marg = true; }
+            if (m.margin_flag >= 0) {
+                int nn = 0;
+                for (int k = 0; k < NB; k++) if (seen[k]) { m.flags[k] |= 4u; const bool drop = m.margin_flag == 0 ? (k == 0 || k == BLK_SB0) : (k == VIWB_WINDOW_SIZE - 1); if (!drop) nn += blk_msize(k); }
+                b->prior_n[w] = nn; b->any_marg = true;
+            }
         }
         // ---- assembly plan (kernels_asm.cuh): per-frame, per-frame-pair and common factor lists cut into chunks = phases
         m.has_common = (m.tcol[BLK_EX0] >= 0 || m.tcol[BLK_EX1] >= 0 || m.tcol[BLK_TD] >= 0) ? 1 : 0;
@@ -322,40 +355,55 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
         ww.status = ST_RUNNING; ww.phase = PH_INIT; ww.first = 1; ww.radius = opt->initial_trust_region_radius; ww.mu = 1e-8; ww.mu_lin = 1e-8;
         ww.term = VIWB_NO_CONVERGENCE;
     }
-    // ---- SoA transpose of the observations
     const size_t nv = vis_type.size();
-    std::vector<double> vis_obs(nv * 12);
-    for (size_t f = 0; f < nv; f++) for (int k = 0; k < 12; k++) vis_obs[(size_t)k * nv + f] = vis_obs_aos[f * 12 + k];
     bd.nvis_total = (int)nv; bd.nlm_total = (int)lm_win.size(); bd.nimu_total = (int)imu_fi.size(); bd.nwheel_total = (int)wheel_fi.size();
     bd.nplane_total = (int)plane_f.size(); bd.nprior = (int)priors.size();
     b->total_state = x_init.size();
-#define UP(vec, field) do { int rc_ = upload(ctx, b, vec, &bd.field); if (rc_) { return rc_; } } while (0)
-    UP(b->meta, meta); UP(priors, prior);
-    UP(vis_type, vis_type); UP(vis_lm, vis_lm); UP(vis_fi, vis_fi); UP(vis_fj, vis_fj); UP(vis_win, vis_win); UP(vis_obs, vis_obs);
-    UP(lm_win, lm_win); UP(lm_fptr, lm_fptr);
     bd.nitems_solve = (int)items_solve.size(); bd.nitems_marg = (int)items_marg.size();
-    { std::vector<AsmItem> all(items_solve); all.insert(all.end(), items_marg.begin(), items_marg.end()); UP(all, items); }
-    UP(asm_list, asm_list);
-    UP(imu_fi, imu_fi); UP(imu_fj, imu_fj); UP(imu_win, imu_win); UP(wheel_fi, wheel_fi); UP(wheel_fj, wheel_fj); UP(wheel_win, wheel_win);
-    UP(plane_f, plane_f); UP(plane_win, plane_win); UP(imu_data, imu_data); UP(wheel_data, wheel_data);
-    UP(prior_J, prior_J); UP(prior_r, prior_r); UP(prior_x0, prior_x0);
-#undef UP
-    { const double *xi = nullptr; int rc = upload(ctx, b, x_init, &xi); if (rc) return rc; bd.x_init = (double *)xi; }
-#define AL(field, count) do { int rc_ = alloc_dev(ctx, b, (size_t)(count), &bd.field); if (rc_) return rc_; } while (0)
-    AL(work, B); AL(x_cur, x_init.size()); AL(x_cand, x_init.size()); AL(x_before, x_init.size());
-    AL(vis_rec, nv * VREC); AL(vis_cost, nv);
-    const size_t nl = lm_win.size();
-    AL(lm_a, nl); AL(lm_g, nl); AL(lm_gamma, nl); AL(lm_scale, nl); AL(lm_cost, nl); AL(lm_W, nl * VSUB);
-    AL(imu_S, imu_fi.size() * 225); AL(wheel_S, wheel_fi.size() * 36);
-    AL(imu_rec, imu_fi.size() * IMU_REC); AL(wheel_rec, wheel_fi.size() * WHEEL_REC); AL(plane_rec, plane_f.size() * PLANE_REC);
-    AL(prior_A, prior_J.size()); AL(prior_res, prior_r.size()); AL(prior_g, prior_r.size());
-    AL(Hpk, (size_t)B * (TFIX * (TFIX + 1) / 2)); AL(gpk, (size_t)B * TFIX); AL(gfix, (size_t)B * (TFIX + 8));
-    AL(asm_out, (size_t)(items_solve.size() + items_marg.size()) * ASM_STRIDE); AL(Tvis, (size_t)B * VSUB * VSUB); AL(tvec, (size_t)B * VSUB);
-    const size_t nvec = (size_t)B * TFIX + nl;
-    AL(v_scale, nvec); AL(v_D, nvec); AL(v_sgrad, nvec); AL(v_gn, nvec);
-    AL(marg_J, (size_t)B * MAXPRI * MAXPRI); AL(marg_r, (size_t)B * MAXPRI); AL(marg_x0, (size_t)B * SFIX);
-    AL(marg_hdr, (size_t)B * (3 + 2 * NB)); AL(marg_A, (size_t)B * (MAXPRI + 16) * (MAXPRI + 16));
-#undef AL
+    std::vector<AsmItem> all_items(items_solve); all_items.insert(all_items.end(), items_marg.begin(), items_marg.end());
+    b->prior_nmax = 0; for (int w = 0; w < B; w++) b->prior_nmax = std::max(b->prior_nmax, b->prior_n[w]);
+    Placer pl;
+    pl.in(b->meta, &bd.meta); pl.in(priors, &bd.prior);
+    pl.in(vis_type, &bd.vis_type); pl.in(vis_lm, &bd.vis_lm); pl.in(vis_fi, &bd.vis_fi); pl.in(vis_fj, &bd.vis_fj); pl.in(vis_win, &bd.vis_win);
+    pl.in_segs(obs_segs, &bd.vis_obs);
+    pl.in(lm_win, &bd.lm_win); pl.in(lm_fptr, &bd.lm_fptr); pl.in(all_items, &bd.items); pl.in(asm_list, &bd.asm_list);
+    pl.in(imu_fi, &bd.imu_fi); pl.in(imu_fj, &bd.imu_fj); pl.in(imu_win, &bd.imu_win); pl.in(wheel_fi, &bd.wheel_fi); pl.in(wheel_fj, &bd.wheel_fj); pl.in(wheel_win, &bd.wheel_win);
+    pl.in(plane_f, &bd.plane_f); pl.in(plane_win, &bd.plane_win);
+    pl.in_segs(imu_segs, &bd.imu_data); pl.in_segs(wheel_segs, &bd.wheel_data);
+    pl.in_segs(priorJ_segs, &bd.prior_J); pl.in(prior_r, &bd.prior_r); pl.in(prior_x0, &bd.prior_x0);
+    { const double *xi = nullptr; pl.in(x_init, &xi); pl.reqs.back().field = (void **)&bd.x_init; }
+    pl.in(b->work, (const WinWork **)&b->work_init_dev);
+    const size_t nl = lm_win.size(), nvec = (size_t)B * TFIX + nl;
+    pl.work(B, &bd.work); pl.work(x_init.size(), &bd.x_cur); pl.work(x_init.size(), &bd.x_cand); pl.work(x_init.size(), &bd.x_before);
+    pl.work(nv * VREC, &bd.vis_rec); pl.work(nv, &bd.vis_cost);
+    pl.work(nl, &bd.lm_a); pl.work(nl, &bd.lm_g); pl.work(nl, &bd.lm_gamma); pl.work(nl, &bd.lm_scale); pl.work(nl, &bd.lm_cost); pl.work(nl * VSUB, &bd.lm_W);
+    pl.work(imu_fi.size() * 225, &bd.imu_S); pl.work(wheel_fi.size() * 36, &bd.wheel_S);
+    pl.work(imu_fi.size() * IMU_REC, &bd.imu_rec); pl.work(wheel_fi.size() * WHEEL_REC, &bd.wheel_rec); pl.work(plane_f.size() * PLANE_REC, &bd.plane_rec);
+    pl.work(priorJ_count, &bd.prior_A); pl.work(prior_r.size(), &bd.prior_res); pl.work(prior_r.size(), &bd.prior_g);
+    pl.work((size_t)B * (TFIX * (TFIX + 1) / 2), &bd.Hpk); pl.work((size_t)B * TFIX, &bd.gpk); pl.work((size_t)B * (TFIX + 8), &bd.gfix);
+    pl.work(all_items.size() * ASM_STRIDE, &bd.asm_out); pl.work((size_t)B * VSUB * VSUB, &bd.Tvis); pl.work((size_t)B * VSUB, &bd.tvec);
+    pl.work(nvec, &bd.v_scale); pl.work(nvec, &bd.v_D); pl.work(nvec, &bd.v_sgrad); pl.work(nvec, &bd.v_gn);
+    pl.work((size_t)B * MAXPRI * MAXPRI, &bd.marg_J); pl.work((size_t)B * MAXPRI, &bd.marg_r); pl.work((size_t)B * SFIX, &bd.marg_x0);
+    pl.work((size_t)B * (3 + 2 * NB), &bd.marg_hdr); pl.work((size_t)B * (MAXPRI + 16) * (MAXPRI + 16), &bd.marg_A);
+    // ---- placement: offsets, slabs, pack + one H2D
+    size_t in_bytes = 0, tot = 0;
+    for (auto &r : pl.reqs) if (r.input) { r.off = tot; tot += align_up(r.bytes); }
+    in_bytes = tot;
+    for (auto &r : pl.reqs) if (!r.input) { r.off = tot; tot += align_up(r.bytes); }
+    b->out_bytes = align_up(b->total_state * 8) + align_up(sizeof(WinWork) * B) + align_up((size_t)B * (3 + 2 * NB) * 4) + align_up((size_t)B * MAXPRI * 8) +
+                   align_up((size_t)B * SFIX * 8) + align_up((size_t)B * b->prior_nmax * b->prior_nmax * 8);
+    const size_t host_need = std::max(in_bytes, b->out_bytes);
+    Arena *ar;
+    if (use_cached && !ctx->arena.busy) { ar = &ctx->arena; b->arena_cached = true; ctx->arena.busy = true; } else { ar = &b->arena; b->arena_cached = false; }
+    if (ar->dev_cap < tot) { if (ar->dev) dev_free(ar->dev); ar->dev = nullptr; ar->dev_cap = 0; void *d = nullptr; int e = dev_malloc(&d, tot + tot / 8); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, std::string("device slab: ") + dev_errstr(e)); } ar->dev = (char *)d; ar->dev_cap = tot + tot / 8; }
+    if (ar->host_cap < host_need) { if (ar->host) host_free(ar->host); ar->host = nullptr; ar->host_cap = 0; void *h = nullptr; int e = host_alloc(&h, host_need + host_need / 8); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, "pinned staging slab"); } ar->host = (char *)h; ar->host_cap = host_need + host_need / 8; }
+    if (b->arena_cached) b->arena = *ar;     // a view; ownership stays with the context
+    for (auto &r : pl.reqs) {
+        *r.field = ar->dev + r.off;
+        if (r.input) { size_t o = r.off; for (auto &sg : r.segs) { memcpy(ar->host + o, sg.src, sg.bytes); o += sg.bytes; } }
+    }
+    { int e = dev_h2d(ar->dev, ar->host, in_bytes, ctx->stream); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, std::string("H2D: ") + dev_errstr(e)); } }
+    { int e = dev_sync(ctx->stream); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, "H2D sync"); } }     // the staging slab is reused for outputs
     *out = b;
     return 0;
 }
@@ -381,7 +429,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     const size_t xs = b->total_state * sizeof(double);
     CK(dev_d2d(bd.x_cur, bd.x_init, xs, st)); CK(dev_d2d(bd.x_cand, bd.x_init, xs, st));
     if (!(what & RUN_REANCHOR) || (what & RUN_SOLVE)) CK(dev_d2d(bd.x_before, bd.x_init, xs, st));
-    CK(dev_h2d(bd.work, b->work.data(), sizeof(WinWork) * B, st));
+    CK(dev_d2d(bd.work, b->work_init_dev, sizeof(WinWork) * B, st));
     const int nt_vis = NT(128), nt_lm = NT(64), nt_small = NT(64), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(512), nt_marg = NT(512);
     const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total + nt_lm - 1) / nt_lm;
     const size_t sm_small = (size_t)(nt_small + MAXPRI + 8) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg) * 8;
@@ -420,59 +468,68 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     return 0;
 }
 
-static void fill_prior_out(const viwb_batch *b, int w, const std::vector<int> &hdr, const std::vector<double> &J, const std::vector<double> &r,
-                           const std::vector<double> &x0, viwb_prior *out) {
-    const int mode = b->out_mode[w];
-    if (mode == 0) {
-        const int *h = hdr.data() + (size_t)w * (3 + 2 * NB);
-        out->valid = h[0]; out->n = h[1]; out->num_blocks = h[2];
-        for (int i = 0; i < h[2]; i++) { out->block_id[i] = h[3 + i]; out->block_idx[i] = h[3 + NB + i]; }
-        const int n = h[1];
-        memcpy(out->J, J.data() + (size_t)w * MAXPRI * MAXPRI, sizeof(double) * n * n);
-        memcpy(out->r, r.data() + (size_t)w * MAXPRI, sizeof(double) * n);
-        memcpy(out->x0, x0.data() + (size_t)w * SFIX, sizeof(double) * SFIX);
-    } else if (mode == 1) {
-        const HostPrior &hp = b->in_prior[w];
-        out->valid = 1; out->n = hp.n; out->num_blocks = hp.nb;
-        memcpy(out->block_id, hp.block_id, sizeof hp.block_id); memcpy(out->block_idx, hp.block_idx, sizeof hp.block_idx);
-        memcpy(out->x0, hp.x0.data(), sizeof(double) * SFIX); memcpy(out->J, hp.J.data(), sizeof(double) * hp.n * hp.n); memcpy(out->r, hp.r.data(), sizeof(double) * hp.n);
-    } else { out->valid = 0; out->n = 0; out->num_blocks = 0; }
-}
-
 static int batch_fetch(viwb_context *ctx, viwb_batch *b, double *const *states, viwb_summary *summaries, viwb_prior *priors_out) {
     BatchDev &bd = b->bd;
-    std::vector<double> x(b->total_state);
-    std::vector<WinWork> work(b->B);
-    CK(dev_d2h(x.data(), bd.x_cur, x.size() * sizeof(double), ctx->stream));
-    CK(dev_d2h(work.data(), bd.work, sizeof(WinWork) * b->B, ctx->stream));
-    std::vector<int> hdr; std::vector<double> J, r, x0;
-    if (priors_out && b->any_marg) {
-        hdr.resize((size_t)b->B * (3 + 2 * NB)); J.resize((size_t)b->B * MAXPRI * MAXPRI); r.resize((size_t)b->B * MAXPRI); x0.resize((size_t)b->B * SFIX);
-        CK(dev_d2h(hdr.data(), bd.marg_hdr, hdr.size() * sizeof(int), ctx->stream));
-        CK(dev_d2h(J.data(), bd.marg_J, J.size() * sizeof(double), ctx->stream));
-        CK(dev_d2h(r.data(), bd.marg_r, r.size() * sizeof(double), ctx->stream));
-        CK(dev_d2h(x0.data(), bd.marg_x0, x0.size() * sizeof(double), ctx->stream));
+    const int B = b->B, nmax = b->prior_nmax;
+    // staging layout inside the pinned slab
+    char *hs = b->arena.host;
+    size_t o = 0;
+    double *x = (double *)(hs + o); o += align_up(b->total_state * 8);
+    WinWork *work = (WinWork *)(hs + o); o += align_up(sizeof(WinWork) * B);
+    int *hdr = (int *)(hs + o); o += align_up((size_t)B * (3 + 2 * NB) * 4);
+    double *r = (double *)(hs + o); o += align_up((size_t)B * MAXPRI * 8);
+    double *x0 = (double *)(hs + o); o += align_up((size_t)B * SFIX * 8);
+    double *J = (double *)(hs + o);
+    CK(dev_d2h(x, bd.x_cur, b->total_state * sizeof(double), ctx->stream));
+    CK(dev_d2h(work, bd.work, sizeof(WinWork) * B, ctx->stream));
+    const bool want_pr = priors_out && b->any_marg;
+    if (want_pr) {
+        CK(dev_d2h(hdr, bd.marg_hdr, (size_t)B * (3 + 2 * NB) * sizeof(int), ctx->stream));
+        CK(dev_d2h(r, bd.marg_r, (size_t)B * MAXPRI * sizeof(double), ctx->stream));
+        CK(dev_d2h(x0, bd.marg_x0, (size_t)B * SFIX * sizeof(double), ctx->stream));
+        // J_lin is n x n (row stride n) at the head of each window's MAXPRI^2 slot: strided copy of the first nmax^2 entries
+        CK(dev_d2h_2d(J, (size_t)nmax * nmax * 8, bd.marg_J, (size_t)MAXPRI * MAXPRI * 8, (size_t)nmax * nmax * 8, B, ctx->stream));
     }
     CK(dev_sync(ctx->stream));
     int rc = 0;
-    for (int w = 0; w < b->B; w++) {
-        if (states && states[w]) memcpy(states[w], x.data() + b->meta[w].state_off, sizeof(double) * b->state_sizes[w]);
+    for (int w = 0; w < B; w++) {
+        if (states && states[w]) memcpy(states[w], x + b->meta[w].state_off, sizeof(double) * b->state_sizes[w]);
         if (summaries) {
-            viwb_summary &s = summaries[w]; const WinWork &ww = work[w];
-            s.termination_type = ww.term; s.num_iterations = ww.num_iterations; s.num_successful_steps = ww.successful; s.num_linear_solves = ww.num_linear;
-            s.initial_cost = ww.initial_cost; s.final_cost = ww.x_cost; s.final_radius = ww.radius; s.final_mu = ww.mu;
+            viwb_summary &sm = summaries[w]; const WinWork &ww = work[w];
+            sm.termination_type = ww.term; sm.num_iterations = ww.num_iterations; sm.num_successful_steps = ww.successful; sm.num_linear_solves = ww.num_linear;
+            sm.initial_cost = ww.initial_cost; sm.final_cost = ww.x_cost; sm.final_radius = ww.radius; sm.final_mu = ww.mu;
         }
-        if (priors_out) {
-            if (b->out_mode[w] == 0 && !b->any_marg) { priors_out[w].valid = 0; continue; }
-            fill_prior_out(b, w, hdr, J, r, x0, &priors_out[w]);
-            if (b->out_mode[w] == 0 && work[w].marg_status < 0) rc = VIWB_ERR_NUMERIC;
-        }
+        if (!priors_out) continue;
+        viwb_prior *out = &priors_out[w];
+        const int mode = b->out_mode[w];
+        if (mode == 0 && want_pr) {
+            const int *h = hdr + (size_t)w * (3 + 2 * NB);
+            out->valid = h[0]; out->n = h[1]; out->num_blocks = h[2];
+            for (int i = 0; i < h[2]; i++) { out->block_id[i] = h[3 + i]; out->block_idx[i] = h[3 + NB + i]; }
+            const int n = h[1];
+            if (h[0]) {
+                memcpy(out->J, J + (size_t)w * nmax * nmax, sizeof(double) * n * n);
+                memcpy(out->r, r + (size_t)w * MAXPRI, sizeof(double) * n);
+                memcpy(out->x0, x0 + (size_t)w * SFIX, sizeof(double) * SFIX);
+            }
+            if (work[w].marg_status < 0) rc = VIWB_ERR_NUMERIC;
+        } else if (mode == 1) {
+            const HostPrior &hp = b->in_prior[w];
+            out->valid = 1; out->n = hp.n; out->num_blocks = hp.nb;
+            memcpy(out->block_id, hp.block_id, sizeof hp.block_id); memcpy(out->block_idx, hp.block_idx, sizeof hp.block_idx);
+            memcpy(out->x0, hp.x0.data(), sizeof(double) * SFIX); memcpy(out->J, hp.J.data(), sizeof(double) * hp.n * hp.n); memcpy(out->r, hp.r.data(), sizeof(double) * hp.n);
+        } else { out->valid = 0; out->n = 0; out->num_blocks = 0; }
     }
     if (rc) return fail(ctx, rc, "marginalisation: kept dimension exceeds the shared-memory eigen solver");
     return 0;
 }
 
-static void batch_free(viwb_batch *b) { if (!b) return; for (void *p : b->allocs) dev_free(p); delete b; }
+static void batch_free(viwb_context *ctx, viwb_batch *b) {
+    if (!b) return;
+    if (b->arena_cached) { if (ctx) ctx->arena.busy = false; }
+    else arena_release(b->arena);
+    delete b;
+}
 
 // ====================================================================================== C ABI
 extern "C" int viwb_create(int device, viwb_context **out) {
@@ -495,6 +552,7 @@ extern "C" void viwb_destroy(viwb_context *ctx) {
     lk_release(ctx->device);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
 #endif
+    arena_release(ctx->arena);
     delete ctx;
 }
 extern "C" const char *viwb_last_error(const viwb_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -550,23 +608,23 @@ extern "C" int viwb_batch_download(viwb_context *ctx, viwb_batch *b, double *con
     return batch_fetch(ctx, b, states, summaries, priors_out);
 }
 extern "C" double viwb_batch_algorithmic_bytes(const viwb_batch *b) { return b ? b->algorithmic_bytes : 0.0; }
-extern "C" void viwb_batch_destroy(viwb_context *ctx, viwb_batch *b) { (void)ctx; batch_free(b); }
+extern "C" void viwb_batch_destroy(viwb_context *ctx, viwb_batch *b) { batch_free(ctx, b); }
 
 static int run_once(viwb_context *ctx, int B, const viwb_problem *problems, double *const *states, const viwb_options *opt,
                     const int32_t *flags, int what, viwb_summary *summaries, viwb_prior *priors, const double *const *before) {
     viwb_batch *b = nullptr;
-    int rc = batch_build(ctx, B, problems, (const double *const *)states, opt, flags, &b);
+    int rc = batch_build(ctx, B, problems, (const double *const *)states, opt, flags, &b, true);
     if (rc) return rc;
     if (before) {   // gauge re-anchoring against an explicit pre-solve state
         std::vector<double> xb(b->total_state);
         for (int w = 0; w < B; w++) memcpy(xb.data() + b->meta[w].state_off, before[w], sizeof(double) * b->state_sizes[w]);
         rc = dev_h2d(b->bd.x_before, xb.data(), xb.size() * sizeof(double), ctx->stream);
         if (!rc) rc = dev_sync(ctx->stream);
-        if (rc) { batch_free(b); return fail(ctx, VIWB_ERR_CUDA, "upload of state_before failed"); }
+        if (rc) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, "upload of state_before failed"); }
     }
     rc = batch_execute(ctx, b, what);
     if (!rc) rc = batch_fetch(ctx, b, states, summaries, priors);
-    batch_free(b);
+    batch_free(ctx, b);
     return rc;
 }
 
@@ -606,7 +664,7 @@ extern "C" int viwb_debug_normal_equations(viwb_context *ctx, const viwb_problem
     int rc = batch_build(ctx, 1, problem, sp, nullptr, nullptr, &b);
     if (rc) return rc;
     rc = batch_execute(ctx, b, RUN_LIN_ONLY);
-    if (rc) { batch_free(b); return rc; }
+    if (rc) { batch_free(ctx, b); return rc; }
     const int N = problem->num_landmarks;
     std::vector<double> Hd((size_t)TFIX * (TFIX + 1) / 2), gd(TFIX), a(N + 1), gl(N + 1), W((size_t)(N + 1) * VSUB), lc(N + 1);
     std::vector<WinWork> ww(1);
@@ -616,7 +674,7 @@ extern "C" int viwb_debug_normal_equations(viwb_context *ctx, const viwb_problem
     e |= dev_d2h(W.data(), b->bd.lm_W, (size_t)N * VSUB * 8, ctx->stream); e |= dev_d2h(lc.data(), b->bd.lm_cost, (size_t)N * 8, ctx->stream);
     e |= dev_d2h(ww.data(), b->bd.work, sizeof(WinWork), ctx->stream);
     e |= dev_sync(ctx->stream);
-    if (e) { batch_free(b); return fail(ctx, VIWB_ERR_CUDA, "download failed"); }
+    if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, "download failed"); }
     // formatting only: scatter the packed active triangle into the caller's fixed-layout arrays
     const WinMeta &m = b->meta[0];
     if (H) { memset(H, 0, sizeof(double) * TFIX * TFIX);
@@ -637,7 +695,7 @@ extern "C" int viwb_debug_normal_equations(viwb_context *ctx, const viwb_problem
             } }
     }
     if (cost) *cost = c;
-    batch_free(b);
+    batch_free(ctx, b);
     return VIWB_OK;
 }
 

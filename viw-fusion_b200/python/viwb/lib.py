@@ -164,6 +164,33 @@ class Context:
                     p.c.block_id[k], p.c.block_idx[k] = parr[i].block_id[k], parr[i].block_idx[k]
         return sts, list(summ), pri
 
+    def prepare_optimization_batch(self, problems, states, flags, options=None):
+        """Marshal the arguments of viwb_optimization_batch once; the returned callable is exactly one C-ABI call
+        (host buffers in, host buffers out).  A C++ caller has no marshalling at all -- this keeps Python's out of timings."""
+        B = len(problems)
+        arr = (abi.Problem * B)()
+        for i, p in enumerate(problems):
+            p.fill(arr[i])
+        src = [np.ascontiguousarray(s, np.float64) for s in states]
+        sts = [s.copy() for s in src]
+        sp = (abi.c_double_p * B)(*[_dp(s) for s in sts])
+        fl = (C.c_int32 * B)(*[int(f) for f in flags])
+        opt = options if options is not None else abi.default_options()
+        summ = (abi.Summary * B)()
+        pri = [abi.PriorData() for _ in range(B)]
+        parr = (abi.Prior * B)()
+        for i, p in enumerate(pri):
+            parr[i] = p.c
+        keep = (arr, src, sts, sp, fl, opt, summ, pri, parr, problems)
+
+        def call():
+            for s, d in zip(src, sts):      # the call updates the states in place: restore the inputs
+                d[:] = s
+            self._ck(self.lib.viwb_optimization_batch(self.h, C.c_int(B), arr, sp, C.byref(opt), fl, summ, parr), "viwb_optimization_batch")
+            return sts, summ, parr
+        call.keep = keep
+        return call
+
     # ---------------------------------------------------------------- feature tracker
     def lk_track(self, prev_img, next_img, prev_pts, next_pts=None, max_level=3, max_iter=30, eps=0.01, flags=0, min_eig=1e-4):
         a = np.ascontiguousarray(prev_img, np.uint8)
