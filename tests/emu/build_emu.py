@@ -15,7 +15,7 @@ def build():
     deps = [os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith((".cu", ".cuh"))] + [os.path.join(ROOT, "include", "viwb.h")]
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DVIWB_HOST_EMU", "-x", "c++", "-Wno-unknown-pragmas",
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DVIWB_HOST_EMU", "-x", "c++", "-Wno-unknown-pragmas",
                            "-o", OUT, os.path.join(SRC, "viwb.cu")])
     return OUT
 

@@ -313,3 +313,27 @@ def check_track_checked(ctx, seed=1):
             assert (st_ref == st_g).mean() >= 0.99, (mode, fb, (st_ref == st_g).mean())
             both = (st_ref == 1) & (st_g == 1)
             assert both.sum() > 100 and np.abs(p_ref[both] - p_g[both]).max() <= 1e-2
+
+
+def check_unsorted_table_and_threads(ctx, oracle):
+    """The visual table may come in any order (the library groups it by landmark), and a batch large enough to use
+    the parallel host lowering gives the same answer as one window at a time."""
+    prob, st, gt = synth.make_window(2)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(prob.vis_type))
+    shuf = abi.WindowProblem(prob.frame_count, prob.num_landmarks, prob.block_flags, prob.subset_mask, prob.vis_type[perm], prob.vis_landmark[perm],
+                             prob.vis_frame_i[perm], prob.vis_frame_j[perm], prob.vis_obs[perm], prob.imu_frame_i, prob.imu_frame_j, prob.imu_data,
+                             globals_=prob.globals)
+    a, sa, qa = ctx.optimization(prob, st, abi.MARGIN_OLD)
+    b, sb, qb = ctx.optimization(shuf, st, abi.MARGIN_OLD)
+    ep, er = synth.pose_errors(a, b)
+    assert ep < 1e-9 and er < 1e-9
+    probs, sts = [], []
+    for i in range(20):
+        p, s, _ = synth.make_window(1 + (i % 4), i % 3)
+        probs.append(p)
+        sts.append(s)
+    out_s, out_sum, out_pr = ctx.optimization_batch(probs, sts, [abi.MARGIN_OLD] * 20)
+    for i in (0, 7, 19):
+        a, sm, q = ctx.optimization(probs[i], sts[i], abi.MARGIN_OLD)
+        assert np.array_equal(a, out_s[i]) and q.n == out_pr[i].n and np.array_equal(q.Jmat(), out_pr[i].Jmat())

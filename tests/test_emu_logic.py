@@ -60,3 +60,7 @@ def test_lk(emu):
 
 def test_track_checked(emu):
     pc.check_track_checked(emu)
+
+
+def test_unsorted_table_and_parallel_lowering(emu, oracle):
+    pc.check_unsorted_table_and_threads(emu, oracle)

@@ -100,3 +100,7 @@ def test_lk_empty_and_tiny(gpu_ctx):
     assert len(p) == 0 and len(st) == 0
     p, st, err = gpu_ctx.lk_track(img0, img1, pts[:1])
     assert st.shape == (1,)
+
+
+def test_unsorted_table_and_parallel_lowering(gpu_ctx, oracle):
+    pc.check_unsorted_table_and_threads(gpu_ctx, oracle)

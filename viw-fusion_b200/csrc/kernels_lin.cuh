@@ -68,7 +68,7 @@ VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, d
     const double *x = eval_state(bd, w, mode);
     double obs[12];
     for (int k = 0; k < 12; k++) obs[k] = bd.vis_obs[(size_t)f * 12 + k];
-    const int lm = bd.vis_lm[f] - m.lm_off;
+    const int lm = bd.vis_lm[f];
     VisOut o;
     vis_eval(bd.vis_type[f], obs, x + 7 * fi, x + 7 * bd.vis_fj[f], x + blk_off(BLK_EX0), x + blk_off(BLK_EX1),
              x[SFIX + lm], x[blk_off(BLK_TD)], m.S_vis, true, o);

@@ -50,8 +50,8 @@ struct WinMeta {        // read-only during a solve
     int nf;             // active fixed tangent columns (compact)
     int namb;
     int margin_flag;
-    int item_off, nitems, nphases;      // assembly items of the solver linearisation (kernels_asm.cuh)
-    int mitem_off, nmitems, nmphases;   // assembly items of the marginalisation linearisation (factors hosted in frame 0)
+    int item_off, nitems, nphases, list_off;     // assembly items of the solver linearisation (kernels_asm.cuh); list entries are window-local
+    int mitem_off, nmitems, nmphases, mlist_off; // assembly items of the marginalisation linearisation (factors hosted in frame 0)
     int has_common;                     // any of ex0 / ex1 / td is an active column (solver); marginalisation always counts them
     short tcol[NB];     // compact column of fixed block b, -1 if constant / absent / unreferenced
     unsigned char flags[NB], mask[NB];
@@ -90,13 +90,13 @@ struct BatchDev {       // passed by value to every kernel
     // states
     double *x_cur, *x_cand, *x_init, *x_before;
     // visual tables
-    const int *vis_type, *vis_lm, *vis_fi, *vis_fj, *vis_win;
+    const int *vis_type, *vis_lm, *vis_fi, *vis_fj, *vis_win;   // vis_lm: landmark index local to the window
     const double *vis_obs;          // [nvis_total][12] exactly as the caller's table (no host transpose)
     double *vis_rec;                // [nvis_total][VREC]
     double *vis_cost;               // [nvis_total]
     // assembly plan (static per batch): items = chunks of per-frame / per-frame-pair / common factor lists
     const struct AsmItem *items;    // solver items of all windows, then marginalisation items
-    const int *asm_list;            // list entries: (global factor index << 1) | role
+    const int *asm_list;            // list entries: (window-local factor index << 1) | role; item.lo/hi are relative to meta.list_off / mlist_off
     double *asm_out;                // [nitems_total][ASM_STRIDE] partial sums written by asm_items
     // landmarks
     const int *lm_win, *lm_fptr;    // [nlm_total], [nlm_total+1] factor range (global factor indices, sorted by landmark)

@@ -12,10 +12,13 @@
 #include "kernels_lk.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <vector>
 
 using namespace viwb;
@@ -90,6 +93,8 @@ DEF_KERNEL(marg, 512)
 // pay cudaMalloc / cudaHostAlloc on every call
 struct Arena { char *dev = nullptr; size_t dev_cap = 0; char *host = nullptr; size_t host_cap = 0; bool busy = false; };
 static void arena_release(Arena &a) { if (a.dev) dev_free(a.dev); if (a.host) host_free(a.host); a = Arena(); }
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static bool g_timing = getenv("VIWB_TIMING") != nullptr;
 struct viwb_context {
     int device;
     stream_t stream;
@@ -113,7 +118,6 @@ struct viwb_batch {
     int prior_nmax;
     WinWork *work_init_dev;              // pristine solver states, copied to bd.work at the start of every run
     std::vector<WinMeta> meta;
-    std::vector<WinWork> work;
     std::vector<int> out_mode;        // 0: prior computed on the device, 1: input prior passes through, 2: invalid / none
     std::vector<HostPrior> in_prior;
     std::vector<int> state_sizes;
@@ -124,16 +128,6 @@ struct viwb_batch {
     size_t nrec_imu, nrec_wheel, nrec_plane;
 };
 
-// deferred placement: every array is first registered (inputs with their host segments), then one device slab and one
-// pinned staging slab are sized, the inputs are packed into the staging slab and go over in a single H2D copy.
-struct Seg { const void *src; size_t bytes; };
-struct Req { void **field; size_t bytes; std::vector<Seg> segs; bool input; size_t off; };
-struct Placer {
-    std::vector<Req> reqs;
-    template <typename T> void in(const std::vector<T> &h, const T **field) { Req r; r.field = (void **)field; r.bytes = h.size() * sizeof(T); r.input = true; r.off = 0; if (r.bytes) r.segs.push_back({h.data(), r.bytes}); reqs.push_back(r); }
-    template <typename T> void in_segs(const std::vector<Seg> &segs, const T **field) { Req r; r.field = (void **)field; r.bytes = 0; for (auto &sg : segs) r.bytes += sg.bytes; r.segs = segs; r.input = true; r.off = 0; reqs.push_back(r); }
-    template <typename T> void work(size_t count, T **field) { Req r; r.field = (void **)field; r.bytes = (count ? count : 1) * sizeof(T); r.input = false; r.off = 0; reqs.push_back(r); }
-};
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static void opts_from(const viwb_options *o, Opts &d) {
@@ -172,15 +166,184 @@ static double window_algorithmic_bytes(const viwb_problem &p, int iters) {
 }
 
 static void batch_free(viwb_context *ctx, viwb_batch *b);
-static int batch_build_impl(viwb_context *ctx, int B, const viwb_problem *problems, const double *const *states,
-                            const viwb_options *options, const int32_t *margin_flags, viwb_batch **out, bool use_cached);
+
+// ---- per-window lowering, phase 1: validation, sizes, active columns, marginalisation plan (no offsets yet)
+struct WinLow {
+    int err; bool grouped, has_prior;
+    int nlist_s, nitems_s, nph_s, nlist_m, nitems_m, nph_m;
+    int prior_n_out;
+};
+static int chunk_count(int n) { return (n + ASM_CHUNK - 1) / ASM_CHUNK; }
+
+static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, int &out_mode) {
+    memset(&m, 0, sizeof m); memset(&lo, 0, sizeof lo);
+    if (p.frame_count < 0 || p.frame_count > VIWB_WINDOW_SIZE || p.num_landmarks < 0 || p.num_landmarks > VIWB_MAX_LANDMARKS) { lo.err = 1; return; }
+    m.nlm = p.num_landmarks; m.frame_count = p.frame_count; m.nvis = p.num_vis; m.nimu = p.num_imu; m.nwheel = p.num_wheel; m.nplane = p.num_plane;
+    for (int k = 0; k < 3; k++) m.G[k] = p.globals.G[k];
+    for (int k = 0; k < 4; k++) m.S_vis[k] = p.globals.vis_sqrt_info[k];
+    for (int k = 0; k < 3; k++) m.w_plane[k] = p.globals.plane_sqrt_info[k];
+    m.huber = p.globals.huber_delta;
+    lo.has_prior = p.prior && p.prior->valid;
+    if (lo.has_prior && (p.prior->n <= 0 || p.prior->n > MAXPRI || p.prior->num_blocks <= 0 || p.prior->num_blocks > NB)) { lo.err = 2; return; }
+    // visual table checks + per-list counts
+    int fcnt[NFR] = {0}, pcnt[NFR * NFR] = {0}, fcnt0[NFR] = {0}, pcnt0[NFR * NFR] = {0}, ncommon0 = 0;
+    bool ref[NB]; for (int k = 0; k < NB; k++) ref[k] = false;
+    bool seen[NB]; for (int k = 0; k < NB; k++) seen[k] = false;
+    bool any_lm0 = false;
+    lo.grouped = true;
+    for (int i = 0; i < p.num_vis; i++) {
+        const int t = p.vis_type[i], l = p.vis_landmark[i], fi = p.vis_frame_i[i], fj = p.vis_frame_j[i];
+        if (t < 0 || t > 2 || l < 0 || l >= p.num_landmarks || fi < 0 || fi > p.frame_count || fj < 0 || fj > p.frame_count) { lo.err = 3; return; }
+        if (i && l < p.vis_landmark[i - 1]) lo.grouped = false;
+        if (t != 2) {
+            ref[fi] = ref[fj] = true; fcnt[fi]++; fcnt[fj]++;
+            const int a = fi < fj ? fi : fj, c = fi < fj ? fj : fi; pcnt[a * NFR + c]++;
+            if (fi == 0) { fcnt0[fi]++; fcnt0[fj]++; pcnt0[a * NFR + c]++; seen[0] = seen[fj] = true; }
+        }
+        ref[BLK_EX0] = true; if (t != 0) ref[BLK_EX1] = true; ref[BLK_TD] = true;
+        if (fi == 0) { any_lm0 = true; ncommon0++; seen[BLK_EX0] = true; if (t != 0) seen[BLK_EX1] = true; seen[BLK_TD] = true; }
+    }
+    if (lo.has_prior) for (int i = 0; i < p.prior->num_blocks; i++) { const int bq = p.prior->block_id[i]; if (bq < 0 || bq >= NB) { lo.err = 2; return; } ref[bq] = true; }
+    for (int i = 0; i < p.num_imu; i++) { const int a = p.imu_frame_i[i], c = p.imu_frame_j[i]; if (a < 0 || a > p.frame_count || c < 0 || c > p.frame_count) { lo.err = 4; return; } ref[a] = ref[BLK_SB0 + a] = ref[c] = ref[BLK_SB0 + c] = true; }
+    for (int i = 0; i < p.num_wheel; i++) { const int a = p.wheel_frame_i[i], c = p.wheel_frame_j[i]; if (a < 0 || a > p.frame_count || c < 0 || c > p.frame_count) { lo.err = 4; return; } ref[a] = ref[c] = ref[BLK_EXW] = ref[BLK_SX] = ref[BLK_SY] = ref[BLK_SW] = ref[BLK_TDW] = true; }
+    for (int i = 0; i < p.num_plane; i++) { const int a = p.plane_frame[i]; if (a < 0 || a > p.frame_count) { lo.err = 4; return; } ref[a] = ref[BLK_EXW] = ref[BLK_PR] = ref[BLK_PZ] = true; }
+    // active blocks (Program::RemoveFixedBlocks) and compact columns
+    int col = 0, amb = 0;
+    for (int k = 0; k < NB; k++) {
+        m.flags[k] = p.block_flags[k] & 3u; m.mask[k] = p.subset_mask[k];
+        const bool active = (p.block_flags[k] & VIWB_BLOCK_PRESENT) && !(p.block_flags[k] & VIWB_BLOCK_CONSTANT) && ref[k];
+        if (active) { m.tcol[k] = (short)col; col += blk_tsize(k); amb += blk_size(k); } else m.tcol[k] = -1;
+    }
+    m.nf = col; m.namb = amb + p.num_landmarks;
+    m.has_common = (m.tcol[BLK_EX0] >= 0 || m.tcol[BLK_EX1] >= 0 || m.tcol[BLK_TD] >= 0) ? 1 : 0;
+    // marginalisation plan (estimator.cpp:1666-1893)
+    m.margin_flag = -1; out_mode = 2; lo.prior_n_out = 0;
+    if (mf >= 0 && p.frame_count == VIWB_WINDOW_SIZE) {
+        if (mf == VIWB_MARGIN_OLD) {
+            if (lo.has_prior) for (int i = 0; i < p.prior->num_blocks; i++) seen[p.prior->block_id[i]] = true;
+            for (int i = 0; i < p.num_imu; i++) if (p.imu_frame_i[i] == 0 && p.imu_frame_j[i] == 1) seen[0] = seen[BLK_SB0] = seen[1] = seen[BLK_SB0 + 1] = true;
+            for (int i = 0; i < p.num_wheel; i++) if (p.wheel_frame_i[i] == 0 && p.wheel_frame_j[i] == 1) seen[0] = seen[1] = seen[BLK_EXW] = seen[BLK_SX] = seen[BLK_SY] = seen[BLK_SW] = seen[BLK_TDW] = true;
+            for (int i = 0; i < p.num_plane; i++) if (p.plane_frame[i] == 0) seen[0] = seen[BLK_EXW] = seen[BLK_PR] = seen[BLK_PZ] = true;
+            if (seen[0] || seen[BLK_SB0] || any_lm0) { m.margin_flag = 0; out_mode = 0; }
+        } else {
+            for (int k = 0; k < NB; k++) seen[k] = false;
+            bool has9 = false;
+            if (lo.has_prior) for (int i = 0; i < p.prior->num_blocks; i++) { seen[p.prior->block_id[i]] = true; if (p.prior->block_id[i] == VIWB_WINDOW_SIZE - 1) has9 = true; }
+            if (has9) { m.margin_flag = 1; out_mode = 0; } else out_mode = lo.has_prior ? 1 : 2;
+        }
+        if (m.margin_flag >= 0) {
+            int nn = 0;
+            for (int k = 0; k < NB; k++) if (seen[k]) { m.flags[k] |= 4u; const bool drop = m.margin_flag == 0 ? (k == 0 || k == BLK_SB0) : (k == VIWB_WINDOW_SIZE - 1); if (!drop) nn += blk_msize(k); }
+            lo.prior_n_out = nn;
+        }
+    }
+    // assembly plan sizes
+    int nframe_ent = 0, npair_ent = 0;
+    for (int a = 0; a < NFR; a++) { nframe_ent += fcnt[a]; lo.nitems_s += chunk_count(fcnt[a]); lo.nph_s = std::max(lo.nph_s, chunk_count(fcnt[a])); }
+    for (int a = 0; a < NFR * NFR; a++) { npair_ent += pcnt[a]; lo.nitems_s += chunk_count(pcnt[a]); lo.nph_s = std::max(lo.nph_s, chunk_count(pcnt[a])); }
+    lo.nlist_s = nframe_ent + npair_ent;
+    if (m.has_common) { lo.nlist_s += p.num_vis; lo.nitems_s += chunk_count(p.num_vis); lo.nph_s = std::max(lo.nph_s, chunk_count(p.num_vis)); }
+    if (m.margin_flag == 0) {
+        for (int a = 0; a < NFR; a++) { lo.nlist_m += fcnt0[a]; lo.nitems_m += chunk_count(fcnt0[a]); lo.nph_m = std::max(lo.nph_m, chunk_count(fcnt0[a])); }
+        for (int a = 0; a < NFR * NFR; a++) { lo.nlist_m += pcnt0[a]; lo.nitems_m += chunk_count(pcnt0[a]); lo.nph_m = std::max(lo.nph_m, chunk_count(pcnt0[a])); }
+        lo.nlist_m += ncommon0; lo.nitems_m += chunk_count(ncommon0); lo.nph_m = std::max(lo.nph_m, chunk_count(ncommon0));
+    }
+    m.nitems = lo.nitems_s; m.nphases = lo.nph_s; m.nmitems = lo.nitems_m; m.nmphases = lo.nph_m;
+}
+
+// ---- phase 3: fill this window's slices of the (pinned) staging arrays; every offset is final
+struct HostArrays {
+    WinMeta *meta; PriorDev *prior; int *vis_type, *vis_lm, *vis_fi, *vis_fj, *vis_win; double *vis_obs; int *lm_win, *lm_fptr;
+    AsmItem *items; int *asm_list; int *imu_fi, *imu_fj, *imu_win, *wheel_fi, *wheel_fj, *wheel_win, *plane_f, *plane_win;
+    double *imu_data, *wheel_data, *prior_J, *prior_r, *prior_x0, *x_init; WinWork *work;
+    int nitems_solve_total;
+};
+static void emit_lists(const int *type, const int *fi, const int *fj, int nvis, bool only_host0, int has_common, int w, AsmItem *items, int *list) {
+    // counting sort of the (factor, role) entries into frame lists, pair lists and the common list, then chunking
+    int fcnt[NFR] = {0}, pcnt[NFR * NFR] = {0}, ncom = 0;
+    for (int i = 0; i < nvis; i++) {
+        if (only_host0 && fi[i] != 0) continue;
+        if (type[i] != 2) { fcnt[fi[i]]++; fcnt[fj[i]]++; const int a = fi[i] < fj[i] ? fi[i] : fj[i], c = fi[i] < fj[i] ? fj[i] : fi[i]; pcnt[a * NFR + c]++; }
+        ncom++;
+    }
+    int foff[NFR], poff[NFR * NFR], pos = 0;
+    for (int a = 0; a < NFR; a++) { foff[a] = pos; pos += fcnt[a]; }
+    for (int a = 0; a < NFR * NFR; a++) { poff[a] = pos; pos += pcnt[a]; }
+    const int coff = pos;
+    int fpos[NFR], ppos[NFR * NFR], cpos = coff;
+    memcpy(fpos, foff, sizeof fpos); memcpy(ppos, poff, sizeof ppos);
+    for (int i = 0; i < nvis; i++) {
+        if (only_host0 && fi[i] != 0) continue;
+        if (type[i] != 2) {
+            list[fpos[fi[i]]++] = (i << 1) | 0; list[fpos[fj[i]]++] = (i << 1) | 1;
+            const int a = fi[i] < fj[i] ? fi[i] : fj[i], c = fi[i] < fj[i] ? fj[i] : fi[i];
+            list[ppos[a * NFR + c]++] = (i << 1) | (fi[i] == a ? 0 : 1);
+        }
+        if (has_common) list[cpos++] = i << 1;
+    }
+    int ni = 0;
+    auto emit = [&](int kind, int a, int c, int off, int cnt) {
+        for (int c0 = 0, ph = 0; c0 < cnt; c0 += ASM_CHUNK, ph++) {
+            AsmItem &it = items[ni++];
+            it.kind = kind; it.win = w; it.a = a; it.b = c; it.lo = off + c0; it.hi = off + std::min(cnt, c0 + (int)ASM_CHUNK); it.phase = ph; it.has_common = has_common;
+        }
+    };
+    for (int a = 0; a < NFR; a++) emit(ITEM_FRAME, a, a, foff[a], fcnt[a]);
+    for (int a = 0; a < NFR; a++) for (int c = a + 1; c < NFR; c++) emit(ITEM_PAIR, a, c, poff[a * NFR + c], pcnt[a * NFR + c]);
+    if (has_common) emit(ITEM_COMMON, 0, 0, coff, ncom);
+}
+
+static void lower_fill(const viwb_problem &p, const double *state, int w, const WinMeta &m, const WinLow &lo, const HostArrays &h, double init_radius) {
+    h.meta[w] = m;
+    // visual factors grouped by landmark
+    int *vt = h.vis_type + m.vis_off, *vl = h.vis_lm + m.vis_off, *vi = h.vis_fi + m.vis_off, *vj = h.vis_fj + m.vis_off, *vw = h.vis_win + m.vis_off;
+    double *vo = h.vis_obs + (size_t)m.vis_off * 12;
+    if (lo.grouped) {
+        memcpy(vt, p.vis_type, sizeof(int) * p.num_vis); memcpy(vl, p.vis_landmark, sizeof(int) * p.num_vis);
+        memcpy(vi, p.vis_frame_i, sizeof(int) * p.num_vis); memcpy(vj, p.vis_frame_j, sizeof(int) * p.num_vis);
+        memcpy(vo, p.vis_obs, sizeof(double) * 12 * p.num_vis);
+    } else {
+        std::vector<int> order(p.num_vis);
+        for (int i = 0; i < p.num_vis; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return p.vis_landmark[a] < p.vis_landmark[c]; });
+        for (int i = 0; i < p.num_vis; i++) { const int sidx = order[i]; vt[i] = p.vis_type[sidx]; vl[i] = p.vis_landmark[sidx]; vi[i] = p.vis_frame_i[sidx]; vj[i] = p.vis_frame_j[sidx]; memcpy(vo + (size_t)i * 12, p.vis_obs + (size_t)sidx * 12, 12 * sizeof(double)); }
+    }
+    for (int i = 0; i < p.num_vis; i++) vw[i] = w;
+    // landmark -> factor ranges (global factor indices)
+    { int *fp = h.lm_fptr + m.lm_off; int run = m.vis_off, i = 0;
+      for (int k = 0; k < p.num_landmarks; k++) { fp[k] = run; while (i < p.num_vis && vl[i] == k) { i++; run++; } h.lm_win[m.lm_off + k] = w; } }
+    // assembly plan
+    emit_lists(vt, vi, vj, p.num_vis, false, m.has_common, w, h.items + m.item_off, h.asm_list + m.list_off);
+    if (m.margin_flag == 0) emit_lists(vt, vi, vj, p.num_vis, true, 1, w, h.items + h.nitems_solve_total + m.mitem_off, h.asm_list + m.mlist_off);
+    // small factors
+    for (int i = 0; i < p.num_imu; i++) { h.imu_fi[m.imu_off + i] = p.imu_frame_i[i]; h.imu_fj[m.imu_off + i] = p.imu_frame_j[i]; h.imu_win[m.imu_off + i] = w; }
+    if (p.num_imu) memcpy(h.imu_data + (size_t)m.imu_off * 287, p.imu_data, sizeof(double) * 287 * p.num_imu);
+    for (int i = 0; i < p.num_wheel; i++) { h.wheel_fi[m.wheel_off + i] = p.wheel_frame_i[i]; h.wheel_fj[m.wheel_off + i] = p.wheel_frame_j[i]; h.wheel_win[m.wheel_off + i] = w; }
+    if (p.num_wheel) memcpy(h.wheel_data + (size_t)m.wheel_off * 78, p.wheel_data, sizeof(double) * 78 * p.num_wheel);
+    for (int i = 0; i < p.num_plane; i++) { h.plane_f[m.plane_off + i] = p.plane_frame[i]; h.plane_win[m.plane_off + i] = w; }
+    // prior
+    if (m.prior_idx >= 0) {
+        const viwb_prior &pr = *p.prior; PriorDev &pd = h.prior[m.prior_idx];
+        memcpy(h.prior_J + pd.J_off, pr.J, sizeof(double) * pr.n * pr.n); memcpy(h.prior_r + pd.r_off, pr.r, sizeof(double) * pr.n);
+        memcpy(h.prior_x0 + pd.x0_off, pr.x0, sizeof(double) * SFIX);
+    }
+    memcpy(h.x_init + m.state_off, state, sizeof(double) * (SFIX + p.num_landmarks));
+    WinWork &ww = h.work[w]; memset(&ww, 0, sizeof ww);
+    ww.status = ST_RUNNING; ww.phase = PH_INIT; ww.first = 1; ww.radius = init_radius; ww.mu = 1e-8; ww.mu_lin = 1e-8; ww.term = VIWB_NO_CONVERGENCE;
+}
+
+template <typename F> static void parallel_for(int n, F f) {
+    int nt = (int)std::thread::hardware_concurrency(); if (nt > 16) nt = 16; if (nt < 1) nt = 1; if (nt > n / 8) nt = n / 8;
+    if (nt <= 1) { for (int i = 0; i < n; i++) f(i); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([=]() { for (int i = t; i < n; i += nt) f(i); });
+    for (auto &t : th) t.join();
+}
+
 static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, const double *const *states,
                        const viwb_options *options, const int32_t *margin_flags, viwb_batch **out, bool use_cached = false) {
-    return batch_build_impl(ctx, B, problems, states, options, margin_flags, out, use_cached);
-}
-static int batch_build_impl(viwb_context *ctx, int B, const viwb_problem *problems, const double *const *states,
-                            const viwb_options *options, const int32_t *margin_flags, viwb_batch **out, bool use_cached) {
     if (B <= 0 || !problems || !states) return fail(ctx, VIWB_ERR_INVALID, "empty batch");
+    const double t_start = now_ms();
     viwb_batch *b = new viwb_batch();
     b->B = B; b->any_marg = false; b->algorithmic_bytes = 0; b->arena_cached = false; b->out_bytes = 0; b->prior_nmax = 0; b->work_init_dev = nullptr;
     viwb_options defopt; viwb_default_options(&defopt);
@@ -188,222 +351,90 @@ static int batch_build_impl(viwb_context *ctx, int B, const viwb_problem *proble
     b->max_iter = opt->max_num_iterations;
     BatchDev &bd = b->bd; memset(&bd, 0, sizeof bd);
     bd.B = B; opts_from(opt, bd.opt);
-    std::vector<int> vis_type, vis_lm, vis_fi, vis_fj, vis_win, lm_win, lm_fptr, asm_list;
-    std::vector<AsmItem> items_solve, items_marg;
-    std::vector<double> x_init;
-    std::vector<Seg> obs_segs, imu_segs, wheel_segs, priorJ_segs;
-    std::vector<int> imu_fi, imu_fj, imu_win, wheel_fi, wheel_fj, wheel_win, plane_f, plane_win;
-    std::vector<double> prior_r, prior_x0;
-    size_t priorJ_count = 0;
-    std::vector<PriorDev> priors;
-    b->meta.resize(B); b->work.resize(B); b->out_mode.assign(B, 2); b->in_prior.resize(B); b->state_sizes.resize(B); b->prior_n.assign(B, 0);
-    lm_fptr.push_back(0);
+    b->meta.resize(B); b->out_mode.assign(B, 2); b->in_prior.resize(B); b->state_sizes.resize(B); b->prior_n.assign(B, 0);
+    std::vector<WinLow> low(B);
+    // ---- phase 1 (parallel): sizes and plans
+    parallel_for(B, [&](int w) { lower_count(problems[w], margin_flags ? margin_flags[w] : -1, b->meta[w], low[w], b->out_mode[w]); });
+    for (int w = 0; w < B; w++) if (low[w].err) { const int e = low[w].err; batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, e == 1 ? "bad frame_count / num_landmarks" : e == 2 ? "bad prior" : e == 3 ? "bad visual factor table" : "bad factor frame index"); }
+    // ---- phase 2: offsets
+    size_t nstate = 0, nvis = 0, nlm = 0, nimu = 0, nwheel = 0, nplane = 0, nlist = 0, nit_s = 0, nit_m = 0, npri = 0, npJ = 0, npr = 0;
     for (int w = 0; w < B; w++) {
-        const viwb_problem &p = problems[w];
-        WinMeta &m = b->meta[w]; memset(&m, 0, sizeof m);
-        if (p.frame_count < 0 || p.frame_count > VIWB_WINDOW_SIZE || p.num_landmarks < 0 || p.num_landmarks > VIWB_MAX_LANDMARKS) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, "bad frame_count / num_landmarks"); }
-        m.state_off = (int)x_init.size(); m.lm_off = (int)lm_win.size(); m.nlm = p.num_landmarks; m.frame_count = p.frame_count;
-        b->state_sizes[w] = SFIX + p.num_landmarks;
-        x_init.insert(x_init.end(), states[w], states[w] + SFIX + p.num_landmarks);
-        for (int k = 0; k < 3; k++) m.G[k] = p.globals.G[k];
-        for (int k = 0; k < 4; k++) m.S_vis[k] = p.globals.vis_sqrt_info[k];
-        for (int k = 0; k < 3; k++) m.w_plane[k] = p.globals.plane_sqrt_info[k];
-        m.huber = p.globals.huber_delta;
-        const bool has_prior = p.prior && p.prior->valid;
-        // ---- visual factors, grouped by landmark (stable sort only if the caller's table is not already grouped)
-        bool grouped = true;
-        for (int i = 0; i < p.num_vis; i++) {
-            const int t = p.vis_type[i], l = p.vis_landmark[i], fi = p.vis_frame_i[i], fj = p.vis_frame_j[i];
-            if (t < 0 || t > 2 || l < 0 || l >= p.num_landmarks || fi < 0 || fi > p.frame_count || fj < 0 || fj > p.frame_count) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, "bad visual factor table"); }
-            if (i && l < p.vis_landmark[i - 1]) grouped = false;
-        }
-        m.vis_off = (int)vis_type.size(); m.nvis = p.num_vis;
-        std::vector<int> cnt(p.num_landmarks + 1, 0);
-        if (grouped) {
-            vis_type.insert(vis_type.end(), p.vis_type, p.vis_type + p.num_vis);
-            vis_fi.insert(vis_fi.end(), p.vis_frame_i, p.vis_frame_i + p.num_vis); vis_fj.insert(vis_fj.end(), p.vis_frame_j, p.vis_frame_j + p.num_vis);
-            for (int i = 0; i < p.num_vis; i++) { vis_lm.push_back(m.lm_off + p.vis_landmark[i]); cnt[p.vis_landmark[i]]++; }
-            vis_win.insert(vis_win.end(), (size_t)p.num_vis, w);
-            if (p.num_vis) obs_segs.push_back({p.vis_obs, (size_t)p.num_vis * 12 * sizeof(double)});
-        } else {
-            std::vector<int> order(p.num_vis);
-            for (int i = 0; i < p.num_vis; i++) order[i] = i;
-            std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return p.vis_landmark[a] < p.vis_landmark[c]; });
-            for (int i = 0; i < p.num_vis; i++) {
-                const int sidx = order[i];
-                vis_type.push_back(p.vis_type[sidx]); vis_lm.push_back(m.lm_off + p.vis_landmark[sidx]); vis_fi.push_back(p.vis_frame_i[sidx]); vis_fj.push_back(p.vis_frame_j[sidx]);
-                vis_win.push_back(w);
-                obs_segs.push_back({p.vis_obs + (size_t)sidx * 12, 12 * sizeof(double)});
-                cnt[p.vis_landmark[sidx]]++;
-            }
-        }
-        for (int k = 0; k < p.num_landmarks; k++) { lm_win.push_back(w); lm_fptr.push_back(lm_fptr.back() + cnt[k]); }
-        // ---- small factors
-        m.imu_off = (int)imu_fi.size(); m.nimu = p.num_imu;
-        for (int i = 0; i < p.num_imu; i++) { imu_fi.push_back(p.imu_frame_i[i]); imu_fj.push_back(p.imu_frame_j[i]); imu_win.push_back(w); }
-        if (p.num_imu) imu_segs.push_back({p.imu_data, (size_t)p.num_imu * 287 * sizeof(double)});
-        m.wheel_off = (int)wheel_fi.size(); m.nwheel = p.num_wheel;
-        for (int i = 0; i < p.num_wheel; i++) { wheel_fi.push_back(p.wheel_frame_i[i]); wheel_fj.push_back(p.wheel_frame_j[i]); wheel_win.push_back(w); }
-        if (p.num_wheel) wheel_segs.push_back({p.wheel_data, (size_t)p.num_wheel * 78 * sizeof(double)});
-        m.plane_off = (int)plane_f.size(); m.nplane = p.num_plane;
-        for (int i = 0; i < p.num_plane; i++) { plane_f.push_back(p.plane_frame[i]); plane_win.push_back(w); }
-        // ---- prior
-        m.prior_idx = -1;
-        HostPrior &hp = b->in_prior[w]; hp.valid = 0; hp.n = 0; hp.nb = 0;
-        if (has_prior) {
-            const viwb_prior &pr = *p.prior;
-            if (pr.n <= 0 || pr.n > MAXPRI || pr.num_blocks <= 0 || pr.num_blocks > NB) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, "bad prior"); }
-            PriorDev pd; memset(&pd, 0, sizeof pd);
-            pd.n = pr.n; pd.nb = pr.num_blocks;
-            for (int i = 0; i < pr.num_blocks; i++) { pd.block_id[i] = pr.block_id[i]; pd.block_idx[i] = pr.block_idx[i]; }
-            pd.J_off = (int)priorJ_count; pd.r_off = (int)prior_r.size(); pd.x0_off = (int)prior_x0.size();
-            priorJ_segs.push_back({pr.J, (size_t)pr.n * pr.n * sizeof(double)}); priorJ_count += (size_t)pr.n * pr.n;
-            prior_r.insert(prior_r.end(), pr.r, pr.r + pr.n);
-            prior_x0.insert(prior_x0.end(), pr.x0, pr.x0 + SFIX);
-            m.prior_idx = (int)priors.size(); priors.push_back(pd);
-            hp.valid = 1; hp.n = pr.n; hp.nb = pr.num_blocks;
-            memcpy(hp.block_id, pd.block_id, sizeof hp.block_id); memcpy(hp.block_idx, pd.block_idx, sizeof hp.block_idx);
-            if (margin_flags && margin_flags[w] == VIWB_MARGIN_SECOND_NEW) { hp.x0.assign(pr.x0, pr.x0 + SFIX); hp.J.assign(pr.J, pr.J + (size_t)pr.n * pr.n); hp.r.assign(pr.r, pr.r + pr.n); }
-        }
-        // ---- active blocks (Program::RemoveFixedBlocks) and compact columns
-        bool ref[NB]; for (int k = 0; k < NB; k++) ref[k] = false;
-        if (has_prior) for (int i = 0; i < p.prior->num_blocks; i++) ref[p.prior->block_id[i]] = true;
-        for (int i = 0; i < p.num_imu; i++) { ref[p.imu_frame_i[i]] = ref[BLK_SB0 + p.imu_frame_i[i]] = ref[p.imu_frame_j[i]] = ref[BLK_SB0 + p.imu_frame_j[i]] = true; }
-        for (int i = 0; i < p.num_wheel; i++) { ref[p.wheel_frame_i[i]] = ref[p.wheel_frame_j[i]] = ref[BLK_EXW] = ref[BLK_SX] = ref[BLK_SY] = ref[BLK_SW] = ref[BLK_TDW] = true; }
-        for (int i = 0; i < p.num_plane; i++) { ref[p.plane_frame[i]] = ref[BLK_EXW] = ref[BLK_PR] = ref[BLK_PZ] = true; }
-        for (int i = 0; i < p.num_vis; i++) {
-            const int t = p.vis_type[i];
-            if (t != 2) { ref[p.vis_frame_i[i]] = ref[p.vis_frame_j[i]] = true; }
-            ref[BLK_EX0] = true; if (t != 0) ref[BLK_EX1] = true; ref[BLK_TD] = true;
-        }
-        int col = 0, amb = 0;
-        for (int k = 0; k < NB; k++) {
-            m.flags[k] = p.block_flags[k] & 3u; m.mask[k] = p.subset_mask[k];
-            const bool active = (p.block_flags[k] & VIWB_BLOCK_PRESENT) && !(p.block_flags[k] & VIWB_BLOCK_CONSTANT) && ref[k];
-            if (active) { m.tcol[k] = (short)col; col += blk_tsize(k); amb += blk_size(k); } else m.tcol[k] = -1;
-        }
-        m.nf = col; m.namb = amb + p.num_landmarks;
-        // ---- marginalisation plan (estimator.cpp:1666-1893)
-        m.margin_flag = -1; b->out_mode[w] = 2;
-        const int mf = margin_flags ? margin_flags[w] : -1;
-        if (mf >= 0 && p.frame_count == VIWB_WINDOW_SIZE) {
-            bool seen[NB]; for (int k = 0; k < NB; k++) seen[k] = false;
-            if (mf == VIWB_MARGIN_OLD) {
-                if (has_prior) for (int i = 0; i < p.prior->num_blocks; i++) seen[p.prior->block_id[i]] = true;
-                for (int i = 0; i < p.num_imu; i++) if (p.imu_frame_i[i] == 0 && p.imu_frame_j[i] == 1) seen[0] = seen[BLK_SB0] = seen[1] = seen[BLK_SB0 + 1] = true;
-                for (int i = 0; i < p.num_wheel; i++) if (p.wheel_frame_i[i] == 0 && p.wheel_frame_j[i] == 1) seen[0] = seen[1] = seen[BLK_EXW] = seen[BLK_SX] = seen[BLK_SY] = seen[BLK_SW] = seen[BLK_TDW] = true;
-                for (int i = 0; i < p.num_plane; i++) if (p.plane_frame[i] == 0) seen[0] = seen[BLK_EXW] = seen[BLK_PR] = seen[BLK_PZ] = true;
-                bool any_lm0 = false;
-                for (int i = 0; i < p.num_vis; i++) if (p.vis_frame_i[i] == 0) {
-                    any_lm0 = true;
-                    const int t = p.vis_type[i];
-                    if (t != 2) seen[0] = seen[p.vis_frame_j[i]] = true;
-                    seen[BLK_EX0] = true; if (t != 0) seen[BLK_EX1] = true; seen[BLK_TD] = true;
-                }
-                if (seen[0] || seen[BLK_SB0] || any_lm0) { m.margin_flag = 0; b->out_mode[w] = 0; }
-            } else {
-                bool has9 = false;
-                if (has_prior) for (int i = 0; i < p.prior->num_blocks; i++) { seen[p.prior->block_id[i]] = true; if (p.prior->block_id[i] == VIWB_WINDOW_SIZE - 1) has9 = true; }
-                if (has9) { m.margin_flag = 1; b->out_mode[w] = 0; }
-                else b->out_mode[w] = has_prior ? 1 : 2;
-            }
-            if (m.margin_flag >= 0) {
-                int nn = 0;
-                for (int k = 0; k < NB; k++) if (seen[k]) { m.flags[k] |= 4u; const bool drop = m.margin_flag == 0 ? (k == 0 || k == BLK_SB0) : (k == VIWB_WINDOW_SIZE - 1); if (!drop) nn += blk_msize(k); }
-                b->prior_n[w] = nn; b->any_marg = true;
-            }
-        }
-        // ---- assembly plan (kernels_asm.cuh): per-frame, per-frame-pair and common factor lists cut into chunks = phases
-        m.has_common = (m.tcol[BLK_EX0] >= 0 || m.tcol[BLK_EX1] >= 0 || m.tcol[BLK_TD] >= 0) ? 1 : 0;
-        for (int pass = 0; pass < 2; pass++) {
-            if (pass == 1 && m.margin_flag != 0) { m.mitem_off = (int)items_marg.size(); m.nmitems = 0; m.nmphases = 0; continue; }
-            std::vector<AsmItem> &items = pass == 0 ? items_solve : items_marg;
-            const int has_common = pass == 0 ? m.has_common : 1;
-            std::vector<std::vector<int>> fl(NFR), pl(NFR * NFR);
-            std::vector<int> cl;
-            for (int i = 0; i < p.num_vis; i++) {
-                const int f = m.vis_off + i, fi = vis_fi[f], fj = vis_fj[f], t = vis_type[f];
-                if (pass == 1 && fi != 0) continue;
-                if (t != 2) {
-                    fl[fi].push_back((f << 1) | 0); fl[fj].push_back((f << 1) | 1);
-                    const int lo = fi < fj ? fi : fj, hi = fi < fj ? fj : fi;
-                    pl[lo * NFR + hi].push_back((f << 1) | (fi == lo ? 0 : 1));
-                }
-                cl.push_back(f << 1);
-            }
-            const int first = (int)items.size();
-            int nph = 0;
-            auto emit = [&](int kind, int a, int bq, const std::vector<int> &lst) {
-                for (size_t c0 = 0, ph = 0; c0 < lst.size(); c0 += ASM_CHUNK, ph++) {
-                    AsmItem it; it.kind = kind; it.win = w; it.a = a; it.b = bq; it.lo = (int)asm_list.size();
-                    const size_t c1 = std::min(lst.size(), c0 + (size_t)ASM_CHUNK);
-                    asm_list.insert(asm_list.end(), lst.begin() + c0, lst.begin() + c1);
-                    it.hi = (int)asm_list.size(); it.phase = (int)ph; it.has_common = has_common;
-                    items.push_back(it);
-                    nph = std::max(nph, (int)ph + 1);
-                }
-            };
-            for (int a = 0; a < NFR; a++) emit(ITEM_FRAME, a, a, fl[a]);
-            for (int a = 0; a < NFR; a++) for (int c = a + 1; c < NFR; c++) emit(ITEM_PAIR, a, c, pl[a * NFR + c]);
-            if (has_common) emit(ITEM_COMMON, 0, 0, cl);
-            if (pass == 0) { m.item_off = first; m.nitems = (int)items.size() - first; m.nphases = nph; }
-            else { m.mitem_off = first; m.nmitems = (int)items.size() - first; m.nmphases = nph; }
-        }
+        const viwb_problem &p = problems[w]; WinMeta &m = b->meta[w]; const WinLow &lo = low[w];
+        m.state_off = (int)nstate; nstate += SFIX + p.num_landmarks; b->state_sizes[w] = SFIX + p.num_landmarks;
+        m.vis_off = (int)nvis; nvis += p.num_vis; m.lm_off = (int)nlm; nlm += p.num_landmarks;
+        m.imu_off = (int)nimu; nimu += p.num_imu; m.wheel_off = (int)nwheel; nwheel += p.num_wheel; m.plane_off = (int)nplane; nplane += p.num_plane;
+        m.item_off = (int)nit_s; nit_s += lo.nitems_s; m.list_off = (int)nlist; nlist += lo.nlist_s;
+        m.prior_idx = lo.has_prior ? (int)npri++ : -1;
+        b->prior_n[w] = lo.prior_n_out; if (m.margin_flag >= 0) b->any_marg = true;
+        b->prior_nmax = std::max(b->prior_nmax, lo.prior_n_out);
         b->algorithmic_bytes += window_algorithmic_bytes(p, opt->max_num_iterations);
-        // ---- initial solver state
-        WinWork &ww = b->work[w]; memset(&ww, 0, sizeof ww);
-        ww.status = ST_RUNNING; ww.phase = PH_INIT; ww.first = 1; ww.radius = opt->initial_trust_region_radius; ww.mu = 1e-8; ww.mu_lin = 1e-8;
-        ww.term = VIWB_NO_CONVERGENCE;
     }
-    const size_t nv = vis_type.size();
-    bd.nvis_total = (int)nv; bd.nlm_total = (int)lm_win.size(); bd.nimu_total = (int)imu_fi.size(); bd.nwheel_total = (int)wheel_fi.size();
-    bd.nplane_total = (int)plane_f.size(); bd.nprior = (int)priors.size();
-    b->total_state = x_init.size();
-    bd.nitems_solve = (int)items_solve.size(); bd.nitems_marg = (int)items_marg.size();
-    std::vector<AsmItem> all_items(items_solve); all_items.insert(all_items.end(), items_marg.begin(), items_marg.end());
-    b->prior_nmax = 0; for (int w = 0; w < B; w++) b->prior_nmax = std::max(b->prior_nmax, b->prior_n[w]);
-    Placer pl;
-    pl.in(b->meta, &bd.meta); pl.in(priors, &bd.prior);
-    pl.in(vis_type, &bd.vis_type); pl.in(vis_lm, &bd.vis_lm); pl.in(vis_fi, &bd.vis_fi); pl.in(vis_fj, &bd.vis_fj); pl.in(vis_win, &bd.vis_win);
-    pl.in_segs(obs_segs, &bd.vis_obs);
-    pl.in(lm_win, &bd.lm_win); pl.in(lm_fptr, &bd.lm_fptr); pl.in(all_items, &bd.items); pl.in(asm_list, &bd.asm_list);
-    pl.in(imu_fi, &bd.imu_fi); pl.in(imu_fj, &bd.imu_fj); pl.in(imu_win, &bd.imu_win); pl.in(wheel_fi, &bd.wheel_fi); pl.in(wheel_fj, &bd.wheel_fj); pl.in(wheel_win, &bd.wheel_win);
-    pl.in(plane_f, &bd.plane_f); pl.in(plane_win, &bd.plane_win);
-    pl.in_segs(imu_segs, &bd.imu_data); pl.in_segs(wheel_segs, &bd.wheel_data);
-    pl.in_segs(priorJ_segs, &bd.prior_J); pl.in(prior_r, &bd.prior_r); pl.in(prior_x0, &bd.prior_x0);
-    { const double *xi = nullptr; pl.in(x_init, &xi); pl.reqs.back().field = (void **)&bd.x_init; }
-    pl.in(b->work, (const WinWork **)&b->work_init_dev);
-    const size_t nl = lm_win.size(), nvec = (size_t)B * TFIX + nl;
-    pl.work(B, &bd.work); pl.work(x_init.size(), &bd.x_cur); pl.work(x_init.size(), &bd.x_cand); pl.work(x_init.size(), &bd.x_before);
-    pl.work(nv * VREC, &bd.vis_rec); pl.work(nv, &bd.vis_cost);
-    pl.work(nl, &bd.lm_a); pl.work(nl, &bd.lm_g); pl.work(nl, &bd.lm_gamma); pl.work(nl, &bd.lm_scale); pl.work(nl, &bd.lm_cost); pl.work(nl * VSUB, &bd.lm_W);
-    pl.work(imu_fi.size() * 225, &bd.imu_S); pl.work(wheel_fi.size() * 36, &bd.wheel_S);
-    pl.work(imu_fi.size() * IMU_REC, &bd.imu_rec); pl.work(wheel_fi.size() * WHEEL_REC, &bd.wheel_rec); pl.work(plane_f.size() * PLANE_REC, &bd.plane_rec);
-    pl.work(priorJ_count, &bd.prior_A); pl.work(prior_r.size(), &bd.prior_res); pl.work(prior_r.size(), &bd.prior_g);
-    pl.work((size_t)B * (TFIX * (TFIX + 1) / 2), &bd.Hpk); pl.work((size_t)B * TFIX, &bd.gpk); pl.work((size_t)B * (TFIX + 8), &bd.gfix);
-    pl.work(all_items.size() * ASM_STRIDE, &bd.asm_out); pl.work((size_t)B * VSUB * VSUB, &bd.Tvis); pl.work((size_t)B * VSUB, &bd.tvec);
-    pl.work(nvec, &bd.v_scale); pl.work(nvec, &bd.v_D); pl.work(nvec, &bd.v_sgrad); pl.work(nvec, &bd.v_gn);
-    pl.work((size_t)B * MAXPRI * MAXPRI, &bd.marg_J); pl.work((size_t)B * MAXPRI, &bd.marg_r); pl.work((size_t)B * SFIX, &bd.marg_x0);
-    pl.work((size_t)B * (3 + 2 * NB), &bd.marg_hdr); pl.work((size_t)B * (MAXPRI + 16) * (MAXPRI + 16), &bd.marg_A);
-    // ---- placement: offsets, slabs, pack + one H2D
-    size_t in_bytes = 0, tot = 0;
-    for (auto &r : pl.reqs) if (r.input) { r.off = tot; tot += align_up(r.bytes); }
-    in_bytes = tot;
-    for (auto &r : pl.reqs) if (!r.input) { r.off = tot; tot += align_up(r.bytes); }
-    b->out_bytes = align_up(b->total_state * 8) + align_up(sizeof(WinWork) * B) + align_up((size_t)B * (3 + 2 * NB) * 4) + align_up((size_t)B * MAXPRI * 8) +
+    for (int w = 0; w < B; w++) { WinMeta &m = b->meta[w]; const WinLow &lo = low[w]; m.mitem_off = (int)nit_m; nit_m += lo.nitems_m; m.mlist_off = (int)nlist; nlist += lo.nlist_m; }
+    if (nstate > 0x7fffffff || nvis * 12 > 0x7fffffffull * 4 || nlist > 0x7fffffff) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, "batch too large"); }
+    std::vector<PriorDev> priors(npri);
+    for (int w = 0; w < B; w++) if (b->meta[w].prior_idx >= 0) {
+        const viwb_prior &pr = *problems[w].prior; PriorDev &pd = priors[b->meta[w].prior_idx]; memset(&pd, 0, sizeof pd);
+        pd.n = pr.n; pd.nb = pr.num_blocks;
+        for (int i = 0; i < pr.num_blocks; i++) { pd.block_id[i] = pr.block_id[i]; pd.block_idx[i] = pr.block_idx[i]; }
+        pd.J_off = (int)npJ; npJ += (size_t)pr.n * pr.n; pd.r_off = (int)npr; npr += pr.n; pd.x0_off = (int)(SFIX * (size_t)b->meta[w].prior_idx);
+        HostPrior &hp = b->in_prior[w]; hp.valid = 1; hp.n = pr.n; hp.nb = pr.num_blocks;
+        memcpy(hp.block_id, pd.block_id, sizeof hp.block_id); memcpy(hp.block_idx, pd.block_idx, sizeof hp.block_idx);
+        if (b->out_mode[w] == 1) { hp.x0.assign(pr.x0, pr.x0 + SFIX); hp.J.assign(pr.J, pr.J + (size_t)pr.n * pr.n); hp.r.assign(pr.r, pr.r + pr.n); }
+    }
+    bd.nvis_total = (int)nvis; bd.nlm_total = (int)nlm; bd.nimu_total = (int)nimu; bd.nwheel_total = (int)nwheel; bd.nplane_total = (int)nplane; bd.nprior = (int)npri;
+    bd.nitems_solve = (int)nit_s; bd.nitems_marg = (int)nit_m;
+    b->total_state = nstate;
+    // ---- placement (inputs first, then work arrays)
+    struct Ent { void **field; size_t bytes; bool input; size_t off; };
+    std::vector<Ent> ents;
+    auto IN = [&](auto **field, size_t count) { ents.push_back({(void **)field, count * sizeof(**field), true, 0}); };
+    auto WK = [&](auto **field, size_t count) { ents.push_back({(void **)field, (count ? count : 1) * sizeof(**field), false, 0}); };
+    IN(&bd.meta, B); IN(&bd.prior, npri); IN(&bd.vis_type, nvis); IN(&bd.vis_lm, nvis); IN(&bd.vis_fi, nvis); IN(&bd.vis_fj, nvis); IN(&bd.vis_win, nvis);
+    IN(&bd.vis_obs, nvis * 12); IN(&bd.lm_win, nlm); IN(&bd.lm_fptr, nlm + 1); IN(&bd.items, nit_s + nit_m); IN(&bd.asm_list, nlist);
+    IN(&bd.imu_fi, nimu); IN(&bd.imu_fj, nimu); IN(&bd.imu_win, nimu); IN(&bd.wheel_fi, nwheel); IN(&bd.wheel_fj, nwheel); IN(&bd.wheel_win, nwheel);
+    IN(&bd.plane_f, nplane); IN(&bd.plane_win, nplane); IN(&bd.imu_data, nimu * 287); IN(&bd.wheel_data, nwheel * 78);
+    IN(&bd.prior_J, npJ); IN(&bd.prior_r, npr); IN(&bd.prior_x0, npri * SFIX); IN(&bd.x_init, nstate); IN(&b->work_init_dev, B);
+    const size_t nvec = (size_t)B * TFIX + nlm;
+    WK(&bd.work, B); WK(&bd.x_cur, nstate); WK(&bd.x_cand, nstate); WK(&bd.x_before, nstate);
+    WK(&bd.vis_rec, nvis * VREC); WK(&bd.vis_cost, nvis);
+    WK(&bd.lm_a, nlm); WK(&bd.lm_g, nlm); WK(&bd.lm_gamma, nlm); WK(&bd.lm_scale, nlm); WK(&bd.lm_cost, nlm); WK(&bd.lm_W, nlm * VSUB);
+    WK(&bd.imu_S, nimu * 225); WK(&bd.wheel_S, nwheel * 36); WK(&bd.imu_rec, nimu * IMU_REC); WK(&bd.wheel_rec, nwheel * WHEEL_REC); WK(&bd.plane_rec, nplane * PLANE_REC);
+    WK(&bd.prior_A, npJ); WK(&bd.prior_res, npr); WK(&bd.prior_g, npr);
+    WK(&bd.Hpk, (size_t)B * (TFIX * (TFIX + 1) / 2)); WK(&bd.gpk, (size_t)B * TFIX); WK(&bd.gfix, (size_t)B * (TFIX + 8));
+    WK(&bd.asm_out, (nit_s + nit_m) * ASM_STRIDE); WK(&bd.Tvis, (size_t)B * VSUB * VSUB); WK(&bd.tvec, (size_t)B * VSUB);
+    WK(&bd.v_scale, nvec); WK(&bd.v_D, nvec); WK(&bd.v_sgrad, nvec); WK(&bd.v_gn, nvec);
+    WK(&bd.marg_J, (size_t)B * MAXPRI * MAXPRI); WK(&bd.marg_r, (size_t)B * MAXPRI); WK(&bd.marg_x0, (size_t)B * SFIX);
+    WK(&bd.marg_hdr, (size_t)B * (3 + 2 * NB)); WK(&bd.marg_A, (size_t)B * (MAXPRI + 16) * (MAXPRI + 16));
+    size_t tot = 0;
+    for (auto &e : ents) if (e.input) { e.off = tot; tot += align_up(e.bytes); }
+    const size_t in_bytes = tot;
+    for (auto &e : ents) if (!e.input) { e.off = tot; tot += align_up(e.bytes); }
+    b->out_bytes = align_up(nstate * 8) + align_up(sizeof(WinWork) * B) + align_up((size_t)B * (3 + 2 * NB) * 4) + align_up((size_t)B * MAXPRI * 8) +
                    align_up((size_t)B * SFIX * 8) + align_up((size_t)B * b->prior_nmax * b->prior_nmax * 8);
     const size_t host_need = std::max(in_bytes, b->out_bytes);
     Arena *ar;
     if (use_cached && !ctx->arena.busy) { ar = &ctx->arena; b->arena_cached = true; ctx->arena.busy = true; } else { ar = &b->arena; b->arena_cached = false; }
     if (ar->dev_cap < tot) { if (ar->dev) dev_free(ar->dev); ar->dev = nullptr; ar->dev_cap = 0; void *d = nullptr; int e = dev_malloc(&d, tot + tot / 8); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, std::string("device slab: ") + dev_errstr(e)); } ar->dev = (char *)d; ar->dev_cap = tot + tot / 8; }
-    if (ar->host_cap < host_need) { if (ar->host) host_free(ar->host); ar->host = nullptr; ar->host_cap = 0; void *h = nullptr; int e = host_alloc(&h, host_need + host_need / 8); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, "pinned staging slab"); } ar->host = (char *)h; ar->host_cap = host_need + host_need / 8; }
+    if (ar->host_cap < host_need) { if (ar->host) host_free(ar->host); ar->host = nullptr; ar->host_cap = 0; void *hm = nullptr; int e = host_alloc(&hm, host_need + host_need / 8); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, "pinned staging slab"); } ar->host = (char *)hm; ar->host_cap = host_need + host_need / 8; }
     if (b->arena_cached) b->arena = *ar;     // a view; ownership stays with the context
-    for (auto &r : pl.reqs) {
-        *r.field = ar->dev + r.off;
-        if (r.input) { size_t o = r.off; for (auto &sg : r.segs) { memcpy(ar->host + o, sg.src, sg.bytes); o += sg.bytes; } }
-    }
+    const double t_alloc = now_ms();
+    // host views of the input arrays inside the staging slab
+    HostArrays h; memset(&h, 0, sizeof h);
+    { size_t k = 0; char *hb = ar->host;
+      auto HP = [&](auto *&dst) { dst = (typename std::remove_reference<decltype(dst)>::type)(hb + ents[k].off); k++; };
+      HP(h.meta); HP(h.prior); HP(h.vis_type); HP(h.vis_lm); HP(h.vis_fi); HP(h.vis_fj); HP(h.vis_win); HP(h.vis_obs); HP(h.lm_win); HP(h.lm_fptr); HP(h.items); HP(h.asm_list);
+      HP(h.imu_fi); HP(h.imu_fj); HP(h.imu_win); HP(h.wheel_fi); HP(h.wheel_fj); HP(h.wheel_win); HP(h.plane_f); HP(h.plane_win); HP(h.imu_data); HP(h.wheel_data);
+      HP(h.prior_J); HP(h.prior_r); HP(h.prior_x0); HP(h.x_init); HP(h.work); }
+    h.nitems_solve_total = (int)nit_s;
+    for (auto &e : ents) *e.field = ar->dev + e.off;
+    if (npri) memcpy(h.prior, priors.data(), sizeof(PriorDev) * npri);
+    h.lm_fptr[nlm] = (int)nvis;
+    // ---- phase 3 (parallel): fill
+    parallel_for(B, [&](int w) { lower_fill(problems[w], states[w], w, b->meta[w], low[w], h, opt->initial_trust_region_radius); });
+    const double t_filled = now_ms();
     { int e = dev_h2d(ar->dev, ar->host, in_bytes, ctx->stream); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, std::string("H2D: ") + dev_errstr(e)); } }
     { int e = dev_sync(ctx->stream); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, "H2D sync"); } }     // the staging slab is reused for outputs
+    if (g_timing) fprintf(stderr, "[viwb] build B=%d: plan+slabs %.1f ms, fill %.1f ms (%.1f MB), h2d %.1f ms\n", B, t_alloc - t_start, t_filled - t_alloc, in_bytes / 1e6, now_ms() - t_filled);
     *out = b;
     return 0;
 }
@@ -622,8 +653,12 @@ static int run_once(viwb_context *ctx, int B, const viwb_problem *problems, doub
         if (!rc) rc = dev_sync(ctx->stream);
         if (rc) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, "upload of state_before failed"); }
     }
+    const double t0 = now_ms();
     rc = batch_execute(ctx, b, what);
+    if (g_timing) { dev_sync(ctx->stream); fprintf(stderr, "[viwb] execute %.1f ms\n", now_ms() - t0); }
+    const double t1 = now_ms();
     if (!rc) rc = batch_fetch(ctx, b, states, summaries, priors);
+    if (g_timing) fprintf(stderr, "[viwb] fetch %.1f ms\n", now_ms() - t1);
     batch_free(ctx, b);
     return rc;
 }
