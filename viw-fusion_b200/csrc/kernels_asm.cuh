@@ -46,7 +46,8 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     double *out = bd.asm_out + (size_t)gi * ASM_STRIDE;
     const WinMeta &wm = bd.meta[item.win];
     const int *list = bd.asm_list + (mode == MODE_SOLVE ? wm.list_off : wm.mlist_off);
-    const double *recs = bd.vis_rec + (size_t)wm.vis_off * VREC;
+    const int rs = rec_stride(bd, mode);
+    const double *recs = bd.vis_rec + (size_t)wm.vis_off * rs;
     int nout;
     if (item.kind == ITEM_FRAME) nout = 105; else if (item.kind == ITEM_PAIR) nout = 36; else nout = 104;
     for (int o = lane; o < nout; o += W) {
@@ -61,7 +62,7 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
         double acc = 0.0;
         for (int e = item.lo; e < item.hi; e++) {
             const int ent = list[e];
-            const double *rec = recs + (size_t)(ent >> 1) * VREC;
+            const double *rec = recs + (size_t)(ent >> 1) * rs;
             const int role = ent & 1;
             int ia, sa, ib, sb;
             if (ka == 0) { ia = (role ? REC_B : REC_A) + pa; sa = 6; } else { ia = common_off(pa); sa = common_stride(pa); }

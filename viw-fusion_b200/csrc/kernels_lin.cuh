@@ -23,6 +23,8 @@ VIWB_HD int blk_moff(int b) { int t = blk_toff(b); return b > BLK_PR ? t + 1 : t
 VIWB_HD bool marg_prior_only(const WinMeta &m, int mode) { return mode == MODE_MARG && m.margin_flag == 1; }
 VIWB_HD bool marg_skip(const WinMeta &m, int mode) { return mode == MODE_MARG && m.margin_flag < 0; }
 
+VIWB_HD int rec_stride(const BatchDev &bd, int mode) { return mode == MODE_SOLVE ? bd.rec_stride_solve : VREC; }
+
 VIWB_HD const double *eval_state(const BatchDev &bd, int w, int mode) {
     return (mode == MODE_SOLVE ? bd.x_cand : bd.x_cur) + bd.meta[w].state_off;
 }
@@ -74,11 +76,15 @@ VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, d
              x[SFIX + lm], x[blk_off(BLK_TD)], m.S_vis, true, o);
     double half_rho;
     const double sc = huber_scale(o.r[0] * o.r[0] + o.r[1] * o.r[1], m.huber, half_rho);
-    double *rec = bd.vis_rec + (size_t)f * VREC;
+    const int rs = rec_stride(bd, mode);
+    double *rec = bd.vis_rec + (size_t)f * rs;
     rec[0] = o.r[0] * sc; rec[1] = o.r[1] * sc;
-    for (int k = 0; k < 12; k++) { rec[REC_A + k] = o.JA[k] * sc; rec[REC_B + k] = o.JB[k] * sc; rec[REC_E0 + k] = o.JE0[k] * sc; rec[REC_E1 + k] = o.JE1[k] * sc; }
+    for (int k = 0; k < 12; k++) { rec[REC_A + k] = o.JA[k] * sc; rec[REC_B + k] = o.JB[k] * sc; }
     rec[REC_L] = o.Jl[0] * sc; rec[REC_L + 1] = o.Jl[1] * sc;
-    rec[REC_TD] = o.Jtd[0] * sc; rec[REC_TD + 1] = o.Jtd[1] * sc;
+    if (rs == VREC) {
+        for (int k = 0; k < 12; k++) { rec[REC_E0 + k] = o.JE0[k] * sc; rec[REC_E1 + k] = o.JE1[k] * sc; }
+        rec[REC_TD] = o.Jtd[0] * sc; rec[REC_TD + 1] = o.Jtd[1] * sc;
+    }
     bd.vis_cost[f] = half_rho;
 }
 
@@ -96,8 +102,9 @@ VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     double wv[VSUB];
     for (int i = 0; i < VSUB; i++) wv[i] = 0.0;
     double a = 0.0, g = 0.0, c = 0.0;
+    const int rs = rec_stride(bd, mode);
     for (int f = f0; f < f1; f++) {
-        const double *rec = bd.vis_rec + (size_t)f * VREC;
+        const double *rec = bd.vis_rec + (size_t)f * rs;
         const double u0 = rec[REC_L], u1 = rec[REC_L + 1];
         a += u0 * u0 + u1 * u1;
         g += u0 * rec[0] + u1 * rec[1];
@@ -110,9 +117,11 @@ VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt,
                 wv[oj + q] += rec[REC_B + q] * u0 + rec[REC_B + 6 + q] * u1;
             }
         }
-        for (int q = 0; q < 6; q++) wv[66 + q] += rec[REC_E0 + q] * u0 + rec[REC_E0 + 6 + q] * u1;
-        if (type != 0) for (int q = 0; q < 6; q++) wv[72 + q] += rec[REC_E1 + q] * u0 + rec[REC_E1 + 6 + q] * u1;
-        wv[78] += rec[REC_TD] * u0 + rec[REC_TD + 1] * u1;
+        if (rs == VREC) {
+            for (int q = 0; q < 6; q++) wv[66 + q] += rec[REC_E0 + q] * u0 + rec[REC_E0 + 6 + q] * u1;
+            if (type != 0) for (int q = 0; q < 6; q++) wv[72 + q] += rec[REC_E1 + q] * u0 + rec[REC_E1 + 6 + q] * u1;
+            wv[78] += rec[REC_TD] * u0 + rec[REC_TD + 1] * u1;
+        }
     }
     for (int i = 0; i < VSUB; i++) W[i] = wv[i];
     bd.lm_a[k] = a; bd.lm_g[k] = g; bd.lm_cost[k] = c;

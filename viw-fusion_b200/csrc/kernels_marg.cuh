@@ -66,65 +66,141 @@ VIWB_D void jacobi_small(double *A, double *V, int n) {
     }
 }
 
-// parallel-ordering cyclic Jacobi in shared memory.  A, V: n x n with leading dimension ld (odd, so that the column
-// walks of the rotation updates are bank-conflict free); on exit diag(A) = eigenvalues, columns of V = eigenvectors.
-// Round r of the circle method pairs (ne-1, r) and ((r+i) mod (ne-1), (r-i) mod (ne-1)), i = 1..ne/2-1: all disjoint.
-VIWB_D void jacobi_pair(int i, int r, int ne, int &p, int &q) {
-    const int m1 = ne - 1;
-    if (i == 0) { p = m1; q = r; } else { p = (r + i) % m1; q = (r - i + m1) % m1; }
-    if (p > q) { const int t = p; p = q; q = t; }
+// Symmetric eigen-decomposition in shared memory: Householder tridiagonalisation + implicit QL with eigenvector
+// accumulation (the EISPACK tred2 / tql2 pair, the algorithm family Eigen::SelfAdjointEigenSolver uses), with the
+// O(n^2)-per-step inner loops spread over the block and the O(n) scalar recurrences kept on thread 0.
+// V (n x n, leading dimension ld): in = symmetric matrix (lower triangle read), out = eigenvectors in columns.
+// d (n): eigenvalues (unsorted).  e (n), cs (2n), sc (8): scratch.
+VIWB_D double blk_reduce_small(double v, int tid, int nt, double *red) {     // sum over the block via a short tree
+    return block_sum(v, tid, nt, red);
 }
-VIWB_D void jacobi_block(double *A, double *V, int n, int ld, double *cs, double *bc, int tid, int nt) {
-    const int ne = n + (n & 1), half = ne / 2;      // pad to even with a dummy index (= n)
-    const int W = nt < 32 ? nt : 32, nw = nt / W, lane = tid % W, wid = tid / W;
-    for (int i = wid; i < n; i += nw) for (int j = lane; j < n; j += W) V[i * ld + j] = (i == j) ? 1.0 : 0.0;
+VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *sc, double *red, int n, int ld, int tid, int nt) {
+#define VV(i, j) V[(i) * ld + (j)]
+    // ---- tred2
+    for (int j = tid; j < n; j += nt) d[j] = VV(n - 1, j);
     VIWB_SYNC();
-    for (int sweep = 0; sweep < 40; sweep++) {
-        if (tid == 0) bc[1] = 0.0;
+    for (int i = n - 1; i > 0; i--) {
+        double part = 0.0;
+        for (int k = tid; k < i; k += nt) part += fabs(d[k]);
+        const double scale = blk_reduce_small(part, tid, nt, red);
+        if (scale == 0.0) {
+            if (tid == 0) e[i] = d[i - 1];
+            VIWB_SYNC();
+            for (int j = tid; j < i; j += nt) { d[j] = VV(i - 1, j); VV(i, j) = 0.0; VV(j, i) = 0.0; }
+            VIWB_SYNC();
+            if (tid == 0) d[i] = 0.0;
+            VIWB_SYNC();
+            continue;
+        }
+        part = 0.0;
+        for (int k = tid; k < i; k += nt) { const double t = d[k] / scale; d[k] = t; part += t * t; }
+        double h = blk_reduce_small(part, tid, nt, red);
+        if (tid == 0) {
+            const double f = d[i - 1];
+            double g = sqrt(h); if (f > 0) g = -g;
+            e[i] = scale * g; h = h - f * g; d[i - 1] = f - g; sc[0] = h;
+        }
         VIWB_SYNC();
-        for (int step = 0; step < ne - 1; step++) {
-            for (int i = tid; i < half; i += nt) {
-                int p, q; jacobi_pair(i, step, ne, p, q);
-                double c = 1.0, s = 0.0;
-                if (q < n) {
-                    const double apq = A[p * ld + q], app = A[p * ld + p], aqq = A[q * ld + q];
-                    if (apq != 0.0 && fabs(apq) > 1e-17 * sqrt(fabs(app) * fabs(aqq))) {
-                        const double tau = (aqq - app) / (2.0 * apq);
-                        const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = 1.0 / sqrt(1.0 + t * t); s = t * c;
-                        bc[1] = 1.0;
-                    }
-                }
-                cs[2 * i] = c; cs[2 * i + 1] = s;
-            }
+        h = sc[0];
+        // e[j] = (A d)[j] over the leading i x i block (lower triangle storage); column i keeps the Householder vector
+        for (int j = tid; j < i; j += nt) {
+            double g = 0.0;
+            for (int k = 0; k <= j; k++) g += VV(j, k) * d[k];
+            for (int k = j + 1; k < i; k++) g += VV(k, j) * d[k];
+            cs[j] = g / h;            // e[j] / h, kept in cs until the reduction below is done
+            VV(j, i) = d[j];
+        }
+        VIWB_SYNC();
+        part = 0.0;
+        for (int j = tid; j < i; j += nt) part += cs[j] * d[j];
+        const double f2 = blk_reduce_small(part, tid, nt, red);
+        const double hh = f2 / (h + h);
+        for (int j = tid; j < i; j += nt) e[j] = cs[j] - hh * d[j];
+        VIWB_SYNC();
+        // rank-2 update of the lower triangle: V[k][j] -= d[j] e[k] + e[j] d[k],  j <= k < i
+        for (int k = tid; k < i; k += nt) { const double ek = e[k], dk = d[k]; for (int j = 0; j <= k; j++) VV(k, j) -= d[j] * ek + e[j] * dk; }
+        VIWB_SYNC();
+        for (int j = tid; j < i; j += nt) { cs[j] = VV(i - 1, j); VV(i, j) = 0.0; }
+        VIWB_SYNC();
+        for (int j = tid; j < i; j += nt) d[j] = cs[j];
+        if (tid == 0) d[i] = h;
+        VIWB_SYNC();
+    }
+    // ---- accumulate the transformations
+    for (int i = 0; i < n - 1; i++) {
+        if (tid == 0) { VV(n - 1, i) = VV(i, i); VV(i, i) = 1.0; }
+        VIWB_SYNC();
+        const double h = d[i + 1];
+        if (h != 0.0) {
+            for (int k = tid; k <= i; k += nt) d[k] = VV(k, i + 1) / h;
             VIWB_SYNC();
-            // A <- A J, V <- V J (columns p,q of every row): warps over pairs, lanes over rows
-            for (int i = wid; i < half; i += nw) {
-                const double c = cs[2 * i], s = cs[2 * i + 1];
-                if (s == 0.0) continue;
-                int p, q; jacobi_pair(i, step, ne, p, q);
-                for (int r = lane; r < n; r += W) {
-                    double a = A[r * ld + p], b = A[r * ld + q]; A[r * ld + p] = c * a - s * b; A[r * ld + q] = s * a + c * b;
-                    a = V[r * ld + p]; b = V[r * ld + q]; V[r * ld + p] = c * a - s * b; V[r * ld + q] = s * a + c * b;
-                }
-            }
-            VIWB_SYNC();
-            // A <- J^T A (rows p,q of every column)
-            for (int i = wid; i < half; i += nw) {
-                const double c = cs[2 * i], s = cs[2 * i + 1];
-                if (s == 0.0) continue;
-                int p, q; jacobi_pair(i, step, ne, p, q);
-                for (int r = lane; r < n; r += W) { const double a = A[p * ld + r], b = A[q * ld + r]; A[p * ld + r] = c * a - s * b; A[q * ld + r] = s * a + c * b; }
+            for (int j = tid; j <= i; j += nt) {
+                double g = 0.0;
+                for (int k = 0; k <= i; k++) g += VV(k, i + 1) * VV(k, j);
+                for (int k = 0; k <= i; k++) VV(k, j) -= g * d[k];
             }
             VIWB_SYNC();
         }
-        if (bc[1] == 0.0) break;
+        for (int k = tid; k <= i; k += nt) VV(k, i + 1) = 0.0;
         VIWB_SYNC();
     }
+    for (int j = tid; j < n; j += nt) { d[j] = VV(n - 1, j); VV(n - 1, j) = 0.0; }
+    VIWB_SYNC();
+    if (tid == 0) { VV(n - 1, n - 1) = 1.0; e[0] = 0.0; }
+    VIWB_SYNC();
+    // ---- tql2
+    for (int i = 1 + tid; i < n; i += nt) cs[i - 1] = e[i];
+    VIWB_SYNC();
+    for (int i = tid; i < n - 1; i += nt) e[i] = cs[i];
+    if (tid == 0) { e[n - 1] = 0.0; sc[1] = 0.0 /* f */; sc[2] = 0.0 /* tst1 */; }
+    VIWB_SYNC();
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; l++) {
+        if (tid == 0) {
+            const double t = fabs(d[l]) + fabs(e[l]); if (t > sc[2]) sc[2] = t;
+            int m = l; while (m < n) { if (fabs(e[m]) <= eps * sc[2]) break; m++; }
+            sc[3] = (double)m;
+        }
+        VIWB_SYNC();
+        const int m = (int)sc[3];
+        if (m > l) {
+            for (int iter = 0; iter < 200; iter++) {
+                if (tid == 0) {
+                    double g = d[l], p = (d[l + 1] - g) / (2.0 * e[l]), r = sqrt(p * p + 1.0);
+                    if (p < 0) r = -r;
+                    d[l] = e[l] / (p + r); d[l + 1] = e[l] * (p + r);
+                    const double dl1 = d[l + 1]; double h = g - d[l];
+                    for (int i = l + 2; i < n; i++) d[i] -= h;
+                    sc[1] += h;
+                    p = d[m];
+                    double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0; const double el1 = e[l + 1];
+                    for (int i = m - 1; i >= l; i--) {
+                        c3 = c2; c2 = c; s2 = s;
+                        g = c * e[i]; h = c * p; r = hypot(p, e[i]);
+                        e[i + 1] = s * r; s = e[i] / r; c = p / r;
+                        p = c * d[i] - s * g; d[i + 1] = h + s * (c * g + s * d[i]);
+                        cs[2 * i] = c; cs[2 * i + 1] = s;
+                    }
+                    p = -s * s2 * c3 * el1 * e[l] / dl1;
+                    e[l] = s * p; d[l] = c * p;
+                    sc[4] = (fabs(e[l]) > eps * sc[2]) ? 1.0 : 0.0;
+                }
+                VIWB_SYNC();
+                for (int k = tid; k < n; k += nt)
+                    for (int i = m - 1; i >= l; i--) { const double c = cs[2 * i], s = cs[2 * i + 1], h = VV(k, i + 1); VV(k, i + 1) = s * VV(k, i) + c * h; VV(k, i) = c * VV(k, i) - s * h; }
+                VIWB_SYNC();
+                if (sc[4] == 0.0) break;
+                VIWB_SYNC();
+            }
+        }
+        if (tid == 0) { d[l] = d[l] + sc[1]; e[l] = 0.0; }
+        VIWB_SYNC();
+    }
+#undef VV
 }
 
 VIWB_HD int vsub_to_mlay(int p) { return p < 66 ? p : p < 72 ? 165 + (p - 66) : p < 78 ? 171 + (p - 72) : 191; }   // td -> blk_moff(BLK_TD) = 191
-VIWB_HD size_t marg_smem_doubles(int nt) { return 24400 + (size_t)nt; }
+VIWB_HD size_t marg_smem_doubles(int nt) { return 100 * 101 + 3 * 256 + 100 * 16 + 216 * 2 + 216 + 16 + 216 + 64 + (size_t)nt; }
 
 VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)mode;
@@ -139,9 +215,10 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
     const double eps = 1e-8;   // marginalization_factor.h:81
     // smem carve
-    double *An = smem, *Vn = An + 100 * 101, *Amm = Vn + 100 * 101, *Vmm = Amm + 256, *Ainv = Vmm + 256, *Tm = Ainv + 256;
-    double *bn = Tm + 100 * 16, *cs = bn + 216, *red = cs + 216 + 216, *bc = red + nt;
+    double *Vn = smem, *Amm = Vn + 100 * 101, *Vmm = Amm + 256, *Ainv = Vmm + 256, *Tm = Ainv + 256;
+    double *bn = Tm + 100 * 16, *cs = bn + 216, *ev = cs + 216, *ee = ev + 108, *red = ee + 108, *bc = red + nt;
     int *keep = (int *)(bc + 16), *dl = keep + 216;
+    double *An = Vn;
     // ---- dense system of the marginalisation factors over the marginalisation layout
     for (int e = tid; e < MLAY * MLAY; e += nt) M[(size_t)(e / MLAY) * LDM + (e % MLAY)] = 0.0;
     for (int i = tid; i < TFIX + 8; i += nt) b[i] = 0.0;
@@ -217,12 +294,12 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     // SelfAdjointEigenSolver reads the lower triangle
     for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e % n; if (j > i) An[i * ld + j] = An[j * ld + i]; }
     VIWB_SYNC();
-    jacobi_block(An, Vn, n, ld, cs, bc, tid, nt);
+    sym_eig_block(Vn, ev, ee, cs, bc + 4, red, n, ld, tid, nt);
     VIWB_SYNC();
     // J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b   (marginalization_factor.cpp:298-306)
     double *Jout = bd.marg_J + (size_t)w * MAXPRI * MAXPRI, *rout = bd.marg_r + (size_t)w * MAXPRI;
     for (int i = tid; i < n; i += nt) {
-        const double l = An[i * ld + i];
+        const double l = ev[i];
         const double S = l > eps ? l : 0.0, Sinv = l > eps ? 1.0 / l : 0.0, ss = sqrt(S), si = sqrt(Sinv);
         double vb = 0.0;
         for (int k = 0; k < n; k++) { Jout[(size_t)i * n + k] = ss * Vn[k * ld + i]; vb += Vn[k * ld + i] * bn[k]; }

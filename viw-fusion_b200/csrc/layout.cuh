@@ -3,7 +3,7 @@
 // HBM layout (all FP64 unless noted; B windows, concatenated):
 //   x_cur / x_cand      [sum(207 + nlm)]        parameter blocks, fixed-state layout of include/viwb.h + inverse depths
 //   vis_*               visual factor table, sorted by landmark; vis_obs stays [nvis][12] as given
-//   vis_rec             [nvis_total][54]  per-factor record written by lin_vis: r(2) A(12) B(12) E0(12) E1(12) Jl(2) Jtd(2)
+//   vis_rec             [nvis_total][28 or 54]  per-factor record written by lin_vis: r(2) A(12) B(12) Jl(2) | Jtd(2) E0(12) E1(12)
 //   lm_*                per landmark: a = |J_l|^2, gl = J_l^T r, gamma = c^2/h (Schur weight), W [80] = J_p^T J_l over the
 //                       "visual subspace" (11 poses x 6 | ex0 6 | ex1 6 | td 1 | pad)
 //   imu_rec / wheel_rec / plane_rec   whitened residual + tangent Jacobian of the small factors
@@ -18,7 +18,9 @@ namespace viwb {
 
 enum { NB = 32, NFR = 11, TFIX = 192, SFIX = 207, VSUB = 80, VREC = 54, IMU_REC = 15 + 15 * 30, WHEEL_REC = 6 + 6 * 22,
        PLANE_REC = 3 + 3 * 16, MAXPRI = 200 };
-enum { REC_R = 0, REC_A = 2, REC_B = 14, REC_E0 = 26, REC_E1 = 38, REC_L = 50, REC_TD = 52 };
+// record layout: the first VREC_COMPACT doubles (r, A, B, J_lambda) are all a solve needs when ex0/ex1/td are constant;
+// td / E0 / E1 follow and are only written (and the stride only widened to VREC) when some window needs them
+enum { REC_R = 0, REC_A = 2, REC_B = 14, REC_L = 26, REC_TD = 28, REC_E0 = 30, REC_E1 = 42, VREC_COMPACT = 28 };
 enum { BLK_SB0 = 11, BLK_EX0 = 22, BLK_EX1 = 23, BLK_EXW = 24, BLK_PR = 25, BLK_PZ = 26, BLK_SX = 27, BLK_SY = 28, BLK_SW = 29,
        BLK_TD = 30, BLK_TDW = 31 };
 
@@ -83,6 +85,7 @@ struct Opts {
 
 struct BatchDev {       // passed by value to every kernel
     int B, nvis_total, nlm_total, nimu_total, nwheel_total, nplane_total, nprior, nitems_solve, nitems_marg;
+    int rec_stride_solve;   // VREC_COMPACT if no window of the batch has ex0/ex1/td active, else VREC (marginalisation always uses VREC)
     const WinMeta *meta;
     WinWork *work;
     const PriorDev *prior;

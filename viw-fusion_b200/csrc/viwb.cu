@@ -83,7 +83,7 @@ DEF_KERNEL(asm_items, 128)
 DEF_KERNEL(syrk, 256)
 DEF_KERNEL(solve, 512)
 DEF_KERNEL(reanchor, 32)
-DEF_KERNEL(marg, 512)
+DEF_KERNEL(marg, 256)
 #define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) \
     do { if ((gx) > 0 && (gy) > 0) { g_prof.begin((mode) == 1 ? #name "_marg" : #name, stream); name##_kernel<<<dim3((gx), (gy)), (nt), (smem_bytes), (stream)>>>(bd, mode); g_prof.end(stream); } } while (0)
 #define NT(n) (n)
@@ -383,6 +383,8 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     }
     bd.nvis_total = (int)nvis; bd.nlm_total = (int)nlm; bd.nimu_total = (int)nimu; bd.nwheel_total = (int)nwheel; bd.nplane_total = (int)nplane; bd.nprior = (int)npri;
     bd.nitems_solve = (int)nit_s; bd.nitems_marg = (int)nit_m;
+    bd.rec_stride_solve = VREC_COMPACT;
+    for (int w = 0; w < B; w++) if (b->meta[w].has_common) bd.rec_stride_solve = VREC;
     b->total_state = nstate;
     // ---- placement (inputs first, then work arrays)
     struct Ent { void **field; size_t bytes; bool input; size_t off; };
@@ -443,7 +445,7 @@ static int ensure_attrs(viwb_context *ctx) {
 #ifndef VIWB_HOST_EMU
     if (!ctx->attrs_set) {
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(512) * 8)));
-        CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(512) * 8)));
+        CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(256) * 8)));
         ctx->attrs_set = true;
     }
 #endif
@@ -461,7 +463,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     CK(dev_d2d(bd.x_cur, bd.x_init, xs, st)); CK(dev_d2d(bd.x_cand, bd.x_init, xs, st));
     if (!(what & RUN_REANCHOR) || (what & RUN_SOLVE)) CK(dev_d2d(bd.x_before, bd.x_init, xs, st));
     CK(dev_d2d(bd.work, b->work_init_dev, sizeof(WinWork) * B, st));
-    const int nt_vis = NT(128), nt_lm = NT(64), nt_small = NT(64), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(512), nt_marg = NT(512);
+    const int nt_vis = NT(128), nt_lm = NT(64), nt_small = NT(64), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(512), nt_marg = NT(256);
     const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total + nt_lm - 1) / nt_lm;
     const size_t sm_small = (size_t)(nt_small + MAXPRI + 8) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg) * 8;
     auto lin = [&](int mode) {
