@@ -161,7 +161,7 @@ VIWB_HD void whiten_upper(int rows, int cols, const double *S, double *J) {
         }
 }
 
-// rec = the 287-double record of include/viwb.h; S = 15x15 upper sqrt-info.  Outputs the whitened residual r[15]
+// rec = the 287-double record of include/viwb.h; S = 15x15 upper sqrt-info (nullptr: leave r and J un-whitened).  Outputs the whitened residual r[15]
 // and, if want_j, whitened tangent Jacobians J (15 x 30 row-major: pose_i 6 | sb_i 9 | pose_j 6 | sb_j 9).
 VIWB_HD void imu_eval(const double *rec, const double *S, const double *G, const double *pose_i, const double *sb_i,
                       const double *pose_j, const double *sb_j, bool want_j, double *r, double *J) {
@@ -187,7 +187,8 @@ VIWB_HD void imu_eval(const double *rec, const double *S, const double *G, const
     st3(raw, a_p - cdp);
     raw[3] = 2.0 * qe.x; raw[4] = 2.0 * qe.y; raw[5] = 2.0 * qe.z;
     st3(raw + 6, a_v - cdv); st3(raw + 9, Baj - Bai); st3(raw + 12, Bgj - Bgi);
-    for (int i = 0; i < 15; i++) { double s = 0.0; for (int k = i; k < 15; k++) s += S[i * 15 + k] * raw[k]; r[i] = s; }
+    if (S) { for (int i = 0; i < 15; i++) { double s = 0.0; for (int k = i; k < 15; k++) s += S[i * 15 + k] * raw[k]; r[i] = s; } }
+    else for (int i = 0; i < 15; i++) r[i] = raw[i];
     if (!want_j) return;
     for (int i = 0; i < 450; i++) J[i] = 0.0;
     // pose_i (cols 0..5)
@@ -216,7 +217,7 @@ VIWB_HD void imu_eval(const double *rec, const double *S, const double *G, const
     put33(J, 30, 6, 21, RiT);
     put33(J, 30, 9, 24, m3_identity());
     put33(J, 30, 12, 27, m3_identity());
-    whiten_upper(15, 30, S, J);
+    if (S) whiten_upper(15, 30, S, J);
 }
 
 // ---------------------------------------------------------------------------------------------- wheel
@@ -250,7 +251,8 @@ VIWB_HD void wheel_eval(const double *rec, const double *S, const double *pose_i
     st3(raw, tmul(Rwo, d) - dp_time);
     const V3 rth = so3_log_q(qinv(dq_time) * q_iio_inv * Qj * qio);
     st3(raw + 3, rth);
-    for (int i = 0; i < 6; i++) { double s = 0.0; for (int k = i; k < 6; k++) s += S[i * 6 + k] * raw[k]; r[i] = s; }
+    if (S) { for (int i = 0; i < 6; i++) { double s = 0.0; for (int k = i; k < 6; k++) s += S[i * 6 + k] * raw[k]; r[i] = s; } }
+    else for (int i = 0; i < 6; i++) r[i] = raw[i];
     if (!want_j) return;
     for (int i = 0; i < 132; i++) J[i] = 0.0;
     const M3 Jri = so3_Jr_inv(rth);
@@ -290,7 +292,7 @@ VIWB_HD void wheel_eval(const double *rec, const double *S, const double *pose_i
         const V3 tr = Jri * (E1 * (E2 * (Rcdq_inv * (Jrtd * (lin_gyr * sw))) - Jr_minus_td * (gyr_1 * sw)));
         for (int k = 0; k < 3; k++) { J[k * 22 + 21] = -comp(tp, k); J[(3 + k) * 22 + 21] = -comp(tr, k); }
     }
-    whiten_upper(6, 22, S, J);
+    if (S) whiten_upper(6, 22, S, J);
 }
 
 // ---------------------------------------------------------------------------------------------- plane

@@ -30,7 +30,12 @@ VIWB_D int plane_slots(int i, Slot *s) { s[0].blk = i; s[0].col = 0; s[1].blk = 
 // offset of common column c (0..12: ex0 6 | ex1 6 | td) inside a visual record, and its row stride
 VIWB_HD int common_off(int c) { return c < 6 ? REC_E0 + c : c < 12 ? REC_E1 + (c - 6) : REC_TD; }
 VIWB_HD int common_stride(int c) { return c < 12 ? 6 : 1; }
-VIWB_HD void sym_unrank(int e, int &p, int &q) { p = 0; while ((p + 1) * (p + 2) / 2 <= e) p++; q = e - p * (p + 1) / 2; }
+VIWB_HD void sym_unrank(int e, int &p, int &q) {   // e = p(p+1)/2 + q, 0 <= q <= p
+    int pp = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+    while ((pp + 1) * (pp + 2) / 2 <= e) pp++;
+    while (pp * (pp + 1) / 2 > e) pp--;
+    p = pp; q = e - pp * (pp + 1) / 2;
+}
 
 // ------------------------------------------------------------------------------------------------ asm_items
 // grid: ceil(nitems / warps_per_block); mode selects the solver or the marginalisation item table.
@@ -48,28 +53,43 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     const int *list = bd.asm_list + (mode == MODE_SOLVE ? wm.list_off : wm.mlist_off);
     const int rs = rec_stride(bd, mode);
     const double *recs = bd.vis_rec + (size_t)wm.vis_off * rs;
+    // outputs of this item; without common columns a FRAME item has only F^T F (21) and F^T r (6 -> stored at 99..104)
     int nout;
-    if (item.kind == ITEM_FRAME) nout = 105; else if (item.kind == ITEM_PAIR) nout = 36; else nout = 104;
-    for (int o = lane; o < nout; o += W) {
-        // (ia, sa): record offset / row stride of the left operand, (ib, sb) of the right one; role-dependent parts resolved per entry
-        int ka = 0, kb = 0, pa = 0, pb = 0;      // k*: 0 = frame slot of a, 1 = frame slot of b (PAIR), 2 = common column, 3 = residual
+    if (item.kind == ITEM_FRAME) nout = item.has_common ? 105 : 27; else if (item.kind == ITEM_PAIR) nout = 36; else nout = 104;
+    if (item.kind == ITEM_FRAME && !item.has_common) for (int o = 21 + lane; o < 99; o += W) out[o] = 0.0;
+    for (int o0 = lane; o0 < nout; o0 += W) {
+        int o = o0;
+        if (item.kind == ITEM_FRAME && !item.has_common && o0 >= 21) o = 99 + (o0 - 21);
+        // operand kinds: 0 = frame slot of a, 1 = frame slot of b (PAIR), 2 = common column, 3 = residual
+        int ka = 0, kb = 0, pa = 0, pb = 0;
         if (item.kind == ITEM_FRAME) {
             if (o < 21) { sym_unrank(o, pa, pb); ka = 0; kb = 0; }
-            else if (o < 99) { if (!item.has_common) { out[o] = 0.0; continue; } pa = (o - 21) / 13; pb = (o - 21) % 13; ka = 0; kb = 2; }
+            else if (o < 99) { pa = (o - 21) / 13; pb = (o - 21) % 13; ka = 0; kb = 2; }
             else { pa = o - 99; ka = 0; kb = 3; }
         } else if (item.kind == ITEM_PAIR) { pa = o / 6; pb = o % 6; ka = 0; kb = 1; }
         else { if (o < 91) { sym_unrank(o, pa, pb); ka = 2; kb = 2; } else { pa = o - 91; ka = 2; kb = 3; } }
+        // role-independent parts of the record offsets
+        const int ia_c = (ka == 2) ? common_off(pa) : pa, sa = (ka == 2) ? common_stride(pa) : 6;
+        const int ib_c = (kb == 2) ? common_off(pb) : (kb == 3 ? 0 : pb), sb = (kb == 2) ? common_stride(pb) : (kb == 3 ? 1 : 6);
         double acc = 0.0;
-        for (int e = item.lo; e < item.hi; e++) {
-            const int ent = list[e];
+        int e = item.lo;
+        for (; e + 4 <= item.hi; e += 4) {        // 4 independent gather chains in flight
+            int en[4]; const double *rc[4]; double va[4], vb[4], wa[4], wb[4];
+            for (int u = 0; u < 4; u++) en[u] = list[e + u];
+            for (int u = 0; u < 4; u++) {
+                const int role = en[u] & 1;
+                rc[u] = recs + (size_t)(en[u] >> 1) * rs;
+                const int ia = (ka == 0) ? (role ? REC_B : REC_A) + ia_c : ia_c;
+                const int ib = (kb == 0) ? (role ? REC_B : REC_A) + ib_c : (kb == 1 ? (role ? REC_A : REC_B) + ib_c : ib_c);
+                va[u] = rc[u][ia]; wa[u] = rc[u][ia + sa]; vb[u] = rc[u][ib]; wb[u] = rc[u][ib + sb];
+            }
+            for (int u = 0; u < 4; u++) acc += va[u] * vb[u] + wa[u] * wb[u];
+        }
+        for (; e < item.hi; e++) {
+            const int ent = list[e], role = ent & 1;
             const double *rec = recs + (size_t)(ent >> 1) * rs;
-            const int role = ent & 1;
-            int ia, sa, ib, sb;
-            if (ka == 0) { ia = (role ? REC_B : REC_A) + pa; sa = 6; } else { ia = common_off(pa); sa = common_stride(pa); }
-            if (kb == 0) { ib = (role ? REC_B : REC_A) + pb; sb = 6; }
-            else if (kb == 1) { ib = (role ? REC_A : REC_B) + pb; sb = 6; }
-            else if (kb == 2) { ib = common_off(pb); sb = common_stride(pb); }
-            else { ib = 0; sb = 1; }
+            const int ia = (ka == 0) ? (role ? REC_B : REC_A) + ia_c : ia_c;
+            const int ib = (kb == 0) ? (role ? REC_B : REC_A) + ib_c : (kb == 1 ? (role ? REC_A : REC_B) + ib_c : ib_c);
             acc += rec[ia] * rec[ib] + rec[ia + sa] * rec[ib + sb];
         }
         out[o] = acc;

@@ -4,7 +4,7 @@
 // barriers only between phases, so the same source runs as a CUDA kernel and (nt = 1) in the CPU emulation.
 //   setup      once per solve: IMU/wheel sqrt-information (imu_factor.h:75, wheel_factor.h:85), prior J^T J
 //   lin_vis    one thread per visual factor: residual, Huber, tangent Jacobians -> 54-double record   (8a-5/6/7, a-12)
-//   lm_reduce  one thread per landmark: a = |J_l|^2, g_l, w = J_p^T J_l, Schur weight gamma, cost      (Schur, Appendix B)
+//   lm_reduce  13 threads per landmark: a = |J_l|^2, g_l, w = J_p^T J_l, Schur weight gamma, cost      (Schur, Appendix B)
 //   lin_small  one block per window: IMU / wheel / plane factors and the prior residual + gradient   (8a-8..a-11)
 //   (assembly of the normal equations: kernels_asm.cuh)
 // mode 0 = solver linearisation at x_cand over the tangent layout, mode 1 = marginalisation at x_cur over the
@@ -89,41 +89,62 @@ VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, d
 }
 
 // ------------------------------------------------------------------------------------------------ lm_reduce
+// 13 threads per landmark, one per block of w_k: role j < 11 owns the 6 entries of pose j (role == host frame also
+// reduces a_k, g_k, the cost and the Schur weight), roles 11 / 12 own [ex0 | td] and [ex1] (wide records only).
+// No dynamic indexing -> everything stays in registers; each factor record is read about once in total.
+enum { LM_ROLES = 13 };
 VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)smem;
-    const int k = bx * nt + tid;
+    const int gid = bx * nt + tid;
+    const int k = gid / LM_ROLES, role = gid % LM_ROLES;
     if (k >= bd.nlm_total) return;
     const int w = bd.lm_win[k];
     const WinWork &ww = bd.work[w];
     if (mode == MODE_SOLVE && ww.status != ST_RUNNING) return;
     const int f0 = bd.lm_fptr[k], f1 = bd.lm_fptr[k + 1];
     double *W = bd.lm_W + (size_t)k * VSUB;
-    if (mode == MODE_MARG && (f0 == f1 || bd.vis_fi[f0] != 0 || bd.meta[w].margin_flag != 0)) { bd.lm_gamma[k] = 0.0; return; }
-    double wv[VSUB];
-    for (int i = 0; i < VSUB; i++) wv[i] = 0.0;
-    double a = 0.0, g = 0.0, c = 0.0;
+    const bool skip = (mode == MODE_MARG) && (f0 == f1 || bd.vis_fi[f0] != 0 || bd.meta[w].margin_flag != 0);
+    if (skip) { if (role == 0) bd.lm_gamma[k] = 0.0; return; }
+    if (f0 == f1) {      // a landmark without factors: contributes nothing
+        if (role == 0) { bd.lm_a[k] = 0.0; bd.lm_g[k] = 0.0; bd.lm_cost[k] = 0.0; bd.lm_gamma[k] = 0.0; if (ww.first) bd.lm_scale[k] = 1.0; }
+        if (role < NFR) for (int q = 0; q < 6; q++) W[6 * role + q] = 0.0;
+        else if (role == 11) { for (int q = 0; q < 6; q++) W[66 + q] = 0.0; W[78] = 0.0; W[79] = 0.0; }
+        else for (int q = 0; q < 6; q++) W[72 + q] = 0.0;
+        return;
+    }
     const int rs = rec_stride(bd, mode);
-    for (int f = f0; f < f1; f++) {
-        const double *rec = bd.vis_rec + (size_t)f * rs;
-        const double u0 = rec[REC_L], u1 = rec[REC_L + 1];
-        a += u0 * u0 + u1 * u1;
-        g += u0 * rec[0] + u1 * rec[1];
-        c += bd.vis_cost[f];
-        const int type = bd.vis_type[f];
-        if (type != 2) {
-            const int oi = 6 * bd.vis_fi[f], oj = 6 * bd.vis_fj[f];
-            for (int q = 0; q < 6; q++) {
-                wv[oi + q] += rec[REC_A + q] * u0 + rec[REC_A + 6 + q] * u1;
-                wv[oj + q] += rec[REC_B + q] * u0 + rec[REC_B + 6 + q] * u1;
+    const int host = (f0 < f1) ? bd.vis_fi[f0] : -1;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    double a = 0.0, g = 0.0, c = 0.0;
+    if (role < NFR) {
+        for (int f = f0; f < f1; f++) {
+            const int type = bd.vis_type[f];
+            const double *rec = bd.vis_rec + (size_t)f * rs;
+            if (role == host) {
+                const double u0 = rec[REC_L], u1 = rec[REC_L + 1];
+                a += u0 * u0 + u1 * u1; g += u0 * rec[0] + u1 * rec[1]; c += bd.vis_cost[f];
+                if (type != 2) for (int q = 0; q < 6; q++) acc[q] += rec[REC_A + q] * u0 + rec[REC_A + 6 + q] * u1;
+            }
+            if (type != 2 && bd.vis_fj[f] == role) {
+                const double u0 = rec[REC_L], u1 = rec[REC_L + 1];
+                for (int q = 0; q < 6; q++) acc[q] += rec[REC_B + q] * u0 + rec[REC_B + 6 + q] * u1;
             }
         }
-        if (rs == VREC) {
-            for (int q = 0; q < 6; q++) wv[66 + q] += rec[REC_E0 + q] * u0 + rec[REC_E0 + 6 + q] * u1;
-            if (type != 0) for (int q = 0; q < 6; q++) wv[72 + q] += rec[REC_E1 + q] * u0 + rec[REC_E1 + 6 + q] * u1;
-            wv[78] += rec[REC_TD] * u0 + rec[REC_TD + 1] * u1;
+        for (int q = 0; q < 6; q++) W[6 * role + q] = acc[q];
+    } else if (rs == VREC) {
+        for (int f = f0; f < f1; f++) {
+            const double *rec = bd.vis_rec + (size_t)f * rs;
+            const double u0 = rec[REC_L], u1 = rec[REC_L + 1];
+            if (role == 11) { for (int q = 0; q < 6; q++) acc[q] += rec[REC_E0 + q] * u0 + rec[REC_E0 + 6 + q] * u1; acc[6] += rec[REC_TD] * u0 + rec[REC_TD + 1] * u1; }
+            else if (bd.vis_type[f] != 0) for (int q = 0; q < 6; q++) acc[q] += rec[REC_E1 + q] * u0 + rec[REC_E1 + 6 + q] * u1;
         }
+        if (role == 11) { for (int q = 0; q < 6; q++) W[66 + q] = acc[q]; W[78] = acc[6]; W[79] = 0.0; }
+        else for (int q = 0; q < 6; q++) W[72 + q] = acc[q];
+    } else {
+        if (role == 11) { for (int q = 0; q < 6; q++) W[66 + q] = 0.0; W[78] = 0.0; W[79] = 0.0; }
+        else for (int q = 0; q < 6; q++) W[72 + q] = 0.0;
     }
-    for (int i = 0; i < VSUB; i++) W[i] = wv[i];
+    if (role != host) return;
     bd.lm_a[k] = a; bd.lm_g[k] = g; bd.lm_cost[k] = c;
     if (mode == MODE_MARG) { bd.lm_gamma[k] = a; return; }     // marginalisation keeps the pivot itself
     // Jacobi scale (first linearisation only) and the Schur weight for the mu this linearisation will be solved with:
@@ -150,6 +171,22 @@ VIWB_D void prior_dx(const PriorDev &p, const double *x, const double *x0, doubl
     }
 }
 
+// One warp per small factor: lane 0 evaluates the un-whitened residual and Jacobian into shared memory, then the lanes
+// whiten one Jacobian column each (r <- S r, J <- S J with S upper triangular) and stream it to the factor's record.
+enum { SMALL_SLOT = 15 + 15 * 30 };
+VIWB_HD size_t lin_small_smem_doubles(int nt) { const int W = nt < 32 ? nt : 32; return (size_t)(nt / W) * SMALL_SLOT + nt + MAXPRI + 8; }
+VIWB_D double whiten_store(const double *raw, const double *S, int rows, int ld, double *rec, int lane, int W) {
+    // raw: [rows residual | rows x ld Jacobian] un-whitened in shared memory -> rec (global), returns this lane's part of 0.5 |r|^2
+    double c = 0.0;
+    for (int col = lane; col <= ld; col += W) {
+        for (int i = 0; i < rows; i++) {
+            double a = 0.0;
+            if (col < ld) { for (int k = i; k < rows; k++) a += S[i * rows + k] * raw[rows + k * ld + col]; rec[rows + i * ld + col] = a; }
+            else { for (int k = i; k < rows; k++) a += S[i * rows + k] * raw[k]; rec[i] = a; c += 0.5 * a * a; }
+        }
+    }
+    return c;
+}
 VIWB_D void lin_small_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by;
     const int w = bx;
@@ -158,31 +195,36 @@ VIWB_D void lin_small_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     if (mode == MODE_SOLVE && ww.status != ST_RUNNING) return;
     if (marg_skip(m, mode)) return;
     const double *x = eval_state(bd, w, mode);
-    double *cost_part = smem;            // [nt]
-    double *dx = smem + nt;              // [MAXPRI]
+    const int W = nt < 32 ? nt : 32, nw = nt / W, wid = tid / W, lane = tid % W;
+    double *slot = smem + (size_t)wid * SMALL_SLOT;
+    double *cost_part = smem + (size_t)nw * SMALL_SLOT;      // [nt]
+    double *dx = cost_part + nt;                             // [MAXPRI]
     double c = 0.0;
     const int n_small = marg_prior_only(m, mode) ? 0 : m.nimu + m.nwheel + m.nplane;
-    for (int t = tid; t < n_small; t += nt) {
+    for (int t = wid; t < n_small; t += nw) {
         if (t < m.nimu) {
             const int f = m.imu_off + t, i = bd.imu_fi[f], j = bd.imu_fj[f];
             if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-            double *rec = bd.imu_rec + (size_t)f * IMU_REC;
-            imu_eval(bd.imu_data + (size_t)f * 287, bd.imu_S + (size_t)f * 225, m.G, x + 7 * i, x + 77 + 9 * i, x + 7 * j, x + 77 + 9 * j,
-                     true, rec, rec + 15);
-            for (int k = 0; k < 15; k++) c += 0.5 * rec[k] * rec[k];
+            if (lane == 0) imu_eval(bd.imu_data + (size_t)f * 287, nullptr, m.G, x + 7 * i, x + 77 + 9 * i, x + 7 * j, x + 77 + 9 * j, true, slot, slot + 15);
+            VIWB_SYNCWARP();
+            c += whiten_store(slot, bd.imu_S + (size_t)f * 225, 15, 30, bd.imu_rec + (size_t)f * IMU_REC, lane, W);
+            VIWB_SYNCWARP();
         } else if (t < m.nimu + m.nwheel) {
             const int f = m.wheel_off + (t - m.nimu), i = bd.wheel_fi[f], j = bd.wheel_fj[f];
             if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-            double *rec = bd.wheel_rec + (size_t)f * WHEEL_REC;
-            wheel_eval(bd.wheel_data + (size_t)f * 78, bd.wheel_S + (size_t)f * 36, x + 7 * i, x + 7 * j, x + blk_off(BLK_EXW),
-                       x[blk_off(BLK_SX)], x[blk_off(BLK_SY)], x[blk_off(BLK_SW)], x[blk_off(BLK_TDW)], true, rec, rec + 6);
-            for (int k = 0; k < 6; k++) c += 0.5 * rec[k] * rec[k];
+            if (lane == 0) wheel_eval(bd.wheel_data + (size_t)f * 78, nullptr, x + 7 * i, x + 7 * j, x + blk_off(BLK_EXW), x[blk_off(BLK_SX)], x[blk_off(BLK_SY)],
+                                      x[blk_off(BLK_SW)], x[blk_off(BLK_TDW)], true, slot, slot + 6);
+            VIWB_SYNCWARP();
+            c += whiten_store(slot, bd.wheel_S + (size_t)f * 36, 6, 22, bd.wheel_rec + (size_t)f * WHEEL_REC, lane, W);
+            VIWB_SYNCWARP();
         } else {
             const int f = m.plane_off + (t - m.nimu - m.nwheel), i = bd.plane_f[f];
             if (mode == MODE_MARG && i != 0) continue;
-            double *rec = bd.plane_rec + (size_t)f * PLANE_REC;
-            plane_eval(m.w_plane, x + 7 * i, x + blk_off(BLK_EXW), x + blk_off(BLK_PR), x[blk_off(BLK_PZ)], true, rec, rec + 3);
-            for (int k = 0; k < 3; k++) c += 0.5 * rec[k] * rec[k];
+            if (lane == 0) {
+                double *rec = bd.plane_rec + (size_t)f * PLANE_REC;
+                plane_eval(m.w_plane, x + 7 * i, x + blk_off(BLK_EXW), x + blk_off(BLK_PR), x[blk_off(BLK_PZ)], true, rec, rec + 3);
+                for (int k = 0; k < 3; k++) c += 0.5 * rec[k] * rec[k];
+            }
         }
     }
     if (m.prior_idx >= 0) {

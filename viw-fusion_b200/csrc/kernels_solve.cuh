@@ -87,43 +87,75 @@ VIWB_D void to_vis(const SolveSmem &s, int nf, const double *u, double *uvis, in
 }
 VIWB_D double dot80(const double *W, const double *v) { double a = 0.0; for (int p = 0; p < 79; p++) a += W[p] * v[p]; return a; }
 
-// in-place packed Cholesky; returns false on a non-positive pivot (Eigen LLT semantics)
-VIWB_D bool cholesky_packed(double *L, int n, int tid, int nt, double *bc) {
-    int TX = 1; while (TX * TX * 2 <= nt) TX *= 2;          // nt = 512 -> TX 16, TY 32 ; nt = 1 -> 1,1
-    const int TY = nt / TX, ty = tid / TX, tx = tid % TX;
+// Blocked (panel width 8) in-place Cholesky of the packed lower triangle with the right-hand side carried as an extra
+// row n, so that on exit y = L^-1 b (forward substitution for free).  Returns false on a non-positive pivot
+// (Eigen LLT semantics: schur_complement_solver.cc -> LINEAR_SOLVER_FAILURE).  3 barriers per panel.
+enum { CHOL_NB = 8 };
+VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, double *bc) {
+#define ROW(i) ((i) < n ? L + (size_t)(i) * ((i) + 1) / 2 : y)
     if (tid == 0) bc[0] = 1.0;
     VIWB_SYNC();
-    for (int j = 0; j < n; j++) {
-        if (tid == 0) { const double d = L[pidx(j, j)]; if (!(d > 0.0)) bc[0] = 0.0; else L[pidx(j, j)] = sqrt(d); }
+    for (int c0 = 0; c0 < n; c0 += CHOL_NB) {
+        const int nb = (n - c0) < CHOL_NB ? (n - c0) : CHOL_NB;
+        if (tid == 0) {      // diagonal block
+            for (int k = 0; k < nb; k++) {
+                double *rk = ROW(c0 + k) + c0;
+                double d = rk[k];
+                for (int m = 0; m < k; m++) d -= rk[m] * rk[m];
+                if (!(d > 0.0)) { bc[0] = 0.0; break; }
+                d = sqrt(d); rk[k] = d;
+                const double inv = 1.0 / d;
+                for (int i = k + 1; i < nb; i++) { double *ri = ROW(c0 + i) + c0; double v = ri[k]; for (int m = 0; m < k; m++) v -= ri[m] * rk[m]; ri[k] = v * inv; }
+            }
+        }
         VIWB_SYNC();
         if (bc[0] == 0.0) return false;
-        const double inv = 1.0 / L[pidx(j, j)];
-        for (int i = j + 1 + tid; i < n; i += nt) L[pidx(i, j)] *= inv;
+        const int r0 = c0 + nb;
+        // panel: rows r0..n (row n = rhs)
+        for (int i = r0 + tid; i <= n; i += nt) {
+            double *ri = ROW(i) + c0;
+            for (int k = 0; k < nb; k++) {
+                const double *rk = ROW(c0 + k) + c0;
+                double v = ri[k];
+                for (int m = 0; m < k; m++) v -= ri[m] * rk[m];
+                ri[k] = v / rk[k];
+            }
+        }
         VIWB_SYNC();
-        for (int i = j + 1 + ty; i < n; i += TY) {
-            const double lij = L[pidx(i, j)];
-            for (int k = j + 1 + tx; k <= i; k += TX) L[i * (i + 1) / 2 + k] -= lij * L[pidx(k, j)];
+        // trailing update with 4x4 register tiles over rows i in [r0, n], columns k in [r0, min(i, n-1)]
+        const int mt = (n + 1 - r0 + 3) / 4, ntile = mt * (mt + 1) / 2;
+        for (int t = tid; t < ntile; t += nt) {
+            int ti, tk; sym_unrank(t, ti, tk);
+            const int ib = r0 + 4 * ti, kb = r0 + 4 * tk;
+            double acc[16];
+            for (int q = 0; q < 16; q++) acc[q] = 0.0;
+            for (int m = 0; m < nb; m++) {
+                double li[4], lk[4];
+                for (int a = 0; a < 4; a++) { li[a] = (ib + a <= n) ? ROW(ib + a)[c0 + m] : 0.0; lk[a] = (kb + a < n) ? ROW(kb + a)[c0 + m] : 0.0; }
+                for (int a = 0; a < 4; a++) for (int b2 = 0; b2 < 4; b2++) acc[a * 4 + b2] += li[a] * lk[b2];
+            }
+            for (int a = 0; a < 4; a++) { const int i = ib + a; if (i > n) break; double *ri = ROW(i);
+                for (int b2 = 0; b2 < 4; b2++) { const int k = kb + b2; if (k >= n || k > i) break; ri[k] -= acc[a * 4 + b2]; } }
         }
         VIWB_SYNC();
     }
+#undef ROW
     return true;
 }
-// solve L L^T y = b in place (b -> y)
-VIWB_D void chol_solve_packed(const double *L, int n, double *b, int tid, int nt) {
-    for (int j = 0; j < n; j++) {
-        if (tid == 0) b[j] /= L[pidx(j, j)];
-        VIWB_SYNC();
-        const double bj = b[j];
-        for (int i = j + 1 + tid; i < n; i += nt) b[i] -= L[pidx(i, j)] * bj;
-        VIWB_SYNC();
+// back substitution L^T x = y in place, by the first warp only (warp-synchronous, no block barriers)
+VIWB_D void chol_backsolve_warp(const double *L, double *y, int n, int tid, int nt) {
+    const int W = nt < 32 ? nt : 32;
+    if (tid < W) {
+        for (int j = n - 1; j >= 0; j--) {
+            const double *rj = L + (size_t)j * (j + 1) / 2;
+            if (tid == 0) y[j] /= rj[j];
+            VIWB_SYNCWARP();
+            const double xj = y[j];
+            for (int i = tid; i < j; i += W) y[i] -= rj[i] * xj;
+            VIWB_SYNCWARP();
+        }
     }
-    for (int j = n - 1; j >= 0; j--) {
-        if (tid == 0) b[j] /= L[pidx(j, j)];
-        VIWB_SYNC();
-        const double bj = b[j];
-        for (int i = tid; i < j; i += nt) b[i] -= L[pidx(j, i)] * bj;
-        VIWB_SYNC();
-    }
+    VIWB_SYNC();
 }
 
 VIWB_D void terminate(WinWork &ww, int term) { ww.status = ST_DONE; ww.term = term; }
@@ -281,12 +313,13 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                 if (h_dirty) load_H(Hpk, s, nf, tid, nt);
                 const double mu = ww.mu;
                 const bool t_ok = (mu == ww.mu_lin);          // gamma / T / tvec were built for mu_lin
-                // S = C (H - T) C + mu D^2 ; rhs = C (g - tvec)
-                for (int i = tid; i < nf; i += nt) {
-                    const int vi = s.vmap[i];
-                    for (int j = 0; j <= i; j++) {
-                        const int vj = s.vmap[j];
-                        double hij = s.L[i * (i + 1) / 2 + j];
+                // S = C (H - T) C + mu D^2 ; rhs = C (g - tvec)     (element-parallel over the packed triangle)
+                const int ne = nf * (nf + 1) / 2;
+                for (int e = tid; e < ne + nf; e += nt) {
+                    if (e < ne) {
+                        int i, j; sym_unrank(e, i, j);
+                        const int vi = s.vmap[i], vj = s.vmap[j];
+                        double hij = s.L[e];
                         if (vi >= 0 && vj >= 0) {
                             if (t_ok) hij -= Tvis[vi * VSUB + vj];
                             else {
@@ -300,21 +333,23 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                         }
                         hij *= s.sc[i] * s.sc[j];
                         if (i == j) hij += mu * s.D[i] * s.D[i];
-                        s.L[i * (i + 1) / 2 + j] = hij;
+                        s.L[e] = hij;
+                    } else {
+                        const int i = e - ne, vi = s.vmap[i];
+                        double r = s.g[i];
+                        if (vi >= 0) {
+                            if (t_ok) r -= tvec[vi];
+                            else { double t = 0.0; for (int k = 0; k < N; k++) { const double c = lm_sc[k], sk = c * c * lm_a[k], Dk = g_D[TFIX + k]; t += (c * c / (sk + mu * Dk * Dk)) * W[(size_t)k * VSUB + vi] * lm_g[k]; } r -= t; }
+                        }
+                        s.y[i] = s.sc[i] * r;
                     }
-                    double r = s.g[i];
-                    if (vi >= 0) {
-                        if (t_ok) r -= tvec[vi];
-                        else { double t = 0.0; for (int k = 0; k < N; k++) { const double c = lm_sc[k], sk = c * c * lm_a[k], Dk = g_D[TFIX + k]; t += (c * c / (sk + mu * Dk * Dk)) * W[(size_t)k * VSUB + vi] * lm_g[k]; } r -= t; }
-                    }
-                    s.y[i] = s.sc[i] * r;
                 }
                 VIWB_SYNC();
                 h_dirty = true;
                 if (tid == 0) ww.num_linear++;
-                bool ok = cholesky_packed(s.L, nf, tid, nt, s.bc);
+                bool ok = cholesky_packed_rhs(s.L, s.y, nf, tid, nt, s.bc);
                 if (ok) {
-                    chol_solve_packed(s.L, nf, s.y, tid, nt);
+                    chol_backsolve_warp(s.L, s.y, nf, tid, nt);
                     // back-substitute the inverse depths (scaled): y_k = (c g_k - c w_k . (C y_f)) / h_k
                     for (int i = tid; i < nf; i += nt) s.u[i] = s.sc[i] * s.y[i];
                     VIWB_SYNC();

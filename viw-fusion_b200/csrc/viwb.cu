@@ -77,8 +77,8 @@ static Profiler g_prof;
 DEF_KERNEL(setup, 128)
 DEF_KERNEL(prior_setup, 256)
 DEF_KERNEL(lin_vis, 128)
-DEF_KERNEL(lm_reduce, 64)
-DEF_KERNEL(lin_small, 64)
+DEF_KERNEL(lm_reduce, 128)
+DEF_KERNEL(lin_small, 128)
 DEF_KERNEL(asm_items, 128)
 DEF_KERNEL(syrk, 256)
 DEF_KERNEL(solve, 512)
@@ -463,9 +463,9 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     CK(dev_d2d(bd.x_cur, bd.x_init, xs, st)); CK(dev_d2d(bd.x_cand, bd.x_init, xs, st));
     if (!(what & RUN_REANCHOR) || (what & RUN_SOLVE)) CK(dev_d2d(bd.x_before, bd.x_init, xs, st));
     CK(dev_d2d(bd.work, b->work_init_dev, sizeof(WinWork) * B, st));
-    const int nt_vis = NT(128), nt_lm = NT(64), nt_small = NT(64), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(512), nt_marg = NT(256);
-    const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total + nt_lm - 1) / nt_lm;
-    const size_t sm_small = (size_t)(nt_small + MAXPRI + 8) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg) * 8;
+    const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(512), nt_marg = NT(256);
+    const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total * LM_ROLES + nt_lm - 1) / nt_lm;
+    const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg) * 8;
     auto lin = [&](int mode) {
         LAUNCH(lin_vis, bd, g_vis, 1, nt_vis, 0, mode, st);
         LAUNCH(lm_reduce, bd, g_lm, 1, nt_lm, 0, mode, st);

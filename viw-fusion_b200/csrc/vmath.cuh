@@ -10,12 +10,14 @@
 #define VIWB_D static inline
 #define VIWB_DM inline
 #define VIWB_SYNC() ((void)0)
+#define VIWB_SYNCWARP() ((void)0)
 #define VIWB_RESTRICT
 #else
 #define VIWB_HD __host__ __device__ __forceinline__
 #define VIWB_D __device__ __forceinline__
 #define VIWB_DM __device__ __forceinline__
 #define VIWB_SYNC() __syncthreads()
+#define VIWB_SYNCWARP() __syncwarp()
 #define VIWB_RESTRICT __restrict__
 #endif
 
