@@ -91,23 +91,14 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_solve_many(vo, probs, states, seconds, threads):
-    """Oracle (C port of the reference algorithm) on `threads` host threads for about `seconds`; returns solves/s."""
-    from concurrent.futures import ThreadPoolExecutor
-    n = len(probs)
-    done = [0] * threads
-    t_end = time.perf_counter() + seconds
-
-    def worker(tid):
-        i = tid
-        while time.perf_counter() < t_end:
-            vo.optimization(probs[i % n], states[i % n], abi.MARGIN_OLD)
-            done[tid] += 1
-            i += threads
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(worker, range(threads)))
-    dt = time.perf_counter() - t0
-    return sum(done) / dt, sum(done), dt
+    """Oracle (C port of the reference algorithm) on `threads` pthreads inside the C library for about `seconds`;
+    each optimisation is single-threaded like Ceres' default.  Returns (solves/s, count, seconds)."""
+    flags = [abi.MARGIN_OLD] * len(probs)
+    n, dt = vo.optimization_throughput(probs, states, flags, threads, 1)         # calibration pass
+    rate = n / dt
+    repeat = max(1, int(round(seconds * rate / max(1, n))))
+    n, dt = vo.optimization_throughput(probs, states, flags, threads, repeat)
+    return n / dt, n, dt
 
 
 def main():
@@ -138,10 +129,10 @@ def main():
             a, sm, q = vo.optimization(p, st, abi.MARGIN_OLD)
             priors.append(q)
             prev.append(a)
-        probs, states = replicate(seqs, priors, prev, 1, 0)
+        probs, states = replicate(seqs, priors, prev, max(1, (2 * cores) // max(1, len(seqs))), 0)
         per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + warmup)))
         for _ in range(warmup):
-            cpu_solve_many(vo, probs, states, 0.5, cores)
+            vo.optimization_throughput(probs, states, [abi.MARGIN_OLD] * len(probs), cores, 1)
         tot_n, tot_t = 0, 0.0
         for _ in range(args.steps):
             rate, n, dt = cpu_solve_many(vo, probs, states, per_step, cores)

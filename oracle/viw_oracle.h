@@ -64,6 +64,10 @@ int vo_marginalize(const viwb_problem *problem, const double *state, int margin_
 int vo_optimization(const viwb_problem *problem, double *state, const viwb_options *options, int margin_flag,
                     viwb_summary *summary, viwb_prior *prior_out);
 
+/* n independent windows on `threads` pthreads, `repeat` passes (bench.py CPU arm); returns the number of optimisations run */
+long vo_optimization_throughput(int n, const viwb_problem *problems, const double *const *states, const int32_t *flags,
+                                const viwb_options *opt, int threads, int repeat);
+
 /* IntegrationBase::propagate (integration_base.h:63-167) on a buffer of samples -> the 287-double record.
  * acc/gyr have (n+1) rows (sample 0 = acc_0/gyr_0), dt has n entries; noise = {ACC_N, GYR_N, ACC_W, GYR_W}. */
 void vo_imu_preintegrate(int n, const double *dt, const double *acc, const double *gyr, const double *ba,

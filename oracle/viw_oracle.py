@@ -183,3 +183,21 @@ def sym_eig(A):
     w, V = np.zeros(n), np.zeros((n, n))
     lib().vo_sym_eig(C.c_int(n), _dp(A), _dp(w), _dp(V))
     return w, V
+
+
+def optimization_throughput(problems, states, flags, threads, repeat=1, options=None):
+    """Run len(problems) * repeat optimisations on `threads` pthreads inside the C library; returns (count, seconds)."""
+    import time
+    B = len(problems)
+    arr = (abi.Problem * B)()
+    for i, p in enumerate(problems):
+        p.fill(arr[i])
+    sts = [np.ascontiguousarray(s, np.float64) for s in states]
+    sp = (abi.c_double_p * B)(*[_dp(s) for s in sts])
+    fl = (C.c_int32 * B)(*[int(f) for f in flags])
+    opt = options if options is not None else abi.default_options()
+    f = lib().vo_optimization_throughput
+    f.restype = C.c_long
+    t0 = time.perf_counter()
+    n = f(C.c_int(B), arr, sp, fl, C.byref(opt), C.c_int(threads), C.c_int(repeat))
+    return int(n), time.perf_counter() - t0

@@ -326,3 +326,38 @@ int vo_optimization(const viwb_problem *pb, double *state, const viwb_options *o
     if (pb->frame_count < VIWB_WINDOW_SIZE || !out) return 0;          /* estimator.cpp:1666 */
     return vo_marginalize(pb, state, flag, out, NULL, NULL, NULL);
 }
+
+/* ------------------------------------------------------------------ multi-threaded batch (CPU baseline arm of bench.py)
+ * n independent windows on `threads` pthreads; each optimisation itself is single-threaded like Ceres' default
+ * (estimator.cpp:1646 leaves num_threads commented out).  repeat > 1 cycles over the windows to fill a time budget. */
+#include <pthread.h>
+typedef struct { const viwb_problem *pb; const double *const *states; const int32_t *flags; const viwb_options *opt; int n, repeat, tid, nthreads; long done; } vo_job;
+static void *vo_worker(void *arg) {
+    vo_job *j = (vo_job *)arg;
+    viwb_prior out; double *x0 = (double *)malloc(sizeof(double) * VIWB_STATE_FIXED), *J = (double *)malloc(sizeof(double) * VIWB_MAX_PRIOR_DIM * VIWB_MAX_PRIOR_DIM), *r = (double *)malloc(sizeof(double) * VIWB_MAX_PRIOR_DIM);
+    out.x0 = x0; out.J = J; out.r = r;
+    double *st = (double *)malloc(sizeof(double) * (VIWB_STATE_FIXED + VIWB_MAX_LANDMARKS));
+    viwb_summary sum;
+    for (int rep = 0; rep < j->repeat; rep++)
+        for (int i = j->tid; i < j->n; i += j->nthreads) {
+            memcpy(st, j->states[i], sizeof(double) * (VIWB_STATE_FIXED + j->pb[i].num_landmarks));
+            vo_optimization(&j->pb[i], st, j->opt, j->flags ? j->flags[i] : -1, &sum, j->flags ? &out : NULL);
+            j->done++;
+        }
+    free(x0); free(J); free(r); free(st);
+    return NULL;
+}
+long vo_optimization_throughput(int n, const viwb_problem *problems, const double *const *states, const int32_t *flags,
+                                const viwb_options *opt, int threads, int repeat) {
+    if (threads < 1) threads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+    vo_job *jobs = (vo_job *)calloc(threads, sizeof(vo_job));
+    for (int t = 0; t < threads; t++) {
+        jobs[t].pb = problems; jobs[t].states = states; jobs[t].flags = flags; jobs[t].opt = opt; jobs[t].n = n; jobs[t].repeat = repeat; jobs[t].tid = t; jobs[t].nthreads = threads;
+        pthread_create(&th[t], NULL, vo_worker, &jobs[t]);
+    }
+    long done = 0;
+    for (int t = 0; t < threads; t++) { pthread_join(th[t], NULL); done += jobs[t].done; }
+    free(th); free(jobs);
+    return done;
+}
