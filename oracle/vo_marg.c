@@ -331,6 +331,7 @@ int vo_optimization(const viwb_problem *pb, double *state, const viwb_options *o
  * n independent windows on `threads` pthreads; each optimisation itself is single-threaded like Ceres' default
  * (estimator.cpp:1646 leaves num_threads commented out).  repeat > 1 cycles over the windows to fill a time budget. */
 #include <pthread.h>
+#include <malloc.h>
 typedef struct { const viwb_problem *pb; const double *const *states; const int32_t *flags; const viwb_options *opt; int n, repeat, tid, nthreads; long done; } vo_job;
 static void *vo_worker(void *arg) {
     vo_job *j = (vo_job *)arg;
@@ -350,6 +351,9 @@ static void *vo_worker(void *arg) {
 long vo_optimization_throughput(int n, const viwb_problem *problems, const double *const *states, const int32_t *flags,
                                 const viwb_options *opt, int threads, int repeat) {
     if (threads < 1) threads = 1;
+    /* the per-solve work buffers (MBs) would otherwise be mmap'ed/unmapped on every call and the threads would serialise on
+     * the process' mm lock: keep them in the per-thread malloc arenas (gives the CPU arm its best case) */
+    mallopt(M_MMAP_THRESHOLD, 1 << 30); mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_TOP_PAD, 64 << 20);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
     vo_job *jobs = (vo_job *)calloc(threads, sizeof(vo_job));
     for (int t = 0; t < threads; t++) {

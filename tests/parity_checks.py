@@ -337,3 +337,18 @@ def check_unsorted_table_and_threads(ctx, oracle):
     for i in (0, 7, 19):
         a, sm, q = ctx.optimization(probs[i], sts[i], abi.MARGIN_OLD)
         assert np.array_equal(a, out_s[i]) and q.n == out_pr[i].n and np.array_equal(q.Jmat(), out_pr[i].Jmat())
+
+
+def check_solver_time_limit(ctx, oracle, cid=4):
+    """SOLVER_TIME (estimator.cpp:1650-1653): an already-expired limit lets exactly one iteration be decided, which is what
+    the oracle gives with max_num_iterations = 1; no limit (0) is the parity configuration."""
+    cfg = synth.make_config(cid)
+    prob, st, _ = synth.Sequence(cfg, 0, 11).window(0)
+    opt = abi.default_options()
+    opt.max_solver_time_in_seconds = 1e-9
+    s1, sm1 = ctx.window_solve(prob, st, opt)
+    o1 = abi.default_options()
+    o1.max_num_iterations = 1
+    s0, sm0 = oracle.window_solve(prob, st, o1)
+    assert sm1.termination_type == abi.NO_CONVERGENCE and sm1.num_iterations == sm0.num_iterations == 2
+    assert np.abs(s1 - s0).max() <= 1e-9

@@ -64,3 +64,7 @@ def test_track_checked(emu):
 
 def test_unsorted_table_and_parallel_lowering(emu, oracle):
     pc.check_unsorted_table_and_threads(emu, oracle)
+
+
+def test_solver_time_limit(emu, oracle):
+    pc.check_solver_time_limit(emu, oracle)

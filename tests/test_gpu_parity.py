@@ -104,3 +104,7 @@ def test_lk_empty_and_tiny(gpu_ctx):
 
 def test_unsorted_table_and_parallel_lowering(gpu_ctx, oracle):
     pc.check_unsorted_table_and_threads(gpu_ctx, oracle)
+
+
+def test_solver_time_limit(gpu_ctx, oracle):
+    pc.check_solver_time_limit(gpu_ctx, oracle)

@@ -234,7 +234,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
         }
         VIWB_SYNC();
         // FinalizeIterationAndCheckIfMinimizerCanContinue (gradient tolerance is tested in phase B)
-        if (ww.iteration >= op.max_num_iterations) { VIWB_SYNC(); if (tid == 0) terminate(ww, 1); return; }
+        if (ww.iteration >= op.max_num_iterations || mode == 3) { VIWB_SYNC(); if (tid == 0) terminate(ww, 1); return; }   // mode 3: max_solver_time reached
         if (ww.radius <= op.min_radius) { VIWB_SYNC(); if (tid == 0) terminate(ww, 0); return; }
     }
     VIWB_SYNC();

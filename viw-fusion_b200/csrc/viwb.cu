@@ -125,6 +125,7 @@ struct viwb_batch {
     double algorithmic_bytes;
     bool any_marg;
     int max_iter;
+    double max_time;       // max_solver_time_in_seconds (0 = off): checked on the host between rounds, like Ceres' wall-clock test
     size_t nrec_imu, nrec_wheel, nrec_plane;
 };
 
@@ -349,6 +350,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     viwb_options defopt; viwb_default_options(&defopt);
     const viwb_options *opt = options ? options : &defopt;
     b->max_iter = opt->max_num_iterations;
+    b->max_time = opt->max_solver_time_in_seconds;
     BatchDev &bd = b->bd; memset(&bd, 0, sizeof bd);
     bd.B = B; opts_from(opt, bd.opt);
     b->meta.resize(B); b->out_mode.assign(B, 2); b->in_prior.resize(B); b->state_sizes.resize(B); b->prior_n.assign(B, 0);
@@ -483,9 +485,18 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     }
     if (what & RUN_LIN_ONLY) { lin(MODE_SOLVE); LAUNCH(solve, bd, B, 1, nt_solve, sm_solve, 2, st); ctx->launches++; }
     if (what & RUN_SOLVE) {
-        for (int round = 0; round <= b->max_iter; round++) {
+        // SOLVER_TIME (estimator.cpp:1650-1653): Ceres tests the wall clock after every iteration; here the host
+        // waits for each round only when a limit is set, and the round after the limit just decides the pending
+        // candidate and stops (NO_CONVERGENCE).  Disabled (0) keeps the whole solve asynchronous.
+        const auto t_start = std::chrono::steady_clock::now();
+        bool last = false;
+        for (int round = 0; round <= b->max_iter && !last; round++) {
+            if (b->max_time > 0.0 && round > 0) {
+                CK(dev_sync(st));
+                last = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() >= b->max_time;
+            }
             lin(MODE_SOLVE);
-            LAUNCH(solve, bd, B, 1, nt_solve, sm_solve, 0, st);
+            LAUNCH(solve, bd, B, 1, nt_solve, sm_solve, last ? 3 : 0, st);
             ctx->launches++;
         }
     }

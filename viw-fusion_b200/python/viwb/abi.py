@@ -22,6 +22,7 @@ BLK_PLANE_R, BLK_PLANE_Z, BLK_SX, BLK_SY, BLK_SW, BLK_TD, BLK_TD_WHEEL, BLK_LAND
 BLOCK_PRESENT, BLOCK_CONSTANT = 1, 2
 F_PROJ_2F1C, F_PROJ_2F2C, F_PROJ_1F2C, F_IMU, F_WHEEL, F_PLANE = 0, 1, 2, 3, 4, 5
 MARGIN_OLD, MARGIN_SECOND_NEW = 0, 1
+CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2      # enum viwb_termination
 LK_USE_INITIAL_FLOW = 4
 
 # parameter block signature of each factor class (global sizes), as in the SizedCostFunction<> templates
