@@ -294,6 +294,36 @@ int viwb_track_checked(viwb_context *ctx, const uint8_t *img_a, const uint8_t *i
                        int stride, const float *pts_a, float *pts_b, int n, int mode, int flow_back,
                        uint8_t *status);
 
+/* ---- batched tracker: one camera tick of `streams` independent VIO sessions per submission --------
+ * Replaces, per stream, the four calcOpticalFlowPyrLK calls of one FeatureTracker::trackImage()
+ * (feature_tracker.cpp:139 temporal forward, :145-146 temporal reverse, :240 stereo forward, :244 stereo
+ * reverse) and the status rules of :147-162 / :245-251.  The object keeps three device image slots per
+ * stream; uploading a new `cur` image turns the previous one (and its pyramid) into `prev`, as
+ * trackImage's prev_img = cur_img (:296) does.  Point arrays are flat [streams][max_points][2] floats,
+ * status arrays [streams][max_points]; n_* give the valid count per stream. */
+typedef struct viwb_lk_batch viwb_lk_batch;
+int viwb_lk_batch_create(viwb_context *ctx, int streams, int width, int height, int max_points, int stereo,
+                         int flow_back /* FLOW_BACK */, viwb_lk_batch **out);
+void viwb_lk_batch_destroy(viwb_lk_batch *b);
+/* Host -> device.  prev/cur/right: `streams` image pointers each (8-bit, `stride` bytes per row) or NULL to
+ * keep what the device holds (prev is only needed on the first tick).  prev_pts: points of the previous
+ * image to follow into cur; stereo_pts: points of cur to follow into right (trackImage runs the stereo
+ * match on cur_pts after goodFeaturesToTrack topped them up, :200-240).  Asynchronous on the context stream;
+ * the host buffers must stay valid until the next synchronising call. */
+int viwb_lk_batch_upload(viwb_lk_batch *b, const uint8_t *const *prev, const uint8_t *const *cur,
+                         const uint8_t *const *right, int stride, const float *prev_pts, const int32_t *n_prev,
+                         const float *stereo_pts, const int32_t *n_stereo);
+/* pyramids of the freshly uploaded images + forward / reverse flows + status rules; device only, asynchronous */
+int viwb_lk_batch_run(viwb_lk_batch *b);
+/* Device -> host (synchronises). Any pointer may be NULL. */
+int viwb_lk_batch_download(viwb_lk_batch *b, float *cur_pts, uint8_t *status, float *right_pts, uint8_t *status_right);
+/* compulsory HBM bytes of one viwb_lk_batch_run (new images read once, coarser levels written once, points) */
+double viwb_lk_batch_algorithmic_bytes(const viwb_lk_batch *b);
+
+/* Page-lock / unlock caller-owned host memory (camera frame buffers) for asynchronous full-rate uploads. */
+int viwb_host_register(viwb_context *ctx, void *ptr, size_t bytes);
+int viwb_host_unregister(viwb_context *ctx, void *ptr);
+
 #ifdef __cplusplus
 }
 #endif

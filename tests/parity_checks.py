@@ -352,3 +352,50 @@ def check_solver_time_limit(ctx, oracle, cid=4):
     s0, sm0 = oracle.window_solve(prob, st, o1)
     assert sm1.termination_type == abi.NO_CONVERGENCE and sm1.num_iterations == sm0.num_iterations == 2
     assert np.abs(s1 - s0).max() <= 1e-9
+
+
+def check_lk_batch(ctx, streams=3, w=320, h=240, min_both=30):
+    """The batched tracker (one tick of several camera streams per submission) reproduces, stream by stream, the
+    trackImage logic restated with cv2 calls, over two consecutive ticks (the second one re-uses the resident
+    previous image and its pyramid) and with ragged point counts."""
+    import cv2
+    maxn = 160
+    ims = [lk_images(10 + s, w, h) for s in range(streams)]
+    img0 = np.stack([i[0] for i in ims]); img1 = np.stack([i[1] for i in ims])
+    right = np.stack([np.ascontiguousarray(np.roll(i[1], -4, axis=1)) for i in ims])          # 4 px disparity
+    img2 = np.stack([np.ascontiguousarray(np.roll(np.roll(i[1], 2, axis=0), -3, axis=1)) for i in ims])
+    right2 = np.stack([np.ascontiguousarray(np.roll(i, -4, axis=1)) for i in img2])
+    pts = np.zeros((streams, maxn, 2), np.float32); n = np.zeros(streams, np.int32)
+    for s in range(streams):
+        p = ims[s][2][: maxn - 7 * s]
+        p = p[: len(p) - 3 * s]                           # ragged counts
+        n[s] = len(p); pts[s, : n[s]] = p
+    lb = ctx.lk_batch(streams, w, h, maxn, stereo=True, flow_back=True)
+    try:
+        def compare(prev, cur, rgt, p_in, n_in, sp_in, ns_in, got):
+            cur_pts, st, rp, sr = got
+            for s in range(streams):
+                k = int(n_in[s])
+                p_ref, st_ref = ref_track_checked(prev[s], cur[s], p_in[s, :k], 0, True)
+                assert (st_ref == st[s, :k]).mean() >= 0.99
+                both = (st_ref == 1) & (st[s, :k] == 1)
+                assert both.sum() > min_both and np.abs(p_ref[both] - cur_pts[s, :k][both]).max() <= 1e-2
+                k2 = int(ns_in[s])
+                q_ref, sq_ref = ref_track_checked(cur[s], rgt[s], sp_in[s, :k2], 1, True)
+                assert (sq_ref == sr[s, :k2]).mean() >= 0.99
+                both = (sq_ref == 1) & (sr[s, :k2] == 1)
+                assert both.sum() > min_both and np.abs(q_ref[both] - rp[s, :k2][both]).max() <= 1e-2
+        # tick 1: prev + cur + right uploaded; stereo runs on the (exactly known) positions of the features in cur
+        sp = pts.copy()
+        lb.upload(prev=img0, cur=img1, right=right, prev_pts=pts, n_prev=n, stereo_pts=sp, n_stereo=n)
+        lb.run()
+        got = [a.copy() for a in lb.download()]
+        compare(img0, img1, right, pts, n, sp, n, got)
+        # tick 2: only the new images travel; the tracked points of tick 1 become prev_pts
+        p2 = got[0].copy(); n2 = n.copy()
+        lb.upload(cur=img2, right=right2, prev_pts=p2, n_prev=n2, stereo_pts=p2, n_stereo=n2)
+        lb.run()
+        got2 = [a.copy() for a in lb.download()]
+        compare(img1, img2, right2, p2, n2, p2, n2, got2)
+    finally:
+        lb.close()

@@ -68,3 +68,7 @@ def test_unsorted_table_and_parallel_lowering(emu, oracle):
 
 def test_solver_time_limit(emu, oracle):
     pc.check_solver_time_limit(emu, oracle)
+
+
+def test_lk_batch(emu):
+    pc.check_lk_batch(emu, streams=2, w=200, h=160, min_both=8)

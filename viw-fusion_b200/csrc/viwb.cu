@@ -102,10 +102,13 @@ struct viwb_context {
     std::string err;
     bool attrs_set;
     Arena arena;
+    struct viwb_lk_batch *lk1;      // one-stream LK state behind viwb_lk_track / viwb_track_checked
 };
 
 static int fail(viwb_context *ctx, int code, const std::string &msg) { if (ctx) ctx->err = msg; return code; }
 #define CK(call) do { int e_ = (call); if (e_) return fail(ctx, VIWB_ERR_CUDA, std::string(#call) + ": " + dev_errstr(e_)); } while (0)
+
+#include "lk_host.inl"
 
 // ====================================================================================== batch
 struct HostPrior { int valid, n, nb; int block_id[NB], block_idx[NB]; std::vector<double> x0, J, r; };
@@ -579,7 +582,7 @@ static void batch_free(viwb_context *ctx, viwb_batch *b) {
 extern "C" int viwb_create(int device, viwb_context **out) {
     if (!out) return VIWB_ERR_INVALID;
     viwb_context *ctx = new viwb_context();
-    ctx->device = device; ctx->launches = 0; ctx->attrs_set = false; ctx->stream = 0;
+    ctx->device = device; ctx->launches = 0; ctx->attrs_set = false; ctx->stream = 0; ctx->lk1 = nullptr;
 #ifndef VIWB_HOST_EMU
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -592,8 +595,8 @@ extern "C" int viwb_create(int device, viwb_context **out) {
 }
 extern "C" void viwb_destroy(viwb_context *ctx) {
     if (!ctx) return;
+    lk_batch_free(ctx->lk1);
 #ifndef VIWB_HOST_EMU
-    lk_release(ctx->device);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
 #endif
     arena_release(ctx->arena);
@@ -873,20 +876,49 @@ extern "C" int viwb_lk_track(viwb_context *ctx, const uint8_t *prev_img, const u
     if (!ctx || !prev_img || !next_img || !prev_pts || !next_pts || !status || n < 0 || width <= 0 || height <= 0) return VIWB_ERR_INVALID;
     if (win_size != 21) return fail(ctx, VIWB_ERR_UNSUPPORTED, "only the reference's 21x21 window is supported");
     if (max_level < 0 || max_level > 3) return fail(ctx, VIWB_ERR_UNSUPPORTED, "maxLevel must be 0..3");
-    long long nl = 0;
-    int rc = lk_track_host(ctx->device, ctx->stream, prev_img, next_img, width, height, stride, prev_pts, next_pts, n, max_level, max_iter, eps, flags,
-                           min_eig_threshold, status, err, &nl);
-    ctx->launches += nl;
-    if (rc) return fail(ctx, VIWB_ERR_CUDA, "lk_track failed");
-    return VIWB_OK;
+    return lk_track_single(ctx, prev_img, next_img, width, height, stride, prev_pts, next_pts, n, max_level, max_iter, eps, flags, min_eig_threshold, status, err);
 }
 
 extern "C" int viwb_track_checked(viwb_context *ctx, const uint8_t *img_a, const uint8_t *img_b, int width, int height, int stride,
                                   const float *pts_a, float *pts_b, int n, int mode, int flow_back, uint8_t *status) {
-    if (!ctx || !img_a || !img_b || !pts_a || !pts_b || !status || n < 0) return VIWB_ERR_INVALID;
-    long long nl = 0;
-    int rc = lk_track_checked_host(ctx->device, ctx->stream, img_a, img_b, width, height, stride, pts_a, pts_b, n, mode, flow_back, status, &nl);
-    ctx->launches += nl;
-    if (rc) return fail(ctx, VIWB_ERR_CUDA, "track_checked failed");
+    if (!ctx || !img_a || !img_b || !pts_a || !pts_b || !status || n < 0 || width <= 0 || height <= 0 || (mode != 0 && mode != 1)) return VIWB_ERR_INVALID;
+    return lk_track_checked_single(ctx, img_a, img_b, width, height, stride, pts_a, pts_b, n, mode, flow_back, status);
+}
+
+extern "C" int viwb_lk_batch_create(viwb_context *ctx, int streams, int width, int height, int max_points, int stereo, int flow_back, viwb_lk_batch **out) {
+    if (!ctx || !out || streams <= 0 || width <= 0 || height <= 0 || max_points <= 0) return VIWB_ERR_INVALID;
+    return lk_batch_build(ctx, streams, width, height, max_points, stereo ? 1 : 0, flow_back ? 1 : 0, out);
+}
+extern "C" void viwb_lk_batch_destroy(viwb_lk_batch *b) { lk_batch_free(b); }
+extern "C" int viwb_lk_batch_upload(viwb_lk_batch *b, const uint8_t *const *prev, const uint8_t *const *cur, const uint8_t *const *right, int stride,
+                                    const float *prev_pts, const int32_t *n_prev, const float *stereo_pts, const int32_t *n_stereo) {
+    if (!b || stride < b->w) return VIWB_ERR_INVALID;
+    return lk_batch_upload(b, prev, cur, right, stride, prev_pts, n_prev, stereo_pts, n_stereo);
+}
+extern "C" int viwb_lk_batch_run(viwb_lk_batch *b) { return b ? lk_batch_execute(b, 3) : VIWB_ERR_INVALID; }
+extern "C" int viwb_lk_batch_download(viwb_lk_batch *b, float *cur_pts, uint8_t *status, float *right_pts, uint8_t *status_right) {
+    return b ? lk_batch_fetch(b, cur_pts, status, right_pts, status_right) : VIWB_ERR_INVALID;
+}
+extern "C" double viwb_lk_batch_algorithmic_bytes(const viwb_lk_batch *b) {
+    if (!b) return 0.0;
+    // per tick: read the new left (+right) level-0 images once, write their three coarser levels; points in/out
+    double img = 0.0; for (int l = 0; l <= b->levels; l++) img += (double)b->lw[l] * b->lh[l];
+    return (double)b->F * ((b->stereo ? 2.0 : 1.0) * img + (double)b->maxn * (b->stereo ? 2 : 1) * (8 + 8 + 1));
+}
+// page-lock caller-owned host buffers (camera frames) so that uploads run at full PCIe rate and asynchronously
+extern "C" int viwb_host_register(viwb_context *ctx, void *ptr, size_t bytes) {
+    if (!ctx || !ptr) return VIWB_ERR_INVALID;
+#ifndef VIWB_HOST_EMU
+    CK((int)cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+#else
+    (void)bytes;
+#endif
+    return VIWB_OK;
+}
+extern "C" int viwb_host_unregister(viwb_context *ctx, void *ptr) {
+    if (!ctx || !ptr) return VIWB_ERR_INVALID;
+#ifndef VIWB_HOST_EMU
+    CK((int)cudaHostUnregister(ptr));
+#endif
     return VIWB_OK;
 }

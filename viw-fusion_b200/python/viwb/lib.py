@@ -18,7 +18,9 @@ EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", 
            "viwb_default_globals", "viwb_factor_evaluate", "viwb_prior_evaluate", "viwb_window_solve", "viwb_gauge_reanchor",
            "viwb_marginalize", "viwb_optimization", "viwb_optimization_batch", "viwb_batch_create", "viwb_batch_reset_states",
            "viwb_batch_run", "viwb_batch_download", "viwb_batch_algorithmic_bytes", "viwb_batch_destroy",
-           "viwb_debug_normal_equations", "viwb_lk_track", "viwb_track_checked"]
+           "viwb_debug_normal_equations", "viwb_lk_track", "viwb_track_checked", "viwb_lk_batch_create", "viwb_lk_batch_destroy",
+           "viwb_lk_batch_upload", "viwb_lk_batch_run", "viwb_lk_batch_download", "viwb_lk_batch_algorithmic_bytes", "viwb_host_register",
+           "viwb_host_unregister"]
 
 
 class ViwbError(RuntimeError):
@@ -33,6 +35,10 @@ def load(libpath=None):
     lib.viwb_last_error.restype = C.c_char_p
     lib.viwb_launch_count.restype = C.c_longlong
     lib.viwb_batch_algorithmic_bytes.restype = C.c_double
+    lib.viwb_lk_batch_algorithmic_bytes.restype = C.c_double
+    lib.viwb_lk_batch_algorithmic_bytes.argtypes = [C.c_void_p]
+    lib.viwb_lk_batch_destroy.argtypes = [C.c_void_p]
+    lib.viwb_lk_batch_destroy.restype = None
     return lib
 
 
@@ -219,6 +225,78 @@ class Context:
                                              p0.ctypes.data_as(C.c_void_p), p1.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(mode),
                                              C.c_int(1 if flow_back else 0), st.ctypes.data_as(C.c_void_p)), "viwb_track_checked")
         return p1, st
+
+    def lk_batch(self, streams, width, height, max_points, stereo=True, flow_back=True):
+        return LkBatch(self, streams, width, height, max_points, stereo, flow_back)
+
+    def host_register(self, arr):
+        self._ck(self.lib.viwb_host_register(self.h, C.c_void_p(arr.ctypes.data), C.c_size_t(arr.nbytes)), "viwb_host_register")
+
+    def host_unregister(self, arr):
+        self._ck(self.lib.viwb_host_unregister(self.h, C.c_void_p(arr.ctypes.data)), "viwb_host_unregister")
+
+
+class LkBatch:
+    """One camera tick of `streams` independent sessions per submission (viwb_lk_batch_*).
+    Images: uint8 arrays [streams, height, width] (C-contiguous); points: float32 [streams, max_points, 2]."""
+
+    def __init__(self, ctx, streams, width, height, max_points, stereo=True, flow_back=True):
+        self.ctx, self.F, self.w, self.h, self.maxn, self.stereo = ctx, streams, width, height, max_points, stereo
+        self.hnd = C.c_void_p()
+        ctx._ck(ctx.lib.viwb_lk_batch_create(ctx.h, C.c_int(streams), C.c_int(width), C.c_int(height), C.c_int(max_points), C.c_int(1 if stereo else 0),
+                                             C.c_int(1 if flow_back else 0), C.byref(self.hnd)), "viwb_lk_batch_create")
+        self.cur_pts = np.zeros((streams, max_points, 2), np.float32)
+        self.right_pts = np.zeros((streams, max_points, 2), np.float32)
+        self.status = np.zeros((streams, max_points), np.uint8)
+        self.status_right = np.zeros((streams, max_points), np.uint8)
+        self._keep = None
+
+    def _ptrs(self, imgs):
+        if imgs is None:
+            return None, None
+        assert imgs.dtype == np.uint8 and imgs.shape == (self.F, self.h, self.w) and imgs.strides[2] == 1
+        arr = (C.c_void_p * self.F)(*[imgs.ctypes.data + f * imgs.strides[0] for f in range(self.F)])
+        return arr, int(imgs.strides[1])
+
+    def upload(self, prev=None, cur=None, right=None, prev_pts=None, n_prev=None, stereo_pts=None, n_stereo=None):
+        strides = set()
+        pp, s0 = self._ptrs(prev); pc, s1 = self._ptrs(cur); pr, s2 = self._ptrs(right)
+        for s in (s0, s1, s2):
+            if s is not None:
+                strides.add(s)
+        assert len(strides) <= 1
+        stride = strides.pop() if strides else self.w
+
+        def f32(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, np.float32)
+            assert a.shape == (self.F, self.maxn, 2)
+            return a
+
+        def i32(a):
+            return None if a is None else np.ascontiguousarray(a, np.int32)
+        a0, a1, c0, c1 = f32(prev_pts), f32(stereo_pts), i32(n_prev), i32(n_stereo)
+        self._keep = (prev, cur, right, a0, a1, c0, c1, pp, pc, pr)      # host buffers must outlive the asynchronous copies
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self.ctx._ck(self.ctx.lib.viwb_lk_batch_upload(self.hnd, pp, pc, pr, C.c_int(stride), vp(a0), vp(c0), vp(a1), vp(c1)), "viwb_lk_batch_upload")
+
+    def run(self):
+        self.ctx._ck(self.ctx.lib.viwb_lk_batch_run(self.hnd), "viwb_lk_batch_run")
+
+    def download(self):
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.ctx._ck(self.ctx.lib.viwb_lk_batch_download(self.hnd, vp(self.cur_pts), vp(self.status), vp(self.right_pts) if self.stereo else None,
+                                                         vp(self.status_right) if self.stereo else None), "viwb_lk_batch_download")
+        return self.cur_pts, self.status, self.right_pts, self.status_right
+
+    def algorithmic_bytes(self):
+        return float(self.ctx.lib.viwb_lk_batch_algorithmic_bytes(self.hnd))
+
+    def close(self):
+        if self.hnd:
+            self.ctx.lib.viwb_lk_batch_destroy(self.hnd)
+            self.hnd = C.c_void_p()
 
 
 class Batch:
