@@ -30,6 +30,8 @@ from viwb import abi, synth  # noqa: E402
 
 METRIC = "sliding-window solves/sec (10 KF, 150 feat)"
 UNIT = "solves/s"
+WORKLOAD = ("C2 EuRoC-shaped stereo+IMU stream, 150 feat/frame: per window one camera tick of LK (4 calcOpticalFlowPyrLK-equivalent passes on "
+            "752x480 stereo frames) + Estimator::optimization() on a window with prior (8 dogleg iterations + gauge re-anchor + MARGIN_OLD marginalisation)")
 
 
 def make_windows(rank, distinct, copies, config_id=2):
@@ -90,6 +92,27 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores():
+    """Host threads this process can really run on: affinity mask, capped by the cgroup CPU quota (a container may see
+    128 CPUs and be allowed 16)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            q, per = open(path).read().split()[:2]
+            if q != "max":
+                n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+        except Exception:
+            pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            n = max(1, min(n, int(q / per + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_solve_many(vo, probs, states, seconds, threads):
     """Oracle (C port of the reference algorithm) on `threads` pthreads inside the C library for about `seconds`;
     each optimisation is single-threaded like Ceres' default.  Returns (solves/s, count, seconds)."""
@@ -98,6 +121,102 @@ def cpu_solve_many(vo, probs, states, seconds, threads):
     rate = n / dt
     repeat = max(1, int(round(seconds * rate / max(1, n))))
     n, dt = vo.optimization_throughput(probs, states, flags, threads, repeat)
+    return n / dt, n, dt
+
+
+# ------------------------------------------------------------------------------------------------ camera frames (LK)
+IMG_W, IMG_H, N_FEAT = 752, 480, 150
+
+
+def make_scenes(rank, scenes):
+    """Synthetic EuRoC-sized stereo scenes: band-limited noise texture seen in two consecutive ticks (sub-pixel image
+    motion) by a left and a right camera (horizontal disparity).  Returns per scene the four images and the feature
+    positions in both ticks (a jittered 15x10 grid: ~150 features per frame, BASELINE.json configs[1])."""
+    from scipy import ndimage
+    out = []
+    for k in range(scenes):
+        rng = np.random.default_rng(5000 + 131 * rank + k)
+        tex = ndimage.gaussian_filter(rng.normal(size=(IMG_H + 64, IMG_W + 64)).astype(np.float32), 2.0)
+        tex = (tex - tex.min()) / (tex.max() - tex.min()) * 255.0
+        dx, dy, disp = rng.uniform(-4, 4), rng.uniform(-3, 3), rng.uniform(3, 12)
+
+        def view(sx, sy):
+            return np.ascontiguousarray(ndimage.shift(tex, (sy, sx), order=1, mode="reflect")[32:32 + IMG_H, 32:32 + IMG_W].astype(np.uint8))
+        gx, gy = np.meshgrid(np.linspace(50, IMG_W - 50, 15), np.linspace(50, IMG_H - 50, 10))
+        p0 = (np.stack([gx.ravel(), gy.ravel()], 1) + rng.uniform(-8, 8, (N_FEAT, 2))).astype(np.float32)
+        out.append({"left": [view(0, 0), view(dx, dy)], "right": [view(-disp, 0), view(dx - disp, dy)],
+                    "pts": [p0, (p0 + np.float32([dx, dy])).astype(np.float32)]})
+    return out
+
+
+class FrameFeed:
+    """Host-side camera buffers of F streams (page-locked): tick t shows image t%2 of each stream's scene."""
+
+    def __init__(self, ctx, scenes, streams):
+        self.ctx, self.F = ctx, streams
+        idx = np.arange(streams) % len(scenes)
+        self.left = [np.ascontiguousarray(np.stack([scenes[i]["left"][t] for i in idx])) for t in (0, 1)]
+        self.right = [np.ascontiguousarray(np.stack([scenes[i]["right"][t] for i in idx])) for t in (0, 1)]
+        self.pts = [np.ascontiguousarray(np.stack([scenes[i]["pts"][t] for i in idx])) for t in (0, 1)]
+        self.n = np.full(streams, N_FEAT, np.int32)
+        if ctx is not None:
+            for a in self.left + self.right:
+                ctx.host_register(a)
+
+    def tick_bytes(self):
+        return self.left[0].nbytes + self.right[0].nbytes + 2 * self.pts[0].nbytes + 2 * self.n.nbytes
+
+    def close(self):
+        if self.ctx is not None:
+            for a in self.left + self.right:
+                self.ctx.host_unregister(a)
+
+
+def cv_track_frame(cv2, prev, cur, right, p_prev, p_cur):
+    """The four calcOpticalFlowPyrLK calls + status rules of one FeatureTracker::trackImage (feature_tracker.cpp:139-162, 240-251)."""
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+    h, w = prev.shape
+    c, st, _ = cv2.calcOpticalFlowPyrLK(prev, cur, p_prev.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3)
+    rp, rs, _ = cv2.calcOpticalFlowPyrLK(cur, prev, c, p_prev.reshape(-1, 1, 2).copy(), winSize=(21, 21), maxLevel=1, criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+    c2, rp2 = c.reshape(-1, 2), rp.reshape(-1, 2)
+    d = np.sqrt(((p_prev.astype(np.float64) - rp2) ** 2).sum(1))
+    ci = np.rint(c2).astype(np.int64)
+    inb = (ci[:, 0] >= 1) & (ci[:, 0] < w - 1) & (ci[:, 1] >= 1) & (ci[:, 1] < h - 1)
+    st_t = (st.reshape(-1) > 0) & (rs.reshape(-1) > 0) & (d <= 0.5) & inb
+    r, st2, _ = cv2.calcOpticalFlowPyrLK(cur, right, p_cur.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3)
+    b, st3, _ = cv2.calcOpticalFlowPyrLK(right, cur, r, None, winSize=(21, 21), maxLevel=3)
+    r2, b2 = r.reshape(-1, 2), b.reshape(-1, 2)
+    d2 = np.sqrt(((p_cur.astype(np.float64) - b2) ** 2).sum(1))
+    ri = np.rint(r2).astype(np.int64)
+    inb2 = (ri[:, 0] >= 1) & (ri[:, 0] < w - 1) & (ri[:, 1] >= 1) & (ri[:, 1] < h - 1)
+    st_s = (st2.reshape(-1) > 0) & (st3.reshape(-1) > 0) & (d2 <= 0.5) & inb2
+    return c2, st_t, r2, st_s
+
+
+def cpu_lk_many(scenes, seconds, threads):
+    """OpenCV's LK (the reference's tracker) on `threads` host threads, one camera frame per task; returns (frames/s, frames, seconds)."""
+    try:
+        import cv2
+    except Exception:
+        return None, 0, 0.0
+    from concurrent.futures import ThreadPoolExecutor
+    cv2.setNumThreads(1 if threads > 1 else 1)
+
+    def one(i):
+        sc = scenes[i % len(scenes)]
+        cv_track_frame(cv2, sc["left"][0], sc["left"][1], sc["right"][1], sc["pts"][0], sc["pts"][1])
+    t0 = time.perf_counter()
+    one(0)
+    per = time.perf_counter() - t0
+    n = max(threads, int(seconds / max(per, 1e-4)) * threads)
+    t0 = time.perf_counter()
+    if threads > 1:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, range(n)))
+    else:
+        for i in range(n):
+            one(i)
+    dt = time.perf_counter() - t0
     return n / dt, n, dt
 
 
@@ -111,6 +230,8 @@ def main():
     ap.add_argument("--copies", type=int, default=32, help="perturbed initial guesses per sequence (batch = distinct*copies)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-lk", action="store_true", help="window solve only (no feature-tracker work in the step)")
+    ap.add_argument("--scenes", type=int, default=8, help="distinct synthetic stereo scenes per rank (replicated over the streams)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -122,7 +243,7 @@ def main():
             return
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import viw_oracle as vo
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         cfg, seqs, first = make_windows(0, min(args.distinct, 16), 1)
         priors, prev = [], []
         for (p, st, _) in first:
@@ -134,17 +255,30 @@ def main():
         for _ in range(warmup):
             vo.optimization_throughput(probs, states, [abi.MARGIN_OLD] * len(probs), cores, 1)
         tot_n, tot_t = 0, 0.0
+        lk_n, lk_t = 0, 0.0
+        scenes = None if args.no_lk else make_scenes(0, min(args.scenes, 4))
         for _ in range(args.steps):
-            rate, n, dt = cpu_solve_many(vo, probs, states, per_step, cores)
+            rate, n, dt = cpu_solve_many(vo, probs, states, per_step * (0.8 if scenes else 1.0), cores)
             tot_n += n
             tot_t += dt
-        value = tot_n / tot_t
+            if scenes:
+                lr, ln, ldt = cpu_lk_many(scenes, per_step * 0.2, cores)
+                if lr is None:
+                    scenes = None
+                else:
+                    lk_n += ln
+                    lk_t += ldt
+        solve_rate = tot_n / tot_t
+        lk_rate = lk_n / lk_t if lk_n else None
+        # one window = one camera tick of LK + one optimisation, both on the same host cores one after the other
+        value = 1.0 / (1.0 / solve_rate + (1.0 / lk_rate if lk_rate else 0.0))
+        sample = "%d oracle optimisations (C FP64 port of the reference algorithm, %d pthreads) over %.1f s = %.1f solves/s" % (tot_n, cores, tot_t, solve_rate)
+        if lk_rate:
+            sample += "; %d camera ticks of OpenCV calcOpticalFlowPyrLK x4 (%d threads) over %.1f s = %.1f frames/s; value = harmonic combination" % (lk_n, cores, lk_t, lk_rate)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
-                "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": {"workload": "C2 EuRoC-shaped stereo+IMU window with prior, 8 dogleg iterations + MARGIN_OLD marginalisation",
-                                                "windows_per_sample": tot_n // max(1, args.steps)},
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": "%d oracle optimisations (C FP64 port, %d threads) over %.1f s" % (tot_n, cores, tot_t)},
+                "ms_per_step": 1e3 * (tot_t + lk_t) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": WORKLOAD, "windows_per_sample": tot_n // max(1, args.steps), "lk_in_step": bool(lk_rate)},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return
@@ -169,6 +303,21 @@ def main():
     flags = [abi.MARGIN_OLD] * B
     batch = ctx.batch(probs, states, flags)
     alg_bytes = batch.algorithmic_bytes()
+    lk, feed, scenes = None, None, None
+    if not args.no_lk:
+        scenes = make_scenes(rank, args.scenes)
+        feed = FrameFeed(ctx, scenes, B)
+        lk = ctx.lk_batch(B, IMG_W, IMG_H, N_FEAT, stereo=True, flow_back=True)
+        # tick 0 (untimed): both left images resident, the resident "current" image is tick 1
+        lk.upload(prev=feed.left[0], cur=feed.left[1], right=feed.right[1], prev_pts=feed.pts[0], n_prev=feed.n, stereo_pts=feed.pts[1], n_stereo=feed.n)
+        lk.run()
+        lk.download()
+        alg_bytes += lk.algorithmic_bytes()
+
+    def step():
+        if lk is not None:
+            lk.run()            # pyramids of the tick's new left/right images + 4 LK passes + status rules
+        batch.run()
 
     def barrier():
         if world > 1:
@@ -176,7 +325,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(warmup):
-        batch.run()
+        step()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -184,7 +333,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        batch.run()
+        step()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -202,12 +351,26 @@ def main():
     # ---- e2e: host buffers in / out through the C ABI
     e2e_steps = max(1, min(args.steps, 5))
     e2e_call = ctx.prepare_optimization_batch(probs, states, flags)
-    e2e_call()
-    e2e_call()
+    lk_out = None
+    if lk is not None:
+        lk_out = [a.copy() for a in lk.download()]        # results of the timed configuration (tick 1), checked below
+    tick = [0]
+
+    def e2e_step():
+        if lk is not None:
+            t = tick[0] % 2       # the camera delivers image t of every stream; the previous tick's image is already resident
+            lk.upload(cur=feed.left[t], right=feed.right[t], prev_pts=feed.pts[1 - t], n_prev=feed.n, stereo_pts=feed.pts[t], n_stereo=feed.n)
+            lk.run()              # asynchronous: overlaps with the host-side lowering of the windows below
+            tick[0] += 1
+        e2e_call()                # lowering + H2D + solve + re-anchor + marginalise + D2H (synchronises)
+        if lk is not None:
+            lk.download()
+    e2e_step()
+    e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_call()
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -217,14 +380,18 @@ def main():
     e2e_value = world * B * e2e_steps / e2e_s
     h2d = sum(p.vis_obs.nbytes + 4 * 4 * len(p.vis_type) + p.imu_data.nbytes + p.wheel_data.nbytes + 8 * p.state_size +
               (8 * (p.prior.n ** 2 + p.prior.n + abi.STATE_FIXED) if p.prior is not None else 0) for p in probs)
-    d2h = sum(8 * p.state_size + 8 * (abi.MAX_PRIOR_DIM ** 2 + abi.MAX_PRIOR_DIM + abi.STATE_FIXED) for p in probs)
+    nmax = max(int(q.n) for q in pri if q is not None and q.valid) if any(q is not None and q.valid for q in pri) else 0
+    d2h = sum(8 * p.state_size + 8 * (nmax * nmax + abi.MAX_PRIOR_DIM + abi.STATE_FIXED) + 4 * 67 for p in probs)
+    if lk is not None:
+        h2d += feed.tick_bytes()
+        d2h += 2 * B * N_FEAT * (8 + 1)
 
     # ---- live per-kernel timing (CUDA events around every launch, separate pass so the headline is unperturbed)
     roofline, kernels = None, None
     if not args.no_profile:
         ctx.set_profiling(True)
         for _ in range(2):
-            batch.run()
+            step()
         torch.cuda.synchronize()
         prof = ctx.profile()
         ctx.set_profiling(False)
@@ -242,6 +409,8 @@ def main():
         R = sum(sum(abi.block_tsize(b) for b in range(32) if (p.block_flags[b] & 1) and not (p.block_flags[b] & 2)) for p in probs) / B
         pg = sum(p.state_size for p in probs)
         per_launch = {"lin_vis": 112.0 * n_vis + 8.0 * pg, "lm_reduce": 0.0, "assemble": 8.0 * B * (R * R + R), "solve": 8.0 * B * (R * R + R) + 8.0 * pg,
+                      "marg": 8.0 * B * (nmax * nmax + nmax + abi.STATE_FIXED), "asm_items": 8.0 * B * (R * R + R), "syrk": 8.0 * B * 80 * 80,
+                      "lk_track": (lk.algorithmic_bytes() if lk is not None else 0.0),
                       "lin_small": sum(2296.0 * len(p.imu_frame_i) + 8.0 * (p.prior.n ** 2 + 2 * p.prior.n if p.prior is not None else 0) for p in probs)}
         a_bytes = per_launch.get(top.replace("_marg", ""), 0.0)
         achieved = a_bytes / (kernels[top]["ms_per_launch"] * 1e-3) / 1e9 if kernels[top]["ms_per_launch"] > 0 else 0.0
@@ -261,19 +430,46 @@ def main():
             ep, er = synth.pose_errors(a, sts[i])
             ep_max, er_max = max(ep_max, ep), max(er_max, er)
         parity = {"pose_err_m": ep_max, "pose_err_rad": er_max, "tolerance": [1e-4, 1e-4], "windows_checked": len(range(0, B, max(1, B // 6)))}
+        lk_cv = None
+        if lk is not None:
+            try:
+                import cv2
+                cv2.setNumThreads(1)
+                worst, agree, cnt = 0.0, 0.0, 0
+                for f in range(0, B, max(1, B // 4)):
+                    sc = scenes[f % len(scenes)]
+                    c, st_t, r, st_s = cv_track_frame(cv2, sc["left"][0], sc["left"][1], sc["right"][1], sc["pts"][0], sc["pts"][1])
+                    for ref_p, ref_s, got_p, got_s in ((c, st_t, lk_out[0][f], lk_out[1][f]), (r, st_s, lk_out[2][f], lk_out[3][f])):
+                        both = ref_s & (got_s > 0)
+                        worst = max(worst, float(np.abs(ref_p[both] - got_p[both]).max()) if both.any() else 0.0)
+                        agree += float((ref_s == (got_s > 0)).mean())
+                        cnt += 1
+                parity.update({"lk_max_px_vs_opencv": worst, "lk_status_agreement": agree / cnt, "lk_tolerance_px": 1e-2, "lk_streams_checked": cnt // 2})
+                lk_cv = cv2
+            except ImportError:
+                parity.update({"lk": "OpenCV not importable on this box: LK parity not checked in bench (see tests)"})
         if world == 1:
-            rate, n, dt = cpu_solve_many(vo, probs, states, args.cpu_seconds, 1)
-            cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                            "sample": "%d sequential oracle optimisations (C FP64 port of the reference algorithm; Ceres default num_threads=1) in %.1f s" % (n, dt)}
+            rate, n, dt = cpu_solve_many(vo, probs, states, args.cpu_seconds * (0.8 if lk_cv else 1.0), 1)
+            sample = "%d sequential oracle optimisations (C FP64 port of the reference algorithm; Ceres default num_threads=1) in %.1f s = %.1f solves/s" % (n, dt, rate)
+            if lk_cv:
+                lr, ln, ldt = cpu_lk_many(scenes, args.cpu_seconds * 0.2, 1)
+                sample += "; %d camera ticks of OpenCV calcOpticalFlowPyrLK x4 (1 thread) in %.1f s = %.1f frames/s; value = harmonic combination" % (ln, ldt, lr)
+                rate = 1.0 / (1.0 / rate + 1.0 / lr)
+            cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "C2 EuRoC-shaped stereo+IMU window with prior (steady state): 8 dogleg iterations + gauge re-anchor + MARGIN_OLD marginalisation per solve",
+                "config": {"workload": WORKLOAD if lk is not None else WORKLOAD + " [--no-lk: window solve only]",
                            "batch_per_gpu": B, "distinct_sequences": args.distinct, "perturbed_copies": args.copies,
                            "mean_visual_factors": sum(len(p.vis_type) for p in probs) / B, "mean_landmarks": sum(p.num_landmarks for p in probs) / B,
-                           "l2": "working set >> 126 MB L2 at this batch; no explicit flush", "lk_in_step": False},
+                           "l2": "working set >> 126 MB L2 at this batch; no explicit flush", "lk_in_step": lk is not None,
+                           "camera": None if lk is None else {"streams": B, "image": [IMG_W, IMG_H], "features": N_FEAT, "distinct_scenes": len(scenes),
+                                                              "e2e_images_uploaded_per_tick": 2}},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity}
         print(json.dumps(line))
+    if lk is not None:
+        lk.close()
+        feed.close()
     batch.destroy()
     ctx.close()
     if world > 1:

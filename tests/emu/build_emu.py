@@ -12,7 +12,7 @@ OUT = os.path.join(HERE, "libviwb_emu.so")
 
 
 def build():
-    deps = [os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith((".cu", ".cuh"))] + [os.path.join(ROOT, "include", "viwb.h")]
+    deps = [os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith((".cu", ".cuh", ".inl"))] + [os.path.join(ROOT, "include", "viwb.h")]
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DVIWB_HOST_EMU", "-x", "c++", "-Wno-unknown-pragmas",

@@ -45,27 +45,6 @@ VIWB_D void reanchor_block(const BatchDev &bd, int bx, int by, int tid, int nt, 
     for (int k = 0; k < m.nlm; k++) st[SFIX + k] = 1.0 / (1.0 / st[SFIX + k]);   // setDepth(1/x), getDepthVector(1/depth)
 }
 
-// serial cyclic Jacobi for a tiny symmetric matrix (n <= 16): A -> eigenvalues on the diagonal, V eigenvectors (columns)
-VIWB_D void jacobi_small(double *A, double *V, int n) {
-    for (int i = 0; i < n * n; i++) V[i] = 0.0;
-    for (int i = 0; i < n; i++) V[i * n + i] = 1.0;
-    for (int sweep = 0; sweep < 60; sweep++) {
-        int rot = 0;
-        for (int p = 0; p < n - 1; p++) for (int q = p + 1; q < n; q++) {
-            const double apq = A[p * n + q], app = A[p * n + p], aqq = A[q * n + q];
-            if (fabs(apq) <= 1e-17 * sqrt(fabs(app) * fabs(aqq)) || apq == 0.0) continue;
-            rot++;
-            const double tau = (aqq - app) / (2.0 * apq);
-            const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
-            for (int r = 0; r < n; r++) { const double a = A[r * n + p], b = A[r * n + q]; A[r * n + p] = c * a - s * b; A[r * n + q] = s * a + c * b; }
-            for (int r = 0; r < n; r++) { const double a = A[p * n + r], b = A[q * n + r]; A[p * n + r] = c * a - s * b; A[q * n + r] = s * a + c * b; }
-            for (int r = 0; r < n; r++) { const double a = V[r * n + p], b = V[r * n + q]; V[r * n + p] = c * a - s * b; V[r * n + q] = s * a + c * b; }
-        }
-        if (!rot) break;
-    }
-}
-
 // Symmetric eigen-decomposition in shared memory: Householder tridiagonalisation + implicit QL with eigenvector
 // accumulation (the EISPACK tred2 / tql2 pair, the algorithm family Eigen::SelfAdjointEigenSolver uses), with the
 // O(n^2)-per-step inner loops spread over the block and the O(n) scalar recurrences kept on thread 0.
@@ -174,12 +153,18 @@ VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *s
                     sc[1] += h;
                     p = d[m];
                     double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0; const double el1 = e[l + 1];
+                    // the rotation chain is the serial critical path of the whole decomposition: operands of the next link are
+                    // fetched before the current link's sqrt / reciprocal, and one reciprocal replaces two divisions
+                    double ei = e[m - 1], di = d[m - 1];
                     for (int i = m - 1; i >= l; i--) {
+                        const double ein = i > l ? e[i - 1] : 0.0, din = i > l ? d[i - 1] : 0.0;
                         c3 = c2; c2 = c; s2 = s;
-                        g = c * e[i]; h = c * p; r = hypot(p, e[i]);
-                        e[i + 1] = s * r; s = e[i] / r; c = p / r;
-                        p = c * d[i] - s * g; d[i + 1] = h + s * (c * g + s * d[i]);
+                        g = c * ei; h = c * p; r = sqrt(p * p + ei * ei);
+                        const double rinv = 1.0 / r;
+                        e[i + 1] = s * r; s = ei * rinv; c = p * rinv;
+                        p = c * di - s * g; d[i + 1] = h + s * (c * g + s * di);
                         cs[2 * i] = c; cs[2 * i + 1] = s;
+                        ei = ein; di = din;
                     }
                     p = -s * s2 * c3 * el1 * e[l] / dl1;
                     e[l] = s * p; d[l] = c * p;
@@ -200,7 +185,8 @@ VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *s
 }
 
 VIWB_HD int vsub_to_mlay(int p) { return p < 66 ? p : p < 72 ? 165 + (p - 66) : p < 78 ? 171 + (p - 72) : 191; }   // td -> blk_moff(BLK_TD) = 191
-VIWB_HD size_t marg_smem_doubles(int nt) { return 100 * 101 + 3 * 256 + 100 * 16 + 216 * 2 + 216 + 16 + 216 + 64 + (size_t)nt; }
+VIWB_HD int marg_cap(int nmax) { return nmax < 16 ? 16 : (nmax > 100 ? 100 : nmax); }
+VIWB_HD size_t marg_smem_doubles(int nt, int nmax) { const int c = marg_cap(nmax); return (size_t)c * (c | 1) + 3 * 256 + (size_t)c * 16 + 216 * 2 + 216 + 16 + 216 + 64 + (size_t)nt; }
 
 VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)mode;
@@ -215,8 +201,9 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
     const double eps = 1e-8;   // marginalization_factor.h:81
     // smem carve
-    double *Vn = smem, *Amm = Vn + 100 * 101, *Vmm = Amm + 256, *Ainv = Vmm + 256, *Tm = Ainv + 256;
-    double *bn = Tm + 100 * 16, *cs = bn + 216, *ev = cs + 216, *ee = ev + 108, *red = ee + 108, *bc = red + nt;
+    const int cap = marg_cap(bd.marg_nmax);
+    double *Vn = smem, *Amm = Vn + (size_t)cap * (cap | 1), *Vmm = Amm + 256, *Ainv = Vmm + 256, *Tm = Ainv + 256;
+    double *bn = Tm + (size_t)cap * 16, *cs = bn + 216, *ev = cs + 216, *ee = ev + 108, *red = ee + 108, *bc = red + nt;
     int *keep = (int *)(bc + 16), *dl = keep + 216;
     double *An = Vn;
     // ---- dense system of the marginalisation factors over the marginalisation layout
@@ -256,16 +243,17 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     }
     VIWB_SYNC();
     const int md = (int)bc[2], n = (int)bc[3];
-    if (n > 100) { if (tid == 0) { ww.marg_status = -1; hdr[0] = 0; } return; }
+    if (n > cap) { if (tid == 0) { ww.marg_status = -1; hdr[0] = 0; } return; }
     // ---- pseudo-inverse of the dropped fixed block (marginalization_factor.cpp:282-287)
     for (int e = tid; e < md * md; e += nt) { const int i = e / md, j = e % md; Amm[e] = 0.5 * (M[(size_t)dl[i] * LDM + dl[j]] + M[(size_t)dl[j] * LDM + dl[i]]); }
     VIWB_SYNC();
-    if (tid == 0) jacobi_small(Amm, Vmm, md);
+    (void)Vmm;
+    sym_eig_block(Amm, ev, ee, cs, bc + 4, red, md, md, tid, nt);      // eigenvalues -> ev, eigenvectors -> columns of Amm
     VIWB_SYNC();
     for (int e = tid; e < md * md; e += nt) {
         const int i = e / md, j = e % md;
         double sacc = 0.0;
-        for (int k = 0; k < md; k++) { const double l = Amm[k * md + k]; if (l > eps) sacc += Vmm[i * md + k] * Vmm[j * md + k] / l; }
+        for (int k = 0; k < md; k++) { const double l = ev[k]; if (l > eps) sacc += Amm[i * md + k] * Amm[j * md + k] / l; }
         Ainv[e] = sacc;
     }
     VIWB_SYNC();

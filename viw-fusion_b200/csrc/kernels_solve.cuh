@@ -17,30 +17,39 @@ namespace viwb {
 
 VIWB_HD int pidx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-// block-wide sum; red has nt doubles.  Every thread gets the result.
+// block-wide sum / max; red has >= 32 doubles.  Every thread gets the result (fixed reduction order: deterministic).
+#ifdef VIWB_HOST_EMU
+VIWB_D double block_sum(double v, int, int, double *) { return v; }
+VIWB_D double block_max(double v, int, int, double *) { return v; }
+#else
 VIWB_D double block_sum(double v, int tid, int nt, double *red) {
-    red[tid] = v;
-    VIWB_SYNC();
-    for (int s = nt >> 1; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; VIWB_SYNC(); }
-    const double r = red[0];
-    VIWB_SYNC();
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    const int nw = nt >> 5;
+    double r = 0.0;
+    for (int k = 0; k < nw; k++) r += red[k];
+    __syncthreads();
     return r;
 }
 VIWB_D double block_max(double v, int tid, int nt, double *red) {
-    red[tid] = v;
-    VIWB_SYNC();
-    for (int s = nt >> 1; s > 0; s >>= 1) { if (tid < s) red[tid] = fmax(red[tid], red[tid + s]); VIWB_SYNC(); }
-    const double r = red[0];
-    VIWB_SYNC();
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    const int nw = nt >> 5;
+    double r = red[0];
+    for (int k = 1; k < nw; k++) r = fmax(r, red[k]);
+    __syncthreads();
     return r;
 }
+#endif
 
 struct SolveSmem {
     double *L;       // packed lower, nf(nf+1)/2
-    double *g, *sc, *D, *sg, *y, *u, *Hu, *ug, *uvis, *red, *bc;
+    double *g, *sc, *D, *sg, *y, *u, *Hu, *ug, *uvis, *red, *bc, *chol;
     int *amap, *vmap;
 };
-VIWB_HD size_t solve_smem_doubles(int nt) { return (size_t)TFIX * (TFIX + 1) / 2 + 9 * TFIX + 2 * VSUB + nt + 16 + TFIX; }   // + ints (2*TFIX ints = TFIX doubles)
+VIWB_HD size_t solve_smem_doubles(int nt) { return (size_t)TFIX * (TFIX + 1) / 2 + 9 * TFIX + 2 * VSUB + nt + 16 + TFIX + (size_t)((nt + 31) / 32) * 48; }   // + ints (2*TFIX ints = TFIX doubles)
 VIWB_D void carve(SolveSmem &s, double *smem, int nt) {
     double *p = smem;
     s.L = p; p += (size_t)TFIX * (TFIX + 1) / 2;
@@ -48,6 +57,7 @@ VIWB_D void carve(SolveSmem &s, double *smem, int nt) {
     s.u = p; p += TFIX; s.Hu = p; p += TFIX; s.ug = p; p += TFIX;
     s.uvis = p; p += 2 * VSUB;
     s.red = p; p += nt; s.bc = p; p += 16;
+    s.chol = p; p += (size_t)((nt + 31) / 32) * 48;
     s.amap = (int *)p; s.vmap = s.amap + TFIX;
 }
 
@@ -89,39 +99,82 @@ VIWB_D double dot80(const double *W, const double *v) { double a = 0.0; for (int
 
 // Blocked (panel width 8) in-place Cholesky of the packed lower triangle with the right-hand side carried as an extra
 // row n, so that on exit y = L^-1 b (forward substitution for free).  Returns false on a non-positive pivot
-// (Eigen LLT semantics: schur_complement_solver.cc -> LINEAR_SOLVER_FAILURE).  3 barriers per panel.
-enum { CHOL_NB = 8 };
-VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, double *bc) {
+// (Eigen LLT semantics: schur_complement_solver.cc -> LINEAR_SOLVER_FAILURE).  2 barriers per panel:
+//   every warp factors the 8x8 diagonal block redundantly (8 lanes, one row each, in registers; pivots through rsqrt so
+//   that the panel rows multiply instead of divide) into its own scratch, so no barrier separates it from the panel solve;
+//   then one thread per panel row, then 4x4 register tiles for the trailing update.
+// scratch: nwarps * 48 doubles (36 packed block entries + 8 inverse pivots + flag).
+enum { CHOL_NB = 8, CHOL_SCR = 48 };
+VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, double *bc, double *scratch) {
 #define ROW(i) ((i) < n ? L + (size_t)(i) * ((i) + 1) / 2 : y)
-    if (tid == 0) bc[0] = 1.0;
-    VIWB_SYNC();
+    const int lane = tid & 31;
+    double *my = scratch + (size_t)(tid >> 5) * CHOL_SCR;      // this warp's copy of the factored diagonal block
     for (int c0 = 0; c0 < n; c0 += CHOL_NB) {
         const int nb = (n - c0) < CHOL_NB ? (n - c0) : CHOL_NB;
-        if (tid == 0) {      // diagonal block
+#ifdef VIWB_HOST_EMU
+        {   // single-thread statement of the same arithmetic
+            my[44] = 1.0;
+            double a[8][8];
+            for (int i = 0; i < nb; i++) for (int j = 0; j <= i; j++) a[i][j] = ROW(c0 + i)[c0 + j];
             for (int k = 0; k < nb; k++) {
-                double *rk = ROW(c0 + k) + c0;
-                double d = rk[k];
-                for (int m = 0; m < k; m++) d -= rk[m] * rk[m];
-                if (!(d > 0.0)) { bc[0] = 0.0; break; }
-                d = sqrt(d); rk[k] = d;
-                const double inv = 1.0 / d;
-                for (int i = k + 1; i < nb; i++) { double *ri = ROW(c0 + i) + c0; double v = ri[k]; for (int m = 0; m < k; m++) v -= ri[m] * rk[m]; ri[k] = v * inv; }
+                const double d = a[k][k];
+                if (!(d > 0.0)) { my[44] = 0.0; break; }
+                const double inv = 1.0 / sqrt(d);
+                a[k][k] = d * inv; my[36 + k] = inv;
+                for (int i = k + 1; i < nb; i++) a[i][k] *= inv;
+                for (int i = k + 1; i < nb; i++) for (int j = k + 1; j <= i; j++) a[i][j] -= a[i][k] * a[j][k];
             }
+            for (int i = 0; i < nb; i++) for (int j = 0; j <= i; j++) my[i * (i + 1) / 2 + j] = a[i][j];
         }
-        VIWB_SYNC();
-        if (bc[0] == 0.0) return false;
+#else
+        {
+            double a[8];
+            const bool act = lane < nb;
+            const double *src = ROW(c0 + (act ? lane : 0)) + c0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[j] = (act && j <= lane) ? src[j] : 0.0;
+            bool okp = true;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const double d = __shfl_sync(0xffffffffu, a[k], k);
+                if (k < nb && !(d > 0.0)) okp = false;
+                const double inv = (k < nb && d > 0.0) ? rsqrt(d) : 0.0;
+                if (lane == k) { a[k] = d * inv; if (k < nb) my[36 + k] = inv; }
+                else if (lane > k) a[k] *= inv;
+#pragma unroll
+                for (int j = k + 1; j < 8; j++) {
+                    const double ljk = __shfl_sync(0xffffffffu, a[k], j);      // L[j][k]
+                    if (lane >= j) a[j] -= a[k] * ljk;
+                }
+            }
+            if (act) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (j <= lane) my[lane * (lane + 1) / 2 + j] = a[j];
+            }
+            if (lane == 0) my[44] = okp ? 1.0 : 0.0;
+            __syncwarp();
+        }
+#endif
+        if (my[44] == 0.0) return false;                    // every warp reaches the same verdict
         const int r0 = c0 + nb;
-        // panel: rows r0..n (row n = rhs)
+        // panel rows r0..n (row n = rhs): x_k = (a_ik - sum_m x_m L_km) / L_kk
         for (int i = r0 + tid; i <= n; i += nt) {
             double *ri = ROW(i) + c0;
-            for (int k = 0; k < nb; k++) {
-                const double *rk = ROW(c0 + k) + c0;
-                double v = ri[k];
-                for (int m = 0; m < k; m++) v -= ri[m] * rk[m];
-                ri[k] = v / rk[k];
+            double x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (k < nb) {
+                    double v = ri[k];
+#pragma unroll
+                    for (int m = 0; m < 8; m++) if (m < k) v -= x[m] * my[k * (k + 1) / 2 + m];
+                    x[k] = v * my[36 + k];
+                    ri[k] = x[k];
+                }
             }
         }
         VIWB_SYNC();
+        // factored diagonal block back into the matrix (only now: the other warps have finished reading the unfactored one)
+        for (int r = tid; r < nb; r += nt) { double *rk = ROW(c0 + r) + c0; for (int j = 0; j <= r; j++) rk[j] = my[r * (r + 1) / 2 + j]; }
         // trailing update with 4x4 register tiles over rows i in [r0, n], columns k in [r0, min(i, n-1)]
         const int mt = (n + 1 - r0 + 3) / 4, ntile = mt * (mt + 1) / 2;
         for (int t = tid; t < ntile; t += nt) {
@@ -129,9 +182,11 @@ VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, do
             const int ib = r0 + 4 * ti, kb = r0 + 4 * tk;
             double acc[16];
             for (int q = 0; q < 16; q++) acc[q] = 0.0;
+            const double *pi[4], *pk[4];
+            for (int a = 0; a < 4; a++) { pi[a] = (ib + a <= n) ? ROW(ib + a) + c0 : nullptr; pk[a] = (kb + a < n) ? ROW(kb + a) + c0 : nullptr; }
             for (int m = 0; m < nb; m++) {
                 double li[4], lk[4];
-                for (int a = 0; a < 4; a++) { li[a] = (ib + a <= n) ? ROW(ib + a)[c0 + m] : 0.0; lk[a] = (kb + a < n) ? ROW(kb + a)[c0 + m] : 0.0; }
+                for (int a = 0; a < 4; a++) { li[a] = pi[a] ? pi[a][m] : 0.0; lk[a] = pk[a] ? pk[a][m] : 0.0; }
                 for (int a = 0; a < 4; a++) for (int b2 = 0; b2 < 4; b2++) acc[a * 4 + b2] += li[a] * lk[b2];
             }
             for (int a = 0; a < 4; a++) { const int i = ib + a; if (i > n) break; double *ri = ROW(i);
@@ -139,6 +194,7 @@ VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, do
         }
         VIWB_SYNC();
     }
+    (void)bc;
 #undef ROW
     return true;
 }
@@ -347,7 +403,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                 VIWB_SYNC();
                 h_dirty = true;
                 if (tid == 0) ww.num_linear++;
-                bool ok = cholesky_packed_rhs(s.L, s.y, nf, tid, nt, s.bc);
+                bool ok = cholesky_packed_rhs(s.L, s.y, nf, tid, nt, s.bc, s.chol);
                 if (ok) {
                     chol_backsolve_warp(s.L, s.y, nf, tid, nt);
                     // back-substitute the inverse depths (scaled): y_k = (c g_k - c w_k . (C y_f)) / h_k

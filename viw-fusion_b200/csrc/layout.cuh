@@ -85,6 +85,7 @@ struct Opts {
 
 struct BatchDev {       // passed by value to every kernel
     int B, nvis_total, nlm_total, nimu_total, nwheel_total, nplane_total, nprior, nitems_solve, nitems_marg;
+    int marg_nmax;          // largest prior dimension any window of the batch produces (sizes the eigen-solver's shared memory)
     int rec_stride_solve;   // VREC_COMPACT if no window of the batch has ex0/ex1/td active, else VREC (marginalisation always uses VREC)
     const WinMeta *meta;
     WinWork *work;

@@ -164,7 +164,11 @@ static int lk_batch_execute(viwb_lk_batch *b, int what) {
     viwb_context *ctx = b->ctx;
     const int F = b->F; stream_t st = ctx->stream;
     if (!b->stereo) what &= 1;
-    for (int s = 0; s < LK_SLOTS; s++) if (b->dirty[s]) {
+    // every tick brings new cur (and right) images, so their pyramids are part of the tick; the previous image keeps the
+    // pyramid it got when it was the current one unless it was (re)uploaded
+    for (int s = 0; s < LK_SLOTS; s++) {
+        const bool need = s == b->cur || (s == 2 && (what & 2)) || (s == 1 - b->cur && (what & 1) && b->dirty[s]);
+        if (!need) continue;
         for (int l = 1; l <= b->levels; l++) { lk_launch_pyr(b->pyr + ((size_t)s * 3 + (l - 1)) * F, b->lw[l] * b->lh[l], F, st); ctx->launches++; }
         b->dirty[s] = false;
     }

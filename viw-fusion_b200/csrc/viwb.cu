@@ -389,6 +389,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     bd.nvis_total = (int)nvis; bd.nlm_total = (int)nlm; bd.nimu_total = (int)nimu; bd.nwheel_total = (int)nwheel; bd.nplane_total = (int)nplane; bd.nprior = (int)npri;
     bd.nitems_solve = (int)nit_s; bd.nitems_marg = (int)nit_m;
     bd.rec_stride_solve = VREC_COMPACT;
+    bd.marg_nmax = b->prior_nmax;
     for (int w = 0; w < B; w++) if (b->meta[w].has_common) bd.rec_stride_solve = VREC;
     b->total_state = nstate;
     // ---- placement (inputs first, then work arrays)
@@ -450,7 +451,7 @@ static int ensure_attrs(viwb_context *ctx) {
 #ifndef VIWB_HOST_EMU
     if (!ctx->attrs_set) {
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(512) * 8)));
-        CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(256) * 8)));
+        CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(256, 100) * 8)));
         ctx->attrs_set = true;
     }
 #endif
@@ -470,7 +471,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     CK(dev_d2d(bd.work, b->work_init_dev, sizeof(WinWork) * B, st));
     const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(512), nt_marg = NT(256);
     const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total * LM_ROLES + nt_lm - 1) / nt_lm;
-    const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg) * 8;
+    const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg, bd.marg_nmax) * 8;
     auto lin = [&](int mode) {
         LAUNCH(lin_vis, bd, g_vis, 1, nt_vis, 0, mode, st);
         LAUNCH(lm_reduce, bd, g_lm, 1, nt_lm, 0, mode, st);
