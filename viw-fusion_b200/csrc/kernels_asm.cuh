@@ -202,37 +202,70 @@ VIWB_HD int common_blk(int c) { return c < 6 ? BLK_EX0 : c < 12 ? BLK_EX1 : BLK_
 VIWB_HD int common_k(int c) { return c < 6 ? c : c < 12 ? c - 6 : 0; }
 
 // Adds every contribution to the (zero-initialised by the caller) target.  All threads of the block must call it.
+// imap: >= MAXPRI ints of block-shared scratch.  Every stage gives each matrix entry exactly one owner thread, and stages
+// that may touch the same entries are separated by a barrier (no atomics; fixed summation order).
 template <typename Target>
-VIWB_D void assemble_into(const Target &t, const BatchDev &bd, int w, int mode, int tid, int nt) {
+VIWB_D void assemble_into(const Target &t, const BatchDev &bd, int w, int mode, int tid, int nt, int *imap) {
     const WinMeta &m = bd.meta[w];
     const bool prior_only = marg_prior_only(m, mode);
-    // ---- prior: A = J_lin^T J_lin (constant during the solve) and g = J_lin^T r
+    // ---- prior: A = J_lin^T J_lin (constant during the solve) and g = J_lin^T r, entry-parallel over the lower triangle
     if (m.prior_idx >= 0) {
         const PriorDev &pr = bd.prior[m.prior_idx];
         const double *A = bd.prior_A + pr.J_off, *g = bd.prior_g + pr.r_off;
-        for (int e = tid; e < pr.nb * (pr.nb + 1) / 2; e += nt) {        // block pairs; entries inside
-            int bi, bj; sym_unrank(e, bi, bj);
-            const int ba = pr.block_id[bi], bb = pr.block_id[bj], ia = pr.block_idx[bi], ib = pr.block_idx[bj];
-            const int sa = blk_msize(ba), sb = blk_msize(bb);
-            for (int p = 0; p < sa; p++) for (int q = 0; q < (bi == bj ? p + 1 : sb); q++) {
-                const int ci = t.col(ba, p), cj = t.col(bb, q);
-                if (ci >= 0 && cj >= 0) t.add(ci, cj, A[(size_t)(ia + p) * pr.n + ib + q]);
-            }
-        }
         for (int bi = tid; bi < pr.nb; bi += nt) {
             const int ba = pr.block_id[bi];
-            for (int p = 0; p < blk_msize(ba); p++) { const int ci = t.col(ba, p); if (ci >= 0) t.addg(ci, g[pr.block_idx[bi] + p]); }
+            for (int p = 0; p < blk_msize(ba); p++) imap[pr.block_idx[bi] + p] = t.col(ba, p);
         }
+        VIWB_SYNC();
+        const int n = pr.n;
+        for (int e = tid; e < n * (n + 1) / 2; e += nt) {
+            int i, j; sym_unrank(e, i, j);
+            const int ci = imap[i], cj = imap[j];
+            if (ci >= 0 && cj >= 0) t.add(ci, cj, A[(size_t)i * n + j]);
+        }
+        for (int i = tid; i < n; i += nt) if (imap[i] >= 0) t.addg(imap[i], g[i]);
     }
     VIWB_SYNC();
-    // ---- IMU / wheel / plane: one factor at a time (consecutive factors share blocks)
+    // ---- IMU: factor k joins frames (i, j = i + 1) (estimator.cpp:1528-1538), so factors of equal parity touch disjoint blocks:
+    //      two barrier-separated passes instead of one per factor.  Wheel / plane factors share the wheel extrinsic and
+    //      intrinsic blocks among all of them and stay one factor at a time.
     Slot sl[8];
     if (!prior_only) {
-        for (int k = 0; k < m.nimu; k++) {
-            const int f = m.imu_off + k, i = bd.imu_fi[f], j = bd.imu_fj[f];
-            if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-            const int ns = imu_slots(i, j, sl);
-            add_small_factor(t, bd.imu_rec + (size_t)f * IMU_REC, 15, 30, sl, ns, tid, nt);
+        bool chain = true;
+        for (int k = 0; k < m.nimu; k++) { const int f = m.imu_off + k; if (bd.imu_fj[f] != bd.imu_fi[f] + 1) chain = false; }
+        if (chain && mode == MODE_SOLVE) {
+            const int per = 30 * 31 / 2 + 30;
+            for (int par = 0; par < 2; par++) {
+                for (int e = tid; e < m.nimu * per; e += nt) {
+                    const int k = e / per, o = e - k * per, f = m.imu_off + k, i = bd.imu_fi[f];
+                    if ((i & 1) != par) continue;
+                    const double *res = bd.imu_rec + (size_t)f * IMU_REC, *J = res + 15;
+                    // local column -> (block, k): [pose_i 6 | sb_i 9 | pose_j 6 | sb_j 9]
+                    auto lc = [&](int p) { return p < 6 ? t.col(i, p) : p < 15 ? t.col(BLK_SB0 + i, p - 6) : p < 21 ? t.col(i + 1, p - 15) : t.col(BLK_SB0 + i + 1, p - 21); };
+                    if (o < 465) {
+                        int p, q; sym_unrank(o, p, q);
+                        const int ci = lc(p), cj = lc(q);
+                        if (ci < 0 || cj < 0) continue;
+                        double v = 0.0;
+                        for (int r = 0; r < 15; r++) v += J[r * 30 + p] * J[r * 30 + q];
+                        t.add(ci, cj, v);
+                    } else {
+                        const int p = o - 465, ci = lc(p);
+                        if (ci < 0) continue;
+                        double v = 0.0;
+                        for (int r = 0; r < 15; r++) v += J[r * 30 + p] * res[r];
+                        t.addg(ci, v);
+                    }
+                }
+                VIWB_SYNC();
+            }
+        } else {
+            for (int k = 0; k < m.nimu; k++) {
+                const int f = m.imu_off + k, i = bd.imu_fi[f], j = bd.imu_fj[f];
+                if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+                const int ns = imu_slots(i, j, sl);
+                add_small_factor(t, bd.imu_rec + (size_t)f * IMU_REC, 15, 30, sl, ns, tid, nt);
+            }
         }
         for (int k = 0; k < m.nwheel; k++) {
             const int f = m.wheel_off + k, i = bd.wheel_fi[f], j = bd.wheel_fj[f];
@@ -247,29 +280,28 @@ VIWB_D void assemble_into(const Target &t, const BatchDev &bd, int w, int mode, 
             add_small_factor(t, bd.plane_rec + (size_t)f * PLANE_REC, 3, 16, sl, ns, tid, nt);
         }
     }
-    // ---- visual partial sums, phase by phase
+    // ---- visual partial sums: the chunks of one target (same frame / frame pair / common block) are consecutive items with
+    //      phase 0, 1, 2, ...; the owner of entry o of the head item gathers the chunks, so one pass and no barriers
     const int ioff = (mode == MODE_SOLVE) ? m.item_off : bd.nitems_solve + m.mitem_off;
     const int ni = (mode == MODE_SOLVE) ? m.nitems : (m.margin_flag == 0 ? m.nmitems : 0);
-    const int nph = (mode == MODE_SOLVE) ? m.nphases : m.nmphases;
-    for (int ph = 0; ph < nph; ph++) {
-        for (int e = tid; e < ni * ASM_STRIDE; e += nt) {
-            const int ii = e / ASM_STRIDE, o = e % ASM_STRIDE;
-            const AsmItem &item = bd.items[ioff + ii];
-            if (item.phase != ph) continue;
-            const double v = bd.asm_out[(size_t)(ioff + ii) * ASM_STRIDE + o];
-            if (item.kind == ITEM_FRAME) {
-                if (o < 21) { int p, q; sym_unrank(o, p, q); const int ci = t.col(item.a, p), cj = t.col(item.a, q); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
-                else if (o < 99) { const int p = (o - 21) / 13, c = (o - 21) % 13; const int ci = t.col(item.a, p), cj = t.col(common_blk(c), common_k(c)); if (ci >= 0 && cj >= 0 && item.has_common) t.add(ci, cj, v); }
-                else if (o < 105) { const int ci = t.col(item.a, o - 99); if (ci >= 0) t.addg(ci, v); }
-            } else if (item.kind == ITEM_PAIR) {
-                if (o < 36) { const int ci = t.col(item.a, o / 6), cj = t.col(item.b, o % 6); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
-            } else {
-                if (o < 91) { int p, q; sym_unrank(o, p, q); const int ci = t.col(common_blk(p), common_k(p)), cj = t.col(common_blk(q), common_k(q)); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
-                else if (o < 104) { const int c = o - 91; const int ci = t.col(common_blk(c), common_k(c)); if (ci >= 0) t.addg(ci, v); }
-            }
+    for (int e = tid; e < ni * ASM_STRIDE; e += nt) {
+        const int ii = e / ASM_STRIDE, o = e - ii * ASM_STRIDE;
+        const AsmItem &item = bd.items[ioff + ii];
+        if (item.phase != 0) continue;
+        double v = bd.asm_out[(size_t)(ioff + ii) * ASM_STRIDE + o];
+        for (int c = 1; ii + c < ni && bd.items[ioff + ii + c].phase == c; c++) v += bd.asm_out[(size_t)(ioff + ii + c) * ASM_STRIDE + o];
+        if (item.kind == ITEM_FRAME) {
+            if (o < 21) { int p, q; sym_unrank(o, p, q); const int ci = t.col(item.a, p), cj = t.col(item.a, q); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
+            else if (o < 99) { const int p = (o - 21) / 13, c = (o - 21) % 13; const int ci = t.col(item.a, p), cj = t.col(common_blk(c), common_k(c)); if (ci >= 0 && cj >= 0 && item.has_common) t.add(ci, cj, v); }
+            else if (o < 105) { const int ci = t.col(item.a, o - 99); if (ci >= 0) t.addg(ci, v); }
+        } else if (item.kind == ITEM_PAIR) {
+            if (o < 36) { const int ci = t.col(item.a, o / 6), cj = t.col(item.b, o % 6); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
+        } else {
+            if (o < 91) { int p, q; sym_unrank(o, p, q); const int ci = t.col(common_blk(p), common_k(p)), cj = t.col(common_blk(q), common_k(q)); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
+            else if (o < 104) { const int c = o - 91; const int ci = t.col(common_blk(c), common_k(c)); if (ci >= 0) t.addg(ci, v); }
         }
-        VIWB_SYNC();
     }
+    VIWB_SYNC();
 }
 
 }  // namespace viwb

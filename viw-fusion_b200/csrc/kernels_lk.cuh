@@ -21,7 +21,7 @@
 
 namespace viwb {
 
-enum { LK_WIN = 21, LK_HALF = 10, LK_MAXLVL = 4, LK_NT = 64, LK_PATCH = 24, LK_DPATCH = 22 };
+enum { LK_WIN = 21, LK_HALF = 10, LK_MAXLVL = 4, LK_PATCH = 24, LK_DPATCH = 22 };
 
 struct LkImage { const uint8_t *img[LK_MAXLVL]; int w[LK_MAXLVL], h[LK_MAXLVL], stride[LK_MAXLVL]; };
 struct LkArgs {
@@ -63,35 +63,51 @@ VIWB_D void pyr_down_item(const PyrArgs &a, int idx) {
     a.dst[(size_t)y * a.dstride + x] = (uint8_t)((acc + 128) >> 8);
 }
 
-// ---- the tracker: one block per point
-// smem (bytes): short patch[576] | short dpatch[968] | short Iptr[441(+1)] | short dI[882] | double red[2 * 3 * warps]
-VIWB_HD size_t lk_smem_bytes(int nt) { return (size_t)(576 + 968 + 442 + 882) * 2 + 8 + (size_t)6 * ((nt + 31) / 32) * 8 + 64; }
-
-// block-wide sum of three exact (integer-valued) doubles; `phase` alternates the scratch half so that one barrier suffices
-VIWB_D void lk_sum3(double &a, double &b, double &c, int tid, int nt, double *red, int phase) {
+// ---- the tracker: one warp per point, no block-level barriers.
+// Per level the warp stages the 24x24 source patch and its 22x22 Scharr samples in its own shared-memory slice, then every
+// lane keeps its 14 template / gradient samples in registers; a Gauss-Newton iteration is 14 bilinear samples of the search
+// image per lane (straight from L1), integer products, and one exact 64-bit warp reduction.
 #ifdef VIWB_HOST_EMU
-    (void)tid; (void)nt; (void)red; (void)phase; (void)a; (void)b; (void)c;
+enum { LK_W = 1 };
 #else
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); c += __shfl_down_sync(0xffffffffu, c, o); }
-    const int nw = (nt + 31) >> 5, wid = tid >> 5;
-    double *r = red + (phase & 1) * 3 * nw;
-    if ((tid & 31) == 0) { r[wid] = a; r[nw + wid] = b; r[2 * nw + wid] = c; }
-    __syncthreads();
-    a = 0; b = 0; c = 0;
-    for (int k = 0; k < nw; k++) { a += r[k]; b += r[nw + k]; c += r[2 * nw + k]; }
+enum { LK_W = 32 };
+#endif
+#ifndef LK_MINB
+#define LK_MINB 6
+#endif
+enum { LK_EPL = (441 + LK_W - 1) / LK_W, LK_PPB = 4, LK_WARP_SMEM = (576 + 968) * 2 + 16 };     // elements per lane, points per block, bytes per warp
+VIWB_HD size_t lk_smem_bytes(int warps) { return (size_t)warps * LK_WARP_SMEM; }
+
+VIWB_D void lk_warp_sum3(long long &a, long long &b, long long &c) {
+#ifndef VIWB_HOST_EMU
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+#else
+    (void)a; (void)b; (void)c;
+#endif
+}
+VIWB_D void lk_warp_sum2(long long &a, long long &b) {
+#ifndef VIWB_HOST_EMU
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+#else
+    (void)a; (void)b;
 #endif
 }
 VIWB_HD bool lk_outside(int ix, int iy, int cols, int rows) { return ix < -LK_WIN || ix >= cols || iy < -LK_WIN || iy >= rows; }
 
-VIWB_D void lk_track_block(const LkArgs &a, int pt, int tid, int nt, unsigned char *smem_raw) {
-    short *patch = (short *)smem_raw, *dpatch = patch + 576, *Iptr = dpatch + 968, *dI = Iptr + 442;
-    double *red = (double *)(smem_raw + (((576 + 968 + 442 + 882) * 2 + 7) / 8) * 8);
+// bilinear sample (before descaling) of the search image at integer corner (sx, sy) with 14-bit weights
+VIWB_D int lk_sample(const LkImage &J, int level, const uint8_t *jimg, int jstr, bool inside, int sx, int sy, int w00, int w01, int w10, int w11) {
+    if (inside) { const uint8_t *q = jimg + (size_t)sy * jstr + sx; return q[0] * w00 + q[1] * w01 + q[jstr] * w10 + q[jstr + 1] * w11; }
+    return lk_pix(J, level, sx, sy) * w00 + lk_pix(J, level, sx + 1, sy) * w01 + lk_pix(J, level, sx, sy + 1) * w10 + lk_pix(J, level, sx + 1, sy + 1) * w11;
+}
+
+VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem_raw) {
+    short *patch = (short *)smem_raw, *dpatch = patch + 576;
     const int npts = a.n_dev ? *a.n_dev : a.n;
     if (pt >= npts) return;
     const float FLT_SCALE = 1.f / (1 << 20);
     bool status = true; float errv = 0.f;
     float npx = 0.f, npy = 0.f;     // nextPts[ptidx] (window centre coordinates)
-    int phase = 0;
+    int Iv[LK_EPL], dxy[LK_EPL];    // template intensity (5 fractional bits) and packed (dx | dy << 16) per owned element
     for (int level = a.max_level; level >= 0; level--) {
         const float sc = (float)(1. / (1 << level));
         float ppx = a.prev_pts[2 * pt] * sc, ppy = a.prev_pts[2 * pt + 1] * sc;
@@ -104,98 +120,108 @@ VIWB_D void lk_track_block(const LkArgs &a, int pt, int tid, int nt, unsigned ch
         const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
         const int cols = a.I.w[level], rows = a.I.h[level];
         if (lk_outside(ipx, ipy, cols, rows)) { if (level == 0) { status = false; errv = 0.f; } continue; }
+        // stage the source patch [ipy-1, ipy+22] x [ipx-1, ipx+22]
+        VIWB_SYNCWARP();
         {
-            // stage the source patch [ipy-1, ipy+22] x [ipx-1, ipx+22]
-            VIWB_SYNC();
-            {
-                const uint8_t *img = a.I.img[level]; const int str = a.I.stride[level];
-                for (int e = tid; e < LK_PATCH * LK_PATCH; e += nt) {
-                    const int y = e / LK_PATCH, x = e - y * LK_PATCH;
-                    patch[e] = (short)img[(size_t)reflect101(ipy - 1 + y, rows) * str + reflect101(ipx - 1 + x, cols)];
-                }
+            const uint8_t *img = a.I.img[level]; const int str = a.I.stride[level];
+            const bool in = ipx >= 1 && ipy >= 1 && ipx + 23 <= cols && ipy + 23 <= rows;
+            for (int e = lane; e < LK_PATCH * LK_PATCH; e += LK_W) {
+                const int y = e / LK_PATCH, x = e - y * LK_PATCH;
+                patch[e] = in ? (short)img[(size_t)(ipy - 1 + y) * str + ipx - 1 + x]
+                              : (short)img[(size_t)reflect101(ipy - 1 + y, rows) * str + reflect101(ipx - 1 + x, cols)];
             }
-            VIWB_SYNC();
-            // Scharr samples at [ipy, ipy+21] x [ipx, ipx+21]; zero outside the image
-            for (int e = tid; e < LK_DPATCH * LK_DPATCH; e += nt) {
-                const int y = e / LK_DPATCH, x = e - y * LK_DPATCH, gx = ipx + x, gy = ipy + y;
-                int ddx = 0, ddy = 0;
-                if (gx >= 0 && gy >= 0 && gx < cols && gy < rows) {
-                    const short *p0 = patch + y * LK_PATCH + x, *p1 = p0 + LK_PATCH, *p2 = p1 + LK_PATCH;
-                    ddx = (p0[2] + p2[2]) * 3 + p1[2] * 10 - ((p0[0] + p2[0]) * 3 + p1[0] * 10);
-                    ddy = ((p2[2] - p0[2]) + (p2[0] - p0[0])) * 3 + (p2[1] - p0[1]) * 10;
-                }
-                dpatch[2 * e] = (short)ddx; dpatch[2 * e + 1] = (short)ddy;
+        }
+        VIWB_SYNCWARP();
+        // Scharr samples at [ipy, ipy+21] x [ipx, ipx+21]; zero outside the image
+        for (int e = lane; e < LK_DPATCH * LK_DPATCH; e += LK_W) {
+            const int y = e / LK_DPATCH, x = e - y * LK_DPATCH, gx = ipx + x, gy = ipy + y;
+            int ddx = 0, ddy = 0;
+            if (gx >= 0 && gy >= 0 && gx < cols && gy < rows) {
+                const short *p0 = patch + y * LK_PATCH + x, *p1 = p0 + LK_PATCH, *p2 = p1 + LK_PATCH;
+                ddx = (p0[2] + p2[2]) * 3 + p1[2] * 10 - ((p0[0] + p2[0]) * 3 + p1[0] * 10);
+                ddy = ((p2[2] - p0[2]) + (p2[0] - p0[0])) * 3 + (p2[1] - p0[1]) * 10;
             }
-            VIWB_SYNC();
-            const float fa = ppx - ipx, fb = ppy - ipy;
-            const int iw00 = cv_round_f((1.f - fa) * (1.f - fb) * (1 << 14)), iw01 = cv_round_f(fa * (1.f - fb) * (1 << 14));
-            const int iw10 = cv_round_f((1.f - fa) * fb * (1 << 14)), iw11 = (1 << 14) - iw00 - iw01 - iw10;
-            double A11 = 0, A12 = 0, A22 = 0;
-            for (int e = tid; e < 441; e += nt) {
+            dpatch[2 * e] = (short)ddx; dpatch[2 * e + 1] = (short)ddy;
+        }
+        VIWB_SYNCWARP();
+        const float fa = ppx - ipx, fb = ppy - ipy;
+        const int iw00 = cv_round_f((1.f - fa) * (1.f - fb) * (1 << 14)), iw01 = cv_round_f(fa * (1.f - fb) * (1 << 14));
+        const int iw10 = cv_round_f((1.f - fa) * fb * (1 << 14)), iw11 = (1 << 14) - iw00 - iw01 - iw10;
+        long long A11 = 0, A12 = 0, A22 = 0;
+#pragma unroll
+        for (int k = 0; k < LK_EPL; k++) {
+            const int e = lane + LK_W * k;
+            if (e < 441) {
                 const int y = e / 21, x = e - y * 21;
                 const short *p = patch + (y + 1) * LK_PATCH + x + 1, *d = dpatch + 2 * (y * LK_DPATCH + x);
                 const int ival = descale(p[0] * iw00 + p[1] * iw01 + p[LK_PATCH] * iw10 + p[LK_PATCH + 1] * iw11, 9);
                 const int ix = descale(d[0] * iw00 + d[2] * iw01 + d[2 * LK_DPATCH] * iw10 + d[2 * LK_DPATCH + 2] * iw11, 14);
                 const int iy = descale(d[1] * iw00 + d[3] * iw01 + d[2 * LK_DPATCH + 1] * iw10 + d[2 * LK_DPATCH + 3] * iw11, 14);
-                Iptr[e] = (short)ival; dI[2 * e] = (short)ix; dI[2 * e + 1] = (short)iy;
-                A11 += (double)(ix * ix); A12 += (double)(ix * iy); A22 += (double)(iy * iy);
+                Iv[k] = ival; dxy[k] = (ix & 0xffff) | (iy << 16);
+                A11 += (long long)(ix * ix); A12 += (long long)(ix * iy); A22 += (long long)(iy * iy);
+            } else { Iv[k] = 0; dxy[k] = 0; }
+        }
+        lk_warp_sum3(A11, A12, A22);
+        const float fA11 = (float)A11 * FLT_SCALE, fA12 = (float)A12 * FLT_SCALE, fA22 = (float)A22 * FLT_SCALE;
+        float D = fA11 * fA22 - fA12 * fA12;
+        const float minEig = (fA22 + fA11 - sqrtf((fA11 - fA22) * (fA11 - fA22) + 4.f * fA12 * fA12)) / (2 * LK_WIN * LK_WIN);
+        if (minEig < a.min_eig || D < 1.1920929e-07f) { if (level == 0) status = false; continue; }
+        D = 1.f / D;
+        nx -= (float)LK_HALF; ny -= (float)LK_HALF;
+        float pdx = 0.f, pdy = 0.f;
+        const int jc = a.J.w[level], jr = a.J.h[level], jstr = a.J.stride[level];
+        const uint8_t *jimg = a.J.img[level];
+        for (int j = 0; j < a.max_iter; j++) {
+            const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+            if (lk_outside(inx, iny, jc, jr)) { if (level == 0) status = false; break; }
+            const float ja = nx - inx, jb = ny - iny;
+            const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
+            const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;
+            const bool inside = inx >= 0 && iny >= 0 && inx + 22 <= jc && iny + 22 <= jr;   // whole 22x22 footprint in the image
+            long long b1 = 0, b2 = 0;
+#pragma unroll
+            for (int k = 0; k < LK_EPL; k++) {
+                const int e = lane + LK_W * k;
+                if (e < 441) {
+                    const int y = e / 21, x = e - y * 21;
+                    const int diff = descale(lk_sample(a.J, level, jimg, jstr, inside, inx + x, iny + y, w00, w01, w10, w11), 9) - Iv[k];
+                    b1 += (long long)(diff * (int)(short)(dxy[k] & 0xffff)); b2 += (long long)(diff * (dxy[k] >> 16));
+                }
             }
-            lk_sum3(A11, A12, A22, tid, nt, red, phase++);
-            const float fA11 = (float)A11 * FLT_SCALE, fA12 = (float)A12 * FLT_SCALE, fA22 = (float)A22 * FLT_SCALE;
-            float D = fA11 * fA22 - fA12 * fA12;
-            const float minEig = (fA22 + fA11 - sqrtf((fA11 - fA22) * (fA11 - fA22) + 4.f * fA12 * fA12)) / (2 * LK_WIN * LK_WIN);
-            if (minEig < a.min_eig || D < 1.1920929e-07f) { if (level == 0) status = false; continue; }
-            D = 1.f / D;
-            nx -= (float)LK_HALF; ny -= (float)LK_HALF;
-            float pdx = 0.f, pdy = 0.f;
-            const int jc = a.J.w[level], jr = a.J.h[level], jstr = a.J.stride[level];
-            const uint8_t *jimg = a.J.img[level];
-            for (int j = 0; j < a.max_iter; j++) {
-                const int inx = (int)floorf(nx), iny = (int)floorf(ny);
-                if (lk_outside(inx, iny, jc, jr)) { if (level == 0) status = false; break; }
-                const float ja = nx - inx, jb = ny - iny;
+            lk_warp_sum2(b1, b2);
+            const float fb1 = (float)b1 * FLT_SCALE, fb2 = (float)b2 * FLT_SCALE;
+            const float dx = (fA12 * fb2 - fA22 * fb1) * D, dy = (fA12 * fb1 - fA11 * fb2) * D;
+            nx += dx; ny += dy;
+            npx = nx + (float)LK_HALF; npy = ny + (float)LK_HALF;
+            if (dx * dx + dy * dy <= a.eps2) break;
+            if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) { npx -= dx * 0.5f; npy -= dy * 0.5f; break; }
+            pdx = dx; pdy = dy;
+        }
+        if (status && level == 0) {   // L1 error of the final patch (flags without OPTFLOW_LK_GET_MIN_EIGENVALS)
+            const float ex = npx - (float)LK_HALF, ey = npy - (float)LK_HALF;
+            const int inx = (int)floorf(ex), iny = (int)floorf(ey);
+            if (lk_outside(inx, iny, jc, jr)) { status = false; }
+            else {
+                const float ja = ex - inx, jb = ey - iny;
                 const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
                 const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;
-                const bool inside = inx >= 0 && iny >= 0 && inx + 22 <= jc && iny + 22 <= jr;   // whole 22x22 footprint in the image
-                double b1 = 0, b2 = 0, dummy = 0;
-                for (int e = tid; e < 441; e += nt) {
-                    const int y = e / 21, x = e - y * 21, sx = inx + x, sy = iny + y;
-                    int v;
-                    if (inside) { const uint8_t *q = jimg + (size_t)sy * jstr + sx; v = q[0] * w00 + q[1] * w01 + q[jstr] * w10 + q[jstr + 1] * w11; }
-                    else v = lk_pix(a.J, level, sx, sy) * w00 + lk_pix(a.J, level, sx + 1, sy) * w01 + lk_pix(a.J, level, sx, sy + 1) * w10 + lk_pix(a.J, level, sx + 1, sy + 1) * w11;
-                    const int diff = descale(v, 9) - Iptr[e];
-                    b1 += (double)(diff * dI[2 * e]); b2 += (double)(diff * dI[2 * e + 1]);
-                }
-                lk_sum3(b1, b2, dummy, tid, nt, red, phase++);
-                const float fb1 = (float)b1 * FLT_SCALE, fb2 = (float)b2 * FLT_SCALE;
-                const float dx = (fA12 * fb2 - fA22 * fb1) * D, dy = (fA12 * fb1 - fA11 * fb2) * D;
-                nx += dx; ny += dy;
-                npx = nx + (float)LK_HALF; npy = ny + (float)LK_HALF;
-                if (dx * dx + dy * dy <= a.eps2) break;
-                if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) { npx -= dx * 0.5f; npy -= dy * 0.5f; break; }
-                pdx = dx; pdy = dy;
-            }
-            if (status && level == 0) {   // L1 error of the final patch (flags without OPTFLOW_LK_GET_MIN_EIGENVALS)
-                const float ex = npx - (float)LK_HALF, ey = npy - (float)LK_HALF;
-                const int inx = (int)floorf(ex), iny = (int)floorf(ey);
-                if (lk_outside(inx, iny, jc, jr)) { status = false; }
-                else {
-                    const float ja = ex - inx, jb = ey - iny;
-                    const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
-                    const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;
-                    double ev = 0, d1 = 0, d2 = 0;
-                    for (int e = tid; e < 441; e += nt) {
-                        const int y = e / 21, x = e - y * 21, sx = inx + x, sy = iny + y;
-                        const int diff = descale(lk_pix(a.J, level, sx, sy) * w00 + lk_pix(a.J, level, sx + 1, sy) * w01 + lk_pix(a.J, level, sx, sy + 1) * w10 + lk_pix(a.J, level, sx + 1, sy + 1) * w11, 9) - Iptr[e];
-                        ev += (double)(diff < 0 ? -diff : diff);
+                const bool inside = inx >= 0 && iny >= 0 && inx + 22 <= jc && iny + 22 <= jr;
+                long long ev = 0, d1 = 0;
+#pragma unroll
+                for (int k = 0; k < LK_EPL; k++) {
+                    const int e = lane + LK_W * k;
+                    if (e < 441) {
+                        const int y = e / 21, x = e - y * 21;
+                        const int diff = descale(lk_sample(a.J, level, jimg, jstr, inside, inx + x, iny + y, w00, w01, w10, w11), 9) - Iv[k];
+                        ev += (long long)(diff < 0 ? -diff : diff);
                     }
-                    lk_sum3(ev, d1, d2, tid, nt, red, phase++);
-                    errv = (float)ev * (1.f / (32 * LK_WIN * LK_WIN));
                 }
+                lk_warp_sum2(ev, d1);
+                errv = (float)ev * (1.f / (32 * LK_WIN * LK_WIN));
             }
         }
     }
-    if (tid == 0) { a.next_pts[2 * pt] = npx; a.next_pts[2 * pt + 1] = npy; a.status[pt] = status ? 1 : 0; if (a.err) a.err[pt] = errv; }
+    if (lane == 0) { a.next_pts[2 * pt] = npx; a.next_pts[2 * pt + 1] = npy; a.status[pt] = status ? 1 : 0; if (a.err) a.err[pt] = errv; }
 }
 
 // ---- status post-processing of trackImage: round trip <= 0.5 px and the 1-px border test after cvRound
@@ -222,9 +248,10 @@ VIWB_D void lk_post_item(const PostArgs &a, int i) {
 // task-table kernels: blockIdx.y selects the task
 __global__ void pyr_down_tasks_kernel(const PyrArgs *t) { pyr_down_item(t[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void lk_post_tasks_kernel(const PostArgs *t) { lk_post_item(t[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x); }
-__global__ void __launch_bounds__(LK_NT) lk_track_tasks_kernel(const LkArgs *t) {
+__global__ void __launch_bounds__(32 * LK_PPB, LK_MINB) lk_track_tasks_kernel(const LkArgs *t) {
     extern __shared__ unsigned char lk_smem[];
-    lk_track_block(t[blockIdx.y], blockIdx.x, threadIdx.x, blockDim.x, lk_smem);
+    const int warp = threadIdx.x >> 5;
+    lk_track_warp(t[blockIdx.y], blockIdx.x * LK_PPB + warp, threadIdx.x & 31, lk_smem + (size_t)warp * LK_WARP_SMEM);
 }
 #endif
 

@@ -210,7 +210,7 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     for (int e = tid; e < MLAY * MLAY; e += nt) M[(size_t)(e / MLAY) * LDM + (e % MLAY)] = 0.0;
     for (int i = tid; i < TFIX + 8; i += nt) b[i] = 0.0;
     VIWB_SYNC();
-    { DenseTarget t; t.M = M; t.g = b; t.ld = LDM; t.flags = m.flags; assemble_into(t, bd, w, MODE_MARG, tid, nt); }
+    { DenseTarget t; t.M = M; t.g = b; t.ld = LDM; t.flags = m.flags; assemble_into(t, bd, w, MODE_MARG, tid, nt, keep); }      // keep[] is filled only afterwards
     VIWB_SYNC();
     // ---- eliminate the dropped landmarks: M -= scatter(T0), b -= scatter(tvec0)   (MARGIN_OLD only)
     if (m.margin_flag == 0) {

@@ -68,7 +68,7 @@ VIWB_D void assemble_H(const BatchDev &bd, int w, const SolveSmem &s, int nf, do
     for (int i = tid; i < nf; i += nt) s.g[i] = 0.0;
     VIWB_SYNC();
     PackedTarget t; t.L = s.L; t.g = s.g; t.tcol = bd.meta[w].tcol;
-    assemble_into(t, bd, w, MODE_SOLVE, tid, nt);
+    assemble_into(t, bd, w, MODE_SOLVE, tid, nt, (int *)s.Hu);      // Hu is free until the step computation
     for (int e = tid; e < ne; e += nt) Hpk[e] = s.L[e];
     for (int i = tid; i < nf; i += nt) gpk[i] = s.g[i];
     VIWB_SYNC();

@@ -8,7 +8,7 @@ static void lk_launch_pyr(const PyrArgs *t, int items, int ntasks, stream_t) { f
 static void lk_launch_post(const PostArgs *t, int items, int ntasks, stream_t) { for (int k = 0; k < ntasks; k++) for (int i = 0; i < items; i++) lk_post_item(t[k], i); }
 static void lk_launch_track(const LkArgs *t, int maxn, int ntasks, stream_t) {
     std::vector<unsigned char> sm(lk_smem_bytes(1) + 64);
-    for (int k = 0; k < ntasks; k++) for (int p = 0; p < maxn; p++) lk_track_block(t[k], p, 0, 1, sm.data());
+    for (int k = 0; k < ntasks; k++) for (int p = 0; p < maxn; p++) lk_track_warp(t[k], p, 0, sm.data());
 }
 static int dev_h2d_2d(void *d, size_t dp, const void *h, size_t hp, size_t w, size_t rows, stream_t) { for (size_t r = 0; r < rows; r++) memcpy((char *)d + r * dp, (const char *)h + r * hp, w); return 0; }
 #else
@@ -22,7 +22,7 @@ static void lk_launch_post(const PostArgs *t, int items, int ntasks, stream_t s)
 }
 static void lk_launch_track(const LkArgs *t, int maxn, int ntasks, stream_t s) {
     if (maxn <= 0 || ntasks <= 0) return;
-    g_prof.begin("lk_track", s); lk_track_tasks_kernel<<<dim3(maxn, ntasks), LK_NT, lk_smem_bytes(LK_NT), s>>>(t); g_prof.end(s);
+    g_prof.begin("lk_track", s); lk_track_tasks_kernel<<<dim3((maxn + LK_PPB - 1) / LK_PPB, ntasks), 32 * LK_PPB, lk_smem_bytes(LK_PPB), s>>>(t); g_prof.end(s);
 }
 static int dev_h2d_2d(void *d, size_t dp, const void *h, size_t hp, size_t w, size_t rows, stream_t s) { return (w && rows) ? (int)cudaMemcpy2DAsync(d, dp, h, hp, w, rows, cudaMemcpyHostToDevice, s) : 0; }
 #endif
