@@ -92,6 +92,22 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def rank_max(x, world, device="cuda"):
+    """Slowest rank's figure (every rank gets it): the job is as fast as its slowest replica."""
+    if world <= 1:
+        return float(x)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def job_throughput(world, per_rank_units, steps, seconds):
+    """Whole-job units/s of `world` independent replicas (weak scaling: every rank processes per_rank_units per step)."""
+    return world * per_rank_units * steps / seconds
+
+
 def usable_cores():
     """Host threads this process can really run on: affinity mask, capped by the cgroup CPU quota (a container may see
     128 CPUs and be allowed 16)."""
@@ -339,11 +355,8 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * B * args.steps / (ms * 1e-3)
+    ms = rank_max(ms, world)
+    value = job_throughput(world, B, args.steps, ms * 1e-3)
 
     # ---- parity spot check of what was just timed (pose error vs the oracle on a few windows, rank 0)
     sts, sums, pri = batch.download()
@@ -373,11 +386,8 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * B * e2e_steps / e2e_s
+    e2e_s = rank_max(e2e_s, world)
+    e2e_value = job_throughput(world, B, e2e_steps, e2e_s)
     h2d = sum(p.vis_obs.nbytes + 4 * 4 * len(p.vis_type) + p.imu_data.nbytes + p.wheel_data.nbytes + 8 * p.state_size +
               (8 * (p.prior.n ** 2 + p.prior.n + abi.STATE_FIXED) if p.prior is not None else 0) for p in probs)
     nmax = max(int(q.n) for q in pri if q is not None and q.valid) if any(q is not None and q.valid for q in pri) else 0
