@@ -7,10 +7,11 @@
 // 3x3 Scharr into int16, 14-bit fixed-point bilinear weights, patch intensities kept with 5 fractional bits,
 // float Gauss-Newton updates, eps^2 / oscillation stopping rules, status and L1 error semantics.
 //
-// Device layout: no derivative images and no padded copies are materialised.  One block tracks one point; per level
+// Device layout: no derivative images and no padded copies are materialised.  One warp tracks one point; per level
 // it stages the 24x24 source patch in shared memory (reflect-101 at the image border), derives the 22x22 Scharr
 // samples from it (zero outside the image, like OpenCV's constant-border derivative buffer), interpolates the 21x21
-// template + gradient into shared memory and keeps them there for all Gauss-Newton iterations.  Work is described by
+// template + gradient into registers (14 samples per lane), and stages a 32x32 region of the search image that the
+// Gauss-Newton iterations sample from shared memory (restaged only if the estimate leaves it).  Work is described by
 // task tables in HBM (one LkArgs per {stream, direction}), so one launch covers every camera stream of a batch.
 #pragma once
 #include <stdint.h>
@@ -75,7 +76,7 @@ enum { LK_W = 32 };
 #ifndef LK_MINB
 #define LK_MINB 6
 #endif
-enum { LK_EPL = (441 + LK_W - 1) / LK_W, LK_PPB = 4, LK_WARP_SMEM = (576 + 968) * 2 + 16 };     // elements per lane, points per block, bytes per warp
+enum { LK_EPL = (441 + LK_W - 1) / LK_W, LK_PPB = 4, LK_WARP_SMEM = (576 + 968) * 2 + 32 * 36 + 16 };     // elements per lane, points per block, bytes per warp
 VIWB_HD size_t lk_smem_bytes(int warps) { return (size_t)warps * LK_WARP_SMEM; }
 
 VIWB_D void lk_warp_sum3(long long &a, long long &b, long long &c) {
@@ -94,26 +95,40 @@ VIWB_D void lk_warp_sum2(long long &a, long long &b) {
 }
 VIWB_HD bool lk_outside(int ix, int iy, int cols, int rows) { return ix < -LK_WIN || ix >= cols || iy < -LK_WIN || iy >= rows; }
 
-// bilinear sample (before descaling) of the search image at integer corner (sx, sy) with 14-bit weights
-VIWB_D int lk_sample(const LkImage &J, int level, const uint8_t *jimg, int jstr, bool inside, int sx, int sy, int w00, int w01, int w10, int w11) {
-    if (inside) { const uint8_t *q = jimg + (size_t)sy * jstr + sx; return q[0] * w00 + q[1] * w01 + q[jstr] * w10 + q[jstr + 1] * w11; }
-    return lk_pix(J, level, sx, sy) * w00 + lk_pix(J, level, sx + 1, sy) * w01 + lk_pix(J, level, sx, sy + 1) * w10 + lk_pix(J, level, sx + 1, sy + 1) * w11;
+// the search-image region a warp keeps in shared memory: (22 + 2*LK_SLACK)^2 bytes around the current estimate, reflect-101
+// resolved while staging, so the Gauss-Newton loop has a single branch-free sampling path
+enum { LK_SLACK = 5, LK_JR = 22 + 2 * LK_SLACK, LK_JS = LK_JR + 4 };
+VIWB_D void lk_stage_search(uint8_t *jbuf, const uint8_t *jimg, int jstr, int jc, int jr, int jx0, int jy0, int lane) {
+    VIWB_SYNCWARP();
+    const bool in = jx0 >= 0 && jy0 >= 0 && jx0 + LK_JR <= jc && jy0 + LK_JR <= jr;
+    for (int e = lane; e < LK_JR * LK_JR; e += LK_W) {
+        const int y = e / LK_JR, x = e - y * LK_JR;
+        jbuf[y * LK_JS + x] = in ? jimg[(size_t)(jy0 + y) * jstr + jx0 + x] : jimg[(size_t)reflect101(jy0 + y, jr) * jstr + reflect101(jx0 + x, jc)];
+    }
+    VIWB_SYNCWARP();
 }
 
 VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem_raw) {
     short *patch = (short *)smem_raw, *dpatch = patch + 576;
+    uint8_t *jbuf = (uint8_t *)(dpatch + 968);
     const int npts = a.n_dev ? *a.n_dev : a.n;
     if (pt >= npts) return;
+    const int max_level = a.max_level, max_iter = a.max_iter, flags = a.flags;
+    const float eps2 = a.eps2, min_eig = a.min_eig;
     const float FLT_SCALE = 1.f / (1 << 20);
+    const float px0 = a.prev_pts[2 * pt], py0 = a.prev_pts[2 * pt + 1];
     bool status = true; float errv = 0.f;
     float npx = 0.f, npy = 0.f;     // nextPts[ptidx] (window centre coordinates)
     int Iv[LK_EPL], dxy[LK_EPL];    // template intensity (5 fractional bits) and packed (dx | dy << 16) per owned element
-    for (int level = a.max_level; level >= 0; level--) {
+    int eoff[LK_EPL];               // offset of the element inside the staged search region
+#pragma unroll
+    for (int k = 0; k < LK_EPL; k++) { const int e = lane + LK_W * k, y = e / 21, x = e - y * 21; eoff[k] = y * LK_JS + x; }
+    for (int level = max_level; level >= 0; level--) {
         const float sc = (float)(1. / (1 << level));
-        float ppx = a.prev_pts[2 * pt] * sc, ppy = a.prev_pts[2 * pt + 1] * sc;
+        float ppx = px0 * sc, ppy = py0 * sc;
         float nx, ny;
-        if (level == a.max_level) {
-            if (a.flags & 4) { nx = a.next_pts[2 * pt] * sc; ny = a.next_pts[2 * pt + 1] * sc; } else { nx = ppx; ny = ppy; }
+        if (level == max_level) {
+            if (flags & 4) { nx = a.next_pts[2 * pt] * sc; ny = a.next_pts[2 * pt + 1] * sc; } else { nx = ppx; ny = ppy; }
         } else { nx = npx * 2.f; ny = npy * 2.f; }
         npx = nx; npy = ny;
         ppx -= (float)LK_HALF; ppy -= (float)LK_HALF;
@@ -165,26 +180,32 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
         const float fA11 = (float)A11 * FLT_SCALE, fA12 = (float)A12 * FLT_SCALE, fA22 = (float)A22 * FLT_SCALE;
         float D = fA11 * fA22 - fA12 * fA12;
         const float minEig = (fA22 + fA11 - sqrtf((fA11 - fA22) * (fA11 - fA22) + 4.f * fA12 * fA12)) / (2 * LK_WIN * LK_WIN);
-        if (minEig < a.min_eig || D < 1.1920929e-07f) { if (level == 0) status = false; continue; }
+        if (minEig < min_eig || D < 1.1920929e-07f) { if (level == 0) status = false; continue; }
         D = 1.f / D;
         nx -= (float)LK_HALF; ny -= (float)LK_HALF;
         float pdx = 0.f, pdy = 0.f;
         const int jc = a.J.w[level], jr = a.J.h[level], jstr = a.J.stride[level];
         const uint8_t *jimg = a.J.img[level];
-        for (int j = 0; j < a.max_iter; j++) {
+        int jx0 = (int)floorf(nx) - LK_SLACK, jy0 = (int)floorf(ny) - LK_SLACK;       // origin of the staged search region
+        bool staged = false;
+        for (int j = 0; j < max_iter; j++) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (lk_outside(inx, iny, jc, jr)) { if (level == 0) status = false; break; }
+            if (!staged || inx < jx0 || iny < jy0 || inx + 22 > jx0 + LK_JR || iny + 22 > jy0 + LK_JR) {
+                jx0 = inx - LK_SLACK; jy0 = iny - LK_SLACK;
+                lk_stage_search(jbuf, jimg, jstr, jc, jr, jx0, jy0, lane);
+                staged = true;
+            }
             const float ja = nx - inx, jb = ny - iny;
             const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
             const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;
-            const bool inside = inx >= 0 && iny >= 0 && inx + 22 <= jc && iny + 22 <= jr;   // whole 22x22 footprint in the image
+            const uint8_t *q0 = jbuf + (iny - jy0) * LK_JS + (inx - jx0);
             long long b1 = 0, b2 = 0;
 #pragma unroll
             for (int k = 0; k < LK_EPL; k++) {
-                const int e = lane + LK_W * k;
-                if (e < 441) {
-                    const int y = e / 21, x = e - y * 21;
-                    const int diff = descale(lk_sample(a.J, level, jimg, jstr, inside, inx + x, iny + y, w00, w01, w10, w11), 9) - Iv[k];
+                if (lane + LK_W * k < 441) {
+                    const uint8_t *q = q0 + eoff[k];
+                    const int diff = descale(q[0] * w00 + q[1] * w01 + q[LK_JS] * w10 + q[LK_JS + 1] * w11, 9) - Iv[k];
                     b1 += (long long)(diff * (int)(short)(dxy[k] & 0xffff)); b2 += (long long)(diff * (dxy[k] >> 16));
                 }
             }
@@ -193,7 +214,7 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
             const float dx = (fA12 * fb2 - fA22 * fb1) * D, dy = (fA12 * fb1 - fA11 * fb2) * D;
             nx += dx; ny += dy;
             npx = nx + (float)LK_HALF; npy = ny + (float)LK_HALF;
-            if (dx * dx + dy * dy <= a.eps2) break;
+            if (dx * dx + dy * dy <= eps2) break;
             if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) { npx -= dx * 0.5f; npy -= dy * 0.5f; break; }
             pdx = dx; pdy = dy;
         }
@@ -202,17 +223,20 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
             const int inx = (int)floorf(ex), iny = (int)floorf(ey);
             if (lk_outside(inx, iny, jc, jr)) { status = false; }
             else {
+                if (!staged || inx < jx0 || iny < jy0 || inx + 22 > jx0 + LK_JR || iny + 22 > jy0 + LK_JR) {
+                    jx0 = inx - LK_SLACK; jy0 = iny - LK_SLACK;
+                    lk_stage_search(jbuf, jimg, jstr, jc, jr, jx0, jy0, lane);
+                }
                 const float ja = ex - inx, jb = ey - iny;
                 const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
                 const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;
-                const bool inside = inx >= 0 && iny >= 0 && inx + 22 <= jc && iny + 22 <= jr;
+                const uint8_t *q0 = jbuf + (iny - jy0) * LK_JS + (inx - jx0);
                 long long ev = 0, d1 = 0;
 #pragma unroll
                 for (int k = 0; k < LK_EPL; k++) {
-                    const int e = lane + LK_W * k;
-                    if (e < 441) {
-                        const int y = e / 21, x = e - y * 21;
-                        const int diff = descale(lk_sample(a.J, level, jimg, jstr, inside, inx + x, iny + y, w00, w01, w10, w11), 9) - Iv[k];
+                    if (lane + LK_W * k < 441) {
+                        const uint8_t *q = q0 + eoff[k];
+                        const int diff = descale(q[0] * w00 + q[1] * w01 + q[LK_JS] * w10 + q[LK_JS + 1] * w11, 9) - Iv[k];
                         ev += (long long)(diff < 0 ? -diff : diff);
                     }
                 }

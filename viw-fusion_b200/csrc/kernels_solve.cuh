@@ -46,10 +46,10 @@ VIWB_D double block_max(double v, int tid, int nt, double *red) {
 
 struct SolveSmem {
     double *L;       // packed lower, nf(nf+1)/2
-    double *g, *sc, *D, *sg, *y, *u, *Hu, *ug, *uvis, *red, *bc, *chol;
+    double *g, *sc, *D, *sg, *y, *u, *Hu, *ug, *uvis, *red, *bc, *chol, *dinv, *xo, *Pt;
     int *amap, *vmap;
 };
-VIWB_HD size_t solve_smem_doubles(int nt) { return (size_t)TFIX * (TFIX + 1) / 2 + 9 * TFIX + 2 * VSUB + nt + 16 + TFIX + (size_t)((nt + 31) / 32) * 48; }   // + ints (2*TFIX ints = TFIX doubles)
+VIWB_HD size_t solve_smem_doubles(int nt) { return (size_t)TFIX * (TFIX + 1) / 2 + 9 * TFIX + 2 * VSUB + nt + 16 + TFIX + (size_t)((nt + 31) / 32) * 48 + 2 * TFIX + 8 * (TFIX + 4) + 2; }   // + ints (2*TFIX ints = TFIX doubles)
 VIWB_D void carve(SolveSmem &s, double *smem, int nt) {
     double *p = smem;
     s.L = p; p += (size_t)TFIX * (TFIX + 1) / 2;
@@ -58,6 +58,9 @@ VIWB_D void carve(SolveSmem &s, double *smem, int nt) {
     s.uvis = p; p += 2 * VSUB;
     s.red = p; p += nt; s.bc = p; p += 16;
     s.chol = p; p += (size_t)((nt + 31) / 32) * 48;
+    s.dinv = p; p += TFIX; s.xo = p; p += TFIX;
+    if ((p - smem) & 1) p++;                    // Pt is read with 16-byte vector loads
+    s.Pt = p; p += 8 * (TFIX + 4);
     s.amap = (int *)p; s.vmap = s.amap + TFIX;
 }
 
@@ -96,16 +99,44 @@ VIWB_D void to_vis(const SolveSmem &s, int nf, const double *u, double *uvis, in
     VIWB_SYNC();
 }
 VIWB_D double dot80(const double *W, const double *v) { double a = 0.0; for (int p = 0; p < 79; p++) a += W[p] * v[p]; return a; }
+// the same product by one warp: coalesced reads of the landmark's W row, every lane gets the sum (fixed order: deterministic)
+VIWB_D double warp_dot80(const double *W, const double *v, int lane) {
+#ifdef VIWB_HOST_EMU
+    (void)lane; return dot80(W, v);
+#else
+    double a = W[lane] * v[lane] + W[lane + 32] * v[lane + 32];
+    if (lane < 15) a += W[lane + 64] * v[lane + 64];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
+#endif
+}
+// landmark loops run one warp per landmark: lane 0 carries the scalar work and the partial sums
+#ifdef VIWB_HOST_EMU
+#define VIWB_LM_LOOP(k, N) for (int k = 0, lane = 0; k < (N); k++)
+#else
+#define VIWB_LM_LOOP(k, N) for (int k = tid >> 5, lane = tid & 31; k < (N); k += nt >> 5)
+#endif
 
 // Blocked (panel width 8) in-place Cholesky of the packed lower triangle with the right-hand side carried as an extra
 // row n, so that on exit y = L^-1 b (forward substitution for free).  Returns false on a non-positive pivot
 // (Eigen LLT semantics: schur_complement_solver.cc -> LINEAR_SOLVER_FAILURE).  2 barriers per panel:
 //   every warp factors the 8x8 diagonal block redundantly (8 lanes, one row each, in registers; pivots through rsqrt so
 //   that the panel rows multiply instead of divide) into its own scratch, so no barrier separates it from the panel solve;
-//   then one thread per panel row, then 4x4 register tiles for the trailing update.
-// scratch: nwarps * 48 doubles (36 packed block entries + 8 inverse pivots + flag).
-enum { CHOL_NB = 8, CHOL_SCR = 48 };
-VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, double *bc, double *scratch) {
+//   one thread per panel row, which also drops its 8 results into a column-major panel buffer Pt[8][rows]; the trailing
+//   update then runs 4x4 register tiles whose operands are 32-byte vector loads from Pt (conflict-free), not strided
+//   reads of the packed triangle.
+// scratch: nwarps * 48 doubles (36 packed block entries + 8 inverse pivots + flag); dinv[n] receives 1 / L_kk;
+// Pt: 8 * CHOL_LDP doubles, 16-byte aligned.
+enum { CHOL_NB = 8, CHOL_SCR = 48, CHOL_LDP = TFIX + 4 };
+VIWB_D void load4(const double *p, double *o) {
+#ifdef VIWB_HOST_EMU
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = p[3];
+#else
+    const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1];
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+#endif
+}
+VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, double *scratch, double *dinv, double *Pt) {
 #define ROW(i) ((i) < n ? L + (size_t)(i) * ((i) + 1) / 2 : y)
     const int lane = tid & 31;
     double *my = scratch + (size_t)(tid >> 5) * CHOL_SCR;      // this warp's copy of the factored diagonal block
@@ -113,6 +144,7 @@ VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, do
         const int nb = (n - c0) < CHOL_NB ? (n - c0) : CHOL_NB;
 #ifdef VIWB_HOST_EMU
         {   // single-thread statement of the same arithmetic
+            (void)lane;
             my[44] = 1.0;
             double a[8][8];
             for (int i = 0; i < nb; i++) for (int j = 0; j <= i; j++) a[i][j] = ROW(c0 + i)[c0 + j];
@@ -157,60 +189,92 @@ VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, do
 #endif
         if (my[44] == 0.0) return false;                    // every warp reaches the same verdict
         const int r0 = c0 + nb;
-        // panel rows r0..n (row n = rhs): x_k = (a_ik - sum_m x_m L_km) / L_kk
-        for (int i = r0 + tid; i <= n; i += nt) {
-            double *ri = ROW(i) + c0;
+        const int nr = n + 1 - r0, mt = (nr + 3) / 4;       // panel rows r0..n (row n = rhs), padded to whole 4-row tiles
+        // panel rows: x_k = (a_ik - sum_m x_m L_km) / L_kk
+        for (int i = r0 + tid; i < r0 + 4 * mt; i += nt) {
             double x[8];
+            if (i <= n) {
+                double *ri = ROW(i) + c0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (k < nb) {
-                    double v = ri[k];
+                for (int k = 0; k < 8; k++) {
+                    x[k] = 0.0;
+                    if (k < nb) {
+                        double v = ri[k];
 #pragma unroll
-                    for (int m = 0; m < 8; m++) if (m < k) v -= x[m] * my[k * (k + 1) / 2 + m];
-                    x[k] = v * my[36 + k];
-                    ri[k] = x[k];
+                        for (int m = 0; m < 8; m++) if (m < k) v -= x[m] * my[k * (k + 1) / 2 + m];
+                        x[k] = v * my[36 + k];
+                        ri[k] = x[k];
+                    }
                 }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[k] = 0.0;
             }
+#pragma unroll
+            for (int k = 0; k < 8; k++) Pt[k * CHOL_LDP + (i - r0)] = x[k];
         }
+        for (int r = tid; r < nb; r += nt) dinv[c0 + r] = my[36 + r];
         VIWB_SYNC();
         // factored diagonal block back into the matrix (only now: the other warps have finished reading the unfactored one)
         for (int r = tid; r < nb; r += nt) { double *rk = ROW(c0 + r) + c0; for (int j = 0; j <= r; j++) rk[j] = my[r * (r + 1) / 2 + j]; }
         // trailing update with 4x4 register tiles over rows i in [r0, n], columns k in [r0, min(i, n-1)]
-        const int mt = (n + 1 - r0 + 3) / 4, ntile = mt * (mt + 1) / 2;
+        const int ntile = mt * (mt + 1) / 2;
         for (int t = tid; t < ntile; t += nt) {
             int ti, tk; sym_unrank(t, ti, tk);
-            const int ib = r0 + 4 * ti, kb = r0 + 4 * tk;
             double acc[16];
+#pragma unroll
             for (int q = 0; q < 16; q++) acc[q] = 0.0;
-            const double *pi[4], *pk[4];
-            for (int a = 0; a < 4; a++) { pi[a] = (ib + a <= n) ? ROW(ib + a) + c0 : nullptr; pk[a] = (kb + a < n) ? ROW(kb + a) + c0 : nullptr; }
-            for (int m = 0; m < nb; m++) {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
                 double li[4], lk[4];
-                for (int a = 0; a < 4; a++) { li[a] = pi[a] ? pi[a][m] : 0.0; lk[a] = pk[a] ? pk[a][m] : 0.0; }
-                for (int a = 0; a < 4; a++) for (int b2 = 0; b2 < 4; b2++) acc[a * 4 + b2] += li[a] * lk[b2];
+                load4(Pt + m * CHOL_LDP + 4 * ti, li); load4(Pt + m * CHOL_LDP + 4 * tk, lk);
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; b2++) acc[a * 4 + b2] += li[a] * lk[b2];
             }
-            for (int a = 0; a < 4; a++) { const int i = ib + a; if (i > n) break; double *ri = ROW(i);
-                for (int b2 = 0; b2 < 4; b2++) { const int k = kb + b2; if (k >= n || k > i) break; ri[k] -= acc[a * 4 + b2]; } }
+            const int ib = r0 + 4 * ti, kb = r0 + 4 * tk;
+#pragma unroll
+            for (int a = 0; a < 4; a++) { const int i = ib + a; if (i <= n) { double *ri = ROW(i);
+#pragma unroll
+                for (int b2 = 0; b2 < 4; b2++) { const int k = kb + b2; if (k < n && k <= i) ri[k] -= acc[a * 4 + b2]; } } }
         }
         VIWB_SYNC();
     }
-    (void)bc;
 #undef ROW
     return true;
 }
-// back substitution L^T x = y in place, by the first warp only (warp-synchronous, no block barriers)
-VIWB_D void chol_backsolve_warp(const double *L, double *y, int n, int tid, int nt) {
-    const int W = nt < 32 ? nt : 32;
-    if (tid < W) {
-        for (int j = n - 1; j >= 0; j--) {
-            const double *rj = L + (size_t)j * (j + 1) / 2;
-            if (tid == 0) y[j] /= rj[j];
-            VIWB_SYNCWARP();
-            const double xj = y[j];
-            for (int i = tid; i < j; i += W) y[i] -= rj[i] * xj;
-            VIWB_SYNCWARP();
+// back substitution L^T x = y (blocks of 8 from the bottom): every thread solves the 8x8 triangular block redundantly from
+// broadcast reads (no barrier between the block solve and the update), then all threads update the rows above.  One barrier
+// per block.  Result in y; xo is scratch of n doubles.
+VIWB_D void chol_backsolve_blocked(const double *L, double *y, const double *dinv, double *xo, int n, int tid, int nt) {
+    const int nblk = (n + CHOL_NB - 1) / CHOL_NB;
+    for (int bi = nblk - 1; bi >= 0; bi--) {
+        const int c0 = bi * CHOL_NB, nb = (n - c0) < CHOL_NB ? (n - c0) : CHOL_NB;
+        double x[8];
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            x[k] = 0.0;
+            if (k < nb) {
+                double v = y[c0 + k];
+#pragma unroll
+                for (int m = 7; m > k; m--) if (m < nb) v -= L[(size_t)(c0 + m) * (c0 + m + 1) / 2 + c0 + k] * x[m];
+                x[k] = v * dinv[c0 + k];
+            }
         }
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k < nb) xo[c0 + k] = x[k];
+        }
+        for (int i = tid; i < c0; i += nt) {
+            double v = y[i];
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k < nb) v -= L[(size_t)(c0 + k) * (c0 + k + 1) / 2 + i] * x[k];
+            y[i] = v;
+        }
+        VIWB_SYNC();
     }
+    for (int i = tid; i < n; i += nt) y[i] = xo[i];
     VIWB_SYNC();
 }
 
@@ -354,10 +418,13 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
             to_vis(s, nf, s.ug, s.uvis, tid, nt);
             double q = 0.0, l = 0.0;
             for (int i = tid; i < nf; i += nt) { q += s.ug[i] * s.Hu[i]; l += s.g[i] * s.ug[i]; }
-            for (int k = tid; k < N; k += nt) {
-                const double ul = lm_sc[k] * g_sg[TFIX + k] / g_D[TFIX + k];
-                q += 2.0 * ul * dot80(W + (size_t)k * VSUB, s.uvis) + lm_a[k] * ul * ul;
-                l += lm_g[k] * ul;
+            VIWB_LM_LOOP(k, N) {
+                const double dw = warp_dot80(W + (size_t)k * VSUB, s.uvis, lane);
+                if (lane == 0) {
+                    const double ul = lm_sc[k] * g_sg[TFIX + k] / g_D[TFIX + k];
+                    q += 2.0 * ul * dw + lm_a[k] * ul * ul;
+                    l += lm_g[k] * ul;
+                }
             }
             q = block_sum(q, tid, nt, s.red); l = block_sum(l, tid, nt, s.red);
             if (tid == 0) { ww.sgrad_norm = sqrt(n2); ww.q_gg = q; ww.l_g = l; ww.alpha = n2 / q; }
@@ -403,20 +470,23 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                 VIWB_SYNC();
                 h_dirty = true;
                 if (tid == 0) ww.num_linear++;
-                bool ok = cholesky_packed_rhs(s.L, s.y, nf, tid, nt, s.bc, s.chol);
+                bool ok = cholesky_packed_rhs(s.L, s.y, nf, tid, nt, s.chol, s.dinv, s.Pt);
                 if (ok) {
-                    chol_backsolve_warp(s.L, s.y, nf, tid, nt);
+                    chol_backsolve_blocked(s.L, s.y, s.dinv, s.xo, nf, tid, nt);
                     // back-substitute the inverse depths (scaled): y_k = (c g_k - c w_k . (C y_f)) / h_k
                     for (int i = tid; i < nf; i += nt) s.u[i] = s.sc[i] * s.y[i];
                     VIWB_SYNC();
                     to_vis(s, nf, s.u, s.uvis, tid, nt);
                     double bad = 0.0;
                     for (int i = tid; i < nf; i += nt) { if (!isfinite(s.y[i])) bad = 1.0; g_gn[i] = -s.D[i] * s.y[i]; }
-                    for (int k = tid; k < N; k += nt) {
-                        const double c = lm_sc[k], Dk = g_D[TFIX + k], hk = c * c * lm_a[k] + mu * Dk * Dk;
-                        const double yk = c * (lm_g[k] - dot80(W + (size_t)k * VSUB, s.uvis)) / hk;
-                        if (!isfinite(yk)) bad = 1.0;
-                        g_gn[TFIX + k] = -Dk * yk;
+                    VIWB_LM_LOOP(k, N) {
+                        const double dw = warp_dot80(W + (size_t)k * VSUB, s.uvis, lane);
+                        if (lane == 0) {
+                            const double c = lm_sc[k], Dk = g_D[TFIX + k], hk = c * c * lm_a[k] + mu * Dk * Dk;
+                            const double yk = c * (lm_g[k] - dw) / hk;
+                            if (!isfinite(yk)) bad = 1.0;
+                            g_gn[TFIX + k] = -Dk * yk;
+                        }
                     }
                     bad = block_sum(bad, tid, nt, s.red);
                     ok = (bad == 0.0);
@@ -439,14 +509,16 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                     qnn += s.u[i] * s.Hu[i]; qgn += s.ug[i] * s.Hu[i]; ln += s.g[i] * s.u[i];
                     nn += g_gn[i] * g_gn[i]; gd += s.sg[i] * g_gn[i];
                 }
-                for (int k = tid; k < N; k += nt) {
-                    const double c = lm_sc[k], Dk = g_D[TFIX + k];
-                    const double un = c * g_gn[TFIX + k] / Dk, ug = c * g_sg[TFIX + k] / Dk;
-                    const double dn = dot80(W + (size_t)k * VSUB, s.uvis), dg = dot80(W + (size_t)k * VSUB, s.uvis + VSUB);
-                    qnn += 2.0 * un * dn + lm_a[k] * un * un;
-                    qgn += ug * dn + un * dg + lm_a[k] * ug * un;
-                    ln += lm_g[k] * un;
-                    nn += g_gn[TFIX + k] * g_gn[TFIX + k]; gd += g_sg[TFIX + k] * g_gn[TFIX + k];
+                VIWB_LM_LOOP(k, N) {
+                    const double dn = warp_dot80(W + (size_t)k * VSUB, s.uvis, lane), dg = warp_dot80(W + (size_t)k * VSUB, s.uvis + VSUB, lane);
+                    if (lane == 0) {
+                        const double c = lm_sc[k], Dk = g_D[TFIX + k];
+                        const double un = c * g_gn[TFIX + k] / Dk, ug = c * g_sg[TFIX + k] / Dk;
+                        qnn += 2.0 * un * dn + lm_a[k] * un * un;
+                        qgn += ug * dn + un * dg + lm_a[k] * ug * un;
+                        ln += lm_g[k] * un;
+                        nn += g_gn[TFIX + k] * g_gn[TFIX + k]; gd += g_sg[TFIX + k] * g_gn[TFIX + k];
+                    }
                 }
                 qnn = block_sum(qnn, tid, nt, s.red); qgn = block_sum(qgn, tid, nt, s.red); ln = block_sum(ln, tid, nt, s.red);
                 nn = block_sum(nn, tid, nt, s.red); gd = block_sum(gd, tid, nt, s.red);

@@ -75,6 +75,7 @@ static void lk_batch_free(viwb_lk_batch *b) {
 }
 
 static int lk_batch_build(viwb_context *ctx, int F, int w, int h, int maxn, int stereo, int flow_back, viwb_lk_batch **out) {
+    bind_device(ctx);
     viwb_lk_batch *b = new viwb_lk_batch();
     memset(b, 0, sizeof *b);
     b->ctx = ctx; b->F = F; b->w = w; b->h = h; b->maxn = maxn; b->stereo = stereo; b->flow_back = flow_back; b->levels = lk_levels(w, h, 3); b->cur = 0;
@@ -131,6 +132,7 @@ static int lk_batch_build(viwb_context *ctx, int F, int w, int h, int maxn, int 
 // F images (host pointer per stream) into one slot; one strided copy when the host images are equally spaced
 static int lk_upload_slot(viwb_lk_batch *b, int slot, const uint8_t *const *imgs, int stride) {
     viwb_context *ctx = b->ctx;
+    bind_device(ctx);
     const int F = b->F;
     bool spaced = stride == b->ls[0];
     const ptrdiff_t gap = F > 1 ? imgs[1] - imgs[0] : (ptrdiff_t)b->lsz[0];
@@ -162,6 +164,7 @@ static int lk_batch_upload(viwb_lk_batch *b, const uint8_t *const *prev, const u
 // what: bit 0 temporal, bit 1 stereo
 static int lk_batch_execute(viwb_lk_batch *b, int what) {
     viwb_context *ctx = b->ctx;
+    bind_device(ctx);
     const int F = b->F; stream_t st = ctx->stream;
     if (!b->stereo) what &= 1;
     // every tick brings new cur (and right) images, so their pyramids are part of the tick; the previous image keeps the
@@ -188,6 +191,7 @@ static int lk_batch_execute(viwb_lk_batch *b, int what) {
 
 static int lk_batch_fetch(viwb_lk_batch *b, float *cur_pts, uint8_t *status, float *right_pts, uint8_t *status_right) {
     viwb_context *ctx = b->ctx;
+    bind_device(ctx);
     const size_t np = (size_t)b->F * b->maxn;
     if (cur_pts) CK(dev_d2h(cur_pts, b->P(1, 0), np * 8, ctx->stream));
     if (status) CK(dev_d2h(status, b->S(0, 0), np, ctx->stream));
@@ -202,6 +206,7 @@ static int lk_single_frames(viwb_context *ctx, int w, int h, int n, viwb_lk_batc
 
 static int lk_track_single(viwb_context *ctx, const uint8_t *prev, const uint8_t *next, int w, int h, int stride, const float *prev_pts, float *next_pts, int n,
                            int max_level, int max_iter, float eps, int flags, float min_eig, uint8_t *status, float *err) {
+    bind_device(ctx);
     if (n == 0) return VIWB_OK;
     viwb_lk_batch *b; int rc = lk_single_frames(ctx, w, h, n, &b); if (rc) return rc;
     const uint8_t *pa[1] = {prev}, *pb[1] = {next};
@@ -243,6 +248,7 @@ static int lk_single_frames(viwb_context *ctx, int w, int h, int n, viwb_lk_batc
 // forward + (optional) reverse LK sharing the two pyramids, then the reference's status rules, all on the device
 static int lk_track_checked_single(viwb_context *ctx, const uint8_t *img_a, const uint8_t *img_b, int w, int h, int stride, const float *pts_a, float *pts_b,
                                    int n, int mode, int flow_back, uint8_t *status) {
+    bind_device(ctx);
     if (n == 0) return VIWB_OK;
     viwb_lk_batch *b; int rc = lk_single_frames(ctx, w, h, n, &b); if (rc) return rc;
     if (b->flow_back != (flow_back ? 1 : 0)) {          // the status rule is baked into the task tables: rebuild them for the other setting

@@ -106,6 +106,16 @@ struct viwb_context {
 };
 
 static int fail(viwb_context *ctx, int code, const std::string &msg) { if (ctx) ctx->err = msg; return code; }
+// CUDA's current device is per host thread: every entry point binds the context's device before touching it, so that
+// contexts can be driven from any thread (one context per thread at a time)
+static inline void bind_device(const viwb_context *ctx) {
+#ifndef VIWB_HOST_EMU
+    static thread_local int cur = -1;
+    if (ctx && cur != ctx->device) { cudaSetDevice(ctx->device); cur = ctx->device; }
+#else
+    (void)ctx;
+#endif
+}
 #define CK(call) do { int e_ = (call); if (e_) return fail(ctx, VIWB_ERR_CUDA, std::string(#call) + ": " + dev_errstr(e_)); } while (0)
 
 #include "lk_host.inl"
@@ -346,6 +356,7 @@ template <typename F> static void parallel_for(int n, F f) {
 
 static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, const double *const *states,
                        const viwb_options *options, const int32_t *margin_flags, viwb_batch **out, bool use_cached = false) {
+    bind_device(ctx);
     if (B <= 0 || !problems || !states) return fail(ctx, VIWB_ERR_INVALID, "empty batch");
     const double t_start = now_ms();
     viwb_batch *b = new viwb_batch();
@@ -461,6 +472,7 @@ static int ensure_attrs(viwb_context *ctx) {
 enum { RUN_SOLVE = 1, RUN_REANCHOR = 2, RUN_MARG = 4, RUN_LIN_ONLY = 8 };
 
 static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
+    bind_device(ctx);
     BatchDev &bd = b->bd;
     int rc = ensure_attrs(ctx); if (rc) return rc;
     stream_t st = ctx->stream;
@@ -517,6 +529,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
 }
 
 static int batch_fetch(viwb_context *ctx, viwb_batch *b, double *const *states, viwb_summary *summaries, viwb_prior *priors_out) {
+    bind_device(ctx);
     BatchDev &bd = b->bd;
     const int B = b->B, nmax = b->prior_nmax;
     // staging layout inside the pinned slab
@@ -781,6 +794,7 @@ __global__ void eval_factor_kernel(EvalArgs a) { if (threadIdx.x == 0 && blockId
 
 extern "C" int viwb_factor_evaluate(viwb_context *ctx, int type, const viwb_globals *gl, const double *consts, const double *const *params,
                                     double *residuals, double **jacobians) {
+    bind_device(ctx);
     if (!ctx || !gl || !params || !residuals || type < 0 || type > 5) return VIWB_ERR_INVALID;
     static const int nblk[6] = {5, 6, 4, 4, 7, 4};
     static const int sizes[6][7] = {{7, 7, 7, 1, 1, 0, 0}, {7, 7, 7, 7, 1, 1, 0}, {7, 7, 1, 1, 0, 0, 0}, {7, 9, 7, 9, 0, 0, 0}, {7, 7, 7, 1, 1, 1, 1}, {7, 7, 4, 1, 0, 0, 0}};
@@ -841,6 +855,7 @@ VIWB_D void prior_eval_device(const PriorEvalArgs &a, int tid, int nt, double *d
 __global__ void prior_eval_kernel(PriorEvalArgs a) { __shared__ double dx[MAXPRI]; prior_eval_device(a, threadIdx.x, blockDim.x, dx); }
 #endif
 extern "C" int viwb_prior_evaluate(viwb_context *ctx, const viwb_prior *prior, const double *state, double *residuals, double *jacobian) {
+    bind_device(ctx);
     if (!ctx || !prior || !state || !residuals || prior->n <= 0 || prior->n > MAXPRI) return VIWB_ERR_INVALID;
     const int n = prior->n;
     double *d = nullptr;
@@ -908,6 +923,7 @@ extern "C" double viwb_lk_batch_algorithmic_bytes(const viwb_lk_batch *b) {
 }
 // page-lock caller-owned host buffers (camera frames) so that uploads run at full PCIe rate and asynchronously
 extern "C" int viwb_host_register(viwb_context *ctx, void *ptr, size_t bytes) {
+    bind_device(ctx);
     if (!ctx || !ptr) return VIWB_ERR_INVALID;
 #ifndef VIWB_HOST_EMU
     CK((int)cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
@@ -917,6 +933,7 @@ extern "C" int viwb_host_register(viwb_context *ctx, void *ptr, size_t bytes) {
     return VIWB_OK;
 }
 extern "C" int viwb_host_unregister(viwb_context *ctx, void *ptr) {
+    bind_device(ctx);
     if (!ctx || !ptr) return VIWB_ERR_INVALID;
 #ifndef VIWB_HOST_EMU
     CK((int)cudaHostUnregister(ptr));
