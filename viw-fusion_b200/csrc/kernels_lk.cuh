@@ -65,52 +65,72 @@ VIWB_D void pyr_down_item(const PyrArgs &a, int idx) {
 }
 
 // ---- the tracker: one warp per point, no block-level barriers.
-// Per level the warp stages the 24x24 source patch and its 22x22 Scharr samples in its own shared-memory slice, then every
-// lane keeps its 14 template / gradient samples in registers; a Gauss-Newton iteration is 14 bilinear samples of the search
-// image per lane (straight from L1), integer products, and one exact 64-bit warp reduction.
+// Work items of a warp: the 21 window rows x 3 segments of 7 pixels = 63 items, two per lane, so that neighbouring samples
+// share their loads and every shared-memory offset inside an item is a compile-time constant.  Per level the warp
+//   1. stages the 24x24 source patch (aligned 32-bit loads when the patch is interior, reflect-101 byte path otherwise),
+//   2. derives the 22x22 Scharr samples from it (zero outside the image, like OpenCV's constant-border derivative buffer),
+//   3. interpolates its 14 template / gradient samples into registers,
+//   4. stages a 32x36 region of the search image around the estimate (again aligned words when interior); the Gauss-Newton
+//      iterations sample it branch-free and restage only if the estimate leaves it,
+//   5. reduces the integer products with the warp-wide integer adder (redux.sync): exact, no shuffle chain.
 #ifdef VIWB_HOST_EMU
 enum { LK_W = 1 };
 #else
 enum { LK_W = 32 };
 #endif
 #ifndef LK_MINB
-#define LK_MINB 6
+#define LK_MINB 8
 #endif
-enum { LK_EPL = (441 + LK_W - 1) / LK_W, LK_PPB = 4, LK_WARP_SMEM = (576 + 968) * 2 + 32 * 36 + 16 };     // elements per lane, points per block, bytes per warp
+enum { LK_ITEMS = 63, LK_IPL = (LK_ITEMS + LK_W - 1) / LK_W, LK_PPB = 4,         // items, items per lane, points per block
+       LK_PS = 28,                                                             // byte stride of the staged source patch (7 words)
+       LK_SLACK = 5, LK_JROWS = 22 + 2 * LK_SLACK, LK_JS = 36,                 // staged search region: 32 rows x 36 bytes (9 words)
+       LK_BS = 23, LK_DBYTES = 2208,                                           // interpolated-intensity image 23 x 23 ints (shares the Scharr sample buffer)
+       LK_WARP_SMEM = 24 * LK_PS + LK_DBYTES + LK_JROWS * LK_JS };             // = 4032 bytes per warp
 VIWB_HD size_t lk_smem_bytes(int warps) { return (size_t)warps * LK_WARP_SMEM; }
 
-VIWB_D void lk_warp_sum3(long long &a, long long &b, long long &c) {
-#ifndef VIWB_HOST_EMU
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+// exact sum over the warp of one int32 per lane (every lane gets it)
+VIWB_D long long lk_warp_sum(int p) {
+#ifdef VIWB_HOST_EMU
+    return (long long)p;
 #else
-    (void)a; (void)b; (void)c;
-#endif
-}
-VIWB_D void lk_warp_sum2(long long &a, long long &b) {
-#ifndef VIWB_HOST_EMU
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-#else
-    (void)a; (void)b;
+    const int hi = __reduce_add_sync(0xffffffffu, p >> 12), lo = __reduce_add_sync(0xffffffffu, p & 0xfff);
+    return ((long long)hi << 12) + (long long)lo;
 #endif
 }
 VIWB_HD bool lk_outside(int ix, int iy, int cols, int rows) { return ix < -LK_WIN || ix >= cols || iy < -LK_WIN || iy >= rows; }
 
-// the search-image region a warp keeps in shared memory: (22 + 2*LK_SLACK)^2 bytes around the current estimate, reflect-101
-// resolved while staging, so the Gauss-Newton loop has a single branch-free sampling path
-enum { LK_SLACK = 5, LK_JR = 22 + 2 * LK_SLACK, LK_JS = LK_JR + 4 };
-VIWB_D void lk_stage_search(uint8_t *jbuf, const uint8_t *jimg, int jstr, int jc, int jr, int jx0, int jy0, int lane) {
+// rows [y0, y0+nrows) x bytes [x0a, x0a + 4*nwords) of an image into a byte buffer with row stride 4*nwords.
+// x0a is a multiple of 4; interior regions use aligned 32-bit loads, the rest resolves reflect-101 byte by byte.
+VIWB_D void lk_stage(uint8_t *buf, const uint8_t *img, int stride, int cols, int rows, int x0a, int y0, int nrows, int nwords, int lane) {
     VIWB_SYNCWARP();
-    const bool in = jx0 >= 0 && jy0 >= 0 && jx0 + LK_JR <= jc && jy0 + LK_JR <= jr;
-    for (int e = lane; e < LK_JR * LK_JR; e += LK_W) {
-        const int y = e / LK_JR, x = e - y * LK_JR;
-        jbuf[y * LK_JS + x] = in ? jimg[(size_t)(jy0 + y) * jstr + jx0 + x] : jimg[(size_t)reflect101(jy0 + y, jr) * jstr + reflect101(jx0 + x, jc)];
+    if (x0a >= 0 && y0 >= 0 && x0a + 4 * nwords <= cols && y0 + nrows <= rows) {
+        const int total = nrows * nwords;
+        for (int e = lane; e < total; e += LK_W) {
+            const int y = e / nwords, x = e - y * nwords;
+            reinterpret_cast<uint32_t *>(buf)[e] = *reinterpret_cast<const uint32_t *>(img + (size_t)(y0 + y) * stride + x0a + 4 * x);
+        }
+    } else {        // border: columns are reflected once per lane, rows once per row
+        const int wb = 4 * nwords;
+#ifdef VIWB_HOST_EMU
+        for (int y = 0; y < nrows; y++) { const uint8_t *src = img + (size_t)reflect101(y0 + y, rows) * stride; for (int x = 0; x < wb; x++) buf[y * wb + x] = src[reflect101(x0a + x, cols)]; }
+#else
+        const int xa = lane, xb = lane + 32;            // wb <= 64
+        const int ca = reflect101(x0a + xa, cols), cb = xb < wb ? reflect101(x0a + xb, cols) : 0;
+        for (int y = 0; y < nrows; y++) {
+            const uint8_t *src = img + (size_t)reflect101(y0 + y, rows) * stride;
+            if (xa < wb) buf[y * wb + xa] = src[ca];
+            if (xb < wb) buf[y * wb + xb] = src[cb];
+        }
+#endif
     }
     VIWB_SYNCWARP();
 }
 
 VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem_raw) {
-    short *patch = (short *)smem_raw, *dpatch = patch + 576;
-    uint8_t *jbuf = (uint8_t *)(dpatch + 968);
+    uint8_t *pbuf = (uint8_t *)smem_raw;                      // 24 rows x 28 bytes
+    short *dpatch = (short *)(smem_raw + 24 * LK_PS);          // 22 x 22 x (dx, dy)
+    int *Bimg = (int *)dpatch;                                // or: 23 x 23 interpolated intensities (interior patches)
+    uint8_t *jbuf = smem_raw + 24 * LK_PS + LK_DBYTES;        // 32 rows x 36 bytes
     const int npts = a.n_dev ? *a.n_dev : a.n;
     if (pt >= npts) return;
     const int max_level = a.max_level, max_iter = a.max_iter, flags = a.flags;
@@ -119,10 +139,10 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
     const float px0 = a.prev_pts[2 * pt], py0 = a.prev_pts[2 * pt + 1];
     bool status = true; float errv = 0.f;
     float npx = 0.f, npy = 0.f;     // nextPts[ptidx] (window centre coordinates)
-    int Iv[LK_EPL], dxy[LK_EPL];    // template intensity (5 fractional bits) and packed (dx | dy << 16) per owned element
-    int eoff[LK_EPL];               // offset of the element inside the staged search region
+    int Iv[LK_IPL][7], dxy[LK_IPL][7];    // template intensity (5 fractional bits) and packed (dx | dy << 16) of the lane's samples
+    int irow[LK_IPL], icol[LK_IPL];
 #pragma unroll
-    for (int k = 0; k < LK_EPL; k++) { const int e = lane + LK_W * k, y = e / 21, x = e - y * 21; eoff[k] = y * LK_JS + x; }
+    for (int s = 0; s < LK_IPL; s++) { const int it = lane + LK_W * s; irow[s] = it / 3; icol[s] = 7 * (it - 3 * irow[s]); }
     for (int level = max_level; level >= 0; level--) {
         const float sc = (float)(1. / (1 << level));
         float ppx = px0 * sc, ppy = py0 * sc;
@@ -135,48 +155,74 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
         const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
         const int cols = a.I.w[level], rows = a.I.h[level];
         if (lk_outside(ipx, ipy, cols, rows)) { if (level == 0) { status = false; errv = 0.f; } continue; }
-        // stage the source patch [ipy-1, ipy+22] x [ipx-1, ipx+22]
-        VIWB_SYNCWARP();
-        {
-            const uint8_t *img = a.I.img[level]; const int str = a.I.stride[level];
-            const bool in = ipx >= 1 && ipy >= 1 && ipx + 23 <= cols && ipy + 23 <= rows;
-            for (int e = lane; e < LK_PATCH * LK_PATCH; e += LK_W) {
-                const int y = e / LK_PATCH, x = e - y * LK_PATCH;
-                patch[e] = in ? (short)img[(size_t)(ipy - 1 + y) * str + ipx - 1 + x]
-                              : (short)img[(size_t)reflect101(ipy - 1 + y, rows) * str + reflect101(ipx - 1 + x, cols)];
-            }
-        }
-        VIWB_SYNCWARP();
-        // Scharr samples at [ipy, ipy+21] x [ipx, ipx+21]; zero outside the image
-        for (int e = lane; e < LK_DPATCH * LK_DPATCH; e += LK_W) {
-            const int y = e / LK_DPATCH, x = e - y * LK_DPATCH, gx = ipx + x, gy = ipy + y;
-            int ddx = 0, ddy = 0;
-            if (gx >= 0 && gy >= 0 && gx < cols && gy < rows) {
-                const short *p0 = patch + y * LK_PATCH + x, *p1 = p0 + LK_PATCH, *p2 = p1 + LK_PATCH;
-                ddx = (p0[2] + p2[2]) * 3 + p1[2] * 10 - ((p0[0] + p2[0]) * 3 + p1[0] * 10);
-                ddy = ((p2[2] - p0[2]) + (p2[0] - p0[0])) * 3 + (p2[1] - p0[1]) * 10;
-            }
-            dpatch[2 * e] = (short)ddx; dpatch[2 * e + 1] = (short)ddy;
-        }
-        VIWB_SYNCWARP();
+        // 1. source patch rows [ipy-1, ipy+22], bytes from the aligned column pxa; pixel (ipx-1+x) sits at byte psx + x
+        const int pxa = (ipx - 1) & ~3, psx = (ipx - 1) - pxa;
+        lk_stage(pbuf, a.I.img[level], a.I.stride[level], cols, rows, pxa, ipy - 1, 24, LK_PS / 4, lane);
         const float fa = ppx - ipx, fb = ppy - ipy;
         const int iw00 = cv_round_f((1.f - fa) * (1.f - fb) * (1 << 14)), iw01 = cv_round_f(fa * (1.f - fb) * (1 << 14));
         const int iw10 = cv_round_f((1.f - fa) * fb * (1 << 14)), iw11 = (1 << 14) - iw00 - iw01 - iw10;
-        long long A11 = 0, A12 = 0, A22 = 0;
+        int sA11 = 0, sA12 = 0, sA22 = 0;              // per lane < 14 * 2^24
+        if (ipx >= 0 && ipy >= 0 && ipx + 22 <= cols && ipy + 22 <= rows) {
+            // 2a/3a. interior patch: the bilinear weights commute with the (integer, unrounded) Scharr stencil, so interpolate the
+            //        intensities once, B(y,x) = sum_i w_i I(.), and take the stencil of B -- the same integers as interpolating the
+            //        four Scharr samples, with a third of the work
+            for (int e = lane; e < LK_BS * LK_BS; e += LK_W) {
+                const int y = e / LK_BS, x = e - y * LK_BS;
+                const uint8_t *p = pbuf + y * LK_PS + psx + x;
+                Bimg[e] = p[0] * iw00 + p[1] * iw01 + p[LK_PS] * iw10 + p[LK_PS + 1] * iw11;
+            }
+            VIWB_SYNCWARP();
 #pragma unroll
-        for (int k = 0; k < LK_EPL; k++) {
-            const int e = lane + LK_W * k;
-            if (e < 441) {
-                const int y = e / 21, x = e - y * 21;
-                const short *p = patch + (y + 1) * LK_PATCH + x + 1, *d = dpatch + 2 * (y * LK_DPATCH + x);
-                const int ival = descale(p[0] * iw00 + p[1] * iw01 + p[LK_PATCH] * iw10 + p[LK_PATCH + 1] * iw11, 9);
-                const int ix = descale(d[0] * iw00 + d[2] * iw01 + d[2 * LK_DPATCH] * iw10 + d[2 * LK_DPATCH + 2] * iw11, 14);
-                const int iy = descale(d[1] * iw00 + d[3] * iw01 + d[2 * LK_DPATCH + 1] * iw10 + d[2 * LK_DPATCH + 3] * iw11, 14);
-                Iv[k] = ival; dxy[k] = (ix & 0xffff) | (iy << 16);
-                A11 += (long long)(ix * ix); A12 += (long long)(ix * iy); A22 += (long long)(iy * iy);
-            } else { Iv[k] = 0; dxy[k] = 0; }
+            for (int s = 0; s < LK_IPL; s++) {
+                if (lane + LK_W * s < LK_ITEMS) {
+                    const int *b0 = Bimg + irow[s] * LK_BS + icol[s], *b1 = b0 + LK_BS, *b2 = b1 + LK_BS;
+#pragma unroll
+                    for (int j = 0; j < 7; j++) {
+                        const int ival = descale(b1[j + 1], 9);
+                        const int ix = descale((b0[j + 2] + b2[j + 2]) * 3 + b1[j + 2] * 10 - ((b0[j] + b2[j]) * 3 + b1[j] * 10), 14);
+                        const int iy = descale(((b2[j + 2] - b0[j + 2]) + (b2[j] - b0[j])) * 3 + (b2[j + 1] - b0[j + 1]) * 10, 14);
+                        Iv[s][j] = ival; dxy[s][j] = (ix & 0xffff) | (iy << 16);
+                        sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 7; j++) { Iv[s][j] = 0; dxy[s][j] = 0; }
+                }
+            }
+        } else {
+            // 2b. Scharr samples at [ipy, ipy+21] x [ipx, ipx+21]; zero outside the image
+            for (int e = lane; e < LK_DPATCH * LK_DPATCH; e += LK_W) {
+                const int y = e / LK_DPATCH, x = e - y * LK_DPATCH, gx = ipx + x, gy = ipy + y;
+                int ddx = 0, ddy = 0;
+                if (gx >= 0 && gy >= 0 && gx < cols && gy < rows) {
+                    const uint8_t *p0 = pbuf + y * LK_PS + psx + x, *p1 = p0 + LK_PS, *p2 = p1 + LK_PS;
+                    ddx = (p0[2] + p2[2]) * 3 + p1[2] * 10 - ((p0[0] + p2[0]) * 3 + p1[0] * 10);
+                    ddy = ((p2[2] - p0[2]) + (p2[0] - p0[0])) * 3 + (p2[1] - p0[1]) * 10;
+                }
+                dpatch[2 * e] = (short)ddx; dpatch[2 * e + 1] = (short)ddy;
+            }
+            VIWB_SYNCWARP();
+            // 3b. template
+#pragma unroll
+            for (int s = 0; s < LK_IPL; s++) {
+                if (lane + LK_W * s < LK_ITEMS) {
+                    const uint8_t *p = pbuf + (irow[s] + 1) * LK_PS + psx + icol[s] + 1;
+                    const short *d = dpatch + 2 * (irow[s] * LK_DPATCH + icol[s]);
+#pragma unroll
+                    for (int j = 0; j < 7; j++) {
+                        const int ival = descale(p[j] * iw00 + p[j + 1] * iw01 + p[j + LK_PS] * iw10 + p[j + LK_PS + 1] * iw11, 9);
+                        const int ix = descale(d[2 * j] * iw00 + d[2 * j + 2] * iw01 + d[2 * j + 2 * LK_DPATCH] * iw10 + d[2 * j + 2 * LK_DPATCH + 2] * iw11, 14);
+                        const int iy = descale(d[2 * j + 1] * iw00 + d[2 * j + 3] * iw01 + d[2 * j + 2 * LK_DPATCH + 1] * iw10 + d[2 * j + 2 * LK_DPATCH + 3] * iw11, 14);
+                        Iv[s][j] = ival; dxy[s][j] = (ix & 0xffff) | (iy << 16);
+                        sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 7; j++) { Iv[s][j] = 0; dxy[s][j] = 0; }
+                }
+            }
         }
-        lk_warp_sum3(A11, A12, A22);
+        const long long A11 = lk_warp_sum(sA11), A12 = lk_warp_sum(sA12), A22 = lk_warp_sum(sA22);
         const float fA11 = (float)A11 * FLT_SCALE, fA12 = (float)A12 * FLT_SCALE, fA22 = (float)A22 * FLT_SCALE;
         float D = fA11 * fA22 - fA12 * fA12;
         const float minEig = (fA22 + fA11 - sqrtf((fA11 - fA22) * (fA11 - fA22) + 4.f * fA12 * fA12)) / (2 * LK_WIN * LK_WIN);
@@ -186,30 +232,33 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
         float pdx = 0.f, pdy = 0.f;
         const int jc = a.J.w[level], jr = a.J.h[level], jstr = a.J.stride[level];
         const uint8_t *jimg = a.J.img[level];
-        int jx0 = (int)floorf(nx) - LK_SLACK, jy0 = (int)floorf(ny) - LK_SLACK;       // origin of the staged search region
+        int jx0 = 0, jy0 = 0;          // origin of the staged search region (jx0 a multiple of 4)
         bool staged = false;
         for (int j = 0; j < max_iter; j++) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (lk_outside(inx, iny, jc, jr)) { if (level == 0) status = false; break; }
-            if (!staged || inx < jx0 || iny < jy0 || inx + 22 > jx0 + LK_JR || iny + 22 > jy0 + LK_JR) {
-                jx0 = inx - LK_SLACK; jy0 = iny - LK_SLACK;
-                lk_stage_search(jbuf, jimg, jstr, jc, jr, jx0, jy0, lane);
+            if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) {
+                jx0 = (inx - LK_SLACK) & ~3; jy0 = iny - LK_SLACK;
+                lk_stage(jbuf, jimg, jstr, jc, jr, jx0, jy0, LK_JROWS, LK_JS / 4, lane);
                 staged = true;
             }
             const float ja = nx - inx, jb = ny - iny;
             const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
             const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;
             const uint8_t *q0 = jbuf + (iny - jy0) * LK_JS + (inx - jx0);
-            long long b1 = 0, b2 = 0;
+            int sb1 = 0, sb2 = 0;      // per lane < 14 * 2^25
 #pragma unroll
-            for (int k = 0; k < LK_EPL; k++) {
-                if (lane + LK_W * k < 441) {
-                    const uint8_t *q = q0 + eoff[k];
-                    const int diff = descale(q[0] * w00 + q[1] * w01 + q[LK_JS] * w10 + q[LK_JS + 1] * w11, 9) - Iv[k];
-                    b1 += (long long)(diff * (int)(short)(dxy[k] & 0xffff)); b2 += (long long)(diff * (dxy[k] >> 16));
+            for (int s = 0; s < LK_IPL; s++) {
+                if (lane + LK_W * s < LK_ITEMS) {
+                    const uint8_t *q = q0 + irow[s] * LK_JS + icol[s];
+#pragma unroll
+                    for (int k = 0; k < 7; k++) {
+                        const int diff = descale(q[k] * w00 + q[k + 1] * w01 + q[k + LK_JS] * w10 + q[k + LK_JS + 1] * w11, 9) - Iv[s][k];
+                        sb1 += diff * (int)(short)(dxy[s][k] & 0xffff); sb2 += diff * (dxy[s][k] >> 16);
+                    }
                 }
             }
-            lk_warp_sum2(b1, b2);
+            const long long b1 = lk_warp_sum(sb1), b2 = lk_warp_sum(sb2);
             const float fb1 = (float)b1 * FLT_SCALE, fb2 = (float)b2 * FLT_SCALE;
             const float dx = (fA12 * fb2 - fA22 * fb1) * D, dy = (fA12 * fb1 - fA11 * fb2) * D;
             nx += dx; ny += dy;
@@ -223,25 +272,27 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
             const int inx = (int)floorf(ex), iny = (int)floorf(ey);
             if (lk_outside(inx, iny, jc, jr)) { status = false; }
             else {
-                if (!staged || inx < jx0 || iny < jy0 || inx + 22 > jx0 + LK_JR || iny + 22 > jy0 + LK_JR) {
-                    jx0 = inx - LK_SLACK; jy0 = iny - LK_SLACK;
-                    lk_stage_search(jbuf, jimg, jstr, jc, jr, jx0, jy0, lane);
+                if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) {
+                    jx0 = (inx - LK_SLACK) & ~3; jy0 = iny - LK_SLACK;
+                    lk_stage(jbuf, jimg, jstr, jc, jr, jx0, jy0, LK_JROWS, LK_JS / 4, lane);
                 }
                 const float ja = ex - inx, jb = ey - iny;
                 const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
                 const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;
                 const uint8_t *q0 = jbuf + (iny - jy0) * LK_JS + (inx - jx0);
-                long long ev = 0, d1 = 0;
+                int sev = 0;
 #pragma unroll
-                for (int k = 0; k < LK_EPL; k++) {
-                    if (lane + LK_W * k < 441) {
-                        const uint8_t *q = q0 + eoff[k];
-                        const int diff = descale(q[0] * w00 + q[1] * w01 + q[LK_JS] * w10 + q[LK_JS + 1] * w11, 9) - Iv[k];
-                        ev += (long long)(diff < 0 ? -diff : diff);
+                for (int s = 0; s < LK_IPL; s++) {
+                    if (lane + LK_W * s < LK_ITEMS) {
+                        const uint8_t *q = q0 + irow[s] * LK_JS + icol[s];
+#pragma unroll
+                        for (int k = 0; k < 7; k++) {
+                            const int diff = descale(q[k] * w00 + q[k + 1] * w01 + q[k + LK_JS] * w10 + q[k + LK_JS + 1] * w11, 9) - Iv[s][k];
+                            sev += diff < 0 ? -diff : diff;
+                        }
                     }
                 }
-                lk_warp_sum2(ev, d1);
-                errv = (float)ev * (1.f / (32 * LK_WIN * LK_WIN));
+                errv = (float)lk_warp_sum(sev) * (1.f / (32 * LK_WIN * LK_WIN));
             }
         }
     }

@@ -252,13 +252,19 @@ VIWB_D void chol_backsolve_blocked(const double *L, double *y, const double *din
     for (int bi = nblk - 1; bi >= 0; bi--) {
         const int c0 = bi * CHOL_NB, nb = (n - c0) < CHOL_NB ? (n - c0) : CHOL_NB;
         double x[8];
+        const double *rp[8];                 // start of the block's rows at column c0 (running offsets: no per-access index products)
+        {
+            const double *r = L + (size_t)c0 * (c0 + 1) / 2 + c0;
+#pragma unroll
+            for (int m = 0; m < 8; m++) { rp[m] = r; r += c0 + m + 1; }
+        }
 #pragma unroll
         for (int k = 7; k >= 0; k--) {
             x[k] = 0.0;
             if (k < nb) {
                 double v = y[c0 + k];
 #pragma unroll
-                for (int m = 7; m > k; m--) if (m < nb) v -= L[(size_t)(c0 + m) * (c0 + m + 1) / 2 + c0 + k] * x[m];
+                for (int m = 7; m > k; m--) if (m < nb) v -= rp[m][k] * x[m];
                 x[k] = v * dinv[c0 + k];
             }
         }
@@ -269,7 +275,7 @@ VIWB_D void chol_backsolve_blocked(const double *L, double *y, const double *din
         for (int i = tid; i < c0; i += nt) {
             double v = y[i];
 #pragma unroll
-            for (int k = 0; k < 8; k++) if (k < nb) v -= L[(size_t)(c0 + k) * (c0 + k + 1) / 2 + i] * x[k];
+            for (int k = 0; k < 8; k++) if (k < nb) v -= rp[k][i - c0] * x[k];
             y[i] = v;
         }
         VIWB_SYNC();

@@ -70,13 +70,17 @@ struct Profiler {
     void collect() { for (auto &r : pending) { cudaEventSynchronize(r.b); float t = 0; cudaEventElapsedTime(&t, r.a, r.b); ms[r.idx] += t; count[r.idx]++; cudaEventDestroy(r.a); cudaEventDestroy(r.b); } pending.clear(); }
 };
 static Profiler g_prof;
-#define DEF_KERNEL(name, maxnt) \
-    __global__ void __launch_bounds__(maxnt) name##_kernel(BatchDev bd, int mode) { \
+#define DEF_KERNEL2(name, maxnt, minb) \
+    __global__ void __launch_bounds__(maxnt, minb) name##_kernel(BatchDev bd, int mode) { \
         extern __shared__ double viwb_smem[]; \
         name##_block(bd, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, viwb_smem, mode); }
+#define DEF_KERNEL(name, maxnt) DEF_KERNEL2(name, maxnt, 1)
+#ifndef LIN_VIS_MINB
+#define LIN_VIS_MINB 1
+#endif
 DEF_KERNEL(setup, 128)
 DEF_KERNEL(prior_setup, 256)
-DEF_KERNEL(lin_vis, 128)
+DEF_KERNEL2(lin_vis, 128, LIN_VIS_MINB)
 DEF_KERNEL(lm_reduce, 128)
 DEF_KERNEL(lin_small, 128)
 DEF_KERNEL(asm_items, 128)
