@@ -246,7 +246,7 @@ def main():
     ap.add_argument("--copies", type=int, default=32, help="perturbed initial guesses per sequence (batch = distinct*copies)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-profile", action="store_true")
-    ap.add_argument("--e2e-lanes", type=int, default=2, help="host threads (each with its own context) driving the e2e measurement")
+    ap.add_argument("--e2e-lanes", type=int, default=4, help="host threads (each with its own context) driving the e2e measurement")
     ap.add_argument("--no-lk", action="store_true", help="window solve only (no feature-tracker work in the step)")
     ap.add_argument("--scenes", type=int, default=8, help="distinct synthetic stereo scenes per rank (replicated over the streams)")
     args = ap.parse_args()

@@ -76,14 +76,17 @@ static Profiler g_prof;
         name##_block(bd, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x, viwb_smem, mode); }
 #define DEF_KERNEL(name, maxnt) DEF_KERNEL2(name, maxnt, 1)
 #ifndef LIN_VIS_MINB
-#define LIN_VIS_MINB 1
+#define LIN_VIS_MINB 3
 #endif
 DEF_KERNEL(setup, 128)
 DEF_KERNEL(prior_setup, 256)
 DEF_KERNEL2(lin_vis, 128, LIN_VIS_MINB)
 DEF_KERNEL(lm_reduce, 128)
 DEF_KERNEL(lin_small, 128)
-DEF_KERNEL(asm_items, 128)
+#ifndef ASM_MINB
+#define ASM_MINB 1
+#endif
+DEF_KERNEL2(asm_items, 128, ASM_MINB)
 DEF_KERNEL(syrk, 256)
 DEF_KERNEL(solve, 512)
 DEF_KERNEL(reanchor, 32)
