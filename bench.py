@@ -464,7 +464,14 @@ def main():
                       "lin_small": sum(2296.0 * len(p.imu_frame_i) + 8.0 * (p.prior.n ** 2 + 2 * p.prior.n if p.prior is not None else 0) for p in probs)}
         a_bytes = per_launch.get(top.replace("_marg", ""), 0.0)
         achieved = a_bytes / (kernels[top]["ms_per_launch"] * 1e-3) / 1e9 if kernels[top]["ms_per_launch"] > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top.replace("_marg", ""))
+            if tr:
+                traffic = tr["bytes_per_unit"] * B      # measured DRAM bytes of one launch (ncu --set full), scaled to this batch
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650",
                     "algorithmic_bytes_per_launch": a_bytes,
                     "whole_step": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes * args.steps / (ms * 1e-3) / 1e9}}

@@ -57,12 +57,7 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     int nout;
     if (item.kind == ITEM_FRAME) nout = item.has_common ? 105 : 27; else if (item.kind == ITEM_PAIR) nout = 36; else nout = 104;
     if (item.kind == ITEM_FRAME && !item.has_common) for (int o = 21 + lane; o < 99; o += W) out[o] = 0.0;
-    // Each lane owns up to two outputs per walk of the factor list (o, o + 32): a PAIR item (36 outputs) is finished in one walk
-    // instead of re-gathering every record for its last 4 entries.
-    struct Op { int ka, kb, ia_c, sa, ib_c, sb, o; bool on; };
-    auto decode = [&](int o0) {
-        Op q; q.on = o0 < nout; q.ka = 0; q.kb = 0; q.ia_c = 0; q.sa = 6; q.ib_c = 0; q.sb = 6; q.o = 0;
-        if (!q.on) return q;
+    for (int o0 = lane; o0 < nout; o0 += W) {
         int o = o0;
         if (item.kind == ITEM_FRAME && !item.has_common && o0 >= 21) o = 99 + (o0 - 21);
         // operand kinds: 0 = frame slot of a, 1 = frame slot of b (PAIR), 2 = common column, 3 = residual
@@ -74,15 +69,9 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
         } else if (item.kind == ITEM_PAIR) { pa = o / 6; pb = o % 6; ka = 0; kb = 1; }
         else { if (o < 91) { sym_unrank(o, pa, pb); ka = 2; kb = 2; } else { pa = o - 91; ka = 2; kb = 3; } }
         // role-independent parts of the record offsets
-        q.ka = ka; q.kb = kb; q.o = o;
-        q.ia_c = (ka == 2) ? common_off(pa) : pa; q.sa = (ka == 2) ? common_stride(pa) : 6;
-        q.ib_c = (kb == 2) ? common_off(pb) : (kb == 3 ? 0 : pb); q.sb = (kb == 2) ? common_stride(pb) : (kb == 3 ? 1 : 6);
-        return q;
-    };
-    for (int base = 0; base < nout; base += 2 * W) {
-        const Op q0 = decode(base + lane), q1 = decode(base + W + lane);
-        const bool two = base + W < nout;          // warp-uniform: does any lane have a second output in this walk
-        double acc0 = 0.0, acc1 = 0.0;
+        const int ia_c = (ka == 2) ? common_off(pa) : pa, sa = (ka == 2) ? common_stride(pa) : 6;
+        const int ib_c = (kb == 2) ? common_off(pb) : (kb == 3 ? 0 : pb), sb = (kb == 2) ? common_stride(pb) : (kb == 3 ? 1 : 6);
+        double acc = 0.0;
         int e = item.lo;
         for (; e + 4 <= item.hi; e += 4) {        // 4 independent gather chains in flight
             int en[4]; const double *rc[4]; double va[4], vb[4], wa[4], wb[4];
@@ -90,37 +79,20 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
             for (int u = 0; u < 4; u++) {
                 const int role = en[u] & 1;
                 rc[u] = recs + (size_t)(en[u] >> 1) * rs;
-                const int ia = (q0.ka == 0) ? (role ? REC_B : REC_A) + q0.ia_c : q0.ia_c;
-                const int ib = (q0.kb == 0) ? (role ? REC_B : REC_A) + q0.ib_c : (q0.kb == 1 ? (role ? REC_A : REC_B) + q0.ib_c : q0.ib_c);
-                va[u] = rc[u][ia]; wa[u] = rc[u][ia + q0.sa]; vb[u] = rc[u][ib]; wb[u] = rc[u][ib + q0.sb];
+                const int ia = (ka == 0) ? (role ? REC_B : REC_A) + ia_c : ia_c;
+                const int ib = (kb == 0) ? (role ? REC_B : REC_A) + ib_c : (kb == 1 ? (role ? REC_A : REC_B) + ib_c : ib_c);
+                va[u] = rc[u][ia]; wa[u] = rc[u][ia + sa]; vb[u] = rc[u][ib]; wb[u] = rc[u][ib + sb];
             }
-            for (int u = 0; u < 4; u++) acc0 += va[u] * vb[u] + wa[u] * wb[u];
-            if (two) {
-                for (int u = 0; u < 4; u++) {
-                    const int role = en[u] & 1;
-                    const int ia = (q1.ka == 0) ? (role ? REC_B : REC_A) + q1.ia_c : q1.ia_c;
-                    const int ib = (q1.kb == 0) ? (role ? REC_B : REC_A) + q1.ib_c : (q1.kb == 1 ? (role ? REC_A : REC_B) + q1.ib_c : q1.ib_c);
-                    va[u] = q1.on ? rc[u][ia] : 0.0; wa[u] = q1.on ? rc[u][ia + q1.sa] : 0.0; vb[u] = q1.on ? rc[u][ib] : 0.0; wb[u] = q1.on ? rc[u][ib + q1.sb] : 0.0;
-                }
-                for (int u = 0; u < 4; u++) acc1 += va[u] * vb[u] + wa[u] * wb[u];
-            }
+            for (int u = 0; u < 4; u++) acc += va[u] * vb[u] + wa[u] * wb[u];
         }
         for (; e < item.hi; e++) {
             const int ent = list[e], role = ent & 1;
             const double *rec = recs + (size_t)(ent >> 1) * rs;
-            if (q0.on) {
-                const int ia = (q0.ka == 0) ? (role ? REC_B : REC_A) + q0.ia_c : q0.ia_c;
-                const int ib = (q0.kb == 0) ? (role ? REC_B : REC_A) + q0.ib_c : (q0.kb == 1 ? (role ? REC_A : REC_B) + q0.ib_c : q0.ib_c);
-                acc0 += rec[ia] * rec[ib] + rec[ia + q0.sa] * rec[ib + q0.sb];
-            }
-            if (q1.on) {
-                const int ia = (q1.ka == 0) ? (role ? REC_B : REC_A) + q1.ia_c : q1.ia_c;
-                const int ib = (q1.kb == 0) ? (role ? REC_B : REC_A) + q1.ib_c : (q1.kb == 1 ? (role ? REC_A : REC_B) + q1.ib_c : q1.ib_c);
-                acc1 += rec[ia] * rec[ib] + rec[ia + q1.sa] * rec[ib + q1.sb];
-            }
+            const int ia = (ka == 0) ? (role ? REC_B : REC_A) + ia_c : ia_c;
+            const int ib = (kb == 0) ? (role ? REC_B : REC_A) + ib_c : (kb == 1 ? (role ? REC_A : REC_B) + ib_c : ib_c);
+            acc += rec[ia] * rec[ib] + rec[ia + sa] * rec[ib + sb];
         }
-        if (q0.on) out[q0.o] = acc0;
-        if (q1.on) out[q1.o] = acc1;
+        out[o] = acc;
     }
 }
 

@@ -89,14 +89,25 @@ VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, d
 }
 
 // ------------------------------------------------------------------------------------------------ lm_reduce
-// 13 threads per landmark, one per block of w_k: role j < 11 owns the 6 entries of pose j (role == host frame also
-// reduces a_k, g_k, the cost and the Schur weight), roles 11 / 12 own [ex0 | td] and [ex1] (wide records only).
-// No dynamic indexing -> everything stays in registers; each factor record is read about once in total.
-enum { LM_ROLES = 13 };
+// One warp per landmark, one lane per factor (chunks of 32 if a landmark has more): every lane streams its own record once
+// (consecutive records -> fully used cache lines), forms its J_p^T J_lambda pieces in registers, and the warp combines them:
+// a_k, g_k, the cost, the host-frame block and the common blocks by shuffle sums; the observing-frame blocks by the lanes that
+// share a frame taking turns in lane order (fixed order -> deterministic).  LM_ROLES = threads per landmark for the launch.
+#ifdef VIWB_HOST_EMU
+enum { LM_ROLES = 1, LM_W = 1 };
+#else
+enum { LM_ROLES = 32, LM_W = 32 };
+#endif
+VIWB_D double lm_warp_sum(double v) {
+#ifndef VIWB_HOST_EMU
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+    return v;
+}
 VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)smem;
     const int gid = bx * nt + tid;
-    const int k = gid / LM_ROLES, role = gid % LM_ROLES;
+    const int k = gid / LM_ROLES, lane = gid % LM_ROLES;
     if (k >= bd.nlm_total) return;
     const int w = bd.lm_win[k];
     const WinWork &ww = bd.work[w];
@@ -104,47 +115,58 @@ VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     const int f0 = bd.lm_fptr[k], f1 = bd.lm_fptr[k + 1];
     double *W = bd.lm_W + (size_t)k * VSUB;
     const bool skip = (mode == MODE_MARG) && (f0 == f1 || bd.vis_fi[f0] != 0 || bd.meta[w].margin_flag != 0);
-    if (skip) { if (role == 0) bd.lm_gamma[k] = 0.0; return; }
+    if (skip) { if (lane == 0) bd.lm_gamma[k] = 0.0; return; }
+    for (int p = lane; p < VSUB; p += LM_W) W[p] = 0.0;
     if (f0 == f1) {      // a landmark without factors: contributes nothing
-        if (role == 0) { bd.lm_a[k] = 0.0; bd.lm_g[k] = 0.0; bd.lm_cost[k] = 0.0; bd.lm_gamma[k] = 0.0; if (ww.first) bd.lm_scale[k] = 1.0; }
-        if (role < NFR) for (int q = 0; q < 6; q++) W[6 * role + q] = 0.0;
-        else if (role == 11) { for (int q = 0; q < 6; q++) W[66 + q] = 0.0; W[78] = 0.0; W[79] = 0.0; }
-        else for (int q = 0; q < 6; q++) W[72 + q] = 0.0;
+        if (lane == 0) { bd.lm_a[k] = 0.0; bd.lm_g[k] = 0.0; bd.lm_cost[k] = 0.0; bd.lm_gamma[k] = 0.0; if (ww.first) bd.lm_scale[k] = 1.0; }
         return;
     }
+    VIWB_SYNCWARP();
     const int rs = rec_stride(bd, mode);
-    const int host = (f0 < f1) ? bd.vis_fi[f0] : -1;
-    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    double a = 0.0, g = 0.0, c = 0.0;
-    if (role < NFR) {
-        for (int f = f0; f < f1; f++) {
+    const int host = bd.vis_fi[f0];
+    double a = 0.0, g = 0.0, c = 0.0, hacc[6] = {0, 0, 0, 0, 0, 0}, e0[6] = {0, 0, 0, 0, 0, 0}, e1[6] = {0, 0, 0, 0, 0, 0}, tdv = 0.0;
+    for (int fb = f0; fb < f1; fb += LM_W) {
+        const int f = fb + lane;
+        const bool on = f < f1;
+        int fj = -1;
+        double bv[6] = {0, 0, 0, 0, 0, 0};
+        if (on) {
             const int type = bd.vis_type[f];
             const double *rec = bd.vis_rec + (size_t)f * rs;
-            if (role == host) {
-                const double u0 = rec[REC_L], u1 = rec[REC_L + 1];
-                a += u0 * u0 + u1 * u1; g += u0 * rec[0] + u1 * rec[1]; c += bd.vis_cost[f];
-                if (type != 2) for (int q = 0; q < 6; q++) acc[q] += rec[REC_A + q] * u0 + rec[REC_A + 6 + q] * u1;
-            }
-            if (type != 2 && bd.vis_fj[f] == role) {
-                const double u0 = rec[REC_L], u1 = rec[REC_L + 1];
-                for (int q = 0; q < 6; q++) acc[q] += rec[REC_B + q] * u0 + rec[REC_B + 6 + q] * u1;
-            }
-        }
-        for (int q = 0; q < 6; q++) W[6 * role + q] = acc[q];
-    } else if (rs == VREC) {
-        for (int f = f0; f < f1; f++) {
-            const double *rec = bd.vis_rec + (size_t)f * rs;
             const double u0 = rec[REC_L], u1 = rec[REC_L + 1];
-            if (role == 11) { for (int q = 0; q < 6; q++) acc[q] += rec[REC_E0 + q] * u0 + rec[REC_E0 + 6 + q] * u1; acc[6] += rec[REC_TD] * u0 + rec[REC_TD + 1] * u1; }
-            else if (bd.vis_type[f] != 0) for (int q = 0; q < 6; q++) acc[q] += rec[REC_E1 + q] * u0 + rec[REC_E1 + 6 + q] * u1;
+            a += u0 * u0 + u1 * u1; g += u0 * rec[0] + u1 * rec[1]; c += bd.vis_cost[f];
+            if (type != 2) {
+                for (int q = 0; q < 6; q++) hacc[q] += rec[REC_A + q] * u0 + rec[REC_A + 6 + q] * u1;
+                for (int q = 0; q < 6; q++) bv[q] = rec[REC_B + q] * u0 + rec[REC_B + 6 + q] * u1;
+                fj = bd.vis_fj[f];
+            }
+            if (rs == VREC) {
+                for (int q = 0; q < 6; q++) e0[q] += rec[REC_E0 + q] * u0 + rec[REC_E0 + 6 + q] * u1;
+                tdv += rec[REC_TD] * u0 + rec[REC_TD + 1] * u1;
+                if (type != 0) for (int q = 0; q < 6; q++) e1[q] += rec[REC_E1 + q] * u0 + rec[REC_E1 + 6 + q] * u1;
+            }
         }
-        if (role == 11) { for (int q = 0; q < 6; q++) W[66 + q] = acc[q]; W[78] = acc[6]; W[79] = 0.0; }
-        else for (int q = 0; q < 6; q++) W[72 + q] = acc[q];
-    } else {
-        if (role == 11) { for (int q = 0; q < 6; q++) W[66 + q] = 0.0; W[78] = 0.0; W[79] = 0.0; }
-        else for (int q = 0; q < 6; q++) W[72 + q] = 0.0;
+        // observing-frame blocks: lanes with the same frame add in lane order
+#ifdef VIWB_HOST_EMU
+        if (fj >= 0) for (int q = 0; q < 6; q++) W[6 * fj + q] += bv[q];
+#else
+        {
+            const unsigned peers = __match_any_sync(0xffffffffu, fj);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            const int rounds = __reduce_max_sync(0xffffffffu, fj >= 0 ? rank : 0);
+            for (int r = 0; r <= rounds; r++) {
+                if (fj >= 0 && rank == r) for (int q = 0; q < 6; q++) W[6 * fj + q] += bv[q];
+                __syncwarp();
+            }
+        }
+#endif
     }
-    if (role != host) return;
+    a = lm_warp_sum(a); g = lm_warp_sum(g); c = lm_warp_sum(c);
+    for (int q = 0; q < 6; q++) hacc[q] = lm_warp_sum(hacc[q]);
+    if (rs == VREC) { for (int q = 0; q < 6; q++) { e0[q] = lm_warp_sum(e0[q]); e1[q] = lm_warp_sum(e1[q]); } tdv = lm_warp_sum(tdv); }
+    if (lane != 0) return;
+    for (int q = 0; q < 6; q++) W[6 * host + q] += hacc[q];
+    if (rs == VREC) { for (int q = 0; q < 6; q++) { W[66 + q] = e0[q]; W[72 + q] = e1[q]; } W[78] = tdv; }
     bd.lm_a[k] = a; bd.lm_g[k] = g; bd.lm_cost[k] = c;
     if (mode == MODE_MARG) { bd.lm_gamma[k] = a; return; }     // marginalisation keeps the pivot itself
     // Jacobi scale (first linearisation only) and the Schur weight for the mu this linearisation will be solved with:

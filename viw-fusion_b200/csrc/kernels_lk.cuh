@@ -41,27 +41,48 @@ VIWB_HD int lk_pix(const LkImage &im, int l, int x, int y) { return im.img[l][(s
 VIWB_HD int cv_round_f(float v) { return (int)lrintf(v); }                 // cvRound: round half to even
 VIWB_HD int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }   // CV_DESCALE
 
-// ---- pyrDown: dst (dw x dh) from src (sw x sh)
+// ---- pyrDown: dst (dw x dh) from src (sw x sh).  One work item = 4 horizontally adjacent outputs: 5 rows x 4 aligned 32-bit
+// loads feed the separable [1 4 6 4 1] sums (the same integers as the 2-D stencil); strips touching the left / right border,
+// and images whose width is not a multiple of 4 at the tail, take the per-pixel reflect-101 path.
 struct PyrArgs { const uint8_t *src; uint8_t *dst; int sw, sh, sstride, dw, dh, dstride; };
-VIWB_D void pyr_down_item(const PyrArgs &a, int idx) {
-    if (idx >= a.dw * a.dh) return;
-    const int x = idx % a.dw, y = idx / a.dw;
+VIWB_D int pyr_down_pixel(const PyrArgs &a, int x, int y) {
     int acc = 0;
     const int wgt[5] = {1, 4, 6, 4, 1};
-    if (x >= 1 && 2 * x + 2 < a.sw) {      // interior columns: no reflection on x
-        for (int dy = -2; dy <= 2; dy++) {
-            const uint8_t *row = a.src + (size_t)reflect101(2 * y + dy, a.sh) * a.sstride + 2 * x;
-            acc += wgt[dy + 2] * (row[-2] + row[2] + 4 * (row[-1] + row[1]) + 6 * row[0]);
-        }
-    } else {
-        for (int dy = -2; dy <= 2; dy++) {
-            const uint8_t *row = a.src + (size_t)reflect101(2 * y + dy, a.sh) * a.sstride;
-            int r = 0;
-            for (int dx = -2; dx <= 2; dx++) r += wgt[dx + 2] * row[reflect101(2 * x + dx, a.sw)];
-            acc += wgt[dy + 2] * r;
-        }
+    for (int dy = -2; dy <= 2; dy++) {
+        const uint8_t *row = a.src + (size_t)reflect101(2 * y + dy, a.sh) * a.sstride;
+        int r = 0;
+        for (int dx = -2; dx <= 2; dx++) r += wgt[dx + 2] * row[reflect101(2 * x + dx, a.sw)];
+        acc += wgt[dy + 2] * r;
     }
-    a.dst[(size_t)y * a.dstride + x] = (uint8_t)((acc + 128) >> 8);
+    return (acc + 128) >> 8;
+}
+VIWB_HD int pyr_items(const PyrArgs &a) { return ((a.dw + 3) / 4) * a.dh; }
+VIWB_D void pyr_down_item(const PyrArgs &a, int idx) {
+    const int sx = (a.dw + 3) / 4;
+    if (idx >= sx * a.dh) return;
+    const int y = idx / sx, x = 4 * (idx - y * sx);
+    // interior strip: source bytes [2x-4, 2x+12) exist and outputs x..x+3 exist
+    if (x >= 2 && 2 * x + 12 <= a.sw && x + 4 <= a.dw) {
+        int h[4] = {0, 0, 0, 0};
+        const int wgt[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+        for (int dy = -2; dy <= 2; dy++) {
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(a.src + (size_t)reflect101(2 * y + dy, a.sh) * a.sstride + 2 * x - 4);
+            const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
+            // bytes b[0..15] = source columns 2x-4 .. 2x+11; output k (0..3) is centred on b[4 + 2k]
+            int b[16];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { b[k] = (w0 >> (8 * k)) & 0xff; b[4 + k] = (w1 >> (8 * k)) & 0xff; b[8 + k] = (w2 >> (8 * k)) & 0xff; b[12 + k] = (w3 >> (8 * k)) & 0xff; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int c = 4 + 2 * k; h[k] += wgt[dy + 2] * (b[c - 2] + b[c + 2] + 4 * (b[c - 1] + b[c + 1]) + 6 * b[c]); }
+        }
+        uint32_t o = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) o |= (uint32_t)((h[k] + 128) >> 8) << (8 * k);
+        *reinterpret_cast<uint32_t *>(a.dst + (size_t)y * a.dstride + x) = o;
+    } else {
+        for (int k = 0; k < 4 && x + k < a.dw; k++) a.dst[(size_t)y * a.dstride + x + k] = (uint8_t)pyr_down_pixel(a, x + k, y);
+    }
 }
 
 // ---- the tracker: one warp per point, no block-level barriers.

@@ -159,8 +159,9 @@ VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *s
                     for (int i = m - 1; i >= l; i--) {
                         const double ein = i > l ? e[i - 1] : 0.0, din = i > l ? d[i - 1] : 0.0;
                         c3 = c2; c2 = c; s2 = s;
-                        g = c * ei; h = c * p; r = sqrt(p * p + ei * ei);
-                        const double rinv = 1.0 / r;
+                        g = c * ei; h = c * p;
+                        const double q2 = p * p + ei * ei, rinv = q2 > 0.0 ? rsqrt(q2) : 0.0;      // r = q2 * rsqrt(q2): one special-function chain, no division
+                        r = q2 * rinv;
                         e[i + 1] = s * r; s = ei * rinv; c = p * rinv;
                         p = c * di - s * g; d[i + 1] = h + s * (c * g + s * di);
                         cs[2 * i] = c; cs[2 * i + 1] = s;

@@ -83,10 +83,7 @@ DEF_KERNEL(prior_setup, 256)
 DEF_KERNEL2(lin_vis, 128, LIN_VIS_MINB)
 DEF_KERNEL(lm_reduce, 128)
 DEF_KERNEL(lin_small, 128)
-#ifndef ASM_MINB
-#define ASM_MINB 1
-#endif
-DEF_KERNEL2(asm_items, 128, ASM_MINB)
+DEF_KERNEL(asm_items, 128)
 DEF_KERNEL(syrk, 256)
 DEF_KERNEL(solve, 512)
 DEF_KERNEL(reanchor, 32)

@@ -12,6 +12,7 @@
 #define VIWB_SYNC() ((void)0)
 #define VIWB_SYNCWARP() ((void)0)
 #define VIWB_RESTRICT
+static inline double rsqrt(double x) { return 1.0 / sqrt(x); }      // CUDA's device intrinsic, for the host emulation
 #else
 #define VIWB_HD __host__ __device__ __forceinline__
 #define VIWB_D __device__ __forceinline__
