@@ -100,14 +100,14 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
 // T = sum_k g_k w_k w_k^T (80 x 80, symmetric, both triangles written), tvec = sum_k g_k w_k gl_k.
 // solver: g_k = gamma_k; marginalisation: g_k = 1 / a_k for the landmarks hosted in frame 0 (gamma holds a_k, 0 = skip).
 enum { SYRK_KC = 32 };
-VIWB_HD size_t syrk_smem_doubles() { return (size_t)SYRK_KC * VSUB + SYRK_KC; }
+VIWB_HD size_t syrk_smem_doubles() { return (size_t)SYRK_KC * VSUB + 2 * SYRK_KC; }
 VIWB_D void syrk_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by;
     const int w = bx;
     const WinMeta &m = bd.meta[w];
     if (mode == MODE_SOLVE && bd.work[w].status != ST_RUNNING) return;
     if (mode == MODE_MARG && m.margin_flag != 0) return;
-    double *Ws = smem, *gs = smem + SYRK_KC * VSUB;      // Ws[k][80] = sqrt(g_k) w_k ; gs[k] = sqrt(g_k) gl_k
+    double *Ws = smem, *gs = smem + SYRK_KC * VSUB, *sgk = gs + SYRK_KC;      // Ws[k][80] = sqrt(g_k) w_k ; gs[k] = sqrt(g_k) gl_k ; sgk[k] = sqrt(g_k)
     const double *W = bd.lm_W + (size_t)m.lm_off * VSUB, *gam = bd.lm_gamma + m.lm_off, *gl = bd.lm_g + m.lm_off;
     double *T = bd.Tvis + (size_t)w * VSUB * VSUB, *tv = bd.tvec + (size_t)w * VSUB;
     // 4x4 tiles of the lower triangle (20 x 20 tile grid -> 210 tiles) + 20 tiles (4 entries each) for tvec
@@ -122,14 +122,14 @@ VIWB_D void syrk_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
         for (int k0 = 0; k0 < m.nlm; k0 += SYRK_KC) {
             const int kc = (m.nlm - k0) < SYRK_KC ? (m.nlm - k0) : SYRK_KC;
             VIWB_SYNC();
-            for (int e = tid; e < kc * VSUB; e += nt) {
-                const int k = e / VSUB, p = e % VSUB;
+            for (int k = tid; k < kc; k += nt) {             // one square root per landmark, not per entry
                 double g = gam[k0 + k];
                 if (mode == MODE_MARG) g = g > 0.0 ? 1.0 / g : 0.0;
                 const double sg = sqrt(g);
-                Ws[e] = sg * W[(size_t)(k0 + k) * VSUB + p];
-                if (p == 0) gs[k] = sg * gl[k0 + k];
+                sgk[k] = sg; gs[k] = sg * gl[k0 + k];
             }
+            VIWB_SYNC();
+            for (int e = tid; e < kc * VSUB; e += nt) Ws[e] = sgk[e / VSUB] * W[(size_t)k0 * VSUB + e];
             VIWB_SYNC();
             if (live && !is_vec) {
                 for (int k = 0; k < kc; k++) {

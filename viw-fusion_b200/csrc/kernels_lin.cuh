@@ -104,8 +104,8 @@ VIWB_D double lm_warp_sum(double v) {
 #endif
     return v;
 }
-VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
-    (void)by; (void)smem;
+template <bool WIDE>
+VIWB_D void lm_reduce_body(const BatchDev &bd, int bx, int tid, int nt, int mode) {
     const int gid = bx * nt + tid;
     const int k = gid / LM_ROLES, lane = gid % LM_ROLES;
     if (k >= bd.nlm_total) return;
@@ -122,9 +122,9 @@ VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt,
         return;
     }
     VIWB_SYNCWARP();
-    const int rs = rec_stride(bd, mode);
+    const int rs = WIDE ? (int)VREC : (int)VREC_COMPACT;
     const int host = bd.vis_fi[f0];
-    double a = 0.0, g = 0.0, c = 0.0, hacc[6] = {0, 0, 0, 0, 0, 0}, e0[6] = {0, 0, 0, 0, 0, 0}, e1[6] = {0, 0, 0, 0, 0, 0}, tdv = 0.0;
+    double a = 0.0, g = 0.0, c = 0.0, hacc[6] = {0, 0, 0, 0, 0, 0}, e0[WIDE ? 6 : 1] = {0}, e1[WIDE ? 6 : 1] = {0}, tdv = 0.0;
     for (int fb = f0; fb < f1; fb += LM_W) {
         const int f = fb + lane;
         const bool on = f < f1;
@@ -140,7 +140,7 @@ VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt,
                 for (int q = 0; q < 6; q++) bv[q] = rec[REC_B + q] * u0 + rec[REC_B + 6 + q] * u1;
                 fj = bd.vis_fj[f];
             }
-            if (rs == VREC) {
+            if (WIDE) {
                 for (int q = 0; q < 6; q++) e0[q] += rec[REC_E0 + q] * u0 + rec[REC_E0 + 6 + q] * u1;
                 tdv += rec[REC_TD] * u0 + rec[REC_TD + 1] * u1;
                 if (type != 0) for (int q = 0; q < 6; q++) e1[q] += rec[REC_E1 + q] * u0 + rec[REC_E1 + 6 + q] * u1;
@@ -163,10 +163,10 @@ VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     }
     a = lm_warp_sum(a); g = lm_warp_sum(g); c = lm_warp_sum(c);
     for (int q = 0; q < 6; q++) hacc[q] = lm_warp_sum(hacc[q]);
-    if (rs == VREC) { for (int q = 0; q < 6; q++) { e0[q] = lm_warp_sum(e0[q]); e1[q] = lm_warp_sum(e1[q]); } tdv = lm_warp_sum(tdv); }
+    if (WIDE) { for (int q = 0; q < 6; q++) { e0[q] = lm_warp_sum(e0[q]); e1[q] = lm_warp_sum(e1[q]); } tdv = lm_warp_sum(tdv); }
     if (lane != 0) return;
     for (int q = 0; q < 6; q++) W[6 * host + q] += hacc[q];
-    if (rs == VREC) { for (int q = 0; q < 6; q++) { W[66 + q] = e0[q]; W[72 + q] = e1[q]; } W[78] = tdv; }
+    if (WIDE) { for (int q = 0; q < 6; q++) { W[66 + q] = e0[q]; W[72 + q] = e1[q]; } W[78] = tdv; }
     bd.lm_a[k] = a; bd.lm_g[k] = g; bd.lm_cost[k] = c;
     if (mode == MODE_MARG) { bd.lm_gamma[k] = a; return; }     // marginalisation keeps the pivot itself
     // Jacobi scale (first linearisation only) and the Schur weight for the mu this linearisation will be solved with:
@@ -177,6 +177,10 @@ VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     double d2 = s; if (d2 < bd.opt.min_lm_diagonal) d2 = bd.opt.min_lm_diagonal; if (d2 > bd.opt.max_lm_diagonal) d2 = bd.opt.max_lm_diagonal;
     bd.lm_gamma[k] = sc * sc / (s + ww.mu_lin * d2);
 }
+
+// two kernels so that the compact-record case is not charged the registers of the wide one (the host picks by rec_stride)
+VIWB_D void lm_reduce_wide_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; (void)smem; lm_reduce_body<true>(bd, bx, tid, nt, mode); }
+VIWB_D void lm_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; (void)smem; lm_reduce_body<false>(bd, bx, tid, nt, mode); }
 
 // ------------------------------------------------------------------------------------------------ lin_small
 // prior residual: r = r_lin + J_lin dx (marginalization_factor.cpp:361-380); dx in the prior's own column layout
@@ -193,10 +197,11 @@ VIWB_D void prior_dx(const PriorDev &p, const double *x, const double *x0, doubl
     }
 }
 
-// One warp per small factor: lane 0 evaluates the un-whitened residual and Jacobian into shared memory, then the lanes
-// whiten one Jacobian column each (r <- S r, J <- S J with S upper triangular) and stream it to the factor's record.
-enum { SMALL_SLOT = 15 + 15 * 30 };
-VIWB_HD size_t lin_small_smem_doubles(int nt) { const int W = nt < 32 ? nt : 32; return (size_t)(nt / W) * SMALL_SLOT + nt + MAXPRI + 8; }
+// Small factors in two phases per group of SMALL_NSLOT: (A) one thread per factor evaluates the un-whitened residual and
+// Jacobian into its shared-memory slot (the factors of a group run side by side in the lanes of one warp), (B) one warp per
+// factor whitens one Jacobian column per lane (r <- S r, J <- S J with S upper triangular) and streams it to the record.
+enum { SMALL_SLOT = 15 + 15 * 30, SMALL_NSLOT = 12 };
+VIWB_HD size_t lin_small_smem_doubles(int nt) { return (size_t)SMALL_NSLOT * SMALL_SLOT + nt + MAXPRI + 8; }
 VIWB_D double whiten_store(const double *raw, const double *S, int rows, int ld, double *rec, int lane, int W) {
     // raw: [rows residual | rows x ld Jacobian] un-whitened in shared memory -> rec (global), returns this lane's part of 0.5 |r|^2
     double c = 0.0;
@@ -218,36 +223,47 @@ VIWB_D void lin_small_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     if (marg_skip(m, mode)) return;
     const double *x = eval_state(bd, w, mode);
     const int W = nt < 32 ? nt : 32, nw = nt / W, wid = tid / W, lane = tid % W;
-    double *slot = smem + (size_t)wid * SMALL_SLOT;
-    double *cost_part = smem + (size_t)nw * SMALL_SLOT;      // [nt]
-    double *dx = cost_part + nt;                             // [MAXPRI]
+    double *cost_part = smem + (size_t)SMALL_NSLOT * SMALL_SLOT;      // [nt]
+    double *dx = cost_part + nt;                                      // [MAXPRI]
     double c = 0.0;
     const int n_small = marg_prior_only(m, mode) ? 0 : m.nimu + m.nwheel + m.nplane;
-    for (int t = wid; t < n_small; t += nw) {
-        if (t < m.nimu) {
-            const int f = m.imu_off + t, i = bd.imu_fi[f], j = bd.imu_fj[f];
-            if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-            if (lane == 0) imu_eval(bd.imu_data + (size_t)f * 287, nullptr, m.G, x + 7 * i, x + 77 + 9 * i, x + 7 * j, x + 77 + 9 * j, true, slot, slot + 15);
-            VIWB_SYNCWARP();
-            c += whiten_store(slot, bd.imu_S + (size_t)f * 225, 15, 30, bd.imu_rec + (size_t)f * IMU_REC, lane, W);
-            VIWB_SYNCWARP();
-        } else if (t < m.nimu + m.nwheel) {
-            const int f = m.wheel_off + (t - m.nimu), i = bd.wheel_fi[f], j = bd.wheel_fj[f];
-            if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-            if (lane == 0) wheel_eval(bd.wheel_data + (size_t)f * 78, nullptr, x + 7 * i, x + 7 * j, x + blk_off(BLK_EXW), x[blk_off(BLK_SX)], x[blk_off(BLK_SY)],
-                                      x[blk_off(BLK_SW)], x[blk_off(BLK_TDW)], true, slot, slot + 6);
-            VIWB_SYNCWARP();
-            c += whiten_store(slot, bd.wheel_S + (size_t)f * 36, 6, 22, bd.wheel_rec + (size_t)f * WHEEL_REC, lane, W);
-            VIWB_SYNCWARP();
-        } else {
-            const int f = m.plane_off + (t - m.nimu - m.nwheel), i = bd.plane_f[f];
-            if (mode == MODE_MARG && i != 0) continue;
-            if (lane == 0) {
+    for (int t0 = 0; t0 < n_small; t0 += SMALL_NSLOT) {
+        const int t1 = (t0 + SMALL_NSLOT < n_small) ? t0 + SMALL_NSLOT : n_small;
+        // ---- A: evaluate
+        for (int t = t0 + tid; t < t1; t += nt) {
+            double *slot = smem + (size_t)(t - t0) * SMALL_SLOT;
+            if (t < m.nimu) {
+                const int f = m.imu_off + t, i = bd.imu_fi[f], j = bd.imu_fj[f];
+                if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+                imu_eval(bd.imu_data + (size_t)f * 287, nullptr, m.G, x + 7 * i, x + 77 + 9 * i, x + 7 * j, x + 77 + 9 * j, true, slot, slot + 15);
+            } else if (t < m.nimu + m.nwheel) {
+                const int f = m.wheel_off + (t - m.nimu), i = bd.wheel_fi[f], j = bd.wheel_fj[f];
+                if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+                wheel_eval(bd.wheel_data + (size_t)f * 78, nullptr, x + 7 * i, x + 7 * j, x + blk_off(BLK_EXW), x[blk_off(BLK_SX)], x[blk_off(BLK_SY)],
+                           x[blk_off(BLK_SW)], x[blk_off(BLK_TDW)], true, slot, slot + 6);
+            } else {
+                const int f = m.plane_off + (t - m.nimu - m.nwheel), i = bd.plane_f[f];
+                if (mode == MODE_MARG && i != 0) continue;
                 double *rec = bd.plane_rec + (size_t)f * PLANE_REC;
                 plane_eval(m.w_plane, x + 7 * i, x + blk_off(BLK_EXW), x + blk_off(BLK_PR), x[blk_off(BLK_PZ)], true, rec, rec + 3);
                 for (int k = 0; k < 3; k++) c += 0.5 * rec[k] * rec[k];
             }
         }
+        VIWB_SYNC();
+        // ---- B: whiten
+        for (int t = t0 + wid; t < t1; t += nw) {
+            const double *slot = smem + (size_t)(t - t0) * SMALL_SLOT;
+            if (t < m.nimu) {
+                const int f = m.imu_off + t, i = bd.imu_fi[f], j = bd.imu_fj[f];
+                if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+                c += whiten_store(slot, bd.imu_S + (size_t)f * 225, 15, 30, bd.imu_rec + (size_t)f * IMU_REC, lane, W);
+            } else if (t < m.nimu + m.nwheel) {
+                const int f = m.wheel_off + (t - m.nimu), i = bd.wheel_fi[f], j = bd.wheel_fj[f];
+                if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
+                c += whiten_store(slot, bd.wheel_S + (size_t)f * 36, 6, 22, bd.wheel_rec + (size_t)f * WHEEL_REC, lane, W);
+            }
+        }
+        VIWB_SYNC();
     }
     if (m.prior_idx >= 0) {
         const PriorDev &p = bd.prior[m.prior_idx];

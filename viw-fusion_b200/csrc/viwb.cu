@@ -81,7 +81,11 @@ static Profiler g_prof;
 DEF_KERNEL(setup, 128)
 DEF_KERNEL(prior_setup, 256)
 DEF_KERNEL2(lin_vis, 128, LIN_VIS_MINB)
-DEF_KERNEL(lm_reduce, 128)
+#ifndef LM_MINB
+#define LM_MINB 8
+#endif
+DEF_KERNEL2(lm_reduce, 128, LM_MINB)
+DEF_KERNEL(lm_reduce_wide, 128)
 DEF_KERNEL(lin_small, 128)
 DEF_KERNEL(asm_items, 128)
 DEF_KERNEL(syrk, 256)
@@ -490,7 +494,8 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg, bd.marg_nmax) * 8;
     auto lin = [&](int mode) {
         LAUNCH(lin_vis, bd, g_vis, 1, nt_vis, 0, mode, st);
-        LAUNCH(lm_reduce, bd, g_lm, 1, nt_lm, 0, mode, st);
+        if ((mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) == VREC) LAUNCH(lm_reduce_wide, bd, g_lm, 1, nt_lm, 0, mode, st);
+        else LAUNCH(lm_reduce, bd, g_lm, 1, nt_lm, 0, mode, st);
         LAUNCH(lin_small, bd, B, 1, nt_small, sm_small, mode, st);
         const int ni = mode == MODE_SOLVE ? bd.nitems_solve : bd.nitems_marg, wpb = nt_asm / (nt_asm < 32 ? nt_asm : 32);
         LAUNCH(asm_items, bd, (ni + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
