@@ -276,6 +276,18 @@ void viwb_batch_destroy(viwb_context *ctx, viwb_batch *b);
 int viwb_debug_normal_equations(viwb_context *ctx, const viwb_problem *problem, const double *state,
                                 double *H, double *g, double *lm, double *cost);
 
+/* ---- pre-integration: the producers of the IMU / wheel records above --------------------
+ * IntegrationBase::propagate over a buffer of samples (factor/integration_base.h:63-167) and
+ * WheelIntegrationBase::propagate (factor/wheel_integration_base.h:67-177), `n` independent intervals per call.
+ * Interval i has counts[i] steps: dt holds the steps of all intervals back to back, the sample arrays hold
+ * counts[i]+1 rows of 3 per interval back to back (row 0 = acc_0 / gyr_0 resp. vel_0 / gyr_0).
+ * ba, bg: [n][3] linearisation biases; noise = {ACC_N, GYR_N, ACC_W, GYR_W} (parameters.cpp) resp.
+ * {VEL_N_wheel, GYR_N_wheel}; s: [n][3] = sx, sy, sw; td: [n] linearized_td.  records: [n][287] / [n][78]. */
+int viwb_imu_preintegrate(viwb_context *ctx, int n, const int32_t *counts, const double *dt, const double *acc,
+                          const double *gyr, const double *ba, const double *bg, const double *noise, double *records);
+int viwb_wheel_preintegrate(viwb_context *ctx, int n, const int32_t *counts, const double *dt, const double *vel,
+                            const double *gyr, const double *s, const double *td, const double *noise, double *records);
+
 /* ---- feature tracker: cv::calcOpticalFlowPyrLK replacement ---------------------------------------
  * Call sites featureTracker/feature_tracker.cpp:125-127,136,139,145-146,240,244.  Images are 8-bit
  * single channel, `stride` in bytes.  next_pts is in/out (read when flags & VIWB_LK_USE_INITIAL_FLOW).

@@ -399,3 +399,29 @@ def check_lk_batch(ctx, streams=3, w=320, h=240, min_both=30):
         compare(img1, img2, right2, p2, n2, p2, n2, got2)
     finally:
         lb.close()
+
+
+def check_preintegration(ctx, oracle, seed=5):
+    """SURVEY 8 f-2: batched IMU / wheel pre-integration against the oracle's restatement of IntegrationBase::propagate /
+    WheelIntegrationBase::propagate, ragged interval lengths (including the 10-sample interval of the 20 Hz / 200 Hz configs)."""
+    rng = np.random.default_rng(seed)
+    lens = [10, 1, 40, 7, 10, 23]
+    dts = [np.full(k, 0.005) + rng.uniform(-1e-4, 1e-4, k) for k in lens]
+    accs = [rng.normal(0, 2.0, (k + 1, 3)) + np.array([0, 0, 9.8]) for k in lens]
+    gyrs = [rng.normal(0, 0.5, (k + 1, 3)) for k in lens]
+    ba, bg = rng.normal(0, 0.05, (len(lens), 3)), rng.normal(0, 0.01, (len(lens), 3))
+    noise = np.array([0.1, 0.01, 1e-3, 1e-4])
+    rec = ctx.imu_preintegrate(dts, accs, gyrs, ba, bg, noise)
+    for i, k in enumerate(lens):
+        ref = oracle.imu_preintegrate(dts[i], accs[i], gyrs[i], ba[i], bg[i], noise)
+        assert np.abs(rec[i] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), (i, np.abs(rec[i] - ref).max())
+    vels = [rng.normal(0, 0.3, (k + 1, 3)) + np.array([1.0, 0, 0]) for k in lens]
+    s = 1.0 + rng.normal(0, 0.01, (len(lens), 3))
+    td = rng.normal(0, 0.002, len(lens))
+    wn = np.array([0.01, 0.004])
+    wrec = ctx.wheel_preintegrate(dts, vels, gyrs, s, td, wn)
+    for i, k in enumerate(lens):
+        ref = oracle.wheel_preintegrate(dts[i], vels[i], gyrs[i], s[i], td[i], wn)
+        assert np.abs(wrec[i] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), (i, np.abs(wrec[i] - ref).max())
+    # the records drive the factors: a record built on the device evaluates to the same residual as one built by the oracle
+    return rec, wrec

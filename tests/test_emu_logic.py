@@ -72,3 +72,7 @@ def test_solver_time_limit(emu, oracle):
 
 def test_lk_batch(emu):
     pc.check_lk_batch(emu, streams=2, w=200, h=160, min_both=8)
+
+
+def test_preintegration(emu, oracle):
+    pc.check_preintegration(emu, oracle)

@@ -113,3 +113,7 @@ def test_solver_time_limit(gpu_ctx, oracle):
 def test_lk_batch(gpu_ctx):
     pc.check_lk_batch(gpu_ctx, streams=3, w=320, h=240)
     pc.check_lk_batch(gpu_ctx, streams=2, w=752, h=480)
+
+
+def test_preintegration(gpu_ctx, oracle):
+    pc.check_preintegration(gpu_ctx, oracle)

@@ -46,13 +46,13 @@ VIWB_HD int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }   // CV_
 // and images whose width is not a multiple of 4 at the tail, take the per-pixel reflect-101 path.
 struct PyrArgs { const uint8_t *src; uint8_t *dst; int sw, sh, sstride, dw, dh, dstride; };
 VIWB_D int pyr_down_pixel(const PyrArgs &a, int x, int y) {
+    int cx[5];
+    for (int d = 0; d < 5; d++) cx[d] = reflect101(2 * x + d - 2, a.sw);       // columns are reflected once per pixel, rows once per row
     int acc = 0;
     const int wgt[5] = {1, 4, 6, 4, 1};
     for (int dy = -2; dy <= 2; dy++) {
         const uint8_t *row = a.src + (size_t)reflect101(2 * y + dy, a.sh) * a.sstride;
-        int r = 0;
-        for (int dx = -2; dx <= 2; dx++) r += wgt[dx + 2] * row[reflect101(2 * x + dx, a.sw)];
-        acc += wgt[dy + 2] * r;
+        acc += wgt[dy + 2] * (row[cx[0]] + row[cx[4]] + 4 * (row[cx[1]] + row[cx[3]]) + 6 * row[cx[2]]);
     }
     return (acc + 128) >> 8;
 }

@@ -10,6 +10,7 @@
 #include "../../include/viwb.h"
 #include "kernels_marg.cuh"
 #include "kernels_lk.cuh"
+#include "kernels_preint.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -892,6 +893,74 @@ extern "C" int viwb_prior_evaluate(viwb_context *ctx, const viwb_prior *prior, c
         }
     }
     return VIWB_OK;
+}
+
+// -------------------------------------------------------------------------------------- pre-integration
+template <typename Args, typename EmuFn>
+static int preint_run(viwb_context *ctx, Args &a, int n, const int32_t *counts, const double *dt, const double *s0, const double *s1, int rec_doubles, double *records,
+                      const double *const *extra, const int *extra_doubles, int nextra, const double **dev_extra, EmuFn emu, int smem_doubles, bool imu) {
+    bind_device(ctx);
+    std::vector<int> off(n + 1, 0);
+    for (int i = 0; i < n; i++) { if (counts[i] < 0) return fail(ctx, VIWB_ERR_INVALID, "negative sample count"); off[i + 1] = off[i] + counts[i]; }
+    const size_t steps = off[n], rows = steps + n;
+    size_t bytes = align_up((n + 1) * sizeof(int)) + align_up(steps * 8) + 2 * align_up(rows * 24) + align_up((size_t)n * rec_doubles * 8);
+    for (int k = 0; k < nextra; k++) bytes += align_up((size_t)n * extra_doubles[k] * 8);
+    char *d = nullptr;
+    CK(dev_malloc((void **)&d, bytes));
+    size_t o = 0;
+    int *d_off = (int *)(d + o); o += align_up((n + 1) * sizeof(int));
+    double *d_dt = (double *)(d + o); o += align_up(steps * 8);
+    double *d_s0 = (double *)(d + o); o += align_up(rows * 24);
+    double *d_s1 = (double *)(d + o); o += align_up(rows * 24);
+    double *d_rec = (double *)(d + o); o += align_up((size_t)n * rec_doubles * 8);
+    int e = dev_h2d(d_off, off.data(), (n + 1) * sizeof(int), ctx->stream);
+    if (!e) e = dev_h2d(d_dt, dt, steps * 8, ctx->stream);
+    if (!e) e = dev_h2d(d_s0, s0, rows * 24, ctx->stream);
+    if (!e) e = dev_h2d(d_s1, s1, rows * 24, ctx->stream);
+    for (int k = 0; k < nextra && !e; k++) { double *p = (double *)(d + o); o += align_up((size_t)n * extra_doubles[k] * 8); e = dev_h2d(p, extra[k], (size_t)n * extra_doubles[k] * 8, ctx->stream); dev_extra[k] = p; }
+    if (e) { dev_free(d); return fail(ctx, VIWB_ERR_CUDA, "pre-integration upload failed"); }
+    a.n = n; a.off = d_off; a.dt = d_dt; a.rec = d_rec;
+    emu(a, d_s0, d_s1);
+    (void)smem_doubles; (void)imu;
+    ctx->launches++;
+    e = dev_d2h(records, d_rec, (size_t)n * rec_doubles * 8, ctx->stream);
+    if (!e) e = dev_sync(ctx->stream);
+    dev_free(d);
+    if (e) return fail(ctx, VIWB_ERR_CUDA, "pre-integration download failed");
+    return VIWB_OK;
+}
+
+extern "C" int viwb_imu_preintegrate(viwb_context *ctx, int n, const int32_t *counts, const double *dt, const double *acc, const double *gyr,
+                                     const double *ba, const double *bg, const double *noise, double *records) {
+    if (!ctx || n < 0 || !counts || !dt || !acc || !gyr || !ba || !bg || !noise || !records) return VIWB_ERR_INVALID;
+    if (n == 0) return VIWB_OK;
+    ImuPreArgs a; for (int k = 0; k < 4; k++) a.noise[k] = noise[k];
+    const double *extra[2] = {ba, bg}; const int ed[2] = {3, 3}; const double *dv[2];
+    stream_t st = ctx->stream;
+    return preint_run(ctx, a, n, counts, dt, acc, gyr, 287, records, extra, ed, 2, dv, [&](ImuPreArgs &q, const double *d0, const double *d1) {
+        q.acc = d0; q.gyr = d1; q.ba = dv[0]; q.bg = dv[1];
+#ifdef VIWB_HOST_EMU
+        std::vector<double> sm(PRE_IMU_SMEM); for (int i = 0; i < q.n; i++) imu_preint_warp(q, i, 0, 1, sm.data());
+#else
+        g_prof.begin("imu_preint", st); imu_preint_kernel<<<(q.n + PRE_WPB - 1) / PRE_WPB, 32 * PRE_WPB, PRE_WPB * PRE_IMU_SMEM * 8, st>>>(q); g_prof.end(st);
+#endif
+    }, PRE_IMU_SMEM, true);
+}
+extern "C" int viwb_wheel_preintegrate(viwb_context *ctx, int n, const int32_t *counts, const double *dt, const double *vel, const double *gyr,
+                                       const double *s, const double *td, const double *noise, double *records) {
+    if (!ctx || n < 0 || !counts || !dt || !vel || !gyr || !s || !td || !noise || !records) return VIWB_ERR_INVALID;
+    if (n == 0) return VIWB_OK;
+    WheelPreArgs a; a.noise[0] = noise[0]; a.noise[1] = noise[1];
+    const double *extra[2] = {s, td}; const int ed[2] = {3, 1}; const double *dv[2];
+    stream_t st = ctx->stream;
+    return preint_run(ctx, a, n, counts, dt, vel, gyr, 78, records, extra, ed, 2, dv, [&](WheelPreArgs &q, const double *d0, const double *d1) {
+        q.vel = d0; q.gyr = d1; q.s = dv[0]; q.td = dv[1];
+#ifdef VIWB_HOST_EMU
+        std::vector<double> sm(PRE_WHEEL_SMEM); for (int i = 0; i < q.n; i++) wheel_preint_warp(q, i, 0, 1, sm.data());
+#else
+        g_prof.begin("wheel_preint", st); wheel_preint_kernel<<<(q.n + PRE_WPB - 1) / PRE_WPB, 32 * PRE_WPB, PRE_WPB * PRE_WHEEL_SMEM * 8, st>>>(q); g_prof.end(st);
+#endif
+    }, PRE_WHEEL_SMEM, false);
 }
 
 // -------------------------------------------------------------------------------------- feature tracker

@@ -20,7 +20,7 @@ EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", 
            "viwb_batch_run", "viwb_batch_download", "viwb_batch_algorithmic_bytes", "viwb_batch_destroy",
            "viwb_debug_normal_equations", "viwb_lk_track", "viwb_track_checked", "viwb_lk_batch_create", "viwb_lk_batch_destroy",
            "viwb_lk_batch_upload", "viwb_lk_batch_run", "viwb_lk_batch_download", "viwb_lk_batch_algorithmic_bytes", "viwb_host_register",
-           "viwb_host_unregister"]
+           "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate"]
 
 
 class ViwbError(RuntimeError):
@@ -225,6 +225,38 @@ class Context:
                                              p0.ctypes.data_as(C.c_void_p), p1.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(mode),
                                              C.c_int(1 if flow_back else 0), st.ctypes.data_as(C.c_void_p)), "viwb_track_checked")
         return p1, st
+
+    # ---------------------------------------------------------------- pre-integration
+    @staticmethod
+    def _pack_intervals(dts, a_list, b_list):
+        counts = np.array([len(d) for d in dts], np.int32)
+        dt = np.ascontiguousarray(np.concatenate([np.asarray(d, np.float64) for d in dts]) if len(dts) else np.zeros(0))
+        a = np.ascontiguousarray(np.concatenate([np.asarray(x, np.float64).reshape(-1, 3) for x in a_list]))
+        b = np.ascontiguousarray(np.concatenate([np.asarray(x, np.float64).reshape(-1, 3) for x in b_list]))
+        assert len(a) == len(dt) + len(dts) and len(b) == len(a)
+        return counts, dt, a, b
+
+    def imu_preintegrate(self, dts, accs, gyrs, ba, bg, noise):
+        """n intervals: dts[i] (k_i,), accs[i] / gyrs[i] (k_i + 1, 3), ba / bg (n, 3), noise = (ACC_N, GYR_N, ACC_W, GYR_W) -> records (n, 287)"""
+        counts, dt, a, g = self._pack_intervals(dts, accs, gyrs)
+        n = len(counts)
+        ba = np.ascontiguousarray(ba, np.float64).reshape(n, 3); bg = np.ascontiguousarray(bg, np.float64).reshape(n, 3)
+        nz = np.ascontiguousarray(noise, np.float64)
+        rec = np.zeros((n, abi.IMU_DOUBLES))
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.viwb_imu_preintegrate(self.h, C.c_int(n), vp(counts), vp(dt), vp(a), vp(g), vp(ba), vp(bg), vp(nz), vp(rec)), "viwb_imu_preintegrate")
+        return rec
+
+    def wheel_preintegrate(self, dts, vels, gyrs, s, td, noise):
+        """n intervals: vels[i] / gyrs[i] (k_i + 1, 3), s (n, 3) = sx, sy, sw, td (n,), noise = (VEL_N_wheel, GYR_N_wheel) -> records (n, 78)"""
+        counts, dt, v, g = self._pack_intervals(dts, vels, gyrs)
+        n = len(counts)
+        s = np.ascontiguousarray(s, np.float64).reshape(n, 3); td = np.ascontiguousarray(td, np.float64).reshape(n)
+        nz = np.ascontiguousarray(noise, np.float64)
+        rec = np.zeros((n, abi.WHEEL_DOUBLES))
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.viwb_wheel_preintegrate(self.h, C.c_int(n), vp(counts), vp(dt), vp(v), vp(g), vp(s), vp(td), vp(nz), vp(rec)), "viwb_wheel_preintegrate")
+        return rec
 
     def lk_batch(self, streams, width, height, max_points, stereo=True, flow_back=True):
         return LkBatch(self, streams, width, height, max_points, stereo, flow_back)
