@@ -305,6 +305,8 @@ def main():
     from viwb import lib
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"           # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = lib.Context(local_rank)           # raises if the CUDA library / device is missing (no CPU path)
     stream = torch.cuda.current_stream()

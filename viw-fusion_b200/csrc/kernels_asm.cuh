@@ -73,9 +73,12 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
         const int ib_c = (kb == 2) ? common_off(pb) : (kb == 3 ? 0 : pb), sb = (kb == 2) ? common_stride(pb) : (kb == 3 ? 1 : 6);
         double acc = 0.0;
         int e = item.lo;
+        int nx[4] = {0, 0, 0, 0};                  // list entries of the next group, fetched one group ahead of the records they index
+        if (e + 4 <= item.hi) for (int u = 0; u < 4; u++) nx[u] = list[e + u];
         for (; e + 4 <= item.hi; e += 4) {        // 4 independent gather chains in flight
             int en[4]; const double *rc[4]; double va[4], vb[4], wa[4], wb[4];
-            for (int u = 0; u < 4; u++) en[u] = list[e + u];
+            for (int u = 0; u < 4; u++) en[u] = nx[u];
+            if (e + 8 <= item.hi) for (int u = 0; u < 4; u++) nx[u] = list[e + 4 + u];
             for (int u = 0; u < 4; u++) {
                 const int role = en[u] & 1;
                 rc[u] = recs + (size_t)(en[u] >> 1) * rs;

@@ -493,15 +493,20 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(512), nt_marg = NT(256);
     const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total * LM_ROLES + nt_lm - 1) / nt_lm;
     const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg, bd.marg_nmax) * 8;
-    auto lin = [&](int mode) {
+    // cost_only: the round after the last allowed iteration only decides accept / reject of the pending candidate (every window
+    // still running is at max_num_iterations there, trust_region_minimizer.cc checks the iteration limit before the gradient),
+    // so the partial sums and the Schur product of that linearisation would never be read
+    auto lin = [&](int mode, bool cost_only) {
         LAUNCH(lin_vis, bd, g_vis, 1, nt_vis, 0, mode, st);
         if ((mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) == VREC) LAUNCH(lm_reduce_wide, bd, g_lm, 1, nt_lm, 0, mode, st);
         else LAUNCH(lm_reduce, bd, g_lm, 1, nt_lm, 0, mode, st);
         LAUNCH(lin_small, bd, B, 1, nt_small, sm_small, mode, st);
+        ctx->launches += (g_vis > 0) + (g_lm > 0) + 1;
+        if (cost_only) return;
         const int ni = mode == MODE_SOLVE ? bd.nitems_solve : bd.nitems_marg, wpb = nt_asm / (nt_asm < 32 ? nt_asm : 32);
         LAUNCH(asm_items, bd, (ni + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
         LAUNCH(syrk, bd, B, 1, nt_syrk, syrk_smem_doubles() * 8, mode, st);
-        ctx->launches += (g_vis > 0) + (g_lm > 0) + (ni > 0) + 2;
+        ctx->launches += (ni > 0) + 1;
     };
     if (what & (RUN_SOLVE | RUN_MARG | RUN_LIN_ONLY)) {
         const int ns = bd.nimu_total + bd.nwheel_total, nt_s = NT(128);
@@ -509,7 +514,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
         LAUNCH(prior_setup, bd, bd.nprior, 1, NT(256), 0, 0, st);
         ctx->launches += (ns > 0) + (bd.nprior > 0);
     }
-    if (what & RUN_LIN_ONLY) { lin(MODE_SOLVE); LAUNCH(solve, bd, B, 1, nt_solve, sm_solve, 2, st); ctx->launches++; }
+    if (what & RUN_LIN_ONLY) { lin(MODE_SOLVE, false); LAUNCH(solve, bd, B, 1, nt_solve, sm_solve, 2, st); ctx->launches++; }
     if (what & RUN_SOLVE) {
         // SOLVER_TIME (estimator.cpp:1650-1653): Ceres tests the wall clock after every iteration; here the host
         // waits for each round only when a limit is set, and the round after the limit just decides the pending
@@ -521,14 +526,14 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
                 CK(dev_sync(st));
                 last = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() >= b->max_time;
             }
-            lin(MODE_SOLVE);
+            lin(MODE_SOLVE, last || (round == b->max_iter && round > 0));
             LAUNCH(solve, bd, B, 1, nt_solve, sm_solve, last ? 3 : 0, st);
             ctx->launches++;
         }
     }
     if (what & RUN_REANCHOR) { LAUNCH(reanchor, bd, B, 1, NT(32), 0, 0, st); ctx->launches++; }
     if ((what & RUN_MARG) && b->any_marg) {
-        lin(MODE_MARG);
+        lin(MODE_MARG, false);
         LAUNCH(marg, bd, B, 1, nt_marg, sm_marg, 0, st);
         ctx->launches++;
     }
