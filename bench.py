@@ -438,6 +438,14 @@ def main():
         h2d += feed.tick_bytes()
         d2h += 2 * B * N_FEAT * (8 + 1)
 
+    # ---- latency of ONE window through the host-buffer call (what a single robot sees per key-frame; not the headline metric)
+    one = ctx.prepare_optimization_batch(probs[:1], states[:1], flags[:1])
+    one(); one()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        one()
+    single_ms = (time.perf_counter() - t0) * 100.0
+
     # ---- live per-kernel timing (CUDA events around every launch, separate pass so the headline is unperturbed)
     roofline, kernels = None, None
     if not args.no_profile:
@@ -524,7 +532,8 @@ def main():
                            "camera": None if lk is None else {"streams": B, "image": [IMG_W, IMG_H], "features": N_FEAT, "distinct_scenes": len(scenes),
                                                               "e2e_images_uploaded_per_tick": 2}},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "host_threads": lanes},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity,
+                "single_window_e2e_ms": single_ms}
         print(json.dumps(line))
     if lk is not None:
         lk.close()

@@ -253,6 +253,12 @@ int viwb_marginalize(viwb_context *ctx, const viwb_problem *problem, const doubl
 int viwb_optimization(viwb_context *ctx, const viwb_problem *problem, double *state, const viwb_options *options,
                       int margin_flag, viwb_summary *summary, viwb_prior *prior_out);
 
+/* Estimator::outliersRejection (estimator.cpp:2127-2185) on a solved window: outliers[k] = 1 when the mean
+ * reprojectionError (:2115-2125) of landmark k over its observations, times focal_length (FOCAL_LENGTH = 460), exceeds
+ * threshold_px (3).  outliers: [num_landmarks]. */
+int viwb_outlier_rejection(viwb_context *ctx, const viwb_problem *problem, const double *state, double focal_length,
+                           double threshold_px, uint8_t *outliers);
+
 /* Batch of B independent windows (one per sequence), host buffers in, host buffers out. */
 int viwb_optimization_batch(viwb_context *ctx, int batch, const viwb_problem *problems, double *const *states,
                             const viwb_options *options, const int32_t *margin_flags, viwb_summary *summaries,
@@ -266,6 +272,9 @@ int viwb_batch_reset_states(viwb_context *ctx, viwb_batch *b);  /* restore the u
 int viwb_batch_run(viwb_context *ctx, viwb_batch *b);           /* solve + reanchor + marginalize, async on the stream */
 int viwb_batch_download(viwb_context *ctx, viwb_batch *b, double *const *states, viwb_summary *summaries,
                         viwb_prior *priors_out);
+/* outliersRejection on the windows as the batch currently holds them (after viwb_batch_run: solved and re-anchored);
+ * outliers[w]: [num_landmarks of window w] or NULL */
+int viwb_batch_outliers(viwb_context *ctx, viwb_batch *b, double focal_length, double threshold_px, uint8_t *const *outliers);
 /* algorithmic bytes of one viwb_batch_run (SURVEY 8(d) B_solve model, summed over the batch) */
 double viwb_batch_algorithmic_bytes(const viwb_batch *b);
 void viwb_batch_destroy(viwb_context *ctx, viwb_batch *b);

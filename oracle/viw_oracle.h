@@ -64,6 +64,9 @@ int vo_marginalize(const viwb_problem *problem, const double *state, int margin_
 int vo_optimization(const viwb_problem *problem, double *state, const viwb_options *options, int margin_flag,
                     viwb_summary *summary, viwb_prior *prior_out);
 
+/* Estimator::outliersRejection (estimator.cpp:2115-2185): out[num_landmarks] */
+int vo_outlier_rejection(const viwb_problem *problem, const double *state, double focal_length, double threshold_px, uint8_t *out);
+
 /* n independent windows on `threads` pthreads, `repeat` passes (bench.py CPU arm); returns the number of optimisations run */
 long vo_optimization_throughput(int n, const viwb_problem *problems, const double *const *states, const int32_t *flags,
                                 const viwb_options *opt, int threads, int repeat);

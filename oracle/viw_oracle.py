@@ -159,6 +159,13 @@ def optimization(problem, state, flag, options=None, want_prior=True):
     return st, summ, out
 
 
+def outlier_rejection(problem, state, focal=460.0, thresh=3.0):
+    st = np.ascontiguousarray(state, np.float64)
+    out = np.zeros(max(problem.num_landmarks, 1), np.uint8)
+    lib().vo_outlier_rejection(C.byref(problem.c), _dp(st), C.c_double(focal), C.c_double(thresh), out.ctypes.data_as(C.c_void_p))
+    return out[: problem.num_landmarks]
+
+
 def imu_preintegrate(dt, acc, gyr, ba, bg, noise):
     dt = np.ascontiguousarray(dt, np.float64)
     acc, gyr = np.ascontiguousarray(acc, np.float64), np.ascontiguousarray(gyr, np.float64)

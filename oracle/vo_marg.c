@@ -327,6 +327,35 @@ int vo_optimization(const viwb_problem *pb, double *state, const viwb_options *o
     return vo_marginalize(pb, state, flag, out, NULL, NULL, NULL);
 }
 
+
+/* ------------------------------------------------------------------ Estimator::outliersRejection (estimator.cpp:2115-2185) */
+static double vo_reproj_err(const double *Pi, const double *Qi, const double *tici, const double *qici, const double *Pj, const double *Qj,
+                            const double *ticj, const double *qicj, double depth, const double *uvi, const double *uvj) {
+    double t[3], a[3], pw[3], Rj[9], Rc[9], c[3], d[3];
+    for (int k = 0; k < 3; k++) t[k] = depth * uvi[k];
+    q_rot(a, qici, t); for (int k = 0; k < 3; k++) a[k] += tici[k];
+    q_rot(pw, Qi, a); for (int k = 0; k < 3; k++) pw[k] += Pi[k];
+    q_to_R(Rj, Qj); q_to_R(Rc, qicj);
+    for (int k = 0; k < 3; k++) d[k] = pw[k] - Pj[k];
+    for (int r = 0; r < 3; r++) c[r] = Rj[0 * 3 + r] * d[0] + Rj[1 * 3 + r] * d[1] + Rj[2 * 3 + r] * d[2] - ticj[r];     /* Rj^T (pw - Pj) - ticj */
+    for (int r = 0; r < 3; r++) a[r] = Rc[0 * 3 + r] * c[0] + Rc[1 * 3 + r] * c[1] + Rc[2 * 3 + r] * c[2];              /* ricj^T (...) */
+    const double rx = a[0] / a[2] - uvj[0], ry = a[1] / a[2] - uvj[1];
+    return sqrt(rx * rx + ry * ry);
+}
+int vo_outlier_rejection(const viwb_problem *pb, const double *state, double focal, double thresh, uint8_t *out) {
+    const int N = pb->num_landmarks;
+    double *err = (double *)calloc(N > 0 ? N : 1, sizeof(double)); int *cnt = (int *)calloc(N > 0 ? N : 1, sizeof(int));
+    for (int f = 0; f < pb->num_vis; f++) {
+        const int type = pb->vis_type[f], k = pb->vis_landmark[f], i = pb->vis_frame_i[f], j = type == 2 ? i : pb->vis_frame_j[f], cam = type == 0 ? 0 : 1;
+        const double *o = pb->vis_obs + (size_t)f * 12, *ex0 = state + 176, *exc = state + 176 + 7 * cam;
+        err[k] += vo_reproj_err(state + 7 * i, state + 7 * i + 3, ex0, ex0 + 3, state + 7 * j, state + 7 * j + 3, exc, exc + 3, 1.0 / state[VIWB_STATE_FIXED + k], o, o + 3);
+        cnt[k]++;
+    }
+    for (int k = 0; k < N; k++) out[k] = (cnt[k] > 0 && (err[k] / cnt[k]) * focal > thresh) ? 1 : 0;
+    free(err); free(cnt);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ multi-threaded batch (CPU baseline arm of bench.py)
  * n independent windows on `threads` pthreads; each optimisation itself is single-threaded like Ceres' default
  * (estimator.cpp:1646 leaves num_threads commented out).  repeat > 1 cycles over the windows to fill a time budget. */

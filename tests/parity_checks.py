@@ -425,3 +425,29 @@ def check_preintegration(ctx, oracle, seed=5):
         assert np.abs(wrec[i] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), (i, np.abs(wrec[i] - ref).max())
     # the records drive the factors: a record built on the device evaluates to the same residual as one built by the oracle
     return rec, wrec
+
+
+def check_outlier_rejection(ctx, oracle):
+    """SURVEY 8 f-3: Estimator::outliersRejection on solved windows (mono and stereo shapes), with a few landmarks pushed far
+    off so that both verdicts occur; single-call and batch entry points."""
+    for cid in (1, 2, 4):
+        cfg = synth.make_config(cid)
+        prob, st, _ = synth.Sequence(cfg, 2, 11).window(0)
+        a, _, _ = ctx.optimization(prob, st, abi.MARGIN_OLD)
+        bad = a.copy()
+        bad[abi.STATE_FIXED: abi.STATE_FIXED + 5] *= 3.0            # wrong inverse depths -> large reprojection errors
+        for x in (a, bad):
+            ref = oracle.outlier_rejection(prob, x)
+            got = ctx.outlier_rejection(prob, x)
+            assert np.array_equal(ref, got)
+        assert oracle.outlier_rejection(prob, bad)[:5].sum() >= 3 and oracle.outlier_rejection(prob, a).mean() < 0.2
+    # batch entry: verdicts on the solved + re-anchored windows the device holds
+    cfg = synth.make_config(2)
+    wins = [synth.Sequence(cfg, s, 11).window(0) for s in range(3)]
+    batch = ctx.batch([w[0] for w in wins], [w[1] for w in wins], [abi.MARGIN_OLD] * 3)
+    batch.run()
+    sts, _, _ = batch.download()
+    outs = batch.outliers()
+    batch.destroy()
+    for (prob, _, _), x, o in zip(wins, sts, outs):
+        assert np.array_equal(o, oracle.outlier_rejection(prob, x))

@@ -76,3 +76,7 @@ def test_lk_batch(emu):
 
 def test_preintegration(emu, oracle):
     pc.check_preintegration(emu, oracle)
+
+
+def test_outlier_rejection(emu, oracle):
+    pc.check_outlier_rejection(emu, oracle)

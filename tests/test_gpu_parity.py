@@ -117,3 +117,7 @@ def test_lk_batch(gpu_ctx):
 
 def test_preintegration(gpu_ctx, oracle):
     pc.check_preintegration(gpu_ctx, oracle)
+
+
+def test_outlier_rejection(gpu_ctx, oracle):
+    pc.check_outlier_rejection(gpu_ctx, oracle)

@@ -297,4 +297,35 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     if (tid == 0) ww.marg_status = 0;
 }
 
+// ---------------------------------------------------------------------------------------------------- outlier rejection
+// Estimator::outliersRejection (estimator.cpp:2127-2185) on the solved window: per landmark the mean of
+// reprojectionError (:2115-2125) over its observations -- left camera of another frame, right camera of another frame, right
+// camera of the host frame; the raw normalised points, no td compensation -- times FOCAL_LENGTH against 3 px.
+// One thread per landmark (its factors are consecutive in the table).
+VIWB_D void outlier_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem; (void)mode;
+    const int k = bx * nt + tid;
+    if (k >= bd.nlm_total) return;
+    const int w = bd.lm_win[k];
+    const WinMeta &m = bd.meta[w];
+    const double *x = bd.x_cur + m.state_off;
+    const int f0 = bd.lm_fptr[k], f1 = bd.lm_fptr[k + 1];
+    if (f0 == f1) { bd.lm_outlier[k] = 0; return; }
+    const double depth = 1.0 / x[SFIX + (k - m.lm_off)];
+    const int ex_off[2] = {blk_off(BLK_EX0), blk_off(BLK_EX1)};
+    double err = 0.0; int cnt = 0;
+    for (int f = f0; f < f1; f++) {
+        const int type = bd.vis_type[f], i = bd.vis_fi[f], j = (type == 2) ? i : bd.vis_fj[f], cam = (type == 0) ? 0 : 1;
+        const double *o = bd.vis_obs + (size_t)f * 12;
+        const V3 uvi = ld3(o), uvj = ld3(o + 3);
+        const V3 Pi = ld3(x + 7 * i), Pj = ld3(x + 7 * j), tici = ld3(x + ex_off[0]), ticj = ld3(x + ex_off[cam]);
+        const Q4 Qi = ldq(x + 7 * i + 3), Qj = ldq(x + 7 * j + 3), qici = ldq(x + ex_off[0] + 3), qicj = ldq(x + ex_off[cam] + 3);
+        const V3 pts_w = qrot(Qi, qrot(qici, depth * uvi) + tici) + Pi;
+        const V3 pts_cj = tmul(qR(qicj), tmul(qR(Qj), pts_w - Pj) - ticj);
+        const double rx = pts_cj.x / pts_cj.z - uvj.x, ry = pts_cj.y / pts_cj.z - uvj.y;
+        err += sqrt(rx * rx + ry * ry); cnt++;
+    }
+    bd.lm_outlier[k] = ((err / cnt) * bd.out_focal > bd.out_thresh) ? 1 : 0;
+}
+
 }  // namespace viwb

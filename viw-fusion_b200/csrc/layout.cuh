@@ -105,6 +105,8 @@ struct BatchDev {       // passed by value to every kernel
     // landmarks
     const int *lm_win, *lm_fptr;    // [nlm_total], [nlm_total+1] factor range (global factor indices, sorted by landmark)
     double *lm_a, *lm_g, *lm_gamma, *lm_scale, *lm_cost, *lm_W;   // lm_W [nlm_total][VSUB]
+    int *lm_outlier;                // [nlm_total] outliersRejection verdict (kernels_marg.cuh: outlier_block)
+    double out_focal, out_thresh;   // FOCAL_LENGTH and the pixel threshold of estimator.cpp:2183
     // small factors
     const int *imu_fi, *imu_fj, *imu_win, *wheel_fi, *wheel_fj, *wheel_win, *plane_f, *plane_win;
     const double *imu_data, *wheel_data;   // [n][287], [n][78]

@@ -93,6 +93,7 @@ DEF_KERNEL(syrk, 256)
 DEF_KERNEL(solve, 512)
 DEF_KERNEL(reanchor, 32)
 DEF_KERNEL(marg, 256)
+DEF_KERNEL(outlier, 128)
 #define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) \
     do { if ((gx) > 0 && (gy) > 0) { g_prof.begin((mode) == 1 ? #name "_marg" : #name, stream); name##_kernel<<<dim3((gx), (gy)), (nt), (smem_bytes), (stream)>>>(bd, mode); g_prof.end(stream); } } while (0)
 #define NT(n) (n)
@@ -425,7 +426,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     const size_t nvec = (size_t)B * TFIX + nlm;
     WK(&bd.work, B); WK(&bd.x_cur, nstate); WK(&bd.x_cand, nstate); WK(&bd.x_before, nstate);
     WK(&bd.vis_rec, nvis * VREC); WK(&bd.vis_cost, nvis);
-    WK(&bd.lm_a, nlm); WK(&bd.lm_g, nlm); WK(&bd.lm_gamma, nlm); WK(&bd.lm_scale, nlm); WK(&bd.lm_cost, nlm); WK(&bd.lm_W, nlm * VSUB);
+    WK(&bd.lm_a, nlm); WK(&bd.lm_g, nlm); WK(&bd.lm_gamma, nlm); WK(&bd.lm_scale, nlm); WK(&bd.lm_cost, nlm); WK(&bd.lm_W, nlm * VSUB); WK(&bd.lm_outlier, nlm);
     WK(&bd.imu_S, nimu * 225); WK(&bd.wheel_S, nwheel * 36); WK(&bd.imu_rec, nimu * IMU_REC); WK(&bd.wheel_rec, nwheel * WHEEL_REC); WK(&bd.plane_rec, nplane * PLANE_REC);
     WK(&bd.prior_A, npJ); WK(&bd.prior_res, npr); WK(&bd.prior_g, npr);
     WK(&bd.Hpk, (size_t)B * (TFIX * (TFIX + 1) / 2)); WK(&bd.gpk, (size_t)B * TFIX); WK(&bd.gfix, (size_t)B * (TFIX + 8));
@@ -683,6 +684,20 @@ extern "C" int viwb_batch_download(viwb_context *ctx, viwb_batch *b, double *con
     if (!ctx || !b) return VIWB_ERR_INVALID;
     return batch_fetch(ctx, b, states, summaries, priors_out);
 }
+// outliersRejection on the states the batch currently holds (after viwb_batch_run: the solved, re-anchored windows)
+extern "C" int viwb_batch_outliers(viwb_context *ctx, viwb_batch *b, double focal_length, double threshold_px, uint8_t *const *outliers) {
+    if (!ctx || !b || !outliers) return VIWB_ERR_INVALID;
+    bind_device(ctx);
+    BatchDev bd = b->bd; bd.out_focal = focal_length; bd.out_thresh = threshold_px;
+    const int nt = NT(128);
+    LAUNCH(outlier, bd, (bd.nlm_total + nt - 1) / nt, 1, nt, 0, 0, ctx->stream);
+    ctx->launches += bd.nlm_total > 0;
+    std::vector<int> h(bd.nlm_total > 0 ? bd.nlm_total : 1);
+    CK(dev_d2h(h.data(), bd.lm_outlier, (size_t)bd.nlm_total * sizeof(int), ctx->stream));
+    CK(dev_sync(ctx->stream));
+    for (int w = 0; w < b->B; w++) if (outliers[w]) { const WinMeta &m = b->meta[w]; for (int k = 0; k < m.nlm; k++) outliers[w][k] = (uint8_t)h[m.lm_off + k]; }
+    return VIWB_OK;
+}
 extern "C" double viwb_batch_algorithmic_bytes(const viwb_batch *b) { return b ? b->algorithmic_bytes : 0.0; }
 extern "C" void viwb_batch_destroy(viwb_context *ctx, viwb_batch *b) { batch_free(ctx, b); }
 
@@ -717,6 +732,19 @@ extern "C" int viwb_gauge_reanchor(viwb_context *ctx, const viwb_problem *proble
     if (!ctx || !problem || !state || !state_before) return VIWB_ERR_INVALID;
     double *sp[1] = {state}; const double *bp[1] = {state_before};
     return run_once(ctx, 1, problem, sp, nullptr, nullptr, RUN_REANCHOR, nullptr, nullptr, bp);
+}
+extern "C" int viwb_outlier_rejection(viwb_context *ctx, const viwb_problem *problem, const double *state, double focal_length, double threshold_px,
+                                      uint8_t *outliers) {
+    if (!ctx || !problem || !state || !outliers) return VIWB_ERR_INVALID;
+    viwb_batch *b = nullptr;
+    const double *sp[1] = {state};
+    int rc = batch_build(ctx, 1, problem, sp, nullptr, nullptr, &b, true);
+    if (rc) return rc;
+    rc = batch_execute(ctx, b, 0);                     // x_cur <- the given state, nothing else
+    uint8_t *op[1] = {outliers};
+    if (!rc) rc = viwb_batch_outliers(ctx, b, focal_length, threshold_px, op);
+    batch_free(ctx, b);
+    return rc;
 }
 extern "C" int viwb_marginalize(viwb_context *ctx, const viwb_problem *problem, const double *state, int margin_flag, viwb_prior *prior_out) {
     if (!ctx || !problem || !state || !prior_out) return VIWB_ERR_INVALID;

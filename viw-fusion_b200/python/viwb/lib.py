@@ -20,7 +20,7 @@ EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", 
            "viwb_batch_run", "viwb_batch_download", "viwb_batch_algorithmic_bytes", "viwb_batch_destroy",
            "viwb_debug_normal_equations", "viwb_lk_track", "viwb_track_checked", "viwb_lk_batch_create", "viwb_lk_batch_destroy",
            "viwb_lk_batch_upload", "viwb_lk_batch_run", "viwb_lk_batch_download", "viwb_lk_batch_algorithmic_bytes", "viwb_host_register",
-           "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate"]
+           "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate", "viwb_outlier_rejection", "viwb_batch_outliers"]
 
 
 class ViwbError(RuntimeError):
@@ -226,6 +226,13 @@ class Context:
                                              C.c_int(1 if flow_back else 0), st.ctypes.data_as(C.c_void_p)), "viwb_track_checked")
         return p1, st
 
+    def outlier_rejection(self, problem, state, focal=460.0, thresh=3.0):
+        st = np.ascontiguousarray(state, np.float64)
+        out = np.zeros(max(problem.num_landmarks, 1), np.uint8)
+        self._ck(self.lib.viwb_outlier_rejection(self.h, C.byref(problem.c), _dp(st), C.c_double(focal), C.c_double(thresh), out.ctypes.data_as(C.c_void_p)),
+                 "viwb_outlier_rejection")
+        return out[: problem.num_landmarks]
+
     # ---------------------------------------------------------------- pre-integration
     @staticmethod
     def _pack_intervals(dts, a_list, b_list):
@@ -371,6 +378,13 @@ class Batch:
                 for k in range(abi.NUM_FIXED_BLOCKS):
                     p.c.block_id[k], p.c.block_idx[k] = parr[i].block_id[k], parr[i].block_idx[k]
         return sts, list(summ), pri
+
+    def outliers(self, focal=460.0, thresh=3.0):
+        """Estimator::outliersRejection on the windows as the batch currently holds them (call after run())."""
+        outs = [np.zeros(max(p.num_landmarks, 1), np.uint8) for p in self.problems]
+        arr = (C.c_void_p * self.B)(*[o.ctypes.data for o in outs])
+        self.ctx._ck(self.ctx.lib.viwb_batch_outliers(self.ctx.h, self.h, C.c_double(focal), C.c_double(thresh), arr), "viwb_batch_outliers")
+        return [o[: p.num_landmarks] for o, p in zip(outs, self.problems)]
 
     def destroy(self):
         if self.h:
