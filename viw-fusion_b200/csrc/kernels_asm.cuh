@@ -83,7 +83,7 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
                 const int role = en[u] & 1;
                 rc[u] = recs + (size_t)(en[u] >> 1) * rs;
                 const int ia = (ka == 0) ? (role ? REC_B : REC_A) + ia_c : ia_c;
-                const int ib = (kb == 0) ? (role ? REC_B : REC_A) + ib_c : (kb == 1 ? (role ? REC_A : REC_B) + ib_c : (kb == 3 && role ? REC_R2 + ib_c : ib_c));
+                const int ib = (kb == 0) ? (role ? REC_B : REC_A) + ib_c : (kb == 1 ? (role ? REC_A : REC_B) + ib_c : ib_c);
                 va[u] = rc[u][ia]; wa[u] = rc[u][ia + sa]; vb[u] = rc[u][ib]; wb[u] = rc[u][ib + sb];
             }
             for (int u = 0; u < 4; u++) acc += va[u] * vb[u] + wa[u] * wb[u];
@@ -92,7 +92,7 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
             const int ent = list[e], role = ent & 1;
             const double *rec = recs + (size_t)(ent >> 1) * rs;
             const int ia = (ka == 0) ? (role ? REC_B : REC_A) + ia_c : ia_c;
-            const int ib = (kb == 0) ? (role ? REC_B : REC_A) + ib_c : (kb == 1 ? (role ? REC_A : REC_B) + ib_c : (kb == 3 && role ? REC_R2 + ib_c : ib_c));
+            const int ib = (kb == 0) ? (role ? REC_B : REC_A) + ib_c : (kb == 1 ? (role ? REC_A : REC_B) + ib_c : ib_c);
             acc += rec[ia] * rec[ib] + rec[ia + sa] * rec[ib + sb];
         }
         out[o] = acc;

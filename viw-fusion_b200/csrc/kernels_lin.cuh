@@ -81,7 +81,6 @@ VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, d
     rec[0] = o.r[0] * sc; rec[1] = o.r[1] * sc;
     for (int k = 0; k < 12; k++) { rec[REC_A + k] = o.JA[k] * sc; rec[REC_B + k] = o.JB[k] * sc; }
     rec[REC_L] = o.Jl[0] * sc; rec[REC_L + 1] = o.Jl[1] * sc;
-    rec[REC_R2] = rec[0]; rec[REC_R2 + 1] = rec[1]; rec[REC_L2] = rec[REC_L]; rec[REC_L2 + 1] = rec[REC_L + 1];
     if (rs == VREC) {
         for (int k = 0; k < 12; k++) { rec[REC_E0 + k] = o.JE0[k] * sc; rec[REC_E1 + k] = o.JE1[k] * sc; }
         rec[REC_TD] = o.Jtd[0] * sc; rec[REC_TD + 1] = o.Jtd[1] * sc;

@@ -16,13 +16,11 @@
 
 namespace viwb {
 
-enum { NB = 32, NFR = 11, TFIX = 192, SFIX = 207, VSUB = 80, VREC = 64, IMU_REC = 15 + 15 * 30, WHEEL_REC = 6 + 6 * 22,
+enum { NB = 32, NFR = 11, TFIX = 192, SFIX = 207, VSUB = 80, VREC = 54, IMU_REC = 15 + 15 * 30, WHEEL_REC = 6 + 6 * 22,
        PLANE_REC = 3 + 3 * 16, MAXPRI = 200 };
-// record layout: two cache-line-sized halves so that a gather touches only what it needs -- the host-frame half
-// [r | A | J_lambda] (16 doubles = 128 B) and the observing-frame half [B | r | J_lambda] (copies of r and J_lambda, 128 B);
-// FRAME items of the assembly read one half, PAIR items both.  td / E0 / E1 follow (wide records, stride VREC = 512 B) and are
-// only written when some window needs them; the first VREC_COMPACT doubles are all a solve needs when ex0/ex1/td are constant
-enum { REC_R = 0, REC_A = 2, REC_L = 14, REC_B = 16, REC_R2 = 28, REC_L2 = 30, REC_TD = 32, REC_E0 = 34, REC_E1 = 46, VREC_COMPACT = 32 };
+// record layout: the first VREC_COMPACT doubles (r, A, B, J_lambda) are all a solve needs when ex0/ex1/td are constant;
+// td / E0 / E1 follow and are only written (and the stride only widened to VREC) when some window needs them
+enum { REC_R = 0, REC_A = 2, REC_B = 14, REC_L = 26, REC_TD = 28, REC_E0 = 30, REC_E1 = 42, VREC_COMPACT = 28 };
 enum { BLK_SB0 = 11, BLK_EX0 = 22, BLK_EX1 = 23, BLK_EXW = 24, BLK_PR = 25, BLK_PZ = 26, BLK_SX = 27, BLK_SY = 28, BLK_SW = 29,
        BLK_TD = 30, BLK_TDW = 31 };
 
