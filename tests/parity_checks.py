@@ -451,3 +451,30 @@ def check_outlier_rejection(ctx, oracle):
     batch.destroy()
     for (prob, _, _), x, o in zip(wins, sts, outs):
         assert np.array_equal(o, oracle.outlier_rejection(prob, x))
+
+
+def check_small_edges(ctx, oracle):
+    """Empty / degenerate inputs of the tracker batch and the widened rows."""
+    import numpy as np
+    # a camera stream with no points, another with one point on the border
+    w, h, maxn = 160, 120, 8
+    img0, img1, _ = lk_images(3, w, h)
+    lb = ctx.lk_batch(2, w, h, maxn, stereo=True, flow_back=True)
+    try:
+        pts = np.zeros((2, maxn, 2), np.float32)
+        pts[1, 0] = [0.5, 0.5]
+        n = np.array([0, 1], np.int32)
+        imgs0, imgs1 = np.stack([img0, img0]), np.stack([img1, img1])
+        lb.upload(prev=imgs0, cur=imgs1, right=imgs1, prev_pts=pts, n_prev=n, stereo_pts=pts, n_stereo=n)
+        lb.run()
+        cur, st, rp, sr = lb.download()
+        p_ref, st_ref = ref_track_checked(img0, img1, pts[1, :1], 0, True)
+        assert st[1, 0] == st_ref[0]
+    finally:
+        lb.close()
+    # pre-integration: zero intervals, and an interval with zero steps (identity pre-integration, zero covariance)
+    noise = np.array([0.1, 0.01, 1e-3, 1e-4])
+    assert ctx.imu_preintegrate([], [], [], np.zeros((0, 3)), np.zeros((0, 3)), noise).shape == (0, abi.IMU_DOUBLES)
+    rec = ctx.imu_preintegrate([np.zeros(0)], [np.array([[0.0, 0, 9.8]])], [np.zeros((1, 3))], np.zeros((1, 3)), np.zeros((1, 3)), noise)
+    ref = oracle.imu_preintegrate(np.zeros(0), np.array([[0.0, 0, 9.8]]), np.zeros((1, 3)), np.zeros(3), np.zeros(3), noise)
+    assert np.array_equal(rec[0], ref) and rec[0][0] == 0.0 and rec[0][7] == 1.0

@@ -80,3 +80,7 @@ def test_preintegration(emu, oracle):
 
 def test_outlier_rejection(emu, oracle):
     pc.check_outlier_rejection(emu, oracle)
+
+
+def test_small_edges(emu, oracle):
+    pc.check_small_edges(emu, oracle)

@@ -121,3 +121,7 @@ def test_preintegration(gpu_ctx, oracle):
 
 def test_outlier_rejection(gpu_ctx, oracle):
     pc.check_outlier_rejection(gpu_ctx, oracle)
+
+
+def test_small_edges(gpu_ctx, oracle):
+    pc.check_small_edges(gpu_ctx, oracle)

@@ -238,8 +238,8 @@ class Context:
     def _pack_intervals(dts, a_list, b_list):
         counts = np.array([len(d) for d in dts], np.int32)
         dt = np.ascontiguousarray(np.concatenate([np.asarray(d, np.float64) for d in dts]) if len(dts) else np.zeros(0))
-        a = np.ascontiguousarray(np.concatenate([np.asarray(x, np.float64).reshape(-1, 3) for x in a_list]))
-        b = np.ascontiguousarray(np.concatenate([np.asarray(x, np.float64).reshape(-1, 3) for x in b_list]))
+        a = np.ascontiguousarray(np.concatenate([np.asarray(x, np.float64).reshape(-1, 3) for x in a_list]) if len(a_list) else np.zeros((0, 3)))
+        b = np.ascontiguousarray(np.concatenate([np.asarray(x, np.float64).reshape(-1, 3) for x in b_list]) if len(b_list) else np.zeros((0, 3)))
         assert len(a) == len(dt) + len(dts) and len(b) == len(a)
         return counts, dt, a, b
 
