@@ -12,6 +12,7 @@
 //                kernel (dense marginalisation layout): prior J^T J, IMU / wheel / plane J^T J factor by factor,
 //                visual partial sums phase by phase.
 #pragma once
+#include <vector>
 #include "layout.cuh"
 #include "factors.cuh"
 #include "kernels_lin.cuh"
@@ -103,54 +104,106 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
 // T = sum_k g_k w_k w_k^T (80 x 80, symmetric, both triangles written), tvec = sum_k g_k w_k gl_k.
 // solver: g_k = gamma_k; marginalisation: g_k = 1 / a_k for the landmarks hosted in frame 0 (gamma holds a_k, 0 = skip).
 enum { SYRK_KC = 32 };
-VIWB_HD size_t syrk_smem_doubles() { return (size_t)SYRK_KC * VSUB + 2 * SYRK_KC; }
+VIWB_HD size_t syrk_smem_doubles() { return (size_t)2 * SYRK_KC * VSUB + 4 * SYRK_KC; }
+// 16-byte asynchronous global -> shared copy (cp.async), commit / wait by groups
+VIWB_D void async_copy16(double *smem_dst, const double *gsrc) {
+#ifdef VIWB_HOST_EMU
+    smem_dst[0] = gsrc[0]; smem_dst[1] = gsrc[1];
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+VIWB_D void async_commit() {
+#ifndef VIWB_HOST_EMU
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+template <int PENDING> VIWB_D void async_wait() {
+#ifndef VIWB_HOST_EMU
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
+#endif
+}
+// Chunks of 32 landmarks stream through two shared-memory buffers: the copy of chunk c+1 is in flight while chunk c is
+// multiplied (4x4 register tiles of the lower triangle, 210 tiles + 20 work items for tvec).
 VIWB_D void syrk_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by;
     const int w = bx;
     const WinMeta &m = bd.meta[w];
     if (mode == MODE_SOLVE && bd.work[w].status != ST_RUNNING) return;
     if (mode == MODE_MARG && m.margin_flag != 0) return;
-    double *Ws = smem, *gs = smem + SYRK_KC * VSUB, *sgk = gs + SYRK_KC;      // Ws[k][80] = sqrt(g_k) w_k ; gs[k] = sqrt(g_k) gl_k ; sgk[k] = sqrt(g_k)
+    double *Wb[2] = {smem, smem + SYRK_KC * VSUB};
+    double *gkb[2] = {smem + 2 * SYRK_KC * VSUB, smem + 2 * SYRK_KC * VSUB + SYRK_KC};              // g_k
+    double *ggb[2] = {smem + 2 * SYRK_KC * VSUB + 2 * SYRK_KC, smem + 2 * SYRK_KC * VSUB + 3 * SYRK_KC};  // g_k * gl_k
     const double *W = bd.lm_W + (size_t)m.lm_off * VSUB, *gam = bd.lm_gamma + m.lm_off, *gl = bd.lm_g + m.lm_off;
     double *T = bd.Tvis + (size_t)w * VSUB * VSUB, *tv = bd.tvec + (size_t)w * VSUB;
-    // 4x4 tiles of the lower triangle (20 x 20 tile grid -> 210 tiles) + 20 tiles (4 entries each) for tvec
     const int NT4 = VSUB / 4, ntiles = NT4 * (NT4 + 1) / 2;
-    for (int base = 0; base < ntiles + NT4; base += nt) {          // every thread walks the same number of rounds (barriers inside)
-        const int t = base + tid;
-        const bool live = t < ntiles + NT4, is_vec = t >= ntiles;
-        int tp = 0, tq = 0;
-        if (live && !is_vec) sym_unrank(t, tp, tq); else if (live) tp = t - ntiles;
-        double acc[16];
-        for (int i = 0; i < 16; i++) acc[i] = 0.0;
-        for (int k0 = 0; k0 < m.nlm; k0 += SYRK_KC) {
-            const int kc = (m.nlm - k0) < SYRK_KC ? (m.nlm - k0) : SYRK_KC;
-            VIWB_SYNC();
-            for (int k = tid; k < kc; k += nt) {             // one square root per landmark, not per entry
-                double g = gam[k0 + k];
-                if (mode == MODE_MARG) g = g > 0.0 ? 1.0 / g : 0.0;
-                const double sg = sqrt(g);
-                sgk[k] = sg; gs[k] = sg * gl[k0 + k];
-            }
-            VIWB_SYNC();
-            for (int e = tid; e < kc * VSUB; e += nt) Ws[e] = sgk[e / VSUB] * W[(size_t)k0 * VSUB + e];
-            VIWB_SYNC();
-            if (live && !is_vec) {
+    const int t = tid;
+    const bool live = t < ntiles + NT4, is_vec = t >= ntiles;       // one round: 230 work items <= block size (256); emulation loops below
+    auto stage = [&](int c, int p) {
+        const int k0 = c * SYRK_KC, kc = (m.nlm - k0) < SYRK_KC ? (m.nlm - k0) : SYRK_KC;
+        for (int e = tid; e < kc * VSUB / 2; e += nt) async_copy16(Wb[p] + 2 * e, W + (size_t)k0 * VSUB + 2 * e);
+        async_commit();
+        for (int k = tid; k < kc; k += nt) {
+            double g = gam[k0 + k];
+            if (mode == MODE_MARG) g = g > 0.0 ? 1.0 / g : 0.0;
+            gkb[p][k] = g; ggb[p][k] = g * gl[k0 + k];
+        }
+    };
+    const int nchunk = (m.nlm + SYRK_KC - 1) / SYRK_KC;
+#ifdef VIWB_HOST_EMU
+    const int nwork = ntiles + NT4;
+    std::vector<double> accs((size_t)nwork * 16, 0.0);
+#else
+    double acc[16];
+    for (int i = 0; i < 16; i++) acc[i] = 0.0;
+    int tp = 0, tq = 0;
+    if (live && !is_vec) sym_unrank(t, tp, tq); else if (live) tp = t - ntiles;
+#endif
+    if (nchunk > 0) stage(0, 0);
+    for (int c = 0, p = 0; c < nchunk; c++, p ^= 1) {
+        if (c + 1 < nchunk) { stage(c + 1, p ^ 1); async_wait<1>(); } else async_wait<0>();
+        VIWB_SYNC();
+        const int k0 = c * SYRK_KC, kc = (m.nlm - k0) < SYRK_KC ? (m.nlm - k0) : SYRK_KC;
+        const double *Ws = Wb[p], *gk = gkb[p], *gg = ggb[p];
+#ifdef VIWB_HOST_EMU
+        for (int wi = 0; wi < nwork; wi++) {
+            double *acc = accs.data() + (size_t)wi * 16;
+            int tp = 0, tq = 0;
+            const bool is_vec = wi >= ntiles;
+            if (!is_vec) sym_unrank(wi, tp, tq); else tp = wi - ntiles;
+            (void)live;
+#else
+        if (live) {
+#endif
+            if (!is_vec) {
                 for (int k = 0; k < kc; k++) {
-                    const double *r = Ws + k * VSUB;
-                    const double a0 = r[4 * tp], a1 = r[4 * tp + 1], a2 = r[4 * tp + 2], a3 = r[4 * tp + 3];
+                    const double *r = Ws + k * VSUB; const double g = gk[k];
+                    const double a0 = g * r[4 * tp], a1 = g * r[4 * tp + 1], a2 = g * r[4 * tp + 2], a3 = g * r[4 * tp + 3];
                     const double b0 = r[4 * tq], b1 = r[4 * tq + 1], b2 = r[4 * tq + 2], b3 = r[4 * tq + 3];
                     acc[0] += a0 * b0; acc[1] += a0 * b1; acc[2] += a0 * b2; acc[3] += a0 * b3;
                     acc[4] += a1 * b0; acc[5] += a1 * b1; acc[6] += a1 * b2; acc[7] += a1 * b3;
                     acc[8] += a2 * b0; acc[9] += a2 * b1; acc[10] += a2 * b2; acc[11] += a2 * b3;
                     acc[12] += a3 * b0; acc[13] += a3 * b1; acc[14] += a3 * b2; acc[15] += a3 * b3;
                 }
-            } else if (live) {
-                for (int k = 0; k < kc; k++) { const double *r = Ws + k * VSUB; const double g = gs[k]; for (int i = 0; i < 4; i++) acc[i] += r[4 * tp + i] * g; }
+            } else {
+                for (int k = 0; k < kc; k++) { const double *r = Ws + k * VSUB; const double g = gg[k]; for (int i = 0; i < 4; i++) acc[i] += r[4 * tp + i] * g; }
             }
         }
-        if (live && !is_vec) {
+        VIWB_SYNC();
+    }
+#ifdef VIWB_HOST_EMU
+    for (int wi = 0; wi < nwork; wi++) {
+        const double *acc = accs.data() + (size_t)wi * 16;
+        int tp = 0, tq = 0;
+        const bool is_vec = wi >= ntiles;
+        if (!is_vec) sym_unrank(wi, tp, tq); else tp = wi - ntiles;
+#else
+    if (live) {
+#endif
+        if (!is_vec) {
             for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { T[(4 * tp + i) * VSUB + 4 * tq + j] = acc[i * 4 + j]; T[(4 * tq + j) * VSUB + 4 * tp + i] = acc[i * 4 + j]; }
-        } else if (live) { for (int i = 0; i < 4; i++) tv[4 * tp + i] = acc[i]; }
+        } else { for (int i = 0; i < 4; i++) tv[4 * tp + i] = acc[i]; }
     }
 }
 

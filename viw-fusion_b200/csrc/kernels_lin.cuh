@@ -58,34 +58,52 @@ VIWB_D void prior_setup_block(const BatchDev &bd, int bx, int by, int tid, int n
 }
 
 // ------------------------------------------------------------------------------------------------ lin_vis
+// One thread per factor.  The records (28 / 54 doubles per factor) are assembled in a shared-memory tile with an odd row stride
+// and leave the block as one contiguous, fully coalesced stream (a thread storing its own record directly would touch 32
+// different sectors per store instruction).
+VIWB_HD size_t lin_vis_smem_doubles(int nt, int rs) { return (size_t)nt * (rs | 1) + (nt + 7) / 8; }
 VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
-    (void)by; (void)smem;
+    (void)by;
+    const int rs = rec_stride(bd, mode), ts = rs | 1;
+    double *tile = smem;
+    unsigned char *act = reinterpret_cast<unsigned char *>(smem + (size_t)nt * ts);
     const int f = bx * nt + tid;
-    if (f >= bd.nvis_total) return;
-    const int w = bd.vis_win[f];
-    if (mode == MODE_SOLVE && bd.work[w].status != ST_RUNNING) return;
-    const int fi = bd.vis_fi[f];
-    const WinMeta &m = bd.meta[w];
-    if (mode == MODE_MARG && (fi != 0 || m.margin_flag != 0)) return;
-    const double *x = eval_state(bd, w, mode);
-    double obs[12];
-    for (int k = 0; k < 12; k++) obs[k] = bd.vis_obs[(size_t)f * 12 + k];
-    const int lm = bd.vis_lm[f];
-    VisOut o;
-    vis_eval(bd.vis_type[f], obs, x + 7 * fi, x + 7 * bd.vis_fj[f], x + blk_off(BLK_EX0), x + blk_off(BLK_EX1),
-             x[SFIX + lm], x[blk_off(BLK_TD)], m.S_vis, true, o);
-    double half_rho;
-    const double sc = huber_scale(o.r[0] * o.r[0] + o.r[1] * o.r[1], m.huber, half_rho);
-    const int rs = rec_stride(bd, mode);
-    double *rec = bd.vis_rec + (size_t)f * rs;
-    rec[0] = o.r[0] * sc; rec[1] = o.r[1] * sc;
-    for (int k = 0; k < 12; k++) { rec[REC_A + k] = o.JA[k] * sc; rec[REC_B + k] = o.JB[k] * sc; }
-    rec[REC_L] = o.Jl[0] * sc; rec[REC_L + 1] = o.Jl[1] * sc;
-    if (rs == VREC) {
-        for (int k = 0; k < 12; k++) { rec[REC_E0 + k] = o.JE0[k] * sc; rec[REC_E1 + k] = o.JE1[k] * sc; }
-        rec[REC_TD] = o.Jtd[0] * sc; rec[REC_TD + 1] = o.Jtd[1] * sc;
+    bool on = f < bd.nvis_total;
+    int w = 0, fi = 0;
+    if (on) {
+        w = bd.vis_win[f];
+        if (mode == MODE_SOLVE && bd.work[w].status != ST_RUNNING) on = false;
     }
-    bd.vis_cost[f] = half_rho;
+    if (on) {
+        fi = bd.vis_fi[f];
+        if (mode == MODE_MARG && (fi != 0 || bd.meta[w].margin_flag != 0)) on = false;
+    }
+    act[tid] = on ? 1 : 0;
+    if (on) {
+        const WinMeta &m = bd.meta[w];
+        const double *x = eval_state(bd, w, mode);
+        double obs[12];
+        for (int k = 0; k < 12; k++) obs[k] = bd.vis_obs[(size_t)f * 12 + k];
+        const int lm = bd.vis_lm[f];
+        VisOut o;
+        vis_eval(bd.vis_type[f], obs, x + 7 * fi, x + 7 * bd.vis_fj[f], x + blk_off(BLK_EX0), x + blk_off(BLK_EX1),
+                 x[SFIX + lm], x[blk_off(BLK_TD)], m.S_vis, true, o);
+        double half_rho;
+        const double sc = huber_scale(o.r[0] * o.r[0] + o.r[1] * o.r[1], m.huber, half_rho);
+        double *rec = tile + (size_t)tid * ts;
+        rec[0] = o.r[0] * sc; rec[1] = o.r[1] * sc;
+        for (int k = 0; k < 12; k++) { rec[REC_A + k] = o.JA[k] * sc; rec[REC_B + k] = o.JB[k] * sc; }
+        rec[REC_L] = o.Jl[0] * sc; rec[REC_L + 1] = o.Jl[1] * sc;
+        if (rs == VREC) {
+            for (int k = 0; k < 12; k++) { rec[REC_E0 + k] = o.JE0[k] * sc; rec[REC_E1 + k] = o.JE1[k] * sc; }
+            rec[REC_TD] = o.Jtd[0] * sc; rec[REC_TD + 1] = o.Jtd[1] * sc;
+        }
+        bd.vis_cost[f] = half_rho;
+    }
+    VIWB_SYNC();
+    double *out = bd.vis_rec + (size_t)bx * nt * rs;
+    const int nrec = (bd.nvis_total - bx * nt) < nt ? (bd.nvis_total - bx * nt) : nt;
+    for (int e = tid; e < nrec * rs; e += nt) { const int r = e / rs, q = e - r * rs; if (act[r]) out[e] = tile[(size_t)r * ts + q]; }
 }
 
 // ------------------------------------------------------------------------------------------------ lm_reduce
@@ -200,10 +218,15 @@ VIWB_D void prior_dx(const PriorDev &p, const double *x, const double *x0, doubl
 // Small factors in two phases per group of SMALL_NSLOT: (A) one thread per factor evaluates the un-whitened residual and
 // Jacobian into its shared-memory slot (the factors of a group run side by side in the lanes of one warp), (B) one warp per
 // factor whitens one Jacobian column per lane (r <- S r, J <- S J with S upper triangular) and streams it to the record.
-enum { SMALL_SLOT = 15 + 15 * 30, SMALL_NSLOT = 12 };
-VIWB_HD size_t lin_small_smem_doubles(int nt) { return (size_t)SMALL_NSLOT * SMALL_SLOT + nt + MAXPRI + 8; }
-VIWB_D double whiten_store(const double *raw, const double *S, int rows, int ld, double *rec, int lane, int W) {
-    // raw: [rows residual | rows x ld Jacobian] un-whitened in shared memory -> rec (global), returns this lane's part of 0.5 |r|^2
+enum { SMALL_SLOT = 15 + 15 * 30, SMALL_NSLOT = 10, SMALL_S = 225 };
+VIWB_HD size_t lin_small_smem_doubles(int nt) { const int W = nt < 32 ? nt : 32; return (size_t)SMALL_NSLOT * SMALL_SLOT + (size_t)(nt / W) * SMALL_S + nt + MAXPRI + 8; }
+VIWB_D double whiten_store(const double *raw, const double *Sg, double *Ss, int rows, int ld, double *rec, int lane, int W) {
+    // raw: [rows residual | rows x ld Jacobian] un-whitened in shared memory -> rec (global), returns this lane's part of 0.5 |r|^2.
+    // The sqrt-information factor is first copied into the warp's shared-memory slice: every lane needs every entry of it.
+    VIWB_SYNCWARP();
+    for (int e = lane; e < rows * rows; e += W) Ss[e] = Sg[e];
+    VIWB_SYNCWARP();
+    const double *S = Ss;
     double c = 0.0;
     for (int col = lane; col <= ld; col += W) {
         for (int i = 0; i < rows; i++) {
@@ -223,7 +246,8 @@ VIWB_D void lin_small_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     if (marg_skip(m, mode)) return;
     const double *x = eval_state(bd, w, mode);
     const int W = nt < 32 ? nt : 32, nw = nt / W, wid = tid / W, lane = tid % W;
-    double *cost_part = smem + (size_t)SMALL_NSLOT * SMALL_SLOT;      // [nt]
+    double *Sw = smem + (size_t)SMALL_NSLOT * SMALL_SLOT + (size_t)wid * SMALL_S;      // this warp's copy of a factor's sqrt-information
+    double *cost_part = smem + (size_t)SMALL_NSLOT * SMALL_SLOT + (size_t)nw * SMALL_S;      // [nt]
     double *dx = cost_part + nt;                                      // [MAXPRI]
     double c = 0.0;
     const int n_small = marg_prior_only(m, mode) ? 0 : m.nimu + m.nwheel + m.nplane;
@@ -256,11 +280,11 @@ VIWB_D void lin_small_block(const BatchDev &bd, int bx, int by, int tid, int nt,
             if (t < m.nimu) {
                 const int f = m.imu_off + t, i = bd.imu_fi[f], j = bd.imu_fj[f];
                 if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-                c += whiten_store(slot, bd.imu_S + (size_t)f * 225, 15, 30, bd.imu_rec + (size_t)f * IMU_REC, lane, W);
+                c += whiten_store(slot, bd.imu_S + (size_t)f * 225, Sw, 15, 30, bd.imu_rec + (size_t)f * IMU_REC, lane, W);
             } else if (t < m.nimu + m.nwheel) {
                 const int f = m.wheel_off + (t - m.nimu), i = bd.wheel_fi[f], j = bd.wheel_fj[f];
                 if (mode == MODE_MARG && !(i == 0 && j == 1)) continue;
-                c += whiten_store(slot, bd.wheel_S + (size_t)f * 36, 6, 22, bd.wheel_rec + (size_t)f * WHEEL_REC, lane, W);
+                c += whiten_store(slot, bd.wheel_S + (size_t)f * 36, Sw, 6, 22, bd.wheel_rec + (size_t)f * WHEEL_REC, lane, W);
             }
         }
         VIWB_SYNC();

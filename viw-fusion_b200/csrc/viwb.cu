@@ -472,6 +472,7 @@ static int ensure_attrs(viwb_context *ctx) {
 #ifndef VIWB_HOST_EMU
     if (!ctx->attrs_set) {
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(512) * 8)));
+        CK(cudaFuncSetAttribute(lin_vis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lin_vis_smem_doubles(128, VREC) * 8)));
         CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(256, 100) * 8)));
         ctx->attrs_set = true;
     }
@@ -498,7 +499,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     // still running is at max_num_iterations there, trust_region_minimizer.cc checks the iteration limit before the gradient),
     // so the partial sums and the Schur product of that linearisation would never be read
     auto lin = [&](int mode, bool cost_only) {
-        LAUNCH(lin_vis, bd, g_vis, 1, nt_vis, 0, mode, st);
+        LAUNCH(lin_vis, bd, g_vis, 1, nt_vis, lin_vis_smem_doubles(nt_vis, mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) * 8, mode, st);
         if ((mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) == VREC) LAUNCH(lm_reduce_wide, bd, g_lm, 1, nt_lm, 0, mode, st);
         else LAUNCH(lm_reduce, bd, g_lm, 1, nt_lm, 0, mode, st);
         LAUNCH(lin_small, bd, B, 1, nt_small, sm_small, mode, st);
