@@ -106,7 +106,7 @@ enum { LK_ITEMS = 63, LK_IPL = (LK_ITEMS + LK_W - 1) / LK_W, LK_PPB = 4,        
        LK_PS = 28,                                                             // byte stride of the staged source patch (7 words)
        LK_SLACK = 5, LK_JROWS = 22 + 2 * LK_SLACK, LK_JS = 36,                 // staged search region: 32 rows x 36 bytes (9 words)
        LK_BS = 23, LK_DBYTES = 2208,                                           // interpolated-intensity image 23 x 23 ints (shares the Scharr sample buffer)
-       LK_WARP_SMEM = 2 * 24 * LK_PS + LK_DBYTES + LK_JROWS * LK_JS };         // = 4704 bytes per warp
+       LK_WARP_SMEM = 24 * LK_PS + LK_DBYTES + LK_JROWS * LK_JS };             // = 4032 bytes per warp
 VIWB_HD size_t lk_smem_bytes(int warps) { return (size_t)warps * LK_WARP_SMEM; }
 
 // exact sum over the warp of one int32 per lane (every lane gets it)
@@ -120,39 +120,15 @@ VIWB_D long long lk_warp_sum(int p) {
 }
 VIWB_HD bool lk_outside(int ix, int iy, int cols, int rows) { return ix < -LK_WIN || ix >= cols || iy < -LK_WIN || iy >= rows; }
 
-// Asynchronous staging (cp.async: global -> shared without passing through registers, completion by commit groups) lets a warp
-// put the loads of its NEXT operands in flight while it computes on the current ones: every level issues three groups in a fixed
-// order -- this level's source patch (empty if it was prefetched), this level's search region, the next level's source patch --
-// and waits for them one by one right before each is read.
-VIWB_D void lk_async_word(void *smem_dst, const void *gsrc) {
-#ifdef VIWB_HOST_EMU
-    *reinterpret_cast<uint32_t *>(smem_dst) = *reinterpret_cast<const uint32_t *>(gsrc);
-#else
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
-#endif
-}
-VIWB_D void lk_async_commit() {
-#ifndef VIWB_HOST_EMU
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-#endif
-}
-template <int PENDING> VIWB_D void lk_async_wait() {          // returns when at most PENDING of the most recent groups are still in flight
-#ifndef VIWB_HOST_EMU
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
-    __syncwarp();
-#endif
-}
-// rows [y0, y0+nrows) x bytes [x0a, x0a + 4*nwords) of an image into a byte buffer with row stride 4*nwords; ends with a commit.
-// x0a is a multiple of 4; interior regions go as asynchronous aligned 32-bit copies, the rest resolves reflect-101 byte by byte
-// (synchronously -- the group it commits is then empty).  The caller waits (lk_async_wait) before reading.
+// rows [y0, y0+nrows) x bytes [x0a, x0a + 4*nwords) of an image into a byte buffer with row stride 4*nwords.
+// x0a is a multiple of 4; interior regions use aligned 32-bit loads, the rest resolves reflect-101 byte by byte.
 VIWB_D void lk_stage(uint8_t *buf, const uint8_t *img, int stride, int cols, int rows, int x0a, int y0, int nrows, int nwords, int lane) {
     VIWB_SYNCWARP();
     if (x0a >= 0 && y0 >= 0 && x0a + 4 * nwords <= cols && y0 + nrows <= rows) {
         const int total = nrows * nwords;
         for (int e = lane; e < total; e += LK_W) {
             const int y = e / nwords, x = e - y * nwords;
-            lk_async_word(buf + 4 * e, img + (size_t)(y0 + y) * stride + x0a + 4 * x);
+            reinterpret_cast<uint32_t *>(buf)[e] = *reinterpret_cast<const uint32_t *>(img + (size_t)(y0 + y) * stride + x0a + 4 * x);
         }
     } else {        // border: columns are reflected once per lane, rows once per row
         const int wb = 4 * nwords;
@@ -168,14 +144,14 @@ VIWB_D void lk_stage(uint8_t *buf, const uint8_t *img, int stride, int cols, int
         }
 #endif
     }
-    lk_async_commit();
+    VIWB_SYNCWARP();
 }
 
 VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem_raw) {
-    uint8_t *pb[2] = {(uint8_t *)smem_raw, (uint8_t *)smem_raw + 24 * LK_PS};      // two source patches of 24 rows x 28 bytes (this level / prefetched next level)
-    short *dpatch = (short *)(smem_raw + 2 * 24 * LK_PS);       // 22 x 22 x (dx, dy)
+    uint8_t *pbuf = (uint8_t *)smem_raw;                      // 24 rows x 28 bytes
+    short *dpatch = (short *)(smem_raw + 24 * LK_PS);          // 22 x 22 x (dx, dy)
     int *Bimg = (int *)dpatch;                                // or: 23 x 23 interpolated intensities (interior patches)
-    uint8_t *jbuf = smem_raw + 2 * 24 * LK_PS + LK_DBYTES;    // 32 rows x 36 bytes
+    uint8_t *jbuf = smem_raw + 24 * LK_PS + LK_DBYTES;        // 32 rows x 36 bytes
     const int npts = a.n_dev ? *a.n_dev : a.n;
     if (pt >= npts) return;
     const int max_level = a.max_level, max_iter = a.max_iter, flags = a.flags;
@@ -188,7 +164,6 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
     int irow[LK_IPL], icol[LK_IPL];
 #pragma unroll
     for (int s = 0; s < LK_IPL; s++) { const int it = lane + LK_W * s; irow[s] = it / 3; icol[s] = 7 * (it - 3 * irow[s]); }
-    int cur = 0; bool have_patch = false;       // pb[cur] already holds (or is receiving) this level's source patch
     for (int level = max_level; level >= 0; level--) {
         const float sc = (float)(1. / (1 << level));
         float ppx = px0 * sc, ppy = py0 * sc;
@@ -200,32 +175,10 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
         ppx -= (float)LK_HALF; ppy -= (float)LK_HALF;
         const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
         const int cols = a.I.w[level], rows = a.I.h[level];
-        lk_async_wait<0>();                      // whatever the previous level left in flight (its prefetch of this level's patch)
-        if (lk_outside(ipx, ipy, cols, rows)) { if (level == 0) { status = false; errv = 0.f; } have_patch = false; continue; }
+        if (lk_outside(ipx, ipy, cols, rows)) { if (level == 0) { status = false; errv = 0.f; } continue; }
         // 1. source patch rows [ipy-1, ipy+22], bytes from the aligned column pxa; pixel (ipx-1+x) sits at byte psx + x
         const int pxa = (ipx - 1) & ~3, psx = (ipx - 1) - pxa;
-        uint8_t *pbuf = pb[cur];
-        if (!have_patch) lk_stage(pbuf, a.I.img[level], a.I.stride[level], cols, rows, pxa, ipy - 1, 24, LK_PS / 4, lane); else lk_async_commit();
-        // search region around the level's initial estimate, and the next level's source patch: in flight during the template work
-        const int jc = a.J.w[level], jr = a.J.h[level], jstr = a.J.stride[level];
-        const uint8_t *jimg = a.J.img[level];
-        int jx0 = 0, jy0 = 0;          // origin of the staged search region (jx0 a multiple of 4)
-        bool staged = false;
-        {
-            const int inx = (int)floorf(nx - (float)LK_HALF), iny = (int)floorf(ny - (float)LK_HALF);
-            if (!lk_outside(inx, iny, jc, jr)) { jx0 = (inx - LK_SLACK) & ~3; jy0 = iny - LK_SLACK; lk_stage(jbuf, jimg, jstr, jc, jr, jx0, jy0, LK_JROWS, LK_JS / 4, lane); staged = true; }
-            else lk_async_commit();
-        }
-        have_patch = false;
-        if (level > 0) {
-            const float sn = (float)(1. / (1 << (level - 1)));
-            const int nipx = (int)floorf(px0 * sn - (float)LK_HALF), nipy = (int)floorf(py0 * sn - (float)LK_HALF);
-            const int ncols = a.I.w[level - 1], nrows = a.I.h[level - 1];
-            if (!lk_outside(nipx, nipy, ncols, nrows)) { lk_stage(pb[1 - cur], a.I.img[level - 1], a.I.stride[level - 1], ncols, nrows, (nipx - 1) & ~3, nipy - 1, 24, LK_PS / 4, lane); have_patch = true; }
-            else lk_async_commit();
-        } else lk_async_commit();
-        cur ^= 1;                                // (pbuf keeps pointing at this level's patch)
-        lk_async_wait<2>();                      // this level's patch has landed; the other two groups may still be in flight
+        lk_stage(pbuf, a.I.img[level], a.I.stride[level], cols, rows, pxa, ipy - 1, 24, LK_PS / 4, lane);
         const float fa = ppx - ipx, fb = ppy - ipy;
         const int iw00 = cv_round_f((1.f - fa) * (1.f - fb) * (1 << 14)), iw01 = cv_round_f(fa * (1.f - fb) * (1 << 14));
         const int iw10 = cv_round_f((1.f - fa) * fb * (1 << 14)), iw11 = (1 << 14) - iw00 - iw01 - iw10;
@@ -298,14 +251,16 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
         D = 1.f / D;
         nx -= (float)LK_HALF; ny -= (float)LK_HALF;
         float pdx = 0.f, pdy = 0.f;
-        lk_async_wait<1>();                      // the search region has landed (the next level's patch may still be in flight)
+        const int jc = a.J.w[level], jr = a.J.h[level], jstr = a.J.stride[level];
+        const uint8_t *jimg = a.J.img[level];
+        int jx0 = 0, jy0 = 0;          // origin of the staged search region (jx0 a multiple of 4)
+        bool staged = false;
         for (int j = 0; j < max_iter; j++) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (lk_outside(inx, iny, jc, jr)) { if (level == 0) status = false; break; }
             if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) {
                 jx0 = (inx - LK_SLACK) & ~3; jy0 = iny - LK_SLACK;
                 lk_stage(jbuf, jimg, jstr, jc, jr, jx0, jy0, LK_JROWS, LK_JS / 4, lane);
-                lk_async_wait<0>();
                 staged = true;
             }
             const float ja = nx - inx, jb = ny - iny;
@@ -341,7 +296,6 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
                 if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) {
                     jx0 = (inx - LK_SLACK) & ~3; jy0 = iny - LK_SLACK;
                     lk_stage(jbuf, jimg, jstr, jc, jr, jx0, jy0, LK_JROWS, LK_JS / 4, lane);
-                    lk_async_wait<0>();
                 }
                 const float ja = ex - inx, jb = ey - iny;
                 const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
