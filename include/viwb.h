@@ -259,6 +259,17 @@ int viwb_optimization(viwb_context *ctx, const viwb_problem *problem, double *st
 int viwb_outlier_rejection(viwb_context *ctx, const viwb_problem *problem, const double *state, double focal_length,
                            double threshold_px, uint8_t *outliers);
 
+/* FeatureManager::triangulate for features without a depth (feature_manager.cpp:309-385; triangulatePoint :198-213): two-view
+ * linear triangulation, stereo[k] = 1: left / right camera of frame[k] (pt0 = point, pt1 = pointRight of the first observation),
+ * stereo[k] = 0: left camera of frame[k] and frame[k]+1 (pt0, pt1 = the first two observations).  pt*: [n][2] normalised
+ * coordinates.  depth[k] = z in the first camera if positive, else init_depth (INIT_DEPTH = 5.0, parameters.cpp:387). */
+int viwb_triangulate(viwb_context *ctx, const double *state, int n, const int32_t *stereo, const int32_t *frame,
+                     const double *pt0, const double *pt1, double init_depth, double *depth);
+/* FeatureManager::removeBackShiftDepth (feature_manager.cpp:457-493) for the features that started in the marginalised frame:
+ * re-express depth in the new frame 0.  uv: [n][3] first-observation points; R row-major 3x3 (camera-to-world), P [3]. */
+int viwb_shift_depth(viwb_context *ctx, int n, const double *uv, const double *depth_in, const double *marg_R, const double *marg_P,
+                     const double *new_R, const double *new_P, double init_depth, double *depth_out);
+
 /* Batch of B independent windows (one per sequence), host buffers in, host buffers out. */
 int viwb_optimization_batch(viwb_context *ctx, int batch, const viwb_problem *problems, double *const *states,
                             const viwb_options *options, const int32_t *margin_flags, viwb_summary *summaries,

@@ -67,6 +67,11 @@ int vo_optimization(const viwb_problem *problem, double *state, const viwb_optio
 /* Estimator::outliersRejection (estimator.cpp:2115-2185): out[num_landmarks] */
 int vo_outlier_rejection(const viwb_problem *problem, const double *state, double focal_length, double threshold_px, uint8_t *out);
 
+/* FeatureManager::triangulate (two-view branches, feature_manager.cpp:309-385) and removeBackShiftDepth (:457-493) */
+int vo_triangulate(const double *state, int n, const int32_t *stereo, const int32_t *frame, const double *pt0, const double *pt1, double init_depth, double *depth);
+int vo_shift_depth(int n, const double *uv, const double *depth_in, const double *marg_R, const double *marg_P, const double *new_R, const double *new_P,
+                   double init_depth, double *depth_out);
+
 /* n independent windows on `threads` pthreads, `repeat` passes (bench.py CPU arm); returns the number of optimisations run */
 long vo_optimization_throughput(int n, const viwb_problem *problems, const double *const *states, const int32_t *flags,
                                 const viwb_options *opt, int threads, int repeat);

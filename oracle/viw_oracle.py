@@ -166,6 +166,24 @@ def outlier_rejection(problem, state, focal=460.0, thresh=3.0):
     return out[: problem.num_landmarks]
 
 
+def triangulate(state, stereo, frame, pt0, pt1, init_depth=5.0):
+    st = np.ascontiguousarray(state, np.float64)
+    s_, f_ = np.ascontiguousarray(stereo, np.int32), np.ascontiguousarray(frame, np.int32)
+    a, b = np.ascontiguousarray(pt0, np.float64), np.ascontiguousarray(pt1, np.float64)
+    out = np.zeros(len(s_))
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    lib().vo_triangulate(_dp(st), C.c_int(len(s_)), vp(s_), vp(f_), _dp(a), _dp(b), C.c_double(init_depth), _dp(out))
+    return out
+
+
+def shift_depth(uv, depth, marg_R, marg_P, new_R, new_P, init_depth=5.0):
+    uv, depth = np.ascontiguousarray(uv, np.float64), np.ascontiguousarray(depth, np.float64)
+    mats = [np.ascontiguousarray(m, np.float64) for m in (marg_R, marg_P, new_R, new_P)]
+    out = np.zeros(len(depth))
+    lib().vo_shift_depth(C.c_int(len(depth)), _dp(uv), _dp(depth), _dp(mats[0]), _dp(mats[1]), _dp(mats[2]), _dp(mats[3]), C.c_double(init_depth), _dp(out))
+    return out
+
+
 def imu_preintegrate(dt, acc, gyr, ba, bg, noise):
     dt = np.ascontiguousarray(dt, np.float64)
     acc, gyr = np.ascontiguousarray(acc, np.float64), np.ascontiguousarray(gyr, np.float64)

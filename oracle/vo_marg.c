@@ -356,6 +356,68 @@ int vo_outlier_rejection(const viwb_problem *pb, const double *state, double foc
     return 0;
 }
 
+
+/* ------------------------------------------------------------------ FeatureManager::triangulate / removeBackShiftDepth
+ * triangulatePoint (feature_manager.cpp:198-213) takes the right singular vector of the smallest singular value of the 4x4
+ * design matrix from Eigen's JacobiSVD; restated with a one-sided Jacobi SVD (any accurate SVD returns the same vector up to
+ * sign, which cancels in the division by its 4th component). */
+static void vo_min_right_singular4(double *D, double *v) {
+    double V[16];
+    for (int i = 0; i < 16; i++) V[i] = (i / 4 == i % 4) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        int rot = 0;
+        for (int p = 0; p < 3; p++) for (int q = p + 1; q < 4; q++) {
+            double a = 0, b = 0, c = 0;
+            for (int r = 0; r < 4; r++) { a += D[r * 4 + p] * D[r * 4 + p]; b += D[r * 4 + q] * D[r * 4 + q]; c += D[r * 4 + p] * D[r * 4 + q]; }
+            if (c == 0.0 || fabs(c) <= 1e-300 + 2.220446049250313e-16 * sqrt(a * b)) continue;
+            rot++;
+            double zeta = (b - a) / (2.0 * c), t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+            for (int r = 0; r < 4; r++) {
+                double dp = D[r * 4 + p], dq = D[r * 4 + q]; D[r * 4 + p] = cs * dp - sn * dq; D[r * 4 + q] = sn * dp + cs * dq;
+                double vp = V[r * 4 + p], vq = V[r * 4 + q]; V[r * 4 + p] = cs * vp - sn * vq; V[r * 4 + q] = sn * vp + cs * vq;
+            }
+        }
+        if (!rot) break;
+    }
+    int best = 0; double nb = 0;
+    for (int c = 0; c < 4; c++) { double n2 = 0; for (int r = 0; r < 4; r++) n2 += D[r * 4 + c] * D[r * 4 + c]; if (c == 0 || n2 < nb) { nb = n2; best = c; } }
+    for (int r = 0; r < 4; r++) v[r] = V[r * 4 + best];
+}
+static void vo_cam_pose34(const double *pose, const double *ex, double *P) {
+    double Rs[9], ric[9], R[9], t[3], a[3];
+    q_to_R(Rs, pose + 3); q_to_R(ric, ex + 3); m3_mul(R, Rs, ric);
+    m3_mulv(a, Rs, ex); for (int k = 0; k < 3; k++) t[k] = pose[k] + a[k];
+    for (int r = 0; r < 3; r++) { double s = 0; for (int c = 0; c < 3; c++) { P[r * 4 + c] = R[c * 3 + r]; s += R[c * 3 + r] * t[c]; } P[r * 4 + 3] = -s; }
+}
+int vo_triangulate(const double *state, int n, const int32_t *stereo, const int32_t *frame, const double *pt0, const double *pt1, double init_depth, double *depth) {
+    for (int k = 0; k < n; k++) {
+        double P0[12], P1[12], D[16], v[4];
+        const int i = frame[k];
+        vo_cam_pose34(state + 7 * i, state + 176, P0);
+        if (stereo[k]) vo_cam_pose34(state + 7 * i, state + 183, P1); else vo_cam_pose34(state + 7 * (i + 1), state + 176, P1);
+        for (int c = 0; c < 4; c++) {
+            D[c] = pt0[2 * k] * P0[8 + c] - P0[c]; D[4 + c] = pt0[2 * k + 1] * P0[8 + c] - P0[4 + c];
+            D[8 + c] = pt1[2 * k] * P1[8 + c] - P1[c]; D[12 + c] = pt1[2 * k + 1] * P1[8 + c] - P1[4 + c];
+        }
+        vo_min_right_singular4(D, v);
+        const double px = v[0] / v[3], py = v[1] / v[3], pz = v[2] / v[3];
+        const double d = P0[8] * px + P0[9] * py + P0[10] * pz + P0[11];
+        depth[k] = d > 0 ? d : init_depth;
+    }
+    return 0;
+}
+int vo_shift_depth(int n, const double *uv, const double *depth_in, const double *margR, const double *margP, const double *newR, const double *newP,
+                   double init_depth, double *depth_out) {
+    for (int k = 0; k < n; k++) {
+        double p[3] = {uv[3 * k] * depth_in[k], uv[3 * k + 1] * depth_in[k], uv[3 * k + 2] * depth_in[k]}, w[3], d[3];
+        m3_mulv(w, margR, p); for (int c = 0; c < 3; c++) d[c] = w[c] + margP[c] - newP[c];
+        const double z = newR[0 * 3 + 2] * d[0] + newR[1 * 3 + 2] * d[1] + newR[2 * 3 + 2] * d[2];      /* (new_R^T d).z */
+        depth_out[k] = z > 0 ? z : init_depth;
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ multi-threaded batch (CPU baseline arm of bench.py)
  * n independent windows on `threads` pthreads; each optimisation itself is single-threaded like Ceres' default
  * (estimator.cpp:1646 leaves num_threads commented out).  repeat > 1 cycles over the windows to fill a time budget. */

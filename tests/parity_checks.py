@@ -478,3 +478,46 @@ def check_small_edges(ctx, oracle):
     rec = ctx.imu_preintegrate([np.zeros(0)], [np.array([[0.0, 0, 9.8]])], [np.zeros((1, 3))], np.zeros((1, 3)), np.zeros((1, 3)), noise)
     ref = oracle.imu_preintegrate(np.zeros(0), np.array([[0.0, 0, 9.8]]), np.zeros((1, 3)), np.zeros(3), np.zeros(3), noise)
     assert np.array_equal(rec[0], ref) and rec[0][0] == 0.0 and rec[0][7] == 1.0
+
+
+def check_triangulation(ctx, oracle, seed=9):
+    """SURVEY 8 f-3: two-view triangulation (stereo and motion branches of FeatureManager::triangulate) and
+    removeBackShiftDepth, against the oracle and against an independent numpy SVD / closed form."""
+    from viwb import geom
+    rng = np.random.default_rng(seed)
+    cfg = synth.make_config(2)
+    prob, st, gt = synth.Sequence(cfg, 1, 11).window(0)
+    x = gt.copy()
+    n = 60
+    stereo = (rng.uniform(size=n) < 0.5).astype(np.int32)
+    frame = rng.integers(0, 9, n).astype(np.int32)
+
+    def cam(i, c):
+        Rs = geom.q_to_R(x[7 * i + 3: 7 * i + 7]); ric = geom.q_to_R(x[176 + 7 * c + 3: 176 + 7 * c + 7])
+        R = Rs @ ric; t = x[7 * i: 7 * i + 3] + Rs @ x[176 + 7 * c: 176 + 7 * c + 3]
+        return np.hstack([R.T, (-R.T @ t)[:, None]])
+    pt0, pt1, ref, truth = np.zeros((n, 2)), np.zeros((n, 2)), np.zeros(n), np.zeros(n)
+    for k in range(n):
+        P0 = cam(frame[k], 0); P1 = cam(frame[k], 1) if stereo[k] else cam(frame[k] + 1, 0)
+        pc = np.array([rng.uniform(-1, 1), rng.uniform(-0.6, 0.6), 1.0]) * rng.uniform(2, 15)       # point in camera 0
+        pw = P0[:, :3].T @ (pc - P0[:, 3])
+        q1 = P1[:, :3] @ pw + P1[:, 3]
+        pt0[k] = pc[:2] / pc[2] + rng.normal(0, 1e-3, 2); pt1[k] = q1[:2] / q1[2] + rng.normal(0, 1e-3, 2)
+        D = np.vstack([pt0[k, 0] * P0[2] - P0[0], pt0[k, 1] * P0[2] - P0[1], pt1[k, 0] * P1[2] - P1[0], pt1[k, 1] * P1[2] - P1[1]])
+        v = np.linalg.svd(D)[2][-1]
+        d = P0[2, :3] @ (v[:3] / v[3]) + P0[2, 3]
+        ref[k] = d if d > 0 else 5.0
+        truth[k] = pc[2]
+    got, orc = ctx.triangulate(x, stereo, frame, pt0, pt1), oracle.triangulate(x, stereo, frame, pt0, pt1)
+    assert np.abs(got - orc).max() <= 1e-9 * np.abs(orc).max()
+    assert np.abs(got - ref).max() <= 1e-7 * np.abs(ref).max()          # numpy's SVD: independent algorithm
+    assert np.median(np.abs(got - truth) / truth) < 0.2                  # and it does triangulate the noisy points
+    # removeBackShiftDepth: closed form
+    uv = np.column_stack([rng.uniform(-1, 1, n), rng.uniform(-0.6, 0.6, n), np.ones(n)])
+    dep = rng.uniform(1, 20, n); dep[:3] = -1.0
+    mR, nR = geom.q_to_R(x[3:7]) @ geom.q_to_R(x[179:183]), geom.q_to_R(x[10:14]) @ geom.q_to_R(x[179:183])
+    mP, nP = x[0:3] + geom.q_to_R(x[3:7]) @ x[176:179], x[7:10] + geom.q_to_R(x[10:14]) @ x[176:179]
+    z = ((uv * dep[:, None]) @ mR.T + mP - nP) @ nR[:, 2]
+    want = np.where(z > 0, z, 5.0)
+    assert np.abs(ctx.shift_depth(uv, dep, mR, mP, nR, nP) - want).max() <= 1e-12 * np.abs(want).max()
+    assert np.abs(oracle.shift_depth(uv, dep, mR, mP, nR, nP) - want).max() <= 1e-12 * np.abs(want).max()

@@ -84,3 +84,7 @@ def test_outlier_rejection(emu, oracle):
 
 def test_small_edges(emu, oracle):
     pc.check_small_edges(emu, oracle)
+
+
+def test_triangulation(emu, oracle):
+    pc.check_triangulation(emu, oracle)

@@ -125,3 +125,7 @@ def test_outlier_rejection(gpu_ctx, oracle):
 
 def test_small_edges(gpu_ctx, oracle):
     pc.check_small_edges(gpu_ctx, oracle)
+
+
+def test_triangulation(gpu_ctx, oracle):
+    pc.check_triangulation(gpu_ctx, oracle)

@@ -11,6 +11,7 @@
 #include "kernels_marg.cuh"
 #include "kernels_lk.cuh"
 #include "kernels_preint.cuh"
+#include "kernels_feat.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -995,6 +996,67 @@ extern "C" int viwb_wheel_preintegrate(viwb_context *ctx, int n, const int32_t *
         g_prof.begin("wheel_preint", st); wheel_preint_kernel<<<(q.n + PRE_WPB - 1) / PRE_WPB, 32 * PRE_WPB, PRE_WPB * PRE_WHEEL_SMEM * 8, st>>>(q); g_prof.end(st);
 #endif
     }, PRE_WHEEL_SMEM, false);
+}
+
+// -------------------------------------------------------------------------------------- triangulation / depth shift
+extern "C" int viwb_triangulate(viwb_context *ctx, const double *state, int n, const int32_t *stereo, const int32_t *frame, const double *pt0, const double *pt1,
+                                double init_depth, double *depth) {
+    if (!ctx || !state || n < 0 || !stereo || !frame || !pt0 || !pt1 || !depth) return VIWB_ERR_INVALID;
+    if (n == 0) return VIWB_OK;
+    for (int k = 0; k < n; k++) if (frame[k] < 0 || frame[k] + (stereo[k] ? 0 : 1) > VIWB_WINDOW_SIZE) return fail(ctx, VIWB_ERR_INVALID, "triangulate: frame index out of the window");
+    bind_device(ctx);
+    const size_t bytes = align_up(SFIX * 8) + 2 * align_up((size_t)n * 4) + 2 * align_up((size_t)n * 16) + align_up((size_t)n * 8);
+    char *d = nullptr; CK(dev_malloc((void **)&d, bytes));
+    size_t o = 0;
+    double *d_x = (double *)(d + o); o += align_up(SFIX * 8);
+    int *d_st = (int *)(d + o); o += align_up((size_t)n * 4);
+    int *d_fr = (int *)(d + o); o += align_up((size_t)n * 4);
+    double *d_p0 = (double *)(d + o); o += align_up((size_t)n * 16);
+    double *d_p1 = (double *)(d + o); o += align_up((size_t)n * 16);
+    double *d_out = (double *)(d + o);
+    int e = dev_h2d(d_x, state, SFIX * 8, ctx->stream);
+    if (!e) e = dev_h2d(d_st, stereo, (size_t)n * 4, ctx->stream);
+    if (!e) e = dev_h2d(d_fr, frame, (size_t)n * 4, ctx->stream);
+    if (!e) e = dev_h2d(d_p0, pt0, (size_t)n * 16, ctx->stream);
+    if (!e) e = dev_h2d(d_p1, pt1, (size_t)n * 16, ctx->stream);
+    TriArgs a; a.n = n; a.state = d_x; a.stereo = d_st; a.frame = d_fr; a.pt0 = d_p0; a.pt1 = d_p1; a.init_depth = init_depth; a.depth = d_out;
+    if (!e) {
+#ifdef VIWB_HOST_EMU
+        for (int k = 0; k < n; k++) triangulate_item(a, k);
+#else
+        g_prof.begin("triangulate", ctx->stream); triangulate_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a); g_prof.end(ctx->stream);
+#endif
+        ctx->launches++;
+        e = dev_d2h(depth, d_out, (size_t)n * 8, ctx->stream);
+    }
+    if (!e) e = dev_sync(ctx->stream);
+    dev_free(d);
+    return e ? fail(ctx, VIWB_ERR_CUDA, "triangulate failed") : VIWB_OK;
+}
+extern "C" int viwb_shift_depth(viwb_context *ctx, int n, const double *uv, const double *depth_in, const double *marg_R, const double *marg_P,
+                                const double *new_R, const double *new_P, double init_depth, double *depth_out) {
+    if (!ctx || n < 0 || !uv || !depth_in || !marg_R || !marg_P || !new_R || !new_P || !depth_out) return VIWB_ERR_INVALID;
+    if (n == 0) return VIWB_OK;
+    bind_device(ctx);
+    const size_t bytes = align_up((size_t)n * 24) + 2 * align_up((size_t)n * 8);
+    char *d = nullptr; CK(dev_malloc((void **)&d, bytes));
+    double *d_uv = (double *)d, *d_in = (double *)(d + align_up((size_t)n * 24)), *d_out = (double *)(d + align_up((size_t)n * 24) + align_up((size_t)n * 8));
+    int e = dev_h2d(d_uv, uv, (size_t)n * 24, ctx->stream);
+    if (!e) e = dev_h2d(d_in, depth_in, (size_t)n * 8, ctx->stream);
+    ShiftArgs a; a.n = n; a.uv = d_uv; a.depth_in = d_in; a.depth_out = d_out; a.init_depth = init_depth;
+    memcpy(a.margR, marg_R, 72); memcpy(a.margP, marg_P, 24); memcpy(a.newR, new_R, 72); memcpy(a.newP, new_P, 24);
+    if (!e) {
+#ifdef VIWB_HOST_EMU
+        for (int k = 0; k < n; k++) shift_depth_item(a, k);
+#else
+        g_prof.begin("shift_depth", ctx->stream); shift_depth_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a); g_prof.end(ctx->stream);
+#endif
+        ctx->launches++;
+        e = dev_d2h(depth_out, d_out, (size_t)n * 8, ctx->stream);
+    }
+    if (!e) e = dev_sync(ctx->stream);
+    dev_free(d);
+    return e ? fail(ctx, VIWB_ERR_CUDA, "shift_depth failed") : VIWB_OK;
 }
 
 // -------------------------------------------------------------------------------------- feature tracker

@@ -20,7 +20,7 @@ EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", 
            "viwb_batch_run", "viwb_batch_download", "viwb_batch_algorithmic_bytes", "viwb_batch_destroy",
            "viwb_debug_normal_equations", "viwb_lk_track", "viwb_track_checked", "viwb_lk_batch_create", "viwb_lk_batch_destroy",
            "viwb_lk_batch_upload", "viwb_lk_batch_run", "viwb_lk_batch_download", "viwb_lk_batch_algorithmic_bytes", "viwb_host_register",
-           "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate", "viwb_outlier_rejection", "viwb_batch_outliers"]
+           "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate", "viwb_outlier_rejection", "viwb_batch_outliers", "viwb_triangulate", "viwb_shift_depth"]
 
 
 class ViwbError(RuntimeError):
@@ -232,6 +232,23 @@ class Context:
         self._ck(self.lib.viwb_outlier_rejection(self.h, C.byref(problem.c), _dp(st), C.c_double(focal), C.c_double(thresh), out.ctypes.data_as(C.c_void_p)),
                  "viwb_outlier_rejection")
         return out[: problem.num_landmarks]
+
+    def triangulate(self, state, stereo, frame, pt0, pt1, init_depth=5.0):
+        st = np.ascontiguousarray(state, np.float64)
+        s_, f_ = np.ascontiguousarray(stereo, np.int32), np.ascontiguousarray(frame, np.int32)
+        a, b = np.ascontiguousarray(pt0, np.float64), np.ascontiguousarray(pt1, np.float64)
+        out = np.zeros(len(s_))
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.viwb_triangulate(self.h, _dp(st), C.c_int(len(s_)), vp(s_), vp(f_), _dp(a), _dp(b), C.c_double(init_depth), _dp(out)), "viwb_triangulate")
+        return out
+
+    def shift_depth(self, uv, depth, marg_R, marg_P, new_R, new_P, init_depth=5.0):
+        uv, depth = np.ascontiguousarray(uv, np.float64), np.ascontiguousarray(depth, np.float64)
+        m = [np.ascontiguousarray(x, np.float64) for x in (marg_R, marg_P, new_R, new_P)]
+        out = np.zeros(len(depth))
+        self._ck(self.lib.viwb_shift_depth(self.h, C.c_int(len(depth)), _dp(uv), _dp(depth), _dp(m[0]), _dp(m[1]), _dp(m[2]), _dp(m[3]), C.c_double(init_depth), _dp(out)),
+                 "viwb_shift_depth")
+        return out
 
     # ---------------------------------------------------------------- pre-integration
     @staticmethod
