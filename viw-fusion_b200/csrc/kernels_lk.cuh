@@ -69,12 +69,18 @@ VIWB_D void pyr_down_item(const PyrArgs &a, int idx) {
         for (int dy = -2; dy <= 2; dy++) {
             const uint32_t *row = reinterpret_cast<const uint32_t *>(a.src + (size_t)reflect101(2 * y + dy, a.sh) * a.sstride + 2 * x - 4);
             const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
-            // bytes b[0..15] = source columns 2x-4 .. 2x+11; output k (0..3) is centred on b[4 + 2k]
+            // bytes b[0..15] = source columns 2x-4 .. 2x+11 (b[0] = low byte of w0); output k (0..3) is centred on b[4 + 2k]:
+            // taps b[2+2k .. 5+2k] are one (funnel-shifted) 32-bit group for a 4-way byte dot product with (1, 4, 6, 4), plus b[6+2k]
+#ifdef VIWB_HOST_EMU
             int b[16];
-#pragma unroll
             for (int k = 0; k < 4; k++) { b[k] = (w0 >> (8 * k)) & 0xff; b[4 + k] = (w1 >> (8 * k)) & 0xff; b[8 + k] = (w2 >> (8 * k)) & 0xff; b[12 + k] = (w3 >> (8 * k)) & 0xff; }
-#pragma unroll
             for (int k = 0; k < 4; k++) { const int c = 4 + 2 * k; h[k] += wgt[dy + 2] * (b[c - 2] + b[c + 2] + 4 * (b[c - 1] + b[c + 1]) + 6 * b[c]); }
+#else
+            const uint32_t g0 = __funnelshift_r(w0, w1, 16), g2 = __funnelshift_r(w1, w2, 16);
+            const uint32_t t0 = __dp4a(g0, 0x04060401u, (w1 >> 16) & 0xffu), t1 = __dp4a(w1, 0x04060401u, w2 & 0xffu);
+            const uint32_t t2 = __dp4a(g2, 0x04060401u, (w2 >> 16) & 0xffu), t3 = __dp4a(w2, 0x04060401u, w3 & 0xffu);
+            h[0] += wgt[dy + 2] * (int)t0; h[1] += wgt[dy + 2] * (int)t1; h[2] += wgt[dy + 2] * (int)t2; h[3] += wgt[dy + 2] * (int)t3;
+#endif
         }
         uint32_t o = 0;
 #pragma unroll

@@ -187,7 +187,9 @@ VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *s
 
 VIWB_HD int vsub_to_mlay(int p) { return p < 66 ? p : p < 72 ? 165 + (p - 66) : p < 78 ? 171 + (p - 72) : 191; }   // td -> blk_moff(BLK_TD) = 191
 VIWB_HD int marg_cap(int nmax) { return nmax < 16 ? 16 : (nmax > 100 ? 100 : nmax); }
-VIWB_HD size_t marg_smem_doubles(int nt, int nmax) { const int c = marg_cap(nmax); return (size_t)c * (c | 1) + 3 * 256 + (size_t)c * 16 + 216 * 2 + 216 + 16 + 216 + 64 + (size_t)nt; }
+// eigenvector matrix c x (c|1), dropped-block matrix and its pseudo-inverse (<= 16 x 16 each), Arm*Ainv (c x 15), five vectors of <= 2c,
+// reduction scratch, scalars, two index lists: 73 KB for the 82-dimensional prior of the stereo+IMU configuration -> three blocks per SM
+VIWB_HD size_t marg_smem_doubles(int nt, int nmax) { (void)nt; const int c = marg_cap(nmax); return (size_t)c * (c | 1) + 2 * 256 + (size_t)c * 15 + (size_t)5 * c + 32 + 16 + 108 + 8; }
 
 VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)mode;
@@ -203,8 +205,8 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     const double eps = 1e-8;   // marginalization_factor.h:81
     // smem carve
     const int cap = marg_cap(bd.marg_nmax);
-    double *Vn = smem, *Amm = Vn + (size_t)cap * (cap | 1), *Vmm = Amm + 256, *Ainv = Vmm + 256, *Tm = Ainv + 256;
-    double *bn = Tm + (size_t)cap * 16, *cs = bn + 216, *ev = cs + 216, *ee = ev + 108, *red = ee + 108, *bc = red + nt;
+    double *Vn = smem, *Amm = Vn + (size_t)cap * (cap | 1), *Ainv = Amm + 256, *Tm = Ainv + 256;
+    double *bn = Tm + (size_t)cap * 15, *cs = bn + cap, *ev = cs + 2 * cap, *ee = ev + cap, *red = ee + cap, *bc = red + 32;
     int *keep = (int *)(bc + 16), *dl = keep + 216;
     double *An = Vn;
     // ---- dense system of the marginalisation factors over the marginalisation layout
@@ -248,7 +250,6 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     // ---- pseudo-inverse of the dropped fixed block (marginalization_factor.cpp:282-287)
     for (int e = tid; e < md * md; e += nt) { const int i = e / md, j = e % md; Amm[e] = 0.5 * (M[(size_t)dl[i] * LDM + dl[j]] + M[(size_t)dl[j] * LDM + dl[i]]); }
     VIWB_SYNC();
-    (void)Vmm;
     sym_eig_block(Amm, ev, ee, cs, bc + 4, red, md, md, tid, nt);      // eigenvalues -> ev, eigenvectors -> columns of Amm
     VIWB_SYNC();
     for (int e = tid; e < md * md; e += nt) {

@@ -90,7 +90,10 @@ DEF_KERNEL2(lm_reduce, 128, LM_MINB)
 DEF_KERNEL(lm_reduce_wide, 128)
 DEF_KERNEL(lin_small, 128)
 DEF_KERNEL(asm_items, 128)
-DEF_KERNEL(syrk, 256)
+#ifndef SYRK_MINB
+#define SYRK_MINB 4
+#endif
+DEF_KERNEL2(syrk, 256, SYRK_MINB)
 DEF_KERNEL(solve, 512)
 DEF_KERNEL(reanchor, 32)
 DEF_KERNEL(marg, 256)
