@@ -521,3 +521,44 @@ def check_triangulation(ctx, oracle, seed=9):
     want = np.where(z > 0, z, 5.0)
     assert np.abs(ctx.shift_depth(uv, dep, mR, mP, nR, nP) - want).max() <= 1e-12 * np.abs(want).max()
     assert np.abs(oracle.shift_depth(uv, dep, mR, mP, nR, nP) - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def check_full_batch_properties(ctx, oracle, distinct, copies):
+    """BASELINE-sized batch (bench.py's workload shape): size-independent properties on EVERY window, oracle parity on a sample.
+    * the robustified cost never increases (trust-region acceptance);
+    * gauge: frame-0 position and yaw equal their pre-solve values after the re-anchoring (estimator.cpp:1224-1276);
+    * the new prior is a square root of a PSD information matrix: J^T J symmetric, eigenvalues >= 0, r in range(J);
+    * identical windows in the batch give bit-identical results (deterministic, order-independent kernels)."""
+    import bench
+    from viwb import geom
+    cfg, seqs, first = bench.make_windows(0, distinct, copies)
+    a0, _, q0 = ctx.optimization_batch([f[0] for f in first], [f[1] for f in first], [abi.MARGIN_OLD] * len(first))
+    probs, states = bench.replicate(seqs, q0, a0, copies, 0)
+    probs = probs + probs[:2]; states = states + [states[0].copy(), states[1].copy()]          # duplicates: must match bit for bit
+    sts, sums, pri = ctx.optimization_batch(probs, states, [abi.MARGIN_OLD] * len(probs))
+    B = len(probs)
+    for i in range(B):
+        assert sums[i].final_cost <= sums[i].initial_cost * (1 + 1e-12)
+        assert 2 <= sums[i].num_iterations <= 9
+        p0, p1 = states[i][0:3], sts[i][0:3]
+        assert np.abs(p0 - p1).max() <= 1e-9
+        y0 = geom.R_to_ypr(geom.q_to_R(states[i][3:7]))[0] if hasattr(geom, "R_to_ypr") else None
+        if y0 is not None:
+            y1 = geom.R_to_ypr(geom.q_to_R(sts[i][3:7]))[0]
+            assert abs(((y0 - y1 + 180.0) % 360.0) - 180.0) <= 1e-7
+        q = pri[i]
+        assert q.valid and 60 <= q.n <= abi.MAX_PRIOR_DIM
+        J, r = q.Jmat(), q.rvec()
+        A = J.T @ J
+        w = np.linalg.eigvalsh(0.5 * (A + A.T))
+        assert w.min() >= -1e-9 * w.max()
+        rr = J @ np.linalg.lstsq(J, r, rcond=None)[0]
+        assert np.abs(rr - r).max() <= 1e-6 * max(1.0, np.abs(r).max())
+    for i in (0, 1):
+        assert np.array_equal(sts[i], sts[B - 2 + i]) and sums[i].final_cost == sums[B - 2 + i].final_cost
+        assert np.array_equal(pri[i].Jmat(), pri[B - 2 + i].Jmat())
+    for i in range(0, B, max(1, B // 5)):
+        a, sm, _ = oracle.optimization(probs[i], states[i], abi.MARGIN_OLD)
+        ep, er = synth.pose_errors(a, sts[i])
+        assert ep <= POSE_TOL_M and er <= POSE_TOL_RAD
+        assert abs(sm.final_cost - sums[i].final_cost) <= 1e-7 * sm.final_cost and sm.num_iterations == sums[i].num_iterations

@@ -88,3 +88,7 @@ def test_small_edges(emu, oracle):
 
 def test_triangulation(emu, oracle):
     pc.check_triangulation(emu, oracle)
+
+
+def test_batch_properties_small(emu, oracle):
+    pc.check_full_batch_properties(emu, oracle, distinct=2, copies=2)

@@ -129,3 +129,7 @@ def test_small_edges(gpu_ctx, oracle):
 
 def test_triangulation(gpu_ctx, oracle):
     pc.check_triangulation(gpu_ctx, oracle)
+
+
+def test_full_batch_properties(gpu_ctx, oracle):
+    pc.check_full_batch_properties(gpu_ctx, oracle, distinct=8, copies=16)
