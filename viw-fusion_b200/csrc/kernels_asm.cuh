@@ -32,7 +32,7 @@ VIWB_D int plane_slots(int i, Slot *s) { s[0].blk = i; s[0].col = 0; s[1].blk = 
 VIWB_HD int common_off(int c) { return c < 6 ? REC_E0 + c : c < 12 ? REC_E1 + (c - 6) : REC_TD; }
 VIWB_HD int common_stride(int c) { return c < 12 ? 6 : 1; }
 VIWB_HD void sym_unrank(int e, int &p, int &q) {   // e = p(p+1)/2 + q, 0 <= q <= p
-    int pp = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+    int pp = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);      // single-precision estimate, made exact by the two loops (e < 2^22)
     while ((pp + 1) * (pp + 2) / 2 <= e) pp++;
     while (pp * (pp + 1) / 2 > e) pp--;
     p = pp; q = e - pp * (pp + 1) / 2;

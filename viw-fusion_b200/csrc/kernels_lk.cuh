@@ -130,13 +130,15 @@ VIWB_HD bool lk_outside(int ix, int iy, int cols, int rows) { return ix < -LK_WI
 // x0a is a multiple of 4; interior regions use aligned 32-bit loads, the rest resolves reflect-101 byte by byte.
 VIWB_D void lk_stage(uint8_t *buf, const uint8_t *img, int stride, int cols, int rows, int x0a, int y0, int nrows, int nwords, int lane) {
     VIWB_SYNCWARP();
-    if (x0a >= 0 && y0 >= 0 && x0a + 4 * nwords <= cols && y0 + nrows <= rows) {
+    if (x0a >= 0 && x0a + 4 * nwords <= cols) {          // columns inside the image: aligned words; only the row index may need reflecting
         const int total = nrows * nwords;
+        const bool rows_in = y0 >= 0 && y0 + nrows <= rows;
         for (int e = lane; e < total; e += LK_W) {
             const int y = e / nwords, x = e - y * nwords;
-            reinterpret_cast<uint32_t *>(buf)[e] = *reinterpret_cast<const uint32_t *>(img + (size_t)(y0 + y) * stride + x0a + 4 * x);
+            const int sy = rows_in ? y0 + y : reflect101(y0 + y, rows);
+            reinterpret_cast<uint32_t *>(buf)[e] = *reinterpret_cast<const uint32_t *>(img + (size_t)sy * stride + x0a + 4 * x);
         }
-    } else {        // border: columns are reflected once per lane, rows once per row
+    } else {        // left / right border: columns are reflected once per lane, rows once per row
         const int wb = 4 * nwords;
 #ifdef VIWB_HOST_EMU
         for (int y = 0; y < nrows; y++) { const uint8_t *src = img + (size_t)reflect101(y0 + y, rows) * stride; for (int x = 0; x < wb; x++) buf[y * wb + x] = src[reflect101(x0a + x, cols)]; }

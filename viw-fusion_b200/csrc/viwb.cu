@@ -96,7 +96,7 @@ DEF_KERNEL(asm_items, 128)
 DEF_KERNEL2(syrk, 256, SYRK_MINB)
 DEF_KERNEL(solve, 512)
 DEF_KERNEL(reanchor, 32)
-DEF_KERNEL(marg, 256)
+DEF_KERNEL2(marg, 256, 3)
 DEF_KERNEL(outlier, 128)
 #define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) \
     do { if ((gx) > 0 && (gy) > 0) { g_prof.begin((mode) == 1 ? #name "_marg" : #name, stream); name##_kernel<<<dim3((gx), (gy)), (nt), (smem_bytes), (stream)>>>(bd, mode); g_prof.end(stream); } } while (0)
