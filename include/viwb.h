@@ -326,6 +326,14 @@ int viwb_track_checked(viwb_context *ctx, const uint8_t *img_a, const uint8_t *i
                        int stride, const float *pts_a, float *pts_b, int n, int mode, int flow_back,
                        uint8_t *status);
 
+/* FeatureTracker::undistortedPts (feature_tracker.cpp:606-617; PinholeCamera::liftProjective, recursive distortion model with
+ * 8 iterations, camera_models/src/camera_models/PinholeCamera.cc:450-517) and FeatureTracker::ptsVelocity (:619-657) for points
+ * paired index-wise with the previous tick.  pts: pixel coordinates [n][2]; un_pts: normalised, narrowed to float
+ * like cv::Point2f; velocity (optional): (un - prev_un) / dt where has_prev[i] (NULL = all) and prev_un_pts are given, else 0. */
+typedef struct viwb_pinhole { double fx, fy, cx, cy, k1, k2, p1, p2; } viwb_pinhole;
+int viwb_undistort_velocity(viwb_context *ctx, const viwb_pinhole *cam, int n, const float *pts, const float *prev_un_pts,
+                            const uint8_t *has_prev, double dt, float *un_pts, float *velocity);
+
 /* ---- batched tracker: one camera tick of `streams` independent VIO sessions per submission --------
  * Replaces, per stream, the four calcOpticalFlowPyrLK calls of one FeatureTracker::trackImage()
  * (feature_tracker.cpp:139 temporal forward, :145-146 temporal reverse, :240 stereo forward, :244 stereo

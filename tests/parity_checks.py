@@ -562,3 +562,36 @@ def check_full_batch_properties(ctx, oracle, distinct, copies):
         ep, er = synth.pose_errors(a, sts[i])
         assert ep <= POSE_TOL_M and er <= POSE_TOL_RAD
         assert abs(sm.final_cost - sums[i].final_cost) <= 1e-7 * sm.final_cost and sm.num_iterations == sums[i].num_iterations
+
+
+def check_undistort_velocity(ctx):
+    """undistortedPts / ptsVelocity restated in numpy with the reference's rounding points
+    (double lift, cv::Point2f narrowing, float difference / double dt)."""
+    rng = np.random.default_rng(4)
+    cam = (461.1586, 459.7529, 362.6593, 248.5236, -0.2847798, 0.08245052, -1.0946e-06, 4.78701e-06)     # config/euroc/cam0_pinhole.yaml
+    n = 300
+    pts = np.column_stack([rng.uniform(0, 752, n), rng.uniform(0, 480, n)]).astype(np.float32)
+    fx, fy, cx, cy, k1, k2, p1, p2 = cam
+
+    def lift(p):
+        mxd, myd = (1.0 / fx) * p[:, 0].astype(np.float64) + (-cx / fx), (1.0 / fy) * p[:, 1].astype(np.float64) + (-cy / fy)
+        mx, my = mxd.copy(), myd.copy()
+        for it in range(8):
+            x, y = (mxd, myd) if it == 0 else (mx, my)
+            mx2, my2, mxy = x * x, y * y, x * y
+            rho2 = mx2 + my2
+            rad = k1 * rho2 + k2 * rho2 * rho2
+            dx = x * rad + 2.0 * p1 * mxy + p2 * (rho2 + 2.0 * mx2)
+            dy = y * rad + 2.0 * p2 * mxy + p1 * (rho2 + 2.0 * my2)
+            mx, my = mxd - dx, myd - dy
+        return np.column_stack([mx, my]).astype(np.float32)
+    ref_un = lift(pts)
+    prev = (ref_un + rng.normal(0, 0.01, (n, 2))).astype(np.float32)
+    has = (rng.uniform(size=n) < 0.8).astype(np.uint8)
+    dt = 0.05
+    ref_vel = np.where(has[:, None] > 0, ((ref_un - prev).astype(np.float64) / dt), 0.0).astype(np.float32)
+    un, vel = ctx.undistort_velocity(cam, pts, prev, has, dt)
+    assert np.abs(un - ref_un).max() <= 2e-7          # one float ulp at |x| < 1 (FMA contraction in the double lift)
+    assert np.abs(vel - ref_vel).max() <= 1e-5
+    un0, vel0 = ctx.undistort_velocity((fx, fy, cx, cy, 0, 0, 0, 0), pts, None, None, dt)
+    assert np.abs(un0[:, 0] - ((pts[:, 0].astype(np.float64) - cx) / fx).astype(np.float32)).max() <= 2e-7 and not vel0.any()

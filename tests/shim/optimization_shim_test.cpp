@@ -41,9 +41,9 @@ int main(int argc, char **argv) {
     // the marginalization info of the previous optimization() (last_marginalization_info / ..._parameter_blocks)
     MarginalizationInfo *last_marginalization_info = nullptr; std::vector<double *> last_marginalization_parameter_blocks;
     auto addr_of_block = [&](int b) -> double * {
-        if (b <= 10) return para_Pose[b]; if (b <= 21) return para_SpeedBias[b - 11]; if (b <= 23) return para_Ex_Pose[b - 22]; if (b == 24) return para_Ex_Pose_wheel[0];
-        if (b == 25) return para_plane_R[0]; if (b == 26) return para_plane_Z[0]; if (b == 27) return para_Ix_sx_wheel[0]; if (b == 28) return para_Ix_sy_wheel[0];
-        if (b == 29) return para_Ix_sw_wheel[0]; if (b == 30) return para_Td[0]; return para_Td_wheel[0]; };
+        return b <= 10 ? para_Pose[b] : b <= 21 ? para_SpeedBias[b - 11] : b <= 23 ? para_Ex_Pose[b - 22] : b == 24 ? para_Ex_Pose_wheel[0] :
+               b == 25 ? para_plane_R[0] : b == 26 ? para_plane_Z[0] : b == 27 ? para_Ix_sx_wheel[0] : b == 28 ? para_Ix_sy_wheel[0] :
+               b == 29 ? para_Ix_sw_wheel[0] : b == 30 ? para_Td[0] : para_Td_wheel[0]; };
     struct LoadedInfo : MarginalizationInfo { };      // a prior loaded from disk stands in for last_marginalization_info
     viwb_prior loaded; std::vector<double> lx0 = pr_x0, lJ = pr_J, lr = pr_r;
     struct PriorFactor : ceres::CostFunction {        // MarginalizationFactor over a loaded prior

@@ -92,3 +92,7 @@ def test_triangulation(emu, oracle):
 
 def test_batch_properties_small(emu, oracle):
     pc.check_full_batch_properties(emu, oracle, distinct=2, copies=2)
+
+
+def test_undistort_velocity(emu):
+    pc.check_undistort_velocity(emu)

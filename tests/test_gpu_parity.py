@@ -133,3 +133,7 @@ def test_triangulation(gpu_ctx, oracle):
 
 def test_full_batch_properties(gpu_ctx, oracle):
     pc.check_full_batch_properties(gpu_ctx, oracle, distinct=8, copies=16)
+
+
+def test_undistort_velocity(gpu_ctx):
+    pc.check_undistort_velocity(gpu_ctx)

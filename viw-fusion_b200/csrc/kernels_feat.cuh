@@ -79,7 +79,38 @@ VIWB_D void shift_depth_item(const ShiftArgs &a, int k) {
     a.depth_out[k] = pts_j.z > 0 ? pts_j.z : a.init_depth;
 }
 
+
+// FeatureTracker::undistortedPts (featureTracker/feature_tracker.cpp:606-617) -> PinholeCamera::liftProjective with the recursive
+// distortion model, n = 8 (camera_models/src/camera_models/PinholeCamera.cc:450-517, distortion :646-662), results narrowed to
+// cv::Point2f; and FeatureTracker::ptsVelocity (:619-657) for points paired index-wise with the previous tick.
+struct UndistArgs { int n; const float *pts, *prev_un; const unsigned char *has_prev; double fx, fy, cx, cy, k1, k2, p1, p2, dt; float *un, *vel; };
+VIWB_D void undistort_item(const UndistArgs &a, int i) {
+    if (i >= a.n) return;
+    const double inv_K11 = 1.0 / a.fx, inv_K13 = -a.cx / a.fx, inv_K22 = 1.0 / a.fy, inv_K23 = -a.cy / a.fy;     // PinholeCamera.cc:105-108
+    const double mx_d = inv_K11 * (double)a.pts[2 * i] + inv_K13, my_d = inv_K22 * (double)a.pts[2 * i + 1] + inv_K23;
+    double mx_u = mx_d, my_u = my_d;
+    if (!(a.k1 == 0.0 && a.k2 == 0.0 && a.p1 == 0.0 && a.p2 == 0.0)) {       // m_noDistortion
+        for (int it = 0; it < 8; it++) {
+            const double x = (it == 0) ? mx_d : mx_u, y = (it == 0) ? my_d : my_u;
+            const double mx2 = x * x, my2 = y * y, mxy = x * y, rho2 = mx2 + my2, rad = a.k1 * rho2 + a.k2 * rho2 * rho2;
+            const double dx = x * rad + 2.0 * a.p1 * mxy + a.p2 * (rho2 + 2.0 * mx2), dy = y * rad + 2.0 * a.p2 * mxy + a.p1 * (rho2 + 2.0 * my2);
+            mx_u = mx_d - dx; my_u = my_d - dy;
+        }
+    }
+    const float ux = (float)(mx_u / 1.0), uy = (float)(my_u / 1.0);          // b.x() / b.z() with b.z() = 1
+    a.un[2 * i] = ux; a.un[2 * i + 1] = uy;
+    if (a.vel) {
+        float vx = 0.f, vy = 0.f;
+        if (a.prev_un && (!a.has_prev || a.has_prev[i])) {
+            vx = (float)((double)(ux - a.prev_un[2 * i]) / a.dt);               // float difference, double division (:640-641)
+            vy = (float)((double)(uy - a.prev_un[2 * i + 1]) / a.dt);
+        }
+        a.vel[2 * i] = vx; a.vel[2 * i + 1] = vy;
+    }
+}
+
 #ifndef VIWB_HOST_EMU
+__global__ void undistort_kernel(UndistArgs a) { undistort_item(a, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void triangulate_kernel(TriArgs a) { triangulate_item(a, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void shift_depth_kernel(ShiftArgs a) { shift_depth_item(a, blockIdx.x * blockDim.x + threadIdx.x); }
 #endif

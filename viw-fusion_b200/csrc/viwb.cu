@@ -1062,6 +1062,36 @@ extern "C" int viwb_shift_depth(viwb_context *ctx, int n, const double *uv, cons
     return e ? fail(ctx, VIWB_ERR_CUDA, "shift_depth failed") : VIWB_OK;
 }
 
+extern "C" int viwb_undistort_velocity(viwb_context *ctx, const viwb_pinhole *cam, int n, const float *pts, const float *prev_un_pts, const uint8_t *has_prev,
+                                       double dt, float *un_pts, float *velocity) {
+    if (!ctx || !cam || n < 0 || !pts || !un_pts) return VIWB_ERR_INVALID;
+    if (n == 0) return VIWB_OK;
+    bind_device(ctx);
+    const size_t pb = align_up((size_t)n * 8);
+    char *d = nullptr; CK(dev_malloc((void **)&d, 4 * pb + align_up((size_t)n)));
+    float *d_pts = (float *)d, *d_prev = (float *)(d + pb), *d_un = (float *)(d + 2 * pb), *d_vel = (float *)(d + 3 * pb);
+    unsigned char *d_hp = (unsigned char *)(d + 4 * pb);
+    int e = dev_h2d(d_pts, pts, (size_t)n * 8, ctx->stream);
+    if (!e && prev_un_pts) e = dev_h2d(d_prev, prev_un_pts, (size_t)n * 8, ctx->stream);
+    if (!e && has_prev) e = dev_h2d(d_hp, has_prev, (size_t)n, ctx->stream);
+    UndistArgs a; a.n = n; a.pts = d_pts; a.prev_un = prev_un_pts ? d_prev : nullptr; a.has_prev = has_prev ? d_hp : nullptr;
+    a.fx = cam->fx; a.fy = cam->fy; a.cx = cam->cx; a.cy = cam->cy; a.k1 = cam->k1; a.k2 = cam->k2; a.p1 = cam->p1; a.p2 = cam->p2; a.dt = dt;
+    a.un = d_un; a.vel = velocity ? d_vel : nullptr;
+    if (!e) {
+#ifdef VIWB_HOST_EMU
+        for (int k = 0; k < n; k++) undistort_item(a, k);
+#else
+        g_prof.begin("undistort", ctx->stream); undistort_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a); g_prof.end(ctx->stream);
+#endif
+        ctx->launches++;
+        e = dev_d2h(un_pts, d_un, (size_t)n * 8, ctx->stream);
+        if (!e && velocity) e = dev_d2h(velocity, d_vel, (size_t)n * 8, ctx->stream);
+    }
+    if (!e) e = dev_sync(ctx->stream);
+    dev_free(d);
+    return e ? fail(ctx, VIWB_ERR_CUDA, "undistort failed") : VIWB_OK;
+}
+
 // -------------------------------------------------------------------------------------- feature tracker
 extern "C" int viwb_lk_track(viwb_context *ctx, const uint8_t *prev_img, const uint8_t *next_img, int width, int height, int stride,
                              const float *prev_pts, float *next_pts, int n, int win_size, int max_level, int max_iter, float eps, int flags,

@@ -20,7 +20,7 @@ EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", 
            "viwb_batch_run", "viwb_batch_download", "viwb_batch_algorithmic_bytes", "viwb_batch_destroy",
            "viwb_debug_normal_equations", "viwb_lk_track", "viwb_track_checked", "viwb_lk_batch_create", "viwb_lk_batch_destroy",
            "viwb_lk_batch_upload", "viwb_lk_batch_run", "viwb_lk_batch_download", "viwb_lk_batch_algorithmic_bytes", "viwb_host_register",
-           "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate", "viwb_outlier_rejection", "viwb_batch_outliers", "viwb_triangulate", "viwb_shift_depth"]
+           "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate", "viwb_outlier_rejection", "viwb_batch_outliers", "viwb_triangulate", "viwb_shift_depth", "viwb_undistort_velocity"]
 
 
 class ViwbError(RuntimeError):
@@ -232,6 +232,19 @@ class Context:
         self._ck(self.lib.viwb_outlier_rejection(self.h, C.byref(problem.c), _dp(st), C.c_double(focal), C.c_double(thresh), out.ctypes.data_as(C.c_void_p)),
                  "viwb_outlier_rejection")
         return out[: problem.num_landmarks]
+
+    def undistort_velocity(self, cam, pts, prev_un=None, has_prev=None, dt=0.05, want_velocity=True):
+        """cam = (fx, fy, cx, cy, k1, k2, p1, p2); pts float32 (n, 2) pixels -> (normalised points, velocities) as float32"""
+        p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        n = len(p)
+        c = (C.c_double * 8)(*[float(v) for v in cam])
+        un, vel = np.zeros((n, 2), np.float32), np.zeros((n, 2), np.float32)
+        pv = None if prev_un is None else np.ascontiguousarray(prev_un, np.float32)
+        hp = None if has_prev is None else np.ascontiguousarray(has_prev, np.uint8)
+        vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.viwb_undistort_velocity(self.h, c, C.c_int(n), vp(p), vp(pv), vp(hp), C.c_double(dt), vp(un), vp(vel) if want_velocity else None),
+                 "viwb_undistort_velocity")
+        return un, vel
 
     def triangulate(self, state, stereo, frame, pt0, pt1, init_depth=5.0):
         st = np.ascontiguousarray(state, np.float64)
