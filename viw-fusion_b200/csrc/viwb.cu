@@ -973,7 +973,7 @@ extern "C" int viwb_imu_preintegrate(viwb_context *ctx, int n, const int32_t *co
     if (!ctx || n < 0 || !counts || !dt || !acc || !gyr || !ba || !bg || !noise || !records) return VIWB_ERR_INVALID;
     if (n == 0) return VIWB_OK;
     ImuPreArgs a; for (int k = 0; k < 4; k++) a.noise[k] = noise[k];
-    const double *extra[2] = {ba, bg}; const int ed[2] = {3, 3}; const double *dv[2];
+    const double *extra[2] = {ba, bg}; const int ed[2] = {3, 3}; const double *dv[2] = {nullptr, nullptr};
     stream_t st = ctx->stream;
     return preint_run(ctx, a, n, counts, dt, acc, gyr, 287, records, extra, ed, 2, dv, [&](ImuPreArgs &q, const double *d0, const double *d1) {
         q.acc = d0; q.gyr = d1; q.ba = dv[0]; q.bg = dv[1];
@@ -989,7 +989,7 @@ extern "C" int viwb_wheel_preintegrate(viwb_context *ctx, int n, const int32_t *
     if (!ctx || n < 0 || !counts || !dt || !vel || !gyr || !s || !td || !noise || !records) return VIWB_ERR_INVALID;
     if (n == 0) return VIWB_OK;
     WheelPreArgs a; a.noise[0] = noise[0]; a.noise[1] = noise[1];
-    const double *extra[2] = {s, td}; const int ed[2] = {3, 1}; const double *dv[2];
+    const double *extra[2] = {s, td}; const int ed[2] = {3, 1}; const double *dv[2] = {nullptr, nullptr};
     stream_t st = ctx->stream;
     return preint_run(ctx, a, n, counts, dt, vel, gyr, 78, records, extra, ed, 2, dv, [&](WheelPreArgs &q, const double *d0, const double *d1) {
         q.vel = d0; q.gyr = d1; q.s = dv[0]; q.td = dv[1];
