@@ -39,12 +39,16 @@ VIWB_HD void sym_unrank(int e, int &p, int &q) {   // e = p(p+1)/2 + q, 0 <= q <
 }
 
 // ------------------------------------------------------------------------------------------------ asm_items
-// grid: ceil(nitems / warps_per_block); mode selects the solver or the marginalisation item table.
-VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
-    (void)by; (void)smem;
+// grid: ceil(nitems * split / warps_per_block); mode selects the solver or the marginalisation item table.
+enum { ASM_SPLIT = 4 };
+template <int SPLIT>
+VIWB_D void asm_items_body(const BatchDev &bd, int bx, int tid, int nt, int mode) {
     const int W = nt < 32 ? nt : 32, wpb = nt / W, lane = tid % W;
+    // Items with the common columns have up to 105 outputs: SPLIT warps share such an item (one slice of the outputs each, the
+    // same list walk) instead of one warp walking the list four times.
     const int nitems = (mode == MODE_SOLVE) ? bd.nitems_solve : bd.nitems_marg;
-    const int it = bx * wpb + tid / W;
+    const int split = SPLIT;
+    const int wi = bx * wpb + tid / W, it = wi / split, part = wi - it * split;
     if (it >= nitems) return;
     const int gi = (mode == MODE_SOLVE) ? it : bd.nitems_solve + it;
     const AsmItem item = bd.items[gi];
@@ -57,8 +61,8 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     // outputs of this item; without common columns a FRAME item has only F^T F (21) and F^T r (6 -> stored at 99..104)
     int nout;
     if (item.kind == ITEM_FRAME) nout = item.has_common ? 105 : 27; else if (item.kind == ITEM_PAIR) nout = 36; else nout = 104;
-    if (item.kind == ITEM_FRAME && !item.has_common) for (int o = 21 + lane; o < 99; o += W) out[o] = 0.0;
-    for (int o0 = lane; o0 < nout; o0 += W) {
+    if (item.kind == ITEM_FRAME && !item.has_common && part == 0) for (int o = 21 + lane; o < 99; o += W) out[o] = 0.0;
+    for (int o0 = lane + W * part; o0 < nout; o0 += W * split) {
         int o = o0;
         if (item.kind == ITEM_FRAME && !item.has_common && o0 >= 21) o = 99 + (o0 - 21);
         // operand kinds: 0 = frame slot of a, 1 = frame slot of b (PAIR), 2 = common column, 3 = residual
@@ -99,6 +103,9 @@ VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt,
         out[o] = acc;
     }
 }
+
+VIWB_D void asm_items_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; (void)smem; asm_items_body<1>(bd, bx, tid, nt, mode); }
+VIWB_D void asm_items_split_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; (void)smem; asm_items_body<ASM_SPLIT>(bd, bx, tid, nt, mode); }
 
 // ------------------------------------------------------------------------------------------------ syrk
 // T = sum_k g_k w_k w_k^T (80 x 80, symmetric, both triangles written), tvec = sum_k g_k w_k gl_k.

@@ -90,6 +90,7 @@ DEF_KERNEL2(lm_reduce, 128, LM_MINB)
 DEF_KERNEL(lm_reduce_wide, 128)
 DEF_KERNEL(lin_small, 128)
 DEF_KERNEL(asm_items, 128)
+DEF_KERNEL(asm_items_split, 128)
 #ifndef SYRK_MINB
 #define SYRK_MINB 4
 #endif
@@ -510,7 +511,9 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
         ctx->launches += (g_vis > 0) + (g_lm > 0) + 1;
         if (cost_only) return;
         const int ni = mode == MODE_SOLVE ? bd.nitems_solve : bd.nitems_marg, wpb = nt_asm / (nt_asm < 32 ? nt_asm : 32);
-        LAUNCH(asm_items, bd, (ni + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
+        const bool wide = (mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) == VREC;     // items carry the common columns
+        if (wide) LAUNCH(asm_items_split, bd, (ni * ASM_SPLIT + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
+        else LAUNCH(asm_items, bd, (ni + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
         LAUNCH(syrk, bd, B, 1, nt_syrk, syrk_smem_doubles() * 8, mode, st);
         ctx->launches += (ni > 0) + 1;
     };
