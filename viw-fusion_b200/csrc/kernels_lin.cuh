@@ -79,11 +79,19 @@ VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, d
         if (mode == MODE_MARG && (fi != 0 || bd.meta[w].margin_flag != 0)) on = false;
     }
     act[tid] = on ? 1 : 0;
+    // the block's observation rows (12 doubles per factor) arrive as one coalesced stream through the tile as well
+    const int nrec = (bd.nvis_total - bx * nt) < nt ? (bd.nvis_total - bx * nt) : nt;
+    {
+        const double *src = bd.vis_obs + (size_t)bx * nt * 12;
+        for (int e = tid; e < nrec * 12; e += nt) tile[(e / 12) * 13 + (e % 12)] = src[e];
+    }
+    VIWB_SYNC();
+    double obs[12];
+    for (int k = 0; k < 12; k++) obs[k] = tile[tid * 13 + k];
+    VIWB_SYNC();
     if (on) {
         const WinMeta &m = bd.meta[w];
         const double *x = eval_state(bd, w, mode);
-        double obs[12];
-        for (int k = 0; k < 12; k++) obs[k] = bd.vis_obs[(size_t)f * 12 + k];
         const int lm = bd.vis_lm[f];
         VisOut o;
         vis_eval(bd.vis_type[f], obs, x + 7 * fi, x + 7 * bd.vis_fj[f], x + blk_off(BLK_EX0), x + blk_off(BLK_EX1),
@@ -102,7 +110,6 @@ VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, d
     }
     VIWB_SYNC();
     double *out = bd.vis_rec + (size_t)bx * nt * rs;
-    const int nrec = (bd.nvis_total - bx * nt) < nt ? (bd.nvis_total - bx * nt) : nt;
     for (int e = tid; e < nrec * rs; e += nt) { const int r = e / rs, q = e - r * rs; if (act[r]) out[e] = tile[(size_t)r * ts + q]; }
 }
 
