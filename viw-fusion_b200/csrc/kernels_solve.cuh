@@ -44,6 +44,21 @@ VIWB_D double block_max(double v, int tid, int nt, double *red) {
 }
 #endif
 
+// several sums in one pass: one barrier pair for all of them (red needs N * 32 doubles)
+template <int N>
+VIWB_D void block_sum_n(double (&v)[N], int tid, int nt, double *red) {
+#ifdef VIWB_HOST_EMU
+    (void)v; (void)tid; (void)nt; (void)red;
+#else
+    for (int q = 0; q < N; q++) for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+    const int nw = nt >> 5;
+    if ((tid & 31) == 0) for (int q = 0; q < N; q++) red[q * 32 + (tid >> 5)] = v[q];
+    __syncthreads();
+    for (int q = 0; q < N; q++) { double r = 0.0; for (int k = 0; k < nw; k++) r += red[q * 32 + k]; v[q] = r; }
+    __syncthreads();
+#endif
+}
+
 struct SolveSmem {
     double *L;       // packed lower, nf(nf+1)/2
     double *g, *sc, *D, *sg, *y, *u, *Hu, *ug, *uvis, *red, *bc, *chol, *dinv, *xo, *Pt;
@@ -432,7 +447,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                     l += lm_g[k] * ul;
                 }
             }
-            q = block_sum(q, tid, nt, s.red); l = block_sum(l, tid, nt, s.red);
+            { double v2[2] = {q, l}; block_sum_n<2>(v2, tid, nt, s.red); q = v2[0]; l = v2[1]; }
             if (tid == 0) { ww.sgrad_norm = sqrt(n2); ww.q_gg = q; ww.l_g = l; ww.alpha = n2 / q; }
             VIWB_SYNC();
             // ---- Gauss-Newton step: (J^T J + mu D^2) y = J^T r through the Schur complement
@@ -526,8 +541,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                         nn += g_gn[TFIX + k] * g_gn[TFIX + k]; gd += g_sg[TFIX + k] * g_gn[TFIX + k];
                     }
                 }
-                qnn = block_sum(qnn, tid, nt, s.red); qgn = block_sum(qgn, tid, nt, s.red); ln = block_sum(ln, tid, nt, s.red);
-                nn = block_sum(nn, tid, nt, s.red); gd = block_sum(gd, tid, nt, s.red);
+                { double v5[5] = {qnn, qgn, ln, nn, gd}; block_sum_n<5>(v5, tid, nt, s.red); qnn = v5[0]; qgn = v5[1]; ln = v5[2]; nn = v5[3]; gd = v5[4]; }
                 if (tid == 0) { ww.q_nn = qnn; ww.q_gn = qgn; ww.l_n = ln; ww.gn_norm = sqrt(nn); ww.sgrad_dot_gn = gd; }
             }
             VIWB_SYNC();
