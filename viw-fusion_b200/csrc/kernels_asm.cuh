@@ -218,10 +218,10 @@ VIWB_D void syrk_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
 // A target provides:  int col(int blk, int k)  (-1 if that column is not part of the system),
 //                     void add(int i, int j, double v)  for an unordered index pair (called once per pair per phase),
 //                     void addg(int i, double v).
-struct PackedTarget {      // solver: packed lower triangle in shared memory over the compact active columns
-    double *L, *g; const short *tcol;
+struct PackedTarget {      // solver: skyline lower triangle in shared memory over the compact active columns
+    double *L, *g; const short *tcol; const int *rp, *fst;
     VIWB_DM int col(int blk, int k) const { return (tcol[blk] >= 0 && k < blk_tsize(blk)) ? tcol[blk] + k : -1; }
-    VIWB_DM void add(int i, int j, double v) const { if (i >= j) L[i * (i + 1) / 2 + j] += v; else L[j * (j + 1) / 2 + i] += v; }
+    VIWB_DM void add(int i, int j, double v) const { if (i < j) { const int t = i; i = j; j = t; } L[rp[i] - fst[i] + j] += v; }
     VIWB_DM void addg(int i, double v) const { g[i] += v; }
 };
 struct DenseTarget {       // marginalisation: dense symmetric matrix in the marginalisation layout (global memory)

@@ -5,8 +5,10 @@
 // (mu x10 on failure), traditional dogleg interpolation, model decrease, candidate = x (+) step; and, one call
 // later, the accept/reject decision with the radius / mu updates and all termination tests.
 //
-// The reduced system (<= 192 active tangent columns) lives in shared memory as a packed lower triangle
-// (<= 148 KB); all quadratic forms are evaluated on the *unscaled* matrices with unscaled directions
+// The reduced system (<= 192 active tangent columns) lives in shared memory as a SKYLINE: row i of the lower triangle is stored
+// from its first structurally non-zero column efirst[i] (host symbolic analysis, csrc/viwb.cu lower_count).  With the speed-bias
+// blocks eliminated first, newest frame first, the stereo+IMU window needs 7.2 K instead of 13.7 K doubles, which lets two
+// windows share an SM.  All quadratic forms are evaluated on the *unscaled* matrices with unscaled directions
 // u = c o (v / D), which equals Ceres' J_scaled products exactly.
 #pragma once
 #include "layout.cuh"
@@ -60,48 +62,53 @@ VIWB_D void block_sum_n(double (&v)[N], int tid, int nt, double *red) {
 }
 
 struct SolveSmem {
-    double *L;       // packed lower, nf(nf+1)/2
+    double *L;       // skyline lower triangle: row i holds columns fst[i]..i at L[rp[i] .. rp[i+1])
+    int *rp, *fst;   // row pointers (nf + 1) and first columns (nf)
     double *g, *sc, *D, *sg, *y, *u, *Hu, *ug, *uvis, *red, *bc, *chol, *dinv, *xo, *Pt;
     int *amap, *vmap;
 };
-VIWB_HD size_t solve_smem_doubles(int nt) { return (size_t)TFIX * (TFIX + 1) / 2 + 9 * TFIX + 2 * VSUB + nt + 16 + TFIX + (size_t)((nt + 31) / 32) * 48 + 2 * TFIX + 8 * (TFIX + 4) + 2; }   // + ints (2*TFIX ints = TFIX doubles)
-VIWB_D void carve(SolveSmem &s, double *smem, int nt) {
+VIWB_HD size_t solve_smem_doubles(int nt, int esize) { return (size_t)((esize + 1) & ~1) + 9 * TFIX + 2 * VSUB + 5 * 32 + 16 + 2 * TFIX + 2 + (size_t)((nt + 31) / 32) * 48 + 2 * TFIX + 8 * (TFIX + 4) + 2; }   // ints: amap, vmap, rp, fst
+VIWB_D void carve(SolveSmem &s, double *smem, int nt, int esize) {
     double *p = smem;
-    s.L = p; p += (size_t)TFIX * (TFIX + 1) / 2;
+    s.L = p; p += (size_t)((esize + 1) & ~1);
     s.g = p; p += TFIX; s.sc = p; p += TFIX; s.D = p; p += TFIX; s.sg = p; p += TFIX; s.y = p; p += TFIX;
     s.u = p; p += TFIX; s.Hu = p; p += TFIX; s.ug = p; p += TFIX;
     s.uvis = p; p += 2 * VSUB;
-    s.red = p; p += nt; s.bc = p; p += 16;
+    s.red = p; p += 5 * 32; s.bc = p; p += 16;
     s.chol = p; p += (size_t)((nt + 31) / 32) * 48;
     s.dinv = p; p += TFIX; s.xo = p; p += TFIX;
     if ((p - smem) & 1) p++;                    // Pt is read with 16-byte vector loads
     s.Pt = p; p += 8 * (TFIX + 4);
-    s.amap = (int *)p; s.vmap = s.amap + TFIX;
+    s.amap = (int *)p; s.vmap = s.amap + TFIX; s.rp = s.vmap + TFIX; s.fst = s.rp + TFIX + 2;
 }
+// entry (i, j), j <= i, of the skyline; must lie inside the envelope
+#define SKY(s, i, j) ((s).L[(s).rp[i] - (s).fst[i] + (j)])
 
-// assemble the active part of H (unscaled) and g into the packed triangle / s.g, and keep a packed copy in HBM
+// assemble the active part of H (unscaled) and g into the skyline / s.g, and keep a copy in HBM
 VIWB_D void assemble_H(const BatchDev &bd, int w, const SolveSmem &s, int nf, double *Hpk, double *gpk, int tid, int nt) {
-    const int ne = nf * (nf + 1) / 2;
+    const int ne = s.rp[nf];
     for (int e = tid; e < ne; e += nt) s.L[e] = 0.0;
     for (int i = tid; i < nf; i += nt) s.g[i] = 0.0;
     VIWB_SYNC();
-    PackedTarget t; t.L = s.L; t.g = s.g; t.tcol = bd.meta[w].tcol;
+    PackedTarget t; t.L = s.L; t.g = s.g; t.tcol = bd.meta[w].tcol; t.rp = s.rp; t.fst = s.fst;
     assemble_into(t, bd, w, MODE_SOLVE, tid, nt, (int *)s.Hu);      // Hu is free until the step computation
     for (int e = tid; e < ne; e += nt) Hpk[e] = s.L[e];
     for (int i = tid; i < nf; i += nt) gpk[i] = s.g[i];
     VIWB_SYNC();
 }
-// reload the packed copy (after the Cholesky factor overwrote it)
+// reload the copy (after the Cholesky factor overwrote it)
 VIWB_D void load_H(const double *Hpk, const SolveSmem &s, int nf, int tid, int nt) {
-    const int ne = nf * (nf + 1) / 2;
+    const int ne = s.rp[nf];
     for (int e = tid; e < ne; e += nt) s.L[e] = Hpk[e];
     VIWB_SYNC();
 }
-// Hu = H u over the packed triangle (u, Hu of length nf)
+// Hu = H u over the skyline (u, Hu of length nf): the stored part of row i, then column i of the rows below that reach it
 VIWB_D void symv(const SolveSmem &s, int nf, const double *u, double *Hu, int tid, int nt) {
     for (int i = tid; i < nf; i += nt) {
         double a = 0.0;
-        for (int j = 0; j < nf; j++) a += s.L[pidx(i, j)] * u[j];
+        const double *ri = s.L + s.rp[i] - s.fst[i];
+        for (int j = s.fst[i]; j <= i; j++) a += ri[j] * u[j];
+        for (int k = i + 1; k < nf; k++) if (s.fst[k] <= i) a += s.L[s.rp[k] - s.fst[k] + i] * u[k];
         Hu[i] = a;
     }
     VIWB_SYNC();
@@ -151,8 +158,10 @@ VIWB_D void load4(const double *p, double *o) {
     o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
 #endif
 }
-VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, double *scratch, double *dinv, double *Pt) {
-#define ROW(i) ((i) < n ? L + (size_t)(i) * ((i) + 1) / 2 : y)
+VIWB_D bool cholesky_packed_rhs(double *L, const int *rp, const int *fst, double *y, int n, int tid, int nt, double *scratch, double *dinv, double *Pt) {
+    // skyline rows: ROW(i)[j] is entry (i, j) for fst[i] <= j <= i; row n is the right-hand side (dense).  FST(i) = first stored column.
+#define ROW(i) ((i) < n ? L + rp[i] - fst[i] : y)
+#define FST(i) ((i) < n ? fst[i] : 0)
     const int lane = tid & 31;
     double *my = scratch + (size_t)(tid >> 5) * CHOL_SCR;      // this warp's copy of the factored diagonal block
     for (int c0 = 0; c0 < n; c0 += CHOL_NB) {
@@ -162,7 +171,7 @@ VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, do
             (void)lane;
             my[44] = 1.0;
             double a[8][8];
-            for (int i = 0; i < nb; i++) for (int j = 0; j <= i; j++) a[i][j] = ROW(c0 + i)[c0 + j];
+            for (int i = 0; i < nb; i++) for (int j = 0; j <= i; j++) a[i][j] = (c0 + j >= FST(c0 + i)) ? ROW(c0 + i)[c0 + j] : 0.0;
             for (int k = 0; k < nb; k++) {
                 const double d = a[k][k];
                 if (!(d > 0.0)) { my[44] = 0.0; break; }
@@ -177,9 +186,10 @@ VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, do
         {
             double a[8];
             const bool act = lane < nb;
-            const double *src = ROW(c0 + (act ? lane : 0)) + c0;
+            const int rr = c0 + (act ? lane : 0), fr = fst[rr];
+            const double *src = ROW(rr) + c0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) a[j] = (act && j <= lane) ? src[j] : 0.0;
+            for (int j = 0; j < 8; j++) a[j] = (act && j <= lane && c0 + j >= fr) ? src[j] : 0.0;
             bool okp = true;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -205,15 +215,17 @@ VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, do
         if (my[44] == 0.0) return false;                    // every warp reaches the same verdict
         const int r0 = c0 + nb;
         const int nr = n + 1 - r0, mt = (nr + 3) / 4;       // panel rows r0..n (row n = rhs), padded to whole 4-row tiles
-        // panel rows: x_k = (a_ik - sum_m x_m L_km) / L_kk
+        // panel rows: x_k = (a_ik - sum_m x_m L_km) / L_kk; columns left of a row's envelope are (and stay) structural zeros
         for (int i = r0 + tid; i < r0 + 4 * mt; i += nt) {
             double x[8];
-            if (i <= n) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = 0.0;
+            if (i <= n && FST(i) < r0) {
                 double *ri = ROW(i) + c0;
+                const int fi = FST(i);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    x[k] = 0.0;
-                    if (k < nb) {
+                    if (k < nb && c0 + k >= fi) {
                         double v = ri[k];
 #pragma unroll
                         for (int m = 0; m < 8; m++) if (m < k) v -= x[m] * my[k * (k + 1) / 2 + m];
@@ -221,9 +233,6 @@ VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, do
                         ri[k] = x[k];
                     }
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; k++) x[k] = 0.0;
             }
 #pragma unroll
             for (int k = 0; k < 8; k++) Pt[k * CHOL_LDP + (i - r0)] = x[k];
@@ -231,11 +240,17 @@ VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, do
         for (int r = tid; r < nb; r += nt) dinv[c0 + r] = my[36 + r];
         VIWB_SYNC();
         // factored diagonal block back into the matrix (only now: the other warps have finished reading the unfactored one)
-        for (int r = tid; r < nb; r += nt) { double *rk = ROW(c0 + r) + c0; for (int j = 0; j <= r; j++) rk[j] = my[r * (r + 1) / 2 + j]; }
-        // trailing update with 4x4 register tiles over rows i in [r0, n], columns k in [r0, min(i, n-1)]
+        for (int r = tid; r < nb; r += nt) { double *rk = ROW(c0 + r) + c0; const int fr = FST(c0 + r); for (int j = 0; j <= r; j++) if (c0 + j >= fr) rk[j] = my[r * (r + 1) / 2 + j]; }
+        // trailing update with 4x4 register tiles over rows i in [r0, n], columns k in [r0, min(i, n-1)]; a tile whose row group or
+        // column group lies entirely right of the panel (first stored column >= r0) has nothing to receive
         const int ntile = mt * (mt + 1) / 2;
         for (int t = tid; t < ntile; t += nt) {
             int ti, tk; sym_unrank(t, ti, tk);
+            const int ib = r0 + 4 * ti, kb = r0 + 4 * tk;
+            bool hit_i = false, hit_k = false;
+#pragma unroll
+            for (int a = 0; a < 4; a++) { if (ib + a <= n && FST(ib + a) < r0) hit_i = true; if (kb + a < n && FST(kb + a) < r0) hit_k = true; }
+            if (!hit_i || !hit_k) continue;
             double acc[16];
 #pragma unroll
             for (int q = 0; q < 16; q++) acc[q] = 0.0;
@@ -248,38 +263,35 @@ VIWB_D bool cholesky_packed_rhs(double *L, double *y, int n, int tid, int nt, do
 #pragma unroll
                     for (int b2 = 0; b2 < 4; b2++) acc[a * 4 + b2] += li[a] * lk[b2];
             }
-            const int ib = r0 + 4 * ti, kb = r0 + 4 * tk;
 #pragma unroll
-            for (int a = 0; a < 4; a++) { const int i = ib + a; if (i <= n) { double *ri = ROW(i);
+            for (int a = 0; a < 4; a++) { const int i = ib + a; if (i <= n && FST(i) < r0) { double *ri = ROW(i);
 #pragma unroll
-                for (int b2 = 0; b2 < 4; b2++) { const int k = kb + b2; if (k < n && k <= i) ri[k] -= acc[a * 4 + b2]; } } }
+                for (int b2 = 0; b2 < 4; b2++) { const int k = kb + b2; if (k < n && k <= i && FST(k) < r0) ri[k] -= acc[a * 4 + b2]; } } }
         }
         VIWB_SYNC();
     }
 #undef ROW
+#undef FST
     return true;
 }
 // back substitution L^T x = y (blocks of 8 from the bottom): every thread solves the 8x8 triangular block redundantly from
 // broadcast reads (no barrier between the block solve and the update), then all threads update the rows above.  One barrier
 // per block.  Result in y; xo is scratch of n doubles.
-VIWB_D void chol_backsolve_blocked(const double *L, double *y, const double *dinv, double *xo, int n, int tid, int nt) {
+VIWB_D void chol_backsolve_blocked(const double *L, const int *rp, const int *fst, double *y, const double *dinv, double *xo, int n, int tid, int nt) {
     const int nblk = (n + CHOL_NB - 1) / CHOL_NB;
     for (int bi = nblk - 1; bi >= 0; bi--) {
         const int c0 = bi * CHOL_NB, nb = (n - c0) < CHOL_NB ? (n - c0) : CHOL_NB;
         double x[8];
-        const double *rp[8];                 // start of the block's rows at column c0 (running offsets: no per-access index products)
-        {
-            const double *r = L + (size_t)c0 * (c0 + 1) / 2 + c0;
+        const double *rw[8]; int fr[8];              // the block's skyline rows and their first columns
 #pragma unroll
-            for (int m = 0; m < 8; m++) { rp[m] = r; r += c0 + m + 1; }
-        }
+        for (int m = 0; m < 8; m++) { const int r = (m < nb) ? c0 + m : c0; rw[m] = L + rp[r] - fst[r]; fr[m] = fst[r]; }
 #pragma unroll
         for (int k = 7; k >= 0; k--) {
             x[k] = 0.0;
             if (k < nb) {
                 double v = y[c0 + k];
 #pragma unroll
-                for (int m = 7; m > k; m--) if (m < nb) v -= rp[m][k] * x[m];
+                for (int m = 7; m > k; m--) if (m < nb && c0 + k >= fr[m]) v -= rw[m][c0 + k] * x[m];
                 x[k] = v * dinv[c0 + k];
             }
         }
@@ -290,7 +302,7 @@ VIWB_D void chol_backsolve_blocked(const double *L, double *y, const double *din
         for (int i = tid; i < c0; i += nt) {
             double v = y[i];
 #pragma unroll
-            for (int k = 0; k < 8; k++) if (k < nb) v -= rp[k][i - c0] * x[k];
+            for (int k = 0; k < 8; k++) if (k < nb && i >= fr[k]) v -= rw[k][i] * x[k];
             y[i] = v;
         }
         VIWB_SYNC();
@@ -319,8 +331,10 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
     WinWork &ww = bd.work[w];
     if (ww.status != ST_RUNNING) return;
     const Opts &op = bd.opt;
-    SolveSmem s; carve(s, smem, nt);
+    SolveSmem s; carve(s, smem, nt, bd.env_max);
     const int nf = m.nf, N = m.nlm, vo = vec_off(bd, w);
+    for (int i = tid; i < nf; i += nt) s.fst[i] = m.efirst[i];
+    if (tid == 0) { int acc = 0; for (int i = 0; i < nf; i++) { s.rp[i] = acc; acc += i - m.efirst[i] + 1; } s.rp[nf] = acc; }
     double *x = bd.x_cur + m.state_off, *xc = bd.x_cand + m.state_off;
     double *g_scale = bd.v_scale + vo, *g_D = bd.v_D + vo, *g_sg = bd.v_sgrad + vo, *g_gn = bd.v_gn + vo;
     const double *lm_a = bd.lm_a + m.lm_off, *lm_g = bd.lm_g + m.lm_off, *lm_gamma = bd.lm_gamma + m.lm_off, *lm_sc = bd.lm_scale + m.lm_off;
@@ -400,7 +414,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
             if (!assembled) { assemble_H(bd, w, s, nf, Hpk, gpk, tid, nt); assembled = true; }
             else { load_H(Hpk, s, nf, tid, nt); for (int i = tid; i < nf; i += nt) s.g[i] = gpk[i]; VIWB_SYNC(); }
             if (ww.first) {
-                for (int i = tid; i < nf; i += nt) g_scale[i] = op.jacobi_scaling ? 1.0 / (1.0 + sqrt(s.L[pidx(i, i)])) : 1.0;
+                for (int i = tid; i < nf; i += nt) g_scale[i] = op.jacobi_scaling ? 1.0 / (1.0 + sqrt(SKY(s, i, i))) : 1.0;
             }
             VIWB_SYNC();
             for (int i = tid; i < nf; i += nt) s.sc[i] = g_scale[i];
@@ -421,7 +435,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
             // D = sqrt(clamp(diag(J_s^T J_s))), scaled gradient, Cauchy direction u_g = c o (sgrad / D)
             double n2 = 0.0;
             for (int i = tid; i < nf; i += nt) {
-                double d2 = s.sc[i] * s.sc[i] * s.L[pidx(i, i)];
+                double d2 = s.sc[i] * s.sc[i] * SKY(s, i, i);
                 d2 = fmin(fmax(d2, op.min_lm_diagonal), op.max_lm_diagonal);
                 const double D = sqrt(d2); s.D[i] = D; g_D[i] = D;
                 const double sg = s.sc[i] * s.g[i] / D; s.sg[i] = sg; g_sg[i] = sg; n2 += sg * sg;
@@ -457,29 +471,33 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                 if (h_dirty) load_H(Hpk, s, nf, tid, nt);
                 const double mu = ww.mu;
                 const bool t_ok = (mu == ww.mu_lin);          // gamma / T / tvec were built for mu_lin
-                // S = C (H - T) C + mu D^2 ; rhs = C (g - tvec)     (element-parallel over the packed triangle)
-                const int ne = nf * (nf + 1) / 2;
-                for (int e = tid; e < ne + nf; e += nt) {
-                    if (e < ne) {
-                        int i, j; sym_unrank(e, i, j);
-                        const int vi = s.vmap[i], vj = s.vmap[j];
-                        double hij = s.L[e];
-                        if (vi >= 0 && vj >= 0) {
-                            if (t_ok) hij -= Tvis[vi * VSUB + vj];
-                            else {
-                                double t = 0.0;
-                                for (int k = 0; k < N; k++) {
-                                    const double c = lm_sc[k], sk = c * c * lm_a[k], Dk = g_D[TFIX + k];
-                                    t += (c * c / (sk + mu * Dk * Dk)) * W[(size_t)k * VSUB + vi] * W[(size_t)k * VSUB + vj];
+                // S = C (H - T) C + mu D^2 ; rhs = C (g - tvec)     (one warp per skyline row, lanes over its stored columns)
+                {
+                    const int Wd = nt < 32 ? nt : 32, nwp = nt / Wd, wid = tid / Wd, ln = tid % Wd;
+                    for (int i = wid; i < nf; i += nwp) {
+                        const int vi = s.vmap[i];
+                        double *ri = s.L + s.rp[i] - s.fst[i];
+                        for (int j = s.fst[i] + ln; j <= i; j += Wd) {
+                            const int vj = s.vmap[j];
+                            double hij = ri[j];
+                            if (vi >= 0 && vj >= 0) {
+                                if (t_ok) hij -= Tvis[vi * VSUB + vj];
+                                else {
+                                    double t = 0.0;
+                                    for (int k = 0; k < N; k++) {
+                                        const double c = lm_sc[k], sk = c * c * lm_a[k], Dk = g_D[TFIX + k];
+                                        t += (c * c / (sk + mu * Dk * Dk)) * W[(size_t)k * VSUB + vi] * W[(size_t)k * VSUB + vj];
+                                    }
+                                    hij -= t;
                                 }
-                                hij -= t;
                             }
+                            hij *= s.sc[i] * s.sc[j];
+                            if (i == j) hij += mu * s.D[i] * s.D[i];
+                            ri[j] = hij;
                         }
-                        hij *= s.sc[i] * s.sc[j];
-                        if (i == j) hij += mu * s.D[i] * s.D[i];
-                        s.L[e] = hij;
-                    } else {
-                        const int i = e - ne, vi = s.vmap[i];
+                    }
+                    for (int i = tid; i < nf; i += nt) {
+                        const int vi = s.vmap[i];
                         double r = s.g[i];
                         if (vi >= 0) {
                             if (t_ok) r -= tvec[vi];
@@ -491,9 +509,9 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                 VIWB_SYNC();
                 h_dirty = true;
                 if (tid == 0) ww.num_linear++;
-                bool ok = cholesky_packed_rhs(s.L, s.y, nf, tid, nt, s.chol, s.dinv, s.Pt);
+                bool ok = cholesky_packed_rhs(s.L, s.rp, s.fst, s.y, nf, tid, nt, s.chol, s.dinv, s.Pt);
                 if (ok) {
-                    chol_backsolve_blocked(s.L, s.y, s.dinv, s.xo, nf, tid, nt);
+                    chol_backsolve_blocked(s.L, s.rp, s.fst, s.y, s.dinv, s.xo, nf, tid, nt);
                     // back-substitute the inverse depths (scaled): y_k = (c g_k - c w_k . (C y_f)) / h_k
                     for (int i = tid; i < nf; i += nt) s.u[i] = s.sc[i] * s.y[i];
                     VIWB_SYNC();

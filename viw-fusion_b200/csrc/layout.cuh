@@ -56,6 +56,8 @@ struct WinMeta {        // read-only during a solve
     int mitem_off, nmitems, nmphases, mlist_off; // assembly items of the marginalisation linearisation (factors hosted in frame 0)
     int has_common;                     // any of ex0 / ex1 / td is an active column (solver); marginalisation always counts them
     short tcol[NB];     // compact column of fixed block b, -1 if constant / absent / unreferenced
+    short efirst[TFIX]; // envelope of the reduced system: first structurally non-zero column of compact row i (<= i)
+    int esize;          // number of stored entries = sum_i (i - efirst[i] + 1)
     unsigned char flags[NB], mask[NB];
     double G[3], S_vis[4], w_plane[3], huber;
 };
@@ -85,6 +87,7 @@ struct Opts {
 
 struct BatchDev {       // passed by value to every kernel
     int B, nvis_total, nlm_total, nimu_total, nwheel_total, nplane_total, nprior, nitems_solve, nitems_marg;
+    int env_max;            // largest esize over the batch (sizes the solve kernel's shared memory)
     int marg_nmax;          // largest prior dimension any window of the batch produces (sizes the eigen-solver's shared memory)
     int rec_stride_solve;   // VREC_COMPACT if no window of the batch has ex0/ex1/td active, else VREC (marginalisation always uses VREC)
     const WinMeta *meta;

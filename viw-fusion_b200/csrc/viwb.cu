@@ -95,7 +95,7 @@ DEF_KERNEL(asm_items_split, 128)
 #define SYRK_MINB 4
 #endif
 DEF_KERNEL2(syrk, 256, SYRK_MINB)
-DEF_KERNEL(solve, 512)
+DEF_KERNEL2(solve, 256, 2)
 DEF_KERNEL(reanchor, 32)
 DEF_KERNEL2(marg, 256, 3)
 DEF_KERNEL(outlier, 128)
@@ -237,13 +237,41 @@ static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, i
     for (int i = 0; i < p.num_wheel; i++) { const int a = p.wheel_frame_i[i], c = p.wheel_frame_j[i]; if (a < 0 || a > p.frame_count || c < 0 || c > p.frame_count) { lo.err = 4; return; } ref[a] = ref[c] = ref[BLK_EXW] = ref[BLK_SX] = ref[BLK_SY] = ref[BLK_SW] = ref[BLK_TDW] = true; }
     for (int i = 0; i < p.num_plane; i++) { const int a = p.plane_frame[i]; if (a < 0 || a > p.frame_count) { lo.err = 4; return; } ref[a] = ref[BLK_EXW] = ref[BLK_PR] = ref[BLK_PZ] = true; }
     // active blocks (Program::RemoveFixedBlocks) and compact columns
+    // Column order = elimination order of the dense Cholesky.  The speed-bias blocks come first, newest frame first: each couples
+    // only with its neighbour in the IMU chain and two poses, so the factor keeps a narrow profile there (a "skyline": row i is
+    // stored from its first structurally non-zero column efirst[i]; Cholesky never fills outside that envelope).
     int col = 0, amb = 0;
+    bool active[NB];
     for (int k = 0; k < NB; k++) {
         m.flags[k] = p.block_flags[k] & 3u; m.mask[k] = p.subset_mask[k];
-        const bool active = (p.block_flags[k] & VIWB_BLOCK_PRESENT) && !(p.block_flags[k] & VIWB_BLOCK_CONSTANT) && ref[k];
-        if (active) { m.tcol[k] = (short)col; col += blk_tsize(k); amb += blk_size(k); } else m.tcol[k] = -1;
+        active[k] = (p.block_flags[k] & VIWB_BLOCK_PRESENT) && !(p.block_flags[k] & VIWB_BLOCK_CONSTANT) && ref[k];
+        m.tcol[k] = -1;
     }
+    for (int f = VIWB_WINDOW_SIZE; f >= 0; f--) { const int k = BLK_SB0 + f; if (active[k]) { m.tcol[k] = (short)col; col += blk_tsize(k); amb += blk_size(k); } }
+    for (int k = 0; k < NB; k++) if (active[k] && m.tcol[k] < 0) { m.tcol[k] = (short)col; col += blk_tsize(k); amb += blk_size(k); }
     m.nf = col; m.namb = amb + p.num_landmarks;
+    {   // symbolic envelope: every factor makes the blocks it touches a clique
+        int first_blk[NB];
+        for (int k = 0; k < NB; k++) first_blk[k] = m.tcol[k];                 // the diagonal block itself
+        auto clique = [&](const int *blks, int n) {
+            int lo = TFIX;
+            for (int q = 0; q < n; q++) if (blks[q] >= 0 && m.tcol[blks[q]] >= 0 && m.tcol[blks[q]] < lo) lo = m.tcol[blks[q]];
+            for (int q = 0; q < n; q++) if (blks[q] >= 0 && m.tcol[blks[q]] >= 0 && lo < first_blk[blks[q]]) first_blk[blks[q]] = lo;
+        };
+        if (lo.has_prior) { int bl[NB]; for (int i = 0; i < p.prior->num_blocks; i++) bl[i] = p.prior->block_id[i]; clique(bl, p.prior->num_blocks); }
+        for (int i = 0; i < p.num_imu; i++) { const int a = p.imu_frame_i[i], c = p.imu_frame_j[i]; const int bl[4] = {a, BLK_SB0 + a, c, BLK_SB0 + c}; clique(bl, 4); }
+        for (int i = 0; i < p.num_wheel; i++) { const int bl[7] = {p.wheel_frame_i[i], p.wheel_frame_j[i], BLK_EXW, BLK_SX, BLK_SY, BLK_SW, BLK_TDW}; clique(bl, 7); }
+        for (int i = 0; i < p.num_plane; i++) { const int bl[4] = {p.plane_frame[i], BLK_EXW, BLK_PR, BLK_PZ}; clique(bl, 4); }
+        if (p.num_vis > 0) {       // after the landmark elimination the visual subspace (all observed poses, ex0, ex1, td) is dense
+            int bl[NFR + 3], n = 0;
+            for (int f = 0; f <= VIWB_WINDOW_SIZE; f++) if (ref[f]) bl[n++] = f;
+            bl[n++] = BLK_EX0; bl[n++] = BLK_EX1; bl[n++] = BLK_TD;
+            clique(bl, n);
+        }
+        int es = 0;
+        for (int k = 0; k < NB; k++) if (m.tcol[k] >= 0) for (int r = 0; r < blk_tsize(k); r++) { const int i = m.tcol[k] + r; m.efirst[i] = (short)first_blk[k]; es += i - first_blk[k] + 1; }
+        m.esize = es;
+    }
     m.has_common = (m.tcol[BLK_EX0] >= 0 || m.tcol[BLK_EX1] >= 0 || m.tcol[BLK_TD] >= 0) ? 1 : 0;
     // marginalisation plan (estimator.cpp:1666-1893)
     m.margin_flag = -1; out_mode = 2; lo.prior_n_out = 0;
@@ -416,6 +444,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     bd.nitems_solve = (int)nit_s; bd.nitems_marg = (int)nit_m;
     bd.rec_stride_solve = VREC_COMPACT;
     bd.marg_nmax = b->prior_nmax;
+    bd.env_max = 1; for (int w = 0; w < B; w++) bd.env_max = std::max(bd.env_max, b->meta[w].esize);
     for (int w = 0; w < B; w++) if (b->meta[w].has_common) bd.rec_stride_solve = VREC;
     b->total_state = nstate;
     // ---- placement (inputs first, then work arrays)
@@ -476,7 +505,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
 static int ensure_attrs(viwb_context *ctx) {
 #ifndef VIWB_HOST_EMU
     if (!ctx->attrs_set) {
-        CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(512) * 8)));
+        CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(256, TFIX * (TFIX + 1) / 2) * 8)));
         CK(cudaFuncSetAttribute(lin_vis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lin_vis_smem_doubles(128, VREC) * 8)));
         CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(256, 100) * 8)));
         ctx->attrs_set = true;
@@ -497,9 +526,9 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     CK(dev_d2d(bd.x_cur, bd.x_init, xs, st)); CK(dev_d2d(bd.x_cand, bd.x_init, xs, st));
     if (!(what & RUN_REANCHOR) || (what & RUN_SOLVE)) CK(dev_d2d(bd.x_before, bd.x_init, xs, st));
     CK(dev_d2d(bd.work, b->work_init_dev, sizeof(WinWork) * B, st));
-    const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(512), nt_marg = NT(256);
+    const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(256), nt_marg = NT(256);
     const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total * LM_ROLES + nt_lm - 1) / nt_lm;
-    const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve) * 8, sm_marg = marg_smem_doubles(nt_marg, bd.marg_nmax) * 8;
+    const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve, bd.env_max) * 8, sm_marg = marg_smem_doubles(nt_marg, bd.marg_nmax) * 8;
     // cost_only: the round after the last allowed iteration only decides accept / reject of the pending candidate (every window
     // still running is at max_num_iterations there, trust_region_minimizer.cc checks the iteration limit before the gradient),
     // so the partial sums and the Schur product of that linearisation would never be read
@@ -794,10 +823,13 @@ extern "C" int viwb_debug_normal_equations(viwb_context *ctx, const viwb_problem
     // formatting only: scatter the packed active triangle into the caller's fixed-layout arrays
     const WinMeta &m = b->meta[0];
     if (H) { memset(H, 0, sizeof(double) * TFIX * TFIX);
+        std::vector<int> rp(m.nf + 1, 0);
+        for (int i = 0; i < m.nf; i++) rp[i + 1] = rp[i] + i - m.efirst[i] + 1;      // skyline row pointers
         for (int ba = 0; ba < NB; ba++) for (int bb = 0; bb < NB; bb++) if (m.tcol[ba] >= 0 && m.tcol[bb] >= 0)
             for (int p = 0; p < blk_tsize(ba); p++) for (int q = 0; q < blk_tsize(bb); q++) {
-                const int ci = m.tcol[ba] + p, cj = m.tcol[bb] + q;
-                H[(blk_toff(ba) + p) * TFIX + blk_toff(bb) + q] = Hd[ci >= cj ? (size_t)ci * (ci + 1) / 2 + cj : (size_t)cj * (cj + 1) / 2 + ci];
+                int ci = m.tcol[ba] + p, cj = m.tcol[bb] + q;
+                if (ci < cj) std::swap(ci, cj);
+                H[(blk_toff(ba) + p) * TFIX + blk_toff(bb) + q] = cj >= m.efirst[ci] ? Hd[(size_t)rp[ci] - m.efirst[ci] + cj] : 0.0;   // outside the envelope: structural zero
             } }
     if (g) { memset(g, 0, sizeof(double) * TFIX); for (int ba = 0; ba < NB; ba++) if (m.tcol[ba] >= 0) for (int p = 0; p < blk_tsize(ba); p++) g[blk_toff(ba) + p] = gd[m.tcol[ba] + p]; }
     double c = ww[0].small_cost;
