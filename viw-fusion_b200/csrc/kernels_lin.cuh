@@ -79,19 +79,12 @@ VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, d
         if (mode == MODE_MARG && (fi != 0 || bd.meta[w].margin_flag != 0)) on = false;
     }
     act[tid] = on ? 1 : 0;
-    // the block's observation rows (12 doubles per factor) arrive as one coalesced stream through the tile as well
     const int nrec = (bd.nvis_total - bx * nt) < nt ? (bd.nvis_total - bx * nt) : nt;
-    {
-        const double *src = bd.vis_obs + (size_t)bx * nt * 12;
-        for (int e = tid; e < nrec * 12; e += nt) tile[(e / 12) * 13 + (e % 12)] = src[e];
-    }
-    VIWB_SYNC();
-    double obs[12];
-    for (int k = 0; k < 12; k++) obs[k] = tile[tid * 13 + k];
-    VIWB_SYNC();
     if (on) {
         const WinMeta &m = bd.meta[w];
         const double *x = eval_state(bd, w, mode);
+        double obs[12];
+        for (int k = 0; k < 12; k++) obs[k] = bd.vis_obs[(size_t)f * 12 + k];      // (staging these through the tile measured slower)
         const int lm = bd.vis_lm[f];
         VisOut o;
         vis_eval(bd.vis_type[f], obs, x + 7 * fi, x + 7 * bd.vis_fj[f], x + blk_off(BLK_EX0), x + blk_off(BLK_EX1),
