@@ -95,7 +95,10 @@ DEF_KERNEL(asm_items_split, 128)
 #define SYRK_MINB 4
 #endif
 DEF_KERNEL2(syrk, 256, SYRK_MINB)
-DEF_KERNEL2(solve, 256, 2)
+#ifndef SOLVE_NT
+#define SOLVE_NT 384
+#endif
+DEF_KERNEL2(solve, SOLVE_NT, 2)
 DEF_KERNEL(reanchor, 32)
 DEF_KERNEL2(marg, 256, 3)
 DEF_KERNEL(outlier, 128)
@@ -505,7 +508,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
 static int ensure_attrs(viwb_context *ctx) {
 #ifndef VIWB_HOST_EMU
     if (!ctx->attrs_set) {
-        CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(256, TFIX * (TFIX + 1) / 2) * 8)));
+        CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(SOLVE_NT, TFIX * (TFIX + 1) / 2) * 8)));
         CK(cudaFuncSetAttribute(lin_vis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lin_vis_smem_doubles(128, VREC) * 8)));
         CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(256, 100) * 8)));
         ctx->attrs_set = true;
@@ -526,7 +529,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     CK(dev_d2d(bd.x_cur, bd.x_init, xs, st)); CK(dev_d2d(bd.x_cand, bd.x_init, xs, st));
     if (!(what & RUN_REANCHOR) || (what & RUN_SOLVE)) CK(dev_d2d(bd.x_before, bd.x_init, xs, st));
     CK(dev_d2d(bd.work, b->work_init_dev, sizeof(WinWork) * B, st));
-    const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(256), nt_marg = NT(256);
+    const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(SOLVE_NT), nt_marg = NT(256);
     const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total * LM_ROLES + nt_lm - 1) / nt_lm;
     const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve, bd.env_max) * 8, sm_marg = marg_smem_doubles(nt_marg, bd.marg_nmax) * 8;
     // cost_only: the round after the last allowed iteration only decides accept / reject of the pending candidate (every window
