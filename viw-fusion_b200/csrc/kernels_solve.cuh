@@ -454,11 +454,13 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
             double q = 0.0, l = 0.0;
             for (int i = tid; i < nf; i += nt) { q += s.ug[i] * s.Hu[i]; l += s.g[i] * s.ug[i]; }
             VIWB_LM_LOOP(k, N) {
+                // the landmark's scalars are fetched (warp-uniform loads) before the dot product so that both latencies overlap
+                const double lsc = lm_sc[k], lsg = g_sg[TFIX + k], lD = g_D[TFIX + k], la = lm_a[k], lg = lm_g[k];
                 const double dw = warp_dot80(W + (size_t)k * VSUB, s.uvis, lane);
                 if (lane == 0) {
-                    const double ul = lm_sc[k] * g_sg[TFIX + k] / g_D[TFIX + k];
-                    q += 2.0 * ul * dw + lm_a[k] * ul * ul;
-                    l += lm_g[k] * ul;
+                    const double ul = lsc * lsg / lD;
+                    q += 2.0 * ul * dw + la * ul * ul;
+                    l += lg * ul;
                 }
             }
             { double v2[2] = {q, l}; block_sum_n<2>(v2, tid, nt, s.red); q = v2[0]; l = v2[1]; }
@@ -519,10 +521,11 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                     double bad = 0.0;
                     for (int i = tid; i < nf; i += nt) { if (!isfinite(s.y[i])) bad = 1.0; g_gn[i] = -s.D[i] * s.y[i]; }
                     VIWB_LM_LOOP(k, N) {
+                        const double c = lm_sc[k], Dk = g_D[TFIX + k], la = lm_a[k], lg = lm_g[k];
                         const double dw = warp_dot80(W + (size_t)k * VSUB, s.uvis, lane);
                         if (lane == 0) {
-                            const double c = lm_sc[k], Dk = g_D[TFIX + k], hk = c * c * lm_a[k] + mu * Dk * Dk;
-                            const double yk = c * (lm_g[k] - dw) / hk;
+                            const double hk = c * c * la + mu * Dk * Dk;
+                            const double yk = c * (lg - dw) / hk;
                             if (!isfinite(yk)) bad = 1.0;
                             g_gn[TFIX + k] = -Dk * yk;
                         }
@@ -549,14 +552,14 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                     nn += g_gn[i] * g_gn[i]; gd += s.sg[i] * g_gn[i];
                 }
                 VIWB_LM_LOOP(k, N) {
+                    const double c = lm_sc[k], Dk = g_D[TFIX + k], ggn = g_gn[TFIX + k], gsg = g_sg[TFIX + k], la = lm_a[k], lg = lm_g[k];
                     const double dn = warp_dot80(W + (size_t)k * VSUB, s.uvis, lane), dg = warp_dot80(W + (size_t)k * VSUB, s.uvis + VSUB, lane);
                     if (lane == 0) {
-                        const double c = lm_sc[k], Dk = g_D[TFIX + k];
-                        const double un = c * g_gn[TFIX + k] / Dk, ug = c * g_sg[TFIX + k] / Dk;
-                        qnn += 2.0 * un * dn + lm_a[k] * un * un;
-                        qgn += ug * dn + un * dg + lm_a[k] * ug * un;
-                        ln += lm_g[k] * un;
-                        nn += g_gn[TFIX + k] * g_gn[TFIX + k]; gd += g_sg[TFIX + k] * g_gn[TFIX + k];
+                        const double un = c * ggn / Dk, ug = c * gsg / Dk;
+                        qnn += 2.0 * un * dn + la * un * un;
+                        qgn += ug * dn + un * dg + la * ug * un;
+                        ln += lg * un;
+                        nn += ggn * ggn; gd += gsg * ggn;
                     }
                 }
                 { double v5[5] = {qnn, qgn, ln, nn, gd}; block_sum_n<5>(v5, tid, nt, s.red); qnn = v5[0]; qgn = v5[1]; ln = v5[2]; nn = v5[3]; gd = v5[4]; }
