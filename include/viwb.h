@@ -360,6 +360,37 @@ int viwb_lk_batch_download(viwb_lk_batch *b, float *cur_pts, uint8_t *status, fl
 /* compulsory HBM bytes of one viwb_lk_batch_run (new images read once, coarser levels written once, points) */
 double viwb_lk_batch_algorithmic_bytes(const viwb_lk_batch *b);
 
+/* ---- feature detection: the rest of FeatureTracker::trackImage() between the LK calls ----------------
+ * viwb_set_mask = FeatureTracker::setMask() (feature_tracker.cpp:59-89): visit the tracked points by descending track count,
+ * keep a point iff the mask is still 255 under its rounded position, blank a filled circle of radius MIN_DIST around every
+ * kept point.  keep[] receives the surviving indices in visiting order (the order cur_pts / ids / track_cnt are rebuilt in);
+ * base_mask (NULL = white) is the FISHEYE mask the reference clones at :62; mask_out (may be NULL) is the [height][width] result.
+ * Points with equal track counts are visited in their original order (std::sort leaves that order unspecified). */
+int viwb_set_mask(viwb_context *ctx, int width, int height, const float *pts, const int32_t *track_cnt, int n, int min_dist,
+                  const uint8_t *base_mask, uint8_t *mask_out, int32_t *keep, int32_t *n_keep);
+/* cv::goodFeaturesToTrack(image, corners, maxCorners, qualityLevel, minDistance, mask) with blockSize 3, gradientSize 3 and
+ * the minimum-eigenvalue measure, the call of feature_tracker.cpp:192.  corners: [capacity][2] floats (capacity <= 1024);
+ * max_corners <= 0 means "all" (still bounded by capacity). */
+int viwb_good_features_to_track(viwb_context *ctx, const uint8_t *image, int width, int height, int stride, int max_corners,
+                                double quality_level, double min_distance, const uint8_t *mask, int mask_stride,
+                                float *corners, int capacity, int32_t *n_corners);
+/* Batched detector: one camera tick of `streams` independent sessions per submission -- setMask over each stream's tracked
+ * points, then goodFeaturesToTrack for the max_cnt - n_keep corners that are missing (feature_tracker.cpp:175-200).
+ * images: `streams` host image pointers, or NULL to detect on the current left images that `resident` (a viwb_lk_batch of the
+ * same geometry) already holds in HBM.  pts [streams][max_pts][2], track_cnt [streams][max_pts], n_pts [streams];
+ * keep [streams][max_pts] / n_keep [streams]; new_pts [streams][max_pts][2] / n_new [streams]; mask_out NULL or
+ * [streams][height][width]; base_masks NULL or `streams` pointers to [height][width] fisheye masks. */
+typedef struct viwb_detector viwb_detector;
+int viwb_detector_create(viwb_context *ctx, int streams, int width, int height, int max_pts, int min_dist /* MIN_DIST */,
+                         viwb_detector **out);
+void viwb_detector_destroy(viwb_detector *d);
+int viwb_detector_detect(viwb_detector *d, const uint8_t *const *images, int stride, const viwb_lk_batch *resident,
+                         const uint8_t *const *base_masks, const float *pts, const int32_t *track_cnt, const int32_t *n_pts,
+                         int max_cnt /* MAX_CNT */, double quality_level, int32_t *keep, int32_t *n_keep, float *new_pts,
+                         int32_t *n_new, uint8_t *mask_out);
+/* compulsory HBM bytes of one viwb_detector_detect: every stream's image read once, the points in, the corners out */
+double viwb_detector_algorithmic_bytes(const viwb_detector *d);
+
 /* Page-lock / unlock caller-owned host memory (camera frame buffers) for asynchronous full-rate uploads. */
 int viwb_host_register(viwb_context *ctx, void *ptr, size_t bytes);
 int viwb_host_unregister(viwb_context *ctx, void *ptr);

@@ -595,3 +595,96 @@ def check_undistort_velocity(ctx):
     assert np.abs(vel - ref_vel).max() <= 1e-5
     un0, vel0 = ctx.undistort_velocity((fx, fy, cx, cy, 0, 0, 0, 0), pts, None, None, dt)
     assert np.abs(un0[:, 0] - ((pts[:, 0].astype(np.float64) - cx) / fx).astype(np.float32)).max() <= 2e-7 and not vel0.any()
+
+
+# ------------------------------------------------------------------------------------------------ feature detection
+def _tracked_points(rng, w, h, n, cap):
+    pts = np.zeros((cap, 2), np.float32)
+    pts[:n] = np.column_stack([rng.uniform(1, w - 2, n), rng.uniform(1, h - 2, n)])
+    cnt = np.zeros(cap, np.int32)
+    cnt[:n] = rng.integers(1, 15, n)
+    return pts, cnt
+
+
+def check_set_mask(ctx, w=752, h=480):
+    """viwb_set_mask against the restated loop of feature_tracker.cpp:59-89 (bit exact: mask bytes and survivor order)."""
+    import feature_oracle as fo
+    rng = np.random.default_rng(11)
+    for n, md, with_base in [(180, 30, False), (40, 30, True), (0, 30, False), (300, 7, False), (120, 1, False)]:
+        pts, cnt = _tracked_points(rng, w, h, n, max(n, 1))
+        base = None
+        if with_base:
+            base = np.full((h, w), 255, np.uint8)
+            base[:, : w // 5] = 0; base[h - 40:, :] = 128          # a fisheye-style mask: only 255 counts as free (== 255 test, :81)
+        m0, k0 = fo.set_mask(w, h, pts[:n], cnt[:n], md, base)
+        m1, k1 = ctx.set_mask(w, h, pts[:n], cnt[:n], md, base)
+        assert np.array_equal(k0, k1), (n, md)
+        assert np.array_equal(m0, m1), (n, md)
+
+
+def check_good_features(ctx, full=True):
+    """viwb_good_features_to_track against the oracle (itself bit-exact with cv2's scalar path): identical corner lists."""
+    import feature_oracle as fo
+    rng = np.random.default_rng(12)
+    cases = [(480, 752, 150, 30.0, True), (480, 752, 60, 30.0, False), (480, 752, 0, 30.0, True), (120, 161, 500, 7.5, False), (67, 90, 40, 0.5, True), (33, 47, 10, 3.0, False)]
+    for k, (h, w, mc, md, use_mask) in enumerate(cases if full else cases[3:]):
+        img = synth.texture_image(h, w, 20 + k)
+        mask = None
+        if use_mask:
+            mask = np.full((h, w), 255, np.uint8)
+            for _ in range(max(2, w * h // 4000)):
+                fo.paint_circle(mask, int(rng.integers(0, w)), int(rng.integers(0, h)), 30 if w > 400 else 9)
+        ref = fo.good_features_to_track(img, mc, 0.01, md, mask)
+        got = ctx.good_features_to_track(img, mc, 0.01, md, mask, capacity=1024)
+        assert ref.shape == got.shape and np.array_equal(ref, got), (h, w, mc, md, len(ref), len(got))
+    # a non-contiguous row stride and an all-zero mask
+    big = synth.texture_image(100, 200, 3)
+    view = big[:, 10:150]
+    assert np.array_equal(fo.good_features_to_track(np.ascontiguousarray(view), 30, 0.01, 10.0), ctx.good_features_to_track(view, 30, 0.01, 10.0))
+    assert len(ctx.good_features_to_track(np.ascontiguousarray(view), 30, 0.01, 10.0, np.zeros(view.shape, np.uint8))) == 0
+    flat = np.full((64, 64), 77, np.uint8)
+    assert len(ctx.good_features_to_track(flat, 30, 0.01, 10.0)) == 0
+
+
+def check_detector_batch(ctx, streams=3, w=752, h=480, max_cnt=150, min_dist=30):
+    """viwb_detector_detect (setMask + goodFeaturesToTrack chained on the device for several streams) against the oracle chain."""
+    import feature_oracle as fo
+    rng = np.random.default_rng(13)
+    cap = 256
+    imgs = np.stack([synth.texture_image(h, w, 40 + f) for f in range(streams)])
+    pts, cnt, n = np.zeros((streams, cap, 2), np.float32), np.zeros((streams, cap), np.int32), np.zeros(streams, np.int32)
+    for f in range(streams):
+        n[f] = [90, 0, 200][f % 3]
+        pts[f], cnt[f] = _tracked_points(rng, w, h, int(n[f]), cap)
+    det = ctx.detector(streams, w, h, cap, min_dist)
+    keep, n_keep, new_pts, n_new, mask = det.detect(imgs, pts, cnt, n, max_cnt, want_mask=True)
+    for f in range(streams):
+        m0, k0, c0 = fo.detect(imgs[f], pts[f, : n[f]], cnt[f, : n[f]], max_cnt, min_dist)
+        assert n_keep[f] == len(k0) and np.array_equal(keep[f, : n_keep[f]], k0), f
+        assert np.array_equal(mask[f], m0), f
+        assert n_new[f] == len(c0) and np.array_equal(new_pts[f, : n_new[f]], c0), (f, n_new[f], len(c0))
+        assert n_keep[f] + n_new[f] <= max(max_cnt, n_keep[f])
+    det.close()
+    return det
+
+
+def check_detector_resident(ctx, w=752, h=480):
+    """The detector reading the tracker's resident current images (no second upload) gives what it gives on host images."""
+    rng = np.random.default_rng(14)
+    F, cap = 2, 192
+    img0 = np.stack([synth.texture_image(h, w, 60 + f) for f in range(F)])
+    img1 = np.stack([np.roll(img0[f], (1, 2), axis=(0, 1)) for f in range(F)])
+    lb = ctx.lk_batch(F, w, h, cap, stereo=False, flow_back=True)
+    pts, cnt, n = np.zeros((F, cap, 2), np.float32), np.zeros((F, cap), np.int32), np.array([100, 30], np.int32)
+    for f in range(F):
+        pts[f], cnt[f] = _tracked_points(rng, w, h, int(n[f]), cap)
+    det = ctx.detector(F, w, h, cap, 30)
+    for tick, cur in enumerate([img1, img0, img1]):              # the tracker alternates its two left slots
+        lb.upload(prev=img0 if tick == 0 else None, cur=cur, prev_pts=pts, n_prev=n)
+        lb.run(); lb.download()
+        a = [x.copy() for x in det.detect(None, pts, cnt, n, 150, resident=lb)[:4]]
+        b = [x.copy() for x in det.detect(cur, pts, cnt, n, 150)[:4]]
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3]), tick
+        for f in range(F):
+            assert np.array_equal(a[0][f, : a[1][f]], b[0][f, : b[1][f]]) and np.array_equal(a[2][f, : a[3][f]], b[2][f, : b[3][f]]), (tick, f)
+    det.close(); lb.close()

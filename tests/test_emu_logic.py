@@ -96,3 +96,19 @@ def test_batch_properties_small(emu, oracle):
 
 def test_undistort_velocity(emu):
     pc.check_undistort_velocity(emu)
+
+
+def test_set_mask(emu):
+    pc.check_set_mask(emu)
+
+
+def test_good_features_to_track(emu):
+    pc.check_good_features(emu, full=False)           # the small images: the emulation runs every pixel on one host thread
+
+
+def test_detector_batch(emu):
+    pc.check_detector_batch(emu, streams=2)
+
+
+def test_detector_resident(emu):
+    pc.check_detector_resident(emu)

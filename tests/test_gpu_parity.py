@@ -137,3 +137,19 @@ def test_full_batch_properties(gpu_ctx, oracle):
 
 def test_undistort_velocity(gpu_ctx):
     pc.check_undistort_velocity(gpu_ctx)
+
+
+def test_set_mask(gpu_ctx):
+    pc.check_set_mask(gpu_ctx)
+
+
+def test_good_features_to_track(gpu_ctx):
+    pc.check_good_features(gpu_ctx)
+
+
+def test_detector_batch(gpu_ctx):
+    pc.check_detector_batch(gpu_ctx, streams=6)
+
+
+def test_detector_resident(gpu_ctx):
+    pc.check_detector_resident(gpu_ctx)

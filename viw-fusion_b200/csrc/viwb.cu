@@ -12,6 +12,7 @@
 #include "kernels_lk.cuh"
 #include "kernels_preint.cuh"
 #include "kernels_feat.cuh"
+#include "kernels_detect.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -121,6 +122,7 @@ struct viwb_context {
     bool attrs_set;
     Arena arena;
     struct viwb_lk_batch *lk1;      // one-stream LK state behind viwb_lk_track / viwb_track_checked
+    struct viwb_detector *det1;     // one-stream detector behind viwb_set_mask / viwb_good_features_to_track
 };
 
 static int fail(viwb_context *ctx, int code, const std::string &msg) { if (ctx) ctx->err = msg; return code; }
@@ -137,6 +139,7 @@ static inline void bind_device(const viwb_context *ctx) {
 #define CK(call) do { int e_ = (call); if (e_) return fail(ctx, VIWB_ERR_CUDA, std::string(#call) + ": " + dev_errstr(e_)); } while (0)
 
 #include "lk_host.inl"
+#include "detect_host.inl"
 
 // ====================================================================================== batch
 struct HostPrior { int valid, n, nb; int block_id[NB], block_idx[NB]; std::vector<double> x0, J, r; };
@@ -652,7 +655,7 @@ static void batch_free(viwb_context *ctx, viwb_batch *b) {
 extern "C" int viwb_create(int device, viwb_context **out) {
     if (!out) return VIWB_ERR_INVALID;
     viwb_context *ctx = new viwb_context();
-    ctx->device = device; ctx->launches = 0; ctx->attrs_set = false; ctx->stream = 0; ctx->lk1 = nullptr;
+    ctx->device = device; ctx->launches = 0; ctx->attrs_set = false; ctx->stream = 0; ctx->lk1 = nullptr; ctx->det1 = nullptr;
 #ifndef VIWB_HOST_EMU
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -666,6 +669,7 @@ extern "C" int viwb_create(int device, viwb_context **out) {
 extern "C" void viwb_destroy(viwb_context *ctx) {
     if (!ctx) return;
     lk_batch_free(ctx->lk1);
+    det_free(ctx->det1);
 #ifndef VIWB_HOST_EMU
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
 #endif
@@ -1159,6 +1163,31 @@ extern "C" int viwb_lk_batch_upload(viwb_lk_batch *b, const uint8_t *const *prev
 extern "C" int viwb_lk_batch_run(viwb_lk_batch *b) { return b ? lk_batch_execute(b, 3) : VIWB_ERR_INVALID; }
 extern "C" int viwb_lk_batch_download(viwb_lk_batch *b, float *cur_pts, uint8_t *status, float *right_pts, uint8_t *status_right) {
     return b ? lk_batch_fetch(b, cur_pts, status, right_pts, status_right) : VIWB_ERR_INVALID;
+}
+extern "C" int viwb_set_mask(viwb_context *ctx, int width, int height, const float *pts, const int32_t *track_cnt, int n, int min_dist,
+                             const uint8_t *base_mask, uint8_t *mask_out, int32_t *keep, int32_t *n_keep) {
+    if (!ctx) return VIWB_ERR_INVALID;
+    return det_set_mask(ctx, width, height, pts, track_cnt, n, min_dist, base_mask, mask_out, keep, n_keep);
+}
+extern "C" int viwb_good_features_to_track(viwb_context *ctx, const uint8_t *image, int width, int height, int stride, int max_corners, double quality_level,
+                                           double min_distance, const uint8_t *mask, int mask_stride, float *corners, int capacity, int32_t *n_corners) {
+    if (!ctx || stride < width || (mask && mask_stride < width)) return VIWB_ERR_INVALID;
+    return det_good_features(ctx, image, width, height, stride, max_corners, quality_level, min_distance, mask, mask_stride, corners, capacity, n_corners);
+}
+extern "C" int viwb_detector_create(viwb_context *ctx, int streams, int width, int height, int max_pts, int min_dist, viwb_detector **out) {
+    if (!ctx || !out) return VIWB_ERR_INVALID;
+    return det_build(ctx, streams, width, height, max_pts, (double)min_dist, out);
+}
+extern "C" void viwb_detector_destroy(viwb_detector *d) { det_free(d); }
+extern "C" int viwb_detector_detect(viwb_detector *d, const uint8_t *const *images, int stride, const viwb_lk_batch *resident, const uint8_t *const *base_masks,
+                                    const float *pts, const int32_t *track_cnt, const int32_t *n_pts, int max_cnt, double quality_level,
+                                    int32_t *keep, int32_t *n_keep, float *new_pts, int32_t *n_new, uint8_t *mask_out) {
+    if (!d || !pts || !track_cnt || !n_pts || !keep || !n_keep || !new_pts || !n_new || (images && stride < d->w) || !(quality_level > 0.0)) return VIWB_ERR_INVALID;
+    return det_detect(d, images, stride, resident, base_masks, pts, track_cnt, n_pts, max_cnt, quality_level, keep, n_keep, new_pts, n_new, mask_out);
+}
+extern "C" double viwb_detector_algorithmic_bytes(const viwb_detector *d) {
+    if (!d) return 0.0;
+    return (double)d->F * ((double)d->w * d->h + (double)d->maxn * (8 + 4 + 4 + 8));
 }
 extern "C" double viwb_lk_batch_algorithmic_bytes(const viwb_lk_batch *b) {
     if (!b) return 0.0;

@@ -20,7 +20,8 @@ EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", 
            "viwb_batch_run", "viwb_batch_download", "viwb_batch_algorithmic_bytes", "viwb_batch_destroy",
            "viwb_debug_normal_equations", "viwb_lk_track", "viwb_track_checked", "viwb_lk_batch_create", "viwb_lk_batch_destroy",
            "viwb_lk_batch_upload", "viwb_lk_batch_run", "viwb_lk_batch_download", "viwb_lk_batch_algorithmic_bytes", "viwb_host_register",
-           "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate", "viwb_outlier_rejection", "viwb_batch_outliers", "viwb_triangulate", "viwb_shift_depth", "viwb_undistort_velocity"]
+           "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate", "viwb_outlier_rejection", "viwb_batch_outliers", "viwb_triangulate", "viwb_shift_depth", "viwb_undistort_velocity",
+           "viwb_set_mask", "viwb_good_features_to_track", "viwb_detector_create", "viwb_detector_destroy", "viwb_detector_detect", "viwb_detector_algorithmic_bytes"]
 
 
 class ViwbError(RuntimeError):
@@ -37,6 +38,9 @@ def load(libpath=None):
     lib.viwb_batch_algorithmic_bytes.restype = C.c_double
     lib.viwb_lk_batch_algorithmic_bytes.restype = C.c_double
     lib.viwb_lk_batch_algorithmic_bytes.argtypes = [C.c_void_p]
+    lib.viwb_detector_algorithmic_bytes.restype = C.c_double
+    lib.viwb_detector_algorithmic_bytes.argtypes = [C.c_void_p]
+    lib.viwb_detector_destroy.argtypes = [C.c_void_p]
     lib.viwb_lk_batch_destroy.argtypes = [C.c_void_p]
     lib.viwb_lk_batch_destroy.restype = None
     return lib
@@ -295,6 +299,34 @@ class Context:
         self._ck(self.lib.viwb_wheel_preintegrate(self.h, C.c_int(n), vp(counts), vp(dt), vp(v), vp(g), vp(s), vp(td), vp(nz), vp(rec)), "viwb_wheel_preintegrate")
         return rec
 
+    def set_mask(self, width, height, pts, track_cnt, min_dist, base_mask=None, want_mask=True):
+        """FeatureTracker::setMask(): returns (mask uint8 [height, width] or None, surviving indices in visiting order)"""
+        p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        c = np.ascontiguousarray(track_cnt, np.int32)
+        n = len(p)
+        keep, nk = np.zeros(max(n, 1), np.int32), C.c_int(0)
+        mask = np.zeros((height, width), np.uint8) if want_mask else None
+        bm = None if base_mask is None else np.ascontiguousarray(base_mask, np.uint8)
+        vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.viwb_set_mask(self.h, C.c_int(width), C.c_int(height), vp(p), vp(c), C.c_int(n), C.c_int(int(min_dist)), vp(bm), vp(mask), vp(keep), C.byref(nk)),
+                 "viwb_set_mask")
+        return mask, keep[: nk.value].copy()
+
+    def good_features_to_track(self, img, max_corners, quality, min_dist, mask=None, capacity=None):
+        """cv2.goodFeaturesToTrack(img, max_corners, quality, min_dist, mask=mask) -> float32 (n, 2)"""
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        h, w = img.shape
+        cap = capacity or (max_corners if max_corners > 0 else 1024)
+        out, n = np.zeros((cap, 2), np.float32), C.c_int(0)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.viwb_good_features_to_track(self.h, vp(img), C.c_int(w), C.c_int(h), C.c_int(img.strides[0]), C.c_int(max_corners), C.c_double(quality),
+                                                      C.c_double(min_dist), vp(m), C.c_int(w), vp(out), C.c_int(cap), C.byref(n)), "viwb_good_features_to_track")
+        return out[: n.value].copy()
+
+    def detector(self, streams, width, height, max_pts, min_dist):
+        return Detector(self, streams, width, height, max_pts, min_dist)
+
     def lk_batch(self, streams, width, height, max_points, stereo=True, flow_back=True):
         return LkBatch(self, streams, width, height, max_points, stereo, flow_back)
 
@@ -303,6 +335,49 @@ class Context:
 
     def host_unregister(self, arr):
         self._ck(self.lib.viwb_host_unregister(self.h, C.c_void_p(arr.ctypes.data)), "viwb_host_unregister")
+
+
+class Detector:
+    """setMask + goodFeaturesToTrack for `streams` sessions per submission (viwb_detector_*).
+    images: uint8 [streams, height, width] host array, or None with resident=<LkBatch> to use the tracker's current left images."""
+
+    def __init__(self, ctx, streams, width, height, max_pts, min_dist):
+        self.ctx, self.F, self.w, self.h, self.maxn = ctx, streams, width, height, max_pts
+        self.hnd = C.c_void_p()
+        ctx._ck(ctx.lib.viwb_detector_create(ctx.h, C.c_int(streams), C.c_int(width), C.c_int(height), C.c_int(max_pts), C.c_int(int(min_dist)), C.byref(self.hnd)),
+                "viwb_detector_create")
+        self.keep = np.zeros((streams, max_pts), np.int32)
+        self.n_keep = np.zeros(streams, np.int32)
+        self.new_pts = np.zeros((streams, max_pts, 2), np.float32)
+        self.n_new = np.zeros(streams, np.int32)
+
+    def detect(self, images, pts, track_cnt, n_pts, max_cnt, quality=0.01, resident=None, base_masks=None, want_mask=False):
+        vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+        ip, stride = None, self.w
+        if images is not None:
+            assert images.dtype == np.uint8 and images.shape == (self.F, self.h, self.w) and images.strides[2] == 1
+            ip = (C.c_void_p * self.F)(*[images.ctypes.data + f * images.strides[0] for f in range(self.F)])
+            stride = int(images.strides[1])
+        bp = None
+        if base_masks is not None:
+            base_masks = np.ascontiguousarray(base_masks, np.uint8)
+            assert base_masks.shape == (self.F, self.h, self.w)
+            bp = (C.c_void_p * self.F)(*[base_masks.ctypes.data + f * base_masks.strides[0] for f in range(self.F)])
+        p = np.ascontiguousarray(pts, np.float32); c = np.ascontiguousarray(track_cnt, np.int32); n = np.ascontiguousarray(n_pts, np.int32)
+        assert p.shape == (self.F, self.maxn, 2) and c.shape == (self.F, self.maxn) and n.shape == (self.F,)
+        mask = np.zeros((self.F, self.h, self.w), np.uint8) if want_mask else None
+        self.ctx._ck(self.ctx.lib.viwb_detector_detect(self.hnd, ip, C.c_int(stride), resident.hnd if resident is not None else None, bp, vp(p), vp(c), vp(n),
+                                                       C.c_int(max_cnt), C.c_double(quality), vp(self.keep), vp(self.n_keep), vp(self.new_pts), vp(self.n_new), vp(mask)),
+                     "viwb_detector_detect")
+        return self.keep, self.n_keep, self.new_pts, self.n_new, mask
+
+    def algorithmic_bytes(self):
+        return float(self.ctx.lib.viwb_detector_algorithmic_bytes(self.hnd))
+
+    def close(self):
+        if self.hnd:
+            self.ctx.lib.viwb_detector_destroy(self.hnd)
+            self.hnd = C.c_void_p()
 
 
 class LkBatch:

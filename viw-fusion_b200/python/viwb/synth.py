@@ -511,3 +511,12 @@ def pose_errors(state_a, state_b, frames=abi.NUM_FRAMES):
         Ra, Rb = q_to_R(q_normalize(state_a[7 * i + 3: 7 * i + 7])), q_to_R(q_normalize(state_b[7 * i + 3: 7 * i + 7]))
         er = max(er, float(np.linalg.norm(so3_log(Ra.T @ Rb))))
     return ep, er
+
+
+def texture_image(h=480, w=752, seed=0):
+    """Band-limited noise texture (two octaves), 8-bit: the synthetic camera image the detector / tracker tests look at."""
+    from scipy import ndimage
+    rng = np.random.default_rng(7000 + seed)
+    t = ndimage.gaussian_filter(rng.normal(size=(h, w)).astype(np.float32), 2.0)
+    t += 0.5 * ndimage.gaussian_filter(rng.normal(size=(h, w)).astype(np.float32), 6.0)
+    return np.ascontiguousarray(((t - t.min()) / (t.max() - t.min()) * 255.0).astype(np.uint8))
