@@ -626,16 +626,18 @@ def check_good_features(ctx, full=True):
     """viwb_good_features_to_track against the oracle (itself bit-exact with cv2's scalar path): identical corner lists."""
     import feature_oracle as fo
     rng = np.random.default_rng(12)
-    cases = [(480, 752, 150, 30.0, True), (480, 752, 60, 30.0, False), (480, 752, 0, 30.0, True), (120, 161, 500, 7.5, False), (67, 90, 40, 0.5, True), (33, 47, 10, 3.0, False)]
-    for k, (h, w, mc, md, use_mask) in enumerate(cases if full else cases[3:]):
+    cases = [(480, 752, 150, 30.0, True, 0.01), (480, 752, 60, 30.0, False, 0.01), (480, 752, 0, 30.0, True, 0.01),
+             (480, 752, 400, 6.0, False, 1e-5),          # > 8192 candidates above the threshold: the in-place global-memory sort
+             (120, 161, 500, 7.5, False, 0.01), (67, 90, 40, 0.5, True, 0.01), (33, 47, 10, 3.0, False, 0.01)]
+    for k, (h, w, mc, md, use_mask, ql) in enumerate(cases if full else cases[3:]):
         img = synth.texture_image(h, w, 20 + k)
         mask = None
         if use_mask:
             mask = np.full((h, w), 255, np.uint8)
             for _ in range(max(2, w * h // 4000)):
                 fo.paint_circle(mask, int(rng.integers(0, w)), int(rng.integers(0, h)), 30 if w > 400 else 9)
-        ref = fo.good_features_to_track(img, mc, 0.01, md, mask)
-        got = ctx.good_features_to_track(img, mc, 0.01, md, mask, capacity=1024)
+        ref = fo.good_features_to_track(img, mc, ql, md, mask)
+        got = ctx.good_features_to_track(img, mc, ql, md, mask, capacity=1024)
         assert ref.shape == got.shape and np.array_equal(ref, got), (h, w, mc, md, len(ref), len(got))
     # a non-contiguous row stride and an all-zero mask
     big = synth.texture_image(100, 200, 3)

@@ -1,6 +1,6 @@
 // detect_host.inl -- host side of the feature detector (kernels_detect.cuh), included by viwb.cu after lk_host.inl.
-// viwb_detector = device state of F camera streams: mask, eigenvalue image, candidate list, cell grid, tracked points in,
-// surviving indices + new corners out, and the per-stream task table the five kernels index.
+// viwb_detector = device state of F camera streams: mask, candidate list, cell grid, tracked points in,
+// surviving indices + new corners out, and the per-stream task table the four kernels index.
 
 #ifdef VIWB_HOST_EMU
 static void det_launch_order(const DetRun &r, int F, stream_t) { std::vector<int> order(DET_MAXPTS); for (int f = 0; f < F; f++) det_order_warp(r.tasks[f], r, 0, 1, order.data()); }
@@ -8,22 +8,23 @@ static void det_launch_mask(const DetRun &r, int F, int h, stream_t) {
     std::vector<short> nx(2 * DET_MAXPTS); int nn = 0;
     for (int f = 0; f < F; f++) for (int b = 0; b < (h + DET_BAND - 1) / DET_BAND; b++) det_mask_band(r.tasks[f], r, b, 0, 1, nx.data(), &nn);
 }
-static void det_launch_eig(const DetRun &r, int F, int w, int h, stream_t) {
-    std::vector<float> sm(det_eig_smem_floats());
-    const int tx = (w + DET_TW - 1) / DET_TW, ty = (h + DET_TH - 1) / DET_TH;
-    for (int f = 0; f < F; f++) for (int t = 0; t < tx * ty; t++) det_eig_tile(r.tasks[f], r, t % tx, t / tx, 0, 1, sm.data());
+static void det_launch_corners(const DetRun &r, int F, int w, int h, stream_t) {
+    std::vector<double> sm(det_tile_smem_bytes() / 8 + 1);
+    const int tx = (w + DET_OW - 1) / DET_OW, ty = (h + DET_OH - 1) / DET_OH;
+    for (int f = 0; f < F; f++) for (int t = 0; t < tx * ty; t++) det_corner_tile(r.tasks[f], r, t % tx, t / tx, 0, 1, (unsigned char *)sm.data());
 }
-static void det_launch_candidates(const DetRun &r, int F, int w, int h, stream_t) { for (int f = 0; f < F; f++) for (int i = 0; i < (w - 2) * (h - 2); i++) det_candidate_item(r.tasks[f], r, i); }
-static void det_launch_select(const DetRun &r, int F, stream_t) { std::vector<unsigned char> sm(det_select_smem_bytes()); for (int f = 0; f < F; f++) det_select_block(r.tasks[f], r, 0, 1, sm.data()); }
+static void det_launch_select(const DetRun &r, int F, stream_t) {
+    std::vector<double> sm(det_select_smem_bytes() / 8 + 1); int counter[2];
+    for (int f = 0; f < F; f++) det_select_block(r.tasks[f], r, 0, 1, (unsigned char *)sm.data(), counter);
+}
 #else
 static void det_launch_order(const DetRun &r, int F, stream_t s) { g_prof.begin("det_order", s); det_order_kernel<<<F, 32, 0, s>>>(r); g_prof.end(s); }
 static void det_launch_mask(const DetRun &r, int F, int h, stream_t s) { g_prof.begin("det_mask", s); det_mask_kernel<<<dim3((h + DET_BAND - 1) / DET_BAND, F), 256, 0, s>>>(r); g_prof.end(s); }
-static void det_launch_eig(const DetRun &r, int F, int w, int h, stream_t s) {
-    const int tx = (w + DET_TW - 1) / DET_TW, ty = (h + DET_TH - 1) / DET_TH;
-    g_prof.begin("det_eig", s); det_eig_kernel<<<dim3(tx * ty, F), 256, det_eig_smem_floats() * sizeof(float), s>>>(r, tx); g_prof.end(s);
-}
-static void det_launch_candidates(const DetRun &r, int F, int w, int h, stream_t s) {
-    g_prof.begin("det_candidates", s); det_candidates_kernel<<<dim3(((w - 2) * (h - 2) + 255) / 256, F), 256, 0, s>>>(r); g_prof.end(s);
+static void det_launch_corners(const DetRun &r, int F, int w, int h, stream_t s) {
+    const int tx = (w + DET_OW - 1) / DET_OW, ty = (h + DET_OH - 1) / DET_OH;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(det_corners_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_tile_smem_bytes()); attr = true; }
+    g_prof.begin("det_corners", s); det_corners_kernel<<<dim3(tx * ty, F), DET_NT, det_tile_smem_bytes(), s>>>(r, tx); g_prof.end(s);
 }
 static void det_launch_select(const DetRun &r, int F, stream_t s) {
     static bool attr = false;
@@ -52,7 +53,7 @@ struct viwb_detector {
     int F, w, h, maxn, radius, cand_cap, gw, gh, cell;
     double min_dist;
     uint8_t *img, *mask, *base;            // [F][h][w] each (img only used when the caller hands host images)
-    float *eig, *pts, *corners;            // [F][h][w], [F][maxn][2], [F][maxn][2]
+    float *pts, *corners;                  // [F][maxn][2], [F][maxn][2]
     int *track_cnt, *keep, *counters;      // [F][maxn], [F][maxn], [DET_COUNTERS][F]
     short *hw, *kept_xy;                   // [radius+1], [F][maxn][2]
     unsigned long long *cand;              // [F][cand_cap]
@@ -64,7 +65,7 @@ struct viwb_detector {
 
 static void det_free(viwb_detector *d) {
     if (!d) return;
-    void *p[] = {d->img, d->mask, d->base, d->eig, d->pts, d->corners, d->track_cnt, d->keep, d->counters, d->hw, d->kept_xy, d->cand, d->grid, d->tasks};
+    void *p[] = {d->img, d->mask, d->base, d->pts, d->corners, d->track_cnt, d->keep, d->counters, d->hw, d->kept_xy, d->cand, d->grid, d->tasks};
     for (void *q : p) if (q) dev_free(q);
     delete d;
 }
@@ -81,7 +82,7 @@ static int det_write_tasks(viwb_detector *d, const viwb_lk_batch *lk) {
         a.pts = d->pts + (size_t)f * d->maxn * 2; a.track_cnt = d->track_cnt + (size_t)f * d->maxn; a.n_dev = d->counters + (size_t)DET_N_PTS * d->F + f;
         a.radius = d->radius; a.hw = d->hw;
         a.keep = d->keep + (size_t)f * d->maxn; a.n_keep = d->counters + (size_t)DET_N_KEEP * d->F + f; a.kept_xy = d->kept_xy + (size_t)f * d->maxn * 2;
-        a.mask = d->mask + px * f; a.eig = d->eig + px * f; a.maxbits = (unsigned *)(d->counters + (size_t)DET_MAXBITS * d->F + f);
+        a.mask = d->mask + px * f; a.maxbits = (unsigned *)(d->counters + (size_t)DET_MAXBITS * d->F + f);
         a.cand = d->cand + (size_t)f * d->cand_cap; a.cand_cap = d->cand_cap; a.n_cand = d->counters + (size_t)DET_N_CAND * d->F + f;
         a.grid = d->grid + cells * f; a.gw = d->gw; a.gh = d->gh; a.cell = d->cell;
         a.corners = d->corners + (size_t)f * d->maxn * 2; a.corner_cap = d->maxn; a.n_corners = d->counters + (size_t)DET_N_CORNERS * d->F + f;
@@ -106,7 +107,7 @@ static int det_build(viwb_context *ctx, int F, int w, int h, int maxn, double mi
     if (d->cand_cap < 1024) d->cand_cap = 1024;
     const size_t px = (size_t)w * h, cells = (size_t)d->gw * d->gh * DET_SLOTS;
 #define DTA(p, n) do { if (dev_malloc((void **)&(p), (n))) { det_free(d); return fail(ctx, VIWB_ERR_CUDA, "detector device allocation failed"); } d->bytes += (n); } while (0)
-    DTA(d->img, px * F); DTA(d->mask, px * F); DTA(d->base, px * F); DTA(d->eig, px * F * 4);
+    DTA(d->img, px * F); DTA(d->mask, px * F); DTA(d->base, px * F);
     DTA(d->pts, (size_t)F * maxn * 8); DTA(d->corners, (size_t)F * maxn * 8); DTA(d->track_cnt, (size_t)F * maxn * 4); DTA(d->keep, (size_t)F * maxn * 4);
     DTA(d->counters, (size_t)DET_COUNTERS * F * 4); DTA(d->hw, (size_t)(d->radius + 1) * 2); DTA(d->kept_xy, (size_t)F * maxn * 4);
     DTA(d->cand, (size_t)F * d->cand_cap * 8); DTA(d->grid, cells * F * 4); DTA(d->tasks, sizeof(DetArgs) * F);
@@ -151,9 +152,8 @@ static int det_detect(viwb_detector *d, const uint8_t *const *images, int stride
     DetRun run; memset(&run, 0, sizeof run);
     run.tasks = d->tasks; run.img_sel = want ? want->cur : 0; run.use_mask = 1; run.use_base = base_masks ? 1 : 0; run.tracker_mode = 1;
     run.max_cnt = max_cnt; run.quality = quality; run.min_dist = d->min_dist;
-    det_launch_order(run, d->F, st); det_launch_mask(run, d->F, d->h, st); det_launch_eig(run, d->F, d->w, d->h, st);
-    det_launch_candidates(run, d->F, d->w, d->h, st); det_launch_select(run, d->F, st);
-    ctx->launches += 5;
+    det_launch_order(run, d->F, st); det_launch_mask(run, d->F, d->h, st); det_launch_corners(run, d->F, d->w, d->h, st); det_launch_select(run, d->F, st);
+    ctx->launches += 4;
     CK(dev_d2h(keep, d->keep, np * 4, st)); CK(dev_d2h(n_keep, d->counters + (size_t)DET_N_KEEP * d->F, (size_t)d->F * 4, st));
     CK(dev_d2h(new_pts, d->corners, np * 8, st)); CK(dev_d2h(n_new, d->counters + (size_t)DET_N_CORNERS * d->F, (size_t)d->F * 4, st));
     if (mask_out) CK(dev_d2h(mask_out, d->mask, (size_t)d->w * d->h * d->F, st));
@@ -189,8 +189,8 @@ static int det_good_features(viwb_context *ctx, const uint8_t *img, int w, int h
     CK(dev_h2d(d->counters, zero, sizeof zero, st));
     DetRun run; memset(&run, 0, sizeof run);
     run.tasks = d->tasks; run.use_mask = mask ? 1 : 0; run.max_corners = max_corners; run.corner_cap = capacity; run.quality = quality; run.min_dist = min_dist;
-    det_launch_eig(run, 1, w, h, st); det_launch_candidates(run, 1, w, h, st); det_launch_select(run, 1, st);
-    ctx->launches += 3;
+    det_launch_corners(run, 1, w, h, st); det_launch_select(run, 1, st);
+    ctx->launches += 2;
     int cnt = 0;
     CK(dev_d2h(&cnt, d->counters + DET_N_CORNERS, 4, st)); CK(dev_sync(st));
     if (cnt < 0) return fail(ctx, VIWB_ERR_INVALID, "goodFeaturesToTrack: candidate list overflow");

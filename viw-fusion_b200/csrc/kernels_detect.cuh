@@ -10,10 +10,10 @@
 // minimum-distance selection over a cell grid.  Every FP32 operation uses the round-to-nearest intrinsics so that nvcc cannot contract
 // a multiply-add: the results are the same bits as the scalar CPU code.
 //
-// Device layout (per camera stream): the image stays where the tracker put it; `mask` u8 [h][w], `eig` f32 [h][w], a candidate list
-// of 64-bit keys (ordered eigenvalue bits << 32 | pixel offset) and a cell grid with four packed (x | y << 16) slots per cell -- cells
-// are min_dist wide, so a cell can never hold more than four accepted corners.  Five launches cover every stream of a batch
-// (blockIdx.y / task index = stream): order -> mask -> eig -> candidates -> select.
+// Device layout (per camera stream): the image stays where the tracker put it; `mask` u8 [h][w], a candidate list of 64-bit keys
+// (ordered eigenvalue bits << 32 | pixel offset) and a cell grid with four packed (x | y << 16) slots per cell -- cells are min_dist
+// wide, so a cell can never hold more than four accepted corners.  The eigenvalue image itself is never written to HBM.  Four
+// launches cover every stream of a batch (blockIdx.y / task index = stream): order -> mask -> corners -> select.
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -21,7 +21,7 @@
 
 namespace viwb {
 
-enum { DET_TW = 64, DET_TH = 16, DET_SLOTS = 4, DET_SORT_SMEM = 8192, DET_GRID_SMEM = 1024, DET_BAND = 8, DET_MAXPTS = 1024 };
+enum { DET_SLOTS = 4, DET_SORT_SMEM = 8192, DET_GRID_SMEM = 1024, DET_BAND = 8, DET_MAXPTS = 1024 };
 
 struct DetArgs {                        // one camera stream
     const unsigned char *img[2];        // candidate image locations (the tracker's two alternating left slots); DetRun::img_sel picks one
@@ -31,7 +31,6 @@ struct DetArgs {                        // one camera stream
     int radius; const short *hw;        // MIN_DIST and the half widths of the filled circle's rows
     int *keep, *n_keep; short *kept_xy; // surviving point indices in visiting order, their rounded centres
     unsigned char *mask;                // [h][w]
-    float *eig;                         // [h][w]
     unsigned int *maxbits;              // masked maximum of eig (ordered-integer encoding)
     unsigned long long *cand; int cand_cap; int *n_cand;
     unsigned int *grid; int gw, gh, cell;
@@ -107,10 +106,18 @@ VIWB_D void det_order_warp(const DetArgs &a, const DetRun &run, int tid, int nt,
 // (cv::circle(mask, pt, MIN_DIST, 0, -1): midpoint circle, one run of 2*hw[|dy|]+1 pixels per row).
 VIWB_D void det_mask_band(const DetArgs &a, const DetRun &run, int band, int tid, int nt, short *near_xy, int *n_near) {
     const int y0 = band * DET_BAND, y1 = (y0 + DET_BAND < a.h) ? y0 + DET_BAND : a.h, r = a.radius, nk = *a.n_keep;
-    if (tid == 0) {
-        int m = 0;
-        for (int j = 0; j < nk; j++) { const int cy = a.kept_xy[2 * j + 1]; if (cy + r >= y0 && cy - r < y1) { near_xy[2 * m] = a.kept_xy[2 * j]; near_xy[2 * m + 1] = (short)cy; m++; } }
-        *n_near = m;
+    if (tid == 0) *n_near = 0;
+    VIWB_SYNC();
+    for (int j = tid; j < nk; j += nt) {                          // the circles that reach into this band (their order does not matter)
+        const int cy = a.kept_xy[2 * j + 1];
+        if (cy + r >= y0 && cy - r < y1) {
+#ifdef VIWB_HOST_EMU
+            const int m = (*n_near)++;
+#else
+            const int m = atomicAdd(n_near, 1);
+#endif
+            near_xy[2 * m] = a.kept_xy[2 * j]; near_xy[2 * m + 1] = (short)cy;
+        }
     }
     VIWB_SYNC();
     const int m = *n_near, words = (a.w + 3) / 4;
@@ -128,8 +135,18 @@ VIWB_D void det_mask_band(const DetArgs &a, const DetRun &run, int band, int tid
     }
 }
 
-// ------------------------------------------------------------------------------------------------------ cornerMinEigenVal
-VIWB_HD int det_eig_smem_floats() { return (DET_TH + 4) * (DET_TW + 4) + 3 * (DET_TH + 2) * (DET_TW + 2); }
+// ------------------------------------------------------------------ cornerMinEigenVal + local maxima, one pass over the image
+// A block owns a DET_OW x DET_OH patch of pixels.  It stages the source patch (+3 px halo, reflected), forms the derivative
+// products over the patch +2 px in FP64, box-sums them with a sliding window (each thread walks 4 rows of one column: row sums
+// (c0+c1)+c2, then (r0+r1)+r2, the order of a separable box filter), evaluates the eigenvalue over the patch +1 px, and then
+//   * folds the masked maximum of its own pixels into DetArgs::maxbits,
+//   * appends every 3x3 local maximum (non-zero, mask != 0, rows / columns 1..n-2) to the candidate list.
+// The eigenvalue image never goes to HBM.  Whether a pixel is a 3x3 maximum of the thresholded image does not depend on the
+// threshold once the pixel itself is above it, so the threshold (max * quality, known only after this pass) is applied to the
+// candidate list by det_select_block.
+enum { DET_OW = 62, DET_OH = 14, DET_EW = DET_OW + 2, DET_EH = DET_OH + 2, DET_CW = DET_OW + 4, DET_CH = DET_OH + 4, DET_SW = DET_OW + 6, DET_SH = DET_OH + 6,
+       DET_NT = DET_EW * (DET_EH / 4) };                              // 64 columns x 4 row groups = 256 threads
+VIWB_HD size_t det_tile_smem_bytes() { return (size_t)3 * DET_CH * DET_CW * 8 + (size_t)DET_SH * DET_SW * 4 + (size_t)DET_EH * DET_EW * 4; }
 VIWB_D void det_commit_max(unsigned *dst, unsigned enc) {
 #ifdef VIWB_HOST_EMU
     if (enc > *dst) *dst = enc;
@@ -138,75 +155,7 @@ VIWB_D void det_commit_max(unsigned *dst, unsigned enc) {
     if ((threadIdx.x & 31) == 0 && enc) atomicMax(dst, enc);
 #endif
 }
-VIWB_D void det_eig_tile(const DetArgs &a, const DetRun &run, int bx, int by, int tid, int nt, float *sm) {
-    const int SW = DET_TW + 4, CW = DET_TW + 2, x0 = bx * DET_TW, y0 = by * DET_TH, w = a.w, h = a.h;
-    const unsigned char *img = a.img[run.img_sel];
-    float *S = sm, *C0 = S + (DET_TH + 4) * SW, *C1 = C0 + (DET_TH + 2) * CW, *C2 = C1 + (DET_TH + 2) * CW;
-    const double scale = 1.0 / (4 * 3) / 255.0;                   // 1 / (2^(ksize-1) * blockSize * 255)
-    const float k1 = (float)scale, k2 = (float)(2.0 * scale);
-    for (int i = tid; i < (DET_TH + 4) * SW; i += nt) {
-        const int rr = i / SW, cc = i - rr * SW;
-        S[i] = (float)img[(size_t)det_reflect(y0 - 2 + rr, h) * a.stride + det_reflect(x0 - 2 + cc, w)];
-    }
-    VIWB_SYNC();
-    for (int i = tid; i < (DET_TH + 2) * CW; i += nt) {
-        const int rr = i / CW, cc = i - rr * CW;
-        // the box filter sees the product image reflected at the border: evaluate the derivatives at the reflected coordinate
-        const int sr = det_reflect(y0 - 1 + rr, h) - (y0 - 2), sc = det_reflect(x0 - 1 + cc, w) - (x0 - 2);
-        float xx = 0.f, xy = 0.f, yy = 0.f;
-        if (sr >= 1 && sr <= DET_TH + 2 && sc >= 1 && sc <= DET_TW + 2) {
-            const float *p0 = S + (sr - 1) * SW + sc, *p1 = p0 + SW, *p2 = p1 + SW;
-            const float r0 = det_sub(p0[1], p0[-1]), r1 = det_sub(p1[1], p1[-1]), r2 = det_sub(p2[1], p2[-1]);
-            const float dx = det_add(det_mul(k2, r1), det_mul(k1, det_add(r0, r2)));
-            const float s0 = det_add(det_add(det_mul(k1, p0[-1]), det_mul(k2, p0[0])), det_mul(k1, p0[1]));
-            const float s2 = det_add(det_add(det_mul(k1, p2[-1]), det_mul(k2, p2[0])), det_mul(k1, p2[1]));
-            const float dy = det_sub(s2, s0);
-            xx = det_mul(dx, dx); xy = det_mul(dx, dy); yy = det_mul(dy, dy);
-        }
-        C0[i] = xx; C1[i] = xy; C2[i] = yy;
-    }
-    VIWB_SYNC();
-    unsigned best = 0u;
-    for (int i = tid; i < DET_TH * DET_TW; i += nt) {
-        const int rr = i / DET_TW, cc = i - rr * DET_TW, y = y0 + rr, x = x0 + cc;
-        if (y >= h || x >= w) continue;
-        double sa = 0.0, sb = 0.0, sc2 = 0.0;
-        for (int dr = 0; dr < 3; dr++) for (int dc = 0; dc < 3; dc++) {
-            const int j = (rr + dr) * CW + cc + dc;
-            sa += (double)C0[j]; sb += (double)C1[j]; sc2 += (double)C2[j];
-        }
-        const float fa = det_mul((float)sa, 0.5f), fb = (float)sb, fc = det_mul((float)sc2, 0.5f), d = det_sub(fa, fc);
-        const float e = det_sub(det_add(fa, fc), det_sqrt(det_add(det_mul(d, d), det_mul(fb, fb))));
-        a.eig[(size_t)y * w + x] = e;
-        if (!run.use_mask || a.mask[(size_t)y * w + x]) { const unsigned enc = det_encode(e); if (enc > best) best = enc; }
-    }
-    det_commit_max(a.maxbits, best);
-}
-
-// -------------------------------------------------------------------------------------------- threshold + local maxima
-VIWB_D float det_threshold(const DetArgs &a, const DetRun &run) {
-    const unsigned mb = *a.maxbits;
-    const float mx = mb ? det_decode(mb) : 0.f;                    // minMaxLoc over an empty mask leaves 0
-    return (float)((double)mx * run.quality);
-}
-VIWB_D void det_candidate_item(const DetArgs &a, const DetRun &run, int idx) {
-    const int w = a.w, h = a.h, iw = w - 2, total = iw * (h - 2);
-    bool ok = idx < total;
-    unsigned long long key = 0ull;
-    if (ok) {
-        const int y = 1 + idx / iw, x = 1 + idx - (idx / iw) * iw;
-        const float thr = det_threshold(a, run);
-        const float *e = a.eig + (size_t)y * w + x;
-        const float v = e[0];
-        ok = v > thr && v != 0.f && (!run.use_mask || a.mask[(size_t)y * w + x]);
-        if (ok) {
-            for (int dy = -1; dy <= 1 && ok; dy++) for (int dx = -1; dx <= 1; dx++) {
-                const float nb = e[dy * w + dx];
-                if ((nb > thr ? nb : 0.f) > v) { ok = false; break; }
-            }
-            key = ((unsigned long long)det_encode(v) << 32) | (unsigned)(y * w + x);
-        }
-    }
+VIWB_D void det_append(const DetArgs &a, bool ok, unsigned long long key) {
 #ifdef VIWB_HOST_EMU
     if (ok) { const int pos = (*a.n_cand)++; if (pos < a.cand_cap) a.cand[pos] = key; }
 #else
@@ -220,6 +169,94 @@ VIWB_D void det_candidate_item(const DetArgs &a, const DetRun &run, int idx) {
         if (ok && pos < a.cand_cap) a.cand[pos] = key;
     }
 #endif
+}
+// stages 1 and 2 of a tile; INTERIOR = the patch and its 3 px halo lie inside the image, so no coordinate is reflected
+template <bool INTERIOR>
+VIWB_D void det_tile_products(const DetArgs &a, const unsigned char *img, int x0, int y0, int tid, int nt, float *S, double *C0, double *C1, double *C2) {
+    const int w = a.w, h = a.h;
+    const double scale = 1.0 / (4 * 3) / 255.0;                   // 1 / (2^(ksize-1) * blockSize * 255)
+    const float k1 = (float)scale, k2 = (float)(2.0 * scale);
+    for (int i = tid; i < DET_SH * DET_SW; i += nt) {             // source patch, origin (x0-3, y0-3)
+        const int rr = i / DET_SW, cc = i - rr * DET_SW;
+        const int y = INTERIOR ? y0 - 3 + rr : det_reflect(y0 - 3 + rr, h), x = INTERIOR ? x0 - 3 + cc : det_reflect(x0 - 3 + cc, w);
+        S[i] = (float)img[y * a.stride + x];
+    }
+    VIWB_SYNC();
+    for (int i = tid; i < DET_CH * DET_CW; i += nt) {             // derivative products, origin (x0-2, y0-2)
+        const int rr = i / DET_CW, cc = i - rr * DET_CW;
+        // the box filter sees the product image reflected at the border: evaluate the derivatives at the reflected coordinate
+        const int sr = INTERIOR ? rr + 1 : det_reflect(y0 - 2 + rr, h) - (y0 - 3), sc = INTERIOR ? cc + 1 : det_reflect(x0 - 2 + cc, w) - (x0 - 3);
+        float xx = 0.f, xy = 0.f, yy = 0.f;
+        if (INTERIOR || (sr >= 1 && sr <= DET_SH - 2 && sc >= 1 && sc <= DET_SW - 2)) {
+            const float *p0 = S + (sr - 1) * DET_SW + sc, *p1 = p0 + DET_SW, *p2 = p1 + DET_SW;
+            const float r0 = det_sub(p0[1], p0[-1]), r1 = det_sub(p1[1], p1[-1]), r2 = det_sub(p2[1], p2[-1]);
+            const float dx = det_add(det_mul(k2, r1), det_mul(k1, det_add(r0, r2)));
+            const float s0 = det_add(det_add(det_mul(k1, p0[-1]), det_mul(k2, p0[0])), det_mul(k1, p0[1]));
+            const float s2 = det_add(det_add(det_mul(k1, p2[-1]), det_mul(k2, p2[0])), det_mul(k1, p2[1]));
+            const float dy = det_sub(s2, s0);
+            xx = det_mul(dx, dx); xy = det_mul(dx, dy); yy = det_mul(dy, dy);
+        }
+        C0[i] = (double)xx; C1[i] = (double)xy; C2[i] = (double)yy;
+    }
+    VIWB_SYNC();
+}
+VIWB_D void det_corner_tile(const DetArgs &a, const DetRun &run, int bx, int by, int tid, int nt, unsigned char *smem) {
+    const int x0 = bx * DET_OW, y0 = by * DET_OH, w = a.w, h = a.h;
+    const unsigned char *img = a.img[run.img_sel];
+    double *C0 = (double *)smem, *C1 = C0 + DET_CH * DET_CW, *C2 = C1 + DET_CH * DET_CW;
+    float *S = (float *)(C2 + DET_CH * DET_CW), *E = S + DET_SH * DET_SW;
+    // the mask bytes of this thread's pixels are fetched first: their latency hides behind the whole tile computation
+    const int rounds = (DET_OW * DET_OH + nt - 1) / nt;
+    unsigned free_bits = 0u;
+    for (int q = 0; q < rounds && q < 32; q++) {
+        const int i = q * nt + tid, rr = i / DET_OW, cc = i - rr * DET_OW, y = y0 + rr, x = x0 + cc;
+        if (i < DET_OW * DET_OH && y < h && x < w && (!run.use_mask || a.mask[(size_t)y * w + x])) free_bits |= 1u << q;
+    }
+    if (x0 >= 3 && y0 >= 3 && x0 + DET_OW + 3 <= w && y0 + DET_OH + 3 <= h) det_tile_products<true>(a, img, x0, y0, tid, nt, S, C0, C1, C2);
+    else det_tile_products<false>(a, img, x0, y0, tid, nt, S, C0, C1, C2);
+    for (int t = tid; t < DET_NT; t += nt) {                      // eigenvalues, origin (x0-1, y0-1): column c, rows 4g..4g+3
+        const int c = t % DET_EW, g = t / DET_EW;
+        double ra[3], rb[3], rc[3];                               // row sums of the three most recent product rows
+        for (int k = 0; k < 6; k++) {
+            const int j = (4 * g + k) * DET_CW + c;
+            const double na = (C0[j] + C0[j + 1]) + C0[j + 2], nb = (C1[j] + C1[j + 1]) + C1[j + 2], nc = (C2[j] + C2[j + 1]) + C2[j + 2];
+            if (k >= 2) {
+                const float fa = det_mul((float)((ra[0] + ra[1]) + na), 0.5f), fb = (float)((rb[0] + rb[1]) + nb), fc = det_mul((float)((rc[0] + rc[1]) + nc), 0.5f);
+                const float d = det_sub(fa, fc);
+                E[(4 * g + k - 2) * DET_EW + c] = det_sub(det_add(fa, fc), det_sqrt(det_add(det_mul(d, d), det_mul(fb, fb))));
+                ra[0] = ra[1]; rb[0] = rb[1]; rc[0] = rc[1];
+                ra[1] = na; rb[1] = nb; rc[1] = nc;
+            } else { ra[k] = na; rb[k] = nb; rc[k] = nc; }
+        }
+    }
+    VIWB_SYNC();
+    unsigned best = 0u;
+    for (int q = 0; q < rounds; q++) {
+        const int i = q * nt + tid;
+        bool ok = false;
+        unsigned long long key = 0ull;
+        if (i < DET_OW * DET_OH) {
+            const int rr = i / DET_OW, cc = i - rr * DET_OW, y = y0 + rr, x = x0 + cc;
+            if (y < h && x < w) {
+                const float *e = E + (rr + 1) * DET_EW + cc + 1;
+                const float v = e[0];
+                const bool free_px = q < 32 ? ((free_bits >> q) & 1u) != 0u : (!run.use_mask || a.mask[(size_t)y * w + x]);
+                if (free_px) { const unsigned enc = det_encode(v); if (enc > best) best = enc; }
+                if (free_px && v != 0.f && x >= 1 && y >= 1 && x <= w - 2 && y <= h - 2) {
+                    ok = e[-DET_EW - 1] <= v && e[-DET_EW] <= v && e[-DET_EW + 1] <= v && e[-1] <= v && e[1] <= v && e[DET_EW - 1] <= v && e[DET_EW] <= v && e[DET_EW + 1] <= v;
+                    key = ((unsigned long long)det_encode(v) << 32) | (unsigned)(y * w + x);
+                }
+            }
+        }
+        det_append(a, ok, key);
+    }
+    det_commit_max(a.maxbits, best);
+}
+
+VIWB_D float det_threshold(const DetArgs &a, const DetRun &run) {
+    const unsigned mb = *a.maxbits;
+    const float mx = mb ? det_decode(mb) : 0.f;                    // minMaxLoc over an empty mask leaves 0
+    return (float)((double)mx * run.quality);
 }
 
 // ------------------------------------------------------------------------------------------------- sort + greedy selection
@@ -255,17 +292,47 @@ VIWB_D void det_grid_insert(unsigned *grid, int gw, int cell, int x, int y) {
 VIWB_HD int det_pow2_at_least(int n) { int p = 2; while (p < n) p <<= 1; return p; }
 VIWB_HD size_t det_select_smem_bytes() { return (size_t)DET_SORT_SMEM * 8 + (size_t)DET_GRID_SMEM * DET_SLOTS * 4; }
 
-VIWB_D void det_select_block(const DetArgs &a, const DetRun &run, int tid, int nt, unsigned char *smem) {
+VIWB_D void det_select_block(const DetArgs &a, const DetRun &run, int tid, int nt, unsigned char *smem, int *counter) {
     const int cap = (run.corner_cap > 0 && run.corner_cap < a.corner_cap) ? run.corner_cap : a.corner_cap;
     int want = run.tracker_mode ? run.max_cnt - *a.n_keep : (run.max_corners > 0 ? run.max_corners : cap);
     if (want > cap) want = cap;
-    const int M = *a.n_cand;
-    if (M > a.cand_cap) { if (tid == 0) *a.n_corners = -1; return; }         // candidate list overflow: reported, never truncated silently
-    if (want <= 0 || M <= 0) { if (tid == 0) *a.n_corners = 0; return; }
-    const int P = det_pow2_at_least(M);
-    unsigned long long *keys = (P <= DET_SORT_SMEM) ? (unsigned long long *)smem : a.cand;
-    if (P <= DET_SORT_SMEM) for (int i = tid; i < M; i += nt) keys[i] = a.cand[i];
-    for (int i = M + tid; i < P; i += nt) keys[i] = 0ull;
+    const int Mall = *a.n_cand;
+    if (Mall > a.cand_cap) { if (tid == 0) *a.n_corners = -1; return; }      // candidate list overflow: reported, never truncated silently
+    if (want <= 0 || Mall <= 0) { if (tid == 0) *a.n_corners = 0; return; }
+    // threshold(eig, max * quality, THRESH_TOZERO): only candidates above it take part
+    const float thr = det_threshold(a, run);
+    if (tid == 0) { counter[0] = 0; counter[1] = 0; }
+    VIWB_SYNC();
+    int mine = 0;
+    for (int i = tid; i < Mall; i += nt) mine += det_decode((unsigned)(a.cand[i] >> 32)) > thr ? 1 : 0;
+#ifdef VIWB_HOST_EMU
+    counter[0] += mine;
+#else
+    if (mine) atomicAdd(&counter[0], mine);
+#endif
+    VIWB_SYNC();
+    const int M = counter[0];
+    if (M <= 0) { if (tid == 0) *a.n_corners = 0; return; }
+    unsigned long long *keys;
+    int P;
+    if (M <= DET_SORT_SMEM) {                                    // the usual case: the survivors are sorted in shared memory
+        keys = (unsigned long long *)smem; P = det_pow2_at_least(M);
+        for (int i = tid; i < Mall; i += nt) {
+            const unsigned long long k = a.cand[i];
+            if (det_decode((unsigned)(k >> 32)) > thr) {
+#ifdef VIWB_HOST_EMU
+                const int pos = counter[1]++;
+#else
+                const int pos = atomicAdd(&counter[1], 1);
+#endif
+                keys[pos] = k;
+            }
+        }
+        for (int i = M + tid; i < P; i += nt) keys[i] = 0ull;
+    } else {                                                     // sort the whole list in place; its first M entries are the survivors
+        keys = a.cand; P = det_pow2_at_least(Mall);
+        for (int i = Mall + tid; i < P; i += nt) keys[i] = 0ull;
+    }
     const int cells = a.gw * a.gh;
     unsigned *grid = (cells <= DET_GRID_SMEM) ? (unsigned *)(smem + (size_t)DET_SORT_SMEM * 8) : a.grid;
     for (int i = tid; i < cells * DET_SLOTS; i += nt) grid[i] = 0xffffffffu;
@@ -324,16 +391,14 @@ __global__ void __launch_bounds__(256) det_mask_kernel(DetRun run) {
     __shared__ int n_near;
     det_mask_band(run.tasks[blockIdx.y], run, blockIdx.x, threadIdx.x, blockDim.x, near_xy, &n_near);
 }
-__global__ void __launch_bounds__(256) det_eig_kernel(DetRun run, int tiles_x) {
-    extern __shared__ float det_sm[];
-    det_eig_tile(run.tasks[blockIdx.y], run, blockIdx.x % tiles_x, blockIdx.x / tiles_x, threadIdx.x, blockDim.x, det_sm);
-}
-__global__ void __launch_bounds__(256) det_candidates_kernel(DetRun run) {
-    det_candidate_item(run.tasks[blockIdx.y], run, blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void __launch_bounds__(DET_NT) det_corners_kernel(DetRun run, int tiles_x) {
+    extern __shared__ __align__(16) unsigned char det_sm[];
+    det_corner_tile(run.tasks[blockIdx.y], run, blockIdx.x % tiles_x, blockIdx.x / tiles_x, threadIdx.x, blockDim.x, det_sm);
 }
 __global__ void __launch_bounds__(1024) det_select_kernel(DetRun run) {
-    extern __shared__ unsigned char det_sel_sm[];
-    det_select_block(run.tasks[blockIdx.x], run, threadIdx.x, blockDim.x, det_sel_sm);
+    extern __shared__ __align__(16) unsigned char det_sel_sm[];
+    __shared__ int counter[2];
+    det_select_block(run.tasks[blockIdx.x], run, threadIdx.x, blockDim.x, det_sel_sm, counter);
 }
 #endif
 
