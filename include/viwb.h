@@ -391,6 +391,37 @@ int viwb_detector_detect(viwb_detector *d, const uint8_t *const *images, int str
 /* compulsory HBM bytes of one viwb_detector_detect: every stream's image read once, the points in, the corners out */
 double viwb_detector_algorithmic_bytes(const viwb_detector *d);
 
+/* ---- session tracker: FeatureTracker::trackImage() as one call (featureTracker/feature_tracker.cpp:99-331) ----------
+ * `streams` independent FeatureTracker sessions (feature_tracker.h:50-95: prev_img, prev_pts, ids, track_cnt, n_id, the id -> point
+ * maps) live in HBM.  One viwb_tracker_track() per camera tick does, per stream and without a host round trip: the temporal flow
+ * (with the hasPrediction branch of :122-137 when predict_pts is given), the reverse check and status rules, reduceVector, track_cnt++,
+ * setMask, goodFeaturesToTrack(MAX_CNT - n, 0.01, MIN_DIST, mask), id assignment (n_id++), undistortedPts + ptsVelocity, the stereo
+ * flow cur -> right with its reverse check, the right camera's undistortedPts + ptsVelocity, and prev_* = cur_*.  Only the images go
+ * up and the featureFrame rows come down.  cam[0] / cam[1]: pinhole + radtan intrinsics of the left / right camera (m_camera[0/1]). */
+typedef struct viwb_tracker_config {
+    int max_cnt;        /* MAX_CNT  (parameters.cpp: "max_cnt"), also the per-stream row capacity of every output array, <= 1024 */
+    int min_dist;       /* MIN_DIST ("min_dist") */
+    int flow_back;      /* FLOW_BACK ("flow_back") */
+    int stereo;         /* stereo_cam && a right image every tick */
+    viwb_pinhole cam[2];
+} viwb_tracker_config;
+typedef struct viwb_tracker viwb_tracker;
+int viwb_tracker_create(viwb_context *ctx, int streams, int width, int height, const viwb_tracker_config *config, viwb_tracker **out);
+void viwb_tracker_destroy(viwb_tracker *t);
+/* trackImage(cur_time, left[s], right[s]) for every stream s.  left / right: `streams` host image pointers (8-bit, `stride` bytes per
+ * row; right may be NULL for a mono session).  predict_pts (optional): [streams][max_cnt][2] = FeatureTracker::setPrediction()'s
+ * predict_pts, aligned with the rows returned by the previous tick; has_prediction: [streams] flags (hasPrediction).  Asynchronous on
+ * the context stream: the host buffers must stay valid until viwb_tracker_download returns. */
+int viwb_tracker_track(viwb_tracker *t, double cur_time, const uint8_t *const *left, const uint8_t *const *right, int stride,
+                       const float *predict_pts, const uint8_t *has_prediction);
+/* The featureFrame of the tick (:307-350), as rows: camera 0 rows in cur_pts order -- ids / track_cnt [streams][max_cnt], feat
+ * [streams][max_cnt][6] = {x, y, p_u, p_v, velocity_x, velocity_y} (z = 1) -- and camera 1 rows in ids_right order.  n_left / n_right:
+ * [streams] row counts.  Any pointer may be NULL.  Synchronises. */
+int viwb_tracker_download(viwb_tracker *t, int32_t *n_left, int32_t *ids, int32_t *track_cnt, float *feat, int32_t *n_right,
+                          int32_t *ids_right, float *feat_right);
+/* compulsory HBM bytes of one tick: the new images read once by the pyramid and once by the detector, pyramid levels written, rows out */
+double viwb_tracker_algorithmic_bytes(const viwb_tracker *t);
+
 /* Page-lock / unlock caller-owned host memory (camera frame buffers) for asynchronous full-rate uploads. */
 int viwb_host_register(viwb_context *ctx, void *ptr, size_t bytes);
 int viwb_host_unregister(viwb_context *ctx, void *ptr);

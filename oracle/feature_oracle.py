@@ -151,3 +151,136 @@ def detect(img, pts, track_cnt, max_cnt, min_dist, quality=0.01, base_mask=None)
     n_new = max_cnt - len(keep)
     new = good_features_to_track(img, n_new, quality, float(min_dist), mask) if n_new > 0 else np.zeros((0, 2), f32)
     return mask, keep, new
+
+
+# ------------------------------------------------------------------------------------------------ FeatureTracker::trackImage()
+def lift_projective(cam, pts):
+    """PinholeCamera::liftProjective with the recursive distortion model, n = 8 (camera_models/src/camera_models/PinholeCamera.cc:450-517),
+    narrowed to cv::Point2f as FeatureTracker::undistortedPts does (feature_tracker.cpp:606-617).  cam = (fx, fy, cx, cy, k1, k2, p1, p2)."""
+    fx, fy, cx, cy, k1, k2, p1, p2 = (float(v) for v in cam)
+    p = np.asarray(pts, f32).reshape(-1, 2)
+    mxd, myd = (1.0 / fx) * p[:, 0].astype(np.float64) + (-cx / fx), (1.0 / fy) * p[:, 1].astype(np.float64) + (-cy / fy)
+    mx, my = mxd.copy(), myd.copy()
+    if not (k1 == 0.0 and k2 == 0.0 and p1 == 0.0 and p2 == 0.0):
+        for it in range(8):
+            x, y = (mxd, myd) if it == 0 else (mx, my)
+            mx2, my2, mxy = x * x, y * y, x * y
+            rho2 = mx2 + my2
+            rad = k1 * rho2 + k2 * rho2 * rho2
+            dx = x * rad + 2.0 * p1 * mxy + p2 * (rho2 + 2.0 * mx2)
+            dy = y * rad + 2.0 * p2 * mxy + p1 * (rho2 + 2.0 * my2)
+            mx, my = mxd - dx, myd - dy
+    return np.column_stack([mx, my]).astype(f32)
+
+
+class FeatureTrackerRef:
+    """FeatureTracker (featureTracker/feature_tracker.h / .cpp) restated line by line, one session.  The two OpenCV calls stay OpenCV
+    calls -- cv2.calcOpticalFlowPyrLK is the very routine the reference links -- so this class is the reference's trackImage() with
+    its own third-party library underneath; setMask / goodFeaturesToTrack go through the restatement above (bit-identical to cv2's
+    scalar path, tests/test_feature_oracle.py) or through cv2 itself (use_cv_detector=True)."""
+
+    def __init__(self, cam0, cam1=None, max_cnt=150, min_dist=30, flow_back=True, use_cv_detector=False):
+        import cv2
+        self.cv2 = cv2
+        self.cam, self.stereo = (cam0, cam1), cam1 is not None
+        self.MAX_CNT, self.MIN_DIST, self.FLOW_BACK, self.use_cv = max_cnt, min_dist, flow_back, use_cv_detector
+        self.n_id = 0
+        self.prev_img = None
+        self.prev_pts = np.zeros((0, 2), f32)
+        self.ids, self.track_cnt = [], []
+        self.prev_un_pts_map, self.prev_un_right_pts_map = {}, {}
+        self.prev_time = 0.0
+        self.hasPrediction, self.predict_pts = False, None
+        self.stats = {"predicted": 0, "repeated": 0}          # how often the hasPrediction branch / its full-pyramid repeat ran
+
+    def set_prediction(self, predict_pts):
+        """FeatureTracker::setPrediction leaves predict_pts aligned with prev_pts (feature_tracker.cpp:715-736)"""
+        self.hasPrediction, self.predict_pts = True, np.asarray(predict_pts, f32).reshape(-1, 2).copy()
+
+    def _in_border(self, p):                                              # feature_tracker.cpp:19-25
+        x, y = int(cv_round(p[0])), int(cv_round(p[1]))
+        return 1 <= x < self.col - 1 and 1 <= y < self.row - 1
+
+    def _lk(self, a, b, pts, init=None, max_level=3):
+        cv2 = self.cv2
+        p = np.ascontiguousarray(pts, f32).reshape(-1, 1, 2)
+        if init is None:
+            q, st, _ = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=(21, 21), maxLevel=max_level)
+        else:
+            q, st, _ = cv2.calcOpticalFlowPyrLK(a, b, p, np.ascontiguousarray(init, f32).reshape(-1, 1, 2).copy(), winSize=(21, 21), maxLevel=max_level,
+                                                criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01), flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        return q.reshape(-1, 2), st.reshape(-1).astype(bool)
+
+    def _velocity(self, ids, un, prev_map, dt):                           # ptsVelocity, :619-657
+        vel = np.zeros((len(ids), 2), f32)
+        if prev_map:
+            for i, fid in enumerate(ids):
+                if fid in prev_map:
+                    vel[i] = ((un[i] - prev_map[fid]).astype(np.float64) / dt).astype(f32)      # float difference, double division
+        return vel
+
+    def track_image(self, cur_time, img, img1=None):
+        """-> (ids, track_cnt, cur_pts, cur_un_pts, pts_velocity, ids_right, cur_right_pts, cur_un_right_pts, right_pts_velocity)"""
+        self.row, self.col = img.shape
+        cur_pts = np.zeros((0, 2), f32)
+        if len(self.prev_pts) > 0:                                        # :117-172
+            if self.hasPrediction:
+                cur_pts, status = self._lk(self.prev_img, img, self.prev_pts, self.predict_pts, 1)
+                self.stats["predicted"] += 1
+                if status.sum() < 10:
+                    self.stats["repeated"] += 1
+                    cur_pts, status = self._lk(self.prev_img, img, self.prev_pts)
+            else:
+                cur_pts, status = self._lk(self.prev_img, img, self.prev_pts)
+            if self.FLOW_BACK:
+                rev, rst = self._lk(img, self.prev_img, cur_pts, self.prev_pts, 1)
+                d = (self.prev_pts - rev).astype(np.float64)
+                status = status & rst & (np.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2) <= 0.5)
+            status = status & np.array([self._in_border(p) for p in cur_pts], bool)
+            cur_pts = cur_pts[status]
+            self.ids = [i for i, s in zip(self.ids, status) if s]
+            self.track_cnt = [c for c, s in zip(self.track_cnt, status) if s]
+        self.track_cnt = [c + 1 for c in self.track_cnt]                  # :174-175
+        # setMask (:59-89) rebuilds cur_pts / ids / track_cnt in visiting order; goodFeaturesToTrack tops up (:181-204)
+        cnt = np.asarray(self.track_cnt, np.int64)
+        mask, keep = set_mask(self.col, self.row, cur_pts, cnt, self.MIN_DIST)
+        cur_pts = cur_pts[keep] if len(keep) else np.zeros((0, 2), f32)
+        self.ids = [self.ids[k] for k in keep]
+        self.track_cnt = [self.track_cnt[k] for k in keep]
+        n_max_cnt = self.MAX_CNT - len(cur_pts)
+        if n_max_cnt > 0:
+            if self.use_cv:
+                n_pts = self.cv2.goodFeaturesToTrack(img, n_max_cnt, 0.01, self.MIN_DIST, mask=mask)
+                n_pts = np.zeros((0, 2), f32) if n_pts is None else n_pts.reshape(-1, 2)
+            else:
+                n_pts = good_features_to_track(img, n_max_cnt, 0.01, float(self.MIN_DIST), mask)
+        else:
+            n_pts = np.zeros((0, 2), f32)
+        for p in n_pts:
+            self.ids.append(self.n_id); self.n_id += 1
+            self.track_cnt.append(1)
+        cur_pts = np.concatenate([cur_pts, n_pts.astype(f32)]).astype(f32)
+        dt = cur_time - self.prev_time
+        cur_un_pts = lift_projective(self.cam[0], cur_pts)                # :207-208
+        pts_velocity = self._velocity(self.ids, cur_un_pts, self.prev_un_pts_map, dt)
+        cur_un_pts_map = {fid: cur_un_pts[i] for i, fid in enumerate(self.ids)}
+        ids_right, cur_right_pts = [], np.zeros((0, 2), f32)
+        cur_un_right_pts, right_pts_velocity = np.zeros((0, 2), f32), np.zeros((0, 2), f32)
+        if img1 is not None and self.stereo:                              # :210-271
+            cur_un_right_pts_map = {}
+            if len(cur_pts) > 0:
+                right, status = self._lk(img, img1, cur_pts)
+                if self.FLOW_BACK:
+                    rev, rst = self._lk(img1, img, right)
+                    d = (cur_pts - rev).astype(np.float64)
+                    status = status & rst & np.array([self._in_border(p) for p in right], bool) & (np.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2) <= 0.5)
+                cur_right_pts = right[status]
+                ids_right = [i for i, s in zip(self.ids, status) if s]
+                cur_un_right_pts = lift_projective(self.cam[1], cur_right_pts)
+                right_pts_velocity = self._velocity(ids_right, cur_un_right_pts, self.prev_un_right_pts_map, dt)
+                cur_un_right_pts_map = {fid: cur_un_right_pts[i] for i, fid in enumerate(ids_right)}
+            self.prev_un_right_pts_map = cur_un_right_pts_map
+        self.prev_img, self.prev_pts, self.prev_un_pts_map, self.prev_time = img, cur_pts, cur_un_pts_map, cur_time      # :296-301
+        self.hasPrediction = False
+        return (np.asarray(self.ids, np.int32), np.asarray(self.track_cnt, np.int32), cur_pts, cur_un_pts, pts_velocity,
+                np.asarray(ids_right, np.int32), cur_right_pts, cur_un_right_pts, right_pts_velocity)

@@ -690,3 +690,78 @@ def check_detector_resident(ctx, w=752, h=480):
         for f in range(F):
             assert np.array_equal(a[0][f, : a[1][f]], b[0][f, : b[1][f]]) and np.array_equal(a[2][f, : a[3][f]], b[2][f, : b[3][f]]), (tick, f)
     det.close(); lb.close()
+
+
+# ------------------------------------------------------------------------------------------------ session tracker
+def camera_sequence(seed, w, h, ticks, disparity=5.0):
+    """A moving camera over a large texture: left / right 8-bit frames per tick and the per-tick image motion (px)."""
+    import cv2
+    world = synth.texture_image(h + 160, w + 160, seed)
+    rng = np.random.default_rng(900 + seed)
+    pos = np.array([80.0, 80.0]); vel = rng.uniform(-2.5, 2.5, 2)
+    left, right, motion = [], [], []
+    for _ in range(ticks):
+        step = vel + rng.normal(0, 0.3, 2)
+        pos = np.clip(pos + step, 20, 140)
+        M = np.float32([[1, 0, -pos[0]], [0, 1, -pos[1]]])
+        left.append(cv2.warpAffine(world, M, (w, h), flags=cv2.INTER_LINEAR))
+        M[0, 2] -= disparity
+        right.append(cv2.warpAffine(world, M, (w, h), flags=cv2.INTER_LINEAR))
+        motion.append(-step)
+    return left, right, motion
+
+
+def check_tracker_session(ctx, streams=2, w=320, h=240, ticks=5, max_cnt=60, min_dist=20, stereo=True, flow_back=True, predict=True):
+    """viwb_tracker_track = FeatureTracker::trackImage() per stream, device-resident session state, against the line-by-line
+    restatement running cv2.calcOpticalFlowPyrLK (oracle/feature_oracle.py:FeatureTrackerRef): ids, track counts and row order
+    identical, pixel positions within the LK tolerance (1e-2 px), undistorted points / velocities within what that allows."""
+    import feature_oracle as fo
+    cam0 = (461.1586 * w / 752, 459.7529 * w / 752, w / 2 - 3.2, h / 2 + 1.7, -0.2847798, 0.08245052, -1.0946e-06, 4.78701e-06)
+    cam1 = (457.5874 * w / 752, 456.1340 * w / 752, w / 2 + 4.1, h / 2 - 2.6, -0.2836831, 0.07395907, 1.9359e-04, 1.7618e-05)
+    seqs = [camera_sequence(70 + f, w, h, ticks) for f in range(streams)]
+    refs = [fo.FeatureTrackerRef(cam0, cam1 if stereo else None, max_cnt, min_dist, flow_back) for _ in range(streams)]
+    trk = ctx.tracker(streams, w, h, cam0, cam1 if stereo else None, max_cnt, min_dist, flow_back)
+    tol_px, dt = 1e-2, 0.05
+    tol_un = 1.5 * tol_px / cam0[0]
+    total_tracked = 0
+    for t in range(ticks):
+        left = np.stack([seqs[f][0][t] for f in range(streams)])
+        right = np.stack([seqs[f][1][t] for f in range(streams)]) if stereo else None
+        pp, hp = None, None
+        if predict and t >= 2:
+            # stream 0: the true image motion as prediction (maxLevel-1 pass succeeds); last stream: a prediction outside the image,
+            # so fewer than 10 points succeed and the full-pyramid pass repeats (feature_tracker.cpp:130-137)
+            pp, hp = np.zeros((streams, max_cnt, 2), np.float32), np.zeros(streams, np.uint8)
+            for f in ([0, streams - 1] if streams > 1 else [0]):
+                prev = refs[f].prev_pts
+                pred = (prev + (seqs[f][2][t] if f == 0 else np.float32([w + 37.0, h + 29.0]))).astype(np.float32)
+                pp[f, : len(prev)] = pred; hp[f] = 1
+                refs[f].set_prediction(pred)
+        trk.track(0.05 * (t + 1) * (dt / 0.05), left, right, pp, hp)
+        n_left, ids, cnt, feat, n_right, ids_r, feat_r = trk.download()
+        for f in range(streams):
+            r = refs[f].track_image(0.05 * (t + 1), seqs[f][0][t], seqs[f][1][t] if stereo else None)
+            rid, rcnt, rpts, run, rvel, rid_r, rpts_r, run_r, rvel_r = r
+            n = int(n_left[f])
+            assert n == len(rid), (t, f, n, len(rid))
+            assert np.array_equal(ids[f, :n], rid) and np.array_equal(cnt[f, :n], rcnt), (t, f)
+            assert np.abs(feat[f, :n, 2:4] - rpts).max() <= tol_px, (t, f, np.abs(feat[f, :n, 2:4] - rpts).max())
+            assert np.abs(feat[f, :n, 0:2] - run).max() <= tol_un
+            assert np.abs(feat[f, :n, 4:6] - rvel).max() <= 2 * tol_un / dt
+            total_tracked += int((rcnt > 1).sum())
+            if stereo:
+                m = int(n_right[f])
+                assert m == len(rid_r) and np.array_equal(ids_r[f, :m], rid_r), (t, f, m, len(rid_r))
+                if m:
+                    assert np.abs(feat_r[f, :m, 2:4] - rpts_r).max() <= tol_px
+                    assert np.abs(feat_r[f, :m, 0:2] - run_r).max() <= tol_un
+                    assert np.abs(feat_r[f, :m, 4:6] - rvel_r).max() <= 2 * tol_un / dt
+                assert m >= 0.5 * n, (t, f, m, n)                 # the synthetic pair is a pure shift: most points must match
+            ff = trk.feature_frame(f)
+            assert len(ff) == n and all(len(v) in (1, 2) and v[0][0] == 0 for v in ff.values())
+    assert total_tracked >= streams * (ticks - 1) * max_cnt // 3, total_tracked      # the sessions really follow features across ticks
+    if predict and ticks > 2:
+        assert refs[0].stats["predicted"] == ticks - 2 and refs[0].stats["repeated"] == 0, refs[0].stats
+        if streams > 1:
+            assert refs[-1].stats["repeated"] == ticks - 2, refs[-1].stats
+    trk.close()

@@ -112,3 +112,11 @@ def test_detector_batch(emu):
 
 def test_detector_resident(emu):
     pc.check_detector_resident(emu)
+
+
+def test_tracker_session(emu):
+    pc.check_tracker_session(emu, streams=2, w=240, h=180, ticks=4, max_cnt=40, min_dist=18)
+
+
+def test_tracker_session_mono_no_flow_back(emu):
+    pc.check_tracker_session(emu, streams=1, w=200, h=160, ticks=3, max_cnt=30, min_dist=15, stereo=False, flow_back=False, predict=False)

@@ -153,3 +153,12 @@ def test_detector_batch(gpu_ctx):
 
 def test_detector_resident(gpu_ctx):
     pc.check_detector_resident(gpu_ctx)
+
+
+def test_tracker_session(gpu_ctx):
+    pc.check_tracker_session(gpu_ctx, streams=3, w=752, h=480, ticks=6, max_cnt=150, min_dist=30)
+
+
+def test_tracker_session_small_mono(gpu_ctx):
+    pc.check_tracker_session(gpu_ctx, streams=2, w=320, h=240, ticks=5, max_cnt=60, min_dist=20, stereo=False)
+    pc.check_tracker_session(gpu_ctx, streams=2, w=320, h=240, ticks=4, max_cnt=60, min_dist=20, stereo=True, flow_back=False, predict=False)

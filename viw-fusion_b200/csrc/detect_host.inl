@@ -132,6 +132,16 @@ static int det_upload_images(viwb_detector *d, uint8_t *dst, const uint8_t *cons
     return VIWB_OK;
 }
 
+// the four launches of one tick over inputs that already sit in the detector's device buffers (points, track counts, counts)
+static void det_run_device(viwb_detector *d, const viwb_lk_batch *resident, int max_cnt, double quality, int use_base) {
+    viwb_context *ctx = d->ctx; stream_t st = ctx->stream;
+    DetRun run; memset(&run, 0, sizeof run);
+    run.tasks = d->tasks; run.img_sel = resident ? resident->cur : 0; run.use_mask = 1; run.use_base = use_base; run.tracker_mode = 1;
+    run.max_cnt = max_cnt; run.quality = quality; run.min_dist = d->min_dist;
+    det_launch_order(run, d->F, st); det_launch_mask(run, d->F, d->h, st); det_launch_corners(run, d->F, d->w, d->h, st); det_launch_select(run, d->F, st);
+    ctx->launches += 4;
+}
+
 // One camera tick of F streams: setMask over the tracked points, goodFeaturesToTrack for the MAX_CNT - n_keep missing corners.
 static int det_detect(viwb_detector *d, const uint8_t *const *images, int stride, const viwb_lk_batch *resident, const uint8_t *const *base_masks,
                       const float *pts, const int *track_cnt, const int *n_pts, int max_cnt, double quality,
@@ -149,11 +159,7 @@ static int det_detect(viwb_detector *d, const uint8_t *const *images, int stride
     if (base_masks) { const int rc = det_upload_images(d, d->base, base_masks, d->w); if (rc) return rc; }
     const size_t np = (size_t)d->F * d->maxn;
     CK(dev_h2d(d->pts, pts, np * 8, st)); CK(dev_h2d(d->track_cnt, track_cnt, np * 4, st)); CK(dev_h2d(d->counters + (size_t)DET_N_PTS * d->F, n_pts, (size_t)d->F * 4, st));
-    DetRun run; memset(&run, 0, sizeof run);
-    run.tasks = d->tasks; run.img_sel = want ? want->cur : 0; run.use_mask = 1; run.use_base = base_masks ? 1 : 0; run.tracker_mode = 1;
-    run.max_cnt = max_cnt; run.quality = quality; run.min_dist = d->min_dist;
-    det_launch_order(run, d->F, st); det_launch_mask(run, d->F, d->h, st); det_launch_corners(run, d->F, d->w, d->h, st); det_launch_select(run, d->F, st);
-    ctx->launches += 4;
+    det_run_device(d, want, max_cnt, quality, base_masks ? 1 : 0);
     CK(dev_d2h(keep, d->keep, np * 4, st)); CK(dev_d2h(n_keep, d->counters + (size_t)DET_N_KEEP * d->F, (size_t)d->F * 4, st));
     CK(dev_d2h(new_pts, d->corners, np * 8, st)); CK(dev_d2h(n_new, d->counters + (size_t)DET_N_CORNERS * d->F, (size_t)d->F * 4, st));
     if (mask_out) CK(dev_d2h(mask_out, d->mask, (size_t)d->w * d->h * d->F, st));

@@ -162,7 +162,9 @@ static int lk_batch_upload(viwb_lk_batch *b, const uint8_t *const *prev, const u
 }
 
 // what: bit 0 temporal, bit 1 stereo
-static int lk_batch_execute(viwb_lk_batch *b, int what) {
+// rebuild_cur = false: the current image's pyramid is only built if the slot is dirty (the session tracker runs the temporal and the
+// stereo half of one tick as two calls)
+static int lk_batch_execute(viwb_lk_batch *b, int what, bool rebuild_cur = true) {
     viwb_context *ctx = b->ctx;
     bind_device(ctx);
     const int F = b->F; stream_t st = ctx->stream;
@@ -170,7 +172,7 @@ static int lk_batch_execute(viwb_lk_batch *b, int what) {
     // every tick brings new cur (and right) images, so their pyramids are part of the tick; the previous image keeps the
     // pyramid it got when it was the current one unless it was (re)uploaded
     for (int s = 0; s < LK_SLOTS; s++) {
-        const bool need = s == b->cur || (s == 2 && (what & 2)) || (s == 1 - b->cur && (what & 1) && b->dirty[s]);
+        const bool need = (s == b->cur && (rebuild_cur || b->dirty[s])) || (s == 2 && (what & 2)) || (s == 1 - b->cur && (what & 1) && b->dirty[s]);
         if (!need) continue;
         for (int l = 1; l <= b->levels; l++) { lk_launch_pyr(b->pyr + ((size_t)s * 3 + (l - 1)) * F, ((b->lw[l] + 3) / 4) * b->lh[l], F, st); ctx->launches++; }
         b->dirty[s] = false;

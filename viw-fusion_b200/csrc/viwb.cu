@@ -13,6 +13,7 @@
 #include "kernels_preint.cuh"
 #include "kernels_feat.cuh"
 #include "kernels_detect.cuh"
+#include "kernels_track.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -140,6 +141,7 @@ static inline void bind_device(const viwb_context *ctx) {
 
 #include "lk_host.inl"
 #include "detect_host.inl"
+#include "track_host.inl"
 
 // ====================================================================================== batch
 struct HostPrior { int valid, n, nb; int block_id[NB], block_idx[NB]; std::vector<double> x0, J, r; };
@@ -1196,6 +1198,26 @@ extern "C" double viwb_lk_batch_algorithmic_bytes(const viwb_lk_batch *b) {
     return (double)b->F * ((b->stereo ? 2.0 : 1.0) * img + (double)b->maxn * (b->stereo ? 2 : 1) * (8 + 8 + 1));
 }
 // page-lock caller-owned host buffers (camera frames) so that uploads run at full PCIe rate and asynchronously
+extern "C" int viwb_tracker_create(viwb_context *ctx, int streams, int width, int height, const viwb_tracker_config *config, viwb_tracker **out) {
+    if (!ctx || !out) return VIWB_ERR_INVALID;
+    return trk_build(ctx, streams, width, height, config, out);
+}
+extern "C" void viwb_tracker_destroy(viwb_tracker *t) { trk_free(t); }
+extern "C" int viwb_tracker_track(viwb_tracker *t, double cur_time, const uint8_t *const *left, const uint8_t *const *right, int stride, const float *predict_pts,
+                                  const uint8_t *has_prediction) {
+    return t ? trk_track(t, cur_time, left, right, stride, predict_pts, has_prediction) : VIWB_ERR_INVALID;
+}
+extern "C" int viwb_tracker_download(viwb_tracker *t, int32_t *n_left, int32_t *ids, int32_t *track_cnt, float *feat, int32_t *n_right, int32_t *ids_right,
+                                     float *feat_right) {
+    return t ? trk_fetch(t, n_left, ids, track_cnt, feat, n_right, ids_right, feat_right) : VIWB_ERR_INVALID;
+}
+extern "C" double viwb_tracker_algorithmic_bytes(const viwb_tracker *t) {
+    if (!t) return 0.0;
+    const viwb_lk_batch *b = t->lk;
+    double px = 0; for (int l = 1; l <= b->levels; l++) px += (double)b->lw[l] * b->lh[l];
+    const double img = (double)t->w * t->h, cams = t->stereo ? 2.0 : 1.0;
+    return (double)t->F * (cams * (img + px) + img + (double)t->maxn * (cams * (24 + 4) + 4));
+}
 extern "C" int viwb_host_register(viwb_context *ctx, void *ptr, size_t bytes) {
     bind_device(ctx);
     if (!ctx || !ptr) return VIWB_ERR_INVALID;

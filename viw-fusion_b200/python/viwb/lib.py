@@ -21,7 +21,8 @@ EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", 
            "viwb_debug_normal_equations", "viwb_lk_track", "viwb_track_checked", "viwb_lk_batch_create", "viwb_lk_batch_destroy",
            "viwb_lk_batch_upload", "viwb_lk_batch_run", "viwb_lk_batch_download", "viwb_lk_batch_algorithmic_bytes", "viwb_host_register",
            "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate", "viwb_outlier_rejection", "viwb_batch_outliers", "viwb_triangulate", "viwb_shift_depth", "viwb_undistort_velocity",
-           "viwb_set_mask", "viwb_good_features_to_track", "viwb_detector_create", "viwb_detector_destroy", "viwb_detector_detect", "viwb_detector_algorithmic_bytes"]
+           "viwb_set_mask", "viwb_good_features_to_track", "viwb_detector_create", "viwb_detector_destroy", "viwb_detector_detect", "viwb_detector_algorithmic_bytes",
+           "viwb_tracker_create", "viwb_tracker_destroy", "viwb_tracker_track", "viwb_tracker_download", "viwb_tracker_algorithmic_bytes"]
 
 
 class ViwbError(RuntimeError):
@@ -43,6 +44,10 @@ def load(libpath=None):
     lib.viwb_detector_destroy.argtypes = [C.c_void_p]
     lib.viwb_lk_batch_destroy.argtypes = [C.c_void_p]
     lib.viwb_lk_batch_destroy.restype = None
+    lib.viwb_tracker_algorithmic_bytes.restype = C.c_double
+    lib.viwb_tracker_algorithmic_bytes.argtypes = [C.c_void_p]
+    lib.viwb_tracker_destroy.argtypes = [C.c_void_p]
+    lib.viwb_tracker_destroy.restype = None
     return lib
 
 
@@ -330,11 +335,79 @@ class Context:
     def lk_batch(self, streams, width, height, max_points, stereo=True, flow_back=True):
         return LkBatch(self, streams, width, height, max_points, stereo, flow_back)
 
+    def tracker(self, streams, width, height, cam0, cam1=None, max_cnt=150, min_dist=30, flow_back=True):
+        return Tracker(self, streams, width, height, cam0, cam1, max_cnt, min_dist, flow_back)
+
     def host_register(self, arr):
         self._ck(self.lib.viwb_host_register(self.h, C.c_void_p(arr.ctypes.data), C.c_size_t(arr.nbytes)), "viwb_host_register")
 
     def host_unregister(self, arr):
         self._ck(self.lib.viwb_host_unregister(self.h, C.c_void_p(arr.ctypes.data)), "viwb_host_unregister")
+
+
+class TrackerConfig(C.Structure):
+    _fields_ = [("max_cnt", C.c_int), ("min_dist", C.c_int), ("flow_back", C.c_int), ("stereo", C.c_int), ("cam", C.c_double * 16)]
+
+
+class Tracker:
+    """`streams` FeatureTracker sessions resident on the device (viwb_tracker_*): track() = FeatureTracker::trackImage() per stream.
+    cam0 / cam1 = (fx, fy, cx, cy, k1, k2, p1, p2); cam1 None = mono sessions."""
+
+    def __init__(self, ctx, streams, width, height, cam0, cam1=None, max_cnt=150, min_dist=30, flow_back=True):
+        self.ctx, self.F, self.w, self.h, self.maxn, self.stereo = ctx, streams, width, height, max_cnt, cam1 is not None
+        cfg = TrackerConfig(max_cnt, int(min_dist), 1 if flow_back else 0, 1 if self.stereo else 0,
+                            (C.c_double * 16)(*([float(v) for v in cam0] + [float(v) for v in (cam1 if cam1 is not None else cam0)])))
+        self.hnd = C.c_void_p()
+        ctx._ck(ctx.lib.viwb_tracker_create(ctx.h, C.c_int(streams), C.c_int(width), C.c_int(height), C.byref(cfg), C.byref(self.hnd)), "viwb_tracker_create")
+        self.n_left, self.n_right = np.zeros(streams, np.int32), np.zeros(streams, np.int32)
+        self.ids, self.track_cnt, self.ids_right = (np.zeros((streams, max_cnt), np.int32) for _ in range(3))
+        self.feat, self.feat_right = np.zeros((streams, max_cnt, 6), np.float32), np.zeros((streams, max_cnt, 6), np.float32)
+        self._keep = None
+
+    def _ptrs(self, imgs):
+        assert imgs.dtype == np.uint8 and imgs.shape == (self.F, self.h, self.w) and imgs.strides[2] == 1
+        return (C.c_void_p * self.F)(*[imgs.ctypes.data + f * imgs.strides[0] for f in range(self.F)]), int(imgs.strides[1])
+
+    def track(self, cur_time, left, right=None, predict_pts=None, has_prediction=None):
+        """asynchronous; call download() for the featureFrame rows"""
+        pl, stride = self._ptrs(left)
+        pr = None
+        if self.stereo:
+            pr, s2 = self._ptrs(right)
+            assert s2 == stride
+        pp = None if predict_pts is None else np.ascontiguousarray(predict_pts, np.float32)
+        hp = None if has_prediction is None else np.ascontiguousarray(has_prediction, np.uint8)
+        assert pp is None or (pp.shape == (self.F, self.maxn, 2) and hp is not None and hp.shape == (self.F,))
+        self._keep = (left, right, pl, pr, pp, hp)
+        vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+        self.ctx._ck(self.ctx.lib.viwb_tracker_track(self.hnd, C.c_double(cur_time), pl, pr, C.c_int(stride), vp(pp), vp(hp)), "viwb_tracker_track")
+
+    def download(self):
+        """-> per stream dicts are left to the caller; returns (n_left, ids, track_cnt, feat, n_right, ids_right, feat_right) views"""
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        self.ctx._ck(self.ctx.lib.viwb_tracker_download(self.hnd, vp(self.n_left), vp(self.ids), vp(self.track_cnt), vp(self.feat), vp(self.n_right) if self.stereo else None,
+                                                        vp(self.ids_right) if self.stereo else None, vp(self.feat_right) if self.stereo else None), "viwb_tracker_download")
+        return self.n_left, self.ids, self.track_cnt, self.feat, self.n_right, self.ids_right, self.feat_right
+
+    def feature_frame(self, f):
+        """featureFrame of stream f as the reference builds it: {feature_id: [(camera_id, [x, y, z, u, v, vx, vy]), ...]}"""
+        out = {}
+        for j in range(self.n_left[f]):
+            x, y, u, v, vx, vy = (float(t) for t in self.feat[f, j])
+            out.setdefault(int(self.ids[f, j]), []).append((0, [x, y, 1.0, u, v, vx, vy]))
+        if self.stereo:
+            for j in range(self.n_right[f]):
+                x, y, u, v, vx, vy = (float(t) for t in self.feat_right[f, j])
+                out.setdefault(int(self.ids_right[f, j]), []).append((1, [x, y, 1.0, u, v, vx, vy]))
+        return out
+
+    def algorithmic_bytes(self):
+        return float(self.ctx.lib.viwb_tracker_algorithmic_bytes(self.hnd))
+
+    def close(self):
+        if self.hnd:
+            self.ctx.lib.viwb_tracker_destroy(self.hnd)
+            self.hnd = C.c_void_p()
 
 
 class Detector:
