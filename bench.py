@@ -248,6 +248,7 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--e2e-lanes", type=int, default=4, help="host threads (each with its own context) driving the e2e measurement")
     ap.add_argument("--no-lk", action="store_true", help="window solve only (no feature-tracker work in the step)")
+    ap.add_argument("--serial-lk", action="store_true", help="run the camera tick on the solver's stream instead of its own (A/B of the overlap)")
     ap.add_argument("--scenes", type=int, default=8, help="distinct synthetic stereo scenes per rank (replicated over the streams)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -322,11 +323,19 @@ def main():
     flags = [abi.MARGIN_OLD] * B
     batch = ctx.batch(probs, states, flags)
     alg_bytes = batch.algorithmic_bytes()
-    lk, feed, scenes = None, None, None
+    lk, feed, scenes, ctx_cam, cam_stream = None, None, None, None, None
     if not args.no_lk:
         scenes = make_scenes(rank, args.scenes)
         feed = FrameFeed(ctx, scenes, B)
-        lk = ctx.lk_batch(B, IMG_W, IMG_H, N_FEAT, stereo=True, flow_back=True)
+        # The reference runs FeatureTracker::trackImage() in its own thread beside the estimator thread (estimator.cpp: processMeasurements vs
+        # inputImage); here the camera tick gets its own context + CUDA stream, so its integer-bound kernels fill issue slots the FP64
+        # latency-bound solver leaves idle.  --serial-lk puts it back on the solver's stream.
+        ctx_cam = ctx
+        if not args.serial_lk:
+            ctx_cam = lib.Context(local_rank)
+            cam_stream = torch.cuda.Stream()
+            ctx_cam.set_stream(cam_stream.cuda_stream)
+        lk = ctx_cam.lk_batch(B, IMG_W, IMG_H, N_FEAT, stereo=True, flow_back=True)
         # tick 0 (untimed): both left images resident, the resident "current" image is tick 1
         lk.upload(prev=feed.left[0], cur=feed.left[1], right=feed.right[1], prev_pts=feed.pts[0], n_prev=feed.n, stereo_pts=feed.pts[1], n_stereo=feed.n)
         lk.run()
@@ -348,15 +357,23 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = ctx.launch_count()
+    def all_launches():
+        return ctx.launch_count() + (ctx_cam.launch_count() if ctx_cam is not None and ctx_cam is not ctx else 0)
+    l0 = all_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    if cam_stream is not None:
+        cam_stream.wait_event(e0)           # the camera stream's first timed tick starts after e0 ...
     for _ in range(args.steps):
         step()
+    if cam_stream is not None:
+        cam_done = torch.cuda.Event()
+        cam_done.record(cam_stream)
+        stream.wait_event(cam_done)         # ... and e1 waits for its last one: the timed region covers K ticks + K solves
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - l0
+    launches = all_launches() - l0
     clocks = sampler.stop()
     ms = rank_max(ms, world)
     value = job_throughput(world, B, args.steps, ms * 1e-3)
@@ -449,12 +466,16 @@ def main():
     # ---- live per-kernel timing (CUDA events around every launch, separate pass so the headline is unperturbed)
     roofline, kernels = None, None
     if not args.no_profile:
+        if cam_stream is not None:
+            ctx_cam.set_stream(stream.cuda_stream)      # per-kernel times are taken with the launches serialised on one stream
         ctx.set_profiling(True)
         for _ in range(2):
             step()
         torch.cuda.synchronize()
         prof = ctx.profile()
         ctx.set_profiling(False)
+        if cam_stream is not None:
+            ctx_cam.set_stream(cam_stream.cuda_stream)
         tot = sum(v[0] for v in prof.values())
         kernels = {k: {"ms_per_launch": v[0] / max(1, v[1]), "launches_per_step": v[1] / 2, "share": v[0] / tot} for k, v in prof.items()}
         top = max(prof.items(), key=lambda kv: kv[1][0])[0]
@@ -529,6 +550,7 @@ def main():
                            "batch_per_gpu": B, "distinct_sequences": args.distinct, "perturbed_copies": args.copies,
                            "mean_visual_factors": sum(len(p.vis_type) for p in probs) / B, "mean_landmarks": sum(p.num_landmarks for p in probs) / B,
                            "l2": "working set >> 126 MB L2 at this batch; no explicit flush", "lk_in_step": lk is not None,
+                           "lk_stream": None if lk is None else ("same stream as the solver" if cam_stream is None else "own CUDA stream, concurrent with the solver (the reference's tracker thread)"),
                            "camera": None if lk is None else {"streams": B, "image": [IMG_W, IMG_H], "features": N_FEAT, "distinct_scenes": len(scenes),
                                                               "e2e_images_uploaded_per_tick": 2}},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "host_threads": lanes},
@@ -539,6 +561,8 @@ def main():
         lk.close()
         feed.close()
     batch.destroy()
+    if ctx_cam is not None and ctx_cam is not ctx:
+        ctx_cam.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
