@@ -247,8 +247,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--e2e-lanes", type=int, default=4, help="host threads (each with its own context) driving the e2e measurement")
+    ap.add_argument("--e2e-lanes-sweep", default="", help="comma-separated host-thread counts to also measure e2e at (tuning aid)")
     ap.add_argument("--no-lk", action="store_true", help="window solve only (no feature-tracker work in the step)")
-    ap.add_argument("--serial-lk", action="store_true", help="run the camera tick on the solver's stream instead of its own (A/B of the overlap)")
+    ap.add_argument("--overlap-lk", action="store_true", help="run the camera tick on its own context + CUDA stream beside the solver (measured: no gain, r01za)")
     ap.add_argument("--scenes", type=int, default=8, help="distinct synthetic stereo scenes per rank (replicated over the streams)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -327,11 +328,11 @@ def main():
     if not args.no_lk:
         scenes = make_scenes(rank, args.scenes)
         feed = FrameFeed(ctx, scenes, B)
-        # The reference runs FeatureTracker::trackImage() in its own thread beside the estimator thread (estimator.cpp: processMeasurements vs
-        # inputImage); here the camera tick gets its own context + CUDA stream, so its integer-bound kernels fill issue slots the FP64
-        # latency-bound solver leaves idle.  --serial-lk puts it back on the solver's stream.
+        # The reference runs FeatureTracker::trackImage() in its own thread beside the estimator thread; --overlap-lk gives the camera tick
+        # its own context + CUDA stream likewise.  Measured on B200 (profiles/r01za_bench_overlap.json vs r01za_bench_serial.json): 26 105 vs
+        # 26 088 solves/s -- both kernel families already keep the SMs' issue slots busy, so the default stays one stream.
         ctx_cam = ctx
-        if not args.serial_lk:
+        if args.overlap_lk:
             ctx_cam = lib.Context(local_rank)
             cam_stream = torch.cuda.Stream()
             ctx_cam.set_stream(cam_stream.cuda_stream)
@@ -388,63 +389,73 @@ def main():
     lk_out = None
     if lk is not None:
         lk_out = [a.copy() for a in lk.download()]        # results of the timed configuration (tick 1), checked below
-    lanes = max(1, min(args.e2e_lanes, B // 32 if B >= 64 else 1))
-    bounds = [B * k // lanes for k in range(lanes + 1)]
+    def measure_e2e(want_lanes):
+        lanes = max(1, min(want_lanes, B // 32 if B >= 64 else 1))
+        bounds = [B * k // lanes for k in range(lanes + 1)]
 
-    class Lane:
-        def __init__(self, k):
-            self.lo, self.hi = bounds[k], bounds[k + 1]
-            self.ctx = ctx if k == 0 else lib.Context(local_rank)
-            self.call = self.ctx.prepare_optimization_batch(probs[self.lo:self.hi], states[self.lo:self.hi], flags[self.lo:self.hi])
-            self.lk = None
-            if lk is not None:
-                n = self.hi - self.lo
-                self.lk = lk if lanes == 1 else self.ctx.lk_batch(n, IMG_W, IMG_H, N_FEAT, stereo=True, flow_back=True)
-                if lanes > 1:
-                    self.lk.upload(prev=feed.left[0][self.lo:self.hi], cur=feed.left[1][self.lo:self.hi], right=feed.right[1][self.lo:self.hi],
-                                   prev_pts=feed.pts[0][self.lo:self.hi], n_prev=feed.n[self.lo:self.hi], stereo_pts=feed.pts[1][self.lo:self.hi],
-                                   n_stereo=feed.n[self.lo:self.hi])
-                    self.lk.run()
+        class Lane:
+            def __init__(self, k):
+                self.lo, self.hi = bounds[k], bounds[k + 1]
+                self.ctx = ctx if k == 0 else lib.Context(local_rank)
+                self.call = self.ctx.prepare_optimization_batch(probs[self.lo:self.hi], states[self.lo:self.hi], flags[self.lo:self.hi])
+                self.lk = None
+                if lk is not None:
+                    n = self.hi - self.lo
+                    self.lk = lk if lanes == 1 else self.ctx.lk_batch(n, IMG_W, IMG_H, N_FEAT, stereo=True, flow_back=True)
+                    if lanes > 1:
+                        self.lk.upload(prev=feed.left[0][self.lo:self.hi], cur=feed.left[1][self.lo:self.hi], right=feed.right[1][self.lo:self.hi],
+                                       prev_pts=feed.pts[0][self.lo:self.hi], n_prev=feed.n[self.lo:self.hi], stereo_pts=feed.pts[1][self.lo:self.hi],
+                                       n_stereo=feed.n[self.lo:self.hi])
+                        self.lk.run()
+                        self.lk.download()
+                self.tick = 0
+
+            def step(self):
+                if self.lk is not None:
+                    t, sl = self.tick % 2, slice(self.lo, self.hi)   # the camera delivers image t of every stream; the previous tick's image is resident
+                    self.lk.upload(cur=feed.left[t][sl], right=feed.right[t][sl], prev_pts=feed.pts[1 - t][sl], n_prev=feed.n[sl],
+                                   stereo_pts=feed.pts[t][sl], n_stereo=feed.n[sl])
+                    self.lk.run()         # asynchronous: overlaps with the host-side lowering of the windows below
+                    self.tick += 1
+                self.call()               # lowering + H2D + solve + re-anchor + marginalise + D2H (synchronises)
+                if self.lk is not None:
                     self.lk.download()
-            self.tick = 0
 
-        def step(self):
-            if self.lk is not None:
-                t, sl = self.tick % 2, slice(self.lo, self.hi)   # the camera delivers image t of every stream; the previous tick's image is resident
-                self.lk.upload(cur=feed.left[t][sl], right=feed.right[t][sl], prev_pts=feed.pts[1 - t][sl], n_prev=feed.n[sl],
-                               stereo_pts=feed.pts[t][sl], n_stereo=feed.n[sl])
-                self.lk.run()         # asynchronous: overlaps with the host-side lowering of the windows below
-                self.tick += 1
-            self.call()               # lowering + H2D + solve + re-anchor + marginalise + D2H (synchronises)
-            if self.lk is not None:
-                self.lk.download()
+            def close(self):
+                if self.lk is not None and self.lk is not lk:
+                    self.lk.close()
+                if self.ctx is not ctx:
+                    self.ctx.close()
 
-        def close(self):
-            if self.lk is not None and self.lk is not lk:
-                self.lk.close()
-            if self.ctx is not ctx:
-                self.ctx.close()
+        lane_objs = [Lane(k) for k in range(lanes)]
 
-    lane_objs = [Lane(k) for k in range(lanes)]
+        def run_lanes(n):
+            if lanes == 1:
+                for _ in range(n):
+                    lane_objs[0].step()
+                return
+            ths = [threading.Thread(target=lambda L=L: [L.step() for _ in range(n)]) for L in lane_objs]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        run_lanes(2)
+        barrier()
+        t0 = time.perf_counter()
+        run_lanes(e2e_steps)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        for L in lane_objs:
+            L.close()
+        return e2e_s, lanes
 
-    def run_lanes(n):
-        if lanes == 1:
-            for _ in range(n):
-                lane_objs[0].step()
-            return
-        ths = [threading.Thread(target=lambda L=L: [L.step() for _ in range(n)]) for L in lane_objs]
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
-    run_lanes(2)
-    barrier()
-    t0 = time.perf_counter()
-    run_lanes(e2e_steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    for L in lane_objs:
-        L.close()
+    e2e_sweep = None
+    if args.e2e_lanes_sweep:                # tuning aid: the same measurement at several host-thread counts (reported, not used for the headline)
+        e2e_sweep = {}
+        for n in [int(v) for v in args.e2e_lanes_sweep.split(",")]:
+            sec, ln = measure_e2e(n)
+            e2e_sweep[str(ln)] = job_throughput(world, B, e2e_steps, rank_max(sec, world))
+    e2e_s, lanes = measure_e2e(args.e2e_lanes)
     e2e_s = rank_max(e2e_s, world)
     e2e_value = job_throughput(world, B, e2e_steps, e2e_s)
     h2d = sum(p.vis_obs.nbytes + 4 * 4 * len(p.vis_type) + p.imu_data.nbytes + p.wheel_data.nbytes + 8 * p.state_size +
@@ -553,7 +564,7 @@ def main():
                            "lk_stream": None if lk is None else ("same stream as the solver" if cam_stream is None else "own CUDA stream, concurrent with the solver (the reference's tracker thread)"),
                            "camera": None if lk is None else {"streams": B, "image": [IMG_W, IMG_H], "features": N_FEAT, "distinct_scenes": len(scenes),
                                                               "e2e_images_uploaded_per_tick": 2}},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "host_threads": lanes},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "host_threads": lanes, "sweep": e2e_sweep},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity,
                 "single_window_e2e_ms": single_ms}
         print(json.dumps(line))

@@ -120,18 +120,38 @@ VIWB_D void det_mask_band(const DetArgs &a, const DetRun &run, int band, int tid
         }
     }
     VIWB_SYNC();
-    const int m = *n_near, words = (a.w + 3) / 4;
-    for (int i = tid; i < (y1 - y0) * words; i += nt) {
-        const int y = y0 + i / words, xb = (i % words) * 4;
-        unsigned char px[4];
-        for (int k = 0; k < 4; k++) px[k] = (run.use_base && xb + k < a.w) ? a.base_mask[(size_t)y * a.w + xb + k] : 255;
+    // 16 pixels per thread and step: a circle is rejected for the whole group with two comparisons (a 61-pixel run meets few of the
+    // 47 groups of a 752-pixel row), the survivors clear their bytes, one 16-byte store when the row start allows it
+    const int m = *n_near, groups = (a.w + 15) / 16;
+    for (int i = tid; i < (y1 - y0) * groups; i += nt) {
+        const int y = y0 + i / groups, xb = (i % groups) * 16;
+        const int nvalid = a.w - xb < 16 ? a.w - xb : 16;
+        unsigned int px[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (run.use_base) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) { const unsigned v = k < nvalid ? a.base_mask[(size_t)y * a.w + xb + k] : 255u; px[k >> 2] = (px[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (v << (8 * (k & 3))); }
+        }
+        unsigned clear = 0u;                                           // bit k: pixel xb + k lies in some circle
         for (int j = 0; j < m; j++) {
             const int dy = abs(y - (int)near_xy[2 * j + 1]);
             if (dy > r) continue;
             const int cx = near_xy[2 * j], half = a.hw[dy];
-            for (int k = 0; k < 4; k++) if (abs(xb + k - cx) <= half) px[k] = 0;
+            int lo = cx - half - xb, hi = cx + half - xb;              // the run, in group coordinates
+            if (hi < 0 || lo > 15) continue;
+            lo = lo < 0 ? 0 : lo; hi = hi > 15 ? 15 : hi;
+            clear |= ((2u << hi) - 1u) & ~((1u << lo) - 1u);
         }
-        for (int k = 0; k < 4; k++) if (xb + k < a.w) a.mask[(size_t)y * a.w + xb + k] = px[k];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {                                  // four mask bits -> four mask bytes
+            unsigned x = (clear >> (4 * q)) & 15u;
+            x = (x | (x << 7) | (x << 14) | (x << 21)) & 0x01010101u;
+            px[q] &= ~(x * 0xffu);
+        }
+        unsigned char *dst = a.mask + (size_t)y * a.w + xb;
+#ifndef VIWB_HOST_EMU
+        if (nvalid == 16 && ((size_t)dst & 15) == 0) { *reinterpret_cast<uint4 *>(dst) = make_uint4(px[0], px[1], px[2], px[3]); continue; }
+#endif
+        for (int k = 0; k < nvalid; k++) dst[k] = (unsigned char)(px[k >> 2] >> (8 * (k & 3)));
     }
 }
 

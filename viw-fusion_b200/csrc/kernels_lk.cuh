@@ -41,9 +41,10 @@ VIWB_HD int lk_pix(const LkImage &im, int l, int x, int y) { return im.img[l][(s
 VIWB_HD int cv_round_f(float v) { return (int)lrintf(v); }                 // cvRound: round half to even
 VIWB_HD int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }   // CV_DESCALE
 
-// ---- pyrDown: dst (dw x dh) from src (sw x sh).  One work item = 4 horizontally adjacent outputs: 5 rows x 4 aligned 32-bit
-// loads feed the separable [1 4 6 4 1] sums (the same integers as the 2-D stencil); strips touching the left / right border,
-// and images whose width is not a multiple of 4 at the tail, take the per-pixel reflect-101 path.
+// ---- pyrDown: dst (dw x dh) from src (sw x sh).  One work item = a 4 x 4 block of outputs: 11 source rows x 4 aligned 32-bit loads,
+// the horizontal [1 4 6 4 1] sums of a row (two funnel shifts + four byte dot products) computed once and added into the (up to three)
+// output rows that use it -- the same integers as the 2-D stencil at 12 instead of 32 instructions per output.  Blocks touching the
+// left / right border, and the tails of images whose size is not a multiple of 4, take the per-pixel reflect-101 path.
 struct PyrArgs { const uint8_t *src; uint8_t *dst; int sw, sh, sstride, dw, dh, dstride; };
 VIWB_D int pyr_down_pixel(const PyrArgs &a, int x, int y) {
     int cx[5];
@@ -56,38 +57,57 @@ VIWB_D int pyr_down_pixel(const PyrArgs &a, int x, int y) {
     }
     return (acc + 128) >> 8;
 }
-VIWB_HD int pyr_items(const PyrArgs &a) { return ((a.dw + 3) / 4) * a.dh; }
+VIWB_HD int pyr_items_wh(int dw, int dh) { return ((dw + 3) / 4) * ((dh + 3) / 4); }
+VIWB_HD int pyr_items(const PyrArgs &a) { return pyr_items_wh(a.dw, a.dh); }
 VIWB_D void pyr_down_item(const PyrArgs &a, int idx) {
-    const int sx = (a.dw + 3) / 4;
-    if (idx >= sx * a.dh) return;
-    const int y = idx / sx, x = 4 * (idx - y * sx);
-    // interior strip: source bytes [2x-4, 2x+12) exist and outputs x..x+3 exist
-    if (x >= 2 && 2 * x + 12 <= a.sw && x + 4 <= a.dw) {
-        int h[4] = {0, 0, 0, 0};
-        const int wgt[5] = {1, 4, 6, 4, 1};
+    const int sx = (a.dw + 3) / 4, sy = (a.dh + 3) / 4;
+    if (idx >= sx * sy) return;
+    const int by = idx / sx, x = 4 * (idx - by * sx), y = 4 * by;
+    // interior block: source bytes [2x-4, 2x+12) exist and outputs x..x+3, y..y+3 exist (rows reflect, which is cheap: 11 per block)
+    if (x >= 2 && 2 * x + 12 <= a.sw && x + 4 <= a.dw && y + 4 <= a.dh) {
+        int acc[4][4];
 #pragma unroll
-        for (int dy = -2; dy <= 2; dy++) {
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(a.src + (size_t)reflect101(2 * y + dy, a.sh) * a.sstride + 2 * x - 4);
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[j][k] = 0;
+        const bool inner = 2 * y - 2 >= 0 && 2 * y + 8 < a.sh;
+#pragma unroll
+        for (int r = 0; r < 11; r++) {                                     // source row 2y - 2 + r feeds output row j with weight wgt[r - 2j]
+            const int ry = inner ? 2 * y - 2 + r : reflect101(2 * y - 2 + r, a.sh);
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(a.src + (size_t)ry * a.sstride + 2 * x - 4);
             const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
             // bytes b[0..15] = source columns 2x-4 .. 2x+11 (b[0] = low byte of w0); output k (0..3) is centred on b[4 + 2k]:
             // taps b[2+2k .. 5+2k] are one (funnel-shifted) 32-bit group for a 4-way byte dot product with (1, 4, 6, 4), plus b[6+2k]
+            int t[4];
 #ifdef VIWB_HOST_EMU
             int b[16];
             for (int k = 0; k < 4; k++) { b[k] = (w0 >> (8 * k)) & 0xff; b[4 + k] = (w1 >> (8 * k)) & 0xff; b[8 + k] = (w2 >> (8 * k)) & 0xff; b[12 + k] = (w3 >> (8 * k)) & 0xff; }
-            for (int k = 0; k < 4; k++) { const int c = 4 + 2 * k; h[k] += wgt[dy + 2] * (b[c - 2] + b[c + 2] + 4 * (b[c - 1] + b[c + 1]) + 6 * b[c]); }
+            for (int k = 0; k < 4; k++) { const int c = 4 + 2 * k; t[k] = b[c - 2] + b[c + 2] + 4 * (b[c - 1] + b[c + 1]) + 6 * b[c]; }
 #else
             const uint32_t g0 = __funnelshift_r(w0, w1, 16), g2 = __funnelshift_r(w1, w2, 16);
-            const uint32_t t0 = __dp4a(g0, 0x04060401u, (w1 >> 16) & 0xffu), t1 = __dp4a(w1, 0x04060401u, w2 & 0xffu);
-            const uint32_t t2 = __dp4a(g2, 0x04060401u, (w2 >> 16) & 0xffu), t3 = __dp4a(w2, 0x04060401u, w3 & 0xffu);
-            h[0] += wgt[dy + 2] * (int)t0; h[1] += wgt[dy + 2] * (int)t1; h[2] += wgt[dy + 2] * (int)t2; h[3] += wgt[dy + 2] * (int)t3;
+            t[0] = (int)__dp4a(g0, 0x04060401u, (w1 >> 16) & 0xffu); t[1] = (int)__dp4a(w1, 0x04060401u, w2 & 0xffu);
+            t[2] = (int)__dp4a(g2, 0x04060401u, (w2 >> 16) & 0xffu); t[3] = (int)__dp4a(w2, 0x04060401u, w3 & 0xffu);
 #endif
-        }
-        uint32_t o = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) o |= (uint32_t)((h[k] + 128) >> 8) << (8 * k);
-        *reinterpret_cast<uint32_t *>(a.dst + (size_t)y * a.dstride + x) = o;
+            for (int j = 0; j < 4; j++) {
+                const int tap = r - 2 * j;                                 // compile-time after unrolling
+                if (tap >= 0 && tap <= 4) {
+                    const int wv = tap == 0 || tap == 4 ? 1 : (tap == 2 ? 6 : 4);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) acc[j][k] += wv * t[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t o = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) o |= (uint32_t)((acc[j][k] + 128) >> 8) << (8 * k);
+            *reinterpret_cast<uint32_t *>(a.dst + (size_t)(y + j) * a.dstride + x) = o;
+        }
     } else {
-        for (int k = 0; k < 4 && x + k < a.dw; k++) a.dst[(size_t)y * a.dstride + x + k] = (uint8_t)pyr_down_pixel(a, x + k, y);
+        for (int j = 0; j < 4 && y + j < a.dh; j++)
+            for (int k = 0; k < 4 && x + k < a.dw; k++) a.dst[(size_t)(y + j) * a.dstride + x + k] = (uint8_t)pyr_down_pixel(a, x + k, y + j);
     }
 }
 

@@ -174,7 +174,7 @@ static int lk_batch_execute(viwb_lk_batch *b, int what, bool rebuild_cur = true)
     for (int s = 0; s < LK_SLOTS; s++) {
         const bool need = (s == b->cur && (rebuild_cur || b->dirty[s])) || (s == 2 && (what & 2)) || (s == 1 - b->cur && (what & 1) && b->dirty[s]);
         if (!need) continue;
-        for (int l = 1; l <= b->levels; l++) { lk_launch_pyr(b->pyr + ((size_t)s * 3 + (l - 1)) * F, ((b->lw[l] + 3) / 4) * b->lh[l], F, st); ctx->launches++; }
+        for (int l = 1; l <= b->levels; l++) { lk_launch_pyr(b->pyr + ((size_t)s * 3 + (l - 1)) * F, pyr_items_wh(b->lw[l], b->lh[l]), F, st); ctx->launches++; }
         b->dirty[s] = false;
     }
     const LkArgs *w1 = b->tasks + ((size_t)b->cur * 2 + 0) * 2 * F, *w2 = b->tasks + ((size_t)b->cur * 2 + 1) * 2 * F;
@@ -215,7 +215,7 @@ static int lk_track_single(viwb_context *ctx, const uint8_t *prev, const uint8_t
     rc = lk_upload_slot(b, 0, pa, stride); if (rc) return rc;
     rc = lk_upload_slot(b, 1, pb, stride); if (rc) return rc;
     stream_t st = ctx->stream;
-    for (int s = 0; s < 2; s++) { for (int l = 1; l <= b->levels; l++) { lk_launch_pyr(b->pyr + ((size_t)s * 3 + (l - 1)) * b->F, ((b->lw[l] + 3) / 4) * b->lh[l], 1, st); ctx->launches++; } b->dirty[s] = false; }
+    for (int s = 0; s < 2; s++) { for (int l = 1; l <= b->levels; l++) { lk_launch_pyr(b->pyr + ((size_t)s * 3 + (l - 1)) * b->F, pyr_items_wh(b->lw[l], b->lh[l]), 1, st); ctx->launches++; } b->dirty[s] = false; }
     CK(dev_h2d(b->P(0, 0), prev_pts, (size_t)n * 8, st));
     CK(dev_h2d(b->P(1, 0), (flags & 4) ? next_pts : prev_pts, (size_t)n * 8, st));
     LkArgs a; memset(&a, 0, sizeof a);

@@ -122,7 +122,7 @@ static int trk_track(viwb_tracker *t, double cur_time, const uint8_t *const *lef
             // pyramids of the new images, then: seeded maxLevel-1 pass for the streams with a prediction, full-pyramid pass for the others
             // and for those with fewer than 10 successes, reverse flow and status rules for everyone
             for (int s = 0; s < 2; s++) if (b->dirty[s]) {
-                for (int l = 1; l <= b->levels; l++) { lk_launch_pyr(b->pyr + ((size_t)s * 3 + (l - 1)) * F, ((b->lw[l] + 3) / 4) * b->lh[l], F, st); ctx->launches++; }
+                for (int l = 1; l <= b->levels; l++) { lk_launch_pyr(b->pyr + ((size_t)s * 3 + (l - 1)) * F, pyr_items_wh(b->lw[l], b->lh[l]), F, st); ctx->launches++; }
                 b->dirty[s] = false;
             }
             CK(dev_h2d(t->has_pred, has_prediction, (size_t)F, st));
