@@ -44,71 +44,128 @@ VIWB_HD int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }   // CV_
 // ---- pyrDown: dst (dw x dh) from src (sw x sh).  One work item = a 4 x 4 block of outputs: 11 source rows x 4 aligned 32-bit loads,
 // the horizontal [1 4 6 4 1] sums of a row (two funnel shifts + four byte dot products) computed once and added into the (up to three)
 // output rows that use it -- the same integers as the 2-D stencil at 12 instead of 32 instructions per output.  Blocks touching the
-// left / right border, and the tails of images whose size is not a multiple of 4, take the per-pixel reflect-101 path.
+// left / right border, and the tails of images whose size is not a multiple of 4, gather their bytes through reflected indices
+// (pyr_down_block_edge) and are numbered AFTER all interior blocks, so they share no warp with them.
+#ifndef PYR_BATCH
+#define PYR_BATCH 6
+#endif
 struct PyrArgs { const uint8_t *src; uint8_t *dst; int sw, sh, sstride, dw, dh, dstride; };
-VIWB_D int pyr_down_pixel(const PyrArgs &a, int x, int y) {
-    int cx[5];
-    for (int d = 0; d < 5; d++) cx[d] = reflect101(2 * x + d - 2, a.sw);       // columns are reflected once per pixel, rows once per row
-    int acc = 0;
-    const int wgt[5] = {1, 4, 6, 4, 1};
-    for (int dy = -2; dy <= 2; dy++) {
-        const uint8_t *row = a.src + (size_t)reflect101(2 * y + dy, a.sh) * a.sstride;
-        acc += wgt[dy + 2] * (row[cx[0]] + row[cx[4]] + 4 * (row[cx[1]] + row[cx[3]]) + 6 * row[cx[2]]);
-    }
-    return (acc + 128) >> 8;
-}
 VIWB_HD int pyr_items_wh(int dw, int dh) { return ((dw + 3) / 4) * ((dh + 3) / 4); }
 VIWB_HD int pyr_items(const PyrArgs &a) { return pyr_items_wh(a.dw, a.dh); }
-VIWB_D void pyr_down_item(const PyrArgs &a, int idx) {
-    const int sx = (a.dw + 3) / 4, sy = (a.dh + 3) / 4;
-    if (idx >= sx * sy) return;
-    const int by = idx / sx, x = 4 * (idx - by * sx), y = 4 * by;
-    // interior block: source bytes [2x-4, 2x+12) exist and outputs x..x+3, y..y+3 exist (rows reflect, which is cheap: 11 per block)
-    if (x >= 2 && 2 * x + 12 <= a.sw && x + 4 <= a.dw && y + 4 <= a.dh) {
-        int acc[4][4];
+// one interior 4 x 4 block; INNER = none of the 11 source rows needs reflecting (straight-line code, no per-row branches)
+template <bool INNER>
+VIWB_D void pyr_down_block(const PyrArgs &a, int x, int y) {
+    int acc[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+    for (int j = 0; j < 4; j++)
 #pragma unroll
-            for (int k = 0; k < 4; k++) acc[j][k] = 0;
-        const bool inner = 2 * y - 2 >= 0 && 2 * y + 8 < a.sh;
+        for (int k = 0; k < 4; k++) acc[j][k] = 0;
+    // the 11 rows are fetched in batches of PYR_BATCH rows: all loads of a batch are in flight before the first one is consumed
+    // (a thread that consumes row by row pays the DRAM latency eleven times in a row and the kernel runs latency-bound)
 #pragma unroll
-        for (int r = 0; r < 11; r++) {                                     // source row 2y - 2 + r feeds output row j with weight wgt[r - 2j]
-            const int ry = inner ? 2 * y - 2 + r : reflect101(2 * y - 2 + r, a.sh);
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(a.src + (size_t)ry * a.sstride + 2 * x - 4);
-            const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
-            // bytes b[0..15] = source columns 2x-4 .. 2x+11 (b[0] = low byte of w0); output k (0..3) is centred on b[4 + 2k]:
-            // taps b[2+2k .. 5+2k] are one (funnel-shifted) 32-bit group for a 4-way byte dot product with (1, 4, 6, 4), plus b[6+2k]
-            int t[4];
-#ifdef VIWB_HOST_EMU
-            int b[16];
-            for (int k = 0; k < 4; k++) { b[k] = (w0 >> (8 * k)) & 0xff; b[4 + k] = (w1 >> (8 * k)) & 0xff; b[8 + k] = (w2 >> (8 * k)) & 0xff; b[12 + k] = (w3 >> (8 * k)) & 0xff; }
-            for (int k = 0; k < 4; k++) { const int c = 4 + 2 * k; t[k] = b[c - 2] + b[c + 2] + 4 * (b[c - 1] + b[c + 1]) + 6 * b[c]; }
+    for (int r0 = 0; r0 < 11; r0 += PYR_BATCH) {
+        uint32_t wd[PYR_BATCH][4];
+#pragma unroll
+        for (int q = 0; q < PYR_BATCH; q++) {
+            const int r = r0 + q;
+            if (r < 11) {
+                const int ry = INNER ? 2 * y - 2 + r : reflect101(2 * y - 2 + r, a.sh);
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(a.src + (size_t)ry * a.sstride + 2 * x - 4);
+#if defined(PYR_ASM_LOADS) && !defined(VIWB_HOST_EMU)
+                // volatile: the loads of a batch keep their program order and are not sunk next to their uses
+                asm volatile("ld.global.nc.u32 %0, [%4];\n\tld.global.nc.u32 %1, [%4+4];\n\tld.global.nc.u32 %2, [%4+8];\n\tld.global.nc.u32 %3, [%4+12];"
+                             : "=r"(wd[q][0]), "=r"(wd[q][1]), "=r"(wd[q][2]), "=r"(wd[q][3]) : "l"(row));
 #else
-            const uint32_t g0 = __funnelshift_r(w0, w1, 16), g2 = __funnelshift_r(w1, w2, 16);
-            t[0] = (int)__dp4a(g0, 0x04060401u, (w1 >> 16) & 0xffu); t[1] = (int)__dp4a(w1, 0x04060401u, w2 & 0xffu);
-            t[2] = (int)__dp4a(g2, 0x04060401u, (w2 >> 16) & 0xffu); t[3] = (int)__dp4a(w2, 0x04060401u, w3 & 0xffu);
+                wd[q][0] = row[0]; wd[q][1] = row[1]; wd[q][2] = row[2]; wd[q][3] = row[3];
 #endif
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int tap = r - 2 * j;                                 // compile-time after unrolling
-                if (tap >= 0 && tap <= 4) {
-                    const int wv = tap == 0 || tap == 4 ? 1 : (tap == 2 ? 6 : 4);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) acc[j][k] += wv * t[k];
-                }
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t o = 0;
+        for (int q = 0; q < PYR_BATCH; q++) {
+            const int r = r0 + q;                                      // source row 2y - 2 + r feeds output row j with weight wgt[r - 2j]
+            if (r < 11) {
+                const uint32_t w0 = wd[q][0], w1 = wd[q][1], w2 = wd[q][2], w3 = wd[q][3];
+                // bytes b[0..15] = source columns 2x-4 .. 2x+11 (b[0] = low byte of w0); output k (0..3) is centred on b[4 + 2k]:
+                // taps b[2+2k .. 5+2k] are one (funnel-shifted) 32-bit group for a 4-way byte dot product with (1, 4, 6, 4), plus b[6+2k]
+                int t[4];
+#ifdef VIWB_HOST_EMU
+                int b[16];
+                for (int k = 0; k < 4; k++) { b[k] = (w0 >> (8 * k)) & 0xff; b[4 + k] = (w1 >> (8 * k)) & 0xff; b[8 + k] = (w2 >> (8 * k)) & 0xff; b[12 + k] = (w3 >> (8 * k)) & 0xff; }
+                for (int k = 0; k < 4; k++) { const int c = 4 + 2 * k; t[k] = b[c - 2] + b[c + 2] + 4 * (b[c - 1] + b[c + 1]) + 6 * b[c]; }
+#else
+                const uint32_t g0 = __funnelshift_r(w0, w1, 16), g2 = __funnelshift_r(w1, w2, 16);
+                t[0] = (int)__dp4a(g0, 0x04060401u, (w1 >> 16) & 0xffu); t[1] = (int)__dp4a(w1, 0x04060401u, w2 & 0xffu);
+                t[2] = (int)__dp4a(g2, 0x04060401u, (w2 >> 16) & 0xffu); t[3] = (int)__dp4a(w2, 0x04060401u, w3 & 0xffu);
+#endif
 #pragma unroll
-            for (int k = 0; k < 4; k++) o |= (uint32_t)((acc[j][k] + 128) >> 8) << (8 * k);
-            *reinterpret_cast<uint32_t *>(a.dst + (size_t)(y + j) * a.dstride + x) = o;
+                for (int j = 0; j < 4; j++) {
+                    const int tap = r - 2 * j;                         // compile-time after unrolling
+                    if (tap >= 0 && tap <= 4) {
+                        const int wv = tap == 0 || tap == 4 ? 1 : (tap == 2 ? 6 : 4);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) acc[j][k] += wv * t[k];
+                    }
+                }
+            }
         }
-    } else {
-        for (int j = 0; j < 4 && y + j < a.dh; j++)
-            for (int k = 0; k < 4 && x + k < a.dw; k++) a.dst[(size_t)(y + j) * a.dstride + x + k] = (uint8_t)pyr_down_pixel(a, x + k, y + j);
     }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) o |= (uint32_t)((acc[j][k] + 128) >> 8) << (8 * k);
+        *reinterpret_cast<uint32_t *>(a.dst + (size_t)(y + j) * a.dstride + x) = o;
+    }
+}
+// a 4 x 4 block at the image border (left / right columns, tails of sizes that are not multiples of 4): the 16 source columns are
+// reflected once per block and the rows once per row, the bytes are gathered into the same four words, and the arithmetic is the
+// interior one -- about 4x an interior block instead of 16 independent 25-tap pixels
+VIWB_D void pyr_down_block_edge(const PyrArgs &a, int x, int y) {
+    int cxi[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) cxi[i] = reflect101(2 * x - 4 + i, a.sw);
+    int acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[j][k] = 0;
+#pragma unroll 1
+    for (int r = 0; r < 11; r++) {
+        const uint8_t *row = a.src + (size_t)reflect101(2 * y - 2 + r, a.sh) * a.sstride;
+        int b[16];
+#pragma unroll
+        for (int i = 2; i < 13; i++) b[i] = row[cxi[i]];            // outputs k = 0..3 use bytes 2 .. 12
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = 4 + 2 * k, t = b[c - 2] + b[c + 2] + 4 * (b[c - 1] + b[c + 1]) + 6 * b[c];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int tap = r - 2 * j;
+                const int wv = (tap == 0 || tap == 4) ? 1 : (tap == 2 ? 6 : ((tap == 1 || tap == 3) ? 4 : 0));
+                acc[j][k] += wv * t;
+            }
+        }
+    }
+    for (int j = 0; j < 4 && y + j < a.dh; j++)
+        for (int k = 0; k < 4 && x + k < a.dw; k++) a.dst[(size_t)(y + j) * a.dstride + x + k] = (uint8_t)((acc[j][k] + 128) >> 8);
+}
+// Item order: first the blocks whose columns are interior (block columns 1 .. ci), row by row, then the border columns -- so that the
+// few border blocks fill warps of their own instead of stalling one lane in most warps (with 94 blocks per row and one slow lane per
+// 47, two warps in three used to wait for a border block).
+VIWB_D void pyr_down_item(const PyrArgs &a, int idx) {
+    const int sx = (a.dw + 3) / 4, sy = (a.dh + 3) / 4;
+    if (idx >= sx * sy) return;
+    int xmax = (a.sw - 12) / 2; if (a.dw - 4 < xmax) xmax = a.dw - 4;     // interior block: x >= 2, 2x + 12 <= sw, x + 4 <= dw
+    int ci = xmax >= 4 ? xmax / 4 : 0; if (ci > sx - 1) ci = sx - 1;
+    const int ce = sx - ci;
+    int bx, by;
+    if (idx < ci * sy) { by = idx / ci; bx = 1 + idx - by * ci; }
+    else { const int e = idx - ci * sy; by = e / ce; const int k = e - by * ce; bx = k == 0 ? 0 : ci + k; }
+    const int x = 4 * bx, y = 4 * by;
+    if (bx >= 1 && bx <= ci && y + 4 <= a.dh) {
+        if (2 * y - 2 >= 0 && 2 * y + 8 < a.sh) pyr_down_block<true>(a, x, y);
+        else pyr_down_block<false>(a, x, y);
+    } else pyr_down_block_edge(a, x, y);
 }
 
 // ---- the tracker: one warp per point, no block-level barriers.
