@@ -41,6 +41,9 @@ VIWB_HD void sym_unrank(int e, int &p, int &q) {   // e = p(p+1)/2 + q, 0 <= q <
 // ------------------------------------------------------------------------------------------------ asm_items
 // grid: ceil(nitems * split / warps_per_block); mode selects the solver or the marginalisation item table.
 enum { ASM_SPLIT = 4 };
+#ifndef ASM_PAIR_U
+#define ASM_PAIR_U 3
+#endif
 template <int SPLIT>
 VIWB_D void asm_items_body(const BatchDev &bd, int bx, int tid, int nt, int mode) {
     const int W = nt < 32 ? nt : 32, wpb = nt / W, lane = tid % W;
@@ -62,6 +65,42 @@ VIWB_D void asm_items_body(const BatchDev &bd, int bx, int tid, int nt, int mode
     int nout;
     if (item.kind == ITEM_FRAME) nout = item.has_common ? 105 : 27; else if (item.kind == ITEM_PAIR) nout = 36; else nout = 104;
     if (item.kind == ITEM_FRAME && !item.has_common && part == 0) for (int o = 21 + lane; o < 99; o += W) out[o] = 0.0;
+#ifndef ASM_NO_PAIR_TILES
+    if (item.kind == ITEM_PAIR && split == 1) {
+        // F_a^T F_b has 36 outputs: one output per lane needs a second list walk for the last four.  18 lanes with two neighbouring
+        // outputs each (6 loads per entry instead of 4, the F_a column shared) cover the block in ONE walk.
+        enum { PU = ASM_PAIR_U };                                     // list entries in flight per lane (6 loads each)
+        for (int t = lane; t < 18; t += W) {
+            const int pa = t / 3, pb = 2 * (t - 3 * pa);
+            double acc0 = 0.0, acc1 = 0.0;
+            int e = item.lo;
+            int nx[PU];
+            for (int u = 0; u < PU; u++) nx[u] = 0;
+            if (e + PU <= item.hi) for (int u = 0; u < PU; u++) nx[u] = list[e + u];
+            for (; e + PU <= item.hi; e += PU) {
+                int en[PU]; double va[PU], wa[PU], vb0[PU], wb0[PU], vb1[PU], wb1[PU];
+                for (int u = 0; u < PU; u++) en[u] = nx[u];
+                if (e + 2 * PU <= item.hi) for (int u = 0; u < PU; u++) nx[u] = list[e + PU + u];
+                for (int u = 0; u < PU; u++) {
+                    const int role = en[u] & 1;
+                    const double *rc = recs + (size_t)(en[u] >> 1) * rs;
+                    const int ia = (role ? REC_B : REC_A) + pa, ib = (role ? REC_A : REC_B) + pb;
+                    va[u] = rc[ia]; wa[u] = rc[ia + 6]; vb0[u] = rc[ib]; wb0[u] = rc[ib + 6]; vb1[u] = rc[ib + 1]; wb1[u] = rc[ib + 7];
+                }
+                for (int u = 0; u < PU; u++) { acc0 += va[u] * vb0[u] + wa[u] * wb0[u]; acc1 += va[u] * vb1[u] + wa[u] * wb1[u]; }
+            }
+            for (; e < item.hi; e++) {
+                const int ent = list[e], role = ent & 1;
+                const double *rec = recs + (size_t)(ent >> 1) * rs;
+                const int ia = (role ? REC_B : REC_A) + pa, ib = (role ? REC_A : REC_B) + pb;
+                acc0 += rec[ia] * rec[ib] + rec[ia + 6] * rec[ib + 6];
+                acc1 += rec[ia] * rec[ib + 1] + rec[ia + 6] * rec[ib + 7];
+            }
+            out[6 * pa + pb] = acc0; out[6 * pa + pb + 1] = acc1;
+        }
+        return;
+    }
+#endif
     for (int o0 = lane + W * part; o0 < nout; o0 += W * split) {
         int o = o0;
         if (item.kind == ITEM_FRAME && !item.has_common && o0 >= 21) o = 99 + (o0 - 21);
