@@ -242,8 +242,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="viwb")
-    ap.add_argument("--distinct", type=int, default=37, help="distinct synthetic sequences per rank (37 x 32 copies = 1184 windows = 8 x 148 SMs: whole waves of the one-block-per-window kernels)")
-    ap.add_argument("--copies", type=int, default=32, help="perturbed initial guesses per sequence (batch = distinct*copies)")
+    ap.add_argument("--distinct", type=int, default=37, help="distinct synthetic sequences per rank (37 x 48 copies = 1776 windows = 12 x 148 SMs: whole waves of every one-block-per-window kernel -- solve at 2 / SM, marg at 3 / SM, syrk at 4 / SM)")
+    ap.add_argument("--copies", type=int, default=48, help="perturbed initial guesses per sequence (batch = distinct*copies)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--e2e-lanes", type=int, default=4, help="host threads (each with its own context) driving the e2e measurement")
