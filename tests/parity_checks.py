@@ -765,3 +765,47 @@ def check_tracker_session(ctx, streams=2, w=320, h=240, ticks=5, max_cnt=60, min
         if streams > 1:
             assert refs[-1].stats["repeated"] == ticks - 2, refs[-1].stats
     trk.close()
+
+
+def check_tracker_edges(ctx):
+    """Degenerate sessions: a featureless stream beside a textured one, error returns that leave the session usable."""
+    import feature_oracle as fo
+    from viwb.lib import ViwbError
+    w, h, max_cnt, min_dist = 200, 160, 25, 15
+    cam = (120.0, 119.0, 99.5, 80.2, -0.28, 0.08, 1e-4, -2e-4)
+    left, right, _ = camera_sequence(75, w, h, 3)
+    flat = np.full((h, w), 128, np.uint8)
+    trk = ctx.tracker(2, w, h, cam, cam, max_cnt, min_dist, True)
+    ref = fo.FeatureTrackerRef(cam, cam, max_cnt, min_dist, True)
+    for t in range(3):
+        trk.track(0.05 * (t + 1), np.stack([flat, left[t]]), np.stack([flat, right[t]]))
+        n_left, ids, cnt, feat, n_right, ids_r, feat_r = trk.download()
+        assert n_left[0] == 0 and n_right[0] == 0                       # goodFeaturesToTrack finds nothing on a constant image, every tick
+        r = ref.track_image(0.05 * (t + 1), left[t], right[t])
+        n = int(n_left[1])
+        assert n == len(r[0]) and np.array_equal(ids[1, :n], r[0]) and np.array_equal(cnt[1, :n], r[1])
+        assert np.abs(feat[1, :n, 2:4] - r[2]).max() <= 1e-2
+    # a stereo session needs a right image; the failed call changes nothing
+    try:
+        trk.track(0.2, np.stack([flat, left[0]]), None)
+        accepted = True
+    except ViwbError:
+        accepted = False
+    assert not accepted
+    trk.track(0.2, np.stack([flat, left[0]]), np.stack([flat, right[0]]))          # the session is still usable
+    assert trk.download()[0][1] > 0
+    trk.close()
+    # the largest point capacity the detector supports, on a mono session
+    trk = ctx.tracker(1, w, h, cam, None, 1024, 2, True)
+    trk.track(0.05, left[0][None])
+    n_left = trk.download()[0]
+    g = fo.FeatureTrackerRef(cam, None, 1024, 2, True)
+    r = g.track_image(0.05, left[0])
+    assert int(n_left[0]) == len(r[0]) and len(r[0]) > 150 and np.array_equal(trk.feat[0, : len(r[0]), 2:4], r[2])
+    trk.close()
+    for bad in (0, 1025):
+        try:
+            ctx.tracker(1, w, h, cam, None, bad, 10, True)
+            raise AssertionError("max_cnt %d accepted" % bad)
+        except ViwbError:
+            pass

@@ -120,3 +120,7 @@ def test_tracker_session(emu):
 
 def test_tracker_session_mono_no_flow_back(emu):
     pc.check_tracker_session(emu, streams=1, w=200, h=160, ticks=3, max_cnt=30, min_dist=15, stereo=False, flow_back=False, predict=False)
+
+
+def test_tracker_edges(emu):
+    pc.check_tracker_edges(emu)

@@ -162,3 +162,7 @@ def test_tracker_session(gpu_ctx):
 def test_tracker_session_small_mono(gpu_ctx):
     pc.check_tracker_session(gpu_ctx, streams=2, w=320, h=240, ticks=5, max_cnt=60, min_dist=20, stereo=False)
     pc.check_tracker_session(gpu_ctx, streams=2, w=320, h=240, ticks=4, max_cnt=60, min_dist=20, stereo=True, flow_back=False, predict=False)
+
+
+def test_tracker_edges(gpu_ctx):
+    pc.check_tracker_edges(gpu_ctx)

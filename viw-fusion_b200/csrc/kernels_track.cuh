@@ -36,7 +36,7 @@ struct TrkArgs {                         // one camera stream; every array holds
     int *out_nr; int *out_ids_r; float *out_feat_r;
     int *flags;                          // bit 0: goodFeaturesToTrack candidate list overflowed in this tick
 };
-struct TrkRun { const TrkArgs *tasks; TrkCam cam[2]; double dt; int maxn, first_tick; };
+struct TrkRun { const TrkArgs *tasks; TrkCam cam[2]; double dt; int maxn; };
 
 // warp-cooperative order-preserving position of an element with `flag` among the flagged ones of a group of nt consecutive indices
 VIWB_D int trk_rank(bool flag, int tid, int &total) {
@@ -78,7 +78,7 @@ VIWB_D void trk_pred_setup(const TrkArgs &a, int tid) {
     *a.redo_n = hp ? 0 : n;
 }
 // succ_num < 10 -> the stream repeats the forward flow over the full pyramid (:130-137)
-VIWB_D void trk_pred_check(const TrkArgs &a, int tid, int nt, int *scratch) {
+VIWB_D void trk_pred_check(const TrkArgs &a, int tid, int nt) {
     const int n = *a.pred_n;
     if (n == 0) return;                                       // stream without a prediction: redo_n already holds its count
     int succ = 0;
@@ -87,7 +87,6 @@ VIWB_D void trk_pred_check(const TrkArgs &a, int tid, int nt, int *scratch) {
         trk_rank(i < n && a.lk_status[i] != 0, tid, tot);
         succ += tot;
     }
-    (void)scratch;
     if (tid == 0) *a.redo_n = succ < 10 ? n : 0;
 }
 
@@ -165,7 +164,7 @@ VIWB_D void trk_stereo(const TrkArgs &a, const TrkRun &r, int tid, int nt) {
 #ifndef VIWB_HOST_EMU
 // one warp per stream for the compactions (ballot ranks), one 128-thread block per stream for the merge
 __global__ void trk_pred_setup_kernel(TrkRun r) { trk_pred_setup(r.tasks[blockIdx.x], threadIdx.x); }
-__global__ void trk_pred_check_kernel(TrkRun r) { trk_pred_check(r.tasks[blockIdx.x], threadIdx.x, 32, nullptr); }
+__global__ void trk_pred_check_kernel(TrkRun r) { trk_pred_check(r.tasks[blockIdx.x], threadIdx.x, 32); }
 __global__ void trk_advance_kernel(TrkRun r) { trk_advance(r.tasks[blockIdx.x], threadIdx.x, 32); }
 __global__ void trk_merge_kernel(TrkRun r) { trk_merge(r.tasks[blockIdx.x], r, threadIdx.x, blockDim.x); }
 __global__ void trk_stereo_kernel(TrkRun r) { trk_stereo(r.tasks[blockIdx.x], r, threadIdx.x, 32); }

@@ -6,7 +6,7 @@
 
 #ifdef VIWB_HOST_EMU
 static void trk_launch_pred_setup(const TrkRun &r, int F, stream_t) { for (int f = 0; f < F; f++) trk_pred_setup(r.tasks[f], 0); }
-static void trk_launch_pred_check(const TrkRun &r, int F, stream_t) { for (int f = 0; f < F; f++) trk_pred_check(r.tasks[f], 0, 1, nullptr); }
+static void trk_launch_pred_check(const TrkRun &r, int F, stream_t) { for (int f = 0; f < F; f++) trk_pred_check(r.tasks[f], 0, 1); }
 static void trk_launch_advance(const TrkRun &r, int F, stream_t) { for (int f = 0; f < F; f++) trk_advance(r.tasks[f], 0, 1); }
 static void trk_launch_merge(const TrkRun &r, int F, stream_t) { for (int f = 0; f < F; f++) trk_merge(r.tasks[f], r, 0, 1); }
 static void trk_launch_stereo(const TrkRun &r, int F, stream_t) { for (int f = 0; f < F; f++) trk_stereo(r.tasks[f], r, 0, 1); }
@@ -112,7 +112,7 @@ static int trk_track(viwb_tracker *t, double cur_time, const uint8_t *const *lef
     if (t->stereo && !right) return fail(ctx, VIWB_ERR_INVALID, "tracker: stereo session without right images");
     int rc = lk_batch_upload(b, nullptr, left, t->stereo ? right : nullptr, stride, nullptr, nullptr, nullptr, nullptr); if (rc) return rc;
     TrkRun run; memset(&run, 0, sizeof run);
-    run.tasks = t->tasks; run.cam[0] = t->cam[0]; run.cam[1] = t->cam[1]; run.maxn = t->maxn; run.first_tick = t->ticks == 0;
+    run.tasks = t->tasks; run.cam[0] = t->cam[0]; run.cam[1] = t->cam[1]; run.maxn = t->maxn;
     run.dt = t->has_prev_time ? cur_time - t->prev_time : 1.0;
     if (t->ticks > 0) {
         bool any_pred = false;

@@ -372,7 +372,7 @@ class Tracker:
         """asynchronous; call download() for the featureFrame rows"""
         pl, stride = self._ptrs(left)
         pr = None
-        if self.stereo:
+        if self.stereo and right is not None:       # a missing right image is the C ABI's error to report
             pr, s2 = self._ptrs(right)
             assert s2 == stride
         pp = None if predict_pts is None else np.ascontiguousarray(predict_pts, np.float32)
