@@ -296,15 +296,11 @@ VIWB_D void lin_small_block(const BatchDev &bd, int bx, int by, int tid, int nt,
         VIWB_SYNC();
         const double *J = bd.prior_J + p.J_off;
         double *res = bd.prior_res + p.r_off, *g = bd.prior_g + p.r_off;
-        // r = r_lin + J_lin dx: one warp per row, lanes along the row (J is row-major: a thread per row reads with stride n)
-        {
-            const int PW = nt < 32 ? nt : 32, pl = tid % PW;
-            for (int i = tid / PW; i < n; i += nt / PW) {
-                double s = 0.0;
-                for (int k = pl; k < n; k += PW) s += J[i * n + k] * dx[k];
-                s = lm_warp_sum(s) + bd.prior_r[p.r_off + i];
-                if (pl == 0) { res[i] = s; c += 0.5 * s * s; }
-            }
+        for (int i = tid; i < n; i += nt) {      // (a warp per row with lanes along the row measured slower: 0.47 vs 0.34 ms per launch, r01zh)
+            double s = bd.prior_r[p.r_off + i];
+            for (int k = 0; k < n; k++) s += J[i * n + k] * dx[k];
+            res[i] = s;
+            c += 0.5 * s * s;
         }
         VIWB_SYNC();
         for (int i = tid; i < n; i += nt) {
