@@ -1,0 +1,484 @@
+// mini_eigen.h -- TEST INFRASTRUCTURE ONLY.  A small, eager, fixed-size stand-in for the subset of Eigen 3 that the reference's factor
+// sources use (vins_estimator/src/factor/*.{h,cpp}, utility/utility.h), written from scratch for this repository so that those
+// sources compile UNMODIFIED, from where they lie under /root/reference, into oracle/_ref/libviw_ref.so (oracle/Makefile: `make ref`).
+// The image has no Eigen; this is not Eigen and shares no code with it.  Every operation returns a concrete Matrix (no expression
+// templates); sums run left to right over the inner index, which is also the order Eigen's fixed-size products reduce to without
+// vectorisation -- agreement with the restated oracle is checked to ~1e-12 relative, not bit for bit (tests/test_reference_factors.py).
+#pragma once
+#include <cassert>
+#include <cmath>
+#include <cstddef>
+#include <iostream>
+#include <type_traits>
+#include <algorithm>
+#include <vector>
+#include <map>
+#include <cstring>
+#include <limits>
+#include <string>
+
+namespace Eigen {
+
+const int Dynamic = -1;
+enum { ColMajor = 0, RowMajor = 1 };
+enum { ComputeThinU = 4, ComputeThinV = 8, ComputeFullU = 16, ComputeFullV = 32 };
+typedef std::ptrdiff_t Index;
+
+template <typename T, int R, int C, int Opt = ColMajor> class Matrix;
+template <typename XprType, int BR, int BC> class Block;
+template <typename PlainType> class Map;
+template <typename T> class Quaternion;
+template <typename MatrixType> class JacobiSVD;               // named by utility.h inside a template that is never instantiated
+template <typename MatrixType> class SelfAdjointEigenSolver;  // idem
+template <typename D> struct traits;
+
+template <typename T, int R, int C, int Opt> struct traits<Matrix<T, R, C, Opt>> { typedef T Scalar; enum { Rows = R, Cols = C }; };
+template <typename X, int BR, int BC> struct traits<Block<X, BR, BC>> { typedef typename traits<X>::Scalar Scalar; enum { Rows = BR, Cols = BC }; };
+template <typename P> struct traits<Map<P>> { typedef typename traits<typename std::remove_const<P>::type>::Scalar Scalar; enum { Rows = traits<typename std::remove_const<P>::type>::Rows, Cols = traits<typename std::remove_const<P>::type>::Cols }; };
+
+template <typename Derived> class MatrixBase;
+// the concrete result type of an operation: fixed when both extents are known at compile time, else run-time sized
+template <typename T, int R, int C> struct plain_type { typedef Matrix<T, (R == Dynamic || C == Dynamic) ? Dynamic : R, (R == Dynamic || C == Dynamic) ? Dynamic : C> type; };
+struct SizeTag {};
+template <typename P> P make_plain(int r, int c) { return P(SizeTag(), r, c); }
+inline constexpr int pick_dim(int a, int b) { return a != Dynamic ? a : b; }
+
+// comma initialiser: m << a, b, c, ... in row-major reading order
+template <typename Derived> class CommaInit {
+    Derived &m; int k;
+  public:
+    typedef typename traits<Derived>::Scalar Scalar;
+    CommaInit(Derived &m_, Scalar first) : m(m_), k(0) { put(first); }
+    void put(Scalar v) { const int cols = m.cols(); assert(k < m.rows() * cols); m.coeffRef(k / cols, k % cols) = v; k++; }
+    CommaInit &operator,(Scalar v) { put(v); return *this; }
+};
+
+// run-time sized head of a vector (velocity_j.head(2)); only multiplication by a fixed matrix and reads are supported
+template <typename T> struct DynHead { T v[8]; int n; T operator()(int i) const { return v[i]; } };
+
+template <typename Derived> class MatrixBase {
+  public:
+    typedef typename traits<Derived>::Scalar Scalar;
+    enum { RowsAtCompileTime = traits<Derived>::Rows, ColsAtCompileTime = traits<Derived>::Cols, SizeAtCompileTime = RowsAtCompileTime * ColsAtCompileTime };
+    typedef typename plain_type<Scalar, RowsAtCompileTime, ColsAtCompileTime>::type PlainObject;
+    typedef typename plain_type<Scalar, ColsAtCompileTime, RowsAtCompileTime>::type TransposeReturn;
+    Derived &derived() { return *static_cast<Derived *>(this); }
+    const Derived &derived() const { return *static_cast<const Derived *>(this); }
+    int rows() const { return derived().rowsImpl(); }
+    int cols() const { return derived().colsImpl(); }
+    int size() const { return rows() * cols(); }
+    PlainObject plain() const { return make_plain<PlainObject>(rows(), cols()); }
+    Scalar coeff(int i, int j) const { return derived().coeff(i, j); }
+    Scalar &coeffRef(int i, int j) { return derived().coeffRef(i, j); }
+    Scalar operator()(int i, int j) const { return coeff(i, j); }
+    Scalar &operator()(int i, int j) { return coeffRef(i, j); }
+    // vector access (row or column vectors)
+    Scalar operator()(int i) const { return ColsAtCompileTime == 1 ? coeff(i, 0) : coeff(0, i); }
+    Scalar &operator()(int i) { return ColsAtCompileTime == 1 ? coeffRef(i, 0) : coeffRef(0, i); }
+    Scalar operator[](int i) const { return (*this)(i); }
+    Scalar &operator[](int i) { return (*this)(i); }
+    Scalar x() const { return (*this)(0); } Scalar &x() { return (*this)(0); }
+    Scalar y() const { return (*this)(1); } Scalar &y() { return (*this)(1); }
+    Scalar z() const { return (*this)(2); } Scalar &z() { return (*this)(2); }
+    Scalar w() const { return (*this)(3); } Scalar &w() { return (*this)(3); }
+
+    PlainObject eval() const { PlainObject r = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = coeff(i, j); return r; }
+    TransposeReturn transpose() const { TransposeReturn r = make_plain<TransposeReturn>(cols(), rows()); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(j, i) = coeff(i, j); return r; }
+
+    // ---- fixed-size sub-blocks (views that can be read and assigned)
+    template <int BR, int BC> Block<Derived, BR, BC> block(int i, int j) { return Block<Derived, BR, BC>(derived(), i, j); }
+    template <int BR, int BC> const Block<Derived, BR, BC> block(int i, int j) const { return Block<Derived, BR, BC>(const_cast<Derived &>(derived()), i, j); }
+    template <int N> Block<Derived, N, ColsAtCompileTime> topRows() { return Block<Derived, N, ColsAtCompileTime>(derived(), 0, 0); }
+    template <int N> const Block<Derived, N, ColsAtCompileTime> topRows() const { return Block<Derived, N, ColsAtCompileTime>(const_cast<Derived &>(derived()), 0, 0); }
+    template <int N> Block<Derived, N, ColsAtCompileTime> bottomRows() { return Block<Derived, N, ColsAtCompileTime>(derived(), rows() - N, 0); }
+    template <int N> const Block<Derived, N, ColsAtCompileTime> bottomRows() const { return Block<Derived, N, ColsAtCompileTime>(const_cast<Derived &>(derived()), rows() - N, 0); }
+    template <int N> Block<Derived, RowsAtCompileTime, N> leftCols() { return Block<Derived, RowsAtCompileTime, N>(derived(), 0, 0); }
+    template <int N> const Block<Derived, RowsAtCompileTime, N> leftCols() const { return Block<Derived, RowsAtCompileTime, N>(const_cast<Derived &>(derived()), 0, 0); }
+    template <int N> Block<Derived, RowsAtCompileTime, N> rightCols() { return Block<Derived, RowsAtCompileTime, N>(derived(), 0, cols() - N); }
+    template <int N> const Block<Derived, RowsAtCompileTime, N> rightCols() const { return Block<Derived, RowsAtCompileTime, N>(const_cast<Derived &>(derived()), 0, cols() - N); }
+    template <int BR, int BC> Block<Derived, BR, BC> bottomRightCorner() { return Block<Derived, BR, BC>(derived(), rows() - BR, cols() - BC); }
+    template <int BR, int BC> const Block<Derived, BR, BC> bottomRightCorner() const { return Block<Derived, BR, BC>(const_cast<Derived &>(derived()), rows() - BR, cols() - BC); }
+    template <int BR, int BC> Block<Derived, BR, BC> topLeftCorner() { return Block<Derived, BR, BC>(derived(), 0, 0); }
+    template <int BR, int BC> const Block<Derived, BR, BC> topLeftCorner() const { return Block<Derived, BR, BC>(const_cast<Derived &>(derived()), 0, 0); }
+    Block<Derived, RowsAtCompileTime, 1> col(int j) { return Block<Derived, RowsAtCompileTime, 1>(derived(), 0, j); }
+    const Block<Derived, RowsAtCompileTime, 1> col(int j) const { return Block<Derived, RowsAtCompileTime, 1>(const_cast<Derived &>(derived()), 0, j); }
+    Block<Derived, 1, ColsAtCompileTime> row(int i) { return Block<Derived, 1, ColsAtCompileTime>(derived(), i, 0); }
+    const Block<Derived, 1, ColsAtCompileTime> row(int i) const { return Block<Derived, 1, ColsAtCompileTime>(const_cast<Derived &>(derived()), i, 0); }
+    // vector segments (column vectors)
+    template <int N> Block<Derived, N, 1> head() { return Block<Derived, N, 1>(derived(), 0, 0); }
+    template <int N> const Block<Derived, N, 1> head() const { return Block<Derived, N, 1>(const_cast<Derived &>(derived()), 0, 0); }
+    template <int N> Block<Derived, N, 1> tail() { return Block<Derived, N, 1>(derived(), rows() - N, 0); }
+    template <int N> const Block<Derived, N, 1> tail() const { return Block<Derived, N, 1>(const_cast<Derived &>(derived()), rows() - N, 0); }
+    template <int N> Block<Derived, N, 1> segment(int i) { return Block<Derived, N, 1>(derived(), i, 0); }
+    template <int N> const Block<Derived, N, 1> segment(int i) const { return Block<Derived, N, 1>(const_cast<Derived &>(derived()), i, 0); }
+    DynHead<Scalar> head(int n) const { DynHead<Scalar> h; h.n = n; assert(n <= 8); for (int i = 0; i < n; i++) h.v[i] = (*this)(i); return h; }
+
+    // ---- assignment from any expression of the same size
+    template <typename O> Derived &assign(const MatrixBase<O> &o) {
+        static_assert(((int)traits<O>::Rows == Dynamic || (int)RowsAtCompileTime == Dynamic || (int)traits<O>::Rows == (int)RowsAtCompileTime) &&
+                      ((int)traits<O>::Cols == Dynamic || (int)ColsAtCompileTime == Dynamic || (int)traits<O>::Cols == (int)ColsAtCompileTime), "mini_eigen: size mismatch in assignment");
+        derived().resizeLike(o.rows(), o.cols());
+        PlainObject t = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) t.coeffRef(i, j) = o.coeff(i, j);    // via a temporary: aliasing-safe
+        for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) = t.coeff(i, j);
+        return derived();
+    }
+    template <typename O> Derived &operator+=(const MatrixBase<O> &o) { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) += o.coeff(i, j); return derived(); }
+    template <typename O> Derived &operator-=(const MatrixBase<O> &o) { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) -= o.coeff(i, j); return derived(); }
+    Derived &operator*=(Scalar s) { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) *= s; return derived(); }
+    Derived &operator/=(Scalar s) { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) /= s; return derived(); }
+    CommaInit<Derived> operator<<(Scalar first) { return CommaInit<Derived>(derived(), first); }
+    Derived &setZero() { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) = Scalar(0); return derived(); }
+    Derived &setIdentity() { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) = i == j ? Scalar(1) : Scalar(0); return derived(); }
+    Derived &setConstant(Scalar v) { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) = v; return derived(); }
+    Derived &noalias() { return derived(); }
+
+    // ---- reductions
+    Scalar squaredNorm() const { Scalar s = 0; for (int j = 0; j < cols(); j++) for (int i = 0; i < rows(); i++) s += coeff(i, j) * coeff(i, j); return s; }
+    Scalar norm() const { return std::sqrt(squaredNorm()); }
+    PlainObject normalized() const { PlainObject r = eval(); const Scalar n2 = squaredNorm(); if (n2 > Scalar(0)) r /= std::sqrt(n2); return r; }
+    void normalize() { const Scalar n2 = squaredNorm(); if (n2 > Scalar(0)) *this /= std::sqrt(n2); }
+    Scalar sum() const { Scalar s = 0; for (int j = 0; j < cols(); j++) for (int i = 0; i < rows(); i++) s += coeff(i, j); return s; }
+    Scalar trace() const { Scalar s = 0; for (int i = 0; i < rows(); i++) s += coeff(i, i); return s; }
+    Scalar maxCoeff() const { Scalar m = coeff(0, 0); for (int j = 0; j < cols(); j++) for (int i = 0; i < rows(); i++) if (coeff(i, j) > m) m = coeff(i, j); return m; }
+    Scalar minCoeff() const { Scalar m = coeff(0, 0); for (int j = 0; j < cols(); j++) for (int i = 0; i < rows(); i++) if (coeff(i, j) < m) m = coeff(i, j); return m; }
+    template <typename O> Scalar dot(const MatrixBase<O> &o) const { Scalar s = 0; for (int i = 0; i < size(); i++) s += (*this)(i) * o(i); return s; }
+    template <typename O> Matrix<Scalar, 3, 1> cross(const MatrixBase<O> &o) const {
+        Matrix<Scalar, 3, 1> r; const MatrixBase &a = *this;
+        r(0) = a(1) * o(2) - a(2) * o(1); r(1) = a(2) * o(0) - a(0) * o(2); r(2) = a(0) * o(1) - a(1) * o(0); return r;
+    }
+    template <typename O> bool operator==(const MatrixBase<O> &o) const { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) if (coeff(i, j) != o.coeff(i, j)) return false; return true; }
+    // vector -> diagonal matrix
+    Matrix<Scalar, SizeAtCompileTime, SizeAtCompileTime> asDiagonal() const {
+        static_assert((int)RowsAtCompileTime != Dynamic && (int)ColsAtCompileTime != Dynamic, "mini_eigen: asDiagonal of a fixed-size vector only");
+        Matrix<Scalar, SizeAtCompileTime, SizeAtCompileTime> r; r.setZero(); for (int i = 0; i < size(); i++) r.coeffRef(i, i) = (*this)(i); return r;
+    }
+    PlainObject cwiseProduct(const PlainObject &o) const { PlainObject r = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = coeff(i, j) * o.coeff(i, j); return r; }
+    PlainObject cwiseAbs() const { PlainObject r = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = std::abs(coeff(i, j)); return r; }
+    // general inverse: Gauss-Jordan with partial pivoting (Eigen uses cofactors up to 4x4 and partial-pivot LU above)
+    PlainObject inverse() const {
+        assert(rows() == cols());
+        const int n = rows();
+        PlainObject a = eval(), inv = plain(); inv.setIdentity();
+        for (int c = 0; c < n; c++) {
+            int p = c; for (int r = c + 1; r < n; r++) if (std::abs(a.coeff(r, c)) > std::abs(a.coeff(p, c))) p = r;
+            if (p != c) for (int k = 0; k < n; k++) { std::swap(a.coeffRef(p, k), a.coeffRef(c, k)); std::swap(inv.coeffRef(p, k), inv.coeffRef(c, k)); }
+            const Scalar d = a.coeff(c, c);
+            for (int k = 0; k < n; k++) { a.coeffRef(c, k) /= d; inv.coeffRef(c, k) /= d; }
+            for (int r = 0; r < n; r++) if (r != c) { const Scalar f = a.coeff(r, c); if (f != Scalar(0)) for (int k = 0; k < n; k++) { a.coeffRef(r, k) -= f * a.coeff(c, k); inv.coeffRef(r, k) -= f * inv.coeff(c, k); } }
+        }
+        return inv;
+    }
+    Scalar determinant() const {
+        static_assert((int)RowsAtCompileTime == 3 && (int)ColsAtCompileTime == 3, "mini_eigen: determinant only for 3x3");
+        return coeff(0, 0) * (coeff(1, 1) * coeff(2, 2) - coeff(1, 2) * coeff(2, 1)) - coeff(0, 1) * (coeff(1, 0) * coeff(2, 2) - coeff(1, 2) * coeff(2, 0)) +
+               coeff(0, 2) * (coeff(1, 0) * coeff(2, 1) - coeff(1, 1) * coeff(2, 0));
+    }
+    static PlainObject Zero() { PlainObject r; r.setZero(); return r; }
+    static PlainObject Identity() { PlainObject r; r.setIdentity(); return r; }
+    static PlainObject Ones() { PlainObject r; r.setConstant(Scalar(1)); return r; }
+    static PlainObject Constant(Scalar v) { PlainObject r; r.setConstant(v); return r; }
+    static PlainObject Zero(int r_, int c_) { PlainObject r = make_plain<PlainObject>(r_, c_); r.setZero(); return r; }
+    static PlainObject Identity(int r_, int c_) { PlainObject r = make_plain<PlainObject>(r_, c_); r.setIdentity(); return r; }
+};
+
+// ------------------------------------------------------------------------------------------------ Matrix
+template <typename T, int R, int C, int Opt> class Matrix : public MatrixBase<Matrix<T, R, C, Opt>> {
+    static_assert(R > 0 && C > 0, "mini_eigen: fixed sizes here; Matrix<T, Dynamic, Dynamic> is specialised below");
+    T d[R * C];
+  public:
+    typedef MatrixBase<Matrix> Base;
+    typedef T Scalar;
+    Matrix() {}
+    explicit Matrix(int) {}                                           // Eigen::Vector3d ypr(3): a size, ignored for fixed sizes
+    Matrix(SizeTag, int r, int c) { assert(r == R && c == C); (void)r; (void)c; }
+    static int rowsImpl() { return R; }
+    static int colsImpl() { return C; }
+    static void resizeLike(int r, int c) { assert(r == R && c == C); (void)r; (void)c; }
+    template <typename A, typename B, typename = typename std::enable_if<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value>::type>
+    Matrix(A a, B b) { if constexpr (R * C == 2) { d[0] = T(a); d[1] = T(b); } else { assert((int)a == R && (int)b == C); } }   // two coefficients, or (rows, cols) of a fixed-size matrix
+    template <typename A, typename B, typename Cc, typename = typename std::enable_if<std::is_arithmetic<A>::value && std::is_arithmetic<B>::value && std::is_arithmetic<Cc>::value>::type>
+    Matrix(A a, B b, Cc c) { static_assert(R * C == 3, "3 coefficients"); d[0] = T(a); d[1] = T(b); d[2] = T(c); }
+    Matrix(T a, T b, T c, T e) { static_assert(R * C == 4, "4 coefficients"); d[0] = a; d[1] = b; d[2] = c; d[3] = e; }
+    Matrix(const Matrix &o) { for (int i = 0; i < R * C; i++) d[i] = o.d[i]; }
+    template <typename O> Matrix(const MatrixBase<O> &o) { Base::assign(o); }
+    Matrix &operator=(const Matrix &o) { for (int i = 0; i < R * C; i++) d[i] = o.d[i]; return *this; }
+    template <typename O> Matrix &operator=(const MatrixBase<O> &o) { return Base::assign(o); }
+    T coeff(int i, int j) const { assert(i >= 0 && i < R && j >= 0 && j < C); return Opt == RowMajor ? d[i * C + j] : d[j * R + i]; }
+    T &coeffRef(int i, int j) { assert(i >= 0 && i < R && j >= 0 && j < C); return Opt == RowMajor ? d[i * C + j] : d[j * R + i]; }
+    T *data() { return d; }
+    const T *data() const { return d; }
+};
+
+// run-time sized matrix (MatrixXd F = MatrixXd::Zero(15, 15) in integration_base.h): column-major std::vector storage
+template <typename T, int Opt> class Matrix<T, Dynamic, Dynamic, Opt> : public MatrixBase<Matrix<T, Dynamic, Dynamic, Opt>> {
+    std::vector<T> d; int r_, c_;
+  public:
+    typedef MatrixBase<Matrix> Base;
+    typedef T Scalar;
+    Matrix() : r_(0), c_(0) {}
+    Matrix(SizeTag, int r, int c) : d((size_t)r * c), r_(r), c_(c) {}
+    Matrix(int r, int c) : d((size_t)r * c), r_(r), c_(c) {}
+    Matrix(const Matrix &o) : d(o.d), r_(o.r_), c_(o.c_) {}
+    template <typename O> Matrix(const MatrixBase<O> &o) : r_(0), c_(0) { Base::assign(o); }
+    Matrix &operator=(const Matrix &o) { d = o.d; r_ = o.r_; c_ = o.c_; return *this; }
+    template <typename O> Matrix &operator=(const MatrixBase<O> &o) { return Base::assign(o); }
+    int rowsImpl() const { return r_; }
+    int colsImpl() const { return c_; }
+    void resizeLike(int r, int c) { if (r != r_ || c != c_) { d.assign((size_t)r * c, T(0)); r_ = r; c_ = c; } }
+    void resize(int r, int c) { resizeLike(r, c); }
+    T coeff(int i, int j) const { assert(i >= 0 && i < r_ && j >= 0 && j < c_); return d[(size_t)j * r_ + i]; }
+    T &coeffRef(int i, int j) { assert(i >= 0 && i < r_ && j >= 0 && j < c_); return d[(size_t)j * r_ + i]; }
+};
+// ------------------------------------------------------------------------------------------------ Block (a view)
+template <typename XprType, int BR, int BC> class Block : public MatrixBase<Block<XprType, BR, BC>> {
+    XprType *x; int i0, j0;
+  public:
+    typedef MatrixBase<Block> Base;
+    typedef typename traits<XprType>::Scalar Scalar;
+    Block(XprType &x_, int i, int j) : x(&x_), i0(i), j0(j) { assert(i >= 0 && j >= 0 && i + BR <= x_.rows() && j + BC <= x_.cols()); }
+    static int rowsImpl() { return BR; }
+    static int colsImpl() { return BC; }
+    static void resizeLike(int r, int c) { assert(r == BR && c == BC); (void)r; (void)c; }
+    Scalar coeff(int i, int j) const { return x->coeff(i0 + i, j0 + j); }
+    Scalar &coeffRef(int i, int j) const { return x->coeffRef(i0 + i, j0 + j); }
+    Block &operator=(const Block &o) { Base::assign(o); return *this; }
+    template <typename O> Block &operator=(const MatrixBase<O> &o) { Base::assign(o); return *this; }
+    template <typename O> const Block &operator=(const MatrixBase<O> &o) const { const_cast<Block *>(this)->assign(o); return *this; }
+};
+
+// ------------------------------------------------------------------------------------------------ Map of a plain matrix
+template <typename T, int R, int C, int Opt> class Map<Matrix<T, R, C, Opt>> : public MatrixBase<Map<Matrix<T, R, C, Opt>>> {
+    T *p;
+  public:
+    typedef MatrixBase<Map> Base;
+    typedef T Scalar;
+    explicit Map(T *p_) : p(p_) {}
+    static int rowsImpl() { return R; }
+    static int colsImpl() { return C; }
+    static void resizeLike(int r, int c) { assert(r == R && c == C); (void)r; (void)c; }
+    T coeff(int i, int j) const { return Opt == RowMajor ? p[i * C + j] : p[j * R + i]; }
+    T &coeffRef(int i, int j) const { return Opt == RowMajor ? p[i * C + j] : p[j * R + i]; }
+    Map &operator=(const Map &o) { Base::assign(o); return *this; }
+    template <typename O> Map &operator=(const MatrixBase<O> &o) { Base::assign(o); return *this; }
+};
+template <typename T, int R, int C, int Opt> class Map<const Matrix<T, R, C, Opt>> : public MatrixBase<Map<const Matrix<T, R, C, Opt>>> {
+    const T *p;
+  public:
+    typedef T Scalar;
+    explicit Map(const T *p_) : p(p_) {}
+    static int rowsImpl() { return R; }
+    static int colsImpl() { return C; }
+    static void resizeLike(int, int) {}
+    T coeff(int i, int j) const { return Opt == RowMajor ? p[i * C + j] : p[j * R + i]; }
+    T &coeffRef(int i, int j) const { return const_cast<T *>(p)[Opt == RowMajor ? i * C + j : j * R + i]; }
+};
+
+// ------------------------------------------------------------------------------------------------ arithmetic (eager)
+#define MINI_EIGEN_SAME(A, B) static_assert(((int)traits<A>::Rows == Dynamic || (int)traits<B>::Rows == Dynamic || (int)traits<A>::Rows == (int)traits<B>::Rows) && \
+    ((int)traits<A>::Cols == Dynamic || (int)traits<B>::Cols == Dynamic || (int)traits<A>::Cols == (int)traits<B>::Cols), "mini_eigen: size mismatch")
+template <typename A, typename B> struct sum_type { typedef typename plain_type<typename traits<A>::Scalar, pick_dim(traits<A>::Rows, traits<B>::Rows), pick_dim(traits<A>::Cols, traits<B>::Cols)>::type type; };
+template <typename A, typename B> typename sum_type<A, B>::type operator+(const MatrixBase<A> &a, const MatrixBase<B> &b) {
+    MINI_EIGEN_SAME(A, B); assert(a.rows() == b.rows() && a.cols() == b.cols());
+    typename sum_type<A, B>::type r = make_plain<typename sum_type<A, B>::type>(a.rows(), a.cols());
+    for (int i = 0; i < a.rows(); i++) for (int j = 0; j < a.cols(); j++) r.coeffRef(i, j) = a.coeff(i, j) + b.coeff(i, j); return r;
+}
+template <typename A, typename B> typename sum_type<A, B>::type operator-(const MatrixBase<A> &a, const MatrixBase<B> &b) {
+    MINI_EIGEN_SAME(A, B); assert(a.rows() == b.rows() && a.cols() == b.cols());
+    typename sum_type<A, B>::type r = make_plain<typename sum_type<A, B>::type>(a.rows(), a.cols());
+    for (int i = 0; i < a.rows(); i++) for (int j = 0; j < a.cols(); j++) r.coeffRef(i, j) = a.coeff(i, j) - b.coeff(i, j); return r;
+}
+template <typename A> typename A::PlainObject operator-(const MatrixBase<A> &a) {
+    typename A::PlainObject r = a.plain(); for (int i = 0; i < a.rows(); i++) for (int j = 0; j < a.cols(); j++) r.coeffRef(i, j) = -a.coeff(i, j); return r;
+}
+template <typename A, typename B> struct prod_type { typedef typename plain_type<typename traits<A>::Scalar, traits<A>::Rows, traits<B>::Cols>::type type; };
+template <typename A, typename B> typename prod_type<A, B>::type operator*(const MatrixBase<A> &a, const MatrixBase<B> &b) {
+    static_assert((int)traits<A>::Cols == Dynamic || (int)traits<B>::Rows == Dynamic || (int)traits<A>::Cols == (int)traits<B>::Rows, "mini_eigen: inner sizes differ in *");
+    assert(a.cols() == b.rows());
+    typename prod_type<A, B>::type r = make_plain<typename prod_type<A, B>::type>(a.rows(), b.cols());
+    for (int i = 0; i < a.rows(); i++) for (int j = 0; j < b.cols(); j++) { typename traits<A>::Scalar s = a.coeff(i, 0) * b.coeff(0, j); for (int k = 1; k < a.cols(); k++) s += a.coeff(i, k) * b.coeff(k, j); r.coeffRef(i, j) = s; }
+    return r;
+}
+template <typename A> Matrix<typename traits<A>::Scalar, traits<A>::Rows, 1> operator*(const MatrixBase<A> &a, const DynHead<typename traits<A>::Scalar> &v) {
+    assert(v.n == a.cols());
+    Matrix<typename traits<A>::Scalar, traits<A>::Rows, 1> r;
+    for (int i = 0; i < a.rows(); i++) { typename traits<A>::Scalar s = a.coeff(i, 0) * v.v[0]; for (int k = 1; k < a.cols(); k++) s += a.coeff(i, k) * v.v[k]; r.coeffRef(i, 0) = s; }
+    return r;
+}
+template <typename A, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type> typename A::PlainObject operator*(const MatrixBase<A> &a, S s) {
+    typename A::PlainObject r = a.plain(); for (int i = 0; i < a.rows(); i++) for (int j = 0; j < a.cols(); j++) r.coeffRef(i, j) = a.coeff(i, j) * typename traits<A>::Scalar(s); return r;
+}
+template <typename A, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type> typename A::PlainObject operator*(S s, const MatrixBase<A> &a) {
+    typename A::PlainObject r = a.plain(); for (int i = 0; i < a.rows(); i++) for (int j = 0; j < a.cols(); j++) r.coeffRef(i, j) = typename traits<A>::Scalar(s) * a.coeff(i, j); return r;
+}
+template <typename A, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type> typename A::PlainObject operator/(const MatrixBase<A> &a, S s) {
+    typename A::PlainObject r = a.plain(); for (int i = 0; i < a.rows(); i++) for (int j = 0; j < a.cols(); j++) r.coeffRef(i, j) = a.coeff(i, j) / typename traits<A>::Scalar(s); return r;
+}
+template <typename A> std::ostream &operator<<(std::ostream &os, const MatrixBase<A> &a) {
+    for (int i = 0; i < a.rows(); i++) { for (int j = 0; j < a.cols(); j++) os << (j ? " " : "") << a.coeff(i, j); if (i + 1 < a.rows()) os << "\n"; }
+    return os;
+}
+
+// ------------------------------------------------------------------------------------------------ Cholesky (LLT), lower factor
+template <typename MatrixType> class LLT {
+    typename MatrixType::PlainObject L; bool ok;
+  public:
+    template <typename O> explicit LLT(const MatrixBase<O> &a) : ok(true) {
+        const int n = a.rows(); L = make_plain<typename MatrixType::PlainObject>(n, n); L.setZero();
+        for (int j = 0; j < n; j++) {
+            typename MatrixType::Scalar s = a.coeff(j, j); for (int k = 0; k < j; k++) s -= L.coeff(j, k) * L.coeff(j, k);
+            if (!(s > 0)) ok = false;
+            const typename MatrixType::Scalar ljj = std::sqrt(s); L.coeffRef(j, j) = ljj;
+            for (int i = j + 1; i < n; i++) { typename MatrixType::Scalar t = a.coeff(i, j); for (int k = 0; k < j; k++) t -= L.coeff(i, k) * L.coeff(j, k); L.coeffRef(i, j) = t / ljj; }
+        }
+    }
+    const typename MatrixType::PlainObject &matrixL() const { return L; }
+    typename MatrixType::PlainObject matrixU() const { return L.transpose(); }
+    bool success() const { return ok; }
+};
+
+// ------------------------------------------------------------------------------------------------ quaternions
+template <typename Derived> struct qtraits;
+template <typename QDerived> class QuatVec;
+template <typename QDerived> struct traits<QuatVec<QDerived>> { typedef typename qtraits<QDerived>::Scalar Scalar; enum { Rows = 3, Cols = 1 }; };
+template <typename QDerived> class QuatVec : public MatrixBase<QuatVec<QDerived>> {
+    QDerived *q;
+  public:
+    typedef typename qtraits<QDerived>::Scalar Scalar;
+    explicit QuatVec(QDerived *q_) : q(q_) {}
+    static int rowsImpl() { return 3; }
+    static int colsImpl() { return 1; }
+    static void resizeLike(int, int) {}
+    Scalar coeff(int i, int) const { return q->c(i); }
+    Scalar &coeffRef(int i, int) const { return q->c(i); }
+    template <typename O> QuatVec &operator=(const MatrixBase<O> &o) { for (int i = 0; i < 3; i++) q->c(i) = o(i); return *this; }
+};
+template <typename Derived> class QuaternionBase {
+  public:
+    typedef typename qtraits<Derived>::Scalar Scalar;
+    typedef Matrix<Scalar, 3, 1> Vector3;
+    typedef Matrix<Scalar, 3, 3> Matrix3;
+    const Derived &derived() const { return *static_cast<const Derived *>(this); }
+    Derived &derived() { return *static_cast<Derived *>(this); }
+    // storage order x, y, z, w
+    Scalar x() const { return derived().c(0); } Scalar y() const { return derived().c(1); } Scalar z() const { return derived().c(2); } Scalar w() const { return derived().c(3); }
+    Scalar &x() { return derived().c(0); } Scalar &y() { return derived().c(1); } Scalar &z() { return derived().c(2); } Scalar &w() { return derived().c(3); }
+    typedef QuatVec<Derived> VecView;                             // q.vec(): the imaginary part, readable and assignable
+    VecView vec() { return VecView(&derived()); }
+    const VecView vec() const { return VecView(const_cast<Derived *>(&derived())); }
+    Matrix<Scalar, 4, 1> coeffs() const { Matrix<Scalar, 4, 1> r; for (int i = 0; i < 4; i++) r(i) = derived().c(i); return r; }
+    Scalar squaredNorm() const { return x() * x() + y() * y() + z() * z() + w() * w(); }
+    Scalar norm() const { return std::sqrt(squaredNorm()); }
+    void normalize() { const Scalar n = norm(); for (int i = 0; i < 4; i++) derived().c(i) /= n; }
+    Quaternion<Scalar> normalized() const { const Scalar n = norm(); return Quaternion<Scalar>(w() / n, x() / n, y() / n, z() / n); }
+    Quaternion<Scalar> conjugate() const { return Quaternion<Scalar>(w(), -x(), -y(), -z()); }
+    Quaternion<Scalar> inverse() const {                           // conjugate / squared norm
+        const Scalar n2 = squaredNorm();
+        if (n2 > Scalar(0)) return Quaternion<Scalar>(w() / n2, -x() / n2, -y() / n2, -z() / n2);
+        return Quaternion<Scalar>(0, 0, 0, 0);
+    }
+    template <typename O> Quaternion<Scalar> operator*(const QuaternionBase<O> &b) const {
+        const QuaternionBase &a = *this;
+        return Quaternion<Scalar>(a.w() * b.w() - a.x() * b.x() - a.y() * b.y() - a.z() * b.z(),
+                                  a.w() * b.x() + a.x() * b.w() + a.y() * b.z() - a.z() * b.y(),
+                                  a.w() * b.y() + a.y() * b.w() + a.z() * b.x() - a.x() * b.z(),
+                                  a.w() * b.z() + a.z() * b.w() + a.x() * b.y() - a.y() * b.x());
+    }
+    // rotation of a vector: v + w * 2(u x v) + u x 2(u x v)
+    template <typename O> Vector3 operator*(const MatrixBase<O> &v) const {
+        static_assert((int)traits<O>::Rows == 3 && (int)traits<O>::Cols == 1, "mini_eigen: quaternion times a 3-vector");
+        Vector3 u; u(0) = x(); u(1) = y(); u(2) = z();
+        Vector3 vv = v.eval();
+        Vector3 uv = u.cross(vv); uv += uv;
+        return vv + w() * uv + u.cross(uv);
+    }
+    Matrix3 toRotationMatrix() const {
+        Matrix3 r;
+        const Scalar tx = Scalar(2) * x(), ty = Scalar(2) * y(), tz = Scalar(2) * z();
+        const Scalar twx = tx * w(), twy = ty * w(), twz = tz * w(), txx = tx * x(), txy = ty * x(), txz = tz * x(), tyy = ty * y(), tyz = tz * y(), tzz = tz * z();
+        r(0, 0) = Scalar(1) - (tyy + tzz); r(0, 1) = txy - twz; r(0, 2) = txz + twy;
+        r(1, 0) = txy + twz; r(1, 1) = Scalar(1) - (txx + tzz); r(1, 2) = tyz - twx;
+        r(2, 0) = txz - twy; r(2, 1) = tyz + twx; r(2, 2) = Scalar(1) - (txx + tyy);
+        return r;
+    }
+    Matrix3 matrix() const { return toRotationMatrix(); }
+    template <typename O> Scalar dot(const QuaternionBase<O> &o) const { return x() * o.x() + y() * o.y() + z() * o.z() + w() * o.w(); }
+    template <typename O> Scalar angularDistance(const QuaternionBase<O> &o) const { const Quaternion<Scalar> d = (*this) * o.conjugate(); Scalar n = std::sqrt(d.x() * d.x() + d.y() * d.y() + d.z() * d.z()); return Scalar(2) * std::atan2(n, std::abs(d.w())); }
+};
+
+template <typename T> struct qtraits<Quaternion<T>> { typedef T Scalar; };
+template <typename T> class Quaternion : public QuaternionBase<Quaternion<T>> {
+    T q[4];
+  public:
+    typedef T Scalar;
+    Quaternion() {}
+    Quaternion(T w, T x, T y, T z) { q[0] = x; q[1] = y; q[2] = z; q[3] = w; }
+    explicit Quaternion(const T *p) { for (int i = 0; i < 4; i++) q[i] = p[i]; }
+    template <typename O> Quaternion(const QuaternionBase<O> &o) { q[0] = o.x(); q[1] = o.y(); q[2] = o.z(); q[3] = o.w(); }
+    template <typename O> Quaternion &operator=(const QuaternionBase<O> &o) { const T a = o.x(), b = o.y(), c_ = o.z(), d = o.w(); q[0] = a; q[1] = b; q[2] = c_; q[3] = d; return *this; }
+    // rotation matrix -> quaternion (Shepperd's branches on the trace)
+    template <typename O, typename = typename std::enable_if<(int)traits<O>::Rows == 3 && (int)traits<O>::Cols == 3>::type> explicit Quaternion(const MatrixBase<O> &m) { *this = m; }
+    template <typename O> typename std::enable_if<(int)traits<O>::Rows == 3 && (int)traits<O>::Cols == 3, Quaternion &>::type operator=(const MatrixBase<O> &m) {
+        T t = m.coeff(0, 0) + m.coeff(1, 1) + m.coeff(2, 2);
+        if (t > T(0)) {
+            t = std::sqrt(t + T(1.0)); q[3] = T(0.5) * t; t = T(0.5) / t;
+            q[0] = (m.coeff(2, 1) - m.coeff(1, 2)) * t; q[1] = (m.coeff(0, 2) - m.coeff(2, 0)) * t; q[2] = (m.coeff(1, 0) - m.coeff(0, 1)) * t;
+        } else {
+            int i = 0; if (m.coeff(1, 1) > m.coeff(0, 0)) i = 1; if (m.coeff(2, 2) > m.coeff(i, i)) i = 2;
+            const int j = (i + 1) % 3, k = (j + 1) % 3;
+            t = std::sqrt(m.coeff(i, i) - m.coeff(j, j) - m.coeff(k, k) + T(1.0)); q[i] = T(0.5) * t; t = T(0.5) / t;
+            q[3] = (m.coeff(k, j) - m.coeff(j, k)) * t; q[j] = (m.coeff(j, i) + m.coeff(i, j)) * t; q[k] = (m.coeff(k, i) + m.coeff(i, k)) * t;
+        }
+        return *this;
+    }
+    T c(int i) const { return q[i]; }
+    T &c(int i) { return q[i]; }
+    static Quaternion Identity() { return Quaternion(T(1), T(0), T(0), T(0)); }
+    Quaternion &setIdentity() { q[0] = q[1] = q[2] = T(0); q[3] = T(1); return *this; }
+};
+template <typename T> struct qtraits<Map<Quaternion<T>>> { typedef T Scalar; };
+template <typename T> struct qtraits<Map<const Quaternion<T>>> { typedef T Scalar; };
+template <typename T> class Map<Quaternion<T>> : public QuaternionBase<Map<Quaternion<T>>> {
+    T *p;
+  public:
+    typedef T Scalar;
+    explicit Map(T *p_) : p(p_) {}
+    T c(int i) const { return p[i]; }
+    T &c(int i) { return p[i]; }
+    template <typename O> Map &operator=(const QuaternionBase<O> &o) { const T a = o.x(), b = o.y(), c_ = o.z(), d = o.w(); p[0] = a; p[1] = b; p[2] = c_; p[3] = d; return *this; }
+    Map &operator=(const Map &o) { for (int i = 0; i < 4; i++) p[i] = o.p[i]; return *this; }
+};
+template <typename T> class Map<const Quaternion<T>> : public QuaternionBase<Map<const Quaternion<T>>> {
+    const T *p;
+  public:
+    typedef T Scalar;
+    explicit Map(const T *p_) : p(p_) {}
+    T c(int i) const { return p[i]; }
+    T &c(int i) { return const_cast<T *>(p)[i]; }
+};
+
+template <typename T> class AngleAxis {
+    T a; Matrix<T, 3, 1> ax;
+  public:
+    template <typename O> AngleAxis(T angle, const MatrixBase<O> &axis) : a(angle), ax(axis) {}
+    T angle() const { return a; }
+    const Matrix<T, 3, 1> &axis() const { return ax; }
+    Matrix<T, 3, 3> toRotationMatrix() const {
+        Matrix<T, 3, 3> r; const T s = std::sin(a), c = std::cos(a);
+        const Matrix<T, 3, 1> cc = ax * (T(1) - c);
+        T tmp;
+        tmp = cc.x() * ax.y(); r(0, 1) = tmp - s * ax.z(); r(1, 0) = tmp + s * ax.z();
+        tmp = cc.x() * ax.z(); r(0, 2) = tmp + s * ax.y(); r(2, 0) = tmp - s * ax.y();
+        tmp = cc.y() * ax.z(); r(1, 2) = tmp - s * ax.x(); r(2, 1) = tmp + s * ax.x();
+        r(0, 0) = cc.x() * ax.x() + c; r(1, 1) = cc.y() * ax.y() + c; r(2, 2) = cc.z() * ax.z() + c;
+        return r;
+    }
+};
+
+typedef Matrix<double, 2, 1> Vector2d; typedef Matrix<double, 3, 1> Vector3d; typedef Matrix<double, 4, 1> Vector4d;
+typedef Matrix<double, 2, 2> Matrix2d; typedef Matrix<double, 3, 3> Matrix3d; typedef Matrix<double, 4, 4> Matrix4d;
+typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
+typedef Matrix<float, 3, 1> Vector3f; typedef Matrix<float, 3, 3> Matrix3f;
+typedef Quaternion<double> Quaterniond; typedef Quaternion<float> Quaternionf;
+typedef AngleAxis<double> AngleAxisd;
+
+}  // namespace Eigen

@@ -1,0 +1,64 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/_ref/libviw_ref.so: the reference's OWN factor / manifold / pre-integration
+sources (vins_estimator/src/factor/*.cpp, *.h), compiled unmodified from /root/reference against the header stand-ins of
+oracle/refshim/ (`make -C oracle ref`).  Used by tests/test_reference_factors.py to pin the restated oracle (and through it the CUDA
+library) to the reference code itself.  The library is git-ignored and rebuilt where /root/reference exists."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libviw_ref.so")
+REF_SRC = "/root/reference/vins_estimator/src"
+_lib = None
+c_double_p = C.POINTER(C.c_double)
+
+
+def available():
+    return os.path.exists(LIB) or os.path.isdir(REF_SRC)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if os.path.isdir(REF_SRC):
+            subprocess.check_call(["make", "-C", HERE, "-s", "ref"])
+        _lib = C.CDLL(LIB)
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def factor_evaluate(ftype, globals_, consts, params, sizes, nres, want_jac=True, null_jac=()):
+    P = [np.ascontiguousarray(p, np.float64) for p in params]
+    pp = (c_double_p * len(P))(*[_dp(p) for p in P])
+    res = np.zeros(nres)
+    cst = np.ascontiguousarray(consts, np.float64) if consts is not None else None
+    jacs = [None if (not want_jac or i in null_jac) else np.zeros((nres, s)) for i, s in enumerate(sizes)]
+    jp = (c_double_p * len(P))(*[(_dp(j) if j is not None else None) for j in jacs]) if want_jac else None
+    rc = lib().ref_factor_evaluate(C.c_int(ftype), C.byref(globals_), _dp(cst) if cst is not None else None, pp, _dp(res), jp)
+    if rc:
+        raise RuntimeError("ref_factor_evaluate rc=%d" % rc)
+    return res, jacs
+
+
+def imu_preintegrate(dt, acc, gyr, ba, bg, noise):
+    dt, acc, gyr = (np.ascontiguousarray(a, np.float64) for a in (dt, acc, gyr))
+    ba, bg, noise = (np.ascontiguousarray(a, np.float64) for a in (ba, bg, noise))
+    rec = np.zeros(287)
+    lib().ref_imu_preintegrate(C.c_int(len(dt)), _dp(dt), _dp(acc), _dp(gyr), _dp(ba), _dp(bg), _dp(noise), _dp(rec))
+    return rec
+
+
+def manifold(kind, mask, x, delta, want_jac=True):
+    """kind 0 PoseLocalParameterization, 1 PoseSubsetParameterization, 2 OrientationSubsetParameterization"""
+    gs, ls = (7, 6) if kind < 2 else (4, 3)
+    x, delta = np.ascontiguousarray(x, np.float64), np.ascontiguousarray(delta, np.float64)
+    out, jac = np.zeros(gs), np.zeros((gs, ls))
+    rc = lib().ref_manifold(C.c_int(kind), C.c_uint(mask), _dp(x), _dp(delta), _dp(out), _dp(jac) if want_jac else None)
+    if rc:
+        raise RuntimeError("ref_manifold rc=%d" % rc)
+    return out, jac

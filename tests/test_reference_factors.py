@@ -1,0 +1,93 @@
+"""Pins the restated oracle to THE REFERENCE'S OWN CODE: vins_estimator/src/factor/{projection*Factor.cpp, imu_factor.h,
+integration_base.h, pose_local_parameterization.cpp, pose_subset_parameterization.cpp, orientation_subset_parameterization.cpp}
+compiled unmodified from /root/reference (oracle/Makefile `ref`, third-party headers replaced by oracle/refshim/) and called on
+the same inputs as oracle/vo_factors.c.  Residuals and every Jacobian block must agree to round-off (measured: 3e-13 relative to the
+block's scale for the projection factors, 5e-16 for the IMU factor, 1e-13 for the pre-integration records)."""
+import numpy as np
+import pytest
+
+from viwb import abi, synth
+
+vr = pytest.importorskip("viw_ref")
+if not vr.available():
+    pytest.skip("neither /root/reference nor a prebuilt oracle/_ref/libviw_ref.so", allow_module_level=True)
+
+from test_oracle_factors import block_ptr, rand_pose  # noqa: E402
+
+
+def close(a, b, tol=1e-11):
+    return np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize("cid,ftype", [(1, abi.F_PROJ_2F1C), (2, abi.F_PROJ_2F1C), (2, abi.F_PROJ_2F2C), (2, abi.F_PROJ_1F2C), (3, abi.F_PROJ_2F1C), (4, abi.F_PROJ_2F2C)])
+def test_projection_factors_match_reference_code(oracle, cid, ftype):
+    prob, st, _ = synth.make_window(cid)
+    st = st.copy()
+    st[abi.block_offset(abi.BLK_TD)] = 0.004
+    idx = np.nonzero(prob.vis_type == ftype)[0][:60]
+    assert len(idx) > 0
+    sizes, nres = abi.FACTOR_BLOCK_SIZES[ftype], abi.FACTOR_RESIDUALS[ftype]
+    for f in idx:
+        fi, fj, lm = prob.vis_frame_i[f], prob.vis_frame_j[f], 32 + prob.vis_landmark[f]
+        blocks = {abi.F_PROJ_2F1C: [fi, fj, 22, lm, 30], abi.F_PROJ_2F2C: [fi, fj, 22, 23, lm, 30], abi.F_PROJ_1F2C: [22, 23, lm, 30]}[ftype]
+        params = [block_ptr(st, b) for b in blocks]
+        r0, J0 = vr.factor_evaluate(ftype, prob.globals, prob.vis_obs[f], params, sizes, nres)
+        r1, J1 = oracle.factor_evaluate(ftype, prob.globals, prob.vis_obs[f], params)
+        assert close(r1, r0), (f, r0, r1)
+        for a, b in zip(J1, J0):
+            assert close(a, b), f
+    # jacobians == NULL and jacobians[i] == NULL are honoured the same way
+    r2, _ = vr.factor_evaluate(ftype, prob.globals, prob.vis_obs[idx[0]], params, sizes, nres, want_jac=False)
+    r3, J3 = vr.factor_evaluate(ftype, prob.globals, prob.vis_obs[idx[0]], params, sizes, nres, null_jac=(1,))
+    assert J3[1] is None and np.array_equal(r2, r3)
+
+
+@pytest.mark.parametrize("cid", [1, 2, 4])
+def test_imu_factor_matches_reference_code(oracle, cid):
+    prob, st, _ = synth.make_window(cid)
+    sizes, nres = abi.FACTOR_BLOCK_SIZES[abi.F_IMU], abi.FACTOR_RESIDUALS[abi.F_IMU]
+    for f in range(len(prob.imu_frame_i)):
+        i, j = prob.imu_frame_i[f], prob.imu_frame_j[f]
+        params = [block_ptr(st, b) for b in [i, 11 + i, j, 11 + j]]
+        r0, J0 = vr.factor_evaluate(abi.F_IMU, prob.globals, prob.imu_data[f], params, sizes, nres)
+        r1, J1 = oracle.factor_evaluate(abi.F_IMU, prob.globals, prob.imu_data[f], params)
+        assert close(r1, r0, 1e-12), (f, np.abs(r1 - r0).max())
+        for a, b in zip(J1, J0):
+            assert close(a, b, 1e-12), f
+
+
+def test_preintegration_matches_reference_code(oracle):
+    rng = np.random.default_rng(12)
+    noise = np.array([0.1, 0.01, 1e-3, 1e-4])
+    for n in (1, 7, 10, 40):
+        dt = np.full(n, 0.005) * rng.uniform(0.8, 1.2, n)
+        acc = rng.normal(0, 1.0, (n + 1, 3)) + [0, 0, 9.8]
+        gyr = rng.normal(0, 0.4, (n + 1, 3))
+        ba, bg = rng.normal(0, 0.05, 3), rng.normal(0, 0.01, 3)
+        r0 = vr.imu_preintegrate(dt, acc, gyr, ba, bg, noise)
+        r1 = oracle.imu_preintegrate(dt, acc, gyr, ba, bg, noise)
+        assert np.abs(r1[:62] - r0[:62]).max() <= 1e-12 * max(1.0, np.abs(r0[:62]).max()), n
+        assert np.abs(r1[62:] - r0[62:]).max() <= 1e-12 * np.abs(r0[62:]).max(), n
+        r2 = synth.imu_preintegrate(dt, acc, gyr, ba, bg, noise)                 # the generator's own restatement, too
+        assert np.abs(r2 - r0).max() <= 1e-10 * max(1.0, np.abs(r0).max())
+
+
+def test_manifolds_match_reference_code(oracle):
+    rng = np.random.default_rng(13)
+    prob, st, _ = synth.make_window(4)
+    for trial in range(20):
+        x = rand_pose(rng)
+        d = rng.normal(0, 0.05, 6)
+        for kind, mask in [(0, 0), (1, 1 << 2), (1, (1 << 2) | (1 << 5)), (1, 0b111000)]:
+            out, jac = vr.manifold(kind, mask, x, d)
+            # the oracle's Plus on a full state: put x into pose block 0, apply delta on its tangent columns
+            s2 = st.copy(); s2[0:7] = x
+            delta = np.zeros(abi.TANGENT_FIXED + prob.num_landmarks); delta[0:6] = d
+            prob.subset_mask[0] = mask
+            got = oracle.state_plus(prob, s2, delta)[0:7]
+            prob.subset_mask[0] = 0
+            assert np.abs(got - out).max() <= 1e-14, (kind, mask)
+            assert np.array_equal(jac, np.vstack([np.eye(6), np.zeros((1, 6))]))       # ComputeJacobian = [I; 0] whatever the mask (quirk 2)
+        q = x[3:7]
+        out, jac = vr.manifold(2, 1 << 2, q, d[:3])
+        assert abs(np.linalg.norm(out) - 1.0) < 1e-12 and np.array_equal(jac, np.vstack([np.eye(3), np.zeros((1, 3))]))
