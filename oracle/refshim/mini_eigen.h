@@ -384,8 +384,10 @@ template <typename Derived> class QuaternionBase {
                                   a.w() * b.z() + a.z() * b.w() + a.x() * b.y() - a.y() * b.x());
     }
     // rotation of a vector: v + w * 2(u x v) + u x 2(u x v)
-    template <typename O> Vector3 operator*(const MatrixBase<O> &v) const {
-        static_assert((int)traits<O>::Rows == 3 && (int)traits<O>::Cols == 1, "mini_eigen: quaternion times a 3-vector");
+    template <typename O> typename std::enable_if<(int)traits<O>::Rows == 3 && (int)traits<O>::Cols == 3, Matrix3>::type operator*(const MatrixBase<O> &m) const {
+        return toRotationMatrix() * m;                              // a rotation times a 3x3 matrix: the rotation matrix times it (RotationBase)
+    }
+    template <typename O> typename std::enable_if<(int)traits<O>::Rows == 3 && (int)traits<O>::Cols == 1, Vector3>::type operator*(const MatrixBase<O> &v) const {
         Vector3 u; u(0) = x(); u(1) = y(); u(2) = z();
         Vector3 vv = v.eval();
         Vector3 uv = u.cross(vv); uv += uv;

@@ -9,10 +9,8 @@
 #include "factor/pose_local_parameterization.h"
 #include "factor/pose_subset_parameterization.h"
 #include "factor/orientation_subset_parameterization.h"
-#ifdef REF_WITH_WHEEL
 #include "factor/wheel_factor.h"
 #include "factor/plane_factor.h"
-#endif
 #include "../../include/viwb.h"
 
 // ---- the globals of estimator/parameters.cpp that the factor code reads (that file itself needs ROS + OpenCV and is not compiled)
@@ -57,7 +55,37 @@ extern "C" int ref_factor_evaluate(int type, const viwb_globals *g, const double
         IMUFactor f(&pre);
         return f.Evaluate(parameters, residuals, jacobians) ? 0 : 1;
     }
+    if (type == VIWB_F_WHEEL) {
+        // record layout of include/viwb.h (VIWB_WHEEL_DOUBLES); linearized_vel / linearized_gyr are const members set by the constructor
+        WheelIntegrationBase pre(Eigen::Vector3d(c[65], c[66], c[67]), Eigen::Vector3d(c[68], c[69], c[70]), c[61], c[62], c[63], c[64]);
+        pre.delta_p = Eigen::Vector3d(c[0], c[1], c[2]);
+        pre.delta_q = Eigen::Quaterniond(c[6], c[3], c[4], c[5]);
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 3; j++) pre.jacobian(i, j) = c[7 + 3 * i + j];
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) pre.covariance(i, j) = c[25 + 6 * i + j];
+        pre.vel_1 = Eigen::Vector3d(c[71], c[72], c[73]);
+        pre.gyr_1 = Eigen::Vector3d(c[74], c[75], c[76]);
+        pre.sum_dt = c[77];
+        WheelFactor f(&pre);
+        return f.Evaluate(parameters, residuals, jacobians) ? 0 : 1;
+    }
+    if (type == VIWB_F_PLANE) {
+        PITCH_N_INV = g->plane_sqrt_info[0]; ROLL_N_INV = g->plane_sqrt_info[1]; ZPW_N_INV = g->plane_sqrt_info[2];
+        PlaneFactor f;
+        return f.Evaluate(parameters, residuals, jacobians) ? 0 : 1;
+    }
     return 2;
+}
+
+// WheelIntegrationBase::push_back over a sample buffer -> the 78-double record (same contract as vo_wheel_preintegrate)
+extern "C" void ref_wheel_preintegrate(int n, const double *dt, const double *vel, const double *gyr, const double *s, double td, const double *noise, double *rec) {
+    VEL_N_wheel = noise[0]; GYR_N_wheel = noise[1];
+    WheelIntegrationBase pre(Eigen::Vector3d(vel[0], vel[1], vel[2]), Eigen::Vector3d(gyr[0], gyr[1], gyr[2]), s[0], s[1], s[2], td);
+    for (int k = 0; k < n; k++) pre.push_back(dt[k], Eigen::Vector3d(vel[3 * (k + 1)], vel[3 * (k + 1) + 1], vel[3 * (k + 1) + 2]), Eigen::Vector3d(gyr[3 * (k + 1)], gyr[3 * (k + 1) + 1], gyr[3 * (k + 1) + 2]));
+    for (int i = 0; i < 3; i++) { rec[i] = pre.delta_p(i); rec[65 + i] = pre.linearized_vel(i); rec[68 + i] = pre.linearized_gyr(i); rec[71 + i] = pre.vel_1(i); rec[74 + i] = pre.gyr_1(i); }
+    rec[3] = pre.delta_q.x(); rec[4] = pre.delta_q.y(); rec[5] = pre.delta_q.z(); rec[6] = pre.delta_q.w();
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 3; j++) rec[7 + 3 * i + j] = pre.jacobian(i, j);
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) rec[25 + 6 * i + j] = pre.covariance(i, j);
+    rec[61] = pre.linearized_sx; rec[62] = pre.linearized_sy; rec[63] = pre.linearized_sw; rec[64] = pre.linearized_td; rec[77] = pre.sum_dt;
 }
 
 // IntegrationBase::push_back over a sample buffer -> the 287-double record (same contract as vo_imu_preintegrate)

@@ -53,6 +53,14 @@ def imu_preintegrate(dt, acc, gyr, ba, bg, noise):
     return rec
 
 
+def wheel_preintegrate(dt, vel, gyr, s, td, noise):
+    dt, vel, gyr = (np.ascontiguousarray(a, np.float64) for a in (dt, vel, gyr))
+    s, noise = np.ascontiguousarray(s, np.float64), np.ascontiguousarray(noise, np.float64)
+    rec = np.zeros(78)
+    lib().ref_wheel_preintegrate(C.c_int(len(dt)), _dp(dt), _dp(vel), _dp(gyr), _dp(s), C.c_double(td), _dp(noise), _dp(rec))
+    return rec
+
+
 def manifold(kind, mask, x, delta, want_jac=True):
     """kind 0 PoseLocalParameterization, 1 PoseSubsetParameterization, 2 OrientationSubsetParameterization"""
     gs, ls = (7, 6) if kind < 2 else (4, 3)

@@ -91,3 +91,62 @@ def test_manifolds_match_reference_code(oracle):
         q = x[3:7]
         out, jac = vr.manifold(2, 1 << 2, q, d[:3])
         assert abs(np.linalg.norm(out) - 1.0) < 1e-12 and np.array_equal(jac, np.vstack([np.eye(3), np.zeros((1, 3))]))
+
+
+@pytest.mark.parametrize("dtd,equal_gyr", [(0.0, False), (0.004, False), (-0.003, True)])
+def test_wheel_factor_matches_reference_code(oracle, dtd, equal_gyr):
+    """WheelFactor::Evaluate (factor/wheel_factor.h:28-246) with WheelIntegrationBase::evaluate (wheel_integration_base.h:179-218)
+    and the reference's own sophus_utils.hpp, all compiled from the reference tree; quirk 4 (inexact sx/sy/sw/td Jacobians for
+    dtd != 0) must come out the same on both sides."""
+    rng = np.random.default_rng(21)
+    sizes, nres = abi.FACTOR_BLOCK_SIZES[abi.F_WHEEL], abi.FACTOR_RESIDUALS[abi.F_WHEEL]
+    for cid in (3, 4):
+        prob, st, _ = synth.make_window(cid)
+        for f in range(len(prob.wheel_frame_i)):
+            i, j = prob.wheel_frame_i[f], prob.wheel_frame_j[f]
+            params = [block_ptr(st, b) for b in [i, j, 24, 27, 28, 29, 31]]
+            params[3][0], params[4][0], params[5][0] = 1.0 + rng.normal(0, 0.01), 1.0 + rng.normal(0, 0.01), 1.0 + rng.normal(0, 0.01)
+            params[6][0] = dtd
+            rec = prob.wheel_data[f].copy()
+            if equal_gyr:
+                rec[74:77] = rec[68:71]
+            r0, J0 = vr.factor_evaluate(abi.F_WHEEL, prob.globals, rec, params, sizes, nres)
+            r1, J1 = oracle.factor_evaluate(abi.F_WHEEL, prob.globals, rec, params)
+            assert close(r1, r0, 1e-10), (cid, f, np.abs(r1 - r0).max())
+            for bi, (a, b) in enumerate(zip(J1, J0)):
+                assert close(a, b, 1e-10), (cid, f, bi, np.abs(a - b).max())
+
+
+def test_plane_factor_matches_reference_code(oracle):
+    rng = np.random.default_rng(22)
+    from viwb.geom import R_to_q, so3_exp
+    prob, st, _ = synth.make_window(4)
+    sizes, nres = abi.FACTOR_BLOCK_SIZES[abi.F_PLANE], abi.FACTOR_RESIDUALS[abi.F_PLANE]
+    for trial in range(20):
+        params = [rand_pose(rng), rand_pose(rng, 0.3), R_to_q(so3_exp(rng.normal(0, 0.2, 3))), np.array([rng.normal()])]
+        r0, J0 = vr.factor_evaluate(abi.F_PLANE, prob.globals, None, params, sizes, nres)
+        r1, J1 = oracle.factor_evaluate(abi.F_PLANE, prob.globals, None, params)
+        assert close(r1, r0, 1e-11)
+        for a, b in zip(J1, J0):
+            assert close(a, b, 1e-11), trial
+    # and on the window's own plane factors
+    for f in prob.plane_frame[:5]:
+        params = [block_ptr(st, b) for b in [int(f), 24, 25, 26]]
+        r0, J0 = vr.factor_evaluate(abi.F_PLANE, prob.globals, None, params, sizes, nres)
+        r1, J1 = oracle.factor_evaluate(abi.F_PLANE, prob.globals, None, params)
+        assert close(r1, r0, 1e-11) and all(close(a, b, 1e-11) for a, b in zip(J1, J0))
+
+
+def test_wheel_preintegration_matches_reference_code(oracle):
+    rng = np.random.default_rng(23)
+    noise = np.array([0.01, 0.004])
+    for n in (1, 3, 10):
+        dt = np.full(n, 0.02) * rng.uniform(0.8, 1.2, n)
+        vel = rng.normal(0, 0.05, (n + 1, 3)) + [0.8, 0.0, 0.0]
+        gyr = rng.normal(0, 0.2, (n + 1, 3))
+        s, td = 1.0 + rng.normal(0, 0.02, 3), 0.002
+        r0 = vr.wheel_preintegrate(dt, vel, gyr, s, td, noise)
+        r1 = oracle.wheel_preintegrate(dt, vel, gyr, s, td, noise)
+        assert np.abs(r1 - r0).max() <= 1e-12 * max(1.0, np.abs(r0).max()), (n, np.abs(r1 - r0).max())
+        r2 = synth.wheel_preintegrate(dt, vel, gyr, s, td, noise)
+        assert np.abs(r2 - r0).max() <= 1e-10 * max(1.0, np.abs(r0).max())
