@@ -3,6 +3,9 @@
 #pragma once
 #include <vector>
 #include <cstdint>
+#include <cmath>
+#include <limits>
+#include <algorithm>
 namespace ceres {
 typedef int int32;
 class CostFunction {
@@ -36,5 +39,20 @@ class LossFunction {
   public:
     virtual ~LossFunction() {}
     virtual void Evaluate(double sq_norm, double out[3]) const = 0;
+};
+// ceres::HuberLoss (third party, loss_function.cc): rho(s) = s for s <= delta^2, 2 delta sqrt(s) - delta^2 above
+class HuberLoss : public LossFunction {
+  public:
+    explicit HuberLoss(double a) : a_(a), b_(a * a) {}
+    virtual void Evaluate(double s, double rho[3]) const {
+        if (s > b_) {
+            const double r = std::sqrt(s);
+            rho[0] = 2.0 * a_ * r - b_;
+            rho[1] = std::max(std::numeric_limits<double>::min(), a_ / r);
+            rho[2] = -rho[1] / (2.0 * s);
+        } else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+    }
+  private:
+    const double a_, b_;
 };
 }  // namespace ceres

@@ -11,6 +11,8 @@
 #include <iostream>
 #include <type_traits>
 #include <algorithm>
+#include <numeric>
+#include <functional>
 #include <vector>
 #include <map>
 #include <cstring>
@@ -29,11 +31,14 @@ template <typename XprType, int BR, int BC> class Block;
 template <typename PlainType> class Map;
 template <typename T> class Quaternion;
 template <typename MatrixType> class JacobiSVD;               // named by utility.h inside a template that is never instantiated
-template <typename MatrixType> class SelfAdjointEigenSolver;  // idem
+template <typename MatrixType> class SelfAdjointEigenSolver;
 template <typename D> struct traits;
+template <typename XprType> class DynBlock;
+template <typename T> class ArrayX;
 
 template <typename T, int R, int C, int Opt> struct traits<Matrix<T, R, C, Opt>> { typedef T Scalar; enum { Rows = R, Cols = C }; };
 template <typename X, int BR, int BC> struct traits<Block<X, BR, BC>> { typedef typename traits<X>::Scalar Scalar; enum { Rows = BR, Cols = BC }; };
+template <typename X> struct traits<DynBlock<X>> { typedef typename traits<X>::Scalar Scalar; enum { Rows = Dynamic, Cols = Dynamic }; };
 template <typename P> struct traits<Map<P>> { typedef typename traits<typename std::remove_const<P>::type>::Scalar Scalar; enum { Rows = traits<typename std::remove_const<P>::type>::Rows, Cols = traits<typename std::remove_const<P>::type>::Cols }; };
 
 template <typename Derived> class MatrixBase;
@@ -53,8 +58,6 @@ template <typename Derived> class CommaInit {
     CommaInit &operator,(Scalar v) { put(v); return *this; }
 };
 
-// run-time sized head of a vector (velocity_j.head(2)); only multiplication by a fixed matrix and reads are supported
-template <typename T> struct DynHead { T v[8]; int n; T operator()(int i) const { return v[i]; } };
 
 template <typename Derived> class MatrixBase {
   public:
@@ -73,8 +76,8 @@ template <typename Derived> class MatrixBase {
     Scalar operator()(int i, int j) const { return coeff(i, j); }
     Scalar &operator()(int i, int j) { return coeffRef(i, j); }
     // vector access (row or column vectors)
-    Scalar operator()(int i) const { return ColsAtCompileTime == 1 ? coeff(i, 0) : coeff(0, i); }
-    Scalar &operator()(int i) { return ColsAtCompileTime == 1 ? coeffRef(i, 0) : coeffRef(0, i); }
+    Scalar operator()(int i) const { return cols() == 1 ? coeff(i, 0) : coeff(0, i); }
+    Scalar &operator()(int i) { return cols() == 1 ? coeffRef(i, 0) : coeffRef(0, i); }
     Scalar operator[](int i) const { return (*this)(i); }
     Scalar &operator[](int i) { return (*this)(i); }
     Scalar x() const { return (*this)(0); } Scalar &x() { return (*this)(0); }
@@ -111,7 +114,27 @@ template <typename Derived> class MatrixBase {
     template <int N> const Block<Derived, N, 1> tail() const { return Block<Derived, N, 1>(const_cast<Derived &>(derived()), rows() - N, 0); }
     template <int N> Block<Derived, N, 1> segment(int i) { return Block<Derived, N, 1>(derived(), i, 0); }
     template <int N> const Block<Derived, N, 1> segment(int i) const { return Block<Derived, N, 1>(const_cast<Derived &>(derived()), i, 0); }
-    DynHead<Scalar> head(int n) const { DynHead<Scalar> h; h.n = n; assert(n <= 8); for (int i = 0; i < n; i++) h.v[i] = (*this)(i); return h; }
+    // ---- run-time sized views
+    DynBlock<Derived> block(int i, int j, int r, int c) { return DynBlock<Derived>(derived(), i, j, r, c); }
+    const DynBlock<Derived> block(int i, int j, int r, int c) const { return DynBlock<Derived>(const_cast<Derived &>(derived()), i, j, r, c); }
+    DynBlock<Derived> segment(int i, int n) { return cols() == 1 ? block(i, 0, n, 1) : block(0, i, 1, n); }
+    const DynBlock<Derived> segment(int i, int n) const { return cols() == 1 ? block(i, 0, n, 1) : block(0, i, 1, n); }
+    DynBlock<Derived> head(int n) { return segment(0, n); }
+    const DynBlock<Derived> head(int n) const { return segment(0, n); }
+    DynBlock<Derived> tail(int n) { return segment(size() - n, n); }
+    const DynBlock<Derived> tail(int n) const { return segment(size() - n, n); }
+    DynBlock<Derived> leftCols(int n) { return block(0, 0, rows(), n); }
+    const DynBlock<Derived> leftCols(int n) const { return block(0, 0, rows(), n); }
+    DynBlock<Derived> rightCols(int n) { return block(0, cols() - n, rows(), n); }
+    const DynBlock<Derived> rightCols(int n) const { return block(0, cols() - n, rows(), n); }
+    DynBlock<Derived> middleCols(int j, int n) { return block(0, j, rows(), n); }
+    const DynBlock<Derived> middleCols(int j, int n) const { return block(0, j, rows(), n); }
+    DynBlock<Derived> topRows(int n) { return block(0, 0, n, cols()); }
+    const DynBlock<Derived> topRows(int n) const { return block(0, 0, n, cols()); }
+    DynBlock<Derived> bottomRows(int n) { return block(rows() - n, 0, n, cols()); }
+    const DynBlock<Derived> bottomRows(int n) const { return block(rows() - n, 0, n, cols()); }
+    ArrayX<Scalar> array() const;
+    PlainObject cwiseSqrt() const { PlainObject r = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = std::sqrt(coeff(i, j)); return r; }
 
     // ---- assignment from any expression of the same size
     template <typename O> Derived &assign(const MatrixBase<O> &o) {
@@ -148,9 +171,11 @@ template <typename Derived> class MatrixBase {
     }
     template <typename O> bool operator==(const MatrixBase<O> &o) const { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) if (coeff(i, j) != o.coeff(i, j)) return false; return true; }
     // vector -> diagonal matrix
-    Matrix<Scalar, SizeAtCompileTime, SizeAtCompileTime> asDiagonal() const {
-        static_assert((int)RowsAtCompileTime != Dynamic && (int)ColsAtCompileTime != Dynamic, "mini_eigen: asDiagonal of a fixed-size vector only");
-        Matrix<Scalar, SizeAtCompileTime, SizeAtCompileTime> r; r.setZero(); for (int i = 0; i < size(); i++) r.coeffRef(i, i) = (*this)(i); return r;
+    typename plain_type<Scalar, ((int)RowsAtCompileTime == Dynamic || (int)ColsAtCompileTime == Dynamic) ? Dynamic : (int)SizeAtCompileTime,
+                        ((int)RowsAtCompileTime == Dynamic || (int)ColsAtCompileTime == Dynamic) ? Dynamic : (int)SizeAtCompileTime>::type asDiagonal() const {
+        typedef typename plain_type<Scalar, ((int)RowsAtCompileTime == Dynamic || (int)ColsAtCompileTime == Dynamic) ? Dynamic : (int)SizeAtCompileTime,
+                                    ((int)RowsAtCompileTime == Dynamic || (int)ColsAtCompileTime == Dynamic) ? Dynamic : (int)SizeAtCompileTime>::type D;
+        D r = make_plain<D>(size(), size()); r.setZero(); for (int i = 0; i < size(); i++) r.coeffRef(i, i) = (*this)(i); return r;
     }
     PlainObject cwiseProduct(const PlainObject &o) const { PlainObject r = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = coeff(i, j) * o.coeff(i, j); return r; }
     PlainObject cwiseAbs() const { PlainObject r = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = std::abs(coeff(i, j)); return r; }
@@ -177,6 +202,7 @@ template <typename Derived> class MatrixBase {
     static PlainObject Identity() { PlainObject r; r.setIdentity(); return r; }
     static PlainObject Ones() { PlainObject r; r.setConstant(Scalar(1)); return r; }
     static PlainObject Constant(Scalar v) { PlainObject r; r.setConstant(v); return r; }
+    static PlainObject Zero(int n_) { PlainObject r = make_plain<PlainObject>(n_, 1); r.setZero(); return r; }
     static PlainObject Zero(int r_, int c_) { PlainObject r = make_plain<PlainObject>(r_, c_); r.setZero(); return r; }
     static PlainObject Identity(int r_, int c_) { PlainObject r = make_plain<PlainObject>(r_, c_); r.setIdentity(); return r; }
 };
@@ -209,7 +235,7 @@ template <typename T, int R, int C, int Opt> class Matrix : public MatrixBase<Ma
     const T *data() const { return d; }
 };
 
-// run-time sized matrix (MatrixXd F = MatrixXd::Zero(15, 15) in integration_base.h): column-major std::vector storage
+// run-time sized matrix (MatrixXd F = MatrixXd::Zero(15, 15) in integration_base.h; the Jacobian buffers of ResidualBlockInfo are RowMajor)
 template <typename T, int Opt> class Matrix<T, Dynamic, Dynamic, Opt> : public MatrixBase<Matrix<T, Dynamic, Dynamic, Opt>> {
     std::vector<T> d; int r_, c_;
   public:
@@ -226,9 +252,69 @@ template <typename T, int Opt> class Matrix<T, Dynamic, Dynamic, Opt> : public M
     int colsImpl() const { return c_; }
     void resizeLike(int r, int c) { if (r != r_ || c != c_) { d.assign((size_t)r * c, T(0)); r_ = r; c_ = c; } }
     void resize(int r, int c) { resizeLike(r, c); }
-    T coeff(int i, int j) const { assert(i >= 0 && i < r_ && j >= 0 && j < c_); return d[(size_t)j * r_ + i]; }
-    T &coeffRef(int i, int j) { assert(i >= 0 && i < r_ && j >= 0 && j < c_); return d[(size_t)j * r_ + i]; }
+    T coeff(int i, int j) const { assert(i >= 0 && i < r_ && j >= 0 && j < c_); return Opt == RowMajor ? d[(size_t)i * c_ + j] : d[(size_t)j * r_ + i]; }
+    T &coeffRef(int i, int j) { assert(i >= 0 && i < r_ && j >= 0 && j < c_); return Opt == RowMajor ? d[(size_t)i * c_ + j] : d[(size_t)j * r_ + i]; }
+    T *data() { return d.data(); }
+    const T *data() const { return d.data(); }
 };
+// run-time sized column vector (VectorXd)
+template <typename T, int Opt> struct traits<Matrix<T, Dynamic, 1, Opt>> { typedef T Scalar; enum { Rows = Dynamic, Cols = 1 }; };
+template <typename T, int Opt> class Matrix<T, Dynamic, 1, Opt> : public MatrixBase<Matrix<T, Dynamic, 1, Opt>> {
+    std::vector<T> d;
+  public:
+    typedef MatrixBase<Matrix> Base;
+    typedef T Scalar;
+    Matrix() {}
+    explicit Matrix(int n) : d((size_t)n) {}
+    Matrix(SizeTag, int r, int c) : d((size_t)r) { assert(c == 1); (void)c; }
+    Matrix(const Matrix &o) : d(o.d) {}
+    template <typename O> Matrix(const MatrixBase<O> &o) { Base::assign(o); }
+    Matrix(const ArrayX<T> &a);
+    Matrix &operator=(const Matrix &o) { d = o.d; return *this; }
+    template <typename O> Matrix &operator=(const MatrixBase<O> &o) { return Base::assign(o); }
+    int rowsImpl() const { return (int)d.size(); }
+    static int colsImpl() { return 1; }
+    void resizeLike(int r, int c) { assert(c == 1); (void)c; if (r != (int)d.size()) d.assign((size_t)r, T(0)); }
+    void resize(int n) { resizeLike(n, 1); }
+    T coeff(int i, int j) const { assert(i >= 0 && i < (int)d.size() && j == 0); (void)j; return d[i]; }
+    T &coeffRef(int i, int j) { assert(i >= 0 && i < (int)d.size() && j == 0); (void)j; return d[i]; }
+    T *data() { return d.data(); }
+    const T *data() const { return d.data(); }
+};
+// run-time sized view
+template <typename XprType> class DynBlock : public MatrixBase<DynBlock<XprType>> {
+    XprType *x; int i0, j0, r_, c_;
+  public:
+    typedef MatrixBase<DynBlock> Base;
+    typedef typename traits<XprType>::Scalar Scalar;
+    DynBlock(XprType &x_, int i, int j, int r, int c) : x(&x_), i0(i), j0(j), r_(r), c_(c) { assert(i >= 0 && j >= 0 && r >= 0 && c >= 0 && i + r <= x_.rows() && j + c <= x_.cols()); }
+    int rowsImpl() const { return r_; }
+    int colsImpl() const { return c_; }
+    void resizeLike(int r, int c) const { assert(r == r_ && c == c_); (void)r; (void)c; }
+    Scalar coeff(int i, int j) const { return x->coeff(i0 + i, j0 + j); }
+    Scalar &coeffRef(int i, int j) const { return x->coeffRef(i0 + i, j0 + j); }
+    DynBlock &operator=(const DynBlock &o) { Base::assign(o); return *this; }
+    template <typename O> DynBlock &operator=(const MatrixBase<O> &o) { Base::assign(o); return *this; }
+    template <typename O> const DynBlock &operator=(const MatrixBase<O> &o) const { const_cast<DynBlock *>(this)->assign(o); return *this; }
+};
+// coefficient-wise view of a vector: (v.array() > eps).select(v.array().inverse(), 0)
+template <typename T> struct BoolArrayX {
+    std::vector<char> b;
+    ArrayX<T> select(const ArrayX<T> &then, T otherwise) const;
+};
+template <typename T> class ArrayX {
+  public:
+    std::vector<T> v;
+    ArrayX() {}
+    explicit ArrayX(size_t n) : v(n) {}
+    BoolArrayX<T> operator>(T s) const { BoolArrayX<T> r; r.b.resize(v.size()); for (size_t i = 0; i < v.size(); i++) r.b[i] = v[i] > s; return r; }
+    ArrayX inverse() const { ArrayX r(v.size()); for (size_t i = 0; i < v.size(); i++) r.v[i] = T(1) / v[i]; return r; }
+    ArrayX sqrt() const { ArrayX r(v.size()); for (size_t i = 0; i < v.size(); i++) r.v[i] = std::sqrt(v[i]); return r; }
+};
+template <typename T> ArrayX<T> BoolArrayX<T>::select(const ArrayX<T> &then, T otherwise) const { ArrayX<T> r(b.size()); for (size_t i = 0; i < b.size(); i++) r.v[i] = b[i] ? then.v[i] : otherwise; return r; }
+template <typename T, int Opt> Matrix<T, Dynamic, 1, Opt>::Matrix(const ArrayX<T> &a) : d(a.v) {}
+template <typename Derived> ArrayX<typename MatrixBase<Derived>::Scalar> MatrixBase<Derived>::array() const { ArrayX<Scalar> r((size_t)size()); for (int i = 0; i < size(); i++) r.v[i] = (*this)(i); return r; }
+
 // ------------------------------------------------------------------------------------------------ Block (a view)
 template <typename XprType, int BR, int BC> class Block : public MatrixBase<Block<XprType, BR, BC>> {
     XprType *x; int i0, j0;
@@ -273,6 +359,47 @@ template <typename T, int R, int C, int Opt> class Map<const Matrix<T, R, C, Opt
     T &coeffRef(int i, int j) const { return const_cast<T *>(p)[Opt == RowMajor ? i * C + j : j * R + i]; }
 };
 
+// run-time sized maps: Map<VectorXd>(p, n), Map<const VectorXd>(p, n), Map<Matrix<T, Dynamic, Dynamic, RowMajor>>(p, r, c)
+template <typename T, int Opt> class Map<Matrix<T, Dynamic, 1, Opt>> : public MatrixBase<Map<Matrix<T, Dynamic, 1, Opt>>> {
+    T *p; int n_;
+  public:
+    typedef MatrixBase<Map> Base;
+    typedef T Scalar;
+    Map(T *p_, int n) : p(p_), n_(n) {}
+    int rowsImpl() const { return n_; }
+    static int colsImpl() { return 1; }
+    void resizeLike(int r, int c) const { assert(r == n_ && c == 1); (void)r; (void)c; }
+    T coeff(int i, int) const { return p[i]; }
+    T &coeffRef(int i, int) const { return p[i]; }
+    Map &operator=(const Map &o) { Base::assign(o); return *this; }
+    template <typename O> Map &operator=(const MatrixBase<O> &o) { Base::assign(o); return *this; }
+};
+template <typename T, int Opt> class Map<const Matrix<T, Dynamic, 1, Opt>> : public MatrixBase<Map<const Matrix<T, Dynamic, 1, Opt>>> {
+    const T *p; int n_;
+  public:
+    typedef T Scalar;
+    Map(const T *p_, int n) : p(p_), n_(n) {}
+    int rowsImpl() const { return n_; }
+    static int colsImpl() { return 1; }
+    void resizeLike(int, int) const {}
+    T coeff(int i, int) const { return p[i]; }
+    T &coeffRef(int i, int) const { return const_cast<T *>(p)[i]; }
+};
+template <typename T, int Opt> class Map<Matrix<T, Dynamic, Dynamic, Opt>> : public MatrixBase<Map<Matrix<T, Dynamic, Dynamic, Opt>>> {
+    T *p; int r_, c_;
+  public:
+    typedef MatrixBase<Map> Base;
+    typedef T Scalar;
+    Map(T *p_, int r, int c) : p(p_), r_(r), c_(c) {}
+    int rowsImpl() const { return r_; }
+    int colsImpl() const { return c_; }
+    void resizeLike(int r, int c) const { assert(r == r_ && c == c_); (void)r; (void)c; }
+    T coeff(int i, int j) const { return Opt == RowMajor ? p[(size_t)i * c_ + j] : p[(size_t)j * r_ + i]; }
+    T &coeffRef(int i, int j) const { return Opt == RowMajor ? p[(size_t)i * c_ + j] : p[(size_t)j * r_ + i]; }
+    Map &operator=(const Map &o) { Base::assign(o); return *this; }
+    template <typename O> Map &operator=(const MatrixBase<O> &o) { Base::assign(o); return *this; }
+};
+
 // ------------------------------------------------------------------------------------------------ arithmetic (eager)
 #define MINI_EIGEN_SAME(A, B) static_assert(((int)traits<A>::Rows == Dynamic || (int)traits<B>::Rows == Dynamic || (int)traits<A>::Rows == (int)traits<B>::Rows) && \
     ((int)traits<A>::Cols == Dynamic || (int)traits<B>::Cols == Dynamic || (int)traits<A>::Cols == (int)traits<B>::Cols), "mini_eigen: size mismatch")
@@ -296,12 +423,6 @@ template <typename A, typename B> typename prod_type<A, B>::type operator*(const
     assert(a.cols() == b.rows());
     typename prod_type<A, B>::type r = make_plain<typename prod_type<A, B>::type>(a.rows(), b.cols());
     for (int i = 0; i < a.rows(); i++) for (int j = 0; j < b.cols(); j++) { typename traits<A>::Scalar s = a.coeff(i, 0) * b.coeff(0, j); for (int k = 1; k < a.cols(); k++) s += a.coeff(i, k) * b.coeff(k, j); r.coeffRef(i, j) = s; }
-    return r;
-}
-template <typename A> Matrix<typename traits<A>::Scalar, traits<A>::Rows, 1> operator*(const MatrixBase<A> &a, const DynHead<typename traits<A>::Scalar> &v) {
-    assert(v.n == a.cols());
-    Matrix<typename traits<A>::Scalar, traits<A>::Rows, 1> r;
-    for (int i = 0; i < a.rows(); i++) { typename traits<A>::Scalar s = a.coeff(i, 0) * v.v[0]; for (int k = 1; k < a.cols(); k++) s += a.coeff(i, k) * v.v[k]; r.coeffRef(i, 0) = s; }
     return r;
 }
 template <typename A, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type> typename A::PlainObject operator*(const MatrixBase<A> &a, S s) {
@@ -334,6 +455,42 @@ template <typename MatrixType> class LLT {
     const typename MatrixType::PlainObject &matrixL() const { return L; }
     typename MatrixType::PlainObject matrixU() const { return L.transpose(); }
     bool success() const { return ok; }
+};
+
+// ------------------------------------------------------------------------------------------------ symmetric eigen decomposition
+// Cyclic Jacobi rotations (Eigen tridiagonalises and runs implicit QR; eigenvalues agree to round-off, eigenvectors up to sign and, for
+// repeated eigenvalues, basis).  eigenvalues() ascending, eigenvectors() in the matching columns.
+template <typename MatrixType> class SelfAdjointEigenSolver {
+    typedef typename traits<MatrixType>::Scalar T;
+    Matrix<T, Dynamic, 1> w; Matrix<T, Dynamic, Dynamic> V;
+  public:
+    template <typename O> explicit SelfAdjointEigenSolver(const MatrixBase<O> &m) {
+        const int n = m.rows(); assert(m.cols() == n);
+        std::vector<T> a((size_t)n * n), v((size_t)n * n, T(0));
+        for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) a[(size_t)i * n + j] = i >= j ? m.coeff(i, j) : m.coeff(j, i);       // lower triangle is read
+        for (int i = 0; i < n; i++) v[(size_t)i * n + i] = T(1);
+        for (int sweep = 0; sweep < 60; sweep++) {
+            T off = 0, diag = 0;
+            for (int i = 0; i < n; i++) { diag += a[(size_t)i * n + i] * a[(size_t)i * n + i]; for (int j = 0; j < i; j++) off += a[(size_t)i * n + j] * a[(size_t)i * n + j]; }
+            if (off <= T(1e-32) * (diag + off) || off == T(0)) break;
+            for (int p = 0; p < n - 1; p++) for (int q = p + 1; q < n; q++) {
+                const T apq = a[(size_t)p * n + q];
+                if (apq == T(0)) continue;
+                const T theta = (a[(size_t)q * n + q] - a[(size_t)p * n + p]) / (T(2) * apq);
+                const T t = (theta >= 0 ? T(1) : T(-1)) / (std::abs(theta) + std::sqrt(theta * theta + T(1)));
+                const T c = T(1) / std::sqrt(t * t + T(1)), sn = t * c;
+                for (int k = 0; k < n; k++) { const T akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q]; a[(size_t)k * n + p] = c * akp - sn * akq; a[(size_t)k * n + q] = sn * akp + c * akq; }
+                for (int k = 0; k < n; k++) { const T apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k]; a[(size_t)p * n + k] = c * apk - sn * aqk; a[(size_t)q * n + k] = sn * apk + c * aqk; }
+                for (int k = 0; k < n; k++) { const T vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q]; v[(size_t)k * n + p] = c * vkp - sn * vkq; v[(size_t)k * n + q] = sn * vkp + c * vkq; }
+            }
+        }
+        std::vector<int> order(n); for (int i = 0; i < n; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int x, int y) { return a[(size_t)x * n + x] < a[(size_t)y * n + y]; });
+        w.resize(n); V.resize(n, n);
+        for (int k = 0; k < n; k++) { w.coeffRef(k, 0) = a[(size_t)order[k] * n + order[k]]; for (int i = 0; i < n; i++) V.coeffRef(i, k) = v[(size_t)i * n + order[k]]; }
+    }
+    const Matrix<T, Dynamic, 1> &eigenvalues() const { return w; }
+    const Matrix<T, Dynamic, Dynamic> &eigenvectors() const { return V; }
 };
 
 // ------------------------------------------------------------------------------------------------ quaternions
@@ -479,6 +636,7 @@ template <typename T> class AngleAxis {
 typedef Matrix<double, 2, 1> Vector2d; typedef Matrix<double, 3, 1> Vector3d; typedef Matrix<double, 4, 1> Vector4d;
 typedef Matrix<double, 2, 2> Matrix2d; typedef Matrix<double, 3, 3> Matrix3d; typedef Matrix<double, 4, 4> Matrix4d;
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
+typedef Matrix<double, Dynamic, 1> VectorXd;
 typedef Matrix<float, 3, 1> Vector3f; typedef Matrix<float, 3, 3> Matrix3f;
 typedef Quaternion<double> Quaterniond; typedef Quaternion<float> Quaternionf;
 typedef AngleAxis<double> AngleAxisd;

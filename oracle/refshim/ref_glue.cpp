@@ -11,6 +11,7 @@
 #include "factor/orientation_subset_parameterization.h"
 #include "factor/wheel_factor.h"
 #include "factor/plane_factor.h"
+#include "factor/marginalization_factor.h"
 #include "../../include/viwb.h"
 
 // ---- the globals of estimator/parameters.cpp that the factor code reads (that file itself needs ROS + OpenCV and is not compiled)
@@ -115,4 +116,128 @@ extern "C" int ref_manifold(int kind, unsigned mask, const double *x, const doub
     if (jacobian) ok = p->ComputeJacobian(x, jacobian) && ok;
     delete p;
     return ok ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------------- marginalization
+// The arithmetic is the reference's (ResidualBlockInfo::Evaluate with the loss corrector, MarginalizationInfo::preMarginalize /
+// marginalize with its four threads, MarginalizationFactor::Evaluate: factor/marginalization_factor.cpp, compiled unmodified).  What
+// this glue restates is only the bookkeeping of Estimator::optimization() that hands the factors over (estimator.cpp:1669-1790 for
+// MARGIN_OLD, :1803-1842 for MARGIN_SECOND_NEW), driven by the same viwb_problem tables the oracle and the CUDA library consume.
+static MarginalizationInfo *info_from_prior(const viwb_prior *pr, std::vector<double *> &x0_blocks) {
+    MarginalizationInfo *info = new MarginalizationInfo();
+    info->n = pr->n; info->m = 0; info->valid = pr->valid != 0;
+    for (int k = 0; k < pr->num_blocks; k++) {
+        const int b = pr->block_id[k], size = viwb_block_size(b);
+        double *d = new double[size];
+        memcpy(d, pr->x0 + viwb_block_offset(b), sizeof(double) * size);
+        x0_blocks.push_back(d);
+        info->keep_block_size.push_back(size);
+        info->keep_block_idx.push_back(pr->block_idx[k]);
+        info->keep_block_data.push_back(d);
+    }
+    info->linearized_jacobians.resize(pr->n, pr->n);
+    info->linearized_residuals.resize(pr->n);
+    for (int i = 0; i < pr->n; i++) { info->linearized_residuals(i) = pr->r[i]; for (int j = 0; j < pr->n; j++) info->linearized_jacobians(i, j) = pr->J[(size_t)i * pr->n + j]; }
+    return info;
+}
+
+// MarginalizationFactor::Evaluate: same contract as vo_prior_evaluate (jacobian n x VIWB_STATE_FIXED row-major, or NULL)
+extern "C" int ref_prior_evaluate(const viwb_prior *pr, const double *state, double *residuals, double *jacobian) {
+    std::vector<double *> x0;
+    MarginalizationInfo *info = info_from_prior(pr, x0);
+    MarginalizationFactor f(info);
+    std::vector<const double *> params; std::vector<std::vector<double>> jb; std::vector<double *> jp;
+    for (int k = 0; k < pr->num_blocks; k++) { const int b = pr->block_id[k]; params.push_back(state + viwb_block_offset(b)); jb.emplace_back((size_t)pr->n * viwb_block_size(b)); }
+    for (auto &v : jb) jp.push_back(v.data());
+    const bool ok = f.Evaluate(params.data(), residuals, jacobian ? jp.data() : nullptr);
+    if (jacobian) {
+        memset(jacobian, 0, sizeof(double) * pr->n * VIWB_STATE_FIXED);
+        for (int k = 0; k < pr->num_blocks; k++) { const int b = pr->block_id[k], size = viwb_block_size(b), off = viwb_block_offset(b);
+            for (int i = 0; i < pr->n; i++) for (int j = 0; j < size; j++) jacobian[(size_t)i * VIWB_STATE_FIXED + off + j] = jb[k][(size_t)i * size + j]; }
+    }
+    for (double *d : x0) delete[] d;
+    delete info;
+    return ok ? 0 : 1;
+}
+
+// Estimator::optimization()'s marginalization step.  Outputs: mn = {m, n, number of kept blocks}; kept block ids / column offsets (idx - m);
+// J (n x n row-major) = linearized_jacobians, r (n) = linearized_residuals.  Returns 0, or 3 when nothing is left to keep.
+extern "C" int ref_marginalize(const viwb_problem *p, const double *state_in, int margin_flag, int32_t *mn, int32_t *block_id, int32_t *block_idx, double *J, double *r) {
+    const viwb_globals *g = &p->globals;
+    G = Eigen::Vector3d(g->G[0], g->G[1], g->G[2]);
+    Eigen::Matrix2d si; si << g->vis_sqrt_info[0], g->vis_sqrt_info[1], g->vis_sqrt_info[2], g->vis_sqrt_info[3];
+    ProjectionTwoFrameOneCamFactor::sqrt_info = si; ProjectionTwoFrameTwoCamFactor::sqrt_info = si; ProjectionOneFrameTwoCamFactor::sqrt_info = si;
+    PITCH_N_INV = g->plane_sqrt_info[0]; ROLL_N_INV = g->plane_sqrt_info[1]; ZPW_N_INV = g->plane_sqrt_info[2];
+    std::vector<double> st(state_in, state_in + VIWB_STATE_FIXED + p->num_landmarks);
+    auto blk = [&](int b) { return st.data() + viwb_block_offset(b); };
+    auto lm = [&](int k) { return st.data() + VIWB_STATE_FIXED + k; };
+    ceres::LossFunction *loss = new ceres::HuberLoss(g->huber_delta);
+    MarginalizationInfo *info = new MarginalizationInfo();
+    MarginalizationInfo *last = nullptr; std::vector<double *> x0;
+    std::vector<IntegrationBase *> imu_pre; std::vector<WheelIntegrationBase *> wheel_pre;
+    const int WS = 10;
+    if (p->prior && p->prior->valid) {
+        last = info_from_prior(p->prior, x0);
+        std::vector<double *> blocks; std::vector<int> drop;
+        for (int k = 0; k < p->prior->num_blocks; k++) {
+            const int b = p->prior->block_id[k];
+            blocks.push_back(blk(b));
+            if (margin_flag == VIWB_MARGIN_OLD ? (b == 0 || b == 11) : (b == WS - 1)) drop.push_back(k);
+        }
+        info->addResidualBlockInfo(new ResidualBlockInfo(new MarginalizationFactor(last), NULL, blocks, drop));
+    }
+    if (margin_flag == VIWB_MARGIN_OLD) {
+        for (int f = 0; f < p->num_imu; f++) if (p->imu_frame_i[f] == 0 && p->imu_frame_j[f] == 1) {
+            IntegrationBase *pre = new IntegrationBase(Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero(), Eigen::Vector3d::Zero());
+            fill_pre_integration(*pre, p->imu_data + (size_t)f * VIWB_IMU_DOUBLES); imu_pre.push_back(pre);
+            if (pre->sum_dt < 10.0) info->addResidualBlockInfo(new ResidualBlockInfo(new IMUFactor(pre), NULL, std::vector<double *>{blk(0), blk(11), blk(1), blk(12)}, std::vector<int>{0, 1}));
+        }
+        for (int f = 0; f < p->num_wheel; f++) if (p->wheel_frame_i[f] == 0 && p->wheel_frame_j[f] == 1) {
+            const double *c = p->wheel_data + (size_t)f * VIWB_WHEEL_DOUBLES;
+            WheelIntegrationBase *pre = new WheelIntegrationBase(Eigen::Vector3d(c[65], c[66], c[67]), Eigen::Vector3d(c[68], c[69], c[70]), c[61], c[62], c[63], c[64]);
+            pre->delta_p = Eigen::Vector3d(c[0], c[1], c[2]); pre->delta_q = Eigen::Quaterniond(c[6], c[3], c[4], c[5]);
+            for (int i = 0; i < 6; i++) for (int j = 0; j < 3; j++) pre->jacobian(i, j) = c[7 + 3 * i + j];
+            for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) pre->covariance(i, j) = c[25 + 6 * i + j];
+            pre->vel_1 = Eigen::Vector3d(c[71], c[72], c[73]); pre->gyr_1 = Eigen::Vector3d(c[74], c[75], c[76]); pre->sum_dt = c[77];
+            wheel_pre.push_back(pre);
+            if (pre->sum_dt < 10.0) info->addResidualBlockInfo(new ResidualBlockInfo(new WheelFactor(pre), NULL, std::vector<double *>{blk(0), blk(1), blk(24), blk(27), blk(28), blk(29), blk(31)}, std::vector<int>{0}));
+        }
+        for (int f = 0; f < p->num_plane; f++) if (p->plane_frame[f] == 0)
+            info->addResidualBlockInfo(new ResidualBlockInfo(new PlaneFactor(), NULL, std::vector<double *>{blk(0), blk(24), blk(25), blk(26)}, std::vector<int>{0}));
+        for (int f = 0; f < p->num_vis; f++) {
+            if (p->vis_frame_i[f] != 0) continue;
+            const double *c = p->vis_obs + (size_t)f * VIWB_VIS_OBS_DOUBLES;
+            const Eigen::Vector3d pi(c[0], c[1], c[2]), pj(c[3], c[4], c[5]); const Eigen::Vector2d vi(c[6], c[7]), vj(c[8], c[9]);
+            const int j = p->vis_frame_j[f]; double *l = lm(p->vis_landmark[f]);
+            if (p->vis_type[f] == VIWB_F_PROJ_2F1C)
+                info->addResidualBlockInfo(new ResidualBlockInfo(new ProjectionTwoFrameOneCamFactor(pi, pj, vi, vj, c[10], c[11]), loss, std::vector<double *>{blk(0), blk(j), blk(22), l, blk(30)}, std::vector<int>{0, 3}));
+            else if (p->vis_type[f] == VIWB_F_PROJ_2F2C)
+                info->addResidualBlockInfo(new ResidualBlockInfo(new ProjectionTwoFrameTwoCamFactor(pi, pj, vi, vj, c[10], c[11]), loss, std::vector<double *>{blk(0), blk(j), blk(22), blk(23), l, blk(30)}, std::vector<int>{0, 4}));
+            else
+                info->addResidualBlockInfo(new ResidualBlockInfo(new ProjectionOneFrameTwoCamFactor(pi, pj, vi, vj, c[10], c[11]), loss, std::vector<double *>{blk(22), blk(23), l, blk(30)}, std::vector<int>{2}));
+        }
+    }
+    int rc = 0;
+    if (info->factors.empty()) rc = 3;
+    else {
+        info->preMarginalize();
+        info->marginalize();
+        std::unordered_map<long, double *> addr_shift;
+        for (auto &it : info->parameter_block_idx) addr_shift[it.first] = reinterpret_cast<double *>(it.first);
+        std::vector<double *> kept = info->getParameterBlocks(addr_shift);
+        mn[0] = info->m; mn[1] = info->n; mn[2] = (int)kept.size();
+        for (size_t k = 0; k < kept.size(); k++) {
+            const long off = kept[k] - st.data();
+            int b = -1;
+            for (int q = 0; q < VIWB_NUM_FIXED_BLOCKS; q++) if (viwb_block_offset(q) == off) b = q;
+            block_id[k] = b; block_idx[k] = info->keep_block_idx[k] - info->m;
+        }
+        for (int i = 0; i < info->n; i++) { r[i] = info->linearized_residuals(i); for (int j = 0; j < info->n; j++) J[(size_t)i * info->n + j] = info->linearized_jacobians(i, j); }
+    }
+    delete info;                       // deletes the factors and the cost functions it was given
+    if (last) { for (double *d : x0) delete[] d; /* `last` itself went with its MarginalizationFactor's owner; the info object is ours */ delete last; }
+    for (auto q : imu_pre) delete q;
+    for (auto q : wheel_pre) delete q;
+    delete loss;
+    return rc;
 }

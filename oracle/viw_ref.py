@@ -70,3 +70,29 @@ def manifold(kind, mask, x, delta, want_jac=True):
     if rc:
         raise RuntimeError("ref_manifold rc=%d" % rc)
     return out, jac
+
+
+def prior_evaluate(prior, state, want_jac=True):
+    """MarginalizationFactor::Evaluate of the reference on a viwb_prior (abi.PriorData)"""
+    st = np.ascontiguousarray(state, np.float64)
+    res = np.zeros(prior.n)
+    jac = np.zeros((prior.n, 207)) if want_jac else None
+    rc = lib().ref_prior_evaluate(C.byref(prior.c), _dp(st), _dp(res), _dp(jac) if want_jac else None)
+    if rc:
+        raise RuntimeError("ref_prior_evaluate rc=%d" % rc)
+    return res, jac
+
+
+def marginalize(problem, state, flag):
+    """MarginalizationInfo::preMarginalize + marginalize of the reference on the factors Estimator::optimization() hands over.
+    Returns dict(m, n, blocks=[(block id BEFORE the addr_shift remap, column offset)], J, r)."""
+    st = np.ascontiguousarray(state, np.float64)
+    cap = 256
+    mn = (C.c_int32 * 3)()
+    bid, bidx = (C.c_int32 * 32)(), (C.c_int32 * 32)()
+    J, r = np.zeros(cap * cap), np.zeros(cap)
+    rc = lib().ref_marginalize(C.byref(problem.c), _dp(st), C.c_int(flag), mn, bid, bidx, _dp(J), _dp(r))
+    if rc:
+        raise RuntimeError("ref_marginalize rc=%d" % rc)
+    n = mn[1]
+    return {"m": mn[0], "n": n, "blocks": [(bid[k], bidx[k]) for k in range(mn[2])], "J": J[: n * n].reshape(n, n).copy(), "r": r[:n].copy()}

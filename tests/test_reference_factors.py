@@ -150,3 +150,79 @@ def test_wheel_preintegration_matches_reference_code(oracle):
         assert np.abs(r1 - r0).max() <= 1e-12 * max(1.0, np.abs(r0).max()), (n, np.abs(r1 - r0).max())
         r2 = synth.wheel_preintegrate(dt, vel, gyr, s, td, noise)
         assert np.abs(r2 - r0).max() <= 1e-10 * max(1.0, np.abs(r0).max())
+
+
+# ------------------------------------------------------------------------------------------------ prior factor + marginalization
+def _information_by_block(blocks, J, r, remap=None):
+    """(A, b) = (J^T J, J^T r) re-ordered into ascending block id, so that two priors whose columns are ordered differently
+    (the reference orders them by the hash of the parameter addresses) can be compared entry by entry."""
+    A, b = J.T @ J, J.T @ r
+    cols, ids = [], []
+    for bid, idx in sorted(((remap(b_) if remap else b_), i_) for b_, i_ in blocks):
+        size = abi.block_tsize(bid) if abi.block_size(bid) != 7 else 6
+        cols += list(range(idx, idx + size)); ids.append(bid)
+    return ids, A[np.ix_(cols, cols)], b[cols]
+
+
+def _shift_old(b):          # addr_shift of MARGIN_OLD (estimator.cpp:1791-1800): pose i -> i-1, speed-bias i -> i-1
+    return b - 1 if (1 <= b <= 10 or 12 <= b <= 21) else b
+
+
+@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+def test_marginalization_matches_reference_code(oracle, cid):
+    """MARGIN_OLD on a first window (no prior) and on the next one (prior present): the reference's ResidualBlockInfo::Evaluate (loss
+    corrector), preMarginalize and marginalize (4 threads, Schur complement, eigen-decomposition with the 1e-8 cut) against the oracle."""
+    seq = synth.Sequence(synth.make_config(cid), 1, 13)
+    prob, st, _ = seq.window(0)
+    a, sm, q = oracle.optimization(prob, st, abi.MARGIN_OLD)
+    for k in range(2):
+        ref = vr.marginalize(prob, a, abi.MARGIN_OLD)
+        got = oracle.marginalize(prob, a, abi.MARGIN_OLD)
+        assert ref["n"] == got.n, (cid, k, ref["n"], got.n)
+        ids0, A0, b0 = _information_by_block(ref["blocks"], ref["J"], ref["r"], _shift_old)
+        ids1, A1, b1 = _information_by_block(got.blocks(), got.Jmat(), got.rvec())
+        assert ids0 == ids1, (ids0, ids1)
+        sA, sb = np.abs(A0).max(), np.abs(b0).max()
+        assert np.abs(A1 - A0).max() <= 1e-7 * sA and np.abs(b1 - b0).max() <= 1e-7 * sb, (cid, k, np.abs(A1 - A0).max() / sA, np.abs(b1 - b0).max() / sb)
+        # next window: the prior just produced takes part, with pose 0 / speed-bias 0 dropped from it
+        prob, st, _ = seq.window(k + 1, prior=got, prev_state=a)
+        a, sm, q = oracle.optimization(prob, st, abi.MARGIN_OLD)
+
+
+@pytest.mark.parametrize("cid", [2, 4])
+def test_prior_factor_matches_reference_code(oracle, cid):
+    seq = synth.Sequence(synth.make_config(cid), 2, 13)
+    prob, st, _ = seq.window(0)
+    a, sm, q = oracle.optimization(prob, st, abi.MARGIN_OLD)
+    prob1, st1, _ = seq.window(1, prior=q, prev_state=a)
+    rng = np.random.default_rng(31)
+    for trial in range(4):
+        x = st1.copy()
+        x[:abi.STATE_FIXED] += rng.normal(0, 0.01 * trial, abi.STATE_FIXED)
+        for f in range(11):
+            x[7 * f + 3: 7 * f + 7] /= np.linalg.norm(x[7 * f + 3: 7 * f + 7])
+        if trial == 3:                                   # the w < 0 branch of the quaternion difference (marginalization_factor.cpp:374-377)
+            x[3:7] *= -1.0
+        r0, J0 = vr.prior_evaluate(q, x)
+        r1, J1 = oracle.prior_evaluate(q, x)
+        assert close(r1, r0, 1e-12) and close(J1, J0, 1e-12), trial
+
+
+def _shift_second_new(b):   # addr_shift of MARGIN_SECOND_NEW (estimator.cpp:1843-1870): frame 10 takes the place of frame 9
+    return 9 if b == 10 else 20 if b == 21 else b
+
+
+@pytest.mark.parametrize("cid", [2, 4])
+def test_marginalization_second_new_matches_reference_code(oracle, cid):
+    seq = synth.Sequence(synth.make_config(cid), 3, 13)
+    prob, st, _ = seq.window(0)
+    a, sm, q = oracle.optimization(prob, st, abi.MARGIN_OLD)
+    prob, st, _ = seq.window(1, prior=q, prev_state=a)
+    a, sm, _ = oracle.optimization(prob, st, abi.MARGIN_SECOND_NEW, want_prior=False)
+    ref = vr.marginalize(prob, a, abi.MARGIN_SECOND_NEW)
+    got = oracle.marginalize(prob, a, abi.MARGIN_SECOND_NEW)
+    assert ref["n"] == got.n
+    ids0, A0, b0 = _information_by_block(ref["blocks"], ref["J"], ref["r"], _shift_second_new)
+    ids1, A1, b1 = _information_by_block(got.blocks(), got.Jmat(), got.rvec())
+    assert ids0 == ids1
+    assert np.abs(A1 - A0).max() <= 1e-7 * np.abs(A0).max() and np.abs(b1 - b0).max() <= 1e-7 * np.abs(b0).max()
