@@ -809,3 +809,29 @@ def check_tracker_edges(ctx):
             raise AssertionError("max_cnt %d accepted" % bad)
         except ViwbError:
             pass
+
+
+# ------------------------------------------------------------------------------------------------ against the reference's own code
+def check_marginalize_vs_reference_code(ctx, oracle, reference_code, cid):
+    """The library's marginalization against MarginalizationInfo::marginalize of the reference, compiled from its sources
+    (oracle/_ref): kept dimension, kept blocks and the information form, block by block (the reference's column order follows the hash
+    of the parameter addresses).  The input state comes from the oracle's solve; the oracle plays no part in the comparison."""
+    from test_reference_factors import _information_by_block, _shift_old
+    seq = synth.Sequence(synth.make_config(cid), 1, 13)
+    prob, st, _ = seq.window(0)
+    a, sm, q = oracle.optimization(prob, st, abi.MARGIN_OLD)
+    for k in range(2):
+        ref = reference_code.marginalize(prob, a, abi.MARGIN_OLD)
+        got = ctx.marginalize(prob, a, abi.MARGIN_OLD)
+        assert ref["n"] == got.n, (cid, k)
+        ids0, A0, b0 = _information_by_block(ref["blocks"], ref["J"], ref["r"], _shift_old)
+        ids1, A1, b1 = _information_by_block(got.blocks(), got.Jmat(), got.rvec())
+        assert ids0 == ids1
+        assert np.abs(A1 - A0).max() <= 1e-6 * np.abs(A0).max() and np.abs(b1 - b0).max() <= 1e-6 * np.abs(b0).max(), (cid, k)
+        # the prior factor on the prior the library just produced
+        x = a.copy(); x[7:10] += 0.01; x[0:3] -= 0.02
+        res0, jac0 = reference_code.prior_evaluate(got, x[:abi.STATE_FIXED])
+        res1, jac1 = ctx.prior_evaluate(got, x)
+        assert np.abs(res0 - res1).max() <= 1e-9 * max(1.0, np.abs(res0).max()) and np.abs(jac0 - jac1).max() <= 1e-12 * max(1.0, np.abs(jac0).max())
+        prob, st, _ = seq.window(k + 1, prior=got, prev_state=a)
+        a, sm, q = oracle.optimization(prob, st, abi.MARGIN_OLD)

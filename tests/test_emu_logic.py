@@ -124,3 +124,14 @@ def test_tracker_session_mono_no_flow_back(emu):
 
 def test_tracker_edges(emu):
     pc.check_tracker_edges(emu)
+
+
+@pytest.mark.parametrize("cid", [2, 4])
+def test_factor_evaluate_vs_reference_code(emu, reference_code, cid):
+    """every factor class of the library against the reference's own Evaluate (oracle/_ref: the reference sources, compiled)"""
+    assert pc.check_factor_evaluate(emu, reference_code, cid, max_each=4) < 1e-9
+
+
+@pytest.mark.parametrize("cid", [2, 4])
+def test_marginalize_vs_reference_code(emu, oracle, reference_code, cid):
+    pc.check_marginalize_vs_reference_code(emu, oracle, reference_code, cid)

@@ -166,3 +166,14 @@ def test_tracker_session_small_mono(gpu_ctx):
 
 def test_tracker_edges(gpu_ctx):
     pc.check_tracker_edges(gpu_ctx)
+
+
+@pytest.mark.parametrize("cid", [2, 4])
+def test_factor_evaluate_vs_reference_code(gpu_ctx, reference_code, cid):
+    """every factor class of the library against the reference's own Evaluate (oracle/_ref: the reference sources, compiled)"""
+    assert pc.check_factor_evaluate(gpu_ctx, reference_code, cid, max_each=4) < 1e-9
+
+
+@pytest.mark.parametrize("cid", [2, 4])
+def test_marginalize_vs_reference_code(gpu_ctx, oracle, reference_code, cid):
+    pc.check_marginalize_vs_reference_code(gpu_ctx, oracle, reference_code, cid)

@@ -133,8 +133,10 @@ VIWB_D void lm_reduce_body(const BatchDev &bd, int bx, int tid, int nt, int mode
     const int f0 = bd.lm_fptr[k], f1 = bd.lm_fptr[k + 1];
     double *W = bd.lm_W + (size_t)k * VSUB;
     const bool skip = (mode == MODE_MARG) && (f0 == f1 || bd.vis_fi[f0] != 0 || bd.meta[w].margin_flag != 0);
-    if (skip) { if (lane == 0) bd.lm_gamma[k] = 0.0; return; }
     for (int p = lane; p < VSUB; p += LM_W) W[p] = 0.0;
+    // a landmark that takes no part in the marginalisation still owns a row of W that syrk multiplies by its zero weight: the row must
+    // hold numbers (a marginalise-only call on a recycled arena would otherwise multiply 0 by whatever an earlier batch left there)
+    if (skip) { if (lane == 0) { bd.lm_gamma[k] = 0.0; bd.lm_a[k] = 0.0; bd.lm_g[k] = 0.0; } return; }
     if (f0 == f1) {      // a landmark without factors: contributes nothing
         if (lane == 0) { bd.lm_a[k] = 0.0; bd.lm_g[k] = 0.0; bd.lm_cost[k] = 0.0; bd.lm_gamma[k] = 0.0; if (ww.first) bd.lm_scale[k] = 1.0; }
         return;
