@@ -241,3 +241,37 @@ extern "C" int ref_marginalize(const viwb_problem *p, const double *state_in, in
     delete loss;
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------------- self-test hooks of the stand-ins
+// tests/test_refshim.py checks oracle/refshim/mini_eigen.h and mini_sophus.h against numpy / scipy on their own, so that agreement
+// between the compiled reference code and the oracle cannot be explained by a shared mistake in the matrix header.
+extern "C" void ref_selftest_linalg15(const double *A_rm, double *inv_rm, double *llt_rm, double *prod_rm) {
+    Eigen::Matrix<double, 15, 15> A;
+    for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) A(i, j) = A_rm[15 * i + j];
+    const Eigen::Matrix<double, 15, 15> inv = A.inverse();
+    const Eigen::Matrix<double, 15, 15> L = Eigen::LLT<Eigen::Matrix<double, 15, 15>>(A).matrixL();
+    Eigen::MatrixXd F = Eigen::MatrixXd::Zero(15, 15);
+    F.block<3, 3>(3, 6) = A.block<3, 3>(0, 0); F.block<3, 3>(0, 0) = Eigen::Matrix3d::Identity() * 2.0;
+    const Eigen::Matrix<double, 15, 15> P = F * A * F.transpose() + A.transpose();
+    for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) { inv_rm[15 * i + j] = inv(i, j); llt_rm[15 * i + j] = L(i, j); prod_rm[15 * i + j] = P(i, j); }
+}
+extern "C" void ref_selftest_eig(int n, const double *A_rm, double *w, double *V_rm) {
+    Eigen::MatrixXd A(n, n);
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) A(i, j) = A_rm[(size_t)n * i + j];
+    Eigen::SelfAdjointEigenSolver<Eigen::MatrixXd> s(A);
+    for (int i = 0; i < n; i++) { w[i] = s.eigenvalues()(i); for (int j = 0; j < n; j++) V_rm[(size_t)n * i + j] = s.eigenvectors()(i, j); }
+}
+// q = [x, y, z, w]; out: R(q) row-major (9), q^-1 (4), q * v (3), quaternion of R (4), (q * p) product (4), SO3::exp(v) quaternion (4), SO3(q).log() (3)
+extern "C" void ref_selftest_rotations(const double *q_, const double *p_, const double *v_, double *out) {
+    const Eigen::Quaterniond q(q_[3], q_[0], q_[1], q_[2]), p(p_[3], p_[0], p_[1], p_[2]);
+    const Eigen::Vector3d v(v_[0], v_[1], v_[2]);
+    const Eigen::Matrix3d R = q.toRotationMatrix();
+    int k = 0;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[k++] = R(i, j);
+    const Eigen::Quaterniond qi = q.inverse(); out[k++] = qi.x(); out[k++] = qi.y(); out[k++] = qi.z(); out[k++] = qi.w();
+    const Eigen::Vector3d qv = q * v; for (int i = 0; i < 3; i++) out[k++] = qv(i);
+    const Eigen::Quaterniond qr(R); out[k++] = qr.x(); out[k++] = qr.y(); out[k++] = qr.z(); out[k++] = qr.w();
+    const Eigen::Quaterniond qp = q * p; out[k++] = qp.x(); out[k++] = qp.y(); out[k++] = qp.z(); out[k++] = qp.w();
+    const Eigen::Quaterniond e = Sophus::SO3d::exp(v).unit_quaternion(); out[k++] = e.x(); out[k++] = e.y(); out[k++] = e.z(); out[k++] = e.w();
+    const Eigen::Vector3d l = Sophus::SO3d(q).log(); for (int i = 0; i < 3; i++) out[k++] = l(i);
+}
