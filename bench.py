@@ -257,7 +257,8 @@ def main():
     warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
-        # the reference's own CPU implementation cannot be built here (ROS/Ceres/Eigen absent): the arm is the oracle port
+        # the reference's own solver (Ceres) cannot be built here: the arm is the oracle port (its factor math is pinned to the reference's
+        # compiled sources, oracle/_ref; the trust-region solve is restated), plus OpenCV's own LK
         if rank != 0:
             return
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -1,7 +1,8 @@
 """ctypes wrapper of the CPU oracle (oracle/libviw_oracle.so).
 
 TEST INFRASTRUCTURE ONLY: may be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs, never by the product package.  PARITY UNPINNED (see oracle/viw_oracle.h).
+--impl reference legs, never by the product package.  Factor / manifold / pre-integration / marginalization math pinned to the reference's own compiled sources (oracle/_ref,
+tests/test_reference_factors.py); the Ceres solve itself is PARITY UNPINNED (see oracle/viw_oracle.h).
 """
 import ctypes as C
 import os

@@ -7,8 +7,8 @@ tracker_golden.npz FeatureTracker::trackImage() over a 5-tick synthetic stereo s
                    oracle/feature_oracle.py:FeatureTrackerRef with cv2.calcOpticalFlowPyrLK AND cv2.goodFeaturesToTrack (scalar path)
                    underneath, i.e. the reference's own third-party calls: ids, track counts, pixel / undistorted points, velocities
                    of both cameras per tick, plus the images.
-window_golden.npz  Regression vectors of the CPU oracle (oracle/, PARITY UNPINNED: the reference ships no known-answer
-                   vectors for the window solve and cannot be built here) for two seeded windows: solved state, iteration
+window_golden.npz  Regression vectors of the CPU oracle (oracle/; its Ceres-solve half is PARITY UNPINNED: the reference ships no known-answer
+                   vectors for the window solve and ceres-solver is not in the image) for two seeded windows: solved state, iteration
                    count, costs and the marginalisation prior's information form (J^T J, J^T r).
 """
 import os

@@ -1,4 +1,5 @@
-"""Pins the CPU oracle's solver / marginalization restatement (PARITY UNPINNED by the reference itself):
+"""Anchors the CPU oracle's solver restatement (the Ceres solve is PARITY UNPINNED: ceres-solver is not in the image; the marginalization
+itself is pinned to the reference's compiled code in tests/test_reference_factors.py):
   * scipy.optimize.least_squares reaches the same minimum of the same robustified objective,
   * dogleg bookkeeping invariants of the Ceres recurrence,
   * marginalization identities J^T J = A, J^T r = b (marginalization_factor.cpp:310-311),
