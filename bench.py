@@ -456,7 +456,9 @@ def main():
         for n in [int(v) for v in args.e2e_lanes_sweep.split(",")]:
             sec, ln = measure_e2e(n)
             e2e_sweep[str(ln)] = job_throughput(world, B, e2e_steps, rank_max(sec, world))
-    e2e_s, lanes = measure_e2e(args.e2e_lanes)
+    # host threads per rank: the default 4 lanes, but never more than this rank's share of the usable cores (8 ranks on a 16-core quota
+    # would otherwise run 32 feeder threads), and at least 2 so that one lane's lowering still overlaps the other's kernels
+    e2e_s, lanes = measure_e2e(max(2, min(args.e2e_lanes, usable_cores() // max(1, world))) if world > 1 else args.e2e_lanes)
     e2e_s = rank_max(e2e_s, world)
     e2e_value = job_throughput(world, B, e2e_steps, e2e_s)
     h2d = sum(p.vis_obs.nbytes + 4 * 4 * len(p.vis_type) + p.imu_data.nbytes + p.wheel_data.nbytes + 8 * p.state_size +
