@@ -30,7 +30,7 @@ template <typename T, int R, int C, int Opt = ColMajor> class Matrix;
 template <typename XprType, int BR, int BC> class Block;
 template <typename PlainType> class Map;
 template <typename T> class Quaternion;
-template <typename MatrixType> class JacobiSVD;               // named by utility.h inside a template that is never instantiated
+template <typename MatrixType> class JacobiSVD;
 template <typename MatrixType> class SelfAdjointEigenSolver;
 template <typename D> struct traits;
 template <typename XprType> class DynBlock;
@@ -91,22 +91,22 @@ template <typename Derived> class MatrixBase {
     // ---- fixed-size sub-blocks (views that can be read and assigned)
     template <int BR, int BC> Block<Derived, BR, BC> block(int i, int j) { return Block<Derived, BR, BC>(derived(), i, j); }
     template <int BR, int BC> const Block<Derived, BR, BC> block(int i, int j) const { return Block<Derived, BR, BC>(const_cast<Derived &>(derived()), i, j); }
-    template <int N> Block<Derived, N, ColsAtCompileTime> topRows() { return Block<Derived, N, ColsAtCompileTime>(derived(), 0, 0); }
-    template <int N> const Block<Derived, N, ColsAtCompileTime> topRows() const { return Block<Derived, N, ColsAtCompileTime>(const_cast<Derived &>(derived()), 0, 0); }
-    template <int N> Block<Derived, N, ColsAtCompileTime> bottomRows() { return Block<Derived, N, ColsAtCompileTime>(derived(), rows() - N, 0); }
-    template <int N> const Block<Derived, N, ColsAtCompileTime> bottomRows() const { return Block<Derived, N, ColsAtCompileTime>(const_cast<Derived &>(derived()), rows() - N, 0); }
-    template <int N> Block<Derived, RowsAtCompileTime, N> leftCols() { return Block<Derived, RowsAtCompileTime, N>(derived(), 0, 0); }
-    template <int N> const Block<Derived, RowsAtCompileTime, N> leftCols() const { return Block<Derived, RowsAtCompileTime, N>(const_cast<Derived &>(derived()), 0, 0); }
-    template <int N> Block<Derived, RowsAtCompileTime, N> rightCols() { return Block<Derived, RowsAtCompileTime, N>(derived(), 0, cols() - N); }
-    template <int N> const Block<Derived, RowsAtCompileTime, N> rightCols() const { return Block<Derived, RowsAtCompileTime, N>(const_cast<Derived &>(derived()), 0, cols() - N); }
+    template <int N> Block<Derived, N, ColsAtCompileTime> topRows() { return Block<Derived, N, ColsAtCompileTime>(derived(), 0, 0, N, cols()); }
+    template <int N> const Block<Derived, N, ColsAtCompileTime> topRows() const { return Block<Derived, N, ColsAtCompileTime>(const_cast<Derived &>(derived()), 0, 0, N, cols()); }
+    template <int N> Block<Derived, N, ColsAtCompileTime> bottomRows() { return Block<Derived, N, ColsAtCompileTime>(derived(), rows() - N, 0, N, cols()); }
+    template <int N> const Block<Derived, N, ColsAtCompileTime> bottomRows() const { return Block<Derived, N, ColsAtCompileTime>(const_cast<Derived &>(derived()), rows() - N, 0, N, cols()); }
+    template <int N> Block<Derived, RowsAtCompileTime, N> leftCols() { return Block<Derived, RowsAtCompileTime, N>(derived(), 0, 0, rows(), N); }
+    template <int N> const Block<Derived, RowsAtCompileTime, N> leftCols() const { return Block<Derived, RowsAtCompileTime, N>(const_cast<Derived &>(derived()), 0, 0, rows(), N); }
+    template <int N> Block<Derived, RowsAtCompileTime, N> rightCols() { return Block<Derived, RowsAtCompileTime, N>(derived(), 0, cols() - N, rows(), N); }
+    template <int N> const Block<Derived, RowsAtCompileTime, N> rightCols() const { return Block<Derived, RowsAtCompileTime, N>(const_cast<Derived &>(derived()), 0, cols() - N, rows(), N); }
     template <int BR, int BC> Block<Derived, BR, BC> bottomRightCorner() { return Block<Derived, BR, BC>(derived(), rows() - BR, cols() - BC); }
     template <int BR, int BC> const Block<Derived, BR, BC> bottomRightCorner() const { return Block<Derived, BR, BC>(const_cast<Derived &>(derived()), rows() - BR, cols() - BC); }
     template <int BR, int BC> Block<Derived, BR, BC> topLeftCorner() { return Block<Derived, BR, BC>(derived(), 0, 0); }
     template <int BR, int BC> const Block<Derived, BR, BC> topLeftCorner() const { return Block<Derived, BR, BC>(const_cast<Derived &>(derived()), 0, 0); }
-    Block<Derived, RowsAtCompileTime, 1> col(int j) { return Block<Derived, RowsAtCompileTime, 1>(derived(), 0, j); }
-    const Block<Derived, RowsAtCompileTime, 1> col(int j) const { return Block<Derived, RowsAtCompileTime, 1>(const_cast<Derived &>(derived()), 0, j); }
-    Block<Derived, 1, ColsAtCompileTime> row(int i) { return Block<Derived, 1, ColsAtCompileTime>(derived(), i, 0); }
-    const Block<Derived, 1, ColsAtCompileTime> row(int i) const { return Block<Derived, 1, ColsAtCompileTime>(const_cast<Derived &>(derived()), i, 0); }
+    Block<Derived, RowsAtCompileTime, 1> col(int j) { return Block<Derived, RowsAtCompileTime, 1>(derived(), 0, j, rows(), 1); }
+    const Block<Derived, RowsAtCompileTime, 1> col(int j) const { return Block<Derived, RowsAtCompileTime, 1>(const_cast<Derived &>(derived()), 0, j, rows(), 1); }
+    Block<Derived, 1, ColsAtCompileTime> row(int i) { return Block<Derived, 1, ColsAtCompileTime>(derived(), i, 0, 1, cols()); }
+    const Block<Derived, 1, ColsAtCompileTime> row(int i) const { return Block<Derived, 1, ColsAtCompileTime>(const_cast<Derived &>(derived()), i, 0, 1, cols()); }
     // vector segments (column vectors)
     template <int N> Block<Derived, N, 1> head() { return Block<Derived, N, 1>(derived(), 0, 0); }
     template <int N> const Block<Derived, N, 1> head() const { return Block<Derived, N, 1>(const_cast<Derived &>(derived()), 0, 0); }
@@ -134,6 +134,7 @@ template <typename Derived> class MatrixBase {
     DynBlock<Derived> bottomRows(int n) { return block(rows() - n, 0, n, cols()); }
     const DynBlock<Derived> bottomRows(int n) const { return block(rows() - n, 0, n, cols()); }
     ArrayX<Scalar> array() const;
+    JacobiSVD<PlainObject> jacobiSvd(unsigned options = 0) const;
     PlainObject cwiseSqrt() const { PlainObject r = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = std::sqrt(coeff(i, j)); return r; }
 
     // ---- assignment from any expression of the same size
@@ -317,14 +318,17 @@ template <typename Derived> ArrayX<typename MatrixBase<Derived>::Scalar> MatrixB
 
 // ------------------------------------------------------------------------------------------------ Block (a view)
 template <typename XprType, int BR, int BC> class Block : public MatrixBase<Block<XprType, BR, BC>> {
-    XprType *x; int i0, j0;
+    XprType *x; int i0, j0, r_, c_;                                   // r_, c_ only matter where BR / BC is Dynamic (a fixed-count slice of a run-time sized parent)
   public:
     typedef MatrixBase<Block> Base;
     typedef typename traits<XprType>::Scalar Scalar;
-    Block(XprType &x_, int i, int j) : x(&x_), i0(i), j0(j) { assert(i >= 0 && j >= 0 && i + BR <= x_.rows() && j + BC <= x_.cols()); }
-    static int rowsImpl() { return BR; }
-    static int colsImpl() { return BC; }
-    static void resizeLike(int r, int c) { assert(r == BR && c == BC); (void)r; (void)c; }
+    Block(XprType &x_, int i, int j, int r = BR, int c = BC) : x(&x_), i0(i), j0(j), r_(r), c_(c) {
+        assert((BR == Dynamic || r == BR) && (BC == Dynamic || c == BC));
+        assert(i >= 0 && j >= 0 && r >= 0 && c >= 0 && i + r <= x_.rows() && j + c <= x_.cols());
+    }
+    int rowsImpl() const { return BR == Dynamic ? r_ : BR; }
+    int colsImpl() const { return BC == Dynamic ? c_ : BC; }
+    void resizeLike(int r, int c) const { assert(r == rowsImpl() && c == colsImpl()); (void)r; (void)c; }
     Scalar coeff(int i, int j) const { return x->coeff(i0 + i, j0 + j); }
     Scalar &coeffRef(int i, int j) const { return x->coeffRef(i0 + i, j0 + j); }
     Block &operator=(const Block &o) { Base::assign(o); return *this; }
@@ -492,6 +496,46 @@ template <typename MatrixType> class SelfAdjointEigenSolver {
     const Matrix<T, Dynamic, 1> &eigenvalues() const { return w; }
     const Matrix<T, Dynamic, Dynamic> &eigenvectors() const { return V; }
 };
+
+// ------------------------------------------------------------------------------------------------ singular value decomposition
+// One-sided (Hestenes) Jacobi on the columns: singular values descending, right singular vectors in the matching columns of matrixV().
+// (Eigen's JacobiSVD is two-sided with a QR preconditioner; the factors agree up to the sign of each singular vector pair.)
+template <typename MatrixType> class JacobiSVD {
+    typedef typename traits<MatrixType>::Scalar T;
+    typedef typename plain_type<T, traits<MatrixType>::Cols, traits<MatrixType>::Cols>::type VType;
+    typedef typename plain_type<T, traits<MatrixType>::Cols, 1>::type SType;
+    VType V_; SType s_;
+  public:
+    template <typename O> explicit JacobiSVD(const MatrixBase<O> &A, unsigned = 0) {
+        const int m = A.rows(), n = A.cols();
+        std::vector<T> u((size_t)m * n), v((size_t)n * n, T(0));
+        for (int i = 0; i < m; i++) for (int j = 0; j < n; j++) u[(size_t)j * m + i] = A.coeff(i, j);                 // column-major
+        for (int j = 0; j < n; j++) v[(size_t)j * n + j] = T(1);
+        for (int sweep = 0; sweep < 60; sweep++) {
+            bool rotated = false;
+            for (int p = 0; p < n - 1; p++) for (int q = p + 1; q < n; q++) {
+                T alpha = 0, beta = 0, gamma = 0;
+                for (int i = 0; i < m; i++) { const T a = u[(size_t)p * m + i], b = u[(size_t)q * m + i]; alpha += a * a; beta += b * b; gamma += a * b; }
+                if (gamma == T(0) || std::abs(gamma) <= T(1e-16) * std::sqrt(alpha * beta)) continue;
+                rotated = true;
+                const T zeta = (beta - alpha) / (T(2) * gamma);
+                const T t = (zeta >= 0 ? T(1) : T(-1)) / (std::abs(zeta) + std::sqrt(T(1) + zeta * zeta));
+                const T c = T(1) / std::sqrt(T(1) + t * t), sn = c * t;
+                for (int i = 0; i < m; i++) { const T a = u[(size_t)p * m + i], b = u[(size_t)q * m + i]; u[(size_t)p * m + i] = c * a - sn * b; u[(size_t)q * m + i] = sn * a + c * b; }
+                for (int i = 0; i < n; i++) { const T a = v[(size_t)p * n + i], b = v[(size_t)q * n + i]; v[(size_t)p * n + i] = c * a - sn * b; v[(size_t)q * n + i] = sn * a + c * b; }
+            }
+            if (!rotated) break;
+        }
+        std::vector<T> sv(n); std::vector<int> order(n);
+        for (int j = 0; j < n; j++) { T a = 0; for (int i = 0; i < m; i++) a += u[(size_t)j * m + i] * u[(size_t)j * m + i]; sv[j] = std::sqrt(a); order[j] = j; }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sv[a] > sv[b]; });
+        V_ = make_plain<VType>(n, n); s_ = make_plain<SType>(n, 1);
+        for (int k = 0; k < n; k++) { s_.coeffRef(k, 0) = sv[order[k]]; for (int i = 0; i < n; i++) V_.coeffRef(i, k) = v[(size_t)order[k] * n + i]; }
+    }
+    const VType &matrixV() const { return V_; }
+    const SType &singularValues() const { return s_; }
+};
+template <typename Derived> JacobiSVD<typename MatrixBase<Derived>::PlainObject> MatrixBase<Derived>::jacobiSvd(unsigned options) const { return JacobiSVD<PlainObject>(*this, options); }
 
 // ------------------------------------------------------------------------------------------------ quaternions
 template <typename Derived> struct qtraits;

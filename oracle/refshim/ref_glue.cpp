@@ -12,6 +12,7 @@
 #include "factor/wheel_factor.h"
 #include "factor/plane_factor.h"
 #include "factor/marginalization_factor.h"
+#include "estimator/feature_manager.h"
 #include "../../include/viwb.h"
 
 // ---- the globals of estimator/parameters.cpp that the factor code reads (that file itself needs ROS + OpenCV and is not compiled)
@@ -24,6 +25,8 @@ std::vector<Eigen::Vector3d> TIC;
 Eigen::Matrix3d RIO;
 Eigen::Vector3d TIO;
 double TD, TD_WHEEL;
+double INIT_DEPTH = 5.0, MIN_PARALLAX = 10.0 / 460.0;
+int NUM_OF_CAM = 2, ROW, COL, MULTIPLE_THREAD, ONLY_INITIAL_WITH_WHEEL;
 int ESTIMATE_EXTRINSIC, ESTIMATE_EXTRINSIC_WHEEL, ESTIMATE_INTRINSIC_WHEEL, ESTIMATE_TD, ESTIMATE_TD_WHEEL, USE_IMU, USE_WHEEL, USE_PLANE, STEREO;
 
 static void fill_pre_integration(IntegrationBase &pre, const double *c) {
@@ -274,4 +277,52 @@ extern "C" void ref_selftest_rotations(const double *q_, const double *p_, const
     const Eigen::Quaterniond qp = q * p; out[k++] = qp.x(); out[k++] = qp.y(); out[k++] = qp.z(); out[k++] = qp.w();
     const Eigen::Quaterniond e = Sophus::SO3d::exp(v).unit_quaternion(); out[k++] = e.x(); out[k++] = e.y(); out[k++] = e.z(); out[k++] = e.w();
     const Eigen::Vector3d l = Sophus::SO3d(q).log(); for (int i = 0; i < 3; i++) out[k++] = l(i);
+}
+
+// ---------------------------------------------------------------------------------------------------- FeatureManager (estimator/feature_manager.cpp)
+static void state_poses(const double *st, Eigen::Vector3d *Ps, Eigen::Matrix3d *Rs, Eigen::Vector3d *tic, Eigen::Matrix3d *ric) {
+    for (int i = 0; i <= 10; i++) { Ps[i] = Eigen::Vector3d(st[7 * i], st[7 * i + 1], st[7 * i + 2]); Rs[i] = Eigen::Quaterniond(st[7 * i + 6], st[7 * i + 3], st[7 * i + 4], st[7 * i + 5]).toRotationMatrix(); }
+    for (int c = 0; c < 2; c++) { const double *e = st + 176 + 7 * c; tic[c] = Eigen::Vector3d(e[0], e[1], e[2]); ric[c] = Eigen::Quaterniond(e[6], e[3], e[4], e[5]).toRotationMatrix(); }
+}
+// FeatureManager::triangulate on features built from (first observation, second observation): same contract as vo_triangulate
+extern "C" int ref_triangulate(const double *state, int n, const int32_t *stereo, const int32_t *frame, const double *pt0, const double *pt1, double init_depth, double *depth) {
+    Eigen::Vector3d Ps[11], tic[2]; Eigen::Matrix3d Rs[11], ric[2];
+    state_poses(state, Ps, Rs, tic, ric);
+    INIT_DEPTH = init_depth; STEREO = 1;
+    FeatureManager fm(Rs);
+    fm.setRic(ric);
+    for (int k = 0; k < n; k++) {
+        Eigen::Matrix<double, 7, 1> a, b;
+        a << pt0[2 * k], pt0[2 * k + 1], 1.0, 0.0, 0.0, 0.0, 0.0;
+        b << pt1[2 * k], pt1[2 * k + 1], 1.0, 0.0, 0.0, 0.0, 0.0;
+        FeaturePerId f(k, frame[k]);
+        f.feature_per_frame.push_back(FeaturePerFrame(a, 0.0));
+        if (stereo[k]) f.feature_per_frame[0].rightObservation(b);
+        else f.feature_per_frame.push_back(FeaturePerFrame(b, 0.0));
+        fm.feature.push_back(f);
+    }
+    fm.triangulate(10, Ps, Rs, tic, ric);
+    int k = 0;
+    for (auto &f : fm.feature) depth[k++] = f.estimated_depth;
+    return 0;
+}
+// FeatureManager::removeBackShiftDepth on features hosted in frame 0 with three observations each: same contract as vo_shift_depth
+extern "C" int ref_shift_depth(int n, const double *uv, const double *depth_in, const double *marg_R, const double *marg_P, const double *new_R, const double *new_P,
+                               double init_depth, double *depth_out) {
+    Eigen::Matrix3d Rs[11], mR, nR; Eigen::Vector3d mP(marg_P[0], marg_P[1], marg_P[2]), nP(new_P[0], new_P[1], new_P[2]);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { mR(i, j) = marg_R[3 * i + j]; nR(i, j) = new_R[3 * i + j]; }
+    INIT_DEPTH = init_depth;
+    FeatureManager fm(Rs);
+    for (int k = 0; k < n; k++) {
+        Eigen::Matrix<double, 7, 1> a; a << uv[3 * k], uv[3 * k + 1], uv[3 * k + 2], 0.0, 0.0, 0.0, 0.0;
+        FeaturePerId f(k, 0);
+        for (int o = 0; o < 3; o++) f.feature_per_frame.push_back(FeaturePerFrame(a, 0.0));
+        f.estimated_depth = depth_in[k];
+        fm.feature.push_back(f);
+    }
+    fm.removeBackShiftDepth(mR, mP, nR, nP);
+    if ((int)fm.feature.size() != n) return 1;
+    int k = 0;
+    for (auto &f : fm.feature) depth_out[k++] = f.estimated_depth;
+    return 0;
 }

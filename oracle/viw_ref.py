@@ -96,3 +96,24 @@ def marginalize(problem, state, flag):
         raise RuntimeError("ref_marginalize rc=%d" % rc)
     n = mn[1]
     return {"m": mn[0], "n": n, "blocks": [(bid[k], bidx[k]) for k in range(mn[2])], "J": J[: n * n].reshape(n, n).copy(), "r": r[:n].copy()}
+
+
+def triangulate(state, stereo, frame, pt0, pt1, init_depth=5.0):
+    """FeatureManager::triangulate (feature_manager.cpp:309-438) of the reference on two-observation features"""
+    st = np.ascontiguousarray(state, np.float64)
+    s_, f_ = np.ascontiguousarray(stereo, np.int32), np.ascontiguousarray(frame, np.int32)
+    a, b = np.ascontiguousarray(pt0, np.float64), np.ascontiguousarray(pt1, np.float64)
+    out = np.zeros(len(s_))
+    ip = lambda x: x.ctypes.data_as(C.POINTER(C.c_int32))
+    rc = lib().ref_triangulate(_dp(st), C.c_int(len(s_)), ip(s_), ip(f_), _dp(a), _dp(b), C.c_double(init_depth), _dp(out))
+    assert rc == 0
+    return out
+
+
+def shift_depth(uv, depth, marg_R, marg_P, new_R, new_P, init_depth=5.0):
+    """FeatureManager::removeBackShiftDepth (feature_manager.cpp:457-495) of the reference"""
+    arrs = [np.ascontiguousarray(x, np.float64) for x in (uv, depth, marg_R, marg_P, new_R, new_P)]
+    out = np.zeros(len(arrs[1]))
+    rc = lib().ref_shift_depth(C.c_int(len(out)), *[_dp(x) for x in arrs], C.c_double(init_depth), _dp(out))
+    assert rc == 0
+    return out

@@ -226,3 +226,41 @@ def test_marginalization_second_new_matches_reference_code(oracle, cid):
     ids1, A1, b1 = _information_by_block(got.blocks(), got.Jmat(), got.rvec())
     assert ids0 == ids1
     assert np.abs(A1 - A0).max() <= 1e-7 * np.abs(A0).max() and np.abs(b1 - b0).max() <= 1e-7 * np.abs(b0).max()
+
+
+# ------------------------------------------------------------------------------------------------ FeatureManager
+def test_triangulation_and_depth_shift_match_reference_code(oracle):
+    """FeatureManager::triangulate (stereo and two-frame branches, triangulatePoint's 4x4 SVD) and removeBackShiftDepth from
+    estimator/feature_manager.cpp, compiled unmodified (cv::solvePnP stubbed out, not exercised), against the oracle's restatement."""
+    from viwb import geom
+    rng = np.random.default_rng(51)
+    prob, st, gt = synth.Sequence(synth.make_config(2), 1, 11).window(0)
+    x = gt.copy()
+    n = 80
+    stereo = (rng.uniform(size=n) < 0.5).astype(np.int32)
+    frame = rng.integers(0, 9, n).astype(np.int32)
+
+    def cam(i, c):
+        Rs = geom.q_to_R(x[7 * i + 3: 7 * i + 7]); ric = geom.q_to_R(x[176 + 7 * c + 3: 176 + 7 * c + 7])
+        R = Rs @ ric; t = x[7 * i: 7 * i + 3] + Rs @ x[176 + 7 * c: 176 + 7 * c + 3]
+        return np.hstack([R.T, (-R.T @ t)[:, None]])
+    pt0, pt1 = np.zeros((n, 2)), np.zeros((n, 2))
+    for k in range(n):
+        P0 = cam(frame[k], 0); P1 = cam(frame[k], 1) if stereo[k] else cam(frame[k] + 1, 0)
+        pc = np.array([rng.uniform(-1, 1), rng.uniform(-0.6, 0.6), 1.0]) * rng.uniform(2, 15)
+        if k % 10 == 9:
+            pc[2] = -abs(pc[2])                                           # behind the camera: the INIT_DEPTH branch
+        pw = P0[:, :3].T @ (pc - P0[:, 3])
+        q1 = P1[:, :3] @ pw + P1[:, 3]
+        pt0[k] = pc[:2] / pc[2] + rng.normal(0, 1e-3, 2); pt1[k] = q1[:2] / q1[2] + rng.normal(0, 1e-3, 2)
+    ref = vr.triangulate(x, stereo, frame, pt0, pt1)
+    got = oracle.triangulate(x, stereo, frame, pt0, pt1)
+    assert (ref == 5.0).sum() >= 4 and np.array_equal(ref == 5.0, got == 5.0)
+    assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max(), np.abs(got - ref).max()
+    uv = np.column_stack([rng.uniform(-1, 1, n), rng.uniform(-0.6, 0.6, n), np.ones(n)])
+    dep = rng.uniform(1, 20, n); dep[:3] = -1.0
+    mR, nR = geom.q_to_R(x[3:7]) @ geom.q_to_R(x[179:183]), geom.q_to_R(x[10:14]) @ geom.q_to_R(x[179:183])
+    mP, nP = x[0:3] + geom.q_to_R(x[3:7]) @ x[176:179], x[7:10] + geom.q_to_R(x[10:14]) @ x[176:179]
+    r0 = vr.shift_depth(uv, dep, mR, mP, nR, nP)
+    r1 = oracle.shift_depth(uv, dep, mR, mP, nR, nP)
+    assert np.abs(r1 - r0).max() <= 1e-13 * np.abs(r0).max()
