@@ -510,6 +510,13 @@ def check_triangulation(ctx, oracle, seed=9):
         truth[k] = pc[2]
     got, orc = ctx.triangulate(x, stereo, frame, pt0, pt1), oracle.triangulate(x, stereo, frame, pt0, pt1)
     assert np.abs(got - orc).max() <= 1e-9 * np.abs(orc).max()
+    try:                                                                 # the reference's own FeatureManager::triangulate, where oracle/_ref exists
+        import viw_ref
+        if viw_ref.available():
+            rc = viw_ref.triangulate(x, stereo, frame, pt0, pt1)
+            assert np.abs(got - rc).max() <= 1e-9 * np.abs(rc).max()
+    except ImportError:
+        pass
     assert np.abs(got - ref).max() <= 1e-7 * np.abs(ref).max()          # numpy's SVD: independent algorithm
     assert np.median(np.abs(got - truth) / truth) < 0.2                  # and it does triangulate the noisy points
     # removeBackShiftDepth: closed form
