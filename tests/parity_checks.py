@@ -816,6 +816,27 @@ def check_tracker_edges(ctx):
             raise AssertionError("max_cnt %d accepted" % bad)
         except ViwbError:
             pass
+    # argument errors of the C entry points: reported with a message, never a crash
+    import ctypes as C
+    hnd = C.c_void_p()
+    cfg = lib_tracker_config(30, 10, cam)
+    assert ctx.lib.viwb_tracker_create(ctx.h, C.c_int(1), C.c_int(2), C.c_int(2), C.byref(cfg), C.byref(hnd)) != 0 and b"image size" in ctx.lib.viwb_last_error(ctx.h)
+    assert ctx.lib.viwb_tracker_create(ctx.h, C.c_int(0), C.c_int(w), C.c_int(h), C.byref(cfg), C.byref(hnd)) != 0
+    assert ctx.lib.viwb_tracker_track(None, C.c_double(0.0), None, None, C.c_int(w), None, None) != 0
+    trk = ctx.tracker(1, w, h, cam, None, 30, 10, True)
+    img = np.ascontiguousarray(left[0][None])
+    ptr = (C.c_void_p * 1)(img.ctypes.data)
+    assert ctx.lib.viwb_tracker_track(trk.hnd, C.c_double(0.05), ptr, None, C.c_int(w - 1), None, None) != 0 and b"stride" in ctx.lib.viwb_last_error(ctx.h)
+    pp = np.zeros((1, 30, 2), np.float32)
+    assert ctx.lib.viwb_tracker_track(trk.hnd, C.c_double(0.05), ptr, None, C.c_int(w), pp.ctypes.data_as(C.c_void_p), None) != 0
+    trk.track(0.05, img); assert trk.download()[0][0] > 0                    # and the session is unharmed
+    trk.close()
+
+
+def lib_tracker_config(max_cnt, min_dist, cam):
+    import ctypes as C
+    from viwb.lib import TrackerConfig
+    return TrackerConfig(max_cnt, min_dist, 1, 0, (C.c_double * 16)(*([float(v) for v in cam] * 2)))
 
 
 # ------------------------------------------------------------------------------------------------ against the reference's own code

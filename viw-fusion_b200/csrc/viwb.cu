@@ -1200,12 +1200,16 @@ extern "C" double viwb_lk_batch_algorithmic_bytes(const viwb_lk_batch *b) {
 // page-lock caller-owned host buffers (camera frames) so that uploads run at full PCIe rate and asynchronously
 extern "C" int viwb_tracker_create(viwb_context *ctx, int streams, int width, int height, const viwb_tracker_config *config, viwb_tracker **out) {
     if (!ctx || !out) return VIWB_ERR_INVALID;
+    if (width < 3 || height < 3) return fail(ctx, VIWB_ERR_INVALID, "tracker: bad image size");
     return trk_build(ctx, streams, width, height, config, out);
 }
 extern "C" void viwb_tracker_destroy(viwb_tracker *t) { trk_free(t); }
 extern "C" int viwb_tracker_track(viwb_tracker *t, double cur_time, const uint8_t *const *left, const uint8_t *const *right, int stride, const float *predict_pts,
                                   const uint8_t *has_prediction) {
-    return t ? trk_track(t, cur_time, left, right, stride, predict_pts, has_prediction) : VIWB_ERR_INVALID;
+    if (!t) return VIWB_ERR_INVALID;
+    if (stride < t->w) return fail(t->ctx, VIWB_ERR_INVALID, "tracker: stride smaller than the image width");
+    if (predict_pts && !has_prediction) return fail(t->ctx, VIWB_ERR_INVALID, "tracker: predict_pts without has_prediction flags");
+    return trk_track(t, cur_time, left, right, stride, predict_pts, has_prediction);
 }
 extern "C" int viwb_tracker_download(viwb_tracker *t, int32_t *n_left, int32_t *ids, int32_t *track_cnt, float *feat, int32_t *n_right, int32_t *ids_right,
                                      float *feat_right) {
