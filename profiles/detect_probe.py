@@ -40,11 +40,6 @@ for path in sys.argv[1:]:
     print(os.path.basename(path), "F=%d tick %.3f ms wall, %.3f ms device" % (F, dt * 1e3, dev_ms), per, "kept %.1f new %.1f" % (n_keep.mean(), n_new.mean()),
           "%.0f frames/s device, image bytes %.1f GB/s" % (F / dev_ms * 1e3, det.algorithmic_bytes() / dev_ms * 1e-6))
     det.close(); lk.close(); ctx.close()
-try:
-    import cv2
-    import feature_oracle  # noqa: F401
-except ImportError:
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import cv2  # noqa: E402
 imgs = feed.left[1][:16]
 t0 = time.perf_counter()

@@ -1,7 +1,7 @@
 """Session tracker (viwb_tracker_*: one FeatureTracker::trackImage() per stream per tick, state resident in HBM) on F streams:
 end-to-end ticks (host images in, featureFrame rows out), the per-kernel CUDA-event times of a tick, and the same trackImage()
-restated over cv2 (oracle/feature_oracle.py:FeatureTrackerRef, real cv2.calcOpticalFlowPyrLK / cv2.goodFeaturesToTrack) on one host
-thread.  Writes one JSON line.  Usage (GPU box): python profiles/track_probe.py [libviwb.so]   (TRK_STREAMS, TRK_TICKS env)"""
+restated over cv2 (tests/parity_checks.py:time_tracker_reference -> the checker's FeatureTrackerRef, real cv2.calcOpticalFlowPyrLK /
+cv2.goodFeaturesToTrack) on one host thread.  Writes one JSON line.  Usage (GPU box): python profiles/track_probe.py [libviwb.so]   (TRK_STREAMS, TRK_TICKS env)"""
 import json
 import os
 import sys
@@ -12,7 +12,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "viw-fusion_b200", "python"))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from viwb import lib  # noqa: E402
 import parity_checks as pc  # noqa: E402
@@ -55,17 +54,8 @@ dev_ms = max(sum(v[0] for v in prof.values()) / 2, 1e-9)
 alg = trk.algorithmic_bytes()
 trk.close()
 
-# CPU: the restated trackImage() over cv2, one stream, one thread
-import cv2  # noqa: E402
-import feature_oracle as fo  # noqa: E402
-cv2.setNumThreads(1)
-ref = fo.FeatureTrackerRef(CAM0, CAM1, MAX_CNT, MIN_DIST, True, use_cv_detector=True)
-for t in range(2):
-    ref.track_image(0.05 * (t + 1), seqs[0][0][t], seqs[0][1][t])
-t0 = time.perf_counter()
-for t in range(2, TICKS + 2):
-    ref.track_image(0.05 * (t + 1), seqs[0][0][t], seqs[0][1][t])
-cpu_ms = (time.perf_counter() - t0) / TICKS * 1e3
+# CPU: the restated trackImage() over cv2, one stream, one thread (the checker lives under tests/ + oracle/; this script only reports its time)
+cpu_ms = pc.time_tracker_reference(CAM0, CAM1, MAX_CNT, MIN_DIST, seqs[0], TICKS)
 
 print(json.dumps({"what": "viwb_tracker_track + download, stereo 752x480, MAX_CNT 150, MIN_DIST 30, FLOW_BACK 1", "streams": F, "ticks": TICKS,
                   "e2e_ms_per_tick": wall * 1e3, "e2e_frames_per_s": F / wall, "device_ms_per_tick": dev_ms, "device_frames_per_s": F / dev_ms * 1e3,

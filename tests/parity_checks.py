@@ -863,3 +863,18 @@ def check_marginalize_vs_reference_code(ctx, oracle, reference_code, cid):
         assert np.abs(res0 - res1).max() <= 1e-9 * max(1.0, np.abs(res0).max()) and np.abs(jac0 - jac1).max() <= 1e-12 * max(1.0, np.abs(jac0).max())
         prob, st, _ = seq.window(k + 1, prior=got, prev_state=a)
         a, sm, q = oracle.optimization(prob, st, abi.MARGIN_OLD)
+
+
+def time_tracker_reference(cam0, cam1, max_cnt, min_dist, seq, ticks):
+    """ms per frame of trackImage() restated over cv2 (one session, one host thread) -- the CPU side of profiles/track_probe.py"""
+    import time
+    import cv2
+    import feature_oracle as fo
+    cv2.setNumThreads(1)
+    ref = fo.FeatureTrackerRef(cam0, cam1, max_cnt, min_dist, True, use_cv_detector=True)
+    for t in range(2):
+        ref.track_image(0.05 * (t + 1), seq[0][t], seq[1][t])
+    t0 = time.perf_counter()
+    for t in range(2, ticks + 2):
+        ref.track_image(0.05 * (t + 1), seq[0][t], seq[1][t])
+    return (time.perf_counter() - t0) / ticks * 1e3
