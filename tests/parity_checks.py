@@ -867,8 +867,11 @@ def check_marginalize_vs_reference_code(ctx, oracle, reference_code, cid):
 
 def time_tracker_reference(cam0, cam1, max_cnt, min_dist, seq, ticks):
     """ms per frame of trackImage() restated over cv2 (one session, one host thread) -- the CPU side of profiles/track_probe.py"""
+    import os
+    import sys
     import time
     import cv2
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
     import feature_oracle as fo
     cv2.setNumThreads(1)
     ref = fo.FeatureTrackerRef(cam0, cam1, max_cnt, min_dist, True, use_cv_detector=True)
