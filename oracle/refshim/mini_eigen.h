@@ -19,6 +19,8 @@
 #include <limits>
 #include <string>
 
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
 namespace Eigen {
 
 const int Dynamic = -1;
@@ -134,6 +136,10 @@ template <typename Derived> class MatrixBase {
     DynBlock<Derived> bottomRows(int n) { return block(rows() - n, 0, n, cols()); }
     const DynBlock<Derived> bottomRows(int n) const { return block(rows() - n, 0, n, cols()); }
     ArrayX<Scalar> array() const;
+    template <typename NewT> typename plain_type<NewT, RowsAtCompileTime, ColsAtCompileTime>::type cast() const {
+        typedef typename plain_type<NewT, RowsAtCompileTime, ColsAtCompileTime>::type R; R r = make_plain<R>(rows(), cols());
+        for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = NewT(coeff(i, j)); return r;
+    }
     JacobiSVD<PlainObject> jacobiSvd(unsigned options = 0) const;
     PlainObject cwiseSqrt() const { PlainObject r = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = std::sqrt(coeff(i, j)); return r; }
 

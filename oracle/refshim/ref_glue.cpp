@@ -13,6 +13,7 @@
 #include "factor/plane_factor.h"
 #include "factor/marginalization_factor.h"
 #include "estimator/feature_manager.h"
+#include "camodocal/camera_models/PinholeCamera.h"
 #include "../../include/viwb.h"
 
 // ---- the globals of estimator/parameters.cpp that the factor code reads (that file itself needs ROS + OpenCV and is not compiled)
@@ -325,4 +326,22 @@ extern "C" int ref_shift_depth(int n, const double *uv, const double *depth_in, 
     int k = 0;
     for (auto &f : fm.feature) depth_out[k++] = f.estimated_depth;
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- camera model (camera_models/src/camera_models/PinholeCamera.cc)
+// FeatureTracker::undistortedPts (featureTracker/feature_tracker.cpp:606-617) is three lines around PinholeCamera::liftProjective; the
+// lift and the distortion model are the reference's.  cam = {fx, fy, cx, cy, k1, k2, p1, p2}; pts / un: n x 2 floats (cv::Point2f).
+extern "C" void ref_undistorted_pts(const double *cam, int width, int height, int n, const float *pts, float *un) {
+    camodocal::PinholeCamera c("cam", width, height, cam[4], cam[5], cam[6], cam[7], cam[0], cam[1], cam[2], cam[3]);
+    for (int i = 0; i < n; i++) {
+        Eigen::Vector2d a(pts[2 * i], pts[2 * i + 1]);
+        Eigen::Vector3d b;
+        c.liftProjective(a, b);
+        un[2 * i] = (float)(b.x() / b.z()); un[2 * i + 1] = (float)(b.y() / b.z());
+    }
+}
+// PinholeCamera::spaceToPlane (projection with distortion): P n x 3 doubles -> pixel n x 2 doubles (FeatureTracker::setPrediction, :729)
+extern "C" void ref_space_to_plane(const double *cam, int width, int height, int n, const double *P, double *uv) {
+    camodocal::PinholeCamera c("cam", width, height, cam[4], cam[5], cam[6], cam[7], cam[0], cam[1], cam[2], cam[3]);
+    for (int i = 0; i < n; i++) { Eigen::Vector2d p; c.spaceToPlane(Eigen::Vector3d(P[3 * i], P[3 * i + 1], P[3 * i + 2]), p); uv[2 * i] = p.x(); uv[2 * i + 1] = p.y(); }
 }

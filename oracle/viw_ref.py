@@ -117,3 +117,21 @@ def shift_depth(uv, depth, marg_R, marg_P, new_R, new_P, init_depth=5.0):
     rc = lib().ref_shift_depth(C.c_int(len(out)), *[_dp(x) for x in arrs], C.c_double(init_depth), _dp(out))
     assert rc == 0
     return out
+
+
+def undistorted_pts(cam, width, height, pts):
+    """FeatureTracker::undistortedPts over the reference's PinholeCamera::liftProjective (camera_models/src/camera_models/PinholeCamera.cc)"""
+    c = np.ascontiguousarray(cam, np.float64)
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    out = np.zeros_like(p)
+    fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    lib().ref_undistorted_pts(_dp(c), C.c_int(width), C.c_int(height), C.c_int(len(p)), fp(p), fp(out))
+    return out
+
+
+def space_to_plane(cam, width, height, P):
+    c = np.ascontiguousarray(cam, np.float64)
+    P = np.ascontiguousarray(P, np.float64).reshape(-1, 3)
+    uv = np.zeros((len(P), 2))
+    lib().ref_space_to_plane(_dp(c), C.c_int(width), C.c_int(height), C.c_int(len(P)), _dp(P), _dp(uv))
+    return uv

@@ -599,6 +599,12 @@ def check_undistort_velocity(ctx):
     ref_vel = np.where(has[:, None] > 0, ((ref_un - prev).astype(np.float64) / dt), 0.0).astype(np.float32)
     un, vel = ctx.undistort_velocity(cam, pts, prev, has, dt)
     assert np.abs(un - ref_un).max() <= 2e-7          # one float ulp at |x| < 1 (FMA contraction in the double lift)
+    try:                                              # and against the reference's own PinholeCamera::liftProjective, where oracle/_ref exists
+        import viw_ref
+        if viw_ref.available():
+            assert np.abs(un - viw_ref.undistorted_pts(cam, 752, 480, pts)).max() <= 2e-7
+    except ImportError:
+        pass
     assert np.abs(vel - ref_vel).max() <= 1e-5
     un0, vel0 = ctx.undistort_velocity((fx, fy, cx, cy, 0, 0, 0, 0), pts, None, None, dt)
     assert np.abs(un0[:, 0] - ((pts[:, 0].astype(np.float64) - cx) / fx).astype(np.float32)).max() <= 2e-7 and not vel0.any()

@@ -264,3 +264,16 @@ def test_triangulation_and_depth_shift_match_reference_code(oracle):
     r0 = vr.shift_depth(uv, dep, mR, mP, nR, nP)
     r1 = oracle.shift_depth(uv, dep, mR, mP, nR, nP)
     assert np.abs(r1 - r0).max() <= 1e-13 * np.abs(r0).max()
+
+
+# ------------------------------------------------------------------------------------------------ camera model
+def test_undistorted_pts_match_reference_code():
+    """FeatureTracker::undistortedPts = PinholeCamera::liftProjective (recursive distortion model, 8 iterations) from
+    camera_models/src/camera_models/PinholeCamera.cc, compiled unmodified, against the checker's restatement: bit for bit."""
+    import feature_oracle as fo
+    rng = np.random.default_rng(61)
+    for cam, (w, h) in (((461.1586, 459.7529, 362.6593, 248.5236, -0.2847798, 0.08245052, -1.0946e-06, 4.78701e-06), (752, 480)),
+                        ((457.5874, 456.1340, 379.9994, 255.2381, -0.2836831, 0.07395907, 1.9359e-04, 1.7618e-05), (752, 480)),
+                        ((384.45, 384.45, 320.0, 240.0, 0.0, 0.0, 0.0, 0.0), (640, 480))):                   # the m_noDistortion branch
+        pts = np.column_stack([rng.uniform(0, w, 400), rng.uniform(0, h, 400)]).astype(np.float32)
+        assert np.array_equal(vr.undistorted_pts(cam, w, h, pts), fo.lift_projective(cam, pts))
