@@ -154,6 +154,8 @@ template <typename Derived> class MatrixBase {
     }
     template <typename O> Derived &operator+=(const MatrixBase<O> &o) { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) += o.coeff(i, j); return derived(); }
     template <typename O> Derived &operator-=(const MatrixBase<O> &o) { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) -= o.coeff(i, j); return derived(); }
+    template <typename O> Derived &operator*=(const MatrixBase<O> &o) { PlainObject t = (*this) * o; return assign(t); }
+    template <typename O> void swap(MatrixBase<O> &o) { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) { const Scalar t = coeff(i, j); coeffRef(i, j) = o.coeff(i, j); o.coeffRef(i, j) = t; } }
     Derived &operator*=(Scalar s) { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) *= s; return derived(); }
     Derived &operator/=(Scalar s) { for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) coeffRef(i, j) /= s; return derived(); }
     CommaInit<Derived> operator<<(Scalar first) { return CommaInit<Derived>(derived(), first); }
@@ -444,6 +446,8 @@ template <typename A, typename S, typename = typename std::enable_if<std::is_ari
 template <typename A, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type> typename A::PlainObject operator/(const MatrixBase<A> &a, S s) {
     typename A::PlainObject r = a.plain(); for (int i = 0; i < a.rows(); i++) for (int j = 0; j < a.cols(); j++) r.coeffRef(i, j) = a.coeff(i, j) / typename traits<A>::Scalar(s); return r;
 }
+// a 1 x 1 product used as a scalar: var += v.transpose() * v
+template <typename S, typename A> typename std::enable_if<std::is_arithmetic<S>::value && (int)traits<A>::Rows == 1 && (int)traits<A>::Cols == 1, S &>::type operator+=(S &s, const MatrixBase<A> &a) { s += a.coeff(0, 0); return s; }
 template <typename A> std::ostream &operator<<(std::ostream &os, const MatrixBase<A> &a) {
     for (int i = 0; i < a.rows(); i++) { for (int j = 0; j < a.cols(); j++) os << (j ? " " : "") << a.coeff(i, j); if (i + 1 < a.rows()) os << "\n"; }
     return os;
@@ -539,6 +543,7 @@ template <typename MatrixType> class JacobiSVD {
         for (int k = 0; k < n; k++) { s_.coeffRef(k, 0) = sv[order[k]]; for (int i = 0; i < n; i++) V_.coeffRef(i, k) = v[(size_t)order[k] * n + i]; }
     }
     const VType &matrixV() const { return V_; }
+    typename plain_type<T, Dynamic, Dynamic>::type matrixU() const { assert(!"mini_eigen: JacobiSVD::matrixU is not provided"); return typename plain_type<T, Dynamic, Dynamic>::type(); }
     const SType &singularValues() const { return s_; }
 };
 template <typename Derived> JacobiSVD<typename MatrixBase<Derived>::PlainObject> MatrixBase<Derived>::jacobiSvd(unsigned options) const { return JacobiSVD<PlainObject>(*this, options); }
@@ -642,6 +647,15 @@ template <typename T> class Quaternion : public QuaternionBase<Quaternion<T>> {
     T c(int i) const { return q[i]; }
     T &c(int i) { return q[i]; }
     static Quaternion Identity() { return Quaternion(T(1), T(0), T(0), T(0)); }
+    // the rotation that takes the direction of a onto the direction of b (Utility::g2R); the antiparallel case picks some orthogonal axis
+    template <typename A, typename B> static Quaternion FromTwoVectors(const MatrixBase<A> &a, const MatrixBase<B> &b) {
+        const Matrix<T, 3, 1> v0 = a.normalized(), v1 = b.normalized();
+        const T c = v1.dot(v0);
+        if (c < T(-1) + T(1e-12)) { Matrix<T, 3, 1> ax = v0.cross(Matrix<T, 3, 1>(T(1), T(0), T(0))); if (ax.norm() < T(1e-6)) ax = v0.cross(Matrix<T, 3, 1>(T(0), T(1), T(0))); ax.normalize(); return Quaternion(T(0), ax.x(), ax.y(), ax.z()); }
+        const Matrix<T, 3, 1> axis = v0.cross(v1);
+        const T s = std::sqrt((T(1) + c) * T(2)), invs = T(1) / s;
+        return Quaternion(s * T(0.5), axis.x() * invs, axis.y() * invs, axis.z() * invs);
+    }
     Quaternion &setIdentity() { q[0] = q[1] = q[2] = T(0); q[3] = T(1); return *this; }
 };
 template <typename T> struct qtraits<Map<Quaternion<T>>> { typedef T Scalar; };
@@ -669,6 +683,11 @@ template <typename T> class AngleAxis {
     T a; Matrix<T, 3, 1> ax;
   public:
     template <typename O> AngleAxis(T angle, const MatrixBase<O> &axis) : a(angle), ax(axis) {}
+    template <typename O, typename = typename std::enable_if<(int)traits<O>::Rows == 3 && (int)traits<O>::Cols == 3>::type> explicit AngleAxis(const MatrixBase<O> &R) {
+        const Quaternion<T> q(R); T n = std::sqrt(q.x() * q.x() + q.y() * q.y() + q.z() * q.z());
+        if (n != T(0)) { a = T(2) * std::atan2(n, std::abs(q.w())); if (q.w() < T(0)) n = -n; ax = Matrix<T, 3, 1>(q.x() / n, q.y() / n, q.z() / n); }
+        else { a = T(0); ax = Matrix<T, 3, 1>(T(1), T(0), T(0)); }
+    }
     T angle() const { return a; }
     const Matrix<T, 3, 1> &axis() const { return ax; }
     Matrix<T, 3, 3> toRotationMatrix() const {

@@ -14,7 +14,9 @@
 #define CV_64F 6
 #define CV_32FC1 5
 #define CV_8UC1 0
+typedef unsigned char uchar;
 namespace cv {
+typedef unsigned char uchar;
 template <typename T> struct Point_ { T x, y; Point_() : x(0), y(0) {} Point_(T x_, T y_) : x(x_), y(y_) {} };
 typedef Point_<float> Point2f; typedef Point_<double> Point2d; typedef Point_<int> Point2i; typedef Point2i Point;
 template <typename T> struct Point3_ { T x, y, z; Point3_() : x(0), y(0), z(0) {} Point3_(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {} };

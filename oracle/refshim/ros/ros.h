@@ -1,2 +1,3 @@
 #pragma once
 #include "assert.h"
+#include "../ros_stub.h"

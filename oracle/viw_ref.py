@@ -135,3 +135,32 @@ def space_to_plane(cam, width, height, P):
     uv = np.zeros((len(P), 2))
     lib().ref_space_to_plane(_dp(c), C.c_int(width), C.c_int(height), C.c_int(len(P)), _dp(P), _dp(uv))
     return uv
+
+
+def estimator_optimization(problem, state, state_solved, flag):
+    """The reference's own Estimator::optimization() (estimator/estimator.cpp compiled unmodified) on the window `state`, with ceres::Solve
+    replaced by a hook that checks the assembled problem against the tables and plays `state_solved` back.  Returns a dict: state_out (the window
+    after double2vector + vector2double), the new prior (m, n, blocks after the address shift, J, r) and the assembly record."""
+    st = np.ascontiguousarray(state, np.float64)
+    so = np.ascontiguousarray(state_solved, np.float64)
+    out = np.zeros_like(st)
+    cap = 256
+    mn, bid, bidx, rec = (C.c_int32 * 3)(), (C.c_int32 * 32)(), (C.c_int32 * 32)(), (C.c_int32 * 11)()
+    J, r = np.zeros(cap * cap), np.zeros(cap)
+    rc = lib().ref_estimator_optimization(C.byref(problem.c), _dp(st), _dp(so), C.c_int(flag), _dp(out), mn, bid, bidx, _dp(J), _dp(r), rec)
+    if rc:
+        raise RuntimeError("ref_estimator_optimization rc=%d" % rc)
+    n = mn[1]
+    names = ("prior", "imu", "wheel", "plane", "proj_2f1c", "proj_2f2c", "proj_1f2c", "parameter_blocks", "structure_mismatches", "vector2double_mismatches", "visual_row_mismatches")
+    return {"state": out, "m": mn[0], "n": n, "blocks": [(bid[k], bidx[k]) for k in range(mn[2])], "J": J[: n * n].reshape(n, n).copy(), "r": r[:n].copy(),
+            "record": dict(zip(names, [int(v) for v in rec]))}
+
+
+def estimator_outliers(problem, state):
+    """Estimator::outliersRejection (estimator.cpp:2127-2185) of the reference"""
+    st = np.ascontiguousarray(state, np.float64)
+    out = np.zeros(max(problem.num_landmarks, 1), np.uint8)
+    rc = lib().ref_estimator_outliers(C.byref(problem.c), _dp(st), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    if rc:
+        raise RuntimeError("ref_estimator_outliers rc=%d" % rc)
+    return out[: problem.num_landmarks]

@@ -277,3 +277,98 @@ def test_undistorted_pts_match_reference_code():
                         ((384.45, 384.45, 320.0, 240.0, 0.0, 0.0, 0.0, 0.0), (640, 480))):                   # the m_noDistortion branch
         pts = np.column_stack([rng.uniform(0, w, 400), rng.uniform(0, h, 400)]).astype(np.float32)
         assert np.array_equal(vr.undistorted_pts(cam, w, h, pts), fo.lift_projective(cam, pts))
+
+
+# ------------------------------------------------------------------------------------------------ Estimator::optimization() itself
+def _as_the_estimator_holds_it(st):
+    """The reference keeps rotations as matrices and vector2double() turns them into quaternions (estimator.cpp:1155-1222, Eigen's
+    matrix -> quaternion: the trace branch, else the largest diagonal entry), so of the two quaternions of a rotation the arrays always hold the
+    one that conversion yields; the synthetic generator's perturbed quaternions may be the other.  Same rotation, the representative the
+    reference would hand to the solver."""
+    from viwb.geom import q_to_R
+    st = st.copy()
+    for off in [7 * i + 3 for i in range(11)] + [179, 186, 193, 197]:
+        q = st[off: off + 4] / np.linalg.norm(st[off: off + 4])
+        m = q_to_R(q)
+        t = m[0, 0] + m[1, 1] + m[2, 2]
+        out = np.zeros(4)
+        if t > 0:
+            t = np.sqrt(t + 1.0); out[3] = 0.5 * t; t = 0.5 / t
+            out[0], out[1], out[2] = (m[2, 1] - m[1, 2]) * t, (m[0, 2] - m[2, 0]) * t, (m[1, 0] - m[0, 1]) * t
+        else:
+            a = 0
+            if m[1, 1] > m[0, 0]:
+                a = 1
+            if m[2, 2] > m[a, a]:
+                a = 2
+            b, c = (a + 1) % 3, (a + 2) % 3
+            t = np.sqrt(m[a, a] - m[b, b] - m[c, c] + 1.0); out[a] = 0.5 * t; t = 0.5 / t
+            out[3] = (m[c, b] - m[b, c]) * t; out[b] = (m[b, a] + m[a, b]) * t; out[c] = (m[c, a] + m[a, c]) * t
+        if np.dot(out, q) < 0:                      # keep the handed-in digits, only pick the representative
+            st[off: off + 4] *= -1.0
+    return st
+
+
+@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+def test_estimator_optimization_of_the_reference_runs_on_the_tables(oracle, cid):
+    """estimator/estimator.cpp compiled unmodified (ROS / OpenCV / camodocal / ceres as name stand-ins, oracle/refshim/): the reference's own
+    Estimator::optimization() is driven on two consecutive windows.  ceres::Problem records, ceres::Solve checks the record against the
+    tables and plays the restated solver's solution back (Ceres itself is not in the image).  Pinned thereby:
+      a-1  vector2double -- the arrays the solver sees are the window handed in; double2vector -- the re-anchored window equals the oracle's;
+      a-2  the problem assembly -- every parameter block (presence, constancy, manifold and its subset mask) and every residual block (type,
+           blocks, constants, order) equals the table row the library consumes;
+      a-13 the marginalization as optimization() orchestrates it (factor hand-over, drop sets, address shift) -- the new prior."""
+    seq = synth.Sequence(synth.make_config(cid), 4, 13)
+    prob, st, _ = seq.window(0)
+    for k in range(2):
+        st = _as_the_estimator_holds_it(st)
+        solved, sm = oracle.window_solve(prob, st)
+        a, sm2, q = oracle.optimization(prob, st, abi.MARGIN_OLD)
+        ref = vr.estimator_optimization(prob, st, solved, abi.MARGIN_OLD)
+        rec = ref["record"]
+        assert rec["structure_mismatches"] == 0 and rec["vector2double_mismatches"] == 0 and rec["visual_row_mismatches"] == 0, (cid, k, rec)
+        assert rec["prior"] == (1 if prob.prior is not None and prob.prior.valid else 0)
+        assert rec["imu"] == len(prob.imu_frame_i) and rec["wheel"] == len(prob.wheel_frame_i) and rec["plane"] == len(prob.plane_frame)
+        assert [rec["proj_2f1c"], rec["proj_2f2c"], rec["proj_1f2c"]] == [int((prob.vis_type == t).sum()) for t in (0, 1, 2)]
+        assert np.abs(ref["state"] - a).max() <= 1e-12 * max(1.0, np.abs(a).max()), (cid, k, np.abs(ref["state"] - a).max())
+        assert ref["n"] == q.n
+        ids0, A0, b0 = _information_by_block(ref["blocks"], ref["J"], ref["r"])
+        ids1, A1, b1 = _information_by_block(q.blocks(), q.Jmat(), q.rvec())
+        assert ids0 == ids1
+        assert np.abs(A1 - A0).max() <= 1e-7 * np.abs(A0).max() and np.abs(b1 - b0).max() <= 1e-7 * np.abs(b0).max(), (cid, k)
+        prob, st, _ = seq.window(k + 1, prior=q, prev_state=a)
+
+
+@pytest.mark.parametrize("cid", [2, 4])
+def test_estimator_optimization_second_new(oracle, cid):
+    seq = synth.Sequence(synth.make_config(cid), 5, 13)
+    prob, st, _ = seq.window(0)
+    a, sm, q = oracle.optimization(prob, st, abi.MARGIN_OLD)
+    prob, st, _ = seq.window(1, prior=q, prev_state=a)
+    st = _as_the_estimator_holds_it(st)
+    solved, sm = oracle.window_solve(prob, st)
+    a, sm2, q2 = oracle.optimization(prob, st, abi.MARGIN_SECOND_NEW)
+    ref = vr.estimator_optimization(prob, st, solved, abi.MARGIN_SECOND_NEW)
+    assert ref["record"]["structure_mismatches"] == 0 and ref["record"]["visual_row_mismatches"] == 0
+    assert np.abs(ref["state"] - a).max() <= 1e-12 * max(1.0, np.abs(a).max())
+    assert ref["n"] == q2.n
+    ids0, A0, b0 = _information_by_block(ref["blocks"], ref["J"], ref["r"])
+    ids1, A1, b1 = _information_by_block(q2.blocks(), q2.Jmat(), q2.rvec())
+    assert ids0 == ids1 and np.abs(A1 - A0).max() <= 1e-7 * np.abs(A0).max() and np.abs(b1 - b0).max() <= 1e-7 * np.abs(b0).max()
+
+
+@pytest.mark.parametrize("cid", [1, 2, 4])
+def test_outlier_rejection_matches_reference_code(oracle, cid):
+    """Estimator::outliersRejection / reprojectionError (estimator.cpp:2115-2185) of the reference on solved and on corrupted windows"""
+    prob, st, _ = synth.make_window(cid)
+    a, sm, q = oracle.optimization(prob, st, abi.MARGIN_OLD)
+    rng = np.random.default_rng(71)
+    for trial in range(3):
+        x = a.copy()
+        if trial:
+            bad = rng.choice(prob.num_landmarks, 12, replace=False)
+            x[abi.STATE_FIXED + bad] *= rng.uniform(0.2, 3.0, 12)              # wrong depths: large reprojection errors
+        r0 = vr.estimator_outliers(prob, x)
+        r1 = oracle.outlier_rejection(prob, x)
+        assert np.array_equal(r0, r1), (cid, trial, int(r0.sum()), int(r1.sum()))
+        assert trial == 0 or r0.sum() >= 3
