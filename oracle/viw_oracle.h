@@ -4,9 +4,9 @@
  * THIS IS TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load it.  The product (libviwb.so) never links or calls it.
  *
- * PINNING: the factor, manifold and pre-integration functions are checked against THE REFERENCE'S OWN SOURCES compiled unmodified
- * into oracle/_ref/libviw_ref.so (oracle/Makefile `ref`, header stand-ins in oracle/refshim/; tests/test_reference_factors.py:
- * 1e-11 or better).  PARITY UNPINNED for the rest: the reference ships no golden vectors / known-answer tests for this path
+ * PINNING: the factor, manifold, pre-integration, prior, marginalization, triangulation and re-anchoring functions are checked against THE
+ * REFERENCE'S OWN SOURCES compiled unmodified into oracle/_ref/libviw_ref.so (oracle/Makefile `ref`, header stand-ins in oracle/refshim/;
+ * tests/test_reference_factors.py), Estimator::optimization() of estimator.cpp included.  PARITY UNPINNED for the arithmetic inside ceres::Solve: the reference ships no golden vectors / known-answer tests for this path
  *  and ceres-solver is not in the image; the trust-region / dense-Schur arithmetic restates
  * ceres-solver 1.14.0 (README.md:41; docker/Dockerfile:3 pins 1.12.0 -- same refactored TrustRegionMinimizer) from its
  * published algorithm (trust_region_minimizer.cc, dogleg_strategy.cc, corrector.cc, schur_complement_solver.cc) and is anchored
