@@ -164,3 +164,35 @@ def estimator_outliers(problem, state):
     if rc:
         raise RuntimeError("ref_estimator_outliers rc=%d" % rc)
     return out[: problem.num_landmarks]
+
+
+def estimator_optimization_with(problem, state, solve, flag):
+    """As estimator_optimization, but ceres::Solve hands the window to `solve(state) -> solved state` (e.g. the library under test): the
+    reference's unmodified Estimator::optimization() then runs on that backend."""
+    from viwb import abi
+    st = np.ascontiguousarray(state, np.float64)
+    out = np.zeros_like(st)
+    size = len(st)
+    CB = C.CFUNCTYPE(C.c_int, C.POINTER(abi.Problem), C.POINTER(C.c_double))
+    err = []
+
+    def cb(_pp, sp):
+        try:
+            window = np.ctypeslib.as_array(sp, shape=(size,))
+            window[:] = solve(window.copy())
+            return 0
+        except Exception as ex:            # noqa: BLE001 -- reported to the caller below
+            err.append(ex)
+            return 1
+    cap = 256
+    mn, bid, bidx, rec = (C.c_int32 * 3)(), (C.c_int32 * 32)(), (C.c_int32 * 32)(), (C.c_int32 * 11)()
+    J, r = np.zeros(cap * cap), np.zeros(cap)
+    rc = lib().ref_estimator_optimization_with(C.byref(problem.c), _dp(st), CB(cb), C.c_int(flag), _dp(out), mn, bid, bidx, _dp(J), _dp(r), rec)
+    if err:
+        raise err[0]
+    if rc:
+        raise RuntimeError("ref_estimator_optimization_with rc=%d" % rc)
+    n = mn[1]
+    names = ("prior", "imu", "wheel", "plane", "proj_2f1c", "proj_2f2c", "proj_1f2c", "parameter_blocks", "structure_mismatches", "vector2double_mismatches", "visual_row_mismatches")
+    return {"state": out, "m": mn[0], "n": n, "blocks": [(bid[k], bidx[k]) for k in range(mn[2])], "J": J[: n * n].reshape(n, n).copy(), "r": r[:n].copy(),
+            "record": dict(zip(names, [int(v) for v in rec]))}

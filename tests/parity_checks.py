@@ -887,3 +887,28 @@ def time_tracker_reference(cam0, cam1, max_cnt, min_dist, seq, ticks):
     for t in range(2, ticks + 2):
         ref.track_image(0.05 * (t + 1), seq[0][t], seq[1][t])
     return (time.perf_counter() - t0) / ticks * 1e3
+
+
+def check_reference_estimator_on_this_backend(ctx, oracle, cid):
+    """The reference's UNMODIFIED Estimator::optimization() (estimator.cpp compiled into oracle/_ref) with ceres::Solve delegated to the
+    library under test (viwb_window_solve through the C ABI): vector2double, problem assembly, double2vector and the marginalization are the
+    reference's own code, the solve is the CUDA backend's.  The result must be what the all-oracle Estimator::optimization() restatement
+    gives: poses to the BASELINE tolerance (tight: 1e-9), the prior in information form."""
+    import viw_ref
+    from test_reference_factors import _as_the_estimator_holds_it, _information_by_block
+    seq = synth.Sequence(synth.make_config(cid), 6, 13)
+    prob, st, _ = seq.window(0)
+    for k in range(2):
+        st = _as_the_estimator_holds_it(st)
+        a, sm, q = oracle.optimization(prob, st, abi.MARGIN_OLD)
+        ref = viw_ref.estimator_optimization_with(prob, st, lambda x: ctx.window_solve(prob, x)[0], abi.MARGIN_OLD)
+        rec = ref["record"]
+        assert rec["structure_mismatches"] == 0 and rec["vector2double_mismatches"] == 0 and rec["visual_row_mismatches"] == 0, (cid, k, rec)
+        ep, er = synth.pose_errors(a, ref["state"])
+        assert ep <= TIGHT_M and er <= TIGHT_RAD, (cid, k, ep, er)
+        assert np.abs(ref["state"] - a).max() <= 1e-8 * max(1.0, np.abs(a).max())
+        assert ref["n"] == q.n
+        ids0, A0, b0 = _information_by_block(ref["blocks"], ref["J"], ref["r"])
+        ids1, A1, b1 = _information_by_block(q.blocks(), q.Jmat(), q.rvec())
+        assert ids0 == ids1 and np.abs(A1 - A0).max() <= 1e-6 * np.abs(A0).max() and np.abs(b1 - b0).max() <= 1e-6 * np.abs(b0).max(), (cid, k)
+        prob, st, _ = seq.window(k + 1, prior=q, prev_state=a)

@@ -135,3 +135,9 @@ def test_factor_evaluate_vs_reference_code(emu, reference_code, cid):
 @pytest.mark.parametrize("cid", [2, 4])
 def test_marginalize_vs_reference_code(emu, oracle, reference_code, cid):
     pc.check_marginalize_vs_reference_code(emu, oracle, reference_code, cid)
+
+
+@pytest.mark.parametrize("cid", [2, 4])
+def test_reference_estimator_runs_on_this_backend(emu, oracle, reference_code, cid):
+    """estimator.cpp of the reference, unmodified, with ceres::Solve answered by the library: north_star's drop-in, literally"""
+    pc.check_reference_estimator_on_this_backend(emu, oracle, cid)
