@@ -56,12 +56,13 @@ def paint_circle(mask, cx, cy, r, hw=None):
                 mask[y, x0:x1 + 1] = 0
 
 
-def set_mask(width, height, pts, track_cnt, min_dist, base_mask=None):
+def set_mask(width, height, pts, track_cnt, min_dist, base_mask=None, order_fn=None):
     """feature_tracker.cpp:59-89.  Returns (mask, keep) where keep lists the surviving indices in their new order.
-    Equal track counts keep their original relative order (std::sort leaves that order unspecified)."""
+    Equal track counts keep their original relative order (std::sort leaves that order unspecified); order_fn(track_cnt) -> visiting order
+    substitutes another valid order (the pinning test passes the one this libstdc++'s std::sort produces)."""
     mask = np.full((height, width), 255, np.uint8) if base_mask is None else base_mask.copy()
     pts = np.asarray(pts, f32).reshape(-1, 2)
-    order = np.argsort(-np.asarray(track_cnt, np.int64), kind="stable")
+    order = np.argsort(-np.asarray(track_cnt, np.int64), kind="stable") if order_fn is None else order_fn(track_cnt)
     hw = circle_half_widths(int(min_dist))
     keep = []
     for i in order:
@@ -179,9 +180,10 @@ class FeatureTrackerRef:
     its own third-party library underneath; setMask / goodFeaturesToTrack go through the restatement above (bit-identical to cv2's
     scalar path, tests/test_feature_oracle.py) or through cv2 itself (use_cv_detector=True)."""
 
-    def __init__(self, cam0, cam1=None, max_cnt=150, min_dist=30, flow_back=True, use_cv_detector=False):
+    def __init__(self, cam0, cam1=None, max_cnt=150, min_dist=30, flow_back=True, use_cv_detector=False, order_fn=None):
         import cv2
         self.cv2 = cv2
+        self.order_fn = order_fn
         self.cam, self.stereo = (cam0, cam1), cam1 is not None
         self.MAX_CNT, self.MIN_DIST, self.FLOW_BACK, self.use_cv = max_cnt, min_dist, flow_back, use_cv_detector
         self.n_id = 0
@@ -243,7 +245,7 @@ class FeatureTrackerRef:
         self.track_cnt = [c + 1 for c in self.track_cnt]                  # :174-175
         # setMask (:59-89) rebuilds cur_pts / ids / track_cnt in visiting order; goodFeaturesToTrack tops up (:181-204)
         cnt = np.asarray(self.track_cnt, np.int64)
-        mask, keep = set_mask(self.col, self.row, cur_pts, cnt, self.MIN_DIST)
+        mask, keep = set_mask(self.col, self.row, cur_pts, cnt, self.MIN_DIST, order_fn=self.order_fn)
         cur_pts = cur_pts[keep] if len(keep) else np.zeros((0, 2), f32)
         self.ids = [self.ids[k] for k in keep]
         self.track_cnt = [self.track_cnt[k] for k in keep]

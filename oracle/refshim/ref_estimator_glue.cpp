@@ -295,3 +295,55 @@ extern "C" int ref_estimator_outliers(const viwb_problem *p, const double *state
     for (int k = 0; k < p->num_landmarks; k++) out[k] = removeIndex.count(k) ? 1 : 0;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------- FeatureTracker (featureTracker/feature_tracker.cpp)
+// The reference's own trackImage(), compiled unmodified.  The OpenCV routines it calls are forwarded to callbacks (refshim/opencv2/opencv.hpp)
+// that the test points at the real cv2, so the tracker code runs on the library the reference links.
+extern "C" void ref_set_cv_callbacks(cv::LkCallback lk, cv::GfttCallback gftt, cv::CircleCallback circle) { cv::g_lk_cb = lk; cv::g_gftt_cb = gftt; cv::g_circle_cb = circle; }
+extern int ROW, COL;
+extern "C" void *ref_tracker_create(const double *cam0, const double *cam1, int width, int height, int max_cnt, int min_dist, int flow_back) {
+    ROW = height; COL = width; MAX_CNT = max_cnt; MIN_DIST = min_dist; FLOW_BACK = flow_back; SHOW_TRACK = 0;
+    FeatureTracker *t = new FeatureTracker();
+    auto mk = [&](const double *c) { return camodocal::CameraPtr(new camodocal::PinholeCamera("cam", width, height, c[4], c[5], c[6], c[7], c[0], c[1], c[2], c[3])); };
+    t->m_camera.push_back(mk(cam0));
+    if (cam1) { t->m_camera.push_back(mk(cam1)); t->stereo_cam = 1; }
+    return t;
+}
+extern "C" void ref_tracker_destroy(void *h) { delete (FeatureTracker *)h; }
+// one trackImage(); outputs in the tracker's own vector order: ids / track_cnt / {x, y, u, v, vx, vy} rows of both cameras
+// hasPrediction / predict_pts as FeatureTracker::setPrediction() leaves them (feature_tracker.cpp:715-736): n points aligned with prev_pts
+extern "C" int ref_tracker_set_prediction(void *h, int n, const float *pts) {
+    FeatureTracker *t = (FeatureTracker *)h;
+    if (n != (int)t->prev_pts.size()) return 1;
+    t->hasPrediction = true; t->predict_pts.clear();
+    for (int i = 0; i < n; i++) t->predict_pts.push_back(cv::Point2f(pts[2 * i], pts[2 * i + 1]));
+    return 0;
+}
+extern "C" int ref_tracker_track(void *h, double time, unsigned char *left, unsigned char *right, int cap, int32_t *n_left, int32_t *ids, int32_t *cnt, float *feat,
+                                 int32_t *n_right, int32_t *ids_r, float *feat_r) {
+    FeatureTracker *t = (FeatureTracker *)h;
+    cv::Mat l(ROW, COL, CV_8UC1, (void *)left), r = right ? cv::Mat(ROW, COL, CV_8UC1, (void *)right) : cv::Mat();
+    t->trackImage(time, l, r);
+    const int n = (int)t->ids.size(), m = (int)t->ids_right.size();
+    if (n > cap || m > cap) return 1;
+    *n_left = n; *n_right = m;
+    for (int i = 0; i < n; i++) {
+        ids[i] = t->ids[i]; cnt[i] = t->track_cnt[i];
+        float *o = feat + 6 * i; o[0] = t->cur_un_pts[i].x; o[1] = t->cur_un_pts[i].y; o[2] = t->cur_pts[i].x; o[3] = t->cur_pts[i].y; o[4] = t->pts_velocity[i].x; o[5] = t->pts_velocity[i].y;
+    }
+    for (int i = 0; i < m; i++) {
+        ids_r[i] = t->ids_right[i];
+        float *o = feat_r + 6 * i; o[0] = t->cur_un_right_pts[i].x; o[1] = t->cur_un_right_pts[i].y; o[2] = t->cur_right_pts[i].x; o[3] = t->cur_right_pts[i].y;
+        o[4] = t->right_pts_velocity[i].x; o[5] = t->right_pts_velocity[i].y;
+    }
+    return 0;
+}
+
+// The permutation std::sort (this libstdc++) gives FeatureTracker::setMask's vector for these track counts: setMask sorts
+// (track_cnt, (point, id)) with `a.first > b.first` (feature_tracker.cpp:70-73), which leaves the order of equal counts to the library.
+extern "C" void ref_std_sort_order(int n, const int32_t *cnt, int32_t *order) {
+    std::vector<std::pair<int, int>> v;
+    for (int i = 0; i < n; i++) v.push_back(std::make_pair(cnt[i], i));
+    std::sort(v.begin(), v.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
+    for (int i = 0; i < n; i++) order[i] = v[i].second;
+}

@@ -196,3 +196,89 @@ def estimator_optimization_with(problem, state, solve, flag):
     names = ("prior", "imu", "wheel", "plane", "proj_2f1c", "proj_2f2c", "proj_1f2c", "parameter_blocks", "structure_mismatches", "vector2double_mismatches", "visual_row_mismatches")
     return {"state": out, "m": mn[0], "n": n, "blocks": [(bid[k], bidx[k]) for k in range(mn[2])], "J": J[: n * n].reshape(n, n).copy(), "r": r[:n].copy(),
             "record": dict(zip(names, [int(v) for v in rec]))}
+
+
+# ---- the reference's FeatureTracker (featureTracker/feature_tracker.cpp, compiled unmodified) with its OpenCV calls answered by the real cv2
+_LK = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_ubyte),
+                  C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int)
+_GFTT = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int, C.c_double, C.c_double, C.POINTER(C.c_float), C.c_int)
+_CIRCLE = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+_cv_keep = []
+
+
+def _install_cv_callbacks():
+    import cv2
+    if _cv_keep:
+        return
+
+    def img(ptr, rows, cols):
+        return np.ctypeslib.as_array(ptr, shape=(rows, cols))
+
+    def lk(prev, nxt, rows, cols, n, p0, p1, status, err, win, max_level, crit_count, crit_eps, flags):
+        a, b = img(prev, rows, cols), img(nxt, rows, cols)
+        pts0 = np.ctypeslib.as_array(p0, shape=(n, 2)).reshape(-1, 1, 2).copy()
+        pts1 = np.ctypeslib.as_array(p1, shape=(n, 2))
+        q, st, er = cv2.calcOpticalFlowPyrLK(a, b, pts0, pts1.reshape(-1, 1, 2).copy() if flags & 4 else None, winSize=(win, win), maxLevel=max_level,
+                                             criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, crit_count, crit_eps), flags=flags)
+        pts1[:] = q.reshape(-1, 2)
+        np.ctypeslib.as_array(status, shape=(n,))[:] = st.reshape(-1)
+        np.ctypeslib.as_array(err, shape=(n,))[:] = er.reshape(-1)
+
+    def gftt(im, rows, cols, mask, max_corners, quality, min_dist, out, cap):
+        m = img(mask, rows, cols) if mask else None
+        c = cv2.goodFeaturesToTrack(img(im, rows, cols), max_corners, quality, min_dist, mask=m)
+        if c is None:
+            return 0
+        c = c.reshape(-1, 2)[:cap]
+        np.ctypeslib.as_array(out, shape=(cap, 2))[: len(c)] = c
+        return len(c)
+
+    def circle(im, rows, cols, cx, cy, radius, color, thickness):
+        cv2.circle(img(im, rows, cols), (cx, cy), radius, color, thickness)
+    cbs = (_LK(lk), _GFTT(gftt), _CIRCLE(circle))
+    _cv_keep.extend(cbs)
+    lib().ref_set_cv_callbacks(*cbs)
+
+
+class ReferenceFeatureTracker:
+    """FeatureTracker of the reference (one session): track_image(t, left, right) -> (ids, track_cnt, feat[n,6], ids_right, feat_right[m,6])"""
+
+    def __init__(self, cam0, cam1, width, height, max_cnt, min_dist, flow_back=True):
+        _install_cv_callbacks()
+        L = lib()
+        L.ref_tracker_create.restype = C.c_void_p
+        c0 = np.ascontiguousarray(cam0, np.float64)
+        c1 = None if cam1 is None else np.ascontiguousarray(cam1, np.float64)
+        self.cap = max(2 * max_cnt, 64)
+        self.h = C.c_void_p(L.ref_tracker_create(_dp(c0), _dp(c1) if c1 is not None else None, C.c_int(width), C.c_int(height), C.c_int(max_cnt), C.c_int(min_dist),
+                                                 C.c_int(1 if flow_back else 0)))
+
+    def set_prediction(self, pts):
+        p = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        rc = lib().ref_tracker_set_prediction(self.h, C.c_int(len(p)), p.ctypes.data_as(C.POINTER(C.c_float)))
+        assert rc == 0, "prediction must have one point per previous point"
+
+    def track_image(self, t, left, right=None):
+        cap = self.cap
+        nl, nr = C.c_int32(), C.c_int32()
+        ids, cnt, ids_r = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        feat, feat_r = np.zeros((cap, 6), np.float32), np.zeros((cap, 6), np.float32)
+        a = np.ascontiguousarray(left, np.uint8)
+        b = None if right is None else np.ascontiguousarray(right, np.uint8)
+        up = lambda x: x.ctypes.data_as(C.POINTER(C.c_ubyte))
+        ip = lambda x: x.ctypes.data_as(C.POINTER(C.c_int32))
+        fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+        rc = lib().ref_tracker_track(self.h, C.c_double(t), up(a), up(b) if b is not None else None, C.c_int(cap), C.byref(nl), ip(ids), ip(cnt), fp(feat),
+                                     C.byref(nr), ip(ids_r), fp(feat_r))
+        if rc:
+            raise RuntimeError("ref_tracker_track rc=%d" % rc)
+        return ids[: nl.value].copy(), cnt[: nl.value].copy(), feat[: nl.value].copy(), ids_r[: nr.value].copy(), feat_r[: nr.value].copy()
+
+
+def std_sort_order(track_cnt):
+    """visiting order of FeatureTracker::setMask under this libstdc++'s std::sort (equal counts: unspecified by the standard)"""
+    c = np.ascontiguousarray(track_cnt, np.int32)
+    out = np.zeros(len(c), np.int32)
+    ip = lambda x: x.ctypes.data_as(C.POINTER(C.c_int32))
+    lib().ref_std_sort_order(C.c_int(len(c)), ip(c), ip(out))
+    return out

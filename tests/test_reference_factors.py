@@ -372,3 +372,45 @@ def test_outlier_rejection_matches_reference_code(oracle, cid):
         r1 = oracle.outlier_rejection(prob, x)
         assert np.array_equal(r0, r1), (cid, trial, int(r0.sum()), int(r1.sum()))
         assert trial == 0 or r0.sum() >= 3
+
+
+# ------------------------------------------------------------------------------------------------ FeatureTracker::trackImage
+def test_track_image_restatement_matches_reference_code():
+    """featureTracker/feature_tracker.cpp compiled unmodified, its three OpenCV calls (calcOpticalFlowPyrLK, goodFeaturesToTrack, circle)
+    answered by the real cv2 through callbacks: the reference's own trackImage() against the checker's line-by-line restatement
+    (oracle/feature_oracle.py:FeatureTrackerRef, the one the device tracker is tested against).  setMask() sorts with std::sort, which
+    leaves the order of equal track counts unspecified; for this test the restatement visits them in the order this libstdc++ produces
+    (vr.std_sort_order; the device tracker documents a stable order, an equally valid choice) and everything must then be IDENTICAL, row by
+    row: ids, track counts, pixels, undistorted points, velocities, both cameras, every tick."""
+    import feature_oracle as fo
+    from parity_checks import camera_sequence
+    cv2 = pytest.importorskip("cv2")
+    w, h, max_cnt, min_dist, ticks = 320, 240, 60, 20, 6
+    cam0 = (461.1586 * w / 752, 459.7529 * w / 752, w / 2 - 3.2, h / 2 + 1.7, -0.2847798, 0.08245052, -1.0946e-06, 4.78701e-06)
+    cam1 = (457.5874 * w / 752, 456.1340 * w / 752, w / 2 + 4.1, h / 2 - 2.6, -0.2836831, 0.07395907, 1.9359e-04, 1.7618e-05)
+    was = cv2.useOptimized(); cv2.setUseOptimized(False)
+    try:
+        for stereo in (True, False):
+            left, right, motion = camera_sequence(81, w, h, ticks)
+            ref = vr.ReferenceFeatureTracker(cam0, cam1 if stereo else None, w, h, max_cnt, min_dist, True)
+            mine = fo.FeatureTrackerRef(cam0, cam1 if stereo else None, max_cnt, min_dist, True, use_cv_detector=True, order_fn=vr.std_sort_order)
+            followed = 0
+            for t in range(ticks):
+                if t in (2, 4):                                          # the hasPrediction branch: a good prediction, then one outside the image (< 10 successes -> full-pyramid repeat)
+                    pred = (mine.prev_pts + (motion[t] if t == 2 else np.float32([w + 30.0, h + 30.0]))).astype(np.float32)
+                    ref.set_prediction(pred); mine.set_prediction(pred)
+                ids0, cnt0, f0, idr0, fr0 = ref.track_image(0.05 * (t + 1), left[t], right[t] if stereo else None)
+                ids1, cnt1, pts1, un1, vel1, idr1, ptsr1, unr1, velr1 = mine.track_image(0.05 * (t + 1), left[t], right[t] if stereo else None)
+                assert np.array_equal(ids0, ids1), (stereo, t)
+                o0, o1 = np.argsort(ids0), np.argsort(ids1)
+                assert np.array_equal(cnt0[o0], cnt1[o1])
+                assert np.array_equal(f0[o0, 2:4], pts1[o1]) and np.array_equal(f0[o0, 0:2], un1[o1]) and np.array_equal(f0[o0, 4:6], vel1[o1]), (stereo, t)
+                assert sorted(idr0) == sorted(idr1)
+                if stereo:
+                    p0, p1 = np.argsort(idr0), np.argsort(idr1)
+                    assert np.array_equal(fr0[p0, 2:4], ptsr1[p1]) and np.array_equal(fr0[p0, 0:2], unr1[p1]) and np.array_equal(fr0[p0, 4:6], velr1[p1])
+                followed += int((cnt0 > 1).sum())
+            assert followed > (ticks - 1) * max_cnt // 3
+            assert mine.stats == {"predicted": 2, "repeated": 1}
+    finally:
+        cv2.setUseOptimized(was)
