@@ -204,6 +204,13 @@ _LK = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_int, C.c
 _GFTT = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int, C.c_double, C.c_double, C.POINTER(C.c_float), C.c_int)
 _CIRCLE = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
 _cv_keep = []
+_cv_backend = [None]          # None: the real cv2 answers FeatureTracker's OpenCV calls; a viwb Context: the library under test does
+
+
+def use_backend(ctx):
+    """ctx = a viwb.lib.Context: cv::calcOpticalFlowPyrLK and cv::goodFeaturesToTrack inside the reference's tracker code are answered by
+    viwb_lk_track / viwb_good_features_to_track (INTEGRATION.md section 2, literally); None: by cv2.  cv::circle stays cv2's drawing."""
+    _cv_backend[0] = ctx
 
 
 def _install_cv_callbacks():
@@ -218,6 +225,12 @@ def _install_cv_callbacks():
         a, b = img(prev, rows, cols), img(nxt, rows, cols)
         pts0 = np.ctypeslib.as_array(p0, shape=(n, 2)).reshape(-1, 1, 2).copy()
         pts1 = np.ctypeslib.as_array(p1, shape=(n, 2))
+        if _cv_backend[0] is not None:
+            q, st, er = _cv_backend[0].lk_track(a, b, pts0.reshape(-1, 2), pts1.copy() if flags & 4 else None, max_level=max_level, max_iter=crit_count, eps=crit_eps, flags=flags)
+            pts1[:] = q
+            np.ctypeslib.as_array(status, shape=(n,))[:] = st
+            np.ctypeslib.as_array(err, shape=(n,))[:] = er
+            return
         q, st, er = cv2.calcOpticalFlowPyrLK(a, b, pts0, pts1.reshape(-1, 1, 2).copy() if flags & 4 else None, winSize=(win, win), maxLevel=max_level,
                                              criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, crit_count, crit_eps), flags=flags)
         pts1[:] = q.reshape(-1, 2)
@@ -226,7 +239,10 @@ def _install_cv_callbacks():
 
     def gftt(im, rows, cols, mask, max_corners, quality, min_dist, out, cap):
         m = img(mask, rows, cols) if mask else None
-        c = cv2.goodFeaturesToTrack(img(im, rows, cols), max_corners, quality, min_dist, mask=m)
+        if _cv_backend[0] is not None:
+            c = _cv_backend[0].good_features_to_track(img(im, rows, cols), max_corners, quality, min_dist, mask=m)
+        else:
+            c = cv2.goodFeaturesToTrack(img(im, rows, cols), max_corners, quality, min_dist, mask=m)
         if c is None:
             return 0
         c = c.reshape(-1, 2)[:cap]

@@ -912,3 +912,33 @@ def check_reference_estimator_on_this_backend(ctx, oracle, cid):
         ids1, A1, b1 = _information_by_block(q.blocks(), q.Jmat(), q.rvec())
         assert ids0 == ids1 and np.abs(A1 - A0).max() <= 1e-6 * np.abs(A0).max() and np.abs(b1 - b0).max() <= 1e-6 * np.abs(b0).max(), (cid, k)
         prob, st, _ = seq.window(k + 1, prior=q, prev_state=a)
+
+
+def check_reference_tracker_on_this_backend(ctx, w=320, h=240, max_cnt=60, min_dist=20, ticks=5):
+    """The reference's UNMODIFIED FeatureTracker::trackImage() (feature_tracker.cpp compiled into oracle/_ref) with cv::calcOpticalFlowPyrLK and
+    cv::goodFeaturesToTrack answered by the library under test (viwb_lk_track, viwb_good_features_to_track) -- the replacement INTEGRATION.md
+    section 2 describes -- against the same tracker code running on the real cv2: same ids in the same order, same track counts, points within
+    the LK tolerance."""
+    import cv2
+    import viw_ref
+    cam0 = (461.1586 * w / 752, 459.7529 * w / 752, w / 2 - 3.2, h / 2 + 1.7, -0.2847798, 0.08245052, -1.0946e-06, 4.78701e-06)
+    cam1 = (457.5874 * w / 752, 456.1340 * w / 752, w / 2 + 4.1, h / 2 - 2.6, -0.2836831, 0.07395907, 1.9359e-04, 1.7618e-05)
+    left, right, _ = camera_sequence(83, w, h, ticks)
+    was = cv2.useOptimized(); cv2.setUseOptimized(False)             # goodFeaturesToTrack's scalar path is the specification (tests/test_feature_oracle.py)
+    try:
+        a = viw_ref.ReferenceFeatureTracker(cam0, cam1, w, h, max_cnt, min_dist, True)
+        b = viw_ref.ReferenceFeatureTracker(cam0, cam1, w, h, max_cnt, min_dist, True)
+        followed = 0
+        for t in range(ticks):
+            viw_ref.use_backend(None)
+            ids0, cnt0, f0, idr0, fr0 = a.track_image(0.05 * (t + 1), left[t], right[t])
+            viw_ref.use_backend(ctx)
+            ids1, cnt1, f1, idr1, fr1 = b.track_image(0.05 * (t + 1), left[t], right[t])
+            assert np.array_equal(ids0, ids1) and np.array_equal(cnt0, cnt1) and np.array_equal(idr0, idr1), t
+            assert np.abs(f0[:, 2:4] - f1[:, 2:4]).max() <= 1e-2 and np.abs(fr0[:, 2:4] - fr1[:, 2:4]).max() <= 1e-2
+            assert np.abs(f0[:, 0:2] - f1[:, 0:2]).max() <= 1.5e-2 / cam0[0]
+            followed += int((cnt0 > 1).sum())
+        assert followed > (ticks - 1) * max_cnt // 3
+    finally:
+        viw_ref.use_backend(None)
+        cv2.setUseOptimized(was)
