@@ -15,10 +15,20 @@
 #include "../../include/viwb.h"
 #include <cstring>
 #include <new>
+#ifdef VIWB_PRODUCT_SHIM
+// Third build (oracle/Makefile `ref_product`): <ceres/ceres.h> is the PRODUCT's shim (viw-fusion_b200/host), not the recording stand-in, and the
+// reference's own factor / manifold classes are lowered by the product's adapter.  ceres::Solve below is then the product's, and what runs is
+// the reference's unmodified estimator.cpp on the library the process has loaded (emulation or libviwb.so).
+#include "viwb_reference_adapter.h"
+#endif
 
 CameraExtrinsicAdjustType CAM_EXT_ADJ_TYPE;
 WheelExtrinsicAdjustType WHEEL_EXT_ADJ_TYPE;
+#ifdef VIWB_PRODUCT_SHIM
+double SOLVER_TIME = 1e9;              // the shim reads >= 1e8 as "no wall-clock limit" (parity runs must not depend on the clock)
+#else
 double SOLVER_TIME = 0.04;
+#endif
 int NUM_ITERATIONS = 8;
 int SHOW_TRACK = 0;
 double BIAS_ACC_THRESHOLD = 0.1, BIAS_GYR_THRESHOLD = 0.1, F_THRESHOLD = 1.0, OFFSET_SIM = 0.0;
@@ -59,6 +69,7 @@ int landmark_of(Estimator *e, const double *ptr) { const long k = (ptr - &e->par
 bool near(double a, double b) { return a == b || std::fabs(a - b) <= 1e-15 * std::max(1.0, std::fabs(b)); }
 }  // namespace
 
+#ifndef VIWB_PRODUCT_SHIM
 ceres::Problem::~Problem() {}         // the objects a played-back problem holds are few and leak on purpose (test process)
 
 void ceres::Solve(const Solver::Options &options, Problem *problem, Solver::Summary *summary) {
@@ -145,6 +156,7 @@ void ceres::Solve(const Solver::Options &options, Problem *problem, Solver::Summ
     summary->iterations.resize(1);
     summary->termination_type = CONVERGENCE;
 }
+#endif  // !VIWB_PRODUCT_SHIM
 
 static Eigen::Quaterniond quat_at(const double *q) { return Eigen::Quaterniond(q[3], q[0], q[1], q[2]); }
 static MarginalizationInfo *estimator_prior(const viwb_prior *pr) {
@@ -267,6 +279,9 @@ static int estimator_optimization(const viwb_problem *p, const double *state_in,
     if (p->frame_count != 10) return 2;
     Estimator *e = make_estimator(p, state_in, margin_flag);
     if (!e) return 3;
+#ifdef VIWB_PRODUCT_SHIM
+    viwb_shim::install_reference_adapter();
+#endif
     g_pb.solve_cb = cb;
     g_pb.p = p; g_pb.solved = state_solved; g_pb.e = e; g_pb.input = state_in; g_pb.record = record; g_pb.active = true;
     for (int k = 0; k < 11; k++) record[k] = -1;

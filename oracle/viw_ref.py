@@ -198,6 +198,43 @@ def estimator_optimization_with(problem, state, solve, flag):
             "record": dict(zip(names, [int(v) for v in rec]))}
 
 
+# ---- third build: the reference's estimator.cpp compiled against the PRODUCT's ceres shim (viw-fusion_b200/host + viwb_reference_adapter.h)
+PRODUCT_LIB = os.path.join(HERE, "_ref", "libviw_ref_product.so")
+_plib = {}
+
+
+def product_lib(under_test_path):
+    """`under_test_path`: the libviwb*.so the shim's viwb_* calls are to land in (loaded RTLD_GLOBAL first: the checker library leaves them undefined)."""
+    if under_test_path not in _plib:
+        if _plib:
+            raise RuntimeError("one library under test per process")
+        if os.path.isdir(REF_SRC):
+            subprocess.check_call(["make", "-C", HERE, "-s", "ref_product"])
+        C.CDLL(under_test_path, mode=C.RTLD_GLOBAL)
+        _plib[under_test_path] = C.CDLL(PRODUCT_LIB)
+    return _plib[under_test_path]
+
+
+def product_available():
+    return os.path.exists(PRODUCT_LIB) or os.path.isdir(REF_SRC)
+
+
+def estimator_optimization_on_product_shim(under_test_path, problem, state, flag):
+    """Estimator::optimization() of the reference, compiled unmodified, with <ceres/ceres.h> = the product shim: ceres::Problem / ceres::Solve are
+    the product's host code, the reference's own factor objects are lowered by the product's adapter, the solve runs in the library under test;
+    the marginalization that follows is the reference's own CPU code on its own factor classes."""
+    st = np.ascontiguousarray(state, np.float64)
+    out = np.zeros_like(st)
+    cap = 256
+    mn, bid, bidx, rec = (C.c_int32 * 3)(), (C.c_int32 * 32)(), (C.c_int32 * 32)(), (C.c_int32 * 11)()
+    J, r = np.zeros(cap * cap), np.zeros(cap)
+    rc = product_lib(under_test_path).ref_estimator_optimization(C.byref(problem.c), _dp(st), None, C.c_int(flag), _dp(out), mn, bid, bidx, _dp(J), _dp(r), rec)
+    if rc:
+        raise RuntimeError("ref_estimator_optimization (product shim) rc=%d" % rc)
+    n = mn[1]
+    return {"state": out, "m": mn[0], "n": n, "blocks": [(bid[k], bidx[k]) for k in range(mn[2])], "J": J[: n * n].reshape(n, n).copy(), "r": r[:n].copy()}
+
+
 # ---- the reference's FeatureTracker (featureTracker/feature_tracker.cpp, compiled unmodified) with its OpenCV calls answered by the real cv2
 _LK = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_ubyte),
                   C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int)

@@ -914,6 +914,38 @@ def check_reference_estimator_on_this_backend(ctx, oracle, cid):
         prob, st, _ = seq.window(k + 1, prior=q, prev_state=a)
 
 
+def check_reference_estimator_on_product_shim(ctx, libpath, cid):
+    """The reference's UNMODIFIED estimator.cpp compiled with <ceres/ceres.h> = the product's shim (viw-fusion_b200/host) and the reference's own
+    factor objects lowered by viw-fusion_b200/host/viwb_reference_adapter.h: what a maintainer gets by changing the include path and adding one
+    install call.  Against the same estimator code with the solve handed to viwb_window_solve on the ORIGINAL tables: if the shim's lowering of the
+    recorded ceres::Problem reproduces the tables, the solved windows and the priors the reference's own marginalization builds from them agree."""
+    import pytest
+    import viw_ref
+    from test_reference_factors import _as_the_estimator_holds_it, _information_by_block
+    if not viw_ref.product_available():
+        pytest.skip("neither /root/reference nor a prebuilt oracle/_ref/libviw_ref_product.so")
+    seq = synth.Sequence(synth.make_config(cid), 6, 13)
+    prob, st, _ = seq.window(0)
+    for k in range(2):
+        st = _as_the_estimator_holds_it(st)
+        try:
+            got = viw_ref.estimator_optimization_on_product_shim(libpath, prob, st, abi.MARGIN_OLD)
+        except RuntimeError as ex:
+            if "one library under test" in str(ex):
+                pytest.skip(str(ex))
+            raise
+        ref = viw_ref.estimator_optimization_with(prob, st, lambda x: ctx.window_solve(prob, x)[0], abi.MARGIN_OLD)
+        ep, er = synth.pose_errors(got["state"], ref["state"])
+        assert ep <= TIGHT_M and er <= TIGHT_RAD, (cid, k, ep, er)
+        assert np.abs(got["state"] - ref["state"]).max() <= 1e-9 * max(1.0, np.abs(ref["state"]).max()), (cid, k)
+        assert got["n"] == ref["n"] and got["m"] == ref["m"] and got["blocks"] == ref["blocks"]
+        ids0, A0, b0 = _information_by_block(ref["blocks"], ref["J"], ref["r"])
+        ids1, A1, b1 = _information_by_block(got["blocks"], got["J"], got["r"])
+        assert ids0 == ids1 and np.abs(A1 - A0).max() <= 1e-7 * np.abs(A0).max() and np.abs(b1 - b0).max() <= 1e-7 * np.abs(b0).max(), (cid, k)
+        a, _, q = ctx.optimization(prob, st, abi.MARGIN_OLD)
+        prob, st, _ = seq.window(k + 1, prior=q, prev_state=a)
+
+
 def check_reference_tracker_on_this_backend(ctx, w=320, h=240, max_cnt=60, min_dist=20, ticks=5):
     """The reference's UNMODIFIED FeatureTracker::trackImage() (feature_tracker.cpp compiled into oracle/_ref) with cv::calcOpticalFlowPyrLK and
     cv::goodFeaturesToTrack answered by the library under test (viwb_lk_track, viwb_good_features_to_track) -- the replacement INTEGRATION.md

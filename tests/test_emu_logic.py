@@ -143,6 +143,13 @@ def test_reference_estimator_runs_on_this_backend(emu, oracle, reference_code, c
     pc.check_reference_estimator_on_this_backend(emu, oracle, cid)
 
 
+@pytest.mark.parametrize("cid", [2, 4])
+def test_reference_estimator_on_product_shim(emu, reference_code, cid):
+    """estimator.cpp of the reference, unmodified, compiled against the product's ceres shim + reference adapter"""
+    from emu import build_emu
+    pc.check_reference_estimator_on_product_shim(emu, build_emu.build(), cid)
+
+
 def test_reference_tracker_runs_on_this_backend(emu, reference_code):
     """feature_tracker.cpp of the reference, unmodified, with its cv:: flow and corner calls answered by the library"""
     pc.check_reference_tracker_on_this_backend(emu)

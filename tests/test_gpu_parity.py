@@ -177,14 +177,3 @@ def test_factor_evaluate_vs_reference_code(gpu_ctx, reference_code, cid):
 @pytest.mark.parametrize("cid", [2, 4])
 def test_marginalize_vs_reference_code(gpu_ctx, oracle, reference_code, cid):
     pc.check_marginalize_vs_reference_code(gpu_ctx, oracle, reference_code, cid)
-
-
-@pytest.mark.parametrize("cid", [2, 4])
-def test_reference_estimator_runs_on_this_backend(gpu_ctx, oracle, reference_code, cid):
-    """estimator.cpp of the reference, unmodified, with ceres::Solve answered by the library: north_star's drop-in, literally"""
-    pc.check_reference_estimator_on_this_backend(gpu_ctx, oracle, cid)
-
-
-def test_reference_tracker_runs_on_this_backend(gpu_ctx, reference_code):
-    """feature_tracker.cpp of the reference, unmodified, with its cv:: flow and corner calls answered by the library"""
-    pc.check_reference_tracker_on_this_backend(gpu_ctx)

@@ -12,6 +12,7 @@
 // Only the reference's seven hot-path factor classes (viw-fusion_b200/host/factor/*.h) can be lowered; any other
 // CostFunction makes Solve() return FAILURE (termination_type) instead of silently solving on the CPU.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -44,6 +45,19 @@ template <int kNumResiduals, int... Ns>
 class SizedCostFunction : public CostFunction {
   public:
     SizedCostFunction() { set_num_residuals(kNumResiduals); *mutable_parameter_block_sizes() = std::vector<int32_t>{Ns...}; }
+};
+
+// estimator.h reaches initial/initial_sfm.h:58, which names this template inside ReprojectionError3D::Create.  The initial structure-from-motion
+// is not on the window path (it stays with the real Ceres in its own target); here the name only has to compile, and a cost
+// function built from it cannot be lowered, so Solve() fails loudly on it like on any other unknown class.
+template <typename Functor, int kNumResiduals, int... Ns>
+class AutoDiffCostFunction : public SizedCostFunction<kNumResiduals, Ns...> {
+  public:
+    explicit AutoDiffCostFunction(Functor *f) : functor_(f) {}
+    ~AutoDiffCostFunction() override { delete functor_; }
+    bool Evaluate(double const *const *, double *, double **) const override { return false; }
+  private:
+    Functor *functor_;
 };
 
 class LocalParameterization {
@@ -134,5 +148,35 @@ class Problem {
 void Solve(const Solver::Options &options, Problem *problem, Solver::Summary *summary);
 
 }  // namespace ceres
+
+// Adapters for cost functions / manifolds / losses that are NOT the shim's own classes -- above all the reference's own factor classes when
+// estimator.cpp is compiled unmodified (viw-fusion_b200/host/viwb_reference_adapter.h installs them).  A class the shim does not know and no
+// adapter claims still makes Solve() fail loudly.
+namespace viwb_shim {
+struct Lowered { int type = -1; const double *record = nullptr; const viwb_prior *prior = nullptr; };   // type as CostFunction::viwb_factor_type()
+typedef bool (*CostAdapter)(const ceres::CostFunction *, Lowered *);
+typedef int (*ManifoldAdapter)(const ceres::LocalParameterization *);      // subset mask, or -1: not mine
+typedef double (*LossAdapter)(const ceres::LossFunction *);                // Huber delta, or -1: not mine
+typedef void (*SolveBegin)();                                              // called at the start of every Solve (adapters drop their scratch records)
+inline CostAdapter &cost_adapter() { static CostAdapter f = nullptr; return f; }
+inline ManifoldAdapter &manifold_adapter() { static ManifoldAdapter f = nullptr; return f; }
+inline LossAdapter &loss_adapter() { static LossAdapter f = nullptr; return f; }
+inline SolveBegin &solve_begin() { static SolveBegin f = nullptr; return f; }
+inline Lowered lower(const ceres::CostFunction *c) {
+    Lowered l; l.type = c->viwb_factor_type(); l.record = c->viwb_record(); l.prior = c->viwb_prior_data();
+    if (l.type == -1 && cost_adapter()) { Lowered a; if (cost_adapter()(c, &a)) l = a; }
+    return l;
+}
+inline unsigned subset_mask(const ceres::LocalParameterization *p) {
+    if (!p) return 0u;
+    if (manifold_adapter()) { const int m = manifold_adapter()(p); if (m >= 0) return (unsigned)m; }
+    return p->viwb_subset_mask();
+}
+inline double huber_delta(const ceres::LossFunction *l) {
+    const double d = l->viwb_huber_delta();
+    if (d < 0 && loss_adapter()) return loss_adapter()(l);
+    return d;
+}
+}  // namespace viwb_shim
 
 #include "../viwb_shim_impl.h"

@@ -66,10 +66,14 @@ inline void Solve(const Solver::Options &options, Problem *problem, Solver::Summ
     double *ex0 = nullptr, *ex1 = nullptr, *exw = nullptr, *sx = nullptr, *sy = nullptr, *sw = nullptr, *tdw = nullptr, *td = nullptr, *plane_r = nullptr, *plane_z = nullptr;
     const viwb_prior *prior = nullptr; const Problem::Residual *prior_res = nullptr;
     double huber = -1.0;
+    if (viwb_shim::solve_begin()) viwb_shim::solve_begin()();
+    std::vector<viwb_shim::Lowered> low(problem->residuals_.size());
+    for (size_t k = 0; k < problem->residuals_.size(); k++) low[k] = viwb_shim::lower(problem->residuals_[k].cost);
+    size_t rk = 0;
     for (auto &r : problem->residuals_) {
-        const int t = r.cost->viwb_factor_type();
+        const int t = low[rk].type;
         const std::vector<double *> &b = r.blocks;
-        if (r.loss) huber = r.loss->viwb_huber_delta();
+        if (r.loss) huber = viwb_shim::huber_delta(r.loss);
         switch (t) {
         case VIWB_F_PROJ_2F1C: poses.insert(b[0]); poses.insert(b[1]); ex0 = b[2]; if (!lm_index.count(b[3])) { lm_index[b[3]] = (int)landmarks.size(); landmarks.push_back(b[3]); } td = b[4]; break;
         case VIWB_F_PROJ_2F2C: poses.insert(b[0]); poses.insert(b[1]); ex0 = b[2]; ex1 = b[3]; if (!lm_index.count(b[4])) { lm_index[b[4]] = (int)landmarks.size(); landmarks.push_back(b[4]); } td = b[5]; break;
@@ -77,9 +81,10 @@ inline void Solve(const Solver::Options &options, Problem *problem, Solver::Summ
         case VIWB_F_IMU: poses.insert(b[0]); sbs.insert(b[1]); poses.insert(b[2]); sbs.insert(b[3]); break;
         case VIWB_F_WHEEL: poses.insert(b[0]); poses.insert(b[1]); exw = b[2]; sx = b[3]; sy = b[4]; sw = b[5]; tdw = b[6]; break;
         case VIWB_F_PLANE: poses.insert(b[0]); exw = b[1]; plane_r = b[2]; plane_z = b[3]; break;
-        case -2: prior = r.cost->viwb_prior_data(); prior_res = &r; break;
+        case -2: prior = low[rk].prior; prior_res = &r; break;
         default: summary->message = "unknown CostFunction: only the hot-path factor classes can be lowered to the GPU"; return;
         }
+        rk++;
     }
     // window poses that carry no factor yet (e.g. registered but unused) still belong to the window: take every size-7
     // block with a plain PoseLocalParameterization that is not an extrinsic
@@ -104,14 +109,15 @@ inline void Solve(const Solver::Options &options, Problem *problem, Solver::Summ
     for (auto &kv : id) {
         const Problem::Block &blk = problem->blocks_[kv.first];
         pb.block_flags[kv.second] = VIWB_BLOCK_PRESENT | (blk.constant ? VIWB_BLOCK_CONSTANT : 0u);
-        pb.subset_mask[kv.second] = blk.lp ? (uint8_t)blk.lp->viwb_subset_mask() : 0;
+        pb.subset_mask[kv.second] = (uint8_t)viwb_shim::subset_mask(blk.lp);
         std::memcpy(state.data() + viwb_block_offset(kv.second), kv.first, sizeof(double) * viwb_block_size(kv.second));
     }
     for (size_t k = 0; k < landmarks.size(); k++) state[VIWB_STATE_FIXED + k] = landmarks[k][0];
     std::vector<int32_t> vt, vl, vi, vj, ii, ij, wi, wj, pf; std::vector<double> vobs, idata, wdata;
     viwb_prior pr_local; std::vector<double> pr_x0;
+    rk = 0;
     for (auto &r : problem->residuals_) {
-        const int t = r.cost->viwb_factor_type(); const std::vector<double *> &b = r.blocks; const double *rec = r.cost->viwb_record();
+        const int t = low[rk].type; const std::vector<double *> &b = r.blocks; const double *rec = low[rk].record; rk++;
         if (t >= 0 && t <= VIWB_F_PROJ_1F2C) {
             const int li = t == VIWB_F_PROJ_2F1C ? 3 : t == VIWB_F_PROJ_2F2C ? 4 : 2;
             vt.push_back(t); vl.push_back(lm_index[b[li]]);
