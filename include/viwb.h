@@ -308,6 +308,22 @@ int viwb_imu_preintegrate(viwb_context *ctx, int n, const int32_t *counts, const
 int viwb_wheel_preintegrate(viwb_context *ctx, int n, const int32_t *counts, const double *dt, const double *vel,
                             const double *gyr, const double *s, const double *td, const double *noise, double *records);
 
+/* ---- initialisation: visual-inertial(-wheel) alignment (SURVEY 8 f-4 ii) -------------------------------
+ * initial/initial_aligment.cpp, the three steps of VisualIMUAlignment (:336-344) as the caller sequences them:
+ *   viwb_solve_gyroscope_bias  = solveGyroscopeBias (:14-48) up to delta_bg; the repropagation that follows it there is
+ *                                viwb_imu_preintegrate with ba = 0, bg = Bgs[0] + delta_bg on the same sample buffers;
+ *   viwb_linear_alignment      = LinearAlignment + RefineGravity (:66-203) when wheel_data is NULL, else
+ *                                LinearAlignmentWithWheel + RefineGravityWithWheel (:204-334).
+ * Frames = all_image_frame in time order: R [num_frames][9] row-major ImageFrame::R, T [num_frames][3]; imu_data / wheel_data
+ * [num_frames-1] records (VIWB_IMU_DOUBLES / VIWB_WHEEL_DOUBLES) of frame j's pre-integration; tic = TIC[0], rio / tio = RIO (row-major) /
+ * TIO, g_norm = G.norm().  Outputs: g, x (capacity 3*num_frames+4; *x_size = 3*num_frames+4 when the first stage already fails its
+ * |g| / scale test, else 3*num_frames+3 with x.tail = s as the reference leaves it), *aligned = the reference's bool. */
+#define VIWB_MAX_INIT_FRAMES 64
+int viwb_solve_gyroscope_bias(viwb_context *ctx, int num_frames, const double *R, const double *imu_data, double *delta_bg);
+int viwb_linear_alignment(viwb_context *ctx, int num_frames, const double *R, const double *T, const double *imu_data,
+                          const double *wheel_data, const double *tic, const double *rio, const double *tio, double g_norm,
+                          double *g, double *x, int32_t *x_size, int32_t *aligned);
+
 /* ---- feature tracker: cv::calcOpticalFlowPyrLK replacement ---------------------------------------
  * Call sites featureTracker/feature_tracker.cpp:125-127,136,139,145-146,240,244.  Images are 8-bit
  * single channel, `stride` in bytes.  next_pts is in/out (read when flags & VIWB_LK_USE_INITIAL_FLOW).

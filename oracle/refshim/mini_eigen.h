@@ -34,6 +34,7 @@ template <typename PlainType> class Map;
 template <typename T> class Quaternion;
 template <typename MatrixType> class JacobiSVD;
 template <typename MatrixType> class SelfAdjointEigenSolver;
+template <typename MatrixType> class LDLT;
 template <typename D> struct traits;
 template <typename XprType> class DynBlock;
 template <typename T> class ArrayX;
@@ -103,6 +104,10 @@ template <typename Derived> class MatrixBase {
     template <int N> const Block<Derived, RowsAtCompileTime, N> rightCols() const { return Block<Derived, RowsAtCompileTime, N>(const_cast<Derived &>(derived()), 0, cols() - N, rows(), N); }
     template <int BR, int BC> Block<Derived, BR, BC> bottomRightCorner() { return Block<Derived, BR, BC>(derived(), rows() - BR, cols() - BC); }
     template <int BR, int BC> const Block<Derived, BR, BC> bottomRightCorner() const { return Block<Derived, BR, BC>(const_cast<Derived &>(derived()), rows() - BR, cols() - BC); }
+    template <int BR, int BC> Block<Derived, BR, BC> topRightCorner() { return Block<Derived, BR, BC>(derived(), 0, cols() - BC); }
+    template <int BR, int BC> const Block<Derived, BR, BC> topRightCorner() const { return Block<Derived, BR, BC>(const_cast<Derived &>(derived()), 0, cols() - BC); }
+    template <int BR, int BC> Block<Derived, BR, BC> bottomLeftCorner() { return Block<Derived, BR, BC>(derived(), rows() - BR, 0); }
+    template <int BR, int BC> const Block<Derived, BR, BC> bottomLeftCorner() const { return Block<Derived, BR, BC>(const_cast<Derived &>(derived()), rows() - BR, 0); }
     template <int BR, int BC> Block<Derived, BR, BC> topLeftCorner() { return Block<Derived, BR, BC>(derived(), 0, 0); }
     template <int BR, int BC> const Block<Derived, BR, BC> topLeftCorner() const { return Block<Derived, BR, BC>(const_cast<Derived &>(derived()), 0, 0); }
     Block<Derived, RowsAtCompileTime, 1> col(int j) { return Block<Derived, RowsAtCompileTime, 1>(derived(), 0, j, rows(), 1); }
@@ -189,6 +194,7 @@ template <typename Derived> class MatrixBase {
     PlainObject cwiseProduct(const PlainObject &o) const { PlainObject r = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = coeff(i, j) * o.coeff(i, j); return r; }
     PlainObject cwiseAbs() const { PlainObject r = plain(); for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) r.coeffRef(i, j) = std::abs(coeff(i, j)); return r; }
     // general inverse: Gauss-Jordan with partial pivoting (Eigen uses cofactors up to 4x4 and partial-pivot LU above)
+    LDLT<PlainObject> ldlt() const;
     PlainObject inverse() const {
         assert(rows() == cols());
         const int n = rows();
@@ -470,6 +476,43 @@ template <typename MatrixType> class LLT {
     typename MatrixType::PlainObject matrixU() const { return L.transpose(); }
     bool success() const { return ok; }
 };
+
+// ------------------------------------------------------------------------------------------------ LDL^T with diagonal pivoting
+// (the pivot rule of Eigen's LDLT: the largest remaining |diagonal|; solve() applies the pseudo-inverse of D)
+template <typename MatrixType> class LDLT {
+    typedef typename traits<MatrixType>::Scalar T;
+    std::vector<T> a; std::vector<int> perm; int n;
+  public:
+    template <typename O> explicit LDLT(const MatrixBase<O> &m) : n(m.rows()) {
+        a.resize((size_t)n * n); perm.resize(n);
+        for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) a[(size_t)i * n + j] = i >= j ? m.coeff(i, j) : m.coeff(j, i);
+        auto A = [&](int i, int j) -> T & { return a[(size_t)i * n + j]; };
+        for (int k = 0; k < n; k++) {
+            int p = k; T best = std::fabs(A(k, k));
+            for (int i = k + 1; i < n; i++) if (std::fabs(A(i, i)) > best) { best = std::fabs(A(i, i)); p = i; }
+            perm[k] = p;
+            if (p != k) {
+                for (int j = 0; j < k; j++) std::swap(A(k, j), A(p, j));
+                for (int i = p + 1; i < n; i++) std::swap(A(i, k), A(i, p));
+                for (int i = k + 1; i < p; i++) std::swap(A(i, k), A(p, i));
+                std::swap(A(k, k), A(p, p));
+            }
+            const T d = A(k, k), inv = std::fabs(d) > std::numeric_limits<T>::min() ? T(1) / d : T(0);
+            for (int i = k + 1; i < n; i++) { const T lik = A(i, k) * inv; for (int j = k + 1; j <= i; j++) A(i, j) -= lik * A(j, k); }
+            for (int i = k + 1; i < n; i++) A(i, k) *= inv;
+        }
+    }
+    template <typename O> typename O::PlainObject solve(const MatrixBase<O> &b) const {
+        typename O::PlainObject x = b.eval();
+        for (int k = 0; k < n; k++) if (perm[k] != k) std::swap(x.coeffRef(k, 0), x.coeffRef(perm[k], 0));
+        for (int i = 0; i < n; i++) { T s = x.coeff(i, 0); for (int j = 0; j < i; j++) s -= a[(size_t)i * n + j] * x.coeff(j, 0); x.coeffRef(i, 0) = s; }
+        for (int i = 0; i < n; i++) { const T d = a[(size_t)i * n + i]; x.coeffRef(i, 0) = std::fabs(d) > std::numeric_limits<T>::min() ? x.coeff(i, 0) / d : T(0); }
+        for (int i = n - 1; i >= 0; i--) { T s = x.coeff(i, 0); for (int j = i + 1; j < n; j++) s -= a[(size_t)j * n + i] * x.coeff(j, 0); x.coeffRef(i, 0) = s; }
+        for (int k = n - 1; k >= 0; k--) if (perm[k] != k) std::swap(x.coeffRef(k, 0), x.coeffRef(perm[k], 0));
+        return x;
+    }
+};
+template <typename Derived> LDLT<typename MatrixBase<Derived>::PlainObject> MatrixBase<Derived>::ldlt() const { return LDLT<PlainObject>(*this); }
 
 // ------------------------------------------------------------------------------------------------ symmetric eigen decomposition
 // Cyclic Jacobi rotations (Eigen tridiagonalises and runs implicit QR; eigenvalues agree to round-off, eigenvectors up to sign and, for

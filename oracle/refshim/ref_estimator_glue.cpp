@@ -311,6 +311,63 @@ extern "C" int ref_estimator_outliers(const viwb_problem *p, const double *state
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------- VisualIMUAlignment (initial/initial_aligment.cpp:336-344)
+// The reference's own solveGyroscopeBias (incl. its repropagate of every pre-integration) + LinearAlignment[WithWheel] + RefineGravity[WithWheel],
+// compiled unmodified.  Frames in time order; interval i (frame i -> i+1) has counts[i] IMU steps, sample rows as in ref_imu_preintegrate.
+// Outputs: delta_bg (what Bgs[] gained), the repropagated 287-double records, g, x, the return value.
+extern std::vector<Eigen::Vector3d> TIC;
+extern Eigen::Matrix3d RIO; extern Eigen::Vector3d TIO;
+extern "C" int ref_visual_imu_alignment(int F, const double *R, const double *T, const int32_t *counts, const double *dt, const double *acc, const double *gyr, const double *noise,
+                                        const double *bg0, const double *wheel_rec, const double *tic, const double *rio, const double *tio, const double *gvec,
+                                        double *delta_bg, double *imu_rec, double *g_out, double *x_out, int32_t *x_size) {
+    ACC_N = noise[0]; GYR_N = noise[1]; ACC_W = noise[2]; GYR_W = noise[3];
+    G = Eigen::Vector3d(gvec[0], gvec[1], gvec[2]);
+    TIC.assign(1, Eigen::Vector3d(tic[0], tic[1], tic[2]));
+    USE_WHEEL = wheel_rec != nullptr;
+    if (wheel_rec) { for (int i = 0; i < 3; i++) { TIO(i) = tio[i]; for (int j = 0; j < 3; j++) RIO(i, j) = rio[3 * i + j]; } }
+    map<double, ImageFrame> frames;
+    Eigen::Vector3d Bgs[WINDOW_SIZE + 1];
+    for (int i = 0; i <= WINDOW_SIZE; i++) Bgs[i] = Eigen::Vector3d(bg0[0], bg0[1], bg0[2]);
+    int s0 = 0;
+    for (int f = 0; f < F; f++) {
+        ImageFrame fr; fr.t = 0.05 * f; fr.is_key_frame = true; fr.pre_integration = nullptr; fr.pre_integration_wheel = nullptr;
+        for (int i = 0; i < 3; i++) { fr.T(i) = T[3 * f + i]; for (int j = 0; j < 3; j++) fr.R(i, j) = R[9 * f + 3 * i + j]; }
+        if (f > 0) {
+            const int it = f - 1, r0 = s0 + it;
+            IntegrationBase *pre = new IntegrationBase(Eigen::Vector3d(acc[3 * r0], acc[3 * r0 + 1], acc[3 * r0 + 2]), Eigen::Vector3d(gyr[3 * r0], gyr[3 * r0 + 1], gyr[3 * r0 + 2]),
+                                                       Eigen::Vector3d::Zero(), Bgs[0]);
+            for (int k = 0; k < counts[it]; k++) { const int r = r0 + k + 1; pre->push_back(dt[s0 + k], Eigen::Vector3d(acc[3 * r], acc[3 * r + 1], acc[3 * r + 2]), Eigen::Vector3d(gyr[3 * r], gyr[3 * r + 1], gyr[3 * r + 2])); }
+            s0 += counts[it];
+            fr.pre_integration = pre;
+            if (wheel_rec) {
+                const double *c = wheel_rec + (size_t)it * VIWB_WHEEL_DOUBLES;
+                WheelIntegrationBase *w = new WheelIntegrationBase(Eigen::Vector3d(c[65], c[66], c[67]), Eigen::Vector3d(c[68], c[69], c[70]), c[61], c[62], c[63], c[64]);
+                w->delta_p = Eigen::Vector3d(c[0], c[1], c[2]);
+                fr.pre_integration_wheel = w;
+            }
+        }
+        frames[fr.t] = fr;
+    }
+    Eigen::Vector3d g; Eigen::VectorXd x;
+    const bool ok = VisualIMUAlignment(frames, Bgs, g, x);
+    for (int i = 0; i < 3; i++) { delta_bg[i] = Bgs[0](i) - bg0[i]; g_out[i] = g(i); }
+    *x_size = (int)x.size();
+    for (int i = 0; i < (int)x.size(); i++) x_out[i] = x(i);
+    int it = 0;
+    for (auto &kv : frames) {
+        IntegrationBase *p = kv.second.pre_integration;
+        if (!p) continue;
+        double *rec = imu_rec + (size_t)it * VIWB_IMU_DOUBLES; it++;
+        rec[0] = p->sum_dt;
+        for (int i = 0; i < 3; i++) { rec[1 + i] = p->delta_p(i); rec[8 + i] = p->delta_v(i); rec[11 + i] = p->linearized_ba(i); rec[14 + i] = p->linearized_bg(i); }
+        rec[4] = p->delta_q.x(); rec[5] = p->delta_q.y(); rec[6] = p->delta_q.z(); rec[7] = p->delta_q.w();
+        const int br[5] = {O_P, O_P, O_R, O_V, O_V}, bc[5] = {O_BA, O_BG, O_BG, O_BA, O_BG};
+        for (int k = 0; k < 5; k++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) rec[17 + 9 * k + 3 * i + j] = p->jacobian(br[k] + i, bc[k] + j);
+        for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) rec[62 + 15 * i + j] = p->covariance(i, j);
+    }
+    return ok ? 1 : 0;
+}
+
 // ---------------------------------------------------------------------------------------------------- FeatureTracker (featureTracker/feature_tracker.cpp)
 // The reference's own trackImage(), compiled unmodified.  The OpenCV routines it calls are forwarded to callbacks (refshim/opencv2/opencv.hpp)
 // that the test points at the real cv2, so the tracker code runs on the library the reference links.

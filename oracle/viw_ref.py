@@ -198,6 +198,25 @@ def estimator_optimization_with(problem, state, solve, flag):
             "record": dict(zip(names, [int(v) for v in rec]))}
 
 
+def visual_imu_alignment(R, T, dts, accs, gyrs, noise, bg0, wheel_rec, tic, rio, tio, gvec):
+    """VisualIMUAlignment of the reference (initial/initial_aligment.cpp compiled unmodified): solveGyroscopeBias with its repropagation, then
+    LinearAlignment[WithWheel] + RefineGravity[WithWheel].  Returns dict(ok, delta_bg, imu (repropagated records), g, x)."""
+    F = len(R)
+    R = np.ascontiguousarray(R, np.float64); T = np.ascontiguousarray(T, np.float64)
+    counts = np.array([len(d) for d in dts], np.int32)
+    dt = np.ascontiguousarray(np.concatenate(dts), np.float64)
+    acc = np.ascontiguousarray(np.concatenate(accs), np.float64); gyr = np.ascontiguousarray(np.concatenate(gyrs), np.float64)
+    noise, bg0, tic, gvec = (np.ascontiguousarray(a, np.float64) for a in (noise, bg0, tic, gvec))
+    w = np.ascontiguousarray(wheel_rec, np.float64) if wheel_rec is not None else None
+    rio = np.ascontiguousarray(rio, np.float64) if rio is not None else None
+    tio = np.ascontiguousarray(tio, np.float64) if tio is not None else None
+    dbg, rec, g, x, xs = np.zeros(3), np.zeros((F - 1, 287)), np.zeros(3), np.zeros(3 * F + 4), C.c_int32(0)
+    ok = lib().ref_visual_imu_alignment(C.c_int(F), _dp(R), _dp(T), counts.ctypes.data_as(C.POINTER(C.c_int32)), _dp(dt), _dp(acc), _dp(gyr), _dp(noise), _dp(bg0),
+                                        _dp(w) if w is not None else None, _dp(tic), _dp(rio) if rio is not None else None, _dp(tio) if tio is not None else None, _dp(gvec),
+                                        _dp(dbg), _dp(rec), _dp(g), _dp(x), C.byref(xs))
+    return {"ok": bool(ok), "delta_bg": dbg, "imu": rec, "g": g, "x": x[: xs.value].copy()}
+
+
 # ---- third build: the reference's estimator.cpp compiled against the PRODUCT's ceres shim (viw-fusion_b200/host + viwb_reference_adapter.h)
 PRODUCT_LIB = os.path.join(HERE, "_ref", "libviw_ref_product.so")
 _plib = {}

@@ -427,6 +427,80 @@ def check_preintegration(ctx, oracle, seed=5):
     return rec, wrec
 
 
+def alignment_case(cid, F=15, seed=3, scale=2.3, c0_tilt=(0.3, -0.2, 0.7), pos_noise=2e-5):
+    """Inputs of VisualIMUAlignment from a synthetic sequence: the up-to-scale camera poses an SfM would give (frame c0 = the world rotated by
+    `c0_tilt`, so that gravity is not along an axis; positions divided by `scale`), the raw IMU buffers, wheel pre-integrations for wheel configs."""
+    cfg = synth.make_config(cid)
+    seq = synth.Sequence(cfg, seed, F)
+    Rc0 = synth.Rz(c0_tilt[2]) @ synth.Ry(c0_tilt[1]) @ synth.Rx(c0_tilt[0])
+    rng = np.random.default_rng(100 * cid + seed)
+    R = np.array([Rc0 @ seq.gt_R[k] for k in range(F)])
+    T = np.array([(Rc0 @ seq.gt_P[k] + R[k] @ cfg.t_ic0) / scale for k in range(F)]) + rng.normal(0, pos_noise, (F, 3))
+    dts, accs, gyrs = [i[0] for i in seq.imu], [i[1] for i in seq.imu], [i[2] for i in seq.imu]
+    case = {"cfg": cfg, "R": R, "T": T, "dts": dts, "accs": accs, "gyrs": gyrs, "noise": np.array([cfg.acc_n, cfg.gyr_n, cfg.acc_w, cfg.gyr_w]), "bg0": np.zeros(3),
+            "tic": cfg.t_ic0, "rio": None, "tio": None, "g_norm": cfg.g_norm, "wheel": None, "scale": scale, "g_true": Rc0 @ np.array([0, 0, cfg.g_norm])}
+    if cfg.use_wheel:
+        case["rio"], case["tio"] = cfg.R_io, cfg.t_io
+        case["wheel_samples"] = seq.wheel
+    return case
+
+
+def _alignment_wheel_records(ctx, case):
+    if case["cfg"].use_wheel and case["wheel"] is None:
+        w = case["wheel_samples"]
+        n = len(w)
+        case["wheel"] = ctx.wheel_preintegrate([i[0] for i in w], [i[1] for i in w], [i[2] for i in w], np.ones((n, 3)), np.zeros(n), np.array([case["cfg"].vel_n_wheel, case["cfg"].gyr_n_wheel]))
+    return case["wheel"]
+
+
+def check_visual_imu_alignment(ctx, oracle, cid, F=15):
+    """SURVEY 8 f-4 ii: solveGyroscopeBias + repropagation + LinearAlignment[WithWheel] + RefineGravity[WithWheel] on the device against the
+    numpy restatement (oracle/init_oracle.py); the result is also physically right (gravity direction and scale of the synthetic sequence)."""
+    import init_oracle as io
+    case = alignment_case(cid, F)
+    wheel = _alignment_wheel_records(ctx, case)
+    got = ctx.visual_imu_alignment(case["R"], case["T"], case["dts"], case["accs"], case["gyrs"], case["noise"], case["bg0"], wheel, case["tic"], case["rio"], case["tio"], case["g_norm"])
+    n = len(case["dts"])
+    rec0 = np.array([oracle.imu_preintegrate(case["dts"][i], case["accs"][i], case["gyrs"][i], np.zeros(3), case["bg0"], case["noise"]) for i in range(n)])
+    dbg = io.solve_gyroscope_bias(case["R"], rec0)
+    assert np.abs(got["delta_bg"] - dbg).max() <= 1e-9 * max(1.0, np.abs(dbg).max()), (cid, got["delta_bg"], dbg)
+    rec = np.array([oracle.imu_preintegrate(case["dts"][i], case["accs"][i], case["gyrs"][i], np.zeros(3), case["bg0"] + dbg, case["noise"]) for i in range(n)])
+    ok, g, x = io.linear_alignment(case["R"], case["T"], rec, wheel, case["tic"], case["rio"], case["tio"], case["g_norm"])
+    assert got["ok"] == ok and ok, (cid, got["ok"], ok)
+    assert len(got["x"]) == len(x)
+    assert np.abs(got["g"] - g).max() <= 1e-7 * case["g_norm"], (cid, got["g"], g)
+    assert np.abs(got["x"] - x).max() <= 1e-7 * max(1.0, np.abs(x).max()), (cid, np.abs(got["x"] - x).max())
+    cosang = got["g"] @ case["g_true"] / (np.linalg.norm(got["g"]) * case["g_norm"])
+    assert cosang > np.cos(np.deg2rad(8.0)) and abs(got["x"][-1] / case["scale"] - 1.0) < 0.25, (cid, cosang, got["x"][-1])    # 0.7 s of motion: a sanity bound, not a parity bound
+    # a sequence the first stage must reject (|g| far from G): the unrefined solution comes back, 3F+4 long, as in the reference
+    bad = ctx.linear_alignment(case["R"], case["T"] * 3.0, rec, wheel, case["tic"], case["rio"], case["tio"], case["g_norm"] + 2.0)
+    okb, gb, xb = io.linear_alignment(case["R"], case["T"] * 3.0, rec, wheel, case["tic"], case["rio"], case["tio"], case["g_norm"] + 2.0)
+    assert bad[0] == okb and len(bad[2]) == len(xb) and np.abs(bad[2] - xb).max() <= 1e-7 * max(1.0, np.abs(xb).max())
+    # argument errors are reported, not computed on: fewer than two frames, more than VIWB_MAX_INIT_FRAMES
+    from viwb.lib import ViwbError
+    for nf in (1, 65):
+        try:
+            ctx.solve_gyroscope_bias(np.tile(np.eye(3), (nf, 1, 1)), np.zeros((max(nf - 1, 1), 287)))
+            raise AssertionError("accepted %d frames" % nf)
+        except ViwbError:
+            pass
+    return got
+
+
+def check_visual_imu_alignment_vs_reference_code(ctx, cid, F=15):
+    """The same call against VisualIMUAlignment of the reference's own compiled initial_aligment.cpp (oracle/_ref)"""
+    import viw_ref
+    case = alignment_case(cid, F)
+    wheel = _alignment_wheel_records(ctx, case)
+    got = ctx.visual_imu_alignment(case["R"], case["T"], case["dts"], case["accs"], case["gyrs"], case["noise"], case["bg0"], wheel, case["tic"], case["rio"], case["tio"], case["g_norm"])
+    ref = viw_ref.visual_imu_alignment(case["R"], case["T"], case["dts"], case["accs"], case["gyrs"], case["noise"], case["bg0"], wheel, case["tic"], case["rio"], case["tio"],
+                                       np.array([0, 0, case["g_norm"]]))
+    assert got["ok"] == ref["ok"] and len(got["x"]) == len(ref["x"])
+    assert np.abs(got["delta_bg"] - ref["delta_bg"]).max() <= 1e-9 * max(1.0, np.abs(ref["delta_bg"]).max())
+    assert np.abs(got["imu"] - ref["imu"]).max() <= 1e-9 * max(1.0, np.abs(ref["imu"]).max())
+    assert np.abs(got["g"] - ref["g"]).max() <= 1e-7 * case["g_norm"] and np.abs(got["x"] - ref["x"]).max() <= 1e-7 * max(1.0, np.abs(ref["x"]).max())
+
+
 def check_outlier_rejection(ctx, oracle):
     """SURVEY 8 f-3: Estimator::outliersRejection on solved windows (mono and stereo shapes), with a few landmarks pushed far
     off so that both verdicts occur; single-call and batch entry points."""

@@ -143,6 +143,16 @@ def test_reference_estimator_runs_on_this_backend(emu, oracle, reference_code, c
     pc.check_reference_estimator_on_this_backend(emu, oracle, cid)
 
 
+@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+def test_visual_imu_alignment(emu, oracle, cid):
+    pc.check_visual_imu_alignment(emu, oracle, cid)
+
+
+@pytest.mark.parametrize("cid", [2, 4])
+def test_visual_imu_alignment_vs_reference_code(emu, reference_code, cid):
+    pc.check_visual_imu_alignment_vs_reference_code(emu, cid)
+
+
 @pytest.mark.parametrize("cid", [2, 4])
 def test_reference_estimator_on_product_shim(emu, reference_code, cid):
     """estimator.cpp of the reference, unmodified, compiled against the product's ceres shim + reference adapter"""

@@ -414,3 +414,33 @@ def test_track_image_restatement_matches_reference_code():
             assert mine.stats == {"predicted": 2, "repeated": 1}
     finally:
         cv2.setUseOptimized(was)
+
+
+@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+def test_visual_imu_alignment_restatement_matches_reference_code(oracle, cid):
+    """SURVEY 8 f-4 ii: VisualIMUAlignment of the reference (initial/initial_aligment.cpp compiled unmodified: solveGyroscopeBias with its
+    repropagation, LinearAlignment[WithWheel], RefineGravity[WithWheel]) against the numpy restatement oracle/init_oracle.py -- gyroscope
+    bias, the repropagated pre-integration records, gravity, the solution vector and the verdict, mono / stereo / wheel shapes."""
+    import init_oracle as io
+    import parity_checks as pc
+    case = pc.alignment_case(cid, F=13, seed=5)
+    n = len(case["dts"])
+    wheel = None
+    if case["cfg"].use_wheel:
+        w = case["wheel_samples"]
+        wheel = np.array([oracle.wheel_preintegrate(i[0], i[1], i[2], np.ones(3), 0.0, np.array([case["cfg"].vel_n_wheel, case["cfg"].gyr_n_wheel])) for i in w])
+    ref = vr.visual_imu_alignment(case["R"], case["T"], case["dts"], case["accs"], case["gyrs"], case["noise"], case["bg0"], wheel, case["tic"], case["rio"], case["tio"],
+                                  np.array([0, 0, case["g_norm"]]))
+    rec0 = np.array([oracle.imu_preintegrate(case["dts"][i], case["accs"][i], case["gyrs"][i], np.zeros(3), case["bg0"], case["noise"]) for i in range(n)])
+    dbg = io.solve_gyroscope_bias(case["R"], rec0)
+    assert close(dbg, ref["delta_bg"], 1e-10)
+    rec = np.array([oracle.imu_preintegrate(case["dts"][i], case["accs"][i], case["gyrs"][i], np.zeros(3), case["bg0"] + dbg, case["noise"]) for i in range(n)])
+    assert close(rec, ref["imu"], 1e-10)
+    ok, g, x = io.linear_alignment(case["R"], case["T"], rec, wheel, case["tic"], case["rio"], case["tio"], case["g_norm"])
+    assert ok == ref["ok"] and ok and len(x) == len(ref["x"])
+    assert close(g, ref["g"], 1e-8) and close(x, ref["x"], 1e-8), (np.abs(g - ref["g"]).max(), np.abs(x - ref["x"]).max())
+    # the rejected branch: |g| off by more than 0.5 -> false, the unrefined 3F+4 vector
+    bad = vr.visual_imu_alignment(case["R"], case["T"], case["dts"], case["accs"], case["gyrs"], case["noise"], case["bg0"], wheel, case["tic"], case["rio"], case["tio"],
+                                  np.array([0, 0, case["g_norm"] + 2.0]))
+    okb, gb, xb = io.linear_alignment(case["R"], case["T"], rec, wheel, case["tic"], case["rio"], case["tio"], case["g_norm"] + 2.0)
+    assert bad["ok"] == okb and not okb and len(bad["x"]) == len(xb) == 3 * len(case["R"]) + 4 and close(xb, bad["x"], 1e-8)

@@ -24,3 +24,14 @@ def test_reference_estimator_on_product_shim(gpu_ctx, reference_code, cid):
     """estimator.cpp of the reference, unmodified, compiled against the product's ceres shim + reference adapter, solving on the GPU"""
     from viwb import lib as viwb_lib
     pc.check_reference_estimator_on_product_shim(gpu_ctx, viwb_lib.DEFAULT_LIB, cid)
+
+
+@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+def test_visual_imu_alignment(gpu_ctx, oracle, cid):
+    """SURVEY 8 f-4 ii: gyroscope bias, repropagation and the linear alignment with gravity refinement, on the device"""
+    pc.check_visual_imu_alignment(gpu_ctx, oracle, cid)
+
+
+@pytest.mark.parametrize("cid", [3, 4])
+def test_visual_imu_alignment_vs_reference_code(gpu_ctx, reference_code, cid):
+    pc.check_visual_imu_alignment_vs_reference_code(gpu_ctx, cid)

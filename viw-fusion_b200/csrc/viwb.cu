@@ -12,6 +12,7 @@
 #include "kernels_lk.cuh"
 #include "kernels_preint.cuh"
 #include "kernels_feat.cuh"
+#include "kernels_init.cuh"
 #include "kernels_detect.cuh"
 #include "kernels_track.cuh"
 
@@ -1043,6 +1044,74 @@ extern "C" int viwb_wheel_preintegrate(viwb_context *ctx, int n, const int32_t *
         g_prof.begin("wheel_preint", st); wheel_preint_kernel<<<(q.n + PRE_WPB - 1) / PRE_WPB, 32 * PRE_WPB, PRE_WPB * PRE_WHEEL_SMEM * 8, st>>>(q); g_prof.end(st);
 #endif
     }, PRE_WHEEL_SMEM, false);
+}
+
+// -------------------------------------------------------------------------------------- initialisation alignment (SURVEY 8 f-4 ii)
+struct InitWork { char *d = nullptr; double *R, *T, *imu, *wheel, *A, *b, *x, *out; int *perm; };
+static int init_work(viwb_context *ctx, InitWork &w, int F, const double *R, const double *T, const double *imu, const double *wheel) {
+    const int n = 3 * F + 4;
+    const size_t sR = align_up((size_t)F * 72), sT = align_up((size_t)F * 24), sI = align_up((size_t)(F - 1) * VIWB_IMU_DOUBLES * 8), sW = align_up((size_t)(F - 1) * VIWB_WHEEL_DOUBLES * 8);
+    const size_t sA = align_up((size_t)2 * n * n * 8), sv = align_up((size_t)(n + 8) * 8);
+    if (dev_malloc((void **)&w.d, sR + sT + sI + sW + sA + 3 * sv + align_up((size_t)n * 4))) return 1;
+    size_t o = 0;
+    w.R = (double *)(w.d + o); o += sR; w.T = (double *)(w.d + o); o += sT; w.imu = (double *)(w.d + o); o += sI; w.wheel = (double *)(w.d + o); o += sW;
+    w.A = (double *)(w.d + o); o += sA; w.b = (double *)(w.d + o); o += sv; w.x = (double *)(w.d + o); o += sv; w.out = (double *)(w.d + o); o += sv;
+    w.perm = (int *)(w.d + o);
+    int e = dev_h2d(w.R, R, (size_t)F * 72, ctx->stream);
+    if (!e && T) e = dev_h2d(w.T, T, (size_t)F * 24, ctx->stream);
+    if (!e) e = dev_h2d(w.imu, imu, (size_t)(F - 1) * VIWB_IMU_DOUBLES * 8, ctx->stream);
+    if (!e && wheel) e = dev_h2d(w.wheel, wheel, (size_t)(F - 1) * VIWB_WHEEL_DOUBLES * 8, ctx->stream);
+    return e;
+}
+
+extern "C" int viwb_solve_gyroscope_bias(viwb_context *ctx, int num_frames, const double *R, const double *imu_data, double *delta_bg) {
+    if (!ctx || !R || !imu_data || !delta_bg) return VIWB_ERR_INVALID;
+    if (num_frames < 2 || num_frames > VIWB_MAX_INIT_FRAMES) return fail(ctx, VIWB_ERR_INVALID, "solve_gyroscope_bias: 2..VIWB_MAX_INIT_FRAMES frames");
+    bind_device(ctx);
+    InitWork w; int e = init_work(ctx, w, num_frames, R, nullptr, imu_data, nullptr);
+    if (!e) {
+        GyroBiasArgs a; a.F = num_frames; a.R = w.R; a.imu = w.imu; a.A = w.A; a.b = w.b; a.x = w.x; a.perm = w.perm; a.out = w.out;
+#ifdef VIWB_HOST_EMU
+        gyro_bias_block(a, 0, 1);
+#else
+        g_prof.begin("gyro_bias", ctx->stream); gyro_bias_kernel<<<1, 32, 0, ctx->stream>>>(a); g_prof.end(ctx->stream);
+#endif
+        ctx->launches++;
+        e = dev_d2h(delta_bg, w.out, 24, ctx->stream);
+    }
+    if (!e) e = dev_sync(ctx->stream);
+    dev_free(w.d);
+    return e ? fail(ctx, VIWB_ERR_CUDA, "solve_gyroscope_bias failed") : VIWB_OK;
+}
+
+extern "C" int viwb_linear_alignment(viwb_context *ctx, int num_frames, const double *R, const double *T, const double *imu_data, const double *wheel_data,
+                                     const double *tic, const double *rio, const double *tio, double g_norm, double *g, double *x, int32_t *x_size, int32_t *aligned) {
+    if (!ctx || !R || !T || !imu_data || !tic || !g || !x || !x_size || !aligned || (wheel_data && (!rio || !tio))) return VIWB_ERR_INVALID;
+    if (num_frames < 2 || num_frames > VIWB_MAX_INIT_FRAMES) return fail(ctx, VIWB_ERR_INVALID, "linear_alignment: 2..VIWB_MAX_INIT_FRAMES frames");
+    bind_device(ctx);
+    const int n = 3 * num_frames + 4;
+    InitWork w; int e = init_work(ctx, w, num_frames, R, T, imu_data, wheel_data);
+    std::vector<double> out((size_t)n + 8);
+    if (!e) {
+        AlignArgs a; a.F = num_frames; a.use_wheel = wheel_data ? 1 : 0; a.R = w.R; a.T = w.T; a.imu = w.imu; a.wheel = wheel_data ? w.wheel : nullptr;
+        memcpy(a.tic, tic, 24); a.g_norm = g_norm;
+        for (int k = 0; k < 9; k++) a.rio[k] = rio ? rio[k] : (k % 4 == 0 ? 1.0 : 0.0);
+        for (int k = 0; k < 3; k++) a.tio[k] = tio ? tio[k] : 0.0;
+        a.A = w.A; a.b = w.b; a.x = w.x; a.perm = w.perm; a.out = w.out;
+#ifdef VIWB_HOST_EMU
+        align_block(a, 0, 1);
+#else
+        g_prof.begin("align", ctx->stream); align_kernel<<<1, 128, 0, ctx->stream>>>(a); g_prof.end(ctx->stream);
+#endif
+        ctx->launches++;
+        e = dev_d2h(out.data(), w.out, (size_t)(n + 5) * 8, ctx->stream);
+    }
+    if (!e) e = dev_sync(ctx->stream);
+    dev_free(w.d);
+    if (e) return fail(ctx, VIWB_ERR_CUDA, "linear_alignment failed");
+    *aligned = out[0] != 0.0; memcpy(g, out.data() + 1, 24); *x_size = (int32_t)out[4];
+    memcpy(x, out.data() + 5, (size_t)*x_size * 8);
+    return VIWB_OK;
 }
 
 // -------------------------------------------------------------------------------------- triangulation / depth shift

@@ -22,7 +22,8 @@ EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", 
            "viwb_lk_batch_upload", "viwb_lk_batch_run", "viwb_lk_batch_download", "viwb_lk_batch_algorithmic_bytes", "viwb_host_register",
            "viwb_host_unregister", "viwb_imu_preintegrate", "viwb_wheel_preintegrate", "viwb_outlier_rejection", "viwb_batch_outliers", "viwb_triangulate", "viwb_shift_depth", "viwb_undistort_velocity",
            "viwb_set_mask", "viwb_good_features_to_track", "viwb_detector_create", "viwb_detector_destroy", "viwb_detector_detect", "viwb_detector_algorithmic_bytes",
-           "viwb_tracker_create", "viwb_tracker_destroy", "viwb_tracker_track", "viwb_tracker_download", "viwb_tracker_algorithmic_bytes"]
+           "viwb_tracker_create", "viwb_tracker_destroy", "viwb_tracker_track", "viwb_tracker_download", "viwb_tracker_algorithmic_bytes",
+           "viwb_solve_gyroscope_bias", "viwb_linear_alignment"]
 
 
 class ViwbError(RuntimeError):
@@ -303,6 +304,38 @@ class Context:
         vp = lambda x: x.ctypes.data_as(C.c_void_p)
         self._ck(self.lib.viwb_wheel_preintegrate(self.h, C.c_int(n), vp(counts), vp(dt), vp(v), vp(g), vp(s), vp(td), vp(nz), vp(rec)), "viwb_wheel_preintegrate")
         return rec
+
+    def solve_gyroscope_bias(self, R, imu_records):
+        """solveGyroscopeBias (initial/initial_aligment.cpp:14-37): R (F, 3, 3), imu_records (F - 1, 287) -> delta_bg (3,)"""
+        R = np.ascontiguousarray(R, np.float64); rec = np.ascontiguousarray(imu_records, np.float64)
+        out = np.zeros(3)
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.viwb_solve_gyroscope_bias(self.h, C.c_int(len(R)), vp(R), vp(rec), vp(out)), "viwb_solve_gyroscope_bias")
+        return out
+
+    def linear_alignment(self, R, T, imu_records, wheel_records, tic, rio, tio, g_norm):
+        """LinearAlignment[WithWheel] + RefineGravity[WithWheel] (:66-334); wheel_records None = camera + IMU only -> (aligned, g, x)"""
+        F = len(R)
+        R = np.ascontiguousarray(R, np.float64); T = np.ascontiguousarray(T, np.float64); rec = np.ascontiguousarray(imu_records, np.float64)
+        w = np.ascontiguousarray(wheel_records, np.float64) if wheel_records is not None else None
+        tic = np.ascontiguousarray(tic, np.float64)
+        rio = np.ascontiguousarray(rio, np.float64) if rio is not None else None
+        tio = np.ascontiguousarray(tio, np.float64) if tio is not None else None
+        g, x, xs, ok = np.zeros(3), np.zeros(3 * F + 4), C.c_int32(0), C.c_int32(0)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        self._ck(self.lib.viwb_linear_alignment(self.h, C.c_int(F), vp(R), vp(T), vp(rec), vp(w), vp(tic), vp(rio), vp(tio), C.c_double(g_norm), vp(g), vp(x),
+                                                C.byref(xs), C.byref(ok)), "viwb_linear_alignment")
+        return bool(ok.value), g, x[: xs.value].copy()
+
+    def visual_imu_alignment(self, R, T, dts, accs, gyrs, noise, bg0, wheel_records, tic, rio, tio, g_norm):
+        """VisualIMUAlignment (:336-344) as the reference sequences it: gyroscope bias from the current pre-integrations, repropagation of every
+        interval with ba = 0, bg = bg0 + delta_bg (viwb_imu_preintegrate on the same buffers), linear alignment.  All three steps on the device."""
+        n = len(dts)
+        rec0 = self.imu_preintegrate(dts, accs, gyrs, np.zeros((n, 3)), np.tile(np.asarray(bg0, np.float64), (n, 1)), noise)
+        dbg = self.solve_gyroscope_bias(R, rec0)
+        rec = self.imu_preintegrate(dts, accs, gyrs, np.zeros((n, 3)), np.tile(np.asarray(bg0, np.float64) + dbg, (n, 1)), noise)
+        ok, g, x = self.linear_alignment(R, T, rec, wheel_records, tic, rio, tio, g_norm)
+        return {"ok": ok, "delta_bg": dbg, "imu": rec, "g": g, "x": x}
 
     def set_mask(self, width, height, pts, track_cnt, min_dist, base_mask=None, want_mask=True):
         """FeatureTracker::setMask(): returns (mask uint8 [height, width] or None, surviving indices in visiting order)"""
