@@ -20,5 +20,21 @@ def build():
     return OUT
 
 
+def build_sanitized():
+    """The same source with -fsanitize=address,undefined (left shifts of negative values excepted: the LK fixed-point arithmetic restates OpenCV's
+    `x << n` on signed operands, well defined on the GPU and for gcc): out-of-bounds indices of the kernels' local arrays, shared-memory carving and
+    workspace offsets show up here, on the CPU box.  Returns (library, libasan to LD_PRELOAD) or None when the toolchain has no libasan."""
+    out = os.path.join(HERE, "libviwb_emu_asan.so")
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        return None
+    deps = [os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith((".cu", ".cuh", ".inl"))] + [os.path.join(ROOT, "include", "viwb.h")]
+    if not (os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps)):
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DVIWB_HOST_EMU", "-x", "c++", "-Wno-unknown-pragmas",
+                               "-fsanitize=address,undefined", "-fno-sanitize=shift", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
+                               "-o", out, os.path.join(SRC, "viwb.cu")])
+    return out, asan
+
+
 if __name__ == "__main__":
     print(build())

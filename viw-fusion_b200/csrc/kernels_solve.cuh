@@ -316,7 +316,7 @@ VIWB_D void terminate(WinWork &ww, int term) { ww.status = ST_DONE; ww.term = te
 // max |x - Plus(x, -g)| over one fixed block (ambient infinity norm of the projected gradient step)
 VIWB_D double block_grad_inf(int b, unsigned mask, const double *x, const double *gneg) {
     const int gs = blk_size(b);
-    double out[7], m = 0.0;
+    double out[9], m = 0.0;          // the largest fixed block is a speed-bias (9)
     if (gs == 7) pose_plus(x, gneg, mask, out);
     else if (gs == 4) quat_plus(x, gneg, mask, out);
     else for (int i = 0; i < gs; i++) out[i] = x[i] + gneg[i];
