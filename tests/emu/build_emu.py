@@ -31,7 +31,7 @@ def build_sanitized():
     deps = [os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith((".cu", ".cuh", ".inl"))] + [os.path.join(ROOT, "include", "viwb.h")]
     if not (os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps)):
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DVIWB_HOST_EMU", "-x", "c++", "-Wno-unknown-pragmas",
-                               "-fsanitize=address,undefined", "-fno-sanitize=shift", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
+                               "-DVIWB_EMU_STRICT", "-fsanitize=address,undefined", "-fno-sanitize=shift", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
                                "-o", out, os.path.join(SRC, "viwb.cu")])
     return out, asan
 

@@ -45,7 +45,11 @@ static const char *dev_errstr(int) { return "emulation"; }
 #define VIWB_EMU_NT 1
 template <typename F>
 static void emu_launch(F f, const BatchDev &bd, int gx, int gy, size_t smem_bytes, int mode) {
+#ifdef VIWB_EMU_STRICT
+    std::vector<double> sm((smem_bytes + 7) / 8);       // sanitizer build: exactly the dynamic shared memory the launch asks for
+#else
     std::vector<double> sm(smem_bytes / 8 + 64);
+#endif
     for (int by = 0; by < gy; by++) for (int bx = 0; bx < gx; bx++) f(bd, bx, by, 0, 1, sm.data(), mode);
 }
 #define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) emu_launch(name##_block, bd, gx, gy, smem_bytes, mode)
