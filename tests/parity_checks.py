@@ -484,6 +484,12 @@ def check_visual_imu_alignment(ctx, oracle, cid, F=15):
             raise AssertionError("accepted %d frames" % nf)
         except ViwbError:
             pass
+    if wheel is not None:                                # wheel rows without the wheel extrinsic: refused
+        try:
+            ctx.linear_alignment(case["R"], case["T"], rec, wheel, case["tic"], None, None, case["g_norm"])
+            raise AssertionError("accepted wheel records without RIO / TIO")
+        except ViwbError:
+            pass
     return got
 
 
