@@ -24,7 +24,7 @@ def test_normal_equations(emu, oracle, cid):
     pc.check_normal_equations(emu, oracle, cid)
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 6])     # 6 = stereo only, USE_IMU = 0 (estimator.cpp:1398-1403)
 def test_solve(emu, oracle, cid):
     pc.check_solve(emu, oracle, cid)
 
@@ -33,17 +33,19 @@ def test_solve_with_prior(emu, oracle):
     pc.check_solve(emu, oracle, 4, prior_chain=True)
 
 
-def test_reanchor(emu, oracle):
-    pc.check_reanchor(emu, oracle, 4)
+@pytest.mark.parametrize("cid", [4, 6])         # 6: double2vector's !USE_IMU branch (estimator.cpp:1288-1297)
+def test_reanchor(emu, oracle, cid):
+    pc.check_reanchor(emu, oracle, cid)
 
 
-@pytest.mark.parametrize("cid", [1, 4])
+@pytest.mark.parametrize("cid", [1, 4, 6])
 def test_marginalize(emu, oracle, cid):
     pc.check_marginalize(emu, oracle, cid)
 
 
-def test_sequence(emu, oracle):
-    pc.check_sequence(emu, oracle, 4)
+@pytest.mark.parametrize("cid", [4, 6])         # both marginalisation flags; 6: drop sets without speed-bias blocks (estimator.cpp:1692,1795)
+def test_sequence(emu, oracle, cid):
+    pc.check_sequence(emu, oracle, cid)
 
 
 def test_batch(emu, oracle):
@@ -132,12 +134,12 @@ def test_factor_evaluate_vs_reference_code(emu, reference_code, cid):
     assert pc.check_factor_evaluate(emu, reference_code, cid, max_each=4) < 1e-9
 
 
-@pytest.mark.parametrize("cid", [2, 4])
+@pytest.mark.parametrize("cid", [2, 4, 6])
 def test_marginalize_vs_reference_code(emu, oracle, reference_code, cid):
     pc.check_marginalize_vs_reference_code(emu, oracle, reference_code, cid)
 
 
-@pytest.mark.parametrize("cid", [2, 4])
+@pytest.mark.parametrize("cid", [2, 4, 6])
 def test_reference_estimator_runs_on_this_backend(emu, oracle, reference_code, cid):
     """estimator.cpp of the reference, unmodified, with ceres::Solve answered by the library: north_star's drop-in, literally"""
     pc.check_reference_estimator_on_this_backend(emu, oracle, cid)
@@ -153,7 +155,7 @@ def test_visual_imu_alignment_vs_reference_code(emu, reference_code, cid):
     pc.check_visual_imu_alignment_vs_reference_code(emu, cid)
 
 
-@pytest.mark.parametrize("cid", [2, 4])
+@pytest.mark.parametrize("cid", [2, 4, 6])
 def test_reference_estimator_on_product_shim(emu, reference_code, cid):
     """estimator.cpp of the reference, unmodified, compiled against the product's ceres shim + reference adapter"""
     from emu import build_emu

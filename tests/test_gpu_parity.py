@@ -22,17 +22,17 @@ def test_factor_evaluate(gpu_ctx, oracle):
     assert worst < 1e-9
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 6])     # 6 = stereo only, USE_IMU = 0
 def test_normal_equations(gpu_ctx, oracle, cid):
     pc.check_normal_equations(gpu_ctx, oracle, cid)
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 6])
 def test_solve_8_iterations(gpu_ctx, oracle, cid):
     pc.check_solve(gpu_ctx, oracle, cid)
 
 
-@pytest.mark.parametrize("cid", [2, 4])
+@pytest.mark.parametrize("cid", [2, 4, 6])
 def test_solve_with_prior(gpu_ctx, oracle, cid):
     pc.check_solve(gpu_ctx, oracle, cid, prior_chain=True)
 
@@ -41,17 +41,17 @@ def test_solve_long_run_matches(gpu_ctx, oracle):
     pc.check_solve(gpu_ctx, oracle, 1, iters=40)
 
 
-@pytest.mark.parametrize("cid", [1, 4])
+@pytest.mark.parametrize("cid", [1, 4, 6])
 def test_reanchor(gpu_ctx, oracle, cid):
     pc.check_reanchor(gpu_ctx, oracle, cid)
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 6])
 def test_marginalize(gpu_ctx, oracle, cid):
     pc.check_marginalize(gpu_ctx, oracle, cid)
 
 
-@pytest.mark.parametrize("cid", [2, 4])
+@pytest.mark.parametrize("cid", [2, 4, 6])
 def test_optimization_sequence(gpu_ctx, oracle, cid):
     pc.check_sequence(gpu_ctx, oracle, cid, nwin=4)
 
@@ -174,6 +174,6 @@ def test_factor_evaluate_vs_reference_code(gpu_ctx, reference_code, cid):
     assert pc.check_factor_evaluate(gpu_ctx, reference_code, cid, max_each=4) < 1e-9
 
 
-@pytest.mark.parametrize("cid", [2, 4])
+@pytest.mark.parametrize("cid", [2, 4, 6])
 def test_marginalize_vs_reference_code(gpu_ctx, oracle, reference_code, cid):
     pc.check_marginalize_vs_reference_code(gpu_ctx, oracle, reference_code, cid)

@@ -168,7 +168,7 @@ def _shift_old(b):          # addr_shift of MARGIN_OLD (estimator.cpp:1791-1800)
     return b - 1 if (1 <= b <= 10 or 12 <= b <= 21) else b
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 6])
 def test_marginalization_matches_reference_code(oracle, cid):
     """MARGIN_OLD on a first window (no prior) and on the next one (prior present): the reference's ResidualBlockInfo::Evaluate (loss
     corrector), preMarginalize and marginalize (4 threads, Schur complement, eigen-decomposition with the 1e-8 cut) against the oracle."""
@@ -212,7 +212,7 @@ def _shift_second_new(b):   # addr_shift of MARGIN_SECOND_NEW (estimator.cpp:184
     return 9 if b == 10 else 20 if b == 21 else b
 
 
-@pytest.mark.parametrize("cid", [2, 4])
+@pytest.mark.parametrize("cid", [2, 4, 6])
 def test_marginalization_second_new_matches_reference_code(oracle, cid):
     seq = synth.Sequence(synth.make_config(cid), 3, 13)
     prob, st, _ = seq.window(0)
@@ -309,7 +309,7 @@ def _as_the_estimator_holds_it(st):
     return st
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 6])
 def test_estimator_optimization_of_the_reference_runs_on_the_tables(oracle, cid):
     """estimator/estimator.cpp compiled unmodified (ROS / OpenCV / camodocal / ceres as name stand-ins, oracle/refshim/): the reference's own
     Estimator::optimization() is driven on two consecutive windows.  ceres::Problem records, ceres::Solve checks the record against the
@@ -339,7 +339,7 @@ def test_estimator_optimization_of_the_reference_runs_on_the_tables(oracle, cid)
         prob, st, _ = seq.window(k + 1, prior=q, prev_state=a)
 
 
-@pytest.mark.parametrize("cid", [2, 4])
+@pytest.mark.parametrize("cid", [2, 4, 6])
 def test_estimator_optimization_second_new(oracle, cid):
     seq = synth.Sequence(synth.make_config(cid), 5, 13)
     prob, st, _ = seq.window(0)
@@ -357,7 +357,7 @@ def test_estimator_optimization_second_new(oracle, cid):
     assert ids0 == ids1 and np.abs(A1 - A0).max() <= 1e-7 * np.abs(A0).max() and np.abs(b1 - b0).max() <= 1e-7 * np.abs(b0).max()
 
 
-@pytest.mark.parametrize("cid", [1, 2, 4])
+@pytest.mark.parametrize("cid", [1, 2, 4, 6])
 def test_outlier_rejection_matches_reference_code(oracle, cid):
     """Estimator::outliersRejection / reprojectionError (estimator.cpp:2115-2185) of the reference on solved and on corrupted windows"""
     prob, st, _ = synth.make_window(cid)

@@ -8,7 +8,7 @@ import parity_checks as pc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("cid", [2, 4])
+@pytest.mark.parametrize("cid", [2, 4, 6])
 def test_reference_estimator_runs_on_this_backend(gpu_ctx, oracle, reference_code, cid):
     """estimator.cpp of the reference, unmodified, with ceres::Solve answered by the library: north_star's drop-in, literally"""
     pc.check_reference_estimator_on_this_backend(gpu_ctx, oracle, cid)
@@ -19,7 +19,7 @@ def test_reference_tracker_runs_on_this_backend(gpu_ctx, reference_code):
     pc.check_reference_tracker_on_this_backend(gpu_ctx)
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 6])
 def test_reference_estimator_on_product_shim(gpu_ctx, reference_code, cid):
     """estimator.cpp of the reference, unmodified, compiled against the product's ceres shim + reference adapter, solving on the GPU"""
     from viwb import lib as viwb_lib

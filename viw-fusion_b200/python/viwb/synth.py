@@ -7,6 +7,8 @@ and lowers any 11-frame window of it to the `viwb_problem` tables of include/viw
   C3  mono + IMU + wheel (D435i shapes), camera extrinsic (subset {2,6}) and td free
   C4  stereo + IMU + wheel + plane, everything shipped in the ridgeback config
   (C5 = several C4 sequences with different seeds, one per GPU)
+  C6  stereo only, USE_IMU = 0 (config/euroc/euroc_stereo_config.yaml:5, config/kitti_odom/*.yaml:4): no speed-bias blocks,
+      no IMU factors, para_Pose[0] constant (estimator.cpp:1398-1403)
 RNG: numpy default_rng(1000*config + sequence).  The pre-integration below is this package's own
 restatement of the upstream step that produces the factor constants (integration_base.h:63-167,
 wheel_integration_base.h:67-177); it is not the oracle and does not import it.
@@ -24,6 +26,7 @@ from .geom import (skew, q_mul, q_normalize, q_to_R, R_to_q, so3_exp, so3_log, s
 class SynthConfig:
     config_id: int = 1
     stereo: bool = False
+    use_imu: bool = True
     use_wheel: bool = False
     use_plane: bool = False
     estimate_extrinsic: bool = False
@@ -82,7 +85,10 @@ def make_config(cid):
                            estimate_extrinsic=True, ex_subset_mask=1 << 2,
                            width=640, height=480, fx=384.45, fy=384.45, cx=320.0, cy=240.0,
                            acc_n=0.1, gyr_n=0.05, acc_w=7.1765713730075628e-04, gyr_w=4.0e-05, g_norm=9.805)
-    raise ValueError("config id must be 1..5")
+    if cid == 6:   # config/euroc/euroc_stereo_config.yaml: imu 0, two cameras, extrinsics trusted
+        return SynthConfig(config_id=6, stereo=True, use_imu=False,
+                           t_ic0=np.array([-0.0216, -0.0647, 0.0098]), t_ic1=np.array([-0.0198, 0.0454, 0.0079]))
+    raise ValueError("config id must be 1..6")
 
 
 # ----------------------------------------------------------------------------- pre-integration
@@ -438,7 +444,10 @@ class Sequence:
         mask = np.zeros(abi.NUM_FIXED_BLOCKS, np.uint8)
         for i in range(abi.NUM_FRAMES):
             flags[abi.BLK_POSE0 + i] = abi.BLOCK_PRESENT
-            flags[abi.BLK_SPEEDBIAS0 + i] = abi.BLOCK_PRESENT
+            if cfg.use_imu:
+                flags[abi.BLK_SPEEDBIAS0 + i] = abi.BLOCK_PRESENT
+        if not cfg.use_imu:
+            flags[abi.BLK_POSE0] |= abi.BLOCK_CONSTANT        # estimator.cpp:1402-1403
         ncam = 2 if cfg.stereo else 1
         for c in range(ncam):
             flags[abi.BLK_EX_POSE0 + c] = abi.BLOCK_PRESENT | (0 if cfg.estimate_extrinsic else abi.BLOCK_CONSTANT)
@@ -477,7 +486,7 @@ class Sequence:
             st[77: 77 + 9 * fc] = prev_state[77 + 9: 77 + 9 * (fc + 1)]
             st[176:abi.STATE_FIXED] = prev_state[176:abi.STATE_FIXED]
         # factor constants are linearised at the *initial* bias estimates of the host frame (estimator.cpp:620-632)
-        for j in range(1, abi.NUM_FRAMES):
+        for j in range(1, abi.NUM_FRAMES if cfg.use_imu else 0):
             dt, acc, gyr = self.imu[k + j - 1]
             ba, bg = st[77 + 9 * j + 3: 77 + 9 * j + 6].copy(), st[77 + 9 * j + 6: 77 + 9 * j + 9].copy()
             imu_i.append(j - 1); imu_j.append(j)
@@ -492,7 +501,7 @@ class Sequence:
             pl = list(range(fc))
         g = abi.default_globals(cfg.g_norm, cfg.pitch_n, cfg.roll_n, cfg.zpw_n)
         prob = abi.WindowProblem(fc, len(landmarks), flags, mask, vt, vl, vi, vj, np.array(vobs) if vobs else np.zeros((0, 12)),
-                                 imu_i, imu_j, np.array(imu_data), wi, wj, np.array(wdata) if wdata else np.zeros((0, 78)),
+                                 imu_i, imu_j, np.array(imu_data) if imu_data else np.zeros((0, abi.IMU_DOUBLES)), wi, wj, np.array(wdata) if wdata else np.zeros((0, 78)),
                                  pl, prior, g)
         return prob, st, gt
 
