@@ -287,7 +287,7 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     sym_eig_block(Vn, ev, ee, cs, bc + 4, red, n, ld, tid, nt);
     VIWB_SYNC();
     // J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b   (marginalization_factor.cpp:298-306)
-    double *Jout = bd.marg_J + (size_t)w * MAXPRI * MAXPRI, *rout = bd.marg_r + (size_t)w * MAXPRI;
+    double *Jout = bd.marg_J + (size_t)w * bd.marg_nmax * bd.marg_nmax, *rout = bd.marg_r + (size_t)w * MAXPRI;
     for (int i = tid; i < n; i += nt) {
         const double l = ev[i];
         const double S = l > eps ? l : 0.0, Sinv = l > eps ? 1.0 / l : 0.0, ss = sqrt(S), si = sqrt(Sinv);

@@ -123,7 +123,7 @@ struct BatchDev {       // passed by value to every kernel
     // solver vectors, per window at work_off = state_off - 15*w ... stored at vec_off = w*TFIX + lm_off
     double *v_scale, *v_D, *v_sgrad, *v_gn;
     // marginalisation outputs
-    double *marg_J, *marg_r, *marg_x0;  // [B][MAXPRI*MAXPRI], [B][MAXPRI], [B][SFIX]
+    double *marg_J, *marg_r, *marg_x0;  // [B][marg_nmax^2] (n x n, row stride n, at the head of the slot), [B][MAXPRI], [B][SFIX]
     int *marg_hdr;                      // [B][2 + 2*NB]: valid, n, nb, block_id[], block_idx[]
     double *marg_A;                     // [B][MAXPRI+16][MAXPRI+16] scratch for the dense system
 };

@@ -40,7 +40,6 @@ static int dev_d2d(void *d, const void *s, size_t n, stream_t) { if (n) memcpy(d
 static int dev_sync(stream_t) { return 0; }
 static int host_alloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
 static void host_free(void *p) { free(p); }
-static int dev_d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t w, size_t rows, stream_t) { for (size_t r = 0; r < rows; r++) memcpy((char *)h + r * hp, (const char *)d + r * dp, w); return 0; }
 static const char *dev_errstr(int) { return "emulation"; }
 #define VIWB_EMU_NT 1
 template <typename F>
@@ -65,7 +64,6 @@ static int dev_d2d(void *d, const void *s_, size_t n, stream_t s) { return n ? (
 static int dev_sync(stream_t s) { return (int)cudaStreamSynchronize(s); }
 static int host_alloc(void **p, size_t n) { return (int)cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault); }
 static void host_free(void *p) { cudaFreeHost(p); }
-static int dev_d2h_2d(void *h, size_t hp, const void *d, size_t dp, size_t w, size_t rows, stream_t s) { return (w && rows) ? (int)cudaMemcpy2DAsync(h, hp, d, dp, w, rows, cudaMemcpyDeviceToHost, s) : 0; }
 static const char *dev_errstr(int e) { return cudaGetErrorString((cudaError_t)e); }
 // optional per-kernel CUDA-event profiler (bench.py's live roofline timing); off by default
 struct Profiler {
@@ -122,7 +120,8 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 static bool g_timing = getenv("VIWB_TIMING") != nullptr;
 struct viwb_context {
     int device;
-    stream_t stream;
+    stream_t stream;        // the stream all work of this context is issued on (own_stream unless viwb_set_stream gave another)
+    stream_t own_stream;    // created by viwb_create, destroyed by viwb_destroy; a caller's stream is never destroyed here
     long long launches;
     std::string err;
     bool attrs_set;
@@ -136,8 +135,7 @@ static int fail(viwb_context *ctx, int code, const std::string &msg) { if (ctx) 
 // contexts can be driven from any thread (one context per thread at a time)
 static inline void bind_device(const viwb_context *ctx) {
 #ifndef VIWB_HOST_EMU
-    static thread_local int cur = -1;
-    if (ctx && cur != ctx->device) { cudaSetDevice(ctx->device); cur = ctx->device; }
+    if (ctx) { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) cudaSetDevice(ctx->device); }   // the host application may have switched devices in between
 #else
     (void)ctx;
 #endif
@@ -220,13 +218,27 @@ static int chunk_count(int n) { return (n + ASM_CHUNK - 1) / ASM_CHUNK; }
 static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, int &out_mode) {
     memset(&m, 0, sizeof m); memset(&lo, 0, sizeof lo);
     if (p.frame_count < 0 || p.frame_count > VIWB_WINDOW_SIZE || p.num_landmarks < 0 || p.num_landmarks > VIWB_MAX_LANDMARKS) { lo.err = 1; return; }
+    if (p.num_vis < 0 || p.num_imu < 0 || p.num_wheel < 0 || p.num_plane < 0) { lo.err = 5; return; }            // counts are added up as size_t below
+    if ((p.num_vis && (!p.vis_type || !p.vis_landmark || !p.vis_frame_i || !p.vis_frame_j || !p.vis_obs)) || (p.num_imu && (!p.imu_frame_i || !p.imu_frame_j || !p.imu_data)) ||
+        (p.num_wheel && (!p.wheel_frame_i || !p.wheel_frame_j || !p.wheel_data)) || (p.num_plane && !p.plane_frame)) { lo.err = 5; return; }
     m.nlm = p.num_landmarks; m.frame_count = p.frame_count; m.nvis = p.num_vis; m.nimu = p.num_imu; m.nwheel = p.num_wheel; m.nplane = p.num_plane;
     for (int k = 0; k < 3; k++) m.G[k] = p.globals.G[k];
     for (int k = 0; k < 4; k++) m.S_vis[k] = p.globals.vis_sqrt_info[k];
     for (int k = 0; k < 3; k++) m.w_plane[k] = p.globals.plane_sqrt_info[k];
     m.huber = p.globals.huber_delta;
     lo.has_prior = p.prior && p.prior->valid;
-    if (lo.has_prior && (p.prior->n <= 0 || p.prior->n > MAXPRI || p.prior->num_blocks <= 0 || p.prior->num_blocks > NB)) { lo.err = 2; return; }
+    if (lo.has_prior && (p.prior->n <= 0 || p.prior->n > MAXPRI || p.prior->num_blocks <= 0 || p.prior->num_blocks > NB || !p.prior->J || !p.prior->r || !p.prior->x0)) { lo.err = 2; return; }
+    if (lo.has_prior) {      // every kept block once, inside [0, n), no two blocks overlapping: prior_dx and the prior's assembly trust the column map
+        unsigned seen_id = 0; unsigned char used[MAXPRI]; memset(used, 0, sizeof used);
+        for (int i = 0; i < p.prior->num_blocks; i++) {
+            const int bq = p.prior->block_id[i], idx = p.prior->block_idx[i];
+            if (bq < 0 || bq >= NB || ((seen_id >> bq) & 1u)) { lo.err = 2; return; }
+            seen_id |= 1u << bq;
+            const int ms = blk_msize(bq);
+            if (idx < 0 || idx + ms > p.prior->n) { lo.err = 2; return; }
+            for (int k = 0; k < ms; k++) { if (used[idx + k]) { lo.err = 2; return; } used[idx + k] = 1; }
+        }
+    }
     // visual table checks + per-list counts
     int fcnt[NFR] = {0}, pcnt[NFR * NFR] = {0}, fcnt0[NFR] = {0}, pcnt0[NFR * NFR] = {0}, ncommon0 = 0;
     bool ref[NB]; for (int k = 0; k < NB; k++) ref[k] = false;
@@ -237,6 +249,7 @@ static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, i
         const int t = p.vis_type[i], l = p.vis_landmark[i], fi = p.vis_frame_i[i], fj = p.vis_frame_j[i];
         if (t < 0 || t > 2 || l < 0 || l >= p.num_landmarks || fi < 0 || fi > p.frame_count || fj < 0 || fj > p.frame_count) { lo.err = 3; return; }
         if (i && l < p.vis_landmark[i - 1]) lo.grouped = false;
+        if (t != 2 && fi == fj) { lo.err = 3; return; }       // a two-frame factor joins two different frames (estimator.cpp:1601-1603); the pair lists have no (a, a) slot
         if (t != 2) {
             ref[fi] = ref[fj] = true; fcnt[fi]++; fcnt[fj]++;
             const int a = fi < fj ? fi : fj, c = fi < fj ? fj : fi; pcnt[a * NFR + c]++;
@@ -245,7 +258,12 @@ static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, i
         ref[BLK_EX0] = true; if (t != 0) ref[BLK_EX1] = true; ref[BLK_TD] = true;
         if (fi == 0) { any_lm0 = true; ncommon0++; seen[BLK_EX0] = true; if (t != 0) seen[BLK_EX1] = true; seen[BLK_TD] = true; }
     }
-    if (lo.has_prior) for (int i = 0; i < p.prior->num_blocks; i++) { const int bq = p.prior->block_id[i]; if (bq < 0 || bq >= NB) { lo.err = 2; return; } ref[bq] = true; }
+    {   // every factor of a landmark is hosted by the landmark's start frame (estimator.cpp:1595-1597): lm_reduce adds the host blocks of a landmark into ONE row of W
+        short host[VIWB_MAX_LANDMARKS];
+        for (int k = 0; k < p.num_landmarks; k++) host[k] = -1;
+        for (int i = 0; i < p.num_vis; i++) { short &h = host[p.vis_landmark[i]]; if (h < 0) h = (short)p.vis_frame_i[i]; else if (h != p.vis_frame_i[i]) { lo.err = 3; return; } }
+    }
+    if (lo.has_prior) for (int i = 0; i < p.prior->num_blocks; i++) ref[p.prior->block_id[i]] = true;
     for (int i = 0; i < p.num_imu; i++) { const int a = p.imu_frame_i[i], c = p.imu_frame_j[i]; if (a < 0 || a > p.frame_count || c < 0 || c > p.frame_count) { lo.err = 4; return; } ref[a] = ref[BLK_SB0 + a] = ref[c] = ref[BLK_SB0 + c] = true; }
     for (int i = 0; i < p.num_wheel; i++) { const int a = p.wheel_frame_i[i], c = p.wheel_frame_j[i]; if (a < 0 || a > p.frame_count || c < 0 || c > p.frame_count) { lo.err = 4; return; } ref[a] = ref[c] = ref[BLK_EXW] = ref[BLK_SX] = ref[BLK_SY] = ref[BLK_SW] = ref[BLK_TDW] = true; }
     for (int i = 0; i < p.num_plane; i++) { const int a = p.plane_frame[i]; if (a < 0 || a > p.frame_count) { lo.err = 4; return; } ref[a] = ref[BLK_EXW] = ref[BLK_PR] = ref[BLK_PZ] = true; }
@@ -427,7 +445,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     std::vector<WinLow> low(B);
     // ---- phase 1 (parallel): sizes and plans
     parallel_for(B, [&](int w) { lower_count(problems[w], margin_flags ? margin_flags[w] : -1, b->meta[w], low[w], b->out_mode[w]); });
-    for (int w = 0; w < B; w++) if (low[w].err) { const int e = low[w].err; batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, e == 1 ? "bad frame_count / num_landmarks" : e == 2 ? "bad prior" : e == 3 ? "bad visual factor table" : "bad factor frame index"); }
+    for (int w = 0; w < B; w++) if (low[w].err) { const int e = low[w].err; batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, e == 1 ? "bad frame_count / num_landmarks" : e == 2 ? "bad prior" : e == 3 ? "bad visual factor table" : e == 5 ? "negative factor count or missing table" : "bad factor frame index"); }
     // ---- phase 2: offsets
     size_t nstate = 0, nvis = 0, nlm = 0, nimu = 0, nwheel = 0, nplane = 0, nlist = 0, nit_s = 0, nit_m = 0, npri = 0, npJ = 0, npr = 0;
     for (int w = 0; w < B; w++) {
@@ -479,8 +497,10 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     WK(&bd.Hpk, (size_t)B * (TFIX * (TFIX + 1) / 2)); WK(&bd.gpk, (size_t)B * TFIX); WK(&bd.gfix, (size_t)B * (TFIX + 8));
     WK(&bd.asm_out, (nit_s + nit_m) * ASM_STRIDE); WK(&bd.Tvis, (size_t)B * VSUB * VSUB); WK(&bd.tvec, (size_t)B * VSUB);
     WK(&bd.v_scale, nvec); WK(&bd.v_D, nvec); WK(&bd.v_sgrad, nvec); WK(&bd.v_gn, nvec);
-    WK(&bd.marg_J, (size_t)B * MAXPRI * MAXPRI); WK(&bd.marg_r, (size_t)B * MAXPRI); WK(&bd.marg_x0, (size_t)B * SFIX);
-    WK(&bd.marg_hdr, (size_t)B * (3 + 2 * NB)); WK(&bd.marg_A, (size_t)B * (MAXPRI + 16) * (MAXPRI + 16));
+    // marginalisation outputs / scratch: sized by the largest prior this batch produces, and not at all when no window marginalises
+    const size_t mJ = b->any_marg ? (size_t)b->prior_nmax * b->prior_nmax : 0, mB = b->any_marg ? (size_t)B : 0;
+    WK(&bd.marg_J, mB * mJ); WK(&bd.marg_r, mB * MAXPRI); WK(&bd.marg_x0, mB * SFIX);
+    WK(&bd.marg_hdr, mB * (3 + 2 * NB)); WK(&bd.marg_A, mB * (MAXPRI + 16) * (MAXPRI + 16));
     size_t tot = 0;
     for (auto &e : ents) if (e.input) { e.off = tot; tot += align_up(e.bytes); }
     const size_t in_bytes = tot;
@@ -614,8 +634,7 @@ static int batch_fetch(viwb_context *ctx, viwb_batch *b, double *const *states, 
         CK(dev_d2h(hdr, bd.marg_hdr, (size_t)B * (3 + 2 * NB) * sizeof(int), ctx->stream));
         CK(dev_d2h(r, bd.marg_r, (size_t)B * MAXPRI * sizeof(double), ctx->stream));
         CK(dev_d2h(x0, bd.marg_x0, (size_t)B * SFIX * sizeof(double), ctx->stream));
-        // J_lin is n x n (row stride n) at the head of each window's MAXPRI^2 slot: strided copy of the first nmax^2 entries
-        CK(dev_d2h_2d(J, (size_t)nmax * nmax * 8, bd.marg_J, (size_t)MAXPRI * MAXPRI * 8, (size_t)nmax * nmax * 8, B, ctx->stream));
+        CK(dev_d2h(J, bd.marg_J, (size_t)B * nmax * nmax * 8, ctx->stream));     // window w's n x n block (row stride n) heads its nmax^2 slot
     }
     CK(dev_sync(ctx->stream));
     int rc = 0;
@@ -662,13 +681,14 @@ static void batch_free(viwb_context *ctx, viwb_batch *b) {
 extern "C" int viwb_create(int device, viwb_context **out) {
     if (!out) return VIWB_ERR_INVALID;
     viwb_context *ctx = new viwb_context();
-    ctx->device = device; ctx->launches = 0; ctx->attrs_set = false; ctx->stream = 0; ctx->lk1 = nullptr; ctx->det1 = nullptr;
+    ctx->device = device; ctx->launches = 0; ctx->attrs_set = false; ctx->stream = 0; ctx->own_stream = 0; ctx->lk1 = nullptr; ctx->det1 = nullptr;
 #ifndef VIWB_HOST_EMU
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || device < 0 || device >= count) { delete ctx; return VIWB_ERR_CUDA; }   // no CPU fallback: fail loudly
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return VIWB_ERR_CUDA; }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return VIWB_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return VIWB_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
 #endif
     *out = ctx;
     return VIWB_OK;
@@ -678,13 +698,21 @@ extern "C" void viwb_destroy(viwb_context *ctx) {
     lk_batch_free(ctx->lk1);
     det_free(ctx->det1);
 #ifndef VIWB_HOST_EMU
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 #endif
     arena_release(ctx->arena);
     delete ctx;
 }
 extern "C" const char *viwb_last_error(const viwb_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-extern "C" int viwb_set_stream(viwb_context *ctx, void *s) { if (!ctx) return VIWB_ERR_INVALID; ctx->stream = (stream_t)s; return VIWB_OK; }
+// NULL restores the context's own stream; work already queued on the previous stream is waited for, so that buffers the context recycles
+// (arena, staging slab) are never touched from two streams at once
+extern "C" int viwb_set_stream(viwb_context *ctx, void *s) {
+    if (!ctx) return VIWB_ERR_INVALID;
+    bind_device(ctx);
+    CK(dev_sync(ctx->stream));
+    ctx->stream = s ? (stream_t)s : ctx->own_stream;
+    return VIWB_OK;
+}
 extern "C" long long viwb_launch_count(const viwb_context *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int viwb_set_profiling(viwb_context *ctx, int enable) {
@@ -958,8 +986,11 @@ extern "C" int viwb_prior_evaluate(viwb_context *ctx, const viwb_prior *prior, c
     double *d = nullptr;
     const size_t tot = (size_t)n * n + n + SFIX + SFIX + n;
     CK(dev_malloc((void **)&d, tot * 8));
-    CK(dev_h2d(d, prior->J, (size_t)n * n * 8, ctx->stream)); CK(dev_h2d(d + (size_t)n * n, prior->r, n * 8, ctx->stream));
-    CK(dev_h2d(d + (size_t)n * n + n, prior->x0, SFIX * 8, ctx->stream)); CK(dev_h2d(d + (size_t)n * n + n + SFIX, state, SFIX * 8, ctx->stream));
+    {   int e = dev_h2d(d, prior->J, (size_t)n * n * 8, ctx->stream);
+        if (!e) e = dev_h2d(d + (size_t)n * n, prior->r, n * 8, ctx->stream);
+        if (!e) e = dev_h2d(d + (size_t)n * n + n, prior->x0, SFIX * 8, ctx->stream);
+        if (!e) e = dev_h2d(d + (size_t)n * n + n + SFIX, state, SFIX * 8, ctx->stream);
+        if (e) { dev_free(d); return fail(ctx, VIWB_ERR_CUDA, std::string("prior upload: ") + dev_errstr(e)); } }
     PriorEvalArgs a; memset(&a, 0, sizeof a);
     a.p.n = n; a.p.nb = prior->num_blocks;
     for (int i = 0; i < prior->num_blocks; i++) { a.p.block_id[i] = prior->block_id[i]; a.p.block_idx[i] = prior->block_idx[i]; }
@@ -970,8 +1001,10 @@ extern "C" int viwb_prior_evaluate(viwb_context *ctx, const viwb_prior *prior, c
     prior_eval_kernel<<<1, 128, 0, ctx->stream>>>(a);
 #endif
     ctx->launches++;
-    CK(dev_d2h(residuals, a.res, n * 8, ctx->stream)); CK(dev_sync(ctx->stream));
-    dev_free(d);
+    {   int e = dev_d2h(residuals, a.res, n * 8, ctx->stream);
+        if (!e) e = dev_sync(ctx->stream);
+        dev_free(d);
+        if (e) return fail(ctx, VIWB_ERR_CUDA, std::string("prior download: ") + dev_errstr(e)); }
     if (jacobian) {   // formatting only (marginalization_factor.cpp:381-394): J_lin columns at the block's state offset
         memset(jacobian, 0, sizeof(double) * n * SFIX);
         for (int i = 0; i < prior->num_blocks; i++) {

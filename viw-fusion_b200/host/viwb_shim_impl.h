@@ -86,12 +86,30 @@ inline void Solve(const Solver::Options &options, Problem *problem, Solver::Summ
         }
         rk++;
     }
-    // window poses that carry no factor yet (e.g. registered but unused) still belong to the window: take every size-7
-    // block with a plain PoseLocalParameterization that is not an extrinsic
-    for (auto &kv : problem->blocks_) if (kv.second.size == 7 && kv.first != ex0 && kv.first != ex1 && kv.first != exw) poses.insert(kv.first);
+    // Window poses: para_Pose[i] are the rows of ONE array (estimator.h:191), so they sit on a lattice of 7 doubles around any pose a factor names
+    // (or around the first size-7 block registered, estimator.cpp:1394-1397, when no factor names one yet).  Every other size-7 block is an
+    // extrinsic: those no factor names are told apart by registration order (camera extrinsics first, estimator.cpp:1405-1437, then the wheel
+    // extrinsic, :1439-1470) and by para_Ex_Pose[1] following para_Ex_Pose[0] in memory (estimator.h:193).
+    {
+        std::vector<std::pair<int, double *>> sevens;        // (registration order, address)
+        for (auto &kv : problem->blocks_) if (kv.second.size == 7) sevens.push_back({kv.second.order, kv.first});
+        std::sort(sevens.begin(), sevens.end());
+        double *anchor = !poses.empty() ? *poses.begin() : nullptr;
+        for (auto &sv : sevens) if (!anchor && sv.second != ex0 && sv.second != ex1 && sv.second != exw) anchor = sv.second;
+        for (auto &sv : sevens) {
+            double *q = sv.second;
+            if (q == ex0 || q == ex1 || q == exw || poses.count(q)) continue;
+            const std::ptrdiff_t d = q - anchor;
+            if (anchor && d % 7 == 0 && d / 7 >= -(std::ptrdiff_t)VIWB_WINDOW_SIZE && d / 7 <= (std::ptrdiff_t)VIWB_WINDOW_SIZE) { poses.insert(q); continue; }
+            if (!ex0) ex0 = q; else if (!ex1 && q == ex0 + 7) ex1 = q; else if (!exw) exw = q;
+            else { summary->message = "a size-7 parameter block is neither a window pose nor an extrinsic"; return; }
+        }
+    }
     for (auto &kv : problem->blocks_) if (kv.second.size == 9) sbs.insert(kv.first);
     std::vector<double *> pose_v(poses.begin(), poses.end()), sb_v(sbs.begin(), sbs.end());      // std::set<double*> iterates in address order
-    if (pose_v.size() > VIWB_NUM_FRAMES || sb_v.size() > VIWB_NUM_FRAMES || landmarks.size() > VIWB_MAX_LANDMARKS) { summary->message = "window too large"; return; }
+    if (pose_v.empty() || pose_v.size() > VIWB_NUM_FRAMES || sb_v.size() > VIWB_NUM_FRAMES || landmarks.size() > VIWB_MAX_LANDMARKS) { summary->message = "window too large (or empty)"; return; }
+    for (size_t i = 0; i < pose_v.size(); i++) if (pose_v[i] - pose_v[0] != 7 * (std::ptrdiff_t)i) { summary->message = "window poses are not consecutive rows of one array"; return; }
+    for (size_t i = 0; i < sb_v.size(); i++) if (sb_v[i] - sb_v[0] != 9 * (std::ptrdiff_t)i) { summary->message = "speed-bias blocks are not consecutive rows of one array"; return; }
     std::map<double *, int> id;
     for (size_t i = 0; i < pose_v.size(); i++) id[pose_v[i]] = VIWB_BLK_POSE0 + (int)i;
     for (size_t i = 0; i < sb_v.size(); i++) id[sb_v[i]] = VIWB_BLK_SPEEDBIAS0 + (int)i;
@@ -135,7 +153,9 @@ inline void Solve(const Solver::Options &options, Problem *problem, Solver::Summ
     if (prior && prior->valid) {      // re-express the prior's kept blocks (identified by address in the reference) as block ids
         pr_local = *prior; pr_x0.assign(VIWB_STATE_FIXED, 0.0);
         for (int i = 0; i < prior->num_blocks && prior_res; i++) {
-            const int bid = id[prior_res->blocks[i]];
+            const auto hit = id.find(prior_res->blocks[i]);
+            if (hit == id.end()) { summary->message = "the prior keeps a parameter block that is not part of the problem"; return; }
+            const int bid = hit->second;
             pr_local.block_id[i] = bid;
             std::memcpy(pr_x0.data() + viwb_block_offset(bid), prior->x0 + viwb_block_offset(prior->block_id[i]), sizeof(double) * viwb_block_size(bid));
         }
