@@ -30,8 +30,27 @@ from viwb import abi, synth  # noqa: E402
 
 METRIC = "sliding-window solves/sec (10 KF, 150 feat)"
 UNIT = "solves/s"
-WORKLOAD = ("C2 EuRoC-shaped stereo+IMU stream, 150 feat/frame: per window one camera tick of LK (4 calcOpticalFlowPyrLK-equivalent passes on "
-            "752x480 stereo frames) + Estimator::optimization() on a window with prior (8 dogleg iterations + gauge re-anchor + MARGIN_OLD marginalisation)")
+OPT = "Estimator::optimization() on a window with prior (8 dogleg iterations + gauge re-anchor + MARGIN_OLD marginalisation)"
+# BASELINE.json configs[0..4] = C1..C5 (+ C6: the stereo-only USE_IMU = 0 window, a parity case with a throughput line).  The metric is quoted on C2,
+# which is therefore the default at every N; the other configs are selected with --config and reported one line each (profiles/).
+WORKLOADS = {
+    1: "C1 single 10-keyframe window shape, mono+IMU, 100 landmarks seen in every frame (the reference's own CPU-runnable case), batched: " + OPT + "; no camera tick",
+    2: "C2 EuRoC-shaped stereo+IMU stream, 150 feat/frame: per window one camera tick of LK (4 calcOpticalFlowPyrLK-equivalent passes on 752x480 stereo frames) + " + OPT,
+    3: "C3 mono+IMU+wheel (realsense_d435i shapes), camera extrinsic + td estimated online: per window one camera tick of LK (2 passes on 640x480 frames) + " + OPT,
+    4: "C4 stereo+IMU+wheel with PlaneFactor and MarginalizationFactor active: per window one camera tick of LK (4 passes on 640x480 stereo frames) + " + OPT,
+    5: "C5 independent C4-shaped sequences sharded one-per-GPU: per window one camera tick of LK (4 passes on 640x480 stereo frames) + " + OPT,
+    6: "C6 stereo only, USE_IMU = 0 (euroc_stereo_config.yaml): per window one camera tick of LK (4 passes on 752x480 stereo frames) + " + OPT,
+}
+CAMERA = {1: None, 2: (752, 480, True), 3: (640, 480, False), 4: (640, 480, True), 5: (640, 480, True), 6: (752, 480, True)}
+
+
+def config_dict(cid, distinct, copies, no_lk):
+    """`config` of the JSON line -- the SAME dict from both arms (the driver compares them): it names the workload, not what a run measured."""
+    cam = None if no_lk else CAMERA[cid]
+    return {"workload": WORKLOADS[cid] + (" [--no-lk: window solve only]" if (no_lk and CAMERA[cid]) else ""), "config_id": cid,
+            "batch_per_gpu": distinct * copies, "distinct_sequences": distinct, "perturbed_copies": copies, "lk_in_step": cam is not None,
+            "camera": None if cam is None else {"image": [cam[0], cam[1]], "stereo": cam[2], "features": N_FEAT, "images_uploaded_per_tick_e2e": 2 if cam[2] else 1},
+            "l2": "working set >> 126 MB L2 at this batch; no explicit flush"}
 
 
 def make_windows(rank, distinct, copies, config_id=2):
@@ -141,7 +160,15 @@ def cpu_solve_many(vo, probs, states, seconds, threads):
 
 
 # ------------------------------------------------------------------------------------------------ camera frames (LK)
-IMG_W, IMG_H, N_FEAT = 752, 480, 150
+IMG_W, IMG_H, N_FEAT = 752, 480, 150          # C2 / C6 camera; --config 3/4/5 switch to 640 x 480 (set_camera)
+
+
+def set_camera(cid):
+    global IMG_W, IMG_H
+    cam = CAMERA[cid]
+    if cam is not None:
+        IMG_W, IMG_H = cam[0], cam[1]
+    return cam
 
 
 def make_scenes(rank, scenes):
@@ -168,11 +195,11 @@ def make_scenes(rank, scenes):
 class FrameFeed:
     """Host-side camera buffers of F streams (page-locked): tick t shows image t%2 of each stream's scene."""
 
-    def __init__(self, ctx, scenes, streams):
-        self.ctx, self.F = ctx, streams
+    def __init__(self, ctx, scenes, streams, stereo=True):
+        self.ctx, self.F, self.stereo = ctx, streams, stereo
         idx = np.arange(streams) % len(scenes)
         self.left = [np.ascontiguousarray(np.stack([scenes[i]["left"][t] for i in idx])) for t in (0, 1)]
-        self.right = [np.ascontiguousarray(np.stack([scenes[i]["right"][t] for i in idx])) for t in (0, 1)]
+        self.right = [np.ascontiguousarray(np.stack([scenes[i]["right"][t] for i in idx])) for t in (0, 1)] if stereo else []
         self.pts = [np.ascontiguousarray(np.stack([scenes[i]["pts"][t] for i in idx])) for t in (0, 1)]
         self.n = np.full(streams, N_FEAT, np.int32)
         if ctx is not None:
@@ -180,7 +207,17 @@ class FrameFeed:
                 ctx.host_register(a)
 
     def tick_bytes(self):
-        return self.left[0].nbytes + self.right[0].nbytes + 2 * self.pts[0].nbytes + 2 * self.n.nbytes
+        k = 2 if self.stereo else 1
+        return self.left[0].nbytes * k + k * self.pts[0].nbytes + k * self.n.nbytes
+
+    def tick_args(self, t, sl=slice(None), first=False):
+        """keyword arguments of LkBatch.upload for camera tick t (image t % 2 of every stream; the previous tick's image is resident)"""
+        kw = dict(cur=self.left[t][sl], prev_pts=self.pts[1 - t][sl], n_prev=self.n[sl])
+        if first:
+            kw["prev"] = self.left[1 - t][sl]
+        if self.stereo:
+            kw.update(right=self.right[t][sl], stereo_pts=self.pts[t][sl], n_stereo=self.n[sl])
+        return kw
 
     def close(self):
         if self.ctx is not None:
@@ -188,7 +225,7 @@ class FrameFeed:
                 self.ctx.host_unregister(a)
 
 
-def cv_track_frame(cv2, prev, cur, right, p_prev, p_cur):
+def cv_track_frame(cv2, prev, cur, right, p_prev, p_cur, stereo=True):
     """The four calcOpticalFlowPyrLK calls + status rules of one FeatureTracker::trackImage (feature_tracker.cpp:139-162, 240-251)."""
     crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
     h, w = prev.shape
@@ -199,6 +236,8 @@ def cv_track_frame(cv2, prev, cur, right, p_prev, p_cur):
     ci = np.rint(c2).astype(np.int64)
     inb = (ci[:, 0] >= 1) & (ci[:, 0] < w - 1) & (ci[:, 1] >= 1) & (ci[:, 1] < h - 1)
     st_t = (st.reshape(-1) > 0) & (rs.reshape(-1) > 0) & (d <= 0.5) & inb
+    if not stereo:
+        return c2, st_t, None, None
     r, st2, _ = cv2.calcOpticalFlowPyrLK(cur, right, p_cur.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3)
     b, st3, _ = cv2.calcOpticalFlowPyrLK(right, cur, r, None, winSize=(21, 21), maxLevel=3)
     r2, b2 = r.reshape(-1, 2), b.reshape(-1, 2)
@@ -209,7 +248,7 @@ def cv_track_frame(cv2, prev, cur, right, p_prev, p_cur):
     return c2, st_t, r2, st_s
 
 
-def cpu_lk_many(scenes, seconds, threads):
+def cpu_lk_many(scenes, seconds, threads, stereo=True):
     """OpenCV's LK (the reference's tracker) on `threads` host threads, one camera frame per task; returns (frames/s, frames, seconds)."""
     try:
         import cv2
@@ -220,7 +259,7 @@ def cpu_lk_many(scenes, seconds, threads):
 
     def one(i):
         sc = scenes[i % len(scenes)]
-        cv_track_frame(cv2, sc["left"][0], sc["left"][1], sc["right"][1], sc["pts"][0], sc["pts"][1])
+        cv_track_frame(cv2, sc["left"][0], sc["left"][1], sc["right"][1], sc["pts"][0], sc["pts"][1], stereo)
     t0 = time.perf_counter()
     one(0)
     per = time.perf_counter() - t0
@@ -234,6 +273,96 @@ def cpu_lk_many(scenes, seconds, threads):
             one(i)
     dt = time.perf_counter() - t0
     return n / dt, n, dt
+
+
+def load_peaks():
+    """Roofline denominators: the driver's HBM copy bandwidth (MEASURED_PEAKS.json) and this repo's FP64 / integer-issue / shared-memory
+    microbenchmarks measured on the same pool (profiles/r02a_microbench.json, source profiles/micro/microbench.cu)."""
+    peaks = {"hbm_gbs": 6650.0, "hbm_source": "fallback 6650", "fp64_tflops": 37.1, "int_tops": 18.4, "smem_tbs": 37.0, "micro_source": "nominal"}
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks["hbm_gbs"], peaks["hbm_source"] = float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, of measured)"
+    except Exception:
+        pass
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02a_microbench.json")))
+        peaks.update({"fp64_tflops": max(float(d["fp64_fma_tflops"]), float(d["dmma_m8n8k4_tflops"])), "int_tops": float(d["imad_tops"]),
+                      "smem_tbs": float(d["smem_ld_tbs"]), "micro_source": "profiles/r02a_microbench.json (measured on this pool's B200)"})
+    except Exception:
+        pass
+    return peaks
+
+
+def kernel_models(probs, pri, B, lk):
+    """Algorithmic bytes (SURVEY 8(d) per-unit figures x units per launch) and FP64 FLOPs (FMA = 2; dense counts of the algebra
+    each kernel owns) / integer sample operations of ONE launch, per kernel."""
+    n_vis = sum(len(p.vis_type) for p in probs)
+    n_lm = sum(p.num_landmarks for p in probs)
+    n_imu = sum(len(p.imu_frame_i) for p in probs)
+    n_wheel = sum(len(p.wheel_frame_i) for p in probs)
+    pg = sum(p.state_size for p in probs)
+    R = [sum(abi.block_tsize(b) for b in range(32) if (p.block_flags[b] & 1) and not (p.block_flags[b] & 2)) for p in probs]
+    npri = [int(p.prior.n) if p.prior is not None else 0 for p in probs]
+    nmax = max([int(q.n) for q in pri if q is not None and q.valid] + [0])
+    sR2 = float(sum(r * r + r for r in R))
+    m = {
+        "lin_vis": (112.0 * n_vis + 8.0 * pg, 700.0 * n_vis),                       # ~350 FMA per projection factor with its Jacobians
+        "lm_reduce": (0.0, 2.0 * 30 * n_vis),
+        "lin_vis_lm": (112.0 * n_vis + 8.0 * pg, 760.0 * n_vis),
+        "asm_items": (0.0, 2.0 * 2 * (21 + 21 + 36 + 12) * n_vis),
+        "asm_pairs": (0.0, 2.0 * 2 * (21 + 21 + 36 + 12) * n_vis),
+        "syrk": (0.0, 2.0 * 80 * 81 / 2 * n_lm),
+        "lin_small": (2296.0 * n_imu + 624.0 * n_wheel + 8.0 * sum(n * n + 2 * n for n in npri), 2.0 * (15 * 15 * 31) * n_imu + 2.0 * 2 * sum(n * n for n in npri)),
+        "solve": (8.0 * sR2 + 8.0 * pg, sum(r ** 3 / 3.0 + 6.0 * r * r for r in R) * 2.0 / 2.0 + 2.0 * 3 * 80 * n_lm + 2.0 * 15 * 465 * n_imu),
+        "marg": (8.0 * B * (nmax * nmax + nmax + abi.STATE_FIXED), B * (4.0 / 3.0 + 3.0) * 2.0 * nmax ** 3),     # tridiagonalisation + eigenvectors + QL
+        "lk_track": ((lk.algorithmic_bytes() if lk is not None else 0.0), 0.0),
+        "lk_pyr_down": (0.0, 0.0),
+    }
+    return m
+
+
+BOUND_HINT = {"lk_track": "issue", "lk_pyr_down": "hbm", "lin_vis": "hbm", "lin_vis_lm": "hbm", "lm_reduce": "hbm", "asm_items": "hbm", "asm_pairs": "hbm", "syrk": "fp64", "solve": "fp64",
+              "marg": "fp64", "lin_small": "hbm"}
+
+
+def roofline_report(prof, probs, pri, B, lk, alg_bytes, steps, ms):
+    peaks = load_peaks()
+    models = kernel_models(probs, pri, B, lk)
+    tot = sum(v[0] for v in prof.values())
+    traffic_db = {}
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    kernels = {}
+    for k, v in prof.items():
+        base = k.replace("_marg", "")
+        ms_l = v[0] / max(1, v[1])
+        ab, fl = models.get(base, (0.0, 0.0)) if not k.endswith("_marg") else (0.0, 0.0)
+        gbs = ab / (ms_l * 1e-3) / 1e9 if ms_l > 0 else 0.0
+        tfl = fl / (ms_l * 1e-3) / 1e12 if ms_l > 0 else 0.0
+        ent = {"ms_per_launch": ms_l, "launches_per_step": v[1] / 2, "share": v[0] / tot, "hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"],
+               "fp64_tflops": tfl, "fp64_frac": tfl / peaks["fp64_tflops"]}
+        hint = BOUND_HINT.get(base, "hbm")
+        # the roof that binds = the hinted resource unless the other fraction is the larger one
+        ent["bound"] = hint if hint == "issue" else ("fp64" if ent["fp64_frac"] > ent["hbm_frac"] else "hbm")
+        tr = traffic_db.get(base)
+        if tr and not k.endswith("_marg"):
+            ent["dram_traffic_bytes"] = tr["bytes_per_unit"] * B
+        kernels[k] = ent
+    top = max(prof.items(), key=lambda kv: kv[1][0])[0]
+    t = kernels[top]
+    ab = models.get(top.replace("_marg", ""), (0.0, 0.0))[0]
+    if t["bound"] == "fp64":
+        roof = {"bound": "fp64", "achieved": t["fp64_tflops"], "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": t["fp64_frac"]}
+    else:
+        roof = {"bound": "hbm" if t["bound"] == "hbm" else "issue", "achieved": t["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": t["hbm_frac"]}
+    roof.update({"kernel": top, "traffic": t.get("dram_traffic_bytes"), "algorithmic_bytes_per_launch": ab, "hbm_gbs": t["hbm_gbs"], "hbm_frac": t["hbm_frac"],
+                 "fp64_tflops": t["fp64_tflops"], "fp64_frac": t["fp64_frac"],
+                 "peak_source": {"hbm": peaks["hbm_source"], "fp64_int_smem": peaks["micro_source"]},
+                 "whole_step": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes * steps / (ms * 1e-3) / 1e9,
+                                "frac_of_hbm": alg_bytes * steps / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}})
+    return roof, kernels
 
 
 def main():
@@ -251,7 +380,16 @@ def main():
     ap.add_argument("--no-lk", action="store_true", help="window solve only (no feature-tracker work in the step)")
     ap.add_argument("--overlap-lk", action="store_true", help="run the camera tick on its own context + CUDA stream beside the solver (measured: no gain, r01za)")
     ap.add_argument("--scenes", type=int, default=8, help="distinct synthetic stereo scenes per rank (replicated over the streams)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5, 6], help="BASELINE.json configuration C1..C5 (C6 = stereo only, USE_IMU = 0); the metric is quoted on C2 = the default")
+    ap.add_argument("--parity-windows", type=int, default=0, help="windows compared with the oracle after the timed region (0 = the whole batch)")
     args = ap.parse_args()
+    cid = args.config
+    synth_cid = 4 if cid == 5 else cid          # C5 = C4-shaped sequences, one shard per GPU
+    cam = set_camera(cid)
+    if cam is None:
+        args.no_lk = True
+    stereo = bool(cam and cam[2])
+    config = config_dict(cid, args.distinct, args.copies, args.no_lk)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     warmup = max(args.warmup, 3)
@@ -264,7 +402,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import viw_oracle as vo
         cores = usable_cores()
-        cfg, seqs, first = make_windows(0, min(args.distinct, 16), 1)
+        cfg, seqs, first = make_windows(0, min(args.distinct, 16), 1, synth_cid)
         priors, prev = [], []
         for (p, st, _) in first:
             a, sm, q = vo.optimization(p, st, abi.MARGIN_OLD)
@@ -282,7 +420,7 @@ def main():
             tot_n += n
             tot_t += dt
             if scenes:
-                lr, ln, ldt = cpu_lk_many(scenes, per_step * 0.2, cores)
+                lr, ln, ldt = cpu_lk_many(scenes, per_step * 0.2, cores, stereo)
                 if lr is None:
                     scenes = None
                 else:
@@ -294,10 +432,10 @@ def main():
         value = 1.0 / (1.0 / solve_rate + (1.0 / lk_rate if lk_rate else 0.0))
         sample = "%d oracle optimisations (C FP64 port of the reference algorithm, %d pthreads) over %.1f s = %.1f solves/s" % (tot_n, cores, tot_t, solve_rate)
         if lk_rate:
-            sample += "; %d camera ticks of OpenCV calcOpticalFlowPyrLK x4 (%d threads) over %.1f s = %.1f frames/s; value = harmonic combination" % (lk_n, cores, lk_t, lk_rate)
+            sample += "; %d camera ticks of OpenCV calcOpticalFlowPyrLK x%d (%d threads) over %.1f s = %.1f frames/s; value = harmonic combination" % (lk_n, 4 if stereo else 2, cores, lk_t, lk_rate)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": 1e3 * (tot_t + lk_t) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": {"workload": WORKLOAD, "windows_per_sample": tot_n // max(1, args.steps), "lk_in_step": bool(lk_rate)},
+                "data": "synthetic", "config": config, "sample": {"windows_per_step": tot_n // max(1, args.steps), "camera_ticks_per_step": lk_n // max(1, args.steps)},
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
@@ -316,7 +454,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
 
     # ---- inputs: window 0 of every sequence is solved + marginalised on the GPU (untimed) to obtain the priors
-    cfg, seqs, first = make_windows(rank, args.distinct, args.copies)
+    cfg, seqs, first = make_windows(rank, args.distinct, args.copies, synth_cid)
     p0 = [f[0] for f in first]
     s0 = [f[1] for f in first]
     a0, _, q0 = ctx.optimization_batch(p0, s0, [abi.MARGIN_OLD] * len(p0))
@@ -328,7 +466,7 @@ def main():
     lk, feed, scenes, ctx_cam, cam_stream = None, None, None, None, None
     if not args.no_lk:
         scenes = make_scenes(rank, args.scenes)
-        feed = FrameFeed(ctx, scenes, B)
+        feed = FrameFeed(ctx, scenes, B, stereo)
         # The reference runs FeatureTracker::trackImage() in its own thread beside the estimator thread; --overlap-lk gives the camera tick
         # its own context + CUDA stream likewise.  Measured on B200 (profiles/r01za_bench_overlap.json vs r01za_bench_serial.json): 26 105 vs
         # 26 088 solves/s -- both kernel families already keep the SMs' issue slots busy, so the default stays one stream.
@@ -337,9 +475,9 @@ def main():
             ctx_cam = lib.Context(local_rank)
             cam_stream = torch.cuda.Stream()
             ctx_cam.set_stream(cam_stream.cuda_stream)
-        lk = ctx_cam.lk_batch(B, IMG_W, IMG_H, N_FEAT, stereo=True, flow_back=True)
+        lk = ctx_cam.lk_batch(B, IMG_W, IMG_H, N_FEAT, stereo=stereo, flow_back=True)
         # tick 0 (untimed): both left images resident, the resident "current" image is tick 1
-        lk.upload(prev=feed.left[0], cur=feed.left[1], right=feed.right[1], prev_pts=feed.pts[0], n_prev=feed.n, stereo_pts=feed.pts[1], n_stereo=feed.n)
+        lk.upload(**feed.tick_args(1, first=True))
         lk.run()
         lk.download()
         alg_bytes += lk.algorithmic_bytes()
@@ -402,11 +540,9 @@ def main():
                 self.lk = None
                 if lk is not None:
                     n = self.hi - self.lo
-                    self.lk = lk if lanes == 1 else self.ctx.lk_batch(n, IMG_W, IMG_H, N_FEAT, stereo=True, flow_back=True)
+                    self.lk = lk if lanes == 1 else self.ctx.lk_batch(n, IMG_W, IMG_H, N_FEAT, stereo=stereo, flow_back=True)
                     if lanes > 1:
-                        self.lk.upload(prev=feed.left[0][self.lo:self.hi], cur=feed.left[1][self.lo:self.hi], right=feed.right[1][self.lo:self.hi],
-                                       prev_pts=feed.pts[0][self.lo:self.hi], n_prev=feed.n[self.lo:self.hi], stereo_pts=feed.pts[1][self.lo:self.hi],
-                                       n_stereo=feed.n[self.lo:self.hi])
+                        self.lk.upload(**feed.tick_args(1, slice(self.lo, self.hi), first=True))
                         self.lk.run()
                         self.lk.download()
                 self.tick = 0
@@ -414,8 +550,7 @@ def main():
             def step(self):
                 if self.lk is not None:
                     t, sl = self.tick % 2, slice(self.lo, self.hi)   # the camera delivers image t of every stream; the previous tick's image is resident
-                    self.lk.upload(cur=feed.left[t][sl], right=feed.right[t][sl], prev_pts=feed.pts[1 - t][sl], n_prev=feed.n[sl],
-                                   stereo_pts=feed.pts[t][sl], n_stereo=feed.n[sl])
+                    self.lk.upload(**feed.tick_args(t, sl))
                     self.lk.run()         # asynchronous: overlaps with the host-side lowering of the windows below
                     self.tick += 1
                 self.call()               # lowering + H2D + solve + re-anchor + marginalise + D2H (synchronises)
@@ -467,7 +602,7 @@ def main():
     d2h = sum(8 * p.state_size + 8 * (nmax * nmax + abi.MAX_PRIOR_DIM + abi.STATE_FIXED) + 4 * 67 for p in probs)
     if lk is not None:
         h2d += feed.tick_bytes()
-        d2h += 2 * B * N_FEAT * (8 + 1)
+        d2h += (2 if stereo else 1) * B * N_FEAT * (8 + 1)
 
     # ---- latency of ONE window through the host-buffer call (what a single robot sees per key-frame; not the headline metric)
     one = ctx.prepare_optimization_batch(probs[:1], states[:1], flags[:1])
@@ -490,63 +625,60 @@ def main():
         ctx.set_profiling(False)
         if cam_stream is not None:
             ctx_cam.set_stream(cam_stream.cuda_stream)
-        tot = sum(v[0] for v in prof.values())
-        kernels = {k: {"ms_per_launch": v[0] / max(1, v[1]), "launches_per_step": v[1] / 2, "share": v[0] / tot} for k, v in prof.items()}
-        top = max(prof.items(), key=lambda kv: kv[1][0])[0]
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        # algorithmic bytes of one launch of the dominant kernel: its share of the SURVEY 8(d) B_iter model (DESIGN.md "Roofline")
-        n_vis = sum(len(p.vis_type) for p in probs)
-        R = sum(sum(abi.block_tsize(b) for b in range(32) if (p.block_flags[b] & 1) and not (p.block_flags[b] & 2)) for p in probs) / B
-        pg = sum(p.state_size for p in probs)
-        per_launch = {"lin_vis": 112.0 * n_vis + 8.0 * pg, "lm_reduce": 0.0, "assemble": 8.0 * B * (R * R + R), "solve": 8.0 * B * (R * R + R) + 8.0 * pg,
-                      "marg": 8.0 * B * (nmax * nmax + nmax + abi.STATE_FIXED), "asm_items": 8.0 * B * (R * R + R), "syrk": 8.0 * B * 80 * 80,
-                      "lk_track": (lk.algorithmic_bytes() if lk is not None else 0.0),
-                      "lin_small": sum(2296.0 * len(p.imu_frame_i) + 8.0 * (p.prior.n ** 2 + 2 * p.prior.n if p.prior is not None else 0) for p in probs)}
-        a_bytes = per_launch.get(top.replace("_marg", ""), 0.0)
-        achieved = a_bytes / (kernels[top]["ms_per_launch"] * 1e-3) / 1e9 if kernels[top]["ms_per_launch"] > 0 else 0.0
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top.replace("_marg", ""))
-            if tr:
-                traffic = tr["bytes_per_unit"] * B      # measured DRAM bytes of one launch (ncu --set full), scaled to this batch
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650",
-                    "algorithmic_bytes_per_launch": a_bytes,
-                    "whole_step": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes * args.steps / (ms * 1e-3) / 1e9}}
+        roofline, kernels = roofline_report(prof, probs, pri, B, lk, alg_bytes, args.steps, ms)
 
     # ---- CPU baseline + parity on rank 0 (the oracle is only used here as checker / baseline, never on the product path)
     cpu_baseline, parity = None, None
     if rank == 0:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import viw_oracle as vo
-        ep_max = er_max = 0.0
-        for i in range(0, B, max(1, B // 6)):
-            a, sm, q = vo.optimization(probs[i], states[i], abi.MARGIN_OLD)
-            ep, er = synth.pose_errors(a, sts[i])
+        cores = usable_cores()
+        # every window of the timed batch against the oracle (all host cores): solved + re-anchored poses, iteration counts and the
+        # order-independent content of the new prior (n, |J_lin|_F^2 = trace(J^T J), |J_lin^T r_lin|^2)
+        npar = B if args.parity_windows <= 0 else min(B, args.parity_windows)
+        pidx = list(range(B)) if npar == B else list(range(0, B, max(1, B // npar)))[:npar]
+        o_states, o_iters, o_digest, o_dt = vo.optimization_many([probs[i] for i in pidx], [states[i] for i in pidx], [abi.MARGIN_OLD] * len(pidx), cores)
+        ep_max = er_max = dig_max = 0.0
+        it_same = n_same = 0
+        for k, i in enumerate(pidx):
+            ep, er = synth.pose_errors(o_states[k], sts[i])
             ep_max, er_max = max(ep_max, ep), max(er_max, er)
-        parity = {"pose_err_m": ep_max, "pose_err_rad": er_max, "tolerance": [1e-4, 1e-4], "windows_checked": len(range(0, B, max(1, B // 6)))}
+            it_same += int(o_iters[k] == sums[i].num_iterations)
+            q = pri[i]
+            if q is not None and q.valid:
+                J, r = q.Jmat(), q.rvec()
+                got = np.array([q.n, float((J * J).sum()), float(((J.T @ r) ** 2).sum())])
+                n_same += int(got[0] == o_digest[k][0])
+                dig_max = max(dig_max, float(np.max(np.abs(got[1:] - o_digest[k][1:]) / np.maximum(1e-300, np.abs(o_digest[k][1:])))))
+            else:
+                n_same += int(o_digest[k][0] == 0)
+        parity = {"pose_err_m": ep_max, "pose_err_rad": er_max, "tolerance": [1e-4, 1e-4], "windows_checked": len(pidx), "of": B,
+                  "iteration_counts_equal": it_same, "prior_dims_equal": n_same, "prior_information_rel_err_max": dig_max,
+                  "oracle_pass": "%d windows on %d host threads in %.1f s" % (len(pidx), cores, o_dt)}
         lk_cv = None
         if lk is not None:
             try:
                 import cv2
+                from concurrent.futures import ThreadPoolExecutor
                 cv2.setNumThreads(1)
+                ref_by_scene = {}
+
+                def ref_scene(k):
+                    sc = scenes[k]
+                    return cv_track_frame(cv2, sc["left"][0], sc["left"][1], sc["right"][1], sc["pts"][0], sc["pts"][1], stereo)
+                with ThreadPoolExecutor(max(1, min(cores, len(scenes)))) as ex:
+                    for k, res in enumerate(ex.map(ref_scene, range(len(scenes)))):
+                        ref_by_scene[k] = res
                 worst, agree, cnt = 0.0, 0.0, 0
-                for f in range(0, B, max(1, B // 4)):
-                    sc = scenes[f % len(scenes)]
-                    c, st_t, r, st_s = cv_track_frame(cv2, sc["left"][0], sc["left"][1], sc["right"][1], sc["pts"][0], sc["pts"][1])
-                    for ref_p, ref_s, got_p, got_s in ((c, st_t, lk_out[0][f], lk_out[1][f]), (r, st_s, lk_out[2][f], lk_out[3][f])):
+                for f in range(B):          # every stream of the timed tick (streams replicate the scenes; the device results are per stream)
+                    c, st_t, r, st_s = ref_by_scene[f % len(scenes)]
+                    pairs = [(c, st_t, lk_out[0][f], lk_out[1][f])] + ([(r, st_s, lk_out[2][f], lk_out[3][f])] if stereo else [])
+                    for ref_p, ref_s, got_p, got_s in pairs:
                         both = ref_s & (got_s > 0)
                         worst = max(worst, float(np.abs(ref_p[both] - got_p[both]).max()) if both.any() else 0.0)
                         agree += float((ref_s == (got_s > 0)).mean())
                         cnt += 1
-                parity.update({"lk_max_px_vs_opencv": worst, "lk_status_agreement": agree / cnt, "lk_tolerance_px": 1e-2, "lk_streams_checked": cnt // 2})
+                parity.update({"lk_max_px_vs_opencv": worst, "lk_status_agreement": agree / cnt, "lk_tolerance_px": 1e-2, "lk_streams_checked": B})
                 lk_cv = cv2
             except ImportError:
                 parity.update({"lk": "OpenCV not importable on this box: LK parity not checked in bench (see tests)"})
@@ -554,19 +686,15 @@ def main():
             rate, n, dt = cpu_solve_many(vo, probs, states, args.cpu_seconds * (0.8 if lk_cv else 1.0), 1)
             sample = "%d sequential oracle optimisations (C FP64 port of the reference algorithm; Ceres default num_threads=1) in %.1f s = %.1f solves/s" % (n, dt, rate)
             if lk_cv:
-                lr, ln, ldt = cpu_lk_many(scenes, args.cpu_seconds * 0.2, 1)
-                sample += "; %d camera ticks of OpenCV calcOpticalFlowPyrLK x4 (1 thread) in %.1f s = %.1f frames/s; value = harmonic combination" % (ln, ldt, lr)
+                lr, ln, ldt = cpu_lk_many(scenes, args.cpu_seconds * 0.2, 1, stereo)
+                sample += "; %d camera ticks of OpenCV calcOpticalFlowPyrLK x%d (1 thread) in %.1f s = %.1f frames/s; value = harmonic combination" % (ln, 4 if stereo else 2, ldt, lr)
                 rate = 1.0 / (1.0 / rate + 1.0 / lr)
             cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD if lk is not None else WORKLOAD + " [--no-lk: window solve only]",
-                           "batch_per_gpu": B, "distinct_sequences": args.distinct, "perturbed_copies": args.copies,
-                           "mean_visual_factors": sum(len(p.vis_type) for p in probs) / B, "mean_landmarks": sum(p.num_landmarks for p in probs) / B,
-                           "l2": "working set >> 126 MB L2 at this batch; no explicit flush", "lk_in_step": lk is not None,
-                           "lk_stream": None if lk is None else ("same stream as the solver" if cam_stream is None else "own CUDA stream, concurrent with the solver (the reference's tracker thread)"),
-                           "camera": None if lk is None else {"streams": B, "image": [IMG_W, IMG_H], "features": N_FEAT, "distinct_scenes": len(scenes),
-                                                              "e2e_images_uploaded_per_tick": 2}},
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "workload_stats": {"mean_visual_factors": sum(len(p.vis_type) for p in probs) / B, "mean_landmarks": sum(p.num_landmarks for p in probs) / B,
+                                   "camera_streams": B if lk is not None else 0, "distinct_scenes": len(scenes) if scenes else 0,
+                                   "lk_stream": None if lk is None else ("same stream as the solver" if cam_stream is None else "own CUDA stream, concurrent with the solver (the reference's tracker thread)")},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "host_threads": lanes, "sweep": e2e_sweep},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity,
                 "single_window_e2e_ms": single_ms}

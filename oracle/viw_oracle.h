@@ -74,6 +74,9 @@ int vo_shift_depth(int n, const double *uv, const double *depth_in, const double
 /* n independent windows on `threads` pthreads, `repeat` passes (bench.py CPU arm); returns the number of optimisations run */
 long vo_optimization_throughput(int n, const viwb_problem *problems, const double *const *states, const int32_t *flags,
                                 const viwb_options *opt, int threads, int repeat);
+/* the same with results: solved states, iteration counts and per window {n, |J_lin|_F^2, |J_lin^T r_lin|^2} of the new prior (any pointer may be NULL) */
+long vo_optimization_many(int n, const viwb_problem *problems, const double *const *states, const int32_t *flags,
+                          const viwb_options *opt, int threads, int repeat, double *const *out_states, int32_t *out_iters, double *out_prior);
 
 /* IntegrationBase::propagate (integration_base.h:63-167) on a buffer of samples -> the 287-double record.
  * acc/gyr have (n+1) rows (sample 0 = acc_0/gyr_0), dt has n entries; noise = {ACC_N, GYR_N, ACC_W, GYR_W}. */

@@ -227,3 +227,27 @@ def optimization_throughput(problems, states, flags, threads, repeat=1, options=
     t0 = time.perf_counter()
     n = f(C.c_int(B), arr, sp, fl, C.byref(opt), C.c_int(threads), C.c_int(repeat))
     return int(n), time.perf_counter() - t0
+
+
+def optimization_many(problems, states, flags, threads, options=None):
+    """len(problems) optimisations on `threads` pthreads; returns (solved states, iteration counts, prior digests [B][3] = n, |J|_F^2,
+    |J^T r|^2, seconds).  bench.py's full-batch parity and its cpu_baseline come from this one pass."""
+    import time
+    B = len(problems)
+    arr = (abi.Problem * B)()
+    for i, p in enumerate(problems):
+        p.fill(arr[i])
+    sts = [np.ascontiguousarray(s, np.float64) for s in states]
+    outs = [np.zeros_like(s) for s in sts]
+    sp = (abi.c_double_p * B)(*[_dp(s) for s in sts])
+    op = (abi.c_double_p * B)(*[_dp(s) for s in outs])
+    fl = (C.c_int32 * B)(*[int(f) for f in flags])
+    iters = np.zeros(B, np.int32)
+    digest = np.zeros((B, 3), np.float64)
+    opt = options if options is not None else abi.default_options()
+    f = lib().vo_optimization_many
+    f.restype = C.c_long
+    t0 = time.perf_counter()
+    f(C.c_int(B), arr, sp, fl, C.byref(opt), C.c_int(threads), C.c_int(1), op, iters.ctypes.data_as(C.POINTER(C.c_int32)), _dp(digest))
+    return outs, iters, digest, time.perf_counter() - t0
+

@@ -423,7 +423,8 @@ int vo_shift_depth(int n, const double *uv, const double *depth_in, const double
  * (estimator.cpp:1646 leaves num_threads commented out).  repeat > 1 cycles over the windows to fill a time budget. */
 #include <pthread.h>
 #include <malloc.h>
-typedef struct { const viwb_problem *pb; const double *const *states; const int32_t *flags; const viwb_options *opt; int n, repeat, tid, nthreads; long done; } vo_job;
+typedef struct { const viwb_problem *pb; const double *const *states; const int32_t *flags; const viwb_options *opt; int n, repeat, tid, nthreads; long done;
+                 double *const *out_states; int32_t *out_iters; double *out_prior; } vo_job;
 static void *vo_worker(void *arg) {
     vo_job *j = (vo_job *)arg;
     viwb_prior out; double *x0 = (double *)malloc(sizeof(double) * VIWB_STATE_FIXED), *J = (double *)malloc(sizeof(double) * VIWB_MAX_PRIOR_DIM * VIWB_MAX_PRIOR_DIM), *r = (double *)malloc(sizeof(double) * VIWB_MAX_PRIOR_DIM);
@@ -435,12 +436,31 @@ static void *vo_worker(void *arg) {
             memcpy(st, j->states[i], sizeof(double) * (VIWB_STATE_FIXED + j->pb[i].num_landmarks));
             vo_optimization(&j->pb[i], st, j->opt, j->flags ? j->flags[i] : -1, &sum, j->flags ? &out : NULL);
             j->done++;
+            /* optional results (bench.py's full-batch parity): solved state, iteration count, and the order-independent content of the new
+             * prior: n, trace(J^T J) = |J|_F^2 and |J^T r|^2 (rows of J_lin are eigen-directions: their order and signs are not defined) */
+            if (j->out_states && j->out_states[i]) memcpy(j->out_states[i], st, sizeof(double) * (VIWB_STATE_FIXED + j->pb[i].num_landmarks));
+            if (j->out_iters) j->out_iters[i] = sum.num_iterations;
+            if (j->out_prior) {
+                double *o = j->out_prior + 3 * (size_t)i; o[0] = o[1] = o[2] = 0.0;
+                if (j->flags && out.valid) {
+                    const int n = out.n; double tr = 0.0, g2 = 0.0;
+                    for (int a = 0; a < n * n; a++) tr += J[a] * J[a];
+                    for (int c = 0; c < n; c++) { double g = 0.0; for (int a = 0; a < n; a++) g += J[a * n + c] * r[a]; g2 += g * g; }
+                    o[0] = n; o[1] = tr; o[2] = g2;
+                }
+            }
         }
     free(x0); free(J); free(r); free(st);
     return NULL;
 }
+long vo_optimization_many(int n, const viwb_problem *problems, const double *const *states, const int32_t *flags,
+                          const viwb_options *opt, int threads, int repeat, double *const *out_states, int32_t *out_iters, double *out_prior);
 long vo_optimization_throughput(int n, const viwb_problem *problems, const double *const *states, const int32_t *flags,
                                 const viwb_options *opt, int threads, int repeat) {
+    return vo_optimization_many(n, problems, states, flags, opt, threads, repeat, NULL, NULL, NULL);
+}
+long vo_optimization_many(int n, const viwb_problem *problems, const double *const *states, const int32_t *flags,
+                          const viwb_options *opt, int threads, int repeat, double *const *out_states, int32_t *out_iters, double *out_prior) {
     if (threads < 1) threads = 1;
     /* the per-solve work buffers (MBs) would otherwise be mmap'ed/unmapped on every call and the threads would serialise on
      * the process' mm lock: keep them in the per-thread malloc arenas (gives the CPU arm its best case) */
@@ -449,6 +469,7 @@ long vo_optimization_throughput(int n, const viwb_problem *problems, const doubl
     vo_job *jobs = (vo_job *)calloc(threads, sizeof(vo_job));
     for (int t = 0; t < threads; t++) {
         jobs[t].pb = problems; jobs[t].states = states; jobs[t].flags = flags; jobs[t].opt = opt; jobs[t].n = n; jobs[t].repeat = repeat; jobs[t].tid = t; jobs[t].nthreads = threads;
+        jobs[t].out_states = out_states; jobs[t].out_iters = out_iters; jobs[t].out_prior = out_prior;
         pthread_create(&th[t], NULL, vo_worker, &jobs[t]);
     }
     long done = 0;
