@@ -43,8 +43,10 @@ VIWB_HD void red_mulv(double *o, const double *red, const V3 &v, double s) {
 
 // type: 0 = 2F1C, 1 = 2F2C, 2 = 1F2C.  obs: pts_i(3) pts_j(3) vel_i(2) vel_j(2) td_i td_j.
 // S = sqrt_info (2x2 row-major).  pose pointers are [p(3), q(x,y,z,w)].
-VIWB_HD void vis_eval(int type, const double *obs, const double *pose_i, const double *pose_j, const double *ex0,
-                      const double *ex1, double inv_dep, double td, const double *S, bool want_j, VisOut &o) {
+// COMMON = false leaves JE0 / JE1 / Jtd unwritten (windows whose extrinsics and td are constant never read them)
+template <bool COMMON>
+VIWB_HD void vis_eval_t(int type, const double *obs, const double *pose_i, const double *pose_j, const double *ex0,
+                        const double *ex1, double inv_dep, double td, const double *S, bool want_j, VisOut &o) {
     const V3 pts_i = ld3(obs), pts_j = ld3(obs + 3);
     const V3 vel_i = v3(obs[6], obs[7], 0.0), vel_j = v3(obs[8], obs[9], 0.0);
     const V3 pi_td = pts_i - (td - obs[10]) * vel_i;
@@ -83,11 +85,13 @@ VIWB_HD void vis_eval(int type, const double *obs, const double *pose_i, const d
     const double sv0 = S[0] * vel_j.x + S[1] * vel_j.y, sv1 = S[2] * vel_j.x + S[3] * vel_j.y;
     if (type == 2) {
         const M3 B = RcT * Ric;                                   // ric2^T ric
-        put26(o.JE0, red, RcT, -(B * skew(Xci)));
-        put26(o.JE1, red, -RcT, skew(Xcj));
+        if (COMMON) {
+            put26(o.JE0, red, RcT, -(B * skew(Xci)));
+            put26(o.JE1, red, -RcT, skew(Xcj));
+            red_mulv(o.Jtd, red, B * vel_i, -inv_l);
+            o.Jtd[0] += sv0; o.Jtd[1] += sv1;
+        }
         red_mulv(o.Jl, red, B * pts_i, -inv_l * inv_l);           // quirk 3: un-compensated pts_i (:119)
-        red_mulv(o.Jtd, red, B * vel_i, -inv_l);
-        o.Jtd[0] += sv0; o.Jtd[1] += sv1;
         for (int k = 0; k < 12; k++) { o.JA[k] = 0.0; o.JB[k] = 0.0; }
         return;
     }
@@ -96,18 +100,24 @@ VIWB_HD void vis_eval(int type, const double *obs, const double *pose_i, const d
     const M3 T = MRi * Ric;
     put26(o.JA, red, M, -(MRi * skew(Xbi)));
     put26(o.JB, red, -M, RcT * skew(Xbj));
-    if (type == 0) {
-        const M3 L = RcT * (transpose(Rj) * Ri - m3_identity());
-        const V3 w = RcT * (tmul(Rj, Ri * tic + ld3(pose_i) - ld3(pose_j)) - tic);
-        put26(o.JE0, red, L, -(T * skew(Xci)) + skew(T * Xci) + skew(w));
-        for (int k = 0; k < 12; k++) o.JE1[k] = 0.0;
-    } else {
-        put26(o.JE0, red, MRi, -(T * skew(Xci)));
-        put26(o.JE1, red, -RcT, skew(Xcj));
+    if (COMMON) {
+        if (type == 0) {
+            const M3 L = RcT * (transpose(Rj) * Ri - m3_identity());
+            const V3 w = RcT * (tmul(Rj, Ri * tic + ld3(pose_i) - ld3(pose_j)) - tic);
+            put26(o.JE0, red, L, -(T * skew(Xci)) + skew(T * Xci) + skew(w));
+            for (int k = 0; k < 12; k++) o.JE1[k] = 0.0;
+        } else {
+            put26(o.JE0, red, MRi, -(T * skew(Xci)));
+            put26(o.JE1, red, -RcT, skew(Xcj));
+        }
+        red_mulv(o.Jtd, red, T * vel_i, -inv_l);
+        o.Jtd[0] += sv0; o.Jtd[1] += sv1;
     }
     red_mulv(o.Jl, red, T * pi_td, -inv_l * inv_l);
-    red_mulv(o.Jtd, red, T * vel_i, -inv_l);
-    o.Jtd[0] += sv0; o.Jtd[1] += sv1;
+}
+VIWB_HD void vis_eval(int type, const double *obs, const double *pose_i, const double *pose_j, const double *ex0,
+                      const double *ex1, double inv_dep, double td, const double *S, bool want_j, VisOut &o) {
+    vis_eval_t<true>(type, obs, pose_i, pose_j, ex0, ex1, inv_dep, td, S, want_j, o);
 }
 
 // ceres::HuberLoss + Corrector for a 2-row residual block: rho'' < 0 whenever s > delta^2, so the corrector always

@@ -299,6 +299,14 @@ VIWB_D void add_small_factor(const Target &t, const double *rec, int rows, int l
     VIWB_SYNC();
 }
 
+// entry (i, j) of a pair chunk's G = sum X^T X as asm_pairs stores it: tiles (0,0), (0,1), (1,1) of the 16 x 16 frame in mma.m8n8k4 accumulator
+// order, out[64 t + 2 l + r] = G[8 tr + l/4][8 tc + 2 (l%4) + r]; G is symmetric, tile (1,0) is read through (0,1)
+VIWB_HD double pair_G_entry(const double *out, int i, int j) {
+    if ((i >> 3) > (j >> 3)) { const int t = i; i = j; j = t; }
+    const int tr = i >> 3, tc = j >> 3, tl = tr == 0 ? (tc == 0 ? 0 : 1) : 2;
+    return out[64 * tl + 2 * (((i & 7) << 2) + ((j & 7) >> 1)) + (j & 1)];
+}
+
 // common column c (0..12) -> (block, k)
 VIWB_HD int common_blk(int c) { return c < 6 ? BLK_EX0 : c < 12 ? BLK_EX1 : BLK_TD; }
 VIWB_HD int common_k(int c) { return c < 6 ? c : c < 12 ? c - 6 : 0; }
@@ -381,6 +389,39 @@ VIWB_D void assemble_into(const Target &t, const BatchDev &bd, int w, int mode, 
             const int ns = plane_slots(i, sl);      // plane_R: 3 tangent columns; its 4th marginalisation column stays zero
             add_small_factor(t, bd.plane_rec + (size_t)f * PLANE_REC, 3, 16, sl, ns, tid, nt);
         }
+    }
+    if (mode == MODE_SOLVE && m.fused) {
+        // ---- fused path: G = sum X^T X per pair chunk (asm_pairs, kernels_fused.cuh), X = [A (host frame a) | B (observer b) | r].
+        //      Diagonal blocks and gradients of frame f: ONE owner per entry walks the chunks of every pair that contains f (fixed order).
+        const int pio = m.pitem_off, npi = m.npitems;
+        for (int e = tid; e < NFR * 27; e += nt) {
+            const int f = e / 27, o = e - 27 * f;
+            int p = 0, q = 0;
+            if (o < 21) sym_unrank(o, p, q); else p = o - 21;
+            double v = 0.0; bool any = false;
+            for (int ii = 0; ii < npi; ii++) {
+                const AsmItem &it = bd.pitems[pio + ii];
+                int base;
+                if (it.a == f) base = 0; else if (it.b == f) base = 6; else continue;
+                v += pair_G_entry(bd.pair_out + (size_t)(pio + ii) * PAIR_OUT, base + p, o < 21 ? base + q : 12);
+                any = true;
+            }
+            if (!any) continue;
+            if (o < 21) { const int ci = t.col(f, p), cj = t.col(f, q); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
+            else { const int ci = t.col(f, p); if (ci >= 0) t.addg(ci, v); }
+        }
+        //      Off-diagonal block of pair (a, b): the owner of entry o of the pair's head chunk adds the chunks (consecutive items, phase 0, 1, ...)
+        for (int e = tid; e < npi * 36; e += nt) {
+            const int ii = e / 36, o = e - 36 * ii;
+            const AsmItem &item = bd.pitems[pio + ii];
+            if (item.phase != 0) continue;
+            double v = pair_G_entry(bd.pair_out + (size_t)(pio + ii) * PAIR_OUT, o / 6, 6 + o % 6);
+            for (int c = 1; ii + c < npi && bd.pitems[pio + ii + c].phase == c; c++) v += pair_G_entry(bd.pair_out + (size_t)(pio + ii + c) * PAIR_OUT, o / 6, 6 + o % 6);
+            const int ci = t.col(item.a, o / 6), cj = t.col(item.b, o % 6);
+            if (ci >= 0 && cj >= 0) t.add(ci, cj, v);
+        }
+        VIWB_SYNC();
+        return;
     }
     // ---- visual partial sums: the chunks of one target (same frame / frame pair / common block) are consecutive items with
     //      phase 0, 1, 2, ...; the owner of entry o of the head item gathers the chunks, so one pass and no barriers

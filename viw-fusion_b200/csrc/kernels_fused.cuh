@@ -1,0 +1,249 @@
+// kernels_fused.cuh -- the solver linearisation of windows whose camera extrinsics and td are constant (C1 / C2 / C6 shapes), and the
+// FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) products of the normal equations.
+//
+//   lin_vis_lm  one block per group of WHOLE landmarks (<= LMB_FACTORS factors): thread per factor evaluates residual, Huber, tangent
+//               Jacobians (the three projection factors, factor/projection*Factor.cpp) into a shared-memory tile; the block then
+//                 - streams one X record per two-frame factor, X = [A | B | r] (2 x 13), to its slot in FRAME-PAIR order (one contiguous
+//                   224-byte store per record), and
+//                 - reduces the per-landmark quantities straight from the tile: a = |J_l|^2, g_l, the cost, the Schur weight gamma and the
+//                   row W = J_p^T J_l -- the 28-double visual records of lin_vis never exist, lm_reduce does not run.
+//   asm_pairs   one warp per chunk of one frame pair's records: G = sum_f X_f^T X_f (13 x 13: A^T A | A^T B | A^T r / B^T B | B^T r) as a
+//               true GEMM on the FP64 tensor pipe: three 8 x 8 accumulator tiles, K = 2 rows per factor, operands read once, coalesced.
+//               Replaces the three gather walks of asm_items (two frame lists + one pair list per factor).
+//   syrk_mma    T = sum_k gamma_k w_k w_k^T (80 x 80) and tvec = sum_k gamma_k g_k w_k as one [80 x K] x [K x 81] DMMA product per window
+//               (the dense Schur block of north_star), operands staged by cp.async into a conflict-free shared-memory layout.
+// The emulation build (VIWB_HOST_EMU) states the same sums in scalar code.
+#pragma once
+#include "kernels_asm.cuh"
+
+namespace viwb {
+
+// D (8x8) += A (8x4, row) * B (4x8, col): lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4) + {0,1}]
+#ifndef VIWB_HOST_EMU
+VIWB_D void dmma884(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------ lin_vis_lm
+enum { LVL_TS = 31, LVL_U = 28, LVL_C = 30 };      // tile row: X record (28) | J_lambda (2) | rho / 2 ; odd stride
+VIWB_HD size_t lin_vis_lm_smem_doubles() { return (size_t)LMB_FACTORS * LVL_TS + 2; }
+VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)mode;                        // solver linearisation at x_cand only
+    const int w = bd.lmb_win[bx];
+    const WinWork &ww = bd.work[w];
+    if (ww.status != ST_RUNNING) return;
+    const WinMeta &m = bd.meta[w];
+    const int k0 = bd.lmb_ptr[2 * bx], k1 = bd.lmb_ptr[2 * bx + 1];    // global landmark range of this block
+    const int f0 = bd.lm_fptr[k0], nf = bd.lm_fptr[k1] - f0;            // its factors (consecutive, <= LMB_FACTORS)
+    double *tile = smem;
+    const double *x = bd.x_cand + m.state_off;
+    // ---- 0: the W rows of these landmarks start from zero (frames that do not observe a landmark keep zero blocks)
+    { double *Wb = bd.lm_W + (size_t)k0 * VSUB; for (int e = tid; e < (k1 - k0) * VSUB; e += nt) Wb[e] = 0.0; }
+    // ---- 1: one thread per factor
+    for (int t = tid; t < nf; t += nt) {
+        const int f = f0 + t;
+        const int type = bd.vis_type[f], fi = bd.vis_fi[f], fj = bd.vis_fj[f];
+        double obs[12];
+        for (int k = 0; k < 12; k++) obs[k] = bd.vis_obs[(size_t)f * 12 + k];
+        VisOut o;
+        vis_eval_t<false>(type, obs, x + 7 * fi, x + 7 * fj, x + blk_off(BLK_EX0), x + blk_off(BLK_EX1), x[SFIX + bd.vis_lm[f]], x[blk_off(BLK_TD)], m.S_vis, true, o);
+        double half_rho;
+        const double sc = huber_scale(o.r[0] * o.r[0] + o.r[1] * o.r[1], m.huber, half_rho);
+        double *row = tile + (size_t)t * LVL_TS;
+        for (int q = 0; q < 6; q++) { row[q] = o.JA[q] * sc; row[6 + q] = o.JB[q] * sc; row[XROW + q] = o.JA[6 + q] * sc; row[XROW + 6 + q] = o.JB[6 + q] * sc; }
+        row[12] = o.r[0] * sc; row[13] = 0.0; row[XROW + 12] = o.r[1] * sc; row[XROW + 13] = 0.0;
+        row[LVL_U] = o.Jl[0] * sc; row[LVL_U + 1] = o.Jl[1] * sc; row[LVL_C] = half_rho;
+    }
+    VIWB_SYNC();
+    // ---- 2a: X records to their frame-pair slots: one warp-wide contiguous store per record
+    {
+        const int Wd = nt < 32 ? nt : 32, nwp = nt / Wd, wid = tid / Wd, lane = tid % Wd;
+        double *xr = bd.xrec + (size_t)m.xrec_off * XREC;
+        for (int t = wid; t < nf; t += nwp) {
+            const int pos = bd.vis_pos[f0 + t];
+            if (pos < 0) continue;                       // one-frame stereo factor: no pose Jacobian
+            for (int q = lane; q < XREC; q += Wd) xr[(size_t)pos * XREC + q] = tile[(size_t)t * LVL_TS + q];
+        }
+    }
+    // ---- 2b: observing-frame blocks of W, item = (factor, component); two factors of one landmark seen from the same frame (left and
+    //          right camera) are consecutive in the table: the first one writes the sum
+    for (int e = tid; e < nf * 6; e += nt) {
+        const int t = e / 6, q = e - 6 * t, f = f0 + t;
+        if (bd.vis_type[f] == 2) continue;
+        const int dup = bd.vis_dup[f];
+        if (dup == 2) continue;
+        const double *row = tile + (size_t)t * LVL_TS;
+        double v = row[6 + q] * row[LVL_U] + row[XROW + 6 + q] * row[LVL_U + 1];
+        if (dup == 1) { const double *r2 = row + LVL_TS; v += r2[6 + q] * r2[LVL_U] + r2[XROW + 6 + q] * r2[LVL_U + 1]; }
+        bd.lm_W[(size_t)(m.lm_off + bd.vis_lm[f]) * VSUB + 6 * bd.vis_fj[f] + q] = v;
+    }
+    // ---- 2c: per landmark, item = (landmark, output): host-frame block of W (6), a, g, cost (+ Jacobi scale and Schur weight)
+    for (int e = tid; e < (k1 - k0) * 9; e += nt) {
+        const int kl = e / 9, q = e - 9 * kl, k = k0 + kl;
+        const int a0 = bd.lm_fptr[k] - f0, a1 = bd.lm_fptr[k + 1] - f0;
+        double s = 0.0;
+        for (int t = a0; t < a1; t++) {
+            const double *row = tile + (size_t)t * LVL_TS;
+            const double u0 = row[LVL_U], u1 = row[LVL_U + 1];
+            if (q < 6) s += row[q] * u0 + row[XROW + q] * u1;              // one-frame factors carry A = 0
+            else if (q == 6) s += u0 * u0 + u1 * u1;
+            else if (q == 7) s += u0 * row[12] + u1 * row[XROW + 12];
+            else s += row[LVL_C];
+        }
+        if (q < 6) { if (a1 > a0) bd.lm_W[(size_t)k * VSUB + 6 * bd.vis_fi[f0 + a0] + q] = s; }
+        else if (q == 7) bd.lm_g[k] = s;
+        else if (q == 8) bd.lm_cost[k] = s;
+        else {
+            bd.lm_a[k] = s;
+            if (a1 == a0) { bd.lm_gamma[k] = 0.0; if (ww.first) bd.lm_scale[k] = 1.0; }
+            else {
+                // Jacobi scale (first linearisation only) and the Schur weight for the mu this linearisation will be solved with:
+                // scaled pivot h = c^2 a + mu * clamp(c^2 a); gamma = c^2 / h  
+                double sc = bd.lm_scale[k];
+                if (ww.first) { sc = bd.opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(s)) : 1.0; bd.lm_scale[k] = sc; }
+                const double s2 = sc * sc * s;
+                double d2 = s2; if (d2 < bd.opt.min_lm_diagonal) d2 = bd.opt.min_lm_diagonal; if (d2 > bd.opt.max_lm_diagonal) d2 = bd.opt.max_lm_diagonal;
+                bd.lm_gamma[k] = sc * sc / (s2 + ww.mu_lin * d2);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ asm_pairs
+// G is 13 x 13 inside a 16 x 16 frame of 8 x 8 tiles; tiles (0,0), (0,1), (1,1) are stored in accumulator order: tile t, lane l, register r at
+// out[64 t + 2 l + r] = G[8 tr + l/4][8 tc + 2 (l%4) + r]; pair_G_entry (kernels_asm.cuh) reads entry (i, j) back.
+VIWB_D void asm_pairs_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem; (void)mode;
+    const int Wd = nt < 32 ? nt : 32, wpb = nt / Wd, lane = tid % Wd;
+    const int it = bx * wpb + tid / Wd;
+    if (it >= bd.npitems_total) return;
+    const AsmItem item = bd.pitems[it];
+    if (bd.work[item.win].status != ST_RUNNING) return;
+    const double *recs = bd.xrec + (size_t)bd.meta[item.win].xrec_off * XREC;
+    double *out = bd.pair_out + (size_t)it * PAIR_OUT;
+#ifdef VIWB_HOST_EMU
+    (void)lane;
+    double G[16][16];
+    for (int a = 0; a < 16; a++) for (int b = 0; b < 16; b++) G[a][b] = 0.0;
+    for (int f = item.lo; f < item.hi; f++) for (int rr = 0; rr < 2; rr++) {
+        const double *xrow = recs + (size_t)f * XREC + rr * XROW;
+        for (int a = 0; a < XROW; a++) for (int b = 0; b < XROW; b++) G[a][b] += xrow[a] * xrow[b];
+    }
+    for (int t = 0; t < 3; t++) { const int tr = t == 2 ? 1 : 0, tc = t == 0 ? 0 : 1;
+        for (int l = 0; l < 32; l++) for (int r = 0; r < 2; r++) out[64 * t + 2 * l + r] = G[8 * tr + l / 4][8 * tc + 2 * (l % 4) + r]; }
+#else
+    // K index of the product = (factor, residual row): k-step of 4 = two records; lane l feeds X[k = l%4][column l/4 (+ 8)] as the A and the B operand
+    const int kk = lane & 3, fo = kk >> 1, rr = kk & 1, c0 = lane >> 2, c1 = c0 + 8;
+    const bool c1ok = c1 < XROW;
+    double acc[2][3][2];
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int t = 0; t < 3; t++) { acc[u][t][0] = 0.0; acc[u][t][1] = 0.0; }
+    for (int f = item.lo; f < item.hi; f += 4) {          // two independent k-steps per trip
+        double a0[2], a1[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int ff = f + 2 * u + fo;
+            const bool ok = ff < item.hi;
+            const double *p = recs + (size_t)ff * XREC + rr * XROW;
+            a0[u] = ok ? p[c0] : 0.0;
+            a1[u] = (ok && c1ok) ? p[c1] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) { dmma884(acc[u][0], a0[u], a0[u]); dmma884(acc[u][1], a0[u], a1[u]); dmma884(acc[u][2], a1[u], a1[u]); }
+    }
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        double2 v; v.x = acc[0][t][0] + acc[1][t][0]; v.y = acc[0][t][1] + acc[1][t][1];
+        reinterpret_cast<double2 *>(out + 64 * t)[lane] = v;
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ syrk_mma
+// T = sum_k g_k w_k w_k^T (80 x 80, both triangles written, exactly symmetric), tvec = sum_k g_k gl_k w_k.
+// solver: g_k = gamma_k; marginalisation: g_k = 1 / a_k for the landmarks hosted in frame 0 (gamma holds a_k, 0 = skip).
+// One [80 x K] x [K x 81] product (column 80 of the right operand = gl): 10 x 11 tiles of 8 x 8, of which the 55 upper-triangular ones
+// and the 10 of the tvec column are computed: five warps, warp v owns tile rows v and 9 - v (13 tiles each).  Chunks of 32 landmarks stream
+// through two shared-memory buffers (cp.async); the row stride 88 makes every operand fetch two conflict-free wavefronts.
+enum { SYRK_LD = 88, SYRK_NT = 160 };
+VIWB_HD size_t syrk_mma_smem_doubles() { return (size_t)2 * SYRK_KC * SYRK_LD + 2 * SYRK_KC; }
+VIWB_D void syrk_mma_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    if (mode == MODE_SOLVE && bd.work[w].status != ST_RUNNING) return;
+    if (mode == MODE_MARG && m.margin_flag != 0) return;
+    const double *W = bd.lm_W + (size_t)m.lm_off * VSUB, *gam = bd.lm_gamma + m.lm_off, *gl = bd.lm_g + m.lm_off;
+    double *T = bd.Tvis + (size_t)w * VSUB * VSUB, *tv = bd.tvec + (size_t)w * VSUB;
+#ifdef VIWB_HOST_EMU
+    (void)smem; (void)tid; (void)nt;
+    for (int i = 0; i < VSUB; i++) { for (int j = 0; j < VSUB; j++) T[i * VSUB + j] = 0.0; tv[i] = 0.0; }
+    for (int k = 0; k < m.nlm; k++) {
+        double g = gam[k];
+        if (mode == MODE_MARG) g = g > 0.0 ? 1.0 / g : 0.0;
+        const double *r = W + (size_t)k * VSUB;
+        for (int i = 0; i < VSUB; i++) { const double a = g * r[i]; for (int j = i; j < VSUB; j++) T[i * VSUB + j] += a * r[j]; tv[i] += a * gl[k]; }
+    }
+    for (int i = 0; i < VSUB; i++) for (int j = 0; j < i; j++) T[i * VSUB + j] = T[j * VSUB + i];
+#else
+    double *Wb[2] = {smem, smem + SYRK_KC * SYRK_LD};
+    double *gkb[2] = {smem + 2 * SYRK_KC * SYRK_LD, smem + 2 * SYRK_KC * SYRK_LD + SYRK_KC};
+    const int lane = tid & 31, wid = tid >> 5;
+    const int tmA = wid, tmB = 9 - wid;                       // tile rows of this warp (tmA <= 4 < tmB)
+    double accA[11][2], accB[6][2];
+#pragma unroll
+    for (int j = 0; j < 11; j++) { accA[j][0] = 0.0; accA[j][1] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < 6; j++) { accB[j][0] = 0.0; accB[j][1] = 0.0; }
+    auto stage = [&](int c, int p) {
+        const int k0 = c * SYRK_KC, kc = (m.nlm - k0) < SYRK_KC ? (m.nlm - k0) : SYRK_KC;
+        for (int e = tid; e < kc * (VSUB / 2); e += nt) { const int r = e / (VSUB / 2), cc = e - r * (VSUB / 2); async_copy16(Wb[p] + r * SYRK_LD + 2 * cc, W + (size_t)(k0 + r) * VSUB + 2 * cc); }
+        async_commit();
+        for (int r = tid; r < SYRK_KC; r += nt) {
+            double g = 0.0, gg = 0.0;
+            if (r < kc) { g = gam[k0 + r]; if (mode == MODE_MARG) g = g > 0.0 ? 1.0 / g : 0.0; gg = gl[k0 + r]; }
+            gkb[p][r] = g;
+            Wb[p][r * SYRK_LD + VSUB] = gg;                   // column 80 of the right operand
+            if (r >= kc) for (int q = 0; q < VSUB; q++) Wb[p][r * SYRK_LD + q] = 0.0;      // rows past the end of the window: zeros, not stale bytes
+        }
+    };
+    for (int e = tid; e < 2 * SYRK_KC * 7; e += nt) { const int r = e / 7, q = e - 7 * r; smem[r * SYRK_LD + VSUB + 1 + q] = 0.0; }      // columns 81..87 of both buffers
+    const int nchunk = (m.nlm + SYRK_KC - 1) / SYRK_KC;
+    if (nchunk > 0) stage(0, 0);
+    for (int c = 0, p = 0; c < nchunk; c++, p ^= 1) {
+        if (c + 1 < nchunk) { stage(c + 1, p ^ 1); async_wait<1>(); } else async_wait<0>();
+        __syncthreads();
+        const double *Ws = Wb[p], *gk = gkb[p];
+#pragma unroll 2
+        for (int ks = 0; ks < SYRK_KC / 4; ks++) {
+            const int k = 4 * ks + (lane & 3), col = lane >> 2;
+            const double *row = Ws + k * SYRK_LD + col;
+            const double g = gk[k];
+            const double aA = g * row[8 * tmA], aB = g * row[8 * tmB];
+#pragma unroll
+            for (int j = 0; j < 11; j++) { const int tn = tmA + j; if (tn <= 10) dmma884(accA[j], aA, row[8 * tn]); }
+#pragma unroll
+            for (int j = 0; j < 6; j++) { const int tn = tmB + j; if (tn <= 10) dmma884(accB[j], aB, row[8 * tn]); }      // (register arrays want compile-time indices: the operand is fetched again)
+        }
+        __syncthreads();
+    }
+    // epilogue: lane l holds rows 8 tm + l/4, columns 8 tn + 2 (l%4) + {0, 1}
+    const int mr = lane >> 2, n0 = 2 * (lane & 3);
+    auto emit = [&](int tm, int tn, const double *v) {
+        const int R = 8 * tm + mr, C = 8 * tn + n0;
+        if (tn == 10) { if (n0 == 0) tv[R] = v[0]; return; }
+        if (tn > tm) { T[R * VSUB + C] = v[0]; T[R * VSUB + C + 1] = v[1]; T[C * VSUB + R] = v[0]; T[(C + 1) * VSUB + R] = v[1]; return; }
+        if (C >= R) { T[R * VSUB + C] = v[0]; T[C * VSUB + R] = v[0]; }
+        if (C + 1 >= R) { T[R * VSUB + C + 1] = v[1]; T[(C + 1) * VSUB + R] = v[1]; }
+    };
+#pragma unroll
+    for (int j = 0; j < 11; j++) if (tmA + j <= 10) emit(tmA, tmA + j, accA[j]);
+#pragma unroll
+    for (int j = 0; j < 6; j++) if (tmB + j <= 10) emit(tmB, tmB + j, accB[j]);
+#endif
+}
+
+}  // namespace viwb

@@ -72,7 +72,7 @@ VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, d
     int w = 0, fi = 0;
     if (on) {
         w = bd.vis_win[f];
-        if (mode == MODE_SOLVE && bd.work[w].status != ST_RUNNING) on = false;
+        if (mode == MODE_SOLVE && (bd.work[w].status != ST_RUNNING || bd.meta[w].fused)) on = false;      // fused windows: lin_vis_lm (kernels_fused.cuh)
     }
     if (on) {
         fi = bd.vis_fi[f];
@@ -129,7 +129,7 @@ VIWB_D void lm_reduce_body(const BatchDev &bd, int bx, int tid, int nt, int mode
     if (k >= bd.nlm_total) return;
     const int w = bd.lm_win[k];
     const WinWork &ww = bd.work[w];
-    if (mode == MODE_SOLVE && ww.status != ST_RUNNING) return;
+    if (mode == MODE_SOLVE && (ww.status != ST_RUNNING || bd.meta[w].fused)) return;
     const int f0 = bd.lm_fptr[k], f1 = bd.lm_fptr[k + 1];
     double *W = bd.lm_W + (size_t)k * VSUB;
     const bool skip = (mode == MODE_MARG) && (f0 == f1 || bd.vis_fi[f0] != 0 || bd.meta[w].margin_flag != 0);

@@ -6,7 +6,8 @@
 // The dropped landmark block is diagonal, so it is eliminated exactly (Schur sum T0 = sum w w^T / a); the remaining
 // dropped block (pose 0 + speed-bias 0, or pose 9) goes through the reference's eigen pseudo-inverse (eps 1e-8),
 // and the kept n x n system through a parallel cyclic Jacobi eigen-decomposition in shared memory
-// (stands in for Eigen::SelfAdjointEigenSolver) to produce J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b.
+// (stands in for Eigen::SelfAdjointEigenSolver) to produce J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b.  The whole system lives in
+// shared memory over the compact (kept | dropped) dimensions: nothing but the prior itself is written to HBM.
 #pragma once
 #include "kernels_lin.cuh"
 #include "kernels_solve.cuh"
@@ -45,151 +46,112 @@ VIWB_D void reanchor_block(const BatchDev &bd, int bx, int by, int tid, int nt, 
     for (int k = 0; k < m.nlm; k++) st[SFIX + k] = 1.0 / (1.0 / st[SFIX + k]);   // setDepth(1/x), getDepthVector(1/depth)
 }
 
-// Symmetric eigen-decomposition in shared memory: Householder tridiagonalisation + implicit QL with eigenvector
-// accumulation (the EISPACK tred2 / tql2 pair, the algorithm family Eigen::SelfAdjointEigenSolver uses), with the
-// O(n^2)-per-step inner loops spread over the block and the O(n) scalar recurrences kept on thread 0.
-// V (n x n, leading dimension ld): in = symmetric matrix (lower triangle read), out = eigenvectors in columns.
-// d (n): eigenvalues (unsorted).  e (n), cs (2n), sc (8): scratch.
-VIWB_D double blk_reduce_small(double v, int tid, int nt, double *red) {     // sum over the block via a short tree
-    return block_sum(v, tid, nt, red);
+// Symmetric eigen-decomposition in shared memory by the parallel cyclic Jacobi method (stands in for Eigen::SelfAdjointEigenSolver,
+// marginalization_factor.cpp:282,294): every round rotates n/2 disjoint index pairs (round-robin tournament order, n - 1 rounds per
+// sweep), so the whole block works on every round -- no serial QL rotation chain.  Per round: (1) one thread per pair computes its
+// rotation from a_pp, a_qq, a_pq; (2) every 2x2 block (pair P x pair Q, P <= Q) of A' = J^T A J is computed by ONE thread from the same
+// 2x2 block of A (rows and columns rotate together, so the update is in place without an intermediate copy) and mirrored, and every
+// (row, pair) item of V' = V J likewise.  Two barriers per round; fixed order, deterministic.  Sweeps stop when the off-diagonal
+// Frobenius norm is below 1e-14 of the diagonal's (or after 16 sweeps).
+// A (n x n, leading dimension lda): in = symmetric matrix (both triangles), out = diagonal holds the eigenvalues.  V (n x n, ldv): out =
+// eigenvectors in columns.  d (n): eigenvalues (unsorted).  rot: 4 * ((n + 1) / 2) doubles of scratch; red: 32 doubles.
+VIWB_HD void jacobi_pair(int m, int r, int k, int &p, int &q) {      // pair k of round r among m (even) players
+    if (k == 0) { p = m - 1; q = r; }
+    else { p = (r + k) % (m - 1); q = (r - k + (m - 1)) % (m - 1); }
 }
-VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *sc, double *red, int n, int ld, int tid, int nt) {
-#define VV(i, j) V[(i) * ld + (j)]
-    // ---- tred2
-    for (int j = tid; j < n; j += nt) d[j] = VV(n - 1, j);
+VIWB_D void sym_eig_jacobi(double *A, int lda, double *V, int ldv, double *d, double *rot, double *red, int n, int tid, int nt) {
+    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; V[i * ldv + j] = (i == j) ? 1.0 : 0.0; }
     VIWB_SYNC();
-    for (int i = n - 1; i > 0; i--) {
-        double part = 0.0;
-        for (int k = tid; k < i; k += nt) part += fabs(d[k]);
-        const double scale = blk_reduce_small(part, tid, nt, red);
-        if (scale == 0.0) {
-            if (tid == 0) e[i] = d[i - 1];
-            VIWB_SYNC();
-            for (int j = tid; j < i; j += nt) { d[j] = VV(i - 1, j); VV(i, j) = 0.0; VV(j, i) = 0.0; }
-            VIWB_SYNC();
-            if (tid == 0) d[i] = 0.0;
-            VIWB_SYNC();
-            continue;
-        }
-        part = 0.0;
-        for (int k = tid; k < i; k += nt) { const double t = d[k] / scale; d[k] = t; part += t * t; }
-        double h = blk_reduce_small(part, tid, nt, red);
-        if (tid == 0) {
-            const double f = d[i - 1];
-            double g = sqrt(h); if (f > 0) g = -g;
-            e[i] = scale * g; h = h - f * g; d[i - 1] = f - g; sc[0] = h;
-        }
-        VIWB_SYNC();
-        h = sc[0];
-        // e[j] = (A d)[j] over the leading i x i block (lower triangle storage); column i keeps the Householder vector
-        for (int j = tid; j < i; j += nt) {
-            double g = 0.0;
-            for (int k = 0; k <= j; k++) g += VV(j, k) * d[k];
-            for (int k = j + 1; k < i; k++) g += VV(k, j) * d[k];
-            cs[j] = g / h;            // e[j] / h, kept in cs until the reduction below is done
-            VV(j, i) = d[j];
-        }
-        VIWB_SYNC();
-        part = 0.0;
-        for (int j = tid; j < i; j += nt) part += cs[j] * d[j];
-        const double f2 = blk_reduce_small(part, tid, nt, red);
-        const double hh = f2 / (h + h);
-        for (int j = tid; j < i; j += nt) e[j] = cs[j] - hh * d[j];
-        VIWB_SYNC();
-        // rank-2 update of the lower triangle: V[k][j] -= d[j] e[k] + e[j] d[k],  j <= k < i
-        for (int k = tid; k < i; k += nt) { const double ek = e[k], dk = d[k]; for (int j = 0; j <= k; j++) VV(k, j) -= d[j] * ek + e[j] * dk; }
-        VIWB_SYNC();
-        for (int j = tid; j < i; j += nt) { cs[j] = VV(i - 1, j); VV(i, j) = 0.0; }
-        VIWB_SYNC();
-        for (int j = tid; j < i; j += nt) d[j] = cs[j];
-        if (tid == 0) d[i] = h;
-        VIWB_SYNC();
-    }
-    // ---- accumulate the transformations
-    for (int i = 0; i < n - 1; i++) {
-        if (tid == 0) { VV(n - 1, i) = VV(i, i); VV(i, i) = 1.0; }
-        VIWB_SYNC();
-        const double h = d[i + 1];
-        if (h != 0.0) {
-            for (int k = tid; k <= i; k += nt) d[k] = VV(k, i + 1) / h;
-            VIWB_SYNC();
-            for (int j = tid; j <= i; j += nt) {
-                double g = 0.0;
-                for (int k = 0; k <= i; k++) g += VV(k, i + 1) * VV(k, j);
-                for (int k = 0; k <= i; k++) VV(k, j) -= g * d[k];
-            }
-            VIWB_SYNC();
-        }
-        for (int k = tid; k <= i; k += nt) VV(k, i + 1) = 0.0;
-        VIWB_SYNC();
-    }
-    for (int j = tid; j < n; j += nt) { d[j] = VV(n - 1, j); VV(n - 1, j) = 0.0; }
-    VIWB_SYNC();
-    if (tid == 0) { VV(n - 1, n - 1) = 1.0; e[0] = 0.0; }
-    VIWB_SYNC();
-    // ---- tql2
-    for (int i = 1 + tid; i < n; i += nt) cs[i - 1] = e[i];
-    VIWB_SYNC();
-    for (int i = tid; i < n - 1; i += nt) e[i] = cs[i];
-    if (tid == 0) { e[n - 1] = 0.0; sc[1] = 0.0 /* f */; sc[2] = 0.0 /* tst1 */; }
-    VIWB_SYNC();
-    const double eps = 2.220446049250313e-16;
-    for (int l = 0; l < n; l++) {
-        if (tid == 0) {
-            const double t = fabs(d[l]) + fabs(e[l]); if (t > sc[2]) sc[2] = t;
-            int m = l; while (m < n) { if (fabs(e[m]) <= eps * sc[2]) break; m++; }
-            sc[3] = (double)m;
-        }
-        VIWB_SYNC();
-        const int m = (int)sc[3];
-        if (m > l) {
-            for (int iter = 0; iter < 200; iter++) {
-                if (tid == 0) {
-                    double g = d[l], p = (d[l + 1] - g) / (2.0 * e[l]), r = sqrt(p * p + 1.0);
-                    if (p < 0) r = -r;
-                    d[l] = e[l] / (p + r); d[l + 1] = e[l] * (p + r);
-                    const double dl1 = d[l + 1]; double h = g - d[l];
-                    for (int i = l + 2; i < n; i++) d[i] -= h;
-                    sc[1] += h;
-                    p = d[m];
-                    double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0; const double el1 = e[l + 1];
-                    // the rotation chain is the serial critical path of the whole decomposition: operands of the next link are
-                    // fetched before the current link's sqrt / reciprocal, and one reciprocal replaces two divisions
-                    double ei = e[m - 1], di = d[m - 1];
-                    for (int i = m - 1; i >= l; i--) {
-                        const double ein = i > l ? e[i - 1] : 0.0, din = i > l ? d[i - 1] : 0.0;
-                        c3 = c2; c2 = c; s2 = s;
-                        g = c * ei; h = c * p;
-                        const double q2 = p * p + ei * ei, rinv = q2 > 0.0 ? rsqrt(q2) : 0.0;      // r = q2 * rsqrt(q2): one special-function chain, no division
-                        r = q2 * rinv;
-                        e[i + 1] = s * r; s = ei * rinv; c = p * rinv;
-                        p = c * di - s * g; d[i + 1] = h + s * (c * g + s * di);
-                        cs[2 * i] = c; cs[2 * i + 1] = s;
-                        ei = ein; di = din;
+    if (n == 1) { if (tid == 0) d[0] = A[0]; VIWB_SYNC(); return; }
+    const int m = n + (n & 1), np = m / 2;      // an odd n gets a bye: pairs with the phantom index m - 1 do not rotate
+    for (int sweep = 0; sweep < 16; sweep++) {
+        // convergence test: off(A)^2 <= (1e-15)^2 * diag(A)^2
+        double off = 0.0, dg = 0.0;
+        for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; const double v = A[i * lda + j]; if (i == j) dg += v * v; else off += v * v; }
+        { double v2[2] = {off, dg}; block_sum_n<2>(v2, tid, nt, red); off = v2[0]; dg = v2[1]; }
+        if (off <= 1e-28 * dg || off == 0.0) break;
+        for (int r = 0; r < m - 1; r++) {
+            for (int k = tid; k < np; k += nt) {
+                int p, q; jacobi_pair(m, r, k, p, q);
+                double c = 1.0, sn = 0.0;
+                if (p < n && q < n) {
+                    const double apq = A[p * lda + q];
+                    if (apq != 0.0) {
+                        const double app = A[p * lda + p], aqq = A[q * lda + q];
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        if (isfinite(t)) { c = 1.0 / sqrt(1.0 + t * t); sn = t * c; }      // |tau| overflowing: the element is negligible, no rotation
                     }
-                    p = -s * s2 * c3 * el1 * e[l] / dl1;
-                    e[l] = s * p; d[l] = c * p;
-                    sc[4] = (fabs(e[l]) > eps * sc[2]) ? 1.0 : 0.0;
                 }
-                VIWB_SYNC();
-                for (int k = tid; k < n; k += nt)
-                    for (int i = m - 1; i >= l; i--) { const double c = cs[2 * i], s = cs[2 * i + 1], h = VV(k, i + 1); VV(k, i + 1) = s * VV(k, i) + c * h; VV(k, i) = c * VV(k, i) - s * h; }
-                VIWB_SYNC();
-                if (sc[4] == 0.0) break;
-                VIWB_SYNC();
+                rot[4 * k] = c; rot[4 * k + 1] = sn; rot[4 * k + 2] = (double)p; rot[4 * k + 3] = (double)q;
             }
+            VIWB_SYNC();
+            const int nblk = np * (np + 1) / 2, nv = n * np;
+            for (int e = tid; e < nblk + nv; e += nt) {
+                if (e < nblk) {
+                    int P, Q; sym_unrank(e, Q, P);          // P <= Q
+                    const int p0 = (int)rot[4 * P + 2], p1 = (int)rot[4 * P + 3], q0 = (int)rot[4 * Q + 2], q1 = (int)rot[4 * Q + 3];
+                    if (p0 >= n || p1 >= n || q0 >= n || q1 >= n) {
+                        // a pair with the phantom index: its real member keeps its row / column, which still rotates with the other pair
+                        const int pr = p0 < n ? p0 : p1, qr = q0 < n ? q0 : q1;
+                        if (P == Q) continue;
+                        if (pr >= n || qr >= n) continue;
+                        if (p0 < n && p1 < n) {            // P rotates, Q is the bye: column qr, rows p0 / p1
+                            const double c = rot[4 * P], s = rot[4 * P + 1], b0 = A[p0 * lda + qr], b1 = A[p1 * lda + qr];
+                            const double n0 = c * b0 - s * b1, n1 = s * b0 + c * b1;
+                            A[p0 * lda + qr] = n0; A[qr * lda + p0] = n0; A[p1 * lda + qr] = n1; A[qr * lda + p1] = n1;
+                        } else if (q0 < n && q1 < n) {     // Q rotates, P is the bye: row pr, columns q0 / q1
+                            const double c = rot[4 * Q], s = rot[4 * Q + 1], b0 = A[pr * lda + q0], b1 = A[pr * lda + q1];
+                            const double n0 = c * b0 - s * b1, n1 = s * b0 + c * b1;
+                            A[pr * lda + q0] = n0; A[q0 * lda + pr] = n0; A[pr * lda + q1] = n1; A[q1 * lda + pr] = n1;
+                        }
+                        continue;
+                    }
+                    const double cP = rot[4 * P], sP = rot[4 * P + 1], cQ = rot[4 * Q], sQ = rot[4 * Q + 1];
+                    if (P == Q) {
+                        const double app = A[p0 * lda + p0], aqq = A[p1 * lda + p1], apq = A[p0 * lda + p1];
+                        // J^T [app apq; apq aqq] J with the rotation that annihilates apq
+                        const double t00 = cP * app - sP * apq, t01 = cP * apq - sP * aqq, t10 = sP * app + cP * apq, t11 = sP * apq + cP * aqq;
+                        A[p0 * lda + p0] = cP * t00 - sP * t01; A[p1 * lda + p1] = sP * t10 + cP * t11;
+                        A[p0 * lda + p1] = 0.0; A[p1 * lda + p0] = 0.0;
+                    } else {
+                        const double b00 = A[p0 * lda + q0], b01 = A[p0 * lda + q1], b10 = A[p1 * lda + q0], b11 = A[p1 * lda + q1];
+                        const double t00 = cP * b00 - sP * b10, t01 = cP * b01 - sP * b11, t10 = sP * b00 + cP * b10, t11 = sP * b01 + cP * b11;
+                        const double n00 = cQ * t00 - sQ * t01, n01 = sQ * t00 + cQ * t01, n10 = cQ * t10 - sQ * t11, n11 = sQ * t10 + cQ * t11;
+                        A[p0 * lda + q0] = n00; A[p0 * lda + q1] = n01; A[p1 * lda + q0] = n10; A[p1 * lda + q1] = n11;
+                        A[q0 * lda + p0] = n00; A[q1 * lda + p0] = n01; A[q0 * lda + p1] = n10; A[q1 * lda + p1] = n11;
+                    }
+                } else {
+                    const int it = e - nblk, i = it / np, Q = it - i * np;
+                    const int q0 = (int)rot[4 * Q + 2], q1 = (int)rot[4 * Q + 3];
+                    if (q0 >= n || q1 >= n) continue;
+                    const double c = rot[4 * Q], s = rot[4 * Q + 1], v0 = V[i * ldv + q0], v1 = V[i * ldv + q1];
+                    V[i * ldv + q0] = c * v0 - s * v1; V[i * ldv + q1] = s * v0 + c * v1;
+                }
+            }
+            VIWB_SYNC();
         }
-        if (tid == 0) { d[l] = d[l] + sc[1]; e[l] = 0.0; }
-        VIWB_SYNC();
     }
-#undef VV
+    for (int i = tid; i < n; i += nt) d[i] = A[i * lda + i];
+    VIWB_SYNC();
 }
 
 VIWB_HD int vsub_to_mlay(int p) { return p < 66 ? p : p < 72 ? 165 + (p - 66) : p < 78 ? 171 + (p - 72) : 191; }   // td -> blk_moff(BLK_TD) = 191
 VIWB_HD int marg_cap(int nmax) { return nmax < 16 ? 16 : (nmax > 100 ? 100 : nmax); }
-// eigenvector matrix c x (c|1), dropped-block matrix and its pseudo-inverse (<= 16 x 16 each), Arm*Ainv (c x 15), five vectors of <= 2c,
-// reduction scratch, scalars, two index lists: 73 KB for the 82-dimensional prior of the stereo+IMU configuration -> three blocks per SM
-VIWB_HD size_t marg_smem_doubles(int nt, int nmax) { (void)nt; const int c = marg_cap(nmax); return (size_t)c * (c | 1) + 2 * 256 + (size_t)c * 15 + (size_t)5 * c + 32 + 16 + 108 + 8; }
+enum { MARG_MD = 15 };      // dimension of the dropped fixed block: pose 0 + speed-bias 0 (MARGIN_OLD) or pose 9 (6, MARGIN_SECOND_NEW)
+// shared memory: the compact system (c + 15)^2 [kept dims first, then the dropped ones], the eigenvectors c^2, Arm*Amm^-1 (c x 15), the dropped
+// block and its eigenvectors / pseudo-inverse (3 x 15^2), right-hand side, eigenvalues, rotation scratch, reductions, index maps: 134 KB for
+// the 82-dimensional prior of the stereo+IMU window -> one 512-thread block per SM
+VIWB_HD size_t marg_smem_doubles(int nt, int nmax) {
+    (void)nt; const int c = marg_cap(nmax), N = c + MARG_MD;
+    return (size_t)N * N + (size_t)c * c + (size_t)c * MARG_MD + 3 * 256 + (size_t)N + (size_t)c + 2 * (size_t)(c + 2) + 3 * 32 + 16 + (MLAY + 1) / 2 + 1 + (size_t)(N + 1) / 2 + 1;
+}
+struct CompactTarget {     // marginalisation: dense symmetric matrix over the compact (kept | dropped) dimensions, in shared memory
+    double *M, *g; int ld; const unsigned char *flags; const int *cmap;
+    VIWB_DM int col(int blk, int k) const { return ((flags[blk] & 1u) && k < blk_msize(blk)) ? cmap[blk_moff(blk) + k] : -1; }
+    VIWB_DM void add(int i, int j, double v) const { M[i * ld + j] += v; if (i != j) M[j * ld + i] += v; }
+    VIWB_DM void addg(int i, double v) const { g[i] += v; }
+};
 
 VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)mode;
@@ -197,49 +159,37 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     const WinMeta &m = bd.meta[w];
     WinWork &ww = bd.work[w];
     if (m.margin_flag < 0) return;
-    const int LDM = MAXPRI + 16;
-    double *M = bd.marg_A + (size_t)w * LDM * LDM;
-    double *b = bd.gfix + (size_t)w * (TFIX + 8);
     const double *T = bd.Tvis + (size_t)w * VSUB * VSUB, *tv = bd.tvec + (size_t)w * VSUB;
     int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
     const double eps = 1e-8;   // marginalization_factor.h:81
     // smem carve
-    const int cap = marg_cap(bd.marg_nmax);
-    double *Vn = smem, *Amm = Vn + (size_t)cap * (cap | 1), *Ainv = Amm + 256, *Tm = Ainv + 256;
-    double *bn = Tm + (size_t)cap * 15, *cs = bn + cap, *ev = cs + 2 * cap, *ee = ev + cap, *red = ee + cap, *bc = red + 32;
-    int *keep = (int *)(bc + 16), *dl = keep + 216;
-    double *An = Vn;
-    // ---- dense system of the marginalisation factors over the marginalisation layout
-    for (int e = tid; e < MLAY * MLAY; e += nt) M[(size_t)(e / MLAY) * LDM + (e % MLAY)] = 0.0;
-    for (int i = tid; i < TFIX + 8; i += nt) b[i] = 0.0;
-    VIWB_SYNC();
-    { DenseTarget t; t.M = M; t.g = b; t.ld = LDM; t.flags = m.flags; assemble_into(t, bd, w, MODE_MARG, tid, nt, keep); }      // keep[] is filled only afterwards
-    VIWB_SYNC();
-    // ---- eliminate the dropped landmarks: M -= scatter(T0), b -= scatter(tvec0)   (MARGIN_OLD only)
-    if (m.margin_flag == 0) {
-        for (int e = tid; e < 79 * 79; e += nt) { const int p = e / 79, q = e % 79; M[(size_t)vsub_to_mlay(p) * LDM + vsub_to_mlay(q)] -= T[p * VSUB + q]; }
-        for (int p = tid; p < 79; p += nt) b[vsub_to_mlay(p)] -= tv[p];
-    }
-    VIWB_SYNC();
-    // ---- dropped / kept dimension lists (marginalisation layout)
+    const int cap = marg_cap(bd.marg_nmax), NC = cap + MARG_MD;
+    double *Mc = smem, *Vn = Mc + (size_t)NC * NC, *Tm = Vn + (size_t)cap * cap, *Amm = Tm + (size_t)cap * MARG_MD, *Vmm = Amm + 256, *Ainv = Vmm + 256;
+    double *bc_ = Ainv + 256, *ev = bc_ + NC, *rot = ev + cap, *red = rot + 2 * (cap + 2), *bc = red + 3 * 32;
+    int *cmap = (int *)(bc + 16), *klist = cmap + ((MLAY + 1) / 2) * 2 + 2;      // klist: marginalisation-layout index of every compact dimension
+    // ---- dropped / kept dimension lists (marginalisation layout -> compact index: kept dims 0..n-1, dropped n..n+md-1)
     if (tid == 0) {
         int md = 0, n = 0, nb = 0;
         unsigned dropped = 0;
+        for (int k = 0; k < MLAY; k++) cmap[k] = -1;
         for (int k = 0; k < SFIX; k++) bd.marg_x0[(size_t)w * SFIX + k] = 0.0;
-        if (m.margin_flag == 0) { for (int k = 0; k < 6; k++) dl[md++] = k; for (int k = 0; k < 9; k++) dl[md++] = 66 + k; dropped = (1u << 0) | (1u << BLK_SB0); }
-        else { for (int k = 0; k < 6; k++) dl[md++] = 54 + k; dropped = (1u << 9); }
-        // a dropped block that no factor references contributes nothing (its rows are zero); keep md as is
+        if (m.margin_flag == 0) dropped = (1u << 0) | (1u << BLK_SB0); else dropped = (1u << 9);
         for (int bq = 0; bq < NB; bq++) {
             if (!(m.flags[bq] & 4u) || ((dropped >> bq) & 1u)) continue;      // bit 2 of flags = seen by a marginalisation factor
             int nid = bq;
             if (m.margin_flag == 0) { if ((bq >= 1 && bq <= 10) || (bq >= 12 && bq <= 21)) nid = bq - 1; }
             else { if (bq == 10 || bq == 21) nid = bq - 1; }
             hdr[3 + nb] = nid; hdr[3 + NB + nb] = n; nb++;
-            for (int k = 0; k < blk_msize(bq); k++) keep[n++] = blk_moff(bq) + k;
+            for (int k = 0; k < blk_msize(bq); k++) { if (n < cap) { cmap[blk_moff(bq) + k] = n; klist[n] = blk_moff(bq) + k; } n++; }
             // linearisation point of the kept block, stored under its new id (keep_block_data + addr_shift)
             const double *src = bd.x_cur + m.state_off + blk_off(bq);
             double *dst = bd.marg_x0 + (size_t)w * SFIX + blk_off(nid);
             for (int k = 0; k < blk_size(bq); k++) dst[k] = src[k];
+        }
+        // a dropped block that no factor references contributes nothing (its rows stay zero, its eigenvalues fall under eps); md as the reference counts it
+        if (n <= cap) {
+            if (m.margin_flag == 0) { for (int k = 0; k < 6; k++) { cmap[k] = n + md; md++; } for (int k = 0; k < 9; k++) { cmap[66 + k] = n + md; md++; } }
+            else { for (int k = 0; k < 6; k++) { cmap[54 + k] = n + md; md++; } }
         }
         hdr[0] = 1; hdr[1] = n; hdr[2] = nb;
         bc[2] = (double)md; bc[3] = (double)n;
@@ -247,15 +197,27 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     VIWB_SYNC();
     const int md = (int)bc[2], n = (int)bc[3];
     if (n > cap) { if (tid == 0) { ww.marg_status = -1; hdr[0] = 0; } return; }
+    const int N = n + md;
+    // ---- dense system of the marginalisation factors over the compact dimensions
+    for (int e = tid; e < N * N; e += nt) Mc[e] = 0.0;
+    for (int i = tid; i < N; i += nt) bc_[i] = 0.0;
+    VIWB_SYNC();
+    { CompactTarget t; t.M = Mc; t.g = bc_; t.ld = N; t.flags = m.flags; t.cmap = cmap; assemble_into(t, bd, w, MODE_MARG, tid, nt, (int *)Vn); }      // Vn: scratch until the eigenvectors
+    VIWB_SYNC();
+    // ---- eliminate the dropped landmarks: M -= scatter(T0), b -= scatter(tvec0)   (MARGIN_OLD only)
+    if (m.margin_flag == 0) {
+        for (int e = tid; e < 79 * 79; e += nt) { const int p = e / 79, q = e % 79, ci = cmap[vsub_to_mlay(p)], cj = cmap[vsub_to_mlay(q)]; if (ci >= 0 && cj >= 0) Mc[ci * N + cj] -= T[p * VSUB + q]; }
+        for (int p = tid; p < 79; p += nt) { const int ci = cmap[vsub_to_mlay(p)]; if (ci >= 0) bc_[ci] -= tv[p]; }
+    }
+    VIWB_SYNC();
     // ---- pseudo-inverse of the dropped fixed block (marginalization_factor.cpp:282-287)
-    for (int e = tid; e < md * md; e += nt) { const int i = e / md, j = e % md; Amm[e] = 0.5 * (M[(size_t)dl[i] * LDM + dl[j]] + M[(size_t)dl[j] * LDM + dl[i]]); }
+    for (int e = tid; e < md * md; e += nt) { const int i = e / md, j = e % md; Amm[e] = 0.5 * (Mc[(n + i) * N + n + j] + Mc[(n + j) * N + n + i]); }
     VIWB_SYNC();
-    sym_eig_block(Amm, ev, ee, cs, bc + 4, red, md, md, tid, nt);      // eigenvalues -> ev, eigenvectors -> columns of Amm
-    VIWB_SYNC();
+    sym_eig_jacobi(Amm, md, Vmm, md, ev, rot, red, md, tid, nt);      // eigenvalues -> ev, eigenvectors -> columns of Vmm
     for (int e = tid; e < md * md; e += nt) {
         const int i = e / md, j = e % md;
         double sacc = 0.0;
-        for (int k = 0; k < md; k++) { const double l = ev[k]; if (l > eps) sacc += Amm[i * md + k] * Amm[j * md + k] / l; }
+        for (int k = 0; k < md; k++) { const double l = ev[k]; if (l > eps) sacc += Vmm[i * md + k] * Vmm[j * md + k] / l; }
         Ainv[e] = sacc;
     }
     VIWB_SYNC();
@@ -263,36 +225,39 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     for (int e = tid; e < n * md; e += nt) {
         const int i = e / md, j = e % md;
         double sacc = 0.0;
-        for (int k = 0; k < md; k++) sacc += M[(size_t)keep[i] * LDM + dl[k]] * Ainv[k * md + j];
+        for (int k = 0; k < md; k++) sacc += Mc[i * N + n + k] * Ainv[k * md + j];
         Tm[e] = sacc;
     }
     VIWB_SYNC();
-    // A = Arr - Arm Amm^-1 Amr ; b = brr - Arm Amm^-1 bmm
-    const int ld = n | 1;
-    for (int e = tid; e < n * n; e += nt) {
-        const int i = e / n, j = e % n;
-        double sacc = M[(size_t)keep[i] * LDM + keep[j]];
-        for (int k = 0; k < md; k++) sacc -= Tm[i * md + k] * M[(size_t)dl[k] * LDM + keep[j]];
-        An[i * ld + j] = sacc;
+    // A = Arr - Arm Amm^-1 Amr (in place: the leading n x n block, leading dimension N) ; b = brr - Arm Amm^-1 bmm.
+    // SelfAdjointEigenSolver reads the lower triangle: entry (i, j) and its mirror both take the lower-triangle value
+    for (int e = tid; e < n * (n + 1) / 2; e += nt) {
+        int i, j; sym_unrank(e, i, j);          // j <= i
+        double sacc = Mc[i * N + j];
+        for (int k = 0; k < md; k++) sacc -= Tm[i * md + k] * Mc[(n + k) * N + j];
+        Mc[i * N + j] = sacc;
     }
     for (int i = tid; i < n; i += nt) {
-        double sacc = b[keep[i]];
-        for (int k = 0; k < md; k++) sacc -= Tm[i * md + k] * b[dl[k]];
-        bn[i] = sacc;
+        double sacc = bc_[i];
+        for (int k = 0; k < md; k++) sacc -= Tm[i * md + k] * bc_[n + k];
+        ev[i] = sacc;          // parked in ev until the mirror pass is done (bc_[n + k] is still read by other threads)
     }
     VIWB_SYNC();
-    // SelfAdjointEigenSolver reads the lower triangle
-    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e % n; if (j > i) An[i * ld + j] = An[j * ld + i]; }
+    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; if (j > i) Mc[i * N + j] = Mc[j * N + i]; }
+    for (int i = tid; i < n; i += nt) bc_[i] = ev[i];
     VIWB_SYNC();
-    sym_eig_block(Vn, ev, ee, cs, bc + 4, red, n, ld, tid, nt);
-    VIWB_SYNC();
+    sym_eig_jacobi(Mc, N, Vn, n, ev, rot, red, n, tid, nt);
     // J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b   (marginalization_factor.cpp:298-306)
     double *Jout = bd.marg_J + (size_t)w * bd.marg_nmax * bd.marg_nmax, *rout = bd.marg_r + (size_t)w * MAXPRI;
-    for (int i = tid; i < n; i += nt) {
+    for (int e = tid; e < n * n; e += nt) {
+        const int i = e / n, k = e - i * n;
         const double l = ev[i];
-        const double S = l > eps ? l : 0.0, Sinv = l > eps ? 1.0 / l : 0.0, ss = sqrt(S), si = sqrt(Sinv);
+        Jout[(size_t)i * n + k] = (l > eps ? sqrt(l) : 0.0) * Vn[k * n + i];
+    }
+    for (int i = tid; i < n; i += nt) {
+        const double l = ev[i], si = l > eps ? sqrt(1.0 / l) : 0.0;
         double vb = 0.0;
-        for (int k = 0; k < n; k++) { Jout[(size_t)i * n + k] = ss * Vn[k * ld + i]; vb += Vn[k * ld + i] * bn[k]; }
+        for (int k = 0; k < n; k++) vb += Vn[k * n + i] * bc_[k];
         rout[i] = si * vb;
     }
     if (tid == 0) ww.marg_status = 0;

@@ -33,6 +33,10 @@ VIWB_HD int blk_msize(int b) { int s = blk_size(b); return s == 7 ? 6 : s; }
 VIWB_HD int blk_voff(int b) { return b < 11 ? 6 * b : b == BLK_EX0 ? 66 : b == BLK_EX1 ? 72 : b == BLK_TD ? 78 : -1; }
 
 enum { ASM_STRIDE = 108, ASM_CHUNK = 256, ITEM_FRAME = 0, ITEM_PAIR = 1, ITEM_COMMON = 2 };
+// Fused path (solver linearisation of batches whose windows keep ex0 / ex1 / td constant): lin_vis_lm evaluates the factors of whole landmarks per
+// block and leaves one X record per two-frame factor, X = [A | B | r] (2 x 13, row stride 14), at the factor's position in FRAME-PAIR order; asm_pairs
+// turns the records of one (host, observer) pair into G = sum X^T X (13 x 13 inside three 8 x 8 FP64 tensor-core tiles) per chunk of PAIR_CHUNK records.
+enum { XREC = 28, XROW = 14, PAIR_CHUNK = 32, PAIR_OUT = 192, LMB_FACTORS = 128 };
 struct AsmItem { int kind, win, a, b, lo, hi, phase, has_common; };
 
 struct PriorDev {       // one per window that has a valid prior
@@ -55,6 +59,10 @@ struct WinMeta {        // read-only during a solve
     int item_off, nitems, nphases, list_off;     // assembly items of the solver linearisation (kernels_asm.cuh); list entries are window-local
     int mitem_off, nmitems, nmphases, mlist_off; // assembly items of the marginalisation linearisation (factors hosted in frame 0)
     int has_common;                     // any of ex0 / ex1 / td is an active column (solver); marginalisation always counts them
+    int xrec_off, nxrec;                // fused path: first X record of the window, number of two-frame factors
+    int pitem_off, npitems;             // fused path: pair items (chunks of one frame pair's records), head item of a pair has phase 0
+    int lmb_off, nlmb;                  // fused path: landmark blocks (whole landmarks, <= LMB_FACTORS factors) of lin_vis_lm
+    int fused;                          // 1: this window's solver linearisation takes the fused path (constant ex0 / ex1 / td, regular factor table)
     short tcol[NB];     // compact column of fixed block b, -1 if constant / absent / unreferenced
     short efirst[TFIX]; // envelope of the reduced system: first structurally non-zero column of compact row i (<= i)
     int esize;          // number of stored entries = sum_i (i - efirst[i] + 1)
@@ -90,6 +98,15 @@ struct BatchDev {       // passed by value to every kernel
     int env_max;            // largest esize over the batch (sizes the solve kernel's shared memory)
     int marg_nmax;          // largest prior dimension any window of the batch produces (sizes the eigen-solver's shared memory)
     int rec_stride_solve;   // VREC_COMPACT if no window of the batch has ex0/ex1/td active, else VREC (marginalisation always uses VREC)
+    int n_unfused;          // windows whose solver linearisation runs lin_vis + lm_reduce + asm_items (the others: lin_vis_lm + asm_pairs, WinMeta.fused)
+    int nlmb_total, npitems_total, nxrec_total;
+    const int *vis_pos;             // [nvis_total] window-local position of the factor's X record in frame-pair order, -1 for one-frame factors
+    const unsigned char *vis_dup;   // [nvis_total] 0: the factor alone observes its landmark from frame j; 1: first of two such factors (adds the next one's part); 2: second (adds nothing)
+    const int *lmb_ptr;             // [nlmb_total][2] global landmark range [first, end) of each landmark block
+    const int *lmb_win;             // [nlmb_total] window of the block
+    double *xrec;                   // [nxrec_total][XREC]
+    const struct AsmItem *pitems;   // [npitems_total] kind = ITEM_PAIR, lo / hi = record range relative to meta.xrec_off
+    double *pair_out;               // [npitems_total][PAIR_OUT] tile (0,0), (0,1), (1,1) of G in mma.m8n8k4 accumulator order
     const WinMeta *meta;
     WinWork *work;
     const PriorDev *prior;
@@ -125,7 +142,6 @@ struct BatchDev {       // passed by value to every kernel
     // marginalisation outputs
     double *marg_J, *marg_r, *marg_x0;  // [B][marg_nmax^2] (n x n, row stride n, at the head of the slot), [B][MAXPRI], [B][SFIX]
     int *marg_hdr;                      // [B][2 + 2*NB]: valid, n, nb, block_id[], block_idx[]
-    double *marg_A;                     // [B][MAXPRI+16][MAXPRI+16] scratch for the dense system
 };
 
 VIWB_HD int vec_off(const BatchDev &bd, int w) { return w * TFIX + bd.meta[w].lm_off; }

@@ -9,6 +9,7 @@
 // the `not gpu` tests (tests/emu); that build is never part of libviwb.so.
 #include "../../include/viwb.h"
 #include "kernels_marg.cuh"
+#include "kernels_fused.cuh"
 #include "kernels_lk.cuh"
 #include "kernels_preint.cuh"
 #include "kernels_feat.cuh"
@@ -104,8 +105,14 @@ DEF_KERNEL2(syrk, 256, SYRK_MINB)
 #define SOLVE_NT 384
 #endif
 DEF_KERNEL2(solve, SOLVE_NT, 2)
+DEF_KERNEL2(lin_vis_lm, LMB_FACTORS, 3)
+DEF_KERNEL(asm_pairs, 128)
+DEF_KERNEL2(syrk_mma, SYRK_NT, 4)
 DEF_KERNEL(reanchor, 32)
-DEF_KERNEL2(marg, 256, 3)
+#ifndef MARG_NT
+#define MARG_NT 512
+#endif
+DEF_KERNEL2(marg, MARG_NT, 1)
 DEF_KERNEL(outlier, 128)
 #define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) \
     do { if ((gx) > 0 && (gy) > 0) { g_prof.begin((mode) == 1 ? #name "_marg" : #name, stream); name##_kernel<<<dim3((gx), (gy)), (nt), (smem_bytes), (stream)>>>(bd, mode); g_prof.end(stream); } } while (0)
@@ -118,6 +125,7 @@ struct Arena { char *dev = nullptr; size_t dev_cap = 0; char *host = nullptr; si
 static void arena_release(Arena &a) { if (a.dev) dev_free(a.dev); if (a.host) host_free(a.host); a = Arena(); }
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static bool g_timing = getenv("VIWB_TIMING") != nullptr;
+static bool g_syrk_dfma = getenv("VIWB_SYRK_DFMA") != nullptr;      // measurement aid: the 4x4 register-tiled DFMA SYRK instead of the DMMA one (profiles/: both builds of the Schur GEMM)
 struct viwb_context {
     int device;
     stream_t stream;        // the stream all work of this context is issued on (own_stream unless viwb_set_stream gave another)
@@ -212,6 +220,8 @@ struct WinLow {
     int err; bool grouped, has_prior;
     int nlist_s, nitems_s, nph_s, nlist_m, nitems_m, nph_m;
     int prior_n_out;
+    bool regular;               // fused path possible: grouped table, <= LMB_FACTORS factors per landmark, at most two factors per (landmark, observer), consecutive
+    int nlmb, npitems, nxrec;   // landmark blocks of lin_vis_lm, pair chunks of asm_pairs, two-frame factors
 };
 static int chunk_count(int n) { return (n + ASM_CHUNK - 1) / ASM_CHUNK; }
 
@@ -337,6 +347,27 @@ static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, i
         lo.nlist_m += ncommon0; lo.nitems_m += chunk_count(ncommon0); lo.nph_m = std::max(lo.nph_m, chunk_count(ncommon0));
     }
     m.nitems = lo.nitems_s; m.nphases = lo.nph_s; m.nmitems = lo.nitems_m; m.nmphases = lo.nph_m;
+    // fused-path plan (kernels_fused.cuh): sizes only; lower_fill builds the tables
+    lo.regular = lo.grouped && !m.has_common;
+    lo.nxrec = 0; lo.npitems = 0; lo.nlmb = 0;
+    for (int a = 0; a < NFR * NFR; a++) { lo.nxrec += pcnt[a]; lo.npitems += (pcnt[a] + PAIR_CHUNK - 1) / PAIR_CHUNK; }
+    if (lo.regular) {
+        int in_blk = 0, i = 0; bool open = false;
+        for (int k = 0; k < p.num_landmarks && lo.regular; k++) {
+            int cnt = 0, seenj[NFR], ndup[NFR];
+            for (int q = 0; q < NFR; q++) { seenj[q] = -2; ndup[q] = 0; }
+            for (; i < p.num_vis && p.vis_landmark[i] == k; i++, cnt++) {
+                if (p.vis_type[i] == 2) continue;
+                const int fj = p.vis_frame_j[i];
+                if (ndup[fj] == 0) { ndup[fj] = 1; seenj[fj] = i; }
+                else if (ndup[fj] == 1 && seenj[fj] == i - 1) ndup[fj] = 2;
+                else lo.regular = false;
+            }
+            if (cnt > LMB_FACTORS) lo.regular = false;
+            if (!open || in_blk + cnt > LMB_FACTORS) { lo.nlmb++; in_blk = 0; open = true; }
+            in_blk += cnt;
+        }
+    }
 }
 
 // ---- phase 3: fill this window's slices of the (pinned) staging arrays; every offset is final
@@ -345,6 +376,7 @@ struct HostArrays {
     AsmItem *items; int *asm_list; int *imu_fi, *imu_fj, *imu_win, *wheel_fi, *wheel_fj, *wheel_win, *plane_f, *plane_win;
     double *imu_data, *wheel_data, *prior_J, *prior_r, *prior_x0, *x_init; WinWork *work;
     int nitems_solve_total;
+    int *vis_pos; unsigned char *vis_dup; int *lmb_ptr, *lmb_win; AsmItem *pitems;
 };
 static void emit_lists(const int *type, const int *fi, const int *fj, int nvis, bool only_host0, int has_common, int w, AsmItem *items, int *list) {
     // counting sort of the (factor, role) entries into frame lists, pair lists and the common list, then chunking
@@ -401,6 +433,37 @@ static void lower_fill(const viwb_problem &p, const double *state, int w, const 
     { int *fp = h.lm_fptr + m.lm_off; int run = m.vis_off, i = 0;
       for (int k = 0; k < p.num_landmarks; k++) { fp[k] = run; while (i < p.num_vis && vl[i] == k) { i++; run++; } h.lm_win[m.lm_off + k] = w; } }
     // assembly plan
+    if (m.fused) {
+        // frame-pair order of the X records (counting sort by (host, observer)), pair chunks, duplicate codes, landmark blocks
+        int pcnt[NFR * NFR] = {0}, poff[NFR * NFR];
+        for (int i = 0; i < p.num_vis; i++) if (vt[i] != 2) pcnt[vi[i] * NFR + vj[i]]++;
+        int pos = 0, ni = 0;
+        AsmItem *pit = h.pitems + m.pitem_off;
+        for (int a = 0; a < NFR * NFR; a++) {
+            poff[a] = pos;
+            for (int c0 = 0, ph = 0; c0 < pcnt[a]; c0 += PAIR_CHUNK, ph++) {
+                AsmItem &it = pit[ni++];
+                it.kind = ITEM_PAIR; it.win = w; it.a = a / NFR; it.b = a % NFR; it.lo = pos + c0; it.hi = pos + std::min(pcnt[a], c0 + (int)PAIR_CHUNK); it.phase = ph; it.has_common = 0;
+            }
+            pos += pcnt[a];
+        }
+        int *vp = h.vis_pos + m.vis_off; unsigned char *vd = h.vis_dup + m.vis_off;
+        for (int i = 0; i < p.num_vis; i++) {
+            vd[i] = 0;
+            if (vt[i] == 2) { vp[i] = -1; continue; }
+            vp[i] = poff[vi[i] * NFR + vj[i]]++;
+            if (i > 0 && vt[i - 1] != 2 && vl[i - 1] == vl[i] && vj[i - 1] == vj[i]) { vd[i - 1] = 1; vd[i] = 2; }
+        }
+        int *lp = h.lmb_ptr + 2 * (size_t)m.lmb_off, *lw = h.lmb_win + m.lmb_off;
+        int nb = 0, in_blk = 0, i = 0; bool open = false;
+        for (int k = 0; k < p.num_landmarks; k++) {
+            int cnt = 0;
+            for (; i < p.num_vis && vl[i] == k; i++) cnt++;
+            if (!open || in_blk + cnt > LMB_FACTORS) { lp[2 * nb] = m.lm_off + k; lw[nb] = w; nb++; in_blk = 0; open = true; }
+            lp[2 * nb - 1] = m.lm_off + k + 1;          // the open block ends after this landmark
+            in_blk += cnt;
+        }
+    } else
     emit_lists(vt, vi, vj, p.num_vis, false, m.has_common, w, h.items + m.item_off, h.asm_list + m.list_off);
     if (m.margin_flag == 0) emit_lists(vt, vi, vj, p.num_vis, true, 1, w, h.items + h.nitems_solve_total + m.mitem_off, h.asm_list + m.mlist_off);
     // small factors
@@ -446,7 +509,18 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     // ---- phase 1 (parallel): sizes and plans
     parallel_for(B, [&](int w) { lower_count(problems[w], margin_flags ? margin_flags[w] : -1, b->meta[w], low[w], b->out_mode[w]); });
     for (int w = 0; w < B; w++) if (low[w].err) { const int e = low[w].err; batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, e == 1 ? "bad frame_count / num_landmarks" : e == 2 ? "bad prior" : e == 3 ? "bad visual factor table" : e == 5 ? "negative factor count or missing table" : "bad factor frame index"); }
+    // fused solver linearisation (kernels_fused.cuh) when every window qualifies; then the solver's gather lists are not built at all
+    // (decided per window, so that a window takes the same path -- and gives the same bits -- whatever else the batch holds)
+    const bool allow_fused = getenv("VIWB_NO_FUSED") == nullptr;
+    int n_unfused = 0;
+    for (int w = 0; w < B; w++) {
+        const bool fused = allow_fused && low[w].regular;
+        b->meta[w].fused = fused ? 1 : 0;
+        if (fused) { low[w].nitems_s = 0; low[w].nlist_s = 0; low[w].nph_s = 0; b->meta[w].nitems = 0; b->meta[w].nphases = 0; }
+        else { low[w].nlmb = 0; low[w].npitems = 0; low[w].nxrec = 0; n_unfused++; }
+    }
     // ---- phase 2: offsets
+    size_t nlmb = 0, npit = 0, nxr = 0;
     size_t nstate = 0, nvis = 0, nlm = 0, nimu = 0, nwheel = 0, nplane = 0, nlist = 0, nit_s = 0, nit_m = 0, npri = 0, npJ = 0, npr = 0;
     for (int w = 0; w < B; w++) {
         const viwb_problem &p = problems[w]; WinMeta &m = b->meta[w]; const WinLow &lo = low[w];
@@ -455,6 +529,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
         m.imu_off = (int)nimu; nimu += p.num_imu; m.wheel_off = (int)nwheel; nwheel += p.num_wheel; m.plane_off = (int)nplane; nplane += p.num_plane;
         m.item_off = (int)nit_s; nit_s += lo.nitems_s; m.list_off = (int)nlist; nlist += lo.nlist_s;
         m.prior_idx = lo.has_prior ? (int)npri++ : -1;
+        m.lmb_off = (int)nlmb; m.nlmb = lo.nlmb; nlmb += lo.nlmb; m.pitem_off = (int)npit; m.npitems = lo.npitems; npit += lo.npitems; m.xrec_off = (int)nxr; m.nxrec = lo.nxrec; nxr += lo.nxrec;
         b->prior_n[w] = lo.prior_n_out; if (m.margin_flag >= 0) b->any_marg = true;
         b->prior_nmax = std::max(b->prior_nmax, lo.prior_n_out);
         b->algorithmic_bytes += window_algorithmic_bytes(p, opt->max_num_iterations);
@@ -474,6 +549,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     bd.nvis_total = (int)nvis; bd.nlm_total = (int)nlm; bd.nimu_total = (int)nimu; bd.nwheel_total = (int)nwheel; bd.nplane_total = (int)nplane; bd.nprior = (int)npri;
     bd.nitems_solve = (int)nit_s; bd.nitems_marg = (int)nit_m;
     bd.rec_stride_solve = VREC_COMPACT;
+    bd.n_unfused = n_unfused; bd.nlmb_total = (int)nlmb; bd.npitems_total = (int)npit; bd.nxrec_total = (int)nxr;
     bd.marg_nmax = b->prior_nmax;
     bd.env_max = 1; for (int w = 0; w < B; w++) bd.env_max = std::max(bd.env_max, b->meta[w].esize);
     for (int w = 0; w < B; w++) if (b->meta[w].has_common) bd.rec_stride_solve = VREC;
@@ -488,9 +564,11 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     IN(&bd.imu_fi, nimu); IN(&bd.imu_fj, nimu); IN(&bd.imu_win, nimu); IN(&bd.wheel_fi, nwheel); IN(&bd.wheel_fj, nwheel); IN(&bd.wheel_win, nwheel);
     IN(&bd.plane_f, nplane); IN(&bd.plane_win, nplane); IN(&bd.imu_data, nimu * 287); IN(&bd.wheel_data, nwheel * 78);
     IN(&bd.prior_J, npJ); IN(&bd.prior_r, npr); IN(&bd.prior_x0, npri * SFIX); IN(&bd.x_init, nstate); IN(&b->work_init_dev, B);
+    IN(&bd.vis_pos, nlmb ? nvis : 0); IN(&bd.vis_dup, nlmb ? nvis : 0); IN(&bd.lmb_ptr, 2 * nlmb); IN(&bd.lmb_win, nlmb); IN(&bd.pitems, npit);
     const size_t nvec = (size_t)B * TFIX + nlm;
     WK(&bd.work, B); WK(&bd.x_cur, nstate); WK(&bd.x_cand, nstate); WK(&bd.x_before, nstate);
     WK(&bd.vis_rec, nvis * VREC); WK(&bd.vis_cost, nvis);
+    WK(&bd.xrec, nxr * XREC); WK(&bd.pair_out, npit * PAIR_OUT);
     WK(&bd.lm_a, nlm); WK(&bd.lm_g, nlm); WK(&bd.lm_gamma, nlm); WK(&bd.lm_scale, nlm); WK(&bd.lm_cost, nlm); WK(&bd.lm_W, nlm * VSUB); WK(&bd.lm_outlier, nlm);
     WK(&bd.imu_S, nimu * 225); WK(&bd.wheel_S, nwheel * 36); WK(&bd.imu_rec, nimu * IMU_REC); WK(&bd.wheel_rec, nwheel * WHEEL_REC); WK(&bd.plane_rec, nplane * PLANE_REC);
     WK(&bd.prior_A, npJ); WK(&bd.prior_res, npr); WK(&bd.prior_g, npr);
@@ -500,7 +578,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     // marginalisation outputs / scratch: sized by the largest prior this batch produces, and not at all when no window marginalises
     const size_t mJ = b->any_marg ? (size_t)b->prior_nmax * b->prior_nmax : 0, mB = b->any_marg ? (size_t)B : 0;
     WK(&bd.marg_J, mB * mJ); WK(&bd.marg_r, mB * MAXPRI); WK(&bd.marg_x0, mB * SFIX);
-    WK(&bd.marg_hdr, mB * (3 + 2 * NB)); WK(&bd.marg_A, mB * (MAXPRI + 16) * (MAXPRI + 16));
+    WK(&bd.marg_hdr, mB * (3 + 2 * NB));
     size_t tot = 0;
     for (auto &e : ents) if (e.input) { e.off = tot; tot += align_up(e.bytes); }
     const size_t in_bytes = tot;
@@ -520,7 +598,8 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
       auto HP = [&](auto *&dst) { dst = (typename std::remove_reference<decltype(dst)>::type)(hb + ents[k].off); k++; };
       HP(h.meta); HP(h.prior); HP(h.vis_type); HP(h.vis_lm); HP(h.vis_fi); HP(h.vis_fj); HP(h.vis_win); HP(h.vis_obs); HP(h.lm_win); HP(h.lm_fptr); HP(h.items); HP(h.asm_list);
       HP(h.imu_fi); HP(h.imu_fj); HP(h.imu_win); HP(h.wheel_fi); HP(h.wheel_fj); HP(h.wheel_win); HP(h.plane_f); HP(h.plane_win); HP(h.imu_data); HP(h.wheel_data);
-      HP(h.prior_J); HP(h.prior_r); HP(h.prior_x0); HP(h.x_init); HP(h.work); }
+      HP(h.prior_J); HP(h.prior_r); HP(h.prior_x0); HP(h.x_init); HP(h.work);
+      HP(h.vis_pos); HP(h.vis_dup); HP(h.lmb_ptr); HP(h.lmb_win); HP(h.pitems); }
     h.nitems_solve_total = (int)nit_s;
     for (auto &e : ents) *e.field = ar->dev + e.off;
     if (npri) memcpy(h.prior, priors.data(), sizeof(PriorDev) * npri);
@@ -540,7 +619,8 @@ static int ensure_attrs(viwb_context *ctx) {
     if (!ctx->attrs_set) {
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(SOLVE_NT, TFIX * (TFIX + 1) / 2) * 8)));
         CK(cudaFuncSetAttribute(lin_vis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lin_vis_smem_doubles(128, VREC) * 8)));
-        CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(256, 100) * 8)));
+        CK(cudaFuncSetAttribute(syrk_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(syrk_mma_smem_doubles() * 8)));
+        CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(MARG_NT, 100) * 8)));
         ctx->attrs_set = true;
     }
 #endif
@@ -559,13 +639,26 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     CK(dev_d2d(bd.x_cur, bd.x_init, xs, st)); CK(dev_d2d(bd.x_cand, bd.x_init, xs, st));
     if (!(what & RUN_REANCHOR) || (what & RUN_SOLVE)) CK(dev_d2d(bd.x_before, bd.x_init, xs, st));
     CK(dev_d2d(bd.work, b->work_init_dev, sizeof(WinWork) * B, st));
-    const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(SOLVE_NT), nt_marg = NT(256);
+    const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(SOLVE_NT), nt_marg = NT(MARG_NT);
     const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total * LM_ROLES + nt_lm - 1) / nt_lm;
     const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve, bd.env_max) * 8, sm_marg = marg_smem_doubles(nt_marg, bd.marg_nmax) * 8;
     // cost_only: the round after the last allowed iteration only decides accept / reject of the pending candidate (every window
     // still running is at max_num_iterations there, trust_region_minimizer.cc checks the iteration limit before the gradient),
     // so the partial sums and the Schur product of that linearisation would never be read
     auto lin = [&](int mode, bool cost_only) {
+        const bool solve = mode == MODE_SOLVE;
+        const bool old_path = !solve || bd.n_unfused > 0;          // marginalisation always takes the gather kernels (it needs the common columns)
+        if (solve && bd.nlmb_total > 0) { LAUNCH(lin_vis_lm, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles() * 8, mode, st); ctx->launches++; }
+        if (!old_path) {
+            LAUNCH(lin_small, bd, B, 1, nt_small, sm_small, mode, st); ctx->launches++;
+            if (cost_only) return;
+            const int wpb2 = NT(128) / (NT(128) < 32 ? NT(128) : 32);
+            LAUNCH(asm_pairs, bd, (bd.npitems_total + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st);
+            if (g_syrk_dfma) LAUNCH(syrk, bd, B, 1, nt_syrk, syrk_smem_doubles() * 8, mode, st);
+            else LAUNCH(syrk_mma, bd, B, 1, NT(SYRK_NT), syrk_mma_smem_doubles() * 8, mode, st);
+            ctx->launches += (bd.npitems_total > 0) + 1;
+            return;
+        }
         LAUNCH(lin_vis, bd, g_vis, 1, nt_vis, lin_vis_smem_doubles(nt_vis, mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) * 8, mode, st);
         if ((mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) == VREC) LAUNCH(lm_reduce_wide, bd, g_lm, 1, nt_lm, 0, mode, st);
         else LAUNCH(lm_reduce, bd, g_lm, 1, nt_lm, 0, mode, st);
@@ -574,9 +667,11 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
         if (cost_only) return;
         const int ni = mode == MODE_SOLVE ? bd.nitems_solve : bd.nitems_marg, wpb = nt_asm / (nt_asm < 32 ? nt_asm : 32);
         const bool wide = (mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) == VREC;     // items carry the common columns
+        if (solve && bd.npitems_total > 0) { const int wpb2 = NT(128) / (NT(128) < 32 ? NT(128) : 32); LAUNCH(asm_pairs, bd, (bd.npitems_total + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st); ctx->launches++; }
         if (wide) LAUNCH(asm_items_split, bd, (ni * ASM_SPLIT + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
         else LAUNCH(asm_items, bd, (ni + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
-        LAUNCH(syrk, bd, B, 1, nt_syrk, syrk_smem_doubles() * 8, mode, st);
+        if (g_syrk_dfma) LAUNCH(syrk, bd, B, 1, nt_syrk, syrk_smem_doubles() * 8, mode, st);
+        else LAUNCH(syrk_mma, bd, B, 1, NT(SYRK_NT), syrk_mma_smem_doubles() * 8, mode, st);
         ctx->launches += (ni > 0) + 1;
     };
     if (what & (RUN_SOLVE | RUN_MARG | RUN_LIN_ONLY)) {
