@@ -312,6 +312,7 @@ def kernel_models(probs, pri, B, lk):
         "asm_items": (0.0, 2.0 * 2 * (21 + 21 + 36 + 12) * n_vis),
         "asm_pairs": (0.0, 2.0 * 2 * (21 + 21 + 36 + 12) * n_vis),
         "syrk": (0.0, 2.0 * 80 * 81 / 2 * n_lm),
+        "syrk_mma": (0.0, 2.0 * 80 * 81 / 2 * n_lm),                                # useful FLOPs of the symmetric product (the tensor tiles compute 65 of 110 8x8 tiles)
         "lin_small": (2296.0 * n_imu + 624.0 * n_wheel + 8.0 * sum(n * n + 2 * n for n in npri), 2.0 * (15 * 15 * 31) * n_imu + 2.0 * 2 * sum(n * n for n in npri)),
         "solve": (8.0 * sR2 + 8.0 * pg, sum(r ** 3 / 3.0 + 6.0 * r * r for r in R) * 2.0 / 2.0 + 2.0 * 3 * 80 * n_lm + 2.0 * 15 * 465 * n_imu),
         "marg": (8.0 * B * (nmax * nmax + nmax + abi.STATE_FIXED), B * (4.0 / 3.0 + 3.0) * 2.0 * nmax ** 3),     # tridiagonalisation + eigenvectors + QL
@@ -321,7 +322,7 @@ def kernel_models(probs, pri, B, lk):
     return m
 
 
-BOUND_HINT = {"lk_track": "issue", "lk_pyr_down": "hbm", "lin_vis": "hbm", "lin_vis_lm": "hbm", "lm_reduce": "hbm", "asm_items": "hbm", "asm_pairs": "hbm", "syrk": "fp64", "solve": "fp64",
+BOUND_HINT = {"lk_track": "issue", "lk_pyr_down": "hbm", "lin_vis": "hbm", "lin_vis_lm": "hbm", "lm_reduce": "hbm", "asm_items": "hbm", "asm_pairs": "hbm", "syrk": "fp64", "syrk_mma": "fp64", "solve": "fp64",
               "marg": "fp64", "lin_small": "hbm"}
 
 
