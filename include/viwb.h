@@ -208,8 +208,8 @@ typedef struct viwb_context viwb_context;
 int viwb_create(int device, viwb_context **out);
 void viwb_destroy(viwb_context *ctx);
 const char *viwb_last_error(const viwb_context *ctx);
-/* run all work of this context on an externally owned cudaStream_t (e.g. torch's current stream); NULL switches back to the context's own
- * stream.  The caller keeps ownership: viwb_destroy only destroys the stream viwb_create made.  Waits for the work queued so far. */
+/* run all work of this context on an externally owned cudaStream_t (e.g. torch's current stream; NULL = CUDA's default stream).  The caller
+ * keeps ownership: viwb_destroy only destroys the stream viwb_create made.  Waits for the work queued so far. */
 int viwb_set_stream(viwb_context *ctx, void *cuda_stream);
 /* number of kernels this context launched since creation (bench.py's gpu_launches) */
 long long viwb_launch_count(const viwb_context *ctx);

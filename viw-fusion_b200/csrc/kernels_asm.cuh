@@ -391,33 +391,23 @@ VIWB_D void assemble_into(const Target &t, const BatchDev &bd, int w, int mode, 
         }
     }
     if (mode == MODE_SOLVE && m.fused) {
-        // ---- fused path: G = sum X^T X per pair chunk (asm_pairs, kernels_fused.cuh), X = [A (host frame a) | B (observer b) | r].
-        //      Diagonal blocks and gradients of frame f: ONE owner per entry walks the chunks of every pair that contains f (fixed order).
-        const int pio = m.pitem_off, npi = m.npitems;
+        // ---- fused path: pair_reduce (kernels_fused.cuh) has folded the pair chunks G = sum X^T X, X = [A (host frame a) | B (observer b) | r],
+        //      into per-frame diagonal blocks + gradients and per-pair off-diagonal blocks.  Exact zeros are frames / pairs without factors
+        //      (their entries may lie outside the envelope) and are skipped.
+        const double *red = bd.pair_red + (size_t)w * PAIR_RED;
         for (int e = tid; e < NFR * 27; e += nt) {
+            const double v = red[e];
+            if (v == 0.0) continue;
             const int f = e / 27, o = e - 27 * f;
-            int p = 0, q = 0;
-            if (o < 21) sym_unrank(o, p, q); else p = o - 21;
-            double v = 0.0; bool any = false;
-            for (int ii = 0; ii < npi; ii++) {
-                const AsmItem &it = bd.pitems[pio + ii];
-                int base;
-                if (it.a == f) base = 0; else if (it.b == f) base = 6; else continue;
-                v += pair_G_entry(bd.pair_out + (size_t)(pio + ii) * PAIR_OUT, base + p, o < 21 ? base + q : 12);
-                any = true;
-            }
-            if (!any) continue;
-            if (o < 21) { const int ci = t.col(f, p), cj = t.col(f, q); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
-            else { const int ci = t.col(f, p); if (ci >= 0) t.addg(ci, v); }
+            if (o < 21) { int p, q; sym_unrank(o, p, q); const int ci = t.col(f, p), cj = t.col(f, q); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
+            else { const int ci = t.col(f, o - 21); if (ci >= 0) t.addg(ci, v); }
         }
-        //      Off-diagonal block of pair (a, b): the owner of entry o of the pair's head chunk adds the chunks (consecutive items, phase 0, 1, ...)
-        for (int e = tid; e < npi * 36; e += nt) {
-            const int ii = e / 36, o = e - 36 * ii;
-            const AsmItem &item = bd.pitems[pio + ii];
-            if (item.phase != 0) continue;
-            double v = pair_G_entry(bd.pair_out + (size_t)(pio + ii) * PAIR_OUT, o / 6, 6 + o % 6);
-            for (int c = 1; ii + c < npi && bd.pitems[pio + ii + c].phase == c; c++) v += pair_G_entry(bd.pair_out + (size_t)(pio + ii + c) * PAIR_OUT, o / 6, 6 + o % 6);
-            const int ci = t.col(item.a, o / 6), cj = t.col(item.b, o % 6);
+        for (int e = tid; e < NPAIR * 36; e += nt) {
+            const double v = red[NFR * 27 + e];
+            if (v == 0.0) continue;
+            int pi = e / 36, a = 0; const int o = e - 36 * pi;
+            while (pi >= NFR - 1 - a) { pi -= NFR - 1 - a; a++; }
+            const int ci = t.col(a, o / 6), cj = t.col(a + 1 + pi, o % 6);
             if (ci >= 0 && cj >= 0) t.add(ci, cj, v);
         }
         VIWB_SYNC();

@@ -27,7 +27,7 @@ VIWB_D void dmma884(double (&c)[2], double a, double b) {
 
 // ------------------------------------------------------------------------------------------------ lin_vis_lm
 enum { LVL_TS = 31, LVL_U = 28, LVL_C = 30 };      // tile row: X record (28) | J_lambda (2) | rho / 2 ; odd stride
-VIWB_HD size_t lin_vis_lm_smem_doubles() { return (size_t)LMB_FACTORS * LVL_TS + 2; }
+VIWB_HD size_t lin_vis_lm_smem_doubles() { return (size_t)LMB_FACTORS * LVL_TS + LMB_FACTORS + 2; }      // tile + per-factor (meta, slot) ints
 VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)mode;                        // solver linearisation at x_cand only
     const int w = bd.lmb_win[bx];
@@ -37,6 +37,7 @@ VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt
     const int k0 = bd.lmb_ptr[2 * bx], k1 = bd.lmb_ptr[2 * bx + 1];    // global landmark range of this block
     const int f0 = bd.lm_fptr[k0], nf = bd.lm_fptr[k1] - f0;            // its factors (consecutive, <= LMB_FACTORS)
     double *tile = smem;
+    int *meta = (int *)(smem + (size_t)LMB_FACTORS * LVL_TS);      // [2 t] = landmark (window-local) << 12 | fi << 8 | fj << 4 | type << 2 | dup ; [2 t + 1] = X-record slot
     const double *x = bd.x_cand + m.state_off;
     // ---- 0: the W rows of these landmarks start from zero (frames that do not observe a landmark keep zero blocks)
     { double *Wb = bd.lm_W + (size_t)k0 * VSUB; for (int e = tid; e < (k1 - k0) * VSUB; e += nt) Wb[e] = 0.0; }
@@ -54,6 +55,8 @@ VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt
         for (int q = 0; q < 6; q++) { row[q] = o.JA[q] * sc; row[6 + q] = o.JB[q] * sc; row[XROW + q] = o.JA[6 + q] * sc; row[XROW + 6 + q] = o.JB[6 + q] * sc; }
         row[12] = o.r[0] * sc; row[13] = 0.0; row[XROW + 12] = o.r[1] * sc; row[XROW + 13] = 0.0;
         row[LVL_U] = o.Jl[0] * sc; row[LVL_U + 1] = o.Jl[1] * sc; row[LVL_C] = half_rho;
+        meta[2 * t] = (bd.vis_lm[f] << 12) | (fi << 8) | (fj << 4) | (type << 2) | bd.vis_dup[f];
+        meta[2 * t + 1] = bd.vis_pos[f];
     }
     VIWB_SYNC();
     // ---- 2a: X records to their frame-pair slots: one warp-wide contiguous store per record
@@ -61,7 +64,7 @@ VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt
         const int Wd = nt < 32 ? nt : 32, nwp = nt / Wd, wid = tid / Wd, lane = tid % Wd;
         double *xr = bd.xrec + (size_t)m.xrec_off * XREC;
         for (int t = wid; t < nf; t += nwp) {
-            const int pos = bd.vis_pos[f0 + t];
+            const int pos = meta[2 * t + 1];
             if (pos < 0) continue;                       // one-frame stereo factor: no pose Jacobian
             for (int q = lane; q < XREC; q += Wd) xr[(size_t)pos * XREC + q] = tile[(size_t)t * LVL_TS + q];
         }
@@ -69,14 +72,14 @@ VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt
     // ---- 2b: observing-frame blocks of W, item = (factor, component); two factors of one landmark seen from the same frame (left and
     //          right camera) are consecutive in the table: the first one writes the sum
     for (int e = tid; e < nf * 6; e += nt) {
-        const int t = e / 6, q = e - 6 * t, f = f0 + t;
-        if (bd.vis_type[f] == 2) continue;
-        const int dup = bd.vis_dup[f];
+        const int t = e / 6, q = e - 6 * t, mt = meta[2 * t];
+        if (((mt >> 2) & 3) == 2) continue;
+        const int dup = mt & 3;
         if (dup == 2) continue;
         const double *row = tile + (size_t)t * LVL_TS;
         double v = row[6 + q] * row[LVL_U] + row[XROW + 6 + q] * row[LVL_U + 1];
         if (dup == 1) { const double *r2 = row + LVL_TS; v += r2[6 + q] * r2[LVL_U] + r2[XROW + 6 + q] * r2[LVL_U + 1]; }
-        bd.lm_W[(size_t)(m.lm_off + bd.vis_lm[f]) * VSUB + 6 * bd.vis_fj[f] + q] = v;
+        bd.lm_W[(size_t)(m.lm_off + (mt >> 12)) * VSUB + 6 * ((mt >> 4) & 15) + q] = v;
     }
     // ---- 2c: per landmark, item = (landmark, output): host-frame block of W (6), a, g, cost (+ Jacobi scale and Schur weight)
     for (int e = tid; e < (k1 - k0) * 9; e += nt) {
@@ -91,7 +94,7 @@ VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt
             else if (q == 7) s += u0 * row[12] + u1 * row[XROW + 12];
             else s += row[LVL_C];
         }
-        if (q < 6) { if (a1 > a0) bd.lm_W[(size_t)k * VSUB + 6 * bd.vis_fi[f0 + a0] + q] = s; }
+        if (q < 6) { if (a1 > a0) bd.lm_W[(size_t)k * VSUB + 6 * ((meta[2 * a0] >> 8) & 15) + q] = s; }
         else if (q == 7) bd.lm_g[k] = s;
         else if (q == 8) bd.lm_cost[k] = s;
         else {
@@ -160,6 +163,43 @@ VIWB_D void asm_pairs_block(const BatchDev &bd, int bx, int by, int tid, int nt,
         reinterpret_cast<double2 *>(out + 64 * t)[lane] = v;
     }
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------ pair_reduce
+// Folds the pair chunks of a window into what the solve kernel adds to H: per frame f the diagonal block and gradient (27 values: every chunk
+// of every pair that contains f, in item order) and per pair (a < b) the 6 x 6 off-diagonal block (36 values, the pair's chunks).  One block per
+// window, one owner per output, fixed order.  Keeps the ~100 dependent L2 reads per entry out of the (latency-bound) solve kernel.
+VIWB_HD int pair_index(int a, int b) { return a * (2 * NFR - a - 1) / 2 + (b - a - 1); }      // a < b
+VIWB_D void pair_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem; (void)mode;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    if (!m.fused || bd.work[w].status != ST_RUNNING) return;
+    double *red = bd.pair_red + (size_t)w * PAIR_RED;
+    const int pio = m.pitem_off, npi = m.npitems;
+    for (int e = tid; e < NFR * 27; e += nt) {
+        const int f = e / 27, o = e - 27 * f;
+        int p = 0, q = 0;
+        if (o < 21) sym_unrank(o, p, q); else p = o - 21;
+        double v = 0.0;
+        for (int ii = 0; ii < npi; ii++) {
+            const AsmItem &it = bd.pitems[pio + ii];
+            int base;
+            if (it.a == f) base = 0; else if (it.b == f) base = 6; else continue;
+            v += pair_G_entry(bd.pair_out + (size_t)(pio + ii) * PAIR_OUT, base + p, o < 21 ? base + q : 12);
+        }
+        red[e] = v;
+    }
+    for (int e = tid; e < NPAIR * 36; e += nt) red[NFR * 27 + e] = 0.0;
+    VIWB_SYNC();
+    for (int e = tid; e < npi * 36; e += nt) {
+        const int ii = e / 36, o = e - 36 * ii;
+        const AsmItem &item = bd.pitems[pio + ii];
+        if (item.phase != 0) continue;
+        double v = pair_G_entry(bd.pair_out + (size_t)(pio + ii) * PAIR_OUT, o / 6, 6 + o % 6);
+        for (int c = 1; ii + c < npi && bd.pitems[pio + ii + c].phase == c; c++) v += pair_G_entry(bd.pair_out + (size_t)(pio + ii + c) * PAIR_OUT, o / 6, 6 + o % 6);
+        red[NFR * 27 + pair_index(item.a, item.b) * 36 + o] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ syrk_mma

@@ -30,6 +30,8 @@ struct LkArgs {
     const float *prev_pts; float *next_pts; uint8_t *status; float *err;
     const int *n_dev;         // optional device-side point count (batched streams); else n
     int n, max_level, max_iter, flags; float eps2, min_eig;
+    int trowI[LK_MAXLVL], trowJ[LK_MAXLVL];      // first row of the template / search image inside the level's stacked tensor (TMA coordinates)
+    int tma;                  // the images live in an LK batch's level stacks: interior windows are staged by TMA tile loads
 };
 
 VIWB_HD int reflect101(int p, int len) {
@@ -171,11 +173,15 @@ VIWB_D void pyr_down_item(const PyrArgs &a, int idx) {
 // ---- the tracker: one warp per point, no block-level barriers.
 // Work items of a warp: the 21 window rows x 3 segments of 7 pixels = 63 items, two per lane, so that neighbouring samples
 // share their loads and every shared-memory offset inside an item is a compile-time constant.  Per level the warp
-//   1. stages the 24x24 source patch (aligned 32-bit loads when the patch is interior, reflect-101 byte path otherwise),
-//   2. derives the 22x22 Scharr samples from it (zero outside the image, like OpenCV's constant-border derivative buffer),
-//   3. interpolates its 14 template / gradient samples into registers,
-//   4. stages a 32x36 region of the search image around the estimate (again aligned words when interior); the Gauss-Newton
-//      iterations sample it branch-free and restage only if the estimate leaves it,
+//   1. stages the source patch: ONE TMA tile load (cp.async.bulk.tensor.2d, 32 x 32 bytes) when the 24 x 24 patch lies inside the image,
+//      the reflect-101 byte / word path otherwise,
+//   2. interpolates the 23 x 23 intensities once (two byte-pair dot products per sample, dp2a) and derives template + Scharr
+//      gradients from them (zero-padded Scharr like OpenCV's constant-border derivative buffer on the border path),
+//   3. keeps its 14 template samples in registers as c0 = 256 - 512 * I (so that one arithmetic shift finishes a residual) with the
+//      gradients unpacked,
+//   4. stages a 32 x 32 region of the search image around the estimate (TMA tile when inside the image) and samples it in the
+//      Gauss-Newton iterations: per row three aligned words, two byte permutes to undo the misalignment, two byte-pair dot products
+//      per sample; restaged only if the estimate leaves it,
 //   5. reduces the integer products with the warp-wide integer adder (redux.sync): exact, no shuffle chain.
 #ifdef VIWB_HOST_EMU
 enum { LK_W = 1 };
@@ -183,13 +189,14 @@ enum { LK_W = 1 };
 enum { LK_W = 32 };
 #endif
 #ifndef LK_MINB
-#define LK_MINB 8
+#define LK_MINB 5
 #endif
 enum { LK_ITEMS = 63, LK_IPL = (LK_ITEMS + LK_W - 1) / LK_W, LK_PPB = 4,         // items, items per lane, points per block
-       LK_PS = 28,                                                             // byte stride of the staged source patch (7 words)
-       LK_SLACK = 5, LK_JROWS = 22 + 2 * LK_SLACK, LK_JS = 36,                 // staged search region: 32 rows x 36 bytes (9 words)
+       LK_PS = 32,                                                             // byte stride of the staged source patch (TMA box row)
+       LK_SLACK = 3, LK_JROWS = 32, LK_JS = 32,                                // staged search region: 32 rows x 32 bytes (TMA box)
        LK_BS = 23, LK_DBYTES = 2208,                                           // interpolated-intensity image 23 x 23 ints (shares the Scharr sample buffer)
-       LK_WARP_SMEM = 24 * LK_PS + LK_DBYTES + LK_JROWS * LK_JS };             // = 4032 bytes per warp
+       LK_OFF_J = 32 * LK_PS, LK_OFF_D = LK_OFF_J + LK_JROWS * LK_JS, LK_OFF_BAR = LK_OFF_D + LK_DBYTES,
+       LK_WARP_SMEM = 4352 };                                                  // 1024 + 1024 + 2208 + 16 (mbarrier) rounded up to a multiple of 128
 VIWB_HD size_t lk_smem_bytes(int warps) { return (size_t)warps * LK_WARP_SMEM; }
 
 // exact sum over the warp of one int32 per lane (every lane gets it)
@@ -232,20 +239,90 @@ VIWB_D void lk_stage(uint8_t *buf, const uint8_t *img, int stride, int cols, int
     VIWB_SYNCWARP();
 }
 
-VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem_raw) {
-    uint8_t *pbuf = (uint8_t *)smem_raw;                      // 24 rows x 28 bytes
-    short *dpatch = (short *)(smem_raw + 24 * LK_PS);          // 22 x 22 x (dx, dy)
+// ---- TMA staging (sm_100a): per pyramid level ONE tensor map over the level's stacked images [slots * streams * rows][width] (u8, row pitch a
+// multiple of 16 bytes), box 32 x 32; a warp's lane 0 arms the warp's mbarrier with the tile's byte count and issues the copy, the warp
+// waits on the barrier's phase.  Columns right of the image are zero-filled by the unit and never read (only windows whose needed
+// pixels are inside the image take this path); rows below the image belong to the next image of the stack and are not read either.
+struct LkMaps { unsigned long long opaque[LK_MAXLVL][16]; };      // LK_MAXLVL x CUtensorMap (128 bytes, 64-byte aligned), encoded by the host
+#ifndef VIWB_HOST_EMU
+VIWB_D unsigned lk_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+VIWB_D void lk_bar_init(unsigned long long *bar, int lane) {
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lk_smem_addr(bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+}
+// tile (x, y) .. (x + 31, y + 31) of the level's stack into dst (128-byte aligned); phase: this warp's count of finished copies & 1
+VIWB_D void lk_tma_tile(uint8_t *dst, const void *map, int x, int y, unsigned long long *bar, unsigned &phase, int lane) {
+    __syncwarp();                                  // every lane is done reading the buffer that is about to be overwritten
+    const unsigned b = lk_smem_addr(bar);
+    if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(32 * 32) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(lk_smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(b) : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(b), "r"(phase) : "memory");
+    }
+    phase ^= 1u;
+}
+#endif
+
+#ifndef VIWB_HOST_EMU
+// c + (signed 16-bit halves of w) . (unsigned bytes 0,1 / 2,3 of px)
+VIWB_D int lk_dp2a_lo(unsigned w, unsigned px, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c)); return d; }
+VIWB_D int lk_dp2a_hi(unsigned w, unsigned px, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c)); return d; }
+#endif
+// bilinear samples of 7 consecutive pixels from two staged rows (row stride 32 bytes) at byte offset xoff (any alignment):
+// out[k] = c[k] + top[k] w00 + top[k+1] w01 + bot[k] w10 + bot[k+1] w11, wt = w00 | w01 << 16, wb = w10 | w11 << 16 as SIGNED 16-bit halves
+// (|w| <= 2^14; w11 = 2^14 - w00 - w01 - w10 can come out as -1, lkpyramid.cpp computes it the same way)
+VIWB_D void lk_sample7(const uint8_t *rowbase, int xoff, unsigned wt, unsigned wb, const int *c, int *out) {
+#ifdef VIWB_HOST_EMU
+    const uint8_t *q = rowbase + xoff;
+    const int w00 = (int)(short)(wt & 0xffffu), w01 = (int)(short)(wt >> 16), w10 = (int)(short)(wb & 0xffffu), w11 = (int)(short)(wb >> 16);
+    for (int k = 0; k < 7; k++) out[k] = c[k] + q[k] * w00 + q[k + 1] * w01 + q[k + 32] * w10 + q[k + 33] * w11;
+#else
+    const int mis = xoff & 3;
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(rowbase + (xoff - mis));
+    const unsigned sel = 0x3210u + 0x1111u * (unsigned)mis;
+    const uint32_t t0 = wp[0], t1 = wp[1], t2 = wp[2], b0 = wp[8], b1 = wp[9], b2 = wp[10];
+    const unsigned ta = __byte_perm(t0, t1, sel), tb = __byte_perm(t1, t2, sel);      // bytes 0..3, 4..7 of the top row
+    const unsigned ba = __byte_perm(b0, b1, sel), bb = __byte_perm(b1, b2, sel);
+    const unsigned ta1 = __byte_perm(ta, tb, 0x4321), tb1 = tb >> 8, ba1 = __byte_perm(ba, bb, 0x4321), bb1 = bb >> 8;      // bytes 1..4, 5..7
+    out[0] = lk_dp2a_lo(wb, ba, lk_dp2a_lo(wt, ta, c[0]));
+    out[1] = lk_dp2a_lo(wb, ba1, lk_dp2a_lo(wt, ta1, c[1]));
+    out[2] = lk_dp2a_hi(wb, ba, lk_dp2a_hi(wt, ta, c[2]));
+    out[3] = lk_dp2a_hi(wb, ba1, lk_dp2a_hi(wt, ta1, c[3]));
+    out[4] = lk_dp2a_lo(wb, bb, lk_dp2a_lo(wt, tb, c[4]));
+    out[5] = lk_dp2a_lo(wb, bb1, lk_dp2a_lo(wt, tb1, c[5]));
+    out[6] = lk_dp2a_hi(wb, bb, lk_dp2a_hi(wt, tb, c[6]));
+#endif
+}
+
+VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane, unsigned char *smem_raw) {
+    uint8_t *pbuf = (uint8_t *)smem_raw;                      // 32 rows x 32 bytes (24 rows used)
+    uint8_t *jbuf = smem_raw + LK_OFF_J;                      // 32 rows x 32 bytes
+    short *dpatch = (short *)(smem_raw + LK_OFF_D);           // 22 x 22 x (dx, dy)
     int *Bimg = (int *)dpatch;                                // or: 23 x 23 interpolated intensities (interior patches)
-    uint8_t *jbuf = smem_raw + 24 * LK_PS + LK_DBYTES;        // 32 rows x 36 bytes
     const int npts = a.n_dev ? *a.n_dev : a.n;
     if (pt >= npts) return;
+#ifndef VIWB_HOST_EMU
+    unsigned long long *bar = (unsigned long long *)(smem_raw + LK_OFF_BAR);
+    unsigned phase = 0;
+    const bool tma = maps != nullptr && a.tma != 0;
+    if (tma) lk_bar_init(bar, lane);
+#else
+    (void)maps;
+#endif
     const int max_level = a.max_level, max_iter = a.max_iter, flags = a.flags;
     const float eps2 = a.eps2, min_eig = a.min_eig;
     const float FLT_SCALE = 1.f / (1 << 20);
     const float px0 = a.prev_pts[2 * pt], py0 = a.prev_pts[2 * pt + 1];
     bool status = true; float errv = 0.f;
     float npx = 0.f, npy = 0.f;     // nextPts[ptidx] (window centre coordinates)
-    int Iv[LK_IPL][7], dxy[LK_IPL][7];    // template intensity (5 fractional bits) and packed (dx | dy << 16) of the lane's samples
+    int Ic[LK_IPL][7], gx[LK_IPL][7], gy[LK_IPL][7];    // 256 - 512 * template intensity (5 fractional bits), template gradients of the lane's samples
     int irow[LK_IPL], icol[LK_IPL];
 #pragma unroll
     for (int s = 0; s < LK_IPL; s++) { const int it = lane + LK_W * s; irow[s] = it / 3; icol[s] = 7 * (it - 3 * irow[s]); }
@@ -261,9 +338,19 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
         const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
         const int cols = a.I.w[level], rows = a.I.h[level];
         if (lk_outside(ipx, ipy, cols, rows)) { if (level == 0) { status = false; errv = 0.f; } continue; }
-        // 1. source patch rows [ipy-1, ipy+22], bytes from the aligned column pxa; pixel (ipx-1+x) sits at byte psx + x
-        const int pxa = (ipx - 1) & ~3, psx = (ipx - 1) - pxa;
-        lk_stage(pbuf, a.I.img[level], a.I.stride[level], cols, rows, pxa, ipy - 1, 24, LK_PS / 4, lane);
+        // 1. source patch rows [ipy-1, ipy+22]; pixel (ipx-1+x) of a row sits at byte psx + x
+        int psx;
+#ifndef VIWB_HOST_EMU
+        if (tma && ipx >= 1 && ipy >= 1 && ipx + 23 <= cols && ipy + 23 <= rows) {
+            lk_tma_tile(pbuf, &maps->opaque[level][0], ipx - 1, a.trowI[level] + ipy - 1, bar, phase, lane);
+            psx = 0;
+        } else
+#endif
+        {
+            const int pxa = (ipx - 1) & ~3;
+            psx = (ipx - 1) - pxa;
+            lk_stage(pbuf, a.I.img[level], a.I.stride[level], cols, rows, pxa, ipy - 1, 24, LK_PS / 4, lane);
+        }
         const float fa = ppx - ipx, fb = ppy - ipy;
         const int iw00 = cv_round_f((1.f - fa) * (1.f - fb) * (1 << 14)), iw01 = cv_round_f(fa * (1.f - fb) * (1 << 14));
         const int iw10 = cv_round_f((1.f - fa) * fb * (1 << 14)), iw11 = (1 << 14) - iw00 - iw01 - iw10;
@@ -271,11 +358,17 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
         if (ipx >= 0 && ipy >= 0 && ipx + 22 <= cols && ipy + 22 <= rows) {
             // 2a/3a. interior patch: the bilinear weights commute with the (integer, unrounded) Scharr stencil, so interpolate the
             //        intensities once, B(y,x) = sum_i w_i I(.), and take the stencil of B -- the same integers as interpolating the
-            //        four Scharr samples, with a third of the work
-            for (int e = lane; e < LK_BS * LK_BS; e += LK_W) {
-                const int y = e / LK_BS, x = e - y * LK_BS;
-                const uint8_t *p = pbuf + y * LK_PS + psx + x;
-                Bimg[e] = p[0] * iw00 + p[1] * iw01 + p[LK_PS] * iw10 + p[LK_PS + 1] * iw11;
+            //        four Scharr samples, with a third of the work.  Items = 23 rows x 4 groups of 7 (the last group has 2 columns).
+            {
+                const unsigned wt = ((unsigned)iw00 & 0xffffu) | ((unsigned)iw01 << 16), wb = ((unsigned)iw10 & 0xffffu) | ((unsigned)iw11 << 16);
+                const int zero7[7] = {0, 0, 0, 0, 0, 0, 0};
+                for (int e = lane; e < LK_BS * 4; e += LK_W) {
+                    const int y = e >> 2, g = e & 3;
+                    int v[7];
+                    lk_sample7(pbuf + y * LK_PS, psx + 7 * g, wt, wb, zero7, v);      // (bytes past column 23 belong to the staged row: read, not used)
+                    const int n = g < 3 ? 7 : 2;
+                    for (int k = 0; k < 7; k++) if (k < n) Bimg[y * LK_BS + 7 * g + k] = v[k];
+                }
             }
             VIWB_SYNCWARP();
 #pragma unroll
@@ -287,20 +380,20 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
                         const int ival = descale(b1[j + 1], 9);
                         const int ix = descale((b0[j + 2] + b2[j + 2]) * 3 + b1[j + 2] * 10 - ((b0[j] + b2[j]) * 3 + b1[j] * 10), 14);
                         const int iy = descale(((b2[j + 2] - b0[j + 2]) + (b2[j] - b0[j])) * 3 + (b2[j + 1] - b0[j + 1]) * 10, 14);
-                        Iv[s][j] = ival; dxy[s][j] = (ix & 0xffff) | (iy << 16);
+                        Ic[s][j] = 256 - (ival << 9); gx[s][j] = ix; gy[s][j] = iy;
                         sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 7; j++) { Iv[s][j] = 0; dxy[s][j] = 0; }
+                    for (int j = 0; j < 7; j++) { Ic[s][j] = 256; gx[s][j] = 0; gy[s][j] = 0; }
                 }
             }
         } else {
             // 2b. Scharr samples at [ipy, ipy+21] x [ipx, ipx+21]; zero outside the image
             for (int e = lane; e < LK_DPATCH * LK_DPATCH; e += LK_W) {
-                const int y = e / LK_DPATCH, x = e - y * LK_DPATCH, gx = ipx + x, gy = ipy + y;
+                const int y = e / LK_DPATCH, x = e - y * LK_DPATCH, gxx = ipx + x, gyy = ipy + y;
                 int ddx = 0, ddy = 0;
-                if (gx >= 0 && gy >= 0 && gx < cols && gy < rows) {
+                if (gxx >= 0 && gyy >= 0 && gxx < cols && gyy < rows) {
                     const uint8_t *p0 = pbuf + y * LK_PS + psx + x, *p1 = p0 + LK_PS, *p2 = p1 + LK_PS;
                     ddx = (p0[2] + p2[2]) * 3 + p1[2] * 10 - ((p0[0] + p2[0]) * 3 + p1[0] * 10);
                     ddy = ((p2[2] - p0[2]) + (p2[0] - p0[0])) * 3 + (p2[1] - p0[1]) * 10;
@@ -319,12 +412,12 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
                         const int ival = descale(p[j] * iw00 + p[j + 1] * iw01 + p[j + LK_PS] * iw10 + p[j + LK_PS + 1] * iw11, 9);
                         const int ix = descale(d[2 * j] * iw00 + d[2 * j + 2] * iw01 + d[2 * j + 2 * LK_DPATCH] * iw10 + d[2 * j + 2 * LK_DPATCH + 2] * iw11, 14);
                         const int iy = descale(d[2 * j + 1] * iw00 + d[2 * j + 3] * iw01 + d[2 * j + 2 * LK_DPATCH + 1] * iw10 + d[2 * j + 2 * LK_DPATCH + 3] * iw11, 14);
-                        Iv[s][j] = ival; dxy[s][j] = (ix & 0xffff) | (iy << 16);
+                        Ic[s][j] = 256 - (ival << 9); gx[s][j] = ix; gy[s][j] = iy;
                         sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 7; j++) { Iv[s][j] = 0; dxy[s][j] = 0; }
+                    for (int j = 0; j < 7; j++) { Ic[s][j] = 256; gx[s][j] = 0; gy[s][j] = 0; }
                 }
             }
         }
@@ -338,30 +431,40 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
         float pdx = 0.f, pdy = 0.f;
         const int jc = a.J.w[level], jr = a.J.h[level], jstr = a.J.stride[level];
         const uint8_t *jimg = a.J.img[level];
-        int jx0 = 0, jy0 = 0;          // origin of the staged search region (jx0 a multiple of 4)
+        int jx0 = 0, jy0 = 0;          // origin of the staged search region
         bool staged = false;
+        // stage the 32 x 32 region that holds the 23 x 23 samples at (inx, iny): one TMA tile clamped into the image when the samples lie inside
+        // it, else the reflect-101 path (origin a multiple of 4 in x)
+        auto stage_j = [&](int inx, int iny) {
+#ifndef VIWB_HOST_EMU
+            if (tma && inx >= 0 && iny >= 0 && inx + 23 <= jc && iny + 23 <= jr && jc >= LK_JS && jr >= LK_JROWS) {
+                jx0 = inx - 4; if (jx0 < 0) jx0 = 0; if (jx0 > jc - LK_JS) jx0 = jc - LK_JS;
+                jy0 = iny - 4; if (jy0 < 0) jy0 = 0; if (jy0 > jr - LK_JROWS) jy0 = jr - LK_JROWS;
+                lk_tma_tile(jbuf, &maps->opaque[level][0], jx0, a.trowJ[level] + jy0, bar, phase, lane);
+                return;
+            }
+#endif
+            jx0 = (inx - LK_SLACK) & ~3; jy0 = iny - 4;
+            lk_stage(jbuf, jimg, jstr, jc, jr, jx0, jy0, LK_JROWS, LK_JS / 4, lane);
+        };
         for (int j = 0; j < max_iter; j++) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (lk_outside(inx, iny, jc, jr)) { if (level == 0) status = false; break; }
-            if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) {
-                jx0 = (inx - LK_SLACK) & ~3; jy0 = iny - LK_SLACK;
-                lk_stage(jbuf, jimg, jstr, jc, jr, jx0, jy0, LK_JROWS, LK_JS / 4, lane);
-                staged = true;
-            }
+            if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) { stage_j(inx, iny); staged = true; }
             const float ja = nx - inx, jb = ny - iny;
             const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
             const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;
-            const uint8_t *q0 = jbuf + (iny - jy0) * LK_JS + (inx - jx0);
+            const unsigned wt = ((unsigned)w00 & 0xffffu) | ((unsigned)w01 << 16), wb = ((unsigned)w10 & 0xffffu) | ((unsigned)w11 << 16);
+            const uint8_t *q0 = jbuf + (iny - jy0) * LK_JS;
+            const int xo = inx - jx0;
             int sb1 = 0, sb2 = 0;      // per lane < 14 * 2^25
 #pragma unroll
             for (int s = 0; s < LK_IPL; s++) {
                 if (lane + LK_W * s < LK_ITEMS) {
-                    const uint8_t *q = q0 + irow[s] * LK_JS + icol[s];
+                    int v[7];
+                    lk_sample7(q0 + irow[s] * LK_JS, xo + icol[s], wt, wb, Ic[s], v);
 #pragma unroll
-                    for (int k = 0; k < 7; k++) {
-                        const int diff = descale(q[k] * w00 + q[k + 1] * w01 + q[k + LK_JS] * w10 + q[k + LK_JS + 1] * w11, 9) - Iv[s][k];
-                        sb1 += diff * (int)(short)(dxy[s][k] & 0xffff); sb2 += diff * (dxy[s][k] >> 16);
-                    }
+                    for (int k = 0; k < 7; k++) { const int diff = v[k] >> 9; sb1 += diff * gx[s][k]; sb2 += diff * gy[s][k]; }
                 }
             }
             const long long b1 = lk_warp_sum(sb1), b2 = lk_warp_sum(sb2);
@@ -378,24 +481,21 @@ VIWB_D void lk_track_warp(const LkArgs &a, int pt, int lane, unsigned char *smem
             const int inx = (int)floorf(ex), iny = (int)floorf(ey);
             if (lk_outside(inx, iny, jc, jr)) { status = false; }
             else {
-                if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) {
-                    jx0 = (inx - LK_SLACK) & ~3; jy0 = iny - LK_SLACK;
-                    lk_stage(jbuf, jimg, jstr, jc, jr, jx0, jy0, LK_JROWS, LK_JS / 4, lane);
-                }
+                if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) stage_j(inx, iny);
                 const float ja = ex - inx, jb = ey - iny;
                 const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
                 const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;
-                const uint8_t *q0 = jbuf + (iny - jy0) * LK_JS + (inx - jx0);
+                const unsigned wt = ((unsigned)w00 & 0xffffu) | ((unsigned)w01 << 16), wb = ((unsigned)w10 & 0xffffu) | ((unsigned)w11 << 16);
+                const uint8_t *q0 = jbuf + (iny - jy0) * LK_JS;
+                const int xo = inx - jx0;
                 int sev = 0;
 #pragma unroll
                 for (int s = 0; s < LK_IPL; s++) {
                     if (lane + LK_W * s < LK_ITEMS) {
-                        const uint8_t *q = q0 + irow[s] * LK_JS + icol[s];
+                        int v[7];
+                        lk_sample7(q0 + irow[s] * LK_JS, xo + icol[s], wt, wb, Ic[s], v);
 #pragma unroll
-                        for (int k = 0; k < 7; k++) {
-                            const int diff = descale(q[k] * w00 + q[k + 1] * w01 + q[k + LK_JS] * w10 + q[k + LK_JS + 1] * w11, 9) - Iv[s][k];
-                            sev += diff < 0 ? -diff : diff;
-                        }
+                        for (int k = 0; k < 7; k++) { const int diff = v[k] >> 9; sev += diff < 0 ? -diff : diff; }
                     }
                 }
                 errv = (float)lk_warp_sum(sev) * (1.f / (32 * LK_WIN * LK_WIN));
@@ -429,10 +529,10 @@ VIWB_D void lk_post_item(const PostArgs &a, int i) {
 // task-table kernels: blockIdx.y selects the task
 __global__ void pyr_down_tasks_kernel(const PyrArgs *t) { pyr_down_item(t[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void lk_post_tasks_kernel(const PostArgs *t) { lk_post_item(t[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x); }
-__global__ void __launch_bounds__(32 * LK_PPB, LK_MINB) lk_track_tasks_kernel(const LkArgs *t) {
-    extern __shared__ unsigned char lk_smem[];
+__global__ void __launch_bounds__(32 * LK_PPB, LK_MINB) lk_track_tasks_kernel(const LkArgs *t, const __grid_constant__ LkMaps maps, int use_tma) {
+    extern __shared__ __align__(128) unsigned char lk_smem[];
     const int warp = threadIdx.x >> 5;
-    lk_track_warp(t[blockIdx.y], blockIdx.x * LK_PPB + warp, threadIdx.x & 31, lk_smem + (size_t)warp * LK_WARP_SMEM);
+    lk_track_warp(t[blockIdx.y], use_tma ? &maps : nullptr, blockIdx.x * LK_PPB + warp, threadIdx.x & 31, lk_smem + (size_t)warp * LK_WARP_SMEM);
 }
 #endif
 

@@ -5,9 +5,9 @@
 //              dense system assembled by assemble_block(MODE_MARG) from the same Jacobian kernels the solver uses.
 // The dropped landmark block is diagonal, so it is eliminated exactly (Schur sum T0 = sum w w^T / a); the remaining
 // dropped block (pose 0 + speed-bias 0, or pose 9) goes through the reference's eigen pseudo-inverse (eps 1e-8),
-// and the kept n x n system through a parallel cyclic Jacobi eigen-decomposition in shared memory
-// (stands in for Eigen::SelfAdjointEigenSolver) to produce J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b.  The whole system lives in
-// shared memory over the compact (kept | dropped) dimensions: nothing but the prior itself is written to HBM.
+// and the kept n x n system through tred2 / tql2 in shared memory (stands in for Eigen::SelfAdjointEigenSolver) to produce
+// J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b.  Two kernels: marg_prep (assembly over the compact kept | dropped dimensions in shared
+// memory, all block-parallel) and marg_eig (the eigen-decomposition, three windows per SM).
 #pragma once
 #include "kernels_lin.cuh"
 #include "kernels_solve.cuh"
@@ -44,6 +44,146 @@ VIWB_D void reanchor_block(const BatchDev &bd, int bx, int by, int tid, int nt, 
         if (m.flags[BLK_PR] & 1u) for (int k = 0; k < 4; k++) st[blk_off(BLK_PR) + k] = e[3 + k];   // quirk 1 (estimator.cpp:1209-1213)
     }
     for (int k = 0; k < m.nlm; k++) st[SFIX + k] = 1.0 / (1.0 / st[SFIX + k]);   // setDepth(1/x), getDepthVector(1/depth)
+}
+
+// Symmetric eigen-decomposition in shared memory: Householder tridiagonalisation + implicit QL with eigenvector
+// accumulation (the EISPACK tred2 / tql2 pair, the algorithm family Eigen::SelfAdjointEigenSolver uses), with the
+// O(n^2)-per-step inner loops spread over the block and the O(n) scalar recurrences kept on thread 0.
+// V (n x n, leading dimension ld): in = symmetric matrix (lower triangle read), out = eigenvectors in columns.
+// d (n): eigenvalues (unsorted).  e (n), cs (2n), sc (8): scratch.
+VIWB_D double blk_reduce_small(double v, int tid, int nt, double *red) {     // sum over the block via a short tree
+    return block_sum(v, tid, nt, red);
+}
+VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *sc, double *red, int n, int ld, int tid, int nt) {
+#define VV(i, j) V[(i) * ld + (j)]
+    // ---- tred2
+    for (int j = tid; j < n; j += nt) d[j] = VV(n - 1, j);
+    VIWB_SYNC();
+    for (int i = n - 1; i > 0; i--) {
+        double part = 0.0;
+        for (int k = tid; k < i; k += nt) part += fabs(d[k]);
+        const double scale = blk_reduce_small(part, tid, nt, red);
+        if (scale == 0.0) {
+            if (tid == 0) e[i] = d[i - 1];
+            VIWB_SYNC();
+            for (int j = tid; j < i; j += nt) { d[j] = VV(i - 1, j); VV(i, j) = 0.0; VV(j, i) = 0.0; }
+            VIWB_SYNC();
+            if (tid == 0) d[i] = 0.0;
+            VIWB_SYNC();
+            continue;
+        }
+        part = 0.0;
+        for (int k = tid; k < i; k += nt) { const double t = d[k] / scale; d[k] = t; part += t * t; }
+        double h = blk_reduce_small(part, tid, nt, red);
+        if (tid == 0) {
+            const double f = d[i - 1];
+            double g = sqrt(h); if (f > 0) g = -g;
+            e[i] = scale * g; h = h - f * g; d[i - 1] = f - g; sc[0] = h;
+        }
+        VIWB_SYNC();
+        h = sc[0];
+        // e[j] = (A d)[j] over the leading i x i block (lower triangle storage); column i keeps the Householder vector
+        for (int j = tid; j < i; j += nt) {
+            double g = 0.0;
+            for (int k = 0; k <= j; k++) g += VV(j, k) * d[k];
+            for (int k = j + 1; k < i; k++) g += VV(k, j) * d[k];
+            cs[j] = g / h;            // e[j] / h, kept in cs until the reduction below is done
+            VV(j, i) = d[j];
+        }
+        VIWB_SYNC();
+        part = 0.0;
+        for (int j = tid; j < i; j += nt) part += cs[j] * d[j];
+        const double f2 = blk_reduce_small(part, tid, nt, red);
+        const double hh = f2 / (h + h);
+        for (int j = tid; j < i; j += nt) e[j] = cs[j] - hh * d[j];
+        VIWB_SYNC();
+        // rank-2 update of the lower triangle: V[k][j] -= d[j] e[k] + e[j] d[k],  j <= k < i
+        for (int k = tid; k < i; k += nt) { const double ek = e[k], dk = d[k]; for (int j = 0; j <= k; j++) VV(k, j) -= d[j] * ek + e[j] * dk; }
+        VIWB_SYNC();
+        for (int j = tid; j < i; j += nt) { cs[j] = VV(i - 1, j); VV(i, j) = 0.0; }
+        VIWB_SYNC();
+        for (int j = tid; j < i; j += nt) d[j] = cs[j];
+        if (tid == 0) d[i] = h;
+        VIWB_SYNC();
+    }
+    // ---- accumulate the transformations
+    for (int i = 0; i < n - 1; i++) {
+        if (tid == 0) { VV(n - 1, i) = VV(i, i); VV(i, i) = 1.0; }
+        VIWB_SYNC();
+        const double h = d[i + 1];
+        if (h != 0.0) {
+            for (int k = tid; k <= i; k += nt) d[k] = VV(k, i + 1) / h;
+            VIWB_SYNC();
+            for (int j = tid; j <= i; j += nt) {
+                double g = 0.0;
+                for (int k = 0; k <= i; k++) g += VV(k, i + 1) * VV(k, j);
+                for (int k = 0; k <= i; k++) VV(k, j) -= g * d[k];
+            }
+            VIWB_SYNC();
+        }
+        for (int k = tid; k <= i; k += nt) VV(k, i + 1) = 0.0;
+        VIWB_SYNC();
+    }
+    for (int j = tid; j < n; j += nt) { d[j] = VV(n - 1, j); VV(n - 1, j) = 0.0; }
+    VIWB_SYNC();
+    if (tid == 0) { VV(n - 1, n - 1) = 1.0; e[0] = 0.0; }
+    VIWB_SYNC();
+    // ---- tql2
+    for (int i = 1 + tid; i < n; i += nt) cs[i - 1] = e[i];
+    VIWB_SYNC();
+    for (int i = tid; i < n - 1; i += nt) e[i] = cs[i];
+    if (tid == 0) { e[n - 1] = 0.0; sc[1] = 0.0 /* f */; sc[2] = 0.0 /* tst1 */; }
+    VIWB_SYNC();
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; l++) {
+        if (tid == 0) {
+            const double t = fabs(d[l]) + fabs(e[l]); if (t > sc[2]) sc[2] = t;
+            int m = l; while (m < n) { if (fabs(e[m]) <= eps * sc[2]) break; m++; }
+            sc[3] = (double)m;
+        }
+        VIWB_SYNC();
+        const int m = (int)sc[3];
+        if (m > l) {
+            for (int iter = 0; iter < 200; iter++) {
+                if (tid == 0) {
+                    double g = d[l], p = (d[l + 1] - g) / (2.0 * e[l]), r = sqrt(p * p + 1.0);
+                    if (p < 0) r = -r;
+                    d[l] = e[l] / (p + r); d[l + 1] = e[l] * (p + r);
+                    const double dl1 = d[l + 1]; double h = g - d[l];
+                    for (int i = l + 2; i < n; i++) d[i] -= h;
+                    sc[1] += h;
+                    p = d[m];
+                    double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0; const double el1 = e[l + 1];
+                    // the rotation chain is the serial critical path of the whole decomposition: operands of the next link are
+                    // fetched before the current link's sqrt / reciprocal, and one reciprocal replaces two divisions
+                    double ei = e[m - 1], di = d[m - 1];
+                    for (int i = m - 1; i >= l; i--) {
+                        const double ein = i > l ? e[i - 1] : 0.0, din = i > l ? d[i - 1] : 0.0;
+                        c3 = c2; c2 = c; s2 = s;
+                        g = c * ei; h = c * p;
+                        const double q2 = p * p + ei * ei, rinv = q2 > 0.0 ? rsqrt(q2) : 0.0;      // r = q2 * rsqrt(q2): one special-function chain, no division
+                        r = q2 * rinv;
+                        e[i + 1] = s * r; s = ei * rinv; c = p * rinv;
+                        p = c * di - s * g; d[i + 1] = h + s * (c * g + s * di);
+                        cs[2 * i] = c; cs[2 * i + 1] = s;
+                        ei = ein; di = din;
+                    }
+                    p = -s * s2 * c3 * el1 * e[l] / dl1;
+                    e[l] = s * p; d[l] = c * p;
+                    sc[4] = (fabs(e[l]) > eps * sc[2]) ? 1.0 : 0.0;
+                }
+                VIWB_SYNC();
+                for (int k = tid; k < n; k += nt)
+                    for (int i = m - 1; i >= l; i--) { const double c = cs[2 * i], s = cs[2 * i + 1], h = VV(k, i + 1); VV(k, i + 1) = s * VV(k, i) + c * h; VV(k, i) = c * VV(k, i) - s * h; }
+                VIWB_SYNC();
+                if (sc[4] == 0.0) break;
+                VIWB_SYNC();
+            }
+        }
+        if (tid == 0) { d[l] = d[l] + sc[1]; e[l] = 0.0; }
+        VIWB_SYNC();
+    }
+#undef VV
 }
 
 // Symmetric eigen-decomposition in shared memory by the parallel cyclic Jacobi method (stands in for Eigen::SelfAdjointEigenSolver,
@@ -139,13 +279,6 @@ VIWB_D void sym_eig_jacobi(double *A, int lda, double *V, int ldv, double *d, do
 VIWB_HD int vsub_to_mlay(int p) { return p < 66 ? p : p < 72 ? 165 + (p - 66) : p < 78 ? 171 + (p - 72) : 191; }   // td -> blk_moff(BLK_TD) = 191
 VIWB_HD int marg_cap(int nmax) { return nmax < 16 ? 16 : (nmax > 100 ? 100 : nmax); }
 enum { MARG_MD = 15 };      // dimension of the dropped fixed block: pose 0 + speed-bias 0 (MARGIN_OLD) or pose 9 (6, MARGIN_SECOND_NEW)
-// shared memory: the compact system (c + 15)^2 [kept dims first, then the dropped ones], the eigenvectors c^2, Arm*Amm^-1 (c x 15), the dropped
-// block and its eigenvectors / pseudo-inverse (3 x 15^2), right-hand side, eigenvalues, rotation scratch, reductions, index maps: 134 KB for
-// the 82-dimensional prior of the stereo+IMU window -> one 512-thread block per SM
-VIWB_HD size_t marg_smem_doubles(int nt, int nmax) {
-    (void)nt; const int c = marg_cap(nmax), N = c + MARG_MD;
-    return (size_t)N * N + (size_t)c * c + (size_t)c * MARG_MD + 3 * 256 + (size_t)N + (size_t)c + 2 * (size_t)(c + 2) + 3 * 32 + 16 + (MLAY + 1) / 2 + 1 + (size_t)(N + 1) / 2 + 1;
-}
 struct CompactTarget {     // marginalisation: dense symmetric matrix over the compact (kept | dropped) dimensions, in shared memory
     double *M, *g; int ld; const unsigned char *flags; const int *cmap;
     VIWB_DM int col(int blk, int k) const { return ((flags[blk] & 1u) && k < blk_msize(blk)) ? cmap[blk_moff(blk) + k] : -1; }
@@ -153,7 +286,14 @@ struct CompactTarget {     // marginalisation: dense symmetric matrix over the c
     VIWB_DM void addg(int i, double v) const { g[i] += v; }
 };
 
-VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+// marg_prep: dense system of the marginalisation factors over the compact (kept | dropped) dimensions in shared memory, landmark elimination,
+// pseudo-inverse of the dropped fixed block, Schur complement -> A (n x n) and b (n) of the kept block to HBM (the head of the window's
+// marg_J slot and marg_r), header and linearisation point.  All phases are block-parallel; nothing serial.
+VIWB_HD size_t marg_prep_smem_doubles(int nt, int nmax) {
+    (void)nt; const int c = marg_cap(nmax), N = c + MARG_MD;
+    return (size_t)N * N + (size_t)c * MARG_MD + 3 * 256 + (size_t)N + (size_t)c + 2 * (size_t)(c + 2) + 3 * 32 + 16 + (MLAY + 1) / 2 + 2;
+}
+VIWB_D void marg_prep_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)mode;
     const int w = bx;
     const WinMeta &m = bd.meta[w];
@@ -162,11 +302,10 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     const double *T = bd.Tvis + (size_t)w * VSUB * VSUB, *tv = bd.tvec + (size_t)w * VSUB;
     int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
     const double eps = 1e-8;   // marginalization_factor.h:81
-    // smem carve
     const int cap = marg_cap(bd.marg_nmax), NC = cap + MARG_MD;
-    double *Mc = smem, *Vn = Mc + (size_t)NC * NC, *Tm = Vn + (size_t)cap * cap, *Amm = Tm + (size_t)cap * MARG_MD, *Vmm = Amm + 256, *Ainv = Vmm + 256;
+    double *Mc = smem, *Tm = Mc + (size_t)NC * NC, *Amm = Tm + (size_t)cap * MARG_MD, *Vmm = Amm + 256, *Ainv = Vmm + 256;
     double *bc_ = Ainv + 256, *ev = bc_ + NC, *rot = ev + cap, *red = rot + 2 * (cap + 2), *bc = red + 3 * 32;
-    int *cmap = (int *)(bc + 16), *klist = cmap + ((MLAY + 1) / 2) * 2 + 2;      // klist: marginalisation-layout index of every compact dimension
+    int *cmap = (int *)(bc + 16);
     // ---- dropped / kept dimension lists (marginalisation layout -> compact index: kept dims 0..n-1, dropped n..n+md-1)
     if (tid == 0) {
         int md = 0, n = 0, nb = 0;
@@ -180,7 +319,7 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
             if (m.margin_flag == 0) { if ((bq >= 1 && bq <= 10) || (bq >= 12 && bq <= 21)) nid = bq - 1; }
             else { if (bq == 10 || bq == 21) nid = bq - 1; }
             hdr[3 + nb] = nid; hdr[3 + NB + nb] = n; nb++;
-            for (int k = 0; k < blk_msize(bq); k++) { if (n < cap) { cmap[blk_moff(bq) + k] = n; klist[n] = blk_moff(bq) + k; } n++; }
+            for (int k = 0; k < blk_msize(bq); k++) { if (n < cap) cmap[blk_moff(bq) + k] = n; n++; }
             // linearisation point of the kept block, stored under its new id (keep_block_data + addr_shift)
             const double *src = bd.x_cur + m.state_off + blk_off(bq);
             double *dst = bd.marg_x0 + (size_t)w * SFIX + blk_off(nid);
@@ -198,11 +337,10 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     const int md = (int)bc[2], n = (int)bc[3];
     if (n > cap) { if (tid == 0) { ww.marg_status = -1; hdr[0] = 0; } return; }
     const int N = n + md;
-    // ---- dense system of the marginalisation factors over the compact dimensions
     for (int e = tid; e < N * N; e += nt) Mc[e] = 0.0;
     for (int i = tid; i < N; i += nt) bc_[i] = 0.0;
     VIWB_SYNC();
-    { CompactTarget t; t.M = Mc; t.g = bc_; t.ld = N; t.flags = m.flags; t.cmap = cmap; assemble_into(t, bd, w, MODE_MARG, tid, nt, (int *)Vn); }      // Vn: scratch until the eigenvectors
+    { CompactTarget t; t.M = Mc; t.g = bc_; t.ld = N; t.flags = m.flags; t.cmap = cmap; assemble_into(t, bd, w, MODE_MARG, tid, nt, (int *)Tm); }      // Tm: scratch until the Schur complement
     VIWB_SYNC();
     // ---- eliminate the dropped landmarks: M -= scatter(T0), b -= scatter(tvec0)   (MARGIN_OLD only)
     if (m.margin_flag == 0) {
@@ -210,7 +348,7 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
         for (int p = tid; p < 79; p += nt) { const int ci = cmap[vsub_to_mlay(p)]; if (ci >= 0) bc_[ci] -= tv[p]; }
     }
     VIWB_SYNC();
-    // ---- pseudo-inverse of the dropped fixed block (marginalization_factor.cpp:282-287)
+    // ---- pseudo-inverse of the dropped fixed block (marginalization_factor.cpp:282-287): 15 x 15 (or 6 x 6) parallel Jacobi
     for (int e = tid; e < md * md; e += nt) { const int i = e / md, j = e % md; Amm[e] = 0.5 * (Mc[(n + i) * N + n + j] + Mc[(n + j) * N + n + i]); }
     VIWB_SYNC();
     sym_eig_jacobi(Amm, md, Vmm, md, ev, rot, red, md, tid, nt);      // eigenvalues -> ev, eigenvectors -> columns of Vmm
@@ -229,35 +367,52 @@ VIWB_D void marg_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
         Tm[e] = sacc;
     }
     VIWB_SYNC();
-    // A = Arr - Arm Amm^-1 Amr (in place: the leading n x n block, leading dimension N) ; b = brr - Arm Amm^-1 bmm.
-    // SelfAdjointEigenSolver reads the lower triangle: entry (i, j) and its mirror both take the lower-triangle value
+    // A = Arr - Arm Amm^-1 Amr ; b = brr - Arm Amm^-1 bmm -> HBM.  SelfAdjointEigenSolver reads the lower triangle: both (i, j) and (j, i)
+    // receive the lower-triangle value
+    double *Aout = bd.marg_J + (size_t)w * bd.marg_nmax * bd.marg_nmax, *bout = bd.marg_r + (size_t)w * MAXPRI;
     for (int e = tid; e < n * (n + 1) / 2; e += nt) {
         int i, j; sym_unrank(e, i, j);          // j <= i
         double sacc = Mc[i * N + j];
         for (int k = 0; k < md; k++) sacc -= Tm[i * md + k] * Mc[(n + k) * N + j];
-        Mc[i * N + j] = sacc;
+        Aout[(size_t)i * n + j] = sacc; Aout[(size_t)j * n + i] = sacc;
     }
     for (int i = tid; i < n; i += nt) {
         double sacc = bc_[i];
         for (int k = 0; k < md; k++) sacc -= Tm[i * md + k] * bc_[n + k];
-        ev[i] = sacc;          // parked in ev until the mirror pass is done (bc_[n + k] is still read by other threads)
+        bout[i] = sacc;
     }
-    VIWB_SYNC();
-    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; if (j > i) Mc[i * N + j] = Mc[j * N + i]; }
-    for (int i = tid; i < n; i += nt) bc_[i] = ev[i];
-    VIWB_SYNC();
-    sym_eig_jacobi(Mc, N, Vn, n, ev, rot, red, n, tid, nt);
-    // J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b   (marginalization_factor.cpp:298-306)
+}
+
+// marg_eig: eigen-decomposition of the kept n x n block in shared memory (tred2 + tql2, the algorithm family of Eigen::SelfAdjointEigenSolver),
+// J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b (marginalization_factor.cpp:289-306), in place over A / b in HBM.
+// (A parallel cyclic Jacobi was measured here: 10 sweeps x 81 rounds of 2x2 block updates cost ten times the QL chain, profiles/r02c_*.)
+VIWB_HD size_t marg_eig_smem_doubles(int nt, int nmax) { (void)nt; const int c = marg_cap(nmax); return (size_t)c * (c | 1) + (size_t)6 * c + 32 + 16 + 8; }
+VIWB_D void marg_eig_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)mode;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    WinWork &ww = bd.work[w];
+    if (m.margin_flag < 0) return;
+    const int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
+    if (hdr[0] == 0) return;                                  // marg_prep gave up (kept dimension beyond the solver's capacity)
+    const int n = hdr[1], cap = marg_cap(bd.marg_nmax), ld = n | 1;
+    const double eps = 1e-8;
+    double *Vn = smem, *bn = Vn + (size_t)cap * (cap | 1), *cs = bn + cap, *ev = cs + 2 * cap, *ee = ev + cap, *red = ee + cap, *bc = red + 32;
     double *Jout = bd.marg_J + (size_t)w * bd.marg_nmax * bd.marg_nmax, *rout = bd.marg_r + (size_t)w * MAXPRI;
+    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; Vn[i * ld + j] = Jout[e]; }
+    for (int i = tid; i < n; i += nt) bn[i] = rout[i];
+    VIWB_SYNC();
+    sym_eig_block(Vn, ev, ee, cs, bc, red, n, ld, tid, nt);
+    VIWB_SYNC();
     for (int e = tid; e < n * n; e += nt) {
         const int i = e / n, k = e - i * n;
         const double l = ev[i];
-        Jout[(size_t)i * n + k] = (l > eps ? sqrt(l) : 0.0) * Vn[k * n + i];
+        Jout[e] = (l > eps ? sqrt(l) : 0.0) * Vn[k * ld + i];
     }
     for (int i = tid; i < n; i += nt) {
         const double l = ev[i], si = l > eps ? sqrt(1.0 / l) : 0.0;
         double vb = 0.0;
-        for (int k = 0; k < n; k++) vb += Vn[k * n + i] * bc_[k];
+        for (int k = 0; k < n; k++) vb += Vn[k * ld + i] * bn[k];
         rout[i] = si * vb;
     }
     if (tid == 0) ww.marg_status = 0;

@@ -36,7 +36,7 @@ enum { ASM_STRIDE = 108, ASM_CHUNK = 256, ITEM_FRAME = 0, ITEM_PAIR = 1, ITEM_CO
 // Fused path (solver linearisation of batches whose windows keep ex0 / ex1 / td constant): lin_vis_lm evaluates the factors of whole landmarks per
 // block and leaves one X record per two-frame factor, X = [A | B | r] (2 x 13, row stride 14), at the factor's position in FRAME-PAIR order; asm_pairs
 // turns the records of one (host, observer) pair into G = sum X^T X (13 x 13 inside three 8 x 8 FP64 tensor-core tiles) per chunk of PAIR_CHUNK records.
-enum { XREC = 28, XROW = 14, PAIR_CHUNK = 32, PAIR_OUT = 192, LMB_FACTORS = 128 };
+enum { XREC = 28, XROW = 14, PAIR_CHUNK = 32, PAIR_OUT = 192, LMB_FACTORS = 128, NPAIR = NFR * (NFR - 1) / 2, PAIR_RED = NFR * 27 + NPAIR * 36 + 3 };
 struct AsmItem { int kind, win, a, b, lo, hi, phase, has_common; };
 
 struct PriorDev {       // one per window that has a valid prior
@@ -107,6 +107,7 @@ struct BatchDev {       // passed by value to every kernel
     double *xrec;                   // [nxrec_total][XREC]
     const struct AsmItem *pitems;   // [npitems_total] kind = ITEM_PAIR, lo / hi = record range relative to meta.xrec_off
     double *pair_out;               // [npitems_total][PAIR_OUT] tile (0,0), (0,1), (1,1) of G in mma.m8n8k4 accumulator order
+    double *pair_red;               // [B][PAIR_RED] per frame: diagonal block (21) + gradient (6); per pair a < b: off-diagonal block (36)  (pair_reduce)
     const WinMeta *meta;
     WinWork *work;
     const PriorDev *prior;

@@ -6,9 +6,9 @@
 #ifdef VIWB_HOST_EMU
 static void lk_launch_pyr(const PyrArgs *t, int items, int ntasks, stream_t) { for (int k = 0; k < ntasks; k++) for (int i = 0; i < items; i++) pyr_down_item(t[k], i); }
 static void lk_launch_post(const PostArgs *t, int items, int ntasks, stream_t) { for (int k = 0; k < ntasks; k++) for (int i = 0; i < items; i++) lk_post_item(t[k], i); }
-static void lk_launch_track(const LkArgs *t, int maxn, int ntasks, stream_t) {
+static void lk_launch_track(const LkArgs *t, int maxn, int ntasks, stream_t, const LkMaps *, bool) {
     std::vector<unsigned char> sm(lk_smem_bytes(1) + 64);
-    for (int k = 0; k < ntasks; k++) for (int p = 0; p < maxn; p++) lk_track_warp(t[k], p, 0, sm.data());
+    for (int k = 0; k < ntasks; k++) for (int p = 0; p < maxn; p++) lk_track_warp(t[k], nullptr, p, 0, sm.data());
 }
 static int dev_h2d_2d(void *d, size_t dp, const void *h, size_t hp, size_t w, size_t rows, stream_t) { for (size_t r = 0; r < rows; r++) memcpy((char *)d + r * dp, (const char *)h + r * hp, w); return 0; }
 #else
@@ -20,9 +20,31 @@ static void lk_launch_post(const PostArgs *t, int items, int ntasks, stream_t s)
     if (items <= 0 || ntasks <= 0) return;
     g_prof.begin("lk_post", s); lk_post_tasks_kernel<<<dim3((items + 127) / 128, ntasks), 128, 0, s>>>(t); g_prof.end(s);
 }
-static void lk_launch_track(const LkArgs *t, int maxn, int ntasks, stream_t s) {
+static void lk_launch_track(const LkArgs *t, int maxn, int ntasks, stream_t s, const LkMaps *maps, bool use_tma) {
     if (maxn <= 0 || ntasks <= 0) return;
-    g_prof.begin("lk_track", s); lk_track_tasks_kernel<<<dim3((maxn + LK_PPB - 1) / LK_PPB, ntasks), 32 * LK_PPB, lk_smem_bytes(LK_PPB), s>>>(t); g_prof.end(s);
+    g_prof.begin("lk_track", s); lk_track_tasks_kernel<<<dim3((maxn + LK_PPB - 1) / LK_PPB, ntasks), 32 * LK_PPB, lk_smem_bytes(LK_PPB), s>>>(t, *maps, use_tma ? 1 : 0); g_prof.end(s);
+}
+// One tensor map per pyramid level over the level's stacked images (u8, [LK_SLOTS * F * rows][width], row pitch a multiple of 16 bytes), box 32 x 32,
+// no swizzle, zero fill outside.  cuTensorMapEncodeTiled is a driver entry point: it is looked up at run time so that libviwb.so does not link libcuda
+// (the library must still load -- and fail loudly in viwb_create -- on a box without a driver).
+#include <cuda.h>
+typedef CUresult (*viwb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int lk_encode_maps(LkMaps *out, uint8_t *const *level_base, const int *lw, const int *lh, const int *ls, int images) {
+    static_assert(sizeof(CUtensorMap) == sizeof(out->opaque[0]), "CUtensorMap is 128 bytes");
+    void *fn = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return 1;
+    for (int l = 0; l < LK_MAXLVL; l++) {
+        const cuuint64_t dims[2] = {(cuuint64_t)lw[l], (cuuint64_t)lh[l] * (cuuint64_t)images};
+        const cuuint64_t strides[1] = {(cuuint64_t)ls[l]};
+        const cuuint32_t box[2] = {LK_JS, LK_JROWS}, estr[2] = {1, 1};
+        CUtensorMap tm;
+        const CUresult r = ((viwb_encode_tiled_fn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, level_base[l], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 2;
+        memcpy(&out->opaque[l][0], &tm, sizeof tm);
+    }
+    return 0;
 }
 static int dev_h2d_2d(void *d, size_t dp, const void *h, size_t hp, size_t w, size_t rows, stream_t s) { return (w && rows) ? (int)cudaMemcpy2DAsync(d, dp, h, hp, w, rows, cudaMemcpyHostToDevice, s) : 0; }
 #endif
@@ -56,6 +78,7 @@ struct viwb_lk_batch {
     PostArgs *post;                   // [2F]
     LkArgs *single;                   // scratch task for the single-call entry points
     size_t bytes_images, bytes_points;
+    LkMaps maps; bool use_tma;        // tensor maps of the level stacks (interior windows of lk_track are staged by TMA)
     uint8_t *image(int l, int slot, int f) const { return img[l] + ((size_t)slot * F + f) * lsz[l]; }
     float *P(int k, int f) const { return pts + ((size_t)k * F + f) * maxn * 2; }
     uint8_t *S(int k, int f) const { return st + ((size_t)k * F + f) * maxn; }
@@ -64,6 +87,11 @@ struct viwb_lk_batch {
 
 static void lk_fill_image(const viwb_lk_batch *b, LkImage &im, int slot, int f) {
     for (int l = 0; l < LK_MAXLVL; l++) { im.img[l] = b->image(l, slot, f); im.w[l] = b->lw[l]; im.h[l] = b->lh[l]; im.stride[l] = b->ls[l]; }
+}
+// rows of (slot, stream) inside the level stacks: the TMA coordinates of a task's template (I) and search (J) images
+static void lk_fill_rows(const viwb_lk_batch *b, LkArgs &a, int slot_i, int slot_j, int f) {
+    for (int l = 0; l < LK_MAXLVL; l++) { a.trowI[l] = (slot_i * b->F + f) * b->lh[l]; a.trowJ[l] = (slot_j * b->F + f) * b->lh[l]; }
+    a.tma = b->use_tma ? 1 : 0;
 }
 
 static void lk_batch_free(viwb_lk_batch *b) {
@@ -87,6 +115,15 @@ static int lk_batch_build(viwb_context *ctx, int F, int w, int h, int maxn, int 
     LKA(b->tasks, sizeof(LkArgs) * 8 * F); LKA(b->pyr, sizeof(PyrArgs) * LK_SLOTS * 3 * F); LKA(b->post, sizeof(PostArgs) * 2 * F); LKA(b->single, sizeof(LkArgs));
 #undef LKA
     b->bytes_points = (size_t)LK_PTS * F * maxn * 8;
+    b->use_tma = false;
+#ifndef VIWB_HOST_EMU
+    if (!getenv("VIWB_LK_NO_TMA")) {
+        if ((size_t)LK_SLOTS * F * h > 0x7fffffffull) { lk_batch_free(b); return fail(ctx, VIWB_ERR_INVALID, "LK batch too large for one tensor map"); }
+        const int e = lk_encode_maps(&b->maps, b->img, b->lw, b->lh, b->ls, LK_SLOTS * F);
+        if (e) { lk_batch_free(b); return fail(ctx, VIWB_ERR_CUDA, e == 1 ? "cuTensorMapEncodeTiled not available from this driver" : "cuTensorMapEncodeTiled failed"); }
+        b->use_tma = true;
+    }
+#endif
     // ---- task tables (they only hold addresses inside this object, so they are built once)
     std::vector<LkArgs> T((size_t)8 * F); std::vector<PyrArgs> Y((size_t)LK_SLOTS * 3 * F); std::vector<PostArgs> Q((size_t)2 * F);
     int mi; float e2; lk_criteria(30, 0.01f, mi, e2);
@@ -95,19 +132,19 @@ static int lk_batch_build(viwb_context *ctx, int F, int w, int h, int maxn, int 
         LkArgs *w1 = T.data() + ((size_t)cur * 2 + 0) * 2 * F, *w2 = T.data() + ((size_t)cur * 2 + 1) * 2 * F;
         LkArgs a; memset(&a, 0, sizeof a); a.max_iter = mi; a.eps2 = e2; a.min_eig = 1e-4f;
         // temporal forward: prev -> cur, maxLevel 3 (feature_tracker.cpp:139)
-        lk_fill_image(b, a.I, prev, f); lk_fill_image(b, a.J, cur, f);
+        lk_fill_image(b, a.I, prev, f); lk_fill_image(b, a.J, cur, f); lk_fill_rows(b, a, prev, cur, f);
         a.prev_pts = b->P(0, f); a.next_pts = b->P(1, f); a.status = b->S(0, f); a.err = b->E(0, f); a.n_dev = b->cnt + f; a.max_level = b->levels; a.flags = 0;
         w1[f] = a;
         // temporal reverse: cur -> prev, maxLevel 1, OPTFLOW_USE_INITIAL_FLOW seeded with prev_pts (:144-146)
-        lk_fill_image(b, a.I, cur, f); lk_fill_image(b, a.J, prev, f);
+        lk_fill_image(b, a.I, cur, f); lk_fill_image(b, a.J, prev, f); lk_fill_rows(b, a, cur, prev, f);
         a.prev_pts = b->P(1, f); a.next_pts = b->P(2, f); a.status = b->S(1, f); a.err = b->E(1, f); a.max_level = b->levels < 1 ? b->levels : 1; a.flags = 4;
         w2[f] = a;
         // stereo forward: cur -> right, maxLevel 3 (:240)
-        lk_fill_image(b, a.I, cur, f); lk_fill_image(b, a.J, 2, f);
+        lk_fill_image(b, a.I, cur, f); lk_fill_image(b, a.J, 2, f); lk_fill_rows(b, a, cur, 2, f);
         a.prev_pts = b->P(3, f); a.next_pts = b->P(4, f); a.status = b->S(2, f); a.err = b->E(2, f); a.n_dev = b->cnt + F + f; a.max_level = b->levels; a.flags = 0;
         w1[F + f] = a;
         // stereo reverse: right -> cur, maxLevel 3, no initial flow (:244)
-        lk_fill_image(b, a.I, 2, f); lk_fill_image(b, a.J, cur, f);
+        lk_fill_image(b, a.I, 2, f); lk_fill_image(b, a.J, cur, f); lk_fill_rows(b, a, 2, cur, f);
         a.prev_pts = b->P(4, f); a.next_pts = b->P(5, f); a.status = b->S(3, f); a.err = b->E(3, f);
         w2[F + f] = a;
     }
@@ -182,8 +219,8 @@ static int lk_batch_execute(viwb_lk_batch *b, int what, bool rebuild_cur = true)
     if (count == 0) return VIWB_OK;
     // forward flows start from the source points (no OPTFLOW_USE_INITIAL_FLOW), the temporal reverse flow from prev_pts
     if (b->flow_back && (what & 1)) CK(dev_d2d(b->P(2, 0), b->P(0, 0), (size_t)F * b->maxn * 8, st));
-    lk_launch_track(w1 + first, b->maxn, count, st); ctx->launches++;
-    if (b->flow_back) { lk_launch_track(w2 + first, b->maxn, count, st); ctx->launches++; }
+    lk_launch_track(w1 + first, b->maxn, count, st, &b->maps, b->use_tma); ctx->launches++;
+    if (b->flow_back) { lk_launch_track(w2 + first, b->maxn, count, st, &b->maps, b->use_tma); ctx->launches++; }
     lk_launch_post(b->post + first, b->maxn, count, st); ctx->launches++;
 #ifndef VIWB_HOST_EMU
     CK((int)cudaGetLastError());
@@ -219,7 +256,7 @@ static int lk_track_single(viwb_context *ctx, const uint8_t *prev, const uint8_t
     CK(dev_h2d(b->P(0, 0), prev_pts, (size_t)n * 8, st));
     CK(dev_h2d(b->P(1, 0), (flags & 4) ? next_pts : prev_pts, (size_t)n * 8, st));
     LkArgs a; memset(&a, 0, sizeof a);
-    lk_fill_image(b, a.I, 0, 0); lk_fill_image(b, a.J, 1, 0);
+    lk_fill_image(b, a.I, 0, 0); lk_fill_image(b, a.J, 1, 0); lk_fill_rows(b, a, 0, 1, 0);
     a.prev_pts = b->P(0, 0); a.next_pts = b->P(1, 0); a.status = b->S(0, 0); a.err = b->E(0, 0); a.n = n; a.n_dev = nullptr;
     a.max_level = max_level < b->levels ? max_level : b->levels; a.flags = flags; a.min_eig = min_eig;
     lk_criteria(max_iter, eps, a.max_iter, a.eps2);
@@ -227,7 +264,7 @@ static int lk_track_single(viwb_context *ctx, const uint8_t *prev, const uint8_t
 #ifndef VIWB_HOST_EMU
     CK(dev_sync(st));                      // `a` lives on this stack frame
 #endif
-    lk_launch_track(b->single, n, 1, st); ctx->launches++;
+    lk_launch_track(b->single, n, 1, st, &b->maps, b->use_tma); ctx->launches++;
     CK(dev_d2h(next_pts, b->P(1, 0), (size_t)n * 8, st));
     CK(dev_d2h(status, b->S(0, 0), (size_t)n, st));
     if (err) CK(dev_d2h(err, b->E(0, 0), (size_t)n * 4, st));

@@ -105,14 +105,16 @@ DEF_KERNEL2(syrk, 256, SYRK_MINB)
 #define SOLVE_NT 384
 #endif
 DEF_KERNEL2(solve, SOLVE_NT, 2)
-DEF_KERNEL2(lin_vis_lm, LMB_FACTORS, 3)
+#ifndef LVL_MINB
+#define LVL_MINB 4
+#endif
+DEF_KERNEL2(lin_vis_lm, LMB_FACTORS, LVL_MINB)
 DEF_KERNEL(asm_pairs, 128)
+DEF_KERNEL(pair_reduce, 256)
 DEF_KERNEL2(syrk_mma, SYRK_NT, 4)
 DEF_KERNEL(reanchor, 32)
-#ifndef MARG_NT
-#define MARG_NT 512
-#endif
-DEF_KERNEL2(marg, MARG_NT, 1)
+DEF_KERNEL2(marg_prep, 256, 2)
+DEF_KERNEL2(marg_eig, 256, 3)
 DEF_KERNEL(outlier, 128)
 #define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) \
     do { if ((gx) > 0 && (gy) > 0) { g_prof.begin((mode) == 1 ? #name "_marg" : #name, stream); name##_kernel<<<dim3((gx), (gy)), (nt), (smem_bytes), (stream)>>>(bd, mode); g_prof.end(stream); } } while (0)
@@ -514,7 +516,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     const bool allow_fused = getenv("VIWB_NO_FUSED") == nullptr;
     int n_unfused = 0;
     for (int w = 0; w < B; w++) {
-        const bool fused = allow_fused && low[w].regular;
+        const bool fused = allow_fused && low[w].regular && low[w].npitems > 0;      // (a window without two-frame factors has nothing to fuse)
         b->meta[w].fused = fused ? 1 : 0;
         if (fused) { low[w].nitems_s = 0; low[w].nlist_s = 0; low[w].nph_s = 0; b->meta[w].nitems = 0; b->meta[w].nphases = 0; }
         else { low[w].nlmb = 0; low[w].npitems = 0; low[w].nxrec = 0; n_unfused++; }
@@ -568,7 +570,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     const size_t nvec = (size_t)B * TFIX + nlm;
     WK(&bd.work, B); WK(&bd.x_cur, nstate); WK(&bd.x_cand, nstate); WK(&bd.x_before, nstate);
     WK(&bd.vis_rec, nvis * VREC); WK(&bd.vis_cost, nvis);
-    WK(&bd.xrec, nxr * XREC); WK(&bd.pair_out, npit * PAIR_OUT);
+    WK(&bd.xrec, nxr * XREC); WK(&bd.pair_out, npit * PAIR_OUT); WK(&bd.pair_red, npit ? (size_t)B * PAIR_RED : 0);
     WK(&bd.lm_a, nlm); WK(&bd.lm_g, nlm); WK(&bd.lm_gamma, nlm); WK(&bd.lm_scale, nlm); WK(&bd.lm_cost, nlm); WK(&bd.lm_W, nlm * VSUB); WK(&bd.lm_outlier, nlm);
     WK(&bd.imu_S, nimu * 225); WK(&bd.wheel_S, nwheel * 36); WK(&bd.imu_rec, nimu * IMU_REC); WK(&bd.wheel_rec, nwheel * WHEEL_REC); WK(&bd.plane_rec, nplane * PLANE_REC);
     WK(&bd.prior_A, npJ); WK(&bd.prior_res, npr); WK(&bd.prior_g, npr);
@@ -620,7 +622,8 @@ static int ensure_attrs(viwb_context *ctx) {
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(SOLVE_NT, TFIX * (TFIX + 1) / 2) * 8)));
         CK(cudaFuncSetAttribute(lin_vis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lin_vis_smem_doubles(128, VREC) * 8)));
         CK(cudaFuncSetAttribute(syrk_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(syrk_mma_smem_doubles() * 8)));
-        CK(cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_smem_doubles(MARG_NT, 100) * 8)));
+        CK(cudaFuncSetAttribute(marg_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_prep_smem_doubles(256, 100) * 8)));
+        CK(cudaFuncSetAttribute(marg_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_eig_smem_doubles(256, 100) * 8)));
         ctx->attrs_set = true;
     }
 #endif
@@ -639,9 +642,9 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     CK(dev_d2d(bd.x_cur, bd.x_init, xs, st)); CK(dev_d2d(bd.x_cand, bd.x_init, xs, st));
     if (!(what & RUN_REANCHOR) || (what & RUN_SOLVE)) CK(dev_d2d(bd.x_before, bd.x_init, xs, st));
     CK(dev_d2d(bd.work, b->work_init_dev, sizeof(WinWork) * B, st));
-    const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(SOLVE_NT), nt_marg = NT(MARG_NT);
+    const int nt_vis = NT(128), nt_lm = NT(128), nt_small = NT(128), nt_asm = NT(128), nt_syrk = NT(256), nt_solve = NT(SOLVE_NT), nt_marg = NT(256);
     const int g_vis = (bd.nvis_total + nt_vis - 1) / nt_vis, g_lm = (bd.nlm_total * LM_ROLES + nt_lm - 1) / nt_lm;
-    const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve, bd.env_max) * 8, sm_marg = marg_smem_doubles(nt_marg, bd.marg_nmax) * 8;
+    const size_t sm_small = lin_small_smem_doubles(nt_small) * 8, sm_solve = solve_smem_doubles(nt_solve, bd.env_max) * 8, sm_marg = marg_prep_smem_doubles(nt_marg, bd.marg_nmax) * 8, sm_eig = marg_eig_smem_doubles(nt_marg, bd.marg_nmax) * 8;
     // cost_only: the round after the last allowed iteration only decides accept / reject of the pending candidate (every window
     // still running is at max_num_iterations there, trust_region_minimizer.cc checks the iteration limit before the gradient),
     // so the partial sums and the Schur product of that linearisation would never be read
@@ -654,6 +657,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
             if (cost_only) return;
             const int wpb2 = NT(128) / (NT(128) < 32 ? NT(128) : 32);
             LAUNCH(asm_pairs, bd, (bd.npitems_total + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st);
+            LAUNCH(pair_reduce, bd, B, 1, NT(256), 0, mode, st); ctx->launches++;
             if (g_syrk_dfma) LAUNCH(syrk, bd, B, 1, nt_syrk, syrk_smem_doubles() * 8, mode, st);
             else LAUNCH(syrk_mma, bd, B, 1, NT(SYRK_NT), syrk_mma_smem_doubles() * 8, mode, st);
             ctx->launches += (bd.npitems_total > 0) + 1;
@@ -667,7 +671,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
         if (cost_only) return;
         const int ni = mode == MODE_SOLVE ? bd.nitems_solve : bd.nitems_marg, wpb = nt_asm / (nt_asm < 32 ? nt_asm : 32);
         const bool wide = (mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) == VREC;     // items carry the common columns
-        if (solve && bd.npitems_total > 0) { const int wpb2 = NT(128) / (NT(128) < 32 ? NT(128) : 32); LAUNCH(asm_pairs, bd, (bd.npitems_total + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st); ctx->launches++; }
+        if (solve && bd.npitems_total > 0) { const int wpb2 = NT(128) / (NT(128) < 32 ? NT(128) : 32); LAUNCH(asm_pairs, bd, (bd.npitems_total + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st); LAUNCH(pair_reduce, bd, B, 1, NT(256), 0, mode, st); ctx->launches += 2; }
         if (wide) LAUNCH(asm_items_split, bd, (ni * ASM_SPLIT + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
         else LAUNCH(asm_items, bd, (ni + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
         if (g_syrk_dfma) LAUNCH(syrk, bd, B, 1, nt_syrk, syrk_smem_doubles() * 8, mode, st);
@@ -700,8 +704,9 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     if (what & RUN_REANCHOR) { LAUNCH(reanchor, bd, B, 1, NT(32), 0, 0, st); ctx->launches++; }
     if ((what & RUN_MARG) && b->any_marg) {
         lin(MODE_MARG, false);
-        LAUNCH(marg, bd, B, 1, nt_marg, sm_marg, 0, st);
-        ctx->launches++;
+        LAUNCH(marg_prep, bd, B, 1, nt_marg, sm_marg, 0, st);
+        LAUNCH(marg_eig, bd, B, 1, nt_marg, sm_eig, 0, st);
+        ctx->launches += 2;
     }
 #ifndef VIWB_HOST_EMU
     CK((int)cudaGetLastError());
@@ -799,13 +804,13 @@ extern "C" void viwb_destroy(viwb_context *ctx) {
     delete ctx;
 }
 extern "C" const char *viwb_last_error(const viwb_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-// NULL restores the context's own stream; work already queued on the previous stream is waited for, so that buffers the context recycles
-// (arena, staging slab) are never touched from two streams at once
+// (NULL is CUDA's legacy default stream, a valid handle -- torch's current stream usually is it.)  Work already queued on the previous stream is
+// waited for, so that buffers the context recycles (arena, staging slab) are never touched from two streams at once
 extern "C" int viwb_set_stream(viwb_context *ctx, void *s) {
     if (!ctx) return VIWB_ERR_INVALID;
     bind_device(ctx);
     CK(dev_sync(ctx->stream));
-    ctx->stream = s ? (stream_t)s : ctx->own_stream;
+    ctx->stream = (stream_t)s;
     return VIWB_OK;
 }
 extern "C" long long viwb_launch_count(const viwb_context *ctx) { return ctx ? ctx->launches : 0; }
