@@ -123,7 +123,7 @@ VIWB_D void asm_pairs_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     if (it >= bd.npitems_total) return;
     const AsmItem item = bd.pitems[it];
     if (bd.work[item.win].status != ST_RUNNING) return;
-    const double *recs = bd.xrec + (size_t)bd.meta[item.win].xrec_off * XREC;
+    const double *recs = bd.xrec;                      // item.lo / item.hi are absolute record indices
     double *out = bd.pair_out + (size_t)it * PAIR_OUT;
 #ifdef VIWB_HOST_EMU
     (void)lane;

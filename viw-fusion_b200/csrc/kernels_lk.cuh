@@ -243,7 +243,7 @@ VIWB_D void lk_stage(uint8_t *buf, const uint8_t *img, int stride, int cols, int
 // multiple of 16 bytes), box 32 x 32; a warp's lane 0 arms the warp's mbarrier with the tile's byte count and issues the copy, the warp
 // waits on the barrier's phase.  Columns right of the image are zero-filled by the unit and never read (only windows whose needed
 // pixels are inside the image take this path); rows below the image belong to the next image of the stack and are not read either.
-struct LkMaps { unsigned long long opaque[LK_MAXLVL][16]; };      // LK_MAXLVL x CUtensorMap (128 bytes, 64-byte aligned), encoded by the host
+struct alignas(64) LkMaps { unsigned long long opaque[LK_MAXLVL][16]; };      // LK_MAXLVL x CUtensorMap (128 bytes each; the descriptor must sit 64-byte aligned, also in kernel parameter space), encoded by the host
 #ifndef VIWB_HOST_EMU
 VIWB_D unsigned lk_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 VIWB_D void lk_bar_init(unsigned long long *bar, int lane) {

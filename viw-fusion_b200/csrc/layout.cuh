@@ -105,7 +105,7 @@ struct BatchDev {       // passed by value to every kernel
     const int *lmb_ptr;             // [nlmb_total][2] global landmark range [first, end) of each landmark block
     const int *lmb_win;             // [nlmb_total] window of the block
     double *xrec;                   // [nxrec_total][XREC]
-    const struct AsmItem *pitems;   // [npitems_total] kind = ITEM_PAIR, lo / hi = record range relative to meta.xrec_off
+    const struct AsmItem *pitems;   // [npitems_total] kind = ITEM_PAIR, lo / hi = absolute record range in xrec
     double *pair_out;               // [npitems_total][PAIR_OUT] tile (0,0), (0,1), (1,1) of G in mma.m8n8k4 accumulator order
     double *pair_red;               // [B][PAIR_RED] per frame: diagonal block (21) + gradient (6); per pair a < b: off-diagonal block (36)  (pair_reduce)
     const WinMeta *meta;

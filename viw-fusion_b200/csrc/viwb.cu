@@ -445,7 +445,7 @@ static void lower_fill(const viwb_problem &p, const double *state, int w, const 
             poff[a] = pos;
             for (int c0 = 0, ph = 0; c0 < pcnt[a]; c0 += PAIR_CHUNK, ph++) {
                 AsmItem &it = pit[ni++];
-                it.kind = ITEM_PAIR; it.win = w; it.a = a / NFR; it.b = a % NFR; it.lo = pos + c0; it.hi = pos + std::min(pcnt[a], c0 + (int)PAIR_CHUNK); it.phase = ph; it.has_common = 0;
+                it.kind = ITEM_PAIR; it.win = w; it.a = a / NFR; it.b = a % NFR; it.lo = m.xrec_off + pos + c0; it.hi = m.xrec_off + pos + std::min(pcnt[a], c0 + (int)PAIR_CHUNK); it.phase = ph; it.has_common = 0;      // absolute record range: asm_pairs needs no second table
             }
             pos += pcnt[a];
         }
