@@ -529,10 +529,11 @@ VIWB_D void lk_post_item(const PostArgs &a, int i) {
 // task-table kernels: blockIdx.y selects the task
 __global__ void pyr_down_tasks_kernel(const PyrArgs *t) { pyr_down_item(t[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void lk_post_tasks_kernel(const PostArgs *t) { lk_post_item(t[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x); }
-__global__ void __launch_bounds__(32 * LK_PPB, LK_MINB) lk_track_tasks_kernel(const LkArgs *t, const __grid_constant__ LkMaps maps, int use_tma) {
+// maps: the level tensor maps in GLOBAL memory (written by the host before the launch), or nullptr = no TMA staging
+__global__ void __launch_bounds__(32 * LK_PPB, LK_MINB) lk_track_tasks_kernel(const LkArgs *t, const LkMaps *maps) {
     extern __shared__ __align__(128) unsigned char lk_smem[];
     const int warp = threadIdx.x >> 5;
-    lk_track_warp(t[blockIdx.y], use_tma ? &maps : nullptr, blockIdx.x * LK_PPB + warp, threadIdx.x & 31, lk_smem + (size_t)warp * LK_WARP_SMEM);
+    lk_track_warp(t[blockIdx.y], maps, blockIdx.x * LK_PPB + warp, threadIdx.x & 31, lk_smem + (size_t)warp * LK_WARP_SMEM);
 }
 #endif
 

@@ -337,6 +337,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
     if (tid == 0) { int acc = 0; for (int i = 0; i < nf; i++) { s.rp[i] = acc; acc += i - m.efirst[i] + 1; } s.rp[nf] = acc; }
     double *x = bd.x_cur + m.state_off, *xc = bd.x_cand + m.state_off;
     double *g_scale = bd.v_scale + vo, *g_D = bd.v_D + vo, *g_sg = bd.v_sgrad + vo, *g_gn = bd.v_gn + vo;
+    double *wug = bd.v_wug + m.lm_off, *wun = bd.v_wun + m.lm_off;      // per landmark: w_k . u_g (Cauchy direction) and w_k . (C y) (Gauss-Newton step), reused by the quadratic forms
     const double *lm_a = bd.lm_a + m.lm_off, *lm_g = bd.lm_g + m.lm_off, *lm_gamma = bd.lm_gamma + m.lm_off, *lm_sc = bd.lm_scale + m.lm_off;
     const double *W = bd.lm_W + (size_t)m.lm_off * VSUB;
     double *Hpk = bd.Hpk + (size_t)w * (TFIX * (TFIX + 1) / 2), *gpk = bd.gpk + (size_t)w * TFIX;
@@ -458,6 +459,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                 const double lsc = lm_sc[k], lsg = g_sg[TFIX + k], lD = g_D[TFIX + k], la = lm_a[k], lg = lm_g[k];
                 const double dw = warp_dot80(W + (size_t)k * VSUB, s.uvis, lane);
                 if (lane == 0) {
+                    wug[k] = dw;
                     const double ul = lsc * lsg / lD;
                     q += 2.0 * ul * dw + la * ul * ul;
                     l += lg * ul;
@@ -524,6 +526,7 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                         const double c = lm_sc[k], Dk = g_D[TFIX + k], la = lm_a[k], lg = lm_g[k];
                         const double dw = warp_dot80(W + (size_t)k * VSUB, s.uvis, lane);
                         if (lane == 0) {
+                            wun[k] = dw;
                             const double hk = c * c * la + mu * Dk * Dk;
                             const double yk = c * (lg - dw) / hk;
                             if (!isfinite(yk)) bad = 1.0;
@@ -539,28 +542,25 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
             }
             VIWB_SYNC();
             if (!ls_failure) {
-                // q_gn, q_nn, l_n with u_n = c o (gn / D) = -c o y
+                // q_gn, q_nn, l_n with u_n = c o (gn / D) = -c o y: s.u still holds c o y from the back-substitution, and the landmark
+                // rows' products with it (wun) and with u_g (wug) are on file -- no third pass over W
                 load_H(Hpk, s, nf, tid, nt);
-                for (int i = tid; i < nf; i += nt) s.u[i] = s.sc[i] * g_gn[i] / s.D[i];
+                for (int i = tid; i < nf; i += nt) s.u[i] = -s.u[i];
                 VIWB_SYNC();
                 symv(s, nf, s.u, s.Hu, tid, nt);
-                to_vis(s, nf, s.u, s.uvis, tid, nt);            // uvis = u_n
-                to_vis(s, nf, s.ug, s.uvis + VSUB, tid, nt);    // second half = u_g
                 double qnn = 0.0, qgn = 0.0, ln = 0.0, nn = 0.0, gd = 0.0;
                 for (int i = tid; i < nf; i += nt) {
                     qnn += s.u[i] * s.Hu[i]; qgn += s.ug[i] * s.Hu[i]; ln += s.g[i] * s.u[i];
                     nn += g_gn[i] * g_gn[i]; gd += s.sg[i] * g_gn[i];
                 }
-                VIWB_LM_LOOP(k, N) {
+                for (int k = tid; k < N; k += nt) {
                     const double c = lm_sc[k], Dk = g_D[TFIX + k], ggn = g_gn[TFIX + k], gsg = g_sg[TFIX + k], la = lm_a[k], lg = lm_g[k];
-                    const double dn = warp_dot80(W + (size_t)k * VSUB, s.uvis, lane), dg = warp_dot80(W + (size_t)k * VSUB, s.uvis + VSUB, lane);
-                    if (lane == 0) {
-                        const double un = c * ggn / Dk, ug = c * gsg / Dk;
-                        qnn += 2.0 * un * dn + la * un * un;
-                        qgn += ug * dn + un * dg + la * ug * un;
-                        ln += lg * un;
-                        nn += ggn * ggn; gd += gsg * ggn;
-                    }
+                    const double dn = -wun[k], dg = wug[k];
+                    const double un = c * ggn / Dk, ug = c * gsg / Dk;
+                    qnn += 2.0 * un * dn + la * un * un;
+                    qgn += ug * dn + un * dg + la * ug * un;
+                    ln += lg * un;
+                    nn += ggn * ggn; gd += gsg * ggn;
                 }
                 { double v5[5] = {qnn, qgn, ln, nn, gd}; block_sum_n<5>(v5, tid, nt, s.red); qnn = v5[0]; qgn = v5[1]; ln = v5[2]; nn = v5[3]; gd = v5[4]; }
                 if (tid == 0) { ww.q_nn = qnn; ww.q_gn = qgn; ww.l_n = ln; ww.gn_norm = sqrt(nn); ww.sgrad_dot_gn = gd; }

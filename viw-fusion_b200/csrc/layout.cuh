@@ -140,6 +140,7 @@ struct BatchDev {       // passed by value to every kernel
     double *Hpk, *gpk, *gfix, *Tvis, *tvec;   // Hpk [B][TFIX*(TFIX+1)/2] packed active H, gpk [B][TFIX] compact gradient
     // solver vectors, per window at work_off = state_off - 15*w ... stored at vec_off = w*TFIX + lm_off
     double *v_scale, *v_D, *v_sgrad, *v_gn;
+    double *v_wug, *v_wun;              // [nlm_total] per landmark w_k . u_g and w_k . (C y) of the current linearisation (solve)
     // marginalisation outputs
     double *marg_J, *marg_r, *marg_x0;  // [B][marg_nmax^2] (n x n, row stride n, at the head of the slot), [B][MAXPRI], [B][SFIX]
     int *marg_hdr;                      // [B][2 + 2*NB]: valid, n, nb, block_id[], block_idx[]

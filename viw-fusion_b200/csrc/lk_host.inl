@@ -22,7 +22,7 @@ static void lk_launch_post(const PostArgs *t, int items, int ntasks, stream_t s)
 }
 static void lk_launch_track(const LkArgs *t, int maxn, int ntasks, stream_t s, const LkMaps *maps, bool use_tma) {
     if (maxn <= 0 || ntasks <= 0) return;
-    g_prof.begin("lk_track", s); lk_track_tasks_kernel<<<dim3((maxn + LK_PPB - 1) / LK_PPB, ntasks), 32 * LK_PPB, lk_smem_bytes(LK_PPB), s>>>(t, *maps, use_tma ? 1 : 0); g_prof.end(s);
+    g_prof.begin("lk_track", s); lk_track_tasks_kernel<<<dim3((maxn + LK_PPB - 1) / LK_PPB, ntasks), 32 * LK_PPB, lk_smem_bytes(LK_PPB), s>>>(t, use_tma ? maps : nullptr); g_prof.end(s);
 }
 // One tensor map per pyramid level over the level's stacked images (u8, [LK_SLOTS * F * rows][width], row pitch a multiple of 16 bytes), box 32 x 32,
 // no swizzle, zero fill outside.  cuTensorMapEncodeTiled is a driver entry point: it is looked up at run time so that libviwb.so does not link libcuda
@@ -78,7 +78,7 @@ struct viwb_lk_batch {
     PostArgs *post;                   // [2F]
     LkArgs *single;                   // scratch task for the single-call entry points
     size_t bytes_images, bytes_points;
-    LkMaps maps; bool use_tma;        // tensor maps of the level stacks (interior windows of lk_track are staged by TMA)
+    LkMaps *maps; bool use_tma;       // device copy of the level stacks' tensor maps (interior windows of lk_track are staged by TMA)
     uint8_t *image(int l, int slot, int f) const { return img[l] + ((size_t)slot * F + f) * lsz[l]; }
     float *P(int k, int f) const { return pts + ((size_t)k * F + f) * maxn * 2; }
     uint8_t *S(int k, int f) const { return st + ((size_t)k * F + f) * maxn; }
@@ -98,6 +98,7 @@ static void lk_batch_free(viwb_lk_batch *b) {
     if (!b) return;
     for (int l = 0; l < LK_MAXLVL; l++) if (b->img[l]) dev_free(b->img[l]);
     if (b->pts) dev_free(b->pts); if (b->st) dev_free(b->st); if (b->err) dev_free(b->err); if (b->cnt) dev_free(b->cnt);
+    if (b->maps) dev_free(b->maps);
     if (b->tasks) dev_free(b->tasks); if (b->pyr) dev_free(b->pyr); if (b->post) dev_free(b->post); if (b->single) dev_free(b->single);
     delete b;
 }
@@ -119,8 +120,10 @@ static int lk_batch_build(viwb_context *ctx, int F, int w, int h, int maxn, int 
 #ifndef VIWB_HOST_EMU
     if (!getenv("VIWB_LK_NO_TMA")) {
         if ((size_t)LK_SLOTS * F * h > 0x7fffffffull) { lk_batch_free(b); return fail(ctx, VIWB_ERR_INVALID, "LK batch too large for one tensor map"); }
-        const int e = lk_encode_maps(&b->maps, b->img, b->lw, b->lh, b->ls, LK_SLOTS * F);
+        LkMaps hm;
+        const int e = lk_encode_maps(&hm, b->img, b->lw, b->lh, b->ls, LK_SLOTS * F);
         if (e) { lk_batch_free(b); return fail(ctx, VIWB_ERR_CUDA, e == 1 ? "cuTensorMapEncodeTiled not available from this driver" : "cuTensorMapEncodeTiled failed"); }
+        if (dev_malloc((void **)&b->maps, sizeof(LkMaps)) || cudaMemcpy(b->maps, &hm, sizeof hm, cudaMemcpyHostToDevice) != cudaSuccess) { lk_batch_free(b); return fail(ctx, VIWB_ERR_CUDA, "tensor map upload failed"); }
         b->use_tma = true;
     }
 #endif
@@ -219,8 +222,8 @@ static int lk_batch_execute(viwb_lk_batch *b, int what, bool rebuild_cur = true)
     if (count == 0) return VIWB_OK;
     // forward flows start from the source points (no OPTFLOW_USE_INITIAL_FLOW), the temporal reverse flow from prev_pts
     if (b->flow_back && (what & 1)) CK(dev_d2d(b->P(2, 0), b->P(0, 0), (size_t)F * b->maxn * 8, st));
-    lk_launch_track(w1 + first, b->maxn, count, st, &b->maps, b->use_tma); ctx->launches++;
-    if (b->flow_back) { lk_launch_track(w2 + first, b->maxn, count, st, &b->maps, b->use_tma); ctx->launches++; }
+    lk_launch_track(w1 + first, b->maxn, count, st, b->maps, b->use_tma); ctx->launches++;
+    if (b->flow_back) { lk_launch_track(w2 + first, b->maxn, count, st, b->maps, b->use_tma); ctx->launches++; }
     lk_launch_post(b->post + first, b->maxn, count, st); ctx->launches++;
 #ifndef VIWB_HOST_EMU
     CK((int)cudaGetLastError());
@@ -264,7 +267,7 @@ static int lk_track_single(viwb_context *ctx, const uint8_t *prev, const uint8_t
 #ifndef VIWB_HOST_EMU
     CK(dev_sync(st));                      // `a` lives on this stack frame
 #endif
-    lk_launch_track(b->single, n, 1, st, &b->maps, b->use_tma); ctx->launches++;
+    lk_launch_track(b->single, n, 1, st, b->maps, b->use_tma); ctx->launches++;
     CK(dev_d2h(next_pts, b->P(1, 0), (size_t)n * 8, st));
     CK(dev_d2h(status, b->S(0, 0), (size_t)n, st));
     if (err) CK(dev_d2h(err, b->E(0, 0), (size_t)n * 4, st));

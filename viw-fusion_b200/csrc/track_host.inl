@@ -128,11 +128,11 @@ static int trk_track(viwb_tracker *t, double cur_time, const uint8_t *const *lef
             CK(dev_h2d(t->has_pred, has_prediction, (size_t)F, st));
             CK(dev_h2d(b->P(1, 0), predict_pts, (size_t)F * t->maxn * 8, st));
             const LkArgs *pt = t->pred_tasks + ((size_t)b->cur * 2 + 0) * F, *rt = t->pred_tasks + ((size_t)b->cur * 2 + 1) * F;
-            trk_launch_pred_setup(run, F, st); lk_launch_track(pt, t->maxn, F, st, &b->maps, b->use_tma);
-            trk_launch_pred_check(run, F, st); lk_launch_track(rt, t->maxn, F, st, &b->maps, b->use_tma);
+            trk_launch_pred_setup(run, F, st); lk_launch_track(pt, t->maxn, F, st, b->maps, b->use_tma);
+            trk_launch_pred_check(run, F, st); lk_launch_track(rt, t->maxn, F, st, b->maps, b->use_tma);
             ctx->launches += 4;
             const LkArgs *w2 = b->tasks + ((size_t)b->cur * 2 + 1) * 2 * F;
-            if (b->flow_back) { CK(dev_d2d(b->P(2, 0), b->P(0, 0), (size_t)F * b->maxn * 8, st)); lk_launch_track(w2, t->maxn, F, st, &b->maps, b->use_tma); ctx->launches++; }
+            if (b->flow_back) { CK(dev_d2d(b->P(2, 0), b->P(0, 0), (size_t)F * b->maxn * 8, st)); lk_launch_track(w2, t->maxn, F, st, b->maps, b->use_tma); ctx->launches++; }
             lk_launch_post(b->post, t->maxn, F, st); ctx->launches++;
         }
     }

@@ -576,7 +576,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     WK(&bd.prior_A, npJ); WK(&bd.prior_res, npr); WK(&bd.prior_g, npr);
     WK(&bd.Hpk, (size_t)B * (TFIX * (TFIX + 1) / 2)); WK(&bd.gpk, (size_t)B * TFIX); WK(&bd.gfix, (size_t)B * (TFIX + 8));
     WK(&bd.asm_out, (nit_s + nit_m) * ASM_STRIDE); WK(&bd.Tvis, (size_t)B * VSUB * VSUB); WK(&bd.tvec, (size_t)B * VSUB);
-    WK(&bd.v_scale, nvec); WK(&bd.v_D, nvec); WK(&bd.v_sgrad, nvec); WK(&bd.v_gn, nvec);
+    WK(&bd.v_scale, nvec); WK(&bd.v_D, nvec); WK(&bd.v_sgrad, nvec); WK(&bd.v_gn, nvec); WK(&bd.v_wug, nlm); WK(&bd.v_wun, nlm);
     // marginalisation outputs / scratch: sized by the largest prior this batch produces, and not at all when no window marginalises
     const size_t mJ = b->any_marg ? (size_t)b->prior_nmax * b->prior_nmax : 0, mB = b->any_marg ? (size_t)B : 0;
     WK(&bd.marg_J, mB * mJ); WK(&bd.marg_r, mB * MAXPRI); WK(&bd.marg_x0, mB * SFIX);
