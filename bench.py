@@ -148,6 +148,30 @@ def usable_cores():
     return n
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank (its feeder lanes inherit the mask) to the CPUs of the NUMA node the GPU hangs off, BEFORE any page-locked slab is allocated, so that
+    staging memory is first-touched on that node and H2D copies do not cross the socket interconnect.  Returns a small report for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith("00000000:"):
+            bdf = "0000:" + bdf[9:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return {"node": None, "note": "no NUMA affinity reported for the GPU"}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"node": node, "note": "node CPUs outside this process' affinity mask"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except Exception as e:      # no sysfs / nvidia-smi: run unbound
+        return {"node": None, "note": "unbound (%s)" % type(e).__name__}
+
+
 def cpu_solve_many(vo, probs, states, seconds, threads):
     """Oracle (C port of the reference algorithm) on `threads` pthreads inside the C library for about `seconds`;
     each optimisation is single-threaded like Ceres' default.  Returns (solves/s, count, seconds)."""
@@ -445,6 +469,7 @@ def main():
     import torch
     import torch.distributed as dist
     from viwb import lib
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else {"node": None, "note": "single rank: unbound"}
     torch.cuda.set_device(local_rank)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -696,7 +721,9 @@ def main():
                 "workload_stats": {"mean_visual_factors": sum(len(p.vis_type) for p in probs) / B, "mean_landmarks": sum(p.num_landmarks for p in probs) / B,
                                    "camera_streams": B if lk is not None else 0, "distinct_scenes": len(scenes) if scenes else 0,
                                    "lk_stream": None if lk is None else ("same stream as the solver" if cam_stream is None else "own CUDA stream, concurrent with the solver (the reference's tracker thread)")},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "host_threads": lanes, "sweep": e2e_sweep},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "host_threads": lanes, "sweep": e2e_sweep,
+                        "numa": numa, "h2d_gbs_per_rank": h2d * e2e_steps / e2e_s / 1e9,
+                        "limiter": "host feed: %.2f GB of page-locked H2D per rank per step (camera frames + whole windows) against the device step" % (h2d / 1e9)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity,
                 "single_window_e2e_ms": single_ms}
         print(json.dumps(line))

@@ -508,7 +508,7 @@ int vo_window_solve(const viwb_problem *pb, double *state, const viwb_options *o
             /* DoglegStrategy::StepAccepted */
             if (relative_decrease < 0.25) radius *= 0.5;
             if (relative_decrease > 0.75) { double r3 = 3.0 * dogleg_step_norm; if (r3 > radius) radius = r3; }
-            if (radius > opt->max_trust_region_radius) radius = opt->max_trust_region_radius;
+            /* (DoglegStrategy::StepAccepted does not clamp to max_trust_region_radius; only LevenbergMarquardtStrategy does) */
             mu = 2.0 * mu / mu_increase; if (mu < min_mu) mu = min_mu;
             reuse = 0;
         } else {

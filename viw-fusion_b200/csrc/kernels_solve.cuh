@@ -382,7 +382,6 @@ VIWB_D void solve_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
                 ww.x_cost = cand_cost; ww.successful++;
                 if (rd < 0.25) ww.radius *= 0.5;                                 // DoglegStrategy::StepAccepted
                 if (rd > 0.75) ww.radius = fmax(ww.radius, 3.0 * ww.dogleg_step_norm);
-                ww.radius = fmin(ww.radius, op.max_radius);
                 ww.mu = fmax(min_mu, 2.0 * ww.mu / mu_inc);
                 ww.reuse = 0;
             } else { ww.radius *= 0.5; ww.reuse = 1; }                           // StepRejected
