@@ -246,22 +246,28 @@ VIWB_D void lk_stage(uint8_t *buf, const uint8_t *img, int stride, int cols, int
 struct alignas(64) LkMaps { unsigned long long opaque[LK_MAXLVL][16]; };      // LK_MAXLVL x CUtensorMap (128 bytes each; the descriptor must sit 64-byte aligned, also in kernel parameter space), encoded by the host
 #ifndef VIWB_HOST_EMU
 VIWB_D unsigned lk_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-VIWB_D void lk_bar_init(unsigned long long *bar, int lane) {
+VIWB_D void lk_bar_init(unsigned long long *bar, int lane) {      // bar[0]: source-patch copies, bar[1]: search-region copies
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lk_smem_addr(bar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lk_smem_addr(bar + 1)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the TMA unit (async proxy) must see the initialised barriers
     }
     __syncwarp();
 }
-// tile (x, y) .. (x + 31, y + 31) of the level's stack into dst (128-byte aligned); phase: this warp's count of finished copies & 1
-VIWB_D void lk_tma_tile(uint8_t *dst, const void *map, int x, int y, unsigned long long *bar, unsigned &phase, int lane) {
+// issue: tile (x, y) .. (x + 31, y + 31) of the level's stack into dst (128-byte aligned), completion on `bar`; returns at once
+VIWB_D void lk_tma_issue(uint8_t *dst, const void *map, int x, int y, unsigned long long *bar, int lane) {
     __syncwarp();                                  // every lane is done reading the buffer that is about to be overwritten
-    const unsigned b = lk_smem_addr(bar);
     if (lane == 0) {
+        const unsigned b = lk_smem_addr(bar);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(32 * 32) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                      ::"r"(lk_smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(b) : "memory");
     }
+}
+// wait: the whole warp spins on the barrier's phase; phase = this barrier's count of finished copies & 1
+VIWB_D void lk_tma_wait(unsigned long long *bar, unsigned &phase) {
+    const unsigned b = lk_smem_addr(bar);
     unsigned done = 0;
     while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(b), "r"(phase) : "memory");
@@ -310,7 +316,8 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
     if (pt >= npts) return;
 #ifndef VIWB_HOST_EMU
     unsigned long long *bar = (unsigned long long *)(smem_raw + LK_OFF_BAR);
-    unsigned phase = 0;
+    unsigned phaseP = 0, phaseJ = 0;
+    bool p_pending = false, j_pending = false;      // a source-patch / search-region copy is in flight
     const bool tma = maps != nullptr && a.tma != 0;
     if (tma) lk_bar_init(bar, lane);
 #else
@@ -338,11 +345,27 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
         const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
         const int cols = a.I.w[level], rows = a.I.h[level];
         if (lk_outside(ipx, ipy, cols, rows)) { if (level == 0) { status = false; errv = 0.f; } continue; }
-        // 1. source patch rows [ipy-1, ipy+22]; pixel (ipx-1+x) of a row sits at byte psx + x
+        // 1. source patch rows [ipy-1, ipy+22]; pixel (ipx-1+x) of a row sits at byte psx + x.  The search region of this level is requested
+        //    first (its position is known), so that its latency hides behind the template construction; the source patch itself was
+        //    requested while the previous level iterated (its position only depends on the tracked point).
         int psx;
+        const int jc = a.J.w[level], jr = a.J.h[level], jstr = a.J.stride[level];
+        const uint8_t *jimg = a.J.img[level];
+        int jx0 = 0, jy0 = 0;          // origin of the staged search region
+        bool staged = false;
 #ifndef VIWB_HOST_EMU
+        if (tma) {
+            const int inx = (int)floorf(nx - (float)LK_HALF), iny = (int)floorf(ny - (float)LK_HALF);
+            if (inx >= 0 && iny >= 0 && inx + 23 <= jc && iny + 23 <= jr && jc >= LK_JS && jr >= LK_JROWS) {
+                jx0 = inx - 4; if (jx0 < 0) jx0 = 0; if (jx0 > jc - LK_JS) jx0 = jc - LK_JS;
+                jy0 = iny - 4; if (jy0 < 0) jy0 = 0; if (jy0 > jr - LK_JROWS) jy0 = jr - LK_JROWS;
+                lk_tma_issue(jbuf, &maps->opaque[level][0], jx0, a.trowJ[level] + jy0, bar + 1, lane);
+                j_pending = true; staged = true;
+            }
+        }
         if (tma && ipx >= 1 && ipy >= 1 && ipx + 23 <= cols && ipy + 23 <= rows) {
-            lk_tma_tile(pbuf, &maps->opaque[level][0], ipx - 1, a.trowI[level] + ipy - 1, bar, phase, lane);
+            if (!p_pending) lk_tma_issue(pbuf, &maps->opaque[level][0], ipx - 1, a.trowI[level] + ipy - 1, bar, lane);
+            lk_tma_wait(bar, phaseP); p_pending = false;
             psx = 0;
         } else
 #endif
@@ -421,18 +444,30 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
                 }
             }
         }
+#ifndef VIWB_HOST_EMU
+        if (tma && level > 0) {      // the template is in registers: the source-patch buffer is free for the next level's patch
+            const float sc2 = (float)(1. / (1 << (level - 1)));
+            const int qx = (int)floorf(px0 * sc2 - (float)LK_HALF), qy = (int)floorf(py0 * sc2 - (float)LK_HALF);
+            if (qx >= 1 && qy >= 1 && qx + 23 <= a.I.w[level - 1] && qy + 23 <= a.I.h[level - 1]) {
+                lk_tma_issue(pbuf, &maps->opaque[level - 1][0], qx - 1, a.trowI[level - 1] + qy - 1, bar, lane);
+                p_pending = true;
+            }
+        }
+#endif
         const long long A11 = lk_warp_sum(sA11), A12 = lk_warp_sum(sA12), A22 = lk_warp_sum(sA22);
         const float fA11 = (float)A11 * FLT_SCALE, fA12 = (float)A12 * FLT_SCALE, fA22 = (float)A22 * FLT_SCALE;
         float D = fA11 * fA22 - fA12 * fA12;
         const float minEig = (fA22 + fA11 - sqrtf((fA11 - fA22) * (fA11 - fA22) + 4.f * fA12 * fA12)) / (2 * LK_WIN * LK_WIN);
-        if (minEig < min_eig || D < 1.1920929e-07f) { if (level == 0) status = false; continue; }
+        if (minEig < min_eig || D < 1.1920929e-07f) {
+#ifndef VIWB_HOST_EMU
+            if (j_pending) { lk_tma_wait(bar + 1, phaseJ); j_pending = false; }
+#endif
+            if (level == 0) status = false;
+            continue;
+        }
         D = 1.f / D;
         nx -= (float)LK_HALF; ny -= (float)LK_HALF;
         float pdx = 0.f, pdy = 0.f;
-        const int jc = a.J.w[level], jr = a.J.h[level], jstr = a.J.stride[level];
-        const uint8_t *jimg = a.J.img[level];
-        int jx0 = 0, jy0 = 0;          // origin of the staged search region
-        bool staged = false;
         // stage the 32 x 32 region that holds the 23 x 23 samples at (inx, iny): one TMA tile clamped into the image when the samples lie inside
         // it, else the reflect-101 path (origin a multiple of 4 in x)
         auto stage_j = [&](int inx, int iny) {
@@ -440,7 +475,8 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
             if (tma && inx >= 0 && iny >= 0 && inx + 23 <= jc && iny + 23 <= jr && jc >= LK_JS && jr >= LK_JROWS) {
                 jx0 = inx - 4; if (jx0 < 0) jx0 = 0; if (jx0 > jc - LK_JS) jx0 = jc - LK_JS;
                 jy0 = iny - 4; if (jy0 < 0) jy0 = 0; if (jy0 > jr - LK_JROWS) jy0 = jr - LK_JROWS;
-                lk_tma_tile(jbuf, &maps->opaque[level][0], jx0, a.trowJ[level] + jy0, bar, phase, lane);
+                lk_tma_issue(jbuf, &maps->opaque[level][0], jx0, a.trowJ[level] + jy0, bar + 1, lane);
+                lk_tma_wait(bar + 1, phaseJ);
                 return;
             }
 #endif
@@ -450,6 +486,9 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
         for (int j = 0; j < max_iter; j++) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (lk_outside(inx, iny, jc, jr)) { if (level == 0) status = false; break; }
+#ifndef VIWB_HOST_EMU
+            if (j_pending) { lk_tma_wait(bar + 1, phaseJ); j_pending = false; }      // the region requested at the top of the level
+#endif
             if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) { stage_j(inx, iny); staged = true; }
             const float ja = nx - inx, jb = ny - iny;
             const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
@@ -476,6 +515,9 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
             if (j > 0 && fabsf(dx + pdx) < 0.01f && fabsf(dy + pdy) < 0.01f) { npx -= dx * 0.5f; npy -= dy * 0.5f; break; }
             pdx = dx; pdy = dy;
         }
+#ifndef VIWB_HOST_EMU
+        if (j_pending) { lk_tma_wait(bar + 1, phaseJ); j_pending = false; }      // (no iteration ran: the requested region is still to be collected)
+#endif
         if (status && level == 0) {   // L1 error of the final patch (flags without OPTFLOW_LK_GET_MIN_EIGENVALS)
             const float ex = npx - (float)LK_HALF, ey = npy - (float)LK_HALF;
             const int inx = (int)floorf(ex), iny = (int)floorf(ey);
