@@ -3,8 +3,8 @@
 //
 //   lin_vis_lm  one block per group of WHOLE landmarks (<= LMB_FACTORS factors): thread per factor evaluates residual, Huber, tangent
 //               Jacobians (the three projection factors, factor/projection*Factor.cpp) into a shared-memory tile; the block then
-//                 - streams one X record per two-frame factor, X = [A | B | r] (2 x 13), to its slot in FRAME-PAIR order (one contiguous
-//                   224-byte store per record), and
+//                 - writes one X record per two-frame factor, X = [A | B | r] (2 x 13), from registers to its slot in FRAME-PAIR order (14 aligned
+//                   16-byte stores per thread), and
 //                 - reduces the per-landmark quantities straight from the tile: a = |J_l|^2, g_l, the cost, the Schur weight gamma and the
 //                   row W = J_p^T J_l -- the 28-double visual records of lin_vis never exist, lm_reduce does not run.
 //   asm_pairs   one warp per chunk of one frame pair's records: G = sum_f X_f^T X_f (13 x 13: A^T A | A^T B | A^T r / B^T B | B^T r) as a
@@ -37,7 +37,7 @@ VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt
     const int k0 = bd.lmb_ptr[2 * bx], k1 = bd.lmb_ptr[2 * bx + 1];    // global landmark range of this block
     const int f0 = bd.lm_fptr[k0], nf = bd.lm_fptr[k1] - f0;            // its factors (consecutive, <= LMB_FACTORS)
     double *tile = smem;
-    int *meta = (int *)(smem + (size_t)LMB_FACTORS * LVL_TS);      // [2 t] = landmark (window-local) << 12 | fi << 8 | fj << 4 | type << 2 | dup ; [2 t + 1] = X-record slot
+    int *meta = (int *)(smem + (size_t)LMB_FACTORS * LVL_TS);      // [2 t] = landmark (window-local) << 12 | fi << 8 | fj << 4 | type << 2 | dup
     const double *x = bd.x_cand + m.state_off;
     // ---- 0: the W rows of these landmarks start from zero (frames that do not observe a landmark keep zero blocks)
     { double *Wb = bd.lm_W + (size_t)k0 * VSUB; for (int e = tid; e < (k1 - k0) * VSUB; e += nt) Wb[e] = 0.0; }
@@ -56,19 +56,26 @@ VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt
         row[12] = o.r[0] * sc; row[13] = 0.0; row[XROW + 12] = o.r[1] * sc; row[XROW + 13] = 0.0;
         row[LVL_U] = o.Jl[0] * sc; row[LVL_U + 1] = o.Jl[1] * sc; row[LVL_C] = half_rho;
         meta[2 * t] = (bd.vis_lm[f] << 12) | (fi << 8) | (fj << 4) | (type << 2) | bd.vis_dup[f];
-        meta[2 * t + 1] = bd.vis_pos[f];
-    }
-    VIWB_SYNC();
-    // ---- 2a: X records to their frame-pair slots: one warp-wide contiguous store per record
-    {
-        const int Wd = nt < 32 ? nt : 32, nwp = nt / Wd, wid = tid / Wd, lane = tid % Wd;
-        double *xr = bd.xrec + (size_t)m.xrec_off * XREC;
-        for (int t = wid; t < nf; t += nwp) {
-            const int pos = meta[2 * t + 1];
-            if (pos < 0) continue;                       // one-frame stereo factor: no pose Jacobian
-            for (int q = lane; q < XREC; q += Wd) xr[(size_t)pos * XREC + q] = tile[(size_t)t * LVL_TS + q];
+        // the X record goes straight from registers to its frame-pair slot: 14 aligned 16-byte stores (one-frame stereo factors have no pose Jacobian: no record)
+        const int pos = bd.vis_pos[f];
+        if (pos >= 0) {
+            double *xr = bd.xrec + ((size_t)m.xrec_off + pos) * XREC;
+#ifdef VIWB_HOST_EMU
+            for (int q = 0; q < XREC; q++) xr[q] = row[q];
+#else
+            double2 *d2 = reinterpret_cast<double2 *>(xr);
+            const double s0 = sc;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {      // row h of X: A[6h..6h+5] | B[6h..6h+5] | r[h] | 0
+                d2[7 * h + 0] = make_double2(o.JA[6 * h] * s0, o.JA[6 * h + 1] * s0); d2[7 * h + 1] = make_double2(o.JA[6 * h + 2] * s0, o.JA[6 * h + 3] * s0);
+                d2[7 * h + 2] = make_double2(o.JA[6 * h + 4] * s0, o.JA[6 * h + 5] * s0); d2[7 * h + 3] = make_double2(o.JB[6 * h] * s0, o.JB[6 * h + 1] * s0);
+                d2[7 * h + 4] = make_double2(o.JB[6 * h + 2] * s0, o.JB[6 * h + 3] * s0); d2[7 * h + 5] = make_double2(o.JB[6 * h + 4] * s0, o.JB[6 * h + 5] * s0);
+                d2[7 * h + 6] = make_double2(o.r[h] * s0, 0.0);
+            }
+#endif
         }
     }
+    VIWB_SYNC();
     // ---- 2b: observing-frame blocks of W, item = (factor, component); two factors of one landmark seen from the same frame (left and
     //          right camera) are consecutive in the table: the first one writes the sum
     for (int e = tid; e < nf * 6; e += nt) {

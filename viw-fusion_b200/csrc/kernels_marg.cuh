@@ -54,7 +54,8 @@ VIWB_D void reanchor_block(const BatchDev &bd, int bx, int by, int tid, int nt, 
 VIWB_D double blk_reduce_small(double v, int tid, int nt, double *red) {     // sum over the block via a short tree
     return block_sum(v, tid, nt, red);
 }
-VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *sc, double *red, int n, int ld, int tid, int nt) {
+// tri_only: stop after tred2 + the accumulation of the Householder transformations: V = Q, d = diagonal, e[0..n-2] = sub-diagonal, e[n-1] = 0
+VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *sc, double *red, int n, int ld, int tid, int nt, bool tri_only = false) {
 #define VV(i, j) V[(i) * ld + (j)]
     // ---- tred2
     for (int j = tid; j < n; j += nt) d[j] = VV(n - 1, j);
@@ -134,6 +135,7 @@ VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *s
     for (int i = tid; i < n - 1; i += nt) e[i] = cs[i];
     if (tid == 0) { e[n - 1] = 0.0; sc[1] = 0.0 /* f */; sc[2] = 0.0 /* tst1 */; }
     VIWB_SYNC();
+    if (tri_only) return;
     const double eps = 2.220446049250313e-16;
     for (int l = 0; l < n; l++) {
         if (tid == 0) {
@@ -404,6 +406,145 @@ VIWB_D void marg_eig_block(const BatchDev &bd, int bx, int by, int tid, int nt, 
     VIWB_SYNC();
     sym_eig_block(Vn, ev, ee, cs, bc, red, n, ld, tid, nt);
     VIWB_SYNC();
+    for (int e = tid; e < n * n; e += nt) {
+        const int i = e / n, k = e - i * n;
+        const double l = ev[i];
+        Jout[e] = (l > eps ? sqrt(l) : 0.0) * Vn[k * ld + i];
+    }
+    for (int i = tid; i < n; i += nt) {
+        const double l = ev[i], si = l > eps ? sqrt(1.0 / l) : 0.0;
+        double vb = 0.0;
+        for (int k = 0; k < n; k++) vb += Vn[k * ld + i] * bn[k];
+        rout[i] = si * vb;
+    }
+    if (tid == 0) ww.marg_status = 0;
+}
+
+// The eigen-decomposition as a three-kernel pipeline.  The implicit QL iteration (tql2) is a strictly serial chain of plane rotations
+// (~n^2 of them, ~120 cycles each): inside a block-per-window kernel it idles 255 threads for 40 % of the run time and only three windows
+// fit an SM.  Splitting it off lets EVERY window's chain run at the same time (one warp each, all resident), while the parallel parts keep
+// whole blocks busy:
+//   marg_tri    block per window : A -> tridiagonal (d, e) + Q (tred2 and the accumulation), Q back to the window's marg_J slot
+//   marg_ql     warp per window  : lane 0 runs tql2 on (d, e) alone and LOGS the rotations (c, s) sweep by sweep; eigenvalues to d
+//   marg_apply  block per window : thread per row of Q applies the logged rotations (the eigenvector half of tql2), then J_lin, r_lin
+// Same arithmetic in the same order as sym_eig_block (the rotations are applied to each row in the order tql2 applies them).
+enum { MARG_ROT_PER_N2 = 3, MARG_SWEEP_PER_N = 12 };      // rotation-log capacity 3 n^2 (a typical run needs ~n^2), sweep-log capacity 12 n
+VIWB_HD size_t marg_rot_cap(int nmax) { const int c = marg_cap(nmax); return (size_t)MARG_ROT_PER_N2 * c * c; }
+VIWB_HD size_t marg_sweep_cap(int nmax) { return (size_t)MARG_SWEEP_PER_N * marg_cap(nmax); }
+VIWB_D void marg_tri_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)mode;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    if (m.margin_flag < 0) return;
+    const int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
+    if (hdr[0] == 0) return;
+    const int n = hdr[1], cap = marg_cap(bd.marg_nmax), ld = n | 1;
+    double *Vn = smem, *bn = Vn + (size_t)cap * (cap | 1), *cs = bn + cap, *ev = cs + 2 * cap, *ee = ev + cap, *red = ee + cap, *bc = red + 32;
+    double *Q = bd.marg_J + (size_t)w * bd.marg_nmax * bd.marg_nmax, *de = bd.marg_de + (size_t)w * 2 * MAXPRI;
+    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; Vn[i * ld + j] = Q[e]; }
+    VIWB_SYNC();
+    sym_eig_block(Vn, ev, ee, cs, bc, red, n, ld, tid, nt, true);
+    VIWB_SYNC();
+    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; Q[e] = Vn[i * ld + j]; }
+    for (int i = tid; i < n; i += nt) { de[i] = ev[i]; de[MAXPRI + i] = ee[i]; }
+}
+// lane 0 of a warp: tql2 on the tridiagonal matrix (the scalar half of sym_eig_block's QL loop, statement for statement), rotations logged
+VIWB_D void marg_ql_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)mode; (void)nt;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    if (m.margin_flag < 0 || tid != 0) return;
+    int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
+    if (hdr[0] == 0) return;
+    const int n = hdr[1];
+    double *d = smem, *e = smem + MAXPRI;
+    double *de = bd.marg_de + (size_t)w * 2 * MAXPRI;
+    const size_t rcap = marg_rot_cap(bd.marg_nmax), scap = marg_sweep_cap(bd.marg_nmax);
+    double *rot = bd.marg_rot + (size_t)w * 2 * rcap;
+    int *swp = bd.marg_sweep + (size_t)w * (2 * scap + 2);
+    for (int i = 0; i < n; i++) { d[i] = de[i]; e[i] = de[MAXPRI + i]; }
+    const double eps = 2.220446049250313e-16;
+    double f = 0.0, tst1 = 0.0;
+    size_t nrot = 0; int nsw = 0; bool overflow = false;
+    for (int l = 0; l < n; l++) {
+        const double t = fabs(d[l]) + fabs(e[l]); if (t > tst1) tst1 = t;
+        int mm = l; while (mm < n) { if (fabs(e[mm]) <= eps * tst1) break; mm++; }
+        if (mm > l) {
+            for (int iter = 0; iter < 200; iter++) {
+                double g = d[l], p = (d[l + 1] - g) / (2.0 * e[l]), r = sqrt(p * p + 1.0);
+                if (p < 0) r = -r;
+                d[l] = e[l] / (p + r); d[l + 1] = e[l] * (p + r);
+                const double dl1 = d[l + 1]; double h = g - d[l];
+                for (int i = l + 2; i < n; i++) d[i] -= h;
+                f += h;
+                p = d[mm];
+                double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0; const double el1 = e[l + 1];
+                if (nrot + (size_t)(mm - l) > rcap || nsw >= (int)scap) { overflow = true; break; }
+                swp[2 + 2 * nsw] = l | (mm << 16); swp[3 + 2 * nsw] = (int)nrot; nsw++;
+                double ei = e[mm - 1], di = d[mm - 1];
+                for (int i = mm - 1; i >= l; i--) {
+                    const double ein = i > l ? e[i - 1] : 0.0, din = i > l ? d[i - 1] : 0.0;
+                    c3 = c2; c2 = c; s2 = s;
+                    g = c * ei; h = c * p;
+                    const double q2 = p * p + ei * ei, rinv = q2 > 0.0 ? rsqrt(q2) : 0.0;
+                    r = q2 * rinv;
+                    e[i + 1] = s * r; s = ei * rinv; c = p * rinv;
+                    p = c * di - s * g; d[i + 1] = h + s * (c * g + s * di);
+                    rot[2 * nrot] = c; rot[2 * nrot + 1] = s; nrot++;
+                    ei = ein; di = din;
+                }
+                p = -s * s2 * c3 * el1 * e[l] / dl1;
+                e[l] = s * p; d[l] = c * p;
+                if (!(fabs(e[l]) > eps * tst1)) break;
+            }
+            if (overflow) break;
+        }
+        d[l] = d[l] + f; e[l] = 0.0;
+    }
+    swp[0] = overflow ? -1 : nsw; swp[1] = (int)nrot;
+    for (int i = 0; i < n; i++) de[i] = d[i];
+    if (overflow) { hdr[0] = 0; bd.work[w].marg_status = -2; }
+}
+VIWB_HD size_t marg_apply_smem_doubles(int nt, int nmax) { (void)nt; const int c = marg_cap(nmax); return (size_t)c * (c | 1) + (size_t)4 * c + 8; }
+VIWB_D void marg_apply_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)mode;
+    const int w = bx;
+    const WinMeta &m = bd.meta[w];
+    WinWork &ww = bd.work[w];
+    if (m.margin_flag < 0) return;
+    const int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
+    if (hdr[0] == 0) return;
+    const int n = hdr[1], cap = marg_cap(bd.marg_nmax), ld = n | 1;
+    const double eps = 1e-8;
+    double *Vn = smem, *bn = Vn + (size_t)cap * (cap | 1), *ev = bn + cap, *rs = ev + cap;      // rs: the current sweep's rotations (2 x n)
+    double *Jout = bd.marg_J + (size_t)w * bd.marg_nmax * bd.marg_nmax, *rout = bd.marg_r + (size_t)w * MAXPRI;
+    const double *de = bd.marg_de + (size_t)w * 2 * MAXPRI;
+    const size_t rcap = marg_rot_cap(bd.marg_nmax), scap = marg_sweep_cap(bd.marg_nmax);
+    const double *rot = bd.marg_rot + (size_t)w * 2 * rcap;
+    const int *swp = bd.marg_sweep + (size_t)w * (2 * scap + 2);
+    for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; Vn[i * ld + j] = Jout[e]; }
+    for (int i = tid; i < n; i += nt) { bn[i] = rout[i]; ev[i] = de[i]; }
+    const int nsw = swp[0];
+    VIWB_SYNC();
+    for (int sw = 0; sw < nsw; sw++) {
+        const int lm = swp[2 + 2 * sw], l = lm & 0xffff, mm = lm >> 16, cnt = mm - l;
+        const double *r0 = rot + 2 * (size_t)swp[3 + 2 * sw];
+        for (int q = tid; q < 2 * cnt; q += nt) rs[q] = r0[q];
+        VIWB_SYNC();
+        for (int k = tid; k < n; k += nt) {          // row k: columns mm .. l, the value of column i carried in a register to the next rotation
+            double *row = Vn + k * ld;
+            double hi = row[mm];                      // V(k, i + 1) for the first rotation (i = mm - 1)
+            for (int q = 0; q < cnt; q++) {
+                const int i = mm - 1 - q;
+                const double c = rs[2 * q], s = rs[2 * q + 1], lo = row[i];
+                row[i + 1] = s * lo + c * hi;
+                hi = c * lo - s * hi;                 // the new V(k, i) is V(k, (i - 1) + 1) of the next rotation
+            }
+            row[l] = hi;
+        }
+        VIWB_SYNC();
+    }
+    // J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b   (marginalization_factor.cpp:298-306)
     for (int e = tid; e < n * n; e += nt) {
         const int i = e / n, k = e - i * n;
         const double l = ev[i];

@@ -144,6 +144,8 @@ struct BatchDev {       // passed by value to every kernel
     // marginalisation outputs
     double *marg_J, *marg_r, *marg_x0;  // [B][marg_nmax^2] (n x n, row stride n, at the head of the slot), [B][MAXPRI], [B][SFIX]
     int *marg_hdr;                      // [B][2 + 2*NB]: valid, n, nb, block_id[], block_idx[]
+    double *marg_de, *marg_rot;         // [B][2 * MAXPRI] tridiagonal (d | e) -> eigenvalues; [B][2 * 3 nmax^2] rotation log (c, s) of the QL iteration
+    int *marg_sweep;                    // [B][2 + 2 * 12 nmax] sweep log: count, rotations, then (l | m << 16, first rotation) per QL sweep
 };
 
 VIWB_HD int vec_off(const BatchDev &bd, int w) { return w * TFIX + bd.meta[w].lm_off; }

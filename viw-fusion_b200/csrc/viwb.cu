@@ -115,6 +115,9 @@ DEF_KERNEL2(syrk_mma, SYRK_NT, 4)
 DEF_KERNEL(reanchor, 32)
 DEF_KERNEL2(marg_prep, 256, 2)
 DEF_KERNEL2(marg_eig, 256, 3)
+DEF_KERNEL2(marg_tri, 256, 3)
+DEF_KERNEL(marg_ql, 32)
+DEF_KERNEL2(marg_apply, 128, 4)
 DEF_KERNEL(outlier, 128)
 #define LAUNCH(name, bd, gx, gy, nt, smem_bytes, mode, stream) \
     do { if ((gx) > 0 && (gy) > 0) { g_prof.begin((mode) == 1 ? #name "_marg" : #name, stream); name##_kernel<<<dim3((gx), (gy)), (nt), (smem_bytes), (stream)>>>(bd, mode); g_prof.end(stream); } } while (0)
@@ -127,6 +130,7 @@ struct Arena { char *dev = nullptr; size_t dev_cap = 0; char *host = nullptr; si
 static void arena_release(Arena &a) { if (a.dev) dev_free(a.dev); if (a.host) host_free(a.host); a = Arena(); }
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static bool g_timing = getenv("VIWB_TIMING") != nullptr;
+static bool g_marg_one_kernel = getenv("VIWB_MARG_ONE_KERNEL") != nullptr;      // measurement aid: tred2 + tql2 in one block-per-window kernel (marg_eig)
 static bool g_syrk_dfma = getenv("VIWB_SYRK_DFMA") != nullptr;      // measurement aid: the 4x4 register-tiled DFMA SYRK instead of the DMMA one (profiles/: both builds of the Schur GEMM)
 struct viwb_context {
     int device;
@@ -580,7 +584,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     // marginalisation outputs / scratch: sized by the largest prior this batch produces, and not at all when no window marginalises
     const size_t mJ = b->any_marg ? (size_t)b->prior_nmax * b->prior_nmax : 0, mB = b->any_marg ? (size_t)B : 0;
     WK(&bd.marg_J, mB * mJ); WK(&bd.marg_r, mB * MAXPRI); WK(&bd.marg_x0, mB * SFIX);
-    WK(&bd.marg_hdr, mB * (3 + 2 * NB));
+    WK(&bd.marg_hdr, mB * (3 + 2 * NB)); WK(&bd.marg_de, mB * 2 * MAXPRI); WK(&bd.marg_rot, mB * 2 * marg_rot_cap(b->prior_nmax)); WK(&bd.marg_sweep, mB * (2 * marg_sweep_cap(b->prior_nmax) + 2));
     size_t tot = 0;
     for (auto &e : ents) if (e.input) { e.off = tot; tot += align_up(e.bytes); }
     const size_t in_bytes = tot;
@@ -623,6 +627,8 @@ static int ensure_attrs(viwb_context *ctx) {
         CK(cudaFuncSetAttribute(lin_vis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lin_vis_smem_doubles(128, VREC) * 8)));
         CK(cudaFuncSetAttribute(syrk_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(syrk_mma_smem_doubles() * 8)));
         CK(cudaFuncSetAttribute(marg_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_prep_smem_doubles(256, 100) * 8)));
+        CK(cudaFuncSetAttribute(marg_tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_eig_smem_doubles(256, 100) * 8)));
+        CK(cudaFuncSetAttribute(marg_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_apply_smem_doubles(128, 100) * 8)));
         CK(cudaFuncSetAttribute(marg_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_eig_smem_doubles(256, 100) * 8)));
         ctx->attrs_set = true;
     }
@@ -705,8 +711,13 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     if ((what & RUN_MARG) && b->any_marg) {
         lin(MODE_MARG, false);
         LAUNCH(marg_prep, bd, B, 1, nt_marg, sm_marg, 0, st);
-        LAUNCH(marg_eig, bd, B, 1, nt_marg, sm_eig, 0, st);
-        ctx->launches += 2;
+        if (g_marg_one_kernel) { LAUNCH(marg_eig, bd, B, 1, nt_marg, sm_eig, 0, st); ctx->launches += 2; }
+        else {
+            LAUNCH(marg_tri, bd, B, 1, nt_marg, sm_eig, 0, st);
+            LAUNCH(marg_ql, bd, B, 1, NT(32), 2 * MAXPRI * 8, 0, st);
+            LAUNCH(marg_apply, bd, B, 1, NT(128), marg_apply_smem_doubles(128, bd.marg_nmax) * 8, 0, st);
+            ctx->launches += 4;
+        }
     }
 #ifndef VIWB_HOST_EMU
     CK((int)cudaGetLastError());
