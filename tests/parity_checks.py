@@ -188,6 +188,14 @@ def check_batch_matches_single(ctx, oracle):
     s1, sum1, pr1 = b.download()
     b.run()
     s2, sum2, pr2 = b.download()
+    # viwb_batch_reset_states: the windows as uploaded again -- the outlier verdicts of the INITIAL guesses, and a third identical run
+    b.reset()
+    for p, s, o in zip(probs, sts, b.outliers()):
+        assert np.array_equal(o, oracle.outlier_rejection(p, s))
+    b.run()
+    s3, _, _ = b.download(want_priors=False)
+    for x, y in zip(s1, s3):
+        assert np.array_equal(x, y)
     b.destroy()
     for x, y, z in zip(s1, s2, out_s):
         assert np.array_equal(x, y) and np.array_equal(x, z)

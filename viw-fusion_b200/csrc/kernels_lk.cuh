@@ -239,10 +239,12 @@ VIWB_D void lk_stage(uint8_t *buf, const uint8_t *img, int stride, int cols, int
     VIWB_SYNCWARP();
 }
 
-// ---- TMA staging (sm_100a): per pyramid level ONE tensor map over the level's stacked images [slots * streams * rows][width] (u8, row pitch a
-// multiple of 16 bytes), box 32 x 32; a warp's lane 0 arms the warp's mbarrier with the tile's byte count and issues the copy, the warp
-// waits on the barrier's phase.  Columns right of the image are zero-filled by the unit and never read (only windows whose needed
-// pixels are inside the image take this path); rows below the image belong to the next image of the stack and are not read either.
+// ---- TMA staging (sm_100a): per pyramid level ONE tensor map over the level's stacked images [slots * streams * rows][pitch / 4] of 32-BIT words
+// (row pitch a multiple of 16 bytes), box 8 words x 32 rows = 32 x 32 bytes, so a tile starts at a byte column that is a multiple of 4; a warp's
+// lane 0 arms the warp's mbarrier with the tile's byte count and issues the copy, the warp waits on the barrier's phase.  (A UINT8 tensor map of
+// the same region is rejected by this driver / GPU pair with "illegal instruction" for every box shape -- profiles/r02i_tma_probe.txt; UINT32 and
+// FLOAT32 maps load fine.)  Columns right of the pitch are zero-filled by the unit; only windows whose needed pixels are inside the image take
+// this path, and samples are only taken from the part of a tile that lies inside the image (rows below it belong to the next image of the stack).
 struct alignas(64) LkMaps { unsigned long long opaque[LK_MAXLVL][16]; };      // LK_MAXLVL x CUtensorMap (128 bytes each; the descriptor must sit 64-byte aligned, also in kernel parameter space), encoded by the host
 #ifndef VIWB_HOST_EMU
 VIWB_D unsigned lk_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -352,21 +354,25 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
         const int jc = a.J.w[level], jr = a.J.h[level], jstr = a.J.stride[level];
         const uint8_t *jimg = a.J.img[level];
         int jx0 = 0, jy0 = 0;          // origin of the staged search region
+        int jx1 = 0, jy1 = 0;          // end of its usable part (a TMA tile may hang over the image's right / bottom edge; the reflect path fills its whole box)
         bool staged = false;
 #ifndef VIWB_HOST_EMU
+        // TMA tile that holds the 23 x 23 samples at (inx, iny), which must lie inside the image: origin a multiple of 4 bytes in x, at most 7 left of inx
+        auto tile_j = [&](int inx, int iny) {
+            jx0 = (inx - 4) & ~3; if (jx0 < 0) jx0 = 0;
+            jy0 = iny - 4; if (jy0 > jr - LK_JROWS) jy0 = jr - LK_JROWS; if (jy0 < 0) jy0 = 0;
+            jx1 = jx0 + LK_JS < jc ? jx0 + LK_JS : jc; jy1 = jy0 + LK_JROWS < jr ? jy0 + LK_JROWS : jr;
+            lk_tma_issue(jbuf, &maps->opaque[level][0], jx0 >> 2, a.trowJ[level] + jy0, bar + 1, lane);
+        };
         if (tma) {
             const int inx = (int)floorf(nx - (float)LK_HALF), iny = (int)floorf(ny - (float)LK_HALF);
-            if (inx >= 0 && iny >= 0 && inx + 23 <= jc && iny + 23 <= jr && jc >= LK_JS && jr >= LK_JROWS) {
-                jx0 = inx - 4; if (jx0 < 0) jx0 = 0; if (jx0 > jc - LK_JS) jx0 = jc - LK_JS;
-                jy0 = iny - 4; if (jy0 < 0) jy0 = 0; if (jy0 > jr - LK_JROWS) jy0 = jr - LK_JROWS;
-                lk_tma_issue(jbuf, &maps->opaque[level][0], jx0, a.trowJ[level] + jy0, bar + 1, lane);
-                j_pending = true; staged = true;
-            }
+            if (inx >= 0 && iny >= 0 && inx + 23 <= jc && iny + 23 <= jr) { tile_j(inx, iny); j_pending = true; staged = true; }
         }
         if (tma && ipx >= 1 && ipy >= 1 && ipx + 23 <= cols && ipy + 23 <= rows) {
-            if (!p_pending) lk_tma_issue(pbuf, &maps->opaque[level][0], ipx - 1, a.trowI[level] + ipy - 1, bar, lane);
+            const int pxa = (ipx - 1) & ~3;
+            if (!p_pending) lk_tma_issue(pbuf, &maps->opaque[level][0], pxa >> 2, a.trowI[level] + ipy - 1, bar, lane);
             lk_tma_wait(bar, phaseP); p_pending = false;
-            psx = 0;
+            psx = (ipx - 1) - pxa;
         } else
 #endif
         {
@@ -449,7 +455,7 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
             const float sc2 = (float)(1. / (1 << (level - 1)));
             const int qx = (int)floorf(px0 * sc2 - (float)LK_HALF), qy = (int)floorf(py0 * sc2 - (float)LK_HALF);
             if (qx >= 1 && qy >= 1 && qx + 23 <= a.I.w[level - 1] && qy + 23 <= a.I.h[level - 1]) {
-                lk_tma_issue(pbuf, &maps->opaque[level - 1][0], qx - 1, a.trowI[level - 1] + qy - 1, bar, lane);
+                lk_tma_issue(pbuf, &maps->opaque[level - 1][0], ((qx - 1) & ~3) >> 2, a.trowI[level - 1] + qy - 1, bar, lane);
                 p_pending = true;
             }
         }
@@ -472,15 +478,9 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
         // it, else the reflect-101 path (origin a multiple of 4 in x)
         auto stage_j = [&](int inx, int iny) {
 #ifndef VIWB_HOST_EMU
-            if (tma && inx >= 0 && iny >= 0 && inx + 23 <= jc && iny + 23 <= jr && jc >= LK_JS && jr >= LK_JROWS) {
-                jx0 = inx - 4; if (jx0 < 0) jx0 = 0; if (jx0 > jc - LK_JS) jx0 = jc - LK_JS;
-                jy0 = iny - 4; if (jy0 < 0) jy0 = 0; if (jy0 > jr - LK_JROWS) jy0 = jr - LK_JROWS;
-                lk_tma_issue(jbuf, &maps->opaque[level][0], jx0, a.trowJ[level] + jy0, bar + 1, lane);
-                lk_tma_wait(bar + 1, phaseJ);
-                return;
-            }
+            if (tma && inx >= 0 && iny >= 0 && inx + 23 <= jc && iny + 23 <= jr) { tile_j(inx, iny); lk_tma_wait(bar + 1, phaseJ); return; }
 #endif
-            jx0 = (inx - LK_SLACK) & ~3; jy0 = iny - 4;
+            jx0 = (inx - LK_SLACK) & ~3; jy0 = iny - 4; jx1 = jx0 + LK_JS; jy1 = jy0 + LK_JROWS;
             lk_stage(jbuf, jimg, jstr, jc, jr, jx0, jy0, LK_JROWS, LK_JS / 4, lane);
         };
         for (int j = 0; j < max_iter; j++) {
@@ -489,7 +489,7 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
 #ifndef VIWB_HOST_EMU
             if (j_pending) { lk_tma_wait(bar + 1, phaseJ); j_pending = false; }      // the region requested at the top of the level
 #endif
-            if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) { stage_j(inx, iny); staged = true; }
+            if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx1 || iny + 23 > jy1) { stage_j(inx, iny); staged = true; }
             const float ja = nx - inx, jb = ny - iny;
             const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
             const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;
@@ -523,7 +523,7 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
             const int inx = (int)floorf(ex), iny = (int)floorf(ey);
             if (lk_outside(inx, iny, jc, jr)) { status = false; }
             else {
-                if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx0 + LK_JS || iny + 23 > jy0 + LK_JROWS) stage_j(inx, iny);
+                if (!staged || inx < jx0 || iny < jy0 || inx + 23 > jx1 || iny + 23 > jy1) stage_j(inx, iny);
                 const float ja = ex - inx, jb = ey - iny;
                 const int w00 = cv_round_f((1.f - ja) * (1.f - jb) * (1 << 14)), w01 = cv_round_f(ja * (1.f - jb) * (1 << 14));
                 const int w10 = cv_round_f((1.f - ja) * jb * (1 << 14)), w11 = (1 << 14) - w00 - w01 - w10;

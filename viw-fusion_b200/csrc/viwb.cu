@@ -865,7 +865,16 @@ extern "C" int viwb_batch_create(viwb_context *ctx, int batch, const viwb_proble
     CK(dev_sync(ctx->stream));
     return VIWB_OK;
 }
-extern "C" int viwb_batch_reset_states(viwb_context *ctx, viwb_batch *b) { (void)ctx; (void)b; return VIWB_OK; }   // batch_run restarts from x_init
+// the windows as uploaded: current and candidate states back to the initial ones, solver bookkeeping cleared (viwb_batch_run does the same before it starts;
+// this entry lets a caller read / evaluate the pristine batch, e.g. viwb_batch_outliers on the initial guess)
+extern "C" int viwb_batch_reset_states(viwb_context *ctx, viwb_batch *b) {
+    if (!ctx || !b) return VIWB_ERR_INVALID;
+    bind_device(ctx);
+    const size_t xs = b->total_state * sizeof(double);
+    CK(dev_d2d(b->bd.x_cur, b->bd.x_init, xs, ctx->stream)); CK(dev_d2d(b->bd.x_cand, b->bd.x_init, xs, ctx->stream)); CK(dev_d2d(b->bd.x_before, b->bd.x_init, xs, ctx->stream));
+    CK(dev_d2d(b->bd.work, b->work_init_dev, sizeof(WinWork) * b->B, ctx->stream));
+    return VIWB_OK;
+}
 extern "C" int viwb_batch_run(viwb_context *ctx, viwb_batch *b) {
     if (!ctx || !b) return VIWB_ERR_INVALID;
     return batch_execute(ctx, b, RUN_SOLVE | RUN_REANCHOR | RUN_MARG);

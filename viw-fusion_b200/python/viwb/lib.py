@@ -569,6 +569,10 @@ class Batch:
     def run(self):
         self.ctx._ck(self.ctx.lib.viwb_batch_run(self.ctx.h, self.h), "viwb_batch_run")
 
+    def reset(self):
+        """The windows as uploaded (viwb_batch_reset_states)."""
+        self.ctx._ck(self.ctx.lib.viwb_batch_reset_states(self.ctx.h, self.h), "viwb_batch_reset_states")
+
     def algorithmic_bytes(self):
         return float(self.ctx.lib.viwb_batch_algorithmic_bytes(self.h))
 
