@@ -10,7 +10,7 @@ import bench  # noqa: E402
 from viwb import abi, lib  # noqa: E402
 
 D, R = int(os.environ.get("PROBE_DISTINCT", "37")), int(os.environ.get("PROBE_COPIES", "32"))
-cfg, seqs, first = bench.make_windows(0, D, R)
+cfg, seqs, first = bench.make_windows(0, D, R, int(os.environ.get("PROBE_CONFIG", "2")))
 for path in sys.argv[1:]:
     ctx = lib.Context(0, os.path.abspath(path))
     a0, _, q0 = ctx.optimization_batch([f[0] for f in first], [f[1] for f in first], [abi.MARGIN_OLD] * len(first))

@@ -299,14 +299,6 @@ VIWB_D void add_small_factor(const Target &t, const double *rec, int rows, int l
     VIWB_SYNC();
 }
 
-// entry (i, j) of a pair chunk's G = sum X^T X as asm_pairs stores it: tiles (0,0), (0,1), (1,1) of the 16 x 16 frame in mma.m8n8k4 accumulator
-// order, out[64 t + 2 l + r] = G[8 tr + l/4][8 tc + 2 (l%4) + r]; G is symmetric, tile (1,0) is read through (0,1)
-VIWB_HD double pair_G_entry(const double *out, int i, int j) {
-    if ((i >> 3) > (j >> 3)) { const int t = i; i = j; j = t; }
-    const int tr = i >> 3, tc = j >> 3, tl = tr == 0 ? (tc == 0 ? 0 : 1) : 2;
-    return out[64 * tl + 2 * (((i & 7) << 2) + ((j & 7) >> 1)) + (j & 1)];
-}
-
 // common column c (0..12) -> (block, k)
 VIWB_HD int common_blk(int c) { return c < 6 ? BLK_EX0 : c < 12 ? BLK_EX1 : BLK_TD; }
 VIWB_HD int common_k(int c) { return c < 6 ? c : c < 12 ? c - 6 : 0; }
@@ -390,25 +382,34 @@ VIWB_D void assemble_into(const Target &t, const BatchDev &bd, int w, int mode, 
             add_small_factor(t, bd.plane_rec + (size_t)f * PLANE_REC, 3, 16, sl, ns, tid, nt);
         }
     }
-    if (mode == MODE_SOLVE && m.fused) {
-        // ---- fused path: pair_reduce (kernels_fused.cuh) has folded the pair chunks G = sum X^T X, X = [A (host frame a) | B (observer b) | r],
-        //      into per-frame diagonal blocks + gradients and per-pair off-diagonal blocks.  Exact zeros are frames / pairs without factors
-        //      (their entries may lie outside the envelope) and are skipped.
+    if (mode == MODE_SOLVE ? m.fused != 0 : m.mfused != 0) {
+        // ---- fused path: pair_reduce (kernels_fused.cuh) has folded the pair chunks G = sum X^T X into per-frame diagonal blocks + gradients
+        //      (+ the frame's block against the common columns ex0 | ex1 | td when the records are WIDE), per-pair off-diagonal blocks and the
+        //      common block.  Exact zeros are frames / pairs without factors (their entries may lie outside the envelope) and are skipped.
+        const bool wide = mode == MODE_MARG || m.has_common != 0;
+        const int FR = wide ? 105 : 27;
         const double *red = bd.pair_red + (size_t)w * PAIR_RED;
-        for (int e = tid; e < NFR * 27; e += nt) {
+        for (int e = tid; e < NFR * FR; e += nt) {
             const double v = red[e];
             if (v == 0.0) continue;
-            const int f = e / 27, o = e - 27 * f;
+            const int f = e / FR, o = e - FR * f;
             if (o < 21) { int p, q; sym_unrank(o, p, q); const int ci = t.col(f, p), cj = t.col(f, q); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
-            else { const int ci = t.col(f, o - 21); if (ci >= 0) t.addg(ci, v); }
+            else if (o < 27) { const int ci = t.col(f, o - 21); if (ci >= 0) t.addg(ci, v); }
+            else { const int p = (o - 27) / 13, c = (o - 27) % 13; const int ci = t.col(f, p), cj = t.col(common_blk(c), common_k(c)); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
         }
         for (int e = tid; e < NPAIR * 36; e += nt) {
-            const double v = red[NFR * 27 + e];
+            const double v = red[NFR * FR + e];
             if (v == 0.0) continue;
             int pi = e / 36, a = 0; const int o = e - 36 * pi;
             while (pi >= NFR - 1 - a) { pi -= NFR - 1 - a; a++; }
             const int ci = t.col(a, o / 6), cj = t.col(a + 1 + pi, o % 6);
             if (ci >= 0 && cj >= 0) t.add(ci, cj, v);
+        }
+        if (wide) for (int e = tid; e < 91 + 13; e += nt) {
+            const double v = red[NFR * FR + NPAIR * 36 + e];
+            if (v == 0.0) continue;
+            if (e < 91) { int p, q; sym_unrank(e, p, q); const int ci = t.col(common_blk(p), common_k(p)), cj = t.col(common_blk(q), common_k(q)); if (ci >= 0 && cj >= 0) t.add(ci, cj, v); }
+            else { const int c = e - 91; const int ci = t.col(common_blk(c), common_k(c)); if (ci >= 0) t.addg(ci, v); }
         }
         VIWB_SYNC();
         return;

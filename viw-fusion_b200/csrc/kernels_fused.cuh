@@ -25,53 +25,77 @@ VIWB_D void dmma884(double (&c)[2], double a, double b) {
 }
 #endif
 
+// ------------------------------------------------------------------------------------------------ record layouts
+// X row of a factor (one per residual row): COMPACT  A(6) | B(6) | r | 0            (14 doubles, 13 used): windows whose ex0 / ex1 / td are constant
+//                                           WIDE     A(6) | B(6) | E0(6) | E1(6) | td | r | 0 0   (28 doubles, 26 used): extrinsics / td estimated, and
+//                                                    every marginalisation (the prior keeps those blocks whatever the solver does with them)
+// G = sum X^T X lives in a frame of NTC x NTC tiles of 8 x 8; the NTILE upper-triangular tiles are stored in mma.m8n8k4 accumulator order.
+template <bool WIDE> struct XL {
+    enum { ROW = WIDE ? 28 : 14, REC = 2 * ROW, USED = WIDE ? 26 : 13, RCOL = WIDE ? 25 : 12, NTC = WIDE ? 4 : 2, NTILE = NTC * (NTC + 1) / 2, OUT = 64 * NTILE,
+           TS = REC + 3, U = REC, C = REC + 2,                      // shared-memory tile row: X record | J_lambda (2) | rho / 2 ; odd stride
+           NLM = WIDE ? 22 : 9,                                     // per-landmark outputs: host block of W (6), a, g, cost (+ E0 (6), E1 (6), td columns of W)
+           FR = WIDE ? 27 + 78 : 27,                                // per-frame reduce outputs: diagonal block (21) + gradient (6) (+ pose x common 6 x 13)
+           RED = NFR * FR + NPAIR * 36 + (WIDE ? 91 + 13 : 0) };    // pair_reduce outputs per window
+};
+// entry (i, j) of a chunk's G as asm_pairs stores it (G is symmetric: tile (tr > tc) is read through its transpose)
+template <bool WIDE> VIWB_HD double pair_G(const double *out, int i, int j) {
+    if ((i >> 3) > (j >> 3)) { const int t = i; i = j; j = t; }
+    const int tr = i >> 3, tc = j >> 3, tl = tr * XL<WIDE>::NTC - tr * (tr - 1) / 2 + (tc - tr);
+    return out[64 * tl + 2 * (((i & 7) << 2) + ((j & 7) >> 1)) + (j & 1)];
+}
+
 // ------------------------------------------------------------------------------------------------ lin_vis_lm
-enum { LVL_TS = 31, LVL_U = 28, LVL_C = 30 };      // tile row: X record (28) | J_lambda (2) | rho / 2 ; odd stride
-VIWB_HD size_t lin_vis_lm_smem_doubles() { return (size_t)LMB_FACTORS * LVL_TS + LMB_FACTORS + 2; }      // tile + per-factor (meta, slot) ints
-VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
-    (void)by; (void)mode;                        // solver linearisation at x_cand only
+VIWB_HD size_t lin_vis_lm_smem_doubles(bool wide) { return (size_t)LMB_FACTORS * (wide ? (int)XL<true>::TS : (int)XL<false>::TS) + LMB_FACTORS / 2 + 2; }      // tile + per-factor meta ints
+// MARG = false: solver linearisation at x_cand of the fused windows whose record width matches WIDE.
+// MARG = true (WIDE): marginalisation linearisation at x_cur of the windows that drop frame 0: only the factors hosted there take part; every other
+//                     landmark of the window gets gamma = 0 and a zero row of W (syrk multiplies its row by that weight).
+template <bool WIDE, bool MARG>
+VIWB_D void lin_vis_lm_body(const BatchDev &bd, int bx, int tid, int nt, double *smem) {
+    typedef XL<WIDE> L;
     const int w = bd.lmb_win[bx];
     const WinWork &ww = bd.work[w];
-    if (ww.status != ST_RUNNING) return;
     const WinMeta &m = bd.meta[w];
+    if (MARG) { if (!m.mfused) return; }
+    else { if (ww.status != ST_RUNNING || !m.fused || (m.has_common != 0) != WIDE) return; }
     const int k0 = bd.lmb_ptr[2 * bx], k1 = bd.lmb_ptr[2 * bx + 1];    // global landmark range of this block
     const int f0 = bd.lm_fptr[k0], nf = bd.lm_fptr[k1] - f0;            // its factors (consecutive, <= LMB_FACTORS)
     double *tile = smem;
-    int *meta = (int *)(smem + (size_t)LMB_FACTORS * LVL_TS);      // [2 t] = landmark (window-local) << 12 | fi << 8 | fj << 4 | type << 2 | dup
-    const double *x = bd.x_cand + m.state_off;
+    int *meta = (int *)(smem + (size_t)LMB_FACTORS * L::TS);      // landmark (window-local) << 12 | fi << 8 | fj << 4 | type << 2 | dup
+    const double *x = (MARG ? bd.x_cur : bd.x_cand) + m.state_off;
+    const int *vpos = MARG ? bd.mvis_pos : bd.vis_pos;
+    double *xbase = bd.xrec + (size_t)(MARG ? m.mxrec_off : m.xrec_off);
     // ---- 0: the W rows of these landmarks start from zero (frames that do not observe a landmark keep zero blocks)
     { double *Wb = bd.lm_W + (size_t)k0 * VSUB; for (int e = tid; e < (k1 - k0) * VSUB; e += nt) Wb[e] = 0.0; }
     // ---- 1: one thread per factor
     for (int t = tid; t < nf; t += nt) {
         const int f = f0 + t;
         const int type = bd.vis_type[f], fi = bd.vis_fi[f], fj = bd.vis_fj[f];
+        meta[t] = (bd.vis_lm[f] << 12) | (fi << 8) | (fj << 4) | (type << 2) | bd.vis_dup[f];
+        double *row = tile + (size_t)t * L::TS;
+        if (MARG && fi != 0) { row[L::U] = 0.0; row[L::U + 1] = 0.0; row[L::C] = 0.0; continue; }      // not hosted in the dropped frame: takes no part
         double obs[12];
         for (int k = 0; k < 12; k++) obs[k] = bd.vis_obs[(size_t)f * 12 + k];
         VisOut o;
-        vis_eval_t<false>(type, obs, x + 7 * fi, x + 7 * fj, x + blk_off(BLK_EX0), x + blk_off(BLK_EX1), x[SFIX + bd.vis_lm[f]], x[blk_off(BLK_TD)], m.S_vis, true, o);
+        vis_eval_t<WIDE>(type, obs, x + 7 * fi, x + 7 * fj, x + blk_off(BLK_EX0), x + blk_off(BLK_EX1), x[SFIX + bd.vis_lm[f]], x[blk_off(BLK_TD)], m.S_vis, true, o);
         double half_rho;
         const double sc = huber_scale(o.r[0] * o.r[0] + o.r[1] * o.r[1], m.huber, half_rho);
-        double *row = tile + (size_t)t * LVL_TS;
-        for (int q = 0; q < 6; q++) { row[q] = o.JA[q] * sc; row[6 + q] = o.JB[q] * sc; row[XROW + q] = o.JA[6 + q] * sc; row[XROW + 6 + q] = o.JB[6 + q] * sc; }
-        row[12] = o.r[0] * sc; row[13] = 0.0; row[XROW + 12] = o.r[1] * sc; row[XROW + 13] = 0.0;
-        row[LVL_U] = o.Jl[0] * sc; row[LVL_U + 1] = o.Jl[1] * sc; row[LVL_C] = half_rho;
-        meta[2 * t] = (bd.vis_lm[f] << 12) | (fi << 8) | (fj << 4) | (type << 2) | bd.vis_dup[f];
-        // the X record goes straight from registers to its frame-pair slot: 14 aligned 16-byte stores (one-frame stereo factors have no pose Jacobian: no record)
-        const int pos = bd.vis_pos[f];
+        for (int h = 0; h < 2; h++) {      // row h of X
+            double *xr = row + h * L::ROW;
+            for (int q = 0; q < 6; q++) { xr[q] = o.JA[6 * h + q] * sc; xr[6 + q] = o.JB[6 * h + q] * sc; }
+            if (WIDE) { for (int q = 0; q < 6; q++) { xr[12 + q] = o.JE0[6 * h + q] * sc; xr[18 + q] = o.JE1[6 * h + q] * sc; } xr[24] = o.Jtd[h] * sc; xr[25] = o.r[h] * sc; xr[26] = 0.0; xr[27] = 0.0; }
+            else { xr[12] = o.r[h] * sc; xr[13] = 0.0; }
+        }
+        row[L::U] = o.Jl[0] * sc; row[L::U + 1] = o.Jl[1] * sc; row[L::C] = half_rho;
+        // the X record goes straight to its frame-pair slot: aligned 16-byte stores (compact: one-frame stereo factors have no pose Jacobian, no record)
+        const int pos = vpos[f];
         if (pos >= 0) {
-            double *xr = bd.xrec + ((size_t)m.xrec_off + pos) * XREC;
+            double *xr = xbase + (size_t)pos * L::REC;
 #ifdef VIWB_HOST_EMU
-            for (int q = 0; q < XREC; q++) xr[q] = row[q];
+            for (int q = 0; q < L::REC; q++) xr[q] = row[q];
 #else
             double2 *d2 = reinterpret_cast<double2 *>(xr);
-            const double s0 = sc;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {      // row h of X: A[6h..6h+5] | B[6h..6h+5] | r[h] | 0
-                d2[7 * h + 0] = make_double2(o.JA[6 * h] * s0, o.JA[6 * h + 1] * s0); d2[7 * h + 1] = make_double2(o.JA[6 * h + 2] * s0, o.JA[6 * h + 3] * s0);
-                d2[7 * h + 2] = make_double2(o.JA[6 * h + 4] * s0, o.JA[6 * h + 5] * s0); d2[7 * h + 3] = make_double2(o.JB[6 * h] * s0, o.JB[6 * h + 1] * s0);
-                d2[7 * h + 4] = make_double2(o.JB[6 * h + 2] * s0, o.JB[6 * h + 3] * s0); d2[7 * h + 5] = make_double2(o.JB[6 * h + 4] * s0, o.JB[6 * h + 5] * s0);
-                d2[7 * h + 6] = make_double2(o.r[h] * s0, 0.0);
-            }
+            for (int q = 0; q < L::REC / 2; q++) d2[q] = make_double2(row[2 * q], row[2 * q + 1]);      // (the thread re-reads its own tile row: values it has just written)
 #endif
         }
     }
@@ -79,34 +103,39 @@ VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt
     // ---- 2b: observing-frame blocks of W, item = (factor, component); two factors of one landmark seen from the same frame (left and
     //          right camera) are consecutive in the table: the first one writes the sum
     for (int e = tid; e < nf * 6; e += nt) {
-        const int t = e / 6, q = e - 6 * t, mt = meta[2 * t];
+        const int t = e / 6, q = e - 6 * t, mt = meta[t];
         if (((mt >> 2) & 3) == 2) continue;
+        if (MARG && ((mt >> 8) & 15) != 0) continue;
         const int dup = mt & 3;
         if (dup == 2) continue;
-        const double *row = tile + (size_t)t * LVL_TS;
-        double v = row[6 + q] * row[LVL_U] + row[XROW + 6 + q] * row[LVL_U + 1];
-        if (dup == 1) { const double *r2 = row + LVL_TS; v += r2[6 + q] * r2[LVL_U] + r2[XROW + 6 + q] * r2[LVL_U + 1]; }
+        const double *row = tile + (size_t)t * L::TS;
+        double v = row[6 + q] * row[L::U] + row[L::ROW + 6 + q] * row[L::U + 1];
+        if (dup == 1) { const double *r2 = row + L::TS; v += r2[6 + q] * r2[L::U] + r2[L::ROW + 6 + q] * r2[L::U + 1]; }
         bd.lm_W[(size_t)(m.lm_off + (mt >> 12)) * VSUB + 6 * ((mt >> 4) & 15) + q] = v;
     }
-    // ---- 2c: per landmark, item = (landmark, output): host-frame block of W (6), a, g, cost (+ Jacobi scale and Schur weight)
-    for (int e = tid; e < (k1 - k0) * 9; e += nt) {
-        const int kl = e / 9, q = e - 9 * kl, k = k0 + kl;
+    // ---- 2c: per landmark, item = (landmark, output): host-frame block of W (6), a, g, cost (+ Jacobi scale and Schur weight) (+ common columns of W)
+    for (int e = tid; e < (k1 - k0) * L::NLM; e += nt) {
+        const int kl = e / L::NLM, q = e - L::NLM * kl, k = k0 + kl;
         const int a0 = bd.lm_fptr[k] - f0, a1 = bd.lm_fptr[k + 1] - f0;
+        const bool part = a1 > a0 && (!MARG || ((meta[a0] >> 8) & 15) == 0);      // the landmark takes part (marginalisation: hosted in frame 0)
         double s = 0.0;
-        for (int t = a0; t < a1; t++) {
-            const double *row = tile + (size_t)t * LVL_TS;
-            const double u0 = row[LVL_U], u1 = row[LVL_U + 1];
-            if (q < 6) s += row[q] * u0 + row[XROW + q] * u1;              // one-frame factors carry A = 0
+        if (part) for (int t = a0; t < a1; t++) {
+            const double *row = tile + (size_t)t * L::TS;
+            const double u0 = row[L::U], u1 = row[L::U + 1];
+            if (q < 6) s += row[q] * u0 + row[L::ROW + q] * u1;              // one-frame factors carry A = 0
             else if (q == 6) s += u0 * u0 + u1 * u1;
-            else if (q == 7) s += u0 * row[12] + u1 * row[XROW + 12];
-            else s += row[LVL_C];
+            else if (q == 7) s += u0 * row[L::RCOL] + u1 * row[L::ROW + L::RCOL];
+            else if (q == 8) s += row[L::C];
+            else s += row[12 + (q - 9)] * u0 + row[L::ROW + 12 + (q - 9)] * u1;      // WIDE: E0 (6) | E1 (6) | td = X columns 12 .. 24
         }
-        if (q < 6) { if (a1 > a0) bd.lm_W[(size_t)k * VSUB + 6 * ((meta[2 * a0] >> 8) & 15) + q] = s; }
+        if (q < 6) { if (part) bd.lm_W[(size_t)k * VSUB + 6 * ((meta[a0] >> 8) & 15) + q] = s; }
         else if (q == 7) bd.lm_g[k] = s;
         else if (q == 8) bd.lm_cost[k] = s;
+        else if (q > 8) { if (part) bd.lm_W[(size_t)k * VSUB + 66 + (q - 9)] = s; }
         else {
             bd.lm_a[k] = s;
-            if (a1 == a0) { bd.lm_gamma[k] = 0.0; if (ww.first) bd.lm_scale[k] = 1.0; }
+            if (MARG) bd.lm_gamma[k] = s;                                    // marginalisation keeps the pivot itself (0: the landmark is skipped)
+            else if (!part) { bd.lm_gamma[k] = 0.0; if (ww.first) bd.lm_scale[k] = 1.0; }
             else {
                 // Jacobi scale (first linearisation only) and the Schur weight for the mu this linearisation will be solved with:
                 // scaled pivot h = c^2 a + mu * clamp(c^2 a); gamma = c^2 / h  
@@ -119,94 +148,117 @@ VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt
         }
     }
 }
-
-// ------------------------------------------------------------------------------------------------ asm_pairs
-// G is 13 x 13 inside a 16 x 16 frame of 8 x 8 tiles; tiles (0,0), (0,1), (1,1) are stored in accumulator order: tile t, lane l, register r at
-// out[64 t + 2 l + r] = G[8 tr + l/4][8 tc + 2 (l%4) + r]; pair_G_entry (kernels_asm.cuh) reads entry (i, j) back.
-VIWB_D void asm_pairs_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
-    (void)by; (void)smem; (void)mode;
-    const int Wd = nt < 32 ? nt : 32, wpb = nt / Wd, lane = tid % Wd;
-    const int it = bx * wpb + tid / Wd;
-    if (it >= bd.npitems_total) return;
-    const AsmItem item = bd.pitems[it];
-    if (bd.work[item.win].status != ST_RUNNING) return;
-    const double *recs = bd.xrec;                      // item.lo / item.hi are absolute record indices
-    double *out = bd.pair_out + (size_t)it * PAIR_OUT;
-#ifdef VIWB_HOST_EMU
-    (void)lane;
-    double G[16][16];
-    for (int a = 0; a < 16; a++) for (int b = 0; b < 16; b++) G[a][b] = 0.0;
-    for (int f = item.lo; f < item.hi; f++) for (int rr = 0; rr < 2; rr++) {
-        const double *xrow = recs + (size_t)f * XREC + rr * XROW;
-        for (int a = 0; a < XROW; a++) for (int b = 0; b < XROW; b++) G[a][b] += xrow[a] * xrow[b];
-    }
-    for (int t = 0; t < 3; t++) { const int tr = t == 2 ? 1 : 0, tc = t == 0 ? 0 : 1;
-        for (int l = 0; l < 32; l++) for (int r = 0; r < 2; r++) out[64 * t + 2 * l + r] = G[8 * tr + l / 4][8 * tc + 2 * (l % 4) + r]; }
-#else
-    // K index of the product = (factor, residual row): k-step of 4 = two records; lane l feeds X[k = l%4][column l/4 (+ 8)] as the A and the B operand
-    const int kk = lane & 3, fo = kk >> 1, rr = kk & 1, c0 = lane >> 2, c1 = c0 + 8;
-    const bool c1ok = c1 < XROW;
-    double acc[2][3][2];
-#pragma unroll
-    for (int u = 0; u < 2; u++)
-#pragma unroll
-        for (int t = 0; t < 3; t++) { acc[u][t][0] = 0.0; acc[u][t][1] = 0.0; }
-    for (int f = item.lo; f < item.hi; f += 4) {          // two independent k-steps per trip
-        double a0[2], a1[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int ff = f + 2 * u + fo;
-            const bool ok = ff < item.hi;
-            const double *p = recs + (size_t)ff * XREC + rr * XROW;
-            a0[u] = ok ? p[c0] : 0.0;
-            a1[u] = (ok && c1ok) ? p[c1] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) { dmma884(acc[u][0], a0[u], a0[u]); dmma884(acc[u][1], a0[u], a1[u]); dmma884(acc[u][2], a1[u], a1[u]); }
-    }
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-        double2 v; v.x = acc[0][t][0] + acc[1][t][0]; v.y = acc[0][t][1] + acc[1][t][1];
-        reinterpret_cast<double2 *>(out + 64 * t)[lane] = v;
-    }
-#endif
+VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; (void)mode; lin_vis_lm_body<false, false>(bd, bx, tid, nt, smem); }
+VIWB_D void lin_vis_lm_wide_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by;
+    if (mode == MODE_MARG) lin_vis_lm_body<true, true>(bd, bx, tid, nt, smem); else lin_vis_lm_body<true, false>(bd, bx, tid, nt, smem);
 }
 
+// ------------------------------------------------------------------------------------------------ asm_pairs
+// One warp per chunk of one frame pair's records: G = sum_f X_f^T X_f on the FP64 tensor pipe.  K index of the product = (factor, residual row): a
+// k-step of 4 = two records; lane l feeds X[k = l%4][column l/4 + 8 t] as the A and the B operand of the tiles in tile row / column t.
+template <bool WIDE>
+VIWB_D void asm_pairs_body(const BatchDev &bd, int bx, int tid, int nt, int mode) {
+    typedef XL<WIDE> L;
+    const int Wd = nt < 32 ? nt : 32, wpb = nt / Wd, lane = tid % Wd;
+    const int it = bx * wpb + tid / Wd;
+    const bool marg = mode == MODE_MARG;
+    if (it >= (marg ? bd.nmpitems_total : bd.npitems_total)) return;
+    const AsmItem item = (marg ? bd.mpitems : bd.pitems)[it];
+    if (marg ? !WIDE : (bd.work[item.win].status != ST_RUNNING || (item.has_common != 0) != WIDE)) return;
+    const double *recs = bd.xrec;                      // item.base: the window's record region (offset in doubles); item.lo / item.hi: records inside it
+    double *out = marg ? bd.mpair_out + (size_t)it * XL<true>::OUT : bd.pair_out + (size_t)it * bd.pout_stride;
+#ifdef VIWB_HOST_EMU
+    (void)lane;
+    double G[32][32];
+    for (int a = 0; a < 32; a++) for (int b = 0; b < 32; b++) G[a][b] = 0.0;
+    for (int f = item.lo; f < item.hi; f++) for (int rr = 0; rr < 2; rr++) {
+        const double *xrow = recs + (size_t)item.base + (size_t)f * L::REC + rr * L::ROW;
+        for (int a = 0; a < L::ROW; a++) for (int b = 0; b < L::ROW; b++) G[a][b] += xrow[a] * xrow[b];
+    }
+    int t = 0;
+    for (int tr = 0; tr < L::NTC; tr++) for (int tc = tr; tc < L::NTC; tc++, t++)
+        for (int l = 0; l < 32; l++) for (int r = 0; r < 2; r++) out[64 * t + 2 * l + r] = G[8 * tr + l / 4][8 * tc + 2 * (l % 4) + r];
+#else
+    const double *base = recs + (size_t)item.base;
+    const int kk = lane & 3, fo = kk >> 1, rr = kk & 1, c0 = lane >> 2;
+    double acc[L::NTILE][2];
+#pragma unroll
+    for (int t = 0; t < L::NTILE; t++) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    for (int f = item.lo; f < item.hi; f += 2) {
+        const int ff = f + fo;
+        const bool ok = ff < item.hi;
+        const double *p = base + (size_t)ff * L::REC + rr * L::ROW;
+        double a[L::NTC];
+#pragma unroll
+        for (int t = 0; t < L::NTC; t++) a[t] = (ok && c0 + 8 * t < L::ROW) ? p[c0 + 8 * t] : 0.0;
+        int t = 0;
+#pragma unroll
+        for (int tr = 0; tr < L::NTC; tr++)
+#pragma unroll
+            for (int tc = tr; tc < L::NTC; tc++, t++) dmma884(acc[t], a[tr], a[tc]);
+    }
+#pragma unroll
+    for (int t = 0; t < L::NTILE; t++) { double2 v; v.x = acc[t][0]; v.y = acc[t][1]; reinterpret_cast<double2 *>(out + 64 * t)[lane] = v; }
+#endif
+}
+VIWB_D void asm_pairs_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; (void)smem; asm_pairs_body<false>(bd, bx, tid, nt, mode); }
+VIWB_D void asm_pairs_wide_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; (void)smem; asm_pairs_body<true>(bd, bx, tid, nt, mode); }
+
 // ------------------------------------------------------------------------------------------------ pair_reduce
-// Folds the pair chunks of a window into what the solve kernel adds to H: per frame f the diagonal block and gradient (27 values: every chunk
-// of every pair that contains f, in item order) and per pair (a < b) the 6 x 6 off-diagonal block (36 values, the pair's chunks).  One block per
-// window, one owner per output, fixed order.  Keeps the ~100 dependent L2 reads per entry out of the (latency-bound) solve kernel.
+// Folds the pair chunks of a window into what the consumer (solve / marg_prep through assemble_into) adds to the normal equations: per frame f the
+// diagonal block and gradient (every chunk of every pair that contains f, in item order) (+ WIDE: its 6 x 13 block against the common columns),
+// per pair (a < b) the 6 x 6 off-diagonal block, (+ WIDE: the 13 x 13 common block and gradient over all chunks).  One block per window, one owner per
+// output, fixed order.  Keeps the ~100 dependent L2 reads per entry out of the (latency-bound) consumer kernels.
 VIWB_HD int pair_index(int a, int b) { return a * (2 * NFR - a - 1) / 2 + (b - a - 1); }      // a < b
-VIWB_D void pair_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
-    (void)by; (void)smem; (void)mode;
-    const int w = bx;
+template <bool WIDE>
+VIWB_D void pair_reduce_body(const BatchDev &bd, int w, int tid, int nt, int mode) {
+    typedef XL<WIDE> L;
     const WinMeta &m = bd.meta[w];
-    if (!m.fused || bd.work[w].status != ST_RUNNING) return;
+    const bool marg = mode == MODE_MARG;
     double *red = bd.pair_red + (size_t)w * PAIR_RED;
-    const int pio = m.pitem_off, npi = m.npitems;
-    for (int e = tid; e < NFR * 27; e += nt) {
-        const int f = e / 27, o = e - 27 * f;
-        int p = 0, q = 0;
-        if (o < 21) sym_unrank(o, p, q); else p = o - 21;
+    const AsmItem *items = marg ? bd.mpitems + m.mpitem_off : bd.pitems + m.pitem_off;
+    const int npi = marg ? m.nmpitems : m.npitems;
+    const size_t PS = marg ? (size_t)XL<true>::OUT : (size_t)bd.pout_stride;
+    const double *outs = marg ? bd.mpair_out + (size_t)m.mpitem_off * PS : bd.pair_out + (size_t)m.pitem_off * PS;
+    for (int e = tid; e < NFR * L::FR; e += nt) {
+        const int f = e / L::FR, o = e - L::FR * f;
+        int p = 0, q = 0;              // G row offset within the frame's slot, G column (absolute unless it is a pose column)
+        bool qpose = false;
+        if (o < 21) { sym_unrank(o, p, q); qpose = true; } else if (o < 27) { p = o - 21; q = L::RCOL; } else { p = (o - 27) / 13; q = 12 + (o - 27) % 13; }
         double v = 0.0;
         for (int ii = 0; ii < npi; ii++) {
-            const AsmItem &it = bd.pitems[pio + ii];
+            const AsmItem &it = items[ii];
             int base;
-            if (it.a == f) base = 0; else if (it.b == f) base = 6; else continue;
-            v += pair_G_entry(bd.pair_out + (size_t)(pio + ii) * PAIR_OUT, base + p, o < 21 ? base + q : 12);
+            if (it.a == f && it.b != f) base = 0; else if (it.b == f && it.a != f) base = 6; else continue;      // (a == b: the one-frame factors of WIDE records, no pose columns)
+            v += pair_G<WIDE>(outs + (size_t)ii * PS, base + p, qpose ? base + q : q);
         }
         red[e] = v;
     }
-    for (int e = tid; e < NPAIR * 36; e += nt) red[NFR * 27 + e] = 0.0;
+    for (int e = tid; e < NPAIR * 36; e += nt) red[NFR * L::FR + e] = 0.0;
     VIWB_SYNC();
     for (int e = tid; e < npi * 36; e += nt) {
         const int ii = e / 36, o = e - 36 * ii;
-        const AsmItem &item = bd.pitems[pio + ii];
-        if (item.phase != 0) continue;
-        double v = pair_G_entry(bd.pair_out + (size_t)(pio + ii) * PAIR_OUT, o / 6, 6 + o % 6);
-        for (int c = 1; ii + c < npi && bd.pitems[pio + ii + c].phase == c; c++) v += pair_G_entry(bd.pair_out + (size_t)(pio + ii + c) * PAIR_OUT, o / 6, 6 + o % 6);
-        red[NFR * 27 + pair_index(item.a, item.b) * 36 + o] = v;
+        const AsmItem &item = items[ii];
+        if (item.phase != 0 || item.a == item.b) continue;
+        double v = pair_G<WIDE>(outs + (size_t)ii * PS, o / 6, 6 + o % 6);
+        for (int c = 1; ii + c < npi && items[ii + c].phase == c; c++) v += pair_G<WIDE>(outs + (size_t)(ii + c) * PS, o / 6, 6 + o % 6);
+        red[NFR * L::FR + pair_index(item.a, item.b) * 36 + o] = v;
     }
+    if (WIDE) for (int e = tid; e < 91 + 13; e += nt) {
+        int p = 0, q = 0;
+        if (e < 91) { sym_unrank(e, p, q); q += 12; } else { p = e - 91; q = L::RCOL; }
+        double v = 0.0;
+        for (int ii = 0; ii < npi; ii++) v += pair_G<WIDE>(outs + (size_t)ii * PS, 12 + p, q);
+        red[NFR * L::FR + NPAIR * 36 + e] = v;
+    }
+}
+VIWB_D void pair_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem;
+    const WinMeta &m = bd.meta[bx];
+    if (mode == MODE_MARG) { if (m.mfused) pair_reduce_body<true>(bd, bx, tid, nt, mode); return; }
+    if (!m.fused || bd.work[bx].status != ST_RUNNING) return;
+    if (m.has_common) pair_reduce_body<true>(bd, bx, tid, nt, mode); else pair_reduce_body<false>(bd, bx, tid, nt, mode);
 }
 
 // ------------------------------------------------------------------------------------------------ syrk_mma

@@ -76,7 +76,7 @@ VIWB_D void lin_vis_block(const BatchDev &bd, int bx, int by, int tid, int nt, d
     }
     if (on) {
         fi = bd.vis_fi[f];
-        if (mode == MODE_MARG && (fi != 0 || bd.meta[w].margin_flag != 0)) on = false;
+        if (mode == MODE_MARG && (fi != 0 || bd.meta[w].margin_flag != 0 || bd.meta[w].mfused)) on = false;      // fused marginalisation: lin_vis_lm_wide
     }
     act[tid] = on ? 1 : 0;
     const int nrec = (bd.nvis_total - bx * nt) < nt ? (bd.nvis_total - bx * nt) : nt;
@@ -130,6 +130,7 @@ VIWB_D void lm_reduce_body(const BatchDev &bd, int bx, int tid, int nt, int mode
     const int w = bd.lm_win[k];
     const WinWork &ww = bd.work[w];
     if (mode == MODE_SOLVE && (ww.status != ST_RUNNING || bd.meta[w].fused)) return;
+    if (mode == MODE_MARG && bd.meta[w].mfused) return;
     const int f0 = bd.lm_fptr[k], f1 = bd.lm_fptr[k + 1];
     double *W = bd.lm_W + (size_t)k * VSUB;
     const bool skip = (mode == MODE_MARG) && (f0 == f1 || bd.vis_fi[f0] != 0 || bd.meta[w].margin_flag != 0);

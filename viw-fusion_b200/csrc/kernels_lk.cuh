@@ -192,11 +192,11 @@ enum { LK_W = 32 };
 #define LK_MINB 8
 #endif
 enum { LK_ITEMS = 63, LK_IPL = (LK_ITEMS + LK_W - 1) / LK_W, LK_PPB = 4,         // items, items per lane, points per block
-       LK_PS = 32,                                                             // byte stride of the staged source patch (TMA box row)
-       LK_SLACK = 3, LK_JROWS = 32, LK_JS = 32,                                // staged search region: 32 rows x 32 bytes (TMA box)
+       LK_PS = 48,                                                             // byte stride of the staged source patch (TMA box row: 48 bytes, its origin 16-byte aligned)
+       LK_SLACK = 4, LK_JROWS = 32, LK_JS = 48,                                // staged search region: 32 rows x 48 bytes (TMA box)
        LK_BS = 23, LK_DBYTES = 2208,                                           // interpolated-intensity image 23 x 23 ints (shares the Scharr sample buffer)
        LK_OFF_J = 32 * LK_PS, LK_OFF_D = LK_OFF_J + LK_JROWS * LK_JS, LK_OFF_BAR = LK_OFF_D + LK_DBYTES,
-       LK_WARP_SMEM = 4352 };                                                  // 1024 + 1024 + 2208 + 16 (mbarrier) rounded up to a multiple of 128
+       LK_WARP_SMEM = 5376 };                                                  // 1536 + 1536 + 2208 + 16 (mbarriers) rounded up to a multiple of 128
 VIWB_HD size_t lk_smem_bytes(int warps) { return (size_t)warps * LK_WARP_SMEM; }
 
 // exact sum over the warp of one int32 per lane (every lane gets it)
@@ -239,12 +239,13 @@ VIWB_D void lk_stage(uint8_t *buf, const uint8_t *img, int stride, int cols, int
     VIWB_SYNCWARP();
 }
 
-// ---- TMA staging (sm_100a): per pyramid level ONE tensor map over the level's stacked images [slots * streams * rows][pitch / 4] of 32-BIT words
-// (row pitch a multiple of 16 bytes), box 8 words x 32 rows = 32 x 32 bytes, so a tile starts at a byte column that is a multiple of 4; a warp's
-// lane 0 arms the warp's mbarrier with the tile's byte count and issues the copy, the warp waits on the barrier's phase.  (A UINT8 tensor map of
-// the same region is rejected by this driver / GPU pair with "illegal instruction" for every box shape -- profiles/r02i_tma_probe.txt; UINT32 and
-// FLOAT32 maps load fine.)  Columns right of the pitch are zero-filled by the unit; only windows whose needed pixels are inside the image take
-// this path, and samples are only taken from the part of a tile that lies inside the image (rows below it belong to the next image of the stack).
+// ---- TMA staging (sm_100a): per pyramid level ONE tensor map over the level's stacked images [slots * streams * rows][width] (u8, row pitch a
+// multiple of 16 bytes), box 48 bytes x 32 rows.  The unit wants the tile's first byte 16-byte aligned (a tile at a byte column that is not a
+// multiple of 16 raises "illegal instruction", profiles/r02i_tma_probe.txt: the probes at x = 8 bytes fault, those at x = 32 bytes load), so
+// the tile starts at the aligned column at or below the window and is 48 bytes wide (23 needed + 15 of misalignment + slack).  A warp's
+// lane 0 arms the warp's mbarrier with the tile's byte count and issues the copy, the warp waits on the barrier's phase.  Columns right of the
+// image are zero-filled by the unit; only windows whose needed pixels are inside the image take this path, and samples are only taken from the
+// part of a tile that lies inside the image (rows below it belong to the next image of the stack).
 struct alignas(64) LkMaps { unsigned long long opaque[LK_MAXLVL][16]; };      // LK_MAXLVL x CUtensorMap (128 bytes each; the descriptor must sit 64-byte aligned, also in kernel parameter space), encoded by the host
 #ifndef VIWB_HOST_EMU
 VIWB_D unsigned lk_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -257,12 +258,12 @@ VIWB_D void lk_bar_init(unsigned long long *bar, int lane) {      // bar[0]: sou
     }
     __syncwarp();
 }
-// issue: tile (x, y) .. (x + 31, y + 31) of the level's stack into dst (128-byte aligned), completion on `bar`; returns at once
+// issue: tile (x, y) .. (x + 47, y + 31) of the level's stack (x a multiple of 16) into dst (128-byte aligned), completion on `bar`; returns at once
 VIWB_D void lk_tma_issue(uint8_t *dst, const void *map, int x, int y, unsigned long long *bar, int lane) {
     __syncwarp();                                  // every lane is done reading the buffer that is about to be overwritten
     if (lane == 0) {
         const unsigned b = lk_smem_addr(bar);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(32 * 32) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(LK_JS * LK_JROWS) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                      ::"r"(lk_smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(b) : "memory");
     }
@@ -283,19 +284,19 @@ VIWB_D void lk_tma_wait(unsigned long long *bar, unsigned &phase) {
 VIWB_D int lk_dp2a_lo(unsigned w, unsigned px, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c)); return d; }
 VIWB_D int lk_dp2a_hi(unsigned w, unsigned px, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c)); return d; }
 #endif
-// bilinear samples of 7 consecutive pixels from two staged rows (row stride 32 bytes) at byte offset xoff (any alignment):
+// bilinear samples of 7 consecutive pixels from two staged rows (row stride LK_JS = LK_PS bytes) at byte offset xoff (any alignment):
 // out[k] = c[k] + top[k] w00 + top[k+1] w01 + bot[k] w10 + bot[k+1] w11, wt = w00 | w01 << 16, wb = w10 | w11 << 16 as SIGNED 16-bit halves
 // (|w| <= 2^14; w11 = 2^14 - w00 - w01 - w10 can come out as -1, lkpyramid.cpp computes it the same way)
 VIWB_D void lk_sample7(const uint8_t *rowbase, int xoff, unsigned wt, unsigned wb, const int *c, int *out) {
 #ifdef VIWB_HOST_EMU
     const uint8_t *q = rowbase + xoff;
     const int w00 = (int)(short)(wt & 0xffffu), w01 = (int)(short)(wt >> 16), w10 = (int)(short)(wb & 0xffffu), w11 = (int)(short)(wb >> 16);
-    for (int k = 0; k < 7; k++) out[k] = c[k] + q[k] * w00 + q[k + 1] * w01 + q[k + 32] * w10 + q[k + 33] * w11;
+    for (int k = 0; k < 7; k++) out[k] = c[k] + q[k] * w00 + q[k + 1] * w01 + q[k + LK_JS] * w10 + q[k + LK_JS + 1] * w11;
 #else
     const int mis = xoff & 3;
     const uint32_t *wp = reinterpret_cast<const uint32_t *>(rowbase + (xoff - mis));
     const unsigned sel = 0x3210u + 0x1111u * (unsigned)mis;
-    const uint32_t t0 = wp[0], t1 = wp[1], t2 = wp[2], b0 = wp[8], b1 = wp[9], b2 = wp[10];
+    const uint32_t t0 = wp[0], t1 = wp[1], t2 = wp[2], b0 = wp[LK_JS / 4], b1 = wp[LK_JS / 4 + 1], b2 = wp[LK_JS / 4 + 2];
     const unsigned ta = __byte_perm(t0, t1, sel), tb = __byte_perm(t1, t2, sel);      // bytes 0..3, 4..7 of the top row
     const unsigned ba = __byte_perm(b0, b1, sel), bb = __byte_perm(b1, b2, sel);
     const unsigned ta1 = __byte_perm(ta, tb, 0x4321), tb1 = tb >> 8, ba1 = __byte_perm(ba, bb, 0x4321), bb1 = bb >> 8;      // bytes 1..4, 5..7
@@ -310,8 +311,8 @@ VIWB_D void lk_sample7(const uint8_t *rowbase, int xoff, unsigned wt, unsigned w
 }
 
 VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane, unsigned char *smem_raw) {
-    uint8_t *pbuf = (uint8_t *)smem_raw;                      // 32 rows x 32 bytes (24 rows used)
-    uint8_t *jbuf = smem_raw + LK_OFF_J;                      // 32 rows x 32 bytes
+    uint8_t *pbuf = (uint8_t *)smem_raw;                      // 32 rows x 48 bytes (24 rows used)
+    uint8_t *jbuf = smem_raw + LK_OFF_J;                      // 32 rows x 48 bytes
     short *dpatch = (short *)(smem_raw + LK_OFF_D);           // 22 x 22 x (dx, dy)
     int *Bimg = (int *)dpatch;                                // or: 23 x 23 interpolated intensities (interior patches)
     const int npts = a.n_dev ? *a.n_dev : a.n;
@@ -357,20 +358,20 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
         int jx1 = 0, jy1 = 0;          // end of its usable part (a TMA tile may hang over the image's right / bottom edge; the reflect path fills its whole box)
         bool staged = false;
 #ifndef VIWB_HOST_EMU
-        // TMA tile that holds the 23 x 23 samples at (inx, iny), which must lie inside the image: origin a multiple of 4 bytes in x, at most 7 left of inx
+        // TMA tile that holds the 23 x 23 samples at (inx, iny), which must lie inside the image: origin a multiple of 16 bytes in x, 4 .. 19 left of inx
         auto tile_j = [&](int inx, int iny) {
-            jx0 = (inx - 4) & ~3; if (jx0 < 0) jx0 = 0;
+            jx0 = (inx - 4) & ~15; if (jx0 < 0) jx0 = 0;
             jy0 = iny - 4; if (jy0 > jr - LK_JROWS) jy0 = jr - LK_JROWS; if (jy0 < 0) jy0 = 0;
             jx1 = jx0 + LK_JS < jc ? jx0 + LK_JS : jc; jy1 = jy0 + LK_JROWS < jr ? jy0 + LK_JROWS : jr;
-            lk_tma_issue(jbuf, &maps->opaque[level][0], jx0 >> 2, a.trowJ[level] + jy0, bar + 1, lane);
+            lk_tma_issue(jbuf, &maps->opaque[level][0], jx0, a.trowJ[level] + jy0, bar + 1, lane);
         };
         if (tma) {
             const int inx = (int)floorf(nx - (float)LK_HALF), iny = (int)floorf(ny - (float)LK_HALF);
             if (inx >= 0 && iny >= 0 && inx + 23 <= jc && iny + 23 <= jr) { tile_j(inx, iny); j_pending = true; staged = true; }
         }
         if (tma && ipx >= 1 && ipy >= 1 && ipx + 23 <= cols && ipy + 23 <= rows) {
-            const int pxa = (ipx - 1) & ~3;
-            if (!p_pending) lk_tma_issue(pbuf, &maps->opaque[level][0], pxa >> 2, a.trowI[level] + ipy - 1, bar, lane);
+            const int pxa = (ipx - 1) & ~15;
+            if (!p_pending) lk_tma_issue(pbuf, &maps->opaque[level][0], pxa, a.trowI[level] + ipy - 1, bar, lane);
             lk_tma_wait(bar, phaseP); p_pending = false;
             psx = (ipx - 1) - pxa;
         } else
@@ -455,7 +456,7 @@ VIWB_D void lk_track_warp(const LkArgs &a, const LkMaps *maps, int pt, int lane,
             const float sc2 = (float)(1. / (1 << (level - 1)));
             const int qx = (int)floorf(px0 * sc2 - (float)LK_HALF), qy = (int)floorf(py0 * sc2 - (float)LK_HALF);
             if (qx >= 1 && qy >= 1 && qx + 23 <= a.I.w[level - 1] && qy + 23 <= a.I.h[level - 1]) {
-                lk_tma_issue(pbuf, &maps->opaque[level - 1][0], ((qx - 1) & ~3) >> 2, a.trowI[level - 1] + qy - 1, bar, lane);
+                lk_tma_issue(pbuf, &maps->opaque[level - 1][0], (qx - 1) & ~15, a.trowI[level - 1] + qy - 1, bar, lane);
                 p_pending = true;
             }
         }

@@ -36,8 +36,8 @@ enum { ASM_STRIDE = 108, ASM_CHUNK = 256, ITEM_FRAME = 0, ITEM_PAIR = 1, ITEM_CO
 // Fused path (solver linearisation of batches whose windows keep ex0 / ex1 / td constant): lin_vis_lm evaluates the factors of whole landmarks per
 // block and leaves one X record per two-frame factor, X = [A | B | r] (2 x 13, row stride 14), at the factor's position in FRAME-PAIR order; asm_pairs
 // turns the records of one (host, observer) pair into G = sum X^T X (13 x 13 inside three 8 x 8 FP64 tensor-core tiles) per chunk of PAIR_CHUNK records.
-enum { XREC = 28, XROW = 14, PAIR_CHUNK = 32, PAIR_OUT = 192, LMB_FACTORS = 128, NPAIR = NFR * (NFR - 1) / 2, PAIR_RED = NFR * 27 + NPAIR * 36 + 3 };
-struct AsmItem { int kind, win, a, b, lo, hi, phase, has_common; };
+enum { PAIR_CHUNK = 32, LMB_FACTORS = 128, NPAIR = NFR * (NFR - 1) / 2, PAIR_RED = NFR * 105 + NPAIR * 36 + 104 + 1 };      // PAIR_RED: the WIDE pair_reduce output (the compact one is a prefix-sized subset)
+struct AsmItem { int kind, win, a, b, lo, hi, phase, has_common, base; };      // base: fused path, offset (doubles) of the window's record region in xrec
 
 struct PriorDev {       // one per window that has a valid prior
     int n, nb;
@@ -59,10 +59,12 @@ struct WinMeta {        // read-only during a solve
     int item_off, nitems, nphases, list_off;     // assembly items of the solver linearisation (kernels_asm.cuh); list entries are window-local
     int mitem_off, nmitems, nmphases, mlist_off; // assembly items of the marginalisation linearisation (factors hosted in frame 0)
     int has_common;                     // any of ex0 / ex1 / td is an active column (solver); marginalisation always counts them
-    int xrec_off, nxrec;                // fused path: first X record of the window, number of two-frame factors
+    int xrec_off, nxrec;                // fused path (solver): the window's record region in xrec (offset in DOUBLES), number of records
     int pitem_off, npitems;             // fused path: pair items (chunks of one frame pair's records), head item of a pair has phase 0
-    int lmb_off, nlmb;                  // fused path: landmark blocks (whole landmarks, <= LMB_FACTORS factors) of lin_vis_lm
-    int fused;                          // 1: this window's solver linearisation takes the fused path (constant ex0 / ex1 / td, regular factor table)
+    int lmb_off, nlmb;                  // landmark blocks (whole landmarks, <= LMB_FACTORS factors) of lin_vis_lm, solver and marginalisation
+    int fused;                          // 1: this window's solver linearisation takes the fused path (regular factor table); records COMPACT unless has_common
+    int mxrec_off, nmxrec, mpitem_off, nmpitems;      // fused marginalisation (MARGIN_OLD, regular table): WIDE records of the factors hosted in frame 0, their pair items
+    int mfused;
     short tcol[NB];     // compact column of fixed block b, -1 if constant / absent / unreferenced
     short efirst[TFIX]; // envelope of the reduced system: first structurally non-zero column of compact row i (<= i)
     int esize;          // number of stored entries = sum_i (i - efirst[i] + 1)
@@ -99,7 +101,12 @@ struct BatchDev {       // passed by value to every kernel
     int marg_nmax;          // largest prior dimension any window of the batch produces (sizes the eigen-solver's shared memory)
     int rec_stride_solve;   // VREC_COMPACT if no window of the batch has ex0/ex1/td active, else VREC (marginalisation always uses VREC)
     int n_unfused;          // windows whose solver linearisation runs lin_vis + lm_reduce + asm_items (the others: lin_vis_lm + asm_pairs, WinMeta.fused)
-    int nlmb_total, npitems_total, nxrec_total;
+    int n_fused_wide, n_fused_compact, n_munfused, n_mfused;      // fused solver windows by record width; marginalising windows by path
+    int nlmb_total, npitems_total, nmpitems_total;
+    int pout_stride;        // doubles per solver pair item in pair_out: 192 (all fused windows compact) or 640
+    const int *mvis_pos;            // [nvis_total] marginalisation: window-local record slot of the factors hosted in frame 0 (-1 otherwise)
+    const struct AsmItem *mpitems;  // [nmpitems_total]
+    double *mpair_out;              // [nmpitems_total][640]
     const int *vis_pos;             // [nvis_total] window-local position of the factor's X record in frame-pair order, -1 for one-frame factors
     const unsigned char *vis_dup;   // [nvis_total] 0: the factor alone observes its landmark from frame j; 1: first of two such factors (adds the next one's part); 2: second (adds nothing)
     const int *lmb_ptr;             // [nlmb_total][2] global landmark range [first, end) of each landmark block

@@ -24,8 +24,8 @@ static void lk_launch_track(const LkArgs *t, int maxn, int ntasks, stream_t s, c
     if (maxn <= 0 || ntasks <= 0) return;
     g_prof.begin("lk_track", s); lk_track_tasks_kernel<<<dim3((maxn + LK_PPB - 1) / LK_PPB, ntasks), 32 * LK_PPB, lk_smem_bytes(LK_PPB), s>>>(t, use_tma ? maps : nullptr); g_prof.end(s);
 }
-// One tensor map per pyramid level over the level's stacked images viewed as 32-bit words ([LK_SLOTS * F * rows][pitch / 4], row pitch a multiple of
-// 16 bytes), box 8 words x 32 rows, no swizzle, zero fill outside (a UINT8 map of the same memory faults on load here, profiles/r02i_tma_probe.txt).  cuTensorMapEncodeTiled is a driver entry point: it is looked up at run time so that libviwb.so does not link libcuda
+// One tensor map per pyramid level over the level's stacked images (u8, [LK_SLOTS * F * rows][width], row pitch a multiple of 16 bytes), box 48 bytes x
+// 32 rows, no swizzle, zero fill outside; tiles are requested at 16-byte aligned byte columns (kernels_lk.cuh).  cuTensorMapEncodeTiled is a driver entry point: it is looked up at run time so that libviwb.so does not link libcuda
 // (the library must still load -- and fail loudly in viwb_create -- on a box without a driver).
 #include <cuda.h>
 typedef CUresult (*viwb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -35,12 +35,11 @@ static int lk_encode_maps(LkMaps *out, uint8_t *const *level_base, const int *lw
     void *fn = nullptr; cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return 1;
     for (int l = 0; l < LK_MAXLVL; l++) {
-        (void)lw;                                          // the map covers the padded pitch: the unit's bounds check runs on whole words
-        const cuuint64_t dims[2] = {(cuuint64_t)(ls[l] / 4), (cuuint64_t)lh[l] * (cuuint64_t)images};
+        const cuuint64_t dims[2] = {(cuuint64_t)lw[l], (cuuint64_t)lh[l] * (cuuint64_t)images};
         const cuuint64_t strides[1] = {(cuuint64_t)ls[l]};
-        const cuuint32_t box[2] = {LK_JS / 4, LK_JROWS}, estr[2] = {1, 1};
+        const cuuint32_t box[2] = {LK_JS, LK_JROWS}, estr[2] = {1, 1};
         CUtensorMap tm;
-        const CUresult r = ((viwb_encode_tiled_fn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, level_base[l], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        const CUresult r = ((viwb_encode_tiled_fn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, level_base[l], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return 2;
         memcpy(&out->opaque[l][0], &tm, sizeof tm);

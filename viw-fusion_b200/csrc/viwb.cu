@@ -109,7 +109,9 @@ DEF_KERNEL2(solve, SOLVE_NT, 2)
 #define LVL_MINB 4
 #endif
 DEF_KERNEL2(lin_vis_lm, LMB_FACTORS, LVL_MINB)
+DEF_KERNEL2(lin_vis_lm_wide, LMB_FACTORS, 3)
 DEF_KERNEL(asm_pairs, 128)
+DEF_KERNEL(asm_pairs_wide, 128)
 DEF_KERNEL(pair_reduce, 256)
 DEF_KERNEL2(syrk_mma, SYRK_NT, 4)
 DEF_KERNEL(reanchor, 32)
@@ -227,7 +229,8 @@ struct WinLow {
     int nlist_s, nitems_s, nph_s, nlist_m, nitems_m, nph_m;
     int prior_n_out;
     bool regular;               // fused path possible: grouped table, <= LMB_FACTORS factors per landmark, at most two factors per (landmark, observer), consecutive
-    int nlmb, npitems, nxrec;   // landmark blocks of lin_vis_lm, pair chunks of asm_pairs, two-frame factors
+    int nlmb, npitems, nxrec;   // landmark blocks of lin_vis_lm, pair chunks of asm_pairs, records (two-frame factors; + the one-frame ones when the records are wide)
+    int nmpitems, nmxrec;       // the same for the marginalisation of frame 0 (factors hosted there, wide records)
 };
 static int chunk_count(int n) { return (n + ASM_CHUNK - 1) / ASM_CHUNK; }
 
@@ -354,9 +357,19 @@ static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, i
     }
     m.nitems = lo.nitems_s; m.nphases = lo.nph_s; m.nmitems = lo.nitems_m; m.nmphases = lo.nph_m;
     // fused-path plan (kernels_fused.cuh): sizes only; lower_fill builds the tables
-    lo.regular = lo.grouped && !m.has_common;
-    lo.nxrec = 0; lo.npitems = 0; lo.nlmb = 0;
+    lo.regular = lo.grouped;
+    lo.nxrec = 0; lo.npitems = 0; lo.nlmb = 0; lo.nmxrec = 0; lo.nmpitems = 0;
     for (int a = 0; a < NFR * NFR; a++) { lo.nxrec += pcnt[a]; lo.npitems += (pcnt[a] + PAIR_CHUNK - 1) / PAIR_CHUNK; }
+    if (m.has_common) {      // wide records: the one-frame factors carry ex0 / ex1 / td columns; they form the "pairs" (host, host), one group per host frame
+        int scnt[NFR] = {0};
+        for (int i = 0; i < p.num_vis; i++) if (p.vis_type[i] == 2) scnt[p.vis_frame_i[i]]++;
+        for (int a = 0; a < NFR; a++) { lo.nxrec += scnt[a]; lo.npitems += (scnt[a] + PAIR_CHUNK - 1) / PAIR_CHUNK; }
+    }
+    if (m.margin_flag == 0) {
+        int two = 0;
+        for (int a = 0; a < NFR * NFR; a++) { two += pcnt0[a]; lo.nmpitems += (pcnt0[a] + PAIR_CHUNK - 1) / PAIR_CHUNK; }
+        lo.nmxrec = ncommon0; lo.nmpitems += (ncommon0 - two + PAIR_CHUNK - 1) / PAIR_CHUNK;
+    }
     if (lo.regular) {
         int in_blk = 0, i = 0; bool open = false;
         for (int k = 0; k < p.num_landmarks && lo.regular; k++) {
@@ -382,7 +395,7 @@ struct HostArrays {
     AsmItem *items; int *asm_list; int *imu_fi, *imu_fj, *imu_win, *wheel_fi, *wheel_fj, *wheel_win, *plane_f, *plane_win;
     double *imu_data, *wheel_data, *prior_J, *prior_r, *prior_x0, *x_init; WinWork *work;
     int nitems_solve_total;
-    int *vis_pos; unsigned char *vis_dup; int *lmb_ptr, *lmb_win; AsmItem *pitems;
+    int *vis_pos; unsigned char *vis_dup; int *lmb_ptr, *lmb_win; AsmItem *pitems; int *mvis_pos; AsmItem *mpitems;
 };
 static void emit_lists(const int *type, const int *fi, const int *fj, int nvis, bool only_host0, int has_common, int w, AsmItem *items, int *list) {
     // counting sort of the (factor, role) entries into frame lists, pair lists and the common list, then chunking
@@ -439,25 +452,36 @@ static void lower_fill(const viwb_problem &p, const double *state, int w, const 
     { int *fp = h.lm_fptr + m.lm_off; int run = m.vis_off, i = 0;
       for (int k = 0; k < p.num_landmarks; k++) { fp[k] = run; while (i < p.num_vis && vl[i] == k) { i++; run++; } h.lm_win[m.lm_off + k] = w; } }
     // assembly plan
-    if (m.fused) {
-        // frame-pair order of the X records (counting sort by (host, observer)), pair chunks, duplicate codes, landmark blocks
+    // frame-pair order of the X records (counting sort by (host, observer); the one-frame factors of WIDE records form the "pair" (host, host)),
+    // pair chunks; for the solver (all factors) and for the marginalisation of frame 0 (the factors hosted there)
+    auto pair_tables = [&](bool marg, int *vp, AsmItem *pit, int base, int wide) {
         int pcnt[NFR * NFR] = {0}, poff[NFR * NFR];
-        for (int i = 0; i < p.num_vis; i++) if (vt[i] != 2) pcnt[vi[i] * NFR + vj[i]]++;
+        for (int i = 0; i < p.num_vis; i++) {
+            if (marg && vi[i] != 0) continue;
+            if (vt[i] != 2) pcnt[vi[i] * NFR + vj[i]]++; else if (wide) pcnt[vi[i] * NFR + vi[i]]++;
+        }
         int pos = 0, ni = 0;
-        AsmItem *pit = h.pitems + m.pitem_off;
         for (int a = 0; a < NFR * NFR; a++) {
             poff[a] = pos;
             for (int c0 = 0, ph = 0; c0 < pcnt[a]; c0 += PAIR_CHUNK, ph++) {
                 AsmItem &it = pit[ni++];
-                it.kind = ITEM_PAIR; it.win = w; it.a = a / NFR; it.b = a % NFR; it.lo = m.xrec_off + pos + c0; it.hi = m.xrec_off + pos + std::min(pcnt[a], c0 + (int)PAIR_CHUNK); it.phase = ph; it.has_common = 0;      // absolute record range: asm_pairs needs no second table
+                it.kind = ITEM_PAIR; it.win = w; it.a = a / NFR; it.b = a % NFR; it.lo = pos + c0; it.hi = pos + std::min(pcnt[a], c0 + (int)PAIR_CHUNK); it.phase = ph; it.has_common = wide; it.base = base;
             }
             pos += pcnt[a];
         }
-        int *vp = h.vis_pos + m.vis_off; unsigned char *vd = h.vis_dup + m.vis_off;
+        for (int i = 0; i < p.num_vis; i++) {
+            if (marg && vi[i] != 0) { vp[i] = -1; continue; }
+            if (vt[i] != 2) vp[i] = poff[vi[i] * NFR + vj[i]]++; else if (wide) vp[i] = poff[vi[i] * NFR + vi[i]]++; else vp[i] = -1;
+        }
+    };
+    if (m.fused) pair_tables(false, h.vis_pos + m.vis_off, h.pitems + m.pitem_off, m.xrec_off, m.has_common);
+    if (m.mfused) pair_tables(true, h.mvis_pos + m.vis_off, h.mpitems + m.mpitem_off, m.mxrec_off, 1);
+    if (m.fused || m.mfused) {
+        // duplicate codes (two factors of one landmark observed from the same frame: left and right camera, consecutive), landmark blocks
+        unsigned char *vd = h.vis_dup + m.vis_off;
         for (int i = 0; i < p.num_vis; i++) {
             vd[i] = 0;
-            if (vt[i] == 2) { vp[i] = -1; continue; }
-            vp[i] = poff[vi[i] * NFR + vj[i]]++;
+            if (vt[i] == 2) continue;
             if (i > 0 && vt[i - 1] != 2 && vl[i - 1] == vl[i] && vj[i - 1] == vj[i]) { vd[i - 1] = 1; vd[i] = 2; }
         }
         int *lp = h.lmb_ptr + 2 * (size_t)m.lmb_off, *lw = h.lmb_win + m.lmb_off;
@@ -469,9 +493,11 @@ static void lower_fill(const viwb_problem &p, const double *state, int w, const 
             lp[2 * nb - 1] = m.lm_off + k + 1;          // the open block ends after this landmark
             in_blk += cnt;
         }
-    } else
+    }
+    if (!m.fused)
     emit_lists(vt, vi, vj, p.num_vis, false, m.has_common, w, h.items + m.item_off, h.asm_list + m.list_off);
-    if (m.margin_flag == 0) emit_lists(vt, vi, vj, p.num_vis, true, 1, w, h.items + h.nitems_solve_total + m.mitem_off, h.asm_list + m.mlist_off);
+    if (m.margin_flag == 0 && !m.mfused) emit_lists(vt, vi, vj, p.num_vis, true, 1, w, h.items + h.nitems_solve_total + m.mitem_off, h.asm_list + m.mlist_off);
+
     // small factors
     for (int i = 0; i < p.num_imu; i++) { h.imu_fi[m.imu_off + i] = p.imu_frame_i[i]; h.imu_fj[m.imu_off + i] = p.imu_frame_j[i]; h.imu_win[m.imu_off + i] = w; }
     if (p.num_imu) memcpy(h.imu_data + (size_t)m.imu_off * 287, p.imu_data, sizeof(double) * 287 * p.num_imu);
@@ -518,15 +544,19 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     // fused solver linearisation (kernels_fused.cuh) when every window qualifies; then the solver's gather lists are not built at all
     // (decided per window, so that a window takes the same path -- and gives the same bits -- whatever else the batch holds)
     const bool allow_fused = getenv("VIWB_NO_FUSED") == nullptr;
-    int n_unfused = 0;
+    int n_unfused = 0, n_fused_wide = 0, n_fused_compact = 0, n_mfused = 0, n_munfused = 0;
     for (int w = 0; w < B; w++) {
         const bool fused = allow_fused && low[w].regular && low[w].npitems > 0;      // (a window without two-frame factors has nothing to fuse)
-        b->meta[w].fused = fused ? 1 : 0;
-        if (fused) { low[w].nitems_s = 0; low[w].nlist_s = 0; low[w].nph_s = 0; b->meta[w].nitems = 0; b->meta[w].nphases = 0; }
-        else { low[w].nlmb = 0; low[w].npitems = 0; low[w].nxrec = 0; n_unfused++; }
+        const bool mfused = allow_fused && low[w].regular && b->meta[w].margin_flag == 0 && low[w].nmpitems > 0;
+        b->meta[w].fused = fused ? 1 : 0; b->meta[w].mfused = mfused ? 1 : 0;
+        if (fused) { low[w].nitems_s = 0; low[w].nlist_s = 0; low[w].nph_s = 0; b->meta[w].nitems = 0; b->meta[w].nphases = 0; if (b->meta[w].has_common) n_fused_wide++; else n_fused_compact++; }
+        else { low[w].npitems = 0; low[w].nxrec = 0; n_unfused++; }
+        if (mfused) { low[w].nitems_m = 0; low[w].nlist_m = 0; low[w].nph_m = 0; b->meta[w].nmitems = 0; b->meta[w].nmphases = 0; n_mfused++; }
+        else { low[w].nmpitems = 0; low[w].nmxrec = 0; if (b->meta[w].margin_flag == 0) n_munfused++; }
+        if (!fused && !mfused) low[w].nlmb = 0;
     }
     // ---- phase 2: offsets
-    size_t nlmb = 0, npit = 0, nxr = 0;
+    size_t nlmb = 0, npit = 0, nxr = 0, nmpit = 0, nmxr = 0;      // nxr / nmxr: record regions in DOUBLES (solver / marginalisation share one buffer)
     size_t nstate = 0, nvis = 0, nlm = 0, nimu = 0, nwheel = 0, nplane = 0, nlist = 0, nit_s = 0, nit_m = 0, npri = 0, npJ = 0, npr = 0;
     for (int w = 0; w < B; w++) {
         const viwb_problem &p = problems[w]; WinMeta &m = b->meta[w]; const WinLow &lo = low[w];
@@ -535,13 +565,14 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
         m.imu_off = (int)nimu; nimu += p.num_imu; m.wheel_off = (int)nwheel; nwheel += p.num_wheel; m.plane_off = (int)nplane; nplane += p.num_plane;
         m.item_off = (int)nit_s; nit_s += lo.nitems_s; m.list_off = (int)nlist; nlist += lo.nlist_s;
         m.prior_idx = lo.has_prior ? (int)npri++ : -1;
-        m.lmb_off = (int)nlmb; m.nlmb = lo.nlmb; nlmb += lo.nlmb; m.pitem_off = (int)npit; m.npitems = lo.npitems; npit += lo.npitems; m.xrec_off = (int)nxr; m.nxrec = lo.nxrec; nxr += lo.nxrec;
+        m.lmb_off = (int)nlmb; m.nlmb = lo.nlmb; nlmb += lo.nlmb; m.pitem_off = (int)npit; m.npitems = lo.npitems; npit += lo.npitems; m.xrec_off = (int)nxr; m.nxrec = lo.nxrec; nxr += (size_t)lo.nxrec * (m.has_common ? (int)XL<true>::REC : (int)XL<false>::REC);
+        m.mpitem_off = (int)nmpit; m.nmpitems = lo.nmpitems; nmpit += lo.nmpitems; m.mxrec_off = (int)nmxr; m.nmxrec = lo.nmxrec; nmxr += (size_t)lo.nmxrec * XL<true>::REC;
         b->prior_n[w] = lo.prior_n_out; if (m.margin_flag >= 0) b->any_marg = true;
         b->prior_nmax = std::max(b->prior_nmax, lo.prior_n_out);
         b->algorithmic_bytes += window_algorithmic_bytes(p, opt->max_num_iterations);
     }
     for (int w = 0; w < B; w++) { WinMeta &m = b->meta[w]; const WinLow &lo = low[w]; m.mitem_off = (int)nit_m; nit_m += lo.nitems_m; m.mlist_off = (int)nlist; nlist += lo.nlist_m; }
-    if (nstate > 0x7fffffff || nvis * 12 > 0x7fffffffull * 4 || nlist > 0x7fffffff) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, "batch too large"); }
+    if (nxr > 0x7fffffff || nmxr > 0x7fffffff || nstate > 0x7fffffff || nvis * 12 > 0x7fffffffull * 4 || nlist > 0x7fffffff) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, "batch too large"); }
     std::vector<PriorDev> priors(npri);
     for (int w = 0; w < B; w++) if (b->meta[w].prior_idx >= 0) {
         const viwb_prior &pr = *problems[w].prior; PriorDev &pd = priors[b->meta[w].prior_idx]; memset(&pd, 0, sizeof pd);
@@ -555,7 +586,9 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     bd.nvis_total = (int)nvis; bd.nlm_total = (int)nlm; bd.nimu_total = (int)nimu; bd.nwheel_total = (int)nwheel; bd.nplane_total = (int)nplane; bd.nprior = (int)npri;
     bd.nitems_solve = (int)nit_s; bd.nitems_marg = (int)nit_m;
     bd.rec_stride_solve = VREC_COMPACT;
-    bd.n_unfused = n_unfused; bd.nlmb_total = (int)nlmb; bd.npitems_total = (int)npit; bd.nxrec_total = (int)nxr;
+    bd.n_unfused = n_unfused; bd.nlmb_total = (int)nlmb; bd.npitems_total = (int)npit; bd.nmpitems_total = (int)nmpit;
+    bd.n_fused_wide = n_fused_wide; bd.n_fused_compact = n_fused_compact; bd.n_mfused = n_mfused; bd.n_munfused = n_munfused;
+    bd.pout_stride = n_fused_wide ? (int)XL<true>::OUT : (int)XL<false>::OUT;
     bd.marg_nmax = b->prior_nmax;
     bd.env_max = 1; for (int w = 0; w < B; w++) bd.env_max = std::max(bd.env_max, b->meta[w].esize);
     for (int w = 0; w < B; w++) if (b->meta[w].has_common) bd.rec_stride_solve = VREC;
@@ -570,11 +603,12 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     IN(&bd.imu_fi, nimu); IN(&bd.imu_fj, nimu); IN(&bd.imu_win, nimu); IN(&bd.wheel_fi, nwheel); IN(&bd.wheel_fj, nwheel); IN(&bd.wheel_win, nwheel);
     IN(&bd.plane_f, nplane); IN(&bd.plane_win, nplane); IN(&bd.imu_data, nimu * 287); IN(&bd.wheel_data, nwheel * 78);
     IN(&bd.prior_J, npJ); IN(&bd.prior_r, npr); IN(&bd.prior_x0, npri * SFIX); IN(&bd.x_init, nstate); IN(&b->work_init_dev, B);
-    IN(&bd.vis_pos, nlmb ? nvis : 0); IN(&bd.vis_dup, nlmb ? nvis : 0); IN(&bd.lmb_ptr, 2 * nlmb); IN(&bd.lmb_win, nlmb); IN(&bd.pitems, npit);
+    IN(&bd.vis_pos, npit ? nvis : 0); IN(&bd.vis_dup, nlmb ? nvis : 0); IN(&bd.lmb_ptr, 2 * nlmb); IN(&bd.lmb_win, nlmb); IN(&bd.pitems, npit);
+    IN(&bd.mvis_pos, nmpit ? nvis : 0); IN(&bd.mpitems, nmpit);
     const size_t nvec = (size_t)B * TFIX + nlm;
     WK(&bd.work, B); WK(&bd.x_cur, nstate); WK(&bd.x_cand, nstate); WK(&bd.x_before, nstate);
     WK(&bd.vis_rec, nvis * VREC); WK(&bd.vis_cost, nvis);
-    WK(&bd.xrec, nxr * XREC); WK(&bd.pair_out, npit * PAIR_OUT); WK(&bd.pair_red, npit ? (size_t)B * PAIR_RED : 0);
+    WK(&bd.xrec, std::max(nxr, nmxr)); WK(&bd.pair_out, npit * (size_t)bd.pout_stride); WK(&bd.mpair_out, nmpit * (size_t)XL<true>::OUT); WK(&bd.pair_red, (npit || nmpit) ? (size_t)B * PAIR_RED : 0);
     WK(&bd.lm_a, nlm); WK(&bd.lm_g, nlm); WK(&bd.lm_gamma, nlm); WK(&bd.lm_scale, nlm); WK(&bd.lm_cost, nlm); WK(&bd.lm_W, nlm * VSUB); WK(&bd.lm_outlier, nlm);
     WK(&bd.imu_S, nimu * 225); WK(&bd.wheel_S, nwheel * 36); WK(&bd.imu_rec, nimu * IMU_REC); WK(&bd.wheel_rec, nwheel * WHEEL_REC); WK(&bd.plane_rec, nplane * PLANE_REC);
     WK(&bd.prior_A, npJ); WK(&bd.prior_res, npr); WK(&bd.prior_g, npr);
@@ -605,7 +639,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
       HP(h.meta); HP(h.prior); HP(h.vis_type); HP(h.vis_lm); HP(h.vis_fi); HP(h.vis_fj); HP(h.vis_win); HP(h.vis_obs); HP(h.lm_win); HP(h.lm_fptr); HP(h.items); HP(h.asm_list);
       HP(h.imu_fi); HP(h.imu_fj); HP(h.imu_win); HP(h.wheel_fi); HP(h.wheel_fj); HP(h.wheel_win); HP(h.plane_f); HP(h.plane_win); HP(h.imu_data); HP(h.wheel_data);
       HP(h.prior_J); HP(h.prior_r); HP(h.prior_x0); HP(h.x_init); HP(h.work);
-      HP(h.vis_pos); HP(h.vis_dup); HP(h.lmb_ptr); HP(h.lmb_win); HP(h.pitems); }
+      HP(h.vis_pos); HP(h.vis_dup); HP(h.lmb_ptr); HP(h.lmb_win); HP(h.pitems); HP(h.mvis_pos); HP(h.mpitems); }
     h.nitems_solve_total = (int)nit_s;
     for (auto &e : ents) *e.field = ar->dev + e.off;
     if (npri) memcpy(h.prior, priors.data(), sizeof(PriorDev) * npri);
@@ -625,6 +659,7 @@ static int ensure_attrs(viwb_context *ctx) {
     if (!ctx->attrs_set) {
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(solve_smem_doubles(SOLVE_NT, TFIX * (TFIX + 1) / 2) * 8)));
         CK(cudaFuncSetAttribute(lin_vis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lin_vis_smem_doubles(128, VREC) * 8)));
+        CK(cudaFuncSetAttribute(lin_vis_lm_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lin_vis_lm_smem_doubles(true) * 8)));
         CK(cudaFuncSetAttribute(syrk_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(syrk_mma_smem_doubles() * 8)));
         CK(cudaFuncSetAttribute(marg_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_prep_smem_doubles(256, 100) * 8)));
         CK(cudaFuncSetAttribute(marg_tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_eig_smem_doubles(256, 100) * 8)));
@@ -656,17 +691,26 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
     // so the partial sums and the Schur product of that linearisation would never be read
     auto lin = [&](int mode, bool cost_only) {
         const bool solve = mode == MODE_SOLVE;
-        const bool old_path = !solve || bd.n_unfused > 0;          // marginalisation always takes the gather kernels (it needs the common columns)
-        if (solve && bd.nlmb_total > 0) { LAUNCH(lin_vis_lm, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles() * 8, mode, st); ctx->launches++; }
+        const bool old_path = solve ? bd.n_unfused > 0 : bd.n_munfused > 0;      // windows outside the fused path (irregular factor tables)
+        const int wpb2 = NT(128) / (NT(128) < 32 ? NT(128) : 32);
+        const int nfi = solve ? bd.npitems_total : bd.nmpitems_total;               // fused pair items of this mode
+        if (solve) {
+            if (bd.n_fused_compact > 0) { LAUNCH(lin_vis_lm, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles(false) * 8, mode, st); ctx->launches++; }
+            if (bd.n_fused_wide > 0) { LAUNCH(lin_vis_lm_wide, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles(true) * 8, mode, st); ctx->launches++; }
+        } else if (bd.n_mfused > 0) { LAUNCH(lin_vis_lm_wide, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles(true) * 8, mode, st); ctx->launches++; }
+        auto fused_asm = [&]() {
+            if (nfi <= 0) return;
+            if (solve && bd.n_fused_compact > 0) { LAUNCH(asm_pairs, bd, (nfi + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st); ctx->launches++; }
+            if (!solve || bd.n_fused_wide > 0) { LAUNCH(asm_pairs_wide, bd, (nfi + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st); ctx->launches++; }
+            LAUNCH(pair_reduce, bd, B, 1, NT(256), 0, mode, st); ctx->launches++;
+        };
         if (!old_path) {
             LAUNCH(lin_small, bd, B, 1, nt_small, sm_small, mode, st); ctx->launches++;
             if (cost_only) return;
-            const int wpb2 = NT(128) / (NT(128) < 32 ? NT(128) : 32);
-            LAUNCH(asm_pairs, bd, (bd.npitems_total + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st);
-            LAUNCH(pair_reduce, bd, B, 1, NT(256), 0, mode, st); ctx->launches++;
+            fused_asm();
             if (g_syrk_dfma) LAUNCH(syrk, bd, B, 1, nt_syrk, syrk_smem_doubles() * 8, mode, st);
             else LAUNCH(syrk_mma, bd, B, 1, NT(SYRK_NT), syrk_mma_smem_doubles() * 8, mode, st);
-            ctx->launches += (bd.npitems_total > 0) + 1;
+            ctx->launches++;
             return;
         }
         LAUNCH(lin_vis, bd, g_vis, 1, nt_vis, lin_vis_smem_doubles(nt_vis, mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) * 8, mode, st);
@@ -677,7 +721,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
         if (cost_only) return;
         const int ni = mode == MODE_SOLVE ? bd.nitems_solve : bd.nitems_marg, wpb = nt_asm / (nt_asm < 32 ? nt_asm : 32);
         const bool wide = (mode == MODE_SOLVE ? bd.rec_stride_solve : (int)VREC) == VREC;     // items carry the common columns
-        if (solve && bd.npitems_total > 0) { const int wpb2 = NT(128) / (NT(128) < 32 ? NT(128) : 32); LAUNCH(asm_pairs, bd, (bd.npitems_total + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st); LAUNCH(pair_reduce, bd, B, 1, NT(256), 0, mode, st); ctx->launches += 2; }
+        fused_asm();
         if (wide) LAUNCH(asm_items_split, bd, (ni * ASM_SPLIT + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
         else LAUNCH(asm_items, bd, (ni + wpb - 1) / wpb, 1, nt_asm, 0, mode, st);
         if (g_syrk_dfma) LAUNCH(syrk, bd, B, 1, nt_syrk, syrk_smem_doubles() * 8, mode, st);
