@@ -611,6 +611,8 @@ def main():
             L.close()
         return e2e_s, lanes
 
+    # the lowering inside each lane's call is itself multi-threaded: give every lane its share of the usable cores instead of 16 threads each
+    os.environ.setdefault("VIWB_HOST_THREADS", str(max(2, usable_cores() // max(1, world) // max(1, args.e2e_lanes))))
     e2e_sweep = None
     if args.e2e_lanes_sweep:                # tuning aid: the same measurement at several host-thread counts (reported, not used for the headline)
         e2e_sweep = {}

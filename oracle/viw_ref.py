@@ -222,23 +222,30 @@ PRODUCT_LIB = os.path.join(HERE, "_ref", "libviw_ref_product.so")
 _plib = {}
 
 
-def product_lib(under_test_path):
+PRODUCT_DEV_LIB = os.path.join(HERE, "_ref", "libviw_ref_product_dev.so")      # the same with the marginalization on the device (marginalization_factor_device.cpp)
+_under_test = []
+
+
+def product_lib(under_test_path, dev=False):
     """`under_test_path`: the libviwb*.so the shim's viwb_* calls are to land in (loaded RTLD_GLOBAL first: the checker library leaves them undefined)."""
-    if under_test_path not in _plib:
-        if _plib:
+    key = (under_test_path, dev)
+    if key not in _plib:
+        if _under_test and _under_test[0] != under_test_path:
             raise RuntimeError("one library under test per process")
         if os.path.isdir(REF_SRC):
-            subprocess.check_call(["make", "-C", HERE, "-s", "ref_product"])
-        C.CDLL(under_test_path, mode=C.RTLD_GLOBAL)
-        _plib[under_test_path] = C.CDLL(PRODUCT_LIB)
-    return _plib[under_test_path]
+            subprocess.check_call(["make", "-C", HERE, "-s", "ref_product_dev" if dev else "ref_product"])
+        if not _under_test:
+            C.CDLL(under_test_path, mode=C.RTLD_GLOBAL)
+            _under_test.append(under_test_path)
+        _plib[key] = C.CDLL(PRODUCT_DEV_LIB if dev else PRODUCT_LIB)
+    return _plib[key]
 
 
-def product_available():
-    return os.path.exists(PRODUCT_LIB) or os.path.isdir(REF_SRC)
+def product_available(dev=False):
+    return os.path.exists(PRODUCT_DEV_LIB if dev else PRODUCT_LIB) or os.path.isdir(REF_SRC)
 
 
-def estimator_optimization_on_product_shim(under_test_path, problem, state, flag):
+def estimator_optimization_on_product_shim(under_test_path, problem, state, flag, dev=False):
     """Estimator::optimization() of the reference, compiled unmodified, with <ceres/ceres.h> = the product shim: ceres::Problem / ceres::Solve are
     the product's host code, the reference's own factor objects are lowered by the product's adapter, the solve runs in the library under test;
     the marginalization that follows is the reference's own CPU code on its own factor classes."""
@@ -247,7 +254,7 @@ def estimator_optimization_on_product_shim(under_test_path, problem, state, flag
     cap = 256
     mn, bid, bidx, rec = (C.c_int32 * 3)(), (C.c_int32 * 32)(), (C.c_int32 * 32)(), (C.c_int32 * 11)()
     J, r = np.zeros(cap * cap), np.zeros(cap)
-    rc = product_lib(under_test_path).ref_estimator_optimization(C.byref(problem.c), _dp(st), None, C.c_int(flag), _dp(out), mn, bid, bidx, _dp(J), _dp(r), rec)
+    rc = product_lib(under_test_path, dev).ref_estimator_optimization(C.byref(problem.c), _dp(st), None, C.c_int(flag), _dp(out), mn, bid, bidx, _dp(J), _dp(r), rec)
     if rc:
         raise RuntimeError("ref_estimator_optimization (product shim) rc=%d" % rc)
     n = mn[1]

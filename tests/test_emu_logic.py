@@ -165,3 +165,12 @@ def test_reference_estimator_on_product_shim(emu, reference_code, cid):
 def test_reference_tracker_runs_on_this_backend(emu, reference_code):
     """feature_tracker.cpp of the reference, unmodified, with its cv:: flow and corner calls answered by the library"""
     pc.check_reference_tracker_on_this_backend(emu)
+
+
+@pytest.mark.parametrize("cid", [2, 4, 6])
+def test_reference_estimator_on_product_shim_with_device_marginalization(emu, reference_code, cid):
+    """adapter route with factor/marginalization_factor.cpp replaced by the product's marginalization_factor_device.cpp: the reference's own
+    MarginalizationInfo class, marginalize() on the library under test"""
+    from emu import build_emu
+    pc.check_reference_estimator_on_product_shim(emu, build_emu.build(), cid, dev=True)
+

@@ -35,3 +35,12 @@ def test_visual_imu_alignment(gpu_ctx, oracle, cid):
 @pytest.mark.parametrize("cid", [3, 4])
 def test_visual_imu_alignment_vs_reference_code(gpu_ctx, reference_code, cid):
     pc.check_visual_imu_alignment_vs_reference_code(gpu_ctx, cid)
+
+
+@pytest.mark.parametrize("cid", [2, 4, 6])
+def test_reference_estimator_on_product_shim_with_device_marginalization(gpu_ctx, reference_code, cid):
+    """the same with factor/marginalization_factor.cpp replaced by the product's marginalization_factor_device.cpp: the reference's own
+    MarginalizationInfo class, its marginalize() on the GPU"""
+    from viwb import lib as viwb_lib
+    pc.check_reference_estimator_on_product_shim(gpu_ctx, viwb_lib.DEFAULT_LIB, cid, dev=True)
+

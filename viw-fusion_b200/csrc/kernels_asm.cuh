@@ -188,7 +188,7 @@ VIWB_D void syrk_block(const BatchDev &bd, int bx, int by, int tid, int nt, doub
     const bool live = t < ntiles + NT4, is_vec = t >= ntiles;       // one round: 230 work items <= block size (256); emulation loops below
     auto stage = [&](int c, int p) {
         const int k0 = c * SYRK_KC, kc = (m.nlm - k0) < SYRK_KC ? (m.nlm - k0) : SYRK_KC;
-        for (int e = tid; e < kc * VSUB / 2; e += nt) async_copy16(Wb[p] + 2 * e, W + (size_t)k0 * VSUB + 2 * e);
+        for (int e = tid; e < kc * VSUB / 2; e += nt) { if (gam[k0 + (2 * e) / VSUB] > 0.0) async_copy16(Wb[p] + 2 * e, W + (size_t)k0 * VSUB + 2 * e); else { Wb[p][2 * e] = 0.0; Wb[p][2 * e + 1] = 0.0; } }
         async_commit();
         for (int k = tid; k < kc; k += nt) {
             double g = gam[k0 + k];

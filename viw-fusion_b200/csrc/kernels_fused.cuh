@@ -64,8 +64,10 @@ VIWB_D void lin_vis_lm_body(const BatchDev &bd, int bx, int tid, int nt, double 
     const double *x = (MARG ? bd.x_cur : bd.x_cand) + m.state_off;
     const int *vpos = MARG ? bd.mvis_pos : bd.vis_pos;
     double *xbase = bd.xrec + (size_t)(MARG ? m.mxrec_off : m.xrec_off);
-    // ---- 0: the W rows of these landmarks start from zero (frames that do not observe a landmark keep zero blocks)
-    { double *Wb = bd.lm_W + (size_t)k0 * VSUB; for (int e = tid; e < (k1 - k0) * VSUB; e += nt) Wb[e] = 0.0; }
+    // ---- 0: the W rows of these landmarks start from zero (frames that do not observe a landmark keep zero blocks).  Marginalisation: only the
+    //         rows of the landmarks hosted in frame 0 (below, once the hosts are known); the other rows keep their finite solver values and are
+    //         multiplied by the weight gamma = 0
+    if (!MARG) { double *Wb = bd.lm_W + (size_t)k0 * VSUB; for (int e = tid; e < (k1 - k0) * VSUB; e += nt) Wb[e] = 0.0; }
     // ---- 1: one thread per factor
     for (int t = tid; t < nf; t += nt) {
         const int f = f0 + t;
@@ -94,12 +96,29 @@ VIWB_D void lin_vis_lm_body(const BatchDev &bd, int bx, int tid, int nt, double 
             for (int q = 0; q < L::REC; q++) xr[q] = row[q];
 #else
             double2 *d2 = reinterpret_cast<double2 *>(xr);
+            if (!WIDE) {      // 14 stores straight from the registers the Jacobians live in
 #pragma unroll
-            for (int q = 0; q < L::REC / 2; q++) d2[q] = make_double2(row[2 * q], row[2 * q + 1]);      // (the thread re-reads its own tile row: values it has just written)
+                for (int h = 0; h < 2; h++) {
+                    d2[7 * h + 0] = make_double2(o.JA[6 * h] * sc, o.JA[6 * h + 1] * sc); d2[7 * h + 1] = make_double2(o.JA[6 * h + 2] * sc, o.JA[6 * h + 3] * sc);
+                    d2[7 * h + 2] = make_double2(o.JA[6 * h + 4] * sc, o.JA[6 * h + 5] * sc); d2[7 * h + 3] = make_double2(o.JB[6 * h] * sc, o.JB[6 * h + 1] * sc);
+                    d2[7 * h + 4] = make_double2(o.JB[6 * h + 2] * sc, o.JB[6 * h + 3] * sc); d2[7 * h + 5] = make_double2(o.JB[6 * h + 4] * sc, o.JB[6 * h + 5] * sc);
+                    d2[7 * h + 6] = make_double2(o.r[h] * sc, 0.0);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < L::REC / 2; q++) d2[q] = make_double2(row[2 * q], row[2 * q + 1]);      // (the thread re-reads its own tile row: values it has just written)
+            }
 #endif
         }
     }
     VIWB_SYNC();
+    if (MARG) {
+        for (int e = tid; e < (k1 - k0) * VSUB; e += nt) {
+            const int kl = e / VSUB, a0 = bd.lm_fptr[k0 + kl] - f0, a1 = bd.lm_fptr[k0 + kl + 1] - f0;
+            if (a1 > a0 && ((meta[a0] >> 8) & 15) == 0) bd.lm_W[(size_t)k0 * VSUB + e] = 0.0;
+        }
+        VIWB_SYNC();
+    }
     // ---- 2b: observing-frame blocks of W, item = (factor, component); two factors of one landmark seen from the same frame (left and
     //          right camera) are consecutive in the table: the first one writes the sum
     for (int e = tid; e < nf * 6; e += nt) {
@@ -283,6 +302,7 @@ VIWB_D void syrk_mma_block(const BatchDev &bd, int bx, int by, int tid, int nt, 
     for (int k = 0; k < m.nlm; k++) {
         double g = gam[k];
         if (mode == MODE_MARG) g = g > 0.0 ? 1.0 / g : 0.0;
+        if (g == 0.0) continue;                           // a landmark that takes no part: its row of W is not even read (it may never have been written)
         const double *r = W + (size_t)k * VSUB;
         for (int i = 0; i < VSUB; i++) { const double a = g * r[i]; for (int j = i; j < VSUB; j++) T[i * VSUB + j] += a * r[j]; tv[i] += a * gl[k]; }
     }
@@ -299,7 +319,12 @@ VIWB_D void syrk_mma_block(const BatchDev &bd, int bx, int by, int tid, int nt, 
     for (int j = 0; j < 6; j++) { accB[j][0] = 0.0; accB[j][1] = 0.0; }
     auto stage = [&](int c, int p) {
         const int k0 = c * SYRK_KC, kc = (m.nlm - k0) < SYRK_KC ? (m.nlm - k0) : SYRK_KC;
-        for (int e = tid; e < kc * (VSUB / 2); e += nt) { const int r = e / (VSUB / 2), cc = e - r * (VSUB / 2); async_copy16(Wb[p] + r * SYRK_LD + 2 * cc, W + (size_t)(k0 + r) * VSUB + 2 * cc); }
+        // rows with weight 0 (landmarks that take no part; marginalisation: not hosted in frame 0) are staged as zeros, never read: they may hold anything
+        for (int e = tid; e < kc * (VSUB / 2); e += nt) {
+            const int r = e / (VSUB / 2), cc = e - r * (VSUB / 2);
+            if (gam[k0 + r] > 0.0) async_copy16(Wb[p] + r * SYRK_LD + 2 * cc, W + (size_t)(k0 + r) * VSUB + 2 * cc);
+            else { Wb[p][r * SYRK_LD + 2 * cc] = 0.0; Wb[p][r * SYRK_LD + 2 * cc + 1] = 0.0; }
+        }
         async_commit();
         for (int r = tid; r < SYRK_KC; r += nt) {
             double g = 0.0, gg = 0.0;

@@ -189,7 +189,7 @@ enum { LK_W = 1 };
 enum { LK_W = 32 };
 #endif
 #ifndef LK_MINB
-#define LK_MINB 8
+#define LK_MINB 5
 #endif
 enum { LK_ITEMS = 63, LK_IPL = (LK_ITEMS + LK_W - 1) / LK_W, LK_PPB = 4,         // items, items per lane, points per block
        LK_PS = 48,                                                             // byte stride of the staged source patch (TMA box row: 48 bytes, its origin 16-byte aligned)

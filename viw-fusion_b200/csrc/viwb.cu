@@ -516,7 +516,11 @@ static void lower_fill(const viwb_problem &p, const double *state, int w, const 
 }
 
 template <typename F> static void parallel_for(int n, F f) {
-    int nt = (int)std::thread::hardware_concurrency(); if (nt > 16) nt = 16; if (nt < 1) nt = 1; if (nt > n / 8) nt = n / 8;
+    // host threads of the lowering: VIWB_HOST_THREADS (a caller that drives several contexts from several threads divides the cores among them), else
+    // all hardware threads up to 16
+    const char *env_nt = getenv("VIWB_HOST_THREADS");
+    const int cap = (env_nt && atoi(env_nt) > 0) ? atoi(env_nt) : 16;
+    int nt = (int)std::thread::hardware_concurrency(); if (nt > cap) nt = cap; if (nt < 1) nt = 1; if (nt > n / 8) nt = n / 8;
     if (nt <= 1) { for (int i = 0; i < n; i++) f(i); return; }
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++) th.emplace_back([=]() { for (int i = t; i < n; i += nt) f(i); });

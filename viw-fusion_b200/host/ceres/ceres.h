@@ -153,7 +153,7 @@ void Solve(const Solver::Options &options, Problem *problem, Solver::Summary *su
 // estimator.cpp is compiled unmodified (viw-fusion_b200/host/viwb_reference_adapter.h installs them).  A class the shim does not know and no
 // adapter claims still makes Solve() fail loudly.
 namespace viwb_shim {
-struct Lowered { int type = -1; const double *record = nullptr; const viwb_prior *prior = nullptr; };   // type as CostFunction::viwb_factor_type()
+struct Lowered { int type = -1; const double *record = nullptr; const viwb_prior *prior = nullptr; bool prior_ids_exact = true; };   // type as CostFunction::viwb_factor_type(); prior_ids_exact: prior->block_id are real block ids (an adapter may only know the block sizes)
 typedef bool (*CostAdapter)(const ceres::CostFunction *, Lowered *);
 typedef int (*ManifoldAdapter)(const ceres::LocalParameterization *);      // subset mask, or -1: not mine
 typedef double (*LossAdapter)(const ceres::LossFunction *);                // Huber delta, or -1: not mine

@@ -19,6 +19,10 @@
 
 namespace viwb_shim {
 
+// exact block ids of the priors produced by factor/marginalization_factor_device.cpp (when that translation unit replaces the reference's
+// marginalization_factor.cpp); weak: absent when the stock CPU marginalization is linked
+std::map<const void *, std::vector<int>> &device_prior_ids() __attribute__((weak));
+
 struct ReferenceScratch {
     std::deque<std::vector<double>> records;          // constant records built for the current Solve
     std::deque<viwb_prior> priors;
@@ -69,11 +73,15 @@ inline bool reference_cost_adapter(const ceres::CostFunction *c, Lowered *out) {
         S.prior_storage.emplace_back(VIWB_STATE_FIXED, 0.0); std::vector<double> &x0 = S.prior_storage.back();
         S.prior_storage.emplace_back((size_t)n * n); std::vector<double> &J = S.prior_storage.back();
         S.prior_storage.emplace_back((size_t)n); std::vector<double> &r = S.prior_storage.back();
-        // provisional block ids: any fixed block of the right size (Solve() re-maps the kept blocks by the addresses of the residual's parameter blocks)
+        // block ids: exact when the prior came from the device marginalization (in column order, like keep_block_* after getParameterBlocks), else
+        // provisional -- any fixed block of the right size (Solve() re-maps the kept blocks by the addresses of the residual's parameter blocks)
+        const std::vector<int> *exact = nullptr;
+        if (&device_prior_ids != nullptr) { auto it = device_prior_ids().find(info); if (it != device_prior_ids().end() && (int)it->second.size() == nb) exact = &it->second; }
         bool used[VIWB_NUM_FIXED_BLOCKS] = {false};
         for (int i = 0; i < nb; i++) {
             const int size = info->keep_block_size[i];
             int slot = -1;
+            if (exact) { slot = (*exact)[i]; if (slot < 0 || slot >= VIWB_NUM_FIXED_BLOCKS || viwb_block_size(slot) != size) return false; }
             for (int b = 0; b < VIWB_NUM_FIXED_BLOCKS && slot < 0; b++) if (!used[b] && viwb_block_size(b) == size) slot = b;
             if (slot < 0) return false;
             used[slot] = true;
@@ -83,7 +91,7 @@ inline bool reference_cost_adapter(const ceres::CostFunction *c, Lowered *out) {
         for (int i = 0; i < n; i++) { r[i] = info->linearized_residuals(i); for (int j = 0; j < n; j++) J[(size_t)i * n + j] = info->linearized_jacobians(i, j); }
         pr.x0 = x0.data(); pr.J = J.data(); pr.r = r.data();
         S.priors.push_back(pr);
-        out->type = -2; out->prior = &S.priors.back(); return true;
+        out->type = -2; out->prior = &S.priors.back(); out->prior_ids_exact = exact != nullptr; return true;
     }
     return false;
 }
