@@ -603,10 +603,12 @@ def main():
                 t.join()
         run_lanes(2)
         barrier()
+        up0 = sum(L.ctx.h2d_bytes() for L in lane_objs)
         t0 = time.perf_counter()
         run_lanes(e2e_steps)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        measure_e2e.table_bytes = (sum(L.ctx.h2d_bytes() for L in lane_objs) - up0) / e2e_steps       # what the library put on the wire for the windows, per step
         for L in lane_objs:
             L.close()
         return e2e_s, lanes
@@ -624,8 +626,9 @@ def main():
     e2e_s, lanes = measure_e2e(max(2, min(args.e2e_lanes, usable_cores() // max(1, world))) if world > 1 else args.e2e_lanes)
     e2e_s = rank_max(e2e_s, world)
     e2e_value = job_throughput(world, B, e2e_steps, e2e_s)
-    h2d = sum(p.vis_obs.nbytes + 4 * 4 * len(p.vis_type) + p.imu_data.nbytes + p.wheel_data.nbytes + 8 * p.state_size +
-              (8 * (p.prior.n ** 2 + p.prior.n + abi.STATE_FIXED) if p.prior is not None else 0) for p in probs)
+    caller_tables = sum(p.vis_obs.nbytes + 4 * 4 * len(p.vis_type) + p.imu_data.nbytes + p.wheel_data.nbytes + 8 * p.state_size +
+                        (8 * (p.prior.n ** 2 + p.prior.n + abi.STATE_FIXED) if p.prior is not None else 0) for p in probs)
+    h2d = measure_e2e.table_bytes          # counted by the library from the slab it copies (viwb_h2d_bytes): the packed wire format of the window tables
     nmax = max(int(q.n) for q in pri if q is not None and q.valid) if any(q is not None and q.valid for q in pri) else 0
     d2h = sum(8 * p.state_size + 8 * (nmax * nmax + abi.MAX_PRIOR_DIM + abi.STATE_FIXED) + 4 * 67 for p in probs)
     if lk is not None:
@@ -723,7 +726,7 @@ def main():
                 "workload_stats": {"mean_visual_factors": sum(len(p.vis_type) for p in probs) / B, "mean_landmarks": sum(p.num_landmarks for p in probs) / B,
                                    "camera_streams": B if lk is not None else 0, "distinct_scenes": len(scenes) if scenes else 0,
                                    "lk_stream": None if lk is None else ("same stream as the solver" if cam_stream is None else "own CUDA stream, concurrent with the solver (the reference's tracker thread)")},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "host_threads": lanes, "sweep": e2e_sweep,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "host_threads": lanes, "sweep": e2e_sweep, "caller_table_bytes_per_step": int(caller_tables),
                         "numa": numa, "h2d_gbs_per_rank": h2d * e2e_steps / e2e_s / 1e9,
                         "limiter": "host feed: %.2f GB of page-locked H2D per rank per step (camera frames + whole windows) against the device step" % (h2d / 1e9)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity,

@@ -213,6 +213,9 @@ const char *viwb_last_error(const viwb_context *ctx);
 int viwb_set_stream(viwb_context *ctx, void *cuda_stream);
 /* number of kernels this context launched since creation (bench.py's gpu_launches) */
 long long viwb_launch_count(const viwb_context *ctx);
+/* Bytes of window tables this context has uploaded so far (host -> device, the library's packed wire format; images of the LK entry points are
+ * not included: their size is the caller's).  Like viwb_launch_count it has no reference counterpart: measurement only. */
+long long viwb_h2d_bytes(const viwb_context *ctx);
 /* optional CUDA-event timing around every kernel launch (used by bench.py for the live roofline numbers) */
 int viwb_set_profiling(viwb_context *ctx, int enable);
 int viwb_profile_count(viwb_context *ctx);

@@ -119,33 +119,49 @@ VIWB_D void lin_vis_lm_body(const BatchDev &bd, int bx, int tid, int nt, double 
         }
         VIWB_SYNC();
     }
-    // ---- 2b: observing-frame blocks of W, item = (factor, component); two factors of one landmark seen from the same frame (left and
-    //          right camera) are consecutive in the table: the first one writes the sum
-    for (int e = tid; e < nf * 6; e += nt) {
-        const int t = e / 6, q = e - 6 * t, mt = meta[t];
-        if (((mt >> 2) & 3) == 2) continue;
+    // ---- 2b: observing-frame blocks of W, one thread per factor (its six components: three 16-byte stores); two factors of one landmark seen
+    //          from the same frame (left and right camera) are consecutive in the table: the first one writes the sum
+    for (int t = tid; t < nf; t += nt) {
+        const int mt = meta[t], dup = mt & 3;
+        if (((mt >> 2) & 3) == 2 || dup == 2) continue;
         if (MARG && ((mt >> 8) & 15) != 0) continue;
-        const int dup = mt & 3;
-        if (dup == 2) continue;
         const double *row = tile + (size_t)t * L::TS;
-        double v = row[6 + q] * row[L::U] + row[L::ROW + 6 + q] * row[L::U + 1];
-        if (dup == 1) { const double *r2 = row + L::TS; v += r2[6 + q] * r2[L::U] + r2[L::ROW + 6 + q] * r2[L::U + 1]; }
-        bd.lm_W[(size_t)(m.lm_off + (mt >> 12)) * VSUB + 6 * ((mt >> 4) & 15) + q] = v;
+        const double u0 = row[L::U], u1 = row[L::U + 1];
+        double v[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) v[q] = row[6 + q] * u0 + row[L::ROW + 6 + q] * u1;
+        if (dup == 1) {
+            const double *r2 = row + L::TS; const double w0 = r2[L::U], w1 = r2[L::U + 1];
+#pragma unroll
+            for (int q = 0; q < 6; q++) v[q] += r2[6 + q] * w0 + r2[L::ROW + 6 + q] * w1;
+        }
+        double *dst = bd.lm_W + (size_t)(m.lm_off + (mt >> 12)) * VSUB + 6 * ((mt >> 4) & 15);      // even offset: 16-byte aligned
+#ifdef VIWB_HOST_EMU
+        for (int q = 0; q < 6; q++) dst[q] = v[q];
+#else
+        double2 *d2 = reinterpret_cast<double2 *>(dst);
+        d2[0] = make_double2(v[0], v[1]); d2[1] = make_double2(v[2], v[3]); d2[2] = make_double2(v[4], v[5]);
+#endif
     }
-    // ---- 2c: per landmark, item = (landmark, output): host-frame block of W (6), a, g, cost (+ Jacobi scale and Schur weight) (+ common columns of W)
+    // ---- 2c: per landmark, item = (landmark, output): host-frame block of W (6), a, g, cost (+ Jacobi scale and Schur weight) (+ common columns of W).
+    //          Every output is sum_t row_t[ca] * p_t + row_t[cb] * q_t with (ca, cb) fixed per output and (p, q) = (u0, u1) or, for the cost, (1, 0):
+    //          no branch inside the factor loop
     for (int e = tid; e < (k1 - k0) * L::NLM; e += nt) {
         const int kl = e / L::NLM, q = e - L::NLM * kl, k = k0 + kl;
         const int a0 = bd.lm_fptr[k] - f0, a1 = bd.lm_fptr[k + 1] - f0;
         const bool part = a1 > a0 && (!MARG || ((meta[a0] >> 8) & 15) == 0);      // the landmark takes part (marginalisation: hosted in frame 0)
+        // q < 6: A column q (one-frame factors carry A = 0); 6: u.u; 7: u.r; 8: cost; > 8 (WIDE): E0 (6) | E1 (6) | td = X columns 12 .. 24
+        const int ca = q < 6 ? q : q == 6 ? (int)L::U : q == 7 ? (int)L::RCOL : q == 8 ? (int)L::C : 12 + (q - 9);
+        const int cb = q < 6 ? (int)L::ROW + q : q == 6 ? (int)L::U + 1 : q == 7 ? (int)L::ROW + (int)L::RCOL : q == 8 ? (int)L::C : (int)L::ROW + 12 + (q - 9);
+        const bool is_cost = q == 8;
         double s = 0.0;
-        if (part) for (int t = a0; t < a1; t++) {
-            const double *row = tile + (size_t)t * L::TS;
-            const double u0 = row[L::U], u1 = row[L::U + 1];
-            if (q < 6) s += row[q] * u0 + row[L::ROW + q] * u1;              // one-frame factors carry A = 0
-            else if (q == 6) s += u0 * u0 + u1 * u1;
-            else if (q == 7) s += u0 * row[L::RCOL] + u1 * row[L::ROW + L::RCOL];
-            else if (q == 8) s += row[L::C];
-            else s += row[12 + (q - 9)] * u0 + row[L::ROW + 12 + (q - 9)] * u1;      // WIDE: E0 (6) | E1 (6) | td = X columns 12 .. 24
+        if (part) {
+            const double *row = tile + (size_t)a0 * L::TS;
+#pragma unroll 4
+            for (int t = a0; t < a1; t++, row += L::TS) {
+                const double u0 = is_cost ? 1.0 : row[L::U], u1 = is_cost ? 0.0 : row[L::U + 1];
+                s += row[ca] * u0 + row[cb] * u1;
+            }
         }
         if (q < 6) { if (part) bd.lm_W[(size_t)k * VSUB + 6 * ((meta[a0] >> 8) & 15) + q] = s; }
         else if (q == 7) bd.lm_g[k] = s;
@@ -231,7 +247,7 @@ VIWB_D void asm_pairs_wide_block(const BatchDev &bd, int bx, int by, int tid, in
 // output, fixed order.  Keeps the ~100 dependent L2 reads per entry out of the (latency-bound) consumer kernels.
 VIWB_HD int pair_index(int a, int b) { return a * (2 * NFR - a - 1) / 2 + (b - a - 1); }      // a < b
 template <bool WIDE>
-VIWB_D void pair_reduce_body(const BatchDev &bd, int w, int tid, int nt, int mode) {
+VIWB_D void pair_reduce_body(const BatchDev &bd, int w, int tid, int nt, int mode, int *ab) {
     typedef XL<WIDE> L;
     const WinMeta &m = bd.meta[w];
     const bool marg = mode == MODE_MARG;
@@ -240,6 +256,9 @@ VIWB_D void pair_reduce_body(const BatchDev &bd, int w, int tid, int nt, int mod
     const int npi = marg ? m.nmpitems : m.npitems;
     const size_t PS = marg ? (size_t)XL<true>::OUT : (size_t)bd.pout_stride;
     const double *outs = marg ? bd.mpair_out + (size_t)m.mpitem_off * PS : bd.pair_out + (size_t)m.pitem_off * PS;
+    // the items' frame pair and chunk phase, staged once: every output below walks the whole list (a | b << 4 | phase << 8)
+    for (int ii = tid; ii < npi; ii += nt) { const AsmItem &it = items[ii]; ab[ii] = it.a | (it.b << 4) | (it.phase << 8); }
+    VIWB_SYNC();
     for (int e = tid; e < NFR * L::FR; e += nt) {
         const int f = e / L::FR, o = e - L::FR * f;
         int p = 0, q = 0;              // G row offset within the frame's slot, G column (absolute unless it is a pose column)
@@ -247,9 +266,9 @@ VIWB_D void pair_reduce_body(const BatchDev &bd, int w, int tid, int nt, int mod
         if (o < 21) { sym_unrank(o, p, q); qpose = true; } else if (o < 27) { p = o - 21; q = L::RCOL; } else { p = (o - 27) / 13; q = 12 + (o - 27) % 13; }
         double v = 0.0;
         for (int ii = 0; ii < npi; ii++) {
-            const AsmItem &it = items[ii];
+            const int ia = ab[ii] & 15, ib = (ab[ii] >> 4) & 15;
             int base;
-            if (it.a == f && it.b != f) base = 0; else if (it.b == f && it.a != f) base = 6; else continue;      // (a == b: the one-frame factors of WIDE records, no pose columns)
+            if (ia == f && ib != f) base = 0; else if (ib == f && ia != f) base = 6; else continue;      // (a == b: the one-frame factors of WIDE records, no pose columns)
             v += pair_G<WIDE>(outs + (size_t)ii * PS, base + p, qpose ? base + q : q);
         }
         red[e] = v;
@@ -258,11 +277,11 @@ VIWB_D void pair_reduce_body(const BatchDev &bd, int w, int tid, int nt, int mod
     VIWB_SYNC();
     for (int e = tid; e < npi * 36; e += nt) {
         const int ii = e / 36, o = e - 36 * ii;
-        const AsmItem &item = items[ii];
-        if (item.phase != 0 || item.a == item.b) continue;
+        const int ia = ab[ii] & 15, ib = (ab[ii] >> 4) & 15;
+        if ((ab[ii] >> 8) != 0 || ia == ib) continue;
         double v = pair_G<WIDE>(outs + (size_t)ii * PS, o / 6, 6 + o % 6);
-        for (int c = 1; ii + c < npi && items[ii + c].phase == c; c++) v += pair_G<WIDE>(outs + (size_t)(ii + c) * PS, o / 6, 6 + o % 6);
-        red[NFR * L::FR + pair_index(item.a, item.b) * 36 + o] = v;
+        for (int c = 1; ii + c < npi && (ab[ii + c] >> 8) == c; c++) v += pair_G<WIDE>(outs + (size_t)(ii + c) * PS, o / 6, 6 + o % 6);
+        red[NFR * L::FR + pair_index(ia, ib) * 36 + o] = v;
     }
     if (WIDE) for (int e = tid; e < 91 + 13; e += nt) {
         int p = 0, q = 0;
@@ -273,11 +292,12 @@ VIWB_D void pair_reduce_body(const BatchDev &bd, int w, int tid, int nt, int mod
     }
 }
 VIWB_D void pair_reduce_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
-    (void)by; (void)smem;
+    (void)by;
     const WinMeta &m = bd.meta[bx];
-    if (mode == MODE_MARG) { if (m.mfused) pair_reduce_body<true>(bd, bx, tid, nt, mode); return; }
+    int *ab = (int *)smem;                  // bd.pitems_max ints
+    if (mode == MODE_MARG) { if (m.mfused) pair_reduce_body<true>(bd, bx, tid, nt, mode, ab); return; }
     if (!m.fused || bd.work[bx].status != ST_RUNNING) return;
-    if (m.has_common) pair_reduce_body<true>(bd, bx, tid, nt, mode); else pair_reduce_body<false>(bd, bx, tid, nt, mode);
+    if (m.has_common) pair_reduce_body<true>(bd, bx, tid, nt, mode, ab); else pair_reduce_body<false>(bd, bx, tid, nt, mode, ab);
 }
 
 // ------------------------------------------------------------------------------------------------ syrk_mma

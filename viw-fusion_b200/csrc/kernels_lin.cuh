@@ -42,6 +42,18 @@ VIWB_D void setup_block(const BatchDev &bd, int bx, int by, int tid, int nt, dou
         sqrt_info_upper(6, bd.wheel_data + (size_t)k * 78 + 25, bd.wheel_S + (size_t)k * 36);
     }
 }
+// wire format -> device tables, one block per window (runs once per upload, before anything reads the visual table)
+VIWB_D void vis_expand_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by; (void)smem; (void)mode;
+    const WinMeta &m = bd.meta[bx];
+    for (int i = tid; i < m.nvis; i += nt) {
+        const int f = m.vis_off + i, code = bd.vis_code[f];
+        bd.vis_type[f] = code & 3; bd.vis_fi[f] = (code >> 2) & 15; bd.vis_fj[f] = (code >> 6) & 15; bd.vis_dup[f] = (unsigned char)((code >> 10) & 3); bd.vis_win[f] = bx;
+        const double *hi = bd.obs_i + (size_t)bd.vis_oi[f] * 6, *hj = bd.obs_j + (size_t)f * 6;
+        double *o = bd.vis_obs + (size_t)f * 12;
+        o[0] = hi[0]; o[1] = hi[1]; o[2] = hi[2]; o[3] = hj[0]; o[4] = hj[1]; o[5] = hj[2]; o[6] = hi[3]; o[7] = hi[4]; o[8] = hj[3]; o[9] = hj[4]; o[10] = hi[5]; o[11] = hj[5];
+    }
+}
 // prior A = J^T J, one block per prior
 VIWB_D void prior_setup_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)smem; (void)mode;
@@ -299,7 +311,7 @@ VIWB_D void lin_small_block(const BatchDev &bd, int bx, int by, int tid, int nt,
         VIWB_SYNC();
         const double *J = bd.prior_J + p.J_off;
         double *res = bd.prior_res + p.r_off, *g = bd.prior_g + p.r_off;
-        for (int i = tid; i < n; i += nt) {      // (a warp per row with lanes along the row measured slower: 0.47 vs 0.34 ms per launch, r01zh)
+        for (int i = tid; i < n; i += nt) {      // thread per row, each walking its own row (measured slower: a warp per row with lanes along the row, 0.47 vs 0.34 ms per launch, r01zh; the same loop over a transposed copy so that neighbouring threads read neighbouring words, 0.38 vs 0.35, r02n)
             double s = bd.prior_r[p.r_off + i];
             for (int k = 0; k < n; k++) s += J[i * n + k] * dx[k];
             res[i] = s;

@@ -102,13 +102,13 @@ struct BatchDev {       // passed by value to every kernel
     int rec_stride_solve;   // VREC_COMPACT if no window of the batch has ex0/ex1/td active, else VREC (marginalisation always uses VREC)
     int n_unfused;          // windows whose solver linearisation runs lin_vis + lm_reduce + asm_items (the others: lin_vis_lm + asm_pairs, WinMeta.fused)
     int n_fused_wide, n_fused_compact, n_munfused, n_mfused;      // fused solver windows by record width; marginalising windows by path
-    int nlmb_total, npitems_total, nmpitems_total;
+    int nlmb_total, npitems_total, nmpitems_total, pitems_max;
     int pout_stride;        // doubles per solver pair item in pair_out: 192 (all fused windows compact) or 640
     const int *mvis_pos;            // [nvis_total] marginalisation: window-local record slot of the factors hosted in frame 0 (-1 otherwise)
     const struct AsmItem *mpitems;  // [nmpitems_total]
     double *mpair_out;              // [nmpitems_total][640]
     const int *vis_pos;             // [nvis_total] window-local position of the factor's X record in frame-pair order, -1 for one-frame factors
-    const unsigned char *vis_dup;   // [nvis_total] 0: the factor alone observes its landmark from frame j; 1: first of two such factors (adds the next one's part); 2: second (adds nothing)
+    unsigned char *vis_dup;         // [nvis_total] 0: the factor alone observes its landmark from frame j; 1: first of two such factors (adds the next one's part); 2: second (adds nothing)
     const int *lmb_ptr;             // [nlmb_total][2] global landmark range [first, end) of each landmark block
     const int *lmb_win;             // [nlmb_total] window of the block
     double *xrec;                   // [nxrec_total][XREC]
@@ -122,8 +122,13 @@ struct BatchDev {       // passed by value to every kernel
     // states
     double *x_cur, *x_cand, *x_init, *x_before;
     // visual tables
-    const int *vis_type, *vis_lm, *vis_fi, *vis_fj, *vis_win;   // vis_lm: landmark index local to the window
-    const double *vis_obs;          // [nvis_total][12] exactly as the caller's table (no host transpose)
+    const int *vis_lm;              // landmark index local to the window
+    int *vis_type, *vis_fi, *vis_fj, *vis_win;   // written on the device by vis_expand from the wire format below
+    double *vis_obs;                // [nvis_total][12] exactly as the caller's table (rebuilt by vis_expand)
+    // wire format of the visual table (what crosses PCIe): per factor one code word (type | fi << 2 | fj << 6 | dup << 10), the observer side of the
+    // observation (pts_j, velocity_j, td_j) and an index into the table of host sides (pts_i, velocity_i, td_i), which every factor of a landmark shares
+    const int *vis_code, *vis_oi;
+    const double *obs_i, *obs_j;    // [nobs_i_total][6], [nvis_total][6]
     double *vis_rec;                // [nvis_total][VREC]
     double *vis_cost;               // [nvis_total]
     // assembly plan (static per batch): items = chunks of per-frame / per-frame-pair / common factor lists

@@ -18,6 +18,7 @@
 #include "kernels_track.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -86,6 +87,7 @@ static Profiler g_prof;
 #ifndef LIN_VIS_MINB
 #define LIN_VIS_MINB 3
 #endif
+DEF_KERNEL(vis_expand, 128)
 DEF_KERNEL(setup, 128)
 DEF_KERNEL(prior_setup, 256)
 DEF_KERNEL2(lin_vis, 128, LIN_VIS_MINB)
@@ -94,7 +96,10 @@ DEF_KERNEL2(lin_vis, 128, LIN_VIS_MINB)
 #endif
 DEF_KERNEL2(lm_reduce, 128, LM_MINB)
 DEF_KERNEL(lm_reduce_wide, 128)
-DEF_KERNEL(lin_small, 128)
+#ifndef LSM_MINB
+#define LSM_MINB 4      // 128 registers, 4 blocks / SM: the spills of the IMU evaluation (10 threads of the block) cost less than the idle SM (r02n: 0.38 -> 0.25 ms per launch)
+#endif
+DEF_KERNEL2(lin_small, 128, LSM_MINB)
 DEF_KERNEL(asm_items, 128)
 DEF_KERNEL(asm_items_split, 128)
 #ifndef SYRK_MINB
@@ -112,12 +117,18 @@ DEF_KERNEL2(lin_vis_lm, LMB_FACTORS, LVL_MINB)
 DEF_KERNEL2(lin_vis_lm_wide, LMB_FACTORS, 3)
 DEF_KERNEL(asm_pairs, 128)
 DEF_KERNEL(asm_pairs_wide, 128)
-DEF_KERNEL(pair_reduce, 256)
+#ifndef PAIR_RED_NT
+#define PAIR_RED_NT 256
+#endif
+DEF_KERNEL(pair_reduce, PAIR_RED_NT)
 DEF_KERNEL2(syrk_mma, SYRK_NT, 4)
 DEF_KERNEL(reanchor, 32)
 DEF_KERNEL2(marg_prep, 256, 2)
 DEF_KERNEL2(marg_eig, 256, 3)
-DEF_KERNEL2(marg_tri, 256, 3)
+#ifndef MARG_TRI_NT
+#define MARG_TRI_NT 128
+#endif
+DEF_KERNEL2(marg_tri, MARG_TRI_NT, 3)
 DEF_KERNEL(marg_ql, 32)
 DEF_KERNEL2(marg_apply, 128, 4)
 DEF_KERNEL(outlier, 128)
@@ -139,6 +150,7 @@ struct viwb_context {
     stream_t stream;        // the stream all work of this context is issued on (own_stream unless viwb_set_stream gave another)
     stream_t own_stream;    // created by viwb_create, destroyed by viwb_destroy; a caller's stream is never destroyed here
     long long launches;
+    long long h2d_bytes;    // bytes of window tables uploaded so far (the wire format, not the caller's tables)
     std::string err;
     bool attrs_set;
     Arena arena;
@@ -231,8 +243,12 @@ struct WinLow {
     bool regular;               // fused path possible: grouped table, <= LMB_FACTORS factors per landmark, at most two factors per (landmark, observer), consecutive
     int nlmb, npitems, nxrec;   // landmark blocks of lin_vis_lm, pair chunks of asm_pairs, records (two-frame factors; + the one-frame ones when the records are wide)
     int nmpitems, nmxrec;       // the same for the marginalisation of frame 0 (factors hosted there, wide records)
+    int nobs_i, obsi_off;       // entries of the host-side observation table (wire format): one per run of factors with an identical (pts_i, velocity_i, td_i)
 };
 static int chunk_count(int n) { return (n + ASM_CHUNK - 1) / ASM_CHUNK; }
+// columns of a visual factor's 12-double observation record (viwb.h): pts_i (0..2) pts_j (3..5) velocity_i (6,7) velocity_j (8,9) td_i (10) td_j (11)
+static bool same_host_side(const double *a, const double *b) { return memcmp(a, b, 3 * sizeof(double)) == 0 && memcmp(a + 6, b + 6, 2 * sizeof(double)) == 0 && memcmp(a + 10, b + 10, sizeof(double)) == 0; }
+static void split_obs(const double *o, double *hi, double *hj) { hi[0] = o[0]; hi[1] = o[1]; hi[2] = o[2]; hi[3] = o[6]; hi[4] = o[7]; hi[5] = o[10]; hj[0] = o[3]; hj[1] = o[4]; hj[2] = o[5]; hj[3] = o[8]; hj[4] = o[9]; hj[5] = o[11]; }
 
 static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, int &out_mode) {
     memset(&m, 0, sizeof m); memset(&lo, 0, sizeof lo);
@@ -357,6 +373,10 @@ static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, i
     }
     m.nitems = lo.nitems_s; m.nphases = lo.nph_s; m.nmitems = lo.nitems_m; m.nmphases = lo.nph_m;
     // fused-path plan (kernels_fused.cuh): sizes only; lower_fill builds the tables
+    // wire format: runs of factors sharing one host-side observation (a grouped table: one run per landmark, estimator.cpp:1595-1597 takes
+    // pts_i / velocity_i / td_i from the landmark's first observation for every factor); an ungrouped table keeps one entry per factor
+    lo.nobs_i = p.num_vis;
+    if (lo.grouped) { lo.nobs_i = 0; for (int i = 0; i < p.num_vis; i++) if (i == 0 || !same_host_side(p.vis_obs + (size_t)i * 12, p.vis_obs + (size_t)(i - 1) * 12)) lo.nobs_i++; }
     lo.regular = lo.grouped;
     lo.nxrec = 0; lo.npitems = 0; lo.nlmb = 0; lo.nmxrec = 0; lo.nmpitems = 0;
     for (int a = 0; a < NFR * NFR; a++) { lo.nxrec += pcnt[a]; lo.npitems += (pcnt[a] + PAIR_CHUNK - 1) / PAIR_CHUNK; }
@@ -391,11 +411,11 @@ static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, i
 
 // ---- phase 3: fill this window's slices of the (pinned) staging arrays; every offset is final
 struct HostArrays {
-    WinMeta *meta; PriorDev *prior; int *vis_type, *vis_lm, *vis_fi, *vis_fj, *vis_win; double *vis_obs; int *lm_win, *lm_fptr;
+    WinMeta *meta; PriorDev *prior; int *vis_code, *vis_lm, *vis_oi; double *obs_i, *obs_j; int *lm_win, *lm_fptr;
     AsmItem *items; int *asm_list; int *imu_fi, *imu_fj, *imu_win, *wheel_fi, *wheel_fj, *wheel_win, *plane_f, *plane_win;
     double *imu_data, *wheel_data, *prior_J, *prior_r, *prior_x0, *x_init; WinWork *work;
     int nitems_solve_total;
-    int *vis_pos; unsigned char *vis_dup; int *lmb_ptr, *lmb_win; AsmItem *pitems; int *mvis_pos; AsmItem *mpitems;
+    int *vis_pos; int *lmb_ptr, *lmb_win; AsmItem *pitems; int *mvis_pos; AsmItem *mpitems;
 };
 static void emit_lists(const int *type, const int *fi, const int *fj, int nvis, bool only_host0, int has_common, int w, AsmItem *items, int *list) {
     // counting sort of the (factor, role) entries into frame lists, pair lists and the common list, then chunking
@@ -435,19 +455,33 @@ static void emit_lists(const int *type, const int *fi, const int *fj, int nvis, 
 static void lower_fill(const viwb_problem &p, const double *state, int w, const WinMeta &m, const WinLow &lo, const HostArrays &h, double init_radius) {
     h.meta[w] = m;
     // visual factors grouped by landmark
-    int *vt = h.vis_type + m.vis_off, *vl = h.vis_lm + m.vis_off, *vi = h.vis_fi + m.vis_off, *vj = h.vis_fj + m.vis_off, *vw = h.vis_win + m.vis_off;
-    double *vo = h.vis_obs + (size_t)m.vis_off * 12;
+    // (the per-factor type / frames / duplicate code travel as ONE code word and are unpacked on the device: the tables below are host scratch)
+    static thread_local std::vector<int> scratch; static thread_local std::vector<unsigned char> scratch_d;
+    scratch.resize((size_t)3 * p.num_vis + 1); scratch_d.assign((size_t)p.num_vis + 1, 0);
+    int *vt = scratch.data(), *vi = vt + p.num_vis, *vj = vi + p.num_vis, *vl = h.vis_lm + m.vis_off;
+    unsigned char *vd = scratch_d.data();
+    double *oj = h.obs_j + (size_t)m.vis_off * 6, *oi = h.obs_i + (size_t)lo.obsi_off * 6;
+    int *voi = h.vis_oi + m.vis_off;
     if (lo.grouped) {
         memcpy(vt, p.vis_type, sizeof(int) * p.num_vis); memcpy(vl, p.vis_landmark, sizeof(int) * p.num_vis);
         memcpy(vi, p.vis_frame_i, sizeof(int) * p.num_vis); memcpy(vj, p.vis_frame_j, sizeof(int) * p.num_vis);
-        memcpy(vo, p.vis_obs, sizeof(double) * 12 * p.num_vis);
+        int run = -1;
+        for (int i = 0; i < p.num_vis; i++) {
+            const double *o = p.vis_obs + (size_t)i * 12;
+            double hi[6];
+            split_obs(o, hi, oj + (size_t)i * 6);
+            if (i == 0 || !same_host_side(o, o - 12)) { run++; memcpy(oi + (size_t)run * 6, hi, sizeof hi); }
+            voi[i] = lo.obsi_off + run;
+        }
     } else {
         std::vector<int> order(p.num_vis);
         for (int i = 0; i < p.num_vis; i++) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return p.vis_landmark[a] < p.vis_landmark[c]; });
-        for (int i = 0; i < p.num_vis; i++) { const int sidx = order[i]; vt[i] = p.vis_type[sidx]; vl[i] = p.vis_landmark[sidx]; vi[i] = p.vis_frame_i[sidx]; vj[i] = p.vis_frame_j[sidx]; memcpy(vo + (size_t)i * 12, p.vis_obs + (size_t)sidx * 12, 12 * sizeof(double)); }
+        for (int i = 0; i < p.num_vis; i++) {
+            const int sidx = order[i]; vt[i] = p.vis_type[sidx]; vl[i] = p.vis_landmark[sidx]; vi[i] = p.vis_frame_i[sidx]; vj[i] = p.vis_frame_j[sidx];
+            split_obs(p.vis_obs + (size_t)sidx * 12, oi + (size_t)i * 6, oj + (size_t)i * 6); voi[i] = lo.obsi_off + i;
+        }
     }
-    for (int i = 0; i < p.num_vis; i++) vw[i] = w;
     // landmark -> factor ranges (global factor indices)
     { int *fp = h.lm_fptr + m.lm_off; int run = m.vis_off, i = 0;
       for (int k = 0; k < p.num_landmarks; k++) { fp[k] = run; while (i < p.num_vis && vl[i] == k) { i++; run++; } h.lm_win[m.lm_off + k] = w; } }
@@ -478,9 +512,7 @@ static void lower_fill(const viwb_problem &p, const double *state, int w, const 
     if (m.mfused) pair_tables(true, h.mvis_pos + m.vis_off, h.mpitems + m.mpitem_off, m.mxrec_off, 1);
     if (m.fused || m.mfused) {
         // duplicate codes (two factors of one landmark observed from the same frame: left and right camera, consecutive), landmark blocks
-        unsigned char *vd = h.vis_dup + m.vis_off;
         for (int i = 0; i < p.num_vis; i++) {
-            vd[i] = 0;
             if (vt[i] == 2) continue;
             if (i > 0 && vt[i - 1] != 2 && vl[i - 1] == vl[i] && vj[i - 1] == vj[i]) { vd[i - 1] = 1; vd[i] = 2; }
         }
@@ -494,6 +526,7 @@ static void lower_fill(const viwb_problem &p, const double *state, int w, const 
             in_blk += cnt;
         }
     }
+    { int *vc = h.vis_code + m.vis_off; for (int i = 0; i < p.num_vis; i++) vc[i] = vt[i] | (vi[i] << 2) | (vj[i] << 6) | ((int)vd[i] << 10); }
     if (!m.fused)
     emit_lists(vt, vi, vj, p.num_vis, false, m.has_common, w, h.items + m.item_off, h.asm_list + m.list_off);
     if (m.margin_flag == 0 && !m.mfused) emit_lists(vt, vi, vj, p.num_vis, true, 1, w, h.items + h.nitems_solve_total + m.mitem_off, h.asm_list + m.mlist_off);
@@ -561,11 +594,13 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     }
     // ---- phase 2: offsets
     size_t nlmb = 0, npit = 0, nxr = 0, nmpit = 0, nmxr = 0;      // nxr / nmxr: record regions in DOUBLES (solver / marginalisation share one buffer)
+    size_t nobsi = 0;
     size_t nstate = 0, nvis = 0, nlm = 0, nimu = 0, nwheel = 0, nplane = 0, nlist = 0, nit_s = 0, nit_m = 0, npri = 0, npJ = 0, npr = 0;
     for (int w = 0; w < B; w++) {
         const viwb_problem &p = problems[w]; WinMeta &m = b->meta[w]; const WinLow &lo = low[w];
         m.state_off = (int)nstate; nstate += SFIX + p.num_landmarks; b->state_sizes[w] = SFIX + p.num_landmarks;
         m.vis_off = (int)nvis; nvis += p.num_vis; m.lm_off = (int)nlm; nlm += p.num_landmarks;
+        low[w].obsi_off = (int)nobsi; nobsi += lo.nobs_i;
         m.imu_off = (int)nimu; nimu += p.num_imu; m.wheel_off = (int)nwheel; nwheel += p.num_wheel; m.plane_off = (int)nplane; nplane += p.num_plane;
         m.item_off = (int)nit_s; nit_s += lo.nitems_s; m.list_off = (int)nlist; nlist += lo.nlist_s;
         m.prior_idx = lo.has_prior ? (int)npri++ : -1;
@@ -591,6 +626,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     bd.nitems_solve = (int)nit_s; bd.nitems_marg = (int)nit_m;
     bd.rec_stride_solve = VREC_COMPACT;
     bd.n_unfused = n_unfused; bd.nlmb_total = (int)nlmb; bd.npitems_total = (int)npit; bd.nmpitems_total = (int)nmpit;
+    bd.pitems_max = 1; for (int w = 0; w < B; w++) bd.pitems_max = std::max(bd.pitems_max, std::max(b->meta[w].npitems, b->meta[w].nmpitems));
     bd.n_fused_wide = n_fused_wide; bd.n_fused_compact = n_fused_compact; bd.n_mfused = n_mfused; bd.n_munfused = n_munfused;
     bd.pout_stride = n_fused_wide ? (int)XL<true>::OUT : (int)XL<false>::OUT;
     bd.marg_nmax = b->prior_nmax;
@@ -602,15 +638,16 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     std::vector<Ent> ents;
     auto IN = [&](auto **field, size_t count) { ents.push_back({(void **)field, count * sizeof(**field), true, 0}); };
     auto WK = [&](auto **field, size_t count) { ents.push_back({(void **)field, (count ? count : 1) * sizeof(**field), false, 0}); };
-    IN(&bd.meta, B); IN(&bd.prior, npri); IN(&bd.vis_type, nvis); IN(&bd.vis_lm, nvis); IN(&bd.vis_fi, nvis); IN(&bd.vis_fj, nvis); IN(&bd.vis_win, nvis);
-    IN(&bd.vis_obs, nvis * 12); IN(&bd.lm_win, nlm); IN(&bd.lm_fptr, nlm + 1); IN(&bd.items, nit_s + nit_m); IN(&bd.asm_list, nlist);
+    IN(&bd.meta, B); IN(&bd.prior, npri); IN(&bd.vis_code, nvis); IN(&bd.vis_lm, nvis); IN(&bd.vis_oi, nvis);
+    IN(&bd.obs_i, nobsi * 6); IN(&bd.obs_j, nvis * 6); IN(&bd.lm_win, nlm); IN(&bd.lm_fptr, nlm + 1); IN(&bd.items, nit_s + nit_m); IN(&bd.asm_list, nlist);
     IN(&bd.imu_fi, nimu); IN(&bd.imu_fj, nimu); IN(&bd.imu_win, nimu); IN(&bd.wheel_fi, nwheel); IN(&bd.wheel_fj, nwheel); IN(&bd.wheel_win, nwheel);
     IN(&bd.plane_f, nplane); IN(&bd.plane_win, nplane); IN(&bd.imu_data, nimu * 287); IN(&bd.wheel_data, nwheel * 78);
     IN(&bd.prior_J, npJ); IN(&bd.prior_r, npr); IN(&bd.prior_x0, npri * SFIX); IN(&bd.x_init, nstate); IN(&b->work_init_dev, B);
-    IN(&bd.vis_pos, npit ? nvis : 0); IN(&bd.vis_dup, nlmb ? nvis : 0); IN(&bd.lmb_ptr, 2 * nlmb); IN(&bd.lmb_win, nlmb); IN(&bd.pitems, npit);
+    IN(&bd.vis_pos, npit ? nvis : 0); IN(&bd.lmb_ptr, 2 * nlmb); IN(&bd.lmb_win, nlmb); IN(&bd.pitems, npit);
     IN(&bd.mvis_pos, nmpit ? nvis : 0); IN(&bd.mpitems, nmpit);
     const size_t nvec = (size_t)B * TFIX + nlm;
     WK(&bd.work, B); WK(&bd.x_cur, nstate); WK(&bd.x_cand, nstate); WK(&bd.x_before, nstate);
+    WK(&bd.vis_type, nvis); WK(&bd.vis_fi, nvis); WK(&bd.vis_fj, nvis); WK(&bd.vis_win, nvis); WK(&bd.vis_dup, nvis); WK(&bd.vis_obs, nvis * 12);
     WK(&bd.vis_rec, nvis * VREC); WK(&bd.vis_cost, nvis);
     WK(&bd.xrec, std::max(nxr, nmxr)); WK(&bd.pair_out, npit * (size_t)bd.pout_stride); WK(&bd.mpair_out, nmpit * (size_t)XL<true>::OUT); WK(&bd.pair_red, (npit || nmpit) ? (size_t)B * PAIR_RED : 0);
     WK(&bd.lm_a, nlm); WK(&bd.lm_g, nlm); WK(&bd.lm_gamma, nlm); WK(&bd.lm_scale, nlm); WK(&bd.lm_cost, nlm); WK(&bd.lm_W, nlm * VSUB); WK(&bd.lm_outlier, nlm);
@@ -640,10 +677,10 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     HostArrays h; memset(&h, 0, sizeof h);
     { size_t k = 0; char *hb = ar->host;
       auto HP = [&](auto *&dst) { dst = (typename std::remove_reference<decltype(dst)>::type)(hb + ents[k].off); k++; };
-      HP(h.meta); HP(h.prior); HP(h.vis_type); HP(h.vis_lm); HP(h.vis_fi); HP(h.vis_fj); HP(h.vis_win); HP(h.vis_obs); HP(h.lm_win); HP(h.lm_fptr); HP(h.items); HP(h.asm_list);
+      HP(h.meta); HP(h.prior); HP(h.vis_code); HP(h.vis_lm); HP(h.vis_oi); HP(h.obs_i); HP(h.obs_j); HP(h.lm_win); HP(h.lm_fptr); HP(h.items); HP(h.asm_list);
       HP(h.imu_fi); HP(h.imu_fj); HP(h.imu_win); HP(h.wheel_fi); HP(h.wheel_fj); HP(h.wheel_win); HP(h.plane_f); HP(h.plane_win); HP(h.imu_data); HP(h.wheel_data);
       HP(h.prior_J); HP(h.prior_r); HP(h.prior_x0); HP(h.x_init); HP(h.work);
-      HP(h.vis_pos); HP(h.vis_dup); HP(h.lmb_ptr); HP(h.lmb_win); HP(h.pitems); HP(h.mvis_pos); HP(h.mpitems); }
+      HP(h.vis_pos); HP(h.lmb_ptr); HP(h.lmb_win); HP(h.pitems); HP(h.mvis_pos); HP(h.mpitems); }
     h.nitems_solve_total = (int)nit_s;
     for (auto &e : ents) *e.field = ar->dev + e.off;
     if (npri) memcpy(h.prior, priors.data(), sizeof(PriorDev) * npri);
@@ -652,8 +689,10 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     parallel_for(B, [&](int w) { lower_fill(problems[w], states[w], w, b->meta[w], low[w], h, opt->initial_trust_region_radius); });
     const double t_filled = now_ms();
     { int e = dev_h2d(ar->dev, ar->host, in_bytes, ctx->stream); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, std::string("H2D: ") + dev_errstr(e)); } }
+    ctx->h2d_bytes += (long long)in_bytes;
+    if (nvis) { LAUNCH(vis_expand, bd, B, 1, NT(128), 0, 0, ctx->stream); ctx->launches++; }      // code words + split observations -> the tables the kernels read
     { int e = dev_sync(ctx->stream); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, "H2D sync"); } }     // the staging slab is reused for outputs
-    if (g_timing) fprintf(stderr, "[viwb] build B=%d: plan+slabs %.1f ms, fill %.1f ms (%.1f MB), h2d %.1f ms\n", B, t_alloc - t_start, t_filled - t_alloc, in_bytes / 1e6, now_ms() - t_filled);
+    if (g_timing) fprintf(stderr, "[viwb] build B=%d: plan+slabs %.2f ms, fill %.2f ms (%.1f MB), h2d %.2f ms\n", B, t_alloc - t_start, t_filled - t_alloc, in_bytes / 1e6, now_ms() - t_filled);
     *out = b;
     return 0;
 }
@@ -706,7 +745,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
             if (nfi <= 0) return;
             if (solve && bd.n_fused_compact > 0) { LAUNCH(asm_pairs, bd, (nfi + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st); ctx->launches++; }
             if (!solve || bd.n_fused_wide > 0) { LAUNCH(asm_pairs_wide, bd, (nfi + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st); ctx->launches++; }
-            LAUNCH(pair_reduce, bd, B, 1, NT(256), 0, mode, st); ctx->launches++;
+            LAUNCH(pair_reduce, bd, B, 1, NT(PAIR_RED_NT), (size_t)bd.pitems_max * sizeof(int), mode, st); ctx->launches++;
         };
         if (!old_path) {
             LAUNCH(lin_small, bd, B, 1, nt_small, sm_small, mode, st); ctx->launches++;
@@ -761,7 +800,7 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
         LAUNCH(marg_prep, bd, B, 1, nt_marg, sm_marg, 0, st);
         if (g_marg_one_kernel) { LAUNCH(marg_eig, bd, B, 1, nt_marg, sm_eig, 0, st); ctx->launches += 2; }
         else {
-            LAUNCH(marg_tri, bd, B, 1, nt_marg, sm_eig, 0, st);
+            LAUNCH(marg_tri, bd, B, 1, NT(MARG_TRI_NT), sm_eig, 0, st);
             LAUNCH(marg_ql, bd, B, 1, NT(32), 2 * MAXPRI * 8, 0, st);
             LAUNCH(marg_apply, bd, B, 1, NT(128), marg_apply_smem_doubles(128, bd.marg_nmax) * 8, 0, st);
             ctx->launches += 4;
@@ -796,15 +835,15 @@ static int batch_fetch(viwb_context *ctx, viwb_batch *b, double *const *states, 
         CK(dev_d2h(J, bd.marg_J, (size_t)B * nmax * nmax * 8, ctx->stream));     // window w's n x n block (row stride n) heads its nmax^2 slot
     }
     CK(dev_sync(ctx->stream));
-    int rc = 0;
-    for (int w = 0; w < B; w++) {
+    std::atomic<int> rc_a(0);
+    parallel_for(B, [&](int w) {           // ~54 KB of prior per window: the unpack into the caller's buffers runs on the host pool
         if (states && states[w]) memcpy(states[w], x + b->meta[w].state_off, sizeof(double) * b->state_sizes[w]);
         if (summaries) {
             viwb_summary &sm = summaries[w]; const WinWork &ww = work[w];
             sm.termination_type = ww.term; sm.num_iterations = ww.num_iterations; sm.num_successful_steps = ww.successful; sm.num_linear_solves = ww.num_linear;
             sm.initial_cost = ww.initial_cost; sm.final_cost = ww.x_cost; sm.final_radius = ww.radius; sm.final_mu = ww.mu;
         }
-        if (!priors_out) continue;
+        if (!priors_out) return;
         viwb_prior *out = &priors_out[w];
         const int mode = b->out_mode[w];
         if (mode == 0 && want_pr) {
@@ -817,14 +856,15 @@ static int batch_fetch(viwb_context *ctx, viwb_batch *b, double *const *states, 
                 memcpy(out->r, r + (size_t)w * MAXPRI, sizeof(double) * n);
                 memcpy(out->x0, x0 + (size_t)w * SFIX, sizeof(double) * SFIX);
             }
-            if (work[w].marg_status < 0) rc = VIWB_ERR_NUMERIC;
+            if (work[w].marg_status < 0) rc_a = VIWB_ERR_NUMERIC;
         } else if (mode == 1) {
             const HostPrior &hp = b->in_prior[w];
             out->valid = 1; out->n = hp.n; out->num_blocks = hp.nb;
             memcpy(out->block_id, hp.block_id, sizeof hp.block_id); memcpy(out->block_idx, hp.block_idx, sizeof hp.block_idx);
             memcpy(out->x0, hp.x0.data(), sizeof(double) * SFIX); memcpy(out->J, hp.J.data(), sizeof(double) * hp.n * hp.n); memcpy(out->r, hp.r.data(), sizeof(double) * hp.n);
         } else { out->valid = 0; out->n = 0; out->num_blocks = 0; }
-    }
+    });
+    const int rc = rc_a;
     if (rc) return fail(ctx, rc, "marginalisation: kept dimension exceeds the shared-memory eigen solver");
     return 0;
 }
@@ -840,7 +880,7 @@ static void batch_free(viwb_context *ctx, viwb_batch *b) {
 extern "C" int viwb_create(int device, viwb_context **out) {
     if (!out) return VIWB_ERR_INVALID;
     viwb_context *ctx = new viwb_context();
-    ctx->device = device; ctx->launches = 0; ctx->attrs_set = false; ctx->stream = 0; ctx->own_stream = 0; ctx->lk1 = nullptr; ctx->det1 = nullptr;
+    ctx->device = device; ctx->launches = 0; ctx->h2d_bytes = 0; ctx->attrs_set = false; ctx->stream = 0; ctx->own_stream = 0; ctx->lk1 = nullptr; ctx->det1 = nullptr;
 #ifndef VIWB_HOST_EMU
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -873,6 +913,7 @@ extern "C" int viwb_set_stream(viwb_context *ctx, void *s) {
     return VIWB_OK;
 }
 extern "C" long long viwb_launch_count(const viwb_context *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" long long viwb_h2d_bytes(const viwb_context *ctx) { return ctx ? ctx->h2d_bytes : 0; }
 
 extern "C" int viwb_set_profiling(viwb_context *ctx, int enable) {
     if (!ctx) return VIWB_ERR_INVALID;
@@ -962,10 +1003,10 @@ static int run_once(viwb_context *ctx, int B, const viwb_problem *problems, doub
     }
     const double t0 = now_ms();
     rc = batch_execute(ctx, b, what);
-    if (g_timing) { dev_sync(ctx->stream); fprintf(stderr, "[viwb] execute %.1f ms\n", now_ms() - t0); }
+    if (g_timing) { dev_sync(ctx->stream); fprintf(stderr, "[viwb] execute %.2f ms\n", now_ms() - t0); }
     const double t1 = now_ms();
     if (!rc) rc = batch_fetch(ctx, b, states, summaries, priors);
-    if (g_timing) fprintf(stderr, "[viwb] fetch %.1f ms\n", now_ms() - t1);
+    if (g_timing) fprintf(stderr, "[viwb] fetch %.2f ms\n", now_ms() - t1);
     batch_free(ctx, b);
     return rc;
 }

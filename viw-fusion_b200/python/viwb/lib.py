@@ -14,7 +14,7 @@ from . import abi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.normpath(os.path.join(_HERE, "..", "..", "csrc", "libviwb.so"))
 
-EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", "viwb_launch_count", "viwb_set_profiling", "viwb_profile_count", "viwb_profile_get", "viwb_default_options",
+EXPORTS = ["viwb_create", "viwb_destroy", "viwb_last_error", "viwb_set_stream", "viwb_launch_count", "viwb_h2d_bytes", "viwb_set_profiling", "viwb_profile_count", "viwb_profile_get", "viwb_default_options",
            "viwb_default_globals", "viwb_factor_evaluate", "viwb_prior_evaluate", "viwb_window_solve", "viwb_gauge_reanchor",
            "viwb_marginalize", "viwb_optimization", "viwb_optimization_batch", "viwb_batch_create", "viwb_batch_reset_states",
            "viwb_batch_run", "viwb_batch_download", "viwb_batch_algorithmic_bytes", "viwb_batch_destroy",
@@ -37,6 +37,7 @@ def load(libpath=None):
     lib = C.CDLL(path)
     lib.viwb_last_error.restype = C.c_char_p
     lib.viwb_launch_count.restype = C.c_longlong
+    lib.viwb_h2d_bytes.restype = C.c_longlong
     lib.viwb_batch_algorithmic_bytes.restype = C.c_double
     lib.viwb_lk_batch_algorithmic_bytes.restype = C.c_double
     lib.viwb_lk_batch_algorithmic_bytes.argtypes = [C.c_void_p]
@@ -78,6 +79,9 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.viwb_launch_count(self.h))
+
+    def h2d_bytes(self):
+        return int(self.lib.viwb_h2d_bytes(self.h))
 
     def set_profiling(self, on):
         self._ck(self.lib.viwb_set_profiling(self.h, C.c_int(1 if on else 0)), "viwb_set_profiling")
