@@ -336,6 +336,24 @@ def check_unsorted_table_and_threads(ctx, oracle):
     b, sb, qb = ctx.optimization(shuf, st, abi.MARGIN_OLD)
     ep, er = synth.pose_errors(a, b)
     assert ep < 1e-9 and er < 1e-9
+    # The packed upload shares one host-side observation (pts_i, velocity_i, td_i) per landmark, as estimator.cpp:1595-1597 produces them; a table whose
+    # factors of one landmark carry DIFFERENT host sides is legal input and must still be solved from its own numbers (the library rebuilds with one entry
+    # per factor): against the oracle, which reads every factor's own 12 doubles, alone and inside a batch of ordinary windows
+    odd_obs = prob.vis_obs.copy()
+    lm0 = int(prob.vis_landmark[0])
+    rows = np.flatnonzero(prob.vis_landmark == lm0)
+    assert len(rows) >= 2
+    odd_obs[rows[1], 0] += 1e-3            # pts_i.x of the landmark's second factor only
+    odd_obs[rows[-1], 10] += 2e-3          # td_i of its last factor only
+    odd = abi.WindowProblem(prob.frame_count, prob.num_landmarks, prob.block_flags, prob.subset_mask, prob.vis_type, prob.vis_landmark, prob.vis_frame_i, prob.vis_frame_j,
+                            odd_obs, prob.imu_frame_i, prob.imu_frame_j, prob.imu_data, globals_=prob.globals)
+    c, sc, qc = ctx.optimization(odd, st, abi.MARGIN_OLD)
+    c0, sc0, qc0 = oracle.optimization(odd, st, abi.MARGIN_OLD)
+    ep, er = synth.pose_errors(c0, c)
+    assert ep < 1e-6 and er < 1e-6 and sc.num_iterations == sc0.num_iterations and qc.n == qc0.n
+    assert np.abs(c - a).max() > 1e-9        # (the perturbation is visible in the solution: the test would notice a library that ignored it)
+    mix_s, _, mix_q = ctx.optimization_batch([prob, odd, prob], [st, st, st], [abi.MARGIN_OLD] * 3)
+    assert np.array_equal(mix_s[1], c) and np.array_equal(mix_s[0], a) and np.array_equal(mix_s[2], a) and np.array_equal(mix_q[1].Jmat(), qc.Jmat())
     probs, sts = [], []
     for i in range(20):
         p, s, _ = synth.make_window(1 + (i % 4), i % 3)

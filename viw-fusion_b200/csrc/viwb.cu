@@ -243,11 +243,14 @@ struct WinLow {
     bool regular;               // fused path possible: grouped table, <= LMB_FACTORS factors per landmark, at most two factors per (landmark, observer), consecutive
     int nlmb, npitems, nxrec;   // landmark blocks of lin_vis_lm, pair chunks of asm_pairs, records (two-frame factors; + the one-frame ones when the records are wide)
     int nmpitems, nmxrec;       // the same for the marginalisation of frame 0 (factors hosted there, wide records)
-    int nobs_i, obsi_off;       // entries of the host-side observation table (wire format): one per run of factors with an identical (pts_i, velocity_i, td_i)
+    bool obs_per_factor; int nobs_i, obsi_off;       // entries of the host-side observation table (wire format): one per run of factors with an identical (pts_i, velocity_i, td_i)
 };
 static int chunk_count(int n) { return (n + ASM_CHUNK - 1) / ASM_CHUNK; }
 // columns of a visual factor's 12-double observation record (viwb.h): pts_i (0..2) pts_j (3..5) velocity_i (6,7) velocity_j (8,9) td_i (10) td_j (11)
-static bool same_host_side(const double *a, const double *b) { return memcmp(a, b, 3 * sizeof(double)) == 0 && memcmp(a + 6, b + 6, 2 * sizeof(double)) == 0 && memcmp(a + 10, b + 10, sizeof(double)) == 0; }
+static inline bool same_host_side(const double *a, const double *b) {      // bitwise (the wire format must reproduce the caller's table exactly)
+    auto bits = [](const double *p) { unsigned long long v; memcpy(&v, p, sizeof v); return v; };
+    return ((bits(a) ^ bits(b)) | (bits(a + 1) ^ bits(b + 1)) | (bits(a + 2) ^ bits(b + 2)) | (bits(a + 6) ^ bits(b + 6)) | (bits(a + 7) ^ bits(b + 7)) | (bits(a + 10) ^ bits(b + 10))) == 0;
+}
 static void split_obs(const double *o, double *hi, double *hj) { hi[0] = o[0]; hi[1] = o[1]; hi[2] = o[2]; hi[3] = o[6]; hi[4] = o[7]; hi[5] = o[10]; hj[0] = o[3]; hj[1] = o[4]; hj[2] = o[5]; hj[3] = o[8]; hj[4] = o[9]; hj[5] = o[11]; }
 
 static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, int &out_mode) {
@@ -375,8 +378,8 @@ static void lower_count(const viwb_problem &p, int mf, WinMeta &m, WinLow &lo, i
     // fused-path plan (kernels_fused.cuh): sizes only; lower_fill builds the tables
     // wire format: runs of factors sharing one host-side observation (a grouped table: one run per landmark, estimator.cpp:1595-1597 takes
     // pts_i / velocity_i / td_i from the landmark's first observation for every factor); an ungrouped table keeps one entry per factor
-    lo.nobs_i = p.num_vis;
-    if (lo.grouped) { lo.nobs_i = 0; for (int i = 0; i < p.num_vis; i++) if (i == 0 || !same_host_side(p.vis_obs + (size_t)i * 12, p.vis_obs + (size_t)(i - 1) * 12)) lo.nobs_i++; }
+    // (assumed here -- the plan never reads the observations --, verified when lower_fill copies them; a table that breaks it is rebuilt with one entry per factor)
+    lo.obs_per_factor = !lo.grouped; lo.nobs_i = lo.grouped ? p.num_landmarks : p.num_vis;
     lo.regular = lo.grouped;
     lo.nxrec = 0; lo.npitems = 0; lo.nlmb = 0; lo.nmxrec = 0; lo.nmpitems = 0;
     for (int a = 0; a < NFR * NFR; a++) { lo.nxrec += pcnt[a]; lo.npitems += (pcnt[a] + PAIR_CHUNK - 1) / PAIR_CHUNK; }
@@ -416,6 +419,7 @@ struct HostArrays {
     double *imu_data, *wheel_data, *prior_J, *prior_r, *prior_x0, *x_init; WinWork *work;
     int nitems_solve_total;
     int *vis_pos; int *lmb_ptr, *lmb_win; AsmItem *pitems; int *mvis_pos; AsmItem *mpitems;
+    unsigned char *obs_viol;        // [B] host only: set by lower_fill when a grouped table does not share one host-side observation per landmark
 };
 static void emit_lists(const int *type, const int *fi, const int *fj, int nvis, bool only_host0, int has_common, int w, AsmItem *items, int *list) {
     // counting sort of the (factor, role) entries into frame lists, pair lists and the common list, then chunking
@@ -470,7 +474,9 @@ static void lower_fill(const viwb_problem &p, const double *state, int w, const 
             const double *o = p.vis_obs + (size_t)i * 12;
             double hi[6];
             split_obs(o, hi, oj + (size_t)i * 6);
-            if (i == 0 || !same_host_side(o, o - 12)) { run++; memcpy(oi + (size_t)run * 6, hi, sizeof hi); }
+            if (lo.obs_per_factor) { memcpy(oi + (size_t)i * 6, hi, sizeof hi); voi[i] = lo.obsi_off + i; continue; }
+            if (i == 0 || vl[i] != vl[i - 1]) { run++; memcpy(oi + (size_t)run * 6, hi, sizeof hi); }
+            else if (!same_host_side(o, o - 12)) h.obs_viol[w] = 1;          // two factors of one landmark with different host-side observations: the caller of lower_fill rebuilds
             voi[i] = lo.obsi_off + run;
         }
     } else {
@@ -561,7 +567,7 @@ template <typename F> static void parallel_for(int n, F f) {
 }
 
 static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, const double *const *states,
-                       const viwb_options *options, const int32_t *margin_flags, viwb_batch **out, bool use_cached = false) {
+                       const viwb_options *options, const int32_t *margin_flags, viwb_batch **out, bool use_cached = false, bool obs_per_factor = false) {
     bind_device(ctx);
     if (B <= 0 || !problems || !states) return fail(ctx, VIWB_ERR_INVALID, "empty batch");
     const double t_start = now_ms();
@@ -577,6 +583,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     std::vector<WinLow> low(B);
     // ---- phase 1 (parallel): sizes and plans
     parallel_for(B, [&](int w) { lower_count(problems[w], margin_flags ? margin_flags[w] : -1, b->meta[w], low[w], b->out_mode[w]); });
+    if (obs_per_factor) for (int w = 0; w < B; w++) { low[w].obs_per_factor = true; low[w].nobs_i = problems[w].num_vis < 0 ? 0 : problems[w].num_vis; }
     for (int w = 0; w < B; w++) if (low[w].err) { const int e = low[w].err; batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, e == 1 ? "bad frame_count / num_landmarks" : e == 2 ? "bad prior" : e == 3 ? "bad visual factor table" : e == 5 ? "negative factor count or missing table" : "bad factor frame index"); }
     // fused solver linearisation (kernels_fused.cuh) when every window qualifies; then the solver's gather lists are not built at all
     // (decided per window, so that a window takes the same path -- and gives the same bits -- whatever else the batch holds)
@@ -686,7 +693,12 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     if (npri) memcpy(h.prior, priors.data(), sizeof(PriorDev) * npri);
     h.lm_fptr[nlm] = (int)nvis;
     // ---- phase 3 (parallel): fill
+    std::vector<unsigned char> obs_viol(B, 0); h.obs_viol = obs_viol.data();
     parallel_for(B, [&](int w) { lower_fill(problems[w], states[w], w, b->meta[w], low[w], h, opt->initial_trust_region_radius); });
+    if (!obs_per_factor && std::find(obs_viol.begin(), obs_viol.end(), 1) != obs_viol.end()) {      // rare: rebuild with one host-side entry per factor
+        batch_free(ctx, b);
+        return batch_build(ctx, B, problems, states, options, margin_flags, out, use_cached, true);
+    }
     const double t_filled = now_ms();
     { int e = dev_h2d(ar->dev, ar->host, in_bytes, ctx->stream); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, std::string("H2D: ") + dev_errstr(e)); } }
     ctx->h2d_bytes += (long long)in_bytes;
