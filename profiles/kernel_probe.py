@@ -26,7 +26,7 @@ for path in sys.argv[1:]:
     prof = ctx.profile()
     ctx.set_profiling(False)
     tot = sum(v[0] for v in prof.values()) / 3
-    print(os.path.basename(path), "B=%d step %.2f ms" % (len(probs), tot), {k: round(v[0] / max(1, v[1]), 3) for k, v in prof.items() if not k.endswith("_marg")},
+    print(os.path.basename(path), "B=%d step %.2f ms" % (len(probs), tot), {k: round(v[0] / max(1, v[1]), 3) for k, v in prof.items()},
           "iters", sums[0].num_iterations)
     batch.destroy()
     ctx.close()

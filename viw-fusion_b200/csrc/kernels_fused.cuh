@@ -49,8 +49,10 @@ VIWB_HD size_t lin_vis_lm_smem_doubles(bool wide) { return (size_t)LMB_FACTORS *
 // MARG = false: solver linearisation at x_cand of the fused windows whose record width matches WIDE.
 // MARG = true (WIDE): marginalisation linearisation at x_cur of the windows that drop frame 0: only the factors hosted there take part; every other
 //                     landmark of the window gets gamma = 0 and a zero row of W (syrk multiplies its row by that weight).
+// cost_only (solver, the round after the last allowed iteration): only the landmark costs are read afterwards (the decision on the pending candidate),
+// so the residuals are evaluated without Jacobians and nothing else is written
 template <bool WIDE, bool MARG>
-VIWB_D void lin_vis_lm_body(const BatchDev &bd, int bx, int tid, int nt, double *smem) {
+VIWB_D void lin_vis_lm_body(const BatchDev &bd, int bx, int tid, int nt, double *smem, bool cost_only = false) {
     typedef XL<WIDE> L;
     const int w = bd.lmb_win[bx];
     const WinWork &ww = bd.work[w];
@@ -64,9 +66,40 @@ VIWB_D void lin_vis_lm_body(const BatchDev &bd, int bx, int tid, int nt, double 
     const double *x = (MARG ? bd.x_cur : bd.x_cand) + m.state_off;
     const int *vpos = MARG ? bd.mvis_pos : bd.vis_pos;
     double *xbase = bd.xrec + (size_t)(MARG ? m.mxrec_off : m.xrec_off);
+    if (MARG) {      // a block without a landmark hosted in frame 0 takes no part: its landmarks get weight 0 and nothing is evaluated
+        if (tid == 0) meta[LMB_FACTORS] = 0;
+        VIWB_SYNC();
+        bool mine = false;
+        for (int t = tid; t < nf; t += nt) if (bd.vis_fi[f0 + t] == 0) mine = true;
+        if (mine) meta[LMB_FACTORS] = 1;
+        VIWB_SYNC();
+        if (!meta[LMB_FACTORS]) {
+            for (int k = k0 + tid; k < k1; k += nt) { bd.lm_a[k] = 0.0; bd.lm_g[k] = 0.0; bd.lm_cost[k] = 0.0; bd.lm_gamma[k] = 0.0; }
+            return;
+        }
+    }
     // ---- 0: the W rows of these landmarks start from zero (frames that do not observe a landmark keep zero blocks).  Marginalisation: only the
     //         rows of the landmarks hosted in frame 0 (below, once the hosts are known); the other rows keep their finite solver values and are
     //         multiplied by the weight gamma = 0
+    if (!MARG && cost_only) {
+        for (int t = tid; t < nf; t += nt) {
+            const int f = f0 + t;
+            double obs[12];
+            for (int k = 0; k < 12; k++) obs[k] = bd.vis_obs[(size_t)f * 12 + k];
+            VisOut o;
+            vis_eval_t<WIDE>(bd.vis_type[f], obs, x + 7 * bd.vis_fi[f], x + 7 * bd.vis_fj[f], x + blk_off(BLK_EX0), x + blk_off(BLK_EX1), x[SFIX + bd.vis_lm[f]], x[blk_off(BLK_TD)], m.S_vis, false, o);
+            double half_rho;
+            huber_scale(o.r[0] * o.r[0] + o.r[1] * o.r[1], m.huber, half_rho);
+            tile[t] = half_rho;
+        }
+        VIWB_SYNC();
+        for (int k = k0 + tid; k < k1; k += nt) {
+            double s = 0.0;
+            for (int t = bd.lm_fptr[k] - f0; t < bd.lm_fptr[k + 1] - f0; t++) s += tile[t];
+            bd.lm_cost[k] = s;
+        }
+        return;
+    }
     if (!MARG) { double *Wb = bd.lm_W + (size_t)k0 * VSUB; for (int e = tid; e < (k1 - k0) * VSUB; e += nt) Wb[e] = 0.0; }
     // ---- 1: one thread per factor
     for (int t = tid; t < nf; t += nt) {
@@ -183,10 +216,10 @@ VIWB_D void lin_vis_lm_body(const BatchDev &bd, int bx, int tid, int nt, double 
         }
     }
 }
-VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; (void)mode; lin_vis_lm_body<false, false>(bd, bx, tid, nt, smem); }
+VIWB_D void lin_vis_lm_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; lin_vis_lm_body<false, false>(bd, bx, tid, nt, smem, mode == MODE_COST); }
 VIWB_D void lin_vis_lm_wide_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by;
-    if (mode == MODE_MARG) lin_vis_lm_body<true, true>(bd, bx, tid, nt, smem); else lin_vis_lm_body<true, false>(bd, bx, tid, nt, smem);
+    if (mode == MODE_MARG) lin_vis_lm_body<true, true>(bd, bx, tid, nt, smem); else lin_vis_lm_body<true, false>(bd, bx, tid, nt, smem, mode == MODE_COST);
 }
 
 // ------------------------------------------------------------------------------------------------ asm_pairs

@@ -15,7 +15,7 @@
 
 namespace viwb {
 
-enum { MODE_SOLVE = 0, MODE_MARG = 1 };
+enum { MODE_SOLVE = 0, MODE_MARG = 1, MODE_COST = 2 };      // MODE_COST: lin_vis_lm only -- the solver's decision-only round (costs at x_cand, no Jacobians)
 enum { MLAY = 193 };   // marginalisation layout dimension over the fixed blocks
 VIWB_HD int blk_moff(int b) { int t = blk_toff(b); return b > BLK_PR ? t + 1 : t; }
 

@@ -750,8 +750,9 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
         const int wpb2 = NT(128) / (NT(128) < 32 ? NT(128) : 32);
         const int nfi = solve ? bd.npitems_total : bd.nmpitems_total;               // fused pair items of this mode
         if (solve) {
-            if (bd.n_fused_compact > 0) { LAUNCH(lin_vis_lm, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles(false) * 8, mode, st); ctx->launches++; }
-            if (bd.n_fused_wide > 0) { LAUNCH(lin_vis_lm_wide, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles(true) * 8, mode, st); ctx->launches++; }
+            const int vmode = cost_only ? (int)MODE_COST : mode;
+            if (bd.n_fused_compact > 0) { LAUNCH(lin_vis_lm, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles(false) * 8, vmode, st); ctx->launches++; }
+            if (bd.n_fused_wide > 0) { LAUNCH(lin_vis_lm_wide, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles(true) * 8, vmode, st); ctx->launches++; }
         } else if (bd.n_mfused > 0) { LAUNCH(lin_vis_lm_wide, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles(true) * 8, mode, st); ctx->launches++; }
         auto fused_asm = [&]() {
             if (nfi <= 0) return;
