@@ -63,9 +63,11 @@ VIWB_D void prior_setup_block(const BatchDev &bd, int bx, int by, int tid, int n
     double *A = bd.prior_A + p.J_off;
     for (int e = tid; e < n * n; e += nt) {
         const int i = e / n, j = e % n;
-        double s = 0.0;
-        for (int k = 0; k < n; k++) s += J[k * n + i] * J[k * n + j];
-        A[e] = s;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four partial sums (one dependent chain of n otherwise)
+        int k = 0;
+        for (; k + 3 < n; k += 4) { s0 += J[k * n + i] * J[k * n + j]; s1 += J[(k + 1) * n + i] * J[(k + 1) * n + j]; s2 += J[(k + 2) * n + i] * J[(k + 2) * n + j]; s3 += J[(k + 3) * n + i] * J[(k + 3) * n + j]; }
+        for (; k < n; k++) s0 += J[k * n + i] * J[k * n + j];
+        A[e] = (s0 + s1) + (s2 + s3);
     }
 }
 
@@ -312,16 +314,22 @@ VIWB_D void lin_small_block(const BatchDev &bd, int bx, int by, int tid, int nt,
         const double *J = bd.prior_J + p.J_off;
         double *res = bd.prior_res + p.r_off, *g = bd.prior_g + p.r_off;
         for (int i = tid; i < n; i += nt) {      // thread per row, each walking its own row (measured slower: a warp per row with lanes along the row, 0.47 vs 0.34 ms per launch, r01zh; the same loop over a transposed copy so that neighbouring threads read neighbouring words, 0.38 vs 0.35, r02n)
-            double s = bd.prior_r[p.r_off + i];
-            for (int k = 0; k < n; k++) s += J[i * n + k] * dx[k];
+            const double *Ji = J + (size_t)i * n;
+            double s0 = bd.prior_r[p.r_off + i], s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four partial sums: one dependent FMA chain of n otherwise
+            int k = 0;
+            for (; k + 3 < n; k += 4) { s0 += Ji[k] * dx[k]; s1 += Ji[k + 1] * dx[k + 1]; s2 += Ji[k + 2] * dx[k + 2]; s3 += Ji[k + 3] * dx[k + 3]; }
+            for (; k < n; k++) s0 += Ji[k] * dx[k];
+            const double s = (s0 + s1) + (s2 + s3);
             res[i] = s;
             c += 0.5 * s * s;
         }
         VIWB_SYNC();
         for (int i = tid; i < n; i += nt) {
-            double s = 0.0;
-            for (int k = 0; k < n; k++) s += J[k * n + i] * res[k];
-            g[i] = s;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int k = 0;
+            for (; k + 3 < n; k += 4) { s0 += J[k * n + i] * res[k]; s1 += J[(k + 1) * n + i] * res[k + 1]; s2 += J[(k + 2) * n + i] * res[k + 2]; s3 += J[(k + 3) * n + i] * res[k + 3]; }
+            for (; k < n; k++) s0 += J[k * n + i] * res[k];
+            g[i] = (s0 + s1) + (s2 + s3);
         }
     }
     cost_part[tid] = c;

@@ -85,9 +85,14 @@ VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *s
         h = sc[0];
         // e[j] = (A d)[j] over the leading i x i block (lower triangle storage); column i keeps the Householder vector
         for (int j = tid; j < i; j += nt) {
-            double g = 0.0;
-            for (int k = 0; k <= j; k++) g += VV(j, k) * d[k];
-            for (int k = j + 1; k < i; k++) g += VV(k, j) * d[k];
+            // four partial sums: the loop is a dependent FMA chain per thread otherwise (the kernel is bound by exactly that latency)
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+            int k = 0;
+            for (; k + 3 <= j; k += 4) { g0 += VV(j, k) * d[k]; g1 += VV(j, k + 1) * d[k + 1]; g2 += VV(j, k + 2) * d[k + 2]; g3 += VV(j, k + 3) * d[k + 3]; }
+            for (; k <= j; k++) g0 += VV(j, k) * d[k];
+            for (; k + 3 < i; k += 4) { g0 += VV(k, j) * d[k]; g1 += VV(k + 1, j) * d[k + 1]; g2 += VV(k + 2, j) * d[k + 2]; g3 += VV(k + 3, j) * d[k + 3]; }
+            for (; k < i; k++) g1 += VV(k, j) * d[k];
+            const double g = (g0 + g1) + (g2 + g3);
             cs[j] = g / h;            // e[j] / h, kept in cs until the reduction below is done
             VV(j, i) = d[j];
         }
@@ -116,9 +121,12 @@ VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *s
             for (int k = tid; k <= i; k += nt) d[k] = VV(k, i + 1) / h;
             VIWB_SYNC();
             for (int j = tid; j <= i; j += nt) {
-                double g = 0.0;
-                for (int k = 0; k <= i; k++) g += VV(k, i + 1) * VV(k, j);
-                for (int k = 0; k <= i; k++) VV(k, j) -= g * d[k];
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+                int k = 0;
+                for (; k + 3 <= i; k += 4) { g0 += VV(k, i + 1) * VV(k, j); g1 += VV(k + 1, i + 1) * VV(k + 1, j); g2 += VV(k + 2, i + 1) * VV(k + 2, j); g3 += VV(k + 3, i + 1) * VV(k + 3, j); }
+                for (; k <= i; k++) g0 += VV(k, i + 1) * VV(k, j);
+                const double g = (g0 + g1) + (g2 + g3);
+                for (k = 0; k <= i; k++) VV(k, j) -= g * d[k];
             }
             VIWB_SYNC();
         }

@@ -105,11 +105,18 @@ VIWB_D void load_H(const double *Hpk, const SolveSmem &s, int nf, int tid, int n
 // Hu = H u over the skyline (u, Hu of length nf): the stored part of row i, then column i of the rows below that reach it
 VIWB_D void symv(const SolveSmem &s, int nf, const double *u, double *Hu, int tid, int nt) {
     for (int i = tid; i < nf; i += nt) {
-        double a = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;            // four partial sums (a dependent FMA chain of up to nf otherwise)
         const double *ri = s.L + s.rp[i] - s.fst[i];
-        for (int j = s.fst[i]; j <= i; j++) a += ri[j] * u[j];
-        for (int k = i + 1; k < nf; k++) if (s.fst[k] <= i) a += s.L[s.rp[k] - s.fst[k] + i] * u[k];
-        Hu[i] = a;
+        int j = s.fst[i];
+        for (; j + 3 <= i; j += 4) { a0 += ri[j] * u[j]; a1 += ri[j + 1] * u[j + 1]; a2 += ri[j + 2] * u[j + 2]; a3 += ri[j + 3] * u[j + 3]; }
+        for (; j <= i; j++) a0 += ri[j] * u[j];
+        int k = i + 1;
+        for (; k + 1 < nf; k += 2) {
+            if (s.fst[k] <= i) a1 += s.L[s.rp[k] - s.fst[k] + i] * u[k];
+            if (s.fst[k + 1] <= i) a2 += s.L[s.rp[k + 1] - s.fst[k + 1] + i] * u[k + 1];
+        }
+        for (; k < nf; k++) if (s.fst[k] <= i) a3 += s.L[s.rp[k] - s.fst[k] + i] * u[k];
+        Hu[i] = (a0 + a1) + (a2 + a3);
     }
     VIWB_SYNC();
 }

@@ -180,7 +180,7 @@ struct viwb_batch {
     int B;
     BatchDev bd;
     Arena arena; bool arena_cached;      // cached: borrowed from the context (host-buffer calls), else owned
-    size_t out_bytes;
+    size_t out_bytes, out_off;           // staging of the results inside the pinned slab: after the inputs (the upload is not waited for, so the regions must not overlap)
     std::vector<int> prior_n;            // n of the prior each window will produce (known from the plan)
     int prior_nmax;
     WinWork *work_init_dev;              // pristine solver states, copied to bd.work at the start of every run
@@ -673,7 +673,8 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     for (auto &e : ents) if (!e.input) { e.off = tot; tot += align_up(e.bytes); }
     b->out_bytes = align_up(nstate * 8) + align_up(sizeof(WinWork) * B) + align_up((size_t)B * (3 + 2 * NB) * 4) + align_up((size_t)B * MAXPRI * 8) +
                    align_up((size_t)B * SFIX * 8) + align_up((size_t)B * b->prior_nmax * b->prior_nmax * 8);
-    const size_t host_need = std::max(in_bytes, b->out_bytes);
+    b->out_off = align_up(in_bytes);
+    const size_t host_need = b->out_off + b->out_bytes;
     Arena *ar;
     if (use_cached && !ctx->arena.busy) { ar = &ctx->arena; b->arena_cached = true; ctx->arena.busy = true; } else { ar = &b->arena; b->arena_cached = false; }
     if (ar->dev_cap < tot) { if (ar->dev) dev_free(ar->dev); ar->dev = nullptr; ar->dev_cap = 0; void *d = nullptr; int e = dev_malloc(&d, tot + tot / 8); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, std::string("device slab: ") + dev_errstr(e)); } ar->dev = (char *)d; ar->dev_cap = tot + tot / 8; }
@@ -703,7 +704,8 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     { int e = dev_h2d(ar->dev, ar->host, in_bytes, ctx->stream); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, std::string("H2D: ") + dev_errstr(e)); } }
     ctx->h2d_bytes += (long long)in_bytes;
     if (nvis) { LAUNCH(vis_expand, bd, B, 1, NT(128), 0, 0, ctx->stream); ctx->launches++; }      // code words + split observations -> the tables the kernels read
-    { int e = dev_sync(ctx->stream); if (e) { batch_free(ctx, b); return fail(ctx, VIWB_ERR_CUDA, "H2D sync"); } }     // the staging slab is reused for outputs
+    // (no wait here: the kernels of the run are queued behind the upload on the same stream, the results are staged in their own region of the slab, and the
+    //  slab is next written by the host only after a fetch has synchronised)
     if (g_timing) fprintf(stderr, "[viwb] build B=%d: plan+slabs %.2f ms, fill %.2f ms (%.1f MB), h2d %.2f ms\n", B, t_alloc - t_start, t_filled - t_alloc, in_bytes / 1e6, now_ms() - t_filled);
     *out = b;
     return 0;
@@ -830,7 +832,7 @@ static int batch_fetch(viwb_context *ctx, viwb_batch *b, double *const *states, 
     BatchDev &bd = b->bd;
     const int B = b->B, nmax = b->prior_nmax;
     // staging layout inside the pinned slab
-    char *hs = b->arena.host;
+    char *hs = b->arena.host + b->out_off;
     size_t o = 0;
     double *x = (double *)(hs + o); o += align_up(b->total_state * 8);
     WinWork *work = (WinWork *)(hs + o); o += align_up(sizeof(WinWork) * B);
@@ -884,6 +886,7 @@ static int batch_fetch(viwb_context *ctx, viwb_batch *b, double *const *states, 
 
 static void batch_free(viwb_context *ctx, viwb_batch *b) {
     if (!b) return;
+    if (ctx) dev_sync(ctx->stream);            // the upload of batch_build is not waited for there: nothing may still read the staging slab when it is released or reused
     if (b->arena_cached) { if (ctx) ctx->arena.busy = false; }
     else arena_release(b->arena);
     delete b;
