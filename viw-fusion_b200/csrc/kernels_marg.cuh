@@ -85,14 +85,9 @@ VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *s
         h = sc[0];
         // e[j] = (A d)[j] over the leading i x i block (lower triangle storage); column i keeps the Householder vector
         for (int j = tid; j < i; j += nt) {
-            // four partial sums: the loop is a dependent FMA chain per thread otherwise (the kernel is bound by exactly that latency)
-            double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
-            int k = 0;
-            for (; k + 3 <= j; k += 4) { g0 += VV(j, k) * d[k]; g1 += VV(j, k + 1) * d[k + 1]; g2 += VV(j, k + 2) * d[k + 2]; g3 += VV(j, k + 3) * d[k + 3]; }
-            for (; k <= j; k++) g0 += VV(j, k) * d[k];
-            for (; k + 3 < i; k += 4) { g0 += VV(k, j) * d[k]; g1 += VV(k + 1, j) * d[k + 1]; g2 += VV(k + 2, j) * d[k + 2]; g3 += VV(k + 3, j) * d[k + 3]; }
-            for (; k < i; k++) g1 += VV(k, j) * d[k];
-            const double g = (g0 + g1) + (g2 + g3);
+            double g = 0.0;
+            for (int k = 0; k <= j; k++) g += VV(j, k) * d[k];
+            for (int k = j + 1; k < i; k++) g += VV(k, j) * d[k];
             cs[j] = g / h;            // e[j] / h, kept in cs until the reduction below is done
             VV(j, i) = d[j];
         }
@@ -121,12 +116,9 @@ VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *s
             for (int k = tid; k <= i; k += nt) d[k] = VV(k, i + 1) / h;
             VIWB_SYNC();
             for (int j = tid; j <= i; j += nt) {
-                double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
-                int k = 0;
-                for (; k + 3 <= i; k += 4) { g0 += VV(k, i + 1) * VV(k, j); g1 += VV(k + 1, i + 1) * VV(k + 1, j); g2 += VV(k + 2, i + 1) * VV(k + 2, j); g3 += VV(k + 3, i + 1) * VV(k + 3, j); }
-                for (; k <= i; k++) g0 += VV(k, i + 1) * VV(k, j);
-                const double g = (g0 + g1) + (g2 + g3);
-                for (k = 0; k <= i; k++) VV(k, j) -= g * d[k];
+                double g = 0.0;
+                for (int k = 0; k <= i; k++) g += VV(k, i + 1) * VV(k, j);
+                for (int k = 0; k <= i; k++) VV(k, j) -= g * d[k];
             }
             VIWB_SYNC();
         }
@@ -196,6 +188,129 @@ VIWB_D void sym_eig_block(double *V, double *d, double *e, double *cs, double *s
 #undef VV
 }
 
+// Householder tridiagonalisation + accumulation of the transformations (the tred2 half of sym_eig_block, same outputs: V = Q, d = diagonal,
+// e[0 .. n-2] = sub-diagonal, e[n-1] = 0), organised for the block instead of statement by statement.  The first version spent 59 % of its warp samples at
+// barriers (profiles/r02m_marg_tri_kernel.ncu.txt): 15 barriers per column with one thread per row walking up to n elements while the others waited.  Here
+//   * the scale, the squared norm and d[i-1] come out of ONE three-way reduction (h = sum d^2 / scale^2 instead of a second pass over d / scale),
+//   * the product A d, the dot product e . d and the rank-2 update use T lanes per row (T = 1, 2, 4, 8 as the shrinking column count frees threads;
+//     partial sums over interleaved columns, combined by shuffles), the scratch vector e is formed on the fly in the update,
+//   * the accumulation runs T lanes per column and merges its zeroing / scaling phases: 7 + 2 barriers per column instead of 11 + 4.
+// Summation orders differ from EISPACK's at rounding level; red: 3 * 32 doubles.
+VIWB_D void tridiag_block(double *V, double *d, double *e, double *cs, double *red, int n, int ld, int tid, int nt) {
+#define VV(i, j) V[(i) * ld + (j)]
+    for (int j = tid; j < n; j += nt) d[j] = VV(n - 1, j);
+    VIWB_SYNC();
+    for (int i = n - 1; i > 0; i--) {
+        int T = 1;
+#ifndef VIWB_HOST_EMU
+        while (T < 8 && 2 * T * i <= nt) T *= 2;
+#endif
+        const int rpp = nt / T > 0 ? nt / T : 1, row0 = tid / T, p = tid % T;       // rows per pass, this thread's row within a pass and its lane in the row
+        double v3[3] = {0.0, 0.0, 0.0};
+        for (int k = tid; k < i; k += nt) { const double x = d[k]; v3[0] += fabs(x); v3[1] += x * x; if (k == i - 1) v3[2] = x; }
+        block_sum_n<3>(v3, tid, nt, red);
+        const double scale = v3[0];
+        if (scale == 0.0) {
+            if (tid == 0) e[i] = d[i - 1];
+            VIWB_SYNC();
+            for (int j = tid; j < i; j += nt) { d[j] = VV(i - 1, j); VV(i, j) = 0.0; VV(j, i) = 0.0; }
+            if (tid == 0) d[i] = 0.0;
+            VIWB_SYNC();
+            continue;
+        }
+        const double f = v3[2] / scale;
+        double g = sqrt(v3[1] / (scale * scale)); if (f > 0) g = -g;
+        const double h = v3[1] / (scale * scale) - f * g;
+        for (int k = tid; k < i; k += nt) d[k] = (k == i - 1) ? f - g : d[k] / scale;
+        if (tid == 0) e[i] = scale * g;
+        VIWB_SYNC();
+        // cs[j] = (A d)[j] / h over the leading i x i block (lower triangle storage); column i keeps the Householder vector
+        double part = 0.0;
+        for (int j0 = 0; j0 < i; j0 += rpp) {
+            const int j = j0 + row0;
+            double a = 0.0;
+            if (j < i) {
+                int k = p;
+                for (; k <= j; k += T) a += VV(j, k) * d[k];
+                for (; k < i; k += T) a += VV(k, j) * d[k];
+            }
+#ifndef VIWB_HOST_EMU
+            for (int o = 1; o < T; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+#endif
+            if (j < i && p == 0) { const double c = a / h; cs[j] = c; VV(j, i) = d[j]; part += c * d[j]; }
+        }
+        const double f2 = block_sum(part, tid, nt, red);
+        const double hh = f2 / (h + h);
+        // rank-2 update of the lower triangle with e[j] = cs[j] - hh d[j] formed on the fly: V[k][j] -= d[j] e[k] + e[j] d[k],  j <= k < i
+        for (int k0 = 0; k0 < i; k0 += rpp) {
+            const int k = k0 + row0;
+            if (k < i) {
+                // batches of four: all loads of a batch are issued before its stores (the compiler cannot move a load of d / cs across a store to V on its own)
+                const double dk = d[k], ek = cs[k] - hh * dk;
+                double *row = &VV(k, 0);
+                int j = p;
+                for (; j + 3 * T <= k; j += 4 * T) {
+                    const double v0 = row[j], v1 = row[j + T], v2 = row[j + 2 * T], v3 = row[j + 3 * T];
+                    const double d0 = d[j], d1 = d[j + T], d2 = d[j + 2 * T], d3 = d[j + 3 * T];
+                    const double c0 = cs[j], c1 = cs[j + T], c2 = cs[j + 2 * T], c3 = cs[j + 3 * T];
+                    row[j] = v0 - (d0 * ek + (c0 - hh * d0) * dk); row[j + T] = v1 - (d1 * ek + (c1 - hh * d1) * dk);
+                    row[j + 2 * T] = v2 - (d2 * ek + (c2 - hh * d2) * dk); row[j + 3 * T] = v3 - (d3 * ek + (c3 - hh * d3) * dk);
+                }
+                for (; j <= k; j += T) row[j] -= d[j] * ek + (cs[j] - hh * d[j]) * dk;
+            }
+        }
+        VIWB_SYNC();
+        for (int j = tid; j < i; j += nt) { d[j] = VV(i - 1, j); VV(i, j) = 0.0; }
+        if (tid == 0) d[i] = h;
+        VIWB_SYNC();
+    }
+    // ---- accumulate the transformations
+    for (int i = 0; i < n - 1; i++) {
+        int T = 1;
+#ifndef VIWB_HOST_EMU
+        while (T < 8 && 2 * T * (i + 1) <= nt) T *= 2;
+#endif
+        const int cpp = nt / T > 0 ? nt / T : 1, col0 = tid / T, p = tid % T;
+        const double h = d[i + 1];
+        if (i > 0) for (int k = tid; k < i; k += nt) VV(k, i) = 0.0;          // the previous column's Householder vector has done its work
+        if (tid == 0) { VV(n - 1, i) = VV(i, i); VV(i, i) = 1.0; }
+        if (h != 0.0) for (int k = tid; k <= i; k += nt) d[k] = VV(k, i + 1) / h;
+        VIWB_SYNC();
+        if (h != 0.0) {
+            for (int j0 = 0; j0 <= i; j0 += cpp) {
+                const int j = j0 + col0;
+                double a = 0.0;
+                if (j <= i) for (int k = p; k <= i; k += T) a += VV(k, i + 1) * VV(k, j);
+#ifndef VIWB_HOST_EMU
+                for (int o = 1; o < T; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+#endif
+                if (j <= i) {
+                    int k = p;
+                    for (; k + 3 * T <= i; k += 4 * T) {
+                        const double v0 = VV(k, j), v1 = VV(k + T, j), v2 = VV(k + 2 * T, j), v3 = VV(k + 3 * T, j);
+                        const double d0 = d[k], d1 = d[k + T], d2 = d[k + 2 * T], d3 = d[k + 3 * T];
+                        VV(k, j) = v0 - a * d0; VV(k + T, j) = v1 - a * d1; VV(k + 2 * T, j) = v2 - a * d2; VV(k + 3 * T, j) = v3 - a * d3;
+                    }
+                    for (; k <= i; k += T) VV(k, j) -= a * d[k];
+                }
+            }
+        }
+        VIWB_SYNC();
+    }
+    for (int k = tid; k < n - 1; k += nt) VV(k, n - 1) = 0.0;
+    VIWB_SYNC();
+    for (int j = tid; j < n; j += nt) { d[j] = VV(n - 1, j); VV(n - 1, j) = 0.0; }
+    VIWB_SYNC();
+    if (tid == 0) VV(n - 1, n - 1) = 1.0;
+    // sub-diagonal: e[i] <- e[i + 1], e[n - 1] = 0
+    for (int i = 1 + tid; i < n; i += nt) cs[i - 1] = e[i];
+    VIWB_SYNC();
+    for (int i = tid; i < n - 1; i += nt) e[i] = cs[i];
+    if (tid == 0) e[n - 1] = 0.0;
+    VIWB_SYNC();
+#undef VV
+}
+
 // Symmetric eigen-decomposition in shared memory by the parallel cyclic Jacobi method (stands in for Eigen::SelfAdjointEigenSolver,
 // marginalization_factor.cpp:282,294): every round rotates n/2 disjoint index pairs (round-robin tournament order, n - 1 rounds per
 // sweep), so the whole block works on every round -- no serial QL rotation chain.  Per round: (1) one thread per pair computes its
@@ -209,16 +324,24 @@ VIWB_HD void jacobi_pair(int m, int r, int k, int &p, int &q) {      // pair k o
     if (k == 0) { p = m - 1; q = r; }
     else { p = (r + k) % (m - 1); q = (r - k + (m - 1)) % (m - 1); }
 }
+// WARP = true: called by ONE warp (tid < 32, nt = 32) while the rest of the block waits at the caller's barrier, the 2 x 14 synchronisations of a sweep being
+// warp-level then.  Measured slower for the 15 x 15 block of marg_prep (156 items per round on 32 lanes instead of 256 threads); kept as the measured alternative.
+template <bool WARP>
 VIWB_D void sym_eig_jacobi(double *A, int lda, double *V, int ldv, double *d, double *rot, double *red, int n, int tid, int nt) {
+#define JSYNC() do { if (WARP) VIWB_SYNCWARP(); else VIWB_SYNC(); } while (0)
     for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; V[i * ldv + j] = (i == j) ? 1.0 : 0.0; }
-    VIWB_SYNC();
-    if (n == 1) { if (tid == 0) d[0] = A[0]; VIWB_SYNC(); return; }
+    JSYNC();
+    if (n == 1) { if (tid == 0) d[0] = A[0]; JSYNC(); return; }
     const int m = n + (n & 1), np = m / 2;      // an odd n gets a bye: pairs with the phantom index m - 1 do not rotate
     for (int sweep = 0; sweep < 16; sweep++) {
         // convergence test: off(A)^2 <= (1e-15)^2 * diag(A)^2
         double off = 0.0, dg = 0.0;
         for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; const double v = A[i * lda + j]; if (i == j) dg += v * v; else off += v * v; }
-        { double v2[2] = {off, dg}; block_sum_n<2>(v2, tid, nt, red); off = v2[0]; dg = v2[1]; }
+        if (WARP) {
+#ifndef VIWB_HOST_EMU
+            for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dg += __shfl_xor_sync(0xffffffffu, dg, o); }
+#endif
+        } else { double v2[2] = {off, dg}; block_sum_n<2>(v2, tid, nt, red); off = v2[0]; dg = v2[1]; }
         if (off <= 1e-28 * dg || off == 0.0) break;
         for (int r = 0; r < m - 1; r++) {
             for (int k = tid; k < np; k += nt) {
@@ -235,7 +358,7 @@ VIWB_D void sym_eig_jacobi(double *A, int lda, double *V, int ldv, double *d, do
                 }
                 rot[4 * k] = c; rot[4 * k + 1] = sn; rot[4 * k + 2] = (double)p; rot[4 * k + 3] = (double)q;
             }
-            VIWB_SYNC();
+            JSYNC();
             const int nblk = np * (np + 1) / 2, nv = n * np;
             for (int e = tid; e < nblk + nv; e += nt) {
                 if (e < nblk) {
@@ -279,11 +402,12 @@ VIWB_D void sym_eig_jacobi(double *A, int lda, double *V, int ldv, double *d, do
                     V[i * ldv + q0] = c * v0 - s * v1; V[i * ldv + q1] = s * v0 + c * v1;
                 }
             }
-            VIWB_SYNC();
+            JSYNC();
         }
     }
     for (int i = tid; i < n; i += nt) d[i] = A[i * lda + i];
-    VIWB_SYNC();
+    JSYNC();
+#undef JSYNC
 }
 
 VIWB_HD int vsub_to_mlay(int p) { return p < 66 ? p : p < 72 ? 165 + (p - 66) : p < 78 ? 171 + (p - 72) : 191; }   // td -> blk_moff(BLK_TD) = 191
@@ -361,7 +485,7 @@ VIWB_D void marg_prep_block(const BatchDev &bd, int bx, int by, int tid, int nt,
     // ---- pseudo-inverse of the dropped fixed block (marginalization_factor.cpp:282-287): 15 x 15 (or 6 x 6) parallel Jacobi
     for (int e = tid; e < md * md; e += nt) { const int i = e / md, j = e % md; Amm[e] = 0.5 * (Mc[(n + i) * N + n + j] + Mc[(n + j) * N + n + i]); }
     VIWB_SYNC();
-    sym_eig_jacobi(Amm, md, Vmm, md, ev, rot, red, md, tid, nt);      // eigenvalues -> ev, eigenvectors -> columns of Vmm
+    sym_eig_jacobi<false>(Amm, md, Vmm, md, ev, rot, red, md, tid, nt);      // eigenvalues -> ev, eigenvectors -> columns of Vmm (the whole block: one warp with warp-level synchronisation measured slower, 1.30 vs 0.90 ms per launch, r02v)
     for (int e = tid; e < md * md; e += nt) {
         const int i = e / md, j = e % md;
         double sacc = 0.0;
@@ -396,7 +520,7 @@ VIWB_D void marg_prep_block(const BatchDev &bd, int bx, int by, int tid, int nt,
 // marg_eig: eigen-decomposition of the kept n x n block in shared memory (tred2 + tql2, the algorithm family of Eigen::SelfAdjointEigenSolver),
 // J_lin = sqrt(S) V^T, r_lin = sqrt(S^-1) V^T b (marginalization_factor.cpp:289-306), in place over A / b in HBM.
 // (A parallel cyclic Jacobi was measured here: 10 sweeps x 81 rounds of 2x2 block updates cost ten times the QL chain, profiles/r02c_*.)
-VIWB_HD size_t marg_eig_smem_doubles(int nt, int nmax) { (void)nt; const int c = marg_cap(nmax); return (size_t)c * (c | 1) + (size_t)6 * c + 32 + 16 + 8; }
+VIWB_HD size_t marg_eig_smem_doubles(int nt, int nmax) { (void)nt; const int c = marg_cap(nmax); return (size_t)c * (c | 1) + (size_t)6 * c + 96 + 16 + 8; }      // V | b | cs (2) | d | e | red (3 x 32: three-way block reductions) | bc
 VIWB_D void marg_eig_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
     (void)by; (void)mode;
     const int w = bx;
@@ -447,11 +571,11 @@ VIWB_D void marg_tri_block(const BatchDev &bd, int bx, int by, int tid, int nt, 
     const int *hdr = bd.marg_hdr + (size_t)w * (3 + 2 * NB);
     if (hdr[0] == 0) return;
     const int n = hdr[1], cap = marg_cap(bd.marg_nmax), ld = n | 1;
-    double *Vn = smem, *bn = Vn + (size_t)cap * (cap | 1), *cs = bn + cap, *ev = cs + 2 * cap, *ee = ev + cap, *red = ee + cap, *bc = red + 32;
+    double *Vn = smem, *bn = Vn + (size_t)cap * (cap | 1), *cs = bn + cap, *ev = cs + 2 * cap, *ee = ev + cap, *red = ee + cap;
     double *Q = bd.marg_J + (size_t)w * bd.marg_nmax * bd.marg_nmax, *de = bd.marg_de + (size_t)w * 2 * MAXPRI;
     for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; Vn[i * ld + j] = Q[e]; }
     VIWB_SYNC();
-    sym_eig_block(Vn, ev, ee, cs, bc, red, n, ld, tid, nt, true);
+    tridiag_block(Vn, ev, ee, cs, red, n, ld, tid, nt);
     VIWB_SYNC();
     for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; Q[e] = Vn[i * ld + j]; }
     for (int i = tid; i < n; i += nt) { de[i] = ev[i]; de[MAXPRI + i] = ee[i]; }
@@ -542,7 +666,20 @@ VIWB_D void marg_apply_block(const BatchDev &bd, int bx, int by, int tid, int nt
         for (int k = tid; k < n; k += nt) {          // row k: columns mm .. l, the value of column i carried in a register to the next rotation
             double *row = Vn + k * ld;
             double hi = row[mm];                      // V(k, i + 1) for the first rotation (i = mm - 1)
-            for (int q = 0; q < cnt; q++) {
+            int q = 0;
+            // four rotations per batch: their (c, s) and the four untouched columns they read are fetched before the first store of the batch (a load of rs
+            // cannot be moved across a store to the row by the compiler), so one shared-memory latency is paid per batch instead of per rotation
+            for (; q + 3 < cnt; q += 4) {
+                const int i = mm - 1 - q;
+                const double c0 = rs[2 * q], s0 = rs[2 * q + 1], c1 = rs[2 * q + 2], s1 = rs[2 * q + 3], c2 = rs[2 * q + 4], s2 = rs[2 * q + 5], c3 = rs[2 * q + 6], s3 = rs[2 * q + 7];
+                const double l0 = row[i], l1 = row[i - 1], l2 = row[i - 2], l3 = row[i - 3];
+                const double n0 = s0 * l0 + c0 * hi; hi = c0 * l0 - s0 * hi;
+                const double n1 = s1 * l1 + c1 * hi; hi = c1 * l1 - s1 * hi;
+                const double n2 = s2 * l2 + c2 * hi; hi = c2 * l2 - s2 * hi;
+                const double n3 = s3 * l3 + c3 * hi; hi = c3 * l3 - s3 * hi;
+                row[i + 1] = n0; row[i] = n1; row[i - 1] = n2; row[i - 2] = n3;
+            }
+            for (; q < cnt; q++) {
                 const int i = mm - 1 - q;
                 const double c = rs[2 * q], s = rs[2 * q + 1], lo = row[i];
                 row[i + 1] = s * lo + c * hi;

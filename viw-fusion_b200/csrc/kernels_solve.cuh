@@ -237,9 +237,11 @@ VIWB_D bool cholesky_packed_rhs(double *L, const int *rp, const int *fst, double
 #pragma unroll
                         for (int m = 0; m < 8; m++) if (m < k) v -= x[m] * my[k * (k + 1) / 2 + m];
                         x[k] = v * my[36 + k];
-                        ri[k] = x[k];
                     }
                 }
+                // (stored after the chain: a store to the row in between would pin every later load of the diagonal block behind it)
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (k < nb && c0 + k >= fi) ri[k] = x[k];
             }
 #pragma unroll
             for (int k = 0; k < 8; k++) Pt[k * CHOL_LDP + (i - r0)] = x[k];
@@ -270,10 +272,29 @@ VIWB_D bool cholesky_packed_rhs(double *L, const int *rp, const int *fst, double
 #pragma unroll
                     for (int b2 = 0; b2 < 4; b2++) acc[a * 4 + b2] += li[a] * lk[b2];
             }
+#ifndef SOLVE_NO_BATCH_RMW
+            // all sixteen current values are fetched before the first store (four different row pointers: the compiler has to assume they alias)
+            {
+                double *rp4[4]; bool rowok[4], colok[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) { const int i = ib + a; rowok[a] = i <= n && FST(i) < r0; rp4[a] = rowok[a] ? ROW(i) : L; }
+#pragma unroll
+                for (int b2 = 0; b2 < 4; b2++) { const int k = kb + b2; colok[b2] = k < n && FST(k) < r0; }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; b2++) { const bool on = rowok[a] && colok[b2] && kb + b2 <= ib + a; acc[a * 4 + b2] = on ? rp4[a][kb + b2] - acc[a * 4 + b2] : 0.0; }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; b2++) { if (rowok[a] && colok[b2] && kb + b2 <= ib + a) rp4[a][kb + b2] = acc[a * 4 + b2]; }
+            }
+#else
 #pragma unroll
             for (int a = 0; a < 4; a++) { const int i = ib + a; if (i <= n && FST(i) < r0) { double *ri = ROW(i);
 #pragma unroll
                 for (int b2 = 0; b2 < 4; b2++) { const int k = kb + b2; if (k < n && k <= i && FST(k) < r0) ri[k] -= acc[a * 4 + b2]; } } }
+#endif
         }
         VIWB_SYNC();
     }

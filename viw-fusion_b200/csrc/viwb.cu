@@ -126,7 +126,7 @@ DEF_KERNEL(reanchor, 32)
 DEF_KERNEL2(marg_prep, 256, 2)
 DEF_KERNEL2(marg_eig, 256, 3)
 #ifndef MARG_TRI_NT
-#define MARG_TRI_NT 128
+#define MARG_TRI_NT 256
 #endif
 DEF_KERNEL2(marg_tri, MARG_TRI_NT, 3)
 DEF_KERNEL(marg_ql, 32)
