@@ -512,7 +512,8 @@ class LkBatch:
         arr = (C.c_void_p * self.F)(*[imgs.ctypes.data + f * imgs.strides[0] for f in range(self.F)])
         return arr, int(imgs.strides[1])
 
-    def upload(self, prev=None, cur=None, right=None, prev_pts=None, n_prev=None, stereo_pts=None, n_stereo=None):
+    def _marshal_upload(self, prev=None, cur=None, right=None, prev_pts=None, n_prev=None, stereo_pts=None, n_stereo=None):
+        """(C arguments, objects that must outlive the asynchronous copies) of viwb_lk_batch_upload"""
         strides = set()
         pp, s0 = self._ptrs(prev); pc, s1 = self._ptrs(cur); pr, s2 = self._ptrs(right)
         for s in (s0, s1, s2):
@@ -531,9 +532,22 @@ class LkBatch:
         def i32(a):
             return None if a is None else np.ascontiguousarray(a, np.int32)
         a0, a1, c0, c1 = f32(prev_pts), f32(stereo_pts), i32(n_prev), i32(n_stereo)
-        self._keep = (prev, cur, right, a0, a1, c0, c1, pp, pc, pr)      # host buffers must outlive the asynchronous copies
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-        self.ctx._ck(self.ctx.lib.viwb_lk_batch_upload(self.hnd, pp, pc, pr, C.c_int(stride), vp(a0), vp(c0), vp(a1), vp(c1)), "viwb_lk_batch_upload")
+        return (self.hnd, pp, pc, pr, C.c_int(stride), vp(a0), vp(c0), vp(a1), vp(c1)), (prev, cur, right, a0, a1, c0, c1, pp, pc, pr)
+
+    def upload(self, **kw):
+        args, self._keep = self._marshal_upload(**kw)      # host buffers must outlive the asynchronous copies
+        self.ctx._ck(self.ctx.lib.viwb_lk_batch_upload(*args), "viwb_lk_batch_upload")
+
+    def prepare_upload(self, **kw):
+        """upload() with the argument marshalling done once: returns a callable that only makes the C call (a camera driver hands over the same ring of
+        page-locked buffers tick after tick; building F-entry pointer arrays in Python costs more than the call)."""
+        args, keep = self._marshal_upload(**kw)
+
+        def call():
+            self._keep = keep
+            self.ctx._ck(self.ctx.lib.viwb_lk_batch_upload(*args), "viwb_lk_batch_upload")
+        return call
 
     def run(self):
         self.ctx._ck(self.ctx.lib.viwb_lk_batch_run(self.hnd), "viwb_lk_batch_run")
