@@ -54,13 +54,12 @@ VIWB_HD size_t lin_vis_lm_smem_doubles(bool wide) { return (size_t)LMB_FACTORS *
 template <bool WIDE, bool MARG>
 VIWB_D void lin_vis_lm_body(const BatchDev &bd, int bx, int tid, int nt, double *smem, bool cost_only = false) {
     typedef XL<WIDE> L;
-    const int w = bd.lmb_win[bx];
+    const LmbDesc &ds = bd.lmb_desc[bx];
+    const int w = ds.win, k0 = ds.k0, k1 = ds.k1, f0 = ds.f0, nf = ds.nf;      // window; global landmark range; its factors (consecutive, <= LMB_FACTORS)
     const WinWork &ww = bd.work[w];
     const WinMeta &m = bd.meta[w];
     if (MARG) { if (!m.mfused) return; }
     else { if (ww.status != ST_RUNNING || !m.fused || (m.has_common != 0) != WIDE) return; }
-    const int k0 = bd.lmb_ptr[2 * bx], k1 = bd.lmb_ptr[2 * bx + 1];    // global landmark range of this block
-    const int f0 = bd.lm_fptr[k0], nf = bd.lm_fptr[k1] - f0;            // its factors (consecutive, <= LMB_FACTORS)
     double *tile = smem;
     int *meta = (int *)(smem + (size_t)LMB_FACTORS * L::TS);      // landmark (window-local) << 12 | fi << 8 | fj << 4 | type << 2 | dup
     const double *x = (MARG ? bd.x_cur : bd.x_cand) + m.state_off;
@@ -104,8 +103,8 @@ VIWB_D void lin_vis_lm_body(const BatchDev &bd, int bx, int tid, int nt, double 
     // ---- 1: one thread per factor
     for (int t = tid; t < nf; t += nt) {
         const int f = f0 + t;
-        const int type = bd.vis_type[f], fi = bd.vis_fi[f], fj = bd.vis_fj[f];
-        meta[t] = (bd.vis_lm[f] << 12) | (fi << 8) | (fj << 4) | (type << 2) | bd.vis_dup[f];
+        const int code = bd.vis_code[f], type = code & 3, fi = (code >> 2) & 15, fj = (code >> 6) & 15;      // the wire format's code word: one load instead of four
+        meta[t] = (bd.vis_lm[f] << 12) | (fi << 8) | (fj << 4) | (type << 2) | ((code >> 10) & 3);
         double *row = tile + (size_t)t * L::TS;
         if (MARG && fi != 0) { row[L::U] = 0.0; row[L::U + 1] = 0.0; row[L::C] = 0.0; continue; }      // not hosted in the dropped frame: takes no part
         double obs[12];

@@ -37,6 +37,7 @@ enum { ASM_STRIDE = 108, ASM_CHUNK = 256, ITEM_FRAME = 0, ITEM_PAIR = 1, ITEM_CO
 // block and leaves one X record per two-frame factor, X = [A | B | r] (2 x 13, row stride 14), at the factor's position in FRAME-PAIR order; asm_pairs
 // turns the records of one (host, observer) pair into G = sum X^T X (13 x 13 inside three 8 x 8 FP64 tensor-core tiles) per chunk of PAIR_CHUNK records.
 enum { PAIR_CHUNK = 32, LMB_FACTORS = 128, NPAIR = NFR * (NFR - 1) / 2, PAIR_RED = NFR * 105 + NPAIR * 36 + 104 + 1 };      // PAIR_RED: the WIDE pair_reduce output (the compact one is a prefix-sized subset)
+struct alignas(32) LmbDesc { int win, k0, k1, f0, nf, pad[3]; };      // window, global landmark range [k0, k1), first factor (global) and factor count (<= LMB_FACTORS)
 struct AsmItem { int kind, win, a, b, lo, hi, phase, has_common, base; };      // base: fused path, offset (doubles) of the window's record region in xrec
 
 struct PriorDev {       // one per window that has a valid prior
@@ -109,8 +110,7 @@ struct BatchDev {       // passed by value to every kernel
     double *mpair_out;              // [nmpitems_total][640]
     const int *vis_pos;             // [nvis_total] window-local position of the factor's X record in frame-pair order, -1 for one-frame factors
     unsigned char *vis_dup;         // [nvis_total] 0: the factor alone observes its landmark from frame j; 1: first of two such factors (adds the next one's part); 2: second (adds nothing)
-    const int *lmb_ptr;             // [nlmb_total][2] global landmark range [first, end) of each landmark block
-    const int *lmb_win;             // [nlmb_total] window of the block
+    const struct LmbDesc *lmb_desc; // [nlmb_total] landmark blocks of lin_vis_lm: everything the block needs to start, in one 32-byte load
     double *xrec;                   // [nxrec_total][XREC]
     const struct AsmItem *pitems;   // [npitems_total] kind = ITEM_PAIR, lo / hi = absolute record range in xrec
     double *pair_out;               // [npitems_total][PAIR_OUT] tile (0,0), (0,1), (1,1) of G in mma.m8n8k4 accumulator order

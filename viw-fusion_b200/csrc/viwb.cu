@@ -418,7 +418,7 @@ struct HostArrays {
     AsmItem *items; int *asm_list; int *imu_fi, *imu_fj, *imu_win, *wheel_fi, *wheel_fj, *wheel_win, *plane_f, *plane_win;
     double *imu_data, *wheel_data, *prior_J, *prior_r, *prior_x0, *x_init; WinWork *work;
     int nitems_solve_total;
-    int *vis_pos; int *lmb_ptr, *lmb_win; AsmItem *pitems; int *mvis_pos; AsmItem *mpitems;
+    int *vis_pos; LmbDesc *lmb_desc; AsmItem *pitems; int *mvis_pos; AsmItem *mpitems;
     unsigned char *obs_viol;        // [B] host only: set by lower_fill when a grouped table does not share one host-side observation per landmark
 };
 static void emit_lists(const int *type, const int *fi, const int *fj, int nvis, bool only_host0, int has_common, int w, AsmItem *items, int *list) {
@@ -522,14 +522,15 @@ static void lower_fill(const viwb_problem &p, const double *state, int w, const 
             if (vt[i] == 2) continue;
             if (i > 0 && vt[i - 1] != 2 && vl[i - 1] == vl[i] && vj[i - 1] == vj[i]) { vd[i - 1] = 1; vd[i] = 2; }
         }
-        int *lp = h.lmb_ptr + 2 * (size_t)m.lmb_off, *lw = h.lmb_win + m.lmb_off;
+        LmbDesc *ld = h.lmb_desc + m.lmb_off;
         int nb = 0, in_blk = 0, i = 0; bool open = false;
         for (int k = 0; k < p.num_landmarks; k++) {
+            const int first = i;
             int cnt = 0;
             for (; i < p.num_vis && vl[i] == k; i++) cnt++;
-            if (!open || in_blk + cnt > LMB_FACTORS) { lp[2 * nb] = m.lm_off + k; lw[nb] = w; nb++; in_blk = 0; open = true; }
-            lp[2 * nb - 1] = m.lm_off + k + 1;          // the open block ends after this landmark
-            in_blk += cnt;
+            if (!open || in_blk + cnt > LMB_FACTORS) { LmbDesc &d = ld[nb++]; memset(&d, 0, sizeof d); d.win = w; d.k0 = m.lm_off + k; d.f0 = m.vis_off + first; in_blk = 0; open = true; }
+            ld[nb - 1].k1 = m.lm_off + k + 1;           // the open block ends after this landmark
+            in_blk += cnt; ld[nb - 1].nf = in_blk;
         }
     }
     { int *vc = h.vis_code + m.vis_off; for (int i = 0; i < p.num_vis; i++) vc[i] = vt[i] | (vi[i] << 2) | (vj[i] << 6) | ((int)vd[i] << 10); }
@@ -650,7 +651,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     IN(&bd.imu_fi, nimu); IN(&bd.imu_fj, nimu); IN(&bd.imu_win, nimu); IN(&bd.wheel_fi, nwheel); IN(&bd.wheel_fj, nwheel); IN(&bd.wheel_win, nwheel);
     IN(&bd.plane_f, nplane); IN(&bd.plane_win, nplane); IN(&bd.imu_data, nimu * 287); IN(&bd.wheel_data, nwheel * 78);
     IN(&bd.prior_J, npJ); IN(&bd.prior_r, npr); IN(&bd.prior_x0, npri * SFIX); IN(&bd.x_init, nstate); IN(&b->work_init_dev, B);
-    IN(&bd.vis_pos, npit ? nvis : 0); IN(&bd.lmb_ptr, 2 * nlmb); IN(&bd.lmb_win, nlmb); IN(&bd.pitems, npit);
+    IN(&bd.vis_pos, npit ? nvis : 0); IN(&bd.lmb_desc, nlmb); IN(&bd.pitems, npit);
     IN(&bd.mvis_pos, nmpit ? nvis : 0); IN(&bd.mpitems, nmpit);
     const size_t nvec = (size_t)B * TFIX + nlm;
     WK(&bd.work, B); WK(&bd.x_cur, nstate); WK(&bd.x_cand, nstate); WK(&bd.x_before, nstate);
@@ -688,7 +689,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
       HP(h.meta); HP(h.prior); HP(h.vis_code); HP(h.vis_lm); HP(h.vis_oi); HP(h.obs_i); HP(h.obs_j); HP(h.lm_win); HP(h.lm_fptr); HP(h.items); HP(h.asm_list);
       HP(h.imu_fi); HP(h.imu_fj); HP(h.imu_win); HP(h.wheel_fi); HP(h.wheel_fj); HP(h.wheel_win); HP(h.plane_f); HP(h.plane_win); HP(h.imu_data); HP(h.wheel_data);
       HP(h.prior_J); HP(h.prior_r); HP(h.prior_x0); HP(h.x_init); HP(h.work);
-      HP(h.vis_pos); HP(h.lmb_ptr); HP(h.lmb_win); HP(h.pitems); HP(h.mvis_pos); HP(h.mpitems); }
+      HP(h.vis_pos); HP(h.lmb_desc); HP(h.pitems); HP(h.mvis_pos); HP(h.mpitems); }
     h.nitems_solve_total = (int)nit_s;
     for (auto &e : ents) *e.field = ar->dev + e.off;
     if (npri) memcpy(h.prior, priors.data(), sizeof(PriorDev) * npri);
