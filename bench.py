@@ -346,6 +346,7 @@ def kernel_models(probs, pri, B, lk):
         "marg_ql": (0.0, B * 30.0 * 2.0 * nmax ** 2),                               # ~2 sweeps per eigenvalue on (d, e): a dependent chain, not a throughput kernel
         "marg_apply": (8.0 * B * (nmax * nmax + nmax), B * 6.0 * 0.8 * nmax ** 3 + B * 2.0 * nmax ** 3),      # ~0.8 n^2 logged rotations (6 flops each) on every one of the n rows + J = S V^T; calibrated on the FP64 pipe utilisation ncu reports (23 %)
         "pair_reduce": (0.0, 0.0),
+        "pair_win": (0.0, 2.0 * 2 * (21 + 21 + 36 + 12) * n_vis),                    # asm_pairs + pair_reduce in one kernel: the same products
         "lk_track": ((lk.algorithmic_bytes() if lk is not None else 0.0), 0.0),
         "lk_pyr_down": (0.0, 0.0),
     }
@@ -355,7 +356,7 @@ def kernel_models(probs, pri, B, lk):
 # which resource binds each kernel, from its ncu capture (profiles/*.ncu.txt): "latency" = dependent chains / barriers at the occupancy the
 # shared-memory or register footprint allows -- neither the byte nor the flop roof is near, both fractions are reported anyway
 BOUND_HINT = {"lk_track": "issue", "lk_pyr_down": "hbm", "lin_vis": "hbm", "lin_vis_lm": "latency", "lin_vis_lm_wide": "latency", "lm_reduce": "hbm", "asm_items": "hbm",
-              "asm_pairs": "fp64", "asm_pairs_wide": "fp64", "syrk": "fp64", "syrk_mma": "fp64", "solve": "latency", "pair_reduce": "latency",
+              "asm_pairs": "fp64", "asm_pairs_wide": "fp64", "syrk": "fp64", "syrk_mma": "fp64", "solve": "latency", "pair_reduce": "latency", "pair_win": "fp64",
               "marg": "latency", "marg_eig": "latency", "marg_prep": "latency", "marg_tri": "latency", "marg_ql": "latency", "marg_apply": "fp64", "lin_small": "latency",
               "setup": "latency", "prior_setup": "fp64", "reanchor": "latency", "lk_post": "hbm"}
 

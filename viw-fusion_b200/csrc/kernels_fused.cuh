@@ -224,17 +224,11 @@ VIWB_D void lin_vis_lm_wide_block(const BatchDev &bd, int bx, int by, int tid, i
 // ------------------------------------------------------------------------------------------------ asm_pairs
 // One warp per chunk of one frame pair's records: G = sum_f X_f^T X_f on the FP64 tensor pipe.  K index of the product = (factor, residual row): a
 // k-step of 4 = two records; lane l feeds X[k = l%4][column l/4 + 8 t] as the A and the B operand of the tiles in tile row / column t.
+// the product of ONE chunk, written to `out` (global: asm_pairs; shared: pair_win) in accumulator order
 template <bool WIDE>
-VIWB_D void asm_pairs_body(const BatchDev &bd, int bx, int tid, int nt, int mode) {
+VIWB_D void pair_chunk(const BatchDev &bd, const AsmItem &item, double *out, int lane) {
     typedef XL<WIDE> L;
-    const int Wd = nt < 32 ? nt : 32, wpb = nt / Wd, lane = tid % Wd;
-    const int it = bx * wpb + tid / Wd;
-    const bool marg = mode == MODE_MARG;
-    if (it >= (marg ? bd.nmpitems_total : bd.npitems_total)) return;
-    const AsmItem item = (marg ? bd.mpitems : bd.pitems)[it];
-    if (marg ? !WIDE : (bd.work[item.win].status != ST_RUNNING || (item.has_common != 0) != WIDE)) return;
     const double *recs = bd.xrec;                      // item.base: the window's record region (offset in doubles); item.lo / item.hi: records inside it
-    double *out = marg ? bd.mpair_out + (size_t)it * XL<true>::OUT : bd.pair_out + (size_t)it * bd.pout_stride;
 #ifdef VIWB_HOST_EMU
     (void)lane;
     double G[32][32];
@@ -269,6 +263,17 @@ VIWB_D void asm_pairs_body(const BatchDev &bd, int bx, int tid, int nt, int mode
     for (int t = 0; t < L::NTILE; t++) { double2 v; v.x = acc[t][0]; v.y = acc[t][1]; reinterpret_cast<double2 *>(out + 64 * t)[lane] = v; }
 #endif
 }
+template <bool WIDE>
+VIWB_D void asm_pairs_body(const BatchDev &bd, int bx, int tid, int nt, int mode) {
+    const int Wd = nt < 32 ? nt : 32, wpb = nt / Wd, lane = tid % Wd;
+    const int it = bx * wpb + tid / Wd;
+    const bool marg = mode == MODE_MARG;
+    if (it >= (marg ? bd.nmpitems_total : bd.npitems_total)) return;
+    const AsmItem item = (marg ? bd.mpitems : bd.pitems)[it];
+    if (marg ? !WIDE : (bd.work[item.win].status != ST_RUNNING || (item.has_common != 0) != WIDE)) return;
+    double *out = marg ? bd.mpair_out + (size_t)it * XL<true>::OUT : bd.pair_out + (size_t)it * bd.pout_stride;
+    pair_chunk<WIDE>(bd, item, out, lane);
+}
 VIWB_D void asm_pairs_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; (void)smem; asm_pairs_body<false>(bd, bx, tid, nt, mode); }
 VIWB_D void asm_pairs_wide_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) { (void)by; (void)smem; asm_pairs_body<true>(bd, bx, tid, nt, mode); }
 
@@ -279,15 +284,16 @@ VIWB_D void asm_pairs_wide_block(const BatchDev &bd, int bx, int by, int tid, in
 // output, fixed order.  Keeps the ~100 dependent L2 reads per entry out of the (latency-bound) consumer kernels.
 VIWB_HD int pair_index(int a, int b) { return a * (2 * NFR - a - 1) / 2 + (b - a - 1); }      // a < b
 template <bool WIDE>
-VIWB_D void pair_reduce_body(const BatchDev &bd, int w, int tid, int nt, int mode, int *ab) {
+VIWB_D void pair_reduce_body(const BatchDev &bd, int w, int tid, int nt, int mode, int *ab, const double *outs_in = nullptr, size_t ps_in = 0) {
     typedef XL<WIDE> L;
     const WinMeta &m = bd.meta[w];
     const bool marg = mode == MODE_MARG;
     double *red = bd.pair_red + (size_t)w * PAIR_RED;
     const AsmItem *items = marg ? bd.mpitems + m.mpitem_off : bd.pitems + m.pitem_off;
     const int npi = marg ? m.nmpitems : m.npitems;
-    const size_t PS = marg ? (size_t)XL<true>::OUT : (size_t)bd.pout_stride;
-    const double *outs = marg ? bd.mpair_out + (size_t)m.mpitem_off * PS : bd.pair_out + (size_t)m.pitem_off * PS;
+    // the chunk products: asm_pairs' global array, or (pair_win) the block's own shared memory
+    const size_t PS = outs_in ? ps_in : (marg ? (size_t)XL<true>::OUT : (size_t)bd.pout_stride);
+    const double *outs = outs_in ? outs_in : (marg ? bd.mpair_out + (size_t)m.mpitem_off * PS : bd.pair_out + (size_t)m.pitem_off * PS);
     // the items' frame pair and chunk phase, staged once: every output below walks the whole list (a | b << 4 | phase << 8)
     for (int ii = tid; ii < npi; ii += nt) { const AsmItem &it = items[ii]; ab[ii] = it.a | (it.b << 4) | (it.phase << 8); }
     VIWB_SYNC();
@@ -330,6 +336,31 @@ VIWB_D void pair_reduce_block(const BatchDev &bd, int bx, int by, int tid, int n
     if (mode == MODE_MARG) { if (m.mfused) pair_reduce_body<true>(bd, bx, tid, nt, mode, ab); return; }
     if (!m.fused || bd.work[bx].status != ST_RUNNING) return;
     if (m.has_common) pair_reduce_body<true>(bd, bx, tid, nt, mode, ab); else pair_reduce_body<false>(bd, bx, tid, nt, mode, ab);
+}
+
+// ------------------------------------------------------------------------------------------------ pair_win
+// asm_pairs + pair_reduce in one kernel, one block per window: the window's chunk products stay in shared memory (compact: 1.5 KB per chunk, wide: 5 KB)
+// instead of a 0.6 MB round trip through HBM per window and iteration; warps take the chunks round robin, then the block folds them exactly as
+// pair_reduce does.  Used when the largest window's chunks fit (bd.pwin_smem; otherwise the two-kernel path above runs).
+VIWB_HD size_t pair_win_smem_bytes(int chunks, int out_doubles) { return (size_t)chunks * out_doubles * 8 + (size_t)((chunks + 1) & ~1) * 4; }
+template <bool WIDE>
+VIWB_D void pair_win_body(const BatchDev &bd, int w, int tid, int nt, double *smem, int mode) {
+    typedef XL<WIDE> L;
+    const WinMeta &m = bd.meta[w];
+    const bool marg = mode == MODE_MARG;
+    const AsmItem *items = marg ? bd.mpitems + m.mpitem_off : bd.pitems + m.pitem_off;
+    const int npi = marg ? m.nmpitems : m.npitems;
+    const int Wd = nt < 32 ? nt : 32, nwp = nt / Wd, wid = tid / Wd, lane = tid % Wd;
+    for (int ii = wid; ii < npi; ii += nwp) pair_chunk<WIDE>(bd, items[ii], smem + (size_t)ii * L::OUT, lane);
+    VIWB_SYNC();
+    pair_reduce_body<WIDE>(bd, w, tid, nt, mode, (int *)(smem + (size_t)npi * L::OUT), smem, (size_t)L::OUT);
+}
+VIWB_D void pair_win_block(const BatchDev &bd, int bx, int by, int tid, int nt, double *smem, int mode) {
+    (void)by;
+    const WinMeta &m = bd.meta[bx];
+    if (mode == MODE_MARG) { if (m.mfused) pair_win_body<true>(bd, bx, tid, nt, smem, mode); return; }
+    if (!m.fused || bd.work[bx].status != ST_RUNNING) return;
+    if (m.has_common) pair_win_body<true>(bd, bx, tid, nt, smem, mode); else pair_win_body<false>(bd, bx, tid, nt, smem, mode);
 }
 
 // ------------------------------------------------------------------------------------------------ syrk_mma

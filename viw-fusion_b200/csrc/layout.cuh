@@ -104,6 +104,7 @@ struct BatchDev {       // passed by value to every kernel
     int n_unfused;          // windows whose solver linearisation runs lin_vis + lm_reduce + asm_items (the others: lin_vis_lm + asm_pairs, WinMeta.fused)
     int n_fused_wide, n_fused_compact, n_munfused, n_mfused;      // fused solver windows by record width; marginalising windows by path
     int nlmb_total, npitems_total, nmpitems_total, pitems_max;
+    int pwin_smem, pwin_smem_marg;      // dynamic shared memory of pair_win (solver / marginalisation mode); 0: a window's chunks do not fit, asm_pairs + pair_reduce run instead
     int pout_stride;        // doubles per solver pair item in pair_out: 192 (all fused windows compact) or 640
     const int *mvis_pos;            // [nvis_total] marginalisation: window-local record slot of the factors hosted in frame 0 (-1 otherwise)
     const struct AsmItem *mpitems;  // [nmpitems_total]

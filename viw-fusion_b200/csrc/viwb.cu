@@ -121,6 +121,7 @@ DEF_KERNEL(asm_pairs_wide, 128)
 #define PAIR_RED_NT 256
 #endif
 DEF_KERNEL(pair_reduce, PAIR_RED_NT)
+DEF_KERNEL2(pair_win, 256, 2)
 DEF_KERNEL2(syrk_mma, SYRK_NT, 4)
 DEF_KERNEL(reanchor, 32)
 DEF_KERNEL2(marg_prep, 256, 2)
@@ -144,6 +145,7 @@ static void arena_release(Arena &a) { if (a.dev) dev_free(a.dev); if (a.host) ho
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static bool g_timing = getenv("VIWB_TIMING") != nullptr;
 static bool g_marg_one_kernel = getenv("VIWB_MARG_ONE_KERNEL") != nullptr;      // measurement aid: tred2 + tql2 in one block-per-window kernel (marg_eig)
+static bool g_no_pair_win = getenv("VIWB_NO_PAIR_WIN") != nullptr;      // measurement aid: asm_pairs + pair_reduce (chunk products through HBM) instead of pair_win
 static bool g_syrk_dfma = getenv("VIWB_SYRK_DFMA") != nullptr;      // measurement aid: the 4x4 register-tiled DFMA SYRK instead of the DMMA one (profiles/: both builds of the Schur GEMM)
 struct viwb_context {
     int device;
@@ -635,6 +637,17 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     bd.rec_stride_solve = VREC_COMPACT;
     bd.n_unfused = n_unfused; bd.nlmb_total = (int)nlmb; bd.npitems_total = (int)npit; bd.nmpitems_total = (int)nmpit;
     bd.pitems_max = 1; for (int w = 0; w < B; w++) bd.pitems_max = std::max(bd.pitems_max, std::max(b->meta[w].npitems, b->meta[w].nmpitems));
+    {   // pair_win keeps a window's chunk products in shared memory: possible when the largest window fits next to a second resident block
+        size_t need_s = 0, need_m = 0;
+        for (int w = 0; w < B; w++) {
+            const WinMeta &mw = b->meta[w];
+            if (mw.fused) need_s = std::max(need_s, pair_win_smem_bytes(mw.npitems, mw.has_common ? (int)XL<true>::OUT : (int)XL<false>::OUT));
+            if (mw.mfused) need_m = std::max(need_m, pair_win_smem_bytes(mw.nmpitems, (int)XL<true>::OUT));
+        }
+        const size_t cap = 110 * 1024;
+        bd.pwin_smem = (!g_no_pair_win && need_s > 0 && need_s <= cap) ? (int)need_s : 0;
+        bd.pwin_smem_marg = (!g_no_pair_win && need_m > 0 && need_m <= cap) ? (int)need_m : 0;
+    }
     bd.n_fused_wide = n_fused_wide; bd.n_fused_compact = n_fused_compact; bd.n_mfused = n_mfused; bd.n_munfused = n_munfused;
     bd.pout_stride = n_fused_wide ? (int)XL<true>::OUT : (int)XL<false>::OUT;
     bd.marg_nmax = b->prior_nmax;
@@ -719,6 +732,7 @@ static int ensure_attrs(viwb_context *ctx) {
         CK(cudaFuncSetAttribute(lin_vis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lin_vis_smem_doubles(128, VREC) * 8)));
         CK(cudaFuncSetAttribute(lin_vis_lm_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lin_vis_lm_smem_doubles(true) * 8)));
         CK(cudaFuncSetAttribute(syrk_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(syrk_mma_smem_doubles() * 8)));
+        CK(cudaFuncSetAttribute(pair_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CK(cudaFuncSetAttribute(marg_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_prep_smem_doubles(256, 100) * 8)));
         CK(cudaFuncSetAttribute(marg_tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_eig_smem_doubles(256, 100) * 8)));
         CK(cudaFuncSetAttribute(marg_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(marg_apply_smem_doubles(128, 100) * 8)));
@@ -759,6 +773,8 @@ static int batch_execute(viwb_context *ctx, viwb_batch *b, int what) {
         } else if (bd.n_mfused > 0) { LAUNCH(lin_vis_lm_wide, bd, bd.nlmb_total, 1, NT(LMB_FACTORS), lin_vis_lm_smem_doubles(true) * 8, mode, st); ctx->launches++; }
         auto fused_asm = [&]() {
             if (nfi <= 0) return;
+            const int pw = solve ? bd.pwin_smem : bd.pwin_smem_marg;
+            if (pw > 0) { LAUNCH(pair_win, bd, B, 1, NT(256), (size_t)pw, mode, st); ctx->launches++; return; }
             if (solve && bd.n_fused_compact > 0) { LAUNCH(asm_pairs, bd, (nfi + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st); ctx->launches++; }
             if (!solve || bd.n_fused_wide > 0) { LAUNCH(asm_pairs_wide, bd, (nfi + wpb2 - 1) / wpb2, 1, NT(128), 0, mode, st); ctx->launches++; }
             LAUNCH(pair_reduce, bd, B, 1, NT(PAIR_RED_NT), (size_t)bd.pitems_max * sizeof(int), mode, st); ctx->launches++;
