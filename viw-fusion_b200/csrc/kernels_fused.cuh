@@ -341,7 +341,8 @@ VIWB_D void pair_reduce_block(const BatchDev &bd, int bx, int by, int tid, int n
 // ------------------------------------------------------------------------------------------------ pair_win
 // asm_pairs + pair_reduce in one kernel, one block per window: the window's chunk products stay in shared memory (compact: 1.5 KB per chunk, wide: 5 KB)
 // instead of a 0.6 MB round trip through HBM per window and iteration; warps take the chunks round robin, then the block folds them exactly as
-// pair_reduce does.  Used when the largest window's chunks fit (bd.pwin_smem; otherwise the two-kernel path above runs).
+// pair_reduce does.  Opt-in (VIWB_PAIR_WIN=1, and only when the largest window's chunks fit: bd.pwin_smem): with 109 KB of products per block for the
+// bench window only two blocks share an SM and the kernel measured slower than the two-kernel path it would replace (0.66 vs 0.35 ms, r02zd).
 VIWB_HD size_t pair_win_smem_bytes(int chunks, int out_doubles) { return (size_t)chunks * out_doubles * 8 + (size_t)((chunks + 1) & ~1) * 4; }
 template <bool WIDE>
 VIWB_D void pair_win_body(const BatchDev &bd, int w, int tid, int nt, double *smem, int mode) {

@@ -36,7 +36,7 @@ enum { ASM_STRIDE = 108, ASM_CHUNK = 256, ITEM_FRAME = 0, ITEM_PAIR = 1, ITEM_CO
 // Fused path (solver linearisation of batches whose windows keep ex0 / ex1 / td constant): lin_vis_lm evaluates the factors of whole landmarks per
 // block and leaves one X record per two-frame factor, X = [A | B | r] (2 x 13, row stride 14), at the factor's position in FRAME-PAIR order; asm_pairs
 // turns the records of one (host, observer) pair into G = sum X^T X (13 x 13 inside three 8 x 8 FP64 tensor-core tiles) per chunk of PAIR_CHUNK records.
-enum { PAIR_CHUNK = 32, LMB_FACTORS = 128, NPAIR = NFR * (NFR - 1) / 2, PAIR_RED = NFR * 105 + NPAIR * 36 + 104 + 1 };      // PAIR_RED: the WIDE pair_reduce output (the compact one is a prefix-sized subset)
+enum { PAIR_CHUNK = 64, LMB_FACTORS = 128, NPAIR = NFR * (NFR - 1) / 2, PAIR_RED = NFR * 105 + NPAIR * 36 + 104 + 1 };      // PAIR_RED: the WIDE pair_reduce output (the compact one is a prefix-sized subset)
 struct alignas(32) LmbDesc { int win, k0, k1, f0, nf, pad[3]; };      // window, global landmark range [k0, k1), first factor (global) and factor count (<= LMB_FACTORS)
 struct AsmItem { int kind, win, a, b, lo, hi, phase, has_common, base; };      // base: fused path, offset (doubles) of the window's record region in xrec
 

@@ -145,7 +145,7 @@ static void arena_release(Arena &a) { if (a.dev) dev_free(a.dev); if (a.host) ho
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static bool g_timing = getenv("VIWB_TIMING") != nullptr;
 static bool g_marg_one_kernel = getenv("VIWB_MARG_ONE_KERNEL") != nullptr;      // measurement aid: tred2 + tql2 in one block-per-window kernel (marg_eig)
-static bool g_no_pair_win = getenv("VIWB_NO_PAIR_WIN") != nullptr;      // measurement aid: asm_pairs + pair_reduce (chunk products through HBM) instead of pair_win
+static bool g_no_pair_win = getenv("VIWB_PAIR_WIN") == nullptr;      // pair_win (chunk products in shared memory, one block per window) is opt-in: at the bench window's 109 KB per block it measured 0.66 ms against 0.21 + 0.14 for asm_pairs + pair_reduce (profiles/r02zd_probe.txt)
 static bool g_syrk_dfma = getenv("VIWB_SYRK_DFMA") != nullptr;      // measurement aid: the 4x4 register-tiled DFMA SYRK instead of the DMMA one (profiles/: both builds of the Schur GEMM)
 struct viwb_context {
     int device;
