@@ -586,6 +586,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     std::vector<WinLow> low(B);
     // ---- phase 1 (parallel): sizes and plans
     parallel_for(B, [&](int w) { lower_count(problems[w], margin_flags ? margin_flags[w] : -1, b->meta[w], low[w], b->out_mode[w]); });
+    const double t_counted = now_ms();
     if (obs_per_factor) for (int w = 0; w < B; w++) { low[w].obs_per_factor = true; low[w].nobs_i = problems[w].num_vis < 0 ? 0 : problems[w].num_vis; }
     for (int w = 0; w < B; w++) if (low[w].err) { const int e = low[w].err; batch_free(ctx, b); return fail(ctx, VIWB_ERR_INVALID, e == 1 ? "bad frame_count / num_landmarks" : e == 2 ? "bad prior" : e == 3 ? "bad visual factor table" : e == 5 ? "negative factor count or missing table" : "bad factor frame index"); }
     // fused solver linearisation (kernels_fused.cuh) when every window qualifies; then the solver's gather lists are not built at all
@@ -720,7 +721,7 @@ static int batch_build(viwb_context *ctx, int B, const viwb_problem *problems, c
     if (nvis) { LAUNCH(vis_expand, bd, B, 1, NT(128), 0, 0, ctx->stream); ctx->launches++; }      // code words + split observations -> the tables the kernels read
     // (no wait here: the kernels of the run are queued behind the upload on the same stream, the results are staged in their own region of the slab, and the
     //  slab is next written by the host only after a fetch has synchronised)
-    if (g_timing) fprintf(stderr, "[viwb] build B=%d: plan+slabs %.2f ms, fill %.2f ms (%.1f MB), h2d %.2f ms\n", B, t_alloc - t_start, t_filled - t_alloc, in_bytes / 1e6, now_ms() - t_filled);
+    if (g_timing) fprintf(stderr, "[viwb] build B=%d: plan+slabs %.2f ms (count %.2f), fill %.2f ms (%.1f MB), h2d %.2f ms\n", B, t_alloc - t_start, t_counted - t_start, t_filled - t_alloc, in_bytes / 1e6, now_ms() - t_filled);
     *out = b;
     return 0;
 }
