@@ -264,7 +264,7 @@ static Estimator *make_estimator(const viwb_problem *p, const double *st, int ma
 // state_out: the window after double2vector() and another vector2double() (the convention of vo_optimization / viwb_optimization);
 // mn = {m, n, kept blocks}; block ids after the address shift; J / r = the new prior; record[11] as documented at Playback.
 static int estimator_optimization(const viwb_problem *p, const double *state_in, const double *state_solved, int (*cb)(const viwb_problem *, double *), int margin_flag,
-                                  double *state_out, int32_t *mn, int32_t *block_id, int32_t *block_idx, double *J, double *r, int32_t *record);
+                                  double *state_out, int32_t *mn, int32_t *block_id, int32_t *block_idx, double *J, double *r, int32_t *record, double *prior_eval = nullptr);
 extern "C" int ref_estimator_optimization(const viwb_problem *p, const double *state_in, const double *state_solved, int margin_flag, double *state_out,
                                           int32_t *mn, int32_t *block_id, int32_t *block_idx, double *J, double *r, int32_t *record) {
     return estimator_optimization(p, state_in, state_solved, nullptr, margin_flag, state_out, mn, block_id, block_idx, J, r, record);
@@ -274,8 +274,15 @@ extern "C" int ref_estimator_optimization_with(const viwb_problem *p, const doub
                                                int32_t *mn, int32_t *block_id, int32_t *block_idx, double *J, double *r, int32_t *record) {
     return estimator_optimization(p, state_in, nullptr, cb, margin_flag, state_out, mn, block_id, block_idx, J, r, record);
 }
+// prior_eval (optional, 3 doubles): MarginalizationFactor::Evaluate (marginalization_factor.cpp:349-397 -- or whatever translation unit defines it in this
+// build) of the NEW prior at a perturbed copy of its blocks: {|res|^2, sum over blocks |J_b^T res|^2, number of residuals}.  Both numbers are invariant
+// under the orthogonal freedom of the square-root factorisation, so builds with different eigen-decompositions can be compared.
+extern "C" int ref_estimator_optimization_prior_eval(const viwb_problem *p, const double *state_in, int margin_flag, double *state_out,
+                                                     int32_t *mn, int32_t *block_id, int32_t *block_idx, double *J, double *r, int32_t *record, double *prior_eval) {
+    return estimator_optimization(p, state_in, nullptr, nullptr, margin_flag, state_out, mn, block_id, block_idx, J, r, record, prior_eval);
+}
 static int estimator_optimization(const viwb_problem *p, const double *state_in, const double *state_solved, int (*cb)(const viwb_problem *, double *), int margin_flag,
-                                  double *state_out, int32_t *mn, int32_t *block_id, int32_t *block_idx, double *J, double *r, int32_t *record) {
+                                  double *state_out, int32_t *mn, int32_t *block_id, int32_t *block_idx, double *J, double *r, int32_t *record, double *prior_eval) {
     if (p->frame_count != 10) return 2;
     Estimator *e = make_estimator(p, state_in, margin_flag);
     if (!e) return 3;
@@ -297,6 +304,24 @@ static int estimator_optimization(const viwb_problem *p, const double *state_in,
         mn[0] = info->m; mn[1] = info->n; mn[2] = (int)e->last_marginalization_parameter_blocks.size();
         for (int k = 0; k < mn[2]; k++) { block_id[k] = block_of(e, e->last_marginalization_parameter_blocks[k]); block_idx[k] = info->keep_block_idx[k] - info->m; }
         for (int i = 0; i < info->n; i++) { r[i] = info->linearized_residuals(i); for (int j = 0; j < info->n; j++) J[(size_t)i * info->n + j] = info->linearized_jacobians(i, j); }
+        if (prior_eval) {
+            MarginalizationFactor factor(info);
+            const int nb = (int)e->last_marginalization_parameter_blocks.size();
+            std::vector<std::vector<double>> xs(nb), jac(nb);
+            std::vector<const double *> params(nb); std::vector<double *> jp(nb);
+            std::vector<double> res(info->n, 0.0);
+            for (int k = 0; k < nb; k++) {
+                const int size = info->keep_block_size[k];
+                xs[k].assign(e->last_marginalization_parameter_blocks[k], e->last_marginalization_parameter_blocks[k] + size);
+                const int bid = block_of(e, e->last_marginalization_parameter_blocks[k]);                 // the block's identity, not its place in this build's list
+                for (int c = 0; c < size && c < 3; c++) xs[k][c] += 1e-3 * (1 + ((bid + c) % 3));        // a fixed, build-independent perturbation (positions / scalars only: unit quaternions stay unit)
+                jac[k].assign((size_t)info->n * size, 0.0); params[k] = xs[k].data(); jp[k] = jac[k].data();
+            }
+            prior_eval[0] = prior_eval[1] = 0.0; prior_eval[2] = info->n;
+            if (!factor.Evaluate(params.data(), res.data(), jp.data())) return 7;
+            for (int i = 0; i < info->n; i++) prior_eval[0] += res[i] * res[i];
+            for (int k = 0; k < nb; k++) { const int size = info->keep_block_size[k]; for (int c = 0; c < size; c++) { double g = 0.0; for (int i = 0; i < info->n; i++) g += jac[k][(size_t)i * size + c] * res[i]; prior_eval[1] += g * g; } }
+        }
     }
     return 0;
 }

@@ -261,6 +261,20 @@ def estimator_optimization_on_product_shim(under_test_path, problem, state, flag
     return {"state": out, "m": mn[0], "n": n, "blocks": [(bid[k], bidx[k]) for k in range(mn[2])], "J": J[: n * n].reshape(n, n).copy(), "r": r[:n].copy()}
 
 
+def prior_factor_digest_on_product_shim(under_test_path, problem, state, flag, dev=False):
+    """As estimator_optimization_on_product_shim, followed by MarginalizationFactor::Evaluate of the NEW prior at a perturbed copy of its blocks:
+    (|res|^2, sum_b |J_b^T res|^2, n) -- the reference's own Evaluate (dev=False) or the device translation unit's (dev=True)."""
+    st = np.ascontiguousarray(state, np.float64)
+    out = np.zeros_like(st)
+    cap = 256
+    mn, bid, bidx, rec = (C.c_int32 * 3)(), (C.c_int32 * 32)(), (C.c_int32 * 32)(), (C.c_int32 * 11)()
+    J, r, dig = np.zeros(cap * cap), np.zeros(cap), np.zeros(3)
+    rc = product_lib(under_test_path, dev).ref_estimator_optimization_prior_eval(C.byref(problem.c), _dp(st), C.c_int(flag), _dp(out), mn, bid, bidx, _dp(J), _dp(r), rec, _dp(dig))
+    if rc:
+        raise RuntimeError("ref_estimator_optimization_prior_eval rc=%d" % rc)
+    return dig
+
+
 # ---- the reference's FeatureTracker (featureTracker/feature_tracker.cpp, compiled unmodified) with its OpenCV calls answered by the real cv2
 _LK = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_ubyte),
                   C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int)

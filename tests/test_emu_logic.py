@@ -174,3 +174,18 @@ def test_reference_estimator_on_product_shim_with_device_marginalization(emu, re
     from emu import build_emu
     pc.check_reference_estimator_on_product_shim(emu, build_emu.build(), cid, dev=True)
 
+
+@pytest.mark.parametrize("cid", [2, 4, 6])
+def test_device_marginalization_prior_factor_evaluate(emu, reference_code, cid):
+    """MarginalizationFactor::Evaluate of the device translation unit (viwb_prior_evaluate underneath) against the reference's own Evaluate
+    (marginalization_factor.cpp:349-397) on the prior each route has just produced, at the same perturbed blocks: |res|^2 and sum_b |J_b^T res|^2
+    (both invariant under the orthogonal freedom of the square-root factorisation) agree"""
+    import viw_ref
+    from emu import build_emu
+    from viwb import abi, synth
+    path = build_emu.build()
+    prob, st, gt = synth.make_window(cid, 0)
+    a = viw_ref.prior_factor_digest_on_product_shim(path, prob, st, abi.MARGIN_OLD, False)
+    b = viw_ref.prior_factor_digest_on_product_shim(path, prob, st, abi.MARGIN_OLD, True)
+    assert a[2] == b[2] and a[2] > 0
+    assert abs(a[0] - b[0]) <= 1e-6 * a[0] and abs(a[1] - b[1]) <= 1e-6 * a[1], (a, b)
